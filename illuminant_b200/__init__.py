@@ -1,0 +1,13 @@
+"""illuminant_b200 -- B200-native (sm_100a) implementation of sq/Illuminant's two data-parallel hot paths:
+the LightingRenderer SDF cone-trace and the ParticleEngine update chain, behind the C-ABI of
+include/illuminant_b200.h.  This package is the host-side mirror of the reference API for those paths."""
+from ._abi import (Context, IlluminantError, EXPORTED_SYMBOLS, LIB_PATH, load_library,
+                   FORMAT_FLOAT4, FORMAT_HALF4, FORMAT_RGBA8)
+from .distance_field import DistanceField, LightObstruction, LightObstructionType, RendererQualitySettings
+from .lighting import (DirectionalLightSource, LightingEnvironment, LightingRenderer, LightProbe, LightSourceRampMode,
+                       LineLightSource, RendererConfiguration, ShadowFilter, SphereLightSource, encode_gbuffer)
+from .particles import (FMA, AreaType, Attractor, AttractorType, Bezier4V, BezierF, Formula, FormulaType, Gravity, MatrixMultiply,
+                        Noise, ParticleCollision, ParticleEngine, ParticleEngineConfiguration, ParticleSystem,
+                        ParticleSystemConfiguration, Spawner, TransformArea)
+
+__version__ = "0.1.0"

@@ -1,0 +1,61 @@
+"""Builds libilluminant_b200.so (sm_100a only) in-tree with nvcc.
+
+`python -m illuminant_b200.build` or `illuminant_b200.build.build()`; invoked by `__graft_entry__.build()`.
+The product has no CPU fallback: if nvcc is missing the build fails loudly.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB = PKG / "libilluminant_b200.so"
+SOURCES = ["api.cu", "lighting.cu", "particles.cu", "dfgen.cu"]
+HEADERS = ["ilb_device.cuh", "ilb_internal.h", "ilb_shapes.cuh", "../../include/illuminant_b200.h"]
+
+# -fmad=false: every fp32 multiply/add rounds separately, in source order (see DESIGN.md "Numerics").
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
+    "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-O2",
+    "-cudart", "static",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found: libilluminant_b200.so cannot be built (there is no CPU fallback)")
+
+
+def _stale() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = [CSRC / s for s in SOURCES] + [(CSRC / h).resolve() for h in HEADERS] + [Path(__file__)]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not _stale():
+        return LIB
+    cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", "/usr/bin/g++", "-o", str(LIB), *[str(CSRC / s) for s in SOURCES]]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd), file=sys.stderr)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout + res.stderr, file=sys.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(LIB)

@@ -1,0 +1,394 @@
+// C-ABI entry points of libilluminant_b200.so (include/illuminant_b200.h): argument validation, device-memory
+// ownership and stream plumbing.  The kernels live in lighting.cu / particles.cu / dfgen.cu.
+#include <cstring>
+#include <mutex>
+
+#include "ilb_internal.h"
+
+size_t ilb_format_bytes(int format);
+
+namespace {
+std::mutex g_error_mutex;
+std::string g_create_error;
+}  // namespace
+
+int ilb_fail(ilb_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->last_error = buf;
+    else {
+        std::lock_guard<std::mutex> lock(g_error_mutex);
+        g_create_error = buf;
+    }
+    return code;
+}
+
+int ilb_cuda_fail(ilb_ctx* ctx, cudaError_t e, const char* what) {
+    const int code = (e == cudaErrorMemoryAllocation) ? ILB_ERR_OUT_OF_MEMORY : ILB_ERR_CUDA;
+    return ilb_fail(ctx, code, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+int ilb_reserve(ilb_ctx* ctx, void** ptr, size_t* capacity, size_t bytes, bool pinned_host) {
+    if (*capacity >= bytes && *ptr) return ILB_OK;
+    if (*ptr) {
+        ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (pinned_host) cudaFreeHost(*ptr); else cudaFree(*ptr);
+        *ptr = nullptr;
+        *capacity = 0;
+    }
+    const size_t want = bytes + bytes / 2;
+    if (pinned_host) ILB_CUDA(ctx, cudaMallocHost(ptr, want));
+    else ILB_CUDA(ctx, cudaMalloc(ptr, want));
+    *capacity = want;
+    return ILB_OK;
+}
+
+bool ilb_make_df_geometry(const ilb_df* df, const ilb_df_uniforms& u, DFGeometry* g) {
+    memset(g, 0, sizeof(*g));
+    if (!df || !(u.Extent.x > 0.0f)) return false;
+    g->tex = df->tex;
+    g->tw = df->tw; g->th = df->th;
+    g->twf = (float)df->tw; g->thf = (float)df->th;
+    g->inv_tw = 1.0f / (float)df->tw;
+    g->zOffset = u.ConeAndMisc.y;
+    g->ex = u.Extent.x; g->ey = u.Extent.y; g->ez = u.Extent.z; g->maxEnc = u.Extent.w;
+    g->maxValidZ = u.Packed1.z; g->zToSlice = u.Packed1.y; g->invSliceCountXTimesOneThird = u.Packed1.x;
+    g->sliceSizeX = u.TextureSliceAndTexelSize.x; g->sliceSizeY = u.TextureSliceAndTexelSize.y;
+    g->texelSizeX = u.TextureSliceAndTexelSize.z; g->texelSizeY = u.TextureSliceAndTexelSize.w;
+    g->invScaleX = u.ConeAndMisc.w; g->invScaleY = u.StepAndMisc2.w;
+    g->sliceCount = u.TextureSliceCount.w;
+    return true;
+}
+
+extern "C" {
+
+int ilb_abi_version(void) { return ILB_ABI_VERSION; }
+
+int ilb_create(int device_ordinal, ilb_ctx** out_ctx) {
+    if (!out_ctx) return ilb_fail(nullptr, ILB_ERR_INVALID_ARGUMENT, "out_ctx is null");
+    *out_ctx = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return ilb_fail(nullptr, ILB_ERR_NO_DEVICE, "no CUDA device (%s); illuminant_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device_ordinal < 0 || device_ordinal >= count)
+        return ilb_fail(nullptr, ILB_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device_ordinal, count);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device_ordinal);
+    if (e != cudaSuccess) return ilb_cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return ilb_fail(nullptr, ILB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device_ordinal, prop.major, prop.minor);
+    e = cudaSetDevice(device_ordinal);
+    if (e != cudaSuccess) return ilb_cuda_fail(nullptr, e, "cudaSetDevice");
+    ilb_ctx* ctx = new ilb_ctx();
+    ctx->device = device_ordinal;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return ilb_cuda_fail(nullptr, e, "cudaStreamCreate");
+    }
+    *out_ctx = ctx;
+    return ILB_OK;
+}
+
+void ilb_destroy(ilb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->gbuffer && ctx->gbuffer_owned) cudaFree(ctx->gbuffer);
+    if (ctx->d_lights) cudaFree(ctx->d_lights);
+    if (ctx->h_lights) cudaFreeHost(ctx->h_lights);
+    if (ctx->d_lightmap) cudaFree(ctx->d_lightmap);
+    if (ctx->d_probe_in) cudaFree(ctx->d_probe_in);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* ilb_last_error(const ilb_ctx* ctx) {
+    if (ctx) return ctx->last_error.c_str();
+    std::lock_guard<std::mutex> lock(g_error_mutex);
+    static thread_local std::string copy;
+    copy = g_create_error;
+    return copy.c_str();
+}
+
+int ilb_synchronize(ilb_ctx* ctx) {
+    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ILB_OK;
+}
+
+void* ilb_stream(ilb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t ilb_launch_count(const ilb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------- distance field
+static int df_alloc(ilb_ctx* ctx, int tw, int th, size_t bytes, bool check_bytes, ilb_df** out_df) {
+    if (!ctx || !out_df) return ILB_ERR_INVALID_ARGUMENT;
+    *out_df = nullptr;
+    if (tw <= 0 || th <= 0 || tw > 8192 || th > 8192)  // DistanceField.MaxSurfaceSize, SDF/DistanceField.cs:19
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "atlas %dx%d outside (0,8192]", tw, th);
+    const size_t need = (size_t)8 * tw * th;
+    if (check_bytes && bytes != need)  // DistanceField.Load "Truncated file", SDF/DistanceField.cs:200-203
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "atlas needs %zu bytes, got %zu", need, bytes);
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ilb_df* df = new ilb_df();
+    df->ctx = ctx; df->tw = tw; df->th = th;
+    cudaError_t e = cudaMalloc(&df->tex, need);
+    if (e != cudaSuccess) {
+        delete df;
+        return ilb_cuda_fail(ctx, e, "cudaMalloc(distance field)");
+    }
+    *out_df = df;
+    return ILB_OK;
+}
+
+int ilb_df_create(ilb_ctx* ctx, int tw, int th, const uint16_t* rgba64, size_t bytes, ilb_df** out_df) {
+    if (!rgba64) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "rgba64 is null");
+    int rc = df_alloc(ctx, tw, th, bytes, true, out_df);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync((*out_df)->tex, rgba64, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        ilb_df_destroy(*out_df);
+        *out_df = nullptr;
+        return ilb_cuda_fail(ctx, e, "upload distance field");
+    }
+    return ILB_OK;
+}
+
+int ilb_df_create_device(ilb_ctx* ctx, int tw, int th, const void* d_rgba64, size_t bytes, ilb_df** out_df) {
+    if (!d_rgba64) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "d_rgba64 is null");
+    int rc = df_alloc(ctx, tw, th, bytes, true, out_df);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync((*out_df)->tex, d_rgba64, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        ilb_df_destroy(*out_df);
+        *out_df = nullptr;
+        return ilb_cuda_fail(ctx, e, "copy distance field");
+    }
+    return ILB_OK;
+}
+
+int ilb_df_generate(ilb_ctx* ctx, int tw, int th, int slice_w, int slice_h, int slice_count, const ilb_df_uniforms* u,
+                    const ilb_obstruction* obstructions, int count, ilb_df** out_df) {
+    if (!u || count < 0 || (count > 0 && !obstructions)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = df_alloc(ctx, tw, th, 0, false, out_df);
+    if (rc) return rc;
+    rc = ilb_dfgen_launch(ctx, (*out_df)->tex, tw, th, slice_w, slice_h, slice_count, u, obstructions, count);
+    if (rc) {
+        ilb_df_destroy(*out_df);
+        *out_df = nullptr;
+    }
+    return rc;
+}
+
+int ilb_df_download(ilb_df* df, uint16_t* rgba64, size_t bytes) {
+    if (!df || !rgba64) return ILB_ERR_INVALID_ARGUMENT;
+    ilb_ctx* ctx = df->ctx;
+    const size_t need = (size_t)8 * df->tw * df->th;
+    if (bytes != need) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "atlas needs %zu bytes, got %zu", need, bytes);
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ILB_CUDA(ctx, cudaMemcpyAsync(rgba64, df->tex, need, cudaMemcpyDeviceToHost, ctx->stream));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ILB_OK;
+}
+
+void ilb_df_destroy(ilb_df* df) {
+    if (!df) return;
+    cudaSetDevice(df->ctx->device);
+    cudaStreamSynchronize(df->ctx->stream);
+    if (df->tex) cudaFree(df->tex);
+    delete df;
+}
+
+// ---------------------------------------------------------------------------------------------- G-buffer
+static int gbuffer_set(ilb_ctx* ctx, int w, int h, int fmt, const void* data, bool device) {
+    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!data) {  // G-buffer disabled (Configuration.EnableGBuffer == false)
+        ctx->gb_w = ctx->gb_h = 0;
+        if (ctx->gbuffer && ctx->gbuffer_owned) {
+            ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->gbuffer);
+        }
+        ctx->gbuffer = nullptr;
+        ctx->gbuffer_capacity = 0;
+        return ILB_OK;
+    }
+    if (w <= 0 || h <= 0) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad G-buffer size %dx%d", w, h);
+    if (fmt != ILB_FORMAT_FLOAT4 && fmt != ILB_FORMAT_HALF4)  // GBuffer.cs:31-39
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "G-buffer format must be FLOAT4 or HALF4");
+    const size_t bytes = ilb_format_bytes(fmt) * (size_t)w * (size_t)h;
+    if (!ctx->gbuffer_owned) { ctx->gbuffer = nullptr; ctx->gbuffer_capacity = 0; }
+    int rc = ilb_reserve(ctx, &ctx->gbuffer, &ctx->gbuffer_capacity, bytes, false);
+    if (rc) return rc;
+    ctx->gbuffer_owned = true;
+    ILB_CUDA(ctx, cudaMemcpyAsync(ctx->gbuffer, data, bytes, device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    if (!device) ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // caller-owned pageable memory
+    ctx->gb_w = w; ctx->gb_h = h; ctx->gb_fmt = fmt;
+    return ILB_OK;
+}
+
+int ilb_gbuffer_upload(ilb_ctx* ctx, int w, int h, int fmt, const void* data) { return gbuffer_set(ctx, w, h, fmt, data, false); }
+int ilb_gbuffer_upload_device(ilb_ctx* ctx, int w, int h, int fmt, const void* d) { return gbuffer_set(ctx, w, h, fmt, d, true); }
+
+// ---------------------------------------------------------------------------------------------- lighting
+int ilb_render_lighting_device(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches,
+                               int batch_count, const ilb_light_vertex* vertices, int vertex_count, void* d_lightmap_out) {
+    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    void* outs[1] = {d_lightmap_out};
+    return ilb_lighting_launch(ctx, df, frame, batches, batch_count, vertices, vertex_count, outs, 1, false);
+}
+
+int ilb_render_lighting_peers(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches,
+                              int batch_count, const ilb_light_vertex* vertices, int vertex_count, void* const* d_peer_lightmaps,
+                              int peer_count) {
+    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!d_peer_lightmaps) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "d_peer_lightmaps is null");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ilb_lighting_launch(ctx, df, frame, batches, batch_count, vertices, vertex_count, d_peer_lightmaps, peer_count, true);
+}
+
+int ilb_render_lighting(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches, int batch_count,
+                        const ilb_light_vertex* vertices, int vertex_count, void* lightmap_out) {
+    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!frame || !lightmap_out) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (frame->width <= 0 || frame->row_end < frame->row_begin) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad frame geometry");
+    const size_t bytes = ilb_format_bytes(frame->lightmap_format) * (size_t)frame->width * (size_t)(frame->row_end - frame->row_begin);
+    int rc = ilb_reserve(ctx, &ctx->d_lightmap, &ctx->d_lightmap_capacity, std::max<size_t>(bytes, 16), false);
+    if (rc) return rc;
+    void* outs[1] = {ctx->d_lightmap};
+    rc = ilb_lighting_launch(ctx, df, frame, batches, batch_count, vertices, vertex_count, outs, 1, false);
+    if (rc) return rc;
+    ILB_CUDA(ctx, cudaMemcpyAsync(lightmap_out, ctx->d_lightmap, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ILB_OK;
+}
+
+int ilb_update_light_probes(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches, int batch_count,
+                            const ilb_light_vertex* vertices, int vertex_count, const ilb_float4* probe_positions,
+                            const ilb_float4* probe_normals, int probe_count, int output_format, void* probes_out) {
+    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ilb_probes_launch(ctx, df, frame, batches, batch_count, vertices, vertex_count, probe_positions, probe_normals, probe_count,
+                             output_format, probes_out);
+}
+
+// ---------------------------------------------------------------------------------------------- particles
+int ilb_particles_create(ilb_ctx* ctx, int chunk_size, int max_chunks, ilb_psys** out_psys) {
+    if (!ctx || !out_psys) return ILB_ERR_INVALID_ARGUMENT;
+    *out_psys = nullptr;
+    if (chunk_size < 16 || chunk_size > 4096 || max_chunks < 1)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "chunk_size %d / max_chunks %d out of range", chunk_size, max_chunks);
+    const size_t per = (size_t)chunk_size * chunk_size, total = per * (size_t)max_chunks;
+    if (total >= (size_t)1 << 31) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "more than 2^31 particles in one system");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ilb_psys* ps = new ilb_psys();
+    ps->ctx = ctx; ps->chunk_size = chunk_size; ps->max_chunks = max_chunks; ps->per_chunk = per;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 5 && e == cudaSuccess; i++) {
+        e = cudaMalloc(&ps->buf[i], sizeof(float4) * total);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ps->buf[i], 0, sizeof(float4) * total, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&ps->d_count, sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        ilb_particles_destroy(ps);
+        return ilb_cuda_fail(ctx, e, "allocate particle storage");
+    }
+    *out_psys = ps;
+    return ILB_OK;
+}
+
+void ilb_particles_destroy(ilb_psys* ps) {
+    if (!ps) return;
+    cudaSetDevice(ps->ctx->device);
+    cudaStreamSynchronize(ps->ctx->stream);
+    for (int i = 0; i < 5; i++)
+        if (ps->buf[i]) cudaFree(ps->buf[i]);
+    if (ps->rng) cudaFree(ps->rng);
+    if (ps->d_count) cudaFree(ps->d_count);
+    delete ps;
+}
+
+int ilb_particles_set_randomness(ilb_psys* ps, const ilb_float4* table, int w, int h) {
+    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    ilb_ctx* ctx = ps->ctx;
+    if (!table || w <= 0 || h <= 0) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad randomness table");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ps->rng) cudaFree(ps->rng);
+    ps->rng = nullptr;
+    const size_t bytes = sizeof(float4) * (size_t)w * (size_t)h;
+    ILB_CUDA(ctx, cudaMalloc(&ps->rng, bytes));
+    ILB_CUDA(ctx, cudaMemcpyAsync(ps->rng, table, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ps->rng_w = w; ps->rng_h = h;
+    return ILB_OK;
+}
+
+int ilb_particles_set_collision_field(ilb_psys* ps, ilb_df* df) {
+    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    if (df && df->ctx != ps->ctx) return ilb_fail(ps->ctx, ILB_ERR_INVALID_ARGUMENT, "distance field belongs to another context");
+    ps->field = df;
+    return ILB_OK;
+}
+
+int ilb_particles_set_live_chunks(ilb_psys* ps, int count) {
+    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    if (count < 0 || count > ps->max_chunks) return ilb_fail(ps->ctx, ILB_ERR_INVALID_ARGUMENT, "live chunk count %d outside [0,%d]", count, ps->max_chunks);
+    ps->live_chunks = count;
+    return ILB_OK;
+}
+
+int ilb_particles_upload_chunk(ilb_psys* ps, int chunk, const ilb_float4* p, const ilb_float4* v, const ilb_float4* a) {
+    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    ilb_ctx* ctx = ps->ctx;
+    if (chunk < 0 || chunk >= ps->max_chunks) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "chunk %d outside [0,%d)", chunk, ps->max_chunks);
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = sizeof(float4) * ps->per_chunk, off = ps->per_chunk * (size_t)chunk;
+    const ilb_float4* src[3] = {p, v, a};
+    for (int i = 0; i < 3; i++)
+        if (src[i]) ILB_CUDA(ctx, cudaMemcpyAsync(ps->buf[i] + off, src[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ILB_OK;
+}
+
+int ilb_particles_download_chunk(ilb_psys* ps, int chunk, ilb_float4* p, ilb_float4* v, ilb_float4* a, ilb_float4* rc, ilb_float4* rd) {
+    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    ilb_ctx* ctx = ps->ctx;
+    if (chunk < 0 || chunk >= ps->max_chunks) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "chunk %d outside [0,%d)", chunk, ps->max_chunks);
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = sizeof(float4) * ps->per_chunk, off = ps->per_chunk * (size_t)chunk;
+    ilb_float4* dst[5] = {p, v, a, rc, rd};
+    for (int i = 0; i < 5; i++)
+        if (dst[i]) ILB_CUDA(ctx, cudaMemcpyAsync(dst[i], ps->buf[i] + off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ILB_OK;
+}
+
+int ilb_particles_step(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spawn* spawns, int spawn_count, const ilb_op* ops,
+                       int op_count, int steps) {
+    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    ILB_CUDA(ps->ctx, cudaSetDevice(ps->ctx->device));
+    return ilb_particles_launch(ps, u, spawns, spawn_count, ops, op_count, steps);
+}
+
+void* ilb_particles_device_buffer(ilb_psys* ps, int which) {
+    if (!ps || which < 0 || which > 4) return nullptr;
+    return ps->buf[which];
+}
+
+int ilb_particles_count_live(ilb_psys* ps, int64_t* out_count) {
+    if (!ps || !out_count) return ILB_ERR_INVALID_ARGUMENT;
+    ILB_CUDA(ps->ctx, cudaSetDevice(ps->ctx->device));
+    return ilb_particles_count_launch(ps, out_count);
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// Host-side internals shared by the translation units of libilluminant_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/illuminant_b200.h"
+#include "ilb_device.cuh"
+
+struct ilb_ctx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    uint64_t launches = 0;
+    // G-buffer (L4)
+    void* gbuffer = nullptr;
+    bool gbuffer_owned = false;
+    size_t gbuffer_capacity = 0;
+    int gb_w = 0, gb_h = 0, gb_fmt = 0;
+    // per-frame staging
+    void* d_lights = nullptr;
+    size_t d_lights_capacity = 0;
+    void* h_lights = nullptr;  // pinned
+    size_t h_lights_capacity = 0;
+    void* d_lightmap = nullptr;  // staging for host-output entry points
+    size_t d_lightmap_capacity = 0;
+    void* d_probe_in = nullptr;
+    size_t d_probe_in_capacity = 0;
+};
+
+struct ilb_df {
+    ilb_ctx* ctx = nullptr;
+    uint2* tex = nullptr;
+    int tw = 0, th = 0;
+};
+
+struct ilb_psys {
+    ilb_ctx* ctx = nullptr;
+    int chunk_size = 0, max_chunks = 0, live_chunks = 0;
+    size_t per_chunk = 0;
+    float4* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // P, V, A, RC, RD
+    float4* rng = nullptr;
+    int rng_w = 0, rng_h = 0;
+    ilb_df* field = nullptr;
+    unsigned long long* d_count = nullptr;
+};
+
+int ilb_fail(ilb_ctx* ctx, int code, const char* fmt, ...);
+int ilb_cuda_fail(ilb_ctx* ctx, cudaError_t e, const char* what);
+int ilb_reserve(ilb_ctx* ctx, void** ptr, size_t* capacity, size_t bytes, bool pinned_host);
+
+#define ILB_CUDA(ctx, expr)                                             \
+    do {                                                                \
+        cudaError_t _e = (expr);                                        \
+        if (_e != cudaSuccess) return ilb_cuda_fail((ctx), _e, #expr);  \
+    } while (0)
+
+// Fills a DFGeometry from the reference uniform block; returns false when Extent.x <= 0 (no field).
+bool ilb_make_df_geometry(const ilb_df* df, const ilb_df_uniforms& u, DFGeometry* out);
+
+// lighting.cu
+int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches,
+                        int batch_count, const ilb_light_vertex* vertices, int vertex_count, void* const* d_outputs,
+                        int output_count, bool outputs_are_full_frames);
+int ilb_probes_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches,
+                      int batch_count, const ilb_light_vertex* vertices, int vertex_count, const ilb_float4* positions,
+                      const ilb_float4* normals, int probe_count, int output_format, void* probes_out_host);
+// dfgen.cu
+int ilb_dfgen_launch(ilb_ctx* ctx, uint2* tex, int tw, int th, int slice_w, int slice_h, int slice_count,
+                     const ilb_df_uniforms* u, const ilb_obstruction* obs, int count);
+// particles.cu
+int ilb_particles_launch(ilb_psys* psys, const ilb_psys_uniforms* u, const ilb_spawn* spawns, int spawn_count,
+                         const ilb_op* ops, int op_count, int steps);
+int ilb_particles_count_launch(ilb_psys* psys, int64_t* out);

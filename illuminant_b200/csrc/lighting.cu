@@ -1,0 +1,800 @@
+// LIGHTING hot path: one fused tile kernel replaces the reference's
+// "one rasterised instanced quad per light + additive ROP blend" (Lighting/LightingRenderer.cs:1149-1166).
+//
+//   per 16x16 tile:  decode the G-buffer once per pixel (L4)            -> registers
+//                    reduce the tile's world-space AABB (warp shuffles) -> per-tile light culling
+//                    ordered compaction of surviving lights (ballot)    -> shared-memory index list
+//                    per pixel: loop lights in draw order, evaluate the sphere / directional / line
+//                    response + AO + cone trace through the packed distance field (L2, L3, L5-L9)
+//                    accumulate in fp32 registers, one lightmap store per pixel (L10)
+//
+// The per-light math keeps the operation order of the reference pixel shaders (file:line cited per function,
+// relative to Illuminant/Shaders/); what changes is data movement: G-buffer and lightmap are touched once per
+// pixel instead of once per light-pixel, the light list is culled per tile, and there is no blend unit.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include <cuda_fp16.h>
+
+#include "ilb_internal.h"
+
+namespace {
+
+constexpr int TILE_W = 16, TILE_H = 16, TILE_THREADS = TILE_W * TILE_H;
+constexpr int MAX_OUTPUTS = 8;
+
+// One light, flattened on the host from (batch, LightVertex): the LightVertex fields (Vertices.cs:10-39) plus
+// the batch's quality uniforms and the rasterised coverage of its quad.
+struct __align__(16) DLight {
+    float4 pos1, pos2;                       // LightPosition1, LightPosition2
+    float4 props, more, evenMore;            // LightProperties, MoreLightProperties, EvenMoreLightProperties
+    float4 color1, color2;                   // Color1, Color2
+    float4 quality;                          // MaxConeRadius, OcclusionToOpacityPower, StepLimit, MinStepSize
+    float longStep;                          // LongStepFactor
+    int hasField;                            // batch.df.Extent.x > 0 && a field is bound
+    int type;                                // ilb_light_type
+    int pad;
+    float4 covX, covY;                       // coverage edges, see coverage()
+    int px0, py0, px1, py1;                  // conservative pixel bounds of the quad (inclusive)
+};
+
+struct LightingParams {
+    DFGeometry df;
+    float4 envZAndScale, envZToY, gbTexelAndMisc, clear;
+    float gbViewportRelative, vpx, vpy;
+    const void* gbuffer;
+    int gw, gh, gfmt;
+    const DLight* lights;
+    int nlights;
+    int width, height, row_begin, row_end;
+    int out_format, stencil;
+    void* outs[MAX_OUTPUTS];
+    int nouts;
+    int out_row_base;  // row index of outs[] row 0 (row_begin for band buffers, 0 for full frames)
+};
+
+struct Pixel {
+    f3 pos, normal, camera;
+    bool enableShadows, fullbright, maskOk;
+};
+
+// ---- cone trace (ConeTrace.fxh) --------------------------------------------------------------------------
+#define MIN_CONE_RADIUS 0.33f
+#define MAX_STEP_RAMP_WINDOW 2.0f
+#define TRACE_INITIAL_OFFSET_PX 0.5f
+#define FULLY_SHADOWED_THRESHOLD 0.075f
+#define UNSHADOWED_THRESHOLD 0.95f
+#define HACK_DISTANCE_OFFSET 1.5f
+#define TRACE_END_MULTIPLIER 100.0f
+
+struct TraceConfig {  // createTraceConfig :122-139 (+ the quality uniforms the step reads)
+    float maxRadius, growth, minStep, longStep, stepLimit, power;
+};
+
+ILB_DEV TraceConfig makeTraceConfig(const DLight& L, float rampX, float rampY, float growthFactor) {
+    TraceConfig c;
+    c.maxRadius = clampf(rampX, MIN_CONE_RADIUS, L.quality.x);
+    const float rampLength = fmaxf(rampY, 16.0f);
+    c.growth = c.maxRadius / rampLength * growthFactor;
+    c.minStep = fmaxf(1.0f, L.quality.w);
+    c.longStep = L.longStep;
+    c.stepLimit = L.quality.z;
+    c.power = L.quality.y;
+    return c;
+}
+
+struct Trace {  // TraceState :31-35
+    f3 origin, direction;
+    float t, len, vis;
+};
+
+ILB_DEV void traceInit(Trace& s, f3 start, f3 end, float lightRadius) {  // coneTraceInitialize :37-49
+    const f3 v = end - start;
+    const float l = length3(v);
+    s.origin = start;
+    s.direction = v / l;
+    s.len = fmaxf(l - lightRadius, 1.0f);
+    s.t = TRACE_INITIAL_OFFSET_PX;
+    s.vis = 1.0f;
+}
+
+ILB_DEV float traceStep(const TraceConfig& c, float d, float offset, float& vis) {  // coneTraceStep :51-71
+    const float localSphereRadius = fminf((c.growth * offset) + MIN_CONE_RADIUS, c.maxRadius);
+    const float localVisibility = ((d + HACK_DISTANCE_OFFSET) / localSphereRadius);
+    vis = fminf(vis, localVisibility);
+    return fmaxf(fabsf(d) * c.longStep, c.minStep);
+}
+
+ILB_DEV float traceFinal(const TraceConfig& c, float visibility) {  // :182-188
+    return powf(saturatef(saturatef(visibility - FULLY_SHADOWED_THRESHOLD) / (UNSHADOWED_THRESHOLD - FULLY_SHADOWED_THRESHOLD)),
+                c.power);
+}
+
+ILB_DEV float coneTrace(const DFGeometry& g, const DLight& L, f3 lightCenter, float rampX, float rampY,
+                        float growthFactor, f3 shaded, bool enable) {  // coneTrace :141-191
+    Trace a;
+    traceInit(a, shaded, lightCenter, rampX);
+    const TraceConfig c = makeTraceConfig(L, rampX, rampY, growthFactor);
+    float stepsRemaining = c.stepLimit;
+    float liveness = (L.hasField && enable) ? 1.0f : 0.0f;
+    while (liveness > 0.0f) {
+        stepsRemaining -= 1.0f;
+        const float d = sampleDistanceField(g, a.origin + (a.direction * a.t));  // coneTraceAdvance :73-82
+        a.t += traceStep(c, d, a.t, a.vis);
+        const float stepLiveness = saturatef(a.vis - FULLY_SHADOWED_THRESHOLD) * saturatef(a.len - a.t);
+        liveness = stepsRemaining * stepLiveness;
+    }
+    const float visibility = fminf(a.vis, stepsRemaining / MAX_STEP_RAMP_WINDOW);
+    return enable ? traceFinal(c, visibility) : 1.0f;
+}
+
+ILB_DEV float traceAdvanceEx(const DFGeometry& g, const TraceConfig& c, Trace& s) {  // coneTraceAdvanceEx :84-96
+    const float d = sampleDistanceField(g, s.origin + (s.direction * s.t));
+    s.t = fminf(s.t + traceStep(c, d, s.t, s.vis), s.len);
+    return saturatef(s.vis - FULLY_SHADOWED_THRESHOLD) * saturatef((s.len - s.t) * TRACE_END_MULTIPLIER);
+}
+
+// ---- light response (LightCommon.fxh, AOCommon.fxh) ---------------------------------------------------------
+#define DOT_EXPONENT 0.85f
+
+ILB_DEV float normalFactorEx(f3 lightNormal, f3 n, float offset, float range) {  // computeNormalFactorEx :154-165
+    if (!any3(n)) return 1.0f;
+    const float d = dot3(-lightNormal, n);
+    return powf(saturatef((d + offset) / range), DOT_EXPONENT);
+}
+
+ILB_DEV float sphereLightOpacity(float lightOcclusion, f3 p, f3 n, f3 center, float4 props, float yFactor) {  // :173-210
+    f3 d3 = p - center;
+    d3.y *= yFactor;
+    const float distance = length3(d3);
+    float distanceFactor = 1.0f - saturatef((distance - props.x) / props.y);
+    if (lightOcclusion > 0.0f) distanceFactor *= 1.0f - saturatef(d3.z / lightOcclusion);
+    const f3 lightNormal = d3 / distance;
+    float normalFactor = normalFactorEx(lightNormal, n, 0.15f, 0.15f);
+    if (props.z >= 2.0f) {
+        distanceFactor = 1.0f - saturatef(distance - props.x);
+        normalFactor = 1.0f;
+    } else if (props.z >= 1.0f) {
+        distanceFactor *= distanceFactor;
+    }
+    return saturatef((normalFactor * distanceFactor) + saturatef(props.x - distance));
+}
+
+ILB_DEV float computeAO(const DFGeometry& g, bool hasField, f3 p, f3 n, float aoRadius, float aoOpacity, bool visible) {  // AOCommon.fxh:1-20
+    if ((aoRadius >= 0.5f) && hasField && visible) {
+        const float distance = sampleDistanceField(g, p + mk3(0.0f, 0.0f, n.z * aoRadius));
+        const float clampedDistance = clampf(distance, 0.0f, aoRadius);
+        float result = 1.0f - saturatef(clampedDistance / aoRadius);
+        result *= result;
+        result = 1.0f - result;
+        return (1.0f - aoOpacity) + (result * aoOpacity);
+    }
+    return 1.0f;
+}
+
+// SphereLightPixelCore (SphereLightCore.fxh:58-158); returns false on discard
+ILB_DEV bool sphereCore(const DFGeometry& g, const DLight& L, float lightOcclusion, f3 p, f3 n, f3 center, float4 props,
+                        float4 more, float& opacity) {
+    const float distanceOpacity = sphereLightOpacity(lightOcclusion, p, n, center, props, more.z);
+    const bool visible = (distanceOpacity > 0.0f) && (p.x > -9999.0f);
+    if (!visible) return false;
+    const float aoRadius = more.x * fmaxf(0.0f, n.z);
+    const float aoOpacity = computeAO(g, L.hasField != 0, p, n, aoRadius, more.w, visible);
+    const float preTraceOpacity = distanceOpacity * aoOpacity;
+    const bool traceShadows = (props.w != 0.0f) && (preTraceOpacity >= (0.75f / 255.0f));
+    const float coneOpacity = coneTrace(g, L, center, props.x, props.y, 1.0f, p + (1.6f * n), traceShadows);
+    opacity = preTraceOpacity * coneOpacity;
+    return true;
+}
+
+// DirectionalLightPixelCore (DirectionalLight.fx:52-93, useOpacityRamp = false)
+ILB_DEV bool directionalCore(const DFGeometry& g, const DLight& L, f3 p, f3 n, float4 dir, float4 props, float4 more,
+                             float& opacity) {
+    float lightOpacity = (dir.w < 0.1f) ? 1.0f : normalFactorEx(mk3(dir.x, dir.y, dir.z), n, 0.35f, 0.35f);
+    const bool visible = (p.x > -9999.0f);
+    const float aoRadius = more.x * fmaxf(0.0f, n.z);
+    lightOpacity *= computeAO(g, L.hasField != 0, p, n, aoRadius, more.w, visible);
+    const bool traceShadows = visible && (props.x != 0.0f) && (lightOpacity >= 1.0f / 256.0f) && (dir.w >= 0.1f);
+    const f3 fakeLightCenter = p - (mk3(dir.x, dir.y, dir.z) * props.y);
+    lightOpacity *= coneTrace(g, L, fakeLightCenter, props.z, more.y, props.w, p + (1.5f * n), traceShadows);
+    if (!visible) return false;
+    opacity = lightOpacity;
+    return true;
+}
+
+// ---- line light (FBPBR.fxh:33-101, LineLightCore.fxh:17-120) -------------------------------------------------
+ILB_DEV f3 closestPointOnLineSegment3(f3 a, f3 b, f3 pt, float& t) {  // DistanceFieldCommon.fxh:151-155
+    const f3 ab = b - a;
+    t = saturatef(dot3(pt - a, ab) / dot3(ab, ab));
+    return a + t * ab;
+}
+
+ILB_DEV float rectangleSolidAngle(f3 wp, f3 p0, f3 p1, f3 p2, f3 p3) {  // FBPBR.fxh:33-51
+    const f3 v0 = p0 - wp, v1 = p1 - wp, v2 = p2 - wp, v3 = p3 - wp;
+    const f3 n0 = normalize3(cross3(v0, v1)), n1 = normalize3(cross3(v1, v2));
+    const f3 n2 = normalize3(cross3(v2, v3)), n3 = normalize3(cross3(v3, v0));
+    const float g0 = acosf(dot3(-n0, n1)), g1 = acosf(dot3(-n1, n2));
+    const float g2 = acosf(dot3(-n2, n3)), g3 = acosf(dot3(-n3, n0));
+    return g0 + g1 + g2 + g3 - 2.0f * ILB_PI;
+}
+
+ILB_DEV float lineLightOpacity(f3 wp, f3 wn, f3 P0, f3 P1, float lightRadius, f3& spherePosition, float& u) {  // :53-101
+    const f3 lightLeft = normalize3(P1 - P0);
+    const f3 lightCenter = lerp3(P0, P1, 0.5f);
+    spherePosition = closestPointOnLineSegment3(P0, P1, wp, u);
+    const f3 forward = normalize3(spherePosition - wp);
+    const f3 up = cross3(lightLeft, forward);
+    const f3 p0 = P0 + lightRadius * up, p1 = P0 - lightRadius * up;
+    const f3 p2 = P1 - lightRadius * up, p3 = P1 + lightRadius * up;
+    const float solidAngle = rectangleSolidAngle(wp, p0, p1, p2, p3);
+    float illuminance = solidAngle * 0.2f *
+                        (saturatef(dot3(normalize3(p0 - wp), wn)) + saturatef(dot3(normalize3(p1 - wp), wn)) +
+                         saturatef(dot3(normalize3(p2 - wp), wn)) + saturatef(dot3(normalize3(p3 - wp), wn)) +
+                         saturatef(dot3(normalize3(lightCenter - wp), wn)));
+    const f3 sphereUnormL = spherePosition - wp;
+    const f3 sphereL = normalize3(sphereUnormL);
+    const float sqrSphereDistance = dot3(sphereUnormL, sphereUnormL);
+    const float illuminanceSphere = ILB_PI * saturatef(dot3(sphereL, wn)) * ((lightRadius * lightRadius) / sqrSphereDistance);
+    illuminance = illuminance + illuminanceSphere;
+    return saturatef(illuminance);
+}
+
+ILB_DEV float lineConeTrace(const DFGeometry& g, const DLight& L, f3 start, f3 end, float u, float rampX, float rampY,
+                            f3 shaded, bool enable) {  // LineLightCore.fxh:17-68
+    Trace a, b, c;
+    const f3 delta = end - start;
+    const float deltaLength = length3(delta);
+    const float offset = fmaxf(saturatef((rampX + 1.0f) / deltaLength), 0.03f);
+    traceInit(a, shaded, start + saturatef(u - offset) * delta, rampX);
+    traceInit(b, shaded, start + u * delta, rampX);
+    traceInit(c, shaded, start + saturatef(u + offset) * delta, rampX);
+    const TraceConfig cfg = makeTraceConfig(L, rampX, rampY, 1.0f);
+    float stepsRemaining = cfg.stepLimit;
+    float liveness = (L.hasField && enable) ? 1.0f : 0.0f;
+    while (liveness > 0.0f) {
+        const float stepLiveness = traceAdvanceEx(g, cfg, a) + traceAdvanceEx(g, cfg, b) + traceAdvanceEx(g, cfg, c);
+        stepsRemaining -= 1.0f;
+        liveness = stepsRemaining * stepLiveness;
+    }
+    const float visibility = fminf((a.vis + b.vis + c.vis) / 3.0f, stepsRemaining / MAX_STEP_RAMP_WINDOW);
+    return enable ? traceFinal(cfg, visibility) : 1.0f;
+}
+
+ILB_DEV bool lineCore(const DFGeometry& g, const DLight& L, f3 p, f3 n, f3 start, f3 end, float4 props, float4 more,
+                      float& u, float& opacity) {  // LineLightPixelCore :70-120
+    f3 lightCenter;
+    const float distanceOpacity = lineLightOpacity(p, n, start, end, props.x, lightCenter, u);
+    const bool visible = (distanceOpacity > 0.0f) && (p.x > -9999.0f);
+    if (!visible) return false;
+    const float aoRadius = more.x * fmaxf(0.0f, n.z);
+    const float aoOpacity = computeAO(g, L.hasField != 0, p, n, aoRadius, more.w, visible);
+    const float preTraceOpacity = distanceOpacity * aoOpacity;
+    const bool traceShadows = (props.w != 0.0f) && (preTraceOpacity >= (0.75f / 255.0f));
+    const float coneOpacity = lineConeTrace(g, L, start, end, u, props.x, props.y, p + (1.5f * n), traceShadows);
+    opacity = preTraceOpacity * coneOpacity;
+    return true;
+}
+
+// ---- G-buffer decode (LightCommon.fxh:58-144, EnvironmentCommon.fxh:42-52) ---------------------------------
+ILB_DEV float4 loadGBufferTexel(const LightingParams& P, int ix, int iy) {
+    ix = min(max(ix, 0), P.gw - 1);
+    iy = min(max(iy, 0), P.gh - 1);
+    const size_t i = (size_t)iy * (size_t)P.gw + (size_t)ix;
+    if (P.gfmt == ILB_FORMAT_FLOAT4) return __ldg((const float4*)P.gbuffer + i);
+    const uint2 raw = __ldg((const uint2*)P.gbuffer + i);
+    const __half2 lo = *reinterpret_cast<const __half2*>(&raw.x), hi = *reinterpret_cast<const __half2*>(&raw.y);
+    const float2 a = __half22float2(lo), b = __half22float2(hi);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+ILB_DEV Pixel decodePixel(const LightingParams& P, int px, int py) {
+    Pixel r;
+    r.enableShadows = true;
+    r.fullbright = false;
+    r.maskOk = true;
+    float sx = (float)px, sy = (float)py;
+    const float rsx = P.envZAndScale.z, rsy = P.envZAndScale.w;
+    const float vsx = P.gbTexelAndMisc.z, vsy = P.gbTexelAndMisc.w;
+    if (any2(P.gbTexelAndMisc.x, P.gbTexelAndMisc.y)) {
+        float srcx = sx, srcy = sy;
+        if (P.gbViewportRelative != 0.0f) {
+            srcx = srcx / vsx;
+            srcy = srcy / vsy;
+            srcx += P.vpx;
+            srcy += P.vpy;
+        }
+        const float u = (srcx + 0.5f) * P.gbTexelAndMisc.x, v = (srcy + 0.5f) * P.gbTexelAndMisc.y;
+        const float4 s = loadGBufferTexel(P, (int)floorf(u * (float)P.gw), (int)floorf(v * (float)P.gh));
+        if (P.stencil) {  // UpdateMaskFromGBuffer, GBufferMask.fx:26-44
+            const float minW = -fabsf(P.envZAndScale.y) - 1.0f, maxW = -fabsf(P.envZAndScale.x) - 1.0f;
+            r.maskOk = !((s.w >= 9999.0f) || (s.w < minW) || ((s.w < 0.0f) && (s.w > maxW)));
+        }
+        const float relativeY = s.z;
+        float worldZ = s.w;
+        if (worldZ < 0.0f) {
+            worldZ += 1.0f;
+            worldZ = -worldZ;
+            r.enableShadows = false;
+        } else if (worldZ >= 9999.0f) {
+            worldZ = 0.0f;
+            r.enableShadows = false;
+            r.fullbright = true;
+        }
+        worldZ *= 1024.0f;
+        worldZ -= 1024.0f;
+        sx = sx / rsx;
+        sy = sy / rsy;
+        r.camera = mk3(sx, sy, P.envZAndScale.y + 0.01f);
+        r.pos = mk3((sx + 0.0f) / vsx + P.vpx, (sy + relativeY) / vsy + P.vpy, worldZ);
+        if (any2(s.x, s.y)) {
+            const float ax = s.x * 2.0f - 1.0f, ay = s.y * 2.0f - 1.0f;
+            float sn, cs;
+            sincosf(ax * ILB_PI, &sn, &cs);
+            const float phx = sqrtf(1.0f - ay * ay);
+            r.normal = mk3(cs * phx, sn * phx, ay);
+        } else {
+            r.normal = mk3(0.0f);
+        }
+    } else {
+        sx = sx / rsx;
+        sy = sy / rsy;
+        r.camera = mk3(sx, sy, P.envZAndScale.y + 0.01f);
+        r.pos = mk3(sx / vsx + P.vpx, sy / vsy + P.vpy, P.envZAndScale.x);
+        r.normal = mk3(0.0f, 0.0f, 1.0f);
+    }
+    return r;
+}
+
+// Rasterised coverage of the light's quad at this pixel centre (world space).
+//   sphere: 12-vertex cross of FillSphereBuffer (LightingRenderer.cs:636-656) through SphereLightVertexShader
+//           (SphereLightCore.fxh:13-56): covX = X(0), X(1/7), X(6/7), X(1); covY likewise (2.5D shift applied to w<0.5)
+//   directional / line: one rectangle covX = (x0, x1), covY = (y0, y1) (DirectionalLight.fx:19-37, LineLightCore.fxh:122-173)
+ILB_DEV bool coverage(const DLight& L, float wx, float wy) {
+    if (L.type == ILB_LIGHT_SPHERE) {
+        const float4 X = L.covX, Y = L.covY;
+        const bool a = (wx >= X.y) && (wx <= X.z) && (wy >= Y.x) && (wy <= Y.w);
+        const bool b = (wx >= X.z) && (wx <= X.w) && (wy >= Y.y) && (wy <= Y.z);
+        const bool c = (wx >= X.x) && (wx <= X.y) && (wy >= Y.y) && (wy <= Y.z);
+        return a || b || c;
+    }
+    return (wx >= L.covX.x) && (wx <= L.covX.y) && (wy >= L.covY.x) && (wy <= L.covY.y);
+}
+
+ILB_DEV bool shadowFilterRejects(float filter, bool enableShadows) {  // checkShadowFilter LightCommon.fxh:146-152
+    if (filter < 0.0f) return false;
+    return (filter > 0.5f) != enableShadows;
+}
+
+// One light at one pixel; returns false when the reference fragment would be discarded.
+ILB_DEV bool shadeLight(const LightingParams& P, const DLight& L, const Pixel& px, f3& rgb) {
+    const float es = px.enableShadows ? 1.0f : 0.0f;
+    if (L.type == ILB_LIGHT_SPHERE) {  // SphereLightPixelShader SphereLight.fx:7-46
+        if (px.fullbright || shadowFilterRejects(L.evenMore.x, px.enableShadows)) return false;
+        float4 props = L.props;
+        props.w *= es;
+        const f3 center = mk3(L.pos1.x, L.pos1.y, L.pos1.z);
+        float opacity;
+        if (!sphereCore(P.df, L, P.envZToY.z, px.pos, px.normal, center, props, L.more, opacity)) return false;
+        const float4 color = L.color1, spec = L.color2;
+        rgb = (mk3(color.x, color.y, color.z) * color.w * opacity);
+        if (any3(mk3(spec.x, spec.y, spec.z))) {  // CalcSphereLightSpecularity LightCommon.fxh:212-222
+            const f3 lightDirection = px.pos - center;
+            const f3 h = normalize3(normalize3(px.camera - px.pos) - lightDirection);
+            const float specularity = powf(saturatef(dot3(h, px.normal)), spec.w);
+            rgb = rgb + (mk3(spec.x, spec.y, spec.z) * specularity * opacity);
+        }
+        return true;
+    } else if (L.type == ILB_LIGHT_DIRECTIONAL) {  // DirectionalLightPixelShader DirectionalLight.fx:95-127
+        if (px.fullbright || shadowFilterRejects(L.evenMore.x, px.enableShadows)) return false;
+        float4 props = L.props;
+        props.x *= es;
+        float opacity;
+        if (!directionalCore(P.df, L, px.pos, px.normal, L.color2, props, L.more, opacity)) return false;
+        rgb = mk3(L.color1.x, L.color1.y, L.color1.z) * L.color1.w * opacity;
+        return true;
+    } else {  // LineLightPixelShader LineLight.fx:7-42
+        if (px.fullbright) return false;
+        float4 props = L.props;
+        props.w *= es;
+        float u, opacity;
+        if (!lineCore(P.df, L, px.pos, px.normal, mk3(L.pos1.x, L.pos1.y, L.pos1.z), mk3(L.pos2.x, L.pos2.y, L.pos2.z), props,
+                      L.more, u, opacity))
+            return false;
+        const f4 color = lerp4(mk4(L.color1), mk4(L.color2), u);
+        rgb = mk3(color.x, color.y, color.z) * color.w * opacity;
+        return true;
+    }
+}
+
+ILB_DEV DLight loadLight(const DLight* lights, int i) {
+    DLight L;
+    const float4* src = reinterpret_cast<const float4*>(lights + i);
+    float4* dst = reinterpret_cast<float4*>(&L);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(DLight) / 16); k++) dst[k] = __ldg(src + k);
+    return L;
+}
+
+ILB_DEV void storeTexel(const LightingParams& P, size_t index, float r, float g, float b, float a) {
+    if (P.out_format == ILB_FORMAT_FLOAT4) {
+        const float4 v = make_float4(r, g, b, a);
+        for (int o = 0; o < P.nouts; o++) reinterpret_cast<float4*>(P.outs[o])[index] = v;
+    } else if (P.out_format == ILB_FORMAT_HALF4) {  // HalfVector4 lightmap (LightingRenderer.cs:477-479)
+        const __half2 lo = __floats2half2_rn(r, g), hi = __floats2half2_rn(b, a);
+        uint2 v;
+        v.x = *reinterpret_cast<const uint32_t*>(&lo);
+        v.y = *reinterpret_cast<const uint32_t*>(&hi);
+        for (int o = 0; o < P.nouts; o++) reinterpret_cast<uint2*>(P.outs[o])[index] = v;
+    } else {  // SurfaceFormat.Color
+        const uint32_t R = (uint32_t)(saturatef(r) * 255.0f + 0.5f), G = (uint32_t)(saturatef(g) * 255.0f + 0.5f);
+        const uint32_t B = (uint32_t)(saturatef(b) * 255.0f + 0.5f), A = (uint32_t)(saturatef(a) * 255.0f + 0.5f);
+        const uint32_t v = R | (G << 8) | (B << 16) | (A << 24);
+        for (int o = 0; o < P.nouts; o++) reinterpret_cast<uint32_t*>(P.outs[o])[index] = v;
+    }
+}
+
+ILB_DEV float warpMin(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    return v;
+}
+ILB_DEV float warpMax(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    return v;
+}
+
+__global__ void __launch_bounds__(TILE_THREADS) light_accumulate_kernel(const __grid_constant__ LightingParams P) {
+    __shared__ float s_box[8][6];
+    __shared__ int s_warpCount[8];
+    __shared__ uint16_t s_list[TILE_THREADS];
+    __shared__ int s_listCount;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // a warp covers an 8x4 pixel patch: neighbouring lanes trace neighbouring rays (coherent DF footprints)
+    const int px = blockIdx.x * TILE_W + (warp & 1) * 8 + (lane & 7);
+    const int py = P.row_begin + blockIdx.y * TILE_H + (warp >> 1) * 4 + (lane >> 3);
+    const bool valid = (px < P.width) && (py < P.row_end);
+
+    Pixel pix;
+    if (valid) pix = decodePixel(P, px, py);
+    const bool shade = valid && pix.maskOk;
+
+    // tile AABB of shaded world positions (warp shuffle + 8-entry shared reduction)
+    const float BIG = 3.0e38f;
+    float bx0 = shade ? pix.pos.x : BIG, bx1 = shade ? pix.pos.x : -BIG;
+    float by0 = shade ? pix.pos.y : BIG, by1 = shade ? pix.pos.y : -BIG;
+    float bz0 = shade ? pix.pos.z : BIG, bz1 = shade ? pix.pos.z : -BIG;
+    bx0 = warpMin(bx0); bx1 = warpMax(bx1);
+    by0 = warpMin(by0); by1 = warpMax(by1);
+    bz0 = warpMin(bz0); bz1 = warpMax(bz1);
+    if (lane == 0) {
+        s_box[warp][0] = bx0; s_box[warp][1] = bx1; s_box[warp][2] = by0;
+        s_box[warp][3] = by1; s_box[warp][4] = bz0; s_box[warp][5] = bz1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        bx0 = fminf(bx0, s_box[w][0]); bx1 = fmaxf(bx1, s_box[w][1]);
+        by0 = fminf(by0, s_box[w][2]); by1 = fmaxf(by1, s_box[w][3]);
+        bz0 = fminf(bz0, s_box[w][4]); bz1 = fmaxf(bz1, s_box[w][5]);
+    }
+    const int tx0 = blockIdx.x * TILE_W, tx1 = tx0 + TILE_W - 1;
+    const int ty0 = P.row_begin + blockIdx.y * TILE_H, ty1 = ty0 + TILE_H - 1;
+
+    // pixel centre in world space for the coverage test (inverse of the light vertex shaders' transform)
+    const float sxs = P.gbTexelAndMisc.z * P.envZAndScale.z, sys = P.gbTexelAndMisc.w * P.envZAndScale.w;
+    const float wx = ((float)px + 0.5f) / sxs + P.vpx, wy = ((float)py + 0.5f) / sys + P.vpy;
+
+    float accR = P.clear.x, accG = P.clear.y, accB = P.clear.z, accA = P.clear.w;
+
+    for (int base = 0; base < P.nlights; base += TILE_THREADS) {
+        // ---- cull: thread t tests light base+t against the tile
+        const int li = base + tid;
+        bool keep = false;
+        if (li < P.nlights) {
+            const DLight* L = P.lights + li;
+            const int4 r = __ldg(reinterpret_cast<const int4*>(&L->px0));
+            keep = (r.x <= tx1) && (r.z >= tx0) && (r.y <= ty1) && (r.w >= ty0) && (bx0 <= bx1);
+            if (keep && __ldg(&L->type) == ILB_LIGHT_SPHERE) {
+                // sphere lights reach radius + rampLength (radius + 1 in RampMode None): reject the tile when the
+                // closest point of its world AABB is farther (1 px of slack covers fp rounding)
+                const float4 c = __ldg(&L->pos1), pr = __ldg(&L->props), mo = __ldg(&L->more);
+                const float dx = fmaxf(fmaxf(bx0 - c.x, c.x - bx1), 0.0f);
+                const float dy = fmaxf(fmaxf(by0 - c.y, c.y - by1), 0.0f) * fabsf(mo.z);
+                const float dz = fmaxf(fmaxf(bz0 - c.z, c.z - bz1), 0.0f);
+                const float reach = pr.x + fmaxf(pr.y, 1.0f) + 1.0f;
+                keep = (dx * dx + dy * dy + dz * dz) <= reach * reach;
+            }
+        }
+        // ---- ordered compaction (draw order is kept so accumulation order matches the reference)
+        const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
+        if (lane == 0) s_warpCount[warp] = __popc(ballot);
+        __syncthreads();
+        int offset = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const int c = s_warpCount[w];
+            if (w < warp) offset += c;
+            total += c;
+        }
+        if (keep) s_list[offset + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)tid;
+        if (tid == 0) s_listCount = total;
+        __syncthreads();
+
+        // ---- shade
+        const int n = s_listCount;
+        for (int k = 0; k < n; k++) {
+            const DLight L = loadLight(P.lights, base + (int)s_list[k]);
+            if (shade && coverage(L, wx, wy)) {
+                f3 rgb;
+                if (shadeLight(P, L, pix, rgb)) {
+                    // BlendState.Additive with PS alpha 1: rgb += src.rgb, a += 1 (LightingRenderer.cs:206)
+                    accR += rgb.x; accG += rgb.y; accB += rgb.z; accA += 1.0f;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    if (valid) storeTexel(P, (size_t)(py - P.out_row_base) * (size_t)P.width + (size_t)px, accR, accG, accB, accA);
+}
+
+// ---- light probes (L11): SphereLightProbe.fx:19-44, DirectionalLight.fx:163-190, LineLightProbe.fx:23-48 ----------
+struct ProbeParams {
+    DFGeometry df;
+    float lightOcclusion;
+    const DLight* lights;
+    int nlights;
+    const float4* positions;
+    const float4* normals;
+    int nprobes;
+    int out_format;
+    void* out;
+};
+
+__global__ void __launch_bounds__(128) probe_accumulate_kernel(const __grid_constant__ ProbeParams P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.nprobes) return;
+    const float4 ps = __ldg(P.positions + i), ns = __ldg(P.normals + i);  // sampleLightProbeBuffer LightCommon.fxh:233-254
+    float accR = 0.0f, accG = 0.0f, accB = 0.0f, accA = 0.0f;
+    if (ps.w > 0.0f) {
+        const f3 p = mk3(ps.x, ps.y, ps.z), n = mk3(ns.x, ns.y, ns.z);
+        for (int k = 0; k < P.nlights; k++) {
+            const DLight L = loadLight(P.lights, k);
+            float4 props = L.props, more = L.more;
+            more.x = 0.0f;
+            more.w = 0.0f;
+            float core;
+            bool lit;
+            if (L.type == ILB_LIGHT_DIRECTIONAL) {
+                props.x *= ns.w;
+                lit = directionalCore(P.df, L, p, n, L.color2, props, more, core);
+            } else {  // sphere, and line lights shaded as spheres at LightPosition1 (reference quirk, LineLightProbe.fx:4)
+                props.w *= ns.w;
+                lit = sphereCore(P.df, L, P.lightOcclusion, p, n, mk3(L.pos1.x, L.pos1.y, L.pos1.z), props, more, core);
+            }
+            if (lit) {
+                const float opacity = ps.w * core;
+                const f3 rgb = mk3(L.color1.x, L.color1.y, L.color1.z) * L.color1.w * opacity;
+                accR += rgb.x; accG += rgb.y; accB += rgb.z; accA += 1.0f;
+            }
+        }
+    }
+    if (P.out_format == ILB_FORMAT_FLOAT4) {
+        reinterpret_cast<float4*>(P.out)[i] = make_float4(accR, accG, accB, accA);
+    } else {
+        const __half2 lo = __floats2half2_rn(accR, accG), hi = __floats2half2_rn(accB, accA);
+        uint2 v;
+        v.x = *reinterpret_cast<const uint32_t*>(&lo);
+        v.y = *reinterpret_cast<const uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(P.out)[i] = v;
+    }
+}
+
+// ---- host: flatten (batch, LightVertex) into DLight ---------------------------------------------------------
+inline float4 h4(const ilb_float4& v) { return make_float4(v.x, v.y, v.z, v.w); }
+inline float hlerp(float a, float b, float t) { return a + t * (b - a); }
+
+int flattenLights(ilb_ctx* ctx, const ilb_df* df, const ilb_lighting_frame* f, const ilb_light_batch* batches, int batch_count,
+                  const ilb_light_vertex* verts, int vertex_count, std::vector<DLight>& out, const ilb_df_uniforms** geometry) {
+    *geometry = nullptr;
+    const float invZToY = f->EnvironmentZToY.y, zToY = f->EnvironmentZToY.x;
+    const float sxs = f->GBufferTexelSizeAndMisc.z * f->EnvironmentZAndScale.z;
+    const float sys = f->GBufferTexelSizeAndMisc.w * f->EnvironmentZAndScale.w;
+    if (!(sxs > 0.0f) || !(sys > 0.0f)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "viewport scale * render scale must be > 0");
+    for (int b = 0; b < batch_count; b++) {
+        const ilb_light_batch& B = batches[b];
+        if (B.light_type != ILB_LIGHT_SPHERE && B.light_type != ILB_LIGHT_DIRECTIONAL && B.light_type != ILB_LIGHT_LINE)
+            return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "light type %d is outside the hot-path scope (sphere=1, directional=2, line=4)", B.light_type);
+        if (B.first_vertex < 0 || B.vertex_count < 0 || B.first_vertex + B.vertex_count > vertex_count)
+            return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "batch %d vertex range [%d,+%d) outside [0,%d)", b, B.first_vertex, B.vertex_count, vertex_count);
+        const bool hasField = (df != nullptr) && (B.df.Extent.x > 0.0f);
+        if (hasField) {
+            if (*geometry) {
+                const ilb_df_uniforms& g = **geometry;
+                // one DistanceField per renderer in the reference: geometry members must agree across batches
+                if (memcmp(&g.TextureSliceAndTexelSize, &B.df.TextureSliceAndTexelSize, sizeof(ilb_float4)) ||
+                    memcmp(&g.TextureSliceCount, &B.df.TextureSliceCount, sizeof(ilb_float4)) ||
+                    memcmp(&g.Extent, &B.df.Extent, sizeof(ilb_float4)) || g.ConeAndMisc.y != B.df.ConeAndMisc.y ||
+                    g.ConeAndMisc.w != B.df.ConeAndMisc.w || g.StepAndMisc2.w != B.df.StepAndMisc2.w ||
+                    g.Packed1.x != B.df.Packed1.x || g.Packed1.y != B.df.Packed1.y || g.Packed1.z != B.df.Packed1.z)
+                    return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "batch %d: distance-field geometry differs from earlier batches", b);
+            } else {
+                *geometry = &B.df;
+            }
+        }
+        for (int i = 0; i < B.vertex_count; i++) {
+            const ilb_light_vertex& v = verts[B.first_vertex + i];
+            DLight L;
+            memset(&L, 0, sizeof(L));
+            L.pos1 = h4(v.LightPosition1); L.pos2 = h4(v.LightPosition2);
+            L.props = h4(v.LightProperties); L.more = h4(v.MoreLightProperties); L.evenMore = h4(v.EvenMoreLightProperties);
+            L.color1 = h4(v.Color1); L.color2 = h4(v.Color2);
+            L.quality = make_float4(B.df.ConeAndMisc.x, B.df.ConeAndMisc.z, B.df.StepAndMisc2.x, B.df.Packed1.w);
+            L.longStep = B.df.StepAndMisc2.z;
+            L.hasField = hasField ? 1 : 0;
+            L.type = B.light_type;
+            float bx0, bx1, by0, by1;  // world-space bounds of the rasterised quad
+            if (B.light_type == ILB_LIGHT_SPHERE) {  // SphereLightVertexShader SphereLightCore.fxh:13-56
+                const float radius = v.LightProperties.x + v.LightProperties.y + 1;
+                const float deltaY = (radius) - (radius / v.MoreLightProperties.z);
+                const float rx = radius, ry = radius - (deltaY / 2.0f);
+                const float tlx = v.LightPosition1.x - rx, brx = v.LightPosition1.x + rx;
+                const float tly = v.LightPosition1.y - ry, bry = v.LightPosition1.y + ry;
+                const float radiusOffset = radius * invZToY, zOffset = v.LightPosition1.z * zToY;
+                const float cOne = 1.0f / 7.0f, mOne = 6.0f / 7.0f;
+                auto Y = [&](float w) {
+                    float y = hlerp(tly, bry, w);
+                    if (w < 0.5f) { y -= radiusOffset; y -= zOffset; }
+                    return y;
+                };
+                L.covX = make_float4(hlerp(tlx, brx, 0.0f), hlerp(tlx, brx, cOne), hlerp(tlx, brx, mOne), hlerp(tlx, brx, 1.0f));
+                L.covY = make_float4(Y(0.0f), Y(cOne), Y(mOne), Y(1.0f));
+                bx0 = std::min(L.covX.x, L.covX.w); bx1 = std::max(L.covX.x, L.covX.w);
+                by0 = std::min(std::min(L.covY.x, L.covY.y), std::min(L.covY.z, L.covY.w));
+                by1 = std::max(std::max(L.covY.x, L.covY.y), std::max(L.covY.z, L.covY.w));
+            } else if (B.light_type == ILB_LIGHT_DIRECTIONAL) {  // DirectionalLight.fx:19-37
+                bx0 = v.LightPosition1.x; bx1 = v.LightPosition2.x; by0 = v.LightPosition1.y; by1 = v.LightPosition2.y;
+                L.covX = make_float4(bx0, bx1, 0, 0);
+                L.covY = make_float4(by0, by1, 0, 0);
+            } else {  // LineLightVertexShader LineLightCore.fxh:122-173 (bounds are +-9999 around the segment)
+                const float radius = v.LightProperties.x + v.LightProperties.y + 1;
+                bx0 = std::min(v.LightPosition1.x, v.LightPosition2.x) - 9999; bx1 = std::max(v.LightPosition1.x, v.LightPosition2.x) + 9999;
+                by0 = std::min(v.LightPosition1.y, v.LightPosition2.y) - 9999; by1 = std::max(v.LightPosition1.y, v.LightPosition2.y) + 9999;
+                by0 -= radius * invZToY;
+                by0 -= v.LightPosition1.z * zToY;
+                L.covX = make_float4(bx0, bx1, 0, 0);
+                L.covY = make_float4(by0, by1, 0, 0);
+            }
+            // conservative pixel bounds: pixel centre (p + 0.5) / s + vp inside [b0, b1], one pixel of slack
+            auto toPx = [](float w, float vp, float s, float slack) {
+                double p = ((double)w - (double)vp) * (double)s - 0.5 + slack;
+                if (!(p > -1.0e9)) p = -1.0e9;
+                if (!(p < 1.0e9)) p = 1.0e9;
+                return (int)std::floor(p);
+            };
+            L.px0 = toPx(bx0, f->ViewportPosition[0], sxs, -1.0f);
+            L.px1 = toPx(bx1, f->ViewportPosition[0], sxs, 2.0f);
+            L.py0 = toPx(by0, f->ViewportPosition[1], sys, -1.0f);
+            L.py1 = toPx(by1, f->ViewportPosition[1], sys, 2.0f);
+            out.push_back(L);
+        }
+    }
+    return ILB_OK;
+}
+
+int uploadLights(ilb_ctx* ctx, const std::vector<DLight>& lights) {
+    const size_t bytes = std::max<size_t>(lights.size(), 1) * sizeof(DLight);
+    int rc = ilb_reserve(ctx, &ctx->d_lights, &ctx->d_lights_capacity, bytes, false);
+    if (rc) return rc;
+    rc = ilb_reserve(ctx, &ctx->h_lights, &ctx->h_lights_capacity, bytes, true);
+    if (rc) return rc;
+    // the pinned staging buffer is reused every frame: wait for the previous frame's copy
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!lights.empty()) {
+        memcpy(ctx->h_lights, lights.data(), lights.size() * sizeof(DLight));
+        ILB_CUDA(ctx, cudaMemcpyAsync(ctx->d_lights, ctx->h_lights, lights.size() * sizeof(DLight), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return ILB_OK;
+}
+
+}  // namespace
+
+size_t ilb_format_bytes(int format) {
+    return format == ILB_FORMAT_FLOAT4 ? 16 : (format == ILB_FORMAT_HALF4 ? 8 : 4);
+}
+
+int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const ilb_light_batch* batches, int batch_count,
+                        const ilb_light_vertex* vertices, int vertex_count, void* const* d_outputs, int output_count,
+                        bool outputs_are_full_frames) {
+    if (!f || (batch_count > 0 && (!batches || !vertices))) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
+    if (f->width <= 0 || f->height <= 0 || f->row_begin < 0 || f->row_end > f->height || f->row_begin > f->row_end)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad frame geometry %dx%d rows [%d,%d)", f->width, f->height, f->row_begin, f->row_end);
+    if (f->lightmap_format != ILB_FORMAT_FLOAT4 && f->lightmap_format != ILB_FORMAT_HALF4 && f->lightmap_format != ILB_FORMAT_RGBA8)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad lightmap format %d", f->lightmap_format);
+    if (output_count < 1 || output_count > MAX_OUTPUTS) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "1..%d outputs", MAX_OUTPUTS);
+    if (df && df->ctx != ctx) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "distance field belongs to another context");
+    if (f->row_begin == f->row_end) return ILB_OK;
+
+    std::vector<DLight> lights;
+    const ilb_df_uniforms* geometry = nullptr;
+    int rc = flattenLights(ctx, df, f, batches, batch_count, vertices, vertex_count, lights, &geometry);
+    if (rc) return rc;
+    if (lights.size() > 65535 * (size_t)TILE_THREADS) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "too many lights");
+    rc = uploadLights(ctx, lights);
+    if (rc) return rc;
+
+    LightingParams P;
+    memset(&P, 0, sizeof(P));
+    if (geometry && !ilb_make_df_geometry(df, *geometry, &P.df)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad distance-field uniforms");
+    P.envZAndScale = h4(f->EnvironmentZAndScale);
+    P.envZToY = h4(f->EnvironmentZToY);
+    P.gbTexelAndMisc = h4(f->GBufferTexelSizeAndMisc);
+    if (!ctx->gbuffer) P.gbTexelAndMisc.x = P.gbTexelAndMisc.y = 0.0f;
+    P.clear = h4(f->ClearColor);
+    P.gbViewportRelative = f->GBufferViewportRelative;
+    P.vpx = f->ViewportPosition[0];
+    P.vpy = f->ViewportPosition[1];
+    P.gbuffer = ctx->gbuffer;
+    P.gw = ctx->gb_w; P.gh = ctx->gb_h; P.gfmt = ctx->gb_fmt;
+    P.lights = reinterpret_cast<const DLight*>(ctx->d_lights);
+    P.nlights = (int)lights.size();
+    P.width = f->width; P.height = f->height; P.row_begin = f->row_begin; P.row_end = f->row_end;
+    P.out_format = f->lightmap_format;
+    P.stencil = f->stencil_culling;
+    for (int o = 0; o < output_count; o++) {
+        if (!d_outputs[o]) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null output %d", o);
+        P.outs[o] = d_outputs[o];
+    }
+    P.nouts = output_count;
+    P.out_row_base = outputs_are_full_frames ? 0 : f->row_begin;
+
+    const dim3 grid((f->width + TILE_W - 1) / TILE_W, (f->row_end - f->row_begin + TILE_H - 1) / TILE_H);
+    light_accumulate_kernel<<<grid, TILE_THREADS, 0, ctx->stream>>>(P);
+    ctx->launches++;
+    ILB_CUDA(ctx, cudaGetLastError());
+    return ILB_OK;
+}
+
+int ilb_probes_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const ilb_light_batch* batches, int batch_count,
+                      const ilb_light_vertex* vertices, int vertex_count, const ilb_float4* positions, const ilb_float4* normals,
+                      int probe_count, int output_format, void* probes_out_host) {
+    if (!f || !positions || !normals || !probes_out_host || probe_count < 0) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
+    if (output_format != ILB_FORMAT_FLOAT4 && output_format != ILB_FORMAT_HALF4) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "probe output must be FLOAT4 or HALF4");
+    if (df && df->ctx != ctx) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "distance field belongs to another context");
+    if (probe_count == 0) return ILB_OK;
+    ilb_lighting_frame fr = *f;  // coverage is irrelevant for probes; guard the scale check
+    if (!(fr.GBufferTexelSizeAndMisc.z > 0)) fr.GBufferTexelSizeAndMisc.z = 1;
+    if (!(fr.GBufferTexelSizeAndMisc.w > 0)) fr.GBufferTexelSizeAndMisc.w = 1;
+    std::vector<DLight> lights;
+    const ilb_df_uniforms* geometry = nullptr;
+    int rc = flattenLights(ctx, df, &fr, batches, batch_count, vertices, vertex_count, lights, &geometry);
+    if (rc) return rc;
+    rc = uploadLights(ctx, lights);
+    if (rc) return rc;
+    const size_t in_bytes = sizeof(float4) * (size_t)probe_count, out_bytes = ilb_format_bytes(output_format) * (size_t)probe_count;
+    rc = ilb_reserve(ctx, &ctx->d_probe_in, &ctx->d_probe_in_capacity, 2 * in_bytes + out_bytes, false);
+    if (rc) return rc;
+    char* base = reinterpret_cast<char*>(ctx->d_probe_in);
+    ILB_CUDA(ctx, cudaMemcpyAsync(base, positions, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ILB_CUDA(ctx, cudaMemcpyAsync(base + in_bytes, normals, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ProbeParams P;
+    memset(&P, 0, sizeof(P));
+    if (geometry && !ilb_make_df_geometry(df, *geometry, &P.df)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad distance-field uniforms");
+    P.lightOcclusion = f->EnvironmentZToY.z;
+    P.lights = reinterpret_cast<const DLight*>(ctx->d_lights);
+    P.nlights = (int)lights.size();
+    P.positions = reinterpret_cast<const float4*>(base);
+    P.normals = reinterpret_cast<const float4*>(base + in_bytes);
+    P.nprobes = probe_count;
+    P.out_format = output_format;
+    P.out = base + 2 * in_bytes;
+    probe_accumulate_kernel<<<(probe_count + 127) / 128, 128, 0, ctx->stream>>>(P);
+    ctx->launches++;
+    ILB_CUDA(ctx, cudaGetLastError());
+    ILB_CUDA(ctx, cudaMemcpyAsync(probes_out_host, P.out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ILB_OK;
+}

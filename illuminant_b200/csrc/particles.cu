@@ -1,0 +1,556 @@
+// PARTICLE hot path: the reference runs one full-chunk rasterised pass per
+// transform per chunk with ping-pong float4 render targets (Particles/ParticleSystem.cs:791-856, >= 304 B per
+// particle-step for Gravity+Noise+FMA+collision).  Here the whole chain is ONE kernel per update over all live
+// chunks: P,V (and attributes for live particles) are read once with 16-byte coalesced loads, the transform list
+// runs in registers in Transforms order, the Update / UpdateWithDistanceField tail follows, and P,V,renderColor,
+// renderData are stored once: 112 B per particle-step, the algorithmic minimum of the reference's contract.
+// State is SoA slabs (max_chunks * ChunkSize^2 float4 per attribute); particles never interact, so the update is
+// done in place (the reference's BufferSet rotation, ParticleSystem.cs:602-616, is not needed).
+//
+// Per-op math keeps the operation order of the reference shaders (file:line per function, relative to
+// Illuminant/Shaders/).
+#include <cstring>
+
+#include "ilb_internal.h"
+#include "ilb_shapes.cuh"
+
+namespace {
+
+constexpr int MAX_OPS = 8;
+constexpr int STEP_THREADS = 256;
+#define VelocityConstantScale 1000.0f
+
+struct StepParams {
+    float4 *P, *V, *A, *RC, *RD;
+    const float4* rng;
+    int rng_w, rng_h;
+    int chunk_size;
+    unsigned per_chunk;  // chunk_size^2
+    unsigned total;      // live_chunks * per_chunk
+    int nops;
+    DFGeometry df;
+    ilb_psys_uniforms u;
+    ilb_op ops[MAX_OPS];
+};
+
+struct SpawnParams {
+    float4 *P, *V, *A;
+    const float4* rng;
+    int rng_w, rng_h;
+    int chunk_size;
+    unsigned chunk_base;  // chunk * per_chunk
+    int first, count;
+    ilb_spawn s;
+};
+
+// ---- randomness (RandomCommon.fxh:17-34): POINT sampled, WRAP/WRAP -------------------------------------------
+ILB_DEV f4 randomFetch(const float4* rng, int w, int h, float u, float v) {
+    int ix = (int)floorf(u * (float)w), iy = (int)floorf(v * (float)h);
+    ix %= w; if (ix < 0) ix += w;
+    iy %= h; if (iy < 0) iy += h;
+    return mk4(__ldg(rng + (size_t)iy * (size_t)w + (size_t)ix));
+}
+ILB_DEV f4 randomCustom(const float4* rng, int w, int h, float x, float y, const float* offset, float ratex, float ratey,
+                        const float* texel) {  // :27-30
+    return randomFetch(rng, w, h, ((x * ratex) + offset[0]) * texel[0], ((y * ratey) + offset[1]) * texel[1]);
+}
+
+// ---- Bezier.fxh ------------------------------------------------------------------------------------------
+ILB_DEV float tForScaledBezier(const ilb_float4& rangeAndCount, float value, float& t) {  // :21-63
+    const float minValue = rangeAndCount.x, invDivisor = rangeAndCount.y;
+    const uint32_t mode = (uint32_t)fabsf(rangeAndCount.w);
+    const bool repeating = mode > 255, bouncing = mode > 511;
+    t = (value - minValue) * fabsf(invDivisor);
+    if (bouncing) {
+        t *= 2.0f;
+        if (invDivisor < 0.0f) t = 2.0f - fmodf(t, 2.0f); else t = fmodf(t, 2.0f);
+        if (t > 1.0f) t = 1.0f - (t - 1.0f);
+    } else if (repeating) {
+        if (invDivisor < 0.0f) t = 1.0f - fmodf(t, 1.0f); else t = fmodf(t, 1.0f);
+    } else {
+        if (invDivisor < 0.0f) t = 1.0f - saturatef(t); else t = saturatef(t);
+    }
+    switch (mode % 256) {
+        default: break;
+        case 1: t = sinf(t * ILB_PI * 0.5f); break;
+        case 2: t = t * t; break;
+    }
+    return rangeAndCount.z;
+}
+ILB_DEV float bezierScalar(float a, float b, float c, float d, float count, float t) {  // :65-95
+    if (count <= 1.5f) return a;
+    const float ab = lerpf(a, b, t);
+    if (count <= 2.5f) return ab;
+    if (count <= 3.5f) return (t <= 0.0f) ? a : ((t >= 1.0f) ? c : b);
+    const float bc = lerpf(b, c, t), abbc = lerpf(ab, bc, t), cd = lerpf(c, d, t), bccd = lerpf(bc, cd, t);
+    return lerpf(abbc, bccd, t);
+}
+ILB_DEV float evaluateBezier1(const ilb_bezier1& b, float value) {  // :97-101
+    float t;
+    const float count = tForScaledBezier(b.RangeAndCount, value, t);
+    return bezierScalar(b.ABCD.x, b.ABCD.y, b.ABCD.z, b.ABCD.w, count, t);
+}
+ILB_DEV f4 evaluateBezier4(const ilb_bezier4& b, float value) {  // :141-177
+    float t;
+    const float count = tForScaledBezier(b.RangeAndCount, value, t);
+    return mk4(bezierScalar(b.A.x, b.B.x, b.C.x, b.D.x, count, t), bezierScalar(b.A.y, b.B.y, b.C.y, b.D.y, count, t),
+               bezierScalar(b.A.z, b.B.z, b.C.z, b.D.z, count, t), bezierScalar(b.A.w, b.B.w, b.C.w, b.D.w, count, t));
+}
+
+// ---- transforms ------------------------------------------------------------------------------------------
+ILB_DEV float computeWeight(const ilb_area& a, f3 worldPosition) {  // FMA.fx:15-20 / Noise.fx:21-26 (scalar rotation broadcast)
+    const float distance = evaluateByTypeId(a.AreaType, worldPosition, mk3(a.AreaCenter[0], a.AreaCenter[1], a.AreaCenter[2]),
+                                            mk3(a.AreaSize[0], a.AreaSize[1], a.AreaSize[2]), mk4(a.AreaRotation));
+    return (1.0f - saturatef(distance / a.AreaFalloff)) * a.Strength;
+}
+ILB_DEV bool checkCategoryFilter(float type, const float* mm) { return (type >= mm[0]) && (type <= mm[1]); }  // ParticleCommon.fxh:198-200
+
+ILB_DEV void opGravity(const ilb_psys_uniforms& u, const ilb_gravity& g, f4& pos, f4& vel) {  // Gravity.fx:12-61
+    if ((pos.w <= 0.0f) || !checkCategoryFilter(vel.w, g.CategoryFilter)) return;
+    const float dt = u.GlobalSettings.x;
+    f3 acceleration = mk3(0.0f);
+    for (int i = 0; i < g.AttractorCount; i++) {
+        const f3 apos = xyz(g.AttractorPositions[i]);
+        const ilb_float4 ars = g.AttractorRadiusesAndStrengths[i];
+        const f3 toCenter = (apos - xyz(pos));
+        float attraction;
+        if (ars.z >= 0.5f) {
+            const float distance = length3(toCenter);
+            attraction = 1.0f - saturatef(distance / ars.x);
+            if (ars.z >= 1.5f) attraction *= attraction;
+            attraction = attraction * dt / VelocityConstantScale;
+        } else {
+            float distanceSquared = dot3(toCenter, toCenter) - ars.x;
+            distanceSquared = fmaxf(distanceSquared, 0.001f);
+            attraction = 1.0f / distanceSquared;
+        }
+        acceleration = acceleration + (normalize3(toCenter) * attraction * ars.y);
+    }
+    const float maximumAcceleration = g.MaximumAcceleration * dt / VelocityConstantScale;
+    const float currentLength = length3(acceleration);
+    if (currentLength > maximumAcceleration) acceleration = normalize3(acceleration) * maximumAcceleration;
+    const float mv = u.GlobalSettings.z;
+    vel = mk4(fminf(mv, vel.x + acceleration.x), fminf(mv, vel.y + acceleration.y), fminf(mv, vel.z + acceleration.z), vel.w);
+}
+
+ILB_DEV void opNoise(const StepParams& P, const ilb_noise& n, float x, float y, f4& pos, f4& vel) {  // Noise.fx:28-72
+    if (!checkCategoryFilter(vel.w, n.area.CategoryFilter)) return;
+    const float weight = computeWeight(n.area, xyz(pos));
+    const float t = weight * P.u.GlobalSettings.x / n.TimeDivisor;
+    const float rx = n.RandomnessTexel[0], ry = n.RandomnessTexel[1];
+    const f4 randomP1 = randomCustom(P.rng, P.rng_w, P.rng_h, x, y, n.RandomnessOffset, rx, ry, n.RandomnessTexel);
+    const f4 randomP2 = randomCustom(P.rng, P.rng_w, P.rng_h, x, y, n.NextRandomnessOffset, rx, ry, n.RandomnessTexel);
+    const f4 randomV1 = randomCustom(P.rng, P.rng_w, P.rng_h, x + 2.0f, y + 1.0f, n.RandomnessOffset, rx, ry, n.RandomnessTexel);
+    const f4 randomV2 = randomCustom(P.rng, P.rng_w, P.rng_h, x + 2.0f, y + 1.0f, n.NextRandomnessOffset, rx, ry, n.RandomnessTexel);
+    const f4 randomP = lerp4(randomP1, randomP2, n.FrequencyLerp);
+    const f4 randomV = lerp4(randomV1, randomV2, n.FrequencyLerp);
+    f4 positionDelta = (randomP + mk4(n.PositionOffset));
+    positionDelta = sign4(positionDelta) * max4(abs4(positionDelta), mk4(n.PositionMinimum));
+    positionDelta = positionDelta * mk4(n.PositionScale);
+    f4 velocityDelta = (randomV + mk4(n.VelocityOffset));
+    velocityDelta = sign4(velocityDelta) * max4(abs4(velocityDelta), mk4(n.VelocityMinimum));
+    velocityDelta = velocityDelta * mk4(n.VelocityScale);
+    const f4 oldPosition = pos;
+    const f3 ov = xyz(vel);
+    pos = lerp4(oldPosition, oldPosition + positionDelta, t);
+    f3 nv;
+    if (n.ReplaceOldVelocity != 0.0f) nv = lerp3(ov, xyz(velocityDelta), weight);
+    else nv = lerp3(ov, ov + xyz(velocityDelta), t);
+    nv = nv + (normalize3(ov) * velocityDelta.w);
+    vel = mk4(nv, vel.w);
+}
+
+ILB_DEV void opFMA(const ilb_psys_uniforms& u, const ilb_fma& f, f4& pos, f4& vel) {  // FMA.fx:22-51
+    if ((pos.w <= 0.0f) || !checkCategoryFilter(vel.w, f.area.CategoryFilter)) return;
+    const float weight = computeWeight(f.area, xyz(pos));
+    const float t = weight * u.GlobalSettings.x / f.TimeDivisor;
+    const f4 oldPosition = pos, oldVelocity = vel;
+    pos = lerp4(oldPosition, (oldPosition * mk4(f.PositionMultiply)) + mk4(f.PositionAdd), t);
+    vel = lerp4(oldVelocity, (oldVelocity * mk4(f.VelocityMultiply)) + mk4(f.VelocityAdd), t);
+}
+
+ILB_DEV f4 mul3(f4 oldValue, const float* mat, float w) {  // ParticleCommon.fxh:187-196
+    const f4 temp = mul_rm(mk4(oldValue.x, oldValue.y, oldValue.z, 1.0f), mat);
+    f3 divided = xyz(temp);
+    if (w != 0.0f) divided = divided / temp.w;
+    return mk4(divided, oldValue.w);
+}
+
+ILB_DEV void opMatrix(const ilb_psys_uniforms& u, const ilb_matrix_multiply& m, f4& pos, f4& vel) {  // MatrixMultiply.fx:14-52
+    if ((pos.w <= 0.0f) || !checkCategoryFilter(vel.w, m.area.CategoryFilter)) return;
+    const float timeScale = (m.TimeDivisor >= 0.0f) ? u.GlobalSettings.x / m.TimeDivisor : 1.0f;
+    const float w = computeWeight(m.area, xyz(pos)) * timeScale;
+    const f4 oldPosition = pos, oldVelocity = vel;
+    pos = lerp4(oldPosition, mul3(oldPosition, m.PositionMatrix, 1.0f), w);
+    vel = lerp4(oldVelocity, mul3(oldVelocity, m.VelocityMatrix, 0.0f), w);
+}
+
+// ---- update tail (UpdateCommon.fxh, UpdateParticleSystem.fx, UpdateParticleSystemWithDistanceField.fx) -------------
+ILB_DEV f3 applyFrictionAndMaximum(const ilb_psys_uniforms& u, f3 velocity) {  // UpdateCommon.fxh:20-35
+    float l = length3(velocity);
+    if (l <= 0.001f) return mk3(0.0f);
+    const float mv = u.GlobalSettings.z;
+    if (l > mv) l = mv;
+    const float friction = l * u.GlobalSettings.y;
+    l -= (friction * (u.GlobalSettings.x / VelocityConstantScale));
+    l = clampf(l, 0.0f, mv);
+    return normalize3(velocity) * l;
+}
+
+ILB_DEV void computeRenderData(const ilb_psys_uniforms& u, float vx, float vy, f4 position, f4 velocity, f4 attributes,
+                               f4& renderColor, f4& renderData) {  // UpdateCommon.fxh:97-117
+    if (position.w <= 0.0f) {
+        renderColor = mk4(0.0f);
+        renderData = mk4(0.0f);
+        return;
+    }
+    const float index = vx + (vy * 256.0f);  // hard-coded 256 (:107)
+    const float velocityLength = fmaxf(length3(xyz(velocity)), 0.0001f);
+    f4 ramped = evaluateBezier4(u.ColorFromLife, position.w);
+    ramped = ramped * evaluateBezier4(u.ColorFromVelocity, velocityLength);
+    renderColor = attributes * ramped;
+    renderColor.w = saturatef(renderColor.w);
+    renderColor.x *= renderColor.w; renderColor.y *= renderColor.w; renderColor.z *= renderColor.w;
+    float size = evaluateBezier1(u.SizeFromLife, position.w);
+    size *= evaluateBezier1(u.SizeFromVelocity, velocityLength);
+    float rotation = 0.0f;  // getRotationForVelocity :82-95
+    if (!((fabsf(velocity.x) < 0.01f) && (fabsf(velocity.y) < 0.01f))) {
+        rotation = atan2f(velocity.y, velocity.x);
+        if (rotation < 0.0f) rotation += 2.0f * ILB_PI;
+    }
+    renderData.x = size;
+    renderData.y = (rotation * u.AnimationRateAndRotationAndZToY.z) +
+                   ((position.w * u.RotationFromLifeAndIndex[0]) + (index * u.RotationFromLifeAndIndex[1]));
+    renderData.z = velocityLength;
+    renderData.w = velocity.w;
+}
+
+ILB_DEV f3 estimateNormal4(const DFGeometry& g, f3 position) {  // VisualizeCommon.fxh:9-63
+    const f3 texel = mk3(g.invScaleX, g.invScaleY, g.ez / fmaxf(g.sliceCount, 1.0f));
+    f3 result = mk3(0.0f);
+    const float wts[4][3] = {{1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {1, 1, 1}};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const f3 weight = mk3(wts[i][0], wts[i][1], wts[i][2]);
+        result = result + (weight * sampleDistanceField(g, position + weight * texel));
+    }
+    return normalize3(result);
+}
+
+// returns false when the reference pass discards (dead on entry): outputs stay at the cleared zeros
+template <bool COLLIDE>
+ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f4 oldVelocity, f4& outP, f4& outV, bool& needAttr) {
+    const ilb_psys_uniforms& u = P.u;
+    outP = mk4(0.0f);
+    outV = mk4(0.0f);
+    needAttr = false;
+    if (oldPosition.w <= 0.0f) return false;  // readStateOrDiscard ParticleCommon.fxh:162-181
+    const float dts = u.GlobalSettings.x / VelocityConstantScale;
+    float newLife = oldPosition.w - (u.GlobalSettings.w * dts);
+    if (!COLLIDE) {  // PS_Update UpdateParticleSystem.fx:9-38
+        const f3 velocity = applyFrictionAndMaximum(u, xyz(oldVelocity));
+        const f3 scaledVelocity = velocity * dts;
+        if (newLife > 0.0f) {
+            outP = mk4(xyz(oldPosition) + scaledVelocity, newLife);
+            outV = mk4(velocity, oldVelocity.w);
+            needAttr = true;
+        }
+        return true;
+    }
+    // PS_Update UpdateParticleSystemWithDistanceField.fx:29-147
+    if (newLife <= 0.0f) return true;
+    const float collisionDistance = u.CollisionSettings.z;
+    const f3 op = xyz(oldPosition);
+    const f3 unitVector = normalize3(xyz(oldVelocity));
+    const f3 velocity = applyFrictionAndMaximum(u, xyz(oldVelocity));
+    bool collided = false, escaping = false;
+    const f3 scaledVelocity = velocity * dts;
+    f3 collisionPosition = mk3(0.0f), newPosition = op;
+    f4 newVelocity = mk4(0.0f);
+
+    const float initialDistance = sampleDistanceField(P.df, op);
+    const bool wasColliding = initialDistance < collisionDistance;
+    float travelDistance = fmaxf(0.0f, fminf(initialDistance, length3(scaledVelocity)));
+    int stepCount = 3;
+    if (wasColliding) stepCount = 1;
+    else if (travelDistance <= 0.001f) stepCount = 0;
+    for (int i = 0; i < stepCount; i++) {
+        const f3 testPosition = op + (travelDistance * unitVector);
+        const float stepDistance = sampleDistanceField(P.df, testPosition);
+        if (stepDistance < collisionDistance) {
+            collided = true;
+            collisionPosition = testPosition;
+        }
+        escaping = stepDistance > initialDistance;
+        if (collided && !escaping) {
+            collisionPosition = testPosition;
+            const float offset = clampf(stepDistance + collisionDistance, 0.05f, 16.0f);
+            travelDistance = fmaxf(0.0f, travelDistance - offset);
+        } else
+            stepCount = 0;
+        if (travelDistance <= 0.001f) stepCount = 0;
+    }
+    if (collided) {
+        const bool bounce = oldVelocity.w <= 0.0f;
+        const bool redirect = wasColliding && !escaping;
+        f3 normal = mk3(0.0f);
+        if (bounce || redirect) normal = estimateNormal4(P.df, collisionPosition);
+        const float maxV = u.GlobalSettings.z;
+        const float escapeSpeed = fminf(maxV, u.CollisionSettings.x);
+        if (redirect) {
+            normal = normal * mk3(1.0f, 1.0f, 0.0f);
+            if (length3(normal) < 0.33f) {
+                float s, c;
+                sincosf((x / 67.0f) + (y / 13.0f), &s, &c);
+                normal = mk3(s, c, 0.0f);
+            }
+            const f3 escapeVector = normalize3(normal);
+            newVelocity = mk4(escapeVector * escapeSpeed * 0.33f, 3.0f);
+            newPosition = op + (xyz(newVelocity) * dts);
+        } else if (bounce) {
+            f3 bounceVector = -(2.0f * dot3(normal, unitVector) * (normal - unitVector));
+            if (length3(bounceVector) < 0.33f) bounceVector = -unitVector;
+            else bounceVector = normalize3(bounceVector);
+            newPosition = collisionPosition;
+            newVelocity = mk4(bounceVector * (fminf(maxV, length3(velocity) * u.CollisionSettings.y)), 3.0f);
+            newLife -= u.CollisionSettings.w;
+        } else {
+            const float currentSpeed = length3(xyz(oldVelocity));
+            const float newSpeed = fmaxf(currentSpeed * 1.1f, escapeSpeed);
+            newVelocity = mk4(unitVector * newSpeed, 0.0f);
+            newPosition = op + (travelDistance * unitVector);
+        }
+    } else {
+        newVelocity = mk4(velocity, fmaxf(oldVelocity.w - 1.0f, 0.0f));
+        newPosition = op + (travelDistance * unitVector);
+    }
+    if (newLife <= 0.0f) {
+        newPosition = mk3(0.0f);
+        newVelocity = mk4(0.0f);
+    }
+    outP = mk4(newPosition, newLife);
+    outV = newVelocity;
+    needAttr = newLife > 0.0f;
+    return true;
+}
+
+template <bool COLLIDE>
+__global__ void __launch_bounds__(STEP_THREADS) particle_step_kernel(const __grid_constant__ StepParams P) {
+    const unsigned gi = blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (gi >= P.total) return;
+    const unsigned i = gi % P.per_chunk;
+    const float x = (float)(i % (unsigned)P.chunk_size), y = (float)(i / (unsigned)P.chunk_size);
+    f4 pos = mk4(P.P[gi]), vel = mk4(P.V[gi]);
+
+    for (int k = 0; k < P.nops; k++) {
+        const ilb_op& op = P.ops[k];
+        switch (op.kind) {
+            case ILB_OP_GRAVITY: opGravity(P.u, op.u.gravity, pos, vel); break;
+            case ILB_OP_NOISE: opNoise(P, op.u.noise, x, y, pos, vel); break;
+            case ILB_OP_FMA: opFMA(P.u, op.u.fma, pos, vel); break;
+            case ILB_OP_MATRIX_MULTIPLY: opMatrix(P.u, op.u.matrix, pos, vel); break;
+            default: break;
+        }
+    }
+
+    f4 outP, outV;
+    bool needAttr;
+    updateTail<COLLIDE>(P, x, y, pos, vel, outP, outV, needAttr);
+    P.P[gi] = to_float4(outP);
+    P.V[gi] = to_float4(outV);
+    if (P.u.write_render_outputs) {
+        f4 rc = mk4(0.0f), rd = mk4(0.0f);
+        if (needAttr) computeRenderData(P.u, x, y, outP, outV, mk4(__ldg(P.A + gi)), rc, rd);
+        P.RC[gi] = to_float4(rc);
+        P.RD[gi] = to_float4(rd);
+    }
+}
+
+// ---- spawner (SpawnerCommon.fxh, SpawnParticles.fx:10-30) -----------------------------------------------------
+ILB_DEV f3 generateRandomNormal3(float rx, float ry) {  // :47-57
+    const float phi = rx * ILB_PI * 2.0f;
+    const float costheta = (ry - 0.5f) * 2.0f;
+    const float theta = acosf(costheta);
+    return mk3(sinf(theta) * cosf(phi), sinf(theta) * sinf(phi), cosf(theta));
+}
+
+ILB_DEV f4 evaluateFormula(const ilb_spawn& s, f4 origin, f4 constant, f4 scale, f4 offset, f4 randomness, float type) {  // :59-104
+    const f4 nonCircular = (randomness + offset) * scale;
+    const f4 type0 = constant + nonCircular;
+    const uint32_t itype = (uint32_t)fabsf(floorf(type));
+    if (itype == 1 || itype == 3) {
+        const f3 axisMask = mk3(s.AxisMask[0], s.AxisMask[1], s.AxisMask[2]);
+        const f3 randomNormal = normalize3(generateRandomNormal3(randomness.x, randomness.y) * axisMask);
+        f3 circular = mk3(randomNormal.x * randomness.z * scale.x, randomNormal.y * randomness.z * scale.y,
+                          randomNormal.z * randomness.z * scale.z);
+        f3 result;
+        if (itype == 3) {
+            const float sqrt2 = 1.41421356237f;
+            const f3 edge = abs3(xyz(offset));
+            result = min3(max3(xyz(offset) * randomNormal * sqrt2, -edge), edge);
+            result = result + (xyz(constant) + circular);
+        } else {
+            circular = circular + (randomNormal * xyz(offset));
+            result = xyz(constant) + circular;
+        }
+        return mk4(result, type0.w);
+    } else if (itype == 2) {
+        const f3 distance = xyz(constant - origin);
+        const float ldistance = length3(distance);
+        if (ldistance < 0.1f) return mk4(0.0f, 0.0f, 0.0f, constant.w);
+        const f3 direction = distance / ldistance;
+        const f3 randomSpeed = (randomness.x * xyz(scale) * direction);
+        const f3 fixedSpeed = (xyz(offset) * direction);
+        return mk4(randomSpeed + fixedSpeed, type0.w);
+    }
+    return type0;
+}
+
+__global__ void __launch_bounds__(STEP_THREADS) particle_spawn_kernel(const __grid_constant__ SpawnParams P) {
+    const int k = blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (k >= P.count) return;
+    const ilb_spawn& s = P.s;
+    const int li = P.first + k;  // index within the chunk, inside [first, last] by construction (Spawn_Stage1 :124-130)
+    const float index = (float)(li % P.chunk_size) + ((float)(li / P.chunk_size) * s.ChunkSizeAndIndices.x);
+    if ((index < s.ChunkSizeAndIndices.y) || (index > s.ChunkSizeAndIndices.z)) return;
+
+    // evaluateRandomForIndex :106-117
+    const float one = 1.0f;
+    f4 random1 = randomCustom(P.rng, P.rng_w, P.rng_h, fmodf(index, 8039.0f), 0.0f + fmodf(index, 57.0f), s.RandomnessOffset, one, one, s.RandomnessTexel);
+    f4 random2 = randomCustom(P.rng, P.rng_w, P.rng_h, fmodf(index, 6180.0f), 1.0f + fmodf(index, 4031.0f), s.RandomnessOffset, one, one, s.RandomnessTexel);
+    const f4 random3 = randomCustom(P.rng, P.rng_w, P.rng_h, fmodf(index, 2025.0f), 2.0f + fmodf(index, 65531.0f), s.RandomnessOffset, one, one, s.RandomnessTexel);
+    if (s.AlignVelocityAndPosition != 0.0f) { random2.x = random1.x; random2.y = random1.y; }
+
+    int index1, index2;
+    float positionIndexT;
+    const float relativeIndex = (index - s.ChunkSizeAndIndices.y);
+    if (s.PolygonRate > 0.05f) {
+        const float positionIndexF = (relativeIndex / s.PolygonRate) + s.ChunkSizeAndIndices.w;
+        const float divisor = s.PositionConstantCount;
+        float positionIndexI;
+        positionIndexT = modff(positionIndexF, &positionIndexI);
+        index1 = (int)fmodf(positionIndexI, divisor);
+        if (s.PolygonLoop != 0.0f) index2 = (int)fmodf(positionIndexI + 1.0f, divisor);
+        else index2 = (int)fminf((float)(index1 + 1), divisor - 1.0f);
+    } else {
+        index1 = index2 = (int)fmodf(relativeIndex + s.ChunkSizeAndIndices.w, s.PositionConstantCount);
+        positionIndexT = 0.0f;
+    }
+    index1 = min(max(index1, 0), 3);
+    index2 = min(max(index2, 0), 3);
+    const f4 position1 = mk4(s.InlinePositionConstants[index1]), position2 = mk4(s.InlinePositionConstants[index2]);
+    const f4 positionConstant = lerp4(position1, position2, positionIndexT);
+    const f4 towardsNext = position2 - position1;
+
+    // Spawn_Stage2 :157-190
+    const ilb_float4* C = s.Configuration;
+    const f4 tempPosition = evaluateFormula(s, mk4(0.0f), positionConstant, mk4(C[0]), mk4(C[1]), random1, s.FormulaTypes.x);
+    f4 newPosition = mul_rm(mk4(tempPosition.x, tempPosition.y, tempPosition.z, 1.0f), s.PositionMatrix);
+    newPosition.w = tempPosition.w;
+    f4 tempVelocity = evaluateFormula(s, tempPosition, mk4(C[2]), mk4(C[3]), mk4(C[4]), random2, s.FormulaTypes.y);
+    const f4 newAttributes = evaluateFormula(s, mk4(0.0f), mk4(C[5]), mk4(C[6]), mk4(C[7]), random3, s.FormulaTypes.z);
+    const float towardsDistance = length4(towardsNext);
+    if (towardsDistance > 0.0001f) {
+        const float towardsSpeed = evaluateFormula(s, mk4(0.0f), mk4(C[8].x), mk4(C[8].y), mk4(C[8].z), mk4(random3.w), s.FormulaTypes.w).x;
+        tempVelocity = tempVelocity + (towardsSpeed * (towardsNext / towardsDistance));
+    }
+    f4 newVelocity = mul_rm(mk4(tempVelocity.x, tempVelocity.y, tempVelocity.z, 1.0f), s.VelocityMatrix);
+    newVelocity.w = tempVelocity.w;
+    if (newAttributes.w < s.AttributeDiscardThreshold) return;  // discard: the texel keeps its old contents
+    const size_t gi = (size_t)P.chunk_base + (size_t)li;
+    P.P[gi] = to_float4(newPosition);
+    P.V[gi] = to_float4(newVelocity);
+    P.A[gi] = to_float4(newAttributes);
+}
+
+__global__ void __launch_bounds__(256) particle_count_live_kernel(const float4* __restrict__ P, unsigned total, unsigned long long* out) {
+    unsigned local = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) local += (__ldg(P + i).w > 0.0f) ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, (unsigned long long)local);
+}
+
+}  // namespace
+
+int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spawn* spawns, int spawn_count, const ilb_op* ops,
+                         int op_count, int steps) {
+    ilb_ctx* ctx = ps->ctx;
+    if (!u || spawn_count < 0 || op_count < 0 || steps < 0 || (spawn_count > 0 && !spawns) || (op_count > 0 && !ops))
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null or negative argument");
+    if (op_count > MAX_OPS) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "at most %d transforms per system", MAX_OPS);
+    if (u->LifeRampSettings.x != 0.0f) return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "life-ramp textures are outside the hot-path scope");
+    if (u->has_collision_field && !ps->field)  // ParticleSystem.cs:834-836
+        return ilb_fail(ctx, ILB_ERR_INVALID_OPERATION, "collision is enabled but no distance field was set");
+    bool needsRng = spawn_count > 0;
+    for (int k = 0; k < op_count; k++) {
+        const int kind = ops[k].kind;
+        if (kind < ILB_OP_GRAVITY || kind > ILB_OP_MATRIX_MULTIPLY) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "op %d: unknown kind %d", k, kind);
+        if (kind == ILB_OP_GRAVITY && (ops[k].u.gravity.AttractorCount < 0 || ops[k].u.gravity.AttractorCount > ILB_MAX_ATTRACTORS))
+            return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "Maximum number of attractors per instance is %d", ILB_MAX_ATTRACTORS);  // Transforms.cs:348-349
+        needsRng |= (kind == ILB_OP_NOISE);
+    }
+    if (needsRng && !ps->rng) return ilb_fail(ctx, ILB_ERR_INVALID_OPERATION, "the randomness texture was not set");
+
+    for (int step = 0; step < steps; step++) {
+        for (int si = 0; si < spawn_count; si++) {
+            const ilb_spawn& s = spawns[si];
+            if (s.chunk < 0 || s.chunk >= ps->live_chunks) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: chunk %d is not live", si, s.chunk);
+            if (s.PositionConstantCount > 4.0f || s.PositionConstantCount < 1.0f)
+                return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "spawn %d: 1..4 inline positions supported (SpawnFromPositionTexture is out of scope)", si);
+            if ((int)s.ChunkSizeAndIndices.x != ps->chunk_size) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: ChunkSize mismatch", si);
+            int first = (int)s.ChunkSizeAndIndices.y, last = (int)s.ChunkSizeAndIndices.z;
+            first = std::max(first, 0);
+            last = std::min(last, (int)ps->per_chunk - 1);
+            if (last < first) continue;
+            SpawnParams SP;
+            memset(&SP, 0, sizeof(SP));
+            SP.P = ps->buf[0]; SP.V = ps->buf[1]; SP.A = ps->buf[2];
+            SP.rng = ps->rng; SP.rng_w = ps->rng_w; SP.rng_h = ps->rng_h;
+            SP.chunk_size = ps->chunk_size;
+            SP.chunk_base = (unsigned)((size_t)s.chunk * ps->per_chunk);
+            SP.first = first; SP.count = last - first + 1;
+            SP.s = s;
+            particle_spawn_kernel<<<(SP.count + STEP_THREADS - 1) / STEP_THREADS, STEP_THREADS, 0, ctx->stream>>>(SP);
+            ctx->launches++;
+        }
+        const size_t total = (size_t)ps->live_chunks * ps->per_chunk;
+        if (total == 0) continue;
+        StepParams SP;
+        memset(&SP, 0, sizeof(SP));
+        SP.P = ps->buf[0]; SP.V = ps->buf[1]; SP.A = ps->buf[2]; SP.RC = ps->buf[3]; SP.RD = ps->buf[4];
+        SP.rng = ps->rng; SP.rng_w = ps->rng_w; SP.rng_h = ps->rng_h;
+        SP.chunk_size = ps->chunk_size;
+        SP.per_chunk = (unsigned)ps->per_chunk;
+        SP.total = (unsigned)total;
+        SP.nops = op_count;
+        SP.u = *u;
+        for (int k = 0; k < op_count; k++) SP.ops[k] = ops[k];
+        const unsigned blocks = (unsigned)((total + STEP_THREADS - 1) / STEP_THREADS);
+        if (u->has_collision_field) {
+            if (!ilb_make_df_geometry(ps->field, u->CollisionField, &SP.df))
+                return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "collision field uniforms describe an empty field");
+            particle_step_kernel<true><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);
+        } else {
+            particle_step_kernel<false><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);
+        }
+        ctx->launches++;
+    }
+    ILB_CUDA(ctx, cudaGetLastError());
+    return ILB_OK;
+}
+
+int ilb_particles_count_launch(ilb_psys* ps, int64_t* out) {
+    ilb_ctx* ctx = ps->ctx;
+    const size_t total = (size_t)ps->live_chunks * ps->per_chunk;
+    ILB_CUDA(ctx, cudaMemsetAsync(ps->d_count, 0, sizeof(unsigned long long), ctx->stream));
+    if (total) {
+        particle_count_live_kernel<<<148 * 4, 256, 0, ctx->stream>>>(ps->buf[0], (unsigned)total, ps->d_count);
+        ctx->launches++;
+    }
+    unsigned long long h = 0;
+    ILB_CUDA(ctx, cudaMemcpyAsync(&h, ps->d_count, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = (int64_t)h;
+    return ILB_OK;
+}

@@ -1,0 +1,375 @@
+"""Host-side mirror of the reference lighting API for the hot path: LightingEnvironment, the three light-source types
+the path covers, RendererConfiguration and LightingRenderer.RenderLighting / UpdateLightProbes.
+
+Names, defaults and packing follow the reference (Illuminant/Lighting/*.cs, cited per member); the work the
+reference enqueues as instanced draws (LightingRenderer.cs:1112-1168) becomes one call into the C-ABI
+(`ilb_render_lighting*`).  Only evaluated values cross the boundary.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import _abi
+from ._abi import (FORMAT_FLOAT4, FORMAT_HALF4, FORMAT_RGBA8, LIGHT_DIRECTIONAL, LIGHT_LINE, LIGHT_SPHERE, DFUniforms, Float4,
+                   LightBatch, LightingFrame, LightVertex)
+from .distance_field import DistanceField, LightObstruction, RendererQualitySettings
+
+F = np.float32
+
+
+class LightSourceRampMode:  # LightSource.cs:622-629
+    Linear, Exponential, None_ = 0, 1, 2
+
+
+class ShadowFilter:  # LightSource.cs:23-27
+    None_, Unshadowed, Shadowed = -1, 0, 1
+
+
+@dataclass
+class LightSource:  # LightSource.cs:58-82
+    Opacity: float = 1.0
+    CastsShadows: bool = True
+    ShadowDistanceFalloff: Optional[float] = None
+    AmbientOcclusionRadius: float = 0.0
+    AmbientOcclusionOpacity: float = 1.0
+    FalloffYFactor: float = 1.0
+    RampOffsetAndRate: Tuple[float, float] = (0.0, 1.0)
+    Quality: Optional[RendererQualitySettings] = None
+    Enabled: bool = True
+    SortKey: int = 0
+
+    @property
+    def RampOffsetForGPU(self) -> float:
+        return float(F(-math.pi) + F(self.RampOffsetAndRate[0]))
+
+    @property
+    def RampRateForGPU(self) -> float:
+        return float(F(1.0 / (math.pi * 2) * self.RampOffsetAndRate[1]))
+
+
+@dataclass
+class SphereLightSource(LightSource):  # LightSource.cs:171-250
+    Position: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    Radius: float = 0.0
+    RampLength: float = 1.0
+    RampMode: int = LightSourceRampMode.Linear
+    Color: Tuple[float, float, float, float] = (1.0, 1.0, 1.0, 1.0)
+    SpecularColor: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    SpecularPower: float = 2.0
+    ShadowFilter: int = ShadowFilter.None_
+    TypeID = LIGHT_SPHERE
+
+
+@dataclass
+class DirectionalLightSource(LightSource):  # LightSource.cs:84-169
+    _Direction: Optional[Tuple[float, float, float]] = None
+    Bounds: Optional[Tuple[Tuple[float, float], Tuple[float, float]]] = None  # (TopLeft, BottomRight)
+    ShadowTraceLength: float = 256
+    ShadowSoftness: float = 12
+    ShadowRampRate: float = 0.5
+    Color: Tuple[float, float, float, float] = (1.0, 1.0, 1.0, 1.0)
+    ShadowFilter: int = ShadowFilter.None_
+    TypeID = LIGHT_DIRECTIONAL
+
+    @property
+    def Direction(self):
+        return self._Direction
+
+    @Direction.setter
+    def Direction(self, value):
+        if value is None:
+            self._Direction = None
+            return
+        v = np.asarray(value, dtype=F)
+        n = F(np.sqrt(F(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])))
+        self._Direction = tuple(float(c) for c in (v / n))  # Vector3.Normalize
+
+
+@dataclass
+class LineLightSource(LightSource):  # LightSource.cs:252-
+    StartPosition: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    EndPosition: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    Radius: float = 0.0
+    RampMode: int = LightSourceRampMode.Linear
+    StartColor: Tuple[float, float, float, float] = (1.0, 1.0, 1.0, 1.0)
+    EndColor: Tuple[float, float, float, float] = (1.0, 1.0, 1.0, 1.0)
+    TypeID = LIGHT_LINE
+
+
+@dataclass
+class LightProbe:  # Lighting/LightProbe.cs
+    Position: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    Normal: Optional[Tuple[float, float, float]] = None
+    EnableShadows: bool = True
+
+
+@dataclass
+class LightingEnvironment:  # Lighting/LightingEnvironment.cs
+    Lights: List[LightSource] = field(default_factory=list)
+    Obstructions: List[LightObstruction] = field(default_factory=list)
+    GroundZ: float = 0.0
+    MaximumZ: float = 128.0
+    ZToYMultiplier: float = 1.0
+    Ambient: Tuple[float, float, float, float] = (0.0, 0.0, 0.0, 1.0)
+
+
+@dataclass
+class RendererConfiguration:  # Lighting/LightingRenderer.Configuration.cs:13-252
+    MaximumRenderSize: Tuple[int, int] = (1920, 1080)
+    HighQuality: bool = True            # HalfVector4 lightmap (LightingRenderer.cs:477-479)
+    HighQualityGBuffer: bool = True     # Vector4 G-buffer (GBuffer.cs:31-39)
+    StencilCulling: bool = False
+    EnableGBuffer: bool = True
+    GBufferViewportRelative: bool = False
+    TwoPointFiveD: bool = False
+    ScaleCompensation: bool = True
+    AllowFullbright: bool = True
+    LightOcclusion: float = 0.0
+    RenderScale: Tuple[float, float] = (1.0, 1.0)
+    MaximumLightProbeCount: int = 256
+    DefaultQuality: RendererQualitySettings = field(default_factory=RendererQualitySettings)
+    Float4Lightmap: bool = False        # not in the reference: fp32 lightmap for parity tests (no half rounding)
+
+
+def _vec4(v, w=None) -> Float4:
+    v = list(v)
+    if w is not None:
+        v = v[:3] + [w]
+    return Float4(*v)
+
+
+def pack_light_vertex(light: LightSource, intensityScale: float, hasDistanceField: bool) -> Optional[LightVertex]:
+    """Render{Sphere,Directional,Line}LightSource (LightingRenderer.cs:1193-1219, :1256-1307, :1309-1337)."""
+    if light.Opacity <= 0:
+        return None
+    v = LightVertex()
+    falloff = -99999.0 if light.ShadowDistanceFalloff is None else light.ShadowDistanceFalloff
+    opacity = F(light.Opacity) * F(intensityScale)
+    if isinstance(light, SphereLightSource):
+        v.LightPosition1 = v.LightPosition2 = v.LightPosition3 = _vec4(list(light.Position) + [0])
+        color = list(light.Color)
+        color[3] = float(F(color[3]) * opacity)
+        v.Color1 = _vec4(color)
+        v.Color2 = _vec4(list(light.SpecularColor) + [light.SpecularPower])
+        v.LightProperties = Float4(light.Radius, light.RampLength, int(light.RampMode), 1.0 if (light.CastsShadows and hasDistanceField) else 0.0)
+        v.MoreLightProperties = Float4(light.AmbientOcclusionRadius, falloff, light.FalloffYFactor, light.AmbientOcclusionOpacity)
+        v.EvenMoreLightProperties = Float4(int(light.ShadowFilter), 0, light.RampOffsetForGPU, light.RampRateForGPU)
+    elif isinstance(light, DirectionalLightSource):
+        if light.Bounds is not None:
+            v.LightPosition1 = Float4(light.Bounds[0][0], light.Bounds[0][1], 0, 0)
+            v.LightPosition2 = Float4(light.Bounds[1][0], light.Bounds[1][1], 0, 0)
+        else:
+            v.LightPosition1 = Float4(-99999, -99999, 0, 0)
+            v.LightPosition2 = Float4(99999, 99999, 0, 0)
+        color = list(light.Color)
+        color[3] = float(F(color[3]) * opacity)
+        v.Color1 = _vec4(color)
+        v.Color2 = _vec4(list(light._Direction) + [1.0]) if light._Direction is not None else Float4()
+        v.LightProperties = Float4(1.0 if light.CastsShadows else 0.0, light.ShadowTraceLength, light.ShadowSoftness, light.ShadowRampRate)
+        v.MoreLightProperties = Float4(light.AmbientOcclusionRadius, falloff, 0, light.AmbientOcclusionOpacity)
+        v.EvenMoreLightProperties = Float4(int(light.ShadowFilter), 0, light.RampOffsetForGPU, light.RampRateForGPU)
+    elif isinstance(light, LineLightSource):
+        v.LightPosition1 = _vec4(list(light.StartPosition) + [0])
+        v.LightPosition2 = _vec4(list(light.EndPosition) + [0])
+        c1, c2 = list(light.StartColor), list(light.EndColor)
+        c1[3] = float(F(c1[3]) * opacity)
+        c2[3] = float(F(c2[3]) * opacity)
+        v.Color1, v.Color2 = _vec4(c1), _vec4(c2)
+        v.LightProperties = Float4(light.Radius, 0, int(light.RampMode), 1.0 if (light.CastsShadows and hasDistanceField) else 0.0)
+        v.MoreLightProperties = Float4(light.AmbientOcclusionRadius, falloff, light.FalloffYFactor, light.AmbientOcclusionOpacity)
+        v.EvenMoreLightProperties = Float4(0, 0, light.RampOffsetForGPU, light.RampRateForGPU)
+    else:
+        raise NotImplementedError(type(light).__name__)  # LightingRenderer.cs:203
+    return v
+
+
+class LightingRenderer:
+    """LightingRenderer(content, coordinator, materials, environment, configuration) -- the parts on the hot path."""
+
+    def __init__(self, ctx: Optional[_abi.Context], environment: LightingEnvironment, configuration: RendererConfiguration):
+        self.ctx = ctx
+        self.Environment = environment
+        self.Configuration = configuration
+        self.DistanceField: Optional[DistanceField] = None
+        self.Probes: List[LightProbe] = []
+        self.ViewportPosition = (0.0, 0.0)   # Materials.ViewportPosition
+        self.ViewportScale = (1.0, 1.0)      # Materials.ViewportScale
+        self._gbuffer_shape = None
+
+    # ---- G-buffer ---------------------------------------------------------------------------------------------
+    def SetGBuffer(self, texels: Optional[np.ndarray]) -> None:
+        """Uploads the G-buffer (encoding GBufferShaderCommon.fxh:10-35): float32 [H,W,4] when HighQualityGBuffer,
+        else float16.  None disables it (Configuration.EnableGBuffer = false)."""
+        if texels is None:
+            self.ctx.check(self.ctx.lib.ilb_gbuffer_upload(self.ctx.handle, 0, 0, FORMAT_FLOAT4, None))
+            self._gbuffer_shape = None
+            return
+        fmt = FORMAT_FLOAT4 if self.Configuration.HighQualityGBuffer else FORMAT_HALF4
+        arr = np.ascontiguousarray(texels, dtype=np.float32 if fmt == FORMAT_FLOAT4 else np.float16)
+        h, w = arr.shape[0], arr.shape[1]
+        self.ctx.check(self.ctx.lib.ilb_gbuffer_upload(self.ctx.handle, w, h, fmt, arr.ctypes.data_as(C.c_void_p)))
+        self._gbuffer_shape = (h, w)
+
+    def SetGBufferDevice(self, device_ptr: int, width: int, height: int) -> None:
+        fmt = FORMAT_FLOAT4 if self.Configuration.HighQualityGBuffer else FORMAT_HALF4
+        self.ctx.check(self.ctx.lib.ilb_gbuffer_upload_device(self.ctx.handle, width, height, fmt, C.c_void_p(device_ptr)))
+        self._gbuffer_shape = (height, width)
+
+    # ---- frame packing ----------------------------------------------------------------------------------------
+    @property
+    def lightmap_format(self) -> int:
+        if self.Configuration.Float4Lightmap:
+            return FORMAT_FLOAT4
+        return FORMAT_HALF4 if self.Configuration.HighQuality else FORMAT_RGBA8
+
+    def _df_uniforms(self, quality: Optional[RendererQualitySettings]) -> DFUniforms:
+        q = quality or self.Configuration.DefaultQuality
+        if self.DistanceField is None or self.DistanceField.handle is None:
+            return DistanceField.empty_uniforms(self.Environment.MaximumZ, q)
+        return self.DistanceField.uniforms(q)
+
+    def build_frame(self, intensityScale: float = 1.0, rows: Optional[Tuple[int, int]] = None) -> LightingFrame:
+        cfg, env = self.Configuration, self.Environment
+        f = LightingFrame()
+        f.width = int(cfg.MaximumRenderSize[0] * cfg.RenderScale[0])   # _BeginLightPass LightingRenderer.cs:729-730
+        f.height = int(cfg.MaximumRenderSize[1] * cfg.RenderScale[1])
+        f.lightmap_format = self.lightmap_format
+        f.row_begin, f.row_end = rows if rows is not None else (0, f.height)
+        f.stencil_culling = 1 if (cfg.StencilCulling and cfg.EnableGBuffer) else 0
+        # ComputeUniforms LightingRenderer.cs:691-701, Uniforms.cs:14-77
+        ztoy = env.ZToYMultiplier if cfg.TwoPointFiveD else 0.0
+        inv = 0.0 if abs(ztoy) <= 0.0001 else float(F(1.0) / F(ztoy))
+        f.EnvironmentZAndScale = Float4(env.GroundZ, env.MaximumZ, cfg.RenderScale[0], cfg.RenderScale[1])
+        f.EnvironmentZToY = Float4(ztoy, inv, cfg.LightOcclusion, 0)
+        # SetGBufferParameters LightingRenderer.GBuffer.cs:520-534
+        if cfg.EnableGBuffer and self._gbuffer_shape is not None:
+            gh, gw = self._gbuffer_shape
+            f.GBufferTexelSizeAndMisc = Float4(F(1) / F(gw), F(1) / F(gh), self.ViewportScale[0], self.ViewportScale[1])
+        else:
+            f.GBufferTexelSizeAndMisc = Float4(0, 0, self.ViewportScale[0], self.ViewportScale[1])
+        f.GBufferViewportRelative = 1.0 if cfg.GBufferViewportRelative else 0.0
+        # PushLightingViewTransform LightingRenderer.cs:711-724
+        vx, vy = F(self.ViewportPosition[0]), F(self.ViewportPosition[1])
+        if cfg.ScaleCompensation:
+            vx = vx + (F(1.0) / F(cfg.RenderScale[0])) * F(0.5)
+            vy = vy + (F(1.0) / F(cfg.RenderScale[1])) * F(0.5)
+        f.ViewportPosition[0], f.ViewportPosition[1] = float(vx), float(vy)
+        # clear colour LightingRenderer.cs:1013-1016
+        amb = [float(F(c) * F(intensityScale)) for c in env.Ambient]
+        if cfg.AllowFullbright and cfg.EnableGBuffer:
+            amb[3] = 0.0
+        f.ClearColor = Float4(*amb)
+        return f
+
+    def build_batches(self, intensityScale: float = 1.0):
+        """Groups enabled lights into LightTypeRenderStates keyed on (type, quality) in first-use order after the
+        stable SortKey sort (LightingRenderer.cs:1050-1110, :801-837) and packs their LightVertex arrays."""
+        hasDF = self.DistanceField is not None and self.DistanceField.handle is not None
+        lights = sorted((l for l in self.Environment.Lights if l.Enabled), key=lambda l: l.SortKey)
+        groups = {}
+        for l in lights:
+            v = pack_light_vertex(l, intensityScale, hasDF)
+            if v is None:
+                continue
+            q = l.Quality or self.Configuration.DefaultQuality
+            key = (l.TypeID, id(q))
+            if key not in groups:
+                groups[key] = (l.TypeID, q, [])
+            groups[key][2].append(v)
+        n = sum(len(g[2]) for g in groups.values())
+        verts = (LightVertex * max(n, 1))()
+        batches = (LightBatch * max(len(groups), 1))()
+        i = 0
+        for b, (typ, q, vs) in enumerate(groups.values()):
+            batches[b].light_type = typ
+            batches[b].first_vertex = i
+            batches[b].vertex_count = len(vs)
+            batches[b].df = self._df_uniforms(q)
+            for v in vs:
+                verts[i] = v
+                i += 1
+        return batches, len(groups), verts, n
+
+    # ---- the hot path -----------------------------------------------------------------------------------------
+    def RenderLighting(self, intensityScale: float = 1.0, rows: Optional[Tuple[int, int]] = None) -> np.ndarray:
+        """LightingRenderer.RenderLighting (LightingRenderer.cs:917): returns the lightmap [rows, W, 4]
+        (float16 when HighQuality, uint8 otherwise, float32 with Float4Lightmap)."""
+        frame = self.build_frame(intensityScale, rows)
+        batches, nb, verts, nv = self.build_batches(intensityScale)
+        h = frame.row_end - frame.row_begin
+        dtype = {FORMAT_FLOAT4: np.float32, FORMAT_HALF4: np.float16, FORMAT_RGBA8: np.uint8}[frame.lightmap_format]
+        out = np.empty((h, frame.width, 4), dtype=dtype)
+        df = self.DistanceField.handle if (self.DistanceField is not None and self.DistanceField.handle) else None
+        self.ctx.check(self.ctx.lib.ilb_render_lighting(self.ctx.handle, df, C.byref(frame), C.cast(batches, C.c_void_p), nb,
+                                                        C.cast(verts, C.c_void_p), nv, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def RenderLightingDevice(self, device_ptr: int, intensityScale: float = 1.0, rows: Optional[Tuple[int, int]] = None,
+                             packed=None) -> None:
+        """Asynchronous variant writing rows [row_begin,row_end) to a device buffer that starts at row_begin."""
+        frame = self.build_frame(intensityScale, rows)
+        batches, nb, verts, nv = packed if packed is not None else self.build_batches(intensityScale)
+        df = self.DistanceField.handle if (self.DistanceField is not None and self.DistanceField.handle) else None
+        self.ctx.check(self.ctx.lib.ilb_render_lighting_device(self.ctx.handle, df, C.byref(frame), C.cast(batches, C.c_void_p), nb,
+                                                               C.cast(verts, C.c_void_p), nv, C.c_void_p(device_ptr)))
+
+    def RenderLightingPeers(self, peer_ptrs, intensityScale: float = 1.0, rows: Optional[Tuple[int, int]] = None, packed=None) -> None:
+        """Band render that stores every texel into each full-frame buffer of `peer_ptrs` (in-kernel all-gather)."""
+        frame = self.build_frame(intensityScale, rows)
+        batches, nb, verts, nv = packed if packed is not None else self.build_batches(intensityScale)
+        df = self.DistanceField.handle if (self.DistanceField is not None and self.DistanceField.handle) else None
+        arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(p) for p in peer_ptrs])
+        self.ctx.check(self.ctx.lib.ilb_render_lighting_peers(self.ctx.handle, df, C.byref(frame), C.cast(batches, C.c_void_p), nb,
+                                                              C.cast(verts, C.c_void_p), nv, arr, len(peer_ptrs)))
+
+    def UpdateLightProbes(self, intensityScale: float = 1.0, float4: bool = False) -> np.ndarray:
+        """UpdateLightProbes (LightingRenderer.LightProbes.cs:49-110): probe values [N,4] (half4 like the reference's
+        HalfVector4 target, or float32 for tests)."""
+        n = len(self.Probes)
+        if n > self.Configuration.MaximumLightProbeCount:
+            raise _abi.IlluminantError(_abi.ERR_INVALID_ARGUMENT, "too many light probes")
+        pos = np.zeros((max(n, 1), 4), dtype=np.float32)
+        nrm = np.zeros((max(n, 1), 4), dtype=np.float32)
+        for i, p in enumerate(self.Probes):   # UpdateLightProbeTexture :88-110
+            pos[i] = list(p.Position) + [1.0]
+            nrm[i] = (list(p.Normal) if p.Normal is not None else [0, 0, 0]) + [1.0 if p.EnableShadows else 0.0]
+        frame = self.build_frame(intensityScale)
+        batches, nb, verts, nv = self.build_batches(intensityScale)
+        fmt = FORMAT_FLOAT4 if float4 else FORMAT_HALF4
+        out = np.zeros((n, 4), dtype=np.float32 if float4 else np.float16)
+        if n == 0:
+            return out
+        df = self.DistanceField.handle if (self.DistanceField is not None and self.DistanceField.handle) else None
+        self.ctx.check(self.ctx.lib.ilb_update_light_probes(self.ctx.handle, df, C.byref(frame), C.cast(batches, C.c_void_p), nb,
+                                                            C.cast(verts, C.c_void_p), nv, pos.ctypes.data_as(C.c_void_p),
+                                                            nrm.ctypes.data_as(C.c_void_p), n, fmt, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+
+def encode_gbuffer(normal: np.ndarray, relativeY: np.ndarray, z: np.ndarray, enableShadows: np.ndarray | bool = True,
+                   fullbright: np.ndarray | bool = False, dead: np.ndarray | bool = False) -> np.ndarray:
+    """Vectorised encodeGBufferSample (Shaders/GBufferShaderCommon.fxh:10-35, EnvironmentCommon.fxh:34-40) -> float32 [...,4].
+    Used to synthesise benchmark scenes; the production G-buffer comes from the caller."""
+    normal = np.asarray(normal, dtype=F)
+    z = np.asarray(z, dtype=F)
+    shape = z.shape
+    out = np.zeros(shape + (4,), dtype=F)
+    nx = normal[..., 0].copy()
+    has_n = (normal != 0).any(axis=-1)
+    nx = np.where(np.abs(nx) < F(0.0001), F(0.0001), nx)
+    ex = ((np.arctan2(normal[..., 1], nx).astype(F) / F(math.pi)) + F(1.0)) * F(0.5)
+    ey = (normal[..., 2] + F(1.0)) * F(0.5)
+    out[..., 0] = np.where(has_n, ex, F(0))
+    out[..., 1] = np.where(has_n, ey, F(0))
+    out[..., 2] = np.asarray(relativeY, dtype=F)
+    es = np.broadcast_to(np.asarray(enableShadows, dtype=bool), shape)
+    w = ((z + F(1024)) / F(1024)) * np.where(es, F(1), F(-1)) + np.where(es, F(0), F(-1))
+    out[..., 3] = np.where(np.broadcast_to(np.asarray(fullbright, dtype=bool), shape), F(99999), w)
+    d = np.broadcast_to(np.asarray(dead, dtype=bool), shape)
+    out[d] = np.array([0, 0, -99999, -99999], dtype=F)
+    return out

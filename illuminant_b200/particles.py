@@ -1,0 +1,645 @@
+"""Host-side mirror of the reference particle API for the hot path: ParticleEngine, ParticleSystem and the
+Spawner / Gravity / Noise / FMA / MatrixMultiply transforms (Illuminant/Particles/*.cs, cited per member).
+
+`ParticleSystem.Update` keeps the reference's order -- spawners first (ParticleSystem.cs:725-741), then for every
+chunk the active transforms in list order and the final Update pass (:791-856) -- but issues it as one call into
+the C-ABI (`ilb_particles_step`).  `Parameter<T>` values are plain numbers here: they cross the boundary already
+evaluated.  Host randomness (spawn counts, RandomnessOffset, Noise U/V) comes from a seedable numpy Generator instead
+of the un-vendored CoreCLR.Xoshiro; every draw is passed explicitly, so results depend only on the seed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import _abi
+from ._abi import (OP_FMA, OP_GRAVITY, OP_MATRIX_MULTIPLY, OP_NOISE, Area, Bezier1, Bezier4, Float4, Op, PsysUniforms, Spawn)
+from .distance_field import DistanceField
+
+F = np.float32
+RandomnessTextureWidth, RandomnessTextureHeight = 807, 653  # ParticleEngine.cs:45-46
+VelocityConstantScale = 1000                                # Uniforms.cs:199
+IDENTITY = (1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0)
+
+
+class AreaType:  # TransformArea types == LightObstructionType ids (DistanceFunctionCommon.fxh:167-186)
+    None_, Ellipsoid, Box, Cylinder, Spheroid, Octagon = 0, 1, 2, 3, 4, 5
+
+
+class FormulaType:  # SpawnerCommon.fxh:34-37
+    Linear, Spherical, Towards, Rectangular = 0, 1, 2, 3
+
+
+class AttractorType:  # Transforms.cs:297-301
+    Physical, Linear, Exponential = 0, 1, 2
+
+
+@dataclass
+class ParticleEngineConfiguration:  # ParticleEngine.cs:616-696
+    ChunkSize: int = 256
+    UpdatesPerSecond: Optional[float] = None
+    MaximumUpdateDeltaTimeSeconds: float = 1 / 20.0
+    RandomSeed: Optional[int] = None
+
+
+@dataclass
+class ParticleCollision:  # ParticleConfiguration.cs:13-45
+    DistanceField: Optional[DistanceField] = None
+    DistanceFieldMaximumZ: Optional[float] = None
+    EscapeVelocity: float = 128.0
+    BounceVelocityMultiplier: float = 0.0
+    Distance: float = 0.33
+    LifePenalty: float = 0.0
+    FullFieldAddressing: bool = False   # not in the reference, see collision_field_uniforms
+
+
+@dataclass
+class BezierF:  # Bezier.cs (BezierF feeding ClampedBezier1, :434-459)
+    Count: int = 1
+    Mode: int = 0
+    MinValue: float = 0.0
+    MaxValue: float = 1.0
+    A: float = 1.0
+    B: float = 1.0
+    C: float = 1.0
+    D: float = 1.0
+
+
+@dataclass
+class Bezier4V:  # Bezier4 feeding ClampedBezier4 (Bezier.cs:589-600)
+    Count: int = 1
+    Mode: int = 0
+    MinValue: float = 0.0
+    MaxValue: float = 1.0
+    A: tuple = (1.0, 1.0, 1.0, 1.0)
+    B: tuple = (1.0, 1.0, 1.0, 1.0)
+    C: tuple = (1.0, 1.0, 1.0, 1.0)
+    D: tuple = (1.0, 1.0, 1.0, 1.0)
+
+
+def _range_and_count(src) -> Float4:
+    rng = F(src.MaxValue) - F(src.MinValue)
+    if rng == 0 or src.Count <= 1:
+        rng = F(1)
+    return Float4(min(src.MinValue, src.MaxValue), F(1.0) / rng, src.Count, int(src.Mode))
+
+
+def clamped_bezier1(src: Optional[BezierF]) -> Bezier1:
+    b = Bezier1()
+    if src is None:  # ClampedBezier1.One
+        b.RangeAndCount, b.ABCD = Float4(0, 1, 1, 0), Float4(1, 1, 1, 1)
+        return b
+    b.RangeAndCount = _range_and_count(src)
+    b.ABCD = Float4(src.A, src.B, src.C, src.D)
+    return b
+
+
+def clamped_bezier4(src: Optional[Bezier4V]) -> Bezier4:
+    b = Bezier4()
+    if src is None:  # ClampedBezier4.One
+        b.RangeAndCount = Float4(0, 1, 1, 0)
+        b.A = b.B = b.C = b.D = Float4(1, 1, 1, 1)
+        return b
+    b.RangeAndCount = _range_and_count(src)
+    b.A, b.B, b.C, b.D = Float4(*src.A), Float4(*src.B), Float4(*src.C), Float4(*src.D)
+    return b
+
+
+@dataclass
+class ParticleSystemConfiguration:  # ParticleConfiguration.cs:187-303
+    Size: Tuple[float, float] = (1.0, 1.0)
+    Friction: float = 0.0
+    MaximumVelocity: float = 9999.0
+    LifeDecayPerSecond: float = 1.0
+    Collision: Optional[ParticleCollision] = None
+    RotationFromLife: float = 0.0       # degrees
+    RotationFromIndex: float = 0.0      # degrees
+    RotationFromVelocity: bool = False
+    AnimationRate: Tuple[float, float] = (0.0, 0.0)
+    ZToY: float = 0.0
+    OpacityFromLife: Optional[float] = None
+    ColorFromLife: Optional[Bezier4V] = None
+    ColorFromVelocity: Optional[Bezier4V] = None
+    SizeFromLife: Optional[BezierF] = None
+    SizeFromVelocity: Optional[BezierF] = None
+    WriteRenderOutputs: bool = True     # not in the reference: False skips renderColor/renderData (64 B/particle mode)
+
+
+@dataclass
+class TransformArea:  # ParticleTransform.cs:299-318
+    Type: int = AreaType.None_
+    Center: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    Size: Tuple[float, float, float] = (1.0, 1.0, 1.0)
+    Falloff: float = 1.0
+    Rotation: float = 0.0
+
+
+class ParticleTransform:
+    IsActive = True
+    IsActive2 = True
+    IsValid = True
+    IsSpawner = False
+
+    def pack(self, system: "ParticleSystem", now: float) -> Op:
+        raise NotImplementedError
+
+
+def _pack_area(area: Optional[TransformArea], strength: float, categoryFilter) -> Area:
+    a = Area()
+    if area is not None:
+        a.AreaType = int(area.Type)
+        a.AreaCenter[:] = [float(v) for v in area.Center]
+        a.AreaSize[:] = [float(v) for v in area.Size]
+        a.AreaFalloff = max(1.0, float(area.Falloff))
+        a.AreaRotation = float(area.Rotation)
+    else:
+        a.AreaType = 0
+        a.AreaFalloff = 1.0   # uniform left at its previous value by the reference; any finite value gives distance 0
+        a.AreaSize[:] = [1.0, 1.0, 1.0]
+    a.Strength = float(strength)
+    cf = categoryFilter if categoryFilter is not None else (-9999.0, 9999.0)
+    a.CategoryFilter[:] = [float(cf[0]), float(cf[1])]
+    return a
+
+
+def _time_divisor(cyclesPerSecond: Optional[float]) -> float:
+    return float(F(VelocityConstantScale) / F(cyclesPerSecond)) if cyclesPerSecond is not None else -1.0
+
+
+@dataclass
+class FMA(ParticleTransform):  # Transforms.cs:16-49
+    CyclesPerSecond: Optional[float] = 10
+    PositionAdd: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    PositionMultiply: Tuple[float, float, float] = (1.0, 1.0, 1.0)
+    VelocityAdd: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    VelocityMultiply: Tuple[float, float, float] = (1.0, 1.0, 1.0)
+    Strength: float = 1.0
+    CategoryFilter: Optional[Tuple[float, float]] = None
+    Area: Optional[TransformArea] = None
+
+    def pack(self, system, now):
+        op = Op()
+        op.kind = OP_FMA
+        f = op.u.fma
+        f.area = _pack_area(self.Area, self.Strength, self.CategoryFilter)
+        f.TimeDivisor = _time_divisor(self.CyclesPerSecond)
+        f.PositionAdd = Float4(*self.PositionAdd, 0)
+        f.PositionMultiply = Float4(*self.PositionMultiply, 1)
+        f.VelocityAdd = Float4(*self.VelocityAdd, 0)
+        f.VelocityMultiply = Float4(*self.VelocityMultiply, 1)
+        return op
+
+
+@dataclass
+class MatrixMultiply(ParticleTransform):  # Transforms.cs:51-80
+    CyclesPerSecond: Optional[float] = 10
+    Position: tuple = IDENTITY
+    Velocity: tuple = IDENTITY
+    Strength: float = 1.0
+    CategoryFilter: Optional[Tuple[float, float]] = None
+    Area: Optional[TransformArea] = None
+
+    def pack(self, system, now):
+        op = Op()
+        op.kind = OP_MATRIX_MULTIPLY
+        m = op.u.matrix
+        m.area = _pack_area(self.Area, self.Strength, self.CategoryFilter)
+        m.TimeDivisor = _time_divisor(self.CyclesPerSecond)
+        m.PositionMatrix[:] = [float(v) for v in self.Position]
+        m.VelocityMatrix[:] = [float(v) for v in self.Velocity]
+        return op
+
+
+@dataclass
+class Noise(ParticleTransform):  # Transforms.cs:82-270
+    IntervalUnit = 1000.0
+    CyclesPerSecond: Optional[float] = 10
+    PositionOffset: tuple = (-0.5, -0.5, -0.5, -0.5)
+    PositionMinimum: tuple = (0.0, 0.0, 0.0, 0.0)
+    PositionScale: tuple = (0.0, 0.0, 0.0, 0.0)
+    VelocityOffset: tuple = (-0.5, -0.5, -0.5)
+    VelocityMinimum: tuple = (0.0, 0.0, 0.0)
+    VelocityScale: tuple = (1.0, 1.0, 1.0)
+    SpeedOffset: float = -0.5
+    SpeedMinimum: float = 0.0
+    SpeedScale: float = 0.0
+    Interval: float = 1000.0            # milliseconds between noise-field changes
+    ReplaceOldVelocity: bool = True
+    Strength: float = 1.0
+    CategoryFilter: Optional[Tuple[float, float]] = None
+    Area: Optional[TransformArea] = None
+    Seed: int = 1
+
+    def __post_init__(self):
+        self._rng = np.random.default_rng(self.Seed)
+        self.Reset()
+
+    def _cycle(self):  # CycleUVs :149-154
+        self.CurrentU, self.CurrentV = self.NextU, self.NextV
+        self.NextU, self.NextV = float(self._rng.random()), float(self._rng.random())
+
+    def Reset(self):  # :156-161
+        self.LastUChangeWhen = 0.0
+        self.NextU = self.NextV = 0.0
+        self._cycle()
+
+    def _auto_cycle(self, now: float, intervalSecs: float) -> float:  # AutoCycleUV :163-181
+        if intervalSecs <= 0.01:
+            return 0.0
+        nextChangeWhen = self.LastUChangeWhen + intervalSecs
+        if now >= nextChangeWhen:
+            elapsed = now - nextChangeWhen
+            self.LastUChangeWhen = now if elapsed >= intervalSecs else nextChangeWhen
+            self._cycle()
+        return float(F((now - self.LastUChangeWhen) / intervalSecs))
+
+    def pack(self, system, now):
+        op = Op()
+        op.kind = OP_NOISE
+        n = op.u.noise
+        n.area = _pack_area(self.Area, self.Strength, self.CategoryFilter)
+        n.TimeDivisor = _time_divisor(self.CyclesPerSecond)
+        n.PositionOffset, n.PositionMinimum, n.PositionScale = Float4(*self.PositionOffset), Float4(*self.PositionMinimum), Float4(*self.PositionScale)
+        n.VelocityOffset = Float4(*self.VelocityOffset, self.SpeedOffset)
+        n.VelocityMinimum = Float4(*self.VelocityMinimum, self.SpeedMinimum)
+        n.VelocityScale = Float4(*self.VelocityScale, self.SpeedScale)
+        t = self._auto_cycle(float(F(now)), self.Interval / self.IntervalUnit)
+        n.RandomnessOffset[:] = [float(F(self.CurrentU * 253)), float(F(self.CurrentV * 127))]
+        n.NextRandomnessOffset[:] = [float(F(self.NextU * 253)), float(F(self.NextV * 127))]
+        n.RandomnessTexel[:] = [float(F(1.0) / F(RandomnessTextureWidth)), float(F(1.0) / F(RandomnessTextureHeight))]
+        n.FrequencyLerp = t
+        n.ReplaceOldVelocity = 1.0 if self.ReplaceOldVelocity else 0.0
+        return op
+
+
+@dataclass
+class Attractor:  # Transforms.cs:306-323
+    Position: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    Radius: float = 1.0
+    Strength: float = 1.0
+    Type: int = AttractorType.Linear
+
+
+@dataclass
+class Gravity(ParticleTransform):  # Transforms.cs:303-372
+    MaxAttractors = 16
+    MaximumAcceleration: float = 8.0
+    Attractors: List[Attractor] = field(default_factory=list)
+    # The reference never sets Gravity.fx's CategoryFilter uniform, so the effect default (0, 0) applies: only
+    # particles whose velocity.w (category / bounce delay) is exactly 0 are attracted.
+    CategoryFilter: Tuple[float, float] = (0.0, 0.0)
+
+    @property
+    def IsValid(self):
+        return len(self.Attractors) > 0
+
+    def pack(self, system, now):
+        if len(self.Attractors) > self.MaxAttractors:
+            raise _abi.IlluminantError(_abi.ERR_INVALID_ARGUMENT, "Maximum number of attractors per instance is 16")
+        op = Op()
+        op.kind = OP_GRAVITY
+        g = op.u.gravity
+        g.AttractorCount = len(self.Attractors)
+        g.MaximumAcceleration = float(self.MaximumAcceleration)
+        g.CategoryFilter[:] = [float(self.CategoryFilter[0]), float(self.CategoryFilter[1])]
+        for i, a in enumerate(self.Attractors):
+            g.AttractorPositions[i] = Float4(*a.Position, 0)
+            g.AttractorRadiusesAndStrengths[i] = Float4(a.Radius, a.Strength, int(a.Type), 0)
+        return op
+
+
+@dataclass
+class Formula:  # Formula.cs: constant + (random + offset) * scale, or a circular variant
+    Constant: tuple = (0.0, 0.0, 0.0)
+    RandomScale: tuple = (0.0, 0.0, 0.0)
+    Offset: tuple = (0.0, 0.0, 0.0)
+    Type: int = FormulaType.Linear
+
+    @property
+    def Circular(self):
+        return self.Type in (FormulaType.Spherical, FormulaType.Rectangular)
+
+
+@dataclass
+class Spawner(ParticleTransform):  # ParticleSpawner.cs:14-419
+    IsSpawner = True
+    MinRate: float = 0.0
+    MaxRate: float = 0.0
+    MaximumTotal: Optional[int] = None
+    AlignVelocityAndPosition: bool = False
+    AxisMask: Tuple[float, float, float] = (1.0, 1.0, 1.0)
+    Position: Formula = field(default_factory=Formula)
+    Velocity: Formula = field(default_factory=lambda: Formula(Type=FormulaType.Spherical))
+    Life: Tuple[float, float, float] = (1.0, 0.0, 0.0)      # Constant, RandomScale, Offset
+    Category: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    ColorConstant: tuple = (1.0, 1.0, 1.0, 1.0)
+    ColorRandomScale: tuple = (0.0, 0.0, 0.0, 0.0)
+    ColorOffset: tuple = (0.0, 0.0, 0.0, 0.0)
+    AlphaDiscardThreshold: float = 1.0
+    PositionPostMatrix: tuple = IDENTITY
+    VelocityPostMatrix: tuple = IDENTITY
+    AdditionalPositions: List[Tuple[float, float, float]] = field(default_factory=list)
+    PolygonRate: Optional[float] = None
+    PolygonLoop: bool = True
+    VelocityAlongPolygon: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    RatePerPosition: bool = True
+    Seed: int = 1
+
+    def __post_init__(self):
+        self._rng = np.random.default_rng(self.Seed)
+        self.RateError = 0.0
+        self.TotalSpawned = 0
+        self.Indices = (0, 0)
+
+    @property
+    def CountScale(self) -> int:  # :301-305
+        return max(len(self.AdditionalPositions) + (1 if self.PolygonLoop else 0) if self.RatePerPosition else 1, 1)
+
+    def BeginTick(self, now: float, deltaTimeSeconds: float) -> int:  # :152-189
+        if not (self.IsActive and self.IsActive2):
+            self.RateError = 0.0
+            return 0
+        minRate, maxRate = min(self.MinRate, self.MaxRate), self.MaxRate
+        currentRate = ((float(self._rng.random()) * (maxRate - minRate)) + minRate) * self.CountScale * deltaTimeSeconds
+        currentRate += self.RateError
+        self.RateError = 0.0
+        if currentRate < 1:
+            self.RateError = max(currentRate, 0.0)
+            spawnCount = 0
+        else:
+            spawnCount = int(currentRate)
+            self.RateError = currentRate - spawnCount
+        if self.MaximumTotal is not None:
+            remaining = self.MaximumTotal * self.CountScale - self.TotalSpawned
+            if spawnCount > remaining:
+                spawnCount = remaining
+                self.RateError = 0.0
+        return spawnCount
+
+    def EndTick(self, requested: int, actual: int):  # :191-194
+        self.RateError += requested - actual
+        self.TotalSpawned += actual
+
+    def pack(self, system, now, chunk: int) -> Spawn:  # SetParameters :200-256, :376-403
+        s = Spawn()
+        s.chunk = chunk
+        a, b = float(self._rng.random()), float(self._rng.random())
+        s.RandomnessOffset[:] = [float(F(a * 253)), float(F(b * 127))]
+        s.RandomnessTexel[:] = [float(F(1.0) / F(RandomnessTextureWidth)), float(F(1.0) / F(RandomnessTextureHeight))]
+        count = 1 + len(self.AdditionalPositions)
+        polygonRate = self.PolygonRate or 0.0
+        if polygonRate >= 1:  # GetChunkSizeAndIndices :361-374
+            c = count - 1 if (not self.PolygonLoop and count > 1) else count
+            w = float(F(math.fmod(float(F(self.TotalSpawned / polygonRate)), float(c))))
+        else:
+            w = float(self.TotalSpawned % count)
+        s.ChunkSizeAndIndices = Float4(system.Engine.Configuration.ChunkSize, self.Indices[0], self.Indices[1], w)
+        lc, ls, lo = self.Life
+        cc, cs, co = self.Category
+        cfg = [Float4(*self.Position.RandomScale, ls), Float4(*self.Position.Offset, lo),
+               Float4(*self.Velocity.Constant, cc), Float4(*self.Velocity.RandomScale, cs), Float4(*self.Velocity.Offset, co),
+               Float4(*self.ColorConstant), Float4(*self.ColorRandomScale), Float4(*self.ColorOffset),
+               Float4(*self.VelocityAlongPolygon, 0)]
+        for i, c in enumerate(cfg):
+            s.Configuration[i] = c
+        s.FormulaTypes = Float4(int(self.Position.Type), int(self.Velocity.Type), 0, 0)
+        s.AlignVelocityAndPosition = 1.0 if (self.AlignVelocityAndPosition and self.Position.Circular and self.Velocity.Circular) else 0.0
+        s.AxisMask[:] = [float(v) for v in self.AxisMask]
+        s.PositionMatrix[:] = [float(v) for v in self.PositionPostMatrix]
+        s.VelocityMatrix[:] = [float(v) for v in self.VelocityPostMatrix]
+        s.AttributeDiscardThreshold = float(F(self.AlphaDiscardThreshold) / F(255.0))
+        if count > 4:  # SpawnFromPositionTexture material (:291-295) is outside the hot-path scope
+            raise _abi.IlluminantError(_abi.ERR_UNSUPPORTED, "more than 3 AdditionalPositions (SpawnFromPositionTexture) is not supported")
+        s.InlinePositionConstants[0] = Float4(*self.Position.Constant, lc)   # BeginTick :343-357
+        for i, ap in enumerate(self.AdditionalPositions[:3]):
+            s.InlinePositionConstants[i + 1] = Float4(*ap, lc)
+        s.PositionConstantCount = float(count)
+        s.PolygonRate = float(polygonRate)
+        s.PolygonLoop = 1.0 if self.PolygonLoop else 0.0
+        return s
+
+
+class ParticleEngine:
+    """ParticleEngine(content, coordinator, materials, configuration) -- ParticleEngine.cs:95-141."""
+
+    def __init__(self, ctx: Optional[_abi.Context], configuration: Optional[ParticleEngineConfiguration] = None):
+        self.ctx = ctx
+        self.Configuration = configuration or ParticleEngineConfiguration()
+        self.RandomnessTexture = generate_randomness_texture(self.Configuration.RandomSeed)
+
+
+def generate_randomness_texture(seed: Optional[int]) -> np.ndarray:
+    """GenerateRandomnessTexture (ParticleEngine.cs:495-544): 807x653 float4 of uniform [0,1) singles.  The reference
+    seeds per-thread Xoshiro instances from the clock; here the table is a function of `seed` only."""
+    rng = np.random.default_rng(0xB200 if seed is None else seed)
+    return rng.random((RandomnessTextureHeight, RandomnessTextureWidth, 4), dtype=np.float32)
+
+
+class ParticleSystem:
+    """ParticleSystem(engine, configuration) -- ParticleSystem.cs:242-330 / Update :634-760."""
+    MaxChunkCount = 64  # ParticleSystem.cs:49 (the capacity passed to the library may be larger, see `maxChunks`)
+
+    def __init__(self, engine: ParticleEngine, configuration: Optional[ParticleSystemConfiguration] = None, maxChunks: Optional[int] = None):
+        self.Engine = engine
+        self.Configuration = configuration or ParticleSystemConfiguration()
+        self.Transforms: List[ParticleTransform] = []
+        self.ctx = engine.ctx
+        self.ChunkSize = engine.Configuration.ChunkSize
+        self.ChunkMaximumCount = self.ChunkSize * self.ChunkSize
+        self.MaxChunks = maxChunks or self.MaxChunkCount
+        self.CurrentFrameIndex = 0
+        self.LastUpdateTimeSeconds: Optional[float] = None
+        self.Now = 0.0
+        self.TotalSpawnCount = 0
+        self._chunk_next_offset: List[int] = []   # Chunk.NextSpawnOffset per live chunk
+        self._spawn_target = -1
+        self.handle = None
+        if self.ctx is not None:
+            h = C.c_void_p()
+            self.ctx.check(self.ctx.lib.ilb_particles_create(self.ctx.handle, self.ChunkSize, self.MaxChunks, C.byref(h)))
+            self.handle = h
+            rt = np.ascontiguousarray(engine.RandomnessTexture, dtype=np.float32)
+            self.ctx.check(self.ctx.lib.ilb_particles_set_randomness(h, rt.ctypes.data_as(C.c_void_p), rt.shape[1], rt.shape[0]))
+
+    # ---- chunks -----------------------------------------------------------------------------------------------
+    @property
+    def LiveChunkCount(self) -> int:
+        return len(self._chunk_next_offset)
+
+    def _create_chunk(self) -> int:  # CreateChunk (ParticleSystem.cs:520-545)
+        if len(self._chunk_next_offset) >= self.MaxChunks:
+            return -1
+        self._chunk_next_offset.append(0)
+        if self.handle:
+            self.ctx.check(self.ctx.lib.ilb_particles_set_live_chunks(self.handle, len(self._chunk_next_offset)))
+        return len(self._chunk_next_offset) - 1
+
+    def Spawn(self, positions: np.ndarray, velocities: np.ndarray, attributes: np.ndarray) -> int:
+        """Spawn(count, initializer) (ParticleSpawning.cs:61-113): fills NEW chunks with caller-provided state
+        (arrays [n,4]); returns the first chunk index used."""
+        n = positions.shape[0]
+        per = self.ChunkMaximumCount
+        first = None
+        for start in range(0, n, per):
+            c = self._create_chunk()
+            if c < 0:
+                raise _abi.IlluminantError(_abi.ERR_INVALID_OPERATION, "out of chunks")
+            first = c if first is None else first
+            m = min(per, n - start)
+            bufs = []
+            for src in (positions, velocities, attributes):
+                b = np.zeros((per, 4), dtype=np.float32)
+                b[:m] = src[start:start + m]
+                bufs.append(b)
+            self.ctx.check(self.ctx.lib.ilb_particles_upload_chunk(self.handle, c, *[b.ctypes.data_as(C.c_void_p) for b in bufs]))
+            self._chunk_next_offset[c] = per   # user chunks are NoLongerASpawnTarget (ParticleSystem.cs:693-695)
+            self.TotalSpawnCount += per
+        return first if first is not None else -1
+
+    def ReadChunk(self, chunk: int):
+        """Readback of one chunk (ParticleReadback.cs:59-61 / GetDataFast): (P, V, attributes, renderColor, renderData)."""
+        per = self.ChunkMaximumCount
+        outs = [np.empty((per, 4), dtype=np.float32) for _ in range(5)]
+        self.ctx.check(self.ctx.lib.ilb_particles_download_chunk(self.handle, chunk, *[o.ctypes.data_as(C.c_void_p) for o in outs]))
+        return tuple(outs)
+
+    @property
+    def LiveCount(self) -> int:
+        out = C.c_int64(0)
+        self.ctx.check(self.ctx.lib.ilb_particles_count_live(self.handle, C.byref(out)))
+        return int(out.value)
+
+    # ---- uniforms ---------------------------------------------------------------------------------------------
+    def system_uniforms(self, deltaTimeSeconds: float) -> PsysUniforms:
+        """Uniforms.ParticleSystem ctor (Uniforms.cs:208-235) + SetSystemUniforms (ParticleSystem.cs:547-575)."""
+        cfg = self.Configuration
+        u = PsysUniforms()
+        cs = self.ChunkSize
+        u.TexelAndSize = Float4(F(1) / F(cs), F(1) / F(cs), cfg.Size[0], cfg.Size[1])
+        u.GlobalSettings = Float4(F(deltaTimeSeconds * VelocityConstantScale), cfg.Friction, cfg.MaximumVelocity, cfg.LifeDecayPerSecond)
+        col = cfg.Collision
+        if col is not None:
+            u.CollisionSettings = Float4(col.EscapeVelocity, col.BounceVelocityMultiplier, col.Distance, col.LifePenalty)
+        ar = cfg.AnimationRate
+        u.AnimationRateAndRotationAndZToY = Float4(F(1.0) / F(ar[0]) if ar[0] != 0 else 0, F(1.0) / F(ar[1]) if ar[1] != 0 else 0,
+                                                    1.0 if cfg.RotationFromVelocity else 0.0, cfg.ZToY)
+        o = cfg.OpacityFromLife or 0
+        if o != 0:
+            b = Bezier4()
+            b.A, b.B = Float4(1, 1, 1, 0), Float4(1, 1, 1, 1)
+            b.RangeAndCount = Float4(0, F(1.0) / F(o), 2, 0)
+            u.ColorFromLife = b
+        else:
+            u.ColorFromLife = clamped_bezier4(cfg.ColorFromLife)
+        u.ColorFromVelocity = clamped_bezier4(cfg.ColorFromVelocity)
+        u.SizeFromLife = clamped_bezier1(cfg.SizeFromLife)
+        u.SizeFromVelocity = clamped_bezier1(cfg.SizeFromVelocity)
+        u.LifeRampSettings = Float4(0, 0, 1, 1)
+        u.RotationFromLifeAndIndex[:] = [float(F(math.radians(cfg.RotationFromLife))), float(F(math.radians(cfg.RotationFromIndex)))]
+        u.write_render_outputs = 1 if cfg.WriteRenderOutputs else 0
+        if col is not None and col.DistanceField is not None:
+            if col.DistanceFieldMaximumZ is None:  # ParticleSystem.cs:835-836
+                raise _abi.IlluminantError(_abi.ERR_INVALID_OPERATION, "If a distance field is active, you must set DistanceFieldMaximumZ")
+            u.has_collision_field = 1
+            u.CollisionField = collision_field_uniforms(col.DistanceField, col.FullFieldAddressing)
+        return u
+
+    # ---- update -----------------------------------------------------------------------------------------------
+    def _delta_time(self, now: float) -> float:  # ParticleSystem.cs:644-669 (variable-timestep branch)
+        ups = self.Engine.Configuration.UpdatesPerSecond
+        maxDelta = min(max(self.Engine.Configuration.MaximumUpdateDeltaTimeSeconds, 1 / 200.0), 10.0)
+        tickUnit = 1.0 / min(max(ups if ups is not None else 60, 5), 200)
+        dt = tickUnit
+        if self.LastUpdateTimeSeconds is not None:
+            dt = min(now - self.LastUpdateTimeSeconds, maxDelta)
+        self.LastUpdateTimeSeconds = now
+        return min(dt, maxDelta)
+
+    def plan_spawns(self, now: float, dt: float):
+        """RunSpawner for every active spawner (ParticleSpawning.cs:115-197); a partial spawn triggers the second
+        RunSpawner pass (ParticleSystem.cs:733-740), which calls BeginTick again exactly like the reference."""
+        spawns = []
+        for t in self.Transforms:
+            if not t.IsSpawner or not (t.IsActive and t.IsActive2) or not t.IsValid:
+                continue
+            for _pass in range(2):
+                requested = t.BeginTick(now, dt)
+                if requested <= 0:
+                    break
+                spawnCount = min(requested, self.ChunkMaximumCount)
+                chunk = self._spawn_target
+                if chunk >= 0 and (self.ChunkMaximumCount - self._chunk_next_offset[chunk]) < 16:  # PickTargetForSpawn :199-231
+                    chunk = -1
+                if chunk < 0:
+                    chunk = self._create_chunk()
+                    if chunk < 0:
+                        break
+                    self._spawn_target = chunk
+                spawnCount = min(spawnCount, self.ChunkMaximumCount - self._chunk_next_offset[chunk])
+                first = self._chunk_next_offset[chunk]
+                t.Indices = (first, first + spawnCount - 1)
+                self._chunk_next_offset[chunk] += spawnCount
+                self.TotalSpawnCount += spawnCount
+                spawns.append(t.pack(self, now, chunk))
+                t.EndTick(requested, spawnCount)
+                if not (requested > spawnCount):
+                    break
+        return spawns
+
+    def plan_ops(self, now: float):
+        ops = [t.pack(self, now) for t in self.Transforms
+               if not t.IsSpawner and t.IsActive and t.IsActive2 and t.IsValid]  # UpdateChunk :800-817
+        return ops
+
+    def Update(self, now: Optional[float] = None, deltaTimeSeconds: Optional[float] = None) -> None:
+        """ParticleSystem.Update (ParticleSystem.cs:634): `now` plays TimeProvider.Seconds; pass deltaTimeSeconds to
+        drive a fixed timestep."""
+        self.CurrentFrameIndex += 1
+        if now is None:
+            now = self.Now + (deltaTimeSeconds if deltaTimeSeconds is not None else 1 / 60.0)
+        dt = deltaTimeSeconds if deltaTimeSeconds is not None else self._delta_time(now)
+        self.Now = now
+        self.LastUpdateTimeSeconds = now
+        spawns = self.plan_spawns(now, dt)
+        ops = self.plan_ops(now)
+        u = self.system_uniforms(dt)
+        self.step_packed(u, spawns, ops, 1)
+
+    def step_packed(self, u: PsysUniforms, spawns, ops, steps: int = 1) -> None:
+        col = self.Configuration.Collision
+        field_handle = col.DistanceField.handle if (col is not None and col.DistanceField is not None) else None
+        self.ctx.check(self.ctx.lib.ilb_particles_set_collision_field(self.handle, field_handle))
+        sp = (Spawn * max(len(spawns), 1))(*spawns)
+        opa = (Op * max(len(ops), 1))(*ops)
+        self.ctx.check(self.ctx.lib.ilb_particles_step(self.handle, C.byref(u), C.cast(sp, C.c_void_p), len(spawns),
+                                                       C.cast(opa, C.c_void_p), len(ops), steps))
+
+    def Dispose(self):
+        if self.handle:
+            self.ctx.lib.ilb_particles_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.Dispose()
+        except Exception:
+            pass
+
+
+def collision_field_uniforms(df: DistanceField, fullFieldAddressing: bool = False):
+    """`new Uniforms.DistanceField(system.Configuration.Collision.DistanceField)` (ParticleTransform.cs:141-148): only the
+    geometry members are initialised by that constructor, and NOTHING on the particle path sets DistanceFieldPacked1
+    (its only writers are LightingRenderer.cs:1913 and :1933), so the update effect keeps the default (0,0,0,0):
+    slicePosition = min(z, 0) * 0 -- particles collide against z-slice 0 of the field only.  That is the reference's
+    behaviour and the default here; `fullFieldAddressing=True` (not in the reference) passes the field's real Packed1."""
+    from .distance_field import RendererQualitySettings
+    u = df.uniforms(RendererQualitySettings())
+    u.ConeAndMisc = Float4(0, 0, 0, u.ConeAndMisc.w)             # Uniforms.cs:106
+    u.StepAndMisc2 = Float4(0, 0, 1, u.StepAndMisc2.w)           # Uniforms.cs:107
+    if not fullFieldAddressing:
+        u.Packed1 = Float4(0, 0, 0, 0)
+    return u

@@ -1,0 +1,319 @@
+/*
+ * illuminant_b200.h -- C-ABI boundary of libilluminant_b200.so
+ *
+ * B200-native (sm_100a) replacement for the two data-parallel hot paths of
+ * sq/Illuminant.  The reference has no FFI for these paths: the seam is its
+ * *material layer* -- renderers fill blittable structs and enqueue one draw per
+ * (effect file, technique).  Every entry point below replaces "enqueue draw(s)
+ * with material X" and accepts the structs that cross at that draw bit-identically.
+ * All `file:line` citations are relative to the reference tree (Illuminant/...).
+ *
+ * Conventions (mirrors the reference's own P/Invoke precedent,
+ * Squared.Nuklear/Squared.Nuklear/Nuklear.cs:10-12 -- Cdecl, plain pointers):
+ *   - every function returns 0 (ILB_OK) or a negative ilb_status; the message is
+ *     available from ilb_last_error().  The C# shim maps codes to the exception
+ *     types the reference throws (ParticleSystem.cs:642, :836).
+ *   - the caller owns every host buffer; the library owns device memory behind
+ *     opaque handles (mirrors Coordinator.DisposeResource, LightingRenderer.cs:658-684).
+ *   - one context == one caller thread at a time (the reference issues all GPU work
+ *     from the draw thread, LightingRenderer.cs:1030).  Work is asynchronous on the
+ *     context's CUDA stream; entry points that fill HOST memory synchronise
+ *     (like Texture2D.GetData), `_device` variants do not.
+ *   - there is NO CPU fallback: without a CUDA device ilb_create fails.
+ */
+#ifndef ILLUMINANT_B200_H
+#define ILLUMINANT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ILB_API __attribute__((visibility("default")))
+#define ILB_ABI_VERSION 1
+
+typedef enum ilb_status {
+    ILB_OK = 0,
+    ILB_ERR_INVALID_ARGUMENT = -1,  /* ArgumentException / ArgumentOutOfRangeException */
+    ILB_ERR_CUDA = -2,              /* device error (message carries cudaGetErrorString) */
+    ILB_ERR_NO_DEVICE = -3,         /* no sm_100 device: the library never falls back to the CPU */
+    ILB_ERR_INVALID_OPERATION = -4, /* InvalidOperationException (e.g. collision without a field, ParticleSystem.cs:836) */
+    ILB_ERR_OUT_OF_MEMORY = -5,
+    ILB_ERR_UNSUPPORTED = -6        /* feature outside the hot-path scope */
+} ilb_status;
+
+typedef struct ilb_float4 { float x, y, z, w; } ilb_float4;
+
+typedef struct ilb_ctx ilb_ctx;   /* one CUDA device + stream                         */
+typedef struct ilb_df ilb_df;     /* a DistanceField atlas resident in HBM            */
+typedef struct ilb_psys ilb_psys; /* one ParticleSystem's chunk storage resident in HBM */
+
+/* ------------------------------------------------------------------ context */
+
+ILB_API int ilb_abi_version(void);
+/* device_ordinal: CUDA device index (one process per GPU; rank r uses LOCAL_RANK). */
+ILB_API int ilb_create(int device_ordinal, ilb_ctx** out_ctx);
+ILB_API void ilb_destroy(ilb_ctx* ctx);
+/* Last error message of this context; ctx == NULL returns the last creation error. */
+ILB_API const char* ilb_last_error(const ilb_ctx* ctx);
+ILB_API int ilb_synchronize(ilb_ctx* ctx);
+/* The CUDA stream (cudaStream_t) all work of this context is enqueued on. */
+ILB_API void* ilb_stream(ilb_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench gpu_launches). */
+ILB_API uint64_t ilb_launch_count(const ilb_ctx* ctx);
+
+/* --------------------------------------------------------- distance field (L1) */
+
+/* The `Uniforms.DistanceField` struct (Uniforms.cs:79-108, 5 x float4) followed by
+ * `DistanceFieldPacked1` (LightingRenderer.cs:1933-1939).  Filled by the host exactly as
+ * SetDistanceFieldParameters does (LightingRenderer.cs:1894-1940); quality-dependent
+ * members make it per light batch / per particle system. */
+typedef struct ilb_df_uniforms {
+    ilb_float4 ConeAndMisc;              /* MaxConeRadius, DistanceFieldZOffset, OcclusionToOpacityPower, InvScaleFactorX */
+    ilb_float4 TextureSliceAndTexelSize; /* 1/Columns, 1/Rows, 1/(VirtualWidth*Columns), 1/(VirtualHeight*Rows) */
+    ilb_float4 StepAndMisc2;             /* StepLimit, MinimumLength, LongStepFactor, InvScaleFactorY */
+    ilb_float4 TextureSliceCount;        /* Columns, Rows, maxValidZ, SliceCount */
+    ilb_float4 Extent;                   /* VirtualWidth, VirtualHeight, VirtualDepth, MaximumEncodedDistance; x<=0 == no field */
+    ilb_float4 Packed1;                  /* 1/Columns*(1/3 as float), SliceCount/Extent.z, maxValidZ, MinStepSize */
+} ilb_df_uniforms;
+
+/* Upload an `Rgba64` atlas in the raw layout of DistanceField.Save (SDF/DistanceField.cs:183-193):
+ * texture_width*texture_height texels, row-major, 4 x uint16 UNORM per texel (r,g,b,a =
+ * z-slices 3p..3p+3 of physical slice p, LightingRenderer.DistanceField.cs:356-361). */
+ILB_API int ilb_df_create(ilb_ctx* ctx, int texture_width, int texture_height,
+                          const uint16_t* rgba64, size_t bytes, ilb_df** out_df);
+/* Same, from a device pointer on ctx's device (multi-GPU broadcast, on-GPU generation). */
+ILB_API int ilb_df_create_device(ilb_ctx* ctx, int texture_width, int texture_height,
+                                 const void* d_rgba64, size_t bytes, ilb_df** out_df);
+ILB_API int ilb_df_download(ilb_df* df, uint16_t* rgba64, size_t bytes);
+ILB_API void ilb_df_destroy(ilb_df* df);
+
+/* "next" row N1 -- analytic obstruction rasterisation (LightObstruction.cs, DistanceFunction.fx:15-48,
+ * LightingRenderer.DistanceField.cs:347-400): MAX-blend of encoded distances, 4 z per texel. */
+typedef struct ilb_obstruction {
+    int32_t type;          /* LightObstructionType: 1 Ellipsoid, 2 Box, 3 Cylinder, 4 Spheroid, 5 Octagon */
+    float center[3];
+    float size[3];
+    float rotation[4];     /* quaternion (x,y,z,w) */
+} ilb_obstruction;
+ILB_API int ilb_df_generate(ilb_ctx* ctx, int texture_width, int texture_height,
+                            int slice_width, int slice_height, int slice_count,
+                            const ilb_df_uniforms* u, const ilb_obstruction* obstructions, int count,
+                            ilb_df** out_df);
+
+/* ------------------------------------------------------------- G-buffer (L4) */
+
+typedef enum ilb_format {
+    ILB_FORMAT_FLOAT4 = 0, /* SurfaceFormat.Vector4     16 B */
+    ILB_FORMAT_HALF4 = 1,  /* SurfaceFormat.HalfVector4  8 B */
+    ILB_FORMAT_RGBA8 = 2   /* SurfaceFormat.Color        4 B (lightmap only) */
+} ilb_format;
+
+/* G-buffer texels in the encoding of GBufferShaderCommon.fxh:10-35 (GBuffer.cs:31-39).
+ * data == NULL disables the G-buffer (flat ground, LightCommon.fxh:132-141). */
+ILB_API int ilb_gbuffer_upload(ilb_ctx* ctx, int width, int height, int format, const void* data);
+ILB_API int ilb_gbuffer_upload_device(ilb_ctx* ctx, int width, int height, int format, const void* d_data);
+
+/* ----------------------------------------------------------- lighting (L2-L11) */
+
+/* `LightVertex` (Vertices.cs:10-39): 8 x float4 = 128 B, Sequential, Pack=4 -- field order as declared
+ * there.  Per-type packing: LightingRenderer.cs:1193-1219 (sphere), :1256-1307 (directional),
+ * :1309-1337 (line); see SURVEY.md appendix A. */
+typedef struct ilb_light_vertex {
+    ilb_float4 LightPosition1, LightPosition2, LightPosition3;
+    ilb_float4 LightProperties, MoreLightProperties, EvenMoreLightProperties;
+    ilb_float4 Color1, Color2;
+} ilb_light_vertex;
+
+typedef enum ilb_light_type { /* LightSourceTypeID, LightSource.cs:12-21 */
+    ILB_LIGHT_SPHERE = 1,
+    ILB_LIGHT_DIRECTIONAL = 2,
+    ILB_LIGHT_LINE = 4
+} ilb_light_type;
+
+/* One LightTypeRenderState (LightingRenderer.cs:801-837) == one instanced draw (:1149-1166):
+ * a light type, the distance-field uniforms its material was given (quality is per batch) and a
+ * range of LightVertex.  Batches are accumulated in array order (= the reference's draw order). */
+typedef struct ilb_light_batch {
+    int32_t light_type;   /* ilb_light_type */
+    int32_t first_vertex;
+    int32_t vertex_count;
+    int32_t reserved;
+    ilb_df_uniforms df;   /* Extent.x <= 0 == rendered without a distance field */
+} ilb_light_batch;
+
+/* Per-frame uniforms of the light pass. */
+typedef struct ilb_lighting_frame {
+    int32_t width, height;            /* lightmap size in pixels (render size) */
+    int32_t lightmap_format;          /* ilb_format: HALF4 (HighQuality, LightingRenderer.cs:477-479), RGBA8, or FLOAT4 (parity tests) */
+    int32_t row_begin, row_end;       /* rows [row_begin,row_end) are rendered: 0,height for a whole frame; a band per GPU */
+    int32_t stencil_culling;          /* Configuration.StencilCulling: mask pixels like UpdateMaskFromGBuffer (GBufferMask.fx:26-44) */
+    ilb_float4 EnvironmentZAndScale;  /* GroundZ, MaximumZ, RenderScale.x, RenderScale.y   (Uniforms.cs:14-77) */
+    ilb_float4 EnvironmentZToY;       /* ZToYMultiplier, InvZToYMultiplier, LightOcclusion, 0 */
+    ilb_float4 GBufferTexelSizeAndMisc; /* 1/w, 1/h (0,0 = G-buffer disabled), ViewportScale.x, .y (LightingRenderer.GBuffer.cs:520-534) */
+    float GBufferViewportRelative;    /* 0 / 1 */
+    float ViewportPosition[2];        /* view transform position incl. ScaleCompensation offset (LightingRenderer.cs:711-724) */
+    float reserved2;
+    ilb_float4 ClearColor;            /* Environment.Ambient * intensityScale, w zeroed in fullbright mode (:1013-1016) */
+} ilb_lighting_frame;
+
+/* RenderLighting (LightingRenderer.cs:917, replacing :1112-1168): clear to ClearColor, then additively
+ * accumulate every light of every batch.  lightmap_out is HOST memory, width*(row_end-row_begin) texels of
+ * lightmap_format, row row_begin first.  Synchronous. */
+ILB_API int ilb_render_lighting(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame,
+                                const ilb_light_batch* batches, int batch_count,
+                                const ilb_light_vertex* vertices, int vertex_count,
+                                void* lightmap_out);
+/* Same with a DEVICE output pointer; asynchronous on ilb_stream(ctx). */
+ILB_API int ilb_render_lighting_device(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame,
+                                       const ilb_light_batch* batches, int batch_count,
+                                       const ilb_light_vertex* vertices, int vertex_count,
+                                       void* d_lightmap_out);
+/* Peer-fused variant: each finished lightmap texel is stored to the same offset of every buffer in
+ * d_peer_lightmaps[0..peer_count) (peer-mapped device pointers, e.g. over NVLink), so the all-gather of
+ * row bands happens inside the kernel.  Buffers are FULL frames (width*height); only this band is written. */
+ILB_API int ilb_render_lighting_peers(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame,
+                                      const ilb_light_batch* batches, int batch_count,
+                                      const ilb_light_vertex* vertices, int vertex_count,
+                                      void* const* d_peer_lightmaps, int peer_count);
+
+/* UpdateLightProbes (LightingRenderer.LightProbes.cs:49-110): probe positions (xyz, opacity=1) and
+ * normals (xyz, enableShadows) as uploaded by UpdateLightProbeTexture; result = probe_count texels
+ * (HALF4 or FLOAT4), cleared to 0 then accumulated like the lightmap. HOST output, synchronous. */
+ILB_API int ilb_update_light_probes(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame,
+                                    const ilb_light_batch* batches, int batch_count,
+                                    const ilb_light_vertex* vertices, int vertex_count,
+                                    const ilb_float4* probe_positions, const ilb_float4* probe_normals,
+                                    int probe_count, int output_format, void* probes_out);
+
+/* ---------------------------------------------------------- particles (P1-P10) */
+
+typedef struct ilb_bezier1 { ilb_float4 RangeAndCount, ABCD; } ilb_bezier1;         /* ClampedBezier1, Bezier.cs:434-459 */
+typedef struct ilb_bezier4 { ilb_float4 RangeAndCount, A, B, C, D; } ilb_bezier4;   /* ClampedBezier4, Bezier.cs:589-600 */
+
+/* Everything SetSystemUniforms / UpdateHandler._BeforeDraw bind for the update pass
+ * (ParticleSystem.cs:547-575, ParticleTransform.cs:84-168, Uniforms.cs:197-236). */
+typedef struct ilb_psys_uniforms {
+    ilb_float4 GlobalSettings;     /* dt*1000, Friction, MaximumVelocity, LifeDecayPerSecond */
+    ilb_float4 CollisionSettings;  /* EscapeVelocity, BounceVelocityMultiplier, Distance, LifePenalty */
+    ilb_float4 TexelAndSize;       /* 1/ChunkSize, 1/ChunkSize, Size.x, Size.y */
+    ilb_float4 AnimationRateAndRotationAndZToY;
+    ilb_bezier4 ColorFromLife, ColorFromVelocity;
+    ilb_bezier1 SizeFromLife, SizeFromVelocity;
+    ilb_float4 LifeRampSettings;   /* x must be 0: the life-ramp texture is outside the hot-path scope */
+    float RotationFromLifeAndIndex[2]; /* radians (ParticleTransform.cs:155-158) */
+    int32_t has_collision_field;   /* Configuration.Collision?.DistanceField != null -> UpdateWithDistanceField */
+    int32_t write_render_outputs;  /* 1 = renderColor/renderData written (reference contract); 0 = 64 B/particle mode */
+    ilb_df_uniforms CollisionField;/* Uniforms.DistanceField(collision field) (ParticleTransform.cs:141-148) */
+} ilb_psys_uniforms;
+
+typedef struct ilb_area { /* TransformArea as set by ParticleAreaTransform.SetParameters (ParticleTransform.cs:299-318) */
+    int32_t AreaType;      /* 0 None, 1 Ellipsoid, 2 Box, 3 Cylinder, 4 Spheroid, 5 Octagon */
+    float AreaCenter[3];
+    float AreaSize[3];
+    float AreaFalloff;     /* >= 1 */
+    float AreaRotation;    /* scalar, broadcast to a float4 by the shader (FMA.fx:11,17) */
+    float Strength;
+    float CategoryFilter[2]; /* default (-9999, 9999) */
+} ilb_area;
+
+#define ILB_MAX_ATTRACTORS 16
+typedef struct ilb_gravity { /* Gravity.fx:5-10, Transforms.cs:347-365 */
+    int32_t AttractorCount;
+    float MaximumAcceleration;
+    float CategoryFilter[2];  /* the reference never sets it for Gravity: the effect default (0,0) applies */
+    ilb_float4 AttractorPositions[ILB_MAX_ATTRACTORS];            /* xyz */
+    ilb_float4 AttractorRadiusesAndStrengths[ILB_MAX_ATTRACTORS]; /* Radius, Strength, Type */
+} ilb_gravity;
+
+typedef struct ilb_noise { /* Noise.fx:5-19, Transforms.cs:243-268 */
+    ilb_area area;
+    float TimeDivisor;
+    float FrequencyLerp;
+    float ReplaceOldVelocity;
+    float reserved;
+    float RandomnessOffset[2], NextRandomnessOffset[2];
+    float RandomnessTexel[2]; /* (1/807, 1/653) -- also used as the `rate` (Noise.fx:49-52) */
+    ilb_float4 PositionOffset, PositionMinimum, PositionScale;
+    ilb_float4 VelocityOffset, VelocityMinimum, VelocityScale;
+} ilb_noise;
+
+typedef struct ilb_fma { /* FMA.fx:4-13, Transforms.cs:38-45 */
+    ilb_area area;
+    float TimeDivisor;
+    float reserved[3];
+    ilb_float4 PositionAdd, PositionMultiply, VelocityAdd, VelocityMultiply;
+} ilb_fma;
+
+typedef struct ilb_matrix_multiply { /* MatrixMultiply.fx:4-12 ("next" row N4) */
+    ilb_area area;
+    float TimeDivisor;
+    float reserved[3];
+    float PositionMatrix[16], VelocityMatrix[16]; /* row-major XNA Matrix, row-vector convention mul(v, M) */
+} ilb_matrix_multiply;
+
+typedef enum ilb_op_kind { ILB_OP_GRAVITY = 1, ILB_OP_NOISE = 2, ILB_OP_FMA = 3, ILB_OP_MATRIX_MULTIPLY = 4 } ilb_op_kind;
+
+typedef struct ilb_op { /* one active non-spawner ParticleTransform, in Transforms list order (ParticleSystem.cs:800-817) */
+    int32_t kind;
+    int32_t reserved[3];
+    union {
+        ilb_gravity gravity;
+        ilb_noise noise;
+        ilb_fma fma;
+        ilb_matrix_multiply matrix;
+    } u;
+} ilb_op;
+
+typedef struct ilb_spawn { /* one RunSpawner draw (ParticleSpawning.cs:115-197; uniforms ParticleSpawner.cs:200-256,361-403) */
+    int32_t chunk;                  /* target chunk index */
+    int32_t reserved[3];
+    ilb_float4 ChunkSizeAndIndices; /* ChunkSize, first, last, polygon phase */
+    ilb_float4 Configuration[9];
+    ilb_float4 FormulaTypes;
+    ilb_float4 InlinePositionConstants[4];
+    float PositionMatrix[16], VelocityMatrix[16];
+    float RandomnessOffset[2];
+    float RandomnessTexel[2];
+    float AxisMask[3];
+    float AlignVelocityAndPosition;
+    float PositionConstantCount;
+    float PolygonRate;
+    float PolygonLoop;
+    float AttributeDiscardThreshold;
+} ilb_spawn;
+
+/* ParticleSystem storage: max_chunks chunks of chunk_size^2 particles (ParticleSystem.cs:73-240). */
+ILB_API int ilb_particles_create(ilb_ctx* ctx, int chunk_size, int max_chunks, ilb_psys** out_psys);
+ILB_API void ilb_particles_destroy(ilb_psys* psys);
+/* The engine-wide randomness texture (ParticleEngine.cs:45-46, :495-544): width*height float4, row-major. */
+ILB_API int ilb_particles_set_randomness(ilb_psys* psys, const ilb_float4* table, int width, int height);
+/* Configuration.Collision.DistanceField (may differ from the lighting field, SimpleParticles.cs:216-219). */
+ILB_API int ilb_particles_set_collision_field(ilb_psys* psys, ilb_df* df);
+/* Spawn(initializer)-style upload / readback of one chunk (ParticleWorkItems.cs:75-78, ParticleReadback.cs:59-61).
+ * Arrays are chunk_size^2 float4, row-major; NULL pointers are skipped. */
+ILB_API int ilb_particles_upload_chunk(ilb_psys* psys, int chunk, const ilb_float4* position_and_life,
+                                       const ilb_float4* velocity, const ilb_float4* attributes);
+ILB_API int ilb_particles_download_chunk(ilb_psys* psys, int chunk, ilb_float4* position_and_life,
+                                         ilb_float4* velocity, ilb_float4* attributes,
+                                         ilb_float4* render_color, ilb_float4* render_data);
+/* Chunks [0, count) are live and updated by ilb_particles_step. */
+ILB_API int ilb_particles_set_live_chunks(ilb_psys* psys, int count);
+/* One ParticleSystem.Update (ParticleSystem.cs:634, replacing the RunSpawner/UpdateChunk loop :725-745):
+ * spawners first, then for every live chunk the transforms in order, then UpdatePositions /
+ * UpdateWithDistanceField.  `steps` repeats the same update (fixed uniforms) steps times. Asynchronous. */
+ILB_API int ilb_particles_step(ilb_psys* psys, const ilb_psys_uniforms* uniforms,
+                               const ilb_spawn* spawns, int spawn_count,
+                               const ilb_op* ops, int op_count, int steps);
+/* Device pointers of the SoA state slabs (max_chunks*chunk_size^2 float4 each) for zero-copy consumers:
+ * 0 PositionAndLife, 1 Velocity, 2 Attributes(Color), 3 RenderColor, 4 RenderData. */
+ILB_API void* ilb_particles_device_buffer(ilb_psys* psys, int which);
+/* Count particles with life > 0 in chunks [0, live) (CountLiveParticles.fx equivalent); synchronous. */
+ILB_API int ilb_particles_count_live(ilb_psys* psys, int64_t* out_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ILLUMINANT_B200_H */

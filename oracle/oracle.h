@@ -1,0 +1,36 @@
+// TEST INFRASTRUCTURE -- exported surface of the CPU oracle (liboracle.so). See oracle/README.md.
+#pragma once
+#include <stdint.h>
+#include "../include/illuminant_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+int orc_render_lighting(const uint16_t* df_tex, int tw, int th, const void* gbuffer, int gw, int gh, int gfmt,
+                        const ilb_lighting_frame* f, const ilb_light_batch* batches, int nbatches,
+                        const ilb_light_vertex* verts, int nverts, float* out, int nthreads);
+int orc_update_light_probes(const uint16_t* df_tex, int tw, int th, const ilb_lighting_frame* f,
+                            const ilb_light_batch* batches, int nbatches, const ilb_light_vertex* verts, int nverts,
+                            const ilb_float4* positions, const ilb_float4* normals, int nprobes, float* out);
+float orc_sample_distance_field(const uint16_t* df_tex, int tw, int th, const ilb_df_uniforms* u, float x, float y, float z);
+float orc_cone_trace(const uint16_t* df_tex, int tw, int th, const ilb_df_uniforms* u, const float* lightCenter,
+                     float radius, float rampLength, float growth, float distanceFalloff, const float* shadedPos,
+                     int enable, int* steps);
+float orc_sphere_light_opacity(const ilb_lighting_frame* f, const float* pos, const float* normal, const float* center,
+                               const float* lightProperties, float yFactor);
+void orc_decode_gbuffer(const ilb_lighting_frame* f, const void* gbuffer, int gw, int gh, int gfmt, int x, int y,
+                        float* worldPos, float* normal, int* enableShadows, int* fullbright);
+float orc_evaluate_by_type_id(int typeId, const float* worldPosition, const float* center, const float* size, const float* rotation);
+float orc_bezier1(const ilb_bezier1* b, float value);
+void orc_bezier4(const ilb_bezier4* b, float value, float* out);
+int orc_particles_step(float* P, float* V, float* A, float* RC, float* RD, int chunk_size, int live_chunks,
+                       const ilb_psys_uniforms* u, const ilb_spawn* spawns, int nspawns, const ilb_op* ops, int nops,
+                       const float* rng_table, int rw, int rh, const uint16_t* df_tex, int tw, int th, int steps,
+                       int nthreads);
+int orc_generate_distance_field(uint16_t* out_rgba64, int tw, int th, int slice_w, int slice_h, int slice_count,
+                                const ilb_df_uniforms* u, const ilb_obstruction* obs, int count, int nthreads);
+void orc_encode_gbuffer_sample(const float* normal, float relativeY, float z, int dead, int enableShadows, int fullbright, float* out4);
+void orc_float_to_half(const float* in, uint16_t* out, long n);
+void orc_half_to_float(const uint16_t* in, float* out, long n);
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,222 @@
+"""TEST INFRASTRUCTURE -- ctypes binding of liboracle.so (the CPU restatement of the reference algorithm).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+It reuses the boundary struct definitions of the product package (`illuminant_b200._abi`) because both sides
+consume the same C structs from include/illuminant_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from illuminant_b200 import _abi
+from illuminant_b200._abi import Bezier1, Bezier4, DFUniforms, LightingFrame, PsysUniforms
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "liboracle.so"
+_lib = None
+P = C.c_void_p
+
+
+def build(force: bool = False) -> Path:
+    srcs = [HERE / n for n in ("oracle_lighting.cpp", "oracle_particles.cpp", "oracle_inputs.cpp", "hlsl.hpp", "oracle.h",
+                               "Makefile")] + [HERE.parent / "include" / "illuminant_b200.h"]
+    if force or not LIB.exists() or any(s.stat().st_mtime > LIB.stat().st_mtime for s in srcs):
+        res = subprocess.run(["make", "-C", str(HERE), "-B", "liboracle.so"], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("oracle build failed:\n" + res.stdout + res.stderr)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(str(LIB))
+        L.orc_render_lighting.restype = C.c_int
+        L.orc_render_lighting.argtypes = [P, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int, C.POINTER(LightingFrame), P, C.c_int, P,
+                                          C.c_int, P, C.c_int]
+        L.orc_update_light_probes.restype = C.c_int
+        L.orc_update_light_probes.argtypes = [P, C.c_int, C.c_int, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, P, P, C.c_int, P]
+        L.orc_sample_distance_field.restype = C.c_float
+        L.orc_sample_distance_field.argtypes = [P, C.c_int, C.c_int, C.POINTER(DFUniforms), C.c_float, C.c_float, C.c_float]
+        L.orc_cone_trace.restype = C.c_float
+        L.orc_cone_trace.argtypes = [P, C.c_int, C.c_int, C.POINTER(DFUniforms), P, C.c_float, C.c_float, C.c_float, C.c_float, P,
+                                     C.c_int, C.POINTER(C.c_int)]
+        L.orc_sphere_light_opacity.restype = C.c_float
+        L.orc_sphere_light_opacity.argtypes = [C.POINTER(LightingFrame), P, P, P, P, C.c_float]
+        L.orc_decode_gbuffer.restype = None
+        L.orc_decode_gbuffer.argtypes = [C.POINTER(LightingFrame), P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, P,
+                                         C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_evaluate_by_type_id.restype = C.c_float
+        L.orc_evaluate_by_type_id.argtypes = [C.c_int, P, P, P, P]
+        L.orc_bezier1.restype = C.c_float
+        L.orc_bezier1.argtypes = [C.POINTER(Bezier1), C.c_float]
+        L.orc_bezier4.restype = None
+        L.orc_bezier4.argtypes = [C.POINTER(Bezier4), C.c_float, P]
+        L.orc_particles_step.restype = C.c_int
+        L.orc_particles_step.argtypes = [P, P, P, P, P, C.c_int, C.c_int, C.POINTER(PsysUniforms), P, C.c_int, P, C.c_int, P, C.c_int,
+                                         C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_generate_distance_field.restype = C.c_int
+        L.orc_generate_distance_field.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DFUniforms), P, C.c_int, C.c_int]
+        L.orc_encode_gbuffer_sample.restype = None
+        L.orc_encode_gbuffer_sample.argtypes = [P, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, P]
+        L.orc_float_to_half.restype = None
+        L.orc_float_to_half.argtypes = [P, P, C.c_long]
+        L.orc_half_to_float.restype = None
+        L.orc_half_to_float.argtypes = [P, P, C.c_long]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(P) if a is not None else None
+
+
+def _f3(v):
+    return np.ascontiguousarray(v, dtype=np.float32)
+
+
+def threads() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def render_lighting(df_tex, gbuffer, frame: LightingFrame, batches, nb, verts, nv, nthreads: int = 0) -> np.ndarray:
+    """fp32 lightmap [rows, W, 4] of the multi-pass reference algorithm. df_tex: uint16 [TH,TW,4] or None;
+    gbuffer: float32/float16 [H,W,4] or None."""
+    tw = th = 0
+    if df_tex is not None:
+        df_tex = np.ascontiguousarray(df_tex, dtype=np.uint16)
+        th, tw = df_tex.shape[0], df_tex.shape[1]
+    gw = gh = gfmt = 0
+    if gbuffer is not None:
+        gfmt = _abi.FORMAT_HALF4 if gbuffer.dtype == np.float16 else _abi.FORMAT_FLOAT4
+        gbuffer = np.ascontiguousarray(gbuffer)
+        gh, gw = gbuffer.shape[0], gbuffer.shape[1]
+    out = np.empty((frame.row_end - frame.row_begin, frame.width, 4), dtype=np.float32)
+    rc = lib().orc_render_lighting(_ptr(df_tex), tw, th, _ptr(gbuffer), gw, gh, gfmt, C.byref(frame), C.cast(batches, P), nb,
+                                   C.cast(verts, P), nv, _ptr(out), nthreads or threads())
+    if rc != 0:
+        raise RuntimeError(f"orc_render_lighting failed: {rc}")
+    return out
+
+
+def update_light_probes(df_tex, frame, batches, nb, verts, nv, positions, normals) -> np.ndarray:
+    tw = th = 0
+    if df_tex is not None:
+        df_tex = np.ascontiguousarray(df_tex, dtype=np.uint16)
+        th, tw = df_tex.shape[0], df_tex.shape[1]
+    positions, normals = np.ascontiguousarray(positions, np.float32), np.ascontiguousarray(normals, np.float32)
+    n = positions.shape[0]
+    out = np.zeros((n, 4), dtype=np.float32)
+    rc = lib().orc_update_light_probes(_ptr(df_tex), tw, th, C.byref(frame), C.cast(batches, P), nb, C.cast(verts, P), nv,
+                                       _ptr(positions), _ptr(normals), n, _ptr(out))
+    if rc != 0:
+        raise RuntimeError(f"orc_update_light_probes failed: {rc}")
+    return out
+
+
+def sample_distance_field(df_tex, u: DFUniforms, x, y, z) -> float:
+    df_tex = np.ascontiguousarray(df_tex, dtype=np.uint16)
+    return float(lib().orc_sample_distance_field(_ptr(df_tex), df_tex.shape[1], df_tex.shape[0], C.byref(u), x, y, z))
+
+
+def cone_trace(df_tex, u: DFUniforms, light_center, radius, ramp_length, shaded, growth=1.0, falloff=-99999.0, enable=True):
+    tw = th = 0
+    if df_tex is not None:
+        df_tex = np.ascontiguousarray(df_tex, dtype=np.uint16)
+        th, tw = df_tex.shape[0], df_tex.shape[1]
+    steps = C.c_int(0)
+    lc, sp = _f3(light_center), _f3(shaded)
+    v = lib().orc_cone_trace(_ptr(df_tex), tw, th, C.byref(u), _ptr(lc), radius, ramp_length, growth, falloff, _ptr(sp),
+                             1 if enable else 0, C.byref(steps))
+    return float(v), steps.value
+
+
+def sphere_light_opacity(frame, pos, normal, center, props, y_factor=1.0) -> float:
+    a, b, c, d = _f3(pos), _f3(normal), _f3(center), _f3(props)
+    return float(lib().orc_sphere_light_opacity(C.byref(frame), _ptr(a), _ptr(b), _ptr(c), _ptr(d), y_factor))
+
+
+def decode_gbuffer(frame, gbuffer, x, y):
+    gfmt = _abi.FORMAT_HALF4 if gbuffer.dtype == np.float16 else _abi.FORMAT_FLOAT4
+    gbuffer = np.ascontiguousarray(gbuffer)
+    wp, n = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    es, fb = C.c_int(0), C.c_int(0)
+    lib().orc_decode_gbuffer(C.byref(frame), _ptr(gbuffer), gbuffer.shape[1], gbuffer.shape[0], gfmt, x, y, _ptr(wp), _ptr(n),
+                             C.byref(es), C.byref(fb))
+    return wp, n, bool(es.value), bool(fb.value)
+
+
+def evaluate_by_type_id(type_id, world_pos, center, size, rotation=(0, 0, 0, 1)) -> float:
+    a, b, c, d = _f3(world_pos), _f3(center), _f3(size), _f3(rotation)
+    return float(lib().orc_evaluate_by_type_id(int(type_id), _ptr(a), _ptr(b), _ptr(c), _ptr(d)))
+
+
+def bezier1(b: Bezier1, value: float) -> float:
+    return float(lib().orc_bezier1(C.byref(b), value))
+
+
+def bezier4(b: Bezier4, value: float) -> np.ndarray:
+    out = np.zeros(4, np.float32)
+    lib().orc_bezier4(C.byref(b), value, _ptr(out))
+    return out
+
+
+def particles_step(P_, V_, A_, chunk_size, u: PsysUniforms, spawns, ops, rng_table, df_tex=None, steps=1, nthreads=0):
+    """In-place multi-pass update of [chunks*chunk_size^2, 4] float32 state. Returns (P, V, A, RC, RD)."""
+    P_, V_, A_ = (np.ascontiguousarray(a, dtype=np.float32).copy() for a in (P_, V_, A_))
+    per = chunk_size * chunk_size
+    live = P_.shape[0] // per
+    RC, RD = np.zeros_like(P_), np.zeros_like(P_)
+    tw = th = 0
+    if df_tex is not None:
+        df_tex = np.ascontiguousarray(df_tex, dtype=np.uint16)
+        th, tw = df_tex.shape[0], df_tex.shape[1]
+    rw = rh = 0
+    if rng_table is not None:
+        rng_table = np.ascontiguousarray(rng_table, dtype=np.float32)
+        rh, rw = rng_table.shape[0], rng_table.shape[1]
+    sp = (_abi.Spawn * max(len(spawns), 1))(*spawns)
+    opa = (_abi.Op * max(len(ops), 1))(*ops)
+    rc = lib().orc_particles_step(_ptr(P_), _ptr(V_), _ptr(A_), _ptr(RC), _ptr(RD), chunk_size, live, C.byref(u), C.cast(sp, P),
+                                  len(spawns), C.cast(opa, P), len(ops), _ptr(rng_table), rw, rh, _ptr(df_tex), tw, th, steps,
+                                  nthreads or threads())
+    if rc != 0:
+        raise RuntimeError(f"orc_particles_step failed: {rc}")
+    return P_, V_, A_, RC, RD
+
+
+def generate_distance_field(df, obstructions, nthreads=0) -> np.ndarray:
+    """df: illuminant_b200.DistanceField descriptor (host arithmetic only). Returns uint16 [TH, TW, 4]."""
+    from illuminant_b200.distance_field import pack_obstructions
+    obs = pack_obstructions(obstructions)
+    saved = df.ValidSliceCount
+    df.ValidSliceCount = df.SliceCount
+    u = df.uniforms()
+    df.ValidSliceCount = saved
+    out = np.zeros((df.TextureHeight, df.TextureWidth, 4), dtype=np.uint16)
+    rc = lib().orc_generate_distance_field(_ptr(out), df.TextureWidth, df.TextureHeight, df.SliceWidth, df.SliceHeight, df.SliceCount,
+                                           C.byref(u), C.cast(obs, P) if len(obstructions) else None, len(obstructions),
+                                           nthreads or threads())
+    if rc != 0:
+        raise RuntimeError(f"orc_generate_distance_field failed: {rc}")
+    return out
+
+
+def encode_gbuffer_sample(normal, relative_y, z, dead=False, enable_shadows=True, fullbright=False) -> np.ndarray:
+    n = _f3(normal)
+    out = np.zeros(4, np.float32)
+    lib().orc_encode_gbuffer_sample(_ptr(n), relative_y, z, int(dead), int(enable_shadows), int(fullbright), _ptr(out))
+    return out
+
+
+def float_to_half(a: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    out = np.empty(a.shape, dtype=np.uint16)
+    lib().orc_float_to_half(_ptr(a), _ptr(out), a.size)
+    return out.view(np.float16)

@@ -1,0 +1,680 @@
+// TEST INFRASTRUCTURE -- CPU oracle for the PARTICLE hot path (P1-P10 of SURVEY.md section 8).
+//
+// fp32 restatement of the reference particle shaders in the reference's own multi-pass form: spawner
+// passes write in place, then one full-chunk pass per transform with ping-pong buffers (first pass's
+// destination cleared), then the final Update pass with 4 outputs.  Only tests/, smoke() and bench.py's
+// cpu_baseline / --impl reference legs may call this; the product never does.
+// PARITY UNPINNED by reference outputs (no reference tests exist); pinned by the reference's own CPU
+// mirror of Bezier.fxh (Bezier.cs ClampedBezier1/4.Evaluate) and closed-form cases (tests/test_oracle_kat.py).
+//
+// Citations are relative to /root/reference/Illuminant/.
+#include <omp.h>
+
+#include <cstring>
+#include <vector>
+
+#include "../include/illuminant_b200.h"
+#include "hlsl.hpp"
+#include "oracle.h"
+
+using namespace hlsl;
+
+namespace {
+
+inline float4 f4(const ilb_float4& v) { return float4(v.x, v.y, v.z, v.w); }
+inline float4 ld4(const float* p, size_t i) { return float4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]); }
+inline void st4(float* p, size_t i, float4 v) { p[4 * i] = v.x; p[4 * i + 1] = v.y; p[4 * i + 2] = v.z; p[4 * i + 3] = v.w; }
+
+const float VelocityConstantScale = 1000;
+
+// ---------------------------------------------------------------- Bezier.fxh
+float tForScaledBezier(float4 rangeAndCount, float value, float& t) {  // Shaders/Bezier.fxh:21-63
+    float minValue = rangeAndCount.x, invDivisor = rangeAndCount.y;
+    uint32_t mode = (uint32_t)fabsf(rangeAndCount.w);
+    bool repeating = mode > 255, bouncing = mode > 511;
+    t = (value - minValue) * fabsf(invDivisor);
+    if (bouncing) {
+        t *= 2;
+        if (invDivisor < 0) t = 2 - fmod(t, 2); else t = fmod(t, 2);
+        if (t > 1) t = 1 - (t - 1);
+    } else if (repeating) {
+        if (invDivisor < 0) t = 1 - fmod(t, 1); else t = fmod(t, 1);
+    } else {
+        if (invDivisor < 0) t = 1 - saturate(t); else t = saturate(t);
+    }
+    switch (mode % 256) {
+        default: break;
+        case 1: t = sinf(t * PI * 0.5f); break;
+        case 2: t = t * t; break;
+    }
+    return rangeAndCount.z;
+}
+
+template <class T>
+T evaluateBezierAtT(T a, T b, T c, T d, float count, float t) {  // Bezier.fxh:65-95, :141-171
+    if (count <= 1.5f) return a;
+    T ab = lerp(a, b, t);
+    if (count <= 2.5f) return ab;
+    if (count <= 3.5f) {
+        if (t <= 0) return a;
+        else if (t >= 1) return c;
+        else return b;
+    }
+    T bc = lerp(b, c, t);
+    T abbc = lerp(ab, bc, t);
+    T cd = lerp(c, d, t);
+    T bccd = lerp(bc, cd, t);
+    return lerp(abbc, bccd, t);
+}
+
+float evaluateBezier1(const ilb_bezier1& b, float value) {  // :97-101
+    float t;
+    float count = tForScaledBezier(f4(b.RangeAndCount), value, t);
+    return evaluateBezierAtT<float>(b.ABCD.x, b.ABCD.y, b.ABCD.z, b.ABCD.w, count, t);
+}
+float4 evaluateBezier4(const ilb_bezier4& b, float value) {  // :173-177
+    float t;
+    float count = tForScaledBezier(f4(b.RangeAndCount), value, t);
+    return evaluateBezierAtT<float4>(f4(b.A), f4(b.B), f4(b.C), f4(b.D), count, t);
+}
+
+// ---------------------------------------------------------------- DistanceFunctionCommon.fxh (area weights)
+float4 qmul(float4 q1, float4 q2) {  // :15-20
+    return float4(q2.xyz() * q1.w + q1.xyz() * q2.w + cross(q1.xyz(), q2.xyz()), q1.w * q2.w - dot(q1.xyz(), q2.xyz()));
+}
+float3 rotateLocalPosition(float3 localPosition, float4 rotation) {  // :23-26
+    float4 r_c = rotation * float4(-1, -1, -1, 1);
+    return qmul(rotation, qmul(float4(localPosition, 0), r_c)).xyz();
+}
+float4 opElongate(float3 p, float3 h) {  // :43-46
+    float3 q = abs(p) - h;
+    return float4(sign(p) * max(q, float3(0.0f)), min(max(q.x, max(q.y, q.z)), 0.0f));
+}
+float evaluateBox(float3 worldPosition, float3 center, float3 size, float4 rotation) {  // :48-63
+    float3 position = rotateLocalPosition(worldPosition - center, rotation);
+    float3 d = abs(position) - size;
+    return min(max(d.x, max(d.y, d.z)), 0.0f) + length(max(d, float3(0.0f)));
+}
+float evaluateSpheroid(float3 worldPosition, float3 center, float3 size, float4 rotation) {  // :65-75
+    float3 position = rotateLocalPosition(worldPosition - center, rotation);
+    float minSize = min(size.x, min(size.y, size.z));
+    float3 elongation = size - minSize;
+    float4 w = opElongate(position, elongation);
+    return w.w + (length(w.xyz()) - minSize);
+}
+float evaluateEllipsoid(float3 worldPosition, float3 center, float3 size, float4 rotation) {  // :92-108
+    float3 p = rotateLocalPosition(worldPosition - center, rotation), r = size;
+    float k0 = length(p / r);
+    float k1 = length(p / (r * r));
+    return (k0 < 1.0f) ? (k0 - 1.0f) * min(min(r.x, r.y), r.z) : k0 * (k0 - 1.0f) / k1;
+}
+float sdCappedCylinder(float3 p, float h, float r) {  // :110-113
+    float2 d = abs(float2(length(p.xy()), p.z)) - float2(r, h);
+    return min(max(d.x, d.y), 0.0f) + length(max(d, float2(0.0f)));
+}
+float evaluateCylinder(float3 worldPosition, float3 center, float3 size, float4 rotation) {  // :115-121
+    float3 position = rotateLocalPosition(worldPosition - center, rotation);
+    return sdCappedCylinder(position, size.z, length(size.xy()));
+}
+float sdOctogonPrism(float3 p, float r, float h) {  // :139-152
+    const float3 k = float3(-0.9238795325f, 0.3826834323f, 0.4142135623f);
+    p = abs(p);
+    float2 pxy = p.xy();
+    pxy -= 2.0f * min(dot(float2(k.x, k.y), pxy), 0.0f) * float2(k.x, k.y);
+    pxy -= 2.0f * min(dot(float2(-k.x, k.y), pxy), 0.0f) * float2(-k.x, k.y);
+    pxy -= float2(clamp(pxy.x, -k.z * r, k.z * r), r);
+    float2 d = float2(length(pxy) * sign(pxy.y), p.z - h);
+    return min(max(d.x, d.y), 0.0f) + length(max(d, float2(0.0f)));
+}
+float evaluateOctagon(float3 worldPosition, float3 center, float3 size, float4 rotation) {  // :154-165
+    float3 position = rotateLocalPosition(worldPosition - center, rotation);
+    float minSize = min(size.x, size.y);
+    float3 elongation = float3(size.xy() - minSize, 0);
+    float4 w = opElongate(position, elongation);
+    return w.w + sdOctogonPrism(w.xyz(), minSize, size.z);
+}
+}  // namespace
+
+float orc_evaluate_by_type_id(int typeId, const float* wp, const float* c, const float* s, const float* rot) {  // :167-186
+    float3 worldPosition(wp[0], wp[1], wp[2]), center(c[0], c[1], c[2]), size(s[0], s[1], s[2]);
+    float4 rotation(rot[0], rot[1], rot[2], rot[3]);
+    switch (typeId < 0 ? -typeId : typeId) {
+        case 1: return evaluateEllipsoid(worldPosition, center, size, rotation);
+        case 2: return evaluateBox(worldPosition, center, size, rotation);
+        case 3: return evaluateCylinder(worldPosition, center, size, rotation);
+        case 4: return evaluateSpheroid(worldPosition, center, size, rotation);
+        case 5: return evaluateOctagon(worldPosition, center, size, rotation);
+        default: return 0;
+    }
+}
+
+namespace {
+
+// computeWeight (FMA.fx:15-20, Noise.fx:21-26): the scalar AreaRotation is broadcast into the float4 quaternion
+float computeWeight(const ilb_area& a, float3 worldPosition) {
+    float rot[4] = {a.AreaRotation, a.AreaRotation, a.AreaRotation, a.AreaRotation};
+    float wp[3] = {worldPosition.x, worldPosition.y, worldPosition.z};
+    float distance = orc_evaluate_by_type_id(a.AreaType, wp, a.AreaCenter, a.AreaSize, rot);
+    return (1 - saturate(distance / a.AreaFalloff)) * a.Strength;
+}
+
+bool checkCategoryFilter(float type, const float* typeMinMax) {  // ParticleCommon.fxh:198-200
+    return (type >= typeMinMax[0]) && (type <= typeMinMax[1]);
+}
+
+// ---------------------------------------------------------------- system uniforms (ParticleCommon.fxh:29-92)
+struct System {
+    const ilb_psys_uniforms& u;
+    explicit System(const ilb_psys_uniforms& u_) : u(u_) {}
+    float getDeltaTimeSeconds() const { return u.GlobalSettings.x / VelocityConstantScale; }
+    float getDeltaTime() const { return u.GlobalSettings.x; }
+    float getFriction() const { return u.GlobalSettings.y; }
+    float getMaximumVelocity() const { return u.GlobalSettings.z; }
+    float getLifeDecayRate() const { return u.GlobalSettings.w; }
+    float getEscapeVelocity() const { return u.CollisionSettings.x; }
+    float getBounceVelocityMultiplier() const { return u.CollisionSettings.y; }
+    float getCollisionDistance() const { return u.CollisionSettings.z; }
+    float getCollisionLifePenalty() const { return u.CollisionSettings.w; }
+    float getVelocityRotation() const { return u.AnimationRateAndRotationAndZToY.z; }
+};
+
+// ---------------------------------------------------------------- randomness (RandomCommon.fxh:17-34)
+struct Randomness {
+    const float* table;
+    int w, h;
+    // POINT sampled, WRAP/WRAP: texel = floor(uv * size) mod size
+    float4 fetch(float2 uv) const {
+        int ix = (int)floorf(uv.x * (float)w), iy = (int)floorf(uv.y * (float)h);
+        ix %= w; if (ix < 0) ix += w;
+        iy %= h; if (iy < 0) iy += h;
+        return ld4(table, (size_t)iy * w + ix);
+    }
+    float4 randomCustom(float2 xy, float2 offset, float2 rate, float2 texel) const {
+        float2 uv = ((xy * rate) + offset) * texel;
+        return fetch(uv);
+    }
+};
+
+// ---------------------------------------------------------------- spawner (SpawnerCommon.fxh, SpawnParticles.fx:10-30)
+float3 generateRandomNormal3(float2 randomness) {  // :47-57
+    float phi = randomness.x * PI * 2;
+    float costheta = (randomness.y - 0.5f) * 2;
+    float theta = acosf(costheta);
+    return float3(sinf(theta) * cosf(phi), sinf(theta) * sinf(phi), cosf(theta));
+}
+
+float4 evaluateFormula(const ilb_spawn& s, float4 origin, float4 constant, float4 scale, float4 offset,
+                       float4 randomness, float type) {  // :59-104
+    float4 nonCircular = (randomness + offset) * scale;
+    float4 type0 = constant + nonCircular;
+    uint32_t itype = (uint32_t)fabsf(floorf(type));
+    switch (itype) {
+        default:
+        case 0: return type0;
+        case 3:
+        case 1: {
+            float3 axisMask(s.AxisMask[0], s.AxisMask[1], s.AxisMask[2]);
+            float3 randomNormal = normalize(generateRandomNormal3(randomness.xy()) * axisMask);
+            float3 circular = float3(randomNormal.x * randomness.z * scale.x, randomNormal.y * randomness.z * scale.y,
+                                     randomNormal.z * randomness.z * scale.z);
+            float3 result;
+            if (itype == 3) {
+                const float sqrt2 = 1.41421356237f;
+                float3 edge = abs(offset.xyz());
+                result = clamp(offset.xyz() * randomNormal * sqrt2, -edge, edge);
+                result += constant.xyz() + circular;
+            } else {
+                circular += randomNormal * offset.xyz();
+                result = constant.xyz() + circular;
+            }
+            return float4(result, type0.w);
+        }
+        case 2: {
+            float3 distance = (constant - origin).xyz();
+            float ldistance = length(distance);
+            if (ldistance < 0.1f) return float4(0, 0, 0, constant.w);
+            float3 direction = distance / ldistance;
+            float3 randomSpeed = (randomness.x * scale.xyz() * direction);
+            float3 fixedSpeed = (offset.xyz() * direction);
+            return float4(randomSpeed + fixedSpeed, type0.w);
+        }
+    }
+}
+
+// returns false when the texel is discarded (outside [first,last] or below the alpha threshold)
+bool PS_Spawn(const ilb_spawn& s, const Randomness& rng, float2 xy, float4& newPosition, float4& newVelocity,
+              float4& newAttributes) {
+    // Spawn_Stage1 :119-155
+    float4 csi = f4(s.ChunkSizeAndIndices);
+    float index = (xy.x) + (xy.y * csi.x);
+    if ((index < csi.y) || (index > csi.z)) return false;
+
+    // evaluateRandomForIndex :106-117 ; random() = randomCustom(xy, RandomnessOffset, 1)
+    float2 ro(s.RandomnessOffset[0], s.RandomnessOffset[1]), rt(s.RandomnessTexel[0], s.RandomnessTexel[1]);
+    float2 randomOffset1 = float2(fmod(index, 8039), 0 + fmod(index, 57));
+    float2 randomOffset2 = float2(fmod(index, 6180), 1 + fmod(index, 4031));
+    float2 randomOffset3 = float2(fmod(index, 2025), 2 + fmod(index, 65531));
+    float4 random1 = rng.randomCustom(randomOffset1, ro, float2(1.0f), rt);
+    float4 random2 = rng.randomCustom(randomOffset2, ro, float2(1.0f), rt);
+    float4 random3 = rng.randomCustom(randomOffset3, ro, float2(1.0f), rt);
+    if (s.AlignVelocityAndPosition != 0) { random2.x = random1.x; random2.y = random1.y; }
+
+    int index1, index2;
+    float positionIndexT;
+    float relativeIndex = (index - csi.y);
+    if (s.PolygonRate > 0.05f) {
+        float polyRate = s.PolygonRate;
+        float positionIndexF = (relativeIndex / polyRate) + csi.w;
+        float divisor = s.PositionConstantCount;
+        float positionIndexI;
+        positionIndexT = modff(positionIndexF, &positionIndexI);
+        if (s.PolygonLoop != 0) {
+            index1 = (int)fmod(positionIndexI, divisor);
+            index2 = (int)fmod(positionIndexI + 1, divisor);
+        } else {
+            index1 = (int)fmod(positionIndexI, divisor);
+            index2 = (int)min((float)(index1 + 1), divisor - 1);
+        }
+    } else {
+        index1 = index2 = (int)fmod(relativeIndex + csi.w, s.PositionConstantCount);
+        positionIndexT = 0;
+    }
+    if (index1 < 0) index1 = 0; if (index1 > 3) index1 = 3;
+    if (index2 < 0) index2 = 0; if (index2 > 3) index2 = 3;
+
+    // PS_Spawn SpawnParticles.fx:25-29
+    float4 position1 = f4(s.InlinePositionConstants[index1]), position2 = f4(s.InlinePositionConstants[index2]);
+    float4 positionConstant = lerp(position1, position2, positionIndexT);
+    float4 towardsNext = position2 - position1;
+
+    // Spawn_Stage2 :157-190
+    const ilb_float4* C = s.Configuration;
+    float4 ft = f4(s.FormulaTypes);
+    float4 tempPosition = evaluateFormula(s, float4(0.0f), positionConstant, f4(C[0]), f4(C[1]), random1, ft.x);
+    newPosition = mul(float4(tempPosition.xyz(), 1), s.PositionMatrix);
+    newPosition.w = tempPosition.w;
+
+    float4 tempVelocity = evaluateFormula(s, tempPosition, f4(C[2]), f4(C[3]), f4(C[4]), random2, ft.y);
+    newAttributes = evaluateFormula(s, float4(0.0f), f4(C[5]), f4(C[6]), f4(C[7]), random3, ft.z);
+
+    float towardsDistance = length(towardsNext);
+    if (towardsDistance > 0.0001f) {
+        float towardsSpeed = evaluateFormula(s, float4(0.0f), float4(C[8].x), float4(C[8].y), float4(C[8].z), float4(random3.w), ft.w).x;
+        tempVelocity += towardsSpeed * (towardsNext / towardsDistance);
+    }
+    newVelocity = mul(float4(tempVelocity.xyz(), 1), s.VelocityMatrix);
+    newVelocity.w = tempVelocity.w;
+    // (#if FNA zero-velocity hack :182-186 is compiled out on the XNA/D3D build this oracle restates)
+    if (newAttributes.w < s.AttributeDiscardThreshold) return false;
+    return true;
+}
+
+// ---------------------------------------------------------------- transforms
+void PS_Gravity(const System& sys, const ilb_gravity& g, float4& newPosition, float4 oldVelocity, float4& newVelocity) {  // Gravity.fx:12-61
+    if ((newPosition.w <= 0) || !checkCategoryFilter(oldVelocity.w, g.CategoryFilter)) {
+        newVelocity = oldVelocity;
+        return;
+    }
+    float3 acceleration(0.0f);
+    for (int i = 0; i < g.AttractorCount; i++) {
+        float3 apos = f4(g.AttractorPositions[i]).xyz();
+        float3 ars = f4(g.AttractorRadiusesAndStrengths[i]).xyz();
+        float3 toCenter = (apos - newPosition.xyz());
+        float attraction = 0;
+        if (ars.z >= 0.5f) {
+            float distance = length(toCenter);
+            attraction = 1 - saturate(distance / ars.x);
+            if (ars.z >= 1.5f) attraction *= attraction;
+            attraction = attraction * sys.getDeltaTime() / VelocityConstantScale;
+        } else {
+            float distanceSquared = dot(toCenter, toCenter) - ars.x;
+            distanceSquared = max(distanceSquared, 0.001f);
+            attraction = 1 / distanceSquared;
+        }
+        float3 newAccel = normalize(toCenter) * attraction * ars.y;
+        acceleration += newAccel;
+    }
+    float maximumAcceleration = g.MaximumAcceleration * sys.getDeltaTime() / VelocityConstantScale;
+    float currentLength = length(acceleration);
+    if (currentLength > maximumAcceleration) acceleration = normalize(acceleration) * maximumAcceleration;
+    // float4 + float3 truncates to float3 (Gravity.fx:59)
+    newVelocity = float4(min(float3(sys.getMaximumVelocity()), oldVelocity.xyz() + acceleration), oldVelocity.w);
+}
+
+void PS_Noise(const System& sys, const ilb_noise& n, const Randomness& rng, float2 xy, float4 oldPosition,
+              float4 oldVelocity, float4& newPosition, float4& newVelocity) {  // Noise.fx:28-72
+    if (!checkCategoryFilter(oldVelocity.w, n.area.CategoryFilter)) {
+        newPosition = oldPosition;
+        newVelocity = oldVelocity;
+        return;
+    }
+    float weight = computeWeight(n.area, oldPosition.xyz());
+    float t = weight * sys.getDeltaTime() / n.TimeDivisor;
+
+    float2 ro(n.RandomnessOffset[0], n.RandomnessOffset[1]), nro(n.NextRandomnessOffset[0], n.NextRandomnessOffset[1]);
+    float2 rt(n.RandomnessTexel[0], n.RandomnessTexel[1]);
+    float4 randomP1 = rng.randomCustom(xy, ro, rt, rt);
+    float4 randomP2 = rng.randomCustom(xy, nro, rt, rt);
+    float4 randomV1 = rng.randomCustom(xy + float2(2, 1), ro, rt, rt);
+    float4 randomV2 = rng.randomCustom(xy + float2(2, 1), nro, rt, rt);
+    float4 randomP = lerp(randomP1, randomP2, n.FrequencyLerp);
+    float4 randomV = lerp(randomV1, randomV2, n.FrequencyLerp);
+
+    float4 positionDelta = (randomP + f4(n.PositionOffset));
+    positionDelta = sign(positionDelta) * max(abs(positionDelta), f4(n.PositionMinimum));
+    positionDelta *= f4(n.PositionScale);
+    float4 velocityDelta = (randomV + f4(n.VelocityOffset));
+    velocityDelta = sign(velocityDelta) * max(abs(velocityDelta), f4(n.VelocityMinimum));
+    velocityDelta *= f4(n.VelocityScale);
+
+    newPosition = lerp(oldPosition, oldPosition + positionDelta, t);
+    float3 nv;
+    if (n.ReplaceOldVelocity != 0)
+        nv = lerp(oldVelocity.xyz(), velocityDelta.xyz(), weight);
+    else
+        nv = lerp(oldVelocity.xyz(), oldVelocity.xyz() + velocityDelta.xyz(), t);
+    nv += normalize(oldVelocity.xyz()) * velocityDelta.w;
+    newVelocity = float4(nv, oldVelocity.w);
+}
+
+void PS_FMA(const System& sys, const ilb_fma& f, float4 oldPosition, float4 oldVelocity, float4& newPosition,
+            float4& newVelocity) {  // FMA.fx:22-51
+    if ((oldPosition.w <= 0) || !checkCategoryFilter(oldVelocity.w, f.area.CategoryFilter)) {
+        newPosition = oldPosition;
+        newVelocity = oldVelocity;
+        return;
+    }
+    float weight = computeWeight(f.area, oldPosition.xyz());
+    float t = weight * sys.getDeltaTime() / f.TimeDivisor;
+    newPosition = lerp(oldPosition, (oldPosition * f4(f.PositionMultiply)) + f4(f.PositionAdd), t);
+    newVelocity = lerp(oldVelocity, (oldVelocity * f4(f.VelocityMultiply)) + f4(f.VelocityAdd), t);
+}
+
+float4 mul3(float4 oldValue, const float* mat, float w) {  // ParticleCommon.fxh:187-196
+    float4 temp = mul(float4(oldValue.xyz(), 1), mat);
+    float3 divided;
+    if (w != 0) divided = temp.xyz() / temp.w;
+    else divided = temp.xyz();
+    return float4(divided, oldValue.w);
+}
+
+void PS_MatrixMultiply(const System& sys, const ilb_matrix_multiply& m, float4 oldPosition, float4 oldVelocity,
+                       float4& newPosition, float4& newVelocity) {  // MatrixMultiply.fx:14-52
+    if ((oldPosition.w <= 0) || !checkCategoryFilter(oldVelocity.w, m.area.CategoryFilter)) {
+        newPosition = oldPosition;
+        newVelocity = oldVelocity;
+        return;
+    }
+    float timeScale = (m.TimeDivisor >= 0) ? sys.getDeltaTime() / m.TimeDivisor : 1;
+    float w = computeWeight(m.area, oldPosition.xyz()) * timeScale;
+    newPosition = lerp(oldPosition, mul3(oldPosition, m.PositionMatrix, 1), w);
+    newVelocity = lerp(oldVelocity, mul3(oldVelocity, m.VelocityMatrix, 0), w);
+}
+
+// ---------------------------------------------------------------- update (UpdateCommon.fxh)
+float3 applyFrictionAndMaximum(const System& sys, float3 velocity) {  // :20-35
+    float l = length(velocity);
+    if (l <= 0.001f) return float3(0.0f);
+    if (l > sys.getMaximumVelocity()) l = sys.getMaximumVelocity();
+    float friction = l * sys.getFriction();
+    l -= (friction * sys.getDeltaTimeSeconds());
+    l = clamp(l, 0, sys.getMaximumVelocity());
+    return normalize(velocity) * l;
+}
+
+float getRotationForVelocity(float3 velocity) {  // :82-95
+    float2 absvel = abs(velocity.xy());
+    if ((absvel.x < 0.01f) && (absvel.y < 0.01f)) return 0;
+    float result = atan2f(velocity.y, velocity.x);
+    if (result < 0) result += 2 * PI;
+    return result;
+}
+
+void computeRenderData(const System& sys, float2 vpos, float4 position, float4 velocity, float4 attributes,
+                       float4& renderColor, float4& renderData) {  // :97-117
+    if (position.w <= 0) {
+        renderColor = renderData = float4(0.0f);
+        return;
+    }
+    float index = vpos.x + (vpos.y * 256);  // hard-coded 256 in the reference (:107)
+    float velocityLength = max(length(velocity.xyz()), 0.0001f);
+    // getRampedColorForLifeValueAndIndex :67-80 with LifeRampSettings.x == 0
+    float4 ramped = evaluateBezier4(sys.u.ColorFromLife, position.w);
+    ramped *= evaluateBezier4(sys.u.ColorFromVelocity, velocityLength);
+    renderColor = attributes * ramped;
+    renderColor.w = saturate(renderColor.w);
+    renderColor.x *= renderColor.w; renderColor.y *= renderColor.w; renderColor.z *= renderColor.w;
+    float size = evaluateBezier1(sys.u.SizeFromLife, position.w);
+    size *= evaluateBezier1(sys.u.SizeFromVelocity, velocityLength);
+    renderData.x = size;
+    renderData.y = (getRotationForVelocity(velocity.xyz()) * sys.getVelocityRotation()) +
+                   ((position.w * sys.u.RotationFromLifeAndIndex[0]) + (index * sys.u.RotationFromLifeAndIndex[1]));
+    renderData.z = velocityLength;
+    renderData.w = velocity.w;
+}
+
+// returns false when discarded (dead): destination keeps its cleared zeros
+bool PS_Update(const System& sys, float2 xy, float4 oldPosition, float4 oldVelocity, float4 attributes,
+               float4& newPosition, float4& newVelocity, float4& renderColor, float4& renderData) {  // UpdateParticleSystem.fx:9-38
+    if (oldPosition.w <= 0) return false;  // readStateOrDiscard ParticleCommon.fxh:162-181
+    float3 velocity = applyFrictionAndMaximum(sys, oldVelocity.xyz());
+    float3 scaledVelocity = velocity * sys.getDeltaTimeSeconds();
+    float newLife = oldPosition.w - (sys.getLifeDecayRate() * sys.getDeltaTimeSeconds());
+    if (newLife <= 0) {
+        newPosition = float4(0.0f);
+        newVelocity = float4(0.0f);
+    } else {
+        newPosition = float4(oldPosition.xyz() + scaledVelocity, newLife);
+        newVelocity = float4(velocity, oldVelocity.w);
+    }
+    computeRenderData(sys, xy, newPosition, newVelocity, attributes, renderColor, renderData);
+    return true;
+}
+
+}  // namespace
+
+// The collision sampler is the lighting oracle's sampleDistanceFieldEx (same header in the reference).
+extern "C" float orc_sample_distance_field(const uint16_t* df_tex, int tw, int th, const ilb_df_uniforms* u, float x, float y, float z);
+
+namespace {
+
+struct Field {
+    const uint16_t* tex; int tw, th; const ilb_df_uniforms* u;
+    float sample(float3 p) const { return orc_sample_distance_field(tex, tw, th, u, p.x, p.y, p.z); }
+};
+
+float3 estimateNormal4(const Field& df, float3 position) {  // VisualizeCommon.fxh:9-63
+    const ilb_df_uniforms& u = *df.u;
+    float3 texel(u.ConeAndMisc.w, u.StepAndMisc2.w, u.Extent.z / max(u.TextureSliceCount.w, 1));
+    const float3 normalWeights[4] = {float3(1, -1, -1), float3(-1, -1, 1), float3(-1, 1, -1), float3(1, 1, 1)};
+    float3 result(0.0f);
+    for (int i = 0; i < 4; i++) {
+        float3 weight = normalWeights[i];
+        result += weight * df.sample(position + weight * texel);
+    }
+    return normalize(result);
+}
+
+bool PS_UpdateWithDistanceField(const System& sys, const Field& df, float2 xy, float4 oldPosition, float4 oldVelocity,
+                                float4 attributes, float4& resultPosition, float4& newVelocity, float4& renderColor,
+                                float4& renderData) {  // UpdateParticleSystemWithDistanceField.fx:29-147
+    const int MAX_STEP_COUNT = 3;
+    const float BOUNCE_DELAY = 3, NO_NORMAL_THRESHOLD = 0.33f;
+    const float INITIAL_ESCAPE_SPEED = 0.33f, ESCAPE_SPEED_ACCELERATION = 1.1f;
+    const float3 ESCAPE_MASK(1, 1, 0);
+
+    resultPosition = newVelocity = renderColor = renderData = float4(0.0f);
+    if (oldPosition.w <= 0) return false;  // readStateOrDiscard
+
+    float newLife = oldPosition.w - (sys.getLifeDecayRate() * sys.getDeltaTimeSeconds());
+    if (newLife <= 0) return true;  // zeros written (:45-51)
+
+    float3 unitVector = normalize(oldVelocity.xyz());
+    float3 velocity = applyFrictionAndMaximum(sys, oldVelocity.xyz());
+
+    bool collided = false, escaping = false;
+    float3 scaledVelocity = velocity * sys.getDeltaTimeSeconds();
+    float3 previousPosition = oldPosition.xyz(), collisionPosition(0.0f), newPosition = previousPosition;
+
+    float initialDistance = df.sample(oldPosition.xyz());
+    bool wasColliding = initialDistance < sys.getCollisionDistance();
+    float travelDistance = max(0, min(initialDistance, length(scaledVelocity)));
+    int stepCount = MAX_STEP_COUNT;
+    if (wasColliding) stepCount = 1;
+    else if (travelDistance <= 0.001f) stepCount = 0;
+
+    for (int i = 0; i < stepCount; i++) {
+        float3 testPosition = oldPosition.xyz() + (travelDistance * unitVector);
+        float stepDistance = df.sample(testPosition);
+        if (stepDistance < sys.getCollisionDistance()) {
+            collided = true;
+            collisionPosition = testPosition;
+        }
+        escaping = stepDistance > initialDistance;
+        if (collided && !escaping) {
+            collisionPosition = testPosition;
+            float offset = clamp(stepDistance + sys.getCollisionDistance(), 0.05f, 16);
+            travelDistance = max(0, travelDistance - offset);
+        } else
+            stepCount = 0;
+        if (travelDistance <= 0.001f) stepCount = 0;
+    }
+
+    if (collided) {
+        bool bounce = oldVelocity.w <= 0;
+        bool redirect = wasColliding && !escaping;
+        float3 normal(0.0f);
+        if (bounce || redirect) normal = estimateNormal4(df, collisionPosition);
+        float escapeSpeed = min(sys.getMaximumVelocity(), sys.getEscapeVelocity());
+        if (redirect) {
+            normal *= ESCAPE_MASK;
+            if (length(normal) < NO_NORMAL_THRESHOLD) {
+                float a = (xy.x / 67) + (xy.y / 13);
+                normal = float3(sinf(a), cosf(a), 0);
+            }
+            float3 escapeVector = normalize(normal);
+            newVelocity = float4(escapeVector * escapeSpeed * INITIAL_ESCAPE_SPEED, BOUNCE_DELAY);
+            float3 escapeDelta = newVelocity.xyz() * sys.getDeltaTimeSeconds();
+            newPosition = oldPosition.xyz() + escapeDelta;
+        } else if (bounce) {
+            float3 bounceVector = -(2 * dot(normal, unitVector) * (normal - unitVector));
+            if (length(bounceVector) < NO_NORMAL_THRESHOLD) bounceVector = -unitVector;
+            else bounceVector = normalize(bounceVector);
+            newPosition = collisionPosition;
+            newVelocity = float4(bounceVector * (min(sys.getMaximumVelocity(), length(velocity) * sys.getBounceVelocityMultiplier())), BOUNCE_DELAY);
+            newLife -= sys.getCollisionLifePenalty();
+        } else {
+            float currentSpeed = length(oldVelocity.xyz());
+            float newSpeed = max(currentSpeed * ESCAPE_SPEED_ACCELERATION, escapeSpeed);
+            float3 nv = unitVector * newSpeed;
+            newVelocity = float4(nv, newVelocity.w);  // .w stays 0 from the initialiser (:36,:133)
+            newPosition = oldPosition.xyz() + (travelDistance * unitVector);
+        }
+    } else {
+        newVelocity = float4(velocity, max(oldVelocity.w - 1, 0));
+        newPosition = oldPosition.xyz() + (travelDistance * unitVector);
+    }
+
+    if (newLife <= 0) {
+        newPosition = float3(0.0f);
+        newVelocity = float4(0.0f);
+    }
+    resultPosition = float4(newPosition, newLife);
+    computeRenderData(sys, xy, resultPosition, newVelocity, attributes, renderColor, renderData);
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+float orc_bezier1(const ilb_bezier1* b, float value) { return evaluateBezier1(*b, value); }
+void orc_bezier4(const ilb_bezier4* b, float value, float* out) {
+    float4 r = evaluateBezier4(*b, value);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+// One or more ParticleSystem.Update calls (Particles/ParticleSystem.cs:634-760) over chunks [0, live_chunks):
+// spawners (in place, ParticleSystem.cs:725-741), then UpdateChunk (:791-856) per chunk.
+// P, V, A, RC, RD: live_chunks * chunk_size^2 float4 each, chunk-major then row-major. In/out.
+int orc_particles_step(float* P, float* V, float* A, float* RC, float* RD, int chunk_size, int live_chunks,
+                       const ilb_psys_uniforms* u, const ilb_spawn* spawns, int nspawns, const ilb_op* ops, int nops,
+                       const float* rng_table, int rw, int rh, const uint16_t* df_tex, int tw, int th, int steps,
+                       int nthreads) {
+    if (u->LifeRampSettings.x != 0) return ILB_ERR_UNSUPPORTED;
+    if (u->has_collision_field && !df_tex) return ILB_ERR_INVALID_OPERATION;
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+    const System sys(*u);
+    const Randomness rng{rng_table, rw, rh};
+    const Field field{df_tex, tw, th, &u->CollisionField};
+    const size_t per = (size_t)chunk_size * chunk_size, total = per * live_chunks;
+    std::vector<float> P2(4 * total), V2(4 * total);
+    float *pPrev = P, *vPrev = V, *pCurr = P2.data(), *vCurr = V2.data();
+
+    for (int step = 0; step < steps; step++) {
+        for (int si = 0; si < nspawns; si++) {
+            const ilb_spawn& s = spawns[si];
+            if (s.chunk < 0 || s.chunk >= live_chunks) return ILB_ERR_INVALID_ARGUMENT;
+            if (s.PositionConstantCount > 4) return ILB_ERR_UNSUPPORTED;
+            const size_t base = per * s.chunk;
+#pragma omp parallel for schedule(static)
+            for (long i = 0; i < (long)per; i++) {
+                float2 xy((float)(i % chunk_size), (float)(i / chunk_size));
+                float4 np, nv, na;
+                if (PS_Spawn(s, rng, xy, np, nv, na)) {
+                    st4(pPrev, base + i, np);
+                    st4(vPrev, base + i, nv);
+                    st4(A, base + i, na);
+                }
+            }
+        }
+        // one full pass per transform, ping-pong (RotateBuffers, ParticleSystem.cs:602-616)
+        for (int oi = 0; oi < nops; oi++) {
+            const ilb_op& op = ops[oi];
+#pragma omp parallel for schedule(static)
+            for (long gi = 0; gi < (long)total; gi++) {
+                long i = gi % (long)per;
+                float2 xy((float)(i % chunk_size), (float)(i / chunk_size));
+                float4 op_ = ld4(pPrev, gi), ov = ld4(vPrev, gi), np, nv;
+                switch (op.kind) {
+                    case ILB_OP_GRAVITY: np = op_; PS_Gravity(sys, op.u.gravity, np, ov, nv); break;
+                    case ILB_OP_NOISE: PS_Noise(sys, op.u.noise, rng, xy, op_, ov, np, nv); break;
+                    case ILB_OP_FMA: PS_FMA(sys, op.u.fma, op_, ov, np, nv); break;
+                    case ILB_OP_MATRIX_MULTIPLY: PS_MatrixMultiply(sys, op.u.matrix, op_, ov, np, nv); break;
+                    default: np = op_; nv = ov; break;
+                }
+                st4(pCurr, gi, np);
+                st4(vCurr, gi, nv);
+            }
+            std::swap(pPrev, pCurr);
+            std::swap(vPrev, vCurr);
+        }
+        // final update pass: destination cleared to 0 (shouldClear = true, ParticleSystem.cs:843,852), dead texels discard
+#pragma omp parallel for schedule(static)
+        for (long gi = 0; gi < (long)total; gi++) {
+            long i = gi % (long)per;
+            float2 xy((float)(i % chunk_size), (float)(i / chunk_size));
+            float4 op_ = ld4(pPrev, gi), ov = ld4(vPrev, gi), at = ld4(A, gi);
+            float4 np(0.0f), nv(0.0f), rc(0.0f), rd(0.0f);
+            bool written = u->has_collision_field
+                               ? PS_UpdateWithDistanceField(sys, field, xy, op_, ov, at, np, nv, rc, rd)
+                               : PS_Update(sys, xy, op_, ov, at, np, nv, rc, rd);
+            if (!written) np = nv = rc = rd = float4(0.0f);
+            st4(pCurr, gi, np);
+            st4(vCurr, gi, nv);
+            if (u->write_render_outputs) {
+                st4(RC, gi, rc);
+                st4(RD, gi, rd);
+            }
+        }
+        std::swap(pPrev, pCurr);
+        std::swap(vPrev, vCurr);
+    }
+    if (pPrev != P) {
+        memcpy(P, pPrev, sizeof(float) * 4 * total);
+        memcpy(V, vPrev, sizeof(float) * 4 * total);
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,172 @@
+"""GPU parity of the lighting hot path (L1-L11) against the CPU oracle, through the C-ABI."""
+import numpy as np
+import pytest
+
+import illuminant_b200 as ib
+from illuminant_b200 import scenes
+from helpers import LIGHTING_RTOL, lighting_rel_err, make_renderer, oracle_lightmap
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(gpu, ref, what):
+    err = lighting_rel_err(gpu, ref)
+    worst = np.unravel_index(np.argmax(err), err.shape)
+    assert err.max() <= LIGHTING_RTOL, f"{what}: max rel err {err.max():.3e} at {worst}: gpu {gpu[worst]} ref {ref[worst]}"
+
+
+def test_c1_single_sphere_light(ctx, oracle):
+    s = scenes.config_c1()
+    s.configuration.Float4Lightmap = True
+    r, tex = make_renderer(ctx, s)
+    _check(r.RenderLighting(), oracle_lightmap(oracle, r, tex, s), "C1")
+
+
+def test_df_generation_matches_oracle(ctx, oracle):
+    s = scenes.lighting_scene(11, 320, 200, 0)
+    df = scenes.make_distance_field(ctx, s)
+    df.Rasterize(s.obstructions)
+    gpu = df.Save().astype(np.int32)
+    ref = oracle.generate_distance_field(df, s.obstructions).astype(np.int32)
+    assert np.abs(gpu - ref).max() <= 1          # UNORM16 LSB
+    assert (gpu != ref).mean() < 1e-3
+
+
+@pytest.mark.parametrize("seed,w,h,ns,nd,nl", [(21, 320, 200, 6, 0, 0), (22, 257, 131, 3, 1, 0), (23, 200, 160, 2, 1, 2), (24, 512, 512, 12, 2, 3)])
+def test_mixed_lights_float4(ctx, oracle, seed, w, h, ns, nd, nl):
+    s = scenes.lighting_scene(seed, w, h, ns, n_directional=nd, n_line=nl, ramp=(60.0, 220.0), ao=True, float4_lightmap=True)
+    r, tex = make_renderer(ctx, s)
+    _check(r.RenderLighting(), oracle_lightmap(oracle, r, tex, s), f"mixed {seed}")
+
+
+def test_half4_and_rgba8_lightmaps(ctx, oracle):
+    s = scenes.lighting_scene(25, 256, 192, 5, n_directional=1, ramp=(60.0, 200.0))
+    r, tex = make_renderer(ctx, s)
+    s.configuration.Float4Lightmap = True
+    ref = oracle_lightmap(oracle, r, tex, s)
+    s.configuration.Float4Lightmap = False
+    half = r.RenderLighting()
+    assert half.dtype == np.float16
+    want = oracle.float_to_half(ref)
+    # identical up to one half ulp where the fp32 values differ by <= 1e-4 relative
+    diff = np.abs(half.view(np.uint16).astype(np.int32) - want.view(np.uint16).astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3
+    s.configuration.HighQuality = False
+    rgba = r.RenderLighting()
+    assert rgba.dtype == np.uint8
+    want8 = np.floor(np.clip(ref, 0, 1) * 255 + 0.5).astype(np.int32)
+    assert np.abs(rgba.astype(np.int32) - want8).max() <= 1
+
+
+def test_row_bands_tile_the_frame(ctx, oracle):
+    s = scenes.lighting_scene(26, 300, 210, 5, n_directional=1, n_line=1, ramp=(60.0, 200.0), float4_lightmap=True)
+    r, tex = make_renderer(ctx, s)
+    full = r.RenderLighting()
+    bands = [r.RenderLighting(rows=(a, b)) for a, b in ((0, 53), (53, 106), (106, 107), (107, 210))]
+    assert np.array_equal(np.concatenate(bands, axis=0), full)   # bit-identical: shards do not change results
+    _check(full, oracle_lightmap(oracle, r, tex, s), "bands")
+
+
+def test_no_distance_field_and_no_gbuffer(ctx, oracle):
+    s = scenes.lighting_scene(27, 200, 120, 4, n_directional=1, ramp=(50.0, 120.0), float4_lightmap=True)
+    s.configuration.EnableGBuffer = False
+    r = ib.LightingRenderer(ctx, s.environment, s.configuration)
+    r.SetGBuffer(None)
+    lm = r.RenderLighting()
+    ref = oracle_lightmap(oracle, r, None, s)
+    _check(lm, ref, "no df / no gbuffer")
+    # closed form: unobstructed, flat ground => ambient + sum(color * a * falloff); alpha counts lights (AllowFullbright off w/o gbuffer)
+    assert lm[..., 3].min() >= s.environment.Ambient[3]
+
+
+def test_shadow_filter_fullbright_and_unshadowed_pixels(ctx, oracle):
+    s = scenes.lighting_scene(28, 192, 128, 3, n_directional=1, ramp=(60.0, 160.0), float4_lightmap=True)
+    rs = np.random.RandomState(5)
+    h, w = s.gbuffer.shape[:2]
+    z = rs.uniform(0, 40, (h, w)).astype(np.float32)
+    n = np.zeros((h, w, 3), np.float32); n[..., 2] = 1
+    tilt = rs.rand(h, w) < 0.3
+    n[tilt] = np.array([0.6, 0.0, 0.8], np.float32)
+    n[rs.rand(h, w) < 0.05] = 0          # "no normal" pixels
+    es = rs.rand(h, w) > 0.3
+    fb = rs.rand(h, w) < 0.1
+    dead = rs.rand(h, w) < 0.05
+    s.gbuffer = ib.encode_gbuffer(n, np.zeros((h, w), np.float32), z, es, fb, dead)
+    s.environment.Lights[0].ShadowFilter = ib.ShadowFilter.Shadowed
+    s.environment.Lights[1].ShadowFilter = ib.ShadowFilter.Unshadowed
+    s.environment.Lights[2].SpecularColor = (0.4, 0.3, 0.2)
+    s.environment.Lights[2].SpecularPower = 6.0
+    for stencil in (False, True):
+        s.configuration.StencilCulling = stencil
+        r, tex = make_renderer(ctx, s)
+        _check(r.RenderLighting(), oracle_lightmap(oracle, r, tex, s), f"flags stencil={stencil}")
+
+
+def test_quality_falloff_modes_and_yfactor(ctx, oracle):
+    q = ib.RendererQualitySettings(MinStepSize=1.0, LongStepFactor=0.5, MaxStepCount=64, MaxConeRadius=24, OcclusionToOpacityPower=0.7)
+    s = scenes.lighting_scene(29, 256, 160, 4, ramp=(50.0, 140.0), quality=q, float4_lightmap=True)
+    L = s.environment.Lights
+    L[0].RampMode = ib.LightSourceRampMode.None_
+    L[0].Radius = 40.0
+    L[1].FalloffYFactor = 2.5
+    L[2].FalloffYFactor = 0.6          # the quad clips lit pixels: coverage test matters
+    L[3].Quality = ib.RendererQualitySettings(MaxStepCount=8)   # second batch; step-limit ramp
+    L[3].ShadowDistanceFalloff = 30.0
+    s.configuration.LightOcclusion = 20.0
+    r, tex = make_renderer(ctx, s)
+    _check(r.RenderLighting(), oracle_lightmap(oracle, r, tex, s), "quality/falloff")
+
+
+def test_light_probes(ctx, oracle):
+    s = scenes.lighting_scene(30, 256, 256, 5, n_directional=1, n_line=2, n_probes=64, ramp=(60.0, 200.0))
+    s.probes[3].Normal = None
+    s.probes[4].EnableShadows = False
+    r, tex = make_renderer(ctx, s)
+    gpu = r.UpdateLightProbes(float4=True)
+    frame = r.build_frame()
+    batches, nb, verts, nv = r.build_batches()
+    pos = np.array([list(p.Position) + [1.0] for p in s.probes], np.float32)
+    nrm = np.array([(list(p.Normal) if p.Normal is not None else [0, 0, 0]) + [1.0 if p.EnableShadows else 0.0] for p in s.probes], np.float32)
+    ref = oracle.update_light_probes(tex, frame, batches, nb, verts, nv, pos, nrm)
+    _check(gpu, ref, "probes")
+    half = r.UpdateLightProbes()
+    assert half.dtype == np.float16 and half.shape == (64, 4)
+
+
+def test_render_scale_and_viewport(ctx, oracle):
+    s = scenes.lighting_scene(31, 240, 160, 4, n_directional=1, ramp=(60.0, 160.0), float4_lightmap=True)
+    s.configuration.RenderScale = (0.5, 0.5)
+    s.gbuffer = s.gbuffer[:80, :120].copy()
+    r, tex = make_renderer(ctx, s)
+    r.ViewportPosition = (10.0, -6.0)
+    r.ViewportScale = (1.25, 1.25)
+    lm = r.RenderLighting()
+    assert lm.shape == (80, 120, 4)
+    _check(lm, oracle_lightmap(oracle, r, tex, s), "render scale")
+
+
+def test_empty_and_degenerate_inputs(ctx):
+    s = scenes.lighting_scene(32, 64, 48, 0, float4_lightmap=True)
+    r, _ = make_renderer(ctx, s)
+    lm = r.RenderLighting()
+    amb = np.array(s.environment.Ambient, np.float32); amb[3] = 0   # fullbright mode zeroes alpha
+    assert np.array_equal(lm, np.broadcast_to(amb, lm.shape))
+    assert r.RenderLighting(rows=(10, 10)).shape == (0, 64, 4)
+    s.environment.Lights = [ib.SphereLightSource(Position=(10, 10, 5), Radius=4, RampLength=20, Opacity=0.0)]
+    assert np.array_equal(r.RenderLighting(), np.broadcast_to(amb, lm.shape))   # Opacity <= 0 lights are skipped on the host
+
+
+def test_error_reporting(ctx):
+    import ctypes as C
+    from illuminant_b200 import _abi
+    s = scenes.lighting_scene(33, 64, 48, 1, float4_lightmap=True)
+    r, _ = make_renderer(ctx, s)
+    frame = r.build_frame()
+    batches, nb, verts, nv = r.build_batches()
+    batches[0].light_type = 5   # Projector: out of scope
+    out = np.empty((48, 64, 4), np.float32)
+    rc = ctx.lib.ilb_render_lighting(ctx.handle, r.DistanceField.handle, C.byref(frame), C.cast(batches, C.c_void_p), nb,
+                                     C.cast(verts, C.c_void_p), nv, out.ctypes.data_as(C.c_void_p))
+    assert rc == _abi.ERR_UNSUPPORTED and b"light type" in ctx.lib.ilb_last_error(ctx.handle)
+    with pytest.raises(ib.IlluminantError):
+        r.DistanceField.Load(np.zeros(16, np.uint16))   # "Truncated file"

@@ -1,0 +1,165 @@
+"""GPU parity of the particle hot path (P1-P10) against the CPU oracle, through the C-ABI."""
+import numpy as np
+import pytest
+
+import illuminant_b200 as ib
+from illuminant_b200 import scenes
+from helpers import PARTICLE_ATOL, particle_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(ctx, oracle, ps, chunk_size, steps, tex=None, seed=3, max_chunks=4, transforms=None):
+    engine = ib.ParticleEngine(ctx, ib.ParticleEngineConfiguration(ChunkSize=chunk_size, RandomSeed=seed))
+    system = ib.ParticleSystem(engine, ps.configuration, maxChunks=max_chunks)
+    system.Transforms = ps.transforms if transforms is None else transforms
+    per = chunk_size * chunk_size
+    system.Spawn(ps.positions, ps.velocities, ps.attributes)
+    n0 = system.LiveChunkCount * per
+    P, V, A = (np.zeros((n0, 4), np.float32) for _ in range(3))
+    P[:ps.count], V[:ps.count], A[:ps.count] = ps.positions, ps.velocities, ps.attributes
+    RC = RD = None
+    now = 0.0
+    for _ in range(steps):
+        now += ps.dt
+        spawns, ops, u = system.plan_spawns(now, ps.dt), system.plan_ops(now), system.system_uniforms(ps.dt)
+        live = system.LiveChunkCount
+        if P.shape[0] < live * per:
+            P, V, A = (np.concatenate([a, np.zeros((live * per - a.shape[0], 4), np.float32)]) for a in (P, V, A))
+        system.step_packed(u, spawns, ops, 1)
+        P, V, A, RC, RD = oracle.particles_step(P, V, A, chunk_size, u, spawns, ops, engine.RandomnessTexture, tex, 1)
+    gpu = [np.concatenate(x) for x in zip(*[system.ReadChunk(c) for c in range(system.LiveChunkCount)])]
+    return system, gpu, (P, V, A, RC, RD)
+
+
+def _check(gpu, ref, what=""):
+    names = ("position", "velocity", "attributes", "renderColor", "renderData")
+    for g, r, n in zip(gpu, ref, names):
+        assert not np.isnan(g).any(), f"{what} {n} NaN"
+        e = particle_err(g, r)
+        assert e <= PARTICLE_ATOL, f"{what} {n}: err {e:.3e}"
+
+
+def test_ballistic_no_transforms_closed_form(ctx, oracle):
+    ps = scenes.particle_scene(40, 5000, 128, 512, 512, steps_hint=16)
+    ps.configuration.Friction = 0.0
+    system, gpu, ref = _run_both(ctx, oracle, ps, 128, 10, transforms=[])
+    _check(gpu, ref, "ballistic")
+    # p(t) = p0 + v t, life linear (friction 0, no transforms, no field)
+    t = 10 * ps.dt
+    want = ps.positions[:, :3] + ps.velocities[:, :3] * np.float32(t)
+    assert np.abs(gpu[0][:5000, :3] - want).max() < 2e-3
+    assert np.allclose(gpu[0][:5000, 3], ps.positions[:, 3] - 1.2 * t, atol=1e-4)
+    assert (gpu[0][5000:] == 0).all()
+
+
+def test_full_chain_with_collision_and_spawner(ctx, oracle):
+    s = scenes.lighting_scene(41, 384, 256, 0)
+    df = scenes.make_distance_field(ctx, s, resolution=0.5)
+    df.Rasterize(s.obstructions)
+    tex = df.Save()
+    ps = scenes.particle_scene(41, 30000, 128, 384, 256, steps_hint=40, collision_field=df, spawn_rate=90000.0)
+    system, gpu, ref = _run_both(ctx, oracle, ps, 128, 12, tex=tex, max_chunks=6)
+    assert system.LiveChunkCount >= 3          # the spawner opened at least one new chunk
+    _check(gpu, ref, "chain")
+    assert system.LiveCount == int((ref[0][:, 3] > 0).sum())
+
+
+def test_full_field_addressing_extension(ctx, oracle):
+    s = scenes.lighting_scene(42, 256, 256, 0)
+    df = scenes.make_distance_field(ctx, s)
+    df.Rasterize(s.obstructions)
+    tex = df.Save()
+    ps = scenes.particle_scene(42, 20000, 256, 256, 256, steps_hint=40, collision_field=df, spawn_rate=0.0)
+    ps.configuration.Collision.FullFieldAddressing = True
+    ps.configuration.Collision.LifePenalty = 0.05
+    _, gpu, ref = _run_both(ctx, oracle, ps, 256, 8, tex=tex, max_chunks=1)
+    _check(gpu, ref, "full-field")
+
+
+def test_each_transform_alone_and_areas(ctx, oracle):
+    base = scenes.particle_scene(43, 9000, 128, 400, 300, steps_hint=20)
+    area = ib.TransformArea(Type=ib.AreaType.Box, Center=(200, 150, 0), Size=(120, 80, 50), Falloff=40.0, Rotation=0.3)
+    variants = {
+        "gravity": [base.transforms[1]],
+        "noise_replace": [ib.Noise(VelocityScale=(30, 30, 30), SpeedScale=4.0, PositionScale=(3, 3, 0, 0), Seed=5, Area=area)],
+        "noise_add": [ib.Noise(VelocityScale=(30, 30, 30), ReplaceOldVelocity=False, Interval=50.0, Seed=6)],
+        "fma": [ib.FMA(PositionAdd=(1, 2, 0), VelocityMultiply=(0.9, 0.9, 1.0), CyclesPerSecond=None, Area=area)],
+        "matrix": [ib.MatrixMultiply(Position=(1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 2, 1, 0, 1),
+                                     Velocity=(0, 1, 0, 0, -1, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1), CategoryFilter=(0, 0),
+                                     Area=ib.TransformArea(Type=ib.AreaType.Cylinder, Center=(200, 150, 0), Size=(90, 90, 40), Falloff=10, Rotation=1.0))],
+        "octagon_spheroid": [ib.FMA(VelocityAdd=(3, 0, 0), Area=ib.TransformArea(Type=ib.AreaType.Octagon, Center=(200, 150, 0), Size=(100, 60, 30), Falloff=20, Rotation=0.7)),
+                             ib.FMA(VelocityAdd=(0, 3, 0), Area=ib.TransformArea(Type=ib.AreaType.Spheroid, Center=(100, 100, 0), Size=(50, 80, 30), Falloff=20, Rotation=0.2))],
+    }
+    for name, tr in variants.items():
+        _, gpu, ref = _run_both(ctx, oracle, base, 128, 5, transforms=tr)
+        _check(gpu, ref, name)
+
+
+def test_spawner_formulas_and_polygon(ctx, oracle):
+    ps = scenes.particle_scene(44, 100, 128, 300, 300, steps_hint=30)
+    for kind, sp in {
+        "rect_towards": ib.Spawner(MinRate=20000, MaxRate=40000, Seed=9,
+                                   Position=ib.Formula(Constant=(150, 150, 0), RandomScale=(40, 40, 0), Offset=(30, 20, 0), Type=ib.FormulaType.Rectangular),
+                                   Velocity=ib.Formula(Constant=(150, 150, 0), RandomScale=(20, 20, 0), Offset=(5, 5, 0), Type=ib.FormulaType.Towards),
+                                   Life=(2.0, 1.0, -0.5), Category=(0.0, 3.0, 0.0), ColorRandomScale=(0.5, 0.5, 0.5, 1.0), ColorOffset=(0, 0, 0, -0.4),
+                                   AlphaDiscardThreshold=20.0),
+        "polygon": ib.Spawner(MinRate=30000, MaxRate=30000, Seed=10, AdditionalPositions=[(250, 50, 0), (250, 250, 0)], PolygonRate=7.0,
+                              PolygonLoop=True, VelocityAlongPolygon=(10.0, 5.0, 0.0), AlignVelocityAndPosition=True,
+                              Position=ib.Formula(Constant=(50, 50, 0), RandomScale=(3, 3, 0), Offset=(0, 0, 0), Type=ib.FormulaType.Spherical),
+                              Velocity=ib.Formula(RandomScale=(10, 10, 0), Offset=(2, 2, 0), Type=ib.FormulaType.Spherical), AxisMask=(1, 1, 0)),
+    }.items():
+        _, gpu, ref = _run_both(ctx, oracle, ps, 128, 6, transforms=[sp], max_chunks=3)
+        _check(gpu, ref, kind)
+        assert (gpu[0][:, 3] > 0).sum() > 1000
+
+
+def test_render_outputs_off_and_beziers(ctx, oracle):
+    ps = scenes.particle_scene(45, 8000, 128, 300, 300, steps_hint=20)
+    ps.configuration.ColorFromLife = ib.Bezier4V(Count=4, MinValue=0.0, MaxValue=3.0, A=(1, 0, 0, 0), B=(1, 1, 0, 1), C=(0, 1, 1, 1), D=(0, 0, 1, 0.2))
+    ps.configuration.SizeFromVelocity = ib.BezierF(Count=2, MinValue=0.0, MaxValue=60.0, A=0.5, B=3.0, Mode=1)
+    ps.configuration.SizeFromLife = ib.BezierF(Count=3, MinValue=4.0, MaxValue=1.0, A=1.0, B=2.0, C=4.0)
+    ps.configuration.ColorFromVelocity = ib.Bezier4V(Count=2, Mode=256 + 2, MinValue=0, MaxValue=20, A=(1, 1, 1, 1), B=(0.5, 0.5, 0.5, 1))
+    _, gpu, ref = _run_both(ctx, oracle, ps, 128, 4)
+    _check(gpu, ref, "beziers")
+    ps.configuration.WriteRenderOutputs = False
+    _, gpu2, ref2 = _run_both(ctx, oracle, ps, 128, 4)
+    _check(gpu2[:3], ref2[:3], "no render outputs")
+    assert (gpu2[3] == 0).all()
+
+
+def test_steps_argument_equals_repeated_calls(ctx):
+    ps = scenes.particle_scene(46, 4000, 128, 300, 300, steps_hint=20)
+    out = []
+    for mode in (0, 1):
+        engine = ib.ParticleEngine(ctx, ib.ParticleEngineConfiguration(ChunkSize=128, RandomSeed=1))
+        system = ib.ParticleSystem(engine, ps.configuration, maxChunks=1)
+        system.Spawn(ps.positions, ps.velocities, ps.attributes)
+        ops = [t.pack(system, 0.0) for t in ps.transforms[1:] if not isinstance(t, ib.Noise)]
+        u = system.system_uniforms(ps.dt)
+        if mode == 0:
+            system.step_packed(u, [], ops, 5)
+        else:
+            for _ in range(5):
+                system.step_packed(u, [], ops, 1)
+        out.append(system.ReadChunk(0))
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
+
+
+def test_errors(ctx):
+    ps = scenes.particle_scene(47, 100, 64, 100, 100)
+    engine = ib.ParticleEngine(ctx, ib.ParticleEngineConfiguration(ChunkSize=64))
+    system = ib.ParticleSystem(engine, ps.configuration, maxChunks=1)
+    system.Spawn(ps.positions, ps.velocities, ps.attributes)
+    ps.configuration.Collision = ib.ParticleCollision(DistanceField=None)
+    u = system.system_uniforms(ps.dt)
+    u.has_collision_field = 1
+    with pytest.raises(ib.IlluminantError) as e:   # collision without a field (ParticleSystem.cs:834-836)
+        system.step_packed(u, [], [], 1)
+    assert e.value.code == -4
+    g = ib.Gravity(Attractors=[ib.Attractor()] * 17)
+    with pytest.raises(ib.IlluminantError):        # Transforms.cs:348-349
+        g.pack(system, 0.0)
+    with pytest.raises(ib.IlluminantError):
+        system.Spawn(ps.positions, ps.velocities, ps.attributes)   # out of chunks
