@@ -17,10 +17,15 @@ LIB = PKG / "libilluminant_b200.so"
 SOURCES = ["api.cu", "lighting.cu", "particles.cu", "dfgen.cu"]
 HEADERS = ["ilb_device.cuh", "ilb_internal.h", "ilb_shapes.cuh", "../../include/illuminant_b200.h"]
 
-# -fmad=false: every fp32 multiply/add rounds separately, in source order (see DESIGN.md "Numerics").
+# FMA contraction on, 2-ulp division / sqrt (MUFU based), denormals flushed; sin/cos/pow/atan2/acos stay the accurate
+# library versions (no -use_fast_math).  See DESIGN.md "Numerics".  ILB_EXACT=1 builds the bit-faithful variant
+# (-fmad=false, IEEE div/sqrt) used to separate arithmetic differences from logic differences when debugging parity.
+EXACT = os.environ.get("ILB_EXACT") == "1"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
+    "-O3", "-lineinfo", "-std=c++17",
+    *(["-fmad=false"] if EXACT else ["-fmad=true", "-prec-div=false", "-prec-sqrt=false", "-ftz=true"]),
+    *[f"-D{d}" for d in os.environ.get("ILB_DEFINES", "").split() if d],
     "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-O2",
     "-cudart", "static",
 ]

@@ -445,7 +445,10 @@ ILB_DEV float warpMax(float v) {
     return v;
 }
 
-__global__ void __launch_bounds__(TILE_THREADS) light_accumulate_kernel(const __grid_constant__ LightingParams P) {
+#ifndef ILB_LIGHT_MINBLOCKS
+#define ILB_LIGHT_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_MINBLOCKS) light_accumulate_kernel(const __grid_constant__ LightingParams P) {
     __shared__ float s_box[8][6];
     __shared__ int s_warpCount[8];
     __shared__ uint16_t s_list[TILE_THREADS];

@@ -25,6 +25,7 @@ struct StepParams {
     const float4* rng;
     int rng_w, rng_h;
     int chunk_size;
+    int chunk_shift;     // log2(chunk_size) when it is a power of two, else -1
     unsigned per_chunk;  // chunk_size^2
     unsigned total;      // live_chunks * per_chunk
     int nops;
@@ -44,10 +45,12 @@ struct SpawnParams {
 };
 
 // ---- randomness (RandomCommon.fxh:17-34): POINT sampled, WRAP/WRAP -------------------------------------------
+ILB_DEV int wrapIndex(float f, int n) {  // floor(f) mod n for |f| < 2^22: (i + 0.5) / n is never within fp error of an integer
+    const float fl = floorf(f);
+    return (int)fl - (int)floorf((fl + 0.5f) * (1.0f / (float)n)) * n;
+}
 ILB_DEV f4 randomFetch(const float4* rng, int w, int h, float u, float v) {
-    int ix = (int)floorf(u * (float)w), iy = (int)floorf(v * (float)h);
-    ix %= w; if (ix < 0) ix += w;
-    iy %= h; if (iy < 0) iy += h;
+    const int ix = wrapIndex(u * (float)w, w), iy = wrapIndex(v * (float)h, h);
     return mk4(__ldg(rng + (size_t)iy * (size_t)w + (size_t)ix));
 }
 ILB_DEV f4 randomCustom(const float4* rng, int w, int h, float x, float y, const float* offset, float ratex, float ratey,
@@ -334,12 +337,24 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
     return true;
 }
 
+#ifndef ILB_PARTICLE_MINBLOCKS
+#define ILB_PARTICLE_MINBLOCKS 4
+#endif
 template <bool COLLIDE>
-__global__ void __launch_bounds__(STEP_THREADS) particle_step_kernel(const __grid_constant__ StepParams P) {
+__global__ void __launch_bounds__(STEP_THREADS, ILB_PARTICLE_MINBLOCKS) particle_step_kernel(const __grid_constant__ StepParams P) {
     const unsigned gi = blockIdx.x * STEP_THREADS + threadIdx.x;
     if (gi >= P.total) return;
-    const unsigned i = gi % P.per_chunk;
-    const float x = (float)(i % (unsigned)P.chunk_size), y = (float)(i / (unsigned)P.chunk_size);
+    unsigned ix, iy;
+    if (P.chunk_shift >= 0) {
+        const unsigned i = gi & (P.per_chunk - 1u);
+        ix = i & ((unsigned)P.chunk_size - 1u);
+        iy = i >> P.chunk_shift;
+    } else {
+        const unsigned i = gi % P.per_chunk;
+        ix = i % (unsigned)P.chunk_size;
+        iy = i / (unsigned)P.chunk_size;
+    }
+    const float x = (float)ix, y = (float)iy;
     f4 pos = mk4(P.P[gi]), vel = mk4(P.V[gi]);
 
     for (int k = 0; k < P.nops; k++) {
@@ -522,6 +537,9 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
         SP.rng = ps->rng; SP.rng_w = ps->rng_w; SP.rng_h = ps->rng_h;
         SP.chunk_size = ps->chunk_size;
         SP.per_chunk = (unsigned)ps->per_chunk;
+        SP.chunk_shift = -1;
+        for (int b = 0; b < 31; b++)
+            if ((1 << b) == ps->chunk_size) SP.chunk_shift = b;
         SP.total = (unsigned)total;
         SP.nops = op_count;
         SP.u = *u;
