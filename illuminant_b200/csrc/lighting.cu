@@ -90,11 +90,11 @@ struct Trace {  // TraceState :31-35
 };
 
 ILB_DEV void traceInit(Trace& s, f3 start, f3 end, float lightRadius) {  // coneTraceInitialize :37-49
-    const f3 v = end - start;
-    const float l = length3(v);
+    const f3 v = xsub3(end, start);
+    const float l = xlength3(v);
     s.origin = start;
-    s.direction = v / l;
-    s.len = fmaxf(l - lightRadius, 1.0f);
+    s.direction = xdivs3(v, l);
+    s.len = fmaxf(xsub(l, lightRadius), 1.0f);
     s.t = TRACE_INITIAL_OFFSET_PX;
     s.vis = 1.0f;
 }
@@ -102,8 +102,8 @@ ILB_DEV void traceInit(Trace& s, f3 start, f3 end, float lightRadius) {  // cone
 ILB_DEV float traceStep(const TraceConfig& c, float d, float offset, float& vis) {  // coneTraceStep :51-71
     const float localSphereRadius = fminf((c.growth * offset) + MIN_CONE_RADIUS, c.maxRadius);
     const float localVisibility = ((d + HACK_DISTANCE_OFFSET) / localSphereRadius);
-    vis = fminf(vis, localVisibility);
-    return fmaxf(fabsf(d) * c.longStep, c.minStep);
+    vis = fminf(vis, localVisibility);  // smooth: a few ulp in vis cannot change the result discontinuously
+    return fmaxf(xmul(fabsf(d), c.longStep), c.minStep);  // exact: the step length moves the march
 }
 
 ILB_DEV float traceFinal(const TraceConfig& c, float visibility) {  // :182-188
@@ -120,9 +120,9 @@ ILB_DEV float coneTrace(const DFGeometry& g, const DLight& L, f3 lightCenter, fl
     float liveness = (L.hasField && enable) ? 1.0f : 0.0f;
     while (liveness > 0.0f) {
         stepsRemaining -= 1.0f;
-        const float d = sampleDistanceField(g, a.origin + (a.direction * a.t));  // coneTraceAdvance :73-82
-        a.t += traceStep(c, d, a.t, a.vis);
-        const float stepLiveness = saturatef(a.vis - FULLY_SHADOWED_THRESHOLD) * saturatef(a.len - a.t);
+        const float d = sampleDistanceField(g, xadd3(a.origin, xscale3(a.direction, a.t)));  // coneTraceAdvance :73-82
+        a.t = xadd(a.t, traceStep(c, d, a.t, a.vis));
+        const float stepLiveness = saturatef(a.vis - FULLY_SHADOWED_THRESHOLD) * saturatef(xsub(a.len, a.t));
         liveness = stepsRemaining * stepLiveness;
     }
     const float visibility = fminf(a.vis, stepsRemaining / MAX_STEP_RAMP_WINDOW);
@@ -130,9 +130,9 @@ ILB_DEV float coneTrace(const DFGeometry& g, const DLight& L, f3 lightCenter, fl
 }
 
 ILB_DEV float traceAdvanceEx(const DFGeometry& g, const TraceConfig& c, Trace& s) {  // coneTraceAdvanceEx :84-96
-    const float d = sampleDistanceField(g, s.origin + (s.direction * s.t));
-    s.t = fminf(s.t + traceStep(c, d, s.t, s.vis), s.len);
-    return saturatef(s.vis - FULLY_SHADOWED_THRESHOLD) * saturatef((s.len - s.t) * TRACE_END_MULTIPLIER);
+    const float d = sampleDistanceField(g, xadd3(s.origin, xscale3(s.direction, s.t)));
+    s.t = fminf(xadd(s.t, traceStep(c, d, s.t, s.vis)), s.len);
+    return saturatef(s.vis - FULLY_SHADOWED_THRESHOLD) * saturatef(xsub(s.len, s.t) * TRACE_END_MULTIPLIER);
 }
 
 // ---- light response (LightCommon.fxh, AOCommon.fxh) ---------------------------------------------------------
@@ -140,30 +140,31 @@ ILB_DEV float traceAdvanceEx(const DFGeometry& g, const TraceConfig& c, Trace& s
 
 ILB_DEV float normalFactorEx(f3 lightNormal, f3 n, float offset, float range) {  // computeNormalFactorEx :154-165
     if (!any3(n)) return 1.0f;
-    const float d = dot3(-lightNormal, n);
-    return powf(saturatef((d + offset) / range), DOT_EXPONENT);
+    const float d = xdot3(-lightNormal, n);  // exact: its sign decides `visible` (discard / alpha count)
+    return powf(saturatef(xdiv(xadd(d, offset), range)), DOT_EXPONENT);
 }
 
 ILB_DEV float sphereLightOpacity(float lightOcclusion, f3 p, f3 n, f3 center, float4 props, float yFactor) {  // :173-210
-    f3 d3 = p - center;
-    d3.y *= yFactor;
-    const float distance = length3(d3);
-    float distanceFactor = 1.0f - saturatef((distance - props.x) / props.y);
-    if (lightOcclusion > 0.0f) distanceFactor *= 1.0f - saturatef(d3.z / lightOcclusion);
-    const f3 lightNormal = d3 / distance;
+    // x-ops: where this falloff reaches exactly 0 the fragment is discarded, which changes the lightmap's alpha count
+    f3 d3 = xsub3(p, center);
+    d3.y = xmul(d3.y, yFactor);
+    const float distance = xlength3(d3);
+    float distanceFactor = xsub(1.0f, saturatef(xdiv(xsub(distance, props.x), props.y)));
+    if (lightOcclusion > 0.0f) distanceFactor = xmul(distanceFactor, xsub(1.0f, saturatef(xdiv(d3.z, lightOcclusion))));
+    const f3 lightNormal = xdivs3(d3, distance);
     float normalFactor = normalFactorEx(lightNormal, n, 0.15f, 0.15f);
     if (props.z >= 2.0f) {
-        distanceFactor = 1.0f - saturatef(distance - props.x);
+        distanceFactor = xsub(1.0f, saturatef(xsub(distance, props.x)));
         normalFactor = 1.0f;
     } else if (props.z >= 1.0f) {
-        distanceFactor *= distanceFactor;
+        distanceFactor = xmul(distanceFactor, distanceFactor);
     }
-    return saturatef((normalFactor * distanceFactor) + saturatef(props.x - distance));
+    return saturatef(xadd(xmul(normalFactor, distanceFactor), saturatef(xsub(props.x, distance))));
 }
 
 ILB_DEV float computeAO(const DFGeometry& g, bool hasField, f3 p, f3 n, float aoRadius, float aoOpacity, bool visible) {  // AOCommon.fxh:1-20
     if ((aoRadius >= 0.5f) && hasField && visible) {
-        const float distance = sampleDistanceField(g, p + mk3(0.0f, 0.0f, n.z * aoRadius));
+        const float distance = sampleDistanceField(g, xadd3(p, mk3(0.0f, 0.0f, xmul(n.z, aoRadius))));
         const float clampedDistance = clampf(distance, 0.0f, aoRadius);
         float result = 1.0f - saturatef(clampedDistance / aoRadius);
         result *= result;
@@ -179,11 +180,11 @@ ILB_DEV bool sphereCore(const DFGeometry& g, const DLight& L, float lightOcclusi
     const float distanceOpacity = sphereLightOpacity(lightOcclusion, p, n, center, props, more.z);
     const bool visible = (distanceOpacity > 0.0f) && (p.x > -9999.0f);
     if (!visible) return false;
-    const float aoRadius = more.x * fmaxf(0.0f, n.z);
+    const float aoRadius = xmul(more.x, fmaxf(0.0f, n.z));
     const float aoOpacity = computeAO(g, L.hasField != 0, p, n, aoRadius, more.w, visible);
     const float preTraceOpacity = distanceOpacity * aoOpacity;
     const bool traceShadows = (props.w != 0.0f) && (preTraceOpacity >= (0.75f / 255.0f));
-    const float coneOpacity = coneTrace(g, L, center, props.x, props.y, 1.0f, p + (1.6f * n), traceShadows);
+    const float coneOpacity = coneTrace(g, L, center, props.x, props.y, 1.0f, xadd3(p, xscale3(n, 1.6f)), traceShadows);
     opacity = preTraceOpacity * coneOpacity;
     return true;
 }
@@ -193,11 +194,11 @@ ILB_DEV bool directionalCore(const DFGeometry& g, const DLight& L, f3 p, f3 n, f
                              float& opacity) {
     float lightOpacity = (dir.w < 0.1f) ? 1.0f : normalFactorEx(mk3(dir.x, dir.y, dir.z), n, 0.35f, 0.35f);
     const bool visible = (p.x > -9999.0f);
-    const float aoRadius = more.x * fmaxf(0.0f, n.z);
+    const float aoRadius = xmul(more.x, fmaxf(0.0f, n.z));
     lightOpacity *= computeAO(g, L.hasField != 0, p, n, aoRadius, more.w, visible);
     const bool traceShadows = visible && (props.x != 0.0f) && (lightOpacity >= 1.0f / 256.0f) && (dir.w >= 0.1f);
-    const f3 fakeLightCenter = p - (mk3(dir.x, dir.y, dir.z) * props.y);
-    lightOpacity *= coneTrace(g, L, fakeLightCenter, props.z, more.y, props.w, p + (1.5f * n), traceShadows);
+    const f3 fakeLightCenter = xsub3(p, xscale3(mk3(dir.x, dir.y, dir.z), props.y));
+    lightOpacity *= coneTrace(g, L, fakeLightCenter, props.z, more.y, props.w, xadd3(p, xscale3(n, 1.5f)), traceShadows);
     if (!visible) return false;
     opacity = lightOpacity;
     return true;
@@ -205,9 +206,9 @@ ILB_DEV bool directionalCore(const DFGeometry& g, const DLight& L, f3 p, f3 n, f
 
 // ---- line light (FBPBR.fxh:33-101, LineLightCore.fxh:17-120) -------------------------------------------------
 ILB_DEV f3 closestPointOnLineSegment3(f3 a, f3 b, f3 pt, float& t) {  // DistanceFieldCommon.fxh:151-155
-    const f3 ab = b - a;
-    t = saturatef(dot3(pt - a, ab) / dot3(ab, ab));
-    return a + t * ab;
+    const f3 ab = xsub3(b, a);  // exact: u places the three trace targets of a line light
+    t = saturatef(xdiv(xdot3(xsub3(pt, a), ab), xdot3(ab, ab)));
+    return xadd3(a, xscale3(ab, t));
 }
 
 ILB_DEV float rectangleSolidAngle(f3 wp, f3 p0, f3 p1, f3 p2, f3 p3) {  // FBPBR.fxh:33-51
@@ -243,12 +244,12 @@ ILB_DEV float lineLightOpacity(f3 wp, f3 wn, f3 P0, f3 P1, float lightRadius, f3
 ILB_DEV float lineConeTrace(const DFGeometry& g, const DLight& L, f3 start, f3 end, float u, float rampX, float rampY,
                             f3 shaded, bool enable) {  // LineLightCore.fxh:17-68
     Trace a, b, c;
-    const f3 delta = end - start;
-    const float deltaLength = length3(delta);
-    const float offset = fmaxf(saturatef((rampX + 1.0f) / deltaLength), 0.03f);
-    traceInit(a, shaded, start + saturatef(u - offset) * delta, rampX);
-    traceInit(b, shaded, start + u * delta, rampX);
-    traceInit(c, shaded, start + saturatef(u + offset) * delta, rampX);
+    const f3 delta = xsub3(end, start);
+    const float deltaLength = xlength3(delta);
+    const float offset = fmaxf(saturatef(xdiv(xadd(rampX, 1.0f), deltaLength)), 0.03f);
+    traceInit(a, shaded, xadd3(start, xscale3(delta, saturatef(xsub(u, offset)))), rampX);
+    traceInit(b, shaded, xadd3(start, xscale3(delta, u)), rampX);
+    traceInit(c, shaded, xadd3(start, xscale3(delta, saturatef(xadd(u, offset)))), rampX);
     const TraceConfig cfg = makeTraceConfig(L, rampX, rampY, 1.0f);
     float stepsRemaining = cfg.stepLimit;
     float liveness = (L.hasField && enable) ? 1.0f : 0.0f;
@@ -267,11 +268,11 @@ ILB_DEV bool lineCore(const DFGeometry& g, const DLight& L, f3 p, f3 n, f3 start
     const float distanceOpacity = lineLightOpacity(p, n, start, end, props.x, lightCenter, u);
     const bool visible = (distanceOpacity > 0.0f) && (p.x > -9999.0f);
     if (!visible) return false;
-    const float aoRadius = more.x * fmaxf(0.0f, n.z);
+    const float aoRadius = xmul(more.x, fmaxf(0.0f, n.z));
     const float aoOpacity = computeAO(g, L.hasField != 0, p, n, aoRadius, more.w, visible);
     const float preTraceOpacity = distanceOpacity * aoOpacity;
     const bool traceShadows = (props.w != 0.0f) && (preTraceOpacity >= (0.75f / 255.0f));
-    const float coneOpacity = lineConeTrace(g, L, start, end, u, props.x, props.y, p + (1.5f * n), traceShadows);
+    const float coneOpacity = lineConeTrace(g, L, start, end, u, props.x, props.y, xadd3(p, xscale3(n, 1.5f)), traceShadows);
     opacity = preTraceOpacity * coneOpacity;
     return true;
 }
@@ -299,13 +300,11 @@ ILB_DEV Pixel decodePixel(const LightingParams& P, int px, int py) {
     if (any2(P.gbTexelAndMisc.x, P.gbTexelAndMisc.y)) {
         float srcx = sx, srcy = sy;
         if (P.gbViewportRelative != 0.0f) {
-            srcx = srcx / vsx;
-            srcy = srcy / vsy;
-            srcx += P.vpx;
-            srcy += P.vpy;
+            srcx = xadd(xdiv(srcx, vsx), P.vpx);
+            srcy = xadd(xdiv(srcy, vsy), P.vpy);
         }
-        const float u = (srcx + 0.5f) * P.gbTexelAndMisc.x, v = (srcy + 0.5f) * P.gbTexelAndMisc.y;
-        const float4 s = loadGBufferTexel(P, (int)floorf(u * (float)P.gw), (int)floorf(v * (float)P.gh));
+        const float u = xmul(xadd(srcx, 0.5f), P.gbTexelAndMisc.x), v = xmul(xadd(srcy, 0.5f), P.gbTexelAndMisc.y);
+        const float4 s = loadGBufferTexel(P, (int)floorf(xmul(u, (float)P.gw)), (int)floorf(xmul(v, (float)P.gh)));
         if (P.stencil) {  // UpdateMaskFromGBuffer, GBufferMask.fx:26-44
             const float minW = -fabsf(P.envZAndScale.y) - 1.0f, maxW = -fabsf(P.envZAndScale.x) - 1.0f;
             r.maskOk = !((s.w >= 9999.0f) || (s.w < minW) || ((s.w < 0.0f) && (s.w > maxW)));
@@ -313,7 +312,7 @@ ILB_DEV Pixel decodePixel(const LightingParams& P, int px, int py) {
         const float relativeY = s.z;
         float worldZ = s.w;
         if (worldZ < 0.0f) {
-            worldZ += 1.0f;
+            worldZ = xadd(worldZ, 1.0f);
             worldZ = -worldZ;
             r.enableShadows = false;
         } else if (worldZ >= 9999.0f) {
@@ -321,26 +320,25 @@ ILB_DEV Pixel decodePixel(const LightingParams& P, int px, int py) {
             r.enableShadows = false;
             r.fullbright = true;
         }
-        worldZ *= 1024.0f;
-        worldZ -= 1024.0f;
-        sx = sx / rsx;
-        sy = sy / rsy;
-        r.camera = mk3(sx, sy, P.envZAndScale.y + 0.01f);
-        r.pos = mk3((sx + 0.0f) / vsx + P.vpx, (sy + relativeY) / vsy + P.vpy, worldZ);
+        worldZ = xsub(xmul(worldZ, 1024.0f), 1024.0f);
+        sx = xdiv(sx, rsx);
+        sy = xdiv(sy, rsy);
+        r.camera = mk3(sx, sy, xadd(P.envZAndScale.y, 0.01f));
+        r.pos = mk3(xadd(xdiv(sx, vsx), P.vpx), xadd(xdiv(xadd(sy, relativeY), vsy), P.vpy), worldZ);
         if (any2(s.x, s.y)) {
-            const float ax = s.x * 2.0f - 1.0f, ay = s.y * 2.0f - 1.0f;
+            const float ax = xsub(xmul(s.x, 2.0f), 1.0f), ay = xsub(xmul(s.y, 2.0f), 1.0f);
             float sn, cs;
-            sincosf(ax * ILB_PI, &sn, &cs);
-            const float phx = sqrtf(1.0f - ay * ay);
-            r.normal = mk3(cs * phx, sn * phx, ay);
+            sincosf(xmul(ax, ILB_PI), &sn, &cs);
+            const float phx = xsqrt(xsub(1.0f, xmul(ay, ay)));
+            r.normal = mk3(xmul(cs, phx), xmul(sn, phx), ay);
         } else {
             r.normal = mk3(0.0f);
         }
     } else {
-        sx = sx / rsx;
-        sy = sy / rsy;
-        r.camera = mk3(sx, sy, P.envZAndScale.y + 0.01f);
-        r.pos = mk3(sx / vsx + P.vpx, sy / vsy + P.vpy, P.envZAndScale.x);
+        sx = xdiv(sx, rsx);
+        sy = xdiv(sy, rsy);
+        r.camera = mk3(sx, sy, xadd(P.envZAndScale.y, 0.01f));
+        r.pos = mk3(xadd(xdiv(sx, vsx), P.vpx), xadd(xdiv(sy, vsy), P.vpy), P.envZAndScale.x);
         r.normal = mk3(0.0f, 0.0f, 1.0f);
     }
     return r;
@@ -487,8 +485,8 @@ __global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_MINBLOCKS) light_accum
     const int ty0 = P.row_begin + blockIdx.y * TILE_H, ty1 = ty0 + TILE_H - 1;
 
     // pixel centre in world space for the coverage test (inverse of the light vertex shaders' transform)
-    const float sxs = P.gbTexelAndMisc.z * P.envZAndScale.z, sys = P.gbTexelAndMisc.w * P.envZAndScale.w;
-    const float wx = ((float)px + 0.5f) / sxs + P.vpx, wy = ((float)py + 0.5f) / sys + P.vpy;
+    const float sxs = xmul(P.gbTexelAndMisc.z, P.envZAndScale.z), sys = xmul(P.gbTexelAndMisc.w, P.envZAndScale.w);
+    const float wx = xadd(xdiv(xadd((float)px, 0.5f), sxs), P.vpx), wy = xadd(xdiv(xadd((float)py, 0.5f), sys), P.vpy);
 
     float accR = P.clear.x, accG = P.clear.y, accB = P.clear.z, accA = P.clear.w;
 

@@ -50,12 +50,12 @@ ILB_DEV int wrapIndex(float f, int n) {  // floor(f) mod n for |f| < 2^22: (i + 
     return (int)fl - (int)floorf((fl + 0.5f) * (1.0f / (float)n)) * n;
 }
 ILB_DEV f4 randomFetch(const float4* rng, int w, int h, float u, float v) {
-    const int ix = wrapIndex(u * (float)w, w), iy = wrapIndex(v * (float)h, h);
+    const int ix = wrapIndex(xmul(u, (float)w), w), iy = wrapIndex(xmul(v, (float)h), h);
     return mk4(__ldg(rng + (size_t)iy * (size_t)w + (size_t)ix));
 }
 ILB_DEV f4 randomCustom(const float4* rng, int w, int h, float x, float y, const float* offset, float ratex, float ratey,
                         const float* texel) {  // :27-30
-    return randomFetch(rng, w, h, ((x * ratex) + offset[0]) * texel[0], ((y * ratey) + offset[1]) * texel[1]);
+    return randomFetch(rng, w, h, xmul(xadd(xmul(x, ratex), offset[0]), texel[0]), xmul(xadd(xmul(y, ratey), offset[1]), texel[1]));
 }
 
 // ---- Bezier.fxh ------------------------------------------------------------------------------------------
@@ -100,11 +100,11 @@ ILB_DEV f4 evaluateBezier4(const ilb_bezier4& b, float value) {  // :141-177
                bezierScalar(b.A.z, b.B.z, b.C.z, b.D.z, count, t), bezierScalar(b.A.w, b.B.w, b.C.w, b.D.w, count, t));
 }
 
-// ---- transforms ------------------------------------------------------------------------------------------
+// ---- transforms: x-ops throughout (particle state feeds the collision thresholds of later steps) -------------
 ILB_DEV float computeWeight(const ilb_area& a, f3 worldPosition) {  // FMA.fx:15-20 / Noise.fx:21-26 (scalar rotation broadcast)
     const float distance = evaluateByTypeId(a.AreaType, worldPosition, mk3(a.AreaCenter[0], a.AreaCenter[1], a.AreaCenter[2]),
                                             mk3(a.AreaSize[0], a.AreaSize[1], a.AreaSize[2]), mk4(a.AreaRotation));
-    return (1.0f - saturatef(distance / a.AreaFalloff)) * a.Strength;
+    return xmul(xsub(1.0f, saturatef(xdiv(distance, a.AreaFalloff))), a.Strength);
 }
 ILB_DEV bool checkCategoryFilter(float type, const float* mm) { return (type >= mm[0]) && (type <= mm[1]); }  // ParticleCommon.fxh:198-200
 
@@ -115,91 +115,92 @@ ILB_DEV void opGravity(const ilb_psys_uniforms& u, const ilb_gravity& g, f4& pos
     for (int i = 0; i < g.AttractorCount; i++) {
         const f3 apos = xyz(g.AttractorPositions[i]);
         const ilb_float4 ars = g.AttractorRadiusesAndStrengths[i];
-        const f3 toCenter = (apos - xyz(pos));
+        const f3 toCenter = xsub3(apos, xyz(pos));
         float attraction;
         if (ars.z >= 0.5f) {
-            const float distance = length3(toCenter);
-            attraction = 1.0f - saturatef(distance / ars.x);
-            if (ars.z >= 1.5f) attraction *= attraction;
-            attraction = attraction * dt / VelocityConstantScale;
+            const float distance = xlength3(toCenter);
+            attraction = xsub(1.0f, saturatef(xdiv(distance, ars.x)));
+            if (ars.z >= 1.5f) attraction = xmul(attraction, attraction);
+            attraction = xdiv(xmul(attraction, dt), VelocityConstantScale);
         } else {
-            float distanceSquared = dot3(toCenter, toCenter) - ars.x;
+            float distanceSquared = xsub(xdot3(toCenter, toCenter), ars.x);
             distanceSquared = fmaxf(distanceSquared, 0.001f);
-            attraction = 1.0f / distanceSquared;
+            attraction = xdiv(1.0f, distanceSquared);
         }
-        acceleration = acceleration + (normalize3(toCenter) * attraction * ars.y);
+        acceleration = xadd3(acceleration, xscale3(xscale3(xnormalize3(toCenter), attraction), ars.y));
     }
-    const float maximumAcceleration = g.MaximumAcceleration * dt / VelocityConstantScale;
-    const float currentLength = length3(acceleration);
-    if (currentLength > maximumAcceleration) acceleration = normalize3(acceleration) * maximumAcceleration;
+    const float maximumAcceleration = xdiv(xmul(g.MaximumAcceleration, dt), VelocityConstantScale);
+    const float currentLength = xlength3(acceleration);
+    if (currentLength > maximumAcceleration) acceleration = xscale3(xnormalize3(acceleration), maximumAcceleration);
     const float mv = u.GlobalSettings.z;
-    vel = mk4(fminf(mv, vel.x + acceleration.x), fminf(mv, vel.y + acceleration.y), fminf(mv, vel.z + acceleration.z), vel.w);
+    vel = mk4(fminf(mv, xadd(vel.x, acceleration.x)), fminf(mv, xadd(vel.y, acceleration.y)), fminf(mv, xadd(vel.z, acceleration.z)), vel.w);
 }
 
 ILB_DEV void opNoise(const StepParams& P, const ilb_noise& n, float x, float y, f4& pos, f4& vel) {  // Noise.fx:28-72
     if (!checkCategoryFilter(vel.w, n.area.CategoryFilter)) return;
     const float weight = computeWeight(n.area, xyz(pos));
-    const float t = weight * P.u.GlobalSettings.x / n.TimeDivisor;
+    const float t = xdiv(xmul(weight, P.u.GlobalSettings.x), n.TimeDivisor);
     const float rx = n.RandomnessTexel[0], ry = n.RandomnessTexel[1];
     const f4 randomP1 = randomCustom(P.rng, P.rng_w, P.rng_h, x, y, n.RandomnessOffset, rx, ry, n.RandomnessTexel);
     const f4 randomP2 = randomCustom(P.rng, P.rng_w, P.rng_h, x, y, n.NextRandomnessOffset, rx, ry, n.RandomnessTexel);
-    const f4 randomV1 = randomCustom(P.rng, P.rng_w, P.rng_h, x + 2.0f, y + 1.0f, n.RandomnessOffset, rx, ry, n.RandomnessTexel);
-    const f4 randomV2 = randomCustom(P.rng, P.rng_w, P.rng_h, x + 2.0f, y + 1.0f, n.NextRandomnessOffset, rx, ry, n.RandomnessTexel);
-    const f4 randomP = lerp4(randomP1, randomP2, n.FrequencyLerp);
-    const f4 randomV = lerp4(randomV1, randomV2, n.FrequencyLerp);
-    f4 positionDelta = (randomP + mk4(n.PositionOffset));
-    positionDelta = sign4(positionDelta) * max4(abs4(positionDelta), mk4(n.PositionMinimum));
-    positionDelta = positionDelta * mk4(n.PositionScale);
-    f4 velocityDelta = (randomV + mk4(n.VelocityOffset));
-    velocityDelta = sign4(velocityDelta) * max4(abs4(velocityDelta), mk4(n.VelocityMinimum));
-    velocityDelta = velocityDelta * mk4(n.VelocityScale);
+    const f4 randomV1 = randomCustom(P.rng, P.rng_w, P.rng_h, xadd(x, 2.0f), xadd(y, 1.0f), n.RandomnessOffset, rx, ry, n.RandomnessTexel);
+    const f4 randomV2 = randomCustom(P.rng, P.rng_w, P.rng_h, xadd(x, 2.0f), xadd(y, 1.0f), n.NextRandomnessOffset, rx, ry, n.RandomnessTexel);
+    const f4 randomP = xlerp4(randomP1, randomP2, n.FrequencyLerp);
+    const f4 randomV = xlerp4(randomV1, randomV2, n.FrequencyLerp);
+    f4 positionDelta = xadd4(randomP, mk4(n.PositionOffset));
+    positionDelta = xmul4(sign4(positionDelta), max4(abs4(positionDelta), mk4(n.PositionMinimum)));
+    positionDelta = xmul4(positionDelta, mk4(n.PositionScale));
+    f4 velocityDelta = xadd4(randomV, mk4(n.VelocityOffset));
+    velocityDelta = xmul4(sign4(velocityDelta), max4(abs4(velocityDelta), mk4(n.VelocityMinimum)));
+    velocityDelta = xmul4(velocityDelta, mk4(n.VelocityScale));
     const f4 oldPosition = pos;
     const f3 ov = xyz(vel);
-    pos = lerp4(oldPosition, oldPosition + positionDelta, t);
+    pos = xlerp4(oldPosition, xadd4(oldPosition, positionDelta), t);
     f3 nv;
-    if (n.ReplaceOldVelocity != 0.0f) nv = lerp3(ov, xyz(velocityDelta), weight);
-    else nv = lerp3(ov, ov + xyz(velocityDelta), t);
-    nv = nv + (normalize3(ov) * velocityDelta.w);
+    if (n.ReplaceOldVelocity != 0.0f) nv = xlerp3(ov, xyz(velocityDelta), weight);
+    else nv = xlerp3(ov, xadd3(ov, xyz(velocityDelta)), t);
+    nv = xadd3(nv, xscale3(xnormalize3(ov), velocityDelta.w));
     vel = mk4(nv, vel.w);
 }
 
 ILB_DEV void opFMA(const ilb_psys_uniforms& u, const ilb_fma& f, f4& pos, f4& vel) {  // FMA.fx:22-51
     if ((pos.w <= 0.0f) || !checkCategoryFilter(vel.w, f.area.CategoryFilter)) return;
     const float weight = computeWeight(f.area, xyz(pos));
-    const float t = weight * u.GlobalSettings.x / f.TimeDivisor;
+    const float t = xdiv(xmul(weight, u.GlobalSettings.x), f.TimeDivisor);
     const f4 oldPosition = pos, oldVelocity = vel;
-    pos = lerp4(oldPosition, (oldPosition * mk4(f.PositionMultiply)) + mk4(f.PositionAdd), t);
-    vel = lerp4(oldVelocity, (oldVelocity * mk4(f.VelocityMultiply)) + mk4(f.VelocityAdd), t);
+    pos = xlerp4(oldPosition, xadd4(xmul4(oldPosition, mk4(f.PositionMultiply)), mk4(f.PositionAdd)), t);
+    vel = xlerp4(oldVelocity, xadd4(xmul4(oldVelocity, mk4(f.VelocityMultiply)), mk4(f.VelocityAdd)), t);
 }
 
 ILB_DEV f4 mul3(f4 oldValue, const float* mat, float w) {  // ParticleCommon.fxh:187-196
-    const f4 temp = mul_rm(mk4(oldValue.x, oldValue.y, oldValue.z, 1.0f), mat);
+    const f4 temp = xmul_rm(mk4(oldValue.x, oldValue.y, oldValue.z, 1.0f), mat);
     f3 divided = xyz(temp);
-    if (w != 0.0f) divided = divided / temp.w;
+    if (w != 0.0f) divided = xdivs3(divided, temp.w);
     return mk4(divided, oldValue.w);
 }
 
 ILB_DEV void opMatrix(const ilb_psys_uniforms& u, const ilb_matrix_multiply& m, f4& pos, f4& vel) {  // MatrixMultiply.fx:14-52
     if ((pos.w <= 0.0f) || !checkCategoryFilter(vel.w, m.area.CategoryFilter)) return;
-    const float timeScale = (m.TimeDivisor >= 0.0f) ? u.GlobalSettings.x / m.TimeDivisor : 1.0f;
-    const float w = computeWeight(m.area, xyz(pos)) * timeScale;
+    const float timeScale = (m.TimeDivisor >= 0.0f) ? xdiv(u.GlobalSettings.x, m.TimeDivisor) : 1.0f;
+    const float w = xmul(computeWeight(m.area, xyz(pos)), timeScale);
     const f4 oldPosition = pos, oldVelocity = vel;
-    pos = lerp4(oldPosition, mul3(oldPosition, m.PositionMatrix, 1.0f), w);
-    vel = lerp4(oldVelocity, mul3(oldVelocity, m.VelocityMatrix, 0.0f), w);
+    pos = xlerp4(oldPosition, mul3(oldPosition, m.PositionMatrix, 1.0f), w);
+    vel = xlerp4(oldVelocity, mul3(oldVelocity, m.VelocityMatrix, 0.0f), w);
 }
 
 // ---- update tail (UpdateCommon.fxh, UpdateParticleSystem.fx, UpdateParticleSystemWithDistanceField.fx) -------------
 ILB_DEV f3 applyFrictionAndMaximum(const ilb_psys_uniforms& u, f3 velocity) {  // UpdateCommon.fxh:20-35
-    float l = length3(velocity);
+    float l = xlength3(velocity);
     if (l <= 0.001f) return mk3(0.0f);
     const float mv = u.GlobalSettings.z;
     if (l > mv) l = mv;
-    const float friction = l * u.GlobalSettings.y;
-    l -= (friction * (u.GlobalSettings.x / VelocityConstantScale));
+    const float friction = xmul(l, u.GlobalSettings.y);
+    l = xsub(l, xmul(friction, xdiv(u.GlobalSettings.x, VelocityConstantScale)));
     l = clampf(l, 0.0f, mv);
-    return normalize3(velocity) * l;
+    return xscale3(xnormalize3(velocity), l);
 }
 
+// Render outputs do not feed back into particle state: plain (FMA / fast division) arithmetic.
 ILB_DEV void computeRenderData(const ilb_psys_uniforms& u, float vx, float vy, f4 position, f4 velocity, f4 attributes,
                                f4& renderColor, f4& renderData) {  // UpdateCommon.fxh:97-117
     if (position.w <= 0.0f) {
@@ -229,15 +230,15 @@ ILB_DEV void computeRenderData(const ilb_psys_uniforms& u, float vx, float vy, f
 }
 
 ILB_DEV f3 estimateNormal4(const DFGeometry& g, f3 position) {  // VisualizeCommon.fxh:9-63
-    const f3 texel = mk3(g.invScaleX, g.invScaleY, g.ez / fmaxf(g.sliceCount, 1.0f));
+    const f3 texel = mk3(g.invScaleX, g.invScaleY, xdiv(g.ez, fmaxf(g.sliceCount, 1.0f)));
     f3 result = mk3(0.0f);
     const float wts[4][3] = {{1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {1, 1, 1}};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const f3 weight = mk3(wts[i][0], wts[i][1], wts[i][2]);
-        result = result + (weight * sampleDistanceField(g, position + weight * texel));
+        result = xadd3(result, xscale3(weight, sampleDistanceField(g, xadd3(position, xmul3(weight, texel)))));
     }
-    return normalize3(result);
+    return xnormalize3(result);
 }
 
 // returns false when the reference pass discards (dead on entry): outputs stay at the cleared zeros
@@ -248,13 +249,13 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
     outV = mk4(0.0f);
     needAttr = false;
     if (oldPosition.w <= 0.0f) return false;  // readStateOrDiscard ParticleCommon.fxh:162-181
-    const float dts = u.GlobalSettings.x / VelocityConstantScale;
-    float newLife = oldPosition.w - (u.GlobalSettings.w * dts);
+    const float dts = xdiv(u.GlobalSettings.x, VelocityConstantScale);
+    float newLife = xsub(oldPosition.w, xmul(u.GlobalSettings.w, dts));
     if (!COLLIDE) {  // PS_Update UpdateParticleSystem.fx:9-38
         const f3 velocity = applyFrictionAndMaximum(u, xyz(oldVelocity));
-        const f3 scaledVelocity = velocity * dts;
+        const f3 scaledVelocity = xscale3(velocity, dts);
         if (newLife > 0.0f) {
-            outP = mk4(xyz(oldPosition) + scaledVelocity, newLife);
+            outP = mk4(xadd3(xyz(oldPosition), scaledVelocity), newLife);
             outV = mk4(velocity, oldVelocity.w);
             needAttr = true;
         }
@@ -264,21 +265,21 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
     if (newLife <= 0.0f) return true;
     const float collisionDistance = u.CollisionSettings.z;
     const f3 op = xyz(oldPosition);
-    const f3 unitVector = normalize3(xyz(oldVelocity));
+    const f3 unitVector = xnormalize3(xyz(oldVelocity));
     const f3 velocity = applyFrictionAndMaximum(u, xyz(oldVelocity));
     bool collided = false, escaping = false;
-    const f3 scaledVelocity = velocity * dts;
+    const f3 scaledVelocity = xscale3(velocity, dts);
     f3 collisionPosition = mk3(0.0f), newPosition = op;
     f4 newVelocity = mk4(0.0f);
 
     const float initialDistance = sampleDistanceField(P.df, op);
     const bool wasColliding = initialDistance < collisionDistance;
-    float travelDistance = fmaxf(0.0f, fminf(initialDistance, length3(scaledVelocity)));
+    float travelDistance = fmaxf(0.0f, fminf(initialDistance, xlength3(scaledVelocity)));
     int stepCount = 3;
     if (wasColliding) stepCount = 1;
     else if (travelDistance <= 0.001f) stepCount = 0;
     for (int i = 0; i < stepCount; i++) {
-        const f3 testPosition = op + (travelDistance * unitVector);
+        const f3 testPosition = xadd3(op, xscale3(unitVector, travelDistance));
         const float stepDistance = sampleDistanceField(P.df, testPosition);
         if (stepDistance < collisionDistance) {
             collided = true;
@@ -287,8 +288,8 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
         escaping = stepDistance > initialDistance;
         if (collided && !escaping) {
             collisionPosition = testPosition;
-            const float offset = clampf(stepDistance + collisionDistance, 0.05f, 16.0f);
-            travelDistance = fmaxf(0.0f, travelDistance - offset);
+            const float offset = clampf(xadd(stepDistance, collisionDistance), 0.05f, 16.0f);
+            travelDistance = fmaxf(0.0f, xsub(travelDistance, offset));
         } else
             stepCount = 0;
         if (travelDistance <= 0.001f) stepCount = 0;
@@ -301,31 +302,32 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
         const float maxV = u.GlobalSettings.z;
         const float escapeSpeed = fminf(maxV, u.CollisionSettings.x);
         if (redirect) {
-            normal = normal * mk3(1.0f, 1.0f, 0.0f);
-            if (length3(normal) < 0.33f) {
+            normal = mk3(normal.x, normal.y, xmul(normal.z, 0.0f));
+            if (xlength3(normal) < 0.33f) {
                 float s, c;
-                sincosf((x / 67.0f) + (y / 13.0f), &s, &c);
+                sincosf(xadd(xdiv(x, 67.0f), xdiv(y, 13.0f)), &s, &c);
                 normal = mk3(s, c, 0.0f);
             }
-            const f3 escapeVector = normalize3(normal);
-            newVelocity = mk4(escapeVector * escapeSpeed * 0.33f, 3.0f);
-            newPosition = op + (xyz(newVelocity) * dts);
+            const f3 escapeVector = xnormalize3(normal);
+            newVelocity = mk4(xscale3(xscale3(escapeVector, escapeSpeed), 0.33f), 3.0f);
+            newPosition = xadd3(op, xscale3(xyz(newVelocity), dts));
         } else if (bounce) {
-            f3 bounceVector = -(2.0f * dot3(normal, unitVector) * (normal - unitVector));
-            if (length3(bounceVector) < 0.33f) bounceVector = -unitVector;
-            else bounceVector = normalize3(bounceVector);
+            const float k = xmul(2.0f, xdot3(normal, unitVector));
+            f3 bounceVector = -xscale3(xsub3(normal, unitVector), k);
+            if (xlength3(bounceVector) < 0.33f) bounceVector = -unitVector;
+            else bounceVector = xnormalize3(bounceVector);
             newPosition = collisionPosition;
-            newVelocity = mk4(bounceVector * (fminf(maxV, length3(velocity) * u.CollisionSettings.y)), 3.0f);
-            newLife -= u.CollisionSettings.w;
+            newVelocity = mk4(xscale3(bounceVector, fminf(maxV, xmul(xlength3(velocity), u.CollisionSettings.y))), 3.0f);
+            newLife = xsub(newLife, u.CollisionSettings.w);
         } else {
-            const float currentSpeed = length3(xyz(oldVelocity));
-            const float newSpeed = fmaxf(currentSpeed * 1.1f, escapeSpeed);
-            newVelocity = mk4(unitVector * newSpeed, 0.0f);
-            newPosition = op + (travelDistance * unitVector);
+            const float currentSpeed = xlength3(xyz(oldVelocity));
+            const float newSpeed = fmaxf(xmul(currentSpeed, 1.1f), escapeSpeed);
+            newVelocity = mk4(xscale3(unitVector, newSpeed), 0.0f);
+            newPosition = xadd3(op, xscale3(unitVector, travelDistance));
         }
     } else {
-        newVelocity = mk4(velocity, fmaxf(oldVelocity.w - 1.0f, 0.0f));
-        newPosition = op + (travelDistance * unitVector);
+        newVelocity = mk4(velocity, fmaxf(xsub(oldVelocity.w, 1.0f), 0.0f));
+        newPosition = xadd3(op, xscale3(unitVector, travelDistance));
     }
     if (newLife <= 0.0f) {
         newPosition = mk3(0.0f);
@@ -383,40 +385,40 @@ __global__ void __launch_bounds__(STEP_THREADS, ILB_PARTICLE_MINBLOCKS) particle
 
 // ---- spawner (SpawnerCommon.fxh, SpawnParticles.fx:10-30) -----------------------------------------------------
 ILB_DEV f3 generateRandomNormal3(float rx, float ry) {  // :47-57
-    const float phi = rx * ILB_PI * 2.0f;
-    const float costheta = (ry - 0.5f) * 2.0f;
+    const float phi = xmul(xmul(rx, ILB_PI), 2.0f);
+    const float costheta = xmul(xsub(ry, 0.5f), 2.0f);
     const float theta = acosf(costheta);
-    return mk3(sinf(theta) * cosf(phi), sinf(theta) * sinf(phi), cosf(theta));
+    return mk3(xmul(sinf(theta), cosf(phi)), xmul(sinf(theta), sinf(phi)), cosf(theta));
 }
 
 ILB_DEV f4 evaluateFormula(const ilb_spawn& s, f4 origin, f4 constant, f4 scale, f4 offset, f4 randomness, float type) {  // :59-104
-    const f4 nonCircular = (randomness + offset) * scale;
-    const f4 type0 = constant + nonCircular;
+    const f4 nonCircular = xmul4(xadd4(randomness, offset), scale);
+    const f4 type0 = xadd4(constant, nonCircular);
     const uint32_t itype = (uint32_t)fabsf(floorf(type));
     if (itype == 1 || itype == 3) {
         const f3 axisMask = mk3(s.AxisMask[0], s.AxisMask[1], s.AxisMask[2]);
-        const f3 randomNormal = normalize3(generateRandomNormal3(randomness.x, randomness.y) * axisMask);
-        f3 circular = mk3(randomNormal.x * randomness.z * scale.x, randomNormal.y * randomness.z * scale.y,
-                          randomNormal.z * randomness.z * scale.z);
+        const f3 randomNormal = xnormalize3(xmul3(generateRandomNormal3(randomness.x, randomness.y), axisMask));
+        f3 circular = mk3(xmul(xmul(randomNormal.x, randomness.z), scale.x), xmul(xmul(randomNormal.y, randomness.z), scale.y),
+                          xmul(xmul(randomNormal.z, randomness.z), scale.z));
         f3 result;
         if (itype == 3) {
             const float sqrt2 = 1.41421356237f;
             const f3 edge = abs3(xyz(offset));
-            result = min3(max3(xyz(offset) * randomNormal * sqrt2, -edge), edge);
-            result = result + (xyz(constant) + circular);
+            result = min3(max3(xscale3(xmul3(xyz(offset), randomNormal), sqrt2), -edge), edge);
+            result = xadd3(result, xadd3(xyz(constant), circular));
         } else {
-            circular = circular + (randomNormal * xyz(offset));
-            result = xyz(constant) + circular;
+            circular = xadd3(circular, xmul3(randomNormal, xyz(offset)));
+            result = xadd3(xyz(constant), circular);
         }
         return mk4(result, type0.w);
     } else if (itype == 2) {
-        const f3 distance = xyz(constant - origin);
-        const float ldistance = length3(distance);
+        const f3 distance = xyz(xsub4(constant, origin));
+        const float ldistance = xlength3(distance);
         if (ldistance < 0.1f) return mk4(0.0f, 0.0f, 0.0f, constant.w);
-        const f3 direction = distance / ldistance;
-        const f3 randomSpeed = (randomness.x * xyz(scale) * direction);
-        const f3 fixedSpeed = (xyz(offset) * direction);
-        return mk4(randomSpeed + fixedSpeed, type0.w);
+        const f3 direction = xdivs3(distance, ldistance);
+        const f3 randomSpeed = xmul3(xscale3(xyz(scale), randomness.x), direction);
+        const f3 fixedSpeed = xmul3(xyz(offset), direction);
+        return mk4(xadd3(randomSpeed, fixedSpeed), type0.w);
     }
     return type0;
 }
@@ -426,50 +428,50 @@ __global__ void __launch_bounds__(STEP_THREADS) particle_spawn_kernel(const __gr
     if (k >= P.count) return;
     const ilb_spawn& s = P.s;
     const int li = P.first + k;  // index within the chunk, inside [first, last] by construction (Spawn_Stage1 :124-130)
-    const float index = (float)(li % P.chunk_size) + ((float)(li / P.chunk_size) * s.ChunkSizeAndIndices.x);
+    const float index = xadd((float)(li % P.chunk_size), xmul((float)(li / P.chunk_size), s.ChunkSizeAndIndices.x));
     if ((index < s.ChunkSizeAndIndices.y) || (index > s.ChunkSizeAndIndices.z)) return;
 
     // evaluateRandomForIndex :106-117
     const float one = 1.0f;
-    f4 random1 = randomCustom(P.rng, P.rng_w, P.rng_h, fmodf(index, 8039.0f), 0.0f + fmodf(index, 57.0f), s.RandomnessOffset, one, one, s.RandomnessTexel);
-    f4 random2 = randomCustom(P.rng, P.rng_w, P.rng_h, fmodf(index, 6180.0f), 1.0f + fmodf(index, 4031.0f), s.RandomnessOffset, one, one, s.RandomnessTexel);
-    const f4 random3 = randomCustom(P.rng, P.rng_w, P.rng_h, fmodf(index, 2025.0f), 2.0f + fmodf(index, 65531.0f), s.RandomnessOffset, one, one, s.RandomnessTexel);
+    f4 random1 = randomCustom(P.rng, P.rng_w, P.rng_h, fmodf(index, 8039.0f), xadd(0.0f, fmodf(index, 57.0f)), s.RandomnessOffset, one, one, s.RandomnessTexel);
+    f4 random2 = randomCustom(P.rng, P.rng_w, P.rng_h, fmodf(index, 6180.0f), xadd(1.0f, fmodf(index, 4031.0f)), s.RandomnessOffset, one, one, s.RandomnessTexel);
+    const f4 random3 = randomCustom(P.rng, P.rng_w, P.rng_h, fmodf(index, 2025.0f), xadd(2.0f, fmodf(index, 65531.0f)), s.RandomnessOffset, one, one, s.RandomnessTexel);
     if (s.AlignVelocityAndPosition != 0.0f) { random2.x = random1.x; random2.y = random1.y; }
 
     int index1, index2;
     float positionIndexT;
-    const float relativeIndex = (index - s.ChunkSizeAndIndices.y);
+    const float relativeIndex = xsub(index, s.ChunkSizeAndIndices.y);
     if (s.PolygonRate > 0.05f) {
-        const float positionIndexF = (relativeIndex / s.PolygonRate) + s.ChunkSizeAndIndices.w;
+        const float positionIndexF = xadd(xdiv(relativeIndex, s.PolygonRate), s.ChunkSizeAndIndices.w);
         const float divisor = s.PositionConstantCount;
         float positionIndexI;
         positionIndexT = modff(positionIndexF, &positionIndexI);
         index1 = (int)fmodf(positionIndexI, divisor);
-        if (s.PolygonLoop != 0.0f) index2 = (int)fmodf(positionIndexI + 1.0f, divisor);
-        else index2 = (int)fminf((float)(index1 + 1), divisor - 1.0f);
+        if (s.PolygonLoop != 0.0f) index2 = (int)fmodf(xadd(positionIndexI, 1.0f), divisor);
+        else index2 = (int)fminf((float)(index1 + 1), xsub(divisor, 1.0f));
     } else {
-        index1 = index2 = (int)fmodf(relativeIndex + s.ChunkSizeAndIndices.w, s.PositionConstantCount);
+        index1 = index2 = (int)fmodf(xadd(relativeIndex, s.ChunkSizeAndIndices.w), s.PositionConstantCount);
         positionIndexT = 0.0f;
     }
     index1 = min(max(index1, 0), 3);
     index2 = min(max(index2, 0), 3);
     const f4 position1 = mk4(s.InlinePositionConstants[index1]), position2 = mk4(s.InlinePositionConstants[index2]);
-    const f4 positionConstant = lerp4(position1, position2, positionIndexT);
-    const f4 towardsNext = position2 - position1;
+    const f4 positionConstant = xlerp4(position1, position2, positionIndexT);
+    const f4 towardsNext = xsub4(position2, position1);
 
     // Spawn_Stage2 :157-190
     const ilb_float4* C = s.Configuration;
     const f4 tempPosition = evaluateFormula(s, mk4(0.0f), positionConstant, mk4(C[0]), mk4(C[1]), random1, s.FormulaTypes.x);
-    f4 newPosition = mul_rm(mk4(tempPosition.x, tempPosition.y, tempPosition.z, 1.0f), s.PositionMatrix);
+    f4 newPosition = xmul_rm(mk4(tempPosition.x, tempPosition.y, tempPosition.z, 1.0f), s.PositionMatrix);
     newPosition.w = tempPosition.w;
     f4 tempVelocity = evaluateFormula(s, tempPosition, mk4(C[2]), mk4(C[3]), mk4(C[4]), random2, s.FormulaTypes.y);
     const f4 newAttributes = evaluateFormula(s, mk4(0.0f), mk4(C[5]), mk4(C[6]), mk4(C[7]), random3, s.FormulaTypes.z);
-    const float towardsDistance = length4(towardsNext);
+    const float towardsDistance = xlength4(towardsNext);
     if (towardsDistance > 0.0001f) {
         const float towardsSpeed = evaluateFormula(s, mk4(0.0f), mk4(C[8].x), mk4(C[8].y), mk4(C[8].z), mk4(random3.w), s.FormulaTypes.w).x;
-        tempVelocity = tempVelocity + (towardsSpeed * (towardsNext / towardsDistance));
+        tempVelocity = xadd4(tempVelocity, xscale4(xdivs4(towardsNext, towardsDistance), towardsSpeed));
     }
-    f4 newVelocity = mul_rm(mk4(tempVelocity.x, tempVelocity.y, tempVelocity.z, 1.0f), s.VelocityMatrix);
+    f4 newVelocity = xmul_rm(mk4(tempVelocity.x, tempVelocity.y, tempVelocity.z, 1.0f), s.VelocityMatrix);
     newVelocity.w = tempVelocity.w;
     if (newAttributes.w < s.AttributeDiscardThreshold) return;  // discard: the texel keeps its old contents
     const size_t gi = (size_t)P.chunk_base + (size_t)li;
