@@ -211,33 +211,37 @@ ILB_DEV f3 closestPointOnLineSegment3(f3 a, f3 b, f3 pt, float& t) {  // Distanc
     return xadd3(a, xscale3(ab, t));
 }
 
+// x-ops: the solid angle is a difference of four arc-cosines that nearly cancel (g0+g1+g2+g3 - 2*pi), so a few ulp in
+// the normalised cross products change the illuminance by far more than 1e-4 relative -- keep it bit-identical.
 ILB_DEV float rectangleSolidAngle(f3 wp, f3 p0, f3 p1, f3 p2, f3 p3) {  // FBPBR.fxh:33-51
-    const f3 v0 = p0 - wp, v1 = p1 - wp, v2 = p2 - wp, v3 = p3 - wp;
-    const f3 n0 = normalize3(cross3(v0, v1)), n1 = normalize3(cross3(v1, v2));
-    const f3 n2 = normalize3(cross3(v2, v3)), n3 = normalize3(cross3(v3, v0));
-    const float g0 = acosf(dot3(-n0, n1)), g1 = acosf(dot3(-n1, n2));
-    const float g2 = acosf(dot3(-n2, n3)), g3 = acosf(dot3(-n3, n0));
-    return g0 + g1 + g2 + g3 - 2.0f * ILB_PI;
+    const f3 v0 = xsub3(p0, wp), v1 = xsub3(p1, wp), v2 = xsub3(p2, wp), v3 = xsub3(p3, wp);
+    const f3 n0 = xnormalize3(xcross3(v0, v1)), n1 = xnormalize3(xcross3(v1, v2));
+    const f3 n2 = xnormalize3(xcross3(v2, v3)), n3 = xnormalize3(xcross3(v3, v0));
+    const float g0 = acosf(xdot3(-n0, n1)), g1 = acosf(xdot3(-n1, n2));
+    const float g2 = acosf(xdot3(-n2, n3)), g3 = acosf(xdot3(-n3, n0));
+    return xsub(xadd(xadd(xadd(g0, g1), g2), g3), xmul(2.0f, ILB_PI));
 }
 
 ILB_DEV float lineLightOpacity(f3 wp, f3 wn, f3 P0, f3 P1, float lightRadius, f3& spherePosition, float& u) {  // :53-101
-    const f3 lightLeft = normalize3(P1 - P0);
-    const f3 lightCenter = lerp3(P0, P1, 0.5f);
+    const f3 lightLeft = xnormalize3(xsub3(P1, P0));
+    const f3 lightCenter = xlerp3(P0, P1, 0.5f);
     spherePosition = closestPointOnLineSegment3(P0, P1, wp, u);
-    const f3 forward = normalize3(spherePosition - wp);
-    const f3 up = cross3(lightLeft, forward);
-    const f3 p0 = P0 + lightRadius * up, p1 = P0 - lightRadius * up;
-    const f3 p2 = P1 - lightRadius * up, p3 = P1 + lightRadius * up;
+    const f3 forward = xnormalize3(xsub3(spherePosition, wp));
+    const f3 up = xcross3(lightLeft, forward);
+    const f3 ru = xscale3(up, lightRadius);
+    const f3 p0 = xadd3(P0, ru), p1 = xsub3(P0, ru);
+    const f3 p2 = xsub3(P1, ru), p3 = xadd3(P1, ru);
     const float solidAngle = rectangleSolidAngle(wp, p0, p1, p2, p3);
-    float illuminance = solidAngle * 0.2f *
-                        (saturatef(dot3(normalize3(p0 - wp), wn)) + saturatef(dot3(normalize3(p1 - wp), wn)) +
-                         saturatef(dot3(normalize3(p2 - wp), wn)) + saturatef(dot3(normalize3(p3 - wp), wn)) +
-                         saturatef(dot3(normalize3(lightCenter - wp), wn)));
-    const f3 sphereUnormL = spherePosition - wp;
-    const f3 sphereL = normalize3(sphereUnormL);
-    const float sqrSphereDistance = dot3(sphereUnormL, sphereUnormL);
-    const float illuminanceSphere = ILB_PI * saturatef(dot3(sphereL, wn)) * ((lightRadius * lightRadius) / sqrSphereDistance);
-    illuminance = illuminance + illuminanceSphere;
+    const float sum = xadd(xadd(xadd(xadd(saturatef(xdot3(xnormalize3(xsub3(p0, wp)), wn)), saturatef(xdot3(xnormalize3(xsub3(p1, wp)), wn))),
+                                     saturatef(xdot3(xnormalize3(xsub3(p2, wp)), wn))),
+                                saturatef(xdot3(xnormalize3(xsub3(p3, wp)), wn))),
+                           saturatef(xdot3(xnormalize3(xsub3(lightCenter, wp)), wn)));
+    float illuminance = xmul(xmul(solidAngle, 0.2f), sum);
+    const f3 sphereUnormL = xsub3(spherePosition, wp);
+    const f3 sphereL = xnormalize3(sphereUnormL);
+    const float sqrSphereDistance = xdot3(sphereUnormL, sphereUnormL);
+    const float illuminanceSphere = xmul(xmul(ILB_PI, saturatef(xdot3(sphereL, wn))), xdiv(xmul(lightRadius, lightRadius), sqrSphereDistance));
+    illuminance = xadd(illuminance, illuminanceSphere);
     return saturatef(illuminance);
 }
 

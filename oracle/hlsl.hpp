@@ -98,11 +98,13 @@ static inline float3 cross(float3 a, float3 b) {
     return float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 // ps_3_0 `nrm` is v * rsq(dot(v,v)); D3D9 defines rsq(0) = FLT_MAX, so normalize(0) = 0 (no NaN).
-// Convention shared with the CUDA path: zero-length input -> zero vector, else v / sqrt(dot).
+// Convention shared with the CUDA path: zero-length input -> zero vector, else v * (1 / sqrt(dot)) with the
+// reciprocal square root formed as an IEEE division of an IEEE square root (reproducible on CPU and GPU).
 static inline float3 normalize(float3 a) {
     float d = dot(a, a);
     if (d == 0.0f) return float3(0.0f);
-    return a / sqrtf(d);
+    float r = 1.0f / sqrtf(d);
+    return a * r;
 }
 static inline bool any(float2 a) { return (a.x != 0.0f) || (a.y != 0.0f); }
 static inline bool any(float3 a) { return (a.x != 0.0f) || (a.y != 0.0f) || (a.z != 0.0f); }
