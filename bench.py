@@ -230,8 +230,9 @@ def run_ours(args):
         renderer.Probes = scene.probes
         gb_host = torch.from_numpy(scene.gbuffer).pin_memory()
         renderer.SetGBuffer(gb_host.numpy())
-        rows_per = (H + world - 1) // world
-        r0, r1 = min(rank * rows_per, H), min((rank + 1) * rows_per, H)
+        from illuminant_b200 import sharding
+        rows_per = sharding.band_height(H, world)
+        r0, r1 = sharding.row_band(rank, world, H)
         full = torch.empty((rows_per * world, W, 4), dtype=torch.float16, device="cuda")
         band = full[rank * rows_per:(rank + 1) * rows_per]
         packed = renderer.build_batches()

@@ -1,0 +1,196 @@
+"""Host-side mirror of the reference API: LightVertex packing, batching, frame uniforms, spawner accounting, sharding."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import illuminant_b200 as ib
+from illuminant_b200 import _abi, scenes, sharding
+from illuminant_b200.lighting import pack_light_vertex
+
+F = np.float32
+
+
+def test_sphere_light_vertex_packing():    # LightingRenderer.cs:1193-1219 / SURVEY appendix A
+    l = ib.SphereLightSource(Position=(1, 2, 3), Radius=4, RampLength=50, RampMode=ib.LightSourceRampMode.Exponential, Color=(0.1, 0.2, 0.3, 0.5),
+                             Opacity=0.5, SpecularColor=(0.9, 0.8, 0.7), SpecularPower=3, AmbientOcclusionRadius=6, AmbientOcclusionOpacity=0.25,
+                             FalloffYFactor=2, ShadowFilter=ib.ShadowFilter.Shadowed)
+    v = pack_light_vertex(l, 2.0, True)
+    assert v.LightPosition1.tuple() == v.LightPosition2.tuple() == v.LightPosition3.tuple() == (1, 2, 3, 0)
+    assert v.LightProperties.tuple() == (4, 50, 1, 1)
+    assert v.MoreLightProperties.tuple() == (6, -99999, 2, 0.25)
+    assert v.Color1.tuple() == pytest.approx((0.1, 0.2, 0.3, 0.5 * 0.5 * 2.0))
+    assert v.Color2.tuple() == pytest.approx((0.9, 0.8, 0.7, 3))
+    assert v.EvenMoreLightProperties.x == 1 and v.EvenMoreLightProperties.z == pytest.approx(-math.pi) and v.EvenMoreLightProperties.w == pytest.approx(1 / (2 * math.pi))
+    assert pack_light_vertex(l, 1.0, False).LightProperties.w == 0          # no distance field -> no shadows
+    l.Opacity = 0
+    assert pack_light_vertex(l, 1.0, True) is None                          # skipped on the host (:1195)
+
+
+def test_directional_and_line_light_vertex_packing():    # :1256-1307, :1309-1337
+    d = ib.DirectionalLightSource(Color=(1, 1, 1, 0.4), ShadowDistanceFalloff=12.0)
+    d.Direction = (0, 3, -4)
+    v = pack_light_vertex(d, 1.0, True)
+    assert v.LightPosition1.tuple() == (-99999, -99999, 0, 0) and v.LightPosition2.tuple() == (99999, 99999, 0, 0)
+    assert v.Color2.tuple() == pytest.approx((0, 0.6, -0.8, 1.0))
+    assert v.LightProperties.tuple() == (1, 256, 12, 0.5) and v.MoreLightProperties.tuple() == (0, 12, 0, 1)
+    d.Direction, d.Bounds = None, ((10, 20), (30, 40))
+    v = pack_light_vertex(d, 1.0, True)
+    assert v.Color2.tuple() == (0, 0, 0, 0) and v.LightPosition1.tuple() == (10, 20, 0, 0) and v.LightPosition2.tuple() == (30, 40, 0, 0)
+    ln = ib.LineLightSource(StartPosition=(0, 0, 5), EndPosition=(100, 0, 5), Radius=8, StartColor=(1, 0, 0, 1), EndColor=(0, 0, 1, 0.5), Opacity=0.5)
+    v = pack_light_vertex(ln, 1.0, True)
+    assert v.LightProperties.tuple() == (8, 0, 0, 1) and v.Color1.w == 0.5 and v.Color2.w == 0.25 and v.EvenMoreLightProperties.x == 0
+
+
+def test_batches_group_by_type_and_quality_in_draw_order():
+    s = scenes.lighting_scene(0, 64, 64, 3, n_directional=1, n_line=1)
+    q2 = ib.RendererQualitySettings(MinStepSize=1.0, LongStepFactor=0.5, OcclusionToOpacityPower=0.7)
+    s.environment.Lights[1].Quality = q2
+    s.environment.Lights[2].Enabled = False
+    s.environment.Lights[0].SortKey = 5                       # sorted after the others (stable)
+    r = ib.LightingRenderer(None, s.environment, s.configuration)
+    batches, nb, verts, nv = r.build_batches()
+    assert (nb, nv) == (4, 4)
+    kinds = [(batches[i].light_type, batches[i].first_vertex, batches[i].vertex_count) for i in range(nb)]
+    assert kinds == [(1, 0, 1), (2, 1, 1), (4, 2, 1), (1, 3, 1)]
+    assert batches[0].df.StepAndMisc2.y == 1.0 and batches[0].df.StepAndMisc2.x == 64      # q2 quality on the first sphere batch
+    assert batches[0].df.Extent.x == 0                        # no field bound: `_DistanceField == null` uniforms (:1906-1916)
+    assert verts[3].LightPosition1.tuple()[:3] == pytest.approx(s.environment.Lights[0].Position)
+
+
+def test_frame_uniforms_scale_compensation_and_clear_colour():
+    s = scenes.lighting_scene(0, 100, 60, 0)
+    s.configuration.RenderScale = (0.5, 0.25)
+    r = ib.LightingRenderer(None, s.environment, s.configuration)
+    r._gbuffer_shape = (15, 50)
+    r.ViewportPosition = (3.0, 4.0)
+    f = r.build_frame(2.0, rows=(2, 9))
+    assert (f.width, f.height, f.row_begin, f.row_end) == (50, 15, 2, 9)
+    assert tuple(f.ViewportPosition) == (3.0 + 1.0, 4.0 + 2.0)                        # + 0.5 / RenderScale (:714-720)
+    assert f.GBufferTexelSizeAndMisc.tuple() == pytest.approx((1 / 50, 1 / 15, 1, 1))
+    assert f.EnvironmentZToY.tuple() == (0, 0, 0, 0)                                  # TwoPointFiveD off -> ZToY 0 (:695-697)
+    assert f.ClearColor.tuple() == pytest.approx((0.1, 0.1, 0.16, 0.0))               # ambient * intensity, alpha zeroed (fullbright mode)
+    s.configuration.TwoPointFiveD = True
+    s.environment.ZToYMultiplier = 2.0
+    assert r.build_frame().EnvironmentZToY.tuple() == (2.0, 0.5, 0, 0)
+    assert r.lightmap_format == _abi.FORMAT_HALF4
+    s.configuration.HighQuality = False
+    assert r.lightmap_format == _abi.FORMAT_RGBA8
+
+
+def test_spawner_rate_accounting_and_indices():    # ParticleSpawner.cs:152-194, ParticleSpawning.cs:115-197
+    engine = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=16))
+    system = ib.ParticleSystem(engine, ib.ParticleSystemConfiguration(), maxChunks=3)
+    sp = ib.Spawner(MinRate=100, MaxRate=100, Seed=1)
+    system.Transforms = [sp]
+    total = 0
+    for step in range(40):
+        spawns = system.plan_spawns(step / 60.0, 1 / 60.0)
+        for s in spawns:
+            first, last = int(s.ChunkSizeAndIndices.y), int(s.ChunkSizeAndIndices.z)
+            assert 0 <= first <= last < 256 and s.ChunkSizeAndIndices.x == 16
+            total += last - first + 1
+    assert total == sp.TotalSpawned == int(100 * 40 / 60.0)          # the fractional part is carried in RateError
+    assert 0 <= sp.RateError < 1
+    # a request larger than the free space of the chunk is split: second RunSpawner pass into a new chunk
+    system2 = ib.ParticleSystem(engine, ib.ParticleSystemConfiguration(), maxChunks=3)
+    big = ib.Spawner(MinRate=60 * 200, MaxRate=60 * 200, Seed=2)
+    system2.Transforms = [big]
+    a = system2.plan_spawns(0.0, 1 / 60.0)
+    b = system2.plan_spawns(1 / 60.0, 1 / 60.0)
+    assert [s.chunk for s in a] == [0] and (a[0].ChunkSizeAndIndices.y, a[0].ChunkSizeAndIndices.z) == (0, 199)
+    assert [s.chunk for s in b] == [0, 1] and (b[0].ChunkSizeAndIndices.y, b[0].ChunkSizeAndIndices.z) == (200, 255)
+    assert system2.LiveChunkCount == 2
+    # MaximumTotal caps the spawner
+    capped = ib.Spawner(MinRate=6000, MaxRate=6000, MaximumTotal=150, Seed=3)
+    system3 = ib.ParticleSystem(engine, ib.ParticleSystemConfiguration(), maxChunks=3)
+    system3.Transforms = [capped]
+    for step in range(5):
+        system3.plan_spawns(step / 60.0, 1 / 60.0)
+    assert capped.TotalSpawned == 150
+
+
+def test_spawner_uniform_packing():    # ParticleSpawner.cs:200-256, :361-403
+    engine = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=32))
+    system = ib.ParticleSystem(engine, ib.ParticleSystemConfiguration(), maxChunks=1)
+    sp = ib.Spawner(Position=ib.Formula(Constant=(1, 2, 3), RandomScale=(4, 5, 6), Offset=(7, 8, 9), Type=ib.FormulaType.Spherical),
+                    Velocity=ib.Formula(Constant=(10, 11, 12), RandomScale=(13, 14, 15), Offset=(16, 17, 18), Type=ib.FormulaType.Linear),
+                    Life=(2.0, 0.5, -0.25), Category=(1.0, 2.0, 3.0), AlphaDiscardThreshold=51.0, AdditionalPositions=[(9, 9, 9)],
+                    AlignVelocityAndPosition=True, PolygonRate=4.0, PolygonLoop=False)
+    sp.Indices = (5, 20)
+    sp.TotalSpawned = 10
+    s = sp.pack(system, 0.0, 0)
+    assert s.Configuration[0].tuple() == (4, 5, 6, 0.5) and s.Configuration[1].tuple() == (7, 8, 9, -0.25)
+    assert s.Configuration[2].tuple() == (10, 11, 12, 1) and s.Configuration[4].tuple() == (16, 17, 18, 3)
+    assert s.InlinePositionConstants[0].tuple() == (1, 2, 3, 2.0) and s.InlinePositionConstants[1].tuple() == (9, 9, 9, 2.0)
+    assert s.FormulaTypes.tuple() == (1, 0, 0, 0) and s.PositionConstantCount == 2
+    assert s.AlignVelocityAndPosition == 0.0                         # only if BOTH formulas are circular (:240-242)
+    assert s.AttributeDiscardThreshold == pytest.approx(0.2)
+    assert s.ChunkSizeAndIndices.tuple() == (32, 5, 20, pytest.approx((10 / 4.0) % 1))   # !PolygonLoop: count - 1 = 1
+    assert 0 <= s.RandomnessOffset[0] < 253 and 0 <= s.RandomnessOffset[1] < 127
+    with pytest.raises(ib.IlluminantError):
+        ib.Spawner(AdditionalPositions=[(0, 0, 0)] * 4).pack(system, 0.0, 0)
+
+
+def test_transform_packing_and_noise_uv_cycle():
+    engine = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=32))
+    system = ib.ParticleSystem(engine, ib.ParticleSystemConfiguration(), maxChunks=1)
+    f = ib.FMA(CyclesPerSecond=None).pack(system, 0.0).u.fma
+    assert f.TimeDivisor == -1 and f.PositionMultiply.w == 1 and f.PositionAdd.w == 0 and tuple(f.area.CategoryFilter) == (-9999, 9999)
+    assert ib.FMA().pack(system, 0.0).u.fma.TimeDivisor == 100.0            # 1000 / CyclesPerSecond (Transforms.cs:40)
+    n = ib.Noise(Interval=500.0, Seed=4)
+    u0 = (n.CurrentU, n.NextU)
+    a = n.pack(system, 0.25).u.noise
+    assert a.FrequencyLerp == pytest.approx(0.5) and tuple(a.RandomnessTexel) == pytest.approx((1 / 807, 1 / 653))
+    assert a.RandomnessOffset[0] == pytest.approx(u0[0] * 253, rel=1e-6) and a.NextRandomnessOffset[0] == pytest.approx(u0[1] * 253, rel=1e-6)
+    b = n.pack(system, 0.55).u.noise                                         # past the interval: UVs cycle
+    assert b.RandomnessOffset[0] == pytest.approx(u0[1] * 253, rel=1e-6) and b.FrequencyLerp == pytest.approx(0.1, abs=1e-6)
+    g = ib.Gravity(Attractors=[ib.Attractor(Position=(1, 2, 3), Radius=4, Strength=5, Type=ib.AttractorType.Exponential)])
+    gp = g.pack(system, 0.0).u.gravity
+    assert gp.AttractorCount == 1 and gp.AttractorRadiusesAndStrengths[0].tuple() == (4, 5, 2, 0) and tuple(gp.CategoryFilter) == (0, 0)
+    assert not ib.Gravity().IsValid and system.plan_ops(0.0) == []
+    area = ib.TransformArea(Type=ib.AreaType.Box, Falloff=0.2)
+    assert ib.FMA(Area=area).pack(system, 0.0).u.fma.area.AreaFalloff == 1.0   # Math.Max(1, falloff) (ParticleTransform.cs:305)
+
+
+def test_system_uniforms():    # Uniforms.cs:208-235, ParticleSystem.cs:547-575
+    engine = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=64))
+    cfg = ib.ParticleSystemConfiguration(Friction=0.2, MaximumVelocity=99, LifeDecayPerSecond=1.5, RotationFromLife=90.0, OpacityFromLife=4.0,
+                                         Collision=ib.ParticleCollision(EscapeVelocity=7, BounceVelocityMultiplier=0.5, Distance=1.5, LifePenalty=0.1))
+    system = ib.ParticleSystem(engine, cfg, maxChunks=1)
+    u = system.system_uniforms(1 / 60.0)
+    assert u.GlobalSettings.tuple() == pytest.approx((1000 / 60.0, 0.2, 99, 1.5)) and u.CollisionSettings.tuple() == pytest.approx((7, 0.5, 1.5, 0.1))
+    assert u.TexelAndSize.x == 1 / 64 and u.has_collision_field == 0 and u.write_render_outputs == 1
+    assert u.ColorFromLife.RangeAndCount.tuple() == (0, 0.25, 2, 0) and u.ColorFromLife.A.tuple() == (1, 1, 1, 0)   # OpacityFromLife ramp
+    assert u.RotationFromLifeAndIndex[0] == pytest.approx(math.pi / 2)
+    df = ib.DistanceField(None, 128, 128, 64.0, 6)
+    cfg.Collision.DistanceField = df
+    with pytest.raises(ib.IlluminantError):          # "If a distance field is active, you must set DistanceFieldMaximumZ"
+        system.system_uniforms(1 / 60.0)
+    cfg.Collision.DistanceFieldMaximumZ = 64.0
+    u = system.system_uniforms(1 / 60.0)
+    assert u.has_collision_field == 1 and u.CollisionField.Packed1.tuple() == (0, 0, 0, 0)     # reference quirk: never set
+    cfg.Collision.FullFieldAddressing = True
+    assert system.system_uniforms(1 / 60.0).CollisionField.Packed1.y > 0
+
+
+def test_sharding_partitions():
+    for height in (2160, 1080, 7, 1):
+        for world in (1, 2, 3, 4, 8):
+            bands = [sharding.row_band(r, world, height) for r in range(world)]
+            assert bands[0][0] == 0 and bands[-1][1] == height
+            assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+            assert all(b - a <= sharding.band_height(height, world) for a, b in bands)
+    for chunks in (32, 5, 1):
+        for world in (1, 2, 4, 8):
+            rs = [sharding.chunk_range(r, world, chunks) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == chunks and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+            sizes = [b - a for a, b in rs]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_randomness_texture_is_seeded():
+    a = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(RandomSeed=5)).RandomnessTexture
+    b = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(RandomSeed=5)).RandomnessTexture
+    assert a.shape == (653, 807, 4) and a.dtype == np.float32 and np.array_equal(a, b) and 0 <= a.min() and a.max() < 1

@@ -1,0 +1,301 @@
+"""Known-answer tests that pin the CPU oracle.  The reference ships no tests, golden images or fixtures for these paths
+ and cannot run here, so the oracle is pinned by (1) an independent transcription of the
+reference's own C# mirror of Bezier.fxh (Bezier.cs:461-492, :759-832), (2) closed forms listed in SURVEY.md section 8c and
+(3) hand-computed vectors.  ("Parity unpinned" by reference outputs -- see oracle/README.md.)"""
+import math
+
+import numpy as np
+import pytest
+
+import illuminant_b200 as ib
+from illuminant_b200 import _abi, scenes
+from illuminant_b200._abi import Float4
+from illuminant_b200.particles import clamped_bezier1, clamped_bezier4
+
+F = np.float32
+
+
+# ---- (1) Bezier: transcription of ClampedBezier4.tForScaledBezier / Evaluate from Bezier.cs, in float32 ----------
+def cs_wrap_exclusive(v, lo, hi):   # Squared.Util Arithmetic.WrapExclusive for positive ranges
+    d = hi - lo
+    return F(v - d * math.floor((v - lo) / d))
+
+
+def cs_t(range_and_count, value):
+    minValue, invDivisor, count, w = (F(x) for x in range_and_count)
+    mode = int(w)
+    repeating, bouncing = mode > 255, mode > 511
+    t = F(F(F(value) - minValue) * F(abs(invDivisor)))
+    if bouncing:
+        t = F(t * F(2))
+        t = F(2 - cs_wrap_exclusive(t, 0, 2)) if invDivisor < 0 else cs_wrap_exclusive(t, 0, 2)
+        if t > 1:
+            t = F(1 - F(t - 1))
+    elif repeating:
+        t = F(1 - cs_wrap_exclusive(t, 0, 1)) if invDivisor < 0 else cs_wrap_exclusive(t, 0, 1)
+    else:
+        s = F(min(max(t, F(0)), F(1)))
+        t = F(1 - s) if invDivisor < 0 else s
+    m = mode % 256
+    if m == 1:
+        t = F(math.sin(float(t) * math.pi * 0.5))
+    elif m == 2:
+        t = F(t * t)
+    return int(count), t
+
+
+def cs_lerp(a, b, t):
+    return F(a + F(F(b - a) * t))    # Arithmetic.Lerp(a, b, x) = a + (b - a) * x
+
+
+def cs_evaluate(range_and_count, a, b, c, d, value):
+    count, t = cs_t(range_and_count, value)
+    if count <= 1.5:
+        return a
+    ab = cs_lerp(a, b, t)
+    if count <= 2.5:
+        return ab
+    if count <= 3.5:
+        return a if t <= 0 else (c if t >= 1 else b)
+    bc, cd = cs_lerp(b, c, t), cs_lerp(c, d, t)
+    return cs_lerp(cs_lerp(ab, bc, t), cs_lerp(bc, cd, t), t)
+
+
+@pytest.mark.parametrize("count", [1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [0, 1, 2, 256, 257, 512, 514])
+@pytest.mark.parametrize("rng", [(0.0, 1.0), (2.0, 5.0), (4.0, 1.0)])
+def test_bezier_matches_reference_cpu_mirror(oracle, count, mode, rng):
+    src = ib.BezierF(Count=count, Mode=mode, MinValue=rng[0], MaxValue=rng[1], A=0.25, B=2.0, C=-1.5, D=0.75)
+    b1 = clamped_bezier1(src)
+    src4 = ib.Bezier4V(Count=count, Mode=mode, MinValue=rng[0], MaxValue=rng[1], A=(0.25, 1, 0, 0.5), B=(2, 0, 1, 1), C=(-1.5, 0.5, 0.25, 0), D=(0.75, 0.1, 0.9, 1))
+    b4 = clamped_bezier4(src4)
+    rc = b1.RangeAndCount.tuple()
+    for value in np.linspace(-1.0, 7.0, 41, dtype=np.float32):
+        # Below the range start the two reference implementations disagree in the repeating / bouncing modes: the
+        # shader's `t % 1` keeps the sign of t (HLSL fmod) while Bezier.cs wraps into [0, 1).  The oracle follows
+        # the shader (that is what runs on the GPU); compare with the C# mirror only where both are defined alike.
+        if mode > 255 and value < min(rng):
+            continue
+        want = cs_evaluate(rc, F(0.25), F(2.0), F(-1.5), F(0.75), float(value))
+        got = oracle.bezier1(b1, float(value))
+        assert got == pytest.approx(float(want), abs=2e-6), (count, mode, rng, value)
+        got4 = oracle.bezier4(b4, float(value))
+        for k, (a, b, c, d) in enumerate(zip(src4.A, src4.B, src4.C, src4.D)):
+            assert got4[k] == pytest.approx(float(cs_evaluate(rc, F(a), F(b), F(c), F(d), float(value))), abs=2e-6)
+
+
+def test_clamped_bezier_constructor_matches_bezier_cs():
+    b = clamped_bezier1(ib.BezierF(Count=2, MinValue=3.0, MaxValue=1.0, A=1, B=2))       # Bezier.cs:444-458
+    assert b.RangeAndCount.tuple() == (1.0, -0.5, 2.0, 0.0)
+    assert clamped_bezier1(None).RangeAndCount.tuple() == (0.0, 1.0, 1.0, 0.0)           # ClampedBezier1.One
+    assert clamped_bezier1(ib.BezierF(Count=1, MinValue=0, MaxValue=9)).RangeAndCount.y == 1.0   # range forced to 1 when Count <= 1
+
+
+# ---- (2) closed forms, lighting -----------------------------------------------------------------------------------
+def _field(width=64, height=48, depth=128.0, slices=8):
+    df = ib.DistanceField(None, width, height, depth, slices)
+    df.ValidSliceCount = df.SliceCount
+    return df
+
+
+def test_distance_field_descriptor_arithmetic():
+    c2 = ib.DistanceField(None, 1920, 1080, 128.0, 8)        # 8 requested -> 9 virtual / 3 physical, 2x2 atlas
+    assert (c2.SliceCount, c2.PhysicalSliceCount, c2.ColumnCount, c2.RowCount) == (9, 3, 2, 2)
+    assert (c2.TextureWidth, c2.TextureHeight) == (3840, 2160)
+    c4 = ib.DistanceField(None, 3840, 2160, 128.0, 8)
+    assert (c4.TextureWidth, c4.TextureHeight, c4.ColumnCount, c4.RowCount) == (7680, 4320, 2, 2)
+    q = ib.DistanceField(None, 1920, 1080, 128.0, 9, 0.25)   # SimpleParticles.cs:216-219
+    assert (q.SliceWidth, q.SliceHeight, q.Resolution) == (480, 270, 0.25)
+    assert ib.DistanceField(None, 100, 100, 64.0, 1).SliceCount == 3
+    many = ib.DistanceField(None, 4096, 4096, 256.0, 64)     # atlas capped at 8192^2: 2x2 cells x 3 slices
+    assert many.SliceCount == 12
+    c2.ValidSliceCount = 9
+    u = c2.uniforms()
+    assert u.Packed1.x == float(F(F(1) / F(2)) * (F(1) / F(3)))
+    assert u.Packed1.y == float(F(1) / F(128) * F(9)) and u.Packed1.z == 128.0 and u.Packed1.w == 3.0
+    assert u.TextureSliceAndTexelSize.tuple() == (0.5, 0.5, float(F(1) / F(3840)), float(F(1) / F(2160)))
+
+
+def test_cleared_texel_decodes_to_192_over_255_of_max(oracle):
+    df = _field()
+    tex = np.zeros((df.TextureHeight, df.TextureWidth, 4), np.uint16)
+    d = oracle.sample_distance_field(tex, df.uniforms(), 10.0, 10.0, 5.0)
+    assert d == pytest.approx(192.0 / 255.0 * 128.0, rel=1e-6)          # DistanceFieldCommon.fxh:8,268-270 -> 96.376
+    # outside the volume the Euclidean distance to the box is added (:320-321, :352)
+    assert oracle.sample_distance_field(tex, df.uniforms(), -3.0, 10.0, 5.0) == pytest.approx(96.37647 + 3.0, rel=1e-6)
+    assert oracle.sample_distance_field(tex, df.uniforms(), 64.0 + 3.0, 48.0 + 4.0, 5.0) == pytest.approx(96.37647 + 5.0, rel=1e-6)
+
+
+def test_sampler_interpolates_z_slices_and_bilinear(oracle):
+    df = _field(8, 8, 90.0, 9)          # 9 slices over depth 90: one slice per 10 z units
+    tex = np.zeros((df.TextureHeight, df.TextureWidth, 4), np.uint16)
+    u = df.uniforms()
+    enc = lambda dist: int(round((192.0 / 255.0 - dist / 128.0) * 65535))
+    # physical slice 0 holds z-slices 0..3 in r,g,b,a: distance = 10 * (slice index + 1) everywhere
+    tex[:8, :8] = [enc(10), enc(20), enc(30), enc(40)]
+    for z, want in [(0.0, 10.0), (5.0, 15.0), (10.0, 20.0), (17.5, 27.5), (25.0, 35.0)]:
+        assert oracle.sample_distance_field(tex, u, 4.0, 4.0, z) == pytest.approx(want, abs=2e-3)
+    # x gradient: texel i holds distance 10 + i at slice 0; texel centres sit at i + 0.5
+    for i in range(8):
+        tex[:8, i, 0] = enc(10 + i)
+    assert oracle.sample_distance_field(tex, u, 3.5, 4.0, 0.0) == pytest.approx(13.0, abs=2e-3)
+    assert oracle.sample_distance_field(tex, u, 4.0, 4.0, 0.0) == pytest.approx(13.5, abs=2e-3)
+
+
+def test_cone_trace_closed_forms(oracle):
+    df = _field()
+    u = df.uniforms()
+    # no field (Extent.x <= 0): coneTrace == 1 (ConeTrace.fxh:159,190)
+    v, steps = oracle.cone_trace(None, ib.DistanceField.empty_uniforms(128.0), (30, 30, 20), 8.0, 100.0, (5, 5, 0))
+    assert (v, steps) == (1.0, 0)
+    # disabled trace returns 1
+    tex = np.zeros((df.TextureHeight, df.TextureWidth, 4), np.uint16)
+    assert oracle.cone_trace(tex, u, (30, 30, 20), 8.0, 100.0, (5, 5, 0), enable=False)[0] == 1.0
+    # empty (cleared) field: every sample is 96.376 -> visibility stays 1, steps = ceil((len - 0.5) / 96.376)
+    v, steps = oracle.cone_trace(tex, u, (60, 40, 20), 8.0, 100.0, (5, 5, 0))
+    length = math.dist((60, 40, 20), (5, 5, 0)) - 8.0
+    assert v == pytest.approx(1.0, abs=1e-6) and steps == math.ceil((length - 0.5) / 96.37647)
+    # fully blocked: a field whose distance is -20 everywhere drives visibility to 0 in one step
+    blocked = np.full_like(tex, int(round((192.0 / 255.0 + 20.0 / 128.0) * 65535)))
+    v, steps = oracle.cone_trace(blocked, u, (60, 40, 20), 8.0, 100.0, (5, 5, 0))
+    assert v == 0.0 and steps == 1
+    # step cap: MaxStepCount 2 with MinStepSize 3 on a field of distance 0 -> stepsRemaining hits 0 -> visibility 0
+    zero = np.full_like(tex, int(round(192.0 / 255.0 * 65535)))
+    q = ib.RendererQualitySettings(MaxStepCount=2)
+    v, steps = oracle.cone_trace(zero, df.uniforms(q), (60, 40, 20), 8.0, 100.0, (5, 5, 0))
+    assert steps == 2 and v == 0.0
+
+
+def test_sphere_light_opacity_closed_forms(oracle):
+    s = scenes.lighting_scene(0, 32, 32, 0)
+    r = ib.LightingRenderer(None, s.environment, s.configuration)
+    f = r.build_frame()
+    up = (0, 0, 1)
+    assert oracle.sphere_light_opacity(f, (10, 10, 0), up, (10, 12, 3), (16, 100, 0, 1)) == 1.0     # inside Radius -> 1 (LightCommon.fxh:209)
+    # linear ramp, light straight above the point: normal factor 1, falloff 1 - (d - R) / ramp
+    assert oracle.sphere_light_opacity(f, (0, 0, 0), up, (0, 0, 60), (10, 100, 0, 1)) == pytest.approx(0.5, abs=1e-6)
+    assert oracle.sphere_light_opacity(f, (0, 0, 0), up, (0, 0, 60), (10, 100, 1, 1)) == pytest.approx(0.25, abs=1e-6)   # exponential
+    assert oracle.sphere_light_opacity(f, (0, 0, 0), up, (0, 0, 200), (10, 100, 0, 1)) == 0.0       # beyond R + ramp
+    assert oracle.sphere_light_opacity(f, (0, 0, 0), up, (0, 0, -60), (10, 100, 0, 1)) == 0.0       # light behind the surface
+    assert oracle.sphere_light_opacity(f, (0, 0, 0), (0, 0, 0), (0, 0, -60), (10, 100, 0, 1)) == pytest.approx(0.5, abs=1e-6)  # no normal
+    assert oracle.sphere_light_opacity(f, (0, 0, 0), up, (0, 30, 0.001), (10, 100, 2, 1)) == 0.0    # RampMode None: 1 - sat(d - R)
+    assert oracle.sphere_light_opacity(f, (0, 0, 0), up, (0, 30, 40), (10, 100, 0, 1), 2.0) == pytest.approx(
+        (1 - (math.hypot(60, 40) - 10) / 100) * min(max((40 / math.hypot(60, 40) + 0.15) / 0.15, 0), 1) ** 0.85, abs=1e-6)   # FalloffYFactor
+
+
+def test_gbuffer_encoding_closed_forms(oracle):
+    g = oracle.encode_gbuffer_sample((0, 0, 1), 0.0, 0.0)
+    assert tuple(g) == (0.5, 1.0, 0.0, 1.0)                  # ground plane z = 0 (GBufferShaderCommon.fxh:22-33)
+    assert tuple(oracle.encode_gbuffer_sample((0, 0, 1), 0.0, 0.0, dead=True)) == (0.0, 0.0, -99999.0, -99999.0)
+    assert oracle.encode_gbuffer_sample((0, 0, 1), 0.0, 32.0, enable_shadows=False)[3] == pytest.approx(-(32 + 1024) / 1024 - 1)
+    assert oracle.encode_gbuffer_sample((0, 0, 1), 0.0, 0.0, fullbright=True)[3] == 99999.0
+    # the vectorised product-side encoder agrees with the oracle's scalar one
+    n = np.array([[0, 0, 1], [0.6, 0, 0.8], [0, 1, 0], [0, 0, 0]], np.float32)
+    z = np.array([0, 12.5, 64, 3], np.float32)
+    enc = ib.encode_gbuffer(n, np.zeros(4, np.float32), z, np.array([True, True, False, True]), np.array([False, False, False, True]))
+    for i in range(4):
+        want = oracle.encode_gbuffer_sample(n[i], 0.0, float(z[i]), enable_shadows=bool([True, True, False, True][i]), fullbright=(i == 3))
+        assert np.allclose(enc[i], want, atol=1e-6)
+    # decode(encode(x)) round trip through sampleGBuffer
+    s = scenes.lighting_scene(0, 4, 1, 0)
+    s.gbuffer = enc.reshape(1, 4, 4)
+    r = ib.LightingRenderer(None, s.environment, s.configuration)
+    r._gbuffer_shape = (1, 4)
+    f = r.build_frame()
+    wp, nn, es, fb = oracle.decode_gbuffer(f, s.gbuffer, 1, 0)
+    assert np.allclose(wp, [1.5, 0.5, 12.5], atol=1e-4) and np.allclose(nn, [0.6, 0, 0.8], atol=1e-6) and es and not fb
+    wp, nn, es, fb = oracle.decode_gbuffer(f, s.gbuffer, 2, 0)
+    assert wp[2] == pytest.approx(64.0, abs=1e-3) and not es and not fb
+    assert oracle.decode_gbuffer(f, s.gbuffer, 3, 0)[3]      # fullbright
+
+
+def test_unobstructed_light_is_ambient_plus_falloff(oracle):
+    """No obstructions, no G-buffer: lightmap = ambient + color.rgb * color.a * computeSphereLightOpacity."""
+    s = scenes.lighting_scene(0, 48, 32, 0, float4_lightmap=True)
+    s.configuration.EnableGBuffer = False
+    light = ib.SphereLightSource(Position=(20.0, 12.0, 30.0), Radius=6.0, RampLength=40.0, Color=(1.0, 0.5, 0.25, 0.8), CastsShadows=True)
+    s.environment.Lights = [light]
+    df = scenes.make_distance_field(None, s)
+    tex = np.zeros((df.TextureHeight, df.TextureWidth, 4), np.uint16)    # cleared field: nothing occludes
+    df.ValidSliceCount, df.handle = df.SliceCount, 1
+    r = ib.LightingRenderer(None, s.environment, s.configuration)
+    r.DistanceField = df
+    frame = r.build_frame()
+    batches, nb, verts, nv = r.build_batches()
+    lm = oracle.render_lighting(tex, None, frame, batches, nb, verts, nv)
+    for (x, y) in [(20, 12), (30, 20), (5, 5), (47, 31), (0, 0)]:
+        pos = (x + 0.5, y + 0.5, 0.0)         # ScaleCompensation: pixel centres
+        op = oracle.sphere_light_opacity(frame, pos, (0, 0, 1), light.Position, (6.0, 40.0, 0, 1))
+        want = np.array(s.environment.Ambient[:3]) + np.array([1.0, 0.5, 0.25]) * 0.8 * op
+        assert np.allclose(lm[y, x, :3], want, atol=2e-6), (x, y)
+        assert lm[y, x, 3] == s.environment.Ambient[3] + (1.0 if op > 0 else 0.0)      # additive blend counts touching lights
+
+
+# ---- closed forms, particles --------------------------------------------------------------------------------------
+def test_ballistic_particles_closed_form(oracle):
+    """friction 0, no transforms, no field: p(t) = p0 + v t, life linear, dead particles become zeros."""
+    engine = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=16))
+    cfg = ib.ParticleSystemConfiguration(Friction=0.0, LifeDecayPerSecond=2.0, MaximumVelocity=1000.0)
+    system = ib.ParticleSystem(engine, cfg, maxChunks=1)
+    P = np.zeros((256, 4), np.float32); V = np.zeros((256, 4), np.float32); A = np.ones((256, 4), np.float32)
+    P[:4] = [[1, 2, 3, 1.0], [0, 0, 0, 0.05], [5, 5, 5, 0.0], [9, 9, 9, 10.0]]
+    V[:4] = [[10, -20, 5, 0], [1, 1, 1, 0], [1, 1, 1, 0], [0, 0, 0, 2]]
+    u = system.system_uniforms(1 / 50.0)
+    P2, V2, A2, RC, RD = oracle.particles_step(P, V, A, 16, u, [], [], engine.RandomnessTexture, None, 5)
+    t = 5 / 50.0
+    assert np.allclose(P2[0], [1 + 10 * t, 2 - 20 * t, 3 + 5 * t, 1.0 - 2.0 * t], atol=1e-5)
+    assert (P2[1] == 0).all() and (V2[1] == 0).all() and (RC[1] == 0).all()          # died: life 0.05 < 2 * 0.1
+    assert (P2[2] == 0).all() and (V2[2] == 0).all()                                 # dead on entry: discarded -> cleared zeros
+    assert np.allclose(P2[3], [9, 9, 9, 10 - 2 * t], atol=1e-5) and V2[3, 3] == 2.0  # |v| <= 0.001 -> velocity 0, category kept
+    assert np.allclose(RD[0], [1.0, 0.0, math.sqrt(100 + 400 + 25), 0.0], atol=1e-4)  # size 1, rotation 0, |v|, category
+    assert np.allclose(RC[0], [1, 1, 1, 1])
+
+
+def test_friction_and_maximum_velocity(oracle):
+    engine = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=16))
+    cfg = ib.ParticleSystemConfiguration(Friction=0.5, LifeDecayPerSecond=0.0, MaximumVelocity=50.0)
+    system = ib.ParticleSystem(engine, cfg, maxChunks=1)
+    P = np.zeros((256, 4), np.float32); V = np.zeros((256, 4), np.float32); A = np.ones((256, 4), np.float32)
+    P[0, 3] = 1.0
+    V[0] = [300, 400, 0, 0]        # |v| = 500 -> clamped to 50, then l -= l * friction * dt
+    u = system.system_uniforms(0.1)
+    P2, V2, *_ = oracle.particles_step(P, V, A, 16, u, [], [], engine.RandomnessTexture, None, 1)
+    speed = 50 - 50 * 0.5 * 0.1
+    assert np.allclose(V2[0, :3], [0.6 * speed, 0.8 * speed, 0], atol=1e-4)
+    assert np.allclose(P2[0, :3], [0.6 * speed * 0.1, 0.8 * speed * 0.1, 0], atol=1e-5)
+
+
+def test_gravity_single_linear_attractor(oracle):
+    engine = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=16))
+    cfg = ib.ParticleSystemConfiguration(Friction=0.0, LifeDecayPerSecond=0.0, MaximumVelocity=1000.0)
+    system = ib.ParticleSystem(engine, cfg, maxChunks=1)
+    system.Transforms = [ib.Gravity(MaximumAcceleration=1000.0, Attractors=[ib.Attractor(Position=(10, 0, 0), Radius=40.0, Strength=6.0, Type=ib.AttractorType.Linear)])]
+    P = np.zeros((256, 4), np.float32); V = np.zeros((256, 4), np.float32); A = np.ones((256, 4), np.float32)
+    P[0] = [0, 0, 0, 1]; P[1] = [0, 0, 0, 1]; V[1, 3] = 3.0     # particle 1 is in bounce delay: Gravity's (0,0) category filter skips it
+    dt = 0.02
+    P2, V2, *_ = oracle.particles_step(P, V, A, 16, system.system_uniforms(dt), [], system.plan_ops(0.0), engine.RandomnessTexture, None, 1)
+    assert V2[0, 0] == pytest.approx((1 - 10 / 40.0) * dt * 6.0, rel=1e-5) and V2[0, 1] == 0        # Gravity.fx:36-48
+    assert V2[1, 0] == 0.0 and V2[1, 3] == 3.0       # untouched (only UpdateWithDistanceField counts the delay down)
+
+
+def test_area_weight_quirk_scalar_rotation(oracle):
+    """AreaRotation is a scalar broadcast into a quaternion (FMA.fx:11,17): rotation 0 collapses the local position to 0,
+    so the weight is `Strength` everywhere (distance = -min size); a unit quaternion would be the identity."""
+    assert oracle.evaluate_by_type_id(2, (100, 0, 0), (0, 0, 0), (5, 6, 7), (0, 0, 0, 0)) == pytest.approx(-5.0)
+    assert oracle.evaluate_by_type_id(2, (100, 0, 0), (0, 0, 0), (5, 6, 7), (0, 0, 0, 1)) == pytest.approx(95.0)
+    assert oracle.evaluate_by_type_id(1, (0, 0, 0), (0, 0, 0), (5, 6, 7)) == pytest.approx(-5.0)     # ellipsoid centre
+    assert oracle.evaluate_by_type_id(3, (0, 0, 30), (0, 0, 0), (3, 4, 10)) == pytest.approx(20.0)   # capped cylinder above the cap
+    assert oracle.evaluate_by_type_id(0, (1, 2, 3), (0, 0, 0), (1, 1, 1)) == 0.0                     # AreaType None
+
+
+def test_distance_field_generation_box_slice(oracle):
+    df = _field(64, 64, 90.0, 9)
+    box = ib.LightObstruction(ib.LightObstructionType.Box, (32.0, 32.0, 0.0), (8.0, 8.0, 200.0))
+    tex = oracle.generate_distance_field(df, [box])
+    dec = lambda c: (192.0 / 255.0 - c / 65535.0) * 128.0
+    assert dec(tex[32, 32, 0]) == pytest.approx(-8.0, abs=2e-3)        # centre of the box: -half size
+    assert dec(tex[32, 50, 0]) == pytest.approx(10.0, abs=2e-3)        # 18 px right of centre, 8 px half size
+    assert dec(tex[32, 50, 3]) == pytest.approx(10.0, abs=2e-3)        # slice 3 (z = 30) still inside the tall box's span
+    # texel (r,g,b,a) = z-slices 3p..3p+3: channel a of physical slice 0 == channel r of physical slice 1
+    ox = df.SliceWidth
+    assert np.array_equal(tex[:64, :64, 3], tex[:64, ox:ox + 64, 0])
