@@ -7,9 +7,19 @@
 
 size_t ilb_format_bytes(int format);
 
+#include <algorithm>
+#include <unordered_set>
+
 namespace {
 std::mutex g_error_mutex;
 std::string g_create_error;
+// Live handles: a destroy call on a handle that is already gone (e.g. a field released after its context at
+// interpreter shutdown) is a no-op instead of a use-after-free.
+std::mutex g_live_mutex;
+std::unordered_set<const void*> g_live;
+void live_add(const void* p) { std::lock_guard<std::mutex> l(g_live_mutex); g_live.insert(p); }
+bool live_take(const void* p) { std::lock_guard<std::mutex> l(g_live_mutex); return g_live.erase(p) != 0; }
+bool live_has(const void* p) { std::lock_guard<std::mutex> l(g_live_mutex); return g_live.count(p) != 0; }
 }  // namespace
 
 int ilb_fail(ilb_ctx* ctx, int code, const char* fmt, ...) {
@@ -90,14 +100,17 @@ int ilb_create(int device_ordinal, ilb_ctx** out_ctx) {
         delete ctx;
         return ilb_cuda_fail(nullptr, e, "cudaStreamCreate");
     }
+    live_add(ctx);
     *out_ctx = ctx;
     return ILB_OK;
 }
 
 void ilb_destroy(ilb_ctx* ctx) {
-    if (!ctx) return;
+    if (!ctx || !live_take(ctx)) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    while (!ctx->fields.empty()) ilb_df_destroy(ctx->fields.back());      // children die with their context
+    while (!ctx->systems.empty()) ilb_particles_destroy(ctx->systems.back());
     if (ctx->gbuffer && ctx->gbuffer_owned) cudaFree(ctx->gbuffer);
     if (ctx->d_lights) cudaFree(ctx->d_lights);
     if (ctx->h_lights) cudaFreeHost(ctx->h_lights);
@@ -142,6 +155,8 @@ static int df_alloc(ilb_ctx* ctx, int tw, int th, size_t bytes, bool check_bytes
         delete df;
         return ilb_cuda_fail(ctx, e, "cudaMalloc(distance field)");
     }
+    ctx->fields.push_back(df);
+    live_add(df);
     *out_df = df;
     return ILB_OK;
 }
@@ -188,7 +203,7 @@ int ilb_df_generate(ilb_ctx* ctx, int tw, int th, int slice_w, int slice_h, int 
 }
 
 int ilb_df_download(ilb_df* df, uint16_t* rgba64, size_t bytes) {
-    if (!df || !rgba64) return ILB_ERR_INVALID_ARGUMENT;
+    if (!df || !rgba64 || !live_has(df)) return ILB_ERR_INVALID_ARGUMENT;
     ilb_ctx* ctx = df->ctx;
     const size_t need = (size_t)8 * df->tw * df->th;
     if (bytes != need) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "atlas needs %zu bytes, got %zu", need, bytes);
@@ -199,7 +214,11 @@ int ilb_df_download(ilb_df* df, uint16_t* rgba64, size_t bytes) {
 }
 
 void ilb_df_destroy(ilb_df* df) {
-    if (!df) return;
+    if (!df || !live_take(df)) return;
+    auto& v = df->ctx->fields;
+    v.erase(std::remove(v.begin(), v.end(), df), v.end());
+    for (ilb_psys* ps : df->ctx->systems)
+        if (ps->field == df) ps->field = nullptr;
     cudaSetDevice(df->ctx->device);
     cudaStreamSynchronize(df->ctx->stream);
     if (df->tex) cudaFree(df->tex);
@@ -292,6 +311,8 @@ int ilb_particles_create(ilb_ctx* ctx, int chunk_size, int max_chunks, ilb_psys*
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
     ilb_psys* ps = new ilb_psys();
     ps->ctx = ctx; ps->chunk_size = chunk_size; ps->max_chunks = max_chunks; ps->per_chunk = per;
+    ctx->systems.push_back(ps);
+    live_add(ps);
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < 5 && e == cudaSuccess; i++) {
         e = cudaMalloc(&ps->buf[i], sizeof(float4) * total);
@@ -307,7 +328,9 @@ int ilb_particles_create(ilb_ctx* ctx, int chunk_size, int max_chunks, ilb_psys*
 }
 
 void ilb_particles_destroy(ilb_psys* ps) {
-    if (!ps) return;
+    if (!ps || !live_take(ps)) return;
+    auto& v = ps->ctx->systems;
+    v.erase(std::remove(v.begin(), v.end(), ps), v.end());
     cudaSetDevice(ps->ctx->device);
     cudaStreamSynchronize(ps->ctx->stream);
     for (int i = 0; i < 5; i++)
@@ -335,7 +358,7 @@ int ilb_particles_set_randomness(ilb_psys* ps, const ilb_float4* table, int w, i
 
 int ilb_particles_set_collision_field(ilb_psys* ps, ilb_df* df) {
     if (!ps) return ILB_ERR_INVALID_ARGUMENT;
-    if (df && df->ctx != ps->ctx) return ilb_fail(ps->ctx, ILB_ERR_INVALID_ARGUMENT, "distance field belongs to another context");
+    if (df && (!live_has(df) || df->ctx != ps->ctx)) return ilb_fail(ps->ctx, ILB_ERR_INVALID_ARGUMENT, "distance field is released or belongs to another context");
     ps->field = df;
     return ILB_OK;
 }

@@ -11,8 +11,13 @@
 #include "../../include/illuminant_b200.h"
 #include "ilb_device.cuh"
 
+struct ilb_df;
+struct ilb_psys;
+
 struct ilb_ctx {
     int device = -1;
+    std::vector<ilb_df*> fields;      // children, destroyed with the context
+    std::vector<ilb_psys*> systems;
     cudaStream_t stream = nullptr;
     std::string last_error;
     uint64_t launches = 0;

@@ -19,24 +19,24 @@ ILB_DEV f4 opElongate(f3 p, f3 h) {  // :43-46
 }
 ILB_DEV float evaluateBox(f3 position, f3 size) {  // :48-63
     const f3 d = xsub3(abs3(position), size);
-    return xadd(fminf(fmaxf(d.x, fmaxf(d.y, d.z)), 0.0f), xlength3(max3(d, mk3(0.0f))));
+    return xadd(fminf(fmaxf(d.x, fmaxf(d.y, d.z)), 0.0f), xlength3z(max3(d, mk3(0.0f))));
 }
 ILB_DEV float evaluateSpheroid(f3 position, f3 size) {  // :65-75
     const float minSize = fminf(size.x, fminf(size.y, size.z));
     const f4 w = opElongate(position, mk3(xsub(size.x, minSize), xsub(size.y, minSize), xsub(size.z, minSize)));
-    return xadd(w.w, xsub(xlength3(xyz(w)), minSize));
+    return xadd(w.w, xsub(xlength3z(xyz(w)), minSize));
 }
 ILB_DEV float evaluateEllipsoid(f3 p, f3 r) {  // sdEllipsoid_improvedV2 :92-108
-    const float k0 = xlength3(xdiv3(p, r));
-    const float k1 = xlength3(xdiv3(p, xmul3(r, r)));
-    return (k0 < 1.0f) ? xmul(xsub(k0, 1.0f), fminf(fminf(r.x, r.y), r.z)) : xdiv(xmul(k0, xsub(k0, 1.0f)), k1);
+    const float k0 = xlength3z(xdiv3z(p, r));
+    const float k1 = xlength3z(xdiv3z(p, xmul3(r, r)));
+    return (k0 < 1.0f) ? xmul(xsub(k0, 1.0f), fminf(fminf(r.x, r.y), r.z)) : xdivz(xmul(k0, xsub(k0, 1.0f)), k1);
 }
 ILB_DEV float sdCappedCylinder(f3 p, float h, float r) {  // :110-113
-    const float dx = xsub(fabsf(xlength2(mk2(p.x, p.y))), r), dy = xsub(fabsf(p.z), h);
-    return xadd(fminf(fmaxf(dx, dy), 0.0f), xlength2(mk2(fmaxf(dx, 0.0f), fmaxf(dy, 0.0f))));
+    const float dx = xsub(fabsf(xlength2z(mk2(p.x, p.y))), r), dy = xsub(fabsf(p.z), h);
+    return xadd(fminf(fmaxf(dx, dy), 0.0f), xlength2z(mk2(fmaxf(dx, 0.0f), fmaxf(dy, 0.0f))));
 }
 ILB_DEV float evaluateCylinder(f3 position, f3 size) {  // :115-121
-    return sdCappedCylinder(position, size.z, xlength2(mk2(size.x, size.y)));
+    return sdCappedCylinder(position, size.z, xlength2z(mk2(size.x, size.y)));
 }
 ILB_DEV float sdOctogonPrism(f3 p, float r, float h) {  // :139-152
     const float kx = -0.9238795325f, ky = 0.3826834323f, kz = 0.4142135623f;
@@ -47,8 +47,8 @@ ILB_DEV float sdOctogonPrism(f3 p, float r, float h) {  // :139-152
     s = xmul(2.0f, fminf(xdot2(mk2(-kx, ky), q), 0.0f));
     q = mk2(xsub(q.x, xmul(s, -kx)), xsub(q.y, xmul(s, ky)));
     q = mk2(xsub(q.x, clampf(q.x, xmul(-kz, r), xmul(kz, r))), xsub(q.y, r));
-    const float dx = xmul(xlength2(q), signf(q.y)), dy = xsub(p.z, h);
-    return xadd(fminf(fmaxf(dx, dy), 0.0f), xlength2(mk2(fmaxf(dx, 0.0f), fmaxf(dy, 0.0f))));
+    const float dx = xmul(xlength2z(q), signf(q.y)), dy = xsub(p.z, h);
+    return xadd(fminf(fmaxf(dx, dy), 0.0f), xlength2z(mk2(fmaxf(dx, 0.0f), fmaxf(dy, 0.0f))));
 }
 ILB_DEV float evaluateOctagon(f3 position, f3 size) {  // :154-165
     const float minSize = fminf(size.x, size.y);

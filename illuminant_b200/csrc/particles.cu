@@ -101,10 +101,15 @@ ILB_DEV f4 evaluateBezier4(const ilb_bezier4& b, float value) {  // :141-177
 }
 
 // ---- transforms: x-ops throughout (particle state feeds the collision thresholds of later steps) -------------
-ILB_DEV float computeWeight(const ilb_area& a, f3 worldPosition) {  // FMA.fx:15-20 / Noise.fx:21-26 (scalar rotation broadcast)
+#if ILB_NOINLINE_WEIGHT
+#define ILB_WEIGHT_QUAL static __device__ __noinline__
+#else
+#define ILB_WEIGHT_QUAL __device__ __forceinline__
+#endif
+ILB_WEIGHT_QUAL float computeWeight(const ilb_area& a, f3 worldPosition) {  // FMA.fx:15-20 / Noise.fx:21-26 (scalar rotation broadcast)
     const float distance = evaluateByTypeId(a.AreaType, worldPosition, mk3(a.AreaCenter[0], a.AreaCenter[1], a.AreaCenter[2]),
                                             mk3(a.AreaSize[0], a.AreaSize[1], a.AreaSize[2]), mk4(a.AreaRotation));
-    return xmul(xsub(1.0f, saturatef(xdiv(distance, a.AreaFalloff))), a.Strength);
+    return xmul(xsub(1.0f, saturatef(xdivz(distance, a.AreaFalloff))), a.Strength);
 }
 ILB_DEV bool checkCategoryFilter(float type, const float* mm) { return (type >= mm[0]) && (type <= mm[1]); }  // ParticleCommon.fxh:198-200
 
@@ -118,19 +123,19 @@ ILB_DEV void opGravity(const ilb_psys_uniforms& u, const ilb_gravity& g, f4& pos
         const f3 toCenter = xsub3(apos, xyz(pos));
         float attraction;
         if (ars.z >= 0.5f) {
-            const float distance = xlength3(toCenter);
-            attraction = xsub(1.0f, saturatef(xdiv(distance, ars.x)));
+            const float distance = xlength3z(toCenter);
+            attraction = xsub(1.0f, saturatef(xdivz(distance, ars.x)));
             if (ars.z >= 1.5f) attraction = xmul(attraction, attraction);
-            attraction = xdiv(xmul(attraction, dt), VelocityConstantScale);
+            attraction = xdivz(xmul(attraction, dt), VelocityConstantScale);
         } else {
             float distanceSquared = xsub(xdot3(toCenter, toCenter), ars.x);
             distanceSquared = fmaxf(distanceSquared, 0.001f);
-            attraction = xdiv(1.0f, distanceSquared);
+            attraction = xdivz(1.0f, distanceSquared);
         }
         acceleration = xadd3(acceleration, xscale3(xscale3(xnormalize3(toCenter), attraction), ars.y));
     }
-    const float maximumAcceleration = xdiv(xmul(g.MaximumAcceleration, dt), VelocityConstantScale);
-    const float currentLength = xlength3(acceleration);
+    const float maximumAcceleration = xdivz(xmul(g.MaximumAcceleration, dt), VelocityConstantScale);
+    const float currentLength = xlength3z(acceleration);
     if (currentLength > maximumAcceleration) acceleration = xscale3(xnormalize3(acceleration), maximumAcceleration);
     const float mv = u.GlobalSettings.z;
     vel = mk4(fminf(mv, xadd(vel.x, acceleration.x)), fminf(mv, xadd(vel.y, acceleration.y)), fminf(mv, xadd(vel.z, acceleration.z)), vel.w);
@@ -139,7 +144,7 @@ ILB_DEV void opGravity(const ilb_psys_uniforms& u, const ilb_gravity& g, f4& pos
 ILB_DEV void opNoise(const StepParams& P, const ilb_noise& n, float x, float y, f4& pos, f4& vel) {  // Noise.fx:28-72
     if (!checkCategoryFilter(vel.w, n.area.CategoryFilter)) return;
     const float weight = computeWeight(n.area, xyz(pos));
-    const float t = xdiv(xmul(weight, P.u.GlobalSettings.x), n.TimeDivisor);
+    const float t = xdivz(xmul(weight, P.u.GlobalSettings.x), n.TimeDivisor);
     const float rx = n.RandomnessTexel[0], ry = n.RandomnessTexel[1];
     const f4 randomP1 = randomCustom(P.rng, P.rng_w, P.rng_h, x, y, n.RandomnessOffset, rx, ry, n.RandomnessTexel);
     const f4 randomP2 = randomCustom(P.rng, P.rng_w, P.rng_h, x, y, n.NextRandomnessOffset, rx, ry, n.RandomnessTexel);
@@ -166,7 +171,7 @@ ILB_DEV void opNoise(const StepParams& P, const ilb_noise& n, float x, float y, 
 ILB_DEV void opFMA(const ilb_psys_uniforms& u, const ilb_fma& f, f4& pos, f4& vel) {  // FMA.fx:22-51
     if ((pos.w <= 0.0f) || !checkCategoryFilter(vel.w, f.area.CategoryFilter)) return;
     const float weight = computeWeight(f.area, xyz(pos));
-    const float t = xdiv(xmul(weight, u.GlobalSettings.x), f.TimeDivisor);
+    const float t = xdivz(xmul(weight, u.GlobalSettings.x), f.TimeDivisor);
     const f4 oldPosition = pos, oldVelocity = vel;
     pos = xlerp4(oldPosition, xadd4(xmul4(oldPosition, mk4(f.PositionMultiply)), mk4(f.PositionAdd)), t);
     vel = xlerp4(oldVelocity, xadd4(xmul4(oldVelocity, mk4(f.VelocityMultiply)), mk4(f.VelocityAdd)), t);
@@ -181,7 +186,7 @@ ILB_DEV f4 mul3(f4 oldValue, const float* mat, float w) {  // ParticleCommon.fxh
 
 ILB_DEV void opMatrix(const ilb_psys_uniforms& u, const ilb_matrix_multiply& m, f4& pos, f4& vel) {  // MatrixMultiply.fx:14-52
     if ((pos.w <= 0.0f) || !checkCategoryFilter(vel.w, m.area.CategoryFilter)) return;
-    const float timeScale = (m.TimeDivisor >= 0.0f) ? xdiv(u.GlobalSettings.x, m.TimeDivisor) : 1.0f;
+    const float timeScale = (m.TimeDivisor >= 0.0f) ? xdivz(u.GlobalSettings.x, m.TimeDivisor) : 1.0f;
     const float w = xmul(computeWeight(m.area, xyz(pos)), timeScale);
     const f4 oldPosition = pos, oldVelocity = vel;
     pos = xlerp4(oldPosition, mul3(oldPosition, m.PositionMatrix, 1.0f), w);
@@ -190,12 +195,12 @@ ILB_DEV void opMatrix(const ilb_psys_uniforms& u, const ilb_matrix_multiply& m, 
 
 // ---- update tail (UpdateCommon.fxh, UpdateParticleSystem.fx, UpdateParticleSystemWithDistanceField.fx) -------------
 ILB_DEV f3 applyFrictionAndMaximum(const ilb_psys_uniforms& u, f3 velocity) {  // UpdateCommon.fxh:20-35
-    float l = xlength3(velocity);
+    float l = xlength3z(velocity);
     if (l <= 0.001f) return mk3(0.0f);
     const float mv = u.GlobalSettings.z;
     if (l > mv) l = mv;
     const float friction = xmul(l, u.GlobalSettings.y);
-    l = xsub(l, xmul(friction, xdiv(u.GlobalSettings.x, VelocityConstantScale)));
+    l = xsub(l, xmul(friction, xdivz(u.GlobalSettings.x, VelocityConstantScale)));
     l = clampf(l, 0.0f, mv);
     return xscale3(xnormalize3(velocity), l);
 }
@@ -230,7 +235,7 @@ ILB_DEV void computeRenderData(const ilb_psys_uniforms& u, float vx, float vy, f
 }
 
 ILB_DEV f3 estimateNormal4(const DFGeometry& g, f3 position) {  // VisualizeCommon.fxh:9-63
-    const f3 texel = mk3(g.invScaleX, g.invScaleY, xdiv(g.ez, fmaxf(g.sliceCount, 1.0f)));
+    const f3 texel = mk3(g.invScaleX, g.invScaleY, xdivz(g.ez, fmaxf(g.sliceCount, 1.0f)));
     f3 result = mk3(0.0f);
     const float wts[4][3] = {{1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {1, 1, 1}};
 #pragma unroll
@@ -249,7 +254,7 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
     outV = mk4(0.0f);
     needAttr = false;
     if (oldPosition.w <= 0.0f) return false;  // readStateOrDiscard ParticleCommon.fxh:162-181
-    const float dts = xdiv(u.GlobalSettings.x, VelocityConstantScale);
+    const float dts = xdivz(u.GlobalSettings.x, VelocityConstantScale);
     float newLife = xsub(oldPosition.w, xmul(u.GlobalSettings.w, dts));
     if (!COLLIDE) {  // PS_Update UpdateParticleSystem.fx:9-38
         const f3 velocity = applyFrictionAndMaximum(u, xyz(oldVelocity));
@@ -274,7 +279,7 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
 
     const float initialDistance = sampleDistanceField(P.df, op);
     const bool wasColliding = initialDistance < collisionDistance;
-    float travelDistance = fmaxf(0.0f, fminf(initialDistance, xlength3(scaledVelocity)));
+    float travelDistance = fmaxf(0.0f, fminf(initialDistance, xlength3z(scaledVelocity)));
     int stepCount = 3;
     if (wasColliding) stepCount = 1;
     else if (travelDistance <= 0.001f) stepCount = 0;
@@ -303,9 +308,9 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
         const float escapeSpeed = fminf(maxV, u.CollisionSettings.x);
         if (redirect) {
             normal = mk3(normal.x, normal.y, xmul(normal.z, 0.0f));
-            if (xlength3(normal) < 0.33f) {
+            if (xlength3z(normal) < 0.33f) {
                 float s, c;
-                sincosf(xadd(xdiv(x, 67.0f), xdiv(y, 13.0f)), &s, &c);
+                sincosf(xadd(xdivz(x, 67.0f), xdivz(y, 13.0f)), &s, &c);
                 normal = mk3(s, c, 0.0f);
             }
             const f3 escapeVector = xnormalize3(normal);
@@ -314,13 +319,13 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
         } else if (bounce) {
             const float k = xmul(2.0f, xdot3(normal, unitVector));
             f3 bounceVector = -xscale3(xsub3(normal, unitVector), k);
-            if (xlength3(bounceVector) < 0.33f) bounceVector = -unitVector;
+            if (xlength3z(bounceVector) < 0.33f) bounceVector = -unitVector;
             else bounceVector = xnormalize3(bounceVector);
             newPosition = collisionPosition;
-            newVelocity = mk4(xscale3(bounceVector, fminf(maxV, xmul(xlength3(velocity), u.CollisionSettings.y))), 3.0f);
+            newVelocity = mk4(xscale3(bounceVector, fminf(maxV, xmul(xlength3z(velocity), u.CollisionSettings.y))), 3.0f);
             newLife = xsub(newLife, u.CollisionSettings.w);
         } else {
-            const float currentSpeed = xlength3(xyz(oldVelocity));
+            const float currentSpeed = xlength3z(xyz(oldVelocity));
             const float newSpeed = fmaxf(xmul(currentSpeed, 1.1f), escapeSpeed);
             newVelocity = mk4(xscale3(unitVector, newSpeed), 0.0f);
             newPosition = xadd3(op, xscale3(unitVector, travelDistance));
@@ -413,7 +418,7 @@ ILB_DEV f4 evaluateFormula(const ilb_spawn& s, f4 origin, f4 constant, f4 scale,
         return mk4(result, type0.w);
     } else if (itype == 2) {
         const f3 distance = xyz(xsub4(constant, origin));
-        const float ldistance = xlength3(distance);
+        const float ldistance = xlength3z(distance);
         if (ldistance < 0.1f) return mk4(0.0f, 0.0f, 0.0f, constant.w);
         const f3 direction = xdivs3(distance, ldistance);
         const f3 randomSpeed = xmul3(xscale3(xyz(scale), randomness.x), direction);
@@ -442,7 +447,7 @@ __global__ void __launch_bounds__(STEP_THREADS) particle_spawn_kernel(const __gr
     float positionIndexT;
     const float relativeIndex = xsub(index, s.ChunkSizeAndIndices.y);
     if (s.PolygonRate > 0.05f) {
-        const float positionIndexF = xadd(xdiv(relativeIndex, s.PolygonRate), s.ChunkSizeAndIndices.w);
+        const float positionIndexF = xadd(xdivz(relativeIndex, s.PolygonRate), s.ChunkSizeAndIndices.w);
         const float divisor = s.PositionConstantCount;
         float positionIndexI;
         positionIndexT = modff(positionIndexF, &positionIndexI);
