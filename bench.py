@@ -233,15 +233,39 @@ def run_ours(args):
         from illuminant_b200 import sharding
         rows_per = sharding.band_height(H, world)
         r0, r1 = sharding.row_band(rank, world, H)
-        full = torch.empty((rows_per * world, W, 4), dtype=torch.float16, device="cuda")
+        # Reassembly of the lit buffer.  Preferred: the kernel itself stores every finished texel into
+        # the full-frame buffer of EVERY rank through NVLink peer mappings (torch symmetric memory provides the mapped
+        # pointers), followed by a device-side barrier -- compute and all-gather are one kernel.  Fallback: a plain NCCL
+        # all-gather of the row bands.
+        gather, hdl, peer_ptrs = "none", None, None
+        if dist is not None and args.gather in ("auto", "peers"):
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                full = symm_mem.empty((rows_per * world, W, 4), dtype=torch.float16, device=torch.device("cuda", local_rank))
+                hdl = symm_mem.rendezvous(full, dist.group.WORLD)
+                peer_ptrs = [int(p) for p in hdl.buffer_ptrs]
+                gather = "peer-stores (in-kernel all-gather over NVLink) + symmetric-memory barrier"
+            except Exception as e:   # noqa: BLE001
+                if args.gather == "peers":
+                    raise
+                hdl, peer_ptrs = None, None
+                print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
+        if peer_ptrs is None:
+            full = torch.empty((rows_per * world, W, 4), dtype=torch.float16, device="cuda")
+            if dist is not None:
+                gather = "nccl all_gather_into_tensor"
         band = full[rank * rows_per:(rank + 1) * rows_per]
         packed = renderer.build_batches()
         launches0 = ctx.launch_count
 
         def light_step():
-            renderer.RenderLightingDevice(band.data_ptr(), rows=(r0, r1), packed=packed)
-            if dist is not None:   # one all-gather of row bands reassembles the lit buffer on every rank
-                dist.all_gather_into_tensor(full, band)
+            if peer_ptrs is not None:
+                renderer.RenderLightingPeers(peer_ptrs, rows=(r0, r1), packed=packed)
+                hdl.barrier(channel=0)
+            else:
+                renderer.RenderLightingDevice(band.data_ptr(), rows=(r0, r1), packed=packed)
+                if dist is not None:   # one all-gather of row bands reassembles the lit buffer on every rank
+                    dist.all_gather_into_tensor(full, band)
 
         sampler.start()
         total_ms, per = timed(light_step, args.steps, args.warmup)
@@ -290,8 +314,17 @@ def run_ours(args):
                          "note": "per-pixel work is O(lights x trace steps): the kernel is issue-bound, not HBM-bound (see DESIGN.md)"},
             "e2e": {"value": W * H / (e_ms * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": int(gb_host.numel() * 4 + nv * 128),
                     "d2h_bytes_per_step": int(out_host.numel() * 2), "ms_per_step": e_ms},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "gather": gather,
         })
+        if world > 1:   # checksum of the reassembled frame: every rank must hold the same lit buffer
+            chk = torch.tensor([float(full[:H].float().sum().item())], device="cuda", dtype=torch.float64)
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            result["gather_checksum_equal"] = bool(lo.item() == hi.item())
+            whole = torch.empty((H, W, 4), dtype=torch.float16, device="cuda")     # unsharded render of the same frame
+            renderer.RenderLightingDevice(whole.data_ptr(), rows=(0, H), packed=packed)
+            barrier()
+            result["gather_matches_single_gpu"] = bool(torch.equal(whole.view(torch.int16), full[:H].view(torch.int16)))
         # probes (config 4's "GI probes"): timed separately, tiny
         t0 = time.perf_counter()
         renderer.UpdateLightProbes()
@@ -383,9 +416,9 @@ def run_ours(args):
                 "scaling": "strong" if primary else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "C4: 3840x2160, 96 sphere + 8 directional + 24 line lights, 256 probes, 9-slice 3840x2160 distance field"
                            if primary else result.get("config", {}).get("workload"),
-                           "parallelism": f"row bands x{world}, one NCCL all-gather" if primary else f"chunk ranges x{world}, no collective",
+                           "parallelism": f"row bands x{world}, gather: {result.get('gather', 'none')}" if primary else f"chunk ranges x{world}, no collective",
                            "l2": "inputs larger than L2 (no flush)"}}
-        for k in ("roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "particles", "probes_ms"):
+        for k in ("roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "gather_checksum_equal", "gather_matches_single_gpu", "particles", "probes_ms"):
             if k in result:
                 line[k] = result[k]
         print(json.dumps(line), flush=True)
@@ -402,6 +435,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="both", choices=["both", "lighting", "particles"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="auto", choices=["auto", "peers", "nccl"], help="N>1 lit-buffer reassembly")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -682,7 +682,7 @@ int orc_render_lighting(const uint16_t* df_tex, int tw, int th, const void* gbuf
             int vi = batch.first_vertex + i;
             if (vi < 0 || vi >= nverts) return ILB_ERR_INVALID_ARGUMENT;
             const ilb_light_vertex& v = verts[vi];
-#pragma omp parallel for schedule(dynamic, 4)
+#pragma omp parallel for collapse(2) schedule(dynamic, 256)
             for (int y = r0; y < r1; y++)
                 for (int x = 0; x < W; x++) {
                     float4 result;
