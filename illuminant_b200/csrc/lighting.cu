@@ -21,7 +21,13 @@
 
 namespace {
 
-constexpr int TILE_W = 16, TILE_H = 16, TILE_THREADS = TILE_W * TILE_H;
+#ifndef ILB_TILE_H
+#define ILB_TILE_H 16
+#endif
+#ifndef ILB_SWIZZLE
+#define ILB_SWIZZLE 8   // CTAs walk down bands of this many tile rows (column-major inside a band): 2-D locality in L1/L2
+#endif
+constexpr int TILE_W = 16, TILE_H = ILB_TILE_H, TILE_THREADS = TILE_W * TILE_H, TILE_WARPS = TILE_THREADS / 32;
 constexpr int MAX_OUTPUTS = 8;
 
 // One light, flattened on the host from (batch, LightVertex): the LightVertex fields (Vertices.cs:10-39) plus
@@ -52,6 +58,7 @@ struct LightingParams {
     void* outs[MAX_OUTPUTS];
     int nouts;
     int out_row_base;  // row index of outs[] row 0 (row_begin for band buffers, 0 for full frames)
+    int tiles_x, tiles_y;
 };
 
 struct Pixel {
@@ -89,7 +96,8 @@ struct Trace {  // TraceState :31-35
     float t, len, vis;
 };
 
-ILB_DEV void traceInit(Trace& s, f3 start, f3 end, float lightRadius) {  // coneTraceInitialize :37-49
+// returns true when the marched interval t < len stays on the segment start -> end
+ILB_DEV bool traceInit(Trace& s, f3 start, f3 end, float lightRadius) {  // coneTraceInitialize :37-49
     const f3 v = xsub3(end, start);
     const float l = xlength3(v);
     s.origin = start;
@@ -97,6 +105,7 @@ ILB_DEV void traceInit(Trace& s, f3 start, f3 end, float lightRadius) {  // cone
     s.len = fmaxf(xsub(l, lightRadius), 1.0f);
     s.t = TRACE_INITIAL_OFFSET_PX;
     s.vis = 1.0f;
+    return s.len <= l;
 }
 
 ILB_DEV float traceStep(const TraceConfig& c, float d, float offset, float& vis) {  // coneTraceStep :51-71
@@ -114,13 +123,21 @@ ILB_DEV float traceFinal(const TraceConfig& c, float visibility) {  // :182-188
 ILB_DEV float coneTrace(const DFGeometry& g, const DLight& L, f3 lightCenter, float rampX, float rampY,
                         float growthFactor, f3 shaded, bool enable) {  // coneTrace :141-191
     Trace a;
-    traceInit(a, shaded, lightCenter, rampX);
+    const bool onSegment = traceInit(a, shaded, lightCenter, rampX);
     const TraceConfig c = makeTraceConfig(L, rampX, rampY, growthFactor);
     float stepsRemaining = c.stepLimit;
     float liveness = (L.hasField && enable) ? 1.0f : 0.0f;
+    // every sample lies on the segment shaded -> lightCenter (t < len <= |v|); the field volume is convex, so when both
+    // ends are inside every sample is inside and the clamp / distance-to-volume work of the sampler is skipped
+    const bool inside = onSegment && insideField(g, shaded) && insideField(g, lightCenter);
     while (liveness > 0.0f) {
         stepsRemaining -= 1.0f;
-        const float d = sampleDistanceField(g, xadd3(a.origin, xscale3(a.direction, a.t)));  // coneTraceAdvance :73-82
+        const f3 sp = xadd3(a.origin, xscale3(a.direction, a.t));  // coneTraceAdvance :73-82
+#if ILB_NO_INSIDE_PATH
+        const float d = sampleDistanceFieldT<false>(g, sp);
+#else
+        const float d = inside ? sampleDistanceFieldT<true>(g, sp) : sampleDistanceFieldT<false>(g, sp);
+#endif
         a.t = xadd(a.t, traceStep(c, d, a.t, a.vis));
         const float stepLiveness = saturatef(a.vis - FULLY_SHADOWED_THRESHOLD) * saturatef(xsub(a.len, a.t));
         liveness = stepsRemaining * stepLiveness;
@@ -448,18 +465,28 @@ ILB_DEV float warpMax(float v) {
 }
 
 #ifndef ILB_LIGHT_MINBLOCKS
-#define ILB_LIGHT_MINBLOCKS 2
+#define ILB_LIGHT_MINBLOCKS (768 / TILE_THREADS)
 #endif
 __global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_MINBLOCKS) light_accumulate_kernel(const __grid_constant__ LightingParams P) {
-    __shared__ float s_box[8][6];
-    __shared__ int s_warpCount[8];
+    __shared__ float s_box[TILE_WARPS][6];
+    __shared__ int s_warpCount[TILE_WARPS];
     __shared__ uint16_t s_list[TILE_THREADS];
     __shared__ int s_listCount;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // a warp covers an 8x4 pixel patch: neighbouring lanes trace neighbouring rays (coherent DF footprints)
-    const int px = blockIdx.x * TILE_W + (warp & 1) * 8 + (lane & 7);
-    const int py = P.row_begin + blockIdx.y * TILE_H + (warp >> 1) * 4 + (lane >> 3);
+    int tileX, tileY;
+    if (ILB_SWIZZLE > 1) {
+        const int band = blockIdx.x / (ILB_SWIZZLE * P.tiles_x), inband = blockIdx.x % (ILB_SWIZZLE * P.tiles_x);
+        const int rowsInBand = min(ILB_SWIZZLE, P.tiles_y - band * ILB_SWIZZLE);
+        tileX = inband / rowsInBand;
+        tileY = band * ILB_SWIZZLE + inband % rowsInBand;
+    } else {
+        tileX = blockIdx.x % P.tiles_x;
+        tileY = blockIdx.x / P.tiles_x;
+    }
+    const int px = tileX * TILE_W + (warp & 1) * 8 + (lane & 7);
+    const int py = P.row_begin + tileY * TILE_H + (warp >> 1) * 4 + (lane >> 3);
     const bool valid = (px < P.width) && (py < P.row_end);
 
     Pixel pix;
@@ -480,13 +507,13 @@ __global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_MINBLOCKS) light_accum
     }
     __syncthreads();
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
+    for (int w = 0; w < TILE_WARPS; w++) {
         bx0 = fminf(bx0, s_box[w][0]); bx1 = fmaxf(bx1, s_box[w][1]);
         by0 = fminf(by0, s_box[w][2]); by1 = fmaxf(by1, s_box[w][3]);
         bz0 = fminf(bz0, s_box[w][4]); bz1 = fmaxf(bz1, s_box[w][5]);
     }
-    const int tx0 = blockIdx.x * TILE_W, tx1 = tx0 + TILE_W - 1;
-    const int ty0 = P.row_begin + blockIdx.y * TILE_H, ty1 = ty0 + TILE_H - 1;
+    const int tx0 = tileX * TILE_W, tx1 = tx0 + TILE_W - 1;
+    const int ty0 = P.row_begin + tileY * TILE_H, ty1 = ty0 + TILE_H - 1;
 
     // pixel centre in world space for the coverage test (inverse of the light vertex shaders' transform)
     const float sxs = xmul(P.gbTexelAndMisc.z, P.envZAndScale.z), sys = xmul(P.gbTexelAndMisc.w, P.envZAndScale.w);
@@ -519,7 +546,7 @@ __global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_MINBLOCKS) light_accum
         __syncthreads();
         int offset = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < 8; w++) {
+        for (int w = 0; w < TILE_WARPS; w++) {
             const int c = s_warpCount[w];
             if (w < warp) offset += c;
             total += c;
@@ -540,7 +567,7 @@ __global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_MINBLOCKS) light_accum
                 }
             }
         }
-        __syncthreads();
+        if (base + TILE_THREADS < P.nlights) __syncthreads();  // the list is rebuilt only when another round follows
     }
 
     if (valid) storeTexel(P, (size_t)(py - P.out_row_base) * (size_t)P.width + (size_t)px, accR, accG, accB, accA);
@@ -756,8 +783,9 @@ int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, c
     P.nouts = output_count;
     P.out_row_base = outputs_are_full_frames ? 0 : f->row_begin;
 
-    const dim3 grid((f->width + TILE_W - 1) / TILE_W, (f->row_end - f->row_begin + TILE_H - 1) / TILE_H);
-    light_accumulate_kernel<<<grid, TILE_THREADS, 0, ctx->stream>>>(P);
+    P.tiles_x = (f->width + TILE_W - 1) / TILE_W;
+    P.tiles_y = (f->row_end - f->row_begin + TILE_H - 1) / TILE_H;
+    light_accumulate_kernel<<<(unsigned)P.tiles_x * (unsigned)P.tiles_y, TILE_THREADS, 0, ctx->stream>>>(P);
     ctx->launches++;
     ILB_CUDA(ctx, cudaGetLastError());
     return ILB_OK;
