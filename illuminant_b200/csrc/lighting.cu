@@ -465,7 +465,7 @@ ILB_DEV float warpMax(float v) {
 }
 
 #ifndef ILB_LIGHT_MINBLOCKS
-#define ILB_LIGHT_MINBLOCKS (768 / TILE_THREADS)
+#define ILB_LIGHT_MINBLOCKS (512 / TILE_THREADS)
 #endif
 __global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_MINBLOCKS) light_accumulate_kernel(const __grid_constant__ LightingParams P) {
     __shared__ float s_box[TILE_WARPS][6];

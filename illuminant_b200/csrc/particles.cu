@@ -9,6 +9,7 @@
 //
 // Per-op math keeps the operation order of the reference shaders (file:line per function, relative to
 // Illuminant/Shaders/).
+#include <cmath>
 #include <cstring>
 
 #include "ilb_internal.h"
@@ -20,6 +21,24 @@ constexpr int MAX_OPS = 8;
 constexpr int STEP_THREADS = 256;
 #define VelocityConstantScale 1000.0f
 
+// Uniform-only arithmetic of the shaders, evaluated once on the host with the same IEEE fp32 operations (x86 SSE
+// division == div.rn), plus correctly rounded reciprocals of the uniform divisors for udiv().
+struct OpDerived {
+    float rFalloff;        // RN(1 / AreaFalloff)
+    float rTimeDivisor;    // RN(1 / TimeDivisor)
+    float rSize[3];        // RN(1 / AreaSize)
+    float size2[3];        // AreaSize * AreaSize
+    float rSize2[3];       // RN(1 / (AreaSize * AreaSize))
+    float maxAccel;        // Gravity: MaximumAcceleration * dt / 1000
+    float timeScale;       // MatrixMultiply: dt / TimeDivisor (or 1)
+    float rRadius[ILB_MAX_ATTRACTORS];  // Gravity: RN(1 / radius)
+};
+struct SysDerived {
+    float dts;             // GlobalSettings.x / 1000 (getDeltaTimeSeconds)
+    float r1000;           // RN(1 / 1000)
+    float texelZ;          // Extent.z / max(SliceCount, 1) (estimateNormal4)
+};
+
 struct StepParams {
     float4 *P, *V, *A, *RC, *RD;
     const float4* rng;
@@ -30,8 +49,10 @@ struct StepParams {
     unsigned total;      // live_chunks * per_chunk
     int nops;
     DFGeometry df;
+    SysDerived sd;
     ilb_psys_uniforms u;
     ilb_op ops[MAX_OPS];
+    OpDerived od[MAX_OPS];
 };
 
 struct SpawnParams {
@@ -101,19 +122,41 @@ ILB_DEV f4 evaluateBezier4(const ilb_bezier4& b, float value) {  // :141-177
 }
 
 // ---- transforms: x-ops throughout (particle state feeds the collision thresholds of later steps) -------------
-#if ILB_NOINLINE_WEIGHT
-#define ILB_WEIGHT_QUAL static __device__ __noinline__
-#else
-#define ILB_WEIGHT_QUAL __device__ __forceinline__
-#endif
-ILB_WEIGHT_QUAL float computeWeight(const ilb_area& a, f3 worldPosition) {  // FMA.fx:15-20 / Noise.fx:21-26 (scalar rotation broadcast)
-    const float distance = evaluateByTypeId(a.AreaType, worldPosition, mk3(a.AreaCenter[0], a.AreaCenter[1], a.AreaCenter[2]),
-                                            mk3(a.AreaSize[0], a.AreaSize[1], a.AreaSize[2]), mk4(a.AreaRotation));
-    return xmul(xsub(1.0f, saturatef(xdivz(distance, a.AreaFalloff))), a.Strength);
+// Division by a uniform divisor y with r = RN(1/y) precomputed on the host (0 when y is not a safe normal number):
+// q = RN(x*r), rho = x - y*q (exact in one FMA), q' = RN(q + rho*r) is the correctly rounded x / y (Markstein), in
+// 3 instructions instead of the ~14 of div.rn's inline sequence + range check.
+ILB_DEV float udiv(float x, float y, float r) {
+    if (r == 0.0f) return xdivz(x, y);  // uniform branch
+    const float q = __fmul_rn(x, r);
+    const float rho = __fmaf_rn(-y, q, x);
+    return __fmaf_rn(rho, r, q);
+}
+
+ILB_DEV float ellipsoidU(f3 p, const ilb_area& a, const OpDerived& d) {  // evaluateEllipsoid with uniform divisors
+    const f3 r = mk3(a.AreaSize[0], a.AreaSize[1], a.AreaSize[2]);
+    const float k0 = xlength3z(mk3(udiv(p.x, r.x, d.rSize[0]), udiv(p.y, r.y, d.rSize[1]), udiv(p.z, r.z, d.rSize[2])));
+    const float k1 = xlength3z(mk3(udiv(p.x, d.size2[0], d.rSize2[0]), udiv(p.y, d.size2[1], d.rSize2[1]), udiv(p.z, d.size2[2], d.rSize2[2])));
+    return (k0 < 1.0f) ? xmul(xsub(k0, 1.0f), fminf(fminf(r.x, r.y), r.z)) : xdivz(xmul(k0, xsub(k0, 1.0f)), k1);
+}
+ILB_DEV float computeWeight(const ilb_area& a, const OpDerived& d, f3 worldPosition) {  // FMA.fx:15-20 / Noise.fx:21-26 (scalar rotation broadcast)
+    const int t = a.AreaType < 0 ? -a.AreaType : a.AreaType;
+    float distance = 0.0f;
+    if (t >= 1 && t <= 5) {
+        const f3 center = mk3(a.AreaCenter[0], a.AreaCenter[1], a.AreaCenter[2]), size = mk3(a.AreaSize[0], a.AreaSize[1], a.AreaSize[2]);
+        const f3 position = rotateLocalPosition(xsub3(worldPosition, center), mk4(a.AreaRotation));
+        switch (t) {
+            case 1: distance = ellipsoidU(position, a, d); break;
+            case 2: distance = evaluateBox(position, size); break;
+            case 3: distance = evaluateCylinder(position, size); break;
+            case 4: distance = evaluateSpheroid(position, size); break;
+            default: distance = evaluateOctagon(position, size); break;
+        }
+    }
+    return xmul(xsub(1.0f, saturatef(udiv(distance, a.AreaFalloff, d.rFalloff))), a.Strength);
 }
 ILB_DEV bool checkCategoryFilter(float type, const float* mm) { return (type >= mm[0]) && (type <= mm[1]); }  // ParticleCommon.fxh:198-200
 
-ILB_DEV void opGravity(const ilb_psys_uniforms& u, const ilb_gravity& g, f4& pos, f4& vel) {  // Gravity.fx:12-61
+ILB_DEV void opGravity(const ilb_psys_uniforms& u, const SysDerived& sd, const ilb_gravity& g, const OpDerived& d, f4& pos, f4& vel) {  // Gravity.fx:12-61
     if ((pos.w <= 0.0f) || !checkCategoryFilter(vel.w, g.CategoryFilter)) return;
     const float dt = u.GlobalSettings.x;
     f3 acceleration = mk3(0.0f);
@@ -124,9 +167,9 @@ ILB_DEV void opGravity(const ilb_psys_uniforms& u, const ilb_gravity& g, f4& pos
         float attraction;
         if (ars.z >= 0.5f) {
             const float distance = xlength3z(toCenter);
-            attraction = xsub(1.0f, saturatef(xdivz(distance, ars.x)));
+            attraction = xsub(1.0f, saturatef(udiv(distance, ars.x, d.rRadius[i])));
             if (ars.z >= 1.5f) attraction = xmul(attraction, attraction);
-            attraction = xdivz(xmul(attraction, dt), VelocityConstantScale);
+            attraction = udiv(xmul(attraction, dt), VelocityConstantScale, sd.r1000);
         } else {
             float distanceSquared = xsub(xdot3(toCenter, toCenter), ars.x);
             distanceSquared = fmaxf(distanceSquared, 0.001f);
@@ -134,17 +177,17 @@ ILB_DEV void opGravity(const ilb_psys_uniforms& u, const ilb_gravity& g, f4& pos
         }
         acceleration = xadd3(acceleration, xscale3(xscale3(xnormalize3(toCenter), attraction), ars.y));
     }
-    const float maximumAcceleration = xdivz(xmul(g.MaximumAcceleration, dt), VelocityConstantScale);
+    const float maximumAcceleration = d.maxAccel;
     const float currentLength = xlength3z(acceleration);
     if (currentLength > maximumAcceleration) acceleration = xscale3(xnormalize3(acceleration), maximumAcceleration);
     const float mv = u.GlobalSettings.z;
     vel = mk4(fminf(mv, xadd(vel.x, acceleration.x)), fminf(mv, xadd(vel.y, acceleration.y)), fminf(mv, xadd(vel.z, acceleration.z)), vel.w);
 }
 
-ILB_DEV void opNoise(const StepParams& P, const ilb_noise& n, float x, float y, f4& pos, f4& vel) {  // Noise.fx:28-72
+ILB_DEV void opNoise(const StepParams& P, const ilb_noise& n, const OpDerived& d, float x, float y, f4& pos, f4& vel) {  // Noise.fx:28-72
     if (!checkCategoryFilter(vel.w, n.area.CategoryFilter)) return;
-    const float weight = computeWeight(n.area, xyz(pos));
-    const float t = xdivz(xmul(weight, P.u.GlobalSettings.x), n.TimeDivisor);
+    const float weight = computeWeight(n.area, d, xyz(pos));
+    const float t = udiv(xmul(weight, P.u.GlobalSettings.x), n.TimeDivisor, d.rTimeDivisor);
     const float rx = n.RandomnessTexel[0], ry = n.RandomnessTexel[1];
     const f4 randomP1 = randomCustom(P.rng, P.rng_w, P.rng_h, x, y, n.RandomnessOffset, rx, ry, n.RandomnessTexel);
     const f4 randomP2 = randomCustom(P.rng, P.rng_w, P.rng_h, x, y, n.NextRandomnessOffset, rx, ry, n.RandomnessTexel);
@@ -168,10 +211,10 @@ ILB_DEV void opNoise(const StepParams& P, const ilb_noise& n, float x, float y, 
     vel = mk4(nv, vel.w);
 }
 
-ILB_DEV void opFMA(const ilb_psys_uniforms& u, const ilb_fma& f, f4& pos, f4& vel) {  // FMA.fx:22-51
+ILB_DEV void opFMA(const ilb_psys_uniforms& u, const ilb_fma& f, const OpDerived& d, f4& pos, f4& vel) {  // FMA.fx:22-51
     if ((pos.w <= 0.0f) || !checkCategoryFilter(vel.w, f.area.CategoryFilter)) return;
-    const float weight = computeWeight(f.area, xyz(pos));
-    const float t = xdivz(xmul(weight, u.GlobalSettings.x), f.TimeDivisor);
+    const float weight = computeWeight(f.area, d, xyz(pos));
+    const float t = udiv(xmul(weight, u.GlobalSettings.x), f.TimeDivisor, d.rTimeDivisor);
     const f4 oldPosition = pos, oldVelocity = vel;
     pos = xlerp4(oldPosition, xadd4(xmul4(oldPosition, mk4(f.PositionMultiply)), mk4(f.PositionAdd)), t);
     vel = xlerp4(oldVelocity, xadd4(xmul4(oldVelocity, mk4(f.VelocityMultiply)), mk4(f.VelocityAdd)), t);
@@ -184,23 +227,22 @@ ILB_DEV f4 mul3(f4 oldValue, const float* mat, float w) {  // ParticleCommon.fxh
     return mk4(divided, oldValue.w);
 }
 
-ILB_DEV void opMatrix(const ilb_psys_uniforms& u, const ilb_matrix_multiply& m, f4& pos, f4& vel) {  // MatrixMultiply.fx:14-52
+ILB_DEV void opMatrix(const ilb_psys_uniforms& u, const ilb_matrix_multiply& m, const OpDerived& d, f4& pos, f4& vel) {  // MatrixMultiply.fx:14-52
     if ((pos.w <= 0.0f) || !checkCategoryFilter(vel.w, m.area.CategoryFilter)) return;
-    const float timeScale = (m.TimeDivisor >= 0.0f) ? xdivz(u.GlobalSettings.x, m.TimeDivisor) : 1.0f;
-    const float w = xmul(computeWeight(m.area, xyz(pos)), timeScale);
+    const float w = xmul(computeWeight(m.area, d, xyz(pos)), d.timeScale);
     const f4 oldPosition = pos, oldVelocity = vel;
     pos = xlerp4(oldPosition, mul3(oldPosition, m.PositionMatrix, 1.0f), w);
     vel = xlerp4(oldVelocity, mul3(oldVelocity, m.VelocityMatrix, 0.0f), w);
 }
 
 // ---- update tail (UpdateCommon.fxh, UpdateParticleSystem.fx, UpdateParticleSystemWithDistanceField.fx) -------------
-ILB_DEV f3 applyFrictionAndMaximum(const ilb_psys_uniforms& u, f3 velocity) {  // UpdateCommon.fxh:20-35
+ILB_DEV f3 applyFrictionAndMaximum(const ilb_psys_uniforms& u, const SysDerived& sd, f3 velocity) {  // UpdateCommon.fxh:20-35
     float l = xlength3z(velocity);
     if (l <= 0.001f) return mk3(0.0f);
     const float mv = u.GlobalSettings.z;
     if (l > mv) l = mv;
     const float friction = xmul(l, u.GlobalSettings.y);
-    l = xsub(l, xmul(friction, xdivz(u.GlobalSettings.x, VelocityConstantScale)));
+    l = xsub(l, xmul(friction, sd.dts));
     l = clampf(l, 0.0f, mv);
     return xscale3(xnormalize3(velocity), l);
 }
@@ -234,8 +276,8 @@ ILB_DEV void computeRenderData(const ilb_psys_uniforms& u, float vx, float vy, f
     renderData.w = velocity.w;
 }
 
-ILB_DEV f3 estimateNormal4(const DFGeometry& g, f3 position) {  // VisualizeCommon.fxh:9-63
-    const f3 texel = mk3(g.invScaleX, g.invScaleY, xdivz(g.ez, fmaxf(g.sliceCount, 1.0f)));
+ILB_DEV f3 estimateNormal4(const DFGeometry& g, float texelZ, f3 position) {  // VisualizeCommon.fxh:9-63
+    const f3 texel = mk3(g.invScaleX, g.invScaleY, texelZ);
     f3 result = mk3(0.0f);
     const float wts[4][3] = {{1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {1, 1, 1}};
 #pragma unroll
@@ -254,10 +296,10 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
     outV = mk4(0.0f);
     needAttr = false;
     if (oldPosition.w <= 0.0f) return false;  // readStateOrDiscard ParticleCommon.fxh:162-181
-    const float dts = xdivz(u.GlobalSettings.x, VelocityConstantScale);
+    const float dts = P.sd.dts;
     float newLife = xsub(oldPosition.w, xmul(u.GlobalSettings.w, dts));
     if (!COLLIDE) {  // PS_Update UpdateParticleSystem.fx:9-38
-        const f3 velocity = applyFrictionAndMaximum(u, xyz(oldVelocity));
+        const f3 velocity = applyFrictionAndMaximum(u, P.sd, xyz(oldVelocity));
         const f3 scaledVelocity = xscale3(velocity, dts);
         if (newLife > 0.0f) {
             outP = mk4(xadd3(xyz(oldPosition), scaledVelocity), newLife);
@@ -271,7 +313,7 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
     const float collisionDistance = u.CollisionSettings.z;
     const f3 op = xyz(oldPosition);
     const f3 unitVector = xnormalize3(xyz(oldVelocity));
-    const f3 velocity = applyFrictionAndMaximum(u, xyz(oldVelocity));
+    const f3 velocity = applyFrictionAndMaximum(u, P.sd, xyz(oldVelocity));
     bool collided = false, escaping = false;
     const f3 scaledVelocity = xscale3(velocity, dts);
     f3 collisionPosition = mk3(0.0f), newPosition = op;
@@ -303,7 +345,7 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
         const bool bounce = oldVelocity.w <= 0.0f;
         const bool redirect = wasColliding && !escaping;
         f3 normal = mk3(0.0f);
-        if (bounce || redirect) normal = estimateNormal4(P.df, collisionPosition);
+        if (bounce || redirect) normal = estimateNormal4(P.df, P.sd.texelZ, collisionPosition);
         const float maxV = u.GlobalSettings.z;
         const float escapeSpeed = fminf(maxV, u.CollisionSettings.x);
         if (redirect) {
@@ -347,7 +389,18 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
 #ifndef ILB_PARTICLE_MINBLOCKS
 #define ILB_PARTICLE_MINBLOCKS 4
 #endif
-template <bool COLLIDE>
+
+template <int KIND>
+ILB_DEV void applyOp(const StepParams& P, const ilb_op& op, const OpDerived& d, float x, float y, f4& pos, f4& vel) {
+    if (KIND == ILB_OP_GRAVITY) opGravity(P.u, P.sd, op.u.gravity, d, pos, vel);
+    else if (KIND == ILB_OP_NOISE) opNoise(P, op.u.noise, d, x, y, pos, vel);
+    else if (KIND == ILB_OP_FMA) opFMA(P.u, op.u.fma, d, pos, vel);
+    else if (KIND == ILB_OP_MATRIX_MULTIPLY) opMatrix(P.u, op.u.matrix, d, pos, vel);
+}
+
+// K0..K2: the transform chain known at compile time (op kinds, 0 = no op): operands come straight from the constant
+// bank with static offsets.  K0 < 0 selects the generic loop over P.ops[0..nops) for every other chain.
+template <bool COLLIDE, int K0, int K1, int K2>
 __global__ void __launch_bounds__(STEP_THREADS, ILB_PARTICLE_MINBLOCKS) particle_step_kernel(const __grid_constant__ StepParams P) {
     const unsigned gi = blockIdx.x * STEP_THREADS + threadIdx.x;
     if (gi >= P.total) return;
@@ -364,15 +417,21 @@ __global__ void __launch_bounds__(STEP_THREADS, ILB_PARTICLE_MINBLOCKS) particle
     const float x = (float)ix, y = (float)iy;
     f4 pos = mk4(P.P[gi]), vel = mk4(P.V[gi]);
 
-    for (int k = 0; k < P.nops; k++) {
-        const ilb_op& op = P.ops[k];
-        switch (op.kind) {
-            case ILB_OP_GRAVITY: opGravity(P.u, op.u.gravity, pos, vel); break;
-            case ILB_OP_NOISE: opNoise(P, op.u.noise, x, y, pos, vel); break;
-            case ILB_OP_FMA: opFMA(P.u, op.u.fma, pos, vel); break;
-            case ILB_OP_MATRIX_MULTIPLY: opMatrix(P.u, op.u.matrix, pos, vel); break;
-            default: break;
+    if (K0 < 0) {
+        for (int k = 0; k < P.nops; k++) {
+            const ilb_op& op = P.ops[k];
+            switch (op.kind) {
+                case ILB_OP_GRAVITY: applyOp<ILB_OP_GRAVITY>(P, op, P.od[k], x, y, pos, vel); break;
+                case ILB_OP_NOISE: applyOp<ILB_OP_NOISE>(P, op, P.od[k], x, y, pos, vel); break;
+                case ILB_OP_FMA: applyOp<ILB_OP_FMA>(P, op, P.od[k], x, y, pos, vel); break;
+                case ILB_OP_MATRIX_MULTIPLY: applyOp<ILB_OP_MATRIX_MULTIPLY>(P, op, P.od[k], x, y, pos, vel); break;
+                default: break;
+            }
         }
+    } else {
+        if (K0 > 0) applyOp<K0>(P, P.ops[0], P.od[0], x, y, pos, vel);
+        if (K1 > 0) applyOp<K1>(P, P.ops[1], P.od[1], x, y, pos, vel);
+        if (K2 > 0) applyOp<K2>(P, P.ops[2], P.od[2], x, y, pos, vel);
     }
 
     f4 outP, outV;
@@ -551,14 +610,53 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
         SP.nops = op_count;
         SP.u = *u;
         for (int k = 0; k < op_count; k++) SP.ops[k] = ops[k];
-        const unsigned blocks = (unsigned)((total + STEP_THREADS - 1) / STEP_THREADS);
-        if (u->has_collision_field) {
+        // host-evaluated uniform arithmetic (same fp32 operations as the shaders) and reciprocals for udiv()
+        auto rcp = [](float y) { const float a = std::fabs(y); return (a >= 1.0e-30f && a <= 1.0e30f) ? 1.0f / y : 0.0f; };
+        const float dtms = u->GlobalSettings.x;
+        SP.sd.dts = dtms / 1000.0f;
+        SP.sd.r1000 = rcp(1000.0f);
+        for (int k = 0; k < op_count; k++) {
+            OpDerived& d = SP.od[k];
+            const ilb_op& op = ops[k];
+            const ilb_area* area = nullptr;
+            float timeDivisor = 0.0f;
+            if (op.kind == ILB_OP_GRAVITY) {
+                d.maxAccel = op.u.gravity.MaximumAcceleration * dtms / 1000.0f;
+                for (int i = 0; i < op.u.gravity.AttractorCount; i++) d.rRadius[i] = rcp(op.u.gravity.AttractorRadiusesAndStrengths[i].x);
+            } else if (op.kind == ILB_OP_NOISE) { area = &op.u.noise.area; timeDivisor = op.u.noise.TimeDivisor; }
+            else if (op.kind == ILB_OP_FMA) { area = &op.u.fma.area; timeDivisor = op.u.fma.TimeDivisor; }
+            else { area = &op.u.matrix.area; timeDivisor = op.u.matrix.TimeDivisor; d.timeScale = (timeDivisor >= 0.0f) ? dtms / timeDivisor : 1.0f; }
+            if (area) {
+                d.rFalloff = rcp(area->AreaFalloff);
+                d.rTimeDivisor = rcp(timeDivisor);
+                for (int c = 0; c < 3; c++) {
+                    d.rSize[c] = rcp(area->AreaSize[c]);
+                    d.size2[c] = area->AreaSize[c] * area->AreaSize[c];
+                    d.rSize2[c] = rcp(d.size2[c]);
+                }
+            }
+        }
+        const bool collide = u->has_collision_field != 0;
+        if (collide) {
             if (!ilb_make_df_geometry(ps->field, u->CollisionField, &SP.df))
                 return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "collision field uniforms describe an empty field");
-            particle_step_kernel<true><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);
-        } else {
-            particle_step_kernel<false><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);
+            SP.sd.texelZ = SP.df.ez / std::fmax(SP.df.sliceCount, 1.0f);
         }
+        const unsigned blocks = (unsigned)((total + STEP_THREADS - 1) / STEP_THREADS);
+        // chains with a compiled specialisation: none, and Gravity -> Noise -> FMA (BASELINE.json configs 3 and 5)
+        const bool chainNone = op_count == 0;
+        const bool chainGNF = op_count == 3 && ops[0].kind == ILB_OP_GRAVITY && ops[1].kind == ILB_OP_NOISE && ops[2].kind == ILB_OP_FMA;
+#define ILB_LAUNCH(C, A, B, D) particle_step_kernel<C, A, B, D><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP)
+        if (collide) {
+            if (chainGNF) ILB_LAUNCH(true, ILB_OP_GRAVITY, ILB_OP_NOISE, ILB_OP_FMA);
+            else if (chainNone) ILB_LAUNCH(true, 0, 0, 0);
+            else ILB_LAUNCH(true, -1, 0, 0);
+        } else {
+            if (chainGNF) ILB_LAUNCH(false, ILB_OP_GRAVITY, ILB_OP_NOISE, ILB_OP_FMA);
+            else if (chainNone) ILB_LAUNCH(false, 0, 0, 0);
+            else ILB_LAUNCH(false, -1, 0, 0);
+        }
+#undef ILB_LAUNCH
         ctx->launches++;
     }
     ILB_CUDA(ctx, cudaGetLastError());
