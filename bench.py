@@ -384,7 +384,7 @@ def run_ours(args):
             "config": {"workload": f"{count} particles per GPU (32 chunks x 512^2), Gravity(4)+Noise+FMA+UpdateWithDistanceField, dt 1/60",
                        "live_fraction": system.LiveCount / count},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ptraffic,
-                         "kernel": "particle_step_kernel<true>", "algorithmic_bytes_per_particle_step": PARTICLE_BYTES_PER_STEP, "peak_source": peak_src},
+                         "kernel": "particle_step_kernel<COLLIDE, Gravity, Noise, FMA>", "algorithmic_bytes_per_particle_step": PARTICLE_BYTES_PER_STEP, "peak_source": peak_src},
             "e2e": {"value": count * world / (e_ms * 1e-3) / 1e6, "unit": "Mparticle-steps/s",
                     "h2d_bytes_per_step": int(C.sizeof(_abi.PsysUniforms) + 3 * C.sizeof(_abi.Op)), "d2h_bytes_per_step": 8, "ms_per_step": e_ms},
             "gpu_launches": int(p_launches), "clocks": pclocks,
