@@ -390,6 +390,32 @@ def run_ours(args):
             "gpu_launches": int(p_launches), "clocks": pclocks,
         }
 
+    # ------------------------------------------------------------------ combined frame loop (config C5)
+    if args.workload == "both":
+        # ParticleLights.cs:333-378: System.Update (collision against the lighting field) -> RenderLighting -> reassemble.
+        c5 = scenes.config_c5_lighting()
+        c5r = ib.LightingRenderer(ctx, c5.environment, c5.configuration)
+        c5r.DistanceField = df                      # particles and lights share the same 4K field
+        c5r._gbuffer_shape = renderer._gbuffer_shape
+        c5packed = c5r.build_batches()
+        system.Configuration.Collision.DistanceField = df
+
+        def frame_step():
+            particle_step()
+            if peer_ptrs is not None:
+                c5r.RenderLightingPeers(peer_ptrs, rows=(r0, r1), packed=c5packed)
+                hdl.barrier(channel=0)
+            else:
+                c5r.RenderLightingDevice(band.data_ptr(), rows=(r0, r1), packed=c5packed)
+                if dist is not None:
+                    dist.all_gather_into_tensor(full, band)
+        f_steps = max(args.steps, 10)
+        total_ms, _ = timed(frame_step, f_steps, 3)
+        ms_frame = max_over_ranks(total_ms) / f_steps
+        result["combined_c5"] = {"metric": "frames/s (8M particles per GPU + 64-light 4K lighting)", "value": 1e3 / ms_frame, "unit": "frames/s",
+                                 "ms_per_frame": ms_frame, "lit_mpixels_per_s": W * H / (ms_frame * 1e-3) / 1e6,
+                                 "mparticle_steps_per_s": count * world / (ms_frame * 1e-3) / 1e6, "steps": f_steps}
+
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
@@ -418,7 +444,7 @@ def run_ours(args):
                            if primary else result.get("config", {}).get("workload"),
                            "parallelism": f"row bands x{world}, gather: {result.get('gather', 'none')}" if primary else f"chunk ranges x{world}, no collective",
                            "l2": "inputs larger than L2 (no flush)"}}
-        for k in ("roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "gather_checksum_equal", "gather_matches_single_gpu", "particles", "probes_ms"):
+        for k in ("roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "gather_checksum_equal", "gather_matches_single_gpu", "particles", "combined_c5", "probes_ms"):
             if k in result:
                 line[k] = result[k]
         print(json.dumps(line), flush=True)
