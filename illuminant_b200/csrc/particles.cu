@@ -96,7 +96,7 @@ ILB_DEV float tForScaledBezier(const ilb_float4& rangeAndCount, float value, flo
     }
     switch (mode % 256) {
         default: break;
-        case 1: t = sinf(t * ILB_PI * 0.5f); break;
+        case 1: t = dm_sinf(xmul(xmul(t, ILB_PI), 0.5f)); break;
         case 2: t = t * t; break;
     }
     return rangeAndCount.z;
@@ -352,7 +352,7 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
             normal = mk3(normal.x, normal.y, xmul(normal.z, 0.0f));
             if (xlength3z(normal) < 0.33f) {
                 float s, c;
-                sincosf(xadd(xdivz(x, 67.0f), xdivz(y, 13.0f)), &s, &c);
+                dm_sincosf(xadd(xdivz(x, 67.0f), xdivz(y, 13.0f)), &s, &c);
                 normal = mk3(s, c, 0.0f);
             }
             const f3 escapeVector = xnormalize3(normal);
@@ -451,8 +451,8 @@ __global__ void __launch_bounds__(STEP_THREADS, ILB_PARTICLE_MINBLOCKS) particle
 ILB_DEV f3 generateRandomNormal3(float rx, float ry) {  // :47-57
     const float phi = xmul(xmul(rx, ILB_PI), 2.0f);
     const float costheta = xmul(xsub(ry, 0.5f), 2.0f);
-    const float theta = acosf(costheta);
-    return mk3(xmul(sinf(theta), cosf(phi)), xmul(sinf(theta), sinf(phi)), cosf(theta));
+    const float theta = dm_acosf(costheta);
+    return mk3(xmul(dm_sinf(theta), dm_cosf(phi)), xmul(dm_sinf(theta), dm_sinf(phi)), dm_cosf(theta));
 }
 
 ILB_DEV f4 evaluateFormula(const ilb_spawn& s, f4 origin, f4 constant, f4 scale, f4 offset, f4 randomness, float type) {  // :59-104

@@ -7,6 +7,9 @@
 #include <cmath>
 #include <cstdint>
 
+// deterministic sin / cos / acos shared bit-for-bit with the CUDA kernels (see the header for why)
+#include "../include/ilb_detmath.h"
+
 namespace hlsl {
 
 static const float PI = 3.14159265358979323846f;

@@ -250,7 +250,7 @@ float4 gbufferPoint(const Frame& fr, float2 uv) {
 float3 decodeNormalSpherical(float2 enc) {  // EnvironmentCommon.fxh:42-52
     if (any(enc)) {
         float2 ang = enc * 2 - 1;
-        float2 scth(sinf(ang.x * PI), cosf(ang.x * PI));
+        float2 scth(dm_sinf(ang.x * PI), dm_cosf(ang.x * PI));  // sincos()
         float2 scphi = float2(sqrtf(1.0f - ang.y * ang.y), ang.y);
         return float3(scth.y * scphi.x, scth.x * scphi.x, scphi.y);
     }
@@ -516,10 +516,10 @@ float rectangleSolidAngle(float3 worldPos, float3 p0, float3 p1, float3 p2, floa
     float3 n1 = normalize(cross(v1, v2));
     float3 n2 = normalize(cross(v2, v3));
     float3 n3 = normalize(cross(v3, v0));
-    float g0 = acosf(dot(-n0, n1));
-    float g1 = acosf(dot(-n1, n2));
-    float g2 = acosf(dot(-n2, n3));
-    float g3 = acosf(dot(-n3, n0));
+    float g0 = dm_acosf(dot(-n0, n1));
+    float g1 = dm_acosf(dot(-n1, n2));
+    float g2 = dm_acosf(dot(-n2, n3));
+    float g3 = dm_acosf(dot(-n3, n0));
     return g0 + g1 + g2 + g3 - 2 * PI;
 }
 

@@ -44,7 +44,7 @@ float tForScaledBezier(float4 rangeAndCount, float value, float& t) {  // Shader
     }
     switch (mode % 256) {
         default: break;
-        case 1: t = sinf(t * PI * 0.5f); break;
+        case 1: t = dm_sinf(t * PI * 0.5f); break;
         case 2: t = t * t; break;
     }
     return rangeAndCount.z;
@@ -199,8 +199,8 @@ struct Randomness {
 float3 generateRandomNormal3(float2 randomness) {  // :47-57
     float phi = randomness.x * PI * 2;
     float costheta = (randomness.y - 0.5f) * 2;
-    float theta = acosf(costheta);
-    return float3(sinf(theta) * cosf(phi), sinf(theta) * sinf(phi), cosf(theta));
+    float theta = dm_acosf(costheta);
+    return float3(dm_sinf(theta) * dm_cosf(phi), dm_sinf(theta) * dm_sinf(phi), dm_cosf(theta));
 }
 
 float4 evaluateFormula(const ilb_spawn& s, float4 origin, float4 constant, float4 scale, float4 offset,
@@ -550,7 +550,7 @@ bool PS_UpdateWithDistanceField(const System& sys, const Field& df, float2 xy, f
             normal *= ESCAPE_MASK;
             if (length(normal) < NO_NORMAL_THRESHOLD) {
                 float a = (xy.x / 67) + (xy.y / 13);
-                normal = float3(sinf(a), cosf(a), 0);
+                normal = float3(dm_sinf(a), dm_cosf(a), 0);  // sincos()
             }
             float3 escapeVector = normalize(normal);
             newVelocity = float4(escapeVector * escapeSpeed * INITIAL_ESCAPE_SPEED, BOUNCE_DELAY);
