@@ -7,7 +7,8 @@
  * state feeds collision tests; decoded normals offset the cone-trace origin; the line-light solid angle is a
  * near-cancelling sum of four arc-cosines), where 1 ulp between two libm implementations becomes an O(1) difference.
  *
- * Algorithms: Cephes single-precision sinf / cosf / asinf / acosf (Moshier), about 1 ulp for |x| < 8192.  Every
+ * Algorithms: Cephes single-precision sinf / cosf (Moshier), about 1 ulp for |x| < 8192; acos from Abramowitz &
+ * Stegun 4.4.46 (absolute error < 1e-7).  Every
  * operation is an individually rounded IEEE fp32 add / multiply / sqrt through the DM_* macros, so the CPU build
  * (-ffp-contract=off) and the GPU build (__fadd_rn / __fmul_rn / __fsqrt_rn: never fused) agree bit for bit.
  *
@@ -92,40 +93,19 @@ DM_FN void dm_sincosf(float x, float* s, float* c) {
     *c = dm_cosf(x);
 }
 
-DM_FN float dm_asinf(float xx) {
-    const int neg = xx < 0.0f;
-    const float a = neg ? -xx : xx;
-    if (!(a <= 1.0f)) return DM_MUL(0.0f, DM_SQRT(-1.0f)); /* domain error / NaN in: NaN out, like acos() */
-    float x, z;
-    int flag = 0;
-    if (a < 1.0e-4f) {
-        z = a;
-    } else {
-        if (a > 0.5f) {
-            z = DM_MUL(0.5f, DM_SUB(1.0f, a));
-            x = DM_SQRT(z);
-            flag = 1;
-        } else {
-            x = a;
-            z = DM_MUL(x, x);
-        }
-        float p = DM_ADD(DM_MUL(4.2163199048E-2f, z), 2.4181311049E-2f);
-        p = DM_ADD(DM_MUL(p, z), 4.5470025998E-2f);
-        p = DM_ADD(DM_MUL(p, z), 7.4953002686E-2f);
-        p = DM_ADD(DM_MUL(p, z), 1.6666752422E-1f);
-        z = DM_ADD(DM_MUL(DM_MUL(p, z), x), x);
-        if (flag) {
-            z = DM_ADD(z, z);
-            z = DM_SUB(DM_PIO2F, z);
-        }
-    }
-    return neg ? -z : z;
-}
-
-DM_FN float dm_acosf(float x) {
-    if (x < -0.5f) return DM_SUB(DM_PIF, DM_MUL(2.0f, dm_asinf(DM_SQRT(DM_MUL(0.5f, DM_ADD(1.0f, x))))));
-    if (x > 0.5f) return DM_MUL(2.0f, dm_asinf(DM_SQRT(DM_MUL(0.5f, DM_SUB(1.0f, x)))));
-    return DM_SUB(DM_PIO2F, dm_asinf(x));
+/* acos: Abramowitz & Stegun 4.4.46, acos(x) = sqrt(1 - x) * P7(x) on [0, 1] (|error| <= 2e-8 before rounding),
+ * reflected for x < 0.  Branch-free apart from the final select; |x| > 1 gives sqrt(negative) = NaN like acos(). */
+DM_FN float dm_acosf(float xx) {
+    const float x = xx < 0.0f ? -xx : xx;
+    float p = DM_ADD(DM_MUL(-0.0012624911f, x), 0.0066700901f);
+    p = DM_ADD(DM_MUL(p, x), -0.0170881256f);
+    p = DM_ADD(DM_MUL(p, x), 0.0308918810f);
+    p = DM_ADD(DM_MUL(p, x), -0.0501743046f);
+    p = DM_ADD(DM_MUL(p, x), 0.0889789874f);
+    p = DM_ADD(DM_MUL(p, x), -0.2145988016f);
+    p = DM_ADD(DM_MUL(p, x), 1.5707963050f);
+    const float r = DM_MUL(DM_SQRT(DM_SUB(1.0f, x)), p);
+    return xx < 0.0f ? DM_SUB(DM_PIF, r) : r;
 }
 
 #endif /* ILB_DETMATH_H */
