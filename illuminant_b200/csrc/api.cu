@@ -1,5 +1,6 @@
 // C-ABI entry points of libilluminant_b200.so (include/illuminant_b200.h): argument validation, device-memory
 // ownership and stream plumbing.  The kernels live in lighting.cu / particles.cu / dfgen.cu.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -313,6 +314,8 @@ int ilb_particles_create(ilb_ctx* ctx, int chunk_size, int max_chunks, ilb_psys*
     ps->ctx = ctx; ps->chunk_size = chunk_size; ps->max_chunks = max_chunks; ps->per_chunk = per;
     ctx->systems.push_back(ps);
     live_add(ps);
+    if (const char* e = getenv("ILB_PARTICLE_TMA")) ps->use_tma = (e[0] != '0');
+    cudaDeviceGetAttribute(&ps->sm_count, cudaDevAttrMultiProcessorCount, ctx->device);
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < 5 && e == cudaSuccess; i++) {
         e = cudaMalloc(&ps->buf[i], sizeof(float4) * total);

@@ -52,6 +52,9 @@ struct ilb_psys {
     int rng_w = 0, rng_h = 0;
     ilb_df* field = nullptr;
     unsigned long long* d_count = nullptr;
+    bool use_tma = false;  // ILB_PARTICLE_TMA=1 selects the TMA-staged persistent step kernel (measured 22 % slower: the
+                           // chain is issue-bound and tile-lockstep adds barrier stalls; the direct kernel is the default)
+    int sm_count = 148;
 };
 
 int ilb_fail(ilb_ctx* ctx, int code, const char* fmt, ...);

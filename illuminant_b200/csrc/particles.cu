@@ -9,7 +9,9 @@
 //
 // Per-op math keeps the operation order of the reference shaders (file:line per function, relative to
 // Illuminant/Shaders/).
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "ilb_internal.h"
@@ -400,10 +402,9 @@ ILB_DEV void applyOp(const StepParams& P, const ilb_op& op, const OpDerived& d, 
 
 // K0..K2: the transform chain known at compile time (op kinds, 0 = no op): operands come straight from the constant
 // bank with static offsets.  K0 < 0 selects the generic loop over P.ops[0..nops) for every other chain.
+// One particle through the whole update: transform chain in registers, then the Update / UpdateWithDistanceField tail.
 template <bool COLLIDE, int K0, int K1, int K2>
-__global__ void __launch_bounds__(STEP_THREADS, ILB_PARTICLE_MINBLOCKS) particle_step_kernel(const __grid_constant__ StepParams P) {
-    const unsigned gi = blockIdx.x * STEP_THREADS + threadIdx.x;
-    if (gi >= P.total) return;
+ILB_DEV void stepParticle(const StepParams& P, unsigned gi, f4 pos, f4 vel, f4& outP, f4& outV, bool& needAttr, float& x, float& y) {
     unsigned ix, iy;
     if (P.chunk_shift >= 0) {
         const unsigned i = gi & (P.per_chunk - 1u);
@@ -414,9 +415,8 @@ __global__ void __launch_bounds__(STEP_THREADS, ILB_PARTICLE_MINBLOCKS) particle
         ix = i % (unsigned)P.chunk_size;
         iy = i / (unsigned)P.chunk_size;
     }
-    const float x = (float)ix, y = (float)iy;
-    f4 pos = mk4(P.P[gi]), vel = mk4(P.V[gi]);
-
+    x = (float)ix;
+    y = (float)iy;
     if (K0 < 0) {
         for (int k = 0; k < P.nops; k++) {
             const ilb_op& op = P.ops[k];
@@ -433,10 +433,18 @@ __global__ void __launch_bounds__(STEP_THREADS, ILB_PARTICLE_MINBLOCKS) particle
         if (K1 > 0) applyOp<K1>(P, P.ops[1], P.od[1], x, y, pos, vel);
         if (K2 > 0) applyOp<K2>(P, P.ops[2], P.od[2], x, y, pos, vel);
     }
+    updateTail<COLLIDE>(P, x, y, pos, vel, outP, outV, needAttr);
+}
 
+// Direct variant: one thread per particle, 16-byte coalesced global loads / stores.
+template <bool COLLIDE, int K0, int K1, int K2>
+__global__ void __launch_bounds__(STEP_THREADS, ILB_PARTICLE_MINBLOCKS) particle_step_kernel(const __grid_constant__ StepParams P) {
+    const unsigned gi = blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (gi >= P.total) return;
     f4 outP, outV;
     bool needAttr;
-    updateTail<COLLIDE>(P, x, y, pos, vel, outP, outV, needAttr);
+    float x, y;
+    stepParticle<COLLIDE, K0, K1, K2>(P, gi, mk4(P.P[gi]), mk4(P.V[gi]), outP, outV, needAttr, x, y);
     P.P[gi] = to_float4(outP);
     P.V[gi] = to_float4(outV);
     if (P.u.write_render_outputs) {
@@ -445,6 +453,111 @@ __global__ void __launch_bounds__(STEP_THREADS, ILB_PARTICLE_MINBLOCKS) particle
         P.RC[gi] = to_float4(rc);
         P.RD[gi] = to_float4(rd);
     }
+}
+
+// ---- TMA-staged variant ------------------------------------------------------------------------------------------
+// Persistent CTAs (a multiple of the SM count) walk the particle slabs in tiles of 256 particles.  One elected thread
+// stages the tile's PositionAndLife / Velocity / Attributes chunks (3 x 4 KB) into shared memory with bulk async copies
+// (cp.async.bulk global -> shared, completion on an mbarrier; SASS: UBLKCP), two tiles deep, so the next tile's 12 KB
+// are in flight while the current one is computed; results go back through shared memory with bulk async stores
+// (shared -> global, 4 x 4 KB), which drain while the CTA already computes the next tile.  No thread ever issues a
+// global load or store for particle state, and no registers are spent on addressing or on in-flight loads.
+constexpr int STAGE_TILE = STEP_THREADS;   // particles per tile == threads per CTA
+constexpr int STAGES = 2;
+
+struct __align__(128) StageSmem {
+    float4 inP[STAGES][STAGE_TILE], inV[STAGES][STAGE_TILE], inA[STAGES][STAGE_TILE];
+    float4 outP[STAGE_TILE], outV[STAGE_TILE], outRC[STAGE_TILE], outRD[STAGE_TILE];
+    unsigned long long full[STAGES];   // mbarriers
+};
+
+ILB_DEV uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+ILB_DEV void mbarInit(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
+}
+ILB_DEV void mbarExpectTx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+ILB_DEV void mbarWait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+ILB_DEV void bulkLoad(void* smemDst, const void* gmemSrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(smemDst)),
+                 "l"(gmemSrc), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+}
+ILB_DEV void bulkStore(void* gmemDst, const void* smemSrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmemDst), "r"(smemAddr(smemSrc)), "r"(bytes) : "memory");
+}
+
+template <bool COLLIDE, int K0, int K1, int K2>
+__global__ void __launch_bounds__(STEP_THREADS, 3) particle_step_tma_kernel(const __grid_constant__ StepParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    StageSmem& S = *reinterpret_cast<StageSmem*>(smem_raw);
+    const unsigned tid = threadIdx.x;
+    const unsigned ntiles = P.total / STAGE_TILE;   // per_chunk is a multiple of 256, so tiles are always full
+    constexpr unsigned TILE_BYTES = STAGE_TILE * sizeof(float4);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) mbarInit(&S.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issueLoads = [&](unsigned tile, int stage) {   // elected thread only
+        const size_t base = (size_t)tile * STAGE_TILE;
+        mbarExpectTx(&S.full[stage], 3 * TILE_BYTES);
+        bulkLoad(S.inP[stage], P.P + base, TILE_BYTES, &S.full[stage]);
+        bulkLoad(S.inV[stage], P.V + base, TILE_BYTES, &S.full[stage]);
+        bulkLoad(S.inA[stage], P.A + base, TILE_BYTES, &S.full[stage]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            const unsigned t = blockIdx.x + (unsigned)s * gridDim.x;
+            if (t < ntiles) issueLoads(t, s);
+        }
+    }
+
+    unsigned it = 0;
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        const int stage = (int)(it % STAGES);
+        mbarWait(&S.full[stage], (it / STAGES) & 1u);
+        const f4 pos = mk4(S.inP[stage][tid]), vel = mk4(S.inV[stage][tid]), attr = mk4(S.inA[stage][tid]);
+        // the previous tile's bulk stores must have finished READING the out buffers before they are overwritten
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();   // every thread holds its inputs in registers: the stage can be refilled
+        if (tid == 0) {
+            const unsigned next = tile + (unsigned)STAGES * gridDim.x;
+            if (next < ntiles) issueLoads(next, stage);
+        }
+
+        const unsigned gi = tile * STAGE_TILE + tid;
+        f4 outP, outV, rc = mk4(0.0f), rd = mk4(0.0f);
+        bool needAttr;
+        float x, y;
+        stepParticle<COLLIDE, K0, K1, K2>(P, gi, pos, vel, outP, outV, needAttr, x, y);
+        if (P.u.write_render_outputs && needAttr) computeRenderData(P.u, x, y, outP, outV, attr, rc, rd);
+
+        S.outP[tid] = to_float4(outP);
+        S.outV[tid] = to_float4(outV);
+        S.outRC[tid] = to_float4(rc);
+        S.outRD[tid] = to_float4(rd);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async proxy
+        __syncthreads();
+        if (tid == 0) {
+            const size_t base = (size_t)tile * STAGE_TILE;
+            bulkStore(P.P + base, S.outP, TILE_BYTES);
+            bulkStore(P.V + base, S.outV, TILE_BYTES);
+            if (P.u.write_render_outputs) {
+                bulkStore(P.RC + base, S.outRC, TILE_BYTES);
+                bulkStore(P.RD + base, S.outRD, TILE_BYTES);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA exits
 }
 
 // ---- spawner (SpawnerCommon.fxh, SpawnParticles.fx:10-30) -----------------------------------------------------
@@ -646,15 +759,32 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
         // chains with a compiled specialisation: none, and Gravity -> Noise -> FMA (BASELINE.json configs 3 and 5)
         const bool chainNone = op_count == 0;
         const bool chainGNF = op_count == 3 && ops[0].kind == ILB_OP_GRAVITY && ops[1].kind == ILB_OP_NOISE && ops[2].kind == ILB_OP_FMA;
-#define ILB_LAUNCH(C, A, B, D) particle_step_kernel<C, A, B, D><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP)
+        // In-place safety of the staged variant: a tile is fully read into registers before its results are stored, and
+        // tiles are disjoint, so reading through one proxy and writing through the other never overlaps in time.
+        const bool staged = ps->use_tma && (chainGNF || chainNone) && (total % STAGE_TILE == 0);
+        const unsigned ntiles = (unsigned)(total / STAGE_TILE);
+        const unsigned persistent = std::min<unsigned>(ntiles, (unsigned)ps->sm_count * 3u);
+#define ILB_LAUNCH(C, A, B, D)                                                                                              \
+    do {                                                                                                                    \
+        if (staged) {                                                                                                       \
+            static bool attr_set = false;                                                                                   \
+            if (!attr_set) {                                                                                                \
+                ILB_CUDA(ctx, cudaFuncSetAttribute(particle_step_tma_kernel<C, A, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem))); \
+                attr_set = true;                                                                                            \
+            }                                                                                                               \
+            particle_step_tma_kernel<C, A, B, D><<<persistent, STEP_THREADS, sizeof(StageSmem), ctx->stream>>>(SP);         \
+        } else {                                                                                                            \
+            particle_step_kernel<C, A, B, D><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);                                  \
+        }                                                                                                                   \
+    } while (0)
         if (collide) {
             if (chainGNF) ILB_LAUNCH(true, ILB_OP_GRAVITY, ILB_OP_NOISE, ILB_OP_FMA);
             else if (chainNone) ILB_LAUNCH(true, 0, 0, 0);
-            else ILB_LAUNCH(true, -1, 0, 0);
+            else particle_step_kernel<true, -1, 0, 0><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);
         } else {
             if (chainGNF) ILB_LAUNCH(false, ILB_OP_GRAVITY, ILB_OP_NOISE, ILB_OP_FMA);
             else if (chainNone) ILB_LAUNCH(false, 0, 0, 0);
-            else ILB_LAUNCH(false, -1, 0, 0);
+            else particle_step_kernel<false, -1, 0, 0><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);
         }
 #undef ILB_LAUNCH
         ctx->launches++;
