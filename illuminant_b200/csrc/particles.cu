@@ -26,6 +26,8 @@ constexpr int STEP_THREADS = 256;
 // Uniform-only arithmetic of the shaders, evaluated once on the host with the same IEEE fp32 operations (x86 SSE
 // division == div.rn), plus correctly rounded reciprocals of the uniform divisors for udiv().
 struct OpDerived {
+    int weightIsUniform;   // the area weight does not depend on the particle (see hostUniformWeight)
+    float uniformWeight;
     float rFalloff;        // RN(1 / AreaFalloff)
     float rTimeDivisor;    // RN(1 / TimeDivisor)
     float rSize[3];        // RN(1 / AreaSize)
@@ -141,6 +143,7 @@ ILB_DEV float ellipsoidU(f3 p, const ilb_area& a, const OpDerived& d) {  // eval
     return (k0 < 1.0f) ? xmul(xsub(k0, 1.0f), fminf(fminf(r.x, r.y), r.z)) : xdivz(xmul(k0, xsub(k0, 1.0f)), k1);
 }
 ILB_DEV float computeWeight(const ilb_area& a, const OpDerived& d, f3 worldPosition) {  // FMA.fx:15-20 / Noise.fx:21-26 (scalar rotation broadcast)
+    if (d.weightIsUniform) return d.uniformWeight;  // uniform branch
     const int t = a.AreaType < 0 ? -a.AreaType : a.AreaType;
     float distance = 0.0f;
     if (t >= 1 && t <= 5) {
@@ -723,6 +726,29 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
         SP.nops = op_count;
         SP.u = *u;
         for (int k = 0; k < op_count; k++) SP.ops[k] = ops[k];
+        // The reference broadcasts the scalar AreaRotation into a float4 "quaternion" (FMA.fx:11,17).  With the default
+        // rotation 0 that quaternion is all zeros and rotateLocalPosition() maps every finite position to the zero vector,
+        // so evaluateByTypeId() -- and with it the area weight -- is the same number for every particle; AreaType None
+        // has distance 0 everywhere.  Evaluate that number once here, with the same fp32 operations, instead of ~200
+        // instructions per particle.  (Non-finite particle positions would give NaN in the reference; they are not
+        // reproduced on this path.)
+        auto hostUniformWeight = [](const ilb_area& a, float* out) -> bool {
+            const int t = a.AreaType < 0 ? -a.AreaType : a.AreaType;
+            float distance;
+            const float sx = a.AreaSize[0], sy = a.AreaSize[1], sz = a.AreaSize[2];
+            if (t < 1 || t > 5) distance = 0.0f;
+            else if (a.AreaRotation != 0.0f) return false;
+            else if (t == 1) {  // ellipsoid at p = 0: k0 = 0 < 1 -> (0 - 1) * min(r)
+                if (!(sx != 0.0f && sy != 0.0f && sz != 0.0f)) return false;
+                distance = (0.0f - 1.0f) * std::fmin(std::fmin(sx, sy), sz);
+            } else if (t == 2) {  // box: d = |0| - size
+                const float dx = 0.0f - sx, dy = 0.0f - sy, dz = 0.0f - sz;
+                const float mx = std::fmax(dx, 0.0f), my = std::fmax(dy, 0.0f), mz = std::fmax(dz, 0.0f);
+                distance = std::fmin(std::fmax(dx, std::fmax(dy, dz)), 0.0f) + std::sqrt(mx * mx + my * my + mz * mz);
+            } else return false;  // cylinder / spheroid / octagon: evaluated per particle
+            *out = (1.0f - std::fmin(std::fmax(distance / a.AreaFalloff, 0.0f), 1.0f)) * a.Strength;
+            return true;
+        };
         // host-evaluated uniform arithmetic (same fp32 operations as the shaders) and reciprocals for udiv()
         auto rcp = [](float y) { const float a = std::fabs(y); return (a >= 1.0e-30f && a <= 1.0e30f) ? 1.0f / y : 0.0f; };
         const float dtms = u->GlobalSettings.x;
@@ -740,6 +766,7 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
             else if (op.kind == ILB_OP_FMA) { area = &op.u.fma.area; timeDivisor = op.u.fma.TimeDivisor; }
             else { area = &op.u.matrix.area; timeDivisor = op.u.matrix.TimeDivisor; d.timeScale = (timeDivisor >= 0.0f) ? dtms / timeDivisor : 1.0f; }
             if (area) {
+                d.weightIsUniform = hostUniformWeight(*area, &d.uniformWeight) ? 1 : 0;
                 d.rFalloff = rcp(area->AreaFalloff);
                 d.rTimeDivisor = rcp(timeDivisor);
                 for (int c = 0; c < 3; c++) {
