@@ -178,7 +178,7 @@ ILB_DEV void opGravity(const ilb_psys_uniforms& u, const SysDerived& sd, const i
         } else {
             float distanceSquared = xsub(xdot3(toCenter, toCenter), ars.x);
             distanceSquared = fmaxf(distanceSquared, 0.001f);
-            attraction = xdivz(1.0f, distanceSquared);
+            attraction = __frcp_rn(distanceSquared);  // 1 / distanceSquared, correctly rounded (distanceSquared >= 0.001)
         }
         acceleration = xadd3(acceleration, xscale3(xscale3(xnormalize3(toCenter), attraction), ars.y));
     }
@@ -281,6 +281,10 @@ ILB_DEV void computeRenderData(const ilb_psys_uniforms& u, float vx, float vy, f
     renderData.w = velocity.w;
 }
 
+template <bool FLAT>
+ILB_DEV float sampleField(const DFGeometry& g, f3 p) { return FLAT ? sampleDistanceFieldFlat(g, p) : sampleDistanceField(g, p); }
+
+template <bool FLAT>
 ILB_DEV f3 estimateNormal4(const DFGeometry& g, float texelZ, f3 position) {  // VisualizeCommon.fxh:9-63
     const f3 texel = mk3(g.invScaleX, g.invScaleY, texelZ);
     f3 result = mk3(0.0f);
@@ -288,13 +292,13 @@ ILB_DEV f3 estimateNormal4(const DFGeometry& g, float texelZ, f3 position) {  //
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const f3 weight = mk3(wts[i][0], wts[i][1], wts[i][2]);
-        result = xadd3(result, xscale3(weight, sampleDistanceField(g, xadd3(position, xmul3(weight, texel)))));
+        result = xadd3(result, xscale3(weight, sampleField<FLAT>(g, xadd3(position, xmul3(weight, texel)))));
     }
     return xnormalize3(result);
 }
 
 // returns false when the reference pass discards (dead on entry): outputs stay at the cleared zeros
-template <bool COLLIDE>
+template <bool COLLIDE, bool FLAT>
 ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f4 oldVelocity, f4& outP, f4& outV, bool& needAttr) {
     const ilb_psys_uniforms& u = P.u;
     outP = mk4(0.0f);
@@ -324,7 +328,7 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
     f3 collisionPosition = mk3(0.0f), newPosition = op;
     f4 newVelocity = mk4(0.0f);
 
-    const float initialDistance = sampleDistanceField(P.df, op);
+    const float initialDistance = sampleField<FLAT>(P.df, op);
     const bool wasColliding = initialDistance < collisionDistance;
     float travelDistance = fmaxf(0.0f, fminf(initialDistance, xlength3z(scaledVelocity)));
     int stepCount = 3;
@@ -332,7 +336,7 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
     else if (travelDistance <= 0.001f) stepCount = 0;
     for (int i = 0; i < stepCount; i++) {
         const f3 testPosition = xadd3(op, xscale3(unitVector, travelDistance));
-        const float stepDistance = sampleDistanceField(P.df, testPosition);
+        const float stepDistance = sampleField<FLAT>(P.df, testPosition);
         if (stepDistance < collisionDistance) {
             collided = true;
             collisionPosition = testPosition;
@@ -350,7 +354,7 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
         const bool bounce = oldVelocity.w <= 0.0f;
         const bool redirect = wasColliding && !escaping;
         f3 normal = mk3(0.0f);
-        if (bounce || redirect) normal = estimateNormal4(P.df, P.sd.texelZ, collisionPosition);
+        if (bounce || redirect) normal = estimateNormal4<FLAT>(P.df, P.sd.texelZ, collisionPosition);
         const float maxV = u.GlobalSettings.z;
         const float escapeSpeed = fminf(maxV, u.CollisionSettings.x);
         if (redirect) {
@@ -436,7 +440,8 @@ ILB_DEV void stepParticle(const StepParams& P, unsigned gi, f4 pos, f4 vel, f4& 
         if (K1 > 0) applyOp<K1>(P, P.ops[1], P.od[1], x, y, pos, vel);
         if (K2 > 0) applyOp<K2>(P, P.ops[2], P.od[2], x, y, pos, vel);
     }
-    updateTail<COLLIDE>(P, x, y, pos, vel, outP, outV, needAttr);
+    if (COLLIDE && fieldIsFlat(P.df)) updateTail<COLLIDE, true>(P, x, y, pos, vel, outP, outV, needAttr);   // uniform branch
+    else updateTail<COLLIDE, false>(P, x, y, pos, vel, outP, outV, needAttr);
 }
 
 // Direct variant: one thread per particle, 16-byte coalesced global loads / stores.
