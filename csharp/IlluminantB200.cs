@@ -1,0 +1,164 @@
+// IlluminantB200.cs -- P/Invoke binding of libilluminant_b200.so for the reference's C# host (Squared.Illuminant).
+//
+// SOURCE ONLY: this image has no .NET toolchain, so the file is not compiled or tested here; it is the artefact a
+// maintainer drops into Illuminant/ (see INTEGRATION.md for where the calls replace the draw submission).  Struct layouts
+// mirror include/illuminant_b200.h field for field; tests/test_abi.py checks the equivalent ctypes mirror against the
+// header's sizeof/offsetof, and the sizes asserted in the static constructor below are the same numbers.
+// Convention follows the reference's own native binding (Squared.Nuklear/Squared.Nuklear/Nuklear.cs:10-12): Cdecl.
+using System;
+using System.Runtime.InteropServices;
+using Microsoft.Xna.Framework;
+
+namespace Squared.Illuminant.Native {
+    public enum IlbStatus : int {
+        OK = 0, InvalidArgument = -1, Cuda = -2, NoDevice = -3, InvalidOperation = -4, OutOfMemory = -5, Unsupported = -6
+    }
+    public enum IlbFormat : int { Float4 = 0, Half4 = 1, Rgba8 = 2 }
+    public enum IlbOpKind : int { Gravity = 1, Noise = 2, FMA = 3, MatrixMultiply = 4 }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct IlbDFUniforms {                       // ilb_df_uniforms: Uniforms.DistanceField (Uniforms.cs:79-108) + Packed1
+        public Vector4 ConeAndMisc, TextureSliceAndTexelSize, StepAndMisc2, TextureSliceCount, Extent, Packed1;
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct IlbLightBatch {                       // ilb_light_batch: one LightTypeRenderState draw (LightingRenderer.cs:1149-1166)
+        public int LightType, FirstVertex, VertexCount, Reserved;
+        public IlbDFUniforms DF;
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct IlbLightingFrame {                    // ilb_lighting_frame
+        public int Width, Height, LightmapFormat, RowBegin, RowEnd, StencilCulling;
+        public Vector4 EnvironmentZAndScale, EnvironmentZToY, GBufferTexelSizeAndMisc;
+        public float GBufferViewportRelative, ViewportPositionX, ViewportPositionY, Reserved2;
+        public Vector4 ClearColor;
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct IlbObstruction {                      // ilb_obstruction (LightObstruction.Vertex)
+        public int Type;
+        public Vector3 Center, Size;
+        public Vector4 Rotation;
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct IlbPsysUniforms {                     // ilb_psys_uniforms
+        public Vector4 GlobalSettings, CollisionSettings, TexelAndSize, AnimationRateAndRotationAndZToY;   // Uniforms.ParticleSystem
+        public Uniforms.ClampedBezier4 ColorFromLife, ColorFromVelocity;                                   // Bezier.cs:589-600
+        public Uniforms.ClampedBezier1 SizeFromLife, SizeFromVelocity;                                     // Bezier.cs:434-459
+        public Vector4 LifeRampSettings;
+        public Vector2 RotationFromLifeAndIndex;
+        public int HasCollisionField, WriteRenderOutputs;
+        public IlbDFUniforms CollisionField;
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public unsafe struct IlbArea {                      // ilb_area
+        public int AreaType;
+        public Vector3 AreaCenter, AreaSize;
+        public float AreaFalloff, AreaRotation, Strength;
+        public Vector2 CategoryFilter;
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public unsafe struct IlbGravity {                   // ilb_gravity
+        public int AttractorCount;
+        public float MaximumAcceleration;
+        public Vector2 CategoryFilter;
+        public fixed float AttractorPositions[16 * 4];
+        public fixed float AttractorRadiusesAndStrengths[16 * 4];
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct IlbNoise {                            // ilb_noise
+        public IlbArea Area;
+        public float TimeDivisor, FrequencyLerp, ReplaceOldVelocity, Reserved;
+        public Vector2 RandomnessOffset, NextRandomnessOffset, RandomnessTexel;
+        public Vector4 PositionOffset, PositionMinimum, PositionScale, VelocityOffset, VelocityMinimum, VelocityScale;
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct IlbFMA {                              // ilb_fma
+        public IlbArea Area;
+        public float TimeDivisor, Reserved0, Reserved1, Reserved2;
+        public Vector4 PositionAdd, PositionMultiply, VelocityAdd, VelocityMultiply;
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct IlbMatrixMultiply {                   // ilb_matrix_multiply
+        public IlbArea Area;
+        public float TimeDivisor, Reserved0, Reserved1, Reserved2;
+        public Matrix PositionMatrix, VelocityMatrix;   // XNA Matrix is row-major M11..M44, row-vector convention
+    }
+
+    [StructLayout(LayoutKind.Explicit, Size = 16 + 528)]
+    public struct IlbOp {                               // ilb_op: 16-byte header + union (largest member: ilb_gravity, 528 B)
+        [FieldOffset(0)] public int Kind;
+        [FieldOffset(16)] public IlbGravity Gravity;
+        [FieldOffset(16)] public IlbNoise Noise;
+        [FieldOffset(16)] public IlbFMA FMA;
+        [FieldOffset(16)] public IlbMatrixMultiply Matrix;
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public unsafe struct IlbSpawn {                     // ilb_spawn
+        public int Chunk, Reserved0, Reserved1, Reserved2;
+        public Vector4 ChunkSizeAndIndices;
+        public fixed float Configuration[9 * 4];
+        public Vector4 FormulaTypes;
+        public fixed float InlinePositionConstants[4 * 4];
+        public Matrix PositionMatrix, VelocityMatrix;
+        public Vector2 RandomnessOffset, RandomnessTexel;
+        public Vector3 AxisMask;
+        public float AlignVelocityAndPosition, PositionConstantCount, PolygonRate, PolygonLoop, AttributeDiscardThreshold;
+    }
+
+    public static unsafe class B200 {
+        public const string DllName = "illuminant_b200";
+        const CallingConvention CC = CallingConvention.Cdecl;
+
+        static B200 () {
+            // same numbers tests/test_abi.py verifies for the ctypes mirror
+            if (Marshal.SizeOf(typeof(LightVertex)) != 128 || Marshal.SizeOf(typeof(IlbDFUniforms)) != 96 ||
+                Marshal.SizeOf(typeof(IlbLightBatch)) != 112 || Marshal.SizeOf(typeof(IlbOp)) != 544)
+                throw new InvalidOperationException("illuminant_b200 struct layout mismatch");
+        }
+
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_abi_version ();
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_create (int deviceOrdinal, out IntPtr ctx);
+        [DllImport(DllName, CallingConvention = CC)] public static extern void ilb_destroy (IntPtr ctx);
+        [DllImport(DllName, CallingConvention = CC)] public static extern IntPtr ilb_last_error (IntPtr ctx);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_synchronize (IntPtr ctx);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_df_create (IntPtr ctx, int w, int h, void* rgba64, UIntPtr bytes, out IntPtr df);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_df_generate (IntPtr ctx, int w, int h, int sliceW, int sliceH, int sliceCount, ref IlbDFUniforms u, IlbObstruction* obstructions, int count, out IntPtr df);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_df_download (IntPtr df, void* rgba64, UIntPtr bytes);
+        [DllImport(DllName, CallingConvention = CC)] public static extern void ilb_df_destroy (IntPtr df);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_gbuffer_upload (IntPtr ctx, int w, int h, int format, void* data);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_render_lighting (IntPtr ctx, IntPtr df, ref IlbLightingFrame frame, IlbLightBatch* batches, int batchCount, LightVertex* vertices, int vertexCount, void* lightmapOut);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_update_light_probes (IntPtr ctx, IntPtr df, ref IlbLightingFrame frame, IlbLightBatch* batches, int batchCount, LightVertex* vertices, int vertexCount, Vector4* probePositions, Vector4* probeNormals, int probeCount, int outputFormat, void* probesOut);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_create (IntPtr ctx, int chunkSize, int maxChunks, out IntPtr psys);
+        [DllImport(DllName, CallingConvention = CC)] public static extern void ilb_particles_destroy (IntPtr psys);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_set_randomness (IntPtr psys, Vector4* table, int w, int h);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_set_collision_field (IntPtr psys, IntPtr df);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_set_live_chunks (IntPtr psys, int count);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_upload_chunk (IntPtr psys, int chunk, Vector4* positionAndLife, Vector4* velocity, Vector4* attributes);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_download_chunk (IntPtr psys, int chunk, Vector4* positionAndLife, Vector4* velocity, Vector4* attributes, Vector4* renderColor, Vector4* renderData);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_step (IntPtr psys, ref IlbPsysUniforms uniforms, IlbSpawn* spawns, int spawnCount, IlbOp* ops, int opCount, int steps);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_count_live (IntPtr psys, out long count);
+
+        /// <summary>Maps an ilb_status to the exception type the reference throws at the same place.</summary>
+        public static void Check (IntPtr ctx, int status) {
+            if (status == 0)
+                return;
+            var message = Marshal.PtrToStringAnsi(ilb_last_error(ctx));
+            switch ((IlbStatus)status) {
+                case IlbStatus.InvalidArgument: throw new ArgumentException(message);
+                case IlbStatus.InvalidOperation: throw new InvalidOperationException(message);   // ParticleSystem.cs:642, :836
+                case IlbStatus.OutOfMemory: throw new OutOfMemoryException(message);
+                case IlbStatus.Unsupported: throw new NotImplementedException(message);          // LightingRenderer.cs:203
+                default: throw new Exception(message);
+            }
+        }
+    }
+}
