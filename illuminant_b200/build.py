@@ -14,7 +14,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libilluminant_b200.so"
-SOURCES = ["api.cu", "lighting.cu", "particles.cu", "dfgen.cu"]
+SOURCES = ["api.cu", "lighting.cu", "particles.cu", "dfgen.cu", "planes.cu"]
 HEADERS = ["ilb_device.cuh", "ilb_internal.h", "ilb_shapes.cuh", "../../include/illuminant_b200.h"]
 
 # FMA contraction on, 2-ulp division / sqrt (MUFU based), denormals flushed; sin/cos/pow/atan2/acos stay the accurate

@@ -222,6 +222,7 @@ void ilb_df_destroy(ilb_df* df) {
         if (ps->field == df) ps->field = nullptr;
     cudaSetDevice(df->ctx->device);
     cudaStreamSynchronize(df->ctx->stream);
+    ilb_planes_release(df);
     if (df->tex) cudaFree(df->tex);
     delete df;
 }

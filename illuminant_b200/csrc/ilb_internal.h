@@ -37,10 +37,21 @@ struct ilb_ctx {
     size_t d_probe_in_capacity = 0;
 };
 
+#define ILB_MAX_VIRTUAL_SLICES 64
+
+// one cached set of expanded planes (planes.cu), keyed by the addressing uniforms it was built for
+struct ilb_df_planes {
+    float key[10];
+    float4* planes = nullptr;
+    float4* vtab = nullptr;
+    int pitch = 0;
+};
+
 struct ilb_df {
     ilb_ctx* ctx = nullptr;
     uint2* tex = nullptr;
     int tw = 0, th = 0;
+    std::vector<ilb_df_planes> planes;
 };
 
 struct ilb_psys {
@@ -70,6 +81,9 @@ int ilb_reserve(ilb_ctx* ctx, void** ptr, size_t* capacity, size_t bytes, bool p
 // Fills a DFGeometry from the reference uniform block; returns false when Extent.x <= 0 (no field).
 bool ilb_make_df_geometry(const ilb_df* df, const ilb_df_uniforms& u, DFGeometry* out);
 
+// planes.cu
+int ilb_planes_attach(ilb_ctx* ctx, ilb_df* df, const ilb_df_uniforms& u, DFGeometry* g);
+void ilb_planes_release(ilb_df* df);
 // lighting.cu
 int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches,
                         int batch_count, const ilb_light_vertex* vertices, int vertex_count, void* const* d_outputs,

@@ -40,9 +40,18 @@ struct __align__(16) DLight {
     float longStep;                          // LongStepFactor
     int hasField;                            // batch.df.Extent.x > 0 && a field is bound
     int type;                                // ilb_light_type
-    int pad;
+    float rcpRamp;                           // RN(1 / LightProperties.y) for udiv(), 0 when that is not a safe normal number
     float4 covX, covY;                       // coverage edges, see coverage()
     int px0, py0, px1, py1;                  // conservative pixel bounds of the quad (inclusive)
+};
+
+// Per-light values of the line-light shaders that do not depend on the pixel, evaluated once on the host with the same
+// IEEE fp32 operations (flattenLights): normalize(P1 - P0), lerp(P0, P1, 0.5), P1 - P0 and its squared / plain length,
+// the reciprocal of the squared length for udiv(), and lineConeTrace's `offset`.  Indexed like the DLight array.
+struct __align__(16) DLine {
+    float4 left;    // lightLeft.xyz, RN(1 / dot(ab, ab)) for udiv() (0 when that is not a safe normal number)
+    float4 center;  // lightCenter.xyz, offset = max(saturate((radius + 1) / |P1 - P0|), 0.03)
+    float4 ab;      // (P1 - P0).xyz, dot(ab, ab)
 };
 
 struct LightingParams {
@@ -52,6 +61,7 @@ struct LightingParams {
     const void* gbuffer;
     int gw, gh, gfmt;
     const DLight* lights;
+    const DLine* lines;   // per-light line constants (valid for line lights)
     int nlights;
     int width, height, row_begin, row_end;
     int out_format, stencil;
@@ -67,6 +77,10 @@ struct Pixel {
 };
 
 // ---- cone trace (ConeTrace.fxh) --------------------------------------------------------------------------
+// Template parameters used throughout the per-light code:
+//   FIELD  0 = sample the Rgba64 atlas, 1 = sample the expanded planes (ilb_device.cuh); bit-identical results
+//   FAST   true = sqrt / reciprocal through the deferred-guard forms (`bad` collects the range checks; when it comes
+//          back set the caller re-evaluates the light with FAST = false), false = plain IEEE x-ops
 #define MIN_CONE_RADIUS 0.33f
 #define MAX_STEP_RAMP_WINDOW 2.0f
 #define TRACE_INITIAL_OFFSET_PX 0.5f
@@ -97,9 +111,10 @@ struct Trace {  // TraceState :31-35
 };
 
 // returns true when the marched interval t < len stays on the segment start -> end
-ILB_DEV bool traceInit(Trace& s, f3 start, f3 end, float lightRadius) {  // coneTraceInitialize :37-49
+template <bool FAST>
+ILB_DEV bool traceInit(Trace& s, f3 start, f3 end, float lightRadius, bool& bad) {  // coneTraceInitialize :37-49
     const f3 v = xsub3(end, start);
-    const float l = xlength3(v);
+    const float l = tlength3<FAST>(v, bad);
     s.origin = start;
     s.direction = xdivs3(v, l);
     s.len = fmaxf(xsub(l, lightRadius), 1.0f);
@@ -120,34 +135,44 @@ ILB_DEV float traceFinal(const TraceConfig& c, float visibility) {  // :182-188
                 c.power);
 }
 
-ILB_DEV float coneTrace(const DFGeometry& g, const DLight& L, f3 lightCenter, float rampX, float rampY,
-                        float growthFactor, f3 shaded, bool enable) {  // coneTrace :141-191
-    Trace a;
-    const bool onSegment = traceInit(a, shaded, lightCenter, rampX);
-    const TraceConfig c = makeTraceConfig(L, rampX, rampY, growthFactor);
-    float stepsRemaining = c.stepLimit;
-    float liveness = (L.hasField && enable) ? 1.0f : 0.0f;
-    // every sample lies on the segment shaded -> lightCenter (t < len <= |v|); the field volume is convex, so when both
-    // ends are inside every sample is inside and the clamp / distance-to-volume work of the sampler is skipped
-    const bool inside = onSegment && insideField(g, shaded) && insideField(g, lightCenter);
+template <int FIELD, bool INSIDE>
+ILB_DEV void coneTraceMarch(const DFGeometry& g, const TraceConfig& c, Trace& a, float& stepsRemaining) {
+    float liveness = 1.0f;
     while (liveness > 0.0f) {
         stepsRemaining -= 1.0f;
         const f3 sp = xadd3(a.origin, xscale3(a.direction, a.t));  // coneTraceAdvance :73-82
-#if ILB_NO_INSIDE_PATH
-        const float d = sampleDistanceFieldT<false>(g, sp);
-#else
-        const float d = inside ? sampleDistanceFieldT<true>(g, sp) : sampleDistanceFieldT<false>(g, sp);
-#endif
+        const float d = sampleFieldT<FIELD, INSIDE>(g, sp);
         a.t = xadd(a.t, traceStep(c, d, a.t, a.vis));
         const float stepLiveness = saturatef(a.vis - FULLY_SHADOWED_THRESHOLD) * saturatef(xsub(a.len, a.t));
         liveness = stepsRemaining * stepLiveness;
+    }
+}
+
+template <int FIELD, bool FAST>
+ILB_DEV float coneTrace(const DFGeometry& g, const DLight& L, f3 lightCenter, float rampX, float rampY,
+                        float growthFactor, f3 shaded, bool enable, bool& bad) {  // coneTrace :141-191
+    Trace a;
+    const bool onSegment = traceInit<FAST>(a, shaded, lightCenter, rampX, bad);
+    const TraceConfig c = makeTraceConfig(L, rampX, rampY, growthFactor);
+    float stepsRemaining = c.stepLimit;
+    if (L.hasField && enable) {
+        // every sample lies on the segment shaded -> lightCenter (t < len <= |v|); the field volume is convex, so when both
+        // ends are inside every sample is inside and the clamp / distance-to-volume work of the sampler is skipped
+        const bool inside = onSegment && insideField(g, shaded) && insideField(g, lightCenter);
+#if ILB_NO_INSIDE_PATH
+        coneTraceMarch<FIELD, false>(g, c, a, stepsRemaining);
+#else
+        if (inside) coneTraceMarch<FIELD, true>(g, c, a, stepsRemaining);
+        else coneTraceMarch<FIELD, false>(g, c, a, stepsRemaining);
+#endif
     }
     const float visibility = fminf(a.vis, stepsRemaining / MAX_STEP_RAMP_WINDOW);
     return enable ? traceFinal(c, visibility) : 1.0f;
 }
 
+template <int FIELD, bool INSIDE>
 ILB_DEV float traceAdvanceEx(const DFGeometry& g, const TraceConfig& c, Trace& s) {  // coneTraceAdvanceEx :84-96
-    const float d = sampleDistanceField(g, xadd3(s.origin, xscale3(s.direction, s.t)));
+    const float d = sampleFieldT<FIELD, INSIDE>(g, xadd3(s.origin, xscale3(s.direction, s.t)));
     s.t = fminf(xadd(s.t, traceStep(c, d, s.t, s.vis)), s.len);
     return saturatef(s.vis - FULLY_SHADOWED_THRESHOLD) * saturatef(xsub(s.len, s.t) * TRACE_END_MULTIPLIER);
 }
@@ -155,21 +180,25 @@ ILB_DEV float traceAdvanceEx(const DFGeometry& g, const TraceConfig& c, Trace& s
 // ---- light response (LightCommon.fxh, AOCommon.fxh) ---------------------------------------------------------
 #define DOT_EXPONENT 0.85f
 
-ILB_DEV float normalFactorEx(f3 lightNormal, f3 n, float offset, float range) {  // computeNormalFactorEx :154-165
+template <int RANGE_1000>  // offset == range == RANGE_1000 / 1000 (0.15 for sphere lights, 0.35 for directional lights)
+ILB_DEV float normalFactorEx(f3 lightNormal, f3 n) {  // computeNormalFactorEx :154-165
     if (!any3(n)) return 1.0f;
+    constexpr float range = (float)RANGE_1000 / 1000.0f;
+    static_assert(RANGE_1000 == 150 || RANGE_1000 == 350, "the two call sites of the reference");
     const float d = xdot3(-lightNormal, n);  // exact: its sign decides `visible` (discard / alpha count)
-    return powf(saturatef(xdiv(xadd(d, offset), range)), DOT_EXPONENT);
+    return powf(saturatef(udiv(xadd(d, range), range, 1.0f / range)), DOT_EXPONENT);
 }
 
-ILB_DEV float sphereLightOpacity(float lightOcclusion, f3 p, f3 n, f3 center, float4 props, float yFactor) {  // :173-210
+template <bool FAST>
+ILB_DEV float sphereLightOpacity(float lightOcclusion, f3 p, f3 n, f3 center, float4 props, float yFactor, float rRamp, bool& bad) {  // :173-210
     // x-ops: where this falloff reaches exactly 0 the fragment is discarded, which changes the lightmap's alpha count
     f3 d3 = xsub3(p, center);
     d3.y = xmul(d3.y, yFactor);
-    const float distance = xlength3(d3);
-    float distanceFactor = xsub(1.0f, saturatef(xdiv(xsub(distance, props.x), props.y)));
+    const float distance = tlength3<FAST>(d3, bad);
+    float distanceFactor = xsub(1.0f, saturatef(udiv(xsub(distance, props.x), props.y, rRamp)));
     if (lightOcclusion > 0.0f) distanceFactor = xmul(distanceFactor, xsub(1.0f, saturatef(xdiv(d3.z, lightOcclusion))));
     const f3 lightNormal = xdivs3(d3, distance);
-    float normalFactor = normalFactorEx(lightNormal, n, 0.15f, 0.15f);
+    float normalFactor = normalFactorEx<150>(lightNormal, n);
     if (props.z >= 2.0f) {
         distanceFactor = xsub(1.0f, saturatef(xsub(distance, props.x)));
         normalFactor = 1.0f;
@@ -179,9 +208,10 @@ ILB_DEV float sphereLightOpacity(float lightOcclusion, f3 p, f3 n, f3 center, fl
     return saturatef(xadd(xmul(normalFactor, distanceFactor), saturatef(xsub(props.x, distance))));
 }
 
+template <int FIELD>
 ILB_DEV float computeAO(const DFGeometry& g, bool hasField, f3 p, f3 n, float aoRadius, float aoOpacity, bool visible) {  // AOCommon.fxh:1-20
     if ((aoRadius >= 0.5f) && hasField && visible) {
-        const float distance = sampleDistanceField(g, xadd3(p, mk3(0.0f, 0.0f, xmul(n.z, aoRadius))));
+        const float distance = sampleFieldT<FIELD, false>(g, xadd3(p, mk3(0.0f, 0.0f, xmul(n.z, aoRadius))));
         const float clampedDistance = clampf(distance, 0.0f, aoRadius);
         float result = 1.0f - saturatef(clampedDistance / aoRadius);
         result *= result;
@@ -192,113 +222,127 @@ ILB_DEV float computeAO(const DFGeometry& g, bool hasField, f3 p, f3 n, float ao
 }
 
 // SphereLightPixelCore (SphereLightCore.fxh:58-158); returns false on discard
+template <int FIELD, bool FAST>
 ILB_DEV bool sphereCore(const DFGeometry& g, const DLight& L, float lightOcclusion, f3 p, f3 n, f3 center, float4 props,
-                        float4 more, float& opacity) {
-    const float distanceOpacity = sphereLightOpacity(lightOcclusion, p, n, center, props, more.z);
+                        float4 more, float& opacity, bool& bad) {
+    const float distanceOpacity = sphereLightOpacity<FAST>(lightOcclusion, p, n, center, props, more.z, L.rcpRamp, bad);
     const bool visible = (distanceOpacity > 0.0f) && (p.x > -9999.0f);
     if (!visible) return false;
     const float aoRadius = xmul(more.x, fmaxf(0.0f, n.z));
-    const float aoOpacity = computeAO(g, L.hasField != 0, p, n, aoRadius, more.w, visible);
+    const float aoOpacity = computeAO<FIELD>(g, L.hasField != 0, p, n, aoRadius, more.w, visible);
     const float preTraceOpacity = distanceOpacity * aoOpacity;
     const bool traceShadows = (props.w != 0.0f) && (preTraceOpacity >= (0.75f / 255.0f));
-    const float coneOpacity = coneTrace(g, L, center, props.x, props.y, 1.0f, xadd3(p, xscale3(n, 1.6f)), traceShadows);
+    const float coneOpacity = coneTrace<FIELD, FAST>(g, L, center, props.x, props.y, 1.0f, xadd3(p, xscale3(n, 1.6f)), traceShadows, bad);
     opacity = preTraceOpacity * coneOpacity;
     return true;
 }
 
 // DirectionalLightPixelCore (DirectionalLight.fx:52-93, useOpacityRamp = false)
+template <int FIELD, bool FAST>
 ILB_DEV bool directionalCore(const DFGeometry& g, const DLight& L, f3 p, f3 n, float4 dir, float4 props, float4 more,
-                             float& opacity) {
-    float lightOpacity = (dir.w < 0.1f) ? 1.0f : normalFactorEx(mk3(dir.x, dir.y, dir.z), n, 0.35f, 0.35f);
+                             float& opacity, bool& bad) {
+    float lightOpacity = (dir.w < 0.1f) ? 1.0f : normalFactorEx<350>(mk3(dir.x, dir.y, dir.z), n);
     const bool visible = (p.x > -9999.0f);
     const float aoRadius = xmul(more.x, fmaxf(0.0f, n.z));
-    lightOpacity *= computeAO(g, L.hasField != 0, p, n, aoRadius, more.w, visible);
+    lightOpacity *= computeAO<FIELD>(g, L.hasField != 0, p, n, aoRadius, more.w, visible);
     const bool traceShadows = visible && (props.x != 0.0f) && (lightOpacity >= 1.0f / 256.0f) && (dir.w >= 0.1f);
     const f3 fakeLightCenter = xsub3(p, xscale3(mk3(dir.x, dir.y, dir.z), props.y));
-    lightOpacity *= coneTrace(g, L, fakeLightCenter, props.z, more.y, props.w, xadd3(p, xscale3(n, 1.5f)), traceShadows);
+    lightOpacity *= coneTrace<FIELD, FAST>(g, L, fakeLightCenter, props.z, more.y, props.w, xadd3(p, xscale3(n, 1.5f)), traceShadows, bad);
     if (!visible) return false;
     opacity = lightOpacity;
     return true;
 }
 
 // ---- line light (FBPBR.fxh:33-101, LineLightCore.fxh:17-120) -------------------------------------------------
-ILB_DEV f3 closestPointOnLineSegment3(f3 a, f3 b, f3 pt, float& t) {  // DistanceFieldCommon.fxh:151-155
-    const f3 ab = xsub3(b, a);  // exact: u places the three trace targets of a line light
-    t = saturatef(xdiv(xdot3(xsub3(pt, a), ab), xdot3(ab, ab)));
-    return xadd3(a, xscale3(ab, t));
-}
-
 // x-ops: the solid angle is a difference of four arc-cosines that nearly cancel (g0+g1+g2+g3 - 2*pi), so a few ulp in
 // the normalised cross products change the illuminance by far more than 1e-4 relative -- keep it bit-identical.
-ILB_DEV float rectangleSolidAngle(f3 wp, f3 p0, f3 p1, f3 p2, f3 p3) {  // FBPBR.fxh:33-51
-    const f3 v0 = xsub3(p0, wp), v1 = xsub3(p1, wp), v2 = xsub3(p2, wp), v3 = xsub3(p3, wp);
-    const f3 n0 = xnormalize3(xcross3(v0, v1)), n1 = xnormalize3(xcross3(v1, v2));
-    const f3 n2 = xnormalize3(xcross3(v2, v3)), n3 = xnormalize3(xcross3(v3, v0));
-#if 1  // deterministic acos (include/ilb_detmath.h): the four angles nearly cancel, so both sides must evaluate the same function
-    const float g0 = dm_acosf(xdot3(-n0, n1)), g1 = dm_acosf(xdot3(-n1, n2));
-    const float g2 = dm_acosf(xdot3(-n2, n3)), g3 = dm_acosf(xdot3(-n3, n0));
-#else  // CUDA's acosf: within 2 ulp of the oracle's; the deterministic variant costs 20 % of the frame for no parity gain
-    const float g0 = acosf(xdot3(-n0, n1)), g1 = acosf(xdot3(-n1, n2));
-    const float g2 = acosf(xdot3(-n2, n3)), g3 = acosf(xdot3(-n3, n0));
-#endif
+template <bool FAST>
+ILB_DEV float acosExact(float x, bool& bad) {  // dm_acosf (include/ilb_detmath.h) with the sqrt of this build
+    return dm_acos_finish(x, tsqrt<FAST>(xsub(1.0f, fabsf(x)), bad));
+}
+template <bool FAST>
+ILB_DEV float rectangleSolidAngle(f3 v0, f3 v1, f3 v2, f3 v3, bool& bad) {  // FBPBR.fxh:33-51, v_i = p_i - worldPos
+    const f3 n0 = tnormalize3<FAST>(xcross3(v0, v1), bad), n1 = tnormalize3<FAST>(xcross3(v1, v2), bad);
+    const f3 n2 = tnormalize3<FAST>(xcross3(v2, v3), bad), n3 = tnormalize3<FAST>(xcross3(v3, v0), bad);
+    // deterministic acos: the four angles nearly cancel, so both sides must evaluate the same function
+    const float g0 = acosExact<FAST>(xdot3(-n0, n1), bad), g1 = acosExact<FAST>(xdot3(-n1, n2), bad);
+    const float g2 = acosExact<FAST>(xdot3(-n2, n3), bad), g3 = acosExact<FAST>(xdot3(-n3, n0), bad);
     return xsub(xadd(xadd(xadd(g0, g1), g2), g3), xmul(2.0f, ILB_PI));
 }
 
-ILB_DEV float lineLightOpacity(f3 wp, f3 wn, f3 P0, f3 P1, float lightRadius, f3& spherePosition, float& u) {  // :53-101
-    const f3 lightLeft = xnormalize3(xsub3(P1, P0));
-    const f3 lightCenter = xlerp3(P0, P1, 0.5f);
-    spherePosition = closestPointOnLineSegment3(P0, P1, wp, u);
-    const f3 forward = xnormalize3(xsub3(spherePosition, wp));
+template <bool FAST>
+ILB_DEV float lineLightOpacity(f3 wp, f3 wn, f3 P0, f3 P1, float lightRadius, const DLine& D, f3& spherePosition, float& u, bool& bad) {  // FBPBR.fxh:53-101
+    const f3 lightLeft = xyz(mk4(D.left)), lightCenter = xyz(mk4(D.center)), ab = xyz(mk4(D.ab));
+    // closestPointOnLineSegment3 DistanceFieldCommon.fxh:151-155 (exact: u places the three trace targets)
+    u = saturatef(udiv(xdot3(xsub3(wp, P0), ab), D.ab.w, D.left.w));
+    spherePosition = xadd3(P0, xscale3(ab, u));
+    const f3 sphereUnormL = xsub3(spherePosition, wp);
+    const float sqrSphereDistance = xdot3(sphereUnormL, sphereUnormL);
+    const f3 forward = tnormalize3<FAST>(sphereUnormL, bad);  // == sphereL
     const f3 up = xcross3(lightLeft, forward);
     const f3 ru = xscale3(up, lightRadius);
     const f3 p0 = xadd3(P0, ru), p1 = xsub3(P0, ru);
     const f3 p2 = xsub3(P1, ru), p3 = xadd3(P1, ru);
-    const float solidAngle = rectangleSolidAngle(wp, p0, p1, p2, p3);
-    const float sum = xadd(xadd(xadd(xadd(saturatef(xdot3(xnormalize3(xsub3(p0, wp)), wn)), saturatef(xdot3(xnormalize3(xsub3(p1, wp)), wn))),
-                                     saturatef(xdot3(xnormalize3(xsub3(p2, wp)), wn))),
-                                saturatef(xdot3(xnormalize3(xsub3(p3, wp)), wn))),
-                           saturatef(xdot3(xnormalize3(xsub3(lightCenter, wp)), wn)));
+    const f3 v0 = xsub3(p0, wp), v1 = xsub3(p1, wp), v2 = xsub3(p2, wp), v3 = xsub3(p3, wp);
+    const float solidAngle = rectangleSolidAngle<FAST>(v0, v1, v2, v3, bad);
+    const float sum = xadd(xadd(xadd(xadd(saturatef(xdot3(tnormalize3<FAST>(v0, bad), wn)), saturatef(xdot3(tnormalize3<FAST>(v1, bad), wn))),
+                                     saturatef(xdot3(tnormalize3<FAST>(v2, bad), wn))),
+                                saturatef(xdot3(tnormalize3<FAST>(v3, bad), wn))),
+                           saturatef(xdot3(tnormalize3<FAST>(xsub3(lightCenter, wp), bad), wn)));
     float illuminance = xmul(xmul(solidAngle, 0.2f), sum);
-    const f3 sphereUnormL = xsub3(spherePosition, wp);
-    const f3 sphereL = xnormalize3(sphereUnormL);
-    const float sqrSphereDistance = xdot3(sphereUnormL, sphereUnormL);
-    const float illuminanceSphere = xmul(xmul(ILB_PI, saturatef(xdot3(sphereL, wn))), xdiv(xmul(lightRadius, lightRadius), sqrSphereDistance));
+    const float illuminanceSphere = xmul(xmul(ILB_PI, saturatef(xdot3(forward, wn))), xdiv(xmul(lightRadius, lightRadius), sqrSphereDistance));
     illuminance = xadd(illuminance, illuminanceSphere);
     return saturatef(illuminance);
 }
 
-ILB_DEV float lineConeTrace(const DFGeometry& g, const DLight& L, f3 start, f3 end, float u, float rampX, float rampY,
-                            f3 shaded, bool enable) {  // LineLightCore.fxh:17-68
-    Trace a, b, c;
-    const f3 delta = xsub3(end, start);
-    const float deltaLength = xlength3(delta);
-    const float offset = fmaxf(saturatef(xdiv(xadd(rampX, 1.0f), deltaLength)), 0.03f);
-    traceInit(a, shaded, xadd3(start, xscale3(delta, saturatef(xsub(u, offset)))), rampX);
-    traceInit(b, shaded, xadd3(start, xscale3(delta, u)), rampX);
-    traceInit(c, shaded, xadd3(start, xscale3(delta, saturatef(xadd(u, offset)))), rampX);
-    const TraceConfig cfg = makeTraceConfig(L, rampX, rampY, 1.0f);
-    float stepsRemaining = cfg.stepLimit;
-    float liveness = (L.hasField && enable) ? 1.0f : 0.0f;
+template <int FIELD, bool INSIDE>
+ILB_DEV void lineTraceMarch(const DFGeometry& g, const TraceConfig& cfg, Trace& a, Trace& b, Trace& c, float& stepsRemaining) {
+    float liveness = 1.0f;
     while (liveness > 0.0f) {
-        const float stepLiveness = traceAdvanceEx(g, cfg, a) + traceAdvanceEx(g, cfg, b) + traceAdvanceEx(g, cfg, c);
+        const float stepLiveness = traceAdvanceEx<FIELD, INSIDE>(g, cfg, a) + traceAdvanceEx<FIELD, INSIDE>(g, cfg, b) + traceAdvanceEx<FIELD, INSIDE>(g, cfg, c);
         stepsRemaining -= 1.0f;
         liveness = stepsRemaining * stepLiveness;
+    }
+}
+
+template <int FIELD, bool FAST>
+ILB_DEV float lineConeTrace(const DFGeometry& g, const DLight& L, const DLine& D, f3 start, float u, float rampX, float rampY,
+                            f3 shaded, bool enable, bool& bad) {  // LineLightCore.fxh:17-68
+    Trace a, b, c;
+    const f3 delta = xyz(mk4(D.ab));
+    const float offset = D.center.w;
+    const f3 ta = xadd3(start, xscale3(delta, saturatef(xsub(u, offset)))), tb = xadd3(start, xscale3(delta, u));
+    const f3 tc = xadd3(start, xscale3(delta, saturatef(xadd(u, offset))));
+    const bool sa = traceInit<FAST>(a, shaded, ta, rampX, bad), sb = traceInit<FAST>(b, shaded, tb, rampX, bad);
+    const bool sc = traceInit<FAST>(c, shaded, tc, rampX, bad);
+    const TraceConfig cfg = makeTraceConfig(L, rampX, rampY, 1.0f);
+    float stepsRemaining = cfg.stepLimit;
+    if (L.hasField && enable) {
+        // t is clamped to len <= |target - shaded| for all three traces: samples stay on their segments
+        const bool inside = sa && sb && sc && insideField(g, shaded) && insideField(g, ta) && insideField(g, tb) && insideField(g, tc);
+#if ILB_NO_INSIDE_PATH
+        lineTraceMarch<FIELD, false>(g, cfg, a, b, c, stepsRemaining);
+#else
+        if (inside) lineTraceMarch<FIELD, true>(g, cfg, a, b, c, stepsRemaining);
+        else lineTraceMarch<FIELD, false>(g, cfg, a, b, c, stepsRemaining);
+#endif
     }
     const float visibility = fminf((a.vis + b.vis + c.vis) / 3.0f, stepsRemaining / MAX_STEP_RAMP_WINDOW);
     return enable ? traceFinal(cfg, visibility) : 1.0f;
 }
 
-ILB_DEV bool lineCore(const DFGeometry& g, const DLight& L, f3 p, f3 n, f3 start, f3 end, float4 props, float4 more,
-                      float& u, float& opacity) {  // LineLightPixelCore :70-120
+template <int FIELD, bool FAST>
+ILB_DEV bool lineCore(const DFGeometry& g, const DLight& L, const DLine& D, f3 p, f3 n, f3 start, f3 end, float4 props, float4 more,
+                      float& u, float& opacity, bool& bad) {  // LineLightPixelCore :70-120
     f3 lightCenter;
-    const float distanceOpacity = lineLightOpacity(p, n, start, end, props.x, lightCenter, u);
+    const float distanceOpacity = lineLightOpacity<FAST>(p, n, start, end, props.x, D, lightCenter, u, bad);
     const bool visible = (distanceOpacity > 0.0f) && (p.x > -9999.0f);
     if (!visible) return false;
     const float aoRadius = xmul(more.x, fmaxf(0.0f, n.z));
-    const float aoOpacity = computeAO(g, L.hasField != 0, p, n, aoRadius, more.w, visible);
+    const float aoOpacity = computeAO<FIELD>(g, L.hasField != 0, p, n, aoRadius, more.w, visible);
     const float preTraceOpacity = distanceOpacity * aoOpacity;
     const bool traceShadows = (props.w != 0.0f) && (preTraceOpacity >= (0.75f / 255.0f));
-    const float coneOpacity = lineConeTrace(g, L, start, end, u, props.x, props.y, xadd3(p, xscale3(n, 1.5f)), traceShadows);
+    const float coneOpacity = lineConeTrace<FIELD, FAST>(g, L, D, start, u, props.x, props.y, xadd3(p, xscale3(n, 1.5f)), traceShadows, bad);
     opacity = preTraceOpacity * coneOpacity;
     return true;
 }
@@ -390,8 +434,25 @@ ILB_DEV bool shadowFilterRejects(float filter, bool enableShadows) {  // checkSh
     return (filter > 0.5f) != enableShadows;
 }
 
+ILB_DEV DLight loadLight(const DLight* lights, int i) {
+    DLight L;
+    const float4* src = reinterpret_cast<const float4*>(lights + i);
+    float4* dst = reinterpret_cast<float4*>(&L);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(DLight) / 16); k++) dst[k] = __ldg(src + k);
+    return L;
+}
+ILB_DEV DLine loadLine(const DLine* lines, int i) {
+    DLine D;
+    const float4* src = reinterpret_cast<const float4*>(lines + i);
+    D.left = __ldg(src); D.center = __ldg(src + 1); D.ab = __ldg(src + 2);
+    return D;
+}
+
 // One light at one pixel; returns false when the reference fragment would be discarded.
-ILB_DEV bool shadeLight(const LightingParams& P, const DLight& L, const Pixel& px, f3& rgb) {
+template <int FIELD, bool FAST>
+ILB_DEV bool shadeLight(const DFGeometry& df, float lightOcclusion, const DLight& L, const DLine* lines, int lightIndex, const Pixel& px,
+                        f3& rgb, bool& bad) {
     const float es = px.enableShadows ? 1.0f : 0.0f;
     if (L.type == ILB_LIGHT_SPHERE) {  // SphereLightPixelShader SphereLight.fx:7-46
         if (px.fullbright || shadowFilterRejects(L.evenMore.x, px.enableShadows)) return false;
@@ -399,7 +460,7 @@ ILB_DEV bool shadeLight(const LightingParams& P, const DLight& L, const Pixel& p
         props.w *= es;
         const f3 center = mk3(L.pos1.x, L.pos1.y, L.pos1.z);
         float opacity;
-        if (!sphereCore(P.df, L, P.envZToY.z, px.pos, px.normal, center, props, L.more, opacity)) return false;
+        if (!sphereCore<FIELD, FAST>(df, L, lightOcclusion, px.pos, px.normal, center, props, L.more, opacity, bad)) return false;
         const float4 color = L.color1, spec = L.color2;
         rgb = (mk3(color.x, color.y, color.z) * color.w * opacity);
         if (any3(mk3(spec.x, spec.y, spec.z))) {  // CalcSphereLightSpecularity LightCommon.fxh:212-222
@@ -414,7 +475,7 @@ ILB_DEV bool shadeLight(const LightingParams& P, const DLight& L, const Pixel& p
         float4 props = L.props;
         props.x *= es;
         float opacity;
-        if (!directionalCore(P.df, L, px.pos, px.normal, L.color2, props, L.more, opacity)) return false;
+        if (!directionalCore<FIELD, FAST>(df, L, px.pos, px.normal, L.color2, props, L.more, opacity, bad)) return false;
         rgb = mk3(L.color1.x, L.color1.y, L.color1.z) * L.color1.w * opacity;
         return true;
     } else {  // LineLightPixelShader LineLight.fx:7-42
@@ -422,8 +483,9 @@ ILB_DEV bool shadeLight(const LightingParams& P, const DLight& L, const Pixel& p
         float4 props = L.props;
         props.w *= es;
         float u, opacity;
-        if (!lineCore(P.df, L, px.pos, px.normal, mk3(L.pos1.x, L.pos1.y, L.pos1.z), mk3(L.pos2.x, L.pos2.y, L.pos2.z), props,
-                      L.more, u, opacity))
+        const DLine D = loadLine(lines, lightIndex);
+        if (!lineCore<FIELD, FAST>(df, L, D, px.pos, px.normal, mk3(L.pos1.x, L.pos1.y, L.pos1.z), mk3(L.pos2.x, L.pos2.y, L.pos2.z), props,
+                                   L.more, u, opacity, bad))
             return false;
         const f4 color = lerp4(mk4(L.color1), mk4(L.color2), u);
         rgb = mk3(color.x, color.y, color.z) * color.w * opacity;
@@ -431,13 +493,46 @@ ILB_DEV bool shadeLight(const LightingParams& P, const DLight& L, const Pixel& p
     }
 }
 
-ILB_DEV DLight loadLight(const DLight* lights, int i) {
-    DLight L;
-    const float4* src = reinterpret_cast<const float4*>(lights + i);
-    float4* dst = reinterpret_cast<float4*>(&L);
-#pragma unroll
-    for (int k = 0; k < (int)(sizeof(DLight) / 16); k++) dst[k] = __ldg(src + k);
-    return L;
+// The IEEE re-evaluation of one light-pixel whose fast evaluation tripped a range guard (an operand of a square root
+// or reciprocal outside the fast window: zero-length vectors, parallel normals, denormal or huge values).  Out of
+// line: it is never on the hot path and must not cost the hot path registers.  Returns rgb, w = 1 when lit.
+template <int FIELD>
+__device__ __noinline__ float4 shadeLightExact(const DFGeometry* df, float lightOcclusion, const DLight* lights, const DLine* lines,
+                                               int lightIndex, float4 posShadows, float4 normalFullbright, float4 camera) {
+    Pixel px;
+    px.pos = mk3(posShadows.x, posShadows.y, posShadows.z);
+    px.normal = mk3(normalFullbright.x, normalFullbright.y, normalFullbright.z);
+    px.camera = mk3(camera.x, camera.y, camera.z);
+    px.enableShadows = posShadows.w != 0.0f;
+    px.fullbright = normalFullbright.w != 0.0f;
+    px.maskOk = true;
+    const DLight L = loadLight(lights, lightIndex);
+    f3 rgb = mk3(0.0f);
+    bool bad = false;
+    const bool lit = shadeLight<FIELD, false>(*df, lightOcclusion, L, lines, lightIndex, px, rgb, bad);
+    return make_float4(rgb.x, rgb.y, rgb.z, lit ? 1.0f : 0.0f);
+}
+
+// fast evaluation + fallback
+template <int FIELD>
+ILB_DEV bool shadeLightGuarded(const DFGeometry& df, float lightOcclusion, const DLight& L, const DLight* lights, const DLine* lines,
+                               int lightIndex, const Pixel& px, f3& rgb) {
+#if ILB_NO_FAST_GUARD
+    bool bad = false;
+    return shadeLight<FIELD, false>(df, lightOcclusion, L, lines, lightIndex, px, rgb, bad);
+#else
+    bool bad = false;
+    bool lit = shadeLight<FIELD, true>(df, lightOcclusion, L, lines, lightIndex, px, rgb, bad);
+    if (bad) {
+        const float4 r = shadeLightExact<FIELD>(&df, lightOcclusion, lights, lines, lightIndex,
+                                                make_float4(px.pos.x, px.pos.y, px.pos.z, px.enableShadows ? 1.0f : 0.0f),
+                                                make_float4(px.normal.x, px.normal.y, px.normal.z, px.fullbright ? 1.0f : 0.0f),
+                                                make_float4(px.camera.x, px.camera.y, px.camera.z, 0.0f));
+        rgb = mk3(r.x, r.y, r.z);
+        lit = r.w != 0.0f;
+    }
+    return lit;
+#endif
 }
 
 ILB_DEV void storeTexel(const LightingParams& P, size_t index, float r, float g, float b, float a) {
@@ -472,6 +567,7 @@ ILB_DEV float warpMax(float v) {
 #ifndef ILB_LIGHT_MINBLOCKS
 #define ILB_LIGHT_MINBLOCKS (512 / TILE_THREADS)
 #endif
+template <int FIELD>
 __global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_MINBLOCKS) light_accumulate_kernel(const __grid_constant__ LightingParams P) {
     __shared__ float s_box[TILE_WARPS][6];
     __shared__ int s_warpCount[TILE_WARPS];
@@ -563,10 +659,11 @@ __global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_MINBLOCKS) light_accum
         // ---- shade
         const int n = s_listCount;
         for (int k = 0; k < n; k++) {
-            const DLight L = loadLight(P.lights, base + (int)s_list[k]);
+            const int lightIndex = base + (int)s_list[k];
+            const DLight L = loadLight(P.lights, lightIndex);
             if (shade && coverage(L, wx, wy)) {
                 f3 rgb;
-                if (shadeLight(P, L, pix, rgb)) {
+                if (shadeLightGuarded<FIELD>(P.df, P.envZToY.z, L, P.lights, P.lines, lightIndex, pix, rgb)) {
                     // BlendState.Additive with PS alpha 1: rgb += src.rgb, a += 1 (LightingRenderer.cs:206)
                     accR += rgb.x; accG += rgb.y; accB += rgb.z; accA += 1.0f;
                 }
@@ -583,6 +680,7 @@ struct ProbeParams {
     DFGeometry df;
     float lightOcclusion;
     const DLight* lights;
+    const DLine* lines;
     int nlights;
     const float4* positions;
     const float4* normals;
@@ -591,6 +689,7 @@ struct ProbeParams {
     void* out;
 };
 
+template <int FIELD>
 __global__ void __launch_bounds__(128) probe_accumulate_kernel(const __grid_constant__ ProbeParams P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.nprobes) return;
@@ -604,13 +703,13 @@ __global__ void __launch_bounds__(128) probe_accumulate_kernel(const __grid_cons
             more.x = 0.0f;
             more.w = 0.0f;
             float core;
-            bool lit;
+            bool lit, bad = false;  // probes are few: plain IEEE x-ops (FAST = false), no guard
             if (L.type == ILB_LIGHT_DIRECTIONAL) {
                 props.x *= ns.w;
-                lit = directionalCore(P.df, L, p, n, L.color2, props, more, core);
+                lit = directionalCore<FIELD, false>(P.df, L, p, n, L.color2, props, more, core, bad);
             } else {  // sphere, and line lights shaded as spheres at LightPosition1 (reference quirk, LineLightProbe.fx:4)
                 props.w *= ns.w;
-                lit = sphereCore(P.df, L, P.lightOcclusion, p, n, mk3(L.pos1.x, L.pos1.y, L.pos1.z), props, more, core);
+                lit = sphereCore<FIELD, false>(P.df, L, P.lightOcclusion, p, n, mk3(L.pos1.x, L.pos1.y, L.pos1.z), props, more, core, bad);
             }
             if (lit) {
                 const float opacity = ps.w * core;
@@ -635,8 +734,11 @@ inline float4 h4(const ilb_float4& v) { return make_float4(v.x, v.y, v.z, v.w); 
 inline float hlerp(float a, float b, float t) { return a + t * (b - a); }
 
 int flattenLights(ilb_ctx* ctx, const ilb_df* df, const ilb_lighting_frame* f, const ilb_light_batch* batches, int batch_count,
-                  const ilb_light_vertex* verts, int vertex_count, std::vector<DLight>& out, const ilb_df_uniforms** geometry) {
+                  const ilb_light_vertex* verts, int vertex_count, std::vector<DLight>& out, std::vector<DLine>& lines,
+                  const ilb_df_uniforms** geometry) {
     *geometry = nullptr;
+    // correctly rounded reciprocal of a uniform divisor for udiv(); 0 selects udiv's IEEE division
+    auto rcp = [](float y) { const float a = std::fabs(y); return (a >= 1.0e-30f && a <= 1.0e30f) ? 1.0f / y : 0.0f; };
     const float invZToY = f->EnvironmentZToY.y, zToY = f->EnvironmentZToY.x;
     const float sxs = f->GBufferTexelSizeAndMisc.z * f->EnvironmentZAndScale.z;
     const float sys = f->GBufferTexelSizeAndMisc.w * f->EnvironmentZAndScale.w;
@@ -673,6 +775,25 @@ int flattenLights(ilb_ctx* ctx, const ilb_df* df, const ilb_lighting_frame* f, c
             L.longStep = B.df.StepAndMisc2.z;
             L.hasField = hasField ? 1 : 0;
             L.type = B.light_type;
+            L.rcpRamp = rcp(v.LightProperties.y);
+            DLine D;
+            memset(&D, 0, sizeof(D));
+            if (B.light_type == ILB_LIGHT_LINE) {
+                // the pixel-independent part of computeLineLightOpacity / lineConeTrace (FBPBR.fxh:53-60, LineLightCore.fxh:24-31),
+                // same fp32 operations in the same order as the shaders (host code is built with -ffp-contract=off)
+                const float P0[3] = {v.LightPosition1.x, v.LightPosition1.y, v.LightPosition1.z};
+                const float P1[3] = {v.LightPosition2.x, v.LightPosition2.y, v.LightPosition2.z};
+                const float ab[3] = {P1[0] - P0[0], P1[1] - P0[1], P1[2] - P0[2]};
+                const float abab = (ab[0] * ab[0] + ab[1] * ab[1]) + ab[2] * ab[2];
+                const float inv = (abab == 0.0f) ? 0.0f : 1.0f / std::sqrt(abab);   // normalize(): zero in, zero out
+                const float deltaLength = std::sqrt(abab);
+                const float ratio = (v.LightProperties.x + 1.0f) / deltaLength;
+                const float sat = std::fmin(std::fmax(ratio, 0.0f), 1.0f);          // NaN -> 0 like saturatef
+                D.left = make_float4(ab[0] * inv, ab[1] * inv, ab[2] * inv, rcp(abab));
+                D.center = make_float4(P0[0] + 0.5f * ab[0], P0[1] + 0.5f * ab[1], P0[2] + 0.5f * ab[2], std::fmax(sat, 0.03f));
+                D.ab = make_float4(ab[0], ab[1], ab[2], abab);
+            }
+            lines.push_back(D);
             float bx0, bx1, by0, by1;  // world-space bounds of the rasterised quad
             if (B.light_type == ILB_LIGHT_SPHERE) {  // SphereLightVertexShader SphereLightCore.fxh:13-56
                 const float radius = v.LightProperties.x + v.LightProperties.y + 1;
@@ -722,18 +843,23 @@ int flattenLights(ilb_ctx* ctx, const ilb_df* df, const ilb_lighting_frame* f, c
     return ILB_OK;
 }
 
-int uploadLights(ilb_ctx* ctx, const std::vector<DLight>& lights) {
-    const size_t bytes = std::max<size_t>(lights.size(), 1) * sizeof(DLight);
+// device layout: DLight[n] followed by DLine[n]
+int uploadLights(ilb_ctx* ctx, const std::vector<DLight>& lights, const std::vector<DLine>& lines, const DLight** d_lights, const DLine** d_lines) {
+    const size_t n = lights.size();
+    const size_t lightBytes = std::max<size_t>(n, 1) * sizeof(DLight), bytes = lightBytes + std::max<size_t>(n, 1) * sizeof(DLine);
     int rc = ilb_reserve(ctx, &ctx->d_lights, &ctx->d_lights_capacity, bytes, false);
     if (rc) return rc;
     rc = ilb_reserve(ctx, &ctx->h_lights, &ctx->h_lights_capacity, bytes, true);
     if (rc) return rc;
     // the pinned staging buffer is reused every frame: wait for the previous frame's copy
     ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (!lights.empty()) {
-        memcpy(ctx->h_lights, lights.data(), lights.size() * sizeof(DLight));
-        ILB_CUDA(ctx, cudaMemcpyAsync(ctx->d_lights, ctx->h_lights, lights.size() * sizeof(DLight), cudaMemcpyHostToDevice, ctx->stream));
+    if (n) {
+        memcpy(ctx->h_lights, lights.data(), n * sizeof(DLight));
+        memcpy(reinterpret_cast<char*>(ctx->h_lights) + lightBytes, lines.data(), n * sizeof(DLine));
+        ILB_CUDA(ctx, cudaMemcpyAsync(ctx->d_lights, ctx->h_lights, bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
+    *d_lights = reinterpret_cast<const DLight*>(ctx->d_lights);
+    *d_lines = reinterpret_cast<const DLine*>(reinterpret_cast<const char*>(ctx->d_lights) + lightBytes);
     return ILB_OK;
 }
 
@@ -756,16 +882,21 @@ int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, c
     if (f->row_begin == f->row_end) return ILB_OK;
 
     std::vector<DLight> lights;
+    std::vector<DLine> lines;
     const ilb_df_uniforms* geometry = nullptr;
-    int rc = flattenLights(ctx, df, f, batches, batch_count, vertices, vertex_count, lights, &geometry);
+    int rc = flattenLights(ctx, df, f, batches, batch_count, vertices, vertex_count, lights, lines, &geometry);
     if (rc) return rc;
     if (lights.size() > 65535 * (size_t)TILE_THREADS) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "too many lights");
-    rc = uploadLights(ctx, lights);
-    if (rc) return rc;
 
     LightingParams P;
     memset(&P, 0, sizeof(P));
-    if (geometry && !ilb_make_df_geometry(df, *geometry, &P.df)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad distance-field uniforms");
+    rc = uploadLights(ctx, lights, lines, &P.lights, &P.lines);
+    if (rc) return rc;
+    if (geometry) {
+        if (!ilb_make_df_geometry(df, *geometry, &P.df)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad distance-field uniforms");
+        rc = ilb_planes_attach(ctx, df, *geometry, &P.df);
+        if (rc) return rc;
+    }
     P.envZAndScale = h4(f->EnvironmentZAndScale);
     P.envZToY = h4(f->EnvironmentZToY);
     P.gbTexelAndMisc = h4(f->GBufferTexelSizeAndMisc);
@@ -776,7 +907,6 @@ int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, c
     P.vpy = f->ViewportPosition[1];
     P.gbuffer = ctx->gbuffer;
     P.gw = ctx->gb_w; P.gh = ctx->gb_h; P.gfmt = ctx->gb_fmt;
-    P.lights = reinterpret_cast<const DLight*>(ctx->d_lights);
     P.nlights = (int)lights.size();
     P.width = f->width; P.height = f->height; P.row_begin = f->row_begin; P.row_end = f->row_end;
     P.out_format = f->lightmap_format;
@@ -790,7 +920,9 @@ int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, c
 
     P.tiles_x = (f->width + TILE_W - 1) / TILE_W;
     P.tiles_y = (f->row_end - f->row_begin + TILE_H - 1) / TILE_H;
-    light_accumulate_kernel<<<(unsigned)P.tiles_x * (unsigned)P.tiles_y, TILE_THREADS, 0, ctx->stream>>>(P);
+    const unsigned tiles = (unsigned)P.tiles_x * (unsigned)P.tiles_y;
+    if (P.df.planes) light_accumulate_kernel<1><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);
+    else light_accumulate_kernel<0><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);
     ctx->launches++;
     ILB_CUDA(ctx, cudaGetLastError());
     return ILB_OK;
@@ -807,10 +939,13 @@ int ilb_probes_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, con
     if (!(fr.GBufferTexelSizeAndMisc.z > 0)) fr.GBufferTexelSizeAndMisc.z = 1;
     if (!(fr.GBufferTexelSizeAndMisc.w > 0)) fr.GBufferTexelSizeAndMisc.w = 1;
     std::vector<DLight> lights;
+    std::vector<DLine> lines;
     const ilb_df_uniforms* geometry = nullptr;
-    int rc = flattenLights(ctx, df, &fr, batches, batch_count, vertices, vertex_count, lights, &geometry);
+    int rc = flattenLights(ctx, df, &fr, batches, batch_count, vertices, vertex_count, lights, lines, &geometry);
     if (rc) return rc;
-    rc = uploadLights(ctx, lights);
+    ProbeParams P;
+    memset(&P, 0, sizeof(P));
+    rc = uploadLights(ctx, lights, lines, &P.lights, &P.lines);
     if (rc) return rc;
     const size_t in_bytes = sizeof(float4) * (size_t)probe_count, out_bytes = ilb_format_bytes(output_format) * (size_t)probe_count;
     rc = ilb_reserve(ctx, &ctx->d_probe_in, &ctx->d_probe_in_capacity, 2 * in_bytes + out_bytes, false);
@@ -818,18 +953,20 @@ int ilb_probes_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, con
     char* base = reinterpret_cast<char*>(ctx->d_probe_in);
     ILB_CUDA(ctx, cudaMemcpyAsync(base, positions, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     ILB_CUDA(ctx, cudaMemcpyAsync(base + in_bytes, normals, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    ProbeParams P;
-    memset(&P, 0, sizeof(P));
-    if (geometry && !ilb_make_df_geometry(df, *geometry, &P.df)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad distance-field uniforms");
+    if (geometry) {
+        if (!ilb_make_df_geometry(df, *geometry, &P.df)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad distance-field uniforms");
+        rc = ilb_planes_attach(ctx, df, *geometry, &P.df);
+        if (rc) return rc;
+    }
     P.lightOcclusion = f->EnvironmentZToY.z;
-    P.lights = reinterpret_cast<const DLight*>(ctx->d_lights);
     P.nlights = (int)lights.size();
     P.positions = reinterpret_cast<const float4*>(base);
     P.normals = reinterpret_cast<const float4*>(base + in_bytes);
     P.nprobes = probe_count;
     P.out_format = output_format;
     P.out = base + 2 * in_bytes;
-    probe_accumulate_kernel<<<(probe_count + 127) / 128, 128, 0, ctx->stream>>>(P);
+    if (P.df.planes) probe_accumulate_kernel<1><<<(probe_count + 127) / 128, 128, 0, ctx->stream>>>(P);
+    else probe_accumulate_kernel<0><<<(probe_count + 127) / 128, 128, 0, ctx->stream>>>(P);
     ctx->launches++;
     ILB_CUDA(ctx, cudaGetLastError());
     ILB_CUDA(ctx, cudaMemcpyAsync(probes_out_host, P.out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));

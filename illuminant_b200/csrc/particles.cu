@@ -126,16 +126,6 @@ ILB_DEV f4 evaluateBezier4(const ilb_bezier4& b, float value) {  // :141-177
 }
 
 // ---- transforms: x-ops throughout (particle state feeds the collision thresholds of later steps) -------------
-// Division by a uniform divisor y with r = RN(1/y) precomputed on the host (0 when y is not a safe normal number):
-// q = RN(x*r), rho = x - y*q (exact in one FMA), q' = RN(q + rho*r) is the correctly rounded x / y (Markstein), in
-// 3 instructions instead of the ~14 of div.rn's inline sequence + range check.
-ILB_DEV float udiv(float x, float y, float r) {
-    if (r == 0.0f) return xdivz(x, y);  // uniform branch
-    const float q = __fmul_rn(x, r);
-    const float rho = __fmaf_rn(-y, q, x);
-    return __fmaf_rn(rho, r, q);
-}
-
 ILB_DEV float ellipsoidU(f3 p, const ilb_area& a, const OpDerived& d) {  // evaluateEllipsoid with uniform divisors
     const f3 r = mk3(a.AreaSize[0], a.AreaSize[1], a.AreaSize[2]);
     const float k0 = xlength3z(mk3(udiv(p.x, r.x, d.rSize[0]), udiv(p.y, r.y, d.rSize[1]), udiv(p.z, r.z, d.rSize[2])));
@@ -281,10 +271,14 @@ ILB_DEV void computeRenderData(const ilb_psys_uniforms& u, float vx, float vy, f
     renderData.w = velocity.w;
 }
 
-template <bool FLAT>
-ILB_DEV float sampleField(const DFGeometry& g, f3 p) { return FLAT ? sampleDistanceFieldFlat(g, p) : sampleDistanceField(g, p); }
+// PL: 0 = sample the Rgba64 atlas, 1 = sample the expanded planes (ilb_device.cuh); FLAT: Packed1 == 0 uniforms
+template <int PL, bool FLAT>
+ILB_DEV float sampleField(const DFGeometry& g, f3 p) {
+    if (PL) return FLAT ? sampleFieldPlanesFlat(g, p) : sampleFieldPlanesT<false>(g, p);
+    return FLAT ? sampleDistanceFieldFlat(g, p) : sampleDistanceField(g, p);
+}
 
-template <bool FLAT>
+template <int PL, bool FLAT>
 ILB_DEV f3 estimateNormal4(const DFGeometry& g, float texelZ, f3 position) {  // VisualizeCommon.fxh:9-63
     const f3 texel = mk3(g.invScaleX, g.invScaleY, texelZ);
     f3 result = mk3(0.0f);
@@ -292,13 +286,13 @@ ILB_DEV f3 estimateNormal4(const DFGeometry& g, float texelZ, f3 position) {  //
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const f3 weight = mk3(wts[i][0], wts[i][1], wts[i][2]);
-        result = xadd3(result, xscale3(weight, sampleField<FLAT>(g, xadd3(position, xmul3(weight, texel)))));
+        result = xadd3(result, xscale3(weight, sampleField<PL, FLAT>(g, xadd3(position, xmul3(weight, texel)))));
     }
     return xnormalize3(result);
 }
 
 // returns false when the reference pass discards (dead on entry): outputs stay at the cleared zeros
-template <bool COLLIDE, bool FLAT>
+template <bool COLLIDE, int PL, bool FLAT>
 ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f4 oldVelocity, f4& outP, f4& outV, bool& needAttr) {
     const ilb_psys_uniforms& u = P.u;
     outP = mk4(0.0f);
@@ -328,7 +322,7 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
     f3 collisionPosition = mk3(0.0f), newPosition = op;
     f4 newVelocity = mk4(0.0f);
 
-    const float initialDistance = sampleField<FLAT>(P.df, op);
+    const float initialDistance = sampleField<PL, FLAT>(P.df, op);
     const bool wasColliding = initialDistance < collisionDistance;
     float travelDistance = fmaxf(0.0f, fminf(initialDistance, xlength3z(scaledVelocity)));
     int stepCount = 3;
@@ -336,7 +330,7 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
     else if (travelDistance <= 0.001f) stepCount = 0;
     for (int i = 0; i < stepCount; i++) {
         const f3 testPosition = xadd3(op, xscale3(unitVector, travelDistance));
-        const float stepDistance = sampleField<FLAT>(P.df, testPosition);
+        const float stepDistance = sampleField<PL, FLAT>(P.df, testPosition);
         if (stepDistance < collisionDistance) {
             collided = true;
             collisionPosition = testPosition;
@@ -354,7 +348,7 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
         const bool bounce = oldVelocity.w <= 0.0f;
         const bool redirect = wasColliding && !escaping;
         f3 normal = mk3(0.0f);
-        if (bounce || redirect) normal = estimateNormal4<FLAT>(P.df, P.sd.texelZ, collisionPosition);
+        if (bounce || redirect) normal = estimateNormal4<PL, FLAT>(P.df, P.sd.texelZ, collisionPosition);
         const float maxV = u.GlobalSettings.z;
         const float escapeSpeed = fminf(maxV, u.CollisionSettings.x);
         if (redirect) {
@@ -410,7 +404,7 @@ ILB_DEV void applyOp(const StepParams& P, const ilb_op& op, const OpDerived& d, 
 // K0..K2: the transform chain known at compile time (op kinds, 0 = no op): operands come straight from the constant
 // bank with static offsets.  K0 < 0 selects the generic loop over P.ops[0..nops) for every other chain.
 // One particle through the whole update: transform chain in registers, then the Update / UpdateWithDistanceField tail.
-template <bool COLLIDE, int K0, int K1, int K2>
+template <bool COLLIDE, int K0, int K1, int K2, int PL>
 ILB_DEV void stepParticle(const StepParams& P, unsigned gi, f4 pos, f4 vel, f4& outP, f4& outV, bool& needAttr, float& x, float& y) {
     unsigned ix, iy;
     if (P.chunk_shift >= 0) {
@@ -440,19 +434,19 @@ ILB_DEV void stepParticle(const StepParams& P, unsigned gi, f4 pos, f4 vel, f4& 
         if (K1 > 0) applyOp<K1>(P, P.ops[1], P.od[1], x, y, pos, vel);
         if (K2 > 0) applyOp<K2>(P, P.ops[2], P.od[2], x, y, pos, vel);
     }
-    if (COLLIDE && fieldIsFlat(P.df)) updateTail<COLLIDE, true>(P, x, y, pos, vel, outP, outV, needAttr);   // uniform branch
-    else updateTail<COLLIDE, false>(P, x, y, pos, vel, outP, outV, needAttr);
+    if (COLLIDE && fieldIsFlat(P.df)) updateTail<COLLIDE, PL, true>(P, x, y, pos, vel, outP, outV, needAttr);   // uniform branch
+    else updateTail<COLLIDE, PL, false>(P, x, y, pos, vel, outP, outV, needAttr);
 }
 
 // Direct variant: one thread per particle, 16-byte coalesced global loads / stores.
-template <bool COLLIDE, int K0, int K1, int K2>
+template <bool COLLIDE, int K0, int K1, int K2, int PL>
 __global__ void __launch_bounds__(STEP_THREADS, ILB_PARTICLE_MINBLOCKS) particle_step_kernel(const __grid_constant__ StepParams P) {
     const unsigned gi = blockIdx.x * STEP_THREADS + threadIdx.x;
     if (gi >= P.total) return;
     f4 outP, outV;
     bool needAttr;
     float x, y;
-    stepParticle<COLLIDE, K0, K1, K2>(P, gi, mk4(P.P[gi]), mk4(P.V[gi]), outP, outV, needAttr, x, y);
+    stepParticle<COLLIDE, K0, K1, K2, PL>(P, gi, mk4(P.P[gi]), mk4(P.V[gi]), outP, outV, needAttr, x, y);
     P.P[gi] = to_float4(outP);
     P.V[gi] = to_float4(outV);
     if (P.u.write_render_outputs) {
@@ -545,7 +539,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 3) particle_step_tma_kernel(cons
         f4 outP, outV, rc = mk4(0.0f), rd = mk4(0.0f);
         bool needAttr;
         float x, y;
-        stepParticle<COLLIDE, K0, K1, K2>(P, gi, pos, vel, outP, outV, needAttr, x, y);
+        stepParticle<COLLIDE, K0, K1, K2, 0>(P, gi, pos, vel, outP, outV, needAttr, x, y);
         if (P.u.write_render_outputs && needAttr) computeRenderData(P.u, x, y, outP, outV, attr, rc, rd);
 
         S.outP[tid] = to_float4(outP);
@@ -786,7 +780,12 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
             if (!ilb_make_df_geometry(ps->field, u->CollisionField, &SP.df))
                 return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "collision field uniforms describe an empty field");
             SP.sd.texelZ = SP.df.ez / std::fmax(SP.df.sliceCount, 1.0f);
+            if (!ps->use_tma) {
+                const int prc = ilb_planes_attach(ctx, ps->field, u->CollisionField, &SP.df);
+                if (prc) return prc;
+            }
         }
+        const bool planes = SP.df.planes != nullptr;
         const unsigned blocks = (unsigned)((total + STEP_THREADS - 1) / STEP_THREADS);
         // chains with a compiled specialisation: none, and Gravity -> Noise -> FMA (BASELINE.json configs 3 and 5)
         const bool chainNone = op_count == 0;
@@ -805,18 +804,21 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
                 attr_set = true;                                                                                            \
             }                                                                                                               \
             particle_step_tma_kernel<C, A, B, D><<<persistent, STEP_THREADS, sizeof(StageSmem), ctx->stream>>>(SP);         \
+        } else if (planes) {                                                                                                \
+            particle_step_kernel<C, A, B, D, (C) ? 1 : 0><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);                     \
         } else {                                                                                                            \
-            particle_step_kernel<C, A, B, D><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);                                  \
+            particle_step_kernel<C, A, B, D, 0><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);                               \
         }                                                                                                                   \
     } while (0)
         if (collide) {
             if (chainGNF) ILB_LAUNCH(true, ILB_OP_GRAVITY, ILB_OP_NOISE, ILB_OP_FMA);
             else if (chainNone) ILB_LAUNCH(true, 0, 0, 0);
-            else particle_step_kernel<true, -1, 0, 0><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);
+            else if (planes) particle_step_kernel<true, -1, 0, 0, 1><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);
+            else particle_step_kernel<true, -1, 0, 0, 0><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);
         } else {
             if (chainGNF) ILB_LAUNCH(false, ILB_OP_GRAVITY, ILB_OP_NOISE, ILB_OP_FMA);
             else if (chainNone) ILB_LAUNCH(false, 0, 0, 0);
-            else particle_step_kernel<false, -1, 0, 0><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);
+            else particle_step_kernel<false, -1, 0, 0, 0><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);
         }
 #undef ILB_LAUNCH
         ctx->launches++;

@@ -95,17 +95,24 @@ DM_FN void dm_sincosf(float x, float* s, float* c) {
 
 /* acos: Abramowitz & Stegun 4.4.46, acos(x) = sqrt(1 - x) * P7(x) on [0, 1] (|error| <= 2e-8 before rounding),
  * reflected for x < 0.  Branch-free apart from the final select; |x| > 1 gives sqrt(negative) = NaN like acos(). */
-DM_FN float dm_acosf(float xx) {
-    const float x = xx < 0.0f ? -xx : xx;
+DM_FN float dm_acos_poly(float x) { /* P7(|x|) */
     float p = DM_ADD(DM_MUL(-0.0012624911f, x), 0.0066700901f);
     p = DM_ADD(DM_MUL(p, x), -0.0170881256f);
     p = DM_ADD(DM_MUL(p, x), 0.0308918810f);
     p = DM_ADD(DM_MUL(p, x), -0.0501743046f);
     p = DM_ADD(DM_MUL(p, x), 0.0889789874f);
     p = DM_ADD(DM_MUL(p, x), -0.2145988016f);
-    p = DM_ADD(DM_MUL(p, x), 1.5707963050f);
-    const float r = DM_MUL(DM_SQRT(DM_SUB(1.0f, x)), p);
+    return DM_ADD(DM_MUL(p, x), 1.5707963050f);
+}
+/* s = sqrt(1 - |xx|), supplied by the caller (the kernels have a cheaper correctly rounded sqrt for in-range operands) */
+DM_FN float dm_acos_finish(float xx, float s) {
+    const float x = xx < 0.0f ? -xx : xx;
+    const float r = DM_MUL(s, dm_acos_poly(x));
     return xx < 0.0f ? DM_SUB(DM_PIF, r) : r;
+}
+DM_FN float dm_acosf(float xx) {
+    const float x = xx < 0.0f ? -xx : xx;
+    return dm_acos_finish(xx, DM_SQRT(DM_SUB(1.0f, x)));
 }
 
 #endif /* ILB_DETMATH_H */

@@ -170,3 +170,25 @@ def test_error_reporting(ctx):
     assert rc == _abi.ERR_UNSUPPORTED and b"light type" in ctx.lib.ilb_last_error(ctx.handle)
     with pytest.raises(ib.IlluminantError):
         r.DistanceField.Load(np.zeros(16, np.uint16))   # "Truncated file"
+
+
+def test_planes_match_atlas_bit_for_bit(ctx, monkeypatch):
+    """The expanded-planes sampler (csrc/planes.cu, sampleFieldPlanesT) and the Rgba64-atlas sampler are two layouts of
+    the same arithmetic: lightmaps and probes must be bit-identical, including a 3-column atlas (1/3 is inexact),
+    a reduced-resolution field and rays that leave the volume."""
+    for seed, w, h, slices, res in ((31, 300, 210, 8, 1.0), (32, 200, 160, 24, 0.5), (33, 257, 131, 3, 1.0)):
+        s = scenes.lighting_scene(seed, w, h, 6, n_directional=2, n_line=2, n_probes=16, ramp=(60.0, 260.0), ao=True, float4_lightmap=True)
+        s.df_slices = slices
+        out = []
+        for flag in ("1", "0"):
+            monkeypatch.setenv("ILB_NO_PLANES", flag)
+            df = scenes.make_distance_field(ctx, s, resolution=res)
+            df.Rasterize(s.obstructions)
+            r = ib.LightingRenderer(ctx, s.environment, s.configuration)
+            r.DistanceField = df
+            r.Probes = s.probes
+            r.SetGBuffer(s.gbuffer)
+            out.append((r.RenderLighting(), r.UpdateLightProbes() if s.probes else None))
+        assert np.array_equal(out[0][0], out[1][0]), f"seed {seed}"
+        if out[0][1] is not None:
+            assert np.array_equal(out[0][1], out[1][1])

@@ -187,3 +187,27 @@ def test_tma_staged_kernel_is_bit_identical_to_direct_kernel(ctx, monkeypatch):
     for a, b in zip(out[0], out[1]):
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
+
+
+def test_planes_match_atlas_bit_for_bit(ctx, monkeypatch):
+    """Collision against the expanded planes (csrc/planes.cu) == collision against the Rgba64 atlas, bit for bit, for
+    the reference's flat addressing and for the FullFieldAddressing extension."""
+    s = scenes.lighting_scene(49, 256, 256, 0)
+    for full in (False, True):
+        out = []
+        for flag in ("1", "0"):
+            monkeypatch.setenv("ILB_NO_PLANES", flag)
+            df = scenes.make_distance_field(ctx, s)
+            df.Rasterize(s.obstructions)
+            ps = scenes.particle_scene(49, 2 * 128 * 128, 128, 256, 256, steps_hint=40, collision_field=df, spawn_rate=0.0)
+            ps.configuration.Collision.FullFieldAddressing = full
+            engine = ib.ParticleEngine(ctx, ib.ParticleEngineConfiguration(ChunkSize=128, RandomSeed=1))
+            system = ib.ParticleSystem(engine, ps.configuration, maxChunks=2)
+            system.Transforms = ps.transforms
+            system.Spawn(ps.positions, ps.velocities, ps.attributes)
+            ops, u = system.plan_ops(ps.dt), system.system_uniforms(ps.dt)
+            system.step_packed(u, [], ops, 9)
+            out.append([system.ReadChunk(c) for c in range(2)])
+        for a, b in zip(out[0], out[1]):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
