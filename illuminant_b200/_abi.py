@@ -6,10 +6,11 @@ Python), but any call that needs the device raises IlluminantError if the CUDA l
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libilluminant_b200.so"
+LIB_PATH = Path(os.environ["ILB_LIB"]) if os.environ.get("ILB_LIB") else PKG / "libilluminant_b200.so"  # ILB_LIB: A/B builds of kernel variants
 
 ILB_OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_INVALID_OPERATION, ERR_OUT_OF_MEMORY, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6

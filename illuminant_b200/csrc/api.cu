@@ -117,6 +117,7 @@ void ilb_destroy(ilb_ctx* ctx) {
     if (ctx->h_lights) cudaFreeHost(ctx->h_lights);
     if (ctx->d_lightmap) cudaFree(ctx->d_lightmap);
     if (ctx->d_probe_in) cudaFree(ctx->d_probe_in);
+    if (ctx->d_accum) cudaFree(ctx->d_accum);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -35,6 +35,8 @@ struct ilb_ctx {
     size_t d_lightmap_capacity = 0;
     void* d_probe_in = nullptr;
     size_t d_probe_in_capacity = 0;
+    void* d_accum = nullptr;     // fp32 sums handed from the line-light pass to the sphere / directional pass
+    size_t d_accum_capacity = 0;
 };
 
 #define ILB_MAX_VIRTUAL_SLICES 64

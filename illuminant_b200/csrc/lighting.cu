@@ -13,6 +13,7 @@
 // pixel instead of once per light-pixel, the light list is culled per tile, and there is no blend unit.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include <cuda_fp16.h>
@@ -69,6 +70,8 @@ struct LightingParams {
     int nouts;
     int out_row_base;  // row index of outs[] row 0 (row_begin for band buffers, 0 for full frames)
     int tiles_x, tiles_y;
+    const float4* accum_in;  // fp32 sums of an earlier pass over this row band (nullptr: start from `clear`)
+    float4* accum_out;       // leave the fp32 sums here instead of storing the lightmap (nullptr: final pass)
 };
 
 struct Pixel {
@@ -141,7 +144,9 @@ ILB_DEV void coneTraceMarch(const DFGeometry& g, const TraceConfig& c, Trace& a,
     while (liveness > 0.0f) {
         stepsRemaining -= 1.0f;
         const f3 sp = xadd3(a.origin, xscale3(a.direction, a.t));  // coneTraceAdvance :73-82
-        const float d = sampleFieldT<FIELD, INSIDE>(g, sp);
+        // a ray that ends outside the volume still spends most of its samples inside it: there the clamp is the
+        // identity and the distance-to-volume term is exactly 0, so the short sampler gives the same bits
+        const float d = (INSIDE || insideField(g, sp)) ? sampleFieldT<FIELD, true>(g, sp) : sampleFieldT<FIELD, false>(g, sp);
         a.t = xadd(a.t, traceStep(c, d, a.t, a.vis));
         const float stepLiveness = saturatef(a.vis - FULLY_SHADOWED_THRESHOLD) * saturatef(xsub(a.len, a.t));
         liveness = stepsRemaining * stepLiveness;
@@ -172,7 +177,8 @@ ILB_DEV float coneTrace(const DFGeometry& g, const DLight& L, f3 lightCenter, fl
 
 template <int FIELD, bool INSIDE>
 ILB_DEV float traceAdvanceEx(const DFGeometry& g, const TraceConfig& c, Trace& s) {  // coneTraceAdvanceEx :84-96
-    const float d = sampleFieldT<FIELD, INSIDE>(g, xadd3(s.origin, xscale3(s.direction, s.t)));
+    const f3 sp = xadd3(s.origin, xscale3(s.direction, s.t));
+    const float d = (INSIDE || insideField(g, sp)) ? sampleFieldT<FIELD, true>(g, sp) : sampleFieldT<FIELD, false>(g, sp);
     s.t = fminf(xadd(s.t, traceStep(c, d, s.t, s.vis)), s.len);
     return saturatef(s.vis - FULLY_SHADOWED_THRESHOLD) * saturatef(xsub(s.len, s.t) * TRACE_END_MULTIPLIER);
 }
@@ -450,11 +456,12 @@ ILB_DEV DLine loadLine(const DLine* lines, int i) {
 }
 
 // One light at one pixel; returns false when the reference fragment would be discarded.
-template <int FIELD, bool FAST>
+// TYPES: bit mask of ilb_light_type values this instantiation can meet (other branches are compiled out)
+template <int FIELD, bool FAST, int TYPES>
 ILB_DEV bool shadeLight(const DFGeometry& df, float lightOcclusion, const DLight& L, const DLine* lines, int lightIndex, const Pixel& px,
                         f3& rgb, bool& bad) {
     const float es = px.enableShadows ? 1.0f : 0.0f;
-    if (L.type == ILB_LIGHT_SPHERE) {  // SphereLightPixelShader SphereLight.fx:7-46
+    if ((TYPES & ILB_LIGHT_SPHERE) && L.type == ILB_LIGHT_SPHERE) {  // SphereLightPixelShader SphereLight.fx:7-46
         if (px.fullbright || shadowFilterRejects(L.evenMore.x, px.enableShadows)) return false;
         float4 props = L.props;
         props.w *= es;
@@ -470,7 +477,7 @@ ILB_DEV bool shadeLight(const DFGeometry& df, float lightOcclusion, const DLight
             rgb = rgb + (mk3(spec.x, spec.y, spec.z) * specularity * opacity);
         }
         return true;
-    } else if (L.type == ILB_LIGHT_DIRECTIONAL) {  // DirectionalLightPixelShader DirectionalLight.fx:95-127
+    } else if ((TYPES & ILB_LIGHT_DIRECTIONAL) && L.type == ILB_LIGHT_DIRECTIONAL) {  // DirectionalLightPixelShader DirectionalLight.fx:95-127
         if (px.fullbright || shadowFilterRejects(L.evenMore.x, px.enableShadows)) return false;
         float4 props = L.props;
         props.x *= es;
@@ -478,7 +485,7 @@ ILB_DEV bool shadeLight(const DFGeometry& df, float lightOcclusion, const DLight
         if (!directionalCore<FIELD, FAST>(df, L, px.pos, px.normal, L.color2, props, L.more, opacity, bad)) return false;
         rgb = mk3(L.color1.x, L.color1.y, L.color1.z) * L.color1.w * opacity;
         return true;
-    } else {  // LineLightPixelShader LineLight.fx:7-42
+    } else if (TYPES & ILB_LIGHT_LINE) {  // LineLightPixelShader LineLight.fx:7-42
         if (px.fullbright) return false;
         float4 props = L.props;
         props.w *= es;
@@ -491,12 +498,13 @@ ILB_DEV bool shadeLight(const DFGeometry& df, float lightOcclusion, const DLight
         rgb = mk3(color.x, color.y, color.z) * color.w * opacity;
         return true;
     }
+    return false;
 }
 
 // The IEEE re-evaluation of one light-pixel whose fast evaluation tripped a range guard (an operand of a square root
 // or reciprocal outside the fast window: zero-length vectors, parallel normals, denormal or huge values).  Out of
 // line: it is never on the hot path and must not cost the hot path registers.  Returns rgb, w = 1 when lit.
-template <int FIELD>
+template <int FIELD, int TYPES>
 __device__ __noinline__ float4 shadeLightExact(const DFGeometry* df, float lightOcclusion, const DLight* lights, const DLine* lines,
                                                int lightIndex, float4 posShadows, float4 normalFullbright, float4 camera) {
     Pixel px;
@@ -509,22 +517,22 @@ __device__ __noinline__ float4 shadeLightExact(const DFGeometry* df, float light
     const DLight L = loadLight(lights, lightIndex);
     f3 rgb = mk3(0.0f);
     bool bad = false;
-    const bool lit = shadeLight<FIELD, false>(*df, lightOcclusion, L, lines, lightIndex, px, rgb, bad);
+    const bool lit = shadeLight<FIELD, false, TYPES>(*df, lightOcclusion, L, lines, lightIndex, px, rgb, bad);
     return make_float4(rgb.x, rgb.y, rgb.z, lit ? 1.0f : 0.0f);
 }
 
 // fast evaluation + fallback
-template <int FIELD>
+template <int FIELD, int TYPES>
 ILB_DEV bool shadeLightGuarded(const DFGeometry& df, float lightOcclusion, const DLight& L, const DLight* lights, const DLine* lines,
                                int lightIndex, const Pixel& px, f3& rgb) {
 #if ILB_NO_FAST_GUARD
     bool bad = false;
-    return shadeLight<FIELD, false>(df, lightOcclusion, L, lines, lightIndex, px, rgb, bad);
+    return shadeLight<FIELD, false, TYPES>(df, lightOcclusion, L, lines, lightIndex, px, rgb, bad);
 #else
     bool bad = false;
-    bool lit = shadeLight<FIELD, true>(df, lightOcclusion, L, lines, lightIndex, px, rgb, bad);
+    bool lit = shadeLight<FIELD, true, TYPES>(df, lightOcclusion, L, lines, lightIndex, px, rgb, bad);
     if (bad) {
-        const float4 r = shadeLightExact<FIELD>(&df, lightOcclusion, lights, lines, lightIndex,
+        const float4 r = shadeLightExact<FIELD, TYPES>(&df, lightOcclusion, lights, lines, lightIndex,
                                                 make_float4(px.pos.x, px.pos.y, px.pos.z, px.enableShadows ? 1.0f : 0.0f),
                                                 make_float4(px.normal.x, px.normal.y, px.normal.z, px.fullbright ? 1.0f : 0.0f),
                                                 make_float4(px.camera.x, px.camera.y, px.camera.z, 0.0f));
@@ -564,11 +572,21 @@ ILB_DEV float warpMax(float v) {
     return v;
 }
 
+// Resident CTAs per SM (register budget = 65536 / (256 * n)): the trace is latency-bound (dependent IEEE ops and
+// gathers through L1/L2), so more resident warps pay even at the price of a few spills.  Line lights (three interleaved
+// traces) need the larger budget; sphere / directional lights run in their own instantiation with more warps.
 #ifndef ILB_LIGHT_MINBLOCKS
-#define ILB_LIGHT_MINBLOCKS (512 / TILE_THREADS)
+#define ILB_LIGHT_MINBLOCKS 3
 #endif
-template <int FIELD>
-__global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_MINBLOCKS) light_accumulate_kernel(const __grid_constant__ LightingParams P) {
+#ifndef ILB_LIGHT_MINBLOCKS_NOLINE
+#define ILB_LIGHT_MINBLOCKS_NOLINE 4
+#endif
+// TYPES: the light types this pass shades (lights of other types are dropped by the tile culling).  A frame is one
+// pass over all types, or -- ILB_SPLIT_PASSES, the default when line lights are present -- a line-light pass that
+// leaves its fp32 sums in P.accum_out followed by a sphere + directional pass that starts from them.
+template <int FIELD, int TYPES>
+__global__ void __launch_bounds__(TILE_THREADS, (TYPES & ILB_LIGHT_LINE) ? ILB_LIGHT_MINBLOCKS : ILB_LIGHT_MINBLOCKS_NOLINE)
+light_accumulate_kernel(const __grid_constant__ LightingParams P) {
     __shared__ float s_box[TILE_WARPS][6];
     __shared__ int s_warpCount[TILE_WARPS];
     __shared__ uint16_t s_list[TILE_THREADS];
@@ -621,6 +639,11 @@ __global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_MINBLOCKS) light_accum
     const float wx = xadd(xdiv(xadd((float)px, 0.5f), sxs), P.vpx), wy = xadd(xdiv(xadd((float)py, 0.5f), sys), P.vpy);
 
     float accR = P.clear.x, accG = P.clear.y, accB = P.clear.z, accA = P.clear.w;
+    const size_t scratchIndex = (size_t)(py - P.row_begin) * (size_t)P.width + (size_t)px;
+    if (P.accum_in && valid) {
+        const float4 a = P.accum_in[scratchIndex];
+        accR = a.x; accG = a.y; accB = a.z; accA = a.w;
+    }
 
     for (int base = 0; base < P.nlights; base += TILE_THREADS) {
         // ---- cull: thread t tests light base+t against the tile
@@ -629,8 +652,9 @@ __global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_MINBLOCKS) light_accum
         if (li < P.nlights) {
             const DLight* L = P.lights + li;
             const int4 r = __ldg(reinterpret_cast<const int4*>(&L->px0));
-            keep = (r.x <= tx1) && (r.z >= tx0) && (r.y <= ty1) && (r.w >= ty0) && (bx0 <= bx1);
-            if (keep && __ldg(&L->type) == ILB_LIGHT_SPHERE) {
+            const int type = __ldg(&L->type);
+            keep = ((type & TYPES) != 0) && (r.x <= tx1) && (r.z >= tx0) && (r.y <= ty1) && (r.w >= ty0) && (bx0 <= bx1);
+            if ((TYPES & ILB_LIGHT_SPHERE) && keep && type == ILB_LIGHT_SPHERE) {
                 // sphere lights reach radius + rampLength (radius + 1 in RampMode None): reject the tile when the
                 // closest point of its world AABB is farther (1 px of slack covers fp rounding)
                 const float4 c = __ldg(&L->pos1), pr = __ldg(&L->props), mo = __ldg(&L->more);
@@ -663,7 +687,7 @@ __global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_MINBLOCKS) light_accum
             const DLight L = loadLight(P.lights, lightIndex);
             if (shade && coverage(L, wx, wy)) {
                 f3 rgb;
-                if (shadeLightGuarded<FIELD>(P.df, P.envZToY.z, L, P.lights, P.lines, lightIndex, pix, rgb)) {
+                if (shadeLightGuarded<FIELD, TYPES>(P.df, P.envZToY.z, L, P.lights, P.lines, lightIndex, pix, rgb)) {
                     // BlendState.Additive with PS alpha 1: rgb += src.rgb, a += 1 (LightingRenderer.cs:206)
                     accR += rgb.x; accG += rgb.y; accB += rgb.z; accA += 1.0f;
                 }
@@ -672,7 +696,9 @@ __global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_MINBLOCKS) light_accum
         if (base + TILE_THREADS < P.nlights) __syncthreads();  // the list is rebuilt only when another round follows
     }
 
-    if (valid) storeTexel(P, (size_t)(py - P.out_row_base) * (size_t)P.width + (size_t)px, accR, accG, accB, accA);
+    if (!valid) return;
+    if (P.accum_out) P.accum_out[scratchIndex] = make_float4(accR, accG, accB, accA);
+    else storeTexel(P, (size_t)(py - P.out_row_base) * (size_t)P.width + (size_t)px, accR, accG, accB, accA);
 }
 
 // ---- light probes (L11): SphereLightProbe.fx:19-44, DirectionalLight.fx:163-190, LineLightProbe.fx:23-48 ----------
@@ -921,9 +947,32 @@ int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, c
     P.tiles_x = (f->width + TILE_W - 1) / TILE_W;
     P.tiles_y = (f->row_end - f->row_begin + TILE_H - 1) / TILE_H;
     const unsigned tiles = (unsigned)P.tiles_x * (unsigned)P.tiles_y;
-    if (P.df.planes) light_accumulate_kernel<1><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);
-    else light_accumulate_kernel<0><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);
-    ctx->launches++;
+    constexpr int ALL = ILB_LIGHT_SPHERE | ILB_LIGHT_DIRECTIONAL | ILB_LIGHT_LINE, NOLINE = ILB_LIGHT_SPHERE | ILB_LIGHT_DIRECTIONAL;
+    int nline = 0;
+    for (const DLight& L : lights) nline += (L.type == ILB_LIGHT_LINE) ? 1 : 0;
+    bool split = nline > 0 && nline < (int)lights.size();
+    if (const char* e = getenv("ILB_SPLIT_PASSES")) split = split && e[0] != '0';
+#define ILB_LIGHT_LAUNCH(TYPES)                                                                                       \
+    do {                                                                                                              \
+        if (P.df.planes) light_accumulate_kernel<1, TYPES><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);               \
+        else light_accumulate_kernel<0, TYPES><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);                           \
+        ctx->launches++;                                                                                              \
+    } while (0)
+    if (split) {
+        const size_t bytes = sizeof(float4) * (size_t)f->width * (size_t)(f->row_end - f->row_begin);
+        rc = ilb_reserve(ctx, &ctx->d_accum, &ctx->d_accum_capacity, bytes, false);
+        if (rc) return rc;
+        P.accum_out = reinterpret_cast<float4*>(ctx->d_accum);
+        ILB_LIGHT_LAUNCH(ILB_LIGHT_LINE);
+        P.accum_in = P.accum_out;
+        P.accum_out = nullptr;
+        ILB_LIGHT_LAUNCH(NOLINE);
+    } else if (nline == 0) {
+        ILB_LIGHT_LAUNCH(NOLINE);
+    } else {
+        ILB_LIGHT_LAUNCH(ALL);
+    }
+#undef ILB_LIGHT_LAUNCH
     ILB_CUDA(ctx, cudaGetLastError());
     return ILB_OK;
 }
