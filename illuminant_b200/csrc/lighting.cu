@@ -952,9 +952,11 @@ int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, c
     for (const DLight& L : lights) nline += (L.type == ILB_LIGHT_LINE) ? 1 : 0;
     bool split = nline > 0 && nline < (int)lights.size();
     if (const char* e = getenv("ILB_SPLIT_PASSES")) split = split && e[0] != '0';
+    int planesMask = 3;  // dev knob: bit 0 = line pass samples the planes, bit 1 = sphere / directional pass does
+    if (const char* e = getenv("ILB_PLANES_MASK")) planesMask = atoi(e);
 #define ILB_LIGHT_LAUNCH(TYPES)                                                                                       \
     do {                                                                                                              \
-        if (P.df.planes) light_accumulate_kernel<1, TYPES><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);               \
+        if (P.df.planes && (planesMask & (((TYPES) & ILB_LIGHT_LINE) ? 1 : 2))) light_accumulate_kernel<1, TYPES><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);               \
         else light_accumulate_kernel<0, TYPES><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);                           \
         ctx->launches++;                                                                                              \
     } while (0)

@@ -151,7 +151,10 @@ ILB_DEV float computeWeight(const ilb_area& a, const OpDerived& d, f3 worldPosit
 }
 ILB_DEV bool checkCategoryFilter(float type, const float* mm) { return (type >= mm[0]) && (type <= mm[1]); }  // ParticleCommon.fxh:198-200
 
-ILB_DEV void opGravity(const ilb_psys_uniforms& u, const SysDerived& sd, const ilb_gravity& g, const OpDerived& d, f4& pos, f4& vel) {  // Gravity.fx:12-61
+// FAST (here and below): square roots / reciprocals through the deferred-guard forms of ilb_device.cuh; `bad` collects
+// the range checks and the caller re-runs the particle through the FAST = false instantiation when it is set.
+template <bool FAST>
+ILB_DEV void opGravity(const ilb_psys_uniforms& u, const SysDerived& sd, const ilb_gravity& g, const OpDerived& d, f4& pos, f4& vel, bool& bad) {  // Gravity.fx:12-61
     if ((pos.w <= 0.0f) || !checkCategoryFilter(vel.w, g.CategoryFilter)) return;
     const float dt = u.GlobalSettings.x;
     f3 acceleration = mk3(0.0f);
@@ -159,27 +162,30 @@ ILB_DEV void opGravity(const ilb_psys_uniforms& u, const SysDerived& sd, const i
         const f3 apos = xyz(g.AttractorPositions[i]);
         const ilb_float4 ars = g.AttractorRadiusesAndStrengths[i];
         const f3 toCenter = xsub3(apos, xyz(pos));
+        f3 direction;
+        const float distance = tlengthdir3z<FAST>(toCenter, direction, bad);  // length() and normalize() share dot and sqrt
         float attraction;
         if (ars.z >= 0.5f) {
-            const float distance = xlength3z(toCenter);
             attraction = xsub(1.0f, saturatef(udiv(distance, ars.x, d.rRadius[i])));
             if (ars.z >= 1.5f) attraction = xmul(attraction, attraction);
             attraction = udiv(xmul(attraction, dt), VelocityConstantScale, sd.r1000);
         } else {
             float distanceSquared = xsub(xdot3(toCenter, toCenter), ars.x);
             distanceSquared = fmaxf(distanceSquared, 0.001f);
-            attraction = __frcp_rn(distanceSquared);  // 1 / distanceSquared, correctly rounded (distanceSquared >= 0.001)
+            attraction = trcp<FAST>(distanceSquared, bad);  // 1 / distanceSquared, correctly rounded (distanceSquared >= 0.001)
         }
-        acceleration = xadd3(acceleration, xscale3(xscale3(xnormalize3(toCenter), attraction), ars.y));
+        acceleration = xadd3(acceleration, xscale3(xscale3(direction, attraction), ars.y));
     }
     const float maximumAcceleration = d.maxAccel;
-    const float currentLength = xlength3z(acceleration);
-    if (currentLength > maximumAcceleration) acceleration = xscale3(xnormalize3(acceleration), maximumAcceleration);
+    f3 accelerationDirection;
+    const float currentLength = tlengthdir3z<FAST>(acceleration, accelerationDirection, bad);
+    if (currentLength > maximumAcceleration) acceleration = xscale3(accelerationDirection, maximumAcceleration);
     const float mv = u.GlobalSettings.z;
     vel = mk4(fminf(mv, xadd(vel.x, acceleration.x)), fminf(mv, xadd(vel.y, acceleration.y)), fminf(mv, xadd(vel.z, acceleration.z)), vel.w);
 }
 
-ILB_DEV void opNoise(const StepParams& P, const ilb_noise& n, const OpDerived& d, float x, float y, f4& pos, f4& vel) {  // Noise.fx:28-72
+template <bool FAST>
+ILB_DEV void opNoise(const StepParams& P, const ilb_noise& n, const OpDerived& d, float x, float y, f4& pos, f4& vel, bool& bad) {  // Noise.fx:28-72
     if (!checkCategoryFilter(vel.w, n.area.CategoryFilter)) return;
     const float weight = computeWeight(n.area, d, xyz(pos));
     const float t = udiv(xmul(weight, P.u.GlobalSettings.x), n.TimeDivisor, d.rTimeDivisor);
@@ -202,7 +208,7 @@ ILB_DEV void opNoise(const StepParams& P, const ilb_noise& n, const OpDerived& d
     f3 nv;
     if (n.ReplaceOldVelocity != 0.0f) nv = xlerp3(ov, xyz(velocityDelta), weight);
     else nv = xlerp3(ov, xadd3(ov, xyz(velocityDelta)), t);
-    nv = xadd3(nv, xscale3(xnormalize3(ov), velocityDelta.w));
+    nv = xadd3(nv, xscale3(tnormalize3z<FAST>(ov, bad), velocityDelta.w));
     vel = mk4(nv, vel.w);
 }
 
@@ -231,15 +237,15 @@ ILB_DEV void opMatrix(const ilb_psys_uniforms& u, const ilb_matrix_multiply& m, 
 }
 
 // ---- update tail (UpdateCommon.fxh, UpdateParticleSystem.fx, UpdateParticleSystemWithDistanceField.fx) -------------
-ILB_DEV f3 applyFrictionAndMaximum(const ilb_psys_uniforms& u, const SysDerived& sd, f3 velocity) {  // UpdateCommon.fxh:20-35
-    float l = xlength3z(velocity);
+// `l` = length(velocity), `direction` = normalize(velocity): computed once by the caller (the collision tail needs both)
+ILB_DEV f3 applyFrictionAndMaximum(const ilb_psys_uniforms& u, const SysDerived& sd, float l, f3 direction) {  // UpdateCommon.fxh:20-35
     if (l <= 0.001f) return mk3(0.0f);
     const float mv = u.GlobalSettings.z;
     if (l > mv) l = mv;
     const float friction = xmul(l, u.GlobalSettings.y);
     l = xsub(l, xmul(friction, sd.dts));
     l = clampf(l, 0.0f, mv);
-    return xscale3(xnormalize3(velocity), l);
+    return xscale3(direction, l);
 }
 
 // Render outputs do not feed back into particle state: plain (FMA / fast division) arithmetic.
@@ -271,29 +277,30 @@ ILB_DEV void computeRenderData(const ilb_psys_uniforms& u, float vx, float vy, f
     renderData.w = velocity.w;
 }
 
-// PL: 0 = sample the Rgba64 atlas, 1 = sample the expanded planes (ilb_device.cuh); FLAT: Packed1 == 0 uniforms
-template <int PL, bool FLAT>
+// FM, the field mode of a kernel instantiation: bit 1 = sample the expanded planes instead of the Rgba64 atlas
+// (ilb_device.cuh), bit 0 = FLAT, the uniforms carry Packed1 == 0 (what the reference's particle update runs with)
+template <int FM>
 ILB_DEV float sampleField(const DFGeometry& g, f3 p) {
-    if (PL) return FLAT ? sampleFieldPlanesFlat(g, p) : sampleFieldPlanesT<false>(g, p);
-    return FLAT ? sampleDistanceFieldFlat(g, p) : sampleDistanceField(g, p);
+    if (FM & 2) return (FM & 1) ? sampleFieldPlanesFlat(g, p) : sampleFieldPlanesT<false>(g, p);
+    return (FM & 1) ? sampleDistanceFieldFlat(g, p) : sampleDistanceField(g, p);
 }
 
-template <int PL, bool FLAT>
-ILB_DEV f3 estimateNormal4(const DFGeometry& g, float texelZ, f3 position) {  // VisualizeCommon.fxh:9-63
+template <int FM, bool FAST>
+ILB_DEV f3 estimateNormal4(const DFGeometry& g, float texelZ, f3 position, bool& bad) {  // VisualizeCommon.fxh:9-63
     const f3 texel = mk3(g.invScaleX, g.invScaleY, texelZ);
     f3 result = mk3(0.0f);
-    const float wts[4][3] = {{1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {1, 1, 1}};
-#pragma unroll
+    // weights (1,-1,-1), (-1,-1,1), (-1,1,-1), (1,1,1): one copy of the sampler in the instruction stream, not four
+#pragma unroll 1
     for (int i = 0; i < 4; i++) {
-        const f3 weight = mk3(wts[i][0], wts[i][1], wts[i][2]);
-        result = xadd3(result, xscale3(weight, sampleField<PL, FLAT>(g, xadd3(position, xmul3(weight, texel)))));
+        const f3 weight = mk3((i == 0 || i == 3) ? 1.0f : -1.0f, (i >= 2) ? 1.0f : -1.0f, (i & 1) ? 1.0f : -1.0f);
+        result = xadd3(result, xscale3(weight, sampleField<FM>(g, xadd3(position, xmul3(weight, texel)))));
     }
-    return xnormalize3(result);
+    return tnormalize3z<FAST>(result, bad);
 }
 
 // returns false when the reference pass discards (dead on entry): outputs stay at the cleared zeros
-template <bool COLLIDE, int PL, bool FLAT>
-ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f4 oldVelocity, f4& outP, f4& outV, bool& needAttr) {
+template <bool COLLIDE, int FM, bool FAST>
+ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f4 oldVelocity, f4& outP, f4& outV, bool& needAttr, bool& bad) {
     const ilb_psys_uniforms& u = P.u;
     outP = mk4(0.0f);
     outV = mk4(0.0f);
@@ -301,8 +308,11 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
     if (oldPosition.w <= 0.0f) return false;  // readStateOrDiscard ParticleCommon.fxh:162-181
     const float dts = P.sd.dts;
     float newLife = xsub(oldPosition.w, xmul(u.GlobalSettings.w, dts));
+    // length(oldVelocity) and normalize(oldVelocity) feed applyFrictionAndMaximum and the collision response
+    f3 unitVector;
+    const float oldSpeed = tlengthdir3z<FAST>(xyz(oldVelocity), unitVector, bad);
     if (!COLLIDE) {  // PS_Update UpdateParticleSystem.fx:9-38
-        const f3 velocity = applyFrictionAndMaximum(u, P.sd, xyz(oldVelocity));
+        const f3 velocity = applyFrictionAndMaximum(u, P.sd, oldSpeed, unitVector);
         const f3 scaledVelocity = xscale3(velocity, dts);
         if (newLife > 0.0f) {
             outP = mk4(xadd3(xyz(oldPosition), scaledVelocity), newLife);
@@ -315,22 +325,22 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
     if (newLife <= 0.0f) return true;
     const float collisionDistance = u.CollisionSettings.z;
     const f3 op = xyz(oldPosition);
-    const f3 unitVector = xnormalize3(xyz(oldVelocity));
-    const f3 velocity = applyFrictionAndMaximum(u, P.sd, xyz(oldVelocity));
+    const f3 velocity = applyFrictionAndMaximum(u, P.sd, oldSpeed, unitVector);
     bool collided = false, escaping = false;
     const f3 scaledVelocity = xscale3(velocity, dts);
     f3 collisionPosition = mk3(0.0f), newPosition = op;
     f4 newVelocity = mk4(0.0f);
 
-    const float initialDistance = sampleField<PL, FLAT>(P.df, op);
+    const float initialDistance = sampleField<FM>(P.df, op);
     const bool wasColliding = initialDistance < collisionDistance;
-    float travelDistance = fmaxf(0.0f, fminf(initialDistance, xlength3z(scaledVelocity)));
+    float travelDistance = fmaxf(0.0f, fminf(initialDistance, tlength3z<FAST>(scaledVelocity, bad)));
     int stepCount = 3;
     if (wasColliding) stepCount = 1;
     else if (travelDistance <= 0.001f) stepCount = 0;
+#pragma unroll 1
     for (int i = 0; i < stepCount; i++) {
         const f3 testPosition = xadd3(op, xscale3(unitVector, travelDistance));
-        const float stepDistance = sampleField<PL, FLAT>(P.df, testPosition);
+        const float stepDistance = sampleField<FM>(P.df, testPosition);
         if (stepDistance < collisionDistance) {
             collided = true;
             collisionPosition = testPosition;
@@ -348,30 +358,29 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
         const bool bounce = oldVelocity.w <= 0.0f;
         const bool redirect = wasColliding && !escaping;
         f3 normal = mk3(0.0f);
-        if (bounce || redirect) normal = estimateNormal4<PL, FLAT>(P.df, P.sd.texelZ, collisionPosition);
+        if (bounce || redirect) normal = estimateNormal4<FM, FAST>(P.df, P.sd.texelZ, collisionPosition, bad);
         const float maxV = u.GlobalSettings.z;
         const float escapeSpeed = fminf(maxV, u.CollisionSettings.x);
         if (redirect) {
             normal = mk3(normal.x, normal.y, xmul(normal.z, 0.0f));
-            if (xlength3z(normal) < 0.33f) {
+            f3 escapeVector;
+            if (tlengthdir3z<FAST>(normal, escapeVector, bad) < 0.33f) {
                 float s, c;
                 dm_sincosf(xadd(xdivz(x, 67.0f), xdivz(y, 13.0f)), &s, &c);
-                normal = mk3(s, c, 0.0f);
+                escapeVector = tnormalize3z<FAST>(mk3(s, c, 0.0f), bad);
             }
-            const f3 escapeVector = xnormalize3(normal);
             newVelocity = mk4(xscale3(xscale3(escapeVector, escapeSpeed), 0.33f), 3.0f);
             newPosition = xadd3(op, xscale3(xyz(newVelocity), dts));
         } else if (bounce) {
             const float k = xmul(2.0f, xdot3(normal, unitVector));
-            f3 bounceVector = -xscale3(xsub3(normal, unitVector), k);
-            if (xlength3z(bounceVector) < 0.33f) bounceVector = -unitVector;
-            else bounceVector = xnormalize3(bounceVector);
+            f3 bounceVector = -xscale3(xsub3(normal, unitVector), k), bounceDirection;
+            if (tlengthdir3z<FAST>(bounceVector, bounceDirection, bad) < 0.33f) bounceVector = -unitVector;
+            else bounceVector = bounceDirection;
             newPosition = collisionPosition;
-            newVelocity = mk4(xscale3(bounceVector, fminf(maxV, xmul(xlength3z(velocity), u.CollisionSettings.y))), 3.0f);
+            newVelocity = mk4(xscale3(bounceVector, fminf(maxV, xmul(tlength3z<FAST>(velocity, bad), u.CollisionSettings.y))), 3.0f);
             newLife = xsub(newLife, u.CollisionSettings.w);
         } else {
-            const float currentSpeed = xlength3z(xyz(oldVelocity));
-            const float newSpeed = fmaxf(xmul(currentSpeed, 1.1f), escapeSpeed);
+            const float newSpeed = fmaxf(xmul(oldSpeed, 1.1f), escapeSpeed);
             newVelocity = mk4(xscale3(unitVector, newSpeed), 0.0f);
             newPosition = xadd3(op, xscale3(unitVector, travelDistance));
         }
@@ -393,19 +402,15 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
 #define ILB_PARTICLE_MINBLOCKS 4
 #endif
 
-template <int KIND>
-ILB_DEV void applyOp(const StepParams& P, const ilb_op& op, const OpDerived& d, float x, float y, f4& pos, f4& vel) {
-    if (KIND == ILB_OP_GRAVITY) opGravity(P.u, P.sd, op.u.gravity, d, pos, vel);
-    else if (KIND == ILB_OP_NOISE) opNoise(P, op.u.noise, d, x, y, pos, vel);
+template <int KIND, bool FAST>
+ILB_DEV void applyOp(const StepParams& P, const ilb_op& op, const OpDerived& d, float x, float y, f4& pos, f4& vel, bool& bad) {
+    if (KIND == ILB_OP_GRAVITY) opGravity<FAST>(P.u, P.sd, op.u.gravity, d, pos, vel, bad);
+    else if (KIND == ILB_OP_NOISE) opNoise<FAST>(P, op.u.noise, d, x, y, pos, vel, bad);
     else if (KIND == ILB_OP_FMA) opFMA(P.u, op.u.fma, d, pos, vel);
     else if (KIND == ILB_OP_MATRIX_MULTIPLY) opMatrix(P.u, op.u.matrix, d, pos, vel);
 }
 
-// K0..K2: the transform chain known at compile time (op kinds, 0 = no op): operands come straight from the constant
-// bank with static offsets.  K0 < 0 selects the generic loop over P.ops[0..nops) for every other chain.
-// One particle through the whole update: transform chain in registers, then the Update / UpdateWithDistanceField tail.
-template <bool COLLIDE, int K0, int K1, int K2, int PL>
-ILB_DEV void stepParticle(const StepParams& P, unsigned gi, f4 pos, f4 vel, f4& outP, f4& outV, bool& needAttr, float& x, float& y) {
+ILB_DEV void particleXY(const StepParams& P, unsigned gi, float& x, float& y) {
     unsigned ix, iy;
     if (P.chunk_shift >= 0) {
         const unsigned i = gi & (P.per_chunk - 1u);
@@ -418,35 +423,74 @@ ILB_DEV void stepParticle(const StepParams& P, unsigned gi, f4 pos, f4 vel, f4& 
     }
     x = (float)ix;
     y = (float)iy;
+}
+
+// K0..K2: the transform chain known at compile time (op kinds, 0 = no op): operands come straight from the constant
+// bank with static offsets.  K0 < 0 selects the generic loop over P.ops[0..nops) for every other chain.
+// One particle through the whole update: transform chain in registers, then the Update / UpdateWithDistanceField tail.
+template <bool COLLIDE, int K0, int K1, int K2, int FM, bool FAST>
+ILB_DEV void stepParticle(const StepParams& P, float x, float y, f4 pos, f4 vel, f4& outP, f4& outV, bool& needAttr, bool& bad) {
     if (K0 < 0) {
         for (int k = 0; k < P.nops; k++) {
             const ilb_op& op = P.ops[k];
             switch (op.kind) {
-                case ILB_OP_GRAVITY: applyOp<ILB_OP_GRAVITY>(P, op, P.od[k], x, y, pos, vel); break;
-                case ILB_OP_NOISE: applyOp<ILB_OP_NOISE>(P, op, P.od[k], x, y, pos, vel); break;
-                case ILB_OP_FMA: applyOp<ILB_OP_FMA>(P, op, P.od[k], x, y, pos, vel); break;
-                case ILB_OP_MATRIX_MULTIPLY: applyOp<ILB_OP_MATRIX_MULTIPLY>(P, op, P.od[k], x, y, pos, vel); break;
+                case ILB_OP_GRAVITY: applyOp<ILB_OP_GRAVITY, FAST>(P, op, P.od[k], x, y, pos, vel, bad); break;
+                case ILB_OP_NOISE: applyOp<ILB_OP_NOISE, FAST>(P, op, P.od[k], x, y, pos, vel, bad); break;
+                case ILB_OP_FMA: applyOp<ILB_OP_FMA, FAST>(P, op, P.od[k], x, y, pos, vel, bad); break;
+                case ILB_OP_MATRIX_MULTIPLY: applyOp<ILB_OP_MATRIX_MULTIPLY, FAST>(P, op, P.od[k], x, y, pos, vel, bad); break;
                 default: break;
             }
         }
     } else {
-        if (K0 > 0) applyOp<K0>(P, P.ops[0], P.od[0], x, y, pos, vel);
-        if (K1 > 0) applyOp<K1>(P, P.ops[1], P.od[1], x, y, pos, vel);
-        if (K2 > 0) applyOp<K2>(P, P.ops[2], P.od[2], x, y, pos, vel);
+        if (K0 > 0) applyOp<K0, FAST>(P, P.ops[0], P.od[0], x, y, pos, vel, bad);
+        if (K1 > 0) applyOp<K1, FAST>(P, P.ops[1], P.od[1], x, y, pos, vel, bad);
+        if (K2 > 0) applyOp<K2, FAST>(P, P.ops[2], P.od[2], x, y, pos, vel, bad);
     }
-    if (COLLIDE && fieldIsFlat(P.df)) updateTail<COLLIDE, PL, true>(P, x, y, pos, vel, outP, outV, needAttr);   // uniform branch
-    else updateTail<COLLIDE, PL, false>(P, x, y, pos, vel, outP, outV, needAttr);
+    updateTail<COLLIDE, FM, FAST>(P, x, y, pos, vel, outP, outV, needAttr, bad);
+}
+
+// The IEEE re-evaluation of a particle whose fast evaluation tripped a range guard (operand of a square root or a
+// reciprocal outside the fast window).  Out of line and generic over the chain: never on the hot path.
+struct ExactResult { float4 p, v; int needAttr; };
+template <bool COLLIDE, int FM>
+__device__ __noinline__ ExactResult stepParticleExact(const StepParams* P, float x, float y, float4 pos, float4 vel) {
+    f4 outP, outV;
+    bool needAttr, bad = false;
+    stepParticle<COLLIDE, -1, 0, 0, FM, false>(*P, x, y, mk4(pos), mk4(vel), outP, outV, needAttr, bad);
+    ExactResult r;
+    r.p = to_float4(outP); r.v = to_float4(outV); r.needAttr = needAttr ? 1 : 0;
+    return r;
+}
+
+// fast evaluation + fallback; the specialised chains (K0 >= 0) take the fast path, the generic chain runs IEEE ops directly
+template <bool COLLIDE, int K0, int K1, int K2, int FM>
+ILB_DEV void stepParticleGuarded(const StepParams& P, float x, float y, f4 pos, f4 vel, f4& outP, f4& outV, bool& needAttr) {
+    bool bad = false;
+#if ILB_NO_FAST_GUARD
+    stepParticle<COLLIDE, K0, K1, K2, FM, false>(P, x, y, pos, vel, outP, outV, needAttr, bad);
+#else
+    if (K0 < 0) {
+        stepParticle<COLLIDE, K0, K1, K2, FM, false>(P, x, y, pos, vel, outP, outV, needAttr, bad);
+        return;
+    }
+    stepParticle<COLLIDE, K0, K1, K2, FM, true>(P, x, y, pos, vel, outP, outV, needAttr, bad);
+    if (bad) {
+        const ExactResult r = stepParticleExact<COLLIDE, FM>(&P, x, y, to_float4(pos), to_float4(vel));
+        outP = mk4(r.p); outV = mk4(r.v); needAttr = r.needAttr != 0;
+    }
+#endif
 }
 
 // Direct variant: one thread per particle, 16-byte coalesced global loads / stores.
-template <bool COLLIDE, int K0, int K1, int K2, int PL>
+template <bool COLLIDE, int K0, int K1, int K2, int FM>
 __global__ void __launch_bounds__(STEP_THREADS, ILB_PARTICLE_MINBLOCKS) particle_step_kernel(const __grid_constant__ StepParams P) {
     const unsigned gi = blockIdx.x * STEP_THREADS + threadIdx.x;
     if (gi >= P.total) return;
     f4 outP, outV;
     bool needAttr;
     float x, y;
-    stepParticle<COLLIDE, K0, K1, K2, PL>(P, gi, mk4(P.P[gi]), mk4(P.V[gi]), outP, outV, needAttr, x, y);
+    particleXY(P, gi, x, y);
+    stepParticleGuarded<COLLIDE, K0, K1, K2, FM>(P, x, y, mk4(P.P[gi]), mk4(P.V[gi]), outP, outV, needAttr);
     P.P[gi] = to_float4(outP);
     P.V[gi] = to_float4(outV);
     if (P.u.write_render_outputs) {
@@ -494,7 +538,7 @@ ILB_DEV void bulkStore(void* gmemDst, const void* smemSrc, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmemDst), "r"(smemAddr(smemSrc)), "r"(bytes) : "memory");
 }
 
-template <bool COLLIDE, int K0, int K1, int K2>
+template <bool COLLIDE, int K0, int K1, int K2, int FM>
 __global__ void __launch_bounds__(STEP_THREADS, 3) particle_step_tma_kernel(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StageSmem& S = *reinterpret_cast<StageSmem*>(smem_raw);
@@ -539,7 +583,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 3) particle_step_tma_kernel(cons
         f4 outP, outV, rc = mk4(0.0f), rd = mk4(0.0f);
         bool needAttr;
         float x, y;
-        stepParticle<COLLIDE, K0, K1, K2, 0>(P, gi, pos, vel, outP, outV, needAttr, x, y);
+        particleXY(P, gi, x, y);
+        stepParticleGuarded<COLLIDE, K0, K1, K2, FM>(P, x, y, pos, vel, outP, outV, needAttr);
         if (P.u.write_render_outputs && needAttr) computeRenderData(P.u, x, y, outP, outV, attr, rc, rd);
 
         S.outP[tid] = to_float4(outP);
@@ -792,35 +837,46 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
         const bool chainGNF = op_count == 3 && ops[0].kind == ILB_OP_GRAVITY && ops[1].kind == ILB_OP_NOISE && ops[2].kind == ILB_OP_FMA;
         // In-place safety of the staged variant: a tile is fully read into registers before its results are stored, and
         // tiles are disjoint, so reading through one proxy and writing through the other never overlaps in time.
-        const bool staged = ps->use_tma && (chainGNF || chainNone) && (total % STAGE_TILE == 0);
+        // (Instantiated for the two chain / collision combinations the bit-identity test exercises.)
+        const bool staged = ps->use_tma && ((chainGNF && collide) || (chainNone && !collide)) && (total % STAGE_TILE == 0);
         const unsigned ntiles = (unsigned)(total / STAGE_TILE);
         const unsigned persistent = std::min<unsigned>(ntiles, (unsigned)ps->sm_count * 3u);
-#define ILB_LAUNCH(C, A, B, D)                                                                                              \
+        const int fm = collide ? ((planes ? 2 : 0) | (ilb_field_is_flat(SP.df) ? 1 : 0)) : 0;  // field mode, see sampleField
+#define ILB_STAGED(C, A, B, D, FM)                                                                                          \
     do {                                                                                                                    \
-        if (staged) {                                                                                                       \
-            static bool attr_set = false;                                                                                   \
-            if (!attr_set) {                                                                                                \
-                ILB_CUDA(ctx, cudaFuncSetAttribute(particle_step_tma_kernel<C, A, B, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem))); \
-                attr_set = true;                                                                                            \
-            }                                                                                                               \
-            particle_step_tma_kernel<C, A, B, D><<<persistent, STEP_THREADS, sizeof(StageSmem), ctx->stream>>>(SP);         \
-        } else if (planes) {                                                                                                \
-            particle_step_kernel<C, A, B, D, (C) ? 1 : 0><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);                     \
-        } else {                                                                                                            \
-            particle_step_kernel<C, A, B, D, 0><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);                               \
+        static bool attr_set = false;                                                                                       \
+        if (!attr_set) {                                                                                                    \
+            ILB_CUDA(ctx, cudaFuncSetAttribute(particle_step_tma_kernel<C, A, B, D, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StageSmem))); \
+            attr_set = true;                                                                                                \
         }                                                                                                                   \
+        particle_step_tma_kernel<C, A, B, D, FM><<<persistent, STEP_THREADS, sizeof(StageSmem), ctx->stream>>>(SP);         \
+    } while (0)
+#define ILB_DIRECT(C, A, B, D, FM) particle_step_kernel<C, A, B, D, FM><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP)
+#define ILB_BY_FIELD(C, A, B, D)                                  \
+    do {                                                          \
+        switch (fm) {                                             \
+            case 0: ILB_DIRECT(C, A, B, D, 0); break;             \
+            case 1: ILB_DIRECT(C, A, B, D, 1); break;             \
+            case 2: ILB_DIRECT(C, A, B, D, 2); break;             \
+            default: ILB_DIRECT(C, A, B, D, 3); break;            \
+        }                                                         \
     } while (0)
         if (collide) {
-            if (chainGNF) ILB_LAUNCH(true, ILB_OP_GRAVITY, ILB_OP_NOISE, ILB_OP_FMA);
-            else if (chainNone) ILB_LAUNCH(true, 0, 0, 0);
-            else if (planes) particle_step_kernel<true, -1, 0, 0, 1><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);
-            else particle_step_kernel<true, -1, 0, 0, 0><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);
+            if (staged) {  // planes are not attached in TMA mode: fm is 0 or 1
+                if (fm & 1) ILB_STAGED(true, ILB_OP_GRAVITY, ILB_OP_NOISE, ILB_OP_FMA, 1);
+                else ILB_STAGED(true, ILB_OP_GRAVITY, ILB_OP_NOISE, ILB_OP_FMA, 0);
+            } else if (chainGNF) ILB_BY_FIELD(true, ILB_OP_GRAVITY, ILB_OP_NOISE, ILB_OP_FMA);
+            else if (chainNone) ILB_BY_FIELD(true, 0, 0, 0);
+            else ILB_BY_FIELD(true, -1, 0, 0);
         } else {
-            if (chainGNF) ILB_LAUNCH(false, ILB_OP_GRAVITY, ILB_OP_NOISE, ILB_OP_FMA);
-            else if (chainNone) ILB_LAUNCH(false, 0, 0, 0);
-            else particle_step_kernel<false, -1, 0, 0, 0><<<blocks, STEP_THREADS, 0, ctx->stream>>>(SP);
+            if (staged) ILB_STAGED(false, 0, 0, 0, 0);
+            else if (chainGNF) ILB_DIRECT(false, ILB_OP_GRAVITY, ILB_OP_NOISE, ILB_OP_FMA, 0);
+            else if (chainNone) ILB_DIRECT(false, 0, 0, 0, 0);
+            else ILB_DIRECT(false, -1, 0, 0, 0);
         }
-#undef ILB_LAUNCH
+#undef ILB_BY_FIELD
+#undef ILB_DIRECT
+#undef ILB_STAGED
         ctx->launches++;
     }
     ILB_CUDA(ctx, cudaGetLastError());
