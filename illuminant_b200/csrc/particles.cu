@@ -298,16 +298,62 @@ ILB_DEV f3 estimateNormal4(const DFGeometry& g, float texelZ, f3 position, bool&
     return tnormalize3z<FAST>(result, bad);
 }
 
-// returns false when the reference pass discards (dead on entry): outputs stay at the cleared zeros
-template <bool COLLIDE, int FM, bool FAST>
-ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f4 oldVelocity, f4& outP, f4& outV, bool& needAttr, bool& bad) {
+// estimateNormal4 for the lanes of a warp that need it (`need`), evaluated cooperatively: colliding particles are a
+// minority, but in almost every warp some lane collides, so the per-lane form makes all 32 lanes walk through four
+// sampler invocations for a handful of results.  Here the requesters are compacted (rank by ballot, lane ids through
+// 32 bytes of shared memory), and each group of four lanes takes one requester's four tetrahedron samples -- one
+// sampler invocation serves eight requesters.  The samples return to their owner by shuffle and are summed there in
+// the reference's order, so the result is bit-identical to estimateNormal4.  Must be reached by all 32 lanes.
+template <int FM, bool FAST>
+ILB_DEV f3 cooperativeNormal4(const DFGeometry& g, float texelZ, f3 position, bool need, unsigned char* warpSlots, bool& bad) {
+    const unsigned full = 0xFFFFFFFFu, lane = threadIdx.x & 31u;
+    const unsigned needMask = __ballot_sync(full, need);
+    f3 normal = mk3(0.0f);
+    if (needMask == 0u) return normal;  // warp-uniform
+    const unsigned rank = __popc(needMask & ((1u << lane) - 1u));
+    if (need) warpSlots[rank] = (unsigned char)lane;
+    __syncwarp();
+    const unsigned count = __popc(needMask), group = lane >> 2, i = lane & 3u;
+    const f3 texel = mk3(g.invScaleX, g.invScaleY, texelZ);
+    const f3 weight = mk3((i == 0u || i == 3u) ? 1.0f : -1.0f, (i >= 2u) ? 1.0f : -1.0f, (i & 1u) ? 1.0f : -1.0f);
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    for (unsigned base = 0; base < count; base += 8u) {
+        const unsigned slot = base + group;
+        const bool helping = slot < count;
+        const unsigned src = helping ? (unsigned)warpSlots[slot] : lane;
+        const f3 p = mk3(__shfl_sync(full, position.x, src), __shfl_sync(full, position.y, src), __shfl_sync(full, position.z, src));
+        float sample = 0.0f;
+        if (helping) sample = sampleField<FM>(g, xadd3(p, xmul3(weight, texel)));
+        const unsigned from = 4u * ((rank - base) & 7u);
+        const float a0 = __shfl_sync(full, sample, from), a1 = __shfl_sync(full, sample, from + 1u);
+        const float a2 = __shfl_sync(full, sample, from + 2u), a3 = __shfl_sync(full, sample, from + 3u);
+        if (need && rank >= base && rank < base + 8u) { s0 = a0; s1 = a1; s2 = a2; s3 = a3; }
+    }
+    __syncwarp();  // the slots are rewritten by the next call
+    if (need) {
+        f3 result = mk3(0.0f);  // weights (1,-1,-1), (-1,-1,1), (-1,1,-1), (1,1,1), VisualizeCommon.fxh:47-63
+        result = xadd3(result, xscale3(mk3(1.0f, -1.0f, -1.0f), s0));
+        result = xadd3(result, xscale3(mk3(-1.0f, -1.0f, 1.0f), s1));
+        result = xadd3(result, xscale3(mk3(-1.0f, 1.0f, -1.0f), s2));
+        result = xadd3(result, xscale3(mk3(1.0f, 1.0f, 1.0f), s3));
+        normal = tnormalize3z<FAST>(result, bad);
+    }
+    return normal;
+}
+
+// returns false when the reference pass discards (dead on entry): outputs stay at the cleared zeros.
+// COOP: every lane of the warp runs through this call together (the normal estimation is shared across lanes, see
+// cooperativeNormal4); COOP = false is the per-lane form for the divergent fallback call.
+template <bool COLLIDE, int FM, bool FAST, bool COOP>
+ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f4 oldVelocity, f4& outP, f4& outV, bool& needAttr, unsigned char* warpSlots, bool& bad) {
     const ilb_psys_uniforms& u = P.u;
     outP = mk4(0.0f);
     outV = mk4(0.0f);
     needAttr = false;
-    if (oldPosition.w <= 0.0f) return false;  // readStateOrDiscard ParticleCommon.fxh:162-181
+    const bool deadOnEntry = oldPosition.w <= 0.0f;  // readStateOrDiscard ParticleCommon.fxh:162-181
+    if (deadOnEntry && !(COLLIDE && COOP)) return false;
     const float dts = P.sd.dts;
-    float newLife = xsub(oldPosition.w, xmul(u.GlobalSettings.w, dts));
+    float newLife = deadOnEntry ? 0.0f : xsub(oldPosition.w, xmul(u.GlobalSettings.w, dts));
     // length(oldVelocity) and normalize(oldVelocity) feed applyFrictionAndMaximum and the collision response
     f3 unitVector;
     const float oldSpeed = tlengthdir3z<FAST>(xyz(oldVelocity), unitVector, bad);
@@ -322,43 +368,49 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
         return true;
     }
     // PS_Update UpdateParticleSystemWithDistanceField.fx:29-147
-    if (newLife <= 0.0f) return true;
+    const bool proceed = newLife > 0.0f;  // (dead-on-entry lanes only get here when COOP keeps them in the flow)
+    if (!COOP && !proceed) return true;
     const float collisionDistance = u.CollisionSettings.z;
     const f3 op = xyz(oldPosition);
     const f3 velocity = applyFrictionAndMaximum(u, P.sd, oldSpeed, unitVector);
-    bool collided = false, escaping = false;
+    bool collided = false, escaping = false, wasColliding = false;
     const f3 scaledVelocity = xscale3(velocity, dts);
     f3 collisionPosition = mk3(0.0f), newPosition = op;
     f4 newVelocity = mk4(0.0f);
-
-    const float initialDistance = sampleField<FM>(P.df, op);
-    const bool wasColliding = initialDistance < collisionDistance;
-    float travelDistance = fmaxf(0.0f, fminf(initialDistance, tlength3z<FAST>(scaledVelocity, bad)));
-    int stepCount = 3;
-    if (wasColliding) stepCount = 1;
-    else if (travelDistance <= 0.001f) stepCount = 0;
+    float travelDistance = 0.0f;
+    if (proceed) {
+        const float initialDistance = sampleField<FM>(P.df, op);
+        wasColliding = initialDistance < collisionDistance;
+        travelDistance = fmaxf(0.0f, fminf(initialDistance, tlength3z<FAST>(scaledVelocity, bad)));
+        int stepCount = 3;
+        if (wasColliding) stepCount = 1;
+        else if (travelDistance <= 0.001f) stepCount = 0;
 #pragma unroll 1
-    for (int i = 0; i < stepCount; i++) {
-        const f3 testPosition = xadd3(op, xscale3(unitVector, travelDistance));
-        const float stepDistance = sampleField<FM>(P.df, testPosition);
-        if (stepDistance < collisionDistance) {
-            collided = true;
-            collisionPosition = testPosition;
+        for (int i = 0; i < stepCount; i++) {
+            const f3 testPosition = xadd3(op, xscale3(unitVector, travelDistance));
+            const float stepDistance = sampleField<FM>(P.df, testPosition);
+            if (stepDistance < collisionDistance) {
+                collided = true;
+                collisionPosition = testPosition;
+            }
+            escaping = stepDistance > initialDistance;
+            if (collided && !escaping) {
+                collisionPosition = testPosition;
+                const float offset = clampf(xadd(stepDistance, collisionDistance), 0.05f, 16.0f);
+                travelDistance = fmaxf(0.0f, xsub(travelDistance, offset));
+            } else
+                stepCount = 0;
+            if (travelDistance <= 0.001f) stepCount = 0;
         }
-        escaping = stepDistance > initialDistance;
-        if (collided && !escaping) {
-            collisionPosition = testPosition;
-            const float offset = clampf(xadd(stepDistance, collisionDistance), 0.05f, 16.0f);
-            travelDistance = fmaxf(0.0f, xsub(travelDistance, offset));
-        } else
-            stepCount = 0;
-        if (travelDistance <= 0.001f) stepCount = 0;
     }
+    const bool bounce = oldVelocity.w <= 0.0f;
+    const bool redirect = wasColliding && !escaping;
+    const bool needNormal = proceed && collided && (bounce || redirect);
+    f3 normal = mk3(0.0f);
+    if (COOP) normal = cooperativeNormal4<FM, FAST>(P.df, P.sd.texelZ, collisionPosition, needNormal, warpSlots, bad);
+    else if (needNormal) normal = estimateNormal4<FM, FAST>(P.df, P.sd.texelZ, collisionPosition, bad);
+    if (!proceed) return !deadOnEntry;
     if (collided) {
-        const bool bounce = oldVelocity.w <= 0.0f;
-        const bool redirect = wasColliding && !escaping;
-        f3 normal = mk3(0.0f);
-        if (bounce || redirect) normal = estimateNormal4<FM, FAST>(P.df, P.sd.texelZ, collisionPosition, bad);
         const float maxV = u.GlobalSettings.z;
         const float escapeSpeed = fminf(maxV, u.CollisionSettings.x);
         if (redirect) {
@@ -428,8 +480,8 @@ ILB_DEV void particleXY(const StepParams& P, unsigned gi, float& x, float& y) {
 // K0..K2: the transform chain known at compile time (op kinds, 0 = no op): operands come straight from the constant
 // bank with static offsets.  K0 < 0 selects the generic loop over P.ops[0..nops) for every other chain.
 // One particle through the whole update: transform chain in registers, then the Update / UpdateWithDistanceField tail.
-template <bool COLLIDE, int K0, int K1, int K2, int FM, bool FAST>
-ILB_DEV void stepParticle(const StepParams& P, float x, float y, f4 pos, f4 vel, f4& outP, f4& outV, bool& needAttr, bool& bad) {
+template <bool COLLIDE, int K0, int K1, int K2, int FM, bool FAST, bool COOP>
+ILB_DEV void stepParticle(const StepParams& P, float x, float y, f4 pos, f4 vel, f4& outP, f4& outV, bool& needAttr, unsigned char* warpSlots, bool& bad) {
     if (K0 < 0) {
         for (int k = 0; k < P.nops; k++) {
             const ilb_op& op = P.ops[k];
@@ -446,7 +498,7 @@ ILB_DEV void stepParticle(const StepParams& P, float x, float y, f4 pos, f4 vel,
         if (K1 > 0) applyOp<K1, FAST>(P, P.ops[1], P.od[1], x, y, pos, vel, bad);
         if (K2 > 0) applyOp<K2, FAST>(P, P.ops[2], P.od[2], x, y, pos, vel, bad);
     }
-    updateTail<COLLIDE, FM, FAST>(P, x, y, pos, vel, outP, outV, needAttr, bad);
+    updateTail<COLLIDE, FM, FAST, COOP>(P, x, y, pos, vel, outP, outV, needAttr, warpSlots, bad);
 }
 
 // The IEEE re-evaluation of a particle whose fast evaluation tripped a range guard (operand of a square root or a
@@ -456,7 +508,7 @@ template <bool COLLIDE, int FM>
 __device__ __noinline__ ExactResult stepParticleExact(const StepParams* P, float x, float y, float4 pos, float4 vel) {
     f4 outP, outV;
     bool needAttr, bad = false;
-    stepParticle<COLLIDE, -1, 0, 0, FM, false>(*P, x, y, mk4(pos), mk4(vel), outP, outV, needAttr, bad);
+    stepParticle<COLLIDE, -1, 0, 0, FM, false, false>(*P, x, y, mk4(pos), mk4(vel), outP, outV, needAttr, nullptr, bad);
     ExactResult r;
     r.p = to_float4(outP); r.v = to_float4(outV); r.needAttr = needAttr ? 1 : 0;
     return r;
@@ -464,16 +516,16 @@ __device__ __noinline__ ExactResult stepParticleExact(const StepParams* P, float
 
 // fast evaluation + fallback; the specialised chains (K0 >= 0) take the fast path, the generic chain runs IEEE ops directly
 template <bool COLLIDE, int K0, int K1, int K2, int FM>
-ILB_DEV void stepParticleGuarded(const StepParams& P, float x, float y, f4 pos, f4 vel, f4& outP, f4& outV, bool& needAttr) {
+ILB_DEV void stepParticleGuarded(const StepParams& P, float x, float y, f4 pos, f4 vel, f4& outP, f4& outV, bool& needAttr, unsigned char* warpSlots) {
     bool bad = false;
 #if ILB_NO_FAST_GUARD
-    stepParticle<COLLIDE, K0, K1, K2, FM, false>(P, x, y, pos, vel, outP, outV, needAttr, bad);
+    stepParticle<COLLIDE, K0, K1, K2, FM, false, true>(P, x, y, pos, vel, outP, outV, needAttr, warpSlots, bad);
 #else
     if (K0 < 0) {
-        stepParticle<COLLIDE, K0, K1, K2, FM, false>(P, x, y, pos, vel, outP, outV, needAttr, bad);
+        stepParticle<COLLIDE, K0, K1, K2, FM, false, true>(P, x, y, pos, vel, outP, outV, needAttr, warpSlots, bad);
         return;
     }
-    stepParticle<COLLIDE, K0, K1, K2, FM, true>(P, x, y, pos, vel, outP, outV, needAttr, bad);
+    stepParticle<COLLIDE, K0, K1, K2, FM, true, true>(P, x, y, pos, vel, outP, outV, needAttr, warpSlots, bad);
     if (bad) {
         const ExactResult r = stepParticleExact<COLLIDE, FM>(&P, x, y, to_float4(pos), to_float4(vel));
         outP = mk4(r.p); outV = mk4(r.v); needAttr = r.needAttr != 0;
@@ -484,13 +536,16 @@ ILB_DEV void stepParticleGuarded(const StepParams& P, float x, float y, f4 pos, 
 // Direct variant: one thread per particle, 16-byte coalesced global loads / stores.
 template <bool COLLIDE, int K0, int K1, int K2, int FM>
 __global__ void __launch_bounds__(STEP_THREADS, ILB_PARTICLE_MINBLOCKS) particle_step_kernel(const __grid_constant__ StepParams P) {
+    __shared__ unsigned char s_slots[STEP_THREADS];  // 32 bytes per warp for cooperativeNormal4
     const unsigned gi = blockIdx.x * STEP_THREADS + threadIdx.x;
-    if (gi >= P.total) return;
+    const bool inRange = gi < P.total;  // out-of-range lanes stay in the flow as dead particles (warp-cooperative code below)
     f4 outP, outV;
     bool needAttr;
     float x, y;
     particleXY(P, gi, x, y);
-    stepParticleGuarded<COLLIDE, K0, K1, K2, FM>(P, x, y, mk4(P.P[gi]), mk4(P.V[gi]), outP, outV, needAttr);
+    const f4 inP = inRange ? mk4(P.P[gi]) : mk4(0.0f), inV = inRange ? mk4(P.V[gi]) : mk4(0.0f);
+    stepParticleGuarded<COLLIDE, K0, K1, K2, FM>(P, x, y, inP, inV, outP, outV, needAttr, s_slots + (threadIdx.x & ~31u));
+    if (!inRange) return;
     P.P[gi] = to_float4(outP);
     P.V[gi] = to_float4(outV);
     if (P.u.write_render_outputs) {
@@ -541,6 +596,7 @@ ILB_DEV void bulkStore(void* gmemDst, const void* smemSrc, unsigned bytes) {
 template <bool COLLIDE, int K0, int K1, int K2, int FM>
 __global__ void __launch_bounds__(STEP_THREADS, 3) particle_step_tma_kernel(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ unsigned char s_slots[STEP_THREADS];
     StageSmem& S = *reinterpret_cast<StageSmem*>(smem_raw);
     const unsigned tid = threadIdx.x;
     const unsigned ntiles = P.total / STAGE_TILE;   // per_chunk is a multiple of 256, so tiles are always full
@@ -584,7 +640,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 3) particle_step_tma_kernel(cons
         bool needAttr;
         float x, y;
         particleXY(P, gi, x, y);
-        stepParticleGuarded<COLLIDE, K0, K1, K2, FM>(P, x, y, pos, vel, outP, outV, needAttr);
+        stepParticleGuarded<COLLIDE, K0, K1, K2, FM>(P, x, y, pos, vel, outP, outV, needAttr, s_slots + (tid & ~31u));
         if (P.u.write_render_outputs && needAttr) computeRenderData(P.u, x, y, outP, outV, attr, rc, rd);
 
         S.outP[tid] = to_float4(outP);
