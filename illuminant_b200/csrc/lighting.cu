@@ -128,7 +128,8 @@ ILB_DEV bool traceInit(Trace& s, f3 start, f3 end, float lightRadius, bool& bad)
 
 ILB_DEV float traceStep(const TraceConfig& c, float d, float offset, float& vis) {  // coneTraceStep :51-71
     const float localSphereRadius = fminf((c.growth * offset) + MIN_CONE_RADIUS, c.maxRadius);
-    const float localVisibility = ((d + HACK_DISTANCE_OFFSET) / localSphereRadius);
+    // smooth factor, and the divisor lies in [0.33, MaxConeRadius]: reciprocal + multiply without the range scaling of `/`
+    const float localVisibility = __fdividef(d + HACK_DISTANCE_OFFSET, localSphereRadius);
     vis = fminf(vis, localVisibility);  // smooth: a few ulp in vis cannot change the result discontinuously
     return fmaxf(xmul(fabsf(d), c.longStep), c.minStep);  // exact: the step length moves the march
 }
@@ -148,8 +149,10 @@ ILB_DEV void coneTraceMarch(const DFGeometry& g, const TraceConfig& c, Trace& a,
         // identity and the distance-to-volume term is exactly 0, so the short sampler gives the same bits
         const float d = (INSIDE || insideField(g, sp)) ? sampleFieldT<FIELD, true>(g, sp) : sampleFieldT<FIELD, false>(g, sp);
         a.t = xadd(a.t, traceStep(c, d, a.t, a.vis));
-        const float stepLiveness = saturatef(a.vis - FULLY_SHADOWED_THRESHOLD) * saturatef(xsub(a.len, a.t));
-        liveness = stepsRemaining * stepLiveness;
+        // liveness = stepsRemaining * saturate(vis - 0.075) * saturate(len - t) > 0 (ConeTrace.fxh:168-176): a product of
+        // non-negative factors that cannot underflow (a non-zero factor is at least one ulp of 0.075 resp. of t >= 0.5), so it
+        // is positive exactly when every factor is
+        liveness = ((stepsRemaining > 0.0f) && (a.vis > FULLY_SHADOWED_THRESHOLD) && (a.len > a.t)) ? 1.0f : 0.0f;
     }
 }
 
@@ -180,7 +183,9 @@ ILB_DEV float traceAdvanceEx(const DFGeometry& g, const TraceConfig& c, Trace& s
     const f3 sp = xadd3(s.origin, xscale3(s.direction, s.t));
     const float d = (INSIDE || insideField(g, sp)) ? sampleFieldT<FIELD, true>(g, sp) : sampleFieldT<FIELD, false>(g, sp);
     s.t = fminf(xadd(s.t, traceStep(c, d, s.t, s.vis)), s.len);
-    return saturatef(s.vis - FULLY_SHADOWED_THRESHOLD) * saturatef(xsub(s.len, s.t) * TRACE_END_MULTIPLIER);
+    // saturate(vis - 0.075) * saturate((len - t) * 100): only its sign is used (lineConeTrace sums three of these and
+    // multiplies by stepsRemaining); positive exactly when both factors are (no underflow, see coneTraceMarch)
+    return ((s.vis > FULLY_SHADOWED_THRESHOLD) && (s.len > s.t)) ? 1.0f : 0.0f;
 }
 
 // ---- light response (LightCommon.fxh, AOCommon.fxh) ---------------------------------------------------------
