@@ -293,10 +293,9 @@ def run_ours(args):
         batches, nb, verts, nv = packed
         gb_ptr, out_ptr = C.c_void_p(gb_host.data_ptr()), C.c_void_p(out_host.data_ptr())
 
-        def e2e_step():
-            ctx.check(ctx.lib.ilb_gbuffer_upload(ctx.handle, W, H, _abi.FORMAT_FLOAT4, gb_ptr))
-            ctx.check(ctx.lib.ilb_render_lighting(ctx.handle, df.handle, C.byref(frame), C.cast(batches, C.c_void_p), nb,
-                                                  C.cast(verts, C.c_void_p), nv, out_ptr))
+        def e2e_step():   # one C-ABI call per frame: G-buffer up, shade, lightmap down (pipelined over row bands inside)
+            ctx.check(ctx.lib.ilb_render_lighting_frame(ctx.handle, df.handle, C.byref(frame), C.cast(batches, C.c_void_p), nb,
+                                                        C.cast(verts, C.c_void_p), nv, W, H, _abi.FORMAT_FLOAT4, gb_ptr, out_ptr))
         e_steps = max(3, args.steps // 2)
         for _ in range(2):
             e2e_step()
@@ -312,7 +311,7 @@ def run_ours(args):
                          "kernel": "light_accumulate_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_pixel": LIGHT_BYTES_PER_PIXEL,
                          "peak_source": peak_src,
                          "note": "per-pixel work is O(lights x trace steps): the kernel is issue-bound, not HBM-bound (see DESIGN.md)"},
-            "e2e": {"value": W * H / (e_ms * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": int(gb_host.numel() * 4 + nv * 128),
+            "e2e": {"value": W * H / (e_ms * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": int((r1 - r0) * W * 16 + nv * 128),
                     "d2h_bytes_per_step": int(out_host.numel() * 2), "ms_per_step": e_ms},
             "gpu_launches": int(launches), "clocks": clocks, "gather": gather,
         })

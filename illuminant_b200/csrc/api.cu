@@ -118,6 +118,11 @@ void ilb_destroy(ilb_ctx* ctx) {
     if (ctx->d_lightmap) cudaFree(ctx->d_lightmap);
     if (ctx->d_probe_in) cudaFree(ctx->d_probe_in);
     if (ctx->d_accum) cudaFree(ctx->d_accum);
+    if (ctx->copy_in) {
+        cudaStreamDestroy(ctx->copy_in);
+        cudaStreamDestroy(ctx->copy_out);
+        for (int i = 0; i < ILB_PIPELINE_BANDS; i++) { cudaEventDestroy(ctx->ev_in[i]); cudaEventDestroy(ctx->ev_done[i]); }
+    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -292,6 +297,15 @@ int ilb_render_lighting(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* fram
     ILB_CUDA(ctx, cudaMemcpyAsync(lightmap_out, ctx->d_lightmap, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ILB_OK;
+}
+
+int ilb_render_lighting_frame(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches, int batch_count,
+                              const ilb_light_vertex* vertices, int vertex_count, int gbuffer_width, int gbuffer_height, int gbuffer_format,
+                              const void* gbuffer, void* lightmap_out) {
+    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ilb_lighting_frame_from_host(ctx, df, frame, batches, batch_count, vertices, vertex_count, gbuffer_width, gbuffer_height,
+                                        gbuffer_format, gbuffer, lightmap_out);
 }
 
 int ilb_update_light_probes(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches, int batch_count,

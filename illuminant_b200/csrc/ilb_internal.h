@@ -14,6 +14,8 @@
 struct ilb_df;
 struct ilb_psys;
 
+#define ILB_PIPELINE_BANDS 8
+
 struct ilb_ctx {
     int device = -1;
     std::vector<ilb_df*> fields;      // children, destroyed with the context
@@ -37,6 +39,9 @@ struct ilb_ctx {
     size_t d_probe_in_capacity = 0;
     void* d_accum = nullptr;     // fp32 sums handed from the line-light pass to the sphere / directional pass
     size_t d_accum_capacity = 0;
+    // host-to-host frame pipeline (ilb_render_lighting_frame): upload / download streams and per-band events
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_in[ILB_PIPELINE_BANDS] = {}, ev_done[ILB_PIPELINE_BANDS] = {};
 };
 
 #define ILB_MAX_VIRTUAL_SLICES 64
@@ -93,6 +98,9 @@ int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* fram
 int ilb_probes_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches,
                       int batch_count, const ilb_light_vertex* vertices, int vertex_count, const ilb_float4* positions,
                       const ilb_float4* normals, int probe_count, int output_format, void* probes_out_host);
+int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches,
+                                 int batch_count, const ilb_light_vertex* vertices, int vertex_count, int gw, int gh, int gfmt,
+                                 const void* gbuffer_host, void* lightmap_out_host);
 // dfgen.cu
 int ilb_dfgen_launch(ilb_ctx* ctx, uint2* tex, int tw, int th, int slice_w, int slice_h, int slice_count,
                      const ilb_df_uniforms* u, const ilb_obstruction* obs, int count);

@@ -900,17 +900,22 @@ size_t ilb_format_bytes(int format) {
     return format == ILB_FORMAT_FLOAT4 ? 16 : (format == ILB_FORMAT_HALF4 ? 8 : 4);
 }
 
-int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const ilb_light_batch* batches, int batch_count,
-                        const ilb_light_vertex* vertices, int vertex_count, void* const* d_outputs, int output_count,
-                        bool outputs_are_full_frames) {
+namespace {
+
+struct LightingPrepared {
+    LightingParams P;   // everything but the row band and the outputs
+    int nline = 0, nlights = 0;
+};
+
+// Per-frame work that does not depend on the row band: validate, flatten + upload the light list, resolve the field.
+int lightingPrepare(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const ilb_light_batch* batches, int batch_count,
+                    const ilb_light_vertex* vertices, int vertex_count, LightingPrepared* out) {
     if (!f || (batch_count > 0 && (!batches || !vertices))) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
     if (f->width <= 0 || f->height <= 0 || f->row_begin < 0 || f->row_end > f->height || f->row_begin > f->row_end)
         return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad frame geometry %dx%d rows [%d,%d)", f->width, f->height, f->row_begin, f->row_end);
     if (f->lightmap_format != ILB_FORMAT_FLOAT4 && f->lightmap_format != ILB_FORMAT_HALF4 && f->lightmap_format != ILB_FORMAT_RGBA8)
         return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad lightmap format %d", f->lightmap_format);
-    if (output_count < 1 || output_count > MAX_OUTPUTS) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "1..%d outputs", MAX_OUTPUTS);
     if (df && df->ctx != ctx) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "distance field belongs to another context");
-    if (f->row_begin == f->row_end) return ILB_OK;
 
     std::vector<DLight> lights;
     std::vector<DLine> lines;
@@ -919,7 +924,7 @@ int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, c
     if (rc) return rc;
     if (lights.size() > 65535 * (size_t)TILE_THREADS) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "too many lights");
 
-    LightingParams P;
+    LightingParams& P = out->P;
     memset(&P, 0, sizeof(P));
     rc = uploadLights(ctx, lights, lines, &P.lights, &P.lines);
     if (rc) return rc;
@@ -939,48 +944,140 @@ int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, c
     P.gbuffer = ctx->gbuffer;
     P.gw = ctx->gb_w; P.gh = ctx->gb_h; P.gfmt = ctx->gb_fmt;
     P.nlights = (int)lights.size();
-    P.width = f->width; P.height = f->height; P.row_begin = f->row_begin; P.row_end = f->row_end;
+    P.width = f->width; P.height = f->height;
     P.out_format = f->lightmap_format;
     P.stencil = f->stencil_culling;
+    out->nlights = (int)lights.size();
+    out->nline = 0;
+    for (const DLight& L : lights) out->nline += (L.type == ILB_LIGHT_LINE) ? 1 : 0;
+    return ILB_OK;
+}
+
+// Shades rows [row_begin, row_end) of a prepared frame into d_outputs (band buffers whose row 0 is `out_row_base`).
+int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin, int row_end, void* const* d_outputs, int output_count,
+                       int out_row_base) {
+    if (output_count < 1 || output_count > MAX_OUTPUTS) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "1..%d outputs", MAX_OUTPUTS);
+    if (row_begin >= row_end) return ILB_OK;
+    LightingParams P = prep.P;
+    P.row_begin = row_begin; P.row_end = row_end;
     for (int o = 0; o < output_count; o++) {
         if (!d_outputs[o]) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null output %d", o);
         P.outs[o] = d_outputs[o];
     }
     P.nouts = output_count;
-    P.out_row_base = outputs_are_full_frames ? 0 : f->row_begin;
-
-    P.tiles_x = (f->width + TILE_W - 1) / TILE_W;
-    P.tiles_y = (f->row_end - f->row_begin + TILE_H - 1) / TILE_H;
+    P.out_row_base = out_row_base;
+    P.tiles_x = (P.width + TILE_W - 1) / TILE_W;
+    P.tiles_y = (row_end - row_begin + TILE_H - 1) / TILE_H;
     const unsigned tiles = (unsigned)P.tiles_x * (unsigned)P.tiles_y;
     constexpr int ALL = ILB_LIGHT_SPHERE | ILB_LIGHT_DIRECTIONAL | ILB_LIGHT_LINE, NOLINE = ILB_LIGHT_SPHERE | ILB_LIGHT_DIRECTIONAL;
-    int nline = 0;
-    for (const DLight& L : lights) nline += (L.type == ILB_LIGHT_LINE) ? 1 : 0;
-    bool split = nline > 0 && nline < (int)lights.size();
+    bool split = prep.nline > 0 && prep.nline < prep.nlights;
     if (const char* e = getenv("ILB_SPLIT_PASSES")) split = split && e[0] != '0';
     int planesMask = 3;  // dev knob: bit 0 = line pass samples the planes, bit 1 = sphere / directional pass does
     if (const char* e = getenv("ILB_PLANES_MASK")) planesMask = atoi(e);
 #define ILB_LIGHT_LAUNCH(TYPES)                                                                                       \
     do {                                                                                                              \
-        if (P.df.planes && (planesMask & (((TYPES) & ILB_LIGHT_LINE) ? 1 : 2))) light_accumulate_kernel<1, TYPES><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);               \
-        else light_accumulate_kernel<0, TYPES><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);                           \
+        if (P.df.planes && (planesMask & (((TYPES) & ILB_LIGHT_LINE) ? 1 : 2)))                                       \
+            light_accumulate_kernel<1, TYPES><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);                            \
+        else                                                                                                          \
+            light_accumulate_kernel<0, TYPES><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);                            \
         ctx->launches++;                                                                                              \
     } while (0)
     if (split) {
-        const size_t bytes = sizeof(float4) * (size_t)f->width * (size_t)(f->row_end - f->row_begin);
-        rc = ilb_reserve(ctx, &ctx->d_accum, &ctx->d_accum_capacity, bytes, false);
+        const size_t bytes = sizeof(float4) * (size_t)P.width * (size_t)(row_end - row_begin);
+        const int rc = ilb_reserve(ctx, &ctx->d_accum, &ctx->d_accum_capacity, bytes, false);
         if (rc) return rc;
         P.accum_out = reinterpret_cast<float4*>(ctx->d_accum);
         ILB_LIGHT_LAUNCH(ILB_LIGHT_LINE);
         P.accum_in = P.accum_out;
         P.accum_out = nullptr;
         ILB_LIGHT_LAUNCH(NOLINE);
-    } else if (nline == 0) {
+    } else if (prep.nline == 0) {
         ILB_LIGHT_LAUNCH(NOLINE);
     } else {
         ILB_LIGHT_LAUNCH(ALL);
     }
 #undef ILB_LIGHT_LAUNCH
     ILB_CUDA(ctx, cudaGetLastError());
+    return ILB_OK;
+}
+
+}  // namespace
+
+int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const ilb_light_batch* batches, int batch_count,
+                        const ilb_light_vertex* vertices, int vertex_count, void* const* d_outputs, int output_count,
+                        bool outputs_are_full_frames) {
+    LightingPrepared prep;
+    int rc = lightingPrepare(ctx, df, f, batches, batch_count, vertices, vertex_count, &prep);
+    if (rc) return rc;
+    return lightingLaunchRows(ctx, prep, f->row_begin, f->row_end, d_outputs, output_count, outputs_are_full_frames ? 0 : f->row_begin);
+}
+
+// Host-to-host frame: G-buffer band up, shade, lightmap band down, software-pipelined over row bands on three streams
+// so that the copies of neighbouring bands hide behind the kernels (the G-buffer decode reads only the pixel's own
+// texel, so a band needs only its own rows).  Synchronous: returns when lightmap_out_host is complete.
+int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const ilb_light_batch* batches, int batch_count,
+                                 const ilb_light_vertex* vertices, int vertex_count, int gw, int gh, int gfmt, const void* gbuffer_host,
+                                 void* lightmap_out_host) {
+    if (!f || !gbuffer_host || !lightmap_out_host) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
+    if (gfmt != ILB_FORMAT_FLOAT4 && gfmt != ILB_FORMAT_HALF4) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "G-buffer format must be FLOAT4 or HALF4");
+    if (gw != f->width || gh != f->height)  // one texel per pixel, so that a row band of the frame needs the same rows of the G-buffer
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "pipelined frames need a G-buffer of the frame's size (%dx%d), got %dx%d", f->width, f->height, gw, gh);
+    if (f->GBufferViewportRelative != 0.0f) return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "pipelined frames need a screen-aligned G-buffer");
+    const size_t gtexel = ilb_format_bytes(gfmt), ltexel = ilb_format_bytes(f->lightmap_format);
+    const size_t gbytes = gtexel * (size_t)gw * (size_t)gh;
+    if (!ctx->gbuffer_owned) { ctx->gbuffer = nullptr; ctx->gbuffer_capacity = 0; }
+    int rc = ilb_reserve(ctx, &ctx->gbuffer, &ctx->gbuffer_capacity, gbytes, false);
+    if (rc) return rc;
+    ctx->gbuffer_owned = true;
+    ctx->gb_w = gw; ctx->gb_h = gh; ctx->gb_fmt = gfmt;
+    const int rows = f->row_end - f->row_begin;
+    if (rows < 0 || f->row_begin < 0 || f->row_end > f->height) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad frame geometry");
+    const size_t lbytes = ltexel * (size_t)f->width * (size_t)std::max(rows, 1);
+    rc = ilb_reserve(ctx, &ctx->d_lightmap, &ctx->d_lightmap_capacity, std::max<size_t>(lbytes, 16), false);
+    if (rc) return rc;
+    if (!ctx->copy_in) {
+        ILB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        ILB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < ILB_PIPELINE_BANDS; i++) {
+            ILB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+            ILB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    LightingPrepared prep;
+    rc = lightingPrepare(ctx, df, f, batches, batch_count, vertices, vertex_count, &prep);
+    if (rc) return rc;
+    if (rows == 0) return ILB_OK;
+    // bands of whole tile rows; the first band is short so that the first kernel starts early, the last so that the
+    // final download is short
+    int bandRows = ((rows + ILB_PIPELINE_BANDS - 1) / ILB_PIPELINE_BANDS + TILE_H - 1) / TILE_H * TILE_H;
+    const char* gsrc = reinterpret_cast<const char*>(gbuffer_host);
+    char* gdst = reinterpret_cast<char*>(ctx->gbuffer);
+    char* ldev = reinterpret_cast<char*>(ctx->d_lightmap);
+    char* lhost = reinterpret_cast<char*>(lightmap_out_host);
+    // everything already queued on the main stream (earlier frames, uploads) must be done before the G-buffer is overwritten
+    ILB_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], ctx->stream));
+    ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_done[0], 0));
+    int nb = 0;
+    for (int r0 = f->row_begin; r0 < f->row_end; r0 += bandRows, nb++) {
+        const int r1 = std::min(r0 + bandRows, f->row_end);
+        const size_t goff = gtexel * (size_t)gw * (size_t)r0, gn = gtexel * (size_t)gw * (size_t)(r1 - r0);
+        ILB_CUDA(ctx, cudaMemcpyAsync(gdst + goff, gsrc + goff, gn, cudaMemcpyHostToDevice, ctx->copy_in));
+        ILB_CUDA(ctx, cudaEventRecord(ctx->ev_in[nb], ctx->copy_in));
+    }
+    nb = 0;
+    for (int r0 = f->row_begin; r0 < f->row_end; r0 += bandRows, nb++) {
+        const int r1 = std::min(r0 + bandRows, f->row_end);
+        ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[nb], 0));
+        void* outs[1] = {ctx->d_lightmap};
+        rc = lightingLaunchRows(ctx, prep, r0, r1, outs, 1, f->row_begin);
+        if (rc) return rc;
+        ILB_CUDA(ctx, cudaEventRecord(ctx->ev_done[nb], ctx->stream));
+        ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[nb], 0));
+        const size_t loff = ltexel * (size_t)f->width * (size_t)(r0 - f->row_begin), ln = ltexel * (size_t)f->width * (size_t)(r1 - r0);
+        ILB_CUDA(ctx, cudaMemcpyAsync(lhost + loff, ldev + loff, ln, cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ILB_OK;
 }
 

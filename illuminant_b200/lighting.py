@@ -309,6 +309,26 @@ class LightingRenderer:
                                                         C.cast(verts, C.c_void_p), nv, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def RenderLightingFrame(self, gbuffer: np.ndarray, intensityScale: float = 1.0, rows: Optional[Tuple[int, int]] = None,
+                            out: Optional[np.ndarray] = None) -> np.ndarray:
+        """One host-to-host frame through `ilb_render_lighting_frame`: this frame's G-buffer goes up, the lightmap comes
+        down, both pipelined behind the kernels over row bands.  Same result as SetGBuffer + RenderLighting."""
+        fmt = FORMAT_FLOAT4 if self.Configuration.HighQualityGBuffer else FORMAT_HALF4
+        arr = np.ascontiguousarray(gbuffer, dtype=np.float32 if fmt == FORMAT_FLOAT4 else np.float16)
+        gh, gw = arr.shape[0], arr.shape[1]
+        self._gbuffer_shape = (gh, gw)
+        frame = self.build_frame(intensityScale, rows)
+        batches, nb, verts, nv = self.build_batches(intensityScale)
+        h = frame.row_end - frame.row_begin
+        dtype = {FORMAT_FLOAT4: np.float32, FORMAT_HALF4: np.float16, FORMAT_RGBA8: np.uint8}[frame.lightmap_format]
+        if out is None:
+            out = np.empty((h, frame.width, 4), dtype=dtype)
+        df = self.DistanceField.handle if (self.DistanceField is not None and self.DistanceField.handle) else None
+        self.ctx.check(self.ctx.lib.ilb_render_lighting_frame(self.ctx.handle, df, C.byref(frame), C.cast(batches, C.c_void_p), nb,
+                                                              C.cast(verts, C.c_void_p), nv, gw, gh, fmt, arr.ctypes.data_as(C.c_void_p),
+                                                              out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def RenderLightingDevice(self, device_ptr: int, intensityScale: float = 1.0, rows: Optional[Tuple[int, int]] = None,
                              packed=None) -> None:
         """Asynchronous variant writing rows [row_begin,row_end) to a device buffer that starts at row_begin."""

@@ -166,6 +166,17 @@ ILB_API int ilb_render_lighting(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fra
                                 const ilb_light_batch* batches, int batch_count,
                                 const ilb_light_vertex* vertices, int vertex_count,
                                 void* lightmap_out);
+/* One whole host-to-host frame in one call: the G-buffer a host-side rasteriser produced for this frame (the input
+ * LightingRenderer.RenderLighting reads through GBufferTexelSizeAndMisc, LightingRenderer.GBuffer.cs:520-534) goes up,
+ * the frame is shaded, the lightmap comes down -- software-pipelined over row bands on three CUDA streams, so the
+ * copies hide behind the kernels.  Equivalent to ilb_gbuffer_upload + ilb_render_lighting (bit-identical lightmap).
+ * The G-buffer must have the frame's size and be screen-aligned (GBufferViewportRelative == 0); pinned host memory
+ * makes the copies asynchronous.  Synchronous: returns when lightmap_out is complete. */
+ILB_API int ilb_render_lighting_frame(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame,
+                                      const ilb_light_batch* batches, int batch_count,
+                                      const ilb_light_vertex* vertices, int vertex_count,
+                                      int gbuffer_width, int gbuffer_height, int gbuffer_format, const void* gbuffer,
+                                      void* lightmap_out);
 /* Same with a DEVICE output pointer; asynchronous on ilb_stream(ctx). */
 ILB_API int ilb_render_lighting_device(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame,
                                        const ilb_light_batch* batches, int batch_count,

@@ -192,3 +192,20 @@ def test_planes_match_atlas_bit_for_bit(ctx, monkeypatch):
         assert np.array_equal(out[0][0], out[1][0]), f"seed {seed}"
         if out[0][1] is not None:
             assert np.array_equal(out[0][1], out[1][1])
+
+
+def test_pipelined_host_frame_equals_upload_plus_render(ctx):
+    """ilb_render_lighting_frame (G-buffer up / shade / lightmap down, pipelined over row bands on three streams) returns
+    the same bits as ilb_gbuffer_upload + ilb_render_lighting, for whole frames, bands and odd sizes."""
+    for seed, w, h in ((34, 300, 211), (35, 640, 400)):
+        s = scenes.lighting_scene(seed, w, h, 6, n_directional=1, n_line=1, ramp=(60.0, 260.0))
+        df = scenes.make_distance_field(ctx, s)
+        df.Rasterize(s.obstructions)
+        r = ib.LightingRenderer(ctx, s.environment, s.configuration)
+        r.DistanceField = df
+        r.SetGBuffer(s.gbuffer)
+        for rows in (None, (16, h - 37)):
+            want = r.RenderLighting(rows=rows)
+            r.SetGBuffer(np.zeros_like(s.gbuffer))          # the pipelined call must bring its own G-buffer
+            got = r.RenderLightingFrame(s.gbuffer, rows=rows)
+            assert np.array_equal(got.view(np.uint16), want.view(np.uint16))
