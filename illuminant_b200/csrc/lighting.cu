@@ -115,7 +115,7 @@ struct Trace {  // TraceState :31-35
 
 // returns true when the marched interval t < len stays on the segment start -> end
 template <bool FAST>
-ILB_DEV bool traceInit(Trace& s, f3 start, f3 end, float lightRadius, bool& bad) {  // coneTraceInitialize :37-49
+ILB_DEV bool traceInit(Trace& s, f3 start, f3 end, float lightRadius, Guard& bad) {  // coneTraceInitialize :37-49
     const f3 v = xsub3(end, start);
     const float l = tlength3<FAST>(v, bad);
     s.origin = start;
@@ -158,7 +158,7 @@ ILB_DEV void coneTraceMarch(const DFGeometry& g, const TraceConfig& c, Trace& a,
 
 template <int FIELD, bool FAST>
 ILB_DEV float coneTrace(const DFGeometry& g, const DLight& L, f3 lightCenter, float rampX, float rampY,
-                        float growthFactor, f3 shaded, bool enable, bool& bad) {  // coneTrace :141-191
+                        float growthFactor, f3 shaded, bool enable, Guard& bad) {  // coneTrace :141-191
     Trace a;
     const bool onSegment = traceInit<FAST>(a, shaded, lightCenter, rampX, bad);
     const TraceConfig c = makeTraceConfig(L, rampX, rampY, growthFactor);
@@ -201,7 +201,7 @@ ILB_DEV float normalFactorEx(f3 lightNormal, f3 n) {  // computeNormalFactorEx :
 }
 
 template <bool FAST>
-ILB_DEV float sphereLightOpacity(float lightOcclusion, f3 p, f3 n, f3 center, float4 props, float yFactor, float rRamp, bool& bad) {  // :173-210
+ILB_DEV float sphereLightOpacity(float lightOcclusion, f3 p, f3 n, f3 center, float4 props, float yFactor, float rRamp, Guard& bad) {  // :173-210
     // x-ops: where this falloff reaches exactly 0 the fragment is discarded, which changes the lightmap's alpha count
     f3 d3 = xsub3(p, center);
     d3.y = xmul(d3.y, yFactor);
@@ -235,7 +235,7 @@ ILB_DEV float computeAO(const DFGeometry& g, bool hasField, f3 p, f3 n, float ao
 // SphereLightPixelCore (SphereLightCore.fxh:58-158); returns false on discard
 template <int FIELD, bool FAST>
 ILB_DEV bool sphereCore(const DFGeometry& g, const DLight& L, float lightOcclusion, f3 p, f3 n, f3 center, float4 props,
-                        float4 more, float& opacity, bool& bad) {
+                        float4 more, float& opacity, Guard& bad) {
     const float distanceOpacity = sphereLightOpacity<FAST>(lightOcclusion, p, n, center, props, more.z, L.rcpRamp, bad);
     const bool visible = (distanceOpacity > 0.0f) && (p.x > -9999.0f);
     if (!visible) return false;
@@ -251,7 +251,7 @@ ILB_DEV bool sphereCore(const DFGeometry& g, const DLight& L, float lightOcclusi
 // DirectionalLightPixelCore (DirectionalLight.fx:52-93, useOpacityRamp = false)
 template <int FIELD, bool FAST>
 ILB_DEV bool directionalCore(const DFGeometry& g, const DLight& L, f3 p, f3 n, float4 dir, float4 props, float4 more,
-                             float& opacity, bool& bad) {
+                             float& opacity, Guard& bad) {
     float lightOpacity = (dir.w < 0.1f) ? 1.0f : normalFactorEx<350>(mk3(dir.x, dir.y, dir.z), n);
     const bool visible = (p.x > -9999.0f);
     const float aoRadius = xmul(more.x, fmaxf(0.0f, n.z));
@@ -268,11 +268,11 @@ ILB_DEV bool directionalCore(const DFGeometry& g, const DLight& L, f3 p, f3 n, f
 // x-ops: the solid angle is a difference of four arc-cosines that nearly cancel (g0+g1+g2+g3 - 2*pi), so a few ulp in
 // the normalised cross products change the illuminance by far more than 1e-4 relative -- keep it bit-identical.
 template <bool FAST>
-ILB_DEV float acosExact(float x, bool& bad) {  // dm_acosf (include/ilb_detmath.h) with the sqrt of this build
+ILB_DEV float acosExact(float x, Guard& bad) {  // dm_acosf (include/ilb_detmath.h) with the sqrt of this build
     return dm_acos_finish(x, tsqrt<FAST>(xsub(1.0f, fabsf(x)), bad));
 }
 template <bool FAST>
-ILB_DEV float rectangleSolidAngle(f3 v0, f3 v1, f3 v2, f3 v3, bool& bad) {  // FBPBR.fxh:33-51, v_i = p_i - worldPos
+ILB_DEV float rectangleSolidAngle(f3 v0, f3 v1, f3 v2, f3 v3, Guard& bad) {  // FBPBR.fxh:33-51, v_i = p_i - worldPos
     const f3 n0 = tnormalize3<FAST>(xcross3(v0, v1), bad), n1 = tnormalize3<FAST>(xcross3(v1, v2), bad);
     const f3 n2 = tnormalize3<FAST>(xcross3(v2, v3), bad), n3 = tnormalize3<FAST>(xcross3(v3, v0), bad);
     // deterministic acos: the four angles nearly cancel, so both sides must evaluate the same function
@@ -282,7 +282,7 @@ ILB_DEV float rectangleSolidAngle(f3 v0, f3 v1, f3 v2, f3 v3, bool& bad) {  // F
 }
 
 template <bool FAST>
-ILB_DEV float lineLightOpacity(f3 wp, f3 wn, f3 P0, f3 P1, float lightRadius, const DLine& D, f3& spherePosition, float& u, bool& bad) {  // FBPBR.fxh:53-101
+ILB_DEV float lineLightOpacity(f3 wp, f3 wn, f3 P0, f3 P1, float lightRadius, const DLine& D, f3& spherePosition, float& u, Guard& bad) {  // FBPBR.fxh:53-101
     const f3 lightLeft = xyz(mk4(D.left)), lightCenter = xyz(mk4(D.center)), ab = xyz(mk4(D.ab));
     // closestPointOnLineSegment3 DistanceFieldCommon.fxh:151-155 (exact: u places the three trace targets)
     u = saturatef(udiv(xdot3(xsub3(wp, P0), ab), D.ab.w, D.left.w));
@@ -318,7 +318,7 @@ ILB_DEV void lineTraceMarch(const DFGeometry& g, const TraceConfig& cfg, Trace& 
 
 template <int FIELD, bool FAST>
 ILB_DEV float lineConeTrace(const DFGeometry& g, const DLight& L, const DLine& D, f3 start, float u, float rampX, float rampY,
-                            f3 shaded, bool enable, bool& bad) {  // LineLightCore.fxh:17-68
+                            f3 shaded, bool enable, Guard& bad) {  // LineLightCore.fxh:17-68
     Trace a, b, c;
     const f3 delta = xyz(mk4(D.ab));
     const float offset = D.center.w;
@@ -344,7 +344,7 @@ ILB_DEV float lineConeTrace(const DFGeometry& g, const DLight& L, const DLine& D
 
 template <int FIELD, bool FAST>
 ILB_DEV bool lineCore(const DFGeometry& g, const DLight& L, const DLine& D, f3 p, f3 n, f3 start, f3 end, float4 props, float4 more,
-                      float& u, float& opacity, bool& bad) {  // LineLightPixelCore :70-120
+                      float& u, float& opacity, Guard& bad) {  // LineLightPixelCore :70-120
     f3 lightCenter;
     const float distanceOpacity = lineLightOpacity<FAST>(p, n, start, end, props.x, D, lightCenter, u, bad);
     const bool visible = (distanceOpacity > 0.0f) && (p.x > -9999.0f);
@@ -464,7 +464,7 @@ ILB_DEV DLine loadLine(const DLine* lines, int i) {
 // TYPES: bit mask of ilb_light_type values this instantiation can meet (other branches are compiled out)
 template <int FIELD, bool FAST, int TYPES>
 ILB_DEV bool shadeLight(const DFGeometry& df, float lightOcclusion, const DLight& L, const DLine* lines, int lightIndex, const Pixel& px,
-                        f3& rgb, bool& bad) {
+                        f3& rgb, Guard& bad) {
     const float es = px.enableShadows ? 1.0f : 0.0f;
     if ((TYPES & ILB_LIGHT_SPHERE) && L.type == ILB_LIGHT_SPHERE) {  // SphereLightPixelShader SphereLight.fx:7-46
         if (px.fullbright || shadowFilterRejects(L.evenMore.x, px.enableShadows)) return false;
@@ -521,7 +521,7 @@ __device__ __noinline__ float4 shadeLightExact(const DFGeometry* df, float light
     px.maskOk = true;
     const DLight L = loadLight(lights, lightIndex);
     f3 rgb = mk3(0.0f);
-    bool bad = false;
+    Guard bad = guardInit();
     const bool lit = shadeLight<FIELD, false, TYPES>(*df, lightOcclusion, L, lines, lightIndex, px, rgb, bad);
     return make_float4(rgb.x, rgb.y, rgb.z, lit ? 1.0f : 0.0f);
 }
@@ -531,12 +531,12 @@ template <int FIELD, int TYPES>
 ILB_DEV bool shadeLightGuarded(const DFGeometry& df, float lightOcclusion, const DLight& L, const DLight* lights, const DLine* lines,
                                int lightIndex, const Pixel& px, f3& rgb) {
 #if ILB_NO_FAST_GUARD
-    bool bad = false;
+    Guard bad = guardInit();
     return shadeLight<FIELD, false, TYPES>(df, lightOcclusion, L, lines, lightIndex, px, rgb, bad);
 #else
-    bool bad = false;
+    Guard bad = guardInit();
     bool lit = shadeLight<FIELD, true, TYPES>(df, lightOcclusion, L, lines, lightIndex, px, rgb, bad);
-    if (bad) {
+    if (guardTripped(bad)) {
         const float4 r = shadeLightExact<FIELD, TYPES>(&df, lightOcclusion, lights, lines, lightIndex,
                                                 make_float4(px.pos.x, px.pos.y, px.pos.z, px.enableShadows ? 1.0f : 0.0f),
                                                 make_float4(px.normal.x, px.normal.y, px.normal.z, px.fullbright ? 1.0f : 0.0f),
@@ -734,7 +734,8 @@ __global__ void __launch_bounds__(128) probe_accumulate_kernel(const __grid_cons
             more.x = 0.0f;
             more.w = 0.0f;
             float core;
-            bool lit, bad = false;  // probes are few: plain IEEE x-ops (FAST = false), no guard
+            bool lit;
+            Guard bad = guardInit();  // probes are few: plain IEEE x-ops (FAST = false), no guard
             if (L.type == ILB_LIGHT_DIRECTIONAL) {
                 props.x *= ns.w;
                 lit = directionalCore<FIELD, false>(P.df, L, p, n, L.color2, props, more, core, bad);

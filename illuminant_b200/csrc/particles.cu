@@ -154,7 +154,7 @@ ILB_DEV bool checkCategoryFilter(float type, const float* mm) { return (type >= 
 // FAST (here and below): square roots / reciprocals through the deferred-guard forms of ilb_device.cuh; `bad` collects
 // the range checks and the caller re-runs the particle through the FAST = false instantiation when it is set.
 template <bool FAST>
-ILB_DEV void opGravity(const ilb_psys_uniforms& u, const SysDerived& sd, const ilb_gravity& g, const OpDerived& d, f4& pos, f4& vel, bool& bad) {  // Gravity.fx:12-61
+ILB_DEV void opGravity(const ilb_psys_uniforms& u, const SysDerived& sd, const ilb_gravity& g, const OpDerived& d, f4& pos, f4& vel, Guard& bad) {  // Gravity.fx:12-61
     if ((pos.w <= 0.0f) || !checkCategoryFilter(vel.w, g.CategoryFilter)) return;
     const float dt = u.GlobalSettings.x;
     f3 acceleration = mk3(0.0f);
@@ -185,7 +185,7 @@ ILB_DEV void opGravity(const ilb_psys_uniforms& u, const SysDerived& sd, const i
 }
 
 template <bool FAST>
-ILB_DEV void opNoise(const StepParams& P, const ilb_noise& n, const OpDerived& d, float x, float y, f4& pos, f4& vel, bool& bad) {  // Noise.fx:28-72
+ILB_DEV void opNoise(const StepParams& P, const ilb_noise& n, const OpDerived& d, float x, float y, f4& pos, f4& vel, Guard& bad) {  // Noise.fx:28-72
     if (!checkCategoryFilter(vel.w, n.area.CategoryFilter)) return;
     const float weight = computeWeight(n.area, d, xyz(pos));
     const float t = udiv(xmul(weight, P.u.GlobalSettings.x), n.TimeDivisor, d.rTimeDivisor);
@@ -286,7 +286,7 @@ ILB_DEV float sampleField(const DFGeometry& g, f3 p) {
 }
 
 template <int FM, bool FAST>
-ILB_DEV f3 estimateNormal4(const DFGeometry& g, float texelZ, f3 position, bool& bad) {  // VisualizeCommon.fxh:9-63
+ILB_DEV f3 estimateNormal4(const DFGeometry& g, float texelZ, f3 position, Guard& bad) {  // VisualizeCommon.fxh:9-63
     const f3 texel = mk3(g.invScaleX, g.invScaleY, texelZ);
     f3 result = mk3(0.0f);
     // weights (1,-1,-1), (-1,-1,1), (-1,1,-1), (1,1,1): one copy of the sampler in the instruction stream, not four
@@ -305,7 +305,7 @@ ILB_DEV f3 estimateNormal4(const DFGeometry& g, float texelZ, f3 position, bool&
 // sampler invocation serves eight requesters.  The samples return to their owner by shuffle and are summed there in
 // the reference's order, so the result is bit-identical to estimateNormal4.  Must be reached by all 32 lanes.
 template <int FM, bool FAST>
-ILB_DEV f3 cooperativeNormal4(const DFGeometry& g, float texelZ, f3 position, bool need, unsigned char* warpSlots, bool& bad) {
+ILB_DEV f3 cooperativeNormal4(const DFGeometry& g, float texelZ, f3 position, bool need, unsigned char* warpSlots, Guard& bad) {
     const unsigned full = 0xFFFFFFFFu, lane = threadIdx.x & 31u;
     const unsigned needMask = __ballot_sync(full, need);
     f3 normal = mk3(0.0f);
@@ -345,7 +345,7 @@ ILB_DEV f3 cooperativeNormal4(const DFGeometry& g, float texelZ, f3 position, bo
 // COOP: every lane of the warp runs through this call together (the normal estimation is shared across lanes, see
 // cooperativeNormal4); COOP = false is the per-lane form for the divergent fallback call.
 template <bool COLLIDE, int FM, bool FAST, bool COOP>
-ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f4 oldVelocity, f4& outP, f4& outV, bool& needAttr, unsigned char* warpSlots, bool& bad) {
+ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f4 oldVelocity, f4& outP, f4& outV, bool& needAttr, unsigned char* warpSlots, Guard& bad) {
     const ilb_psys_uniforms& u = P.u;
     outP = mk4(0.0f);
     outV = mk4(0.0f);
@@ -455,7 +455,7 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
 #endif
 
 template <int KIND, bool FAST>
-ILB_DEV void applyOp(const StepParams& P, const ilb_op& op, const OpDerived& d, float x, float y, f4& pos, f4& vel, bool& bad) {
+ILB_DEV void applyOp(const StepParams& P, const ilb_op& op, const OpDerived& d, float x, float y, f4& pos, f4& vel, Guard& bad) {
     if (KIND == ILB_OP_GRAVITY) opGravity<FAST>(P.u, P.sd, op.u.gravity, d, pos, vel, bad);
     else if (KIND == ILB_OP_NOISE) opNoise<FAST>(P, op.u.noise, d, x, y, pos, vel, bad);
     else if (KIND == ILB_OP_FMA) opFMA(P.u, op.u.fma, d, pos, vel);
@@ -481,7 +481,7 @@ ILB_DEV void particleXY(const StepParams& P, unsigned gi, float& x, float& y) {
 // bank with static offsets.  K0 < 0 selects the generic loop over P.ops[0..nops) for every other chain.
 // One particle through the whole update: transform chain in registers, then the Update / UpdateWithDistanceField tail.
 template <bool COLLIDE, int K0, int K1, int K2, int FM, bool FAST, bool COOP>
-ILB_DEV void stepParticle(const StepParams& P, float x, float y, f4 pos, f4 vel, f4& outP, f4& outV, bool& needAttr, unsigned char* warpSlots, bool& bad) {
+ILB_DEV void stepParticle(const StepParams& P, float x, float y, f4 pos, f4 vel, f4& outP, f4& outV, bool& needAttr, unsigned char* warpSlots, Guard& bad) {
     if (K0 < 0) {
         for (int k = 0; k < P.nops; k++) {
             const ilb_op& op = P.ops[k];
@@ -507,7 +507,8 @@ struct ExactResult { float4 p, v; int needAttr; };
 template <bool COLLIDE, int FM>
 __device__ __noinline__ ExactResult stepParticleExact(const StepParams* P, float x, float y, float4 pos, float4 vel) {
     f4 outP, outV;
-    bool needAttr, bad = false;
+    bool needAttr;
+    Guard bad = guardInit();
     stepParticle<COLLIDE, -1, 0, 0, FM, false, false>(*P, x, y, mk4(pos), mk4(vel), outP, outV, needAttr, nullptr, bad);
     ExactResult r;
     r.p = to_float4(outP); r.v = to_float4(outV); r.needAttr = needAttr ? 1 : 0;
@@ -517,7 +518,7 @@ __device__ __noinline__ ExactResult stepParticleExact(const StepParams* P, float
 // fast evaluation + fallback; the specialised chains (K0 >= 0) take the fast path, the generic chain runs IEEE ops directly
 template <bool COLLIDE, int K0, int K1, int K2, int FM>
 ILB_DEV void stepParticleGuarded(const StepParams& P, float x, float y, f4 pos, f4 vel, f4& outP, f4& outV, bool& needAttr, unsigned char* warpSlots) {
-    bool bad = false;
+    Guard bad = guardInit();
 #if ILB_NO_FAST_GUARD
     stepParticle<COLLIDE, K0, K1, K2, FM, false, true>(P, x, y, pos, vel, outP, outV, needAttr, warpSlots, bad);
 #else
@@ -526,7 +527,7 @@ ILB_DEV void stepParticleGuarded(const StepParams& P, float x, float y, f4 pos, 
         return;
     }
     stepParticle<COLLIDE, K0, K1, K2, FM, true, true>(P, x, y, pos, vel, outP, outV, needAttr, warpSlots, bad);
-    if (bad) {
+    if (guardTripped(bad)) {
         const ExactResult r = stepParticleExact<COLLIDE, FM>(&P, x, y, to_float4(pos), to_float4(vel));
         outP = mk4(r.p); outV = mk4(r.v); needAttr = r.needAttr != 0;
     }
