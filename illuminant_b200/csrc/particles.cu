@@ -166,9 +166,9 @@ ILB_DEV void opGravity(const ilb_psys_uniforms& u, const SysDerived& sd, const i
         const float distance = tlengthdir3z<FAST>(toCenter, direction, bad);  // length() and normalize() share dot and sqrt
         float attraction;
         if (ars.z >= 0.5f) {
-            attraction = xsub(1.0f, saturatef(udiv(distance, ars.x, d.rRadius[i])));
+            attraction = xsub(1.0f, saturatef(tudiv<!FAST>(distance, ars.x, d.rRadius[i])));
             if (ars.z >= 1.5f) attraction = xmul(attraction, attraction);
-            attraction = udiv(xmul(attraction, dt), VelocityConstantScale, sd.r1000);
+            attraction = tudiv<!FAST>(xmul(attraction, dt), VelocityConstantScale, sd.r1000);
         } else {
             float distanceSquared = xsub(xdot3(toCenter, toCenter), ars.x);
             distanceSquared = fmaxf(distanceSquared, 0.001f);
@@ -188,7 +188,7 @@ template <bool FAST>
 ILB_DEV void opNoise(const StepParams& P, const ilb_noise& n, const OpDerived& d, float x, float y, f4& pos, f4& vel, Guard& bad) {  // Noise.fx:28-72
     if (!checkCategoryFilter(vel.w, n.area.CategoryFilter)) return;
     const float weight = computeWeight(n.area, d, xyz(pos));
-    const float t = udiv(xmul(weight, P.u.GlobalSettings.x), n.TimeDivisor, d.rTimeDivisor);
+    const float t = tudiv<!FAST>(xmul(weight, P.u.GlobalSettings.x), n.TimeDivisor, d.rTimeDivisor);
     const float rx = n.RandomnessTexel[0], ry = n.RandomnessTexel[1];
     const f4 randomP1 = randomCustom(P.rng, P.rng_w, P.rng_h, x, y, n.RandomnessOffset, rx, ry, n.RandomnessTexel);
     const f4 randomP2 = randomCustom(P.rng, P.rng_w, P.rng_h, x, y, n.NextRandomnessOffset, rx, ry, n.RandomnessTexel);
@@ -379,16 +379,24 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
     f4 newVelocity = mk4(0.0f);
     float travelDistance = 0.0f;
     if (proceed) {
-        const float initialDistance = sampleField<FM>(P.df, op);
-        wasColliding = initialDistance < collisionDistance;
-        travelDistance = fmaxf(0.0f, fminf(initialDistance, tlength3z<FAST>(scaledVelocity, bad)));
-        int stepCount = 3;
-        if (wasColliding) stepCount = 1;
-        else if (travelDistance <= 0.001f) stepCount = 0;
+        const float stepLength = tlength3z<FAST>(scaledVelocity, bad);
+        float initialDistance = 0.0f;
+        int stepCount = 0;
+        // iteration -1 is the sample at the old position (:52-60), iterations 0.. the march (:62-88): one copy of the
+        // sampler in the instruction stream
 #pragma unroll 1
-        for (int i = 0; i < stepCount; i++) {
-            const f3 testPosition = xadd3(op, xscale3(unitVector, travelDistance));
+        for (int i = -1; i < stepCount; i++) {
+            const f3 testPosition = (i < 0) ? op : xadd3(op, xscale3(unitVector, travelDistance));
             const float stepDistance = sampleField<FM>(P.df, testPosition);
+            if (i < 0) {
+                initialDistance = stepDistance;
+                wasColliding = initialDistance < collisionDistance;
+                travelDistance = fmaxf(0.0f, fminf(initialDistance, stepLength));
+                stepCount = 3;
+                if (wasColliding) stepCount = 1;
+                else if (travelDistance <= 0.001f) stepCount = 0;
+                continue;
+            }
             if (stepDistance < collisionDistance) {
                 collided = true;
                 collisionPosition = testPosition;
@@ -877,6 +885,15 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
                 }
             }
         }
+        // the fast instantiations divide by uniform divisors through their reciprocals without checking them
+        bool reciprocalsOk = true;
+        for (int k = 0; k < op_count; k++) {
+            const ilb_op& op = ops[k];
+            if (op.kind == ILB_OP_GRAVITY) {
+                for (int i = 0; i < op.u.gravity.AttractorCount; i++)
+                    if (op.u.gravity.AttractorRadiusesAndStrengths[i].z >= 0.5f && SP.od[k].rRadius[i] == 0.0f) reciprocalsOk = false;
+            } else if (op.kind == ILB_OP_NOISE && SP.od[k].rTimeDivisor == 0.0f) reciprocalsOk = false;
+        }
         const bool collide = u->has_collision_field != 0;
         if (collide) {
             if (!ilb_make_df_geometry(ps->field, u->CollisionField, &SP.df))
@@ -891,7 +908,7 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
         const unsigned blocks = (unsigned)((total + STEP_THREADS - 1) / STEP_THREADS);
         // chains with a compiled specialisation: none, and Gravity -> Noise -> FMA (BASELINE.json configs 3 and 5)
         const bool chainNone = op_count == 0;
-        const bool chainGNF = op_count == 3 && ops[0].kind == ILB_OP_GRAVITY && ops[1].kind == ILB_OP_NOISE && ops[2].kind == ILB_OP_FMA;
+        const bool chainGNF = reciprocalsOk && op_count == 3 && ops[0].kind == ILB_OP_GRAVITY && ops[1].kind == ILB_OP_NOISE && ops[2].kind == ILB_OP_FMA;
         // In-place safety of the staged variant: a tile is fully read into registers before its results are stored, and
         // tiles are disjoint, so reading through one proxy and writing through the other never overlaps in time.
         // (Instantiated for the two chain / collision combinations the bit-identity test exercises.)
