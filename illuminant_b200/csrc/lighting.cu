@@ -584,7 +584,7 @@ ILB_DEV float warpMax(float v) {
 #define ILB_LIGHT_MINBLOCKS 3
 #endif
 #ifndef ILB_LIGHT_MINBLOCKS_NOLINE
-#define ILB_LIGHT_MINBLOCKS_NOLINE 4
+#define ILB_LIGHT_MINBLOCKS_NOLINE 5
 #endif
 // TYPES: the light types this pass shades (lights of other types are dropped by the tile culling).  A frame is one
 // pass over all types, or -- ILB_SPLIT_PASSES, the default when line lights are present -- a line-light pass that
