@@ -45,16 +45,50 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed region: NVML in a thread every 5 ms (the timed region of
+    the default run is ~0.1 s), `nvidia-smi -lms` as the fallback when NVML cannot be loaded."""
 
     def __init__(self, device: int):
         self.device, self.rows, self.proc = device, [], None
+        self.sm, self.mx, self.reasons = [], [], set()
+        self._stop, self._thread, self._nvml = threading.Event(), None, None
+
+    def _nvml_loop(self):
+        n, h = self._nvml
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)))
+                mask = int(get_reasons(h))
+                for name, attr in names:
+                    if mask & int(getattr(n, attr, 0)):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
 
     def start(self):
+        try:
+            import pynvml as n
+            n.nvmlInit()
+            # NVML enumerates all GPUs of the box; map the CUDA ordinal through CUDA_VISIBLE_DEVICES when it is a plain list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.device
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[self.device])
+            self._nvml = (n, n.nvmlDeviceGetHandleByIndex(idx))
+            self._thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self._nvml = None
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -65,10 +99,13 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons = list(self.sm), list(self.mx), set(self.reasons)
         for r in self.rows:
             parts = [p.strip() for p in r.split(",")]
             if len(parts) < 6:
@@ -308,9 +345,10 @@ def run_ours(args):
         result.update({
             "metric": "lit Mpixels/s (4K, 128 lights)", "value": mpx, "unit": "Mpixels/s", "ms_per_step": ms_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "light_accumulate_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_pixel": LIGHT_BYTES_PER_PIXEL,
-                         "peak_source": peak_src,
-                         "note": "per-pixel work is O(lights x trace steps): the kernel is issue-bound, not HBM-bound (see DESIGN.md)"},
+                         "kernel": "light_accumulate_kernel (line-light pass + sphere/directional pass, both launches of the step)",
+                         "kernel_ms": k_ms, "algorithmic_bytes_per_pixel": LIGHT_BYTES_PER_PIXEL, "peak_source": peak_src,
+                         "note": "per-pixel work is O(lights x trace steps): issue- and latency-bound, not HBM-bound (see DESIGN.md); "
+                                 "traffic = ncu DRAM bytes of both passes (the expanded distance-field planes trade traffic for instructions)"},
             "e2e": {"value": W * H / (e_ms * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": int((r1 - r0) * W * 16 + nv * 128),
                     "d2h_bytes_per_step": int(out_host.numel() * 2), "ms_per_step": e_ms},
             "gpu_launches": int(launches), "clocks": clocks, "gather": gather,
