@@ -523,6 +523,9 @@ __device__ __noinline__ float4 shadeLightExact(const DFGeometry* df, float light
     f3 rgb = mk3(0.0f);
     Guard bad = guardInit();
     const bool lit = shadeLight<FIELD, false, TYPES>(*df, lightOcclusion, L, lines, lightIndex, px, rgb, bad);
+#if ILB_BREAK_FALLBACK  // test hook: proves that a test reaches this path (tests/README: degenerate-geometry tests must fail with it)
+    rgb.x += 1.0f;
+#endif
     return make_float4(rgb.x, rgb.y, rgb.z, lit ? 1.0f : 0.0f);
 }
 

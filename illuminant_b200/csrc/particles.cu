@@ -520,6 +520,9 @@ __device__ __noinline__ ExactResult stepParticleExact(const StepParams* P, float
     stepParticle<COLLIDE, -1, 0, 0, FM, false, false>(*P, x, y, mk4(pos), mk4(vel), outP, outV, needAttr, nullptr, bad);
     ExactResult r;
     r.p = to_float4(outP); r.v = to_float4(outV); r.needAttr = needAttr ? 1 : 0;
+#if ILB_BREAK_FALLBACK  // test hook: proves that a test reaches this path
+    r.v.x += 1.0f;
+#endif
     return r;
 }
 

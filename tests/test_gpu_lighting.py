@@ -209,3 +209,26 @@ def test_pipelined_host_frame_equals_upload_plus_render(ctx):
             r.SetGBuffer(np.zeros_like(s.gbuffer))          # the pipelined call must bring its own G-buffer
             got = r.RenderLightingFrame(s.gbuffer, rows=rows)
             assert np.array_equal(got.view(np.uint16), want.view(np.uint16))
+
+
+def test_degenerate_geometry_takes_the_ieee_fallback(ctx, oracle):
+    """Operands outside the fast window of the deferred-guard square roots / reciprocals (zero-length vectors: a light
+    exactly at a shaded point, at a trace origin, a pixel on a line light's axis, a zero-length line light) must come out
+    of the IEEE re-evaluation exactly like the oracle, NaN for NaN."""
+    s = scenes.lighting_scene(36, 160, 96, 0, float4_lightmap=True)
+    s.gbuffer[...] = scenes.make_gbuffer(np.random.RandomState(1), 160, 96, 0)       # flat ground: world = (px + 0.5, py + 0.5, 0)
+    c = (0.8, 0.6, 0.4, 1.0)
+    s.environment.Lights = [
+        ib.SphereLightSource(Position=(40.5, 30.5, 0.0), Radius=6.0, RampLength=60.0, Color=c, CastsShadows=True),     # on a shaded point
+        ib.SphereLightSource(Position=(80.5, 50.5, 1.6), Radius=4.0, RampLength=50.0, Color=c, CastsShadows=True),     # on a trace origin
+        ib.SphereLightSource(Position=(20.5, 70.5, 0.0), Radius=0.0, RampLength=40.0, Color=c, CastsShadows=False),
+        ib.LineLightSource(StartPosition=(100.5, 20.5, 0.0), EndPosition=(140.5, 20.5, 0.0), Radius=5.0, StartColor=c, EndColor=c, CastsShadows=True),
+        ib.LineLightSource(StartPosition=(60.5, 80.5, 12.0), EndPosition=(60.5, 80.5, 12.0), Radius=5.0, StartColor=c, EndColor=c, CastsShadows=True),
+        ib.LineLightSource(StartPosition=(10.5, 10.5, 1.5), EndPosition=(10.5, 40.5, 1.5), Radius=3.0, StartColor=c, EndColor=c, CastsShadows=True),
+    ]
+    r, tex = make_renderer(ctx, s)
+    gpu, ref = r.RenderLighting(), oracle_lightmap(oracle, r, tex, s)
+    assert np.array_equal(np.isnan(gpu), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    err = lighting_rel_err(gpu[ok], ref[ok])
+    assert err.max() <= LIGHTING_RTOL, f"max rel err {err.max():.3e}"

@@ -216,3 +216,41 @@ def test_planes_match_atlas_bit_for_bit(ctx, monkeypatch):
         for a, b in zip(out[0], out[1]):
             for x, y in zip(a, b):
                 assert np.array_equal(x, y)
+
+
+def _check_nan_aware(gpu, ref):
+    for g, r_, n in zip(gpu, ref, ("position", "velocity", "attributes", "renderColor", "renderData")):
+        assert np.array_equal(np.isnan(g), np.isnan(r_)), n
+        ok = np.isfinite(r_) & np.isfinite(g)
+        assert np.array_equal(np.isfinite(g), np.isfinite(r_)), n
+        e = particle_err(g[ok], r_[ok])
+        assert e <= PARTICLE_ATOL, f"{n}: err {e:.3e}"
+
+
+def test_degenerate_vectors_take_the_ieee_fallback(ctx, oracle):
+    """Operands outside the fast window of the guarded square roots / reciprocals of the fast chains -- squared lengths
+    that are tiny but not zero, or overflow -- must come out of the IEEE re-evaluation like the oracle; exactly-zero
+    vectors (a particle on an attractor, live particles at rest) stay on the fast path through the zero select.
+    (A build with -DILB_BREAK_FALLBACK=1 fails this test: it does reach stepParticleExact.)"""
+    s = scenes.lighting_scene(51, 256, 256, 0)
+    df = scenes.make_distance_field(ctx, s)
+    df.Rasterize(s.obstructions)
+    tex = df.Save()
+    # (a) the Gravity -> Noise -> FMA chain: an attractor at the origin with particles 1e-17 away from it, particles
+    #     exactly on the other attractors, particles at rest
+    ps = scenes.particle_scene(51, 6000, 128, 256, 256, steps_hint=40, collision_field=df, spawn_rate=0.0)
+    gravity = ps.transforms[1]
+    gravity.Attractors[0] = ib.Attractor(Position=(0.0, 0.0, 0.0), Radius=150.0, Strength=400.0, Type=ib.AttractorType.Linear)
+    ps.positions[0:60, :3] = np.float32(1e-17)
+    for k, a in enumerate(gravity.Attractors[1:], start=1):
+        ps.positions[100 * k:100 * k + 40, :3] = np.asarray(a.Position, np.float32)
+    ps.velocities[1000:1400, :3] = 0.0
+    _, gpu, ref = _run_both(ctx, oracle, ps, 128, 3, tex=tex, max_chunks=1)
+    _check_nan_aware(gpu, ref)
+    # (b) the empty chain with collision: |v|^2 below / above the window
+    ps = scenes.particle_scene(52, 6000, 128, 256, 256, steps_hint=40, collision_field=df, spawn_rate=0.0)
+    ps.velocities[0:300, :3] = np.float32(1e-17)
+    ps.velocities[300:600, :3] = np.float32(3e19)
+    ps.velocities[600:900, :3] = 0.0
+    _, gpu, ref = _run_both(ctx, oracle, ps, 128, 3, tex=tex, max_chunks=1, transforms=[])
+    _check_nan_aware(gpu, ref)
