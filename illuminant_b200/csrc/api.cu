@@ -355,6 +355,7 @@ void ilb_particles_destroy(ilb_psys* ps) {
     for (int i = 0; i < 5; i++)
         if (ps->buf[i]) cudaFree(ps->buf[i]);
     if (ps->rng) cudaFree(ps->rng);
+    if (ps->noise_table) cudaFree(ps->noise_table);
     if (ps->d_count) cudaFree(ps->d_count);
     delete ps;
 }

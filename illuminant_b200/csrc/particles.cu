@@ -57,6 +57,7 @@ struct StepParams {
     ilb_psys_uniforms u;
     ilb_op ops[MAX_OPS];
     OpDerived od[MAX_OPS];
+    const float4* noiseTable;  // fast chains: positionDelta[per_chunk] then velocityDelta[per_chunk] of the chain's Noise op (noise_table_kernel)
 };
 
 struct SpawnParams {
@@ -184,24 +185,38 @@ ILB_DEV void opGravity(const ilb_psys_uniforms& u, const SysDerived& sd, const i
     vel = mk4(fminf(mv, xadd(vel.x, acceleration.x)), fminf(mv, xadd(vel.y, acceleration.y)), fminf(mv, xadd(vel.z, acceleration.z)), vel.w);
 }
 
+// The random part of PS_Noise (Noise.fx:42-60): positionDelta and velocityDelta depend on the particle's texel (x, y) and
+// on the op's uniforms only -- not on the particle's state and not on the chunk.
+ILB_DEV void noiseDeltas(const float4* rng, int rng_w, int rng_h, const ilb_noise& n, float x, float y, f4& positionDelta, f4& velocityDelta) {
+    const float rx = n.RandomnessTexel[0], ry = n.RandomnessTexel[1];
+    const f4 randomP1 = randomCustom(rng, rng_w, rng_h, x, y, n.RandomnessOffset, rx, ry, n.RandomnessTexel);
+    const f4 randomP2 = randomCustom(rng, rng_w, rng_h, x, y, n.NextRandomnessOffset, rx, ry, n.RandomnessTexel);
+    const f4 randomV1 = randomCustom(rng, rng_w, rng_h, xadd(x, 2.0f), xadd(y, 1.0f), n.RandomnessOffset, rx, ry, n.RandomnessTexel);
+    const f4 randomV2 = randomCustom(rng, rng_w, rng_h, xadd(x, 2.0f), xadd(y, 1.0f), n.NextRandomnessOffset, rx, ry, n.RandomnessTexel);
+    const f4 randomP = xlerp4(randomP1, randomP2, n.FrequencyLerp);
+    const f4 randomV = xlerp4(randomV1, randomV2, n.FrequencyLerp);
+    positionDelta = xadd4(randomP, mk4(n.PositionOffset));
+    positionDelta = xmul4(sign4(positionDelta), max4(abs4(positionDelta), mk4(n.PositionMinimum)));
+    positionDelta = xmul4(positionDelta, mk4(n.PositionScale));
+    velocityDelta = xadd4(randomV, mk4(n.VelocityOffset));
+    velocityDelta = xmul4(sign4(velocityDelta), max4(abs4(velocityDelta), mk4(n.VelocityMinimum)));
+    velocityDelta = xmul4(velocityDelta, mk4(n.VelocityScale));
+}
+
+// FAST chains read the deltas from the per-step table (one entry per texel of a chunk, shared by all chunks: the
+// reference recomputes them for every particle of every chunk); `li` = index of the particle inside its chunk.
 template <bool FAST>
-ILB_DEV void opNoise(const StepParams& P, const ilb_noise& n, const OpDerived& d, float x, float y, f4& pos, f4& vel, Guard& bad) {  // Noise.fx:28-72
+ILB_DEV void opNoise(const StepParams& P, const ilb_noise& n, const OpDerived& d, float x, float y, unsigned li, f4& pos, f4& vel, Guard& bad) {  // Noise.fx:28-72
     if (!checkCategoryFilter(vel.w, n.area.CategoryFilter)) return;
     const float weight = computeWeight(n.area, d, xyz(pos));
     const float t = tudiv<!FAST>(xmul(weight, P.u.GlobalSettings.x), n.TimeDivisor, d.rTimeDivisor);
-    const float rx = n.RandomnessTexel[0], ry = n.RandomnessTexel[1];
-    const f4 randomP1 = randomCustom(P.rng, P.rng_w, P.rng_h, x, y, n.RandomnessOffset, rx, ry, n.RandomnessTexel);
-    const f4 randomP2 = randomCustom(P.rng, P.rng_w, P.rng_h, x, y, n.NextRandomnessOffset, rx, ry, n.RandomnessTexel);
-    const f4 randomV1 = randomCustom(P.rng, P.rng_w, P.rng_h, xadd(x, 2.0f), xadd(y, 1.0f), n.RandomnessOffset, rx, ry, n.RandomnessTexel);
-    const f4 randomV2 = randomCustom(P.rng, P.rng_w, P.rng_h, xadd(x, 2.0f), xadd(y, 1.0f), n.NextRandomnessOffset, rx, ry, n.RandomnessTexel);
-    const f4 randomP = xlerp4(randomP1, randomP2, n.FrequencyLerp);
-    const f4 randomV = xlerp4(randomV1, randomV2, n.FrequencyLerp);
-    f4 positionDelta = xadd4(randomP, mk4(n.PositionOffset));
-    positionDelta = xmul4(sign4(positionDelta), max4(abs4(positionDelta), mk4(n.PositionMinimum)));
-    positionDelta = xmul4(positionDelta, mk4(n.PositionScale));
-    f4 velocityDelta = xadd4(randomV, mk4(n.VelocityOffset));
-    velocityDelta = xmul4(sign4(velocityDelta), max4(abs4(velocityDelta), mk4(n.VelocityMinimum)));
-    velocityDelta = xmul4(velocityDelta, mk4(n.VelocityScale));
+    f4 positionDelta, velocityDelta;
+    if (FAST) {
+        positionDelta = mk4(__ldg(P.noiseTable + li));
+        velocityDelta = mk4(__ldg(P.noiseTable + P.per_chunk + li));
+    } else {
+        noiseDeltas(P.rng, P.rng_w, P.rng_h, n, x, y, positionDelta, velocityDelta);
+    }
     const f4 oldPosition = pos;
     const f3 ov = xyz(vel);
     pos = xlerp4(oldPosition, xadd4(oldPosition, positionDelta), t);
@@ -463,48 +478,50 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
 #endif
 
 template <int KIND, bool FAST>
-ILB_DEV void applyOp(const StepParams& P, const ilb_op& op, const OpDerived& d, float x, float y, f4& pos, f4& vel, Guard& bad) {
+ILB_DEV void applyOp(const StepParams& P, const ilb_op& op, const OpDerived& d, float x, float y, unsigned li, f4& pos, f4& vel, Guard& bad) {
     if (KIND == ILB_OP_GRAVITY) opGravity<FAST>(P.u, P.sd, op.u.gravity, d, pos, vel, bad);
-    else if (KIND == ILB_OP_NOISE) opNoise<FAST>(P, op.u.noise, d, x, y, pos, vel, bad);
+    else if (KIND == ILB_OP_NOISE) opNoise<FAST>(P, op.u.noise, d, x, y, li, pos, vel, bad);
     else if (KIND == ILB_OP_FMA) opFMA(P.u, op.u.fma, d, pos, vel);
     else if (KIND == ILB_OP_MATRIX_MULTIPLY) opMatrix(P.u, op.u.matrix, d, pos, vel);
 }
 
-ILB_DEV void particleXY(const StepParams& P, unsigned gi, float& x, float& y) {
-    unsigned ix, iy;
+// texel (x, y) of particle gi inside its chunk; returns the index inside the chunk
+ILB_DEV unsigned particleXY(const StepParams& P, unsigned gi, float& x, float& y) {
+    unsigned ix, iy, i;
     if (P.chunk_shift >= 0) {
-        const unsigned i = gi & (P.per_chunk - 1u);
+        i = gi & (P.per_chunk - 1u);
         ix = i & ((unsigned)P.chunk_size - 1u);
         iy = i >> P.chunk_shift;
     } else {
-        const unsigned i = gi % P.per_chunk;
+        i = gi % P.per_chunk;
         ix = i % (unsigned)P.chunk_size;
         iy = i / (unsigned)P.chunk_size;
     }
     x = (float)ix;
     y = (float)iy;
+    return i;
 }
 
 // K0..K2: the transform chain known at compile time (op kinds, 0 = no op): operands come straight from the constant
 // bank with static offsets.  K0 < 0 selects the generic loop over P.ops[0..nops) for every other chain.
 // One particle through the whole update: transform chain in registers, then the Update / UpdateWithDistanceField tail.
 template <bool COLLIDE, int K0, int K1, int K2, int FM, bool FAST, bool COOP>
-ILB_DEV void stepParticle(const StepParams& P, float x, float y, f4 pos, f4 vel, f4& outP, f4& outV, bool& needAttr, unsigned char* warpSlots, Guard& bad) {
+ILB_DEV void stepParticle(const StepParams& P, float x, float y, unsigned li, f4 pos, f4 vel, f4& outP, f4& outV, bool& needAttr, unsigned char* warpSlots, Guard& bad) {
     if (K0 < 0) {
         for (int k = 0; k < P.nops; k++) {
             const ilb_op& op = P.ops[k];
             switch (op.kind) {
-                case ILB_OP_GRAVITY: applyOp<ILB_OP_GRAVITY, FAST>(P, op, P.od[k], x, y, pos, vel, bad); break;
-                case ILB_OP_NOISE: applyOp<ILB_OP_NOISE, FAST>(P, op, P.od[k], x, y, pos, vel, bad); break;
-                case ILB_OP_FMA: applyOp<ILB_OP_FMA, FAST>(P, op, P.od[k], x, y, pos, vel, bad); break;
-                case ILB_OP_MATRIX_MULTIPLY: applyOp<ILB_OP_MATRIX_MULTIPLY, FAST>(P, op, P.od[k], x, y, pos, vel, bad); break;
+                case ILB_OP_GRAVITY: applyOp<ILB_OP_GRAVITY, FAST>(P, op, P.od[k], x, y, li, pos, vel, bad); break;
+                case ILB_OP_NOISE: applyOp<ILB_OP_NOISE, FAST>(P, op, P.od[k], x, y, li, pos, vel, bad); break;
+                case ILB_OP_FMA: applyOp<ILB_OP_FMA, FAST>(P, op, P.od[k], x, y, li, pos, vel, bad); break;
+                case ILB_OP_MATRIX_MULTIPLY: applyOp<ILB_OP_MATRIX_MULTIPLY, FAST>(P, op, P.od[k], x, y, li, pos, vel, bad); break;
                 default: break;
             }
         }
     } else {
-        if (K0 > 0) applyOp<K0, FAST>(P, P.ops[0], P.od[0], x, y, pos, vel, bad);
-        if (K1 > 0) applyOp<K1, FAST>(P, P.ops[1], P.od[1], x, y, pos, vel, bad);
-        if (K2 > 0) applyOp<K2, FAST>(P, P.ops[2], P.od[2], x, y, pos, vel, bad);
+        if (K0 > 0) applyOp<K0, FAST>(P, P.ops[0], P.od[0], x, y, li, pos, vel, bad);
+        if (K1 > 0) applyOp<K1, FAST>(P, P.ops[1], P.od[1], x, y, li, pos, vel, bad);
+        if (K2 > 0) applyOp<K2, FAST>(P, P.ops[2], P.od[2], x, y, li, pos, vel, bad);
     }
     updateTail<COLLIDE, FM, FAST, COOP>(P, x, y, pos, vel, outP, outV, needAttr, warpSlots, bad);
 }
@@ -513,11 +530,11 @@ ILB_DEV void stepParticle(const StepParams& P, float x, float y, f4 pos, f4 vel,
 // reciprocal outside the fast window).  Out of line and generic over the chain: never on the hot path.
 struct ExactResult { float4 p, v; int needAttr; };
 template <bool COLLIDE, int FM>
-__device__ __noinline__ ExactResult stepParticleExact(const StepParams* P, float x, float y, float4 pos, float4 vel) {
+__device__ __noinline__ ExactResult stepParticleExact(const StepParams* P, float x, float y, unsigned li, float4 pos, float4 vel) {
     f4 outP, outV;
     bool needAttr;
     Guard bad = guardInit();
-    stepParticle<COLLIDE, -1, 0, 0, FM, false, false>(*P, x, y, mk4(pos), mk4(vel), outP, outV, needAttr, nullptr, bad);
+    stepParticle<COLLIDE, -1, 0, 0, FM, false, false>(*P, x, y, li, mk4(pos), mk4(vel), outP, outV, needAttr, nullptr, bad);
     ExactResult r;
     r.p = to_float4(outP); r.v = to_float4(outV); r.needAttr = needAttr ? 1 : 0;
 #if ILB_BREAK_FALLBACK  // test hook: proves that a test reaches this path
@@ -528,18 +545,18 @@ __device__ __noinline__ ExactResult stepParticleExact(const StepParams* P, float
 
 // fast evaluation + fallback; the specialised chains (K0 >= 0) take the fast path, the generic chain runs IEEE ops directly
 template <bool COLLIDE, int K0, int K1, int K2, int FM>
-ILB_DEV void stepParticleGuarded(const StepParams& P, float x, float y, f4 pos, f4 vel, f4& outP, f4& outV, bool& needAttr, unsigned char* warpSlots) {
+ILB_DEV void stepParticleGuarded(const StepParams& P, float x, float y, unsigned li, f4 pos, f4 vel, f4& outP, f4& outV, bool& needAttr, unsigned char* warpSlots) {
     Guard bad = guardInit();
 #if ILB_NO_FAST_GUARD
-    stepParticle<COLLIDE, K0, K1, K2, FM, false, true>(P, x, y, pos, vel, outP, outV, needAttr, warpSlots, bad);
+    stepParticle<COLLIDE, K0, K1, K2, FM, false, true>(P, x, y, li, pos, vel, outP, outV, needAttr, warpSlots, bad);
 #else
     if (K0 < 0) {
-        stepParticle<COLLIDE, K0, K1, K2, FM, false, true>(P, x, y, pos, vel, outP, outV, needAttr, warpSlots, bad);
+        stepParticle<COLLIDE, K0, K1, K2, FM, false, true>(P, x, y, li, pos, vel, outP, outV, needAttr, warpSlots, bad);
         return;
     }
-    stepParticle<COLLIDE, K0, K1, K2, FM, true, true>(P, x, y, pos, vel, outP, outV, needAttr, warpSlots, bad);
+    stepParticle<COLLIDE, K0, K1, K2, FM, true, true>(P, x, y, li, pos, vel, outP, outV, needAttr, warpSlots, bad);
     if (guardTripped(bad)) {
-        const ExactResult r = stepParticleExact<COLLIDE, FM>(&P, x, y, to_float4(pos), to_float4(vel));
+        const ExactResult r = stepParticleExact<COLLIDE, FM>(&P, x, y, li, to_float4(pos), to_float4(vel));
         outP = mk4(r.p); outV = mk4(r.v); needAttr = r.needAttr != 0;
     }
 #endif
@@ -554,9 +571,9 @@ __global__ void __launch_bounds__(STEP_THREADS, ILB_PARTICLE_MINBLOCKS) particle
     f4 outP, outV;
     bool needAttr;
     float x, y;
-    particleXY(P, gi, x, y);
+    const unsigned li = particleXY(P, gi, x, y);
     const f4 inP = inRange ? mk4(P.P[gi]) : mk4(0.0f), inV = inRange ? mk4(P.V[gi]) : mk4(0.0f);
-    stepParticleGuarded<COLLIDE, K0, K1, K2, FM>(P, x, y, inP, inV, outP, outV, needAttr, s_slots + (threadIdx.x & ~31u));
+    stepParticleGuarded<COLLIDE, K0, K1, K2, FM>(P, x, y, li, inP, inV, outP, outV, needAttr, s_slots + (threadIdx.x & ~31u));
     if (!inRange) return;
     P.P[gi] = to_float4(outP);
     P.V[gi] = to_float4(outV);
@@ -651,8 +668,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 3) particle_step_tma_kernel(cons
         f4 outP, outV, rc = mk4(0.0f), rd = mk4(0.0f);
         bool needAttr;
         float x, y;
-        particleXY(P, gi, x, y);
-        stepParticleGuarded<COLLIDE, K0, K1, K2, FM>(P, x, y, pos, vel, outP, outV, needAttr, s_slots + (tid & ~31u));
+        const unsigned li = particleXY(P, gi, x, y);
+        stepParticleGuarded<COLLIDE, K0, K1, K2, FM>(P, x, y, li, pos, vel, outP, outV, needAttr, s_slots + (tid & ~31u));
         if (P.u.write_render_outputs && needAttr) computeRenderData(P.u, x, y, outP, outV, attr, rc, rd);
 
         S.outP[tid] = to_float4(outP);
@@ -673,6 +690,24 @@ __global__ void __launch_bounds__(STEP_THREADS, 3) particle_step_tma_kernel(cons
         }
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA exits
+}
+
+// ---- per-step Noise table ------------------------------------------------------------------------------------------
+struct NoiseTableParams {
+    ilb_noise n;
+    const float4* rng;
+    int rng_w, rng_h, chunk_size;
+    unsigned per_chunk;
+    float4* table;
+};
+__global__ void __launch_bounds__(STEP_THREADS) noise_table_kernel(const __grid_constant__ NoiseTableParams P) {
+    const unsigned i = blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (i >= P.per_chunk) return;
+    const float x = (float)(i % (unsigned)P.chunk_size), y = (float)(i / (unsigned)P.chunk_size);
+    f4 positionDelta, velocityDelta;
+    noiseDeltas(P.rng, P.rng_w, P.rng_h, P.n, x, y, positionDelta, velocityDelta);
+    P.table[i] = to_float4(positionDelta);
+    P.table[P.per_chunk + i] = to_float4(velocityDelta);
 }
 
 // ---- spawner (SpawnerCommon.fxh, SpawnParticles.fx:10-30) -----------------------------------------------------
@@ -918,6 +953,18 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
         const bool staged = ps->use_tma && ((chainGNF && collide) || (chainNone && !collide)) && (total % STAGE_TILE == 0);
         const unsigned ntiles = (unsigned)(total / STAGE_TILE);
         const unsigned persistent = std::min<unsigned>(ntiles, (unsigned)ps->sm_count * 3u);
+        if (chainGNF) {  // the fast chain reads the Noise deltas from a per-step table shared by all chunks
+            if (!ps->noise_table) ILB_CUDA(ctx, cudaMalloc(&ps->noise_table, sizeof(float4) * 2 * ps->per_chunk));
+            NoiseTableParams NT;
+            memset(&NT, 0, sizeof(NT));
+            NT.n = ops[1].u.noise;
+            NT.rng = ps->rng; NT.rng_w = ps->rng_w; NT.rng_h = ps->rng_h;
+            NT.chunk_size = ps->chunk_size; NT.per_chunk = (unsigned)ps->per_chunk;
+            NT.table = ps->noise_table;
+            noise_table_kernel<<<(unsigned)((ps->per_chunk + STEP_THREADS - 1) / STEP_THREADS), STEP_THREADS, 0, ctx->stream>>>(NT);
+            ctx->launches++;
+            SP.noiseTable = ps->noise_table;
+        }
         const int fm = collide ? ((planes ? 2 : 0) | (ilb_field_is_flat(SP.df) ? 1 : 0)) : 0;  // field mode, see sampleField
 #define ILB_STAGED(C, A, B, D, FM)                                                                                          \
     do {                                                                                                                    \
