@@ -141,6 +141,7 @@ namespace Squared.Illuminant.Native {
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_create (IntPtr ctx, int chunkSize, int maxChunks, out IntPtr psys);
         [DllImport(DllName, CallingConvention = CC)] public static extern void ilb_particles_destroy (IntPtr psys);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_set_randomness (IntPtr psys, Vector4* table, int w, int h);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_set_life_ramp (IntPtr psys, Vector4* texels, int w, int h);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_set_collision_field (IntPtr psys, IntPtr df);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_set_live_chunks (IntPtr psys, int count);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_upload_chunk (IntPtr psys, int chunk, Vector4* positionAndLife, Vector4* velocity, Vector4* attributes);

@@ -7,7 +7,7 @@ from .distance_field import DistanceField, LightObstruction, LightObstructionTyp
 from .lighting import (DirectionalLightSource, LightingEnvironment, LightingRenderer, LightProbe, LightSourceRampMode,
                        LineLightSource, RendererConfiguration, ShadowFilter, SphereLightSource, encode_gbuffer)
 from .particles import (FMA, AreaType, Attractor, AttractorType, Bezier4V, BezierF, Formula, FormulaType, Gravity, MatrixMultiply,
-                        Noise, ParticleCollision, ParticleEngine, ParticleEngineConfiguration, ParticleSystem,
+                        Noise, ParticleCollision, ParticleColorLifeRamp, ParticleEngine, ParticleEngineConfiguration, ParticleSystem,
                         ParticleSystemConfiguration, Spawner, TransformArea)
 
 __version__ = "0.1.0"

@@ -156,6 +156,7 @@ _PROTOTYPES = [
     ("ilb_particles_create", C.c_int, [P, C.c_int, C.c_int, C.POINTER(P)]),
     ("ilb_particles_destroy", None, [P]),
     ("ilb_particles_set_randomness", C.c_int, [P, P, C.c_int, C.c_int]),
+    ("ilb_particles_set_life_ramp", C.c_int, [P, P, C.c_int, C.c_int]),
     ("ilb_particles_set_collision_field", C.c_int, [P, P]),
     ("ilb_particles_upload_chunk", C.c_int, [P, C.c_int, P, P, P]),
     ("ilb_particles_download_chunk", C.c_int, [P, C.c_int, P, P, P, P, P]),

@@ -356,6 +356,7 @@ void ilb_particles_destroy(ilb_psys* ps) {
         if (ps->buf[i]) cudaFree(ps->buf[i]);
     if (ps->rng) cudaFree(ps->rng);
     if (ps->noise_table) cudaFree(ps->noise_table);
+    if (ps->life_ramp) cudaFree(ps->life_ramp);
     if (ps->d_count) cudaFree(ps->d_count);
     delete ps;
 }
@@ -373,6 +374,24 @@ int ilb_particles_set_randomness(ilb_psys* ps, const ilb_float4* table, int w, i
     ILB_CUDA(ctx, cudaMemcpyAsync(ps->rng, table, bytes, cudaMemcpyHostToDevice, ctx->stream));
     ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ps->rng_w = w; ps->rng_h = h;
+    return ILB_OK;
+}
+
+int ilb_particles_set_life_ramp(ilb_psys* ps, const ilb_float4* texels, int w, int h) {
+    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    ilb_ctx* ctx = ps->ctx;
+    if (texels && (w <= 0 || h <= 0 || w > 16384 || h > 16384)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad life ramp size %dx%d", w, h);
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ps->life_ramp) cudaFree(ps->life_ramp);
+    ps->life_ramp = nullptr;
+    ps->life_ramp_w = ps->life_ramp_h = 0;
+    if (!texels) return ILB_OK;
+    const size_t bytes = sizeof(float4) * (size_t)w * (size_t)h;
+    ILB_CUDA(ctx, cudaMalloc(&ps->life_ramp, bytes));
+    ILB_CUDA(ctx, cudaMemcpyAsync(ps->life_ramp, texels, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ps->life_ramp_w = w; ps->life_ramp_h = h;
     return ILB_OK;
 }
 

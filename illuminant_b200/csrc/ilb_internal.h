@@ -69,6 +69,8 @@ struct ilb_psys {
     float4* rng = nullptr;
     int rng_w = 0, rng_h = 0;
     ilb_df* field = nullptr;
+    float4* life_ramp = nullptr;    // LifeRampTexture, float4 texels
+    int life_ramp_w = 0, life_ramp_h = 0;
     float4* noise_table = nullptr;  // 2 * per_chunk float4, see noise_table_kernel
     unsigned long long* d_count = nullptr;
     bool use_tma = false;  // ILB_PARTICLE_TMA=1 selects the TMA-staged persistent step kernel (measured 22 % slower: the

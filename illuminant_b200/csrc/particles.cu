@@ -57,6 +57,8 @@ struct StepParams {
     ilb_psys_uniforms u;
     ilb_op ops[MAX_OPS];
     OpDerived od[MAX_OPS];
+    const float4* lifeRamp;    // LifeRampTexture (float4 texels) or nullptr
+    int lifeRampW, lifeRampH;
     const float4* noiseTable;  // fast chains: positionDelta[per_chunk] then velocityDelta[per_chunk] of the chain's Noise op (noise_table_kernel)
 };
 
@@ -264,8 +266,17 @@ ILB_DEV f3 applyFrictionAndMaximum(const ilb_psys_uniforms& u, const SysDerived&
 }
 
 // Render outputs do not feed back into particle state: plain (FMA / fast division) arithmetic.
-ILB_DEV void computeRenderData(const ilb_psys_uniforms& u, float vx, float vy, f4 position, f4 velocity, f4 attributes,
+// LifeRampSampler (UpdateCommon.fxh:6-13): POINT, U clamp, V wrap; texel selection with x-ops (a flipped texel is an O(1) difference)
+ILB_DEV f4 readLifeRamp(const float4* ramp, int w, int h, float u, float v) {
+    if (!ramp) return mk4(1.0f);  // Engine.DummyRampTexture
+    const int ix = min(max((int)floorf(xmul(u, (float)w)), 0), w - 1);
+    const int iy = min(max(wrapIndex(xmul(v, (float)h), h), 0), h - 1);
+    return mk4(__ldg(ramp + (size_t)iy * (size_t)w + (size_t)ix));
+}
+
+ILB_DEV void computeRenderData(const StepParams& P, float vx, float vy, f4 position, f4 velocity, f4 attributes,
                                f4& renderColor, f4& renderData) {  // UpdateCommon.fxh:97-117
+    const ilb_psys_uniforms& u = P.u;
     if (position.w <= 0.0f) {
         renderColor = mk4(0.0f);
         renderData = mk4(0.0f);
@@ -275,6 +286,12 @@ ILB_DEV void computeRenderData(const ilb_psys_uniforms& u, float vx, float vy, f
     const float velocityLength = fmaxf(length3(xyz(velocity)), 0.0001f);
     f4 ramped = evaluateBezier4(u.ColorFromLife, position.w);
     ramped = ramped * evaluateBezier4(u.ColorFromVelocity, velocityLength);
+    if (u.LifeRampSettings.x != 0.0f) {  // getRampedColorForLifeValueAndIndex :67-80 (uniform branch)
+        float ru = xdiv(xsub(position.w, u.LifeRampSettings.y), u.LifeRampSettings.z);
+        if (u.LifeRampSettings.x < 0.0f) ru = xsub(1.0f, saturatef(ru));
+        const float rv = xdiv(index, u.LifeRampSettings.w);
+        ramped = lerp4(ramped, readLifeRamp(P.lifeRamp, P.lifeRampW, P.lifeRampH, ru, rv) * ramped, saturatef(fabsf(u.LifeRampSettings.x)));
+    }
     renderColor = attributes * ramped;
     renderColor.w = saturatef(renderColor.w);
     renderColor.x *= renderColor.w; renderColor.y *= renderColor.w; renderColor.z *= renderColor.w;
@@ -579,7 +596,7 @@ __global__ void __launch_bounds__(STEP_THREADS, ILB_PARTICLE_MINBLOCKS) particle
     P.V[gi] = to_float4(outV);
     if (P.u.write_render_outputs) {
         f4 rc = mk4(0.0f), rd = mk4(0.0f);
-        if (needAttr) computeRenderData(P.u, x, y, outP, outV, mk4(__ldg(P.A + gi)), rc, rd);
+        if (needAttr) computeRenderData(P, x, y, outP, outV, mk4(__ldg(P.A + gi)), rc, rd);
         P.RC[gi] = to_float4(rc);
         P.RD[gi] = to_float4(rd);
     }
@@ -670,7 +687,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 3) particle_step_tma_kernel(cons
         float x, y;
         const unsigned li = particleXY(P, gi, x, y);
         stepParticleGuarded<COLLIDE, K0, K1, K2, FM>(P, x, y, li, pos, vel, outP, outV, needAttr, s_slots + (tid & ~31u));
-        if (P.u.write_render_outputs && needAttr) computeRenderData(P.u, x, y, outP, outV, attr, rc, rd);
+        if (P.u.write_render_outputs && needAttr) computeRenderData(P, x, y, outP, outV, attr, rc, rd);
 
         S.outP[tid] = to_float4(outP);
         S.outV[tid] = to_float4(outV);
@@ -823,7 +840,6 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
     if (!u || spawn_count < 0 || op_count < 0 || steps < 0 || (spawn_count > 0 && !spawns) || (op_count > 0 && !ops))
         return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null or negative argument");
     if (op_count > MAX_OPS) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "at most %d transforms per system", MAX_OPS);
-    if (u->LifeRampSettings.x != 0.0f) return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "life-ramp textures are outside the hot-path scope");
     if (u->has_collision_field && !ps->field)  // ParticleSystem.cs:834-836
         return ilb_fail(ctx, ILB_ERR_INVALID_OPERATION, "collision is enabled but no distance field was set");
     bool needsRng = spawn_count > 0;
@@ -864,6 +880,7 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
         memset(&SP, 0, sizeof(SP));
         SP.P = ps->buf[0]; SP.V = ps->buf[1]; SP.A = ps->buf[2]; SP.RC = ps->buf[3]; SP.RD = ps->buf[4];
         SP.rng = ps->rng; SP.rng_w = ps->rng_w; SP.rng_h = ps->rng_h;
+        SP.lifeRamp = ps->life_ramp; SP.lifeRampW = ps->life_ramp_w; SP.lifeRampH = ps->life_ramp_h;
         SP.chunk_size = ps->chunk_size;
         SP.per_chunk = (unsigned)ps->per_chunk;
         SP.chunk_shift = -1;

@@ -126,7 +126,17 @@ class ParticleSystemConfiguration:  # ParticleConfiguration.cs:187-303
     ColorFromVelocity: Optional[Bezier4V] = None
     SizeFromLife: Optional[BezierF] = None
     SizeFromVelocity: Optional[BezierF] = None
+    LifeRamp: Optional["ParticleColorLifeRamp"] = None   # Configuration.Color.LifeRamp (ParticleConfiguration.cs:111-137)
     WriteRenderOutputs: bool = True     # not in the reference: False skips renderColor/renderData (64 B/particle mode)
+
+
+@dataclass
+class ParticleColorLifeRamp:  # ParticleConfiguration.cs:111-137
+    Minimum: float = 0.0
+    Maximum: float = 100.0
+    Strength: float = 1.0
+    Invert: bool = False
+    Texture: Optional[np.ndarray] = None   # float32 [H, W, 4] texels of the ramp texture
 
 
 @dataclass
@@ -464,6 +474,20 @@ class ParticleSystem:
             self.handle = h
             rt = np.ascontiguousarray(engine.RandomnessTexture, dtype=np.float32)
             self.ctx.check(self.ctx.lib.ilb_particles_set_randomness(h, rt.ctypes.data_as(C.c_void_p), rt.shape[1], rt.shape[0]))
+        self._life_ramp_uploaded = None
+
+    def _sync_life_ramp(self) -> None:
+        """MaybeSetLifeRampParameters (ParticleSystem.cs:911-925): binds Configuration.LifeRamp.Texture."""
+        lr = self.Configuration.LifeRamp
+        tex = lr.Texture if lr is not None else None
+        if tex is self._life_ramp_uploaded or self.handle is None:
+            return
+        if tex is None:
+            self.ctx.check(self.ctx.lib.ilb_particles_set_life_ramp(self.handle, None, 0, 0))
+        else:
+            arr = np.ascontiguousarray(tex, dtype=np.float32)
+            self.ctx.check(self.ctx.lib.ilb_particles_set_life_ramp(self.handle, arr.ctypes.data_as(C.c_void_p), arr.shape[1], arr.shape[0]))
+        self._life_ramp_uploaded = tex
 
     # ---- chunks -----------------------------------------------------------------------------------------------
     @property
@@ -538,7 +562,13 @@ class ParticleSystem:
         u.ColorFromVelocity = clamped_bezier4(cfg.ColorFromVelocity)
         u.SizeFromLife = clamped_bezier1(cfg.SizeFromLife)
         u.SizeFromVelocity = clamped_bezier1(cfg.SizeFromVelocity)
-        u.LifeRampSettings = Float4(0, 0, 1, 1)
+        lr = cfg.LifeRamp
+        if lr is not None and lr.Texture is not None:   # MaybeSetLifeRampParameters ParticleSystem.cs:927-940
+            rangeSize = max(F(lr.Maximum) - F(lr.Minimum), F(0.001))
+            u.LifeRampSettings = Float4(F(lr.Strength) * (-1 if lr.Invert else 1), lr.Minimum, rangeSize, float(np.asarray(lr.Texture).shape[0]))
+        else:
+            u.LifeRampSettings = Float4(0, 0, 1, 1)
+        self._sync_life_ramp()
         u.RotationFromLifeAndIndex[:] = [float(F(math.radians(cfg.RotationFromLife))), float(F(math.radians(cfg.RotationFromIndex)))]
         u.write_render_outputs = 1 if cfg.WriteRenderOutputs else 0
         if col is not None and col.DistanceField is not None:

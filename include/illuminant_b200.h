@@ -213,7 +213,7 @@ typedef struct ilb_psys_uniforms {
     ilb_float4 AnimationRateAndRotationAndZToY;
     ilb_bezier4 ColorFromLife, ColorFromVelocity;
     ilb_bezier1 SizeFromLife, SizeFromVelocity;
-    ilb_float4 LifeRampSettings;   /* x must be 0: the life-ramp texture is outside the hot-path scope */
+    ilb_float4 LifeRampSettings;   /* strength (negative = inverted), minimum, range, index divisor (ParticleSystem.cs:911-941); x == 0: no ramp */
     float RotationFromLifeAndIndex[2]; /* radians (ParticleTransform.cs:155-158) */
     int32_t has_collision_field;   /* Configuration.Collision?.DistanceField != null -> UpdateWithDistanceField */
     int32_t write_render_outputs;  /* 1 = renderColor/renderData written (reference contract); 0 = 64 B/particle mode */
@@ -301,6 +301,10 @@ ILB_API int ilb_particles_create(ilb_ctx* ctx, int chunk_size, int max_chunks, i
 ILB_API void ilb_particles_destroy(ilb_psys* psys);
 /* The engine-wide randomness texture (ParticleEngine.cs:45-46, :495-544): width*height float4, row-major. */
 ILB_API int ilb_particles_set_randomness(ilb_psys* psys, const ilb_float4* table, int width, int height);
+/* LifeRampTexture (Configuration.Color.LifeRamp.Texture, ParticleSystem.cs:911-925; sampled POINT / U clamp / V wrap by
+ * getRampedColorForLifeValueAndIndex, UpdateCommon.fxh:6-13,67-80): width*height float4 texels, row-major.  NULL removes
+ * it (the reference then binds its white dummy ramp). */
+ILB_API int ilb_particles_set_life_ramp(ilb_psys* psys, const ilb_float4* texels, int width, int height);
 /* Configuration.Collision.DistanceField (may differ from the lighting field, SimpleParticles.cs:216-219). */
 ILB_API int ilb_particles_set_collision_field(ilb_psys* psys, ilb_df* df);
 /* Spawn(initializer)-style upload / readback of one chunk (ParticleWorkItems.cs:75-78, ParticleReadback.cs:59-61).

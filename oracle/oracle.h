@@ -20,6 +20,8 @@ float orc_sphere_light_opacity(const ilb_lighting_frame* f, const float* pos, co
 void orc_decode_gbuffer(const ilb_lighting_frame* f, const void* gbuffer, int gw, int gh, int gfmt, int x, int y,
                         float* worldPos, float* normal, int* enableShadows, int* fullbright);
 float orc_evaluate_by_type_id(int typeId, const float* worldPosition, const float* center, const float* size, const float* rotation);
+/* LifeRampTexture of the particle update (UpdateCommon.fxh:6-13): float4 texels, row-major; NULL = none. The pointer must stay valid. */
+void orc_set_life_ramp(const float* texels, int w, int h);
 float orc_bezier1(const ilb_bezier1* b, float value);
 void orc_bezier4(const ilb_bezier4* b, float value, float* out);
 int orc_particles_step(float* P, float* V, float* A, float* RC, float* RD, int chunk_size, int live_chunks,

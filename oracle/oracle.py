@@ -54,6 +54,8 @@ def lib():
                                          C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_evaluate_by_type_id.restype = C.c_float
         L.orc_evaluate_by_type_id.argtypes = [C.c_int, P, P, P, P]
+        L.orc_set_life_ramp.restype = None
+        L.orc_set_life_ramp.argtypes = [P, C.c_int, C.c_int]
         L.orc_bezier1.restype = C.c_float
         L.orc_bezier1.argtypes = [C.POINTER(Bezier1), C.c_float]
         L.orc_bezier4.restype = None
@@ -167,8 +169,14 @@ def bezier4(b: Bezier4, value: float) -> np.ndarray:
     return out
 
 
-def particles_step(P_, V_, A_, chunk_size, u: PsysUniforms, spawns, ops, rng_table, df_tex=None, steps=1, nthreads=0):
-    """In-place multi-pass update of [chunks*chunk_size^2, 4] float32 state. Returns (P, V, A, RC, RD)."""
+def particles_step(P_, V_, A_, chunk_size, u: PsysUniforms, spawns, ops, rng_table, df_tex=None, steps=1, nthreads=0, life_ramp=None):
+    """In-place multi-pass update of [chunks*chunk_size^2, 4] float32 state. Returns (P, V, A, RC, RD).
+    life_ramp: float32 [H, W, 4] LifeRampTexture or None."""
+    if life_ramp is not None:
+        life_ramp = np.ascontiguousarray(life_ramp, dtype=np.float32)
+        lib().orc_set_life_ramp(_ptr(life_ramp), life_ramp.shape[1], life_ramp.shape[0])
+    else:
+        lib().orc_set_life_ramp(None, 0, 0)
     P_, V_, A_ = (np.ascontiguousarray(a, dtype=np.float32).copy() for a in (P_, V_, A_))
     per = chunk_size * chunk_size
     live = P_.shape[0] // per

@@ -422,6 +422,21 @@ float3 applyFrictionAndMaximum(const System& sys, float3 velocity) {  // :20-35
     return normalize(velocity) * l;
 }
 
+// LifeRampSampler (UpdateCommon.fxh:6-13): POINT filter, AddressU CLAMP, AddressV WRAP.  The texture is set once per
+// system with orc_set_life_ramp (float4 texels, row-major).
+static const float* g_lifeRamp = nullptr;
+static int g_lifeRampW = 0, g_lifeRampH = 0;
+float4 readLifeRamp(float u, float v) {  // :36-38
+    if (!g_lifeRamp) return float4(1.0f);  // Engine.DummyRampTexture (ParticleSystem.cs:921-924): white
+    int ix = (int)floorf(u * (float)g_lifeRampW);
+    ix = ix < 0 ? 0 : (ix > g_lifeRampW - 1 ? g_lifeRampW - 1 : ix);
+    const float fy = floorf(v * (float)g_lifeRampH);
+    int iy = (int)(fy - floorf(fy / (float)g_lifeRampH) * (float)g_lifeRampH);
+    iy = iy < 0 ? 0 : (iy > g_lifeRampH - 1 ? g_lifeRampH - 1 : iy);
+    const float* t = g_lifeRamp + 4 * ((size_t)iy * g_lifeRampW + ix);
+    return float4(t[0], t[1], t[2], t[3]);
+}
+
 float getRotationForVelocity(float3 velocity) {  // :82-95
     float2 absvel = abs(velocity.xy());
     if ((absvel.x < 0.01f) && (absvel.y < 0.01f)) return 0;
@@ -438,9 +453,16 @@ void computeRenderData(const System& sys, float2 vpos, float4 position, float4 v
     }
     float index = vpos.x + (vpos.y * 256);  // hard-coded 256 in the reference (:107)
     float velocityLength = max(length(velocity.xyz()), 0.0001f);
-    // getRampedColorForLifeValueAndIndex :67-80 with LifeRampSettings.x == 0
+    // getRampedColorForLifeValueAndIndex :67-80
     float4 ramped = evaluateBezier4(sys.u.ColorFromLife, position.w);
     ramped *= evaluateBezier4(sys.u.ColorFromVelocity, velocityLength);
+    const ilb_float4 lrs = sys.u.LifeRampSettings;
+    if (lrs.x != 0) {
+        float u = (position.w - lrs.y) / lrs.z;
+        if (lrs.x < 0) u = 1 - saturate(u);
+        float v = index / lrs.w;
+        ramped = lerp(ramped, readLifeRamp(u, v) * ramped, saturate(fabsf(lrs.x)));
+    }
     renderColor = attributes * ramped;
     renderColor.w = saturate(renderColor.w);
     renderColor.x *= renderColor.w; renderColor.y *= renderColor.w; renderColor.z *= renderColor.w;
@@ -588,6 +610,8 @@ bool PS_UpdateWithDistanceField(const System& sys, const Field& df, float2 xy, f
 
 extern "C" {
 
+void orc_set_life_ramp(const float* texels, int w, int h) { g_lifeRamp = texels; g_lifeRampW = w; g_lifeRampH = h; }
+
 float orc_bezier1(const ilb_bezier1* b, float value) { return evaluateBezier1(*b, value); }
 void orc_bezier4(const ilb_bezier4* b, float value, float* out) {
     float4 r = evaluateBezier4(*b, value);
@@ -601,7 +625,6 @@ int orc_particles_step(float* P, float* V, float* A, float* RC, float* RD, int c
                        const ilb_psys_uniforms* u, const ilb_spawn* spawns, int nspawns, const ilb_op* ops, int nops,
                        const float* rng_table, int rw, int rh, const uint16_t* df_tex, int tw, int th, int steps,
                        int nthreads) {
-    if (u->LifeRampSettings.x != 0) return ILB_ERR_UNSUPPORTED;
     if (u->has_collision_field && !df_tex) return ILB_ERR_INVALID_OPERATION;
     if (nthreads > 0) omp_set_num_threads(nthreads);
     const System sys(*u);

@@ -9,7 +9,7 @@ from helpers import PARTICLE_ATOL, particle_err
 pytestmark = pytest.mark.gpu
 
 
-def _run_both(ctx, oracle, ps, chunk_size, steps, tex=None, seed=3, max_chunks=4, transforms=None):
+def _run_both(ctx, oracle, ps, chunk_size, steps, tex=None, seed=3, max_chunks=4, transforms=None, life_ramp=None):
     engine = ib.ParticleEngine(ctx, ib.ParticleEngineConfiguration(ChunkSize=chunk_size, RandomSeed=seed))
     system = ib.ParticleSystem(engine, ps.configuration, maxChunks=max_chunks)
     system.Transforms = ps.transforms if transforms is None else transforms
@@ -27,7 +27,7 @@ def _run_both(ctx, oracle, ps, chunk_size, steps, tex=None, seed=3, max_chunks=4
         if P.shape[0] < live * per:
             P, V, A = (np.concatenate([a, np.zeros((live * per - a.shape[0], 4), np.float32)]) for a in (P, V, A))
         system.step_packed(u, spawns, ops, 1)
-        P, V, A, RC, RD = oracle.particles_step(P, V, A, chunk_size, u, spawns, ops, engine.RandomnessTexture, tex, 1)
+        P, V, A, RC, RD = oracle.particles_step(P, V, A, chunk_size, u, spawns, ops, engine.RandomnessTexture, tex, 1, life_ramp=life_ramp)
     gpu = [np.concatenate(x) for x in zip(*[system.ReadChunk(c) for c in range(system.LiveChunkCount)])]
     return system, gpu, (P, V, A, RC, RD)
 
@@ -254,3 +254,19 @@ def test_degenerate_vectors_take_the_ieee_fallback(ctx, oracle):
     ps.velocities[600:900, :3] = 0.0
     _, gpu, ref = _run_both(ctx, oracle, ps, 128, 3, tex=tex, max_chunks=1, transforms=[])
     _check_nan_aware(gpu, ref)
+
+
+def test_life_ramp_texture(ctx, oracle):
+    """getRampedColorForLifeValueAndIndex with a LifeRampTexture (UpdateCommon.fxh:6-13,67-80): POINT sampled, U clamped,
+    V wrapped by the particle index; normal and inverted, partial strength."""
+    rs = np.random.RandomState(7)
+    for invert, strength, shape in ((False, 1.0, (4, 16, 4)), (True, 0.6, (3, 7, 4))):
+        ps = scenes.particle_scene(53, 9000, 128, 300, 300, steps_hint=20)
+        ramp = rs.uniform(0.0, 1.0, shape).astype(np.float32)
+        ps.configuration.LifeRamp = ib.ParticleColorLifeRamp(Minimum=0.5, Maximum=3.0, Strength=strength, Invert=invert, Texture=ramp)
+        _, gpu, ref = _run_both(ctx, oracle, ps, 128, 4, life_ramp=ramp)
+        _check(gpu, ref, f"life ramp invert={invert}")
+        fresh = scenes.particle_scene(53, 9000, 128, 300, 300, steps_hint=20)   # same seed, fresh host-side spawner state
+        _, plain, _ = _run_both(ctx, oracle, fresh, 128, 4)
+        assert not np.allclose(gpu[3], plain[3])      # the ramp really changes renderColor
+        assert np.array_equal(gpu[0], plain[0])       # ... and nothing else
