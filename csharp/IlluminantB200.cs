@@ -132,6 +132,7 @@ namespace Squared.Illuminant.Native {
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_synchronize (IntPtr ctx);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_df_create (IntPtr ctx, int w, int h, void* rgba64, UIntPtr bytes, out IntPtr df);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_df_generate (IntPtr ctx, int w, int h, int sliceW, int sliceH, int sliceCount, ref IlbDFUniforms u, IlbObstruction* obstructions, int count, out IntPtr df);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_df_update_dynamic (IntPtr df, IntPtr staticDf, int sliceW, int sliceH, int sliceCount, ref IlbDFUniforms u, IlbObstruction* dynamicObstructions, int count);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_df_download (IntPtr df, void* rgba64, UIntPtr bytes);
         [DllImport(DllName, CallingConvention = CC)] public static extern void ilb_df_destroy (IntPtr df);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_gbuffer_upload (IntPtr ctx, int w, int h, int format, void* data);

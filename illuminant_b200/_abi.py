@@ -145,6 +145,7 @@ _PROTOTYPES = [
     ("ilb_df_create_device", C.c_int, [P, C.c_int, C.c_int, P, C.c_size_t, C.POINTER(P)]),
     ("ilb_df_download", C.c_int, [P, P, C.c_size_t]),
     ("ilb_df_destroy", None, [P]),
+    ("ilb_df_update_dynamic", C.c_int, [P, P, C.c_int, C.c_int, C.c_int, C.POINTER(DFUniforms), P, C.c_int]),
     ("ilb_df_generate", C.c_int, [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DFUniforms), P, C.c_int, C.POINTER(P)]),
     ("ilb_gbuffer_upload", C.c_int, [P, C.c_int, C.c_int, C.c_int, P]),
     ("ilb_gbuffer_upload_device", C.c_int, [P, C.c_int, C.c_int, C.c_int, P]),

@@ -201,12 +201,26 @@ int ilb_df_generate(ilb_ctx* ctx, int tw, int th, int slice_w, int slice_h, int 
     if (!u || count < 0 || (count > 0 && !obstructions)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
     int rc = df_alloc(ctx, tw, th, 0, false, out_df);
     if (rc) return rc;
-    rc = ilb_dfgen_launch(ctx, (*out_df)->tex, tw, th, slice_w, slice_h, slice_count, u, obstructions, count);
+    rc = ilb_dfgen_launch(ctx, (*out_df)->tex, nullptr, tw, th, slice_w, slice_h, slice_count, u, obstructions, count);
     if (rc) {
         ilb_df_destroy(*out_df);
         *out_df = nullptr;
     }
     return rc;
+}
+
+int ilb_df_update_dynamic(ilb_df* df, const ilb_df* static_df, int slice_w, int slice_h, int slice_count, const ilb_df_uniforms* u,
+                          const ilb_obstruction* obstructions, int count) {
+    if (!df || !live_has(df)) return ILB_ERR_INVALID_ARGUMENT;
+    ilb_ctx* ctx = df->ctx;
+    if (!static_df || !live_has(static_df) || static_df->ctx != ctx || static_df == df)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "static field is released, the same as the dynamic field, or belongs to another context");
+    if (static_df->tw != df->tw || static_df->th != df->th)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "static field is %dx%d, dynamic field %dx%d", static_df->tw, static_df->th, df->tw, df->th);
+    if (!u || count < 0 || (count > 0 && !obstructions)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    df->version++;  // derived planes are rebuilt (in place) the next time the field is sampled
+    return ilb_dfgen_launch(ctx, df->tex, static_df->tex, df->tw, df->th, slice_w, slice_h, slice_count, u, obstructions, count);
 }
 
 int ilb_df_download(ilb_df* df, uint16_t* rgba64, size_t bytes) {

@@ -11,6 +11,7 @@ namespace {
 
 struct DFGenParams {
     uint2* tex;
+    const uint2* base;  // static field of a DynamicDistanceField (same atlas geometry) or nullptr
     int tw, th, slice_w, slice_h, slice_count, columns, physical;
     float maxEnc, zOffset, depth, invX, invY;
     const ilb_obstruction* obs;
@@ -37,6 +38,12 @@ __global__ void __launch_bounds__(GEN_TILE * GEN_TILE) df_generate_kernel(const 
         sliceZ[k] = (s * P.depth) + P.zOffset;
     }
     float best[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // ClearDistanceField.fx:27-39
+    const int cellX = (p % P.columns) * P.slice_w, cellY = (p / P.columns) * P.slice_h;
+    if (P.base && valid) {  // dynamic field: the slice starts as a copy of the static texture (LightingRenderer.DistanceField.cs:113-118)
+        const uint2 b = __ldg(P.base + (size_t)(cellY + y) * (size_t)P.tw + (size_t)(cellX + x));
+        const float k = 1.0f / 65535.0f;
+        best[0] = xmul(u16lo(b.x), k); best[1] = xmul(u16hi(b.x), k); best[2] = xmul(u16lo(b.y), k); best[3] = xmul(u16hi(b.y), k);
+    }
     for (int base = 0; base < P.count; base += GEN_TILE * GEN_TILE) {
         const int oi = base + tid;
         bool keep = false;
@@ -85,11 +92,11 @@ __global__ void __launch_bounds__(GEN_TILE * GEN_TILE) df_generate_kernel(const 
 
 }  // namespace
 
-int ilb_dfgen_launch(ilb_ctx* ctx, uint2* tex, int tw, int th, int slice_w, int slice_h, int slice_count,
+int ilb_dfgen_launch(ilb_ctx* ctx, uint2* tex, const uint2* base, int tw, int th, int slice_w, int slice_h, int slice_count,
                      const ilb_df_uniforms* u, const ilb_obstruction* obs, int count) {
     DFGenParams P;
     memset(&P, 0, sizeof(P));
-    P.tex = tex; P.tw = tw; P.th = th; P.slice_w = slice_w; P.slice_h = slice_h; P.slice_count = slice_count;
+    P.tex = tex; P.base = base; P.tw = tw; P.th = th; P.slice_w = slice_w; P.slice_h = slice_h; P.slice_count = slice_count;
     P.columns = (int)u->TextureSliceCount.x;
     P.physical = (slice_count + 2) / 3;
     if (P.columns < 1 || slice_w < 1 || slice_h < 1 || slice_count < 1)
@@ -105,7 +112,8 @@ int ilb_dfgen_launch(ilb_ctx* ctx, uint2* tex, int tw, int th, int slice_w, int 
         ILB_CUDA(ctx, cudaMemcpyAsync(d_obs, obs, sizeof(ilb_obstruction) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
     }
     P.obs = d_obs; P.count = count;
-    ILB_CUDA(ctx, cudaMemsetAsync(tex, 0, sizeof(uint2) * (size_t)tw * (size_t)th, ctx->stream));
+    if (base) ILB_CUDA(ctx, cudaMemcpyAsync(tex, base, sizeof(uint2) * (size_t)tw * (size_t)th, cudaMemcpyDeviceToDevice, ctx->stream));
+    else ILB_CUDA(ctx, cudaMemsetAsync(tex, 0, sizeof(uint2) * (size_t)tw * (size_t)th, ctx->stream));
     const dim3 grid((slice_w + GEN_TILE - 1) / GEN_TILE, (slice_h + GEN_TILE - 1) / GEN_TILE, P.physical);
     df_generate_kernel<<<grid, dim3(GEN_TILE, GEN_TILE), 0, ctx->stream>>>(P);
     ctx->launches++;

@@ -49,6 +49,8 @@ struct ilb_ctx {
 // one cached set of expanded planes (planes.cu), keyed by the addressing uniforms it was built for
 struct ilb_df_planes {
     float key[10];
+    uint64_t version = 0;   // ilb_df::version the planes were built from
+    int nv = 0, sw = 0, sh = 0;
     float4* planes = nullptr;
     float4* vtab = nullptr;
     int pitch = 0;
@@ -58,6 +60,7 @@ struct ilb_df {
     ilb_ctx* ctx = nullptr;
     uint2* tex = nullptr;
     int tw = 0, th = 0;
+    uint64_t version = 0;   // bumped when the atlas is rewritten in place (ilb_df_update_dynamic)
     std::vector<ilb_df_planes> planes;
 };
 
@@ -105,7 +108,7 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
                                  int batch_count, const ilb_light_vertex* vertices, int vertex_count, int gw, int gh, int gfmt,
                                  const void* gbuffer_host, void* lightmap_out_host);
 // dfgen.cu
-int ilb_dfgen_launch(ilb_ctx* ctx, uint2* tex, int tw, int th, int slice_w, int slice_h, int slice_count,
+int ilb_dfgen_launch(ilb_ctx* ctx, uint2* tex, const uint2* base, int tw, int th, int slice_w, int slice_h, int slice_count,
                      const ilb_df_uniforms* u, const ilb_obstruction* obs, int count);
 // particles.cu
 int ilb_particles_launch(ilb_psys* psys, const ilb_psys_uniforms* u, const ilb_spawn* spawns, int spawn_count,

@@ -63,10 +63,14 @@ int ilb_planes_attach(ilb_ctx* ctx, ilb_df* df, const ilb_df_uniforms& u, DFGeom
     if (!df || !g->tex) return ILB_OK;
     if (const char* e = getenv("ILB_NO_PLANES"))  // read per call: the parity tests flip it to compare both samplers
         if (e[0] != '0') return ILB_OK;
-    for (const ilb_df_planes& p : df->planes)
+    ilb_df_planes* stale = nullptr;
+    for (ilb_df_planes& p : df->planes)
         if (sameKey(p, *g)) {
-            g->planes = p.planes; g->vtab = p.vtab; g->pitch = p.pitch;
-            return ILB_OK;
+            if (p.version == df->version) {
+                g->planes = p.planes; g->vtab = p.vtab; g->pitch = p.pitch;
+                return ILB_OK;
+            }
+            stale = &p;  // the atlas was rewritten in place: same geometry, same allocation, new contents
         }
     const int columns = (int)u.TextureSliceCount.x, rows = (int)u.TextureSliceCount.y;
     if (columns < 1 || rows < 1 || (float)columns != u.TextureSliceCount.x || (float)rows != u.TextureSliceCount.y) return ILB_OK;
@@ -106,7 +110,17 @@ int ilb_planes_attach(ilb_ctx* ctx, ilb_df* df, const ilb_df_uniforms& u, DFGeom
         vtab[(size_t)v] = make_float4(cu, rv, basef, 0.0f);
     }
 
+    if (stale && stale->nv == nv && stale->sw == sw && stale->sh == sh) {
+        B.tex = df->tex; B.planes = stale->planes;
+        B.tw = df->tw; B.th = df->th; B.sw = sw; B.sh = sh; B.pw = pw; B.ph = ph; B.nv = nv;
+        df_planes_build_kernel<<<dim3((pw + 255) / 256, ph, nv), 256, 0, ctx->stream>>>(B);
+        ILB_CUDA(ctx, cudaGetLastError());
+        stale->version = df->version;
+        g->planes = stale->planes; g->vtab = stale->vtab; g->pitch = stale->pitch;
+        return ILB_OK;
+    }
     ilb_df_planes P;
+    P.version = df->version; P.nv = nv; P.sw = sw; P.sh = sh;
     const size_t bytes = sizeof(float4) * (size_t)nv * pw * ph;
     if (cudaMalloc(&P.planes, bytes) != cudaSuccess) {
         cudaGetLastError();  // not enough HBM for the derived copy: keep sampling the atlas

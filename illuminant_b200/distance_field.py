@@ -178,6 +178,55 @@ class DistanceField:
     def Dispose(self):
         self._release()
 
+
+class DynamicDistanceField(DistanceField):
+    """DynamicDistanceField (SDF/DistanceField.cs:248-310): keeps a static field (obstructions with IsDynamic == false)
+    and derives the sampled field from it every time the dynamic obstructions move: the slices are cleared to the static
+    texture and only the dynamic obstructions are rasterised on top (LightingRenderer.DistanceField.cs:99-118)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.static_handle = None
+
+    def _release(self):
+        super()._release()
+        if getattr(self, "static_handle", None):
+            self.ctx.lib.ilb_df_destroy(self.static_handle)
+            self.static_handle = None
+
+    def _generate(self, obstructions):
+        obs = pack_obstructions(obstructions)
+        self.ValidSliceCount = self.SliceCount
+        u = self.uniforms()
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.ilb_df_generate(self.ctx.handle, self.TextureWidth, self.TextureHeight, self.SliceWidth,
+                                                    self.SliceHeight, self.SliceCount, C.byref(u),
+                                                    C.cast(obs, C.c_void_p) if len(obs) else None, len(obs), C.byref(h)))
+        return h
+
+    def Rasterize(self, obstructions) -> None:
+        """Invalidate(invalidateStatic = true) + a full update: static field from the static obstructions, then the
+        sampled field from it and the dynamic ones."""
+        static = [o for o in obstructions if not o.IsDynamic]
+        self._release()
+        self.static_handle = self._generate(static)
+        self.handle = self._generate(static)            # a second atlas of the same size to hold the sampled field
+        self.RasterizeDynamic([o for o in obstructions if o.IsDynamic])
+
+    def RasterizeDynamic(self, dynamic_obstructions) -> None:
+        """Invalidate(invalidateStatic = false) + update: per-frame path, rewrites the sampled field in place."""
+        if self.static_handle is None or self.handle is None:
+            raise _abi.IlluminantError(_abi.ERR_INVALID_OPERATION, "Rasterize() the static field first")
+        obs = pack_obstructions(dynamic_obstructions)
+        u = self.uniforms()
+        self.ctx.check(self.ctx.lib.ilb_df_update_dynamic(self.handle, self.static_handle, self.SliceWidth, self.SliceHeight, self.SliceCount,
+                                                          C.byref(u), C.cast(obs, C.c_void_p) if len(obs) else None, len(obs)))
+
+    def SaveStatic(self) -> np.ndarray:
+        out = np.empty((self.TextureHeight, self.TextureWidth, 4), dtype=np.uint16)
+        self.ctx.check(self.ctx.lib.ilb_df_download(self.static_handle, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
     def __del__(self):
         try:
             self._release()

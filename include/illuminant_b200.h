@@ -102,6 +102,12 @@ ILB_API int ilb_df_generate(ilb_ctx* ctx, int texture_width, int texture_height,
                             int slice_width, int slice_height, int slice_count,
                             const ilb_df_uniforms* u, const ilb_obstruction* obstructions, int count,
                             ilb_df** out_df);
+/* DynamicDistanceField (SDF/DistanceField.cs:248-310): the field a frame samples is the STATIC field with the dynamic
+ * obstructions MAX-blended on top -- the slice is "cleared" to the static texture and only IsDynamic obstructions are
+ * rasterised (LightingRenderer.DistanceField.cs:99-118, ClearDistanceField.fx:27-39).  Rewrites `df` in place from
+ * `static_df` (same atlas size; no allocation, derived data is refreshed lazily), so it can run every frame. */
+ILB_API int ilb_df_update_dynamic(ilb_df* df, const ilb_df* static_df, int slice_width, int slice_height, int slice_count,
+                                  const ilb_df_uniforms* uniforms, const ilb_obstruction* dynamic_obstructions, int count);
 
 /* ------------------------------------------------------------- G-buffer (L4) */
 

@@ -28,7 +28,7 @@ int orc_particles_step(float* P, float* V, float* A, float* RC, float* RD, int c
                        const ilb_psys_uniforms* u, const ilb_spawn* spawns, int nspawns, const ilb_op* ops, int nops,
                        const float* rng_table, int rw, int rh, const uint16_t* df_tex, int tw, int th, int steps,
                        int nthreads);
-int orc_generate_distance_field(uint16_t* out_rgba64, int tw, int th, int slice_w, int slice_h, int slice_count,
+int orc_generate_distance_field(uint16_t* out_rgba64, const uint16_t* base_rgba64 /* static field or NULL */, int tw, int th, int slice_w, int slice_h, int slice_count,
                                 const ilb_df_uniforms* u, const ilb_obstruction* obs, int count, int nthreads);
 void orc_encode_gbuffer_sample(const float* normal, float relativeY, float z, int dead, int enableShadows, int fullbright, float* out4);
 void orc_float_to_half(const float* in, uint16_t* out, long n);

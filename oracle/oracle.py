@@ -64,7 +64,7 @@ def lib():
         L.orc_particles_step.argtypes = [P, P, P, P, P, C.c_int, C.c_int, C.POINTER(PsysUniforms), P, C.c_int, P, C.c_int, P, C.c_int,
                                          C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_generate_distance_field.restype = C.c_int
-        L.orc_generate_distance_field.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DFUniforms), P, C.c_int, C.c_int]
+        L.orc_generate_distance_field.argtypes = [P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DFUniforms), P, C.c_int, C.c_int]
         L.orc_encode_gbuffer_sample.restype = None
         L.orc_encode_gbuffer_sample.argtypes = [P, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, P]
         L.orc_float_to_half.restype = None
@@ -199,8 +199,9 @@ def particles_step(P_, V_, A_, chunk_size, u: PsysUniforms, spawns, ops, rng_tab
     return P_, V_, A_, RC, RD
 
 
-def generate_distance_field(df, obstructions, nthreads=0) -> np.ndarray:
-    """df: illuminant_b200.DistanceField descriptor (host arithmetic only). Returns uint16 [TH, TW, 4]."""
+def generate_distance_field(df, obstructions, nthreads=0, base=None) -> np.ndarray:
+    """df: illuminant_b200.DistanceField descriptor (host arithmetic only). Returns uint16 [TH, TW, 4].
+    base: the static field (uint16 [TH, TW, 4]) of a DynamicDistanceField, or None."""
     from illuminant_b200.distance_field import pack_obstructions
     obs = pack_obstructions(obstructions)
     saved = df.ValidSliceCount
@@ -208,7 +209,9 @@ def generate_distance_field(df, obstructions, nthreads=0) -> np.ndarray:
     u = df.uniforms()
     df.ValidSliceCount = saved
     out = np.zeros((df.TextureHeight, df.TextureWidth, 4), dtype=np.uint16)
-    rc = lib().orc_generate_distance_field(_ptr(out), df.TextureWidth, df.TextureHeight, df.SliceWidth, df.SliceHeight, df.SliceCount,
+    if base is not None:
+        base = np.ascontiguousarray(base, dtype=np.uint16)
+    rc = lib().orc_generate_distance_field(_ptr(out), _ptr(base), df.TextureWidth, df.TextureHeight, df.SliceWidth, df.SliceHeight, df.SliceCount,
                                            C.byref(u), C.cast(obs, P) if len(obstructions) else None, len(obstructions),
                                            nthreads or threads())
     if rc != 0:

@@ -20,7 +20,9 @@ extern "C" {
 // center.xy +- (max|size| + MaximumEncodedDistance + 4) (Shaders/DistanceFunction.fx:15-27) and is MAX-blended
 // (LoadMaterials.cs:171-175) with encodeDistance(evaluateX(...)) (DistanceFunction.fx:34-48,
 // DistanceFieldCommon.fxh:264-266); the render target is UNORM16 (round-to-nearest, saturating).
-int orc_generate_distance_field(uint16_t* out, int tw, int th, int slice_w, int slice_h, int slice_count,
+// `base` (nullable): the static field of a DynamicDistanceField; the slice is then "cleared" to the static texel
+// (ClearDistanceField.fx:27-39 with ClearTexture = StaticTexture, LightingRenderer.DistanceField.cs:113-118) instead of 0.
+int orc_generate_distance_field(uint16_t* out, const uint16_t* base, int tw, int th, int slice_w, int slice_h, int slice_count,
                                 const ilb_df_uniforms* u, const ilb_obstruction* obs, int count, int nthreads) {
     if (nthreads > 0) omp_set_num_threads(nthreads);
     const int physical = (slice_count + 2) / 3;
@@ -28,7 +30,8 @@ int orc_generate_distance_field(uint16_t* out, int tw, int th, int slice_w, int 
     const float maxEnc = u->Extent.w, zOffset = u->ConeAndMisc.y, depth = u->Extent.z;
     const float invX = u->ConeAndMisc.w, invY = u->StepAndMisc2.w;
     const float DISTANCE_ZERO = 192.0f / 255.0f;
-    memset(out, 0, sizeof(uint16_t) * 4 * (size_t)tw * th);
+    if (base) memcpy(out, base, sizeof(uint16_t) * 4 * (size_t)tw * th);
+    else memset(out, 0, sizeof(uint16_t) * 4 * (size_t)tw * th);
     for (int p = 0; p < physical; p++) {
         const int ox = (p % columns) * slice_w, oy = (p / columns) * slice_h;
         if (ox + slice_w > tw || oy + slice_h > th) return ILB_ERR_INVALID_ARGUMENT;
@@ -42,6 +45,10 @@ int orc_generate_distance_field(uint16_t* out, int tw, int th, int slice_w, int 
             for (int x = 0; x < slice_w; x++) {
                 float wx = (float)x * invX, wy = (float)y * invY;  // getPositionXy, DistanceFunction.fx:29-32
                 float best[4] = {0, 0, 0, 0};
+                if (base) {
+                    const uint16_t* b = base + 4 * ((size_t)(oy + y) * tw + (ox + x));
+                    for (int k = 0; k < 4; k++) best[k] = (float)b[k] * (1.0f / 65535.0f);
+                }
                 for (int i = 0; i < count; i++) {
                     const ilb_obstruction& o = obs[i];
                     float msize = fmaxf(fmaxf(fabsf(o.size[0]), fabsf(o.size[1])), fabsf(o.size[2])) + maxEnc + 4;

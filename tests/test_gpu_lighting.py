@@ -232,3 +232,38 @@ def test_degenerate_geometry_takes_the_ieee_fallback(ctx, oracle):
     ok = ~np.isnan(ref)
     err = lighting_rel_err(gpu[ok], ref[ok])
     assert err.max() <= LIGHTING_RTOL, f"max rel err {err.max():.3e}"
+
+
+def test_dynamic_distance_field(ctx, oracle):
+    """DynamicDistanceField (SDF/DistanceField.cs:248-310): sampled field = static field with the dynamic obstructions
+    MAX-blended on top, rewritten in place per frame; the derived planes follow the new contents."""
+    s = scenes.lighting_scene(37, 320, 200, 5, n_directional=1, ramp=(60.0, 220.0), float4_lightmap=True)
+    rs = np.random.RandomState(5)
+    dynamic = [ib.LightObstruction(ib.LightObstructionType.Ellipsoid, (float(rs.uniform(40, 280)), float(rs.uniform(30, 170)), 10.0), (18.0, 12.0, 40.0),
+                                   IsDynamic=True) for _ in range(3)]
+    df = ib.DynamicDistanceField(ctx, s.width, s.height, s.df_depth, s.df_slices, s.df_resolution, 128)
+    df.Rasterize(s.obstructions + dynamic)
+    static_ref = oracle.generate_distance_field(df, s.obstructions)
+    assert np.abs(df.SaveStatic().astype(np.int32) - static_ref.astype(np.int32)).max() <= 1
+    static_gpu = df.SaveStatic()
+    ref = oracle.generate_distance_field(df, dynamic, base=static_gpu)
+    got = df.Save()
+    assert np.abs(got.astype(np.int32) - ref.astype(np.int32)).max() <= 1 and (got != ref).mean() < 1e-3
+    # all obstructions at once is the same field (MAX is associative; re-quantising the static part is idempotent)
+    whole = scenes.make_distance_field(ctx, s)
+    whole.Rasterize(s.obstructions + dynamic)
+    assert np.array_equal(whole.Save(), got)
+
+    r = ib.LightingRenderer(ctx, s.environment, s.configuration)
+    r.DistanceField = df
+    r.SetGBuffer(s.gbuffer)
+    before = r.RenderLighting()
+    _check(before, oracle_lightmap(oracle, r, got, s), "dynamic field, frame 0")
+    for o in dynamic:                                   # next frame: the dynamic obstructions moved
+        o.Center = (o.Center[0] + 25.0, o.Center[1] - 10.0, o.Center[2])
+    df.RasterizeDynamic(dynamic)
+    moved = df.Save()
+    assert not np.array_equal(moved, got)
+    after = r.RenderLighting()                          # same handle, rewritten atlas: the planes must have been refreshed
+    assert not np.array_equal(after, before)
+    _check(after, oracle_lightmap(oracle, r, moved, s), "dynamic field, frame 1")
