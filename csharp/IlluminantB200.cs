@@ -138,6 +138,13 @@ namespace Squared.Illuminant.Native {
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_gbuffer_upload (IntPtr ctx, int w, int h, int format, void* data);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_render_lighting (IntPtr ctx, IntPtr df, ref IlbLightingFrame frame, IlbLightBatch* batches, int batchCount, LightVertex* vertices, int vertexCount, void* lightmapOut);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_render_lighting_frame (IntPtr ctx, IntPtr df, ref IlbLightingFrame frame, IlbLightBatch* batches, int batchCount, LightVertex* vertices, int vertexCount, int gbufferWidth, int gbufferHeight, int gbufferFormat, void* gbuffer, void* lightmapOut);
+        [StructLayout(LayoutKind.Sequential, Pack = 4)]
+        public struct IlbParticleLightSource {   // ilb_particle_light_source
+            public IntPtr System;
+            public Vector4 LightProperties, MoreLightProperties, LightColor, LightSpecularColor;
+            public IlbDFUniforms DF;
+        }
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_lighting_set_particle_lights (IntPtr ctx, IlbParticleLightSource* sources, int count);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_update_light_probes (IntPtr ctx, IntPtr df, ref IlbLightingFrame frame, IlbLightBatch* batches, int batchCount, LightVertex* vertices, int vertexCount, Vector4* probePositions, Vector4* probeNormals, int probeCount, int outputFormat, void* probesOut);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_create (IntPtr ctx, int chunkSize, int maxChunks, out IntPtr psys);
         [DllImport(DllName, CallingConvention = CC)] public static extern void ilb_particles_destroy (IntPtr psys);

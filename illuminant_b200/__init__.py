@@ -5,7 +5,7 @@ from ._abi import (Context, IlluminantError, EXPORTED_SYMBOLS, LIB_PATH, load_li
                    FORMAT_FLOAT4, FORMAT_HALF4, FORMAT_RGBA8)
 from .distance_field import DistanceField, DynamicDistanceField, LightObstruction, LightObstructionType, RendererQualitySettings
 from .lighting import (DirectionalLightSource, LightingEnvironment, LightingRenderer, LightProbe, LightSourceRampMode,
-                       LineLightSource, RendererConfiguration, ShadowFilter, SphereLightSource, encode_gbuffer)
+                       LineLightSource, ParticleLightSource, RendererConfiguration, ShadowFilter, SphereLightSource, encode_gbuffer)
 from .particles import (FMA, AreaType, Attractor, AttractorType, Bezier4V, BezierF, Formula, FormulaType, Gravity, MatrixMultiply,
                         Noise, ParticleCollision, ParticleColorLifeRamp, ParticleEngine, ParticleEngineConfiguration, ParticleSystem,
                         ParticleSystemConfiguration, Spawner, TransformArea)

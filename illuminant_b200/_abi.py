@@ -15,7 +15,7 @@ LIB_PATH = Path(os.environ["ILB_LIB"]) if os.environ.get("ILB_LIB") else PKG / "
 ILB_OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_INVALID_OPERATION, ERR_OUT_OF_MEMORY, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 FORMAT_FLOAT4, FORMAT_HALF4, FORMAT_RGBA8 = 0, 1, 2
-LIGHT_SPHERE, LIGHT_DIRECTIONAL, LIGHT_LINE = 1, 2, 4
+LIGHT_SPHERE, LIGHT_DIRECTIONAL, LIGHT_PARTICLE, LIGHT_LINE = 1, 2, 3, 4
 OP_GRAVITY, OP_NOISE, OP_FMA, OP_MATRIX_MULTIPLY = 1, 2, 3, 4
 MAX_ATTRACTORS = 16
 FORMAT_BYTES = {FORMAT_FLOAT4: 16, FORMAT_HALF4: 8, FORMAT_RGBA8: 4}
@@ -54,6 +54,11 @@ class LightVertex(C.Structure):
 class LightBatch(C.Structure):
     _fields_ = [("light_type", C.c_int32), ("first_vertex", C.c_int32), ("vertex_count", C.c_int32), ("reserved", C.c_int32),
                 ("df", DFUniforms)]
+
+
+class ParticleLightSourceStruct(C.Structure):  # ilb_particle_light_source
+    _fields_ = [("system", C.c_void_p), ("LightProperties", Float4), ("MoreLightProperties", Float4), ("LightColor", Float4),
+                ("LightSpecularColor", Float4), ("df", DFUniforms)]
 
 
 class LightingFrame(C.Structure):
@@ -151,6 +156,7 @@ _PROTOTYPES = [
     ("ilb_gbuffer_upload_device", C.c_int, [P, C.c_int, C.c_int, C.c_int, P]),
     ("ilb_render_lighting", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, P]),
     ("ilb_render_lighting_frame", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_int, P, P]),
+    ("ilb_lighting_set_particle_lights", C.c_int, [P, P, C.c_int]),
     ("ilb_render_lighting_device", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, P]),
     ("ilb_render_lighting_peers", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, C.POINTER(P), C.c_int]),
     ("ilb_update_light_probes", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, P, P, C.c_int, C.c_int, P]),

@@ -118,6 +118,7 @@ void ilb_destroy(ilb_ctx* ctx) {
     if (ctx->d_lightmap) cudaFree(ctx->d_lightmap);
     if (ctx->d_probe_in) cudaFree(ctx->d_probe_in);
     if (ctx->d_accum) cudaFree(ctx->d_accum);
+    if (ctx->d_plight_scratch) cudaFree(ctx->d_plight_scratch);
     if (ctx->copy_in) {
         cudaStreamDestroy(ctx->copy_in);
         cudaStreamDestroy(ctx->copy_out);
@@ -322,6 +323,16 @@ int ilb_render_lighting_frame(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame
                                         gbuffer_format, gbuffer, lightmap_out);
 }
 
+int ilb_lighting_set_particle_lights(ilb_ctx* ctx, const ilb_particle_light_source* sources, int count) {
+    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (count < 0 || (count > 0 && !sources)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null or negative argument");
+    for (int i = 0; i < count; i++)
+        if (!sources[i].system || !live_has(sources[i].system) || sources[i].system->ctx != ctx)
+            return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "particle light source %d: system is released or belongs to another context", i);
+    ctx->particle_lights.assign(sources, sources + count);
+    return ILB_OK;
+}
+
 int ilb_update_light_probes(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches, int batch_count,
                             const ilb_light_vertex* vertices, int vertex_count, const ilb_float4* probe_positions,
                             const ilb_float4* probe_normals, int probe_count, int output_format, void* probes_out) {
@@ -364,6 +375,8 @@ void ilb_particles_destroy(ilb_psys* ps) {
     if (!ps || !live_take(ps)) return;
     auto& v = ps->ctx->systems;
     v.erase(std::remove(v.begin(), v.end(), ps), v.end());
+    auto& pl = ps->ctx->particle_lights;
+    pl.erase(std::remove_if(pl.begin(), pl.end(), [ps](const ilb_particle_light_source& s) { return s.system == ps; }), pl.end());
     cudaSetDevice(ps->ctx->device);
     cudaStreamSynchronize(ps->ctx->stream);
     for (int i = 0; i < 5; i++)

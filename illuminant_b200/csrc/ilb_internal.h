@@ -39,6 +39,10 @@ struct ilb_ctx {
     size_t d_probe_in_capacity = 0;
     void* d_accum = nullptr;     // fp32 sums handed from the line-light pass to the sphere / directional pass
     size_t d_accum_capacity = 0;
+    // ParticleLightSources applied to every frame until replaced (ilb_lighting_set_particle_lights)
+    std::vector<ilb_particle_light_source> particle_lights;
+    void* d_plight_scratch = nullptr;
+    size_t d_plight_scratch_capacity = 0;
     // host-to-host frame pipeline (ilb_render_lighting_frame): upload / download streams and per-band events
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_in[ILB_PIPELINE_BANDS] = {}, ev_done[ILB_PIPELINE_BANDS] = {};

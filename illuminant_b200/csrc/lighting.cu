@@ -30,6 +30,7 @@ namespace {
 #endif
 constexpr int TILE_W = 16, TILE_H = ILB_TILE_H, TILE_THREADS = TILE_W * TILE_H, TILE_WARPS = TILE_THREADS / 32;
 constexpr int MAX_OUTPUTS = 8;
+constexpr int ILB_LIGHT_PARTICLE_BIT = 8;  // DLight::type of a particle light (a bit for the TYPES masks; the public id, ILB_LIGHT_PARTICLE, is 3)
 
 // One light, flattened on the host from (batch, LightVertex): the LightVertex fields (Vertices.cs:10-39) plus
 // the batch's quality uniforms and the rasterised coverage of its quad.
@@ -466,7 +467,7 @@ template <int FIELD, bool FAST, int TYPES>
 ILB_DEV bool shadeLight(const DFGeometry& df, float lightOcclusion, const DLight& L, const DLine* lines, int lightIndex, const Pixel& px,
                         f3& rgb, Guard& bad) {
     const float es = px.enableShadows ? 1.0f : 0.0f;
-    if ((TYPES & ILB_LIGHT_SPHERE) && L.type == ILB_LIGHT_SPHERE) {  // SphereLightPixelShader SphereLight.fx:7-46
+    if ((TYPES & ILB_LIGHT_SPHERE) && (L.type == ILB_LIGHT_SPHERE || L.type == ILB_LIGHT_PARTICLE_BIT)) {  // SphereLightPixelShader SphereLight.fx:7-46, ParticleLightPixelShader ParticleLight.fx:84-118
         if (px.fullbright || shadowFilterRejects(L.evenMore.x, px.enableShadows)) return false;
         float4 props = L.props;
         props.w *= es;
@@ -475,7 +476,7 @@ ILB_DEV bool shadeLight(const DFGeometry& df, float lightOcclusion, const DLight
         if (!sphereCore<FIELD, FAST>(df, L, lightOcclusion, px.pos, px.normal, center, props, L.more, opacity, bad)) return false;
         const float4 color = L.color1, spec = L.color2;
         rgb = (mk3(color.x, color.y, color.z) * color.w * opacity);
-        if (any3(mk3(spec.x, spec.y, spec.z))) {  // CalcSphereLightSpecularity LightCommon.fxh:212-222
+        if (any3(mk3(spec.x, spec.y, spec.z)) || L.type == ILB_LIGHT_PARTICLE_BIT) {  // CalcSphereLightSpecularity LightCommon.fxh:212-222
             const f3 lightDirection = px.pos - center;
             const f3 h = normalize3(normalize3(px.camera - px.pos) - lightDirection);
             const float specularity = powf(saturatef(dot3(h, px.normal)), spec.w);
@@ -662,7 +663,7 @@ light_accumulate_kernel(const __grid_constant__ LightingParams P) {
             const int4 r = __ldg(reinterpret_cast<const int4*>(&L->px0));
             const int type = __ldg(&L->type);
             keep = ((type & TYPES) != 0) && (r.x <= tx1) && (r.z >= tx0) && (r.y <= ty1) && (r.w >= ty0) && (bx0 <= bx1);
-            if ((TYPES & ILB_LIGHT_SPHERE) && keep && type == ILB_LIGHT_SPHERE) {
+            if ((TYPES & ILB_LIGHT_SPHERE) && keep && (type == ILB_LIGHT_SPHERE || type == ILB_LIGHT_PARTICLE_BIT)) {
                 // sphere lights reach radius + rampLength (radius + 1 in RampMode None): reject the tile when the
                 // closest point of its world AABB is farther (1 px of slack covers fp rounding)
                 const float4 c = __ldg(&L->pos1), pr = __ldg(&L->props), mo = __ldg(&L->more);
@@ -878,24 +879,139 @@ int flattenLights(ilb_ctx* ctx, const ilb_df* df, const ilb_lighting_frame* f, c
     return ILB_OK;
 }
 
-// device layout: DLight[n] followed by DLine[n]
-int uploadLights(ilb_ctx* ctx, const std::vector<DLight>& lights, const std::vector<DLine>& lines, const DLight** d_lights, const DLine** d_lines) {
+// device layout: DLine[n] (host lights only) followed by DLight[n + extra]; the `extra` records are appended on the device
+// (particle lights)
+int uploadLights(ilb_ctx* ctx, const std::vector<DLight>& lights, const std::vector<DLine>& lines, size_t extra, const DLight** d_lights,
+                 const DLine** d_lines) {
     const size_t n = lights.size();
-    const size_t lightBytes = std::max<size_t>(n, 1) * sizeof(DLight), bytes = lightBytes + std::max<size_t>(n, 1) * sizeof(DLine);
-    int rc = ilb_reserve(ctx, &ctx->d_lights, &ctx->d_lights_capacity, bytes, false);
+    const size_t lineBytes = std::max<size_t>(n, 1) * sizeof(DLine), hostBytes = lineBytes + std::max<size_t>(n, 1) * sizeof(DLight);
+    int rc = ilb_reserve(ctx, &ctx->d_lights, &ctx->d_lights_capacity, hostBytes + extra * sizeof(DLight), false);
     if (rc) return rc;
-    rc = ilb_reserve(ctx, &ctx->h_lights, &ctx->h_lights_capacity, bytes, true);
+    rc = ilb_reserve(ctx, &ctx->h_lights, &ctx->h_lights_capacity, hostBytes, true);
     if (rc) return rc;
     // the pinned staging buffer is reused every frame: wait for the previous frame's copy
     ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (n) {
-        memcpy(ctx->h_lights, lights.data(), n * sizeof(DLight));
-        memcpy(reinterpret_cast<char*>(ctx->h_lights) + lightBytes, lines.data(), n * sizeof(DLine));
-        ILB_CUDA(ctx, cudaMemcpyAsync(ctx->d_lights, ctx->h_lights, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        memcpy(ctx->h_lights, lines.data(), n * sizeof(DLine));
+        memcpy(reinterpret_cast<char*>(ctx->h_lights) + lineBytes, lights.data(), n * sizeof(DLight));
+        ILB_CUDA(ctx, cudaMemcpyAsync(ctx->d_lights, ctx->h_lights, hostBytes, cudaMemcpyHostToDevice, ctx->stream));
     }
-    *d_lights = reinterpret_cast<const DLight*>(ctx->d_lights);
-    *d_lines = reinterpret_cast<const DLine*>(reinterpret_cast<const char*>(ctx->d_lights) + lightBytes);
+    *d_lines = reinterpret_cast<const DLine*>(ctx->d_lights);
+    *d_lights = reinterpret_cast<const DLight*>(reinterpret_cast<const char*>(ctx->d_lights) + lineBytes);
     return ILB_OK;
+}
+
+// ---- particle lights ("next" row N4): ParticleLightSource (LightSource.cs:466-500) ---------------------------------------
+// The reference draws the particle system's instanced quads with the ParticleLight material (LightingRenderer.cs:1126-1144):
+// ParticleLightVertexShader (ParticleLight.fx:16-82) turns every live particle into a sphere light at its position with the
+// template's properties and colour = unpremultiplied attribute colour * LightColor; the pixel shader is the sphere-light
+// core without the shadow filter (:84-118).  Here the particle state never leaves HBM: three small kernels append one
+// DLight per live, visible particle to the frame's light list in particle order (count per block, scan, ordered write),
+// and the tile kernel shades them like sphere lights with a rectangular quad.  StippleFactor is taken as 1 (StippleReject
+// lives in the un-vendored sq/Fracture DitherCommon.fxh).
+
+struct PLightParams {
+    const float4* P;      // PositionAndLife
+    const float4* A;      // attributes (AttributeSampler)
+    unsigned total;       // live_chunks * per_chunk
+    unsigned* counts;     // per block of 256 particles
+    unsigned* offsets;    // exclusive scan of counts; offsets[nblocks] = total lights
+    unsigned nblocks;
+    DLight* out;          // first particle light record
+    float4 props, more, color, spec, quality;
+    float longStep, rcpRamp;
+    int hasField;
+    float zToY, invZToY, sxs, sys, vpx, vpy;
+};
+
+ILB_DEV bool particleLightColor(const PLightParams& P, unsigned i, float4& position, float4& lightColor) {  // ParticleLight.fx:36-51,73-81
+    position = __ldg(P.P + i);
+    if (!(position.w > 0.0f)) return false;
+    float4 c = __ldg(P.A + i);
+    if (c.w > 0.0f) { c.x = xdiv(c.x, c.w); c.y = xdiv(c.y, c.w); c.z = xdiv(c.z, c.w); }  // unpremultiply
+    lightColor = make_float4(xmul(c.x, P.color.x), xmul(c.y, P.color.y), xmul(c.z, P.color.z), xmul(c.w, P.color.w));
+    return lightColor.w > 0.0f;
+}
+
+__global__ void __launch_bounds__(256) particle_light_count_kernel(const __grid_constant__ PLightParams P) {
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    float4 pos, col;
+    const bool keep = (i < P.total) && particleLightColor(P, i, pos, col);
+    const int n = __syncthreads_count(keep);
+    if (threadIdx.x == 0) P.counts[blockIdx.x] = (unsigned)n;
+}
+
+__global__ void __launch_bounds__(1024) particle_light_scan_kernel(const __grid_constant__ PLightParams P) {  // one block
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_carry;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (unsigned base = 0; base < P.nblocks; base += 1024u) {
+        const unsigned v = (base + tid < P.nblocks) ? P.counts[base + tid] : 0u;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        if (lane == 31u) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+                if (lane >= (unsigned)o) wi += t;
+            }
+            s_warp[lane] = wi - w;  // exclusive warp offsets
+        }
+        __syncthreads();
+        const unsigned carry = s_carry;
+        if (base + tid < P.nblocks) P.offsets[base + tid] = carry + s_warp[warp] + incl - v;
+        __syncthreads();
+        if (tid == 1023u) s_carry = carry + s_warp[warp] + incl;
+        __syncthreads();
+    }
+    if (tid == 0) P.offsets[P.nblocks] = s_carry;
+}
+
+__global__ void __launch_bounds__(256) particle_light_write_kernel(const __grid_constant__ PLightParams P) {
+    __shared__ unsigned s_warp[8];
+    const unsigned i = blockIdx.x * 256u + threadIdx.x, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    float4 pos, col;
+    const bool keep = (i < P.total) && particleLightColor(P, i, pos, col);
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    if (!keep) return;
+    unsigned rank = __popc(ballot & ((1u << lane) - 1u));
+    for (unsigned w = 0; w < warp; w++) rank += s_warp[w];
+    DLight L;
+    L.pos1 = L.pos2 = make_float4(pos.x, pos.y, pos.z, 0.0f);
+    L.props = P.props; L.more = P.more;
+    L.evenMore = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);  // no shadow filter in ParticleLightPixelShader
+    L.color1 = col; L.color2 = P.spec;
+    L.quality = P.quality; L.longStep = P.longStep; L.hasField = P.hasField; L.type = ILB_LIGHT_PARTICLE_BIT; L.rcpRamp = P.rcpRamp;
+    // quad: lerp(tl, br, corner) with tl = center - radius, br = center + radius, tl.y -= radius * invZToY + z * zToY (:53-64)
+    const float radius = xadd(xadd(P.props.x, P.props.y), 1.0f);
+    const float x0 = xsub(pos.x, radius), x1 = xadd(pos.x, radius);
+    float y0 = xsub(pos.y, radius);
+    const float y1 = xadd(pos.y, radius);
+    y0 = xsub(y0, xmul(radius, P.invZToY));
+    y0 = xsub(y0, xmul(pos.z, P.zToY));
+    L.covX = make_float4(x0, x1, 0.0f, 0.0f);
+    L.covY = make_float4(y0, y1, 0.0f, 0.0f);
+    // conservative pixel bounds (pixel centre (p + 0.5) / s + vp inside [b0, b1]), one pixel of slack plus float rounding
+    const float BIG = 1.0e9f;
+    L.px0 = (int)floorf(fminf(fmaxf((x0 - P.vpx) * P.sxs - 2.5f, -BIG), BIG));
+    L.px1 = (int)floorf(fminf(fmaxf((x1 - P.vpx) * P.sxs + 2.5f, -BIG), BIG));
+    L.py0 = (int)floorf(fminf(fmaxf((y0 - P.vpy) * P.sys - 2.5f, -BIG), BIG));
+    L.py1 = (int)floorf(fminf(fmaxf((y1 - P.vpy) * P.sys + 2.5f, -BIG), BIG));
+    float4* dst = reinterpret_cast<float4*>(P.out + P.offsets[blockIdx.x] + rank);
+    const float4* src = reinterpret_cast<const float4*>(&L);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(DLight) / 16); k++) dst[k] = src[k];
 }
 
 }  // namespace
@@ -924,14 +1040,76 @@ int lightingPrepare(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const
     std::vector<DLight> lights;
     std::vector<DLine> lines;
     const ilb_df_uniforms* geometry = nullptr;
+    auto rcp = [](float y) { const float a = std::fabs(y); return (a >= 1.0e-30f && a <= 1.0e30f) ? 1.0f / y : 0.0f; };
     int rc = flattenLights(ctx, df, f, batches, batch_count, vertices, vertex_count, lights, lines, &geometry);
     if (rc) return rc;
     if (lights.size() > 65535 * (size_t)TILE_THREADS) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "too many lights");
 
     LightingParams& P = out->P;
     memset(&P, 0, sizeof(P));
-    rc = uploadLights(ctx, lights, lines, &P.lights, &P.lines);
+    // particle light sources: count the live, visible particles of every source (device), then append their records
+    struct Pending { PLightParams pp; unsigned count; };
+    std::vector<Pending> pending;
+    size_t extra = 0;
+    if (!ctx->particle_lights.empty()) {
+        const float sxs = f->GBufferTexelSizeAndMisc.z * f->EnvironmentZAndScale.z, sys = f->GBufferTexelSizeAndMisc.w * f->EnvironmentZAndScale.w;
+        size_t words = 0;
+        for (const ilb_particle_light_source& src : ctx->particle_lights) {
+            const ilb_psys* ps = src.system;
+            const size_t total = (size_t)ps->live_chunks * ps->per_chunk;
+            words += 2 * ((total + 255) / 256) + 1;
+        }
+        rc = ilb_reserve(ctx, &ctx->d_plight_scratch, &ctx->d_plight_scratch_capacity, std::max<size_t>(words, 1) * sizeof(unsigned), false);
+        if (rc) return rc;
+        unsigned* scratch = reinterpret_cast<unsigned*>(ctx->d_plight_scratch);
+        for (const ilb_particle_light_source& src : ctx->particle_lights) {
+            const ilb_psys* ps = src.system;
+            const size_t total = (size_t)ps->live_chunks * ps->per_chunk;
+            if (total == 0) continue;
+            Pending pd;
+            memset(&pd, 0, sizeof(pd));
+            PLightParams& pp = pd.pp;
+            pp.P = ps->buf[0]; pp.A = ps->buf[2];
+            pp.total = (unsigned)total;
+            pp.nblocks = (unsigned)((total + 255) / 256);
+            pp.counts = scratch; pp.offsets = scratch + pp.nblocks;
+            scratch += 2 * pp.nblocks + 1;
+            pp.props = h4(src.LightProperties); pp.more = h4(src.MoreLightProperties);
+            pp.color = h4(src.LightColor); pp.spec = h4(src.LightSpecularColor);
+            const bool hasField = (df != nullptr) && (src.df.Extent.x > 0.0f);
+            if (hasField) {
+                if (!geometry) geometry = &src.df;
+            }
+            pp.quality = make_float4(src.df.ConeAndMisc.x, src.df.ConeAndMisc.z, src.df.StepAndMisc2.x, src.df.Packed1.w);
+            pp.longStep = src.df.StepAndMisc2.z;
+            pp.hasField = hasField ? 1 : 0;
+            pp.rcpRamp = rcp(src.LightProperties.y);
+            pp.zToY = f->EnvironmentZToY.x; pp.invZToY = f->EnvironmentZToY.y;
+            pp.sxs = sxs; pp.sys = sys; pp.vpx = f->ViewportPosition[0]; pp.vpy = f->ViewportPosition[1];
+            particle_light_count_kernel<<<pp.nblocks, 256, 0, ctx->stream>>>(pp);
+            particle_light_scan_kernel<<<1, 1024, 0, ctx->stream>>>(pp);
+            ctx->launches += 2;
+            ILB_CUDA(ctx, cudaMemcpyAsync(&pd.count, pp.offsets + pp.nblocks, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+            pending.push_back(pd);
+        }
+        ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (const Pending& pd : pending) extra += pd.count;
+        if (extra > ((size_t)1 << 20))
+            return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "%zu particle lights in one frame (limit 1048576): the tile culling is brute force over the light list", extra);
+    }
+    rc = uploadLights(ctx, lights, lines, extra, &P.lights, &P.lines);
     if (rc) return rc;
+    {
+        size_t at = lights.size();
+        for (Pending& pd : pending) {
+            if (pd.count == 0) continue;
+            pd.pp.out = const_cast<DLight*>(P.lights) + at;
+            particle_light_write_kernel<<<pd.pp.nblocks, 256, 0, ctx->stream>>>(pd.pp);
+            ctx->launches++;
+            at += pd.count;
+        }
+        ILB_CUDA(ctx, cudaGetLastError());
+    }
     if (geometry) {
         if (!ilb_make_df_geometry(df, *geometry, &P.df)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad distance-field uniforms");
         rc = ilb_planes_attach(ctx, df, *geometry, &P.df);
@@ -947,11 +1125,11 @@ int lightingPrepare(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const
     P.vpy = f->ViewportPosition[1];
     P.gbuffer = ctx->gbuffer;
     P.gw = ctx->gb_w; P.gh = ctx->gb_h; P.gfmt = ctx->gb_fmt;
-    P.nlights = (int)lights.size();
+    P.nlights = (int)(lights.size() + extra);
     P.width = f->width; P.height = f->height;
     P.out_format = f->lightmap_format;
     P.stencil = f->stencil_culling;
-    out->nlights = (int)lights.size();
+    out->nlights = (int)(lights.size() + extra);
     out->nline = 0;
     for (const DLight& L : lights) out->nline += (L.type == ILB_LIGHT_LINE) ? 1 : 0;
     return ILB_OK;
@@ -973,7 +1151,7 @@ int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin
     P.tiles_x = (P.width + TILE_W - 1) / TILE_W;
     P.tiles_y = (row_end - row_begin + TILE_H - 1) / TILE_H;
     const unsigned tiles = (unsigned)P.tiles_x * (unsigned)P.tiles_y;
-    constexpr int ALL = ILB_LIGHT_SPHERE | ILB_LIGHT_DIRECTIONAL | ILB_LIGHT_LINE, NOLINE = ILB_LIGHT_SPHERE | ILB_LIGHT_DIRECTIONAL;
+    constexpr int NOLINE = ILB_LIGHT_SPHERE | ILB_LIGHT_DIRECTIONAL | ILB_LIGHT_PARTICLE_BIT, ALL = NOLINE | ILB_LIGHT_LINE;
     bool split = prep.nline > 0 && prep.nline < prep.nlights;
     if (const char* e = getenv("ILB_SPLIT_PASSES")) split = split && e[0] != '0';
     int planesMask = 3;  // dev knob: bit 0 = line pass samples the planes, bit 1 = sphere / directional pass does
@@ -1102,7 +1280,7 @@ int ilb_probes_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, con
     if (rc) return rc;
     ProbeParams P;
     memset(&P, 0, sizeof(P));
-    rc = uploadLights(ctx, lights, lines, &P.lights, &P.lines);
+    rc = uploadLights(ctx, lights, lines, 0, &P.lights, &P.lines);
     if (rc) return rc;
     const size_t in_bytes = sizeof(float4) * (size_t)probe_count, out_bytes = ilb_format_bytes(output_format) * (size_t)probe_count;
     rc = ilb_reserve(ctx, &ctx->d_probe_in, &ctx->d_probe_in_capacity, 2 * in_bytes + out_bytes, false);

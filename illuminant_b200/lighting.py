@@ -15,7 +15,7 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 from . import _abi
-from ._abi import (FORMAT_FLOAT4, FORMAT_HALF4, FORMAT_RGBA8, LIGHT_DIRECTIONAL, LIGHT_LINE, LIGHT_SPHERE, DFUniforms, Float4,
+from ._abi import (FORMAT_FLOAT4, FORMAT_HALF4, FORMAT_RGBA8, LIGHT_DIRECTIONAL, LIGHT_LINE, LIGHT_PARTICLE, LIGHT_SPHERE, DFUniforms, Float4,
                    LightBatch, LightingFrame, LightVertex)
 from .distance_field import DistanceField, LightObstruction, RendererQualitySettings
 
@@ -99,6 +99,50 @@ class LineLightSource(LightSource):  # LightSource.cs:252-
     StartColor: Tuple[float, float, float, float] = (1.0, 1.0, 1.0, 1.0)
     EndColor: Tuple[float, float, float, float] = (1.0, 1.0, 1.0, 1.0)
     TypeID = LIGHT_LINE
+
+
+@dataclass
+class ParticleLightSource(LightSource):  # LightSource.cs:466-500
+    """Every live particle of `System` is a sphere light with `Template`'s properties (ParticleLight.fx); the particle
+    state is read on the device when the frame is rendered."""
+    Template: SphereLightSource = field(default_factory=SphereLightSource)
+    System: object = None          # illuminant_b200.ParticleSystem
+    IsActive: bool = True
+    TypeID = LIGHT_PARTICLE
+
+    def uniforms(self, hasDistanceField: bool):
+        """_ParticleLightBatchSetup (LightingRenderer.cs:769-789): (LightProperties, MoreLightProperties, LightColor, LightSpecularColor)."""
+        t = self.Template
+        falloff = -99999.0 if t.ShadowDistanceFalloff is None else t.ShadowDistanceFalloff
+        props = Float4(t.Radius, t.RampLength, int(t.RampMode), 1.0 if (t.CastsShadows and hasDistanceField) else 0.0)
+        more = Float4(t.AmbientOcclusionRadius if t.AmbientOcclusionOpacity > 0.001 else 0.0, falloff, t.FalloffYFactor,
+                      min(max(t.AmbientOcclusionOpacity, 0.0), 1.0))
+        return props, more, _vec4(list(t.Color)), _vec4(list(t.SpecularColor) + [t.SpecularPower])
+
+    def light_vertices(self, positions: np.ndarray, attributes: np.ndarray, hasDistanceField: bool):
+        """What ParticleLightVertexShader (ParticleLight.fx:16-82) hands to the pixel shader for particle state
+        [n,4] / [n,4] (float32 arithmetic, StippleFactor 1): a LightVertex per live particle whose light colour has
+        alpha > 0.  Used to drive the oracle with the same lights the device builds."""
+        props, more, color, spec = self.uniforms(hasDistanceField)
+        lc = np.array([color.x, color.y, color.z, color.w], dtype=F)
+        out = []
+        for p, a in zip(np.asarray(positions, dtype=F), np.asarray(attributes, dtype=F)):
+            if not (p[3] > 0):
+                continue
+            c = a.copy()
+            if c[3] > 0:
+                c[:3] = c[:3] / c[3]
+            c = c * lc
+            if not (c[3] > 0):
+                continue
+            v = LightVertex()
+            v.LightPosition1 = v.LightPosition2 = v.LightPosition3 = Float4(float(p[0]), float(p[1]), float(p[2]), 0.0)
+            v.LightProperties, v.MoreLightProperties = props, more
+            v.EvenMoreLightProperties = Float4(-1, 0, 0, 0)
+            v.Color1 = Float4(*[float(x) for x in c])
+            v.Color2 = spec
+            out.append(v)
+        return out
 
 
 @dataclass
@@ -270,7 +314,8 @@ class LightingRenderer:
         """Groups enabled lights into LightTypeRenderStates keyed on (type, quality) in first-use order after the
         stable SortKey sort (LightingRenderer.cs:1050-1110, :801-837) and packs their LightVertex arrays."""
         hasDF = self.DistanceField is not None and self.DistanceField.handle is not None
-        lights = sorted((l for l in self.Environment.Lights if l.Enabled), key=lambda l: l.SortKey)
+        lights = sorted((l for l in self.Environment.Lights if l.Enabled and l.TypeID != LIGHT_PARTICLE), key=lambda l: l.SortKey)
+        self._sync_particle_lights()
         groups = {}
         for l in lights:
             v = pack_light_vertex(l, intensityScale, hasDF)
@@ -294,6 +339,22 @@ class LightingRenderer:
                 verts[i] = v
                 i += 1
         return batches, len(groups), verts, n
+
+    def _sync_particle_lights(self) -> None:
+        """Hands the enabled, active ParticleLightSources to the library (LightingRenderer.cs:1126-1144)."""
+        if self.ctx is None:
+            return
+        hasDF = self.DistanceField is not None and self.DistanceField.handle is not None
+        srcs = [l for l in self.Environment.Lights if l.Enabled and l.TypeID == LIGHT_PARTICLE and l.IsActive and l.System is not None]
+        if not srcs and not getattr(self, "_had_particle_lights", False):
+            return
+        arr = (_abi.ParticleLightSourceStruct * max(len(srcs), 1))()
+        for i, l in enumerate(srcs):
+            arr[i].system = l.System.handle
+            arr[i].LightProperties, arr[i].MoreLightProperties, arr[i].LightColor, arr[i].LightSpecularColor = l.uniforms(hasDF)
+            arr[i].df = self._df_uniforms(l.Template.Quality)
+        self.ctx.check(self.ctx.lib.ilb_lighting_set_particle_lights(self.ctx.handle, C.cast(arr, C.c_void_p) if srcs else None, len(srcs)))
+        self._had_particle_lights = bool(srcs)
 
     # ---- the hot path -----------------------------------------------------------------------------------------
     def RenderLighting(self, intensityScale: float = 1.0, rows: Optional[Tuple[int, int]] = None) -> np.ndarray:

@@ -136,6 +136,7 @@ typedef struct ilb_light_vertex {
 typedef enum ilb_light_type { /* LightSourceTypeID, LightSource.cs:12-21 */
     ILB_LIGHT_SPHERE = 1,
     ILB_LIGHT_DIRECTIONAL = 2,
+    ILB_LIGHT_PARTICLE = 3,   /* never in a batch: see ilb_lighting_set_particle_lights */
     ILB_LIGHT_LINE = 4
 } ilb_light_type;
 
@@ -195,6 +196,22 @@ ILB_API int ilb_render_lighting_peers(ilb_ctx* ctx, ilb_df* df, const ilb_lighti
                                       const ilb_light_batch* batches, int batch_count,
                                       const ilb_light_vertex* vertices, int vertex_count,
                                       void* const* d_peer_lightmaps, int peer_count);
+
+/* "next" row N4 -- ParticleLightSource (LightSource.cs:466-500): every live particle of `system` whose attribute colour
+ * has alpha > 0 is a sphere light at the particle's position (ParticleLightVertexShader, ParticleLight.fx:16-82) with the
+ * template's properties exactly as _ParticleLightBatchSetup sets them (LightingRenderer.cs:769-789):
+ * LightProperties = (Radius, RampLength, RampMode, castsShadows && field ? 1 : 0), MoreLightProperties = (AO radius,
+ * ShadowDistanceFalloff ?? -99999, FalloffYFactor, saturate(AO opacity)), LightColor = Template.Color,
+ * LightSpecularColor = (SpecularColor, SpecularPower); `df` = the uniforms SetDistanceFieldParameters gives the batch.
+ * The sources apply to every following ilb_render_lighting* call of the context (after the batches, in array order) until
+ * replaced; count = 0 clears them.  The particle state is read on the device when the frame is rendered -- render before
+ * ilb_particles_step to reproduce the reference's usePreviousData (LightingRenderer.cs:1137-1143).  StippleFactor is 1. */
+typedef struct ilb_particle_light_source {
+    ilb_psys* system;
+    ilb_float4 LightProperties, MoreLightProperties, LightColor, LightSpecularColor;
+    ilb_df_uniforms df;
+} ilb_particle_light_source;
+ILB_API int ilb_lighting_set_particle_lights(ilb_ctx* ctx, const ilb_particle_light_source* sources, int count);
 
 /* UpdateLightProbes (LightingRenderer.LightProbes.cs:49-110): probe positions (xyz, opacity=1) and
  * normals (xyz, enableShadows) as uploaded by UpdateLightProbeTexture; result = probe_count texels

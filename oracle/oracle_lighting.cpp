@@ -455,6 +455,44 @@ bool SphereLightPixelShader(const Frame& fr, const DistanceField& df, const ilb_
     return true;
 }
 
+// ---------------------------------------------------------------- particle light (N4)
+// ParticleLightVertexShader (ParticleLight.fx:53-68): one axis-aligned quad lerp(tl, br, corner), tl = center - radius,
+// br = center + radius, tl.y -= radius * invZToY + center.z * zToY.  The LightVertex carries what the vertex shader hands
+// to the pixel shader: LightPosition1 = particle position, LightProperties / MoreLightProperties = the template's,
+// Color1 = unpremultiplied attribute colour * LightColor, Color2 = LightSpecularColor.
+bool particleLightCovers(const Frame& fr, const ilb_light_vertex& v, float px, float py) {
+    float3 lightCenter(v.LightPosition1.x, v.LightPosition1.y, v.LightPosition1.z);
+    float radius = v.LightProperties.x + v.LightProperties.y + 1;
+    float3 radius3 = float3(radius, radius, 0);
+    float3 tl = lightCenter - radius3, br = lightCenter + radius3;
+    tl.y -= radius * fr.getInvZToYMultiplier();
+    tl.y -= lightCenter.z * fr.getZToYMultiplier();
+    float2 s = fr.GetViewportScale() * fr.getEnvironmentRenderScale();
+    float wx = (px + 0.5f) / s.x + fr.GetViewportPosition().x;
+    float wy = (py + 0.5f) / s.y + fr.GetViewportPosition().y;
+    return (wx >= tl.x) && (wx <= br.x) && (wy >= tl.y) && (wy <= br.y);
+}
+
+bool ParticleLightPixelShader(const Frame& fr, const DistanceField& df, const ilb_light_vertex& v, float2 vpos,
+                              float4& result) {  // ParticleLight.fx:84-118
+    float3 lightCenter(v.LightPosition1.x, v.LightPosition1.y, v.LightPosition1.z);
+    float4 lightProperties = f4(v.LightProperties), moreLightProperties = f4(v.MoreLightProperties);
+    float4 lightColor = f4(v.Color1), specular = f4(v.Color2);
+    float3 shadedPixelPosition, shadedPixelNormal;
+    bool enableShadows, fullbright;
+    float3 cameraPosition = sampleGBuffer(fr, vpos, shadedPixelPosition, shadedPixelNormal, enableShadows, fullbright);
+    if (fullbright) return false;
+    lightProperties.w *= enableShadows ? 1.0f : 0.0f;
+    float opacity;
+    if (!SphereLightPixelCore(fr, df, shadedPixelPosition, shadedPixelNormal, lightCenter, lightProperties,
+                              moreLightProperties, opacity))
+        return false;
+    float specularity = CalcSphereLightSpecularity(cameraPosition, shadedPixelPosition, shadedPixelNormal, lightCenter, specular.w);
+    float3 rgb = (lightColor.xyz() * lightColor.w * opacity) + (specular.xyz() * specularity * opacity);
+    result = float4(rgb, 1);
+    return true;
+}
+
 // ---------------------------------------------------------------- directional light (L8)
 bool DirectionalLightPixelCore(const DistanceField& df, float3 shadedPixelPosition, float3 shadedPixelNormal,
                                float4 lightDirection, float4 lightProperties, float4 moreLightProperties,
@@ -702,6 +740,9 @@ int orc_render_lighting(const uint16_t* df_tex, int tw, int th, const void* gbuf
                             break;
                         case ILB_LIGHT_LINE:
                             lit = lineLightCovers(fr, v, (float)x, (float)y) && LineLightPixelShader(fr, df, v, vpos, result);
+                            break;
+                        case ILB_LIGHT_PARTICLE:
+                            lit = particleLightCovers(fr, v, (float)x, (float)y) && ParticleLightPixelShader(fr, df, v, vpos, result);
                             break;
                         default:
                             break;

@@ -267,3 +267,58 @@ def test_dynamic_distance_field(ctx, oracle):
     after = r.RenderLighting()                          # same handle, rewritten atlas: the planes must have been refreshed
     assert not np.array_equal(after, before)
     _check(after, oracle_lightmap(oracle, r, moved, s), "dynamic field, frame 1")
+
+
+def test_particle_light_source(ctx, oracle):
+    """ParticleLightSource ("next" row N4; ParticleLight.fx, LightingRenderer.cs:769-789, :1126-1144): every live particle
+    with a visible colour lights the frame like a sphere light with the template's properties; the light list is built on
+    the device from the particle state.  The oracle gets the same lights as LightVertex records."""
+    s = scenes.lighting_scene(38, 320, 200, 2, n_directional=1, n_line=1, ramp=(60.0, 160.0), float4_lightmap=True)
+    df = scenes.make_distance_field(ctx, s)
+    df.Rasterize(s.obstructions)
+    tex = df.Save()
+    rs = np.random.RandomState(9)
+    n = 700
+    pos = np.zeros((n, 4), np.float32)
+    pos[:, 0], pos[:, 1], pos[:, 2] = rs.uniform(0, 320, n), rs.uniform(0, 200, n), rs.uniform(2, 40, n)
+    pos[:, 3] = rs.uniform(-0.5, 3.0, n)                       # some are dead
+    vel = np.zeros((n, 4), np.float32)
+    attr = rs.uniform(0.0, 1.0, (n, 4)).astype(np.float32)
+    attr[::7, 3] = 0.0                                         # some are invisible
+    attr[:, :3] *= attr[:, 3:4]                                # premultiplied like the spawner output
+    engine = ib.ParticleEngine(ctx, ib.ParticleEngineConfiguration(ChunkSize=16, RandomSeed=1))
+    system = ib.ParticleSystem(engine, ib.ParticleSystemConfiguration(), maxChunks=4)
+    system.Spawn(pos, vel, attr)
+    template = ib.SphereLightSource(Radius=3.0, RampLength=24.0, Color=(0.9, 0.7, 0.5, 0.6), SpecularColor=(0.2, 0.2, 0.3), SpecularPower=4.0,
+                                    CastsShadows=True, AmbientOcclusionRadius=6.0, AmbientOcclusionOpacity=0.5)
+    pls = ib.ParticleLightSource(Template=template, System=system)
+    s.environment.Lights.append(pls)
+    r = ib.LightingRenderer(ctx, s.environment, s.configuration)
+    r.DistanceField = df
+    r.SetGBuffer(s.gbuffer)
+    gpu = r.RenderLighting()
+
+    # oracle: the host lights' batches plus one ILB_LIGHT_PARTICLE batch with the vertex-shader outputs, in particle order
+    frame = r.build_frame()
+    batches, nb, verts, nv = r.build_batches()
+    per = 16 * 16
+    P = np.zeros((system.LiveChunkCount * per, 4), np.float32)
+    A = np.zeros_like(P)
+    P[:n], A[:n] = pos, attr
+    pv = pls.light_vertices(P, A, True)
+    assert 300 < len(pv) < n
+    from illuminant_b200._abi import LightBatch, LightVertex
+    allv = (LightVertex * (nv + len(pv)))(*([verts[i] for i in range(nv)] + pv))
+    allb = (LightBatch * (nb + 1))(*[batches[i] for i in range(nb)])
+    allb[nb].light_type, allb[nb].first_vertex, allb[nb].vertex_count = 3, nv, len(pv)
+    allb[nb].df = r._df_uniforms(None)
+    ref = oracle.render_lighting(tex, s.gbuffer, frame, allb, nb + 1, allv, nv + len(pv))
+    _check(gpu, ref, "particle lights")
+    assert np.array_equal(gpu[..., 3], ref[..., 3])            # alpha counts the lights touching each pixel
+    # the source really contributes, and goes away with the list
+    pls.Enabled = False
+    assert not np.array_equal(r.RenderLighting(), gpu)
+    bands = None
+    pls.Enabled = True
+    bands = [r.RenderLighting(rows=(a, b)) for a, b in ((0, 64), (64, 200))]
+    assert np.array_equal(np.concatenate(bands, axis=0), gpu)
