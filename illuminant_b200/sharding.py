@@ -26,3 +26,31 @@ def chunk_range(rank: int, world: int, chunks: int) -> Tuple[int, int]:
     base, rem = divmod(chunks, world)
     begin = rank * base + min(rank, rem)
     return begin, begin + base + (1 if rank < rem else 0)
+
+
+def rebalance_rows(bounds, times, height: int, quantum: int = 16):
+    """Row bands of equal measured COST instead of equal height.  `bounds` = the current band edges [b0=0, b1, ..., bN=height],
+    `times[k]` = the measured time of band k.  Lights are spatially clustered, so equal-height bands finish at different
+    times and the frame waits for the slowest rank; treating each band's cost as uniform over its rows gives a piecewise
+    linear cumulative cost whose N-quantiles are the new edges (rounded to whole tile rows).  Iterating this over a few
+    frames of a static scene converges to bands that finish together."""
+    n = len(times)
+    assert len(bounds) == n + 1
+    total = float(sum(times))
+    if total <= 0.0:
+        return list(bounds)
+    new = [0]
+    k, acc = 0, 0.0            # acc = cost of the bands before band k
+    for j in range(1, n):
+        target = total * j / n
+        while k < n - 1 and acc + times[k] < target:
+            acc += times[k]
+            k += 1
+        rows = bounds[k + 1] - bounds[k]
+        frac = (target - acc) / times[k] if times[k] > 0 else 0.0
+        edge = bounds[k] + frac * rows
+        edge = int(round(edge / quantum)) * quantum
+        edge = min(max(edge, new[-1]), height)
+        new.append(edge)
+    new.append(height)
+    return new

@@ -194,3 +194,19 @@ def test_randomness_texture_is_seeded():
     a = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(RandomSeed=5)).RandomnessTexture
     b = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(RandomSeed=5)).RandomnessTexture
     assert a.shape == (653, 807, 4) and a.dtype == np.float32 and np.array_equal(a, b) and 0 <= a.min() and a.max() < 1
+
+
+def test_rebalance_rows_equalises_measured_cost():
+    from illuminant_b200 import sharding
+    H, n = 2160, 8
+    rng = np.random.RandomState(3)
+    density = 1.0 + 2.0 * np.exp(-((np.arange(H) - 700) / 200.0) ** 2)      # a cluster of lights around row 700
+    bounds = [min(k * sharding.band_height(H, n), H) for k in range(n)] + [H]
+    for _ in range(4):
+        times = [float(density[bounds[k]:bounds[k + 1]].sum()) for k in range(n)]
+        bounds = sharding.rebalance_rows(bounds, times, H)
+        assert bounds[0] == 0 and bounds[-1] == H and all(b % 16 == 0 for b in bounds[1:-1])
+        assert all(bounds[k] <= bounds[k + 1] for k in range(n))
+    times = np.array([density[bounds[k]:bounds[k + 1]].sum() for k in range(n)])
+    assert times.max() / times.mean() < 1.10            # equal-height bands of this profile: 1.5 (16-row quantisation limits the fit)
+    assert sharding.rebalance_rows([0, 1080, 2160], [0.0, 0.0], 2160) == [0, 1080, 2160]
