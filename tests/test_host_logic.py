@@ -210,3 +210,45 @@ def test_rebalance_rows_equalises_measured_cost():
     times = np.array([density[bounds[k]:bounds[k + 1]].sum() for k in range(n)])
     assert times.max() / times.mean() < 1.10            # equal-height bands of this profile: 1.5 (16-row quantisation limits the fit)
     assert sharding.rebalance_rows([0, 1080, 2160], [0.0, 0.0], 2160) == [0, 1080, 2160]
+
+
+def test_particle_light_source_uniforms_and_vertices():    # LightingRenderer.cs:769-789, ParticleLight.fx:16-82
+    t = ib.SphereLightSource(Radius=3, RampLength=20, RampMode=ib.LightSourceRampMode.Exponential, Color=(0.5, 1.0, 2.0, 0.5),
+                             SpecularColor=(0.1, 0.2, 0.3), SpecularPower=5, AmbientOcclusionRadius=7, AmbientOcclusionOpacity=1.5, FalloffYFactor=2)
+    pls = ib.ParticleLightSource(Template=t)
+    props, more, color, spec = pls.uniforms(True)
+    assert props.tuple() == (3, 20, 1, 1) and pls.uniforms(False)[0].w == 0
+    assert more.tuple() == (7, -99999, 2, 1.0)                      # AO opacity saturated
+    assert color.tuple() == (0.5, 1.0, 2.0, 0.5) and spec.tuple() == pytest.approx((0.1, 0.2, 0.3, 5))
+    t.AmbientOcclusionOpacity = 0.0005
+    assert pls.uniforms(True)[1].x == 0                             # AO radius dropped when its opacity is <= 0.001
+    P = np.array([[1, 2, 3, 1.0], [4, 5, 6, 0.0], [7, 8, 9, 2.0], [1, 1, 1, 1.0]], np.float32)
+    A = np.array([[0.2, 0.4, 0.1, 0.5], [1, 1, 1, 1], [0.3, 0.3, 0.3, 0.0], [0.5, 0.25, 0.125, 1.0]], np.float32)
+    vs = pls.light_vertices(P, A, True)
+    assert len(vs) == 2                                             # particle 1 is dead, particle 2 has alpha 0
+    assert vs[0].LightPosition1.tuple() == (1, 2, 3, 0) and vs[0].EvenMoreLightProperties.x == -1
+    assert vs[0].Color1.tuple() == pytest.approx((0.4 * 0.5, 0.8 * 1.0, 0.2 * 2.0, 0.5 * 0.5))   # unpremultiplied, times LightColor
+    assert vs[1].Color1.tuple() == pytest.approx((0.25, 0.25, 0.25, 0.5))
+    # a particle light source never enters the host batches
+    s = scenes.lighting_scene(0, 64, 64, 1)
+    s.environment.Lights.append(pls)
+    r = ib.LightingRenderer(None, s.environment, s.configuration)
+    _, nb, _, nv = r.build_batches()
+    assert (nb, nv) == (1, 1)
+
+
+def test_life_ramp_settings():                             # MaybeSetLifeRampParameters ParticleSystem.cs:911-941
+    engine = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=16))
+    cfg = ib.ParticleSystemConfiguration()
+    system = ib.ParticleSystem(engine, cfg, maxChunks=1)
+    assert system.system_uniforms(1 / 60).LifeRampSettings.tuple() == (0, 0, 1, 1)
+    cfg.LifeRamp = ib.ParticleColorLifeRamp(Minimum=1.0, Maximum=1.0002, Strength=0.75, Invert=True, Texture=np.zeros((5, 9, 4), np.float32))
+    u = system.system_uniforms(1 / 60)
+    assert u.LifeRampSettings.x == -0.75 and u.LifeRampSettings.y == 1.0 and u.LifeRampSettings.w == 5
+    assert u.LifeRampSettings.z == pytest.approx(0.001)             # max(range, 0.001)
+
+
+def test_dynamic_distance_field_is_a_distance_field():
+    df = ib.DynamicDistanceField(None, 320, 200, 128.0, 8)
+    assert (df.SliceCount, df.PhysicalSliceCount, df.TextureWidth, df.TextureHeight) == (9, 3, 640, 400)
+    assert df.static_handle is None
