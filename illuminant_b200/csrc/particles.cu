@@ -491,7 +491,7 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
 }
 
 #ifndef ILB_PARTICLE_MINBLOCKS
-#define ILB_PARTICLE_MINBLOCKS 4
+#define ILB_PARTICLE_MINBLOCKS 5
 #endif
 
 template <int KIND, bool FAST>
