@@ -6,6 +6,8 @@ from ._abi import (Context, IlluminantError, EXPORTED_SYMBOLS, LIB_PATH, load_li
 from .distance_field import DistanceField, DynamicDistanceField, LightObstruction, LightObstructionType, RendererQualitySettings
 from .lighting import (DirectionalLightSource, LightingEnvironment, LightingRenderer, LightProbe, LightSourceRampMode,
                        LineLightSource, ParticleLightSource, RendererConfiguration, ShadowFilter, SphereLightSource, encode_gbuffer)
+from .hdr import (DitheringSettings, GammaCompressionConfiguration, HDRConfiguration, HDRMode, Histogram, RenderedLighting,
+                  ToneMappingConfiguration, pack_resolve)
 from .particles import (FMA, AreaType, Attractor, AttractorType, Bezier4V, BezierF, Formula, FormulaType, Gravity, MatrixMultiply,
                         Noise, ParticleCollision, ParticleColorLifeRamp, ParticleEngine, ParticleEngineConfiguration, ParticleSystem,
                         ParticleSystemConfiguration, Spawner, TransformArea)

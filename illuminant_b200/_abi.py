@@ -16,6 +16,7 @@ ILB_OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_INVALID_OPERATION, ERR_OUT_OF_MEMORY, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 FORMAT_FLOAT4, FORMAT_HALF4, FORMAT_RGBA8 = 0, 1, 2
 LIGHT_SPHERE, LIGHT_DIRECTIONAL, LIGHT_PARTICLE, LIGHT_LINE = 1, 2, 3, 4
+HDR_NONE, HDR_GAMMA_COMPRESS, HDR_TONE_MAP = 0, 1, 2
 OP_GRAVITY, OP_NOISE, OP_FMA, OP_MATRIX_MULTIPLY = 1, 2, 3, 4
 MAX_ATTRACTORS = 16
 FORMAT_BYTES = {FORMAT_FLOAT4: 16, FORMAT_HALF4: 8, FORMAT_RGBA8: 4}
@@ -67,6 +68,15 @@ class LightingFrame(C.Structure):
                 ("EnvironmentZAndScale", Float4), ("EnvironmentZToY", Float4), ("GBufferTexelSizeAndMisc", Float4),
                 ("GBufferViewportRelative", C.c_float), ("ViewportPosition", C.c_float * 2), ("reserved2", C.c_float),
                 ("ClearColor", Float4)]
+
+
+class Resolve(C.Structure):  # ilb_resolve
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("lightmap_format", C.c_int32), ("albedo_format", C.c_int32),
+                ("output_format", C.c_int32), ("hdr_mode", C.c_int32), ("InverseScaleFactor", C.c_float),
+                ("AlbedoIsSRGB", C.c_float), ("ResolveToSRGB", C.c_float), ("Offset", C.c_float), ("ExposureMinusOne", C.c_float),
+                ("GammaMinusOne", C.c_float), ("MiddleGray", C.c_float), ("AverageLuminance", C.c_float),
+                ("MaximumLuminanceSquared", C.c_float), ("WhitePoint", C.c_float), ("LightmapUVOffset", C.c_float * 2),
+                ("DitheringStrength", C.c_float), ("reserved", C.c_float)]
 
 
 class Bezier1(C.Structure):
@@ -160,6 +170,9 @@ _PROTOTYPES = [
     ("ilb_render_lighting_device", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, P]),
     ("ilb_render_lighting_peers", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, C.POINTER(P), C.c_int]),
     ("ilb_update_light_probes", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, P, P, C.c_int, C.c_int, P]),
+    ("ilb_resolve_lighting", C.c_int, [P, C.POINTER(Resolve), P, P, P]),
+    ("ilb_resolve_lighting_device", C.c_int, [P, C.POINTER(Resolve), P, P, P]),
+    ("ilb_compute_luminance", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, C.c_int, P]),
     ("ilb_particles_create", C.c_int, [P, C.c_int, C.c_int, C.POINTER(P)]),
     ("ilb_particles_destroy", None, [P]),
     ("ilb_particles_set_randomness", C.c_int, [P, P, C.c_int, C.c_int]),

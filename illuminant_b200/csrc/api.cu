@@ -118,6 +118,10 @@ void ilb_destroy(ilb_ctx* ctx) {
     if (ctx->d_lightmap) cudaFree(ctx->d_lightmap);
     if (ctx->d_probe_in) cudaFree(ctx->d_probe_in);
     if (ctx->d_accum) cudaFree(ctx->d_accum);
+    if (ctx->d_resolve_in) cudaFree(ctx->d_resolve_in);
+    if (ctx->d_resolve_albedo) cudaFree(ctx->d_resolve_albedo);
+    if (ctx->d_resolve_out) cudaFree(ctx->d_resolve_out);
+    for (int i = 0; i < 2; i++) if (ctx->d_luminance[i]) cudaFree(ctx->d_luminance[i]);
     if (ctx->d_plight_scratch) cudaFree(ctx->d_plight_scratch);
     if (ctx->copy_in) {
         cudaStreamDestroy(ctx->copy_in);
@@ -307,8 +311,10 @@ int ilb_render_lighting(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* fram
     int rc = ilb_reserve(ctx, &ctx->d_lightmap, &ctx->d_lightmap_capacity, std::max<size_t>(bytes, 16), false);
     if (rc) return rc;
     void* outs[1] = {ctx->d_lightmap};
+    ctx->lm_fmt = -1;
     rc = ilb_lighting_launch(ctx, df, frame, batches, batch_count, vertices, vertex_count, outs, 1, false);
     if (rc) return rc;
+    ctx->lm_w = frame->width; ctx->lm_rows = frame->row_end - frame->row_begin; ctx->lm_fmt = frame->lightmap_format;
     ILB_CUDA(ctx, cudaMemcpyAsync(lightmap_out, ctx->d_lightmap, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ILB_OK;
@@ -319,8 +325,78 @@ int ilb_render_lighting_frame(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame
                               const void* gbuffer, void* lightmap_out) {
     if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
-    return ilb_lighting_frame_from_host(ctx, df, frame, batches, batch_count, vertices, vertex_count, gbuffer_width, gbuffer_height,
-                                        gbuffer_format, gbuffer, lightmap_out);
+    ctx->lm_fmt = -1;
+    const int rc = ilb_lighting_frame_from_host(ctx, df, frame, batches, batch_count, vertices, vertex_count, gbuffer_width, gbuffer_height,
+                                                gbuffer_format, gbuffer, lightmap_out);
+    if (rc == ILB_OK) { ctx->lm_w = frame->width; ctx->lm_rows = frame->row_end - frame->row_begin; ctx->lm_fmt = frame->lightmap_format; }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------- resolve / luminance (N3)
+// The lightmap a resolve / luminance call reads: the caller's host texels (staged), or the context's resident one.
+static int resolve_source(ilb_ctx* ctx, int w, int h, int fmt, const void* lightmap_host, const void** d_out) {
+    if (w <= 0 || h <= 0) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad size %dx%d", w, h);
+    if (fmt != ILB_FORMAT_FLOAT4 && fmt != ILB_FORMAT_HALF4 && fmt != ILB_FORMAT_RGBA8) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad lightmap format %d", fmt);
+    if (!lightmap_host) {
+        if (ctx->lm_fmt < 0 || !ctx->d_lightmap) return ilb_fail(ctx, ILB_ERR_INVALID_OPERATION, "no resident lightmap: render a frame first or pass the texels");
+        if (ctx->lm_w != w || ctx->lm_rows != h || ctx->lm_fmt != fmt)
+            return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "resident lightmap is %dx%d format %d, asked for %dx%d format %d", ctx->lm_w, ctx->lm_rows, ctx->lm_fmt, w, h, fmt);
+        *d_out = ctx->d_lightmap;
+        return ILB_OK;
+    }
+    const size_t bytes = ilb_format_bytes(fmt) * (size_t)w * (size_t)h;
+    int rc = ilb_reserve(ctx, &ctx->d_resolve_in, &ctx->d_resolve_in_capacity, bytes, false);
+    if (rc) return rc;
+    ILB_CUDA(ctx, cudaMemcpyAsync(ctx->d_resolve_in, lightmap_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *d_out = ctx->d_resolve_in;
+    return ILB_OK;
+}
+
+int ilb_resolve_lighting_device(ilb_ctx* ctx, const ilb_resolve* params, const void* d_lightmap, const void* d_albedo, void* d_output) {
+    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!params || !d_lightmap || !d_output) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ilb_resolve_launch(ctx, params, d_lightmap, d_albedo, d_output);
+}
+
+int ilb_resolve_lighting(ilb_ctx* ctx, const ilb_resolve* params, const void* lightmap, const void* albedo, void* output) {
+    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!params || !output) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void* d_lm = nullptr;
+    int rc = resolve_source(ctx, params->width, params->height, params->lightmap_format, lightmap, &d_lm);
+    if (rc) return rc;
+    const size_t n = (size_t)params->width * (size_t)params->height;
+    const void* d_al = nullptr;
+    if (albedo) {
+        if (params->albedo_format != ILB_FORMAT_FLOAT4 && params->albedo_format != ILB_FORMAT_RGBA8)
+            return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "albedo format must be RGBA8 or FLOAT4");
+        const size_t abytes = ilb_format_bytes(params->albedo_format) * n;
+        rc = ilb_reserve(ctx, &ctx->d_resolve_albedo, &ctx->d_resolve_albedo_capacity, abytes, false);
+        if (rc) return rc;
+        ILB_CUDA(ctx, cudaMemcpyAsync(ctx->d_resolve_albedo, albedo, abytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_al = ctx->d_resolve_albedo;
+    }
+    if (params->output_format != ILB_FORMAT_FLOAT4 && params->output_format != ILB_FORMAT_RGBA8)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "output format must be RGBA8 or FLOAT4");
+    const size_t obytes = ilb_format_bytes(params->output_format) * n;
+    rc = ilb_reserve(ctx, &ctx->d_resolve_out, &ctx->d_resolve_out_capacity, obytes, false);
+    if (rc) return rc;
+    rc = ilb_resolve_launch(ctx, params, d_lm, d_al, ctx->d_resolve_out);
+    if (rc) return rc;
+    ILB_CUDA(ctx, cudaMemcpyAsync(output, ctx->d_resolve_out, obytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ILB_OK;
+}
+
+int ilb_compute_luminance(ilb_ctx* ctx, int width, int height, int lightmap_format, const void* lightmap, int level, float* out_luminance) {
+    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!out_luminance) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void* d_lm = nullptr;
+    int rc = resolve_source(ctx, width, height, lightmap_format, lightmap, &d_lm);
+    if (rc) return rc;
+    return ilb_luminance_launch(ctx, width, height, lightmap_format, d_lm, level, out_luminance);
 }
 
 int ilb_lighting_set_particle_lights(ilb_ctx* ctx, const ilb_particle_light_source* sources, int count) {

@@ -37,6 +37,12 @@ struct ilb_ctx {
     size_t d_lightmap_capacity = 0;
     void* d_probe_in = nullptr;
     size_t d_probe_in_capacity = 0;
+    int lm_w = 0, lm_rows = 0, lm_fmt = -1;  // what d_lightmap holds after the last host-output frame (-1: nothing)
+    // N3 resolve / luminance staging (resolve.cu)
+    void* d_resolve_in = nullptr;   size_t d_resolve_in_capacity = 0;
+    void* d_resolve_albedo = nullptr; size_t d_resolve_albedo_capacity = 0;
+    void* d_resolve_out = nullptr;  size_t d_resolve_out_capacity = 0;
+    void* d_luminance[2] = {nullptr, nullptr}; size_t d_luminance_capacity[2] = {0, 0};
     void* d_accum = nullptr;     // fp32 sums handed from the line-light pass to the sphere / directional pass
     size_t d_accum_capacity = 0;
     // ParticleLightSources applied to every frame until replaced (ilb_lighting_set_particle_lights)
@@ -111,6 +117,11 @@ int ilb_probes_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame,
 int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches,
                                  int batch_count, const ilb_light_vertex* vertices, int vertex_count, int gw, int gh, int gfmt,
                                  const void* gbuffer_host, void* lightmap_out_host);
+// resolve.cu (N3)
+int ilb_resolve_launch(ilb_ctx* ctx, const ilb_resolve* params, const void* d_lightmap, const void* d_albedo, void* d_output);
+int ilb_luminance_launch(ilb_ctx* ctx, int width, int height, int lightmap_format, const void* d_lightmap, int level,
+                         float* out_host);
+size_t ilb_format_bytes(int format);
 // dfgen.cu
 int ilb_dfgen_launch(ilb_ctx* ctx, uint2* tex, const uint2* base, int tw, int th, int slice_w, int slice_h, int slice_count,
                      const ilb_df_uniforms* u, const ilb_obstruction* obs, int count);

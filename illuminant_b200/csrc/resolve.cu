@@ -1,0 +1,257 @@
+// "Next" row N3: the lightmap resolve of Illuminant/Shaders/Resolve.fx + HDR.fxh as ONE streaming
+// kernel, and the luminance buffer / mip chain behind RenderedLighting.TryComputeHistogram.
+//
+// resolve_kernel<MODE, ALBEDO, VEC>: one thread per group of four consecutive pixels (the screen-aligned 1:1 resolve has no
+// dependence on the pixel's row, so the frame is a flat array).  HBM-bound by construction: per pixel it reads the lightmap
+// texel (8 B HalfVector4) and the albedo texel (4 B Color) and writes one backbuffer texel (4 B Color) = 16 B (12 B without
+// albedo); four pixels per thread make every access a 16- or 32-byte vector, loads are streaming (__ldcs: read once),
+// stores too (__stcs).  Uniform branches skip pow() when Gamma == 1 and the sRGB transfer when it is off, otherwise the
+// three accurate powf per pixel would make the kernel ALU-bound.
+//
+// The reference does this as a full-screen BitmapBatch draw with material {Screen,World}Space{,GammaCompressed,ToneMapped}
+// LightingResolve{,WithAlbedo} (LightingRenderer.cs:1537-1645).
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "ilb_internal.h"
+
+namespace {
+
+struct ResolveParams {
+    const void* lightmap;
+    const void* albedo;
+    void* out;
+    unsigned long long n;  // pixels
+    int lm_fmt, al_fmt, out_fmt;
+    float invScale, invScale2;  // InverseScaleFactor, InverseScaleFactor * 2 (Resolve.fx:40, :61)
+    float offset, exposure, gamma;
+    float middleGray, averageLuminance, maxLumSq;
+    float whiteScale;  // Uncharted2Tonemap1(WhitePoint), host-evaluated (HDR.fxh:32-38, Resolve.fx:131)
+    int albedoIsSRGB, resolveToSRGB;
+};
+
+// ---- texel access ---------------------------------------------------------------------------------------------------
+ILB_DEV f4 unpackHalf4(uint2 v) {
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    return mk4(lo.x, lo.y, hi.x, hi.y);
+}
+ILB_DEV f4 unpackRgba8(uint32_t v) {  // UNORM8 -> float is c / 255
+    return mk4(xdiv((float)(v & 255u), 255.0f), xdiv((float)((v >> 8) & 255u), 255.0f), xdiv((float)((v >> 16) & 255u), 255.0f),
+               xdiv((float)(v >> 24), 255.0f));
+}
+ILB_DEV uint32_t packRgba8(f4 c) {  // float -> UNORM8: round to nearest, NaN -> 0 (saturatef)
+    const uint32_t R = (uint32_t)(saturatef(c.x) * 255.0f + 0.5f), G = (uint32_t)(saturatef(c.y) * 255.0f + 0.5f);
+    const uint32_t B = (uint32_t)(saturatef(c.z) * 255.0f + 0.5f), A = (uint32_t)(saturatef(c.w) * 255.0f + 0.5f);
+    return R | (G << 8) | (B << 16) | (A << 24);
+}
+ILB_DEV f4 loadTexel(const void* base, int fmt, unsigned long long i) {
+    if (fmt == ILB_FORMAT_HALF4) return unpackHalf4(__ldcs(reinterpret_cast<const uint2*>(base) + i));
+    if (fmt == ILB_FORMAT_FLOAT4) return mk4(__ldcs(reinterpret_cast<const float4*>(base) + i));
+    return unpackRgba8(__ldcs(reinterpret_cast<const unsigned int*>(base) + i));
+}
+ILB_DEV void loadTexels4(const void* base, int fmt, unsigned long long g, f4 t[4]) {  // texels 4g .. 4g+3, 16-byte aligned base
+    if (fmt == ILB_FORMAT_HALF4) {
+        const uint4 a = __ldcs(reinterpret_cast<const uint4*>(base) + 2 * g), b = __ldcs(reinterpret_cast<const uint4*>(base) + 2 * g + 1);
+        t[0] = unpackHalf4(make_uint2(a.x, a.y)); t[1] = unpackHalf4(make_uint2(a.z, a.w));
+        t[2] = unpackHalf4(make_uint2(b.x, b.y)); t[3] = unpackHalf4(make_uint2(b.z, b.w));
+    } else if (fmt == ILB_FORMAT_FLOAT4) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) t[k] = mk4(__ldcs(reinterpret_cast<const float4*>(base) + 4 * g + k));
+    } else {
+        const uint4 a = __ldcs(reinterpret_cast<const uint4*>(base) + g);
+        t[0] = unpackRgba8(a.x); t[1] = unpackRgba8(a.y); t[2] = unpackRgba8(a.z); t[3] = unpackRgba8(a.w);
+    }
+}
+
+// ---- sq/Fracture sRGBCommon.fxh (un-vendored): IEC 61966-2-1 on the un-premultiplied colour, as in the oracle
+ILB_DEV float srgbToLinear1(float s) { return (s <= 0.04045f) ? s / 12.92f : powf((s + 0.055f) / 1.055f, 2.4f); }
+ILB_DEV float linearToSrgb1(float l) { return (l <= 0.0031308f) ? l * 12.92f : 1.055f * powf(l, 1.0f / 2.4f) - 0.055f; }
+ILB_DEV f4 pSRGBToPLinear(f4 c) {
+    if (!(c.w > 0.0f)) return mk4(0.0f, 0.0f, 0.0f, c.w);
+    const f3 s = xyz(c) / c.w;
+    return mk4(mk3(srgbToLinear1(s.x), srgbToLinear1(s.y), srgbToLinear1(s.z)) * c.w, c.w);
+}
+ILB_DEV f4 pLinearToPSRGB(f4 c) {
+    if (!(c.w > 0.0f)) return mk4(0.0f, 0.0f, 0.0f, c.w);
+    const f3 l = xyz(c) / c.w;
+    return mk4(mk3(linearToSrgb1(l.x), linearToSrgb1(l.y), linearToSrgb1(l.z)) * c.w, c.w);
+}
+
+// ---- HDR.fxh
+// The quotient is an IEEE division: at value == 0 (unlit texels) the result is the difference of two nearly equal numbers
+// (kD*kE / (kD*kF) - kE/kF = +7.45e-9 in fp32) whose SIGN decides whether the following pow(x, Gamma) is a number or NaN,
+// so it must not depend on the approximate-division path.
+ILB_DEV float uncharted2Tonemap1(float value) {  // HDR.fxh:32-46
+    const float kA = 0.15f, kB = 0.50f, kC = 0.10f, kD = 0.20f, kE = 0.02f, kF = 0.30f;
+    return xdiv(value * (kA * value + kC * kB) + kD * kE, value * (kA * value + kB) + kD * kF) - kE / kF;
+}
+
+ILB_DEV f3 pow3u(f3 v, float e) {  // pow(x, 1) == x exactly: skip the three powf when Gamma == 1 (uniform branch)
+    if (e == 1.0f) return v;
+    return mk3(powf(v.x, e), powf(v.y, e), powf(v.z, e));
+}
+
+template <int MODE, bool ALBEDO>
+ILB_DEV f4 resolvePixel(const ResolveParams& P, f4 light, f4 albedo) {
+    f4 result;
+    if (ALBEDO) {  // ResolveWithAlbedoCommon, Resolve.fx:47-68
+        if (P.albedoIsSRGB) albedo = pSRGBToPLinear(albedo);
+        light = light * P.invScale2;
+        const f3 a = xyz(albedo);
+        result = mk4(lerp3(a, a * xyz(light), saturatef(light.w)), albedo.w);
+    } else {  // ResolveCommon, Resolve.fx:30-45
+        result = light * P.invScale;
+        result.w = 1.0f;
+    }
+    if (MODE == ILB_HDR_GAMMA_COMPRESS) {  // GammaCompress, HDR.fxh:12-19
+        const f3 rgb = max3(xyz(result) + P.offset, mk3(0.0f));
+        const float resultLuminance = rgb.x * 0.299f + rgb.y * 0.587f + rgb.z * 0.114f;
+        const float scaledLuminance = (resultLuminance * P.middleGray) / P.averageLuminance;
+        const float compressedLuminance = (scaledLuminance * (1.0f + (scaledLuminance / P.maxLumSq))) / (1.0f + scaledLuminance);
+        const float rescaleFactor = compressedLuminance / resultLuminance;  // 0 / 0 = NaN for black, like the shader
+        result = mk4(rgb * rescaleFactor, result.w);
+    } else if (MODE == ILB_HDR_TONE_MAP) {  // Resolve.fx:127-133
+        const f3 pre = max3(mk3(0.0f), xyz(result) + P.offset) * P.exposure;
+        const f3 tm = mk3(uncharted2Tonemap1(pre.x), uncharted2Tonemap1(pre.y), uncharted2Tonemap1(pre.z)) / P.whiteScale;
+        result = mk4(pow3u(tm, P.gamma), result.w);
+    } else {  // Resolve.fx:84-86
+        f3 rgb = max3(mk3(0.0f), xyz(result) + P.offset);
+        rgb = rgb * P.exposure;
+        result = mk4(pow3u(rgb, P.gamma), result.w);
+    }
+    if (P.resolveToSRGB) result = pLinearToPSRGB(result);
+    return result;  // ApplyDither: identity at Strength 0 (the only value the boundary accepts)
+}
+
+template <int MODE, bool ALBEDO, bool VEC>
+__global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ ResolveParams P) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long groups = P.n >> 2;
+    if (VEC) for (unsigned long long g = tid; g < groups; g += stride) {
+        f4 l[4], a[4], r[4];
+        loadTexels4(P.lightmap, P.lm_fmt, g, l);
+        if (ALBEDO) loadTexels4(P.albedo, P.al_fmt, g, a);
+#pragma unroll
+        for (int k = 0; k < 4; k++) r[k] = resolvePixel<MODE, ALBEDO>(P, l[k], ALBEDO ? a[k] : mk4(0.0f));
+        if (P.out_fmt == ILB_FORMAT_RGBA8) {
+            __stcs(reinterpret_cast<uint4*>(P.out) + g, make_uint4(packRgba8(r[0]), packRgba8(r[1]), packRgba8(r[2]), packRgba8(r[3])));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) __stcs(reinterpret_cast<float4*>(P.out) + 4 * g + k, to_float4(r[k]));
+        }
+    }
+    // tail (n % 4 pixels), or every pixel when a pointer is not 16-byte aligned
+    for (unsigned long long i = (VEC ? (groups << 2) : 0ull) + tid; i < P.n; i += stride) {
+        const f4 l = loadTexel(P.lightmap, P.lm_fmt, i);
+        const f4 a = ALBEDO ? loadTexel(P.albedo, P.al_fmt, i) : mk4(0.0f);
+        const f4 r = resolvePixel<MODE, ALBEDO>(P, l, a);
+        if (P.out_fmt == ILB_FORMAT_RGBA8) reinterpret_cast<uint32_t*>(P.out)[i] = packRgba8(r);
+        else reinterpret_cast<float4*>(P.out)[i] = to_float4(r);
+    }
+}
+
+// ---- luminance ------------------------------------------------------------------------------------------------------
+// CalculateLuminancePixelShader (Resolve.fx:219-234) drawn into the half-size Single target (LightingRenderer.cs:839-898):
+// texel (x, y) point-samples lightmap texel (2x+1, 2y+1).  Individually rounded products / sums: bit-identical to the oracle.
+__global__ void __launch_bounds__(256) luminance_level0_kernel(const void* lightmap, int fmt, int w, int lw, int lh, float* out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= lw || y >= lh) return;
+    const f4 t = loadTexel(lightmap, fmt, (unsigned long long)(2 * y + 1) * (unsigned long long)w + (unsigned long long)(2 * x + 1));
+    out[(size_t)y * lw + x] = xadd(xadd(xmul(t.x, 0.299f), xmul(t.y, 0.587f)), xmul(t.z, 0.144f));  // 0.144: Resolve.fx:15 (sic)
+}
+// one mip step: 2x2 box filter, size floor(size / 2)
+__global__ void __launch_bounds__(256) luminance_downsample_kernel(const float* in, int lw, float* out, int nw, int nh) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nw || y >= nh) return;
+    const float* p0 = in + (size_t)(2 * y) * lw + 2 * x;
+    const float* p1 = p0 + lw;
+    out[(size_t)y * nw + x] = xmul(xadd(xadd(p0[0], p0[1]), xadd(p1[0], p1[1])), 0.25f);
+}
+
+float hostTonemap1(float value) {  // same expression as the device / oracle function, evaluated in fp32 (-ffp-contract=off)
+    const float kA = 0.15f, kB = 0.50f, kC = 0.10f, kD = 0.20f, kE = 0.02f, kF = 0.30f;
+    return ((value * (kA * value + kC * kB) + kD * kE) / (value * (kA * value + kB) + kD * kF)) - kE / kF;
+}
+
+template <int MODE, bool ALBEDO>
+void launchResolve(ilb_ctx* ctx, const ResolveParams& P, bool vec, int grid) {
+    if (vec) resolve_kernel<MODE, ALBEDO, true><<<grid, 256, 0, ctx->stream>>>(P);
+    else resolve_kernel<MODE, ALBEDO, false><<<grid, 256, 0, ctx->stream>>>(P);
+}
+
+}  // namespace
+
+int ilb_resolve_launch(ilb_ctx* ctx, const ilb_resolve* r, const void* d_lightmap, const void* d_albedo, void* d_output) {
+    if (r->width <= 0 || r->height <= 0) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad size %dx%d", r->width, r->height);
+    if (r->lightmap_format != ILB_FORMAT_FLOAT4 && r->lightmap_format != ILB_FORMAT_HALF4 && r->lightmap_format != ILB_FORMAT_RGBA8)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad lightmap format %d", r->lightmap_format);
+    if (d_albedo && r->albedo_format != ILB_FORMAT_FLOAT4 && r->albedo_format != ILB_FORMAT_RGBA8)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "albedo format must be RGBA8 or FLOAT4");
+    if (r->output_format != ILB_FORMAT_FLOAT4 && r->output_format != ILB_FORMAT_RGBA8)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "output format must be RGBA8 or FLOAT4");
+    if (r->hdr_mode < ILB_HDR_NONE || r->hdr_mode > ILB_HDR_TONE_MAP) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad hdr_mode %d", r->hdr_mode);
+    if (r->LightmapUVOffset[0] != 0.0f || r->LightmapUVOffset[1] != 0.0f)
+        return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "LightmapUVOffset != 0 (scaled / offset resolves are outside the hot-path scope)");
+    if (r->DitheringStrength != 0.0f)
+        return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "DitheringStrength != 0 (ApplyDither lives in the un-vendored sq/Fracture DitherCommon.fxh)");
+    ResolveParams P;
+    memset(&P, 0, sizeof(P));
+    P.lightmap = d_lightmap; P.albedo = d_albedo; P.out = d_output;
+    P.n = (unsigned long long)r->width * (unsigned long long)r->height;
+    P.lm_fmt = r->lightmap_format; P.al_fmt = r->albedo_format; P.out_fmt = r->output_format;
+    const float inv = (r->InverseScaleFactor != 0.0f) ? r->InverseScaleFactor : 1.0f;  // LightingRenderer.cs:1469-1473
+    P.invScale = inv; P.invScale2 = inv * 2;
+    P.offset = r->Offset; P.exposure = r->ExposureMinusOne + 1; P.gamma = r->GammaMinusOne + 1;
+    P.middleGray = r->MiddleGray; P.averageLuminance = r->AverageLuminance; P.maxLumSq = r->MaximumLuminanceSquared;
+    P.whiteScale = hostTonemap1(r->WhitePoint);
+    P.albedoIsSRGB = r->AlbedoIsSRGB != 0.0f; P.resolveToSRGB = r->ResolveToSRGB != 0.0f;
+    const bool vec = (((uintptr_t)d_lightmap | (uintptr_t)d_albedo | (uintptr_t)d_output) & 15u) == 0;
+    // enough 256-thread CTAs for every group of four pixels, capped at 8 waves of 148 SMs x 8 resident CTAs (grid-stride)
+    const unsigned long long work = vec ? std::max<unsigned long long>(P.n >> 2, 1) : P.n;
+    const int grid = (int)std::min<unsigned long long>((work + 255) / 256, 148ull * 8 * 8);
+    const bool albedo = d_albedo != nullptr;
+    switch (r->hdr_mode * 2 + (albedo ? 1 : 0)) {
+        case 0: launchResolve<ILB_HDR_NONE, false>(ctx, P, vec, grid); break;
+        case 1: launchResolve<ILB_HDR_NONE, true>(ctx, P, vec, grid); break;
+        case 2: launchResolve<ILB_HDR_GAMMA_COMPRESS, false>(ctx, P, vec, grid); break;
+        case 3: launchResolve<ILB_HDR_GAMMA_COMPRESS, true>(ctx, P, vec, grid); break;
+        case 4: launchResolve<ILB_HDR_TONE_MAP, false>(ctx, P, vec, grid); break;
+        default: launchResolve<ILB_HDR_TONE_MAP, true>(ctx, P, vec, grid); break;
+    }
+    ctx->launches++;
+    ILB_CUDA(ctx, cudaGetLastError());
+    return ILB_OK;
+}
+
+int ilb_luminance_launch(ilb_ctx* ctx, int width, int height, int fmt, const void* d_lightmap, int level, float* out_host) {
+    int lw = width / 2, lh = height / 2;
+    if (level < 0 || lw <= 0 || lh <= 0 || (lw >> level) <= 0 || (lh >> level) <= 0)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "luminance level %d does not exist for a %dx%d lightmap", level, width, height);
+    const size_t bytes0 = sizeof(float) * (size_t)lw * (size_t)lh;
+    int rc = ilb_reserve(ctx, &ctx->d_luminance[0], &ctx->d_luminance_capacity[0], bytes0, false);
+    if (rc) return rc;
+    if (level > 0) {
+        rc = ilb_reserve(ctx, &ctx->d_luminance[1], &ctx->d_luminance_capacity[1], std::max<size_t>(bytes0 / 4, 16), false);
+        if (rc) return rc;
+    }
+    float* cur = reinterpret_cast<float*>(ctx->d_luminance[0]);
+    float* nxt = reinterpret_cast<float*>(ctx->d_luminance[1]);
+    luminance_level0_kernel<<<dim3((lw + 255) / 256, lh), 256, 0, ctx->stream>>>(d_lightmap, fmt, width, lw, lh, cur);
+    ctx->launches++;
+    ILB_CUDA(ctx, cudaGetLastError());
+    for (int k = 0; k < level; k++) {
+        const int nw = lw / 2, nh = lh / 2;
+        luminance_downsample_kernel<<<dim3((nw + 255) / 256, nh), 256, 0, ctx->stream>>>(cur, lw, nxt, nw, nh);
+        ctx->launches++;
+        ILB_CUDA(ctx, cudaGetLastError());
+        std::swap(cur, nxt);
+        lw = nw; lh = nh;
+    }
+    ILB_CUDA(ctx, cudaMemcpyAsync(out_host, cur, sizeof(float) * (size_t)lw * (size_t)lh, cudaMemcpyDeviceToHost, ctx->stream));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ILB_OK;
+}

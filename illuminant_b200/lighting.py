@@ -244,6 +244,7 @@ class LightingRenderer:
         self.ViewportPosition = (0.0, 0.0)   # Materials.ViewportPosition
         self.ViewportScale = (1.0, 1.0)      # Materials.ViewportScale
         self._gbuffer_shape = None
+        self.LastRendered = None             # hdr.RenderedLighting of the most recent host-output frame
 
     # ---- G-buffer ---------------------------------------------------------------------------------------------
     def SetGBuffer(self, texels: Optional[np.ndarray]) -> None:
@@ -368,7 +369,15 @@ class LightingRenderer:
         df = self.DistanceField.handle if (self.DistanceField is not None and self.DistanceField.handle) else None
         self.ctx.check(self.ctx.lib.ilb_render_lighting(self.ctx.handle, df, C.byref(frame), C.cast(batches, C.c_void_p), nb,
                                                         C.cast(verts, C.c_void_p), nv, out.ctypes.data_as(C.c_void_p)))
+        self._set_last_rendered(frame, intensityScale)
         return out
+
+    def _set_last_rendered(self, frame: LightingFrame, intensityScale: float) -> None:
+        """RenderLighting returns a RenderedLighting in the reference (LightingRenderer.cs:951-954: lightmap + 1 / intensityScale);
+        here the texels are the return value and the handle to the device-resident lightmap is `LastRendered`."""
+        from .hdr import RenderedLighting
+        self.LastRendered = RenderedLighting(self, frame.width, frame.row_end - frame.row_begin, frame.lightmap_format,
+                                             1.0 / intensityScale)
 
     def RenderLightingFrame(self, gbuffer: np.ndarray, intensityScale: float = 1.0, rows: Optional[Tuple[int, int]] = None,
                             out: Optional[np.ndarray] = None) -> np.ndarray:
@@ -388,6 +397,7 @@ class LightingRenderer:
         self.ctx.check(self.ctx.lib.ilb_render_lighting_frame(self.ctx.handle, df, C.byref(frame), C.cast(batches, C.c_void_p), nb,
                                                               C.cast(verts, C.c_void_p), nv, gw, gh, fmt, arr.ctypes.data_as(C.c_void_p),
                                                               out.ctypes.data_as(C.c_void_p)))
+        self._set_last_rendered(frame, intensityScale)
         return out
 
     def RenderLightingDevice(self, device_ptr: int, intensityScale: float = 1.0, rows: Optional[Tuple[int, int]] = None,

@@ -222,6 +222,59 @@ ILB_API int ilb_update_light_probes(ilb_ctx* ctx, ilb_df* df, const ilb_lighting
                                     const ilb_float4* probe_positions, const ilb_float4* probe_normals,
                                     int probe_count, int output_format, void* probes_out);
 
+/* ------------------------------------------ "next" row N3: lightmap resolve / luminance */
+
+typedef enum ilb_hdr_mode { /* HDRMode, LightingRenderer.HDR.cs:269-273 */
+    ILB_HDR_NONE = 0,
+    ILB_HDR_GAMMA_COMPRESS = 1,
+    ILB_HDR_TONE_MAP = 2
+} ilb_hdr_mode;
+
+/* Everything LightingResolveHandler._Before binds for one resolve draw (LightingRenderer.cs:1464-1523) and the material
+ * ResolveLighting picks (:1537-1591): hdr_mode + albedo select one of the six pixel shaders of Resolve.fx
+ * ({,GammaCompressed,ToneMapped}LightingResolve{,WithAlbedo}PixelShader, Resolve.fx:66-217).  Values are the ones the
+ * reference sets on the effect, clamps included (IlluminantMaterials.cs:81-137): the shim passes ExposureMinusOne =
+ * clamp(Exposure, 1/256, 99999) - 1, GammaMinusOne = clamp(Gamma, 0.1, 4) - 1, WhitePoint (1 in mode NONE),
+ * MaximumLuminanceSquared = clamp(MaximumLuminance)^2, InverseScaleFactor (0 means 1, :1469-1473).
+ * Scope: the screen-aligned 1:1 resolve (RenderedLighting.Resolve with width/height = the lightmap's size, position 0;
+ * with the LinearClamp sampler that fetches exactly one texel per pixel) -- LightmapUVOffset must be (0,0) and the
+ * albedo has the lightmap's size.  ApplyDither (Resolve.fx:88) lives in the un-vendored sq/Fracture (DitherCommon.fxh);
+ * the handler's default is Strength 0 (:1489-1494), i.e. the identity -- DitheringStrength must be 0.  LUT blending
+ * (LUTResolve.fx) is out of scope.  Other values return ILB_ERR_UNSUPPORTED. */
+typedef struct ilb_resolve {
+    int32_t width, height;     /* lightmap (= output) size in pixels */
+    int32_t lightmap_format;   /* ilb_format of the lightmap: HALF4, RGBA8 or FLOAT4 */
+    int32_t albedo_format;     /* RGBA8 (SurfaceFormat.Color) or FLOAT4; ignored without albedo */
+    int32_t output_format;     /* RGBA8 (backbuffer, UNORM round-to-nearest) or FLOAT4 (parity tests) */
+    int32_t hdr_mode;          /* ilb_hdr_mode */
+    float InverseScaleFactor;
+    float AlbedoIsSRGB, ResolveToSRGB;          /* 0 / 1 */
+    float Offset, ExposureMinusOne, GammaMinusOne;
+    float MiddleGray, AverageLuminance, MaximumLuminanceSquared; /* GammaCompress (HDR.fxh:6-18) */
+    float WhitePoint;                                            /* ToneMap (HDR.fxh:22-44) */
+    float LightmapUVOffset[2];
+    float DitheringStrength;
+    float reserved;
+} ilb_resolve;
+
+/* One resolve draw, host to host: lightmap (NULL = the device-resident lightmap the context's most recent
+ * ilb_render_lighting / ilb_render_lighting_frame call produced -- like RenderedLighting.Resolve, which never reads the
+ * lightmap back) and albedo (NULL = the Resolve.fx shaders without albedo) are width*height texels; output is
+ * width*height texels of output_format.  Synchronous. */
+ILB_API int ilb_resolve_lighting(ilb_ctx* ctx, const ilb_resolve* params, const void* lightmap, const void* albedo, void* output);
+/* Same with DEVICE pointers (16-byte aligned); asynchronous on ilb_stream(ctx). */
+ILB_API int ilb_resolve_lighting_device(ilb_ctx* ctx, const ilb_resolve* params, const void* d_lightmap, const void* d_albedo,
+                                        void* d_output);
+/* UpdateLuminanceBuffer + the mip chain TryComputeHistogram reads (LightingRenderer.cs:855-898, LightingRenderer.HDR.cs:154-186):
+ * level 0 is (width/2) x (height/2) SurfaceFormat.Single texels, texel (x,y) = dot(lightmap texel (2x+1, 2y+1).rgb,
+ * (0.299, 0.587, 0.144)) (CalculateLuminancePixelShader, Resolve.fx:219-234; point-sampled at the half-size target's pixel
+ * centres; 0.144 is the reference's constant); level k+1 = 2x2 box filter of level k, size floor(size/2).  Writes level
+ * `level` (level_width = width/2 >> level, level_height likewise; the reference's accuracyFactor, default 3) to HOST memory
+ * out_luminance[level_width*level_height].  lightmap == NULL as for ilb_resolve_lighting.  Synchronous.  The histogram
+ * itself (Histogram.cs) is host code in the reference and stays host code (illuminant_b200.hdr.Histogram). */
+ILB_API int ilb_compute_luminance(ilb_ctx* ctx, int width, int height, int lightmap_format, const void* lightmap, int level,
+                                  float* out_luminance);
+
 /* ---------------------------------------------------------- particles (P1-P10) */
 
 typedef struct ilb_bezier1 { ilb_float4 RangeAndCount, ABCD; } ilb_bezier1;         /* ClampedBezier1, Bezier.cs:434-459 */

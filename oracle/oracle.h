@@ -31,6 +31,10 @@ int orc_particles_step(float* P, float* V, float* A, float* RC, float* RD, int c
 int orc_generate_distance_field(uint16_t* out_rgba64, const uint16_t* base_rgba64 /* static field or NULL */, int tw, int th, int slice_w, int slice_h, int slice_count,
                                 const ilb_df_uniforms* u, const ilb_obstruction* obs, int count, int nthreads);
 void orc_encode_gbuffer_sample(const float* normal, float relativeY, float z, int dead, int enableShadows, int fullbright, float* out4);
+/* N3: Resolve.fx / HDR.fxh on fp32-decoded texels (lightmap, albedo: w*h*4 floats; albedo may be NULL); out: w*h*4 floats, not quantised. */
+int orc_resolve_lighting(const ilb_resolve* p, const float* lightmap, const float* albedo, float* out);
+/* N3: luminance buffer level `level` ((w/2 >> level) x (h/2 >> level) floats) of a fp32-decoded lightmap. */
+int orc_compute_luminance(const float* lightmap, int w, int h, int level, float* out);
 void orc_float_to_half(const float* in, uint16_t* out, long n);
 void orc_half_to_float(const uint16_t* in, float* out, long n);
 #ifdef __cplusplus

@@ -23,7 +23,7 @@ P = C.c_void_p
 
 
 def build(force: bool = False) -> Path:
-    srcs = [HERE / n for n in ("oracle_lighting.cpp", "oracle_particles.cpp", "oracle_inputs.cpp", "hlsl.hpp", "oracle.h",
+    srcs = [HERE / n for n in ("oracle_lighting.cpp", "oracle_particles.cpp", "oracle_inputs.cpp", "oracle_resolve.cpp", "hlsl.hpp", "oracle.h",
                                "Makefile")] + [HERE.parent / "include" / "illuminant_b200.h"]
     if force or not LIB.exists() or any(s.stat().st_mtime > LIB.stat().st_mtime for s in srcs):
         res = subprocess.run(["make", "-C", str(HERE), "-B", "liboracle.so"], capture_output=True, text=True)
@@ -67,6 +67,10 @@ def lib():
         L.orc_generate_distance_field.argtypes = [P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DFUniforms), P, C.c_int, C.c_int]
         L.orc_encode_gbuffer_sample.restype = None
         L.orc_encode_gbuffer_sample.argtypes = [P, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, P]
+        L.orc_resolve_lighting.restype = C.c_int
+        L.orc_resolve_lighting.argtypes = [C.POINTER(_abi.Resolve), P, P, P]
+        L.orc_compute_luminance.restype = C.c_int
+        L.orc_compute_luminance.argtypes = [P, C.c_int, C.c_int, C.c_int, P]
         L.orc_float_to_half.restype = None
         L.orc_float_to_half.argtypes = [P, P, C.c_long]
         L.orc_half_to_float.restype = None
@@ -231,3 +235,32 @@ def float_to_half(a: np.ndarray) -> np.ndarray:
     out = np.empty(a.shape, dtype=np.uint16)
     lib().orc_float_to_half(_ptr(a), _ptr(out), a.size)
     return out.view(np.float16)
+
+
+def resolve_lighting(params, lightmap, albedo=None) -> np.ndarray:
+    """Resolve.fx on fp32-decoded texels: lightmap [H, W, 4] (any float dtype, or uint8 UNORM), albedo likewise or None.
+    Returns the un-quantised float32 [H, W, 4] pixel-shader output."""
+    def decode(a):
+        if a is None:
+            return None
+        a = np.asarray(a)
+        if a.dtype == np.uint8:
+            return np.ascontiguousarray(a.astype(np.float32) / np.float32(255.0))
+        return np.ascontiguousarray(a, dtype=np.float32)
+    lm, al = decode(lightmap), decode(albedo)
+    out = np.empty((params.height, params.width, 4), dtype=np.float32)
+    rc = lib().orc_resolve_lighting(C.byref(params), _ptr(lm), _ptr(al), _ptr(out))
+    if rc != 0:
+        raise RuntimeError(f"orc_resolve_lighting failed: {rc}")
+    return out
+
+
+def compute_luminance(lightmap, level: int) -> np.ndarray:
+    lm = np.asarray(lightmap)
+    lm = np.ascontiguousarray(lm.astype(np.float32) / np.float32(255.0)) if lm.dtype == np.uint8 else np.ascontiguousarray(lm, dtype=np.float32)
+    h, w = lm.shape[0], lm.shape[1]
+    out = np.empty(((h // 2) >> level, (w // 2) >> level), dtype=np.float32)
+    rc = lib().orc_compute_luminance(_ptr(lm), w, h, level, _ptr(out))
+    if rc != 0:
+        raise RuntimeError(f"orc_compute_luminance failed: {rc}")
+    return out
