@@ -8,7 +8,7 @@ from .lighting import (DirectionalLightSource, LightingEnvironment, LightingRend
                        LineLightSource, ParticleLightSource, RendererConfiguration, ShadowFilter, SphereLightSource, encode_gbuffer)
 from .hdr import (DitheringSettings, GammaCompressionConfiguration, HDRConfiguration, HDRMode, Histogram, RenderedLighting,
                   ToneMappingConfiguration, pack_resolve)
-from .particles import (FMA, AreaType, Attractor, AttractorType, Bezier4V, BezierF, Formula, FormulaType, Gravity, MatrixMultiply,
+from .particles import (FMA, AreaType, Attractor, AttractorType, Bezier4V, BezierF, FeedbackSpawner, Formula, FormulaType, Gravity, MatrixMultiply,
                         Noise, ParticleCollision, ParticleColorLifeRamp, ParticleEngine, ParticleEngineConfiguration, ParticleSystem,
                         ParticleSystemConfiguration, Spawner, TransformArea)
 

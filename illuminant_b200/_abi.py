@@ -17,6 +17,7 @@ ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_INVALID_OPERATION, ERR_OUT_OF
 FORMAT_FLOAT4, FORMAT_HALF4, FORMAT_RGBA8 = 0, 1, 2
 LIGHT_SPHERE, LIGHT_DIRECTIONAL, LIGHT_PARTICLE, LIGHT_LINE = 1, 2, 3, 4
 HDR_NONE, HDR_GAMMA_COMPRESS, HDR_TONE_MAP = 0, 1, 2
+SPAWN_INLINE, SPAWN_POSITION_TEXTURE, SPAWN_FEEDBACK = 0, 1, 2
 OP_GRAVITY, OP_NOISE, OP_FMA, OP_MATRIX_MULTIPLY = 1, 2, 3, 4
 MAX_ATTRACTORS = 16
 FORMAT_BYTES = {FORMAT_FLOAT4: 16, FORMAT_HALF4: 8, FORMAT_RGBA8: 4}
@@ -138,6 +139,13 @@ class Spawn(C.Structure):
                 ("PolygonRate", C.c_float), ("PolygonLoop", C.c_float), ("AttributeDiscardThreshold", C.c_float)]
 
 
+class SpawnSource(C.Structure):  # ilb_spawn_source
+    _fields_ = [("kind", C.c_int32), ("position_count", C.c_int32), ("positions", C.c_void_p), ("source_system", C.c_void_p),
+                ("source_chunk", C.c_int32), ("FeedbackSourceIndex", C.c_float), ("InstanceMultiplier", C.c_float),
+                ("SourceVelocityFactor", C.c_float), ("AlignPositionConstant", C.c_float), ("MultiplyLife", C.c_float),
+                ("MultiplyAttributeConstant", C.c_float), ("SourceLifeRange", C.c_float * 2), ("reserved", C.c_int32)]
+
+
 class IlluminantError(RuntimeError):
     """Raised for every non-zero ilb_status; `.code` carries the status."""
 
@@ -182,6 +190,7 @@ _PROTOTYPES = [
     ("ilb_particles_download_chunk", C.c_int, [P, C.c_int, P, P, P, P, P]),
     ("ilb_particles_set_live_chunks", C.c_int, [P, C.c_int]),
     ("ilb_particles_step", C.c_int, [P, C.POINTER(PsysUniforms), P, C.c_int, P, C.c_int, C.c_int]),
+    ("ilb_particles_step_sources", C.c_int, [P, C.POINTER(PsysUniforms), P, P, C.c_int, P, C.c_int, C.c_int]),
     ("ilb_particles_device_buffer", P, [P, C.c_int]),
     ("ilb_particles_count_live", C.c_int, [P, C.POINTER(C.c_int64)]),
 ]

@@ -459,6 +459,7 @@ void ilb_particles_destroy(ilb_psys* ps) {
         if (ps->buf[i]) cudaFree(ps->buf[i]);
     if (ps->rng) cudaFree(ps->rng);
     if (ps->noise_table) cudaFree(ps->noise_table);
+    if (ps->positions) cudaFree(ps->positions);
     if (ps->life_ramp) cudaFree(ps->life_ramp);
     if (ps->d_count) cudaFree(ps->d_count);
     delete ps;
@@ -542,7 +543,18 @@ int ilb_particles_step(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spawn
                        int op_count, int steps) {
     if (!ps) return ILB_ERR_INVALID_ARGUMENT;
     ILB_CUDA(ps->ctx, cudaSetDevice(ps->ctx->device));
-    return ilb_particles_launch(ps, u, spawns, spawn_count, ops, op_count, steps);
+    return ilb_particles_launch(ps, u, spawns, nullptr, spawn_count, ops, op_count, steps);
+}
+
+int ilb_particles_step_sources(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spawn* spawns, const ilb_spawn_source* sources,
+                               int spawn_count, const ilb_op* ops, int op_count, int steps) {
+    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    ILB_CUDA(ps->ctx, cudaSetDevice(ps->ctx->device));
+    if (sources)
+        for (int i = 0; i < spawn_count; i++)
+            if (sources[i].kind == ILB_SPAWN_FEEDBACK && (!sources[i].source_system || !live_has(sources[i].source_system)))
+                return ilb_fail(ps->ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: the feedback source system is null or released", i);
+    return ilb_particles_launch(ps, u, spawns, sources, spawn_count, ops, op_count, steps);
 }
 
 void* ilb_particles_device_buffer(ilb_psys* ps, int which) {

@@ -84,6 +84,8 @@ struct ilb_psys {
     ilb_df* field = nullptr;
     float4* life_ramp = nullptr;    // LifeRampTexture, float4 texels
     int life_ramp_w = 0, life_ramp_h = 0;
+    float4* positions = nullptr;    // PositionBuffer of an ILB_SPAWN_POSITION_TEXTURE spawn
+    size_t positions_capacity = 0;
     float4* noise_table = nullptr;  // 2 * per_chunk float4, see noise_table_kernel
     unsigned long long* d_count = nullptr;
     bool use_tma = false;  // ILB_PARTICLE_TMA=1 selects the TMA-staged persistent step kernel (measured 22 % slower: the
@@ -126,6 +128,6 @@ size_t ilb_format_bytes(int format);
 int ilb_dfgen_launch(ilb_ctx* ctx, uint2* tex, const uint2* base, int tw, int th, int slice_w, int slice_h, int slice_count,
                      const ilb_df_uniforms* u, const ilb_obstruction* obs, int count);
 // particles.cu
-int ilb_particles_launch(ilb_psys* psys, const ilb_psys_uniforms* u, const ilb_spawn* spawns, int spawn_count,
-                         const ilb_op* ops, int op_count, int steps);
+int ilb_particles_launch(ilb_psys* psys, const ilb_psys_uniforms* u, const ilb_spawn* spawns, const ilb_spawn_source* sources,
+                         int spawn_count, const ilb_op* ops, int op_count, int steps);
 int ilb_particles_count_launch(ilb_psys* psys, int64_t* out);

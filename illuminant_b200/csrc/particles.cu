@@ -70,6 +70,14 @@ struct SpawnParams {
     unsigned chunk_base;  // chunk * per_chunk
     int first, count;
     ilb_spawn s;
+    // N4: spawn sources (ilb_spawn_source)
+    const float4* positions;  // POSITION_TEXTURE: the PositionBuffer texels
+    int position_count;
+    const float4 *srcP, *srcV, *srcRC;  // FEEDBACK: the source chunk's PositionAndLife / Velocity / RenderColor
+    int src_size;
+    float feedbackSourceIndex, instanceMultiplier, sourceVelocityFactor;
+    int alignPositionConstant, multiplyLife, multiplyAttributeConstant;
+    float sourceLifeMin, sourceLifeMax;
 };
 
 // ---- randomness (RandomCommon.fxh:17-34): POINT sampled, WRAP/WRAP -------------------------------------------
@@ -767,6 +775,19 @@ ILB_DEV f4 evaluateFormula(const ilb_spawn& s, f4 origin, f4 constant, f4 scale,
     return type0;
 }
 
+// evaluateRandomForIndex :106-117
+ILB_DEV void evaluateRandomForIndex(const SpawnParams& P, float index, f4& random1, f4& random2, f4& random3) {
+    const ilb_spawn& s = P.s;
+    const float one = 1.0f;
+    random1 = randomCustom(P.rng, P.rng_w, P.rng_h, fmodf(index, 8039.0f), xadd(0.0f, fmodf(index, 57.0f)), s.RandomnessOffset, one, one, s.RandomnessTexel);
+    random2 = randomCustom(P.rng, P.rng_w, P.rng_h, fmodf(index, 6180.0f), xadd(1.0f, fmodf(index, 4031.0f)), s.RandomnessOffset, one, one, s.RandomnessTexel);
+    random3 = randomCustom(P.rng, P.rng_w, P.rng_h, fmodf(index, 2025.0f), xadd(2.0f, fmodf(index, 65531.0f)), s.RandomnessOffset, one, one, s.RandomnessTexel);
+    if (s.AlignVelocityAndPosition != 0.0f) { random2.x = random1.x; random2.y = random1.y; }
+}
+
+// One thread per texel of [first, last] of the target chunk.  KIND (ilb_spawn_kind) selects the pixel shader of
+// SpawnParticles.fx: PS_Spawn (:10-30), PS_SpawnFromPositionTexture (:32-52) or PS_SpawnFeedback (:54-120).
+template <int KIND>
 __global__ void __launch_bounds__(STEP_THREADS) particle_spawn_kernel(const __grid_constant__ SpawnParams P) {
     const int k = blockIdx.x * STEP_THREADS + threadIdx.x;
     if (k >= P.count) return;
@@ -774,13 +795,47 @@ __global__ void __launch_bounds__(STEP_THREADS) particle_spawn_kernel(const __gr
     const int li = P.first + k;  // index within the chunk, inside [first, last] by construction (Spawn_Stage1 :124-130)
     const float index = xadd((float)(li % P.chunk_size), xmul((float)(li / P.chunk_size), s.ChunkSizeAndIndices.x));
     if ((index < s.ChunkSizeAndIndices.y) || (index > s.ChunkSizeAndIndices.z)) return;
+    const ilb_float4* C = s.Configuration;
+    const size_t gi = (size_t)P.chunk_base + (size_t)li;
 
-    // evaluateRandomForIndex :106-117
-    const float one = 1.0f;
-    f4 random1 = randomCustom(P.rng, P.rng_w, P.rng_h, fmodf(index, 8039.0f), xadd(0.0f, fmodf(index, 57.0f)), s.RandomnessOffset, one, one, s.RandomnessTexel);
-    f4 random2 = randomCustom(P.rng, P.rng_w, P.rng_h, fmodf(index, 6180.0f), xadd(1.0f, fmodf(index, 4031.0f)), s.RandomnessOffset, one, one, s.RandomnessTexel);
-    const f4 random3 = randomCustom(P.rng, P.rng_w, P.rng_h, fmodf(index, 2025.0f), xadd(2.0f, fmodf(index, 65531.0f)), s.RandomnessOffset, one, one, s.RandomnessTexel);
-    if (s.AlignVelocityAndPosition != 0.0f) { random2.x = random1.x; random2.y = random1.y; }
+    if (KIND == ILB_SPAWN_FEEDBACK) {
+        // the source particle: texel (floor(sourceX), sourceY) of the source chunk, CLAMP addressing (:69-79)
+        const float sourceIndex = xadd(xdiv(xsub(index, s.ChunkSizeAndIndices.y), P.instanceMultiplier), P.feedbackSourceIndex);
+        float sourceY;
+        const float sourceX = xmul(modff(xdiv(sourceIndex, (float)P.src_size), &sourceY), (float)P.src_size);
+        const int tx = min(max((int)floorf(sourceX), 0), P.src_size - 1), ty = min(max((int)sourceY, 0), P.src_size - 1);
+        const size_t si = (size_t)ty * (size_t)P.src_size + (size_t)tx;
+        const f4 sourcePosition = mk4(P.srcP[si]);
+        if ((sourcePosition.w <= P.sourceLifeMin) || (sourcePosition.w >= P.sourceLifeMax)) return;
+        const f4 sourceVelocity = mk4(P.srcV[si]), sourceAttributes = mk4(P.srcRC[si]);
+        f4 random1, random2, random3;
+        evaluateRandomForIndex(P, index, random1, random2, random3);
+        f4 positionConstant = mk4(s.InlinePositionConstants[0]);
+        if (P.alignPositionConstant) {
+            positionConstant.x = xadd(positionConstant.x, sourcePosition.x);
+            positionConstant.y = xadd(positionConstant.y, sourcePosition.y);
+            positionConstant.z = xadd(positionConstant.z, sourcePosition.z);
+        }
+        const f4 tempPosition = evaluateFormula(s, mk4(0.0f), positionConstant, mk4(C[0]), mk4(C[1]), random1, s.FormulaTypes.x);
+        f4 attributeConstant = mk4(C[5]);
+        if (P.multiplyAttributeConstant) attributeConstant = xmul4(attributeConstant, sourceAttributes);
+        f4 newPosition = xmul_rm(mk4(tempPosition.x, tempPosition.y, tempPosition.z, 1.0f), s.PositionMatrix);
+        newPosition.w = tempPosition.w;
+        if (P.multiplyLife) newPosition.w = xmul(newPosition.w, sourcePosition.w);
+        f4 tempVelocity = evaluateFormula(s, tempPosition, mk4(C[2]), mk4(C[3]), mk4(C[4]), random2, s.FormulaTypes.y);
+        tempVelocity = xadd4(tempVelocity, xscale4(sourceVelocity, P.sourceVelocityFactor));
+        f4 newVelocity = xmul_rm(mk4(tempVelocity.x, tempVelocity.y, tempVelocity.z, 1.0f), s.VelocityMatrix);
+        newVelocity.w = tempVelocity.w;
+        const f4 newAttributes = evaluateFormula(s, tempPosition, attributeConstant, mk4(C[6]), mk4(C[7]), random3, s.FormulaTypes.z);
+        if (newAttributes.w < s.AttributeDiscardThreshold) return;
+        P.P[gi] = to_float4(newPosition);
+        P.V[gi] = to_float4(newVelocity);
+        P.A[gi] = to_float4(newAttributes);
+        return;
+    }
+
+    f4 random1, random2, random3;
+    evaluateRandomForIndex(P, index, random1, random2, random3);
 
     int index1, index2;
     float positionIndexT;
@@ -797,14 +852,18 @@ __global__ void __launch_bounds__(STEP_THREADS) particle_spawn_kernel(const __gr
         index1 = index2 = (int)fmodf(xadd(relativeIndex, s.ChunkSizeAndIndices.w), s.PositionConstantCount);
         positionIndexT = 0.0f;
     }
-    index1 = min(max(index1, 0), 3);
-    index2 = min(max(index2, 0), 3);
-    const f4 position1 = mk4(s.InlinePositionConstants[index1]), position2 = mk4(s.InlinePositionConstants[index2]);
+    f4 position1, position2;
+    if (KIND == ILB_SPAWN_POSITION_TEXTURE) {  // texel `index` of the W x 1 PositionBuffer, CLAMP addressing (:45-47)
+        position1 = mk4(P.positions[min(max(index1, 0), P.position_count - 1)]);
+        position2 = mk4(P.positions[min(max(index2, 0), P.position_count - 1)]);
+    } else {
+        position1 = mk4(s.InlinePositionConstants[min(max(index1, 0), 3)]);
+        position2 = mk4(s.InlinePositionConstants[min(max(index2, 0), 3)]);
+    }
     const f4 positionConstant = xlerp4(position1, position2, positionIndexT);
     const f4 towardsNext = xsub4(position2, position1);
 
     // Spawn_Stage2 :157-190
-    const ilb_float4* C = s.Configuration;
     const f4 tempPosition = evaluateFormula(s, mk4(0.0f), positionConstant, mk4(C[0]), mk4(C[1]), random1, s.FormulaTypes.x);
     f4 newPosition = xmul_rm(mk4(tempPosition.x, tempPosition.y, tempPosition.z, 1.0f), s.PositionMatrix);
     newPosition.w = tempPosition.w;
@@ -818,7 +877,6 @@ __global__ void __launch_bounds__(STEP_THREADS) particle_spawn_kernel(const __gr
     f4 newVelocity = xmul_rm(mk4(tempVelocity.x, tempVelocity.y, tempVelocity.z, 1.0f), s.VelocityMatrix);
     newVelocity.w = tempVelocity.w;
     if (newAttributes.w < s.AttributeDiscardThreshold) return;  // discard: the texel keeps its old contents
-    const size_t gi = (size_t)P.chunk_base + (size_t)li;
     P.P[gi] = to_float4(newPosition);
     P.V[gi] = to_float4(newVelocity);
     P.A[gi] = to_float4(newAttributes);
@@ -834,8 +892,8 @@ __global__ void __launch_bounds__(256) particle_count_live_kernel(const float4* 
 
 }  // namespace
 
-int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spawn* spawns, int spawn_count, const ilb_op* ops,
-                         int op_count, int steps) {
+int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spawn* spawns, const ilb_spawn_source* sources,
+                         int spawn_count, const ilb_op* ops, int op_count, int steps) {
     ilb_ctx* ctx = ps->ctx;
     if (!u || spawn_count < 0 || op_count < 0 || steps < 0 || (spawn_count > 0 && !spawns) || (op_count > 0 && !ops))
         return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null or negative argument");
@@ -856,8 +914,10 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
         for (int si = 0; si < spawn_count; si++) {
             const ilb_spawn& s = spawns[si];
             if (s.chunk < 0 || s.chunk >= ps->live_chunks) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: chunk %d is not live", si, s.chunk);
-            if (s.PositionConstantCount > 4.0f || s.PositionConstantCount < 1.0f)
-                return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "spawn %d: 1..4 inline positions supported (SpawnFromPositionTexture is out of scope)", si);
+            const int kind = sources ? sources[si].kind : ILB_SPAWN_INLINE;
+            if (kind < ILB_SPAWN_INLINE || kind > ILB_SPAWN_FEEDBACK) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: unknown source kind %d", si, kind);
+            if (s.PositionConstantCount < 1.0f || (kind == ILB_SPAWN_INLINE && s.PositionConstantCount > 4.0f))
+                return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: 1..4 inline positions (more need an ILB_SPAWN_POSITION_TEXTURE source, ParticleSpawner.cs:331-352)", si);
             if ((int)s.ChunkSizeAndIndices.x != ps->chunk_size) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: ChunkSize mismatch", si);
             int first = (int)s.ChunkSizeAndIndices.y, last = (int)s.ChunkSizeAndIndices.z;
             first = std::max(first, 0);
@@ -871,8 +931,42 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
             SP.chunk_base = (unsigned)((size_t)s.chunk * ps->per_chunk);
             SP.first = first; SP.count = last - first + 1;
             SP.s = s;
-            particle_spawn_kernel<<<(SP.count + STEP_THREADS - 1) / STEP_THREADS, STEP_THREADS, 0, ctx->stream>>>(SP);
+            const int sgrid = (SP.count + STEP_THREADS - 1) / STEP_THREADS;
+            if (kind == ILB_SPAWN_POSITION_TEXTURE) {
+                const ilb_spawn_source& src = sources[si];
+                if (!src.positions || src.position_count < 1 || s.PositionConstantCount > (float)src.position_count)
+                    return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: position texture has %d texels for %g positions", si, src.position_count, (double)s.PositionConstantCount);
+                const size_t bytes = sizeof(float4) * (size_t)src.position_count;
+                if (ps->positions_capacity < bytes) {  // EnsurePositionBufferExists (ParticleSpawner.cs:306-319)
+                    if (ps->positions) { ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ps->positions); ps->positions = nullptr; ps->positions_capacity = 0; }
+                    ILB_CUDA(ctx, cudaMalloc(&ps->positions, bytes * 2));
+                    ps->positions_capacity = bytes * 2;
+                }
+                // the caller's array is pageable host memory: the copy is staged before cudaMemcpyAsync returns
+                ILB_CUDA(ctx, cudaMemcpyAsync(ps->positions, src.positions, bytes, cudaMemcpyHostToDevice, ctx->stream));
+                SP.positions = ps->positions; SP.position_count = src.position_count;
+                particle_spawn_kernel<ILB_SPAWN_POSITION_TEXTURE><<<sgrid, STEP_THREADS, 0, ctx->stream>>>(SP);
+            } else if (kind == ILB_SPAWN_FEEDBACK) {
+                const ilb_spawn_source& src = sources[si];
+                ilb_psys* from = src.source_system;
+                if (!from || from == ps || from->ctx != ctx)  // SpecialSpawners.cs:333-335: a system cannot feed itself
+                    return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: the feedback source must be another live system of the same context", si);
+                if (src.source_chunk < 0 || src.source_chunk >= from->live_chunks) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: source chunk %d is not live", si, src.source_chunk);
+                if (!(src.InstanceMultiplier >= 1.0f)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: InstanceMultiplier must be >= 1", si);
+                const size_t sbase = (size_t)src.source_chunk * from->per_chunk;
+                SP.srcP = from->buf[0] + sbase; SP.srcV = from->buf[1] + sbase; SP.srcRC = from->buf[3] + sbase;
+                SP.src_size = from->chunk_size;
+                SP.feedbackSourceIndex = src.FeedbackSourceIndex; SP.instanceMultiplier = src.InstanceMultiplier;
+                SP.sourceVelocityFactor = src.SourceVelocityFactor;
+                SP.alignPositionConstant = src.AlignPositionConstant != 0.0f; SP.multiplyLife = src.MultiplyLife != 0.0f;
+                SP.multiplyAttributeConstant = src.MultiplyAttributeConstant != 0.0f;
+                SP.sourceLifeMin = src.SourceLifeRange[0]; SP.sourceLifeMax = src.SourceLifeRange[1];
+                particle_spawn_kernel<ILB_SPAWN_FEEDBACK><<<sgrid, STEP_THREADS, 0, ctx->stream>>>(SP);
+            } else {
+                particle_spawn_kernel<ILB_SPAWN_INLINE><<<sgrid, STEP_THREADS, 0, ctx->stream>>>(SP);
+            }
             ctx->launches++;
+            ILB_CUDA(ctx, cudaGetLastError());
         }
         const size_t total = (size_t)ps->live_chunks * ps->per_chunk;
         if (total == 0) continue;

@@ -17,12 +17,13 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 from . import _abi
-from ._abi import (OP_FMA, OP_GRAVITY, OP_MATRIX_MULTIPLY, OP_NOISE, Area, Bezier1, Bezier4, Float4, Op, PsysUniforms, Spawn)
+from ._abi import (OP_FMA, OP_GRAVITY, OP_MATRIX_MULTIPLY, OP_NOISE, Area, Bezier1, Bezier4, Float4, Op, PsysUniforms, Spawn, SpawnSource)
 from .distance_field import DistanceField
 
 F = np.float32
 RandomnessTextureWidth, RandomnessTextureHeight = 807, 653  # ParticleEngine.cs:45-46
 VelocityConstantScale = 1000                                # Uniforms.cs:199
+MaxInlinePositions = 4                                      # ParticleSpawner.cs:263
 IDENTITY = (1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0)
 
 
@@ -422,14 +423,114 @@ class Spawner(ParticleTransform):  # ParticleSpawner.cs:14-419
         s.PositionMatrix[:] = [float(v) for v in self.PositionPostMatrix]
         s.VelocityMatrix[:] = [float(v) for v in self.VelocityPostMatrix]
         s.AttributeDiscardThreshold = float(F(self.AlphaDiscardThreshold) / F(255.0))
-        if count > 4:  # SpawnFromPositionTexture material (:291-295) is outside the hot-path scope
-            raise _abi.IlluminantError(_abi.ERR_UNSUPPORTED, "more than 3 AdditionalPositions (SpawnFromPositionTexture) is not supported")
-        s.InlinePositionConstants[0] = Float4(*self.Position.Constant, lc)   # BeginTick :343-357
-        for i, ap in enumerate(self.AdditionalPositions[:3]):
-            s.InlinePositionConstants[i + 1] = Float4(*ap, lc)
+        self._source = None
+        if count > MaxInlinePositions:  # SpawnParticlesFromPositionTexture (:291-295): PositionBuffer of (count + 127) / 128 * 128 texels (:306-352)
+            buf = np.zeros(((count + 127) // 128 * 128, 4), dtype=np.float32)
+            buf[0] = [*self.Position.Constant, lc]
+            for i, ap in enumerate(self.AdditionalPositions):
+                buf[i + 1] = [*ap, lc]
+            src = SpawnSource()
+            src.kind, src.position_count = _abi.SPAWN_POSITION_TEXTURE, buf.shape[0]
+            src.positions = buf.ctypes.data
+            self._position_buffer = buf   # keeps the host array alive until the step call returns
+            self._source = src
+        else:
+            s.InlinePositionConstants[0] = Float4(*self.Position.Constant, lc)   # BeginTick :343-357
+            for i, ap in enumerate(self.AdditionalPositions[:MaxInlinePositions - 1]):
+                s.InlinePositionConstants[i + 1] = Float4(*ap, lc)
         s.PositionConstantCount = float(count)
         s.PolygonRate = float(polygonRate)
         s.PolygonLoop = 1.0 if self.PolygonLoop else 0.0
+        return s
+
+
+@dataclass
+class FeedbackSpawner(Spawner):  # SpecialSpawners.cs:266-437 (derives from SpawnerBase: no additional positions / polygon)
+    """Spawns from the particles of another system: position / velocity / colour constants come from a source particle."""
+    SourceSystem: Optional["ParticleSystem"] = None
+    SlidingWindowSize: Optional[int] = None
+    SlidingWindowMargin: int = 0
+    SpawnFromEntireWindow: bool = False
+    InstanceMultiplier: int = 1
+    AlignPositionConstant: bool = True
+    SourceVelocityFactor: float = 0.0
+    MultiplyLife: bool = False
+    MultiplyColorConstant: bool = False
+    SourceLifeRange: Tuple[float, float] = (0.0, 9999.0)
+
+    IsFeedback = True
+
+    def __post_init__(self):
+        super().__post_init__()
+        self.CurrentFeedbackSource = -1
+        self.CurrentFeedbackSourceIndex = 0
+
+    @property
+    def CountScale(self) -> int:  # SpawnerBase :119-123
+        return 1
+
+    def BeginTickFeedback(self, system: "ParticleSystem", now: float, deltaTimeSeconds: float) -> Tuple[int, int]:
+        """FeedbackSpawner.BeginTick (:325-403) -> (spawnCount, sourceChunk or -1)."""
+        if self.InstanceMultiplier < 1:
+            self.InstanceMultiplier = 1
+        self.CurrentFeedbackSource = -1
+        src = self.SourceSystem
+        if src is None or src is system:      # :329-335
+            return 0, -1
+        spawnCount = Spawner.BeginTick(self, now, deltaTimeSeconds)
+        if spawnCount < self.InstanceMultiplier and not self.SpawnFromEntireWindow:
+            self.RateError += spawnCount       # AddError
+            return 0, -1
+        instances = spawnCount // self.InstanceMultiplier
+        rounded = instances * self.InstanceMultiplier
+        if rounded < spawnCount and rounded > 0:
+            self.RateError += spawnCount - rounded
+            spawnCount = rounded
+        sourceChunk = src.PickSourceForFeedback(instances)
+        if sourceChunk < 0:
+            return 0, -1
+        windowSize = self.SlidingWindowSize if self.SlidingWindowSize is not None else 999999
+        available = src.AvailableForFeedback(sourceChunk)
+        if src._chunk_no_longer_target[sourceChunk]:
+            cw = src._spawn_target
+            if cw >= 0:
+                available += src.AvailableForFeedback(cw)
+        windowedAvailable = min(available, windowSize)
+        src.SkipFeedbackInput(sourceChunk, max(0, available - windowedAvailable))
+        availableLessMargin = max(0, windowedAvailable - self.SlidingWindowMargin)
+        spawnCount = min(spawnCount, availableLessMargin * self.InstanceMultiplier)
+        spawnCount = min(spawnCount, src.AvailableForFeedback(sourceChunk) * self.InstanceMultiplier)
+        self.CurrentFeedbackSource = sourceChunk
+        self.CurrentFeedbackSourceIndex = src._chunk_consumed[sourceChunk]       # Chunk.FeedbackSourceIndex
+        if self.SpawnFromEntireWindow:
+            sourceCount = max(spawnCount // self.InstanceMultiplier, 1)
+            maxOffset = availableLessMargin - sourceCount
+            if maxOffset > 1:
+                self.CurrentFeedbackSourceIndex += int(self._rng.integers(0, maxOffset))
+        return spawnCount, sourceChunk
+
+    def pack(self, system, now, chunk: int) -> Spawn:  # SetParameters :409-430 on top of SpawnerBase.SetParameters
+        saved = self.AdditionalPositions, self.PolygonRate
+        self.AdditionalPositions, self.PolygonRate = [], None
+        try:
+            s = Spawner.pack(self, system, now, chunk)
+        finally:
+            self.AdditionalPositions, self.PolygonRate = saved
+        s.ChunkSizeAndIndices = Float4(system.Engine.Configuration.ChunkSize, self.Indices[0], self.Indices[1], 0)  # SpawnerBase :137-141
+        s.Configuration[8] = Float4(0, 0, 0, 0)
+        s.PolygonLoop = 0.0
+        src = SpawnSource()
+        src.kind = _abi.SPAWN_FEEDBACK
+        src.source_system = self.SourceSystem.handle
+        src.source_chunk = self.CurrentFeedbackSource
+        src.FeedbackSourceIndex = float(self.CurrentFeedbackSourceIndex)
+        src.InstanceMultiplier = float(self.InstanceMultiplier)
+        src.SourceVelocityFactor = float(self.SourceVelocityFactor)
+        src.AlignPositionConstant = 1.0 if self.AlignPositionConstant else 0.0
+        src.MultiplyLife = 1.0 if self.MultiplyLife else 0.0
+        src.MultiplyAttributeConstant = 1.0 if self.MultiplyColorConstant else 0.0
+        src.SourceLifeRange[:] = [float(self.SourceLifeRange[0]), float(self.SourceLifeRange[1])]
+        self._source = src
         return s
 
 
@@ -465,8 +566,15 @@ class ParticleSystem:
         self.LastUpdateTimeSeconds: Optional[float] = None
         self.Now = 0.0
         self.TotalSpawnCount = 0
-        self._chunk_next_offset: List[int] = []   # Chunk.NextSpawnOffset per live chunk
+        self._chunk_next_offset: List[int] = []   # Chunk.NextSpawnOffset per live chunk (ParticleSystem.cs:148-240)
+        self._chunk_total_spawned: List[int] = []      # Chunk.TotalSpawned
+        self._chunk_consumed: List[int] = []           # Chunk.TotalConsumedForFeedback (== FeedbackSourceIndex)
+        self._chunk_no_longer_target: List[bool] = []  # Chunk.NoLongerASpawnTarget
+        self._chunk_is_feedback: List[bool] = []       # Chunk.IsFeedbackSource (set on the chunks a FeedbackSpawner fills)
         self._spawn_target = -1
+        self._feedback_spawn_target = -1               # CurrentFeedbackSpawnTarget
+        self._feedback_source = -1                     # CurrentFeedbackSource
+        self.last_sources = None                       # ilb_spawn_source list of the most recent plan_spawns (None: all inline)
         self.handle = None
         if self.ctx is not None:
             h = C.c_void_p()
@@ -494,10 +602,21 @@ class ParticleSystem:
     def LiveChunkCount(self) -> int:
         return len(self._chunk_next_offset)
 
+    def _sync_chunk_lists(self) -> None:
+        """Chunks that were registered by assigning `_chunk_next_offset` directly (tests that model a pre-filled user chunk)
+        get the bookkeeping of a chunk whose NextSpawnOffset particles were all spawned."""
+        for c in range(len(self._chunk_total_spawned), len(self._chunk_next_offset)):
+            self._chunk_total_spawned.append(self._chunk_next_offset[c])
+            self._chunk_consumed.append(0)
+            self._chunk_no_longer_target.append(self._chunk_next_offset[c] >= self.ChunkMaximumCount)
+            self._chunk_is_feedback.append(False)
+
     def _create_chunk(self) -> int:  # CreateChunk (ParticleSystem.cs:520-545)
         if len(self._chunk_next_offset) >= self.MaxChunks:
             return -1
+        self._sync_chunk_lists()
         self._chunk_next_offset.append(0)
+        self._sync_chunk_lists()
         if self.handle:
             self.ctx.check(self.ctx.lib.ilb_particles_set_live_chunks(self.handle, len(self._chunk_next_offset)))
         return len(self._chunk_next_offset) - 1
@@ -521,6 +640,8 @@ class ParticleSystem:
                 bufs.append(b)
             self.ctx.check(self.ctx.lib.ilb_particles_upload_chunk(self.handle, c, *[b.ctypes.data_as(C.c_void_p) for b in bufs]))
             self._chunk_next_offset[c] = per   # user chunks are NoLongerASpawnTarget (ParticleSystem.cs:693-695)
+            self._chunk_total_spawned[c] = m
+            self._chunk_no_longer_target[c] = True
             self.TotalSpawnCount += per
         return first if first is not None else -1
 
@@ -589,35 +710,72 @@ class ParticleSystem:
         self.LastUpdateTimeSeconds = now
         return min(dt, maxDelta)
 
+    # ---- feedback bookkeeping (ParticleSystem.Chunk :166-182, :234-238; ParticleSpawning.cs:246-264) ---------------
+    def AvailableForFeedback(self, chunk: int) -> int:
+        return self._chunk_total_spawned[chunk] - self._chunk_consumed[chunk]
+
+    def SkipFeedbackInput(self, chunk: int, skipAmount: int) -> None:
+        self._chunk_consumed[chunk] = min(self._chunk_consumed[chunk] + skipAmount, self._chunk_total_spawned[chunk])
+
+    def PickSourceForFeedback(self, count: int) -> int:
+        for c in range(self.LiveChunkCount):
+            if self.AvailableForFeedback(c) >= count // 2 and not self._chunk_is_feedback[c]:
+                self._feedback_source = c
+                return c
+        return -1
+
+    def _pick_target_for_spawn(self, feedback: bool, count: int, partialSpawnAllowed: bool) -> int:  # PickTargetForSpawn :199-231
+        chunk = self._feedback_spawn_target if feedback else self._spawn_target
+        if chunk >= 0 and (self.ChunkMaximumCount - self._chunk_next_offset[chunk]) < (16 if partialSpawnAllowed else count):
+            self._chunk_no_longer_target[chunk] = True
+            chunk = -1
+        if chunk < 0:
+            chunk = self._create_chunk()
+            if chunk < 0:
+                return -1
+            self._chunk_is_feedback[chunk] = feedback
+        if feedback:
+            self._feedback_spawn_target = chunk
+        else:
+            self._spawn_target = chunk
+        return chunk
+
     def plan_spawns(self, now: float, dt: float):
         """RunSpawner for every active spawner (ParticleSpawning.cs:115-197); a partial spawn triggers the second
-        RunSpawner pass (ParticleSystem.cs:733-740), which calls BeginTick again exactly like the reference."""
-        spawns = []
+        RunSpawner pass (ParticleSystem.cs:733-740), which calls BeginTick again exactly like the reference.  The
+        ilb_spawn_source of each spawn (None when every spawn is inline) is left in `self.last_sources`."""
+        spawns, sources = [], []
+        self._sync_chunk_lists()
         for t in self.Transforms:
             if not t.IsSpawner or not (t.IsActive and t.IsActive2) or not t.IsValid:
                 continue
+            feedback = bool(getattr(t, "IsFeedback", False))
             for _pass in range(2):
-                requested = t.BeginTick(now, dt)
+                sourceChunk = -1
+                if feedback:
+                    requested, sourceChunk = t.BeginTickFeedback(self, now, dt)
+                else:
+                    requested = t.BeginTick(now, dt)
                 if requested <= 0:
                     break
                 spawnCount = min(requested, self.ChunkMaximumCount)
-                chunk = self._spawn_target
-                if chunk >= 0 and (self.ChunkMaximumCount - self._chunk_next_offset[chunk]) < 16:  # PickTargetForSpawn :199-231
-                    chunk = -1
+                chunk = self._pick_target_for_spawn(feedback, spawnCount, True)
                 if chunk < 0:
-                    chunk = self._create_chunk()
-                    if chunk < 0:
-                        break
-                    self._spawn_target = chunk
+                    break
                 spawnCount = min(spawnCount, self.ChunkMaximumCount - self._chunk_next_offset[chunk])
                 first = self._chunk_next_offset[chunk]
                 t.Indices = (first, first + spawnCount - 1)
                 self._chunk_next_offset[chunk] += spawnCount
                 self.TotalSpawnCount += spawnCount
+                if sourceChunk >= 0 and not t.SpawnFromEntireWindow:   # :163-170
+                    t.SourceSystem._chunk_consumed[sourceChunk] += max(spawnCount // t.InstanceMultiplier, 1)
                 spawns.append(t.pack(self, now, chunk))
+                sources.append(getattr(t, "_source", None))
                 t.EndTick(requested, spawnCount)
+                self._chunk_total_spawned[chunk] += spawnCount
                 if not (requested > spawnCount):
                     break
+        self.last_sources = sources if any(x is not None for x in sources) else None
         return spawns
 
     def plan_ops(self, now: float):
@@ -637,16 +795,22 @@ class ParticleSystem:
         spawns = self.plan_spawns(now, dt)
         ops = self.plan_ops(now)
         u = self.system_uniforms(dt)
-        self.step_packed(u, spawns, ops, 1)
+        self.step_packed(u, spawns, ops, 1, self.last_sources)
 
-    def step_packed(self, u: PsysUniforms, spawns, ops, steps: int = 1) -> None:
+    def step_packed(self, u: PsysUniforms, spawns, ops, steps: int = 1, sources=None) -> None:
+        """`sources`: None (every spawn is inline) or one ilb_spawn_source / None per spawn (ilb_particles_step_sources)."""
         col = self.Configuration.Collision
         field_handle = col.DistanceField.handle if (col is not None and col.DistanceField is not None) else None
         self.ctx.check(self.ctx.lib.ilb_particles_set_collision_field(self.handle, field_handle))
         sp = (Spawn * max(len(spawns), 1))(*spawns)
         opa = (Op * max(len(ops), 1))(*ops)
-        self.ctx.check(self.ctx.lib.ilb_particles_step(self.handle, C.byref(u), C.cast(sp, C.c_void_p), len(spawns),
-                                                       C.cast(opa, C.c_void_p), len(ops), steps))
+        if sources is None:
+            self.ctx.check(self.ctx.lib.ilb_particles_step(self.handle, C.byref(u), C.cast(sp, C.c_void_p), len(spawns),
+                                                           C.cast(opa, C.c_void_p), len(ops), steps))
+            return
+        src = (SpawnSource * max(len(spawns), 1))(*[x if x is not None else SpawnSource() for x in sources])
+        self.ctx.check(self.ctx.lib.ilb_particles_step_sources(self.handle, C.byref(u), C.cast(sp, C.c_void_p), C.cast(src, C.c_void_p),
+                                                               len(spawns), C.cast(opa, C.c_void_p), len(ops), steps))
 
     def Dispose(self):
         if self.handle:

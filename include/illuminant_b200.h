@@ -372,6 +372,29 @@ typedef struct ilb_spawn { /* one RunSpawner draw (ParticleSpawning.cs:115-197; 
     float AttributeDiscardThreshold;
 } ilb_spawn;
 
+/* "next" row N4 -- the spawner materials that read a source besides the uniforms: SpawnParticlesFromPositionTexture (a Spawner
+ * with more than MaxInlinePositions = 4 positions, ParticleSpawner.cs:268,331-352,376-384) and SpawnFeedbackParticles
+ * (FeedbackSpawner, SpecialSpawners.cs:266-437).  One entry per ilb_spawn of the same call. */
+typedef enum ilb_spawn_kind {
+    ILB_SPAWN_INLINE = 0,            /* PS_Spawn, SpawnParticles.fx:10-30: positions from ilb_spawn.InlinePositionConstants */
+    ILB_SPAWN_POSITION_TEXTURE = 1,  /* PS_SpawnFromPositionTexture, :32-52 */
+    ILB_SPAWN_FEEDBACK = 2           /* PS_SpawnFeedback, :54-120 */
+} ilb_spawn_kind;
+typedef struct ilb_spawn_source {
+    int32_t kind;                 /* ilb_spawn_kind */
+    int32_t position_count;       /* POSITION_TEXTURE: texels of the PositionBuffer (ParticleSpawner.cs:306-319) */
+    const ilb_float4* positions;  /* POSITION_TEXTURE: HOST array of (position, life) (:337-352); ilb_spawn.PositionConstantCount of them are addressed */
+    ilb_psys* source_system;      /* FEEDBACK: SourceSystem.Instance -- another system of the same context (:333-335) */
+    int32_t source_chunk;         /* FEEDBACK: the chunk PickSourceForFeedback chose (ParticleSpawning.cs:246-264); its PositionAndLife,
+                                     Velocity and RenderColor are read as they are when the step runs */
+    float FeedbackSourceIndex;    /* SpecialSpawners.cs:425 */
+    float InstanceMultiplier;     /* >= 1 (:321-323) */
+    float SourceVelocityFactor;
+    float AlignPositionConstant, MultiplyLife, MultiplyAttributeConstant; /* 0 / 1 */
+    float SourceLifeRange[2];
+    int32_t reserved;
+} ilb_spawn_source;
+
 /* ParticleSystem storage: max_chunks chunks of chunk_size^2 particles (ParticleSystem.cs:73-240). */
 ILB_API int ilb_particles_create(ilb_ctx* ctx, int chunk_size, int max_chunks, ilb_psys** out_psys);
 ILB_API void ilb_particles_destroy(ilb_psys* psys);
@@ -398,6 +421,10 @@ ILB_API int ilb_particles_set_live_chunks(ilb_psys* psys, int count);
 ILB_API int ilb_particles_step(ilb_psys* psys, const ilb_psys_uniforms* uniforms,
                                const ilb_spawn* spawns, int spawn_count,
                                const ilb_op* ops, int op_count, int steps);
+/* ilb_particles_step with a source per spawn: sources == NULL means every spawn is ILB_SPAWN_INLINE. */
+ILB_API int ilb_particles_step_sources(ilb_psys* psys, const ilb_psys_uniforms* uniforms,
+                                       const ilb_spawn* spawns, const ilb_spawn_source* sources, int spawn_count,
+                                       const ilb_op* ops, int op_count, int steps);
 /* Device pointers of the SoA state slabs (max_chunks*chunk_size^2 float4 each) for zero-copy consumers:
  * 0 PositionAndLife, 1 Velocity, 2 Attributes(Color), 3 RenderColor, 4 RenderData. */
 ILB_API void* ilb_particles_device_buffer(ilb_psys* psys, int which);

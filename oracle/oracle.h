@@ -28,6 +28,14 @@ int orc_particles_step(float* P, float* V, float* A, float* RC, float* RD, int c
                        const ilb_psys_uniforms* u, const ilb_spawn* spawns, int nspawns, const ilb_op* ops, int nops,
                        const float* rng_table, int rw, int rh, const uint16_t* df_tex, int tw, int th, int steps,
                        int nthreads);
+/* N4: spawners that read a source -- `sources` as for ilb_particles_step_sources (source_system is ignored); for FEEDBACK entries
+ * states[i] holds the SOURCE CHUNK's PositionAndLife / Velocity / RenderColor (chunk_size^2 float4 each). */
+typedef struct orc_source_state { const float *P, *V, *RC; int chunk_size; } orc_source_state;
+int orc_particles_step_sources(float* P, float* V, float* A, float* RC, float* RD, int chunk_size, int live_chunks,
+                               const ilb_psys_uniforms* u, const ilb_spawn* spawns, const ilb_spawn_source* sources,
+                               const orc_source_state* states, int nspawns, const ilb_op* ops, int nops,
+                               const float* rng_table, int rw, int rh, const uint16_t* df_tex, int tw, int th, int steps,
+                               int nthreads);
 int orc_generate_distance_field(uint16_t* out_rgba64, const uint16_t* base_rgba64 /* static field or NULL */, int tw, int th, int slice_w, int slice_h, int slice_count,
                                 const ilb_df_uniforms* u, const ilb_obstruction* obs, int count, int nthreads);
 void orc_encode_gbuffer_sample(const float* normal, float relativeY, float z, int dead, int enableShadows, int fullbright, float* out4);

@@ -63,6 +63,9 @@ def lib():
         L.orc_particles_step.restype = C.c_int
         L.orc_particles_step.argtypes = [P, P, P, P, P, C.c_int, C.c_int, C.POINTER(PsysUniforms), P, C.c_int, P, C.c_int, P, C.c_int,
                                          C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_particles_step_sources.restype = C.c_int
+        L.orc_particles_step_sources.argtypes = [P, P, P, P, P, C.c_int, C.c_int, C.POINTER(PsysUniforms), P, P, P, C.c_int, P, C.c_int, P,
+                                                 C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_generate_distance_field.restype = C.c_int
         L.orc_generate_distance_field.argtypes = [P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DFUniforms), P, C.c_int, C.c_int]
         L.orc_encode_gbuffer_sample.restype = None
@@ -173,9 +176,16 @@ def bezier4(b: Bezier4, value: float) -> np.ndarray:
     return out
 
 
-def particles_step(P_, V_, A_, chunk_size, u: PsysUniforms, spawns, ops, rng_table, df_tex=None, steps=1, nthreads=0, life_ramp=None):
+class SourceState(C.Structure):  # orc_source_state
+    _fields_ = [("P", C.c_void_p), ("V", C.c_void_p), ("RC", C.c_void_p), ("chunk_size", C.c_int)]
+
+
+def particles_step(P_, V_, A_, chunk_size, u: PsysUniforms, spawns, ops, rng_table, df_tex=None, steps=1, nthreads=0, life_ramp=None,
+                   sources=None, source_states=None):
     """In-place multi-pass update of [chunks*chunk_size^2, 4] float32 state. Returns (P, V, A, RC, RD).
-    life_ramp: float32 [H, W, 4] LifeRampTexture or None."""
+    life_ramp: float32 [H, W, 4] LifeRampTexture or None.
+    sources: None or one ilb_spawn_source / None per spawn; source_states: for FEEDBACK entries a tuple
+    (P, V, RC, chunk_size) of float32 [chunk_size^2, 4] arrays holding the SOURCE CHUNK's state."""
     if life_ramp is not None:
         life_ramp = np.ascontiguousarray(life_ramp, dtype=np.float32)
         lib().orc_set_life_ramp(_ptr(life_ramp), life_ramp.shape[1], life_ramp.shape[0])
@@ -195,9 +205,23 @@ def particles_step(P_, V_, A_, chunk_size, u: PsysUniforms, spawns, ops, rng_tab
         rh, rw = rng_table.shape[0], rng_table.shape[1]
     sp = (_abi.Spawn * max(len(spawns), 1))(*spawns)
     opa = (_abi.Op * max(len(ops), 1))(*ops)
-    rc = lib().orc_particles_step(_ptr(P_), _ptr(V_), _ptr(A_), _ptr(RC), _ptr(RD), chunk_size, live, C.byref(u), C.cast(sp, P),
-                                  len(spawns), C.cast(opa, P), len(ops), _ptr(rng_table), rw, rh, _ptr(df_tex), tw, th, steps,
-                                  nthreads or threads())
+    if sources is not None:
+        n = max(len(spawns), 1)
+        src = (_abi.SpawnSource * n)(*[x if x is not None else _abi.SpawnSource() for x in sources])
+        keep, st = [], (SourceState * n)()
+        for i, ss in enumerate(source_states or []):
+            if ss is None:
+                continue
+            arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in ss[:3]]
+            keep.append(arrs)
+            st[i].P, st[i].V, st[i].RC, st[i].chunk_size = arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, int(ss[3])
+        rc = lib().orc_particles_step_sources(_ptr(P_), _ptr(V_), _ptr(A_), _ptr(RC), _ptr(RD), chunk_size, live, C.byref(u), C.cast(sp, P),
+                                              C.cast(src, P), C.cast(st, P), len(spawns), C.cast(opa, P), len(ops), _ptr(rng_table), rw, rh,
+                                              _ptr(df_tex), tw, th, steps, nthreads or threads())
+    else:
+        rc = lib().orc_particles_step(_ptr(P_), _ptr(V_), _ptr(A_), _ptr(RC), _ptr(RD), chunk_size, live, C.byref(u), C.cast(sp, P),
+                                      len(spawns), C.cast(opa, P), len(ops), _ptr(rng_table), rw, rh, _ptr(df_tex), tw, th, steps,
+                                      nthreads or threads())
     if rc != 0:
         raise RuntimeError(f"orc_particles_step failed: {rc}")
     return P_, V_, A_, RC, RD

@@ -241,26 +241,27 @@ float4 evaluateFormula(const ilb_spawn& s, float4 origin, float4 constant, float
     }
 }
 
-// returns false when the texel is discarded (outside [first,last] or below the alpha threshold)
-bool PS_Spawn(const ilb_spawn& s, const Randomness& rng, float2 xy, float4& newPosition, float4& newVelocity,
-              float4& newAttributes) {
-    // Spawn_Stage1 :119-155
-    float4 csi = f4(s.ChunkSizeAndIndices);
-    float index = (xy.x) + (xy.y * csi.x);
-    if ((index < csi.y) || (index > csi.z)) return false;
-
-    // evaluateRandomForIndex :106-117 ; random() = randomCustom(xy, RandomnessOffset, 1)
+// evaluateRandomForIndex :106-117 ; random() = randomCustom(xy, RandomnessOffset, 1)
+void evaluateRandomForIndex(const ilb_spawn& s, const Randomness& rng, float index, float4& random1, float4& random2, float4& random3) {
     float2 ro(s.RandomnessOffset[0], s.RandomnessOffset[1]), rt(s.RandomnessTexel[0], s.RandomnessTexel[1]);
     float2 randomOffset1 = float2(fmod(index, 8039), 0 + fmod(index, 57));
     float2 randomOffset2 = float2(fmod(index, 6180), 1 + fmod(index, 4031));
     float2 randomOffset3 = float2(fmod(index, 2025), 2 + fmod(index, 65531));
-    float4 random1 = rng.randomCustom(randomOffset1, ro, float2(1.0f), rt);
-    float4 random2 = rng.randomCustom(randomOffset2, ro, float2(1.0f), rt);
-    float4 random3 = rng.randomCustom(randomOffset3, ro, float2(1.0f), rt);
+    random1 = rng.randomCustom(randomOffset1, ro, float2(1.0f), rt);
+    random2 = rng.randomCustom(randomOffset2, ro, float2(1.0f), rt);
+    random3 = rng.randomCustom(randomOffset3, ro, float2(1.0f), rt);
     if (s.AlignVelocityAndPosition != 0) { random2.x = random1.x; random2.y = random1.y; }
+}
 
-    int index1, index2;
-    float positionIndexT;
+// Spawn_Stage1 :119-155.  Returns false when the texel is outside [first, last] (discard).
+bool Spawn_Stage1(const ilb_spawn& s, const Randomness& rng, float2 xy, float4& random1, float4& random2, float4& random3,
+                  int& index1, int& index2, float& positionIndexT) {
+    float4 csi = f4(s.ChunkSizeAndIndices);
+    float index = (xy.x) + (xy.y * csi.x);
+    if ((index < csi.y) || (index > csi.z)) return false;
+
+    evaluateRandomForIndex(s, rng, index, random1, random2, random3);
+
     float relativeIndex = (index - csi.y);
     if (s.PolygonRate > 0.05f) {
         float polyRate = s.PolygonRate;
@@ -279,15 +280,12 @@ bool PS_Spawn(const ilb_spawn& s, const Randomness& rng, float2 xy, float4& newP
         index1 = index2 = (int)fmod(relativeIndex + csi.w, s.PositionConstantCount);
         positionIndexT = 0;
     }
-    if (index1 < 0) index1 = 0; if (index1 > 3) index1 = 3;
-    if (index2 < 0) index2 = 0; if (index2 > 3) index2 = 3;
+    return true;
+}
 
-    // PS_Spawn SpawnParticles.fx:25-29
-    float4 position1 = f4(s.InlinePositionConstants[index1]), position2 = f4(s.InlinePositionConstants[index2]);
-    float4 positionConstant = lerp(position1, position2, positionIndexT);
-    float4 towardsNext = position2 - position1;
-
-    // Spawn_Stage2 :157-190
+// Spawn_Stage2 :157-190.  Returns false when the new particle is below the alpha threshold (discard).
+bool Spawn_Stage2(const ilb_spawn& s, float4 positionConstant, float4 towardsNext, float4 random1, float4 random2, float4 random3,
+                  float4& newPosition, float4& newVelocity, float4& newAttributes) {
     const ilb_float4* C = s.Configuration;
     float4 ft = f4(s.FormulaTypes);
     float4 tempPosition = evaluateFormula(s, float4(0.0f), positionConstant, f4(C[0]), f4(C[1]), random1, ft.x);
@@ -305,6 +303,81 @@ bool PS_Spawn(const ilb_spawn& s, const Randomness& rng, float2 xy, float4& newP
     newVelocity = mul(float4(tempVelocity.xyz(), 1), s.VelocityMatrix);
     newVelocity.w = tempVelocity.w;
     // (#if FNA zero-velocity hack :182-186 is compiled out on the XNA/D3D build this oracle restates)
+    if (newAttributes.w < s.AttributeDiscardThreshold) return false;
+    return true;
+}
+
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// PS_Spawn SpawnParticles.fx:10-30
+bool PS_Spawn(const ilb_spawn& s, const Randomness& rng, float2 xy, float4& newPosition, float4& newVelocity,
+              float4& newAttributes) {
+    int index1, index2;
+    float positionIndexT;
+    float4 random1, random2, random3;
+    if (!Spawn_Stage1(s, rng, xy, random1, random2, random3, index1, index2, positionIndexT)) return false;
+    index1 = clampi(index1, 0, 3);
+    index2 = clampi(index2, 0, 3);
+    float4 position1 = f4(s.InlinePositionConstants[index1]), position2 = f4(s.InlinePositionConstants[index2]);
+    float4 positionConstant = lerp(position1, position2, positionIndexT);
+    return Spawn_Stage2(s, positionConstant, position2 - position1, random1, random2, random3, newPosition, newVelocity, newAttributes);
+}
+
+// PS_SpawnFromPositionTexture SpawnParticles.fx:32-52.  The PositionBuffer (ParticleSpawner.cs:306-319) is a W x 1 Vector4
+// texture point-sampled at u = index * (1 / W): texel `index` (CLAMP addressing).
+bool PS_SpawnFromPositionTexture(const ilb_spawn& s, const float* positions, int positionCount, const Randomness& rng, float2 xy,
+                                 float4& newPosition, float4& newVelocity, float4& newAttributes) {
+    int index1, index2;
+    float positionIndexT;
+    float4 random1, random2, random3;
+    if (!Spawn_Stage1(s, rng, xy, random1, random2, random3, index1, index2, positionIndexT)) return false;
+    float4 position1 = ld4(positions, clampi(index1, 0, positionCount - 1)), position2 = ld4(positions, clampi(index2, 0, positionCount - 1));
+    float4 positionConstant = lerp(position1, position2, positionIndexT);
+    return Spawn_Stage2(s, positionConstant, position2 - position1, random1, random2, random3, newPosition, newVelocity, newAttributes);
+}
+
+// PS_SpawnFeedback SpawnParticles.fx:54-120.  srcP / srcV / srcRC: the source chunk's PositionAndLife, Velocity and RenderColor
+// (ParticleTransform.cs:122-139: AttributeTexture = SourceChunk.RenderColor), srcSize^2 float4 each; point-sampled at
+// sourceXy * (1 / srcSize): texel (floor(sourceX), sourceY), CLAMP addressing.
+bool PS_SpawnFeedback(const ilb_spawn& s, const ilb_spawn_source& f, const float* srcP, const float* srcV, const float* srcRC, int srcSize,
+                      const Randomness& rng, float2 xy, float4& newPosition, float4& newVelocity, float4& newAttributes) {
+    float4 csi = f4(s.ChunkSizeAndIndices);
+    float index = (xy.x) + (xy.y * csi.x);
+    if ((index < csi.y) || (index > csi.z)) return false;
+
+    float sourceIndex = ((index - csi.y) / f.InstanceMultiplier) + f.FeedbackSourceIndex;
+    float sourceY, sourceX = modff(sourceIndex / (float)srcSize, &sourceY) * (float)srcSize;
+    const int tx = clampi((int)floorf(sourceX), 0, srcSize - 1), ty = clampi((int)sourceY, 0, srcSize - 1);
+    const size_t si = (size_t)ty * srcSize + tx;
+    float4 sourcePosition = ld4(srcP, si), sourceVelocity = ld4(srcV, si), sourceAttributes = ld4(srcRC, si);
+    if ((sourcePosition.w <= f.SourceLifeRange[0]) || (sourcePosition.w >= f.SourceLifeRange[1])) return false;
+
+    float4 random1, random2, random3;
+    evaluateRandomForIndex(s, rng, index, random1, random2, random3);
+
+    const ilb_float4* C = s.Configuration;
+    float4 ft = f4(s.FormulaTypes);
+    float4 positionConstant = f4(s.InlinePositionConstants[0]);
+    if (f.AlignPositionConstant != 0) {
+        positionConstant.x += sourcePosition.x; positionConstant.y += sourcePosition.y; positionConstant.z += sourcePosition.z;
+    }
+    float4 tempPosition = evaluateFormula(s, float4(0.0f), positionConstant, f4(C[0]), f4(C[1]), random1, ft.x);
+
+    float4 attributeConstant = f4(C[5]);
+    if (f.MultiplyAttributeConstant != 0) attributeConstant *= sourceAttributes;
+
+    newPosition = mul(float4(tempPosition.xyz(), 1), s.PositionMatrix);
+    newPosition.w = tempPosition.w;
+    if (f.MultiplyLife != 0) newPosition.w *= sourcePosition.w;
+
+    float4 velocityConstant = f4(C[2]);
+    float4 tempVelocity = evaluateFormula(s, tempPosition, velocityConstant, f4(C[3]), f4(C[4]), random2, ft.y);
+    tempVelocity += sourceVelocity * f.SourceVelocityFactor;
+
+    newVelocity = mul(float4(tempVelocity.xyz(), 1), s.VelocityMatrix);
+    newVelocity.w = tempVelocity.w;
+
+    newAttributes = evaluateFormula(s, tempPosition, attributeConstant, f4(C[6]), f4(C[7]), random3, ft.z);
     if (newAttributes.w < s.AttributeDiscardThreshold) return false;
     return true;
 }
@@ -621,10 +694,11 @@ void orc_bezier4(const ilb_bezier4* b, float value, float* out) {
 // One or more ParticleSystem.Update calls (Particles/ParticleSystem.cs:634-760) over chunks [0, live_chunks):
 // spawners (in place, ParticleSystem.cs:725-741), then UpdateChunk (:791-856) per chunk.
 // P, V, A, RC, RD: live_chunks * chunk_size^2 float4 each, chunk-major then row-major. In/out.
-int orc_particles_step(float* P, float* V, float* A, float* RC, float* RD, int chunk_size, int live_chunks,
-                       const ilb_psys_uniforms* u, const ilb_spawn* spawns, int nspawns, const ilb_op* ops, int nops,
-                       const float* rng_table, int rw, int rh, const uint16_t* df_tex, int tw, int th, int steps,
-                       int nthreads) {
+int orc_particles_step_sources(float* P, float* V, float* A, float* RC, float* RD, int chunk_size, int live_chunks,
+                               const ilb_psys_uniforms* u, const ilb_spawn* spawns, const ilb_spawn_source* sources,
+                               const orc_source_state* states, int nspawns, const ilb_op* ops, int nops,
+                               const float* rng_table, int rw, int rh, const uint16_t* df_tex, int tw, int th, int steps,
+                               int nthreads) {
     if (u->has_collision_field && !df_tex) return ILB_ERR_INVALID_OPERATION;
     if (nthreads > 0) omp_set_num_threads(nthreads);
     const System sys(*u);
@@ -638,13 +712,23 @@ int orc_particles_step(float* P, float* V, float* A, float* RC, float* RD, int c
         for (int si = 0; si < nspawns; si++) {
             const ilb_spawn& s = spawns[si];
             if (s.chunk < 0 || s.chunk >= live_chunks) return ILB_ERR_INVALID_ARGUMENT;
-            if (s.PositionConstantCount > 4) return ILB_ERR_UNSUPPORTED;
+            const int kind = sources ? sources[si].kind : ILB_SPAWN_INLINE;
+            if (kind == ILB_SPAWN_INLINE && s.PositionConstantCount > 4) return ILB_ERR_UNSUPPORTED;
+            if (kind == ILB_SPAWN_POSITION_TEXTURE && (!sources[si].positions || sources[si].position_count < 1)) return ILB_ERR_INVALID_ARGUMENT;
+            if (kind == ILB_SPAWN_FEEDBACK && (!states || !states[si].P || states[si].chunk_size < 1)) return ILB_ERR_INVALID_ARGUMENT;
             const size_t base = per * s.chunk;
 #pragma omp parallel for schedule(static)
             for (long i = 0; i < (long)per; i++) {
                 float2 xy((float)(i % chunk_size), (float)(i / chunk_size));
                 float4 np, nv, na;
-                if (PS_Spawn(s, rng, xy, np, nv, na)) {
+                bool spawned;
+                if (kind == ILB_SPAWN_POSITION_TEXTURE)
+                    spawned = PS_SpawnFromPositionTexture(s, &sources[si].positions[0].x, sources[si].position_count, rng, xy, np, nv, na);
+                else if (kind == ILB_SPAWN_FEEDBACK)
+                    spawned = PS_SpawnFeedback(s, sources[si], states[si].P, states[si].V, states[si].RC, states[si].chunk_size, rng, xy, np, nv, na);
+                else
+                    spawned = PS_Spawn(s, rng, xy, np, nv, na);
+                if (spawned) {
                     st4(pPrev, base + i, np);
                     st4(vPrev, base + i, nv);
                     st4(A, base + i, na);
@@ -698,6 +782,14 @@ int orc_particles_step(float* P, float* V, float* A, float* RC, float* RD, int c
         memcpy(V, vPrev, sizeof(float) * 4 * total);
     }
     return 0;
+}
+
+int orc_particles_step(float* P, float* V, float* A, float* RC, float* RD, int chunk_size, int live_chunks,
+                       const ilb_psys_uniforms* u, const ilb_spawn* spawns, int nspawns, const ilb_op* ops, int nops,
+                       const float* rng_table, int rw, int rh, const uint16_t* df_tex, int tw, int th, int steps,
+                       int nthreads) {
+    return orc_particles_step_sources(P, V, A, RC, RD, chunk_size, live_chunks, u, spawns, nullptr, nullptr, nspawns, ops, nops, rng_table,
+                                      rw, rh, df_tex, tw, th, steps, nthreads);
 }
 
 }  // extern "C"

@@ -129,8 +129,49 @@ def test_spawner_uniform_packing():    # ParticleSpawner.cs:200-256, :361-403
     assert s.AttributeDiscardThreshold == pytest.approx(0.2)
     assert s.ChunkSizeAndIndices.tuple() == (32, 5, 20, pytest.approx((10 / 4.0) % 1))   # !PolygonLoop: count - 1 = 1
     assert 0 <= s.RandomnessOffset[0] < 253 and 0 <= s.RandomnessOffset[1] < 127
-    with pytest.raises(ib.IlluminantError):
-        ib.Spawner(AdditionalPositions=[(0, 0, 0)] * 4).pack(system, 0.0, 0)
+    # more than MaxInlinePositions = 4 positions: the SpawnParticlesFromPositionTexture material and its PositionBuffer
+    # ((count + 127) / 128 * 128 texels of (position, life), ParticleSpawner.cs:306-352, :376-384)
+    big = ib.Spawner(Position=ib.Formula(Constant=(1, 2, 3)), Life=(9.0, 0, 0), AdditionalPositions=[(i, 0, -i) for i in range(1, 5)])
+    s = big.pack(system, 0.0, 0)
+    src = big._source
+    assert s.PositionConstantCount == 5 and src.kind == _abi.SPAWN_POSITION_TEXTURE and src.position_count == 128
+    assert np.array_equal(big._position_buffer[:6], np.array([[1, 2, 3, 9], [1, 0, -1, 9], [2, 0, -2, 9], [3, 0, -3, 9], [4, 0, -4, 9], [0, 0, 0, 0]], np.float32))
+    assert src.positions == big._position_buffer.ctypes.data
+    assert ib.Spawner(AdditionalPositions=[(0, 0, 0)] * 3).pack(system, 0.0, 0) is not None and ib.Spawner()._rng is not None
+
+
+def test_feedback_spawner_bookkeeping():
+    """FeedbackSpawner.BeginTick / RunSpawner bookkeeping (SpecialSpawners.cs:325-403, ParticleSpawning.cs:115-197, :246-264)."""
+    engine = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=16))
+    source = ib.ParticleSystem(engine, ib.ParticleSystemConfiguration(), maxChunks=2)
+    target = ib.ParticleSystem(engine, ib.ParticleSystemConfiguration(), maxChunks=2)
+    source.handle = 12345     # packed into ilb_spawn_source.source_system; no device here
+    source._chunk_next_offset = [100]      # a chunk with 100 spawned particles that is still the spawn target
+    source._sync_chunk_lists()
+    source._spawn_target = 0
+    fs = ib.FeedbackSpawner(MinRate=600, MaxRate=600, SourceSystem=source, InstanceMultiplier=3, SlidingWindowMargin=10,
+                            SourceVelocityFactor=0.5, MultiplyLife=True, SourceLifeRange=(0.1, 50.0))
+    target.Transforms = [fs]
+    spawns = target.plan_spawns(1.0, 1 / 60.0)           # 600/s * 1/60 = 10 -> 3 instances x 3, one left as rate error
+    assert len(spawns) == 1 and target.last_sources is not None
+    s, src = spawns[0], target.last_sources[0]
+    assert (s.ChunkSizeAndIndices.y, s.ChunkSizeAndIndices.z, s.ChunkSizeAndIndices.w) == (0, 8, 0)
+    assert src.kind == _abi.SPAWN_FEEDBACK and src.source_system == 12345 and src.source_chunk == 0
+    assert (src.FeedbackSourceIndex, src.InstanceMultiplier, src.SourceVelocityFactor) == (0.0, 3.0, 0.5)
+    assert (src.AlignPositionConstant, src.MultiplyLife, src.MultiplyAttributeConstant) == (1.0, 1.0, 0.0)
+    assert tuple(src.SourceLifeRange) == (pytest.approx(0.1), 50.0)
+    assert fs.RateError == pytest.approx(1.0) and fs.TotalSpawned == 9
+    assert source._chunk_consumed[0] == 3 and source.AvailableForFeedback(0) == 97       # consumed 9 / 3 source particles
+    assert target._chunk_is_feedback == [True] and target._feedback_spawn_target == 0 and target._spawn_target == -1
+    spawns = target.plan_spawns(1.0 + 1 / 60.0, 1 / 60.0)   # 10 + 1 carried = 11 -> 3 instances again, FeedbackSourceIndex advanced
+    assert target.last_sources[0].FeedbackSourceIndex == 3.0 and spawns[0].ChunkSizeAndIndices.y == 9
+    # sliding window: only the newest 20 source particles are eligible -> the older ones are skipped
+    fs.SlidingWindowSize = 20
+    target.plan_spawns(1.0 + 2 / 60.0, 1 / 60.0)
+    assert target.last_sources[0].FeedbackSourceIndex == 80.0          # 100 - 20
+    # a system cannot feed itself (SpecialSpawners.cs:333-335)
+    fs.SourceSystem = target
+    assert target.plan_spawns(2.0, 1 / 60.0) == [] and target.last_sources is None
 
 
 def test_transform_packing_and_noise_uv_cycle():
