@@ -10,7 +10,9 @@ from helpers import make_renderer
 pytestmark = pytest.mark.gpu
 
 RESOLVE_RTOL = 1e-4      # same bar as the lightmap itself (north_star: 1e-4 relative per channel)
-RESOLVE_FLOOR = 1e-3
+RESOLVE_FLOOR = 1 / 255  # |ref| floor of the relative error: one LSB of the Color backbuffer the values are resolved into, i.e. an
+                         # absolute tolerance of 1e-4 LSB.  (Uncharted2Tonemap subtracts two nearly equal numbers near black --
+                         # q - kE/kF with q ~ 0.0667 -- so values below the floor carry the absolute rounding error of q.)
 
 
 def _rendered(ctx, w, h, fmt=_abi.FORMAT_HALF4):
