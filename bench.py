@@ -367,6 +367,35 @@ def run_ours(args):
         renderer.UpdateLightProbes()
         result["probes_ms"] = (time.perf_counter() - t0) * 1e3
 
+        # N3: resolve of the lit buffer -- HalfVector4 lightmap + Color albedo -> Color backbuffer, tone-mapped.
+        # A streaming kernel: 16 algorithmic bytes per pixel.  Two buffer sets alternate (2 x 133 MB > L2) so every launch
+        # streams from HBM.  Reported next to the headline, never part of it.
+        try:
+            from illuminant_b200 import hdr as hdr_mod
+            hdr_cfg = ib.HDRConfiguration(Mode=ib.HDRMode.ToneMap, Exposure=1.2, ToneMapping=ib.ToneMappingConfiguration(WhitePoint=3.0))
+            rp = hdr_mod.pack_resolve(W, H, _abi.FORMAT_HALF4, hdr_cfg, _abi.FORMAT_RGBA8, _abi.FORMAT_RGBA8)
+            lms = [full[:H].contiguous(), full[:H].clone()]
+            als = [torch.randint(0, 256, (H, W, 4), dtype=torch.uint8, device="cuda") for _ in range(2)]
+            outs = [torch.empty((H, W, 4), dtype=torch.uint8, device="cuda") for _ in range(2)]
+            flip = {"i": 0}
+
+            def resolve_step():
+                i = flip["i"] = flip["i"] ^ 1
+                ctx.check(ctx.lib.ilb_resolve_lighting_device(ctx.handle, C.byref(rp), C.c_void_p(lms[i].data_ptr()),
+                                                              C.c_void_p(als[i].data_ptr()), C.c_void_p(outs[i].data_ptr())))
+            r_steps = max(20, 2 * args.steps)
+            r_total, r_per = timed(resolve_step, r_steps, 3)
+            r_ms = float(np.median(r_per))
+            r_ach = 16 * W * H / (r_ms * 1e-3) / 1e9
+            result["resolve"] = {"metric": "resolved Mpixels/s (4K, tone-mapped, with albedo)", "value": W * H / (r_ms * 1e-3) / 1e6,
+                                 "unit": "Mpixels/s", "ms_per_step": r_ms, "steps": r_steps,
+                                 "roofline": {"bound": "hbm", "achieved": r_ach, "peak": peak, "unit": "GB/s", "frac": r_ach / peak,
+                                              "traffic": None, "kernel": "resolve_kernel<ToneMap, albedo, vec4>",
+                                              "algorithmic_bytes_per_pixel": 16, "peak_source": peak_src}}
+            del lms, als, outs
+        except Exception as e:   # noqa: BLE001 -- the headline must not depend on the N3 side measurement
+            result["resolve"] = {"error": f"{type(e).__name__}: {e}"}
+
     # ------------------------------------------------------------------ particles (weak: 8M particles per GPU)
     if args.workload in ("both", "particles"):
         chunk, nchunks = 512, 32
@@ -481,7 +510,7 @@ def run_ours(args):
                            if primary else result.get("config", {}).get("workload"),
                            "parallelism": f"row bands x{world}, gather: {result.get('gather', 'none')}" if primary else f"chunk ranges x{world}, no collective",
                            "l2": "inputs larger than L2 (no flush)"}}
-        for k in ("roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "gather_checksum_equal", "gather_matches_single_gpu", "particles", "combined_c5", "probes_ms"):
+        for k in ("roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "gather_checksum_equal", "gather_matches_single_gpu", "particles", "combined_c5", "probes_ms", "resolve"):
             if k in result:
                 line[k] = result[k]
         print(json.dumps(line), flush=True)

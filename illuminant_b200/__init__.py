@@ -10,6 +10,6 @@ from .hdr import (DitheringSettings, GammaCompressionConfiguration, HDRConfigura
                   ToneMappingConfiguration, pack_resolve)
 from .particles import (FMA, AreaType, Attractor, AttractorType, Bezier4V, BezierF, FeedbackSpawner, Formula, FormulaType, Gravity, MatrixMultiply,
                         Noise, ParticleCollision, ParticleColorLifeRamp, ParticleEngine, ParticleEngineConfiguration, ParticleSystem,
-                        ParticleSystemConfiguration, Spawner, TransformArea)
+                        ParticleSystemConfiguration, PatternSpawner, Spawner, TransformArea)
 
 __version__ = "0.1.0"

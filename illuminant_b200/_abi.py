@@ -17,7 +17,7 @@ ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_INVALID_OPERATION, ERR_OUT_OF
 FORMAT_FLOAT4, FORMAT_HALF4, FORMAT_RGBA8 = 0, 1, 2
 LIGHT_SPHERE, LIGHT_DIRECTIONAL, LIGHT_PARTICLE, LIGHT_LINE = 1, 2, 3, 4
 HDR_NONE, HDR_GAMMA_COMPRESS, HDR_TONE_MAP = 0, 1, 2
-SPAWN_INLINE, SPAWN_POSITION_TEXTURE, SPAWN_FEEDBACK = 0, 1, 2
+SPAWN_INLINE, SPAWN_POSITION_TEXTURE, SPAWN_FEEDBACK, SPAWN_PATTERN = 0, 1, 2, 3
 OP_GRAVITY, OP_NOISE, OP_FMA, OP_MATRIX_MULTIPLY = 1, 2, 3, 4
 MAX_ATTRACTORS = 16
 FORMAT_BYTES = {FORMAT_FLOAT4: 16, FORMAT_HALF4: 8, FORMAT_RGBA8: 4}
@@ -143,7 +143,10 @@ class SpawnSource(C.Structure):  # ilb_spawn_source
     _fields_ = [("kind", C.c_int32), ("position_count", C.c_int32), ("positions", C.c_void_p), ("source_system", C.c_void_p),
                 ("source_chunk", C.c_int32), ("FeedbackSourceIndex", C.c_float), ("InstanceMultiplier", C.c_float),
                 ("SourceVelocityFactor", C.c_float), ("AlignPositionConstant", C.c_float), ("MultiplyLife", C.c_float),
-                ("MultiplyAttributeConstant", C.c_float), ("SourceLifeRange", C.c_float * 2), ("reserved", C.c_int32)]
+                ("MultiplyAttributeConstant", C.c_float), ("SourceLifeRange", C.c_float * 2), ("reserved", C.c_int32),
+                ("pattern_texels", C.c_void_p), ("pattern_width", C.c_int32), ("pattern_height", C.c_int32),
+                ("StepWidthAndSizeScale", Float4), ("YOffsetsAndCoordScale", Float4), ("TexelOffsetAndMipBias", Float4),
+                ("CenteringOffset", C.c_float * 2), ("reserved2", C.c_float * 2)]
 
 
 class IlluminantError(RuntimeError):

@@ -460,6 +460,7 @@ void ilb_particles_destroy(ilb_psys* ps) {
     if (ps->rng) cudaFree(ps->rng);
     if (ps->noise_table) cudaFree(ps->noise_table);
     if (ps->positions) cudaFree(ps->positions);
+    if (ps->pattern) cudaFree(ps->pattern);
     if (ps->life_ramp) cudaFree(ps->life_ramp);
     if (ps->d_count) cudaFree(ps->d_count);
     delete ps;

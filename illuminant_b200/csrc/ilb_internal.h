@@ -86,6 +86,8 @@ struct ilb_psys {
     int life_ramp_w = 0, life_ramp_h = 0;
     float4* positions = nullptr;    // PositionBuffer of an ILB_SPAWN_POSITION_TEXTURE spawn
     size_t positions_capacity = 0;
+    uint8_t* pattern = nullptr;     // packed mip chain of an ILB_SPAWN_PATTERN spawn's texture
+    size_t pattern_capacity = 0;
     float4* noise_table = nullptr;  // 2 * per_chunk float4, see noise_table_kernel
     unsigned long long* d_count = nullptr;
     bool use_tma = false;  // ILB_PARTICLE_TMA=1 selects the TMA-staged persistent step kernel (measured 22 % slower: the

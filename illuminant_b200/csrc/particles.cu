@@ -62,6 +62,7 @@ struct StepParams {
     const float4* noiseTable;  // fast chains: positionDelta[per_chunk] then velocityDelta[per_chunk] of the chain's Noise op (noise_table_kernel)
 };
 
+#define PATTERN_MAX_LEVELS 15  // up to 16384 x 16384
 struct SpawnParams {
     float4 *P, *V, *A;
     const float4* rng;
@@ -78,6 +79,13 @@ struct SpawnParams {
     float feedbackSourceIndex, instanceMultiplier, sourceVelocityFactor;
     int alignPositionConstant, multiplyLife, multiplyAttributeConstant;
     float sourceLifeMin, sourceLifeMax;
+    // PATTERN: packed mip chain of the pattern texture (Color texels) + the PatternSpawner uniforms
+    const uint8_t* pattern;
+    int pat_levels;
+    int pat_w[PATTERN_MAX_LEVELS], pat_h[PATTERN_MAX_LEVELS];
+    unsigned pat_off[PATTERN_MAX_LEVELS];  // texel offset of each level
+    float4 stepWidthAndSizeScale, yOffsetsAndCoordScale, texelOffsetAndMipBias;
+    float centeringX, centeringY;
 };
 
 // ---- randomness (RandomCommon.fxh:17-34): POINT sampled, WRAP/WRAP -------------------------------------------
@@ -785,6 +793,31 @@ ILB_DEV void evaluateRandomForIndex(const SpawnParams& P, float index, f4& rando
     if (s.AlignVelocityAndPosition != 0.0f) { random2.x = random1.x; random2.y = random1.y; }
 }
 
+// ---- PatternSpawner.fx: the pattern texture (Color, packed mip chain), LINEAR min/mag, POINT mip, CLAMP (:11-19) ----------
+__global__ void __launch_bounds__(256) pattern_mip_kernel(const uchar4* __restrict__ src, int pw, int ph, uchar4* __restrict__ dst, int nw, int nh) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= nw || y >= nh) return;
+    const int x0 = min(2 * x, pw - 1), x1 = min(2 * x + 1, pw - 1), y0 = min(2 * y, ph - 1), y1 = min(2 * y + 1, ph - 1);
+    const uchar4 a = src[(size_t)y0 * pw + x0], b = src[(size_t)y0 * pw + x1], c = src[(size_t)y1 * pw + x0], d = src[(size_t)y1 * pw + x1];
+    dst[(size_t)y * nw + x] = make_uchar4((unsigned char)((a.x + b.x + c.x + d.x + 2) >> 2), (unsigned char)((a.y + b.y + c.y + d.y + 2) >> 2),
+                                          (unsigned char)((a.z + b.z + c.z + d.z + 2) >> 2), (unsigned char)((a.w + b.w + c.w + d.w + 2) >> 2));
+}
+ILB_DEV f4 patternTexel(const SpawnParams& P, int l, int x, int y) {
+    x = min(max(x, 0), P.pat_w[l] - 1);
+    y = min(max(y, 0), P.pat_h[l] - 1);
+    const uchar4 t = reinterpret_cast<const uchar4*>(P.pattern)[(size_t)P.pat_off[l] + (size_t)y * P.pat_w[l] + x];
+    return mk4(xdiv((float)t.x, 255.0f), xdiv((float)t.y, 255.0f), xdiv((float)t.z, 255.0f), xdiv((float)t.w, 255.0f));
+}
+ILB_DEV f4 patternSample(const SpawnParams& P, float u, float v, float lod) {
+    const int l = min(max((int)floorf(xadd(lod, 0.5f)), 0), P.pat_levels - 1);
+    const float fx = xsub(xmul(u, (float)P.pat_w[l]), 0.5f), fy = xsub(xmul(v, (float)P.pat_h[l]), 0.5f);
+    const float x0 = floorf(fx), y0 = floorf(fy);
+    const float tx = xsub(fx, x0), ty = xsub(fy, y0);
+    const f4 top = xlerp4(patternTexel(P, l, (int)x0, (int)y0), patternTexel(P, l, (int)x0 + 1, (int)y0), tx);
+    const f4 bottom = xlerp4(patternTexel(P, l, (int)x0, (int)y0 + 1), patternTexel(P, l, (int)x0 + 1, (int)y0 + 1), tx);
+    return xlerp4(top, bottom, ty);
+}
+
 // One thread per texel of [first, last] of the target chunk.  KIND (ilb_spawn_kind) selects the pixel shader of
 // SpawnParticles.fx: PS_Spawn (:10-30), PS_SpawnFromPositionTexture (:32-52) or PS_SpawnFeedback (:54-120).
 template <int KIND>
@@ -797,6 +830,35 @@ __global__ void __launch_bounds__(STEP_THREADS) particle_spawn_kernel(const __gr
     if ((index < s.ChunkSizeAndIndices.y) || (index > s.ChunkSizeAndIndices.z)) return;
     const ilb_float4* C = s.Configuration;
     const size_t gi = (size_t)P.chunk_base + (size_t)li;
+
+    if (KIND == ILB_SPAWN_PATTERN) {  // PS_SpawnPattern, PatternSpawner.fx:21-96
+        const float relativeIndex = floorf(xsub(index, s.ChunkSizeAndIndices.y));
+        const float particlesPerRow = P.stepWidthAndSizeScale.y;
+        const float ix = floorf(fmodf(relativeIndex, particlesPerRow));
+        const float iy = xadd(floorf(xdiv(relativeIndex, particlesPerRow)), P.yOffsetsAndCoordScale.x);
+        const float u = xadd(xmul(ix, P.stepWidthAndSizeScale.z), P.texelOffsetAndMipBias.x);
+        const float v = xadd(xadd(xmul(iy, P.stepWidthAndSizeScale.w), P.texelOffsetAndMipBias.y), P.yOffsetsAndCoordScale.y);
+        const float px = xadd(xmul(ix, P.yOffsetsAndCoordScale.z), P.centeringX), py = xadd(xmul(iy, P.yOffsetsAndCoordScale.w), P.centeringY);
+        if ((u > 1.0f) || (v > 1.0f)) return;  // the next-power-of-two padding of the spawn rectangle (:50-53)
+        const f4 patternColor = patternSample(P, u, v, P.texelOffsetAndMipBias.w);
+        f4 random1, random2, random3;
+        evaluateRandomForIndex(P, index, random1, random2, random3);
+        f4 tempPosition = evaluateFormula(s, mk4(0.0f), mk4(s.InlinePositionConstants[0]), mk4(C[0]), mk4(C[1]), random1, s.FormulaTypes.x);
+        tempPosition.x = xadd(tempPosition.x, px);
+        tempPosition.y = xadd(tempPosition.y, py);
+        const f4 attributeConstant = P.multiplyAttributeConstant ? xmul4(patternColor, mk4(C[5])) : xadd4(patternColor, mk4(C[5]));
+        f4 newPosition = xmul_rm(mk4(tempPosition.x, tempPosition.y, tempPosition.z, 1.0f), s.PositionMatrix);
+        newPosition.w = tempPosition.w;
+        const f4 tempVelocity = evaluateFormula(s, tempPosition, mk4(C[2]), mk4(C[3]), mk4(C[4]), random2, s.FormulaTypes.y);
+        f4 newVelocity = xmul_rm(mk4(tempVelocity.x, tempVelocity.y, tempVelocity.z, 1.0f), s.VelocityMatrix);
+        newVelocity.w = tempVelocity.w;
+        const f4 newAttributes = evaluateFormula(s, tempPosition, attributeConstant, mk4(C[6]), mk4(C[7]), random3, s.FormulaTypes.z);
+        if (newAttributes.w < s.AttributeDiscardThreshold) return;
+        P.P[gi] = to_float4(newPosition);
+        P.V[gi] = to_float4(newVelocity);
+        P.A[gi] = to_float4(newAttributes);
+        return;
+    }
 
     if (KIND == ILB_SPAWN_FEEDBACK) {
         // the source particle: texel (floor(sourceX), sourceY) of the source chunk, CLAMP addressing (:69-79)
@@ -915,7 +977,7 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
             const ilb_spawn& s = spawns[si];
             if (s.chunk < 0 || s.chunk >= ps->live_chunks) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: chunk %d is not live", si, s.chunk);
             const int kind = sources ? sources[si].kind : ILB_SPAWN_INLINE;
-            if (kind < ILB_SPAWN_INLINE || kind > ILB_SPAWN_FEEDBACK) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: unknown source kind %d", si, kind);
+            if (kind < ILB_SPAWN_INLINE || kind > ILB_SPAWN_PATTERN) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: unknown source kind %d", si, kind);
             if (s.PositionConstantCount < 1.0f || (kind == ILB_SPAWN_INLINE && s.PositionConstantCount > 4.0f))
                 return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: 1..4 inline positions (more need an ILB_SPAWN_POSITION_TEXTURE source, ParticleSpawner.cs:331-352)", si);
             if ((int)s.ChunkSizeAndIndices.x != ps->chunk_size) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: ChunkSize mismatch", si);
@@ -946,6 +1008,40 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
                 ILB_CUDA(ctx, cudaMemcpyAsync(ps->positions, src.positions, bytes, cudaMemcpyHostToDevice, ctx->stream));
                 SP.positions = ps->positions; SP.position_count = src.position_count;
                 particle_spawn_kernel<ILB_SPAWN_POSITION_TEXTURE><<<sgrid, STEP_THREADS, 0, ctx->stream>>>(SP);
+            } else if (kind == ILB_SPAWN_PATTERN) {
+                const ilb_spawn_source& src = sources[si];
+                if (!src.pattern_texels || src.pattern_width < 1 || src.pattern_height < 1 || src.pattern_width > 16384 || src.pattern_height > 16384)
+                    return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: bad pattern texture %dx%d", si, src.pattern_width, src.pattern_height);
+                if (!(src.StepWidthAndSizeScale.y >= 1.0f)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: ParticlesPerRow must be >= 1", si);
+                size_t texels = 0;
+                int lw = src.pattern_width, lh = src.pattern_height, levels = 0;
+                for (;;) {
+                    SP.pat_w[levels] = lw; SP.pat_h[levels] = lh; SP.pat_off[levels] = (unsigned)texels;
+                    texels += (size_t)lw * lh;
+                    levels++;
+                    if ((lw == 1 && lh == 1) || levels == PATTERN_MAX_LEVELS) break;
+                    lw = lw > 1 ? lw / 2 : 1; lh = lh > 1 ? lh / 2 : 1;
+                }
+                SP.pat_levels = levels;
+                if (ps->pattern_capacity < texels * 4) {
+                    if (ps->pattern) { ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ps->pattern); ps->pattern = nullptr; ps->pattern_capacity = 0; }
+                    ILB_CUDA(ctx, cudaMalloc(&ps->pattern, texels * 4));
+                    ps->pattern_capacity = texels * 4;
+                }
+                ILB_CUDA(ctx, cudaMemcpyAsync(ps->pattern, src.pattern_texels, (size_t)src.pattern_width * src.pattern_height * 4, cudaMemcpyHostToDevice, ctx->stream));
+                for (int l = 1; l < levels; l++) {
+                    pattern_mip_kernel<<<dim3((SP.pat_w[l] + 255) / 256, SP.pat_h[l]), 256, 0, ctx->stream>>>(
+                        reinterpret_cast<const uchar4*>(ps->pattern) + SP.pat_off[l - 1], SP.pat_w[l - 1], SP.pat_h[l - 1],
+                        reinterpret_cast<uchar4*>(ps->pattern) + SP.pat_off[l], SP.pat_w[l], SP.pat_h[l]);
+                    ctx->launches++;
+                }
+                SP.pattern = ps->pattern;
+                SP.stepWidthAndSizeScale = make_float4(src.StepWidthAndSizeScale.x, src.StepWidthAndSizeScale.y, src.StepWidthAndSizeScale.z, src.StepWidthAndSizeScale.w);
+                SP.yOffsetsAndCoordScale = make_float4(src.YOffsetsAndCoordScale.x, src.YOffsetsAndCoordScale.y, src.YOffsetsAndCoordScale.z, src.YOffsetsAndCoordScale.w);
+                SP.texelOffsetAndMipBias = make_float4(src.TexelOffsetAndMipBias.x, src.TexelOffsetAndMipBias.y, src.TexelOffsetAndMipBias.z, src.TexelOffsetAndMipBias.w);
+                SP.centeringX = src.CenteringOffset[0]; SP.centeringY = src.CenteringOffset[1];
+                SP.multiplyAttributeConstant = src.MultiplyAttributeConstant != 0.0f;
+                particle_spawn_kernel<ILB_SPAWN_PATTERN><<<sgrid, STEP_THREADS, 0, ctx->stream>>>(SP);
             } else if (kind == ILB_SPAWN_FEEDBACK) {
                 const ilb_spawn_source& src = sources[si];
                 ilb_psys* from = src.source_system;

@@ -378,6 +378,7 @@ class Spawner(ParticleTransform):  # ParticleSpawner.cs:14-419
         currentRate = ((float(self._rng.random()) * (maxRate - minRate)) + minRate) * self.CountScale * deltaTimeSeconds
         currentRate += self.RateError
         self.RateError = 0.0
+        currentRate = self._adjust_current_rate(currentRate)
         if currentRate < 1:
             self.RateError = max(currentRate, 0.0)
             spawnCount = 0
@@ -390,6 +391,9 @@ class Spawner(ParticleTransform):  # ParticleSpawner.cs:14-419
                 spawnCount = remaining
                 self.RateError = 0.0
         return spawnCount
+
+    def _adjust_current_rate(self, rate: float) -> float:  # AdjustCurrentRate :143-145
+        return rate
 
     def EndTick(self, requested: int, actual: int):  # :191-194
         self.RateError += requested - actual
@@ -530,6 +534,122 @@ class FeedbackSpawner(Spawner):  # SpecialSpawners.cs:266-437 (derives from Spaw
         src.MultiplyLife = 1.0 if self.MultiplyLife else 0.0
         src.MultiplyAttributeConstant = 1.0 if self.MultiplyColorConstant else 0.0
         src.SourceLifeRange[:] = [float(self.SourceLifeRange[0]), float(self.SourceLifeRange[1])]
+        self._source = src
+        return s
+
+
+def _next_power_of_two(v: int) -> int:  # Squared.Util.Arithmetic.NextPowerOfTwo (un-vendored sq/Fracture): smallest 2^k >= v
+    v = int(v)
+    return 0 if v <= 0 else 1 << (v - 1).bit_length()
+
+
+@dataclass
+class PatternSpawner(Spawner):  # SpecialSpawners.cs:15-262 (derives from SpawnerBase)
+    """One particle per `Divisor`-th pixel of `Texture` (uint8 [H, W, 4], SurfaceFormat.Color), coloured by the pixel."""
+    Texture: Optional[np.ndarray] = None
+    TextureTopLeftPx: Optional[Tuple[float, float]] = None
+    TextureSizePx: Optional[Tuple[float, float]] = None
+    MipBiasBase: float = -0.5
+    Divisor: int = 1
+    WholeSpawn: bool = False
+    InstantInitialSpawn: bool = True
+    MultiplyColorConstant: bool = True
+
+    PartialSpawnAllowed = False      # :137-141
+
+    def __post_init__(self):
+        super().__post_init__()
+        self.RowsSpawned = 0
+        self.Divisor = min(max(int(self.Divisor), 1), 10)     # :45-52
+
+    @property
+    def IsValid(self) -> bool:
+        return self.Texture is not None
+
+    @property
+    def DirectTextureSize(self) -> Tuple[float, float]:  # :76-97
+        if self.Texture is None:
+            return (0.0, 0.0)
+        w, h = float(self.Texture.shape[1]), float(self.Texture.shape[0])
+        if self.TextureSizePx is not None:
+            if self.TextureSizePx[0] > 0:
+                w = float(self.TextureSizePx[0])
+            if self.TextureSizePx[1] > 0:
+                h = float(self.TextureSizePx[1])
+        if self.TextureTopLeftPx is not None:
+            w, h = w - self.TextureTopLeftPx[0], h - self.TextureTopLeftPx[1]
+        return (w, h)
+
+    @property
+    def ParticlesPerRow(self) -> int:   # :111-115
+        return _next_power_of_two(int(self.DirectTextureSize[0]) // self.Divisor)
+
+    @property
+    def RowsPerInstance(self) -> int:   # :117-121
+        return _next_power_of_two(int(self.DirectTextureSize[1]) // self.Divisor)
+
+    @property
+    def ParticlesPerInstance(self) -> int:
+        return self.ParticlesPerRow * self.RowsPerInstance
+
+    @property
+    def CountScale(self) -> int:        # :129-136
+        return self.ParticlesPerInstance if self.WholeSpawn else self.ParticlesPerRow
+
+    def _adjust_current_rate(self, rate: float) -> float:   # AdjustCurrentRate :148-166
+        if self.WholeSpawn and self.TotalSpawned == 0 and (self.MaximumTotal or 0) > 0 and rate >= 1 and self.InstantInitialSpawn:
+            result = max(self.ParticlesPerInstance, rate)
+            self.RateError += rate - result
+            return result
+        return rate
+
+    def BeginTick(self, now: float, deltaTimeSeconds: float) -> int:  # :168-194
+        if self.Texture is None:
+            return 0
+        spawnCount = Spawner.BeginTick(self, now, deltaTimeSeconds)
+        minCount = self.ParticlesPerInstance if self.WholeSpawn else self.ParticlesPerRow
+        if minCount <= 0:
+            return 0
+        requested = spawnCount
+        if spawnCount < minCount:
+            self.RateError += spawnCount
+            return 0
+        spawnCount = (spawnCount // minCount) * minCount
+        self.RateError += requested - spawnCount
+        return spawnCount
+
+    def pack(self, system, now, chunk: int) -> Spawn:  # SetParameters :196-249 on top of SpawnerBase.SetParameters
+        saved = self.AdditionalPositions, self.PolygonRate
+        self.AdditionalPositions, self.PolygonRate = [], None
+        try:
+            s = Spawner.pack(self, system, now, chunk)
+        finally:
+            self.AdditionalPositions, self.PolygonRate = saved
+        s.ChunkSizeAndIndices = Float4(system.Engine.Configuration.ChunkSize, self.Indices[0], self.Indices[1], 0)
+        s.Configuration[8] = Float4(0, 0, 0, 0)
+        s.PolygonLoop = 0.0
+        tex = np.ascontiguousarray(self.Texture, dtype=np.uint8)
+        th, tw = tex.shape[0], tex.shape[1]
+        if self.WholeSpawn:
+            currentRow, self.RowsSpawned = 0, 0
+        else:
+            currentRow = self.RowsSpawned % self.RowsPerInstance
+            self.RowsSpawned += 1
+        d = self.Divisor
+        src = SpawnSource()
+        src.kind = _abi.SPAWN_PATTERN
+        src.pattern_texels, src.pattern_width, src.pattern_height = tex.ctypes.data, tw, th
+        self._pattern_texels = tex      # keeps the host array alive until the step call returns
+        src.StepWidthAndSizeScale = Float4(d, self.ParticlesPerRow, F(d) / F(tw), F(d) / F(th))
+        baseX = baseY = F(0)
+        if self.TextureTopLeftPx is not None:
+            baseX, baseY = F(self.TextureTopLeftPx[0]) / F(tw), F(self.TextureTopLeftPx[1]) / F(th)
+        # (currentRow * Divisor) / tex.Height is an INTEGER division in the reference (:231-234)
+        src.YOffsetsAndCoordScale = Float4(currentRow, (currentRow * d) // th, d, d)
+        src.TexelOffsetAndMipBias = Float4(F(-0.5) / F(tw) + baseX, F(-0.5) / F(th) + baseY, 0, F(math.log(d, 2)) + F(self.MipBiasBase))
+        dts = self.DirectTextureSize
+        src.CenteringOffset[:] = [float(F(dts[0]) * F(-0.5)), float(F(dts[1]) * F(-0.5))]
+        src.MultiplyAttributeConstant = 1.0 if self.MultiplyColorConstant else 0.0
         self._source = src
         return s
 
@@ -759,10 +879,15 @@ class ParticleSystem:
                 if requested <= 0:
                     break
                 spawnCount = min(requested, self.ChunkMaximumCount)
-                chunk = self._pick_target_for_spawn(feedback, spawnCount, True)
+                partial = bool(getattr(t, "PartialSpawnAllowed", True))
+                chunk = self._pick_target_for_spawn(feedback, spawnCount, partial)
                 if chunk < 0:
                     break
-                spawnCount = min(spawnCount, self.ChunkMaximumCount - self._chunk_next_offset[chunk])
+                free = self.ChunkMaximumCount - self._chunk_next_offset[chunk]
+                if spawnCount > free:          # ParticleSpawning.cs:144-149
+                    if not partial:
+                        break
+                    spawnCount = free
                 first = self._chunk_next_offset[chunk]
                 t.Indices = (first, first + spawnCount - 1)
                 self._chunk_next_offset[chunk] += spawnCount

@@ -378,7 +378,8 @@ typedef struct ilb_spawn { /* one RunSpawner draw (ParticleSpawning.cs:115-197; 
 typedef enum ilb_spawn_kind {
     ILB_SPAWN_INLINE = 0,            /* PS_Spawn, SpawnParticles.fx:10-30: positions from ilb_spawn.InlinePositionConstants */
     ILB_SPAWN_POSITION_TEXTURE = 1,  /* PS_SpawnFromPositionTexture, :32-52 */
-    ILB_SPAWN_FEEDBACK = 2           /* PS_SpawnFeedback, :54-120 */
+    ILB_SPAWN_FEEDBACK = 2,          /* PS_SpawnFeedback, :54-120 */
+    ILB_SPAWN_PATTERN = 3            /* PS_SpawnPattern, PatternSpawner.fx:21-96 (PatternSpawner, SpecialSpawners.cs:15-262) */
 } ilb_spawn_kind;
 typedef struct ilb_spawn_source {
     int32_t kind;                 /* ilb_spawn_kind */
@@ -393,6 +394,19 @@ typedef struct ilb_spawn_source {
     float AlignPositionConstant, MultiplyLife, MultiplyAttributeConstant; /* 0 / 1 */
     float SourceLifeRange[2];
     int32_t reserved;
+    /* PATTERN: one particle per `Divisor`-th pixel of a texture.  pattern_texels is the HOST level-0 image, SurfaceFormat.Color
+     * (pattern_width*pattern_height*4 bytes, row-major); the mip chain the shader's tex2Dlod addresses through
+     * TexelOffsetAndMipBias.w = log2(Divisor) + MipBiasBase is built on the device with a rounding 2x2 box filter.  Sampler as
+     * declared in PatternSpawner.fx:11-19: LINEAR min/mag, POINT mip (level = floor(lod + 0.5) clamped), CLAMP addressing.
+     * The four uniforms are the ones PatternSpawner.SetParameters computes (SpecialSpawners.cs:196-249);
+     * MultiplyAttributeConstant (above) = MultiplyColorConstant. */
+    const uint8_t* pattern_texels;
+    int32_t pattern_width, pattern_height;
+    ilb_float4 StepWidthAndSizeScale;  /* Divisor, ParticlesPerRow, Divisor / tex.Width, Divisor / tex.Height */
+    ilb_float4 YOffsetsAndCoordScale;  /* currentRow, currentRow * Divisor / tex.Height, Divisor, Divisor */
+    ilb_float4 TexelOffsetAndMipBias;  /* -0.5 / tex.Width + baseX, -0.5 / tex.Height + baseY, 0, log2(Divisor) + MipBiasBase */
+    float CenteringOffset[2];
+    float reserved2[2];
 } ilb_spawn_source;
 
 /* ParticleSystem storage: max_chunks chunks of chunk_size^2 particles (ParticleSystem.cs:73-240). */

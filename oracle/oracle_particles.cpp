@@ -11,6 +11,7 @@
 #include <omp.h>
 
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "../include/illuminant_b200.h"
@@ -382,6 +383,96 @@ bool PS_SpawnFeedback(const ilb_spawn& s, const ilb_spawn_source& f, const float
     return true;
 }
 
+// ---- PatternSpawner.fx.  The pattern texture with its mip chain: SurfaceFormat.Color levels, level k+1 = rounding 2x2 box
+// filter of level k (the reference's mips come from its content loader; un-pinned).
+struct PatternTexture {
+    std::vector<std::vector<uint8_t>> levels;
+    std::vector<int> w, h;
+    PatternTexture(const uint8_t* texels, int w0, int h0) {
+        levels.emplace_back(texels, texels + (size_t)w0 * h0 * 4);
+        w.push_back(w0); h.push_back(h0);
+        while (w.back() > 1 || h.back() > 1) {
+            const int pw = w.back(), ph = h.back(), nw = pw > 1 ? pw / 2 : 1, nh = ph > 1 ? ph / 2 : 1;
+            const std::vector<uint8_t>& src = levels.back();
+            std::vector<uint8_t> dst((size_t)nw * nh * 4);
+            for (int y = 0; y < nh; y++)
+                for (int x = 0; x < nw; x++) {
+                    const int x0 = 2 * x < pw ? 2 * x : pw - 1, x1 = 2 * x + 1 < pw ? 2 * x + 1 : pw - 1;
+                    const int y0 = 2 * y < ph ? 2 * y : ph - 1, y1 = 2 * y + 1 < ph ? 2 * y + 1 : ph - 1;
+                    for (int c = 0; c < 4; c++) {
+                        const unsigned sum = src[((size_t)y0 * pw + x0) * 4 + c] + src[((size_t)y0 * pw + x1) * 4 + c] +
+                                             src[((size_t)y1 * pw + x0) * 4 + c] + src[((size_t)y1 * pw + x1) * 4 + c];
+                        dst[((size_t)y * nw + x) * 4 + c] = (uint8_t)((sum + 2) >> 2);
+                    }
+                }
+            levels.push_back(std::move(dst));
+            w.push_back(nw); h.push_back(nh);
+        }
+    }
+    float4 texel(int l, int x, int y) const {
+        x = x < 0 ? 0 : (x >= w[l] ? w[l] - 1 : x);
+        y = y < 0 ? 0 : (y >= h[l] ? h[l] - 1 : y);
+        const uint8_t* t = &levels[l][((size_t)y * w[l] + x) * 4];
+        return float4(t[0] / 255.0f, t[1] / 255.0f, t[2] / 255.0f, t[3] / 255.0f);
+    }
+    // tex2Dlod with PatternSampler (PatternSpawner.fx:11-19): LINEAR min/mag, POINT mip, CLAMP
+    float4 sample(float2 uv, float lod) const {
+        int l = (int)floorf(lod + 0.5f);
+        l = l < 0 ? 0 : (l >= (int)levels.size() ? (int)levels.size() - 1 : l);
+        const float fx = uv.x * (float)w[l] - 0.5f, fy = uv.y * (float)h[l] - 0.5f;
+        const float x0 = floorf(fx), y0 = floorf(fy);
+        const float tx = fx - x0, ty = fy - y0;
+        const float4 top = lerp(texel(l, (int)x0, (int)y0), texel(l, (int)x0 + 1, (int)y0), tx);
+        const float4 bottom = lerp(texel(l, (int)x0, (int)y0 + 1), texel(l, (int)x0 + 1, (int)y0 + 1), tx);
+        return lerp(top, bottom, ty);
+    }
+};
+
+// PS_SpawnPattern PatternSpawner.fx:21-96
+bool PS_SpawnPattern(const ilb_spawn& s, const ilb_spawn_source& f, const PatternTexture& tex, const Randomness& rng, float2 xy,
+                     float4& newPosition, float4& newVelocity, float4& newAttributes) {
+    float4 csi = f4(s.ChunkSizeAndIndices);
+    float index = floorf(xy.x) + (floorf(xy.y) * csi.x);
+    if ((index < csi.y) || (index > csi.z)) return false;
+
+    float relativeIndex = floorf(index - csi.y);
+    float particlesPerRow = f.StepWidthAndSizeScale.y;
+    float2 indexXy = float2(floorf(fmod(relativeIndex, particlesPerRow)), floorf(relativeIndex / particlesPerRow));
+    indexXy.y += f.YOffsetsAndCoordScale.x;
+    float2 texCoordXy = (indexXy * float2(f.StepWidthAndSizeScale.z, f.StepWidthAndSizeScale.w)) + float2(f.TexelOffsetAndMipBias.x, f.TexelOffsetAndMipBias.y);
+    texCoordXy.y += f.YOffsetsAndCoordScale.y;
+    float2 positionXy = indexXy * float2(f.YOffsetsAndCoordScale.z, f.YOffsetsAndCoordScale.w) + float2(f.CenteringOffset[0], f.CenteringOffset[1]);
+    if ((texCoordXy.x > 1) || (texCoordXy.y > 1)) return false;
+
+    float4 patternColor = tex.sample(texCoordXy, f.TexelOffsetAndMipBias.w);
+
+    float4 random1, random2, random3;
+    evaluateRandomForIndex(s, rng, index, random1, random2, random3);
+
+    const ilb_float4* C = s.Configuration;
+    float4 ft = f4(s.FormulaTypes);
+    float4 positionConstant = f4(s.InlinePositionConstants[0]);
+    float4 tempPosition = evaluateFormula(s, float4(0.0f), positionConstant, f4(C[0]), f4(C[1]), random1, ft.x);
+    tempPosition.x += positionXy.x;
+    tempPosition.y += positionXy.y;
+
+    float4 attributeConstant = patternColor;
+    if (f.MultiplyAttributeConstant != 0) attributeConstant *= f4(C[5]);
+    else attributeConstant += f4(C[5]);
+
+    newPosition = mul(float4(tempPosition.xyz(), 1), s.PositionMatrix);
+    newPosition.w = tempPosition.w;
+
+    float4 velocityConstant = f4(C[2]);
+    float4 tempVelocity = evaluateFormula(s, tempPosition, velocityConstant, f4(C[3]), f4(C[4]), random2, ft.y);
+    newVelocity = mul(float4(tempVelocity.xyz(), 1), s.VelocityMatrix);
+    newVelocity.w = tempVelocity.w;
+
+    newAttributes = evaluateFormula(s, tempPosition, attributeConstant, f4(C[6]), f4(C[7]), random3, ft.z);
+    if (newAttributes.w < s.AttributeDiscardThreshold) return false;
+    return true;
+}
+
 // ---------------------------------------------------------------- transforms
 void PS_Gravity(const System& sys, const ilb_gravity& g, float4& newPosition, float4 oldVelocity, float4& newVelocity) {  // Gravity.fx:12-61
     if ((newPosition.w <= 0) || !checkCategoryFilter(oldVelocity.w, g.CategoryFilter)) {
@@ -716,6 +807,9 @@ int orc_particles_step_sources(float* P, float* V, float* A, float* RC, float* R
             if (kind == ILB_SPAWN_INLINE && s.PositionConstantCount > 4) return ILB_ERR_UNSUPPORTED;
             if (kind == ILB_SPAWN_POSITION_TEXTURE && (!sources[si].positions || sources[si].position_count < 1)) return ILB_ERR_INVALID_ARGUMENT;
             if (kind == ILB_SPAWN_FEEDBACK && (!states || !states[si].P || states[si].chunk_size < 1)) return ILB_ERR_INVALID_ARGUMENT;
+            if (kind == ILB_SPAWN_PATTERN && (!sources[si].pattern_texels || sources[si].pattern_width < 1 || sources[si].pattern_height < 1)) return ILB_ERR_INVALID_ARGUMENT;
+            std::unique_ptr<PatternTexture> pattern;
+            if (kind == ILB_SPAWN_PATTERN) pattern.reset(new PatternTexture(sources[si].pattern_texels, sources[si].pattern_width, sources[si].pattern_height));
             const size_t base = per * s.chunk;
 #pragma omp parallel for schedule(static)
             for (long i = 0; i < (long)per; i++) {
@@ -724,6 +818,8 @@ int orc_particles_step_sources(float* P, float* V, float* A, float* RC, float* R
                 bool spawned;
                 if (kind == ILB_SPAWN_POSITION_TEXTURE)
                     spawned = PS_SpawnFromPositionTexture(s, &sources[si].positions[0].x, sources[si].position_count, rng, xy, np, nv, na);
+                else if (kind == ILB_SPAWN_PATTERN)
+                    spawned = PS_SpawnPattern(s, sources[si], *pattern, rng, xy, np, nv, na);
                 else if (kind == ILB_SPAWN_FEEDBACK)
                     spawned = PS_SpawnFeedback(s, sources[si], states[si].P, states[si].V, states[si].RC, states[si].chunk_size, rng, xy, np, nv, na);
                 else

@@ -58,7 +58,7 @@ def test_struct_layouts_match_the_header(tmp_path):
              "ilb_op": _abi.Op, "ilb_spawn": _abi.Spawn, "ilb_resolve": _abi.Resolve, "ilb_spawn_source": _abi.SpawnSource}
     probes = {"ilb_lighting_frame": ["ClearColor", "ViewportPosition", "stencil_culling"], "ilb_psys_uniforms": ["CollisionField", "has_collision_field"],
               "ilb_spawn": ["AttributeDiscardThreshold", "PositionMatrix"], "ilb_noise": ["VelocityScale", "RandomnessTexel"], "ilb_op": ["u"],
-              "ilb_light_batch": ["df"], "ilb_spawn_source": ["positions", "source_system", "source_chunk", "SourceLifeRange"], "ilb_resolve": ["InverseScaleFactor", "WhitePoint", "DitheringStrength"], "ilb_gravity": ["AttractorRadiusesAndStrengths"]}
+              "ilb_light_batch": ["df"], "ilb_spawn_source": ["positions", "source_system", "source_chunk", "SourceLifeRange", "pattern_texels", "StepWidthAndSizeScale", "CenteringOffset"], "ilb_resolve": ["InverseScaleFactor", "WhitePoint", "DitheringStrength"], "ilb_gravity": ["AttractorRadiusesAndStrengths"]}
     src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
     for n in names:
         src.append(f'printf("{n} %zu\\n", sizeof({n}));')

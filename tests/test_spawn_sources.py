@@ -198,3 +198,89 @@ def test_gpu_spawn_source_errors(ctx):
     with pytest.raises(ib.IlluminantError) as e:         # 6 positions without the position texture
         system.step_packed(u, spawns, [], 1, None)
     assert e.value.code == _abi.ERR_INVALID_ARGUMENT
+
+
+# ------------------------------------------------------------------------------------------------ PatternSpawner
+def _pattern_texture(w, h, seed=5):
+    rs = np.random.RandomState(seed)
+    t = rs.randint(0, 256, size=(h, w, 4), dtype=np.uint8)
+    t[..., 3] = np.where(rs.rand(h, w) < 0.2, 0, 255)      # transparent pixels spawn nothing (alpha below the discard threshold)
+    return t
+
+
+def test_pattern_spawner_known_answers(oracle):
+    engine = _engine()
+    system = _system(engine)
+    tex = _pattern_texture(8, 4)
+    sp = ib.PatternSpawner(MinRate=120, MaxRate=120, MaximumTotal=1, Texture=tex, WholeSpawn=True, Divisor=1,
+                           Position=ib.Formula(Constant=(100.0, 50.0, 0.0)), Velocity=ib.Formula(Type=ib.FormulaType.Linear),
+                           Life=(3.0, 0, 0), ColorConstant=(1.0, 0.5, 1.0, 1.0), AlphaDiscardThreshold=1.0)
+    assert (sp.ParticlesPerRow, sp.RowsPerInstance, sp.CountScale) == (8, 4, 32)
+    spawns, sources, u = _plan(system, sp)
+    assert len(spawns) == 1 and sources[0].kind == _abi.SPAWN_PATTERN
+    s, src = spawns[0], sources[0]
+    assert (s.ChunkSizeAndIndices.y, s.ChunkSizeAndIndices.z) == (0, 31) and sp.RateError == 0      # the instant whole spawn (:148-166)
+    assert src.StepWidthAndSizeScale.tuple() == (1, 8, 1 / 8, 1 / 4) and tuple(src.CenteringOffset) == (-4.0, -2.0)
+    assert src.TexelOffsetAndMipBias.tuple() == (-0.5 / 8, -0.5 / 4, 0, -0.5) and src.YOffsetsAndCoordScale.tuple() == (0, 0, 1, 1)
+    Z = np.zeros((PER, 4), np.float32)
+    P, V, A, _, _ = oracle.particles_step(Z, Z, Z, CS, u, spawns, [], engine.RandomnessTexture, sources=sources)
+    ix, iy = np.arange(32) % 8, np.arange(32) // 8
+    # texCoord = index / size - half a texel: exactly the centre of texel (index - 1), CLAMP at the border
+    texel = tex[np.maximum(iy - 1, 0), np.maximum(ix - 1, 0)].astype(np.float32) / np.float32(255)
+    spawned = texel[:, 3] >= 1 / 255
+    assert np.array_equal(P[:32, 3] > 0, spawned)
+    want = np.stack([100.0 + ix - 4.0, 50.0 + iy - 2.0, 0 * ix], 1)
+    assert np.allclose(P[:32][spawned][:, :3], want[spawned]) and np.all(P[:32][spawned][:, 3] == 3.0)
+    assert np.allclose(A[:32][spawned], texel[spawned] * np.array([1.0, 0.5, 1.0, 1.0], np.float32), rtol=1e-6)
+    assert system.plan_spawns(2.0, 1 / 60.0) == []             # MaximumTotal reached
+
+
+def test_pattern_spawner_rows_and_rates():
+    engine = _engine()
+    system = _system(engine)
+    tex = _pattern_texture(20, 12)
+    sp = ib.PatternSpawner(MinRate=60, MaxRate=60, Texture=tex, Divisor=2, TextureTopLeftPx=(2, 2))
+    assert sp.DirectTextureSize == (18.0, 10.0) and (sp.ParticlesPerRow, sp.RowsPerInstance) == (16, 8)
+    system.Transforms = [sp]
+    rows = []
+    for k in range(10):
+        spawns = system.plan_spawns(k / 60.0, 1 / 60.0)       # 60/s * CountScale 16 / 60 = one row per frame
+        assert len(spawns) == 1 and spawns[0].ChunkSizeAndIndices.z - spawns[0].ChunkSizeAndIndices.y == 15
+        src = system.last_sources[0]
+        rows.append(int(src.YOffsetsAndCoordScale.x))
+        assert src.TexelOffsetAndMipBias.w == pytest.approx(0.5) and src.StepWidthAndSizeScale.tuple() == (2, 16, pytest.approx(0.1), pytest.approx(1 / 6))
+        assert src.TexelOffsetAndMipBias.x == pytest.approx(-0.5 / 20 + 2 / 20)
+    assert rows == [0, 1, 2, 3, 4, 5, 6, 7, 0, 1]               # RowsSpawned % RowsPerInstance (:205-209)
+    # a row never straddles a chunk: PartialSpawnAllowed is false (:137-141) -- 1024 / 16 = 64 rows fill chunk 0 exactly
+    for k in range(10, 70):
+        system.plan_spawns(k / 60.0, 1 / 60.0)
+    assert system.LiveChunkCount == 2 and system._chunk_next_offset == [1024, 96]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,divisor,whole,topleft,multiply", [(8, 4, 1, True, None, True), (20, 12, 2, False, (2, 2), False),
+                                                               (64, 48, 3, True, None, True), (31, 17, 4, False, (1, 0), True)])
+def test_gpu_pattern_spawner(ctx, oracle, w, h, divisor, whole, topleft, multiply):
+    engine = _engine(ctx)
+    system = _system(engine, max_chunks=3)
+    tex = _pattern_texture(w, h, seed=w + divisor)
+    sp = ib.PatternSpawner(MinRate=600, MaxRate=600, Texture=tex, WholeSpawn=whole, Divisor=divisor, TextureTopLeftPx=topleft,
+                           MultiplyColorConstant=multiply, Position=ib.Formula(Constant=(300.0, 200.0, 4.0), RandomScale=(1.5, 1.5, 0.0)),
+                           Velocity=ib.Formula(Constant=(0, 0, 0), RandomScale=(12, 12, 3), Type=ib.FormulaType.Spherical),
+                           Life=(2.0, 1.0, 0), ColorConstant=(0.8, 0.9, 1.0, 1.0) if multiply else (0.05, 0.0, 0.1, 0.0),
+                           ColorRandomScale=(0.1, 0.1, 0.1, 0.0), AlphaDiscardThreshold=8.0)
+    P = V = A = np.zeros((0, 4), np.float32)
+    now, total = 0.0, 0
+    for _ in range(4):
+        now += 1 / 60.0
+        spawns, sources, u = _plan(system, sp, now)
+        total += len(spawns)
+        live = system.LiveChunkCount
+        if P.shape[0] < live * PER:
+            P, V, A = (np.concatenate([a, np.zeros((live * PER - a.shape[0], 4), np.float32)]) for a in (P, V, A))
+        system.step_packed(u, spawns, [], 1, sources)
+        P, V, A, RC, RD = oracle.particles_step(P, V, A, CS, u, spawns, [], engine.RandomnessTexture, sources=sources)
+    assert total >= 1
+    gpu = [np.concatenate(x) for x in zip(*[system.ReadChunk(c) for c in range(system.LiveChunkCount)])]
+    assert (gpu[0][:, 3] > 0).sum() == (P[:, 3] > 0).sum() > 0
+    _check(gpu, (P, V, A, RC, RD), f"pattern {w}x{h} /{divisor}")
