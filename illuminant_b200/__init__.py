@@ -9,7 +9,7 @@ from .lighting import (DirectionalLightSource, LightingEnvironment, LightingRend
 from .hdr import (DitheringSettings, GammaCompressionConfiguration, HDRConfiguration, HDRMode, Histogram, RenderedLighting,
                   ToneMappingConfiguration, pack_resolve)
 from .particles import (FMA, AreaType, Attractor, AttractorType, Bezier4V, BezierF, FeedbackSpawner, Formula, FormulaType, Gravity, MatrixMultiply,
-                        Noise, ParticleCollision, ParticleColorLifeRamp, ParticleEngine, ParticleEngineConfiguration, ParticleSystem,
+                        Noise, ParticleAppearance, ParticleCollision, ParticleColorLifeRamp, ParticleEngine, ParticleEngineConfiguration, ParticleRenderParameters, ParticleSystem,
                         ParticleSystemConfiguration, PatternSpawner, Spawner, TransformArea)
 
 __version__ = "0.1.0"

@@ -18,6 +18,8 @@ FORMAT_FLOAT4, FORMAT_HALF4, FORMAT_RGBA8 = 0, 1, 2
 LIGHT_SPHERE, LIGHT_DIRECTIONAL, LIGHT_PARTICLE, LIGHT_LINE = 1, 2, 3, 4
 HDR_NONE, HDR_GAMMA_COMPRESS, HDR_TONE_MAP = 0, 1, 2
 SPAWN_INLINE, SPAWN_POSITION_TEXTURE, SPAWN_FEEDBACK, SPAWN_PATTERN = 0, 1, 2, 3
+BLEND_ALPHA, BLEND_ADDITIVE, BLEND_OPAQUE = 0, 1, 2
+TEXTURE_NONE, TEXTURE_POINT, TEXTURE_LINEAR = 0, 1, 2
 OP_GRAVITY, OP_NOISE, OP_FMA, OP_MATRIX_MULTIPLY = 1, 2, 3, 4
 MAX_ATTRACTORS = 16
 FORMAT_BYTES = {FORMAT_FLOAT4: 16, FORMAT_HALF4: 8, FORMAT_RGBA8: 4}
@@ -149,6 +151,16 @@ class SpawnSource(C.Structure):  # ilb_spawn_source
                 ("CenteringOffset", C.c_float * 2), ("reserved2", C.c_float * 2)]
 
 
+class ParticleRender(C.Structure):  # ilb_particle_render
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("target_format", C.c_int32), ("blend", C.c_int32),
+                ("texture_filter", C.c_int32), ("texture_width", C.c_int32), ("texture_height", C.c_int32), ("clear", C.c_int32),
+                ("ClearColor", Float4), ("GlobalColor", Float4), ("BitmapTextureRegion", Float4), ("SizeFactorAndPosition", Float4),
+                ("Scale", Float4), ("ZFormula", Float4), ("ZConfiguration", Float4), ("RoundingPowerFromLife", Bezier1),
+                ("RenderingOptions", Float4), ("TexelAndSize", Float4), ("AnimationRateAndRotationAndZToY", Float4),
+                ("ViewportPosition", C.c_float * 2), ("ViewportScale", C.c_float * 2), ("StippleFactor", C.c_float),
+                ("reserved", C.c_float * 3)]
+
+
 class IlluminantError(RuntimeError):
     """Raised for every non-zero ilb_status; `.code` carries the status."""
 
@@ -190,10 +202,13 @@ _PROTOTYPES = [
     ("ilb_particles_set_life_ramp", C.c_int, [P, P, C.c_int, C.c_int]),
     ("ilb_particles_set_collision_field", C.c_int, [P, P]),
     ("ilb_particles_upload_chunk", C.c_int, [P, C.c_int, P, P, P]),
+    ("ilb_particles_upload_buffer", C.c_int, [P, C.c_int, C.c_int, P]),
     ("ilb_particles_download_chunk", C.c_int, [P, C.c_int, P, P, P, P, P]),
     ("ilb_particles_set_live_chunks", C.c_int, [P, C.c_int]),
     ("ilb_particles_step", C.c_int, [P, C.POINTER(PsysUniforms), P, C.c_int, P, C.c_int, C.c_int]),
     ("ilb_particles_step_sources", C.c_int, [P, C.POINTER(PsysUniforms), P, P, C.c_int, P, C.c_int, C.c_int]),
+    ("ilb_particles_render", C.c_int, [P, C.POINTER(ParticleRender), P, P]),
+    ("ilb_particles_render_device", C.c_int, [P, C.POINTER(ParticleRender), P, P]),
     ("ilb_particles_device_buffer", P, [P, C.c_int]),
     ("ilb_particles_count_live", C.c_int, [P, C.POINTER(C.c_int64)]),
 ]

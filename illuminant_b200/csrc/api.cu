@@ -461,6 +461,7 @@ void ilb_particles_destroy(ilb_psys* ps) {
     if (ps->noise_table) cudaFree(ps->noise_table);
     if (ps->positions) cudaFree(ps->positions);
     if (ps->pattern) cudaFree(ps->pattern);
+    ilb_raster_release(ps);
     if (ps->life_ramp) cudaFree(ps->life_ramp);
     if (ps->d_count) cudaFree(ps->d_count);
     delete ps;
@@ -527,6 +528,17 @@ int ilb_particles_upload_chunk(ilb_psys* ps, int chunk, const ilb_float4* p, con
     return ILB_OK;
 }
 
+int ilb_particles_upload_buffer(ilb_psys* ps, int chunk, int which, const ilb_float4* data) {
+    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    ilb_ctx* ctx = ps->ctx;
+    if (!data || which < 0 || which > 4) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null data or bad buffer index %d", which);
+    if (chunk < 0 || chunk >= ps->max_chunks) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "chunk %d out of range [0,%d)", chunk, ps->max_chunks);
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ILB_CUDA(ctx, cudaMemcpyAsync(ps->buf[which] + (size_t)chunk * ps->per_chunk, data, sizeof(float4) * ps->per_chunk, cudaMemcpyHostToDevice, ctx->stream));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ILB_OK;
+}
+
 int ilb_particles_download_chunk(ilb_psys* ps, int chunk, ilb_float4* p, ilb_float4* v, ilb_float4* a, ilb_float4* rc, ilb_float4* rd) {
     if (!ps) return ILB_ERR_INVALID_ARGUMENT;
     ilb_ctx* ctx = ps->ctx;
@@ -556,6 +568,42 @@ int ilb_particles_step_sources(ilb_psys* ps, const ilb_psys_uniforms* u, const i
             if (sources[i].kind == ILB_SPAWN_FEEDBACK && (!sources[i].source_system || !live_has(sources[i].source_system)))
                 return ilb_fail(ps->ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: the feedback source system is null or released", i);
     return ilb_particles_launch(ps, u, spawns, sources, spawn_count, ops, op_count, steps);
+}
+
+// ---------------------------------------------------------------------------------------------- particle rasterisation (N2)
+int ilb_particles_render_device(ilb_psys* ps, const ilb_particle_render* params, const void* d_texture, void* d_target) {
+    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    ILB_CUDA(ps->ctx, cudaSetDevice(ps->ctx->device));
+    return ilb_raster_launch(ps, params, d_texture, d_target);
+}
+
+int ilb_particles_render(ilb_psys* ps, const ilb_particle_render* r, const void* texture, void* target) {
+    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    ilb_ctx* ctx = ps->ctx;
+    if (!r || !target) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (r->width <= 0 || r->height <= 0 || r->width > 32768 || r->height > 32768) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad target size %dx%d", r->width, r->height);
+    if (r->target_format != ILB_FORMAT_FLOAT4 && r->target_format != ILB_FORMAT_HALF4 && r->target_format != ILB_FORMAT_RGBA8)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad target format %d", r->target_format);
+    const void* d_tex = nullptr;
+    if (r->texture_filter != ILB_TEXTURE_NONE) {
+        if (!texture || r->texture_width < 1 || r->texture_height < 1 || r->texture_width > 16384 || r->texture_height > 16384)
+            return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "textured material without a texture");
+        const size_t tbytes = (size_t)r->texture_width * (size_t)r->texture_height * 4;
+        int rc = ilb_reserve(ctx, &ps->raster[9], &ps->raster_capacity[9], tbytes, false);
+        if (rc) return rc;
+        ILB_CUDA(ctx, cudaMemcpyAsync(ps->raster[9], texture, tbytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_tex = ps->raster[9];
+    }
+    const size_t bytes = ilb_format_bytes(r->target_format) * (size_t)r->width * (size_t)r->height;
+    int rc = ilb_reserve(ctx, &ps->raster[10], &ps->raster_capacity[10], bytes, false);
+    if (rc) return rc;
+    if (!r->clear) ILB_CUDA(ctx, cudaMemcpyAsync(ps->raster[10], target, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = ilb_raster_launch(ps, r, d_tex, ps->raster[10]);
+    if (rc) return rc;
+    ILB_CUDA(ctx, cudaMemcpyAsync(target, ps->raster[10], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ILB_OK;
 }
 
 void* ilb_particles_device_buffer(ilb_psys* ps, int which) {

@@ -74,6 +74,7 @@ struct ilb_df {
     std::vector<ilb_df_planes> planes;
 };
 
+#define ILB_RASTER_BUFFERS 11
 struct ilb_psys {
     ilb_ctx* ctx = nullptr;
     int chunk_size = 0, max_chunks = 0, live_chunks = 0;
@@ -86,6 +87,8 @@ struct ilb_psys {
     int life_ramp_w = 0, life_ramp_h = 0;
     float4* positions = nullptr;    // PositionBuffer of an ILB_SPAWN_POSITION_TEXTURE spawn
     size_t positions_capacity = 0;
+    void* raster[ILB_RASTER_BUFFERS] = {};   // N2 rasteriser: counts, offsets, tile ranges, CUB temp, pairs x4, pair total, texture, target
+    size_t raster_capacity[ILB_RASTER_BUFFERS] = {};
     uint8_t* pattern = nullptr;     // packed mip chain of an ILB_SPAWN_PATTERN spawn's texture
     size_t pattern_capacity = 0;
     float4* noise_table = nullptr;  // 2 * per_chunk float4, see noise_table_kernel
@@ -126,6 +129,9 @@ int ilb_resolve_launch(ilb_ctx* ctx, const ilb_resolve* params, const void* d_li
 int ilb_luminance_launch(ilb_ctx* ctx, int width, int height, int lightmap_format, const void* d_lightmap, int level,
                          float* out_host);
 size_t ilb_format_bytes(int format);
+// raster.cu (N2)
+int ilb_raster_launch(ilb_psys* psys, const ilb_particle_render* params, const void* d_texture, void* d_target);
+void ilb_raster_release(ilb_psys* psys);
 // dfgen.cu
 int ilb_dfgen_launch(ilb_ctx* ctx, uint2* tex, const uint2* base, int tw, int th, int slice_w, int slice_h, int slice_count,
                      const ilb_df_uniforms* u, const ilb_obstruction* obs, int count);

@@ -111,6 +111,28 @@ def clamped_bezier4(src: Optional[Bezier4V]) -> Bezier4:
 
 
 @dataclass
+class ParticleAppearance:  # ParticleConfiguration.cs:42-109
+    Texture: Optional[np.ndarray] = None            # uint8 [H, W, 4] (SurfaceFormat.Color) sprite sheet; None = solid quads
+    OffsetPx: Tuple[float, float] = (0.0, 0.0)
+    SizePx: Optional[Tuple[float, float]] = None
+    AnimationRate: Tuple[float, float] = (0.0, 0.0)
+    Rounded: bool = False
+    DitheredOpacity: bool = False
+    RoundingPowerFromLife: Optional["BezierF"] = None   # default BezierF(0.8) (:82)
+    Bilinear: bool = True
+    RelativeSize: bool = True
+    RowFromVelocity: bool = False
+    ColumnFromVelocity: bool = False
+
+
+@dataclass
+class ParticleRenderParameters:  # ParticleConfiguration.cs:305-310
+    Origin: Tuple[float, float] = (0.0, 0.0)
+    Scale: Tuple[float, float] = (1.0, 1.0)
+    StippleFactor: Optional[float] = None
+
+
+@dataclass
 class ParticleSystemConfiguration:  # ParticleConfiguration.cs:187-303
     Size: Tuple[float, float] = (1.0, 1.0)
     Friction: float = 0.0
@@ -128,6 +150,11 @@ class ParticleSystemConfiguration:  # ParticleConfiguration.cs:187-303
     SizeFromLife: Optional[BezierF] = None
     SizeFromVelocity: Optional[BezierF] = None
     LifeRamp: Optional["ParticleColorLifeRamp"] = None   # Configuration.Color.LifeRamp (ParticleConfiguration.cs:111-137)
+    Appearance: ParticleAppearance = field(default_factory=ParticleAppearance)
+    GlobalColor: Tuple[float, float, float, float] = (1.0, 1.0, 1.0, 1.0)   # Configuration.Color.Global (un-premultiplied)
+    SizeFromZ: float = 0.0
+    ZFormula: Tuple[float, float, float, float] = (0.0, 0.0, 0.0, 0.0)
+    StippleFactor: float = 1.0
     WriteRenderOutputs: bool = True     # not in the reference: False skips renderColor/renderData (64 B/particle mode)
 
 
@@ -765,6 +792,13 @@ class ParticleSystem:
             self.TotalSpawnCount += per
         return first if first is not None else -1
 
+    def WriteChunkBuffer(self, chunk: int, which: int, data: np.ndarray) -> None:
+        """SetData on one texture of a chunk (0 PositionAndLife, 1 Velocity, 2 Attributes, 3 RenderColor, 4 RenderData)."""
+        arr = np.ascontiguousarray(data, dtype=np.float32)
+        if arr.shape != (self.ChunkMaximumCount, 4):
+            raise _abi.IlluminantError(_abi.ERR_INVALID_ARGUMENT, f"expected [{self.ChunkMaximumCount}, 4] texels, got {arr.shape}")
+        self.ctx.check(self.ctx.lib.ilb_particles_upload_buffer(self.handle, chunk, which, arr.ctypes.data_as(C.c_void_p)))
+
     def ReadChunk(self, chunk: int):
         """Readback of one chunk (ParticleReadback.cs:59-61 / GetDataFast): (P, V, attributes, renderColor, renderData)."""
         per = self.ChunkMaximumCount
@@ -936,6 +970,75 @@ class ParticleSystem:
         src = (SpawnSource * max(len(spawns), 1))(*[x if x is not None else SpawnSource() for x in sources])
         self.ctx.check(self.ctx.lib.ilb_particles_step_sources(self.handle, C.byref(u), C.cast(sp, C.c_void_p), C.cast(src, C.c_void_p),
                                                                len(spawns), C.cast(opa, C.c_void_p), len(ops), steps))
+
+    # ---- rasterisation (N2) ---------------------------------------------------------------------------------------
+    def render_params(self, width: int, height: int, blendState: str = "AlphaBlend", renderParams: Optional[ParticleRenderParameters] = None,
+                      viewportPosition=(0.0, 0.0), viewportScale=(1.0, 1.0), clearColor=None, target_format: int = _abi.FORMAT_FLOAT4):
+        """The uniforms of one ParticleSystem.Render draw: Uniforms.RasterizeParticleSystem (Uniforms.cs:238-290), the material
+        choice and RenderingOptions of Render (ParticleSystem.cs:943-1039), RoundingPowerFromLife (:568-572)."""
+        cfg, ap = self.Configuration, self.Configuration.Appearance
+        rp = renderParams or ParticleRenderParameters()
+        r = _abi.ParticleRender()
+        r.width, r.height, r.target_format = int(width), int(height), target_format
+        r.blend = {"AlphaBlend": _abi.BLEND_ALPHA, "Additive": _abi.BLEND_ADDITIVE, "Opaque": _abi.BLEND_OPAQUE}[blendState]
+        tex = ap.Texture
+        if tex is not None:
+            th, tw = tex.shape[0], tex.shape[1]
+            r.texture_filter = _abi.TEXTURE_LINEAR if ap.Bilinear else _abi.TEXTURE_POINT
+            r.texture_width, r.texture_height = tw, th
+            size = ap.SizePx if ap.SizePx is not None else (float(tw), float(th))
+            ox, oy = F(ap.OffsetPx[0]) / F(tw), F(ap.OffsetPx[1]) / F(th)
+            r.BitmapTextureRegion = Float4(ox, oy, ox + F(size[0]) / F(tw), oy + F(size[1]) / F(th))
+            if ap.RelativeSize:
+                r.SizeFactorAndPosition = Float4(F(size[0]) * F(0.5), F(size[1]) * F(0.5), rp.Origin[0], rp.Origin[1])
+            else:
+                r.SizeFactorAndPosition = Float4(1, 1, rp.Origin[0], rp.Origin[1])
+        else:
+            r.texture_filter = _abi.TEXTURE_NONE
+            r.BitmapTextureRegion = Float4(0, 0, 1, 1)
+            r.SizeFactorAndPosition = Float4(1, 1, rp.Origin[0], rp.Origin[1])
+        r.Scale = Float4(rp.Scale[0], rp.Scale[1], 0, 0)
+        g = cfg.GlobalColor
+        r.GlobalColor = Float4(F(g[0]) * F(g[3]), F(g[1]) * F(g[3]), F(g[2]) * F(g[3]), g[3])
+        r.ZFormula = Float4(*cfg.ZFormula)
+        r.ZConfiguration = Float4(cfg.SizeFromZ, 0, 0, 0)
+        r.RoundingPowerFromLife = clamped_bezier1(ap.RoundingPowerFromLife if ap.RoundingPowerFromLife is not None else BezierF(A=0.8, B=0.8, C=0.8, D=0.8))
+        r.RenderingOptions = Float4(1 if ap.Rounded else 0, 1 if ap.DitheredOpacity else 0, 1 if ap.ColumnFromVelocity else 0,
+                                    1 if ap.RowFromVelocity else 0)
+        u = self.system_uniforms(0.0)
+        r.TexelAndSize = u.TexelAndSize
+        # the rasteriser's animation rate is the APPEARANCE's (ParticleSystem.cs:556-560 packs Appearance.AnimationRate)
+        ar = ap.AnimationRate if (ap.AnimationRate[0] or ap.AnimationRate[1]) else cfg.AnimationRate
+        r.AnimationRateAndRotationAndZToY = Float4(F(1.0) / F(ar[0]) if ar[0] != 0 else 0, F(1.0) / F(ar[1]) if ar[1] != 0 else 0,
+                                                    u.AnimationRateAndRotationAndZToY.z, cfg.ZToY)
+        r.ViewportPosition[:] = [float(viewportPosition[0]), float(viewportPosition[1])]
+        r.ViewportScale[:] = [float(viewportScale[0]), float(viewportScale[1])]
+        r.StippleFactor = float(rp.StippleFactor if rp.StippleFactor is not None else cfg.StippleFactor)
+        if clearColor is not None:
+            r.clear, r.ClearColor = 1, Float4(*clearColor)
+        return r
+
+    def Render(self, width: int, height: int, target: Optional[np.ndarray] = None, blendState: str = "AlphaBlend",
+               renderParams: Optional[ParticleRenderParameters] = None, viewportPosition=(0.0, 0.0), viewportScale=(1.0, 1.0),
+               clearColor=(0.0, 0.0, 0.0, 0.0)) -> np.ndarray:
+        """ParticleSystem.Render (ParticleSystem.cs:943-1039) into a render target [H, W, 4] (float32, float16 or uint8).
+        `target` = None renders over `clearColor`; an array is blended over and returned (a copy)."""
+        fmt = _abi.FORMAT_FLOAT4
+        if target is not None:
+            target = np.array(target, copy=True, order="C")
+            fmt = {np.dtype(np.float32): _abi.FORMAT_FLOAT4, np.dtype(np.float16): _abi.FORMAT_HALF4, np.dtype(np.uint8): _abi.FORMAT_RGBA8}[target.dtype]
+            height, width = target.shape[0], target.shape[1]
+        r = self.render_params(width, height, blendState, renderParams, viewportPosition, viewportScale,
+                               clearColor if target is None else None, fmt)
+        if target is None:
+            target = np.empty((height, width, 4), dtype=np.float32)
+        tex = self.Configuration.Appearance.Texture
+        tex_ptr = None
+        if tex is not None:
+            tex = np.ascontiguousarray(tex, dtype=np.uint8)
+            tex_ptr = tex.ctypes.data_as(C.c_void_p)
+        self.ctx.check(self.ctx.lib.ilb_particles_render(self.handle, C.byref(r), tex_ptr, target.ctypes.data_as(C.c_void_p)))
+        return target
 
     def Dispose(self):
         if self.handle:

@@ -427,6 +427,10 @@ ILB_API int ilb_particles_upload_chunk(ilb_psys* psys, int chunk, const ilb_floa
 ILB_API int ilb_particles_download_chunk(ilb_psys* psys, int chunk, ilb_float4* position_and_life,
                                          ilb_float4* velocity, ilb_float4* attributes,
                                          ilb_float4* render_color, ilb_float4* render_data);
+/* SetData on one of a chunk's five textures (`which` as for ilb_particles_device_buffer: 0 PositionAndLife, 1 Velocity,
+ * 2 Attributes, 3 RenderColor, 4 RenderData): chunk_size^2 float4 from HOST memory.  RenderColor / RenderData are outputs of the
+ * update pass; uploading them restores a saved system for ilb_particles_render without stepping it. */
+ILB_API int ilb_particles_upload_buffer(ilb_psys* psys, int chunk, int which, const ilb_float4* data);
 /* Chunks [0, count) are live and updated by ilb_particles_step. */
 ILB_API int ilb_particles_set_live_chunks(ilb_psys* psys, int count);
 /* One ParticleSystem.Update (ParticleSystem.cs:634, replacing the RunSpawner/UpdateChunk loop :725-745):
@@ -444,6 +448,55 @@ ILB_API int ilb_particles_step_sources(ilb_psys* psys, const ilb_psys_uniforms* 
 ILB_API void* ilb_particles_device_buffer(ilb_psys* psys, int which);
 /* Count particles with life > 0 in chunks [0, live) (CountLiveParticles.fx equivalent); synchronous. */
 ILB_API int ilb_particles_count_live(ilb_psys* psys, int64_t* out_count);
+
+/* ------------------------------------------ "next" row N2: particle rasterisation (ParticleSystem.Render) */
+
+typedef enum ilb_blend {
+    ILB_BLEND_ALPHA = 0,    /* BlendState.AlphaBlend (premultiplied): dst = src + dst * (1 - src.a) */
+    ILB_BLEND_ADDITIVE = 1, /* BlendState.Additive: dst = src * src.a + dst */
+    ILB_BLEND_OPAQUE = 2    /* BlendState.Opaque: dst = src */
+} ilb_blend;
+typedef enum ilb_texture_filter { ILB_TEXTURE_NONE = 0, ILB_TEXTURE_POINT = 1, ILB_TEXTURE_LINEAR = 2 } ilb_texture_filter;
+
+/* One ParticleSystem.Render (ParticleSystem.cs:943-1039): every live chunk in order, every particle of the chunk in index order
+ * (RenderChunk :876-907 draws quadCount instances), as the material RasterizeParticles{NoTexture,TexturePoint,TextureLinear} of
+ * RasterizeParticleSystem.fx would: VS_PosVelAttr (:62-150) builds a rotated quad per live particle from PositionAndLife,
+ * RenderData (size, rotation, |v|, category) and RenderColor; PS_NoTexture / PS_Texture / PS_TexturePoint (:190-254) shade it;
+ * the output-merger blends in draw order.  Members are the uniforms of that draw:
+ *   RasterizeSettings = `Uniforms.RasterizeParticleSystem` (Uniforms.cs:238-290): GlobalColor (premultiplied), BitmapTextureRegion,
+ *   SizeFactorAndPosition, Scale, ZFormula (depth only: unused), ZConfiguration; RoundingPowerFromLife (ParticleSystem.cs:568-572);
+ *   RenderingOptions = (Rounded, DitheredOpacity, ColumnFromVelocity, RowFromVelocity) (:1021-1028); TexelAndSize and
+ *   AnimationRateAndRotationAndZToY from the system uniforms (Uniforms.cs:197-236).
+ * Scope / conventions (the view transform, StippleReject and Dither64 live in the un-vendored sq/Fracture):
+ *   - screen-space orthographic view: pixel = (world - ViewportPosition) * ViewportScale, pixel centres at +0.5; a pixel is
+ *     covered when its centre lies in the quad's half-open unit square (-1 <= u < 1, -1 <= v < 1 in the quad's own frame);
+ *   - StippleFactor must be 1 and DitheredOpacity 0 (ILB_ERR_UNSUPPORTED otherwise);
+ *   - the sprite texture is SurfaceFormat.Color with one mip level (XNA Texture2D without mipmaps), CLAMP addressing;
+ *   - blending accumulates in fp32 and converts to target_format once per pixel (the reference's output-merger rounds to the
+ *     target's format after every quad). */
+typedef struct ilb_particle_render {
+    int32_t width, height;           /* render target size in pixels */
+    int32_t target_format;           /* ilb_format: FLOAT4, HALF4 or RGBA8 */
+    int32_t blend;                   /* ilb_blend */
+    int32_t texture_filter;          /* ilb_texture_filter: NONE = RasterizeParticlesNoTexture */
+    int32_t texture_width, texture_height;
+    int32_t clear;                   /* 1: the target is cleared to ClearColor first; 0: blend over its contents */
+    ilb_float4 ClearColor;
+    ilb_float4 GlobalColor, BitmapTextureRegion, SizeFactorAndPosition, Scale, ZFormula, ZConfiguration;
+    ilb_bezier1 RoundingPowerFromLife;
+    ilb_float4 RenderingOptions;
+    ilb_float4 TexelAndSize, AnimationRateAndRotationAndZToY;
+    float ViewportPosition[2], ViewportScale[2];
+    float StippleFactor;
+    float reserved[3];
+} ilb_particle_render;
+
+/* texture: HOST Color texels (texture_width*texture_height*4 bytes) or NULL; target: HOST width*height texels of target_format,
+ * read first when clear == 0, always written.  Synchronous. */
+ILB_API int ilb_particles_render(ilb_psys* psys, const ilb_particle_render* params, const void* texture, void* target);
+/* Same with DEVICE pointers (texture may be NULL); asynchronous on the context's stream apart from one 4-byte read-back of
+ * the quad/tile pair count. */
+ILB_API int ilb_particles_render_device(ilb_psys* psys, const ilb_particle_render* params, const void* d_texture, void* d_target);
 
 #ifdef __cplusplus
 }

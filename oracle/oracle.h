@@ -36,6 +36,9 @@ int orc_particles_step_sources(float* P, float* V, float* A, float* RC, float* R
                                const orc_source_state* states, int nspawns, const ilb_op* ops, int nops,
                                const float* rng_table, int rw, int rh, const uint16_t* df_tex, int tw, int th, int steps,
                                int nthreads);
+/* N2: ParticleSystem.Render over `total` particles in draw order; target: width*height float4 (read when clear == 0, written). */
+int orc_particles_render(const float* P, const float* RD, const float* RC, long total, const ilb_particle_render* r,
+                         const uint8_t* texture, float* target);
 int orc_generate_distance_field(uint16_t* out_rgba64, const uint16_t* base_rgba64 /* static field or NULL */, int tw, int th, int slice_w, int slice_h, int slice_count,
                                 const ilb_df_uniforms* u, const ilb_obstruction* obs, int count, int nthreads);
 void orc_encode_gbuffer_sample(const float* normal, float relativeY, float z, int dead, int enableShadows, int fullbright, float* out4);

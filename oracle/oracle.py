@@ -66,6 +66,8 @@ def lib():
         L.orc_particles_step_sources.restype = C.c_int
         L.orc_particles_step_sources.argtypes = [P, P, P, P, P, C.c_int, C.c_int, C.POINTER(PsysUniforms), P, P, P, C.c_int, P, C.c_int, P,
                                                  C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_particles_render.restype = C.c_int
+        L.orc_particles_render.argtypes = [P, P, P, C.c_long, C.POINTER(_abi.ParticleRender), P, P]
         L.orc_generate_distance_field.restype = C.c_int
         L.orc_generate_distance_field.argtypes = [P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DFUniforms), P, C.c_int, C.c_int]
         L.orc_encode_gbuffer_sample.restype = None
@@ -287,4 +289,17 @@ def compute_luminance(lightmap, level: int) -> np.ndarray:
     rc = lib().orc_compute_luminance(_ptr(lm), w, h, level, _ptr(out))
     if rc != 0:
         raise RuntimeError(f"orc_compute_luminance failed: {rc}")
+    return out
+
+
+def particles_render(P_, RD, RC, params, texture=None, target=None) -> np.ndarray:
+    """ParticleSystem.Render in the reference's form (one quad per particle in draw order).  P_, RD, RC: float32 [n, 4];
+    texture: uint8 [H, W, 4] or None; target: float32 [H, W, 4] blended over when params.clear == 0.  Returns float32 [H, W, 4]."""
+    P_, RD, RC = (np.ascontiguousarray(a, dtype=np.float32) for a in (P_, RD, RC))
+    out = np.zeros((params.height, params.width, 4), dtype=np.float32) if target is None else np.array(target, dtype=np.float32, copy=True, order="C")
+    if texture is not None:
+        texture = np.ascontiguousarray(texture, dtype=np.uint8)
+    rc = lib().orc_particles_render(_ptr(P_), _ptr(RD), _ptr(RC), P_.shape[0], C.byref(params), _ptr(texture), _ptr(out))
+    if rc != 0:
+        raise RuntimeError(f"orc_particles_render failed: {rc}")
     return out

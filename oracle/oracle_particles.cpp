@@ -888,4 +888,115 @@ int orc_particles_step(float* P, float* V, float* A, float* RC, float* RD, int c
                                       rw, rh, df_tex, tw, th, steps, nthreads);
 }
 
+
+// ---------------------------------------------------------------- N2: ParticleSystem.Render (RasterizeParticleSystem.fx)
+// The reference's own form: one quad per particle, in draw order, each covered pixel shaded and blended into the target at once.
+// P, RD, RC: PositionAndLife / RenderData / RenderColor of the live chunks (total float4 each); texture: Color texels or NULL;
+// target: width*height float4, read (clear == 0) and written.  Conventions as documented for ilb_particle_render.
+int orc_particles_render(const float* P, const float* RD, const float* RC, long total, const ilb_particle_render* r,
+                         const uint8_t* texture, float* target) {
+    if (!P || !RD || !RC || !r || !target) return ILB_ERR_INVALID_ARGUMENT;
+    if (r->StippleFactor != 1.0f || r->RenderingOptions.y >= 0.5f) return ILB_ERR_UNSUPPORTED;
+    if (r->texture_filter != ILB_TEXTURE_NONE && !texture) return ILB_ERR_INVALID_ARGUMENT;
+    const int W = r->width, H = r->height;
+    if (r->clear)
+        for (long i = 0; i < (long)W * H; i++) st4(target, i, f4(r->ClearColor));
+    const float4 region = f4(r->BitmapTextureRegion), sfp = f4(r->SizeFactorAndPosition), scale = f4(r->Scale);
+    const float4 texelAndSize = f4(r->TexelAndSize), anim = f4(r->AnimationRateAndRotationAndZToY), options = f4(r->RenderingOptions);
+    const float4 globalColor = f4(r->GlobalColor);
+    const float vpx = r->ViewportPosition[0], vpy = r->ViewportPosition[1], vsx = r->ViewportScale[0], vsy = r->ViewportScale[1];
+    const int texW = r->texture_width, texH = r->texture_height;
+    auto texel = [&](int x, int y) {
+        x = x < 0 ? 0 : (x >= texW ? texW - 1 : x);
+        y = y < 0 ? 0 : (y >= texH ? texH - 1 : y);
+        const uint8_t* t = texture + ((size_t)y * texW + x) * 4;
+        return float4(t[0] / 255.0f, t[1] / 255.0f, t[2] / 255.0f, t[3] / 255.0f);
+    };
+    auto sample = [&](float u, float v) {  // BitmapSampler (LINEAR) / BitmapPointSampler, CLAMP, one mip level
+        if (r->texture_filter == ILB_TEXTURE_POINT) return texel((int)floorf(u * (float)texW), (int)floorf(v * (float)texH));
+        const float fx = u * (float)texW - 0.5f, fy = v * (float)texH - 0.5f;
+        const float x0 = floorf(fx), y0 = floorf(fy);
+        const float tx = fx - x0, ty = fy - y0;
+        const float4 top = lerp(texel((int)x0, (int)y0), texel((int)x0 + 1, (int)y0), tx);
+        const float4 bottom = lerp(texel((int)x0, (int)y0 + 1), texel((int)x0 + 1, (int)y0 + 1), tx);
+        return lerp(top, bottom, ty);
+    };
+    for (long i = 0; i < total; i++) {
+        // ---- VS_PosVelAttr :62-150
+        const float4 position = ld4(P, i), renderData = ld4(RD, i), color = ld4(RC, i);
+        const float life = position.w;
+        if (!(life > 0)) continue;
+        const float angle = fmod(renderData.y, 2 * PI);
+        const float zf = max(0.0f, 1.0f + (position.z * r->ZConfiguration.x));
+        const float sx = ((renderData.x * texelAndSize.z) * sfp.x) * zf, sy = ((renderData.x * texelAndSize.w) * sfp.y) * zf;
+        const float sn = dm_sinf(angle), cs = dm_cosf(angle);
+        const float dispx = position.x * scale.x + sfp.z, dispy = (position.y - (position.z * anim.w)) * scale.y + sfp.w;
+        const float cx = (dispx - vpx) * vsx, cy = (dispy - vpy) * vsy;
+        const float kx = scale.x * vsx, ky = scale.y * vsy;
+        const float ax = (cs * sx) * kx, ay = (sn * sx) * ky, bx = -((sn * sy) * kx), by = (cs * sy) * ky;
+        const float det = ax * by - ay * bx;
+        if (!(fabsf(det) > 0)) continue;
+        const float m00 = by / det, m01 = -bx / det, m10 = -ay / det, m11 = ax / det;
+        const float ex = fabsf(ax) + fabsf(bx), ey = fabsf(ay) + fabsf(by);
+        const float fx0 = (cx - ex) - 1, fx1 = (cx + ex) + 1, fy0 = (cy - ey) - 1, fy1 = (cy + ey) + 1;
+        if (!(fx0 <= fx1) || !(fy0 <= fy1) || std::isinf(fx0) || std::isinf(fx1) || std::isinf(fy0) || std::isinf(fy1)) continue;
+        if (fx1 < 0 || fy1 < 0 || fx0 > (float)(W - 1) || fy0 > (float)(H - 1)) continue;
+        const int x0 = (int)floorf(fmaxf(fx0, 0.0f)), x1 = (int)ceilf(fminf(fx1, (float)(W - 1)));
+        const int y0 = (int)floorf(fmaxf(fy0, 0.0f)), y1 = (int)ceilf(fminf(fy1, (float)(H - 1)));
+        float frameU = 0, frameV = 0;
+        if (r->texture_filter != ILB_TEXTURE_NONE) {
+            const float tsx = region.z - region.x, tsy = region.w - region.y;
+            const float fcx = floorf(1.0f / tsx), fcy = floorf(1.0f / tsy);
+            float fix = floorf(fabsf(anim.x) * life), fiy = floorf(fabsf(anim.y) * life);
+            const float maxAngleX = (2 * PI) / fcx, maxAngleY = (2 * PI) / fcy;
+            const float ffvx = floorf(angle / maxAngleX + 0.5f), ffvy = floorf(angle / maxAngleY + 0.5f);
+            fiy += floorf(renderData.w);
+            if (options.z != 0) fix += ffvx;
+            if (options.w != 0) fiy += ffvy;
+            fix = fmod(max(fix, 0.0f), fcx);
+            fiy = clamp(fiy, 0.0f, fcy - 1);
+            if (anim.x < 0) fix = (fcx - fix) - 1;
+            if (anim.y < 0) fiy = (fcy - fiy) - 1;
+            frameU = fix * tsx; frameV = fiy * tsy;
+        }
+        const float rounding = clamp(evaluateBezier1(r->RoundingPowerFromLife, life), 0.001f, 1.0f);
+        for (int y = y0; y <= y1; y++)
+            for (int x = x0; x <= x1; x++) {
+                const float dx = ((float)x + 0.5f) - cx, dy = ((float)y + 0.5f) - cy;
+                const float u = dx * m00 + dy * m01, v = dx * m10 + dy * m11;
+                if (!(u >= -1 && u < 1 && v >= -1 && v < 1)) continue;
+                // ---- PS_NoTexture / PS_Texture / PS_TexturePoint :190-254 ((1 / 512) is an integer division: 0)
+                float4 result = color;
+                if (r->texture_filter != ILB_TEXTURE_NONE) {
+                    if (color.w > 0) {
+                        const float ccx = u / 2 + 0.5f, ccy = v / 2 + 0.5f;
+                        const float tu = lerp(region.x, region.z, ccx) + frameU, tv = lerp(region.y, region.w, ccy) + frameV;
+                        result = result * sample(tu, tv);
+                        result = result * globalColor;
+                    }
+                } else {
+                    result = result * globalColor;
+                }
+                float circular = 1;
+                if (options.x != 0) {  // computeCircularAlpha :152-163
+                    const float distance = sqrtf(u * u + v * v);
+                    const float power = max(rounding, 0.01f);
+                    const float divisor = max(saturate(1 - power), 0.001f);
+                    const float distanceFromEdge = saturate(distance - power) / divisor;
+                    circular = saturate(1 - powf(distanceFromEdge, power));
+                }
+                result = result * circular;
+                if (!(result.w > 0)) continue;
+                const size_t pi = (size_t)y * W + x;
+                const float4 dst = ld4(target, pi);
+                float4 out;
+                if (r->blend == ILB_BLEND_ALPHA) out = result + dst * (1 - result.w);
+                else if (r->blend == ILB_BLEND_ADDITIVE) out = result * result.w + dst;
+                else out = result;
+                st4(target, pi, out);
+            }
+    }
+    return 0;
+}
+
 }  // extern "C"
