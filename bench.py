@@ -456,6 +456,31 @@ def run_ours(args):
             "gpu_launches": int(p_launches), "clocks": pclocks,
         }
 
+        # N2: ParticleSystem.Render of the same 8M particles into a 4K half4 target, additive (the whole
+        # render: vertex work, binning, stable sort, ordered per-tile shading).  Reported next to the headline, never part of it.
+        try:
+            rparams = system.render_params(W, H, "Additive", ib.ParticleRenderParameters(Scale=(2.0, 2.0)), clearColor=(0, 0, 0, 0),
+                                           target_format=_abi.FORMAT_HALF4)
+            rtarget = torch.empty((H, W, 4), dtype=torch.float16, device="cuda")
+
+            def render_step():
+                ctx.check(ctx.lib.ilb_particles_render_device(system.handle, C.byref(rparams), None, C.c_void_p(rtarget.data_ptr())))
+            rn = 10
+            _, rper = timed(render_step, rn, 2)
+            rms = float(np.median(rper))
+            rbytes = 48 * count + 8 * W * H
+            result["render"] = {"metric": "rasterised Mparticles/s (8M particles per GPU -> 4K half4 target, additive)",
+                                "value": count / (rms * 1e-3) / 1e6, "unit": "Mparticles/s", "ms_per_step": rms, "steps": rn,
+                                "lit_fraction": float((rtarget[..., 3] > 0).float().mean().item()),
+                                "roofline": {"bound": "hbm", "achieved": rbytes / (rms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                             "frac": rbytes / (rms * 1e-3) / 1e9 / peak, "traffic": None,
+                                             "kernel": "raster_count + scan + raster_emit + radix sort + raster_ranges + raster_shade (one render)",
+                                             "algorithmic_bytes": "48 B per particle (P, RenderData, RenderColor) + 8 B per target pixel",
+                                             "peak_source": peak_src}}
+            del rtarget
+        except Exception as e:   # noqa: BLE001 -- the headline must not depend on the N2 side measurement
+            result["render"] = {"error": f"{type(e).__name__}: {e}"}
+
     # ------------------------------------------------------------------ combined frame loop (config C5)
     if args.workload == "both":
         # ParticleLights.cs:333-378: System.Update (collision against the lighting field) -> RenderLighting -> reassemble.
@@ -510,7 +535,7 @@ def run_ours(args):
                            if primary else result.get("config", {}).get("workload"),
                            "parallelism": f"row bands x{world}, gather: {result.get('gather', 'none')}" if primary else f"chunk ranges x{world}, no collective",
                            "l2": "inputs larger than L2 (no flush)"}}
-        for k in ("roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "gather_checksum_equal", "gather_matches_single_gpu", "particles", "combined_c5", "probes_ms", "resolve"):
+        for k in ("roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "gather_checksum_equal", "gather_matches_single_gpu", "particles", "combined_c5", "probes_ms", "resolve", "render"):
             if k in result:
                 line[k] = result[k]
         print(json.dumps(line), flush=True)
