@@ -379,13 +379,16 @@ def run_ours(args):
             outs = [torch.empty((H, W, 4), dtype=torch.uint8, device="cuda") for _ in range(2)]
             flip = {"i": 0}
 
+            R_INNER = 8   # launches per timed step: one 4K resolve is shorter than the Python launch path, so a step is 8 back to back
+
             def resolve_step():
-                i = flip["i"] = flip["i"] ^ 1
-                ctx.check(ctx.lib.ilb_resolve_lighting_device(ctx.handle, C.byref(rp), C.c_void_p(lms[i].data_ptr()),
-                                                              C.c_void_p(als[i].data_ptr()), C.c_void_p(outs[i].data_ptr())))
+                for _ in range(R_INNER):
+                    i = flip["i"] = flip["i"] ^ 1
+                    ctx.check(ctx.lib.ilb_resolve_lighting_device(ctx.handle, C.byref(rp), C.c_void_p(lms[i].data_ptr()),
+                                                                  C.c_void_p(als[i].data_ptr()), C.c_void_p(outs[i].data_ptr())))
             r_steps = max(20, 2 * args.steps)
             r_total, r_per = timed(resolve_step, r_steps, 3)
-            r_ms = float(np.median(r_per))
+            r_ms = float(np.median(r_per)) / R_INNER
             r_ach = 16 * W * H / (r_ms * 1e-3) / 1e9
             result["resolve"] = {"metric": "resolved Mpixels/s (4K, tone-mapped, with albedo)", "value": W * H / (r_ms * 1e-3) / 1e6,
                                  "unit": "Mpixels/s", "ms_per_step": r_ms, "steps": r_steps,

@@ -60,6 +60,8 @@ struct Sprite {           // one quad in pixel space + the per-quad varyings of 
 
 // VS_PosVelAttr (RasterizeParticleSystem.fx:62-150).  Returns false for particles that draw nothing.  x0..y1: the pixel
 // bounding box (conservative, clamped to the target).
+// FULL = false: geometry only (the binning kernels need neither the colour nor the per-quad varyings).
+template <bool FULL>
 ILB_DEV bool makeSprite(const RasterParams& R, unsigned i, Sprite& s, int& x0, int& y0, int& x1, int& y1) {
     const float4 position = __ldg(R.P + i);
     const float life = position.w;
@@ -83,12 +85,16 @@ ILB_DEV bool makeSprite(const RasterParams& R, unsigned i, Sprite& s, int& x0, i
     if (!(fabsf(det) > 0.0f)) return false;  // zero-area quad (also NaN)
     s.m00 = xdiv(by, det); s.m01 = xdiv(-bx, det); s.m10 = xdiv(-ay, det); s.m11 = xdiv(ax, det);
     const float ex = xadd(fabsf(ax), fabsf(bx)), ey = xadd(fabsf(ay), fabsf(by));
-    const float fx0 = xsub(xsub(s.cx, ex), 1.0f), fx1 = xadd(xadd(s.cx, ex), 1.0f);
-    const float fy0 = xsub(xsub(s.cy, ey), 1.0f), fy1 = xadd(xadd(s.cy, ey), 1.0f);
+    // pixel x can be covered only if its centre x + 0.5 lies within cx -+ ex: x in [cx - ex - 0.5, cx + ex - 0.5]; 1/64 px of slack
+    // covers the rounding of the sums (one ulp at 16384 is 1/1024 px).  Conservative is all this has to be: coverage itself is
+    // decided per pixel by the exact (u, v) test.
+    const float fx0 = xsub(xsub(s.cx, ex), 0.515625f), fx1 = xsub(xadd(s.cx, ex), 0.484375f);
+    const float fy0 = xsub(xsub(s.cy, ey), 0.515625f), fy1 = xsub(xadd(s.cy, ey), 0.484375f);
     if (!(fx0 <= fx1) || !(fy0 <= fy1) || isinf(fx0) || isinf(fx1) || isinf(fy0) || isinf(fy1)) return false;
     if (fx1 < 0.0f || fy1 < 0.0f || fx0 > (float)(R.W - 1) || fy0 > (float)(R.H - 1)) return false;  // off-screen
     x0 = (int)floorf(fmaxf(fx0, 0.0f)); x1 = (int)ceilf(fminf(fx1, (float)(R.W - 1)));
     y0 = (int)floorf(fmaxf(fy0, 0.0f)); y1 = (int)ceilf(fminf(fy1, (float)(R.H - 1)));
+    if (!FULL) return true;
     const float4 color = __ldg(R.RC + i);
     s.r = color.x; s.g = color.y; s.b = color.z; s.a = color.w;
     s.frameU = 0.0f; s.frameV = 0.0f;
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(256) raster_count_kernel(const __grid_constant
     if (i < R.total) {
         Sprite s;
         int x0, y0, x1, y1;
-        if (makeSprite(R, i, s, x0, y0, x1, y1)) {
+        if (makeSprite<false>(R, i, s, x0, y0, x1, y1)) {
             int tx0, ty0, tx1, ty1;
             tileRange(R, x0, y0, x1, y1, tx0, ty0, tx1, ty1);
             n = (unsigned)(tx1 - tx0 + 1) * (unsigned)(ty1 - ty0 + 1);
@@ -142,7 +148,7 @@ __global__ void __launch_bounds__(256) raster_emit_kernel(const __grid_constant_
     if (R.counts[i] == 0) return;
     Sprite s;
     int x0, y0, x1, y1;
-    if (!makeSprite(R, i, s, x0, y0, x1, y1)) return;
+    if (!makeSprite<false>(R, i, s, x0, y0, x1, y1)) return;
     int tx0, ty0, tx1, ty1;
     tileRange(R, x0, y0, x1, y1, tx0, ty0, tx1, ty1);
     unsigned o = R.offsets[i];
@@ -213,11 +219,17 @@ ILB_DEV void storeTarget(void* base, int fmt, size_t i, f4 c) {
     }
 }
 
+// One CTA per 16x16 tile.  Each of the 8 warps owns an 8x4 pixel block of the tile (lane -> (lane & 7, lane >> 3)), so that a
+// quad whose pixel bounding box misses the block is rejected by one warp-uniform test instead of 32 per-lane (u, v) evaluations:
+// quads are typically a few pixels wide, while the tile's list holds every quad that touches any of its 256 pixels.
 __global__ void __launch_bounds__(RBATCH) raster_shade_kernel(const __grid_constant__ RasterParams R) {
     __shared__ Sprite batch[RBATCH];
+    __shared__ int4 boxes[RBATCH];  // pixel bounding box (x0, y0, x1, y1) of each staged quad; x1 < x0 for quads that draw nothing
     const int tile = blockIdx.x;
     const int tx = tile % R.tilesX, ty = tile / R.tilesX;
-    const int px = tx * RTILE + (threadIdx.x % RTILE), py = ty * RTILE + (threadIdx.x / RTILE);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bx0 = tx * RTILE + (warp & 1) * 8, by0 = ty * RTILE + (warp >> 1) * 4;  // the warp's 8x4 block
+    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
     const bool inside = px < R.W && py < R.H;
     const size_t pi = (size_t)py * (size_t)R.W + (size_t)px;
     f4 acc = mk4(R.clearColor);
@@ -229,16 +241,16 @@ __global__ void __launch_bounds__(RBATCH) raster_shade_kernel(const __grid_const
         __syncthreads();  // the previous batch is consumed
         if (threadIdx.x < n) {
             Sprite s;
-            int x0, y0, x1, y1;
-            s.valid = 0.0f;
-            if (!makeSprite(R, R.vals[base + threadIdx.x], s, x0, y0, x1, y1)) s.valid = 0.0f;
+            int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
+            if (!makeSprite<true>(R, R.vals[base + threadIdx.x], s, x0, y0, x1, y1)) { x0 = 0; x1 = -1; }
             batch[threadIdx.x] = s;
+            boxes[threadIdx.x] = make_int4(x0, y0, x1, y1);
         }
         __syncthreads();
-        if (!inside) continue;
         for (unsigned k = 0; k < n; k++) {
+            const int4 box = boxes[k];
+            if (box.z < bx0 || box.x > bx0 + 7 || box.w < by0 || box.y > by0 + 3) continue;  // warp-uniform
             const Sprite& s = batch[k];
-            if (s.valid == 0.0f) continue;
             const float dx = xsub(pcx, s.cx), dy = xsub(pcy, s.cy);
             const float u = xadd(xmul(dx, s.m00), xmul(dy, s.m01)), v = xadd(xmul(dx, s.m10), xmul(dy, s.m11));
             if (!(u >= -1.0f && u < 1.0f && v >= -1.0f && v < 1.0f)) continue;

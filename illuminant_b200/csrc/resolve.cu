@@ -28,7 +28,7 @@ struct ResolveParams {
     float invScale, invScale2;  // InverseScaleFactor, InverseScaleFactor * 2 (Resolve.fx:40, :61)
     float offset, exposure, gamma;
     float middleGray, averageLuminance, maxLumSq;
-    float whiteScale;  // Uncharted2Tonemap1(WhitePoint), host-evaluated (HDR.fxh:32-38, Resolve.fx:131)
+    float invWhiteScale;  // 1 / Uncharted2Tonemap1(WhitePoint), host-evaluated (HDR.fxh:32-38, Resolve.fx:131)
     int albedoIsSRGB, resolveToSRGB;
 };
 
@@ -81,12 +81,13 @@ ILB_DEV f4 pLinearToPSRGB(f4 c) {
 }
 
 // ---- HDR.fxh
-// The quotient is an IEEE division: at value == 0 (unlit texels) the result is the difference of two nearly equal numbers
-// (kD*kE / (kD*kF) - kE/kF = +7.45e-9 in fp32) whose SIGN decides whether the following pow(x, Gamma) is a number or NaN,
-// so it must not depend on the approximate-division path.
+// value >= 0.  The curve is the difference of two nearly equal numbers near black (kD*kE / (kD*kF) - kE/kF = +7.45e-9 in IEEE
+// fp32 at value == 0) and its SIGN decides whether a following pow(x, Gamma != 1) is a number or NaN.  In exact arithmetic the
+// curve is >= 0 for value >= 0, so the quotient uses the fast division (with IEEE divisions the kernel is ALU-bound: 72 us per 4K
+// frame, profiles/r1_n2n3_launches.csv) and the result is clamped at 0: within 1e-8 of the IEEE value at black, never NaN.
 ILB_DEV float uncharted2Tonemap1(float value) {  // HDR.fxh:32-46
     const float kA = 0.15f, kB = 0.50f, kC = 0.10f, kD = 0.20f, kE = 0.02f, kF = 0.30f;
-    return xdiv(value * (kA * value + kC * kB) + kD * kE, value * (kA * value + kB) + kD * kF) - kE / kF;
+    return fmaxf(__fdividef(value * (kA * value + kC * kB) + kD * kE, value * (kA * value + kB) + kD * kF) - kE / kF, 0.0f);
 }
 
 ILB_DEV f3 pow3u(f3 v, float e) {  // pow(x, 1) == x exactly: skip the three powf when Gamma == 1 (uniform branch)
@@ -115,7 +116,7 @@ ILB_DEV f4 resolvePixel(const ResolveParams& P, f4 light, f4 albedo) {
         result = mk4(rgb * rescaleFactor, result.w);
     } else if (MODE == ILB_HDR_TONE_MAP) {  // Resolve.fx:127-133
         const f3 pre = max3(mk3(0.0f), xyz(result) + P.offset) * P.exposure;
-        const f3 tm = mk3(uncharted2Tonemap1(pre.x), uncharted2Tonemap1(pre.y), uncharted2Tonemap1(pre.z)) / P.whiteScale;
+        const f3 tm = mk3(uncharted2Tonemap1(pre.x), uncharted2Tonemap1(pre.y), uncharted2Tonemap1(pre.z)) * P.invWhiteScale;
         result = mk4(pow3u(tm, P.gamma), result.w);
     } else {  // Resolve.fx:84-86
         f3 rgb = max3(mk3(0.0f), xyz(result) + P.offset);
@@ -207,7 +208,7 @@ int ilb_resolve_launch(ilb_ctx* ctx, const ilb_resolve* r, const void* d_lightma
     P.invScale = inv; P.invScale2 = inv * 2;
     P.offset = r->Offset; P.exposure = r->ExposureMinusOne + 1; P.gamma = r->GammaMinusOne + 1;
     P.middleGray = r->MiddleGray; P.averageLuminance = r->AverageLuminance; P.maxLumSq = r->MaximumLuminanceSquared;
-    P.whiteScale = hostTonemap1(r->WhitePoint);
+    P.invWhiteScale = 1.0f / hostTonemap1(r->WhitePoint);
     P.albedoIsSRGB = r->AlbedoIsSRGB != 0.0f; P.resolveToSRGB = r->ResolveToSRGB != 0.0f;
     const bool vec = (((uintptr_t)d_lightmap | (uintptr_t)d_albedo | (uintptr_t)d_output) & 15u) == 0;
     // enough 256-thread CTAs for every group of four pixels, capped at 8 waves of 148 SMs x 8 resident CTAs (grid-stride)
