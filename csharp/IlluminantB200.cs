@@ -157,6 +157,51 @@ namespace Squared.Illuminant.Native {
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_step (IntPtr psys, ref IlbPsysUniforms uniforms, IlbSpawn* spawns, int spawnCount, IlbOp* ops, int opCount, int steps);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_count_live (IntPtr psys, out long count);
 
+        // ---- "next" rows of SURVEY.md section 8f ------------------------------------------------------------------------
+        // N3: lightmap resolve (Resolve.fx / HDR.fxh) and the luminance buffer behind RenderedLighting.TryComputeHistogram
+        [StructLayout(LayoutKind.Sequential, Pack = 4)]
+        public struct IlbResolve {                // ilb_resolve == what LightingResolveHandler._Before binds (LightingRenderer.cs:1464-1523)
+            public int Width, Height, LightmapFormat, AlbedoFormat, OutputFormat, HdrMode;
+            public float InverseScaleFactor, AlbedoIsSRGB, ResolveToSRGB, Offset, ExposureMinusOne, GammaMinusOne;
+            public float MiddleGray, AverageLuminance, MaximumLuminanceSquared, WhitePoint;
+            public float LightmapUVOffsetX, LightmapUVOffsetY, DitheringStrength, Reserved;
+        }
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_resolve_lighting (IntPtr ctx, ref IlbResolve parameters, void* lightmapOrNull, void* albedoOrNull, void* output);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_resolve_lighting_device (IntPtr ctx, ref IlbResolve parameters, void* dLightmap, void* dAlbedoOrNull, void* dOutput);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_compute_luminance (IntPtr ctx, int width, int height, int lightmapFormat, void* lightmapOrNull, int level, float* outLuminance);
+
+        // N4: spawner materials that read a source (SpawnParticlesFromPositionTexture, SpawnFeedbackParticles, SpawnPatternParticles)
+        [StructLayout(LayoutKind.Sequential, Pack = 8)]
+        public struct IlbSpawnSource {            // ilb_spawn_source, one per IlbSpawn of the same call
+            public int Kind, PositionCount;       // 0 inline, 1 position texture, 2 feedback, 3 pattern
+            public Vector4* Positions;            // Spawner.Temp4 (ParticleSpawner.cs:331-352)
+            public IntPtr SourceSystem;           // FeedbackSpawner.SourceSystem.Instance's handle
+            public int SourceChunk;
+            public float FeedbackSourceIndex, InstanceMultiplier, SourceVelocityFactor;
+            public float AlignPositionConstant, MultiplyLife, MultiplyAttributeConstant;
+            public float SourceLifeRangeMin, SourceLifeRangeMax;
+            public int Reserved;
+            public byte* PatternTexels;           // PatternSpawner.Texture level 0 (SurfaceFormat.Color)
+            public int PatternWidth, PatternHeight;
+            public Vector4 StepWidthAndSizeScale, YOffsetsAndCoordScale, TexelOffsetAndMipBias;   // SpecialSpawners.cs:213-241
+            public float CenteringOffsetX, CenteringOffsetY, Reserved2, Reserved3;
+        }
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_step_sources (IntPtr psys, ref IlbPsysUniforms uniforms, IlbSpawn* spawns, IlbSpawnSource* sourcesOrNull, int spawnCount, IlbOp* ops, int opCount, int steps);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_upload_buffer (IntPtr psys, int chunk, int which, Vector4* data);
+
+        // N2: ParticleSystem.Render (RasterizeParticleSystem.fx)
+        [StructLayout(LayoutKind.Sequential, Pack = 4)]
+        public struct IlbParticleRender {         // ilb_particle_render
+            public int Width, Height, TargetFormat, Blend, TextureFilter, TextureWidth, TextureHeight, Clear;
+            public Vector4 ClearColor;
+            public Uniforms.RasterizeParticleSystem RasterizeSettings;   // 6 x Vector4, Uniforms.cs:238-290
+            public Uniforms.ClampedBezier1 RoundingPowerFromLife;
+            public Vector4 RenderingOptions, TexelAndSize, AnimationRateAndRotationAndZToY;
+            public float ViewportPositionX, ViewportPositionY, ViewportScaleX, ViewportScaleY, StippleFactor, R0, R1, R2;
+        }
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_render (IntPtr psys, ref IlbParticleRender parameters, void* textureOrNull, void* target);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_render_device (IntPtr psys, ref IlbParticleRender parameters, void* dTextureOrNull, void* dTarget);
+
         /// <summary>Maps an ilb_status to the exception type the reference throws at the same place.</summary>
         public static void Check (IntPtr ctx, int status) {
             if (status == 0)
