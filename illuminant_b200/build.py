@@ -23,7 +23,7 @@ HEADERS = ["ilb_device.cuh", "ilb_internal.h", "ilb_shapes.cuh", "ilb_bezier.cuh
 EXACT = os.environ.get("ILB_EXACT") == "1"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17",
+    "-O3", "-lineinfo", "-std=c++17", "--threads", "0",   # the translation units compile in parallel
     *(["-fmad=false"] if EXACT else ["-fmad=true", "-prec-div=false", "-prec-sqrt=false", "-ftz=true"]),
     *[f"-D{d}" for d in os.environ.get("ILB_DEFINES", "").split() if d],
     "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-O2",
