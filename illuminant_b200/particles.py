@@ -463,7 +463,8 @@ class Spawner(ParticleTransform):  # ParticleSpawner.cs:14-419
             src = SpawnSource()
             src.kind, src.position_count = _abi.SPAWN_POSITION_TEXTURE, buf.shape[0]
             src.positions = buf.ctypes.data
-            self._position_buffer = buf   # keeps the host array alive until the step call returns
+            self._position_buffer = buf
+            system._spawn_keepalive.append(buf)   # the source holds a raw pointer: alive until the next plan_spawns
             self._source = src
         else:
             s.InlinePositionConstants[0] = Float4(*self.Position.Constant, lc)   # BeginTick :343-357
@@ -666,7 +667,8 @@ class PatternSpawner(Spawner):  # SpecialSpawners.cs:15-262 (derives from Spawne
         src = SpawnSource()
         src.kind = _abi.SPAWN_PATTERN
         src.pattern_texels, src.pattern_width, src.pattern_height = tex.ctypes.data, tw, th
-        self._pattern_texels = tex      # keeps the host array alive until the step call returns
+        self._pattern_texels = tex
+        system._spawn_keepalive.append(tex)   # the source holds a raw pointer: alive until the next plan_spawns
         src.StepWidthAndSizeScale = Float4(d, self.ParticlesPerRow, F(d) / F(tw), F(d) / F(th))
         baseX = baseY = F(0)
         if self.TextureTopLeftPx is not None:
@@ -722,6 +724,7 @@ class ParticleSystem:
         self._feedback_spawn_target = -1               # CurrentFeedbackSpawnTarget
         self._feedback_source = -1                     # CurrentFeedbackSource
         self.last_sources = None                       # ilb_spawn_source list of the most recent plan_spawns (None: all inline)
+        self._spawn_keepalive: list = []
         self.handle = None
         if self.ctx is not None:
             h = C.c_void_p()
@@ -899,6 +902,7 @@ class ParticleSystem:
         RunSpawner pass (ParticleSystem.cs:733-740), which calls BeginTick again exactly like the reference.  The
         ilb_spawn_source of each spawn (None when every spawn is inline) is left in `self.last_sources`."""
         spawns, sources = [], []
+        self._spawn_keepalive = []   # host arrays the ilb_spawn_source records of this plan point into (a spawner may pack twice per plan)
         self._sync_chunk_lists()
         for t in self.Transforms:
             if not t.IsSpawner or not (t.IsActive and t.IsActive2) or not t.IsValid:

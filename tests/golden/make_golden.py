@@ -59,8 +59,64 @@ def golden_particles():
     return {"P": P, "V": V, "A": A, "RC": RC, "RD": RD}
 
 
+def golden_next_rows():
+    """Regression vectors of the oracle for the "next" rows: N3 resolve + luminance, N2 render, N4 spawner sources."""
+    from illuminant_b200 import _abi
+    out = {}
+    rs = np.random.RandomState(79)
+    # N3: tone-mapped resolve with an sRGB Color albedo of a half4 lightmap, and level 1 of its luminance chain
+    lm = (rs.rand(16, 32, 4) ** 2 * 3).astype(np.float16)
+    al = rs.randint(0, 256, size=(16, 32, 4), dtype=np.uint8)
+    hdr = ib.HDRConfiguration(Mode=ib.HDRMode.ToneMap, Exposure=1.3, Gamma=0.9, InverseScaleFactor=0.5, AlbedoIsSRGB=True,
+                              ToneMapping=ib.ToneMappingConfiguration(WhitePoint=2.8))
+    out["resolve"] = oracle.resolve_lighting(ib.pack_resolve(32, 16, _abi.FORMAT_HALF4, hdr, _abi.FORMAT_RGBA8, _abi.FORMAT_FLOAT4), lm, al)
+    out["luminance1"] = oracle.compute_luminance(lm, 1)
+    # N2: 200 rotated, rounded, textured quads blended over a grey target
+    engine = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=16, RandomSeed=79))
+    cfg = ib.ParticleSystemConfiguration()
+    cfg.Size = (1.5, 1.0)
+    tex = rs.randint(0, 256, size=(8, 16, 4), dtype=np.uint8)
+    cfg.Appearance = ib.ParticleAppearance(Texture=tex, SizePx=(4, 4), AnimationRate=(1.5, 0.0), Rounded=True, RelativeSize=False)
+    system = ib.ParticleSystem(engine, cfg)
+    n = 200
+    P = np.zeros((n, 4), np.float32)
+    P[:, 0], P[:, 1], P[:, 3] = rs.rand(n) * 48, rs.rand(n) * 32, np.where(rs.rand(n) < 0.1, 0, rs.rand(n) * 3 + 0.1)
+    RD = np.zeros((n, 4), np.float32)
+    RD[:, 0], RD[:, 1], RD[:, 3] = rs.rand(n) * 4 + 1, rs.rand(n) * 12 - 2, rs.randint(0, 2, n)
+    RC = rs.rand(n, 4).astype(np.float32)
+    RC[:, :3] *= RC[:, 3:4]
+    r = system.render_params(48, 32, "AlphaBlend")
+    out["render"] = oracle.particles_render(P, RD, RC, r, texture=tex, target=np.full((32, 48, 4), 0.25, np.float32))
+    # N4: one frame of a 7-position polygon spawner (position texture) and of a pattern spawner
+    def fresh():
+        c = ib.ParticleSystemConfiguration()
+        c.Friction, c.LifeDecayPerSecond = 0.0, 0.0
+        return ib.ParticleSystem(ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=16, RandomSeed=79)), c, maxChunks=2)
+    sysA = fresh()
+    poly = ib.Spawner(MinRate=6000, MaxRate=6000, Seed=79, Position=ib.Formula(Constant=(1.0, 2.0, 3.0), RandomScale=(2, 2, 0), Type=ib.FormulaType.Spherical),
+                      Velocity=ib.Formula(RandomScale=(10, 10, 2), Type=ib.FormulaType.Spherical), Life=(4.0, 1.0, 0),
+                      AdditionalPositions=[(10.0 * i, 5.0 * (i % 3), float(i)) for i in range(1, 7)], PolygonRate=2.5, RatePerPosition=False,
+                      VelocityAlongPolygon=(3.0, 1.0, 0.0), AlphaDiscardThreshold=0.0)
+    sysA.Transforms = [poly]
+    spawns = sysA.plan_spawns(1.0, 1 / 60.0)
+    Z = np.zeros((256 * sysA.LiveChunkCount, 4), np.float32)
+    out["spawn_polygon"] = np.concatenate(oracle.particles_step(Z, Z, Z, 16, sysA.system_uniforms(1 / 60.0), spawns, [], sysA.Engine.RandomnessTexture,
+                                                                sources=sysA.last_sources)[:3], axis=1)
+    sysB = fresh()
+    pat = ib.PatternSpawner(MinRate=600, MaxRate=600, Seed=79, Texture=rs.randint(64, 256, size=(10, 12, 4), dtype=np.uint8), Divisor=2, WholeSpawn=True,
+                            Position=ib.Formula(Constant=(50.0, 40.0, 0.0)), Velocity=ib.Formula(Type=ib.FormulaType.Linear), Life=(2.0, 0, 0),
+                            AlphaDiscardThreshold=1.0)
+    sysB.Transforms = [pat]
+    spawns = sysB.plan_spawns(1.0, 1 / 60.0)      # 640 requested: two RunSpawner passes fill two chunks of 256
+    Z = np.zeros((256 * sysB.LiveChunkCount, 4), np.float32)
+    out["spawn_pattern"] = np.concatenate(oracle.particles_step(Z, Z, Z, 16, sysB.system_uniforms(1 / 60.0), spawns, [], sysB.Engine.RandomnessTexture,
+                                                                sources=sysB.last_sources)[:3], axis=1)
+    return out
+
+
 if __name__ == "__main__":
     out = Path(__file__).resolve().parent
     np.savez_compressed(out / "lighting_96x64.npz", **golden_lighting())
     np.savez_compressed(out / "particles_64.npz", **golden_particles())
+    np.savez_compressed(out / "next_rows.npz", **golden_next_rows())
     print("wrote", [p.name for p in out.glob("*.npz")])
