@@ -284,3 +284,59 @@ def test_gpu_pattern_spawner(ctx, oracle, w, h, divisor, whole, topleft, multipl
     gpu = [np.concatenate(x) for x in zip(*[system.ReadChunk(c) for c in range(system.LiveChunkCount)])]
     assert (gpu[0][:, 3] > 0).sum() == (P[:, 3] > 0).sum() > 0
     _check(gpu, (P, V, A, RC, RD), f"pattern {w}x{h} /{divisor}")
+
+
+def test_pattern_spawner_rows_rebuild_the_image(oracle):
+    """Row-by-row mode end to end on the CPU: after RowsPerInstance frames every texel of the pattern has produced one particle at
+    its pixel's position (centred on the spawner's position constant), coloured by that texel."""
+    engine = _engine()
+    system = _system(engine, max_chunks=1)
+    tex = _pattern_texture(8, 8, seed=9)
+    tex[..., 3] = 255
+    sp = ib.PatternSpawner(MinRate=60, MaxRate=60, Texture=tex, Divisor=1, Position=ib.Formula(Constant=(100.0, 50.0, 0.0)),
+                           Velocity=ib.Formula(Type=ib.FormulaType.Linear), Life=(3.0, 0, 0), ColorConstant=(1, 1, 1, 1), AlphaDiscardThreshold=1.0)
+    system.Transforms = [sp]
+    P = V = A = np.zeros((PER, 4), np.float32)
+    for k in range(8):                                     # 60/s * CountScale 8 / 60 = one row of 8 particles per frame
+        spawns = system.plan_spawns((k + 1) / 60.0, 1 / 60.0)
+        assert len(spawns) == 1 and int(system.last_sources[0].YOffsetsAndCoordScale.x) == k
+        P, V, A, _, _ = oracle.particles_step(P, V, A, CS, system.system_uniforms(1 / 60.0), spawns, [], engine.RandomnessTexture,
+                                              sources=system.last_sources)
+    assert (P[:, 3] > 0).sum() == 64
+    ix, iy = np.arange(64) % 8, np.arange(64) // 8
+    assert np.allclose(P[:64, :2], np.stack([100.0 + ix - 4.0, 50.0 + iy - 4.0], 1))
+    texel = tex[np.maximum(iy - 1, 0), np.maximum(ix - 1, 0)].astype(np.float32) / np.float32(255)     # half-texel offset: texel (index - 1)
+    assert np.allclose(A[:64], texel, rtol=1e-6)
+
+
+def test_feedback_spawner_follows_its_source_across_frames(oracle):
+    """Two systems on the CPU: a source that keeps spawning and a feedback spawner that consumes its particles in order, one new
+    particle per source particle, at the source particle's position."""
+    engine = _engine()
+    source, target = _system(engine, max_chunks=1), _system(engine, max_chunks=1)
+    emitter = ib.Spawner(MinRate=600, MaxRate=600, Position=ib.Formula(Constant=(0.0, 0.0, 0.0), RandomScale=(100, 100, 0)),
+                         Velocity=ib.Formula(Type=ib.FormulaType.Linear), Life=(5.0, 0, 0), AlphaDiscardThreshold=0.0)
+    source.Transforms = [emitter]
+    fs = ib.FeedbackSpawner(MinRate=300, MaxRate=300, SourceSystem=source, Position=ib.Formula(Constant=(0.0, 0.0, 1.0)),
+                            Velocity=ib.Formula(Type=ib.FormulaType.Linear), Life=(1.0, 0, 0), AlphaDiscardThreshold=0.0)
+    target.Transforms = [fs]
+    sP = sV = sA = np.zeros((PER, 4), np.float32)
+    tP = tV = tA = np.zeros((PER, 4), np.float32)
+    sRC = np.zeros((PER, 4), np.float32)
+    consumed = []
+    for k in range(6):
+        now = (k + 1) / 60.0
+        spawns = source.plan_spawns(now, 1 / 60.0)                      # 10 new source particles per frame
+        sP, sV, sA, sRC, _ = oracle.particles_step(sP, sV, sA, CS, source.system_uniforms(1 / 60.0), spawns, [], engine.RandomnessTexture)
+        source.handle = 1                                               # what ilb_spawn_source.source_system carries (no device here)
+        spawns = target.plan_spawns(now, 1 / 60.0)                      # 5 feedback particles per frame
+        assert len(spawns) == 1
+        src = target.last_sources[0]
+        consumed.append(int(src.FeedbackSourceIndex))
+        first = int(spawns[0].ChunkSizeAndIndices.y)
+        tP, tV, tA, _, _ = oracle.particles_step(tP, tV, tA, CS, target.system_uniforms(1 / 60.0), spawns, [], engine.RandomnessTexture,
+                                                 sources=target.last_sources, source_states=[(sP, sV, sRC, CS)])
+        got = tP[first:first + 5, :3]
+        want = sP[consumed[-1]:consumed[-1] + 5, :3] + np.array([0, 0, 1], np.float32)
+        assert np.allclose(got, want, atol=1e-5), k
+    assert consumed == [0, 5, 10, 15, 20, 25] and source.AvailableForFeedback(0) == 60 - 30
