@@ -169,6 +169,9 @@ class IlluminantError(RuntimeError):
         self.code = code
 
 
+# ilb_option
+OPT_LIGHT_CONCURRENT, OPT_LIGHT_LINE_CTAS, OPT_LIGHT_OTHER_CTAS, OPT_LIGHT_LINE_HELPERS, OPT_LIGHT_OTHER_HELPERS = range(5)
+
 # every symbol include/illuminant_b200.h declares: (name, restype, argtypes)
 P = C.c_void_p
 _PROTOTYPES = [
@@ -179,6 +182,9 @@ _PROTOTYPES = [
     ("ilb_synchronize", C.c_int, [P]),
     ("ilb_stream", P, [P]),
     ("ilb_launch_count", C.c_uint64, [P]),
+    ("ilb_set_option", C.c_int, [P, C.c_int, C.c_int]),
+    ("ilb_get_option", C.c_int, [P, C.c_int, C.POINTER(C.c_int)]),
+    ("ilb_debug_detmath", C.c_int, [P, C.c_int, P, P, C.c_int]),
     ("ilb_df_create", C.c_int, [P, C.c_int, C.c_int, P, C.c_size_t, C.POINTER(P)]),
     ("ilb_df_create_device", C.c_int, [P, C.c_int, C.c_int, P, C.c_size_t, C.POINTER(P)]),
     ("ilb_df_download", C.c_int, [P, P, C.c_size_t]),
@@ -193,6 +199,7 @@ _PROTOTYPES = [
     ("ilb_render_lighting_device", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, P]),
     ("ilb_render_lighting_peers", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, C.POINTER(P), C.c_int]),
     ("ilb_update_light_probes", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, P, P, C.c_int, C.c_int, P]),
+    ("ilb_update_light_probes_device", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, P, P, C.c_int, C.c_int, P]),
     ("ilb_resolve_lighting", C.c_int, [P, C.POINTER(Resolve), P, P, P]),
     ("ilb_resolve_lighting_device", C.c_int, [P, C.POINTER(Resolve), P, P, P]),
     ("ilb_compute_luminance", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, C.c_int, P]),
@@ -267,6 +274,15 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.ilb_launch_count(self.handle))
+
+    def set_option(self, option: int, value: int):
+        """Scheduling knobs (ilb_option): never change results."""
+        self.check(self.lib.ilb_set_option(self.handle, int(option), int(value)))
+
+    def get_option(self, option: int) -> int:
+        v = C.c_int(0)
+        self.check(self.lib.ilb_get_option(self.handle, int(option), C.byref(v)))
+        return int(v.value)
 
     def close(self):
         if getattr(self, "handle", None):

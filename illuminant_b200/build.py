@@ -15,7 +15,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = Path(os.environ["ILB_OUT"]) if os.environ.get("ILB_OUT") else PKG / "libilluminant_b200.so"  # ILB_OUT: variant builds
 SOURCES = ["api.cu", "lighting.cu", "particles.cu", "dfgen.cu", "planes.cu", "resolve.cu", "raster.cu"]
-HEADERS = ["ilb_device.cuh", "ilb_internal.h", "ilb_shapes.cuh", "ilb_bezier.cuh", "../../include/illuminant_b200.h"]
+HEADERS = ["ilb_device.cuh", "ilb_internal.h", "ilb_shapes.cuh", "ilb_bezier.cuh", "../../include/illuminant_b200.h", "../../include/ilb_detmath.h"]
 
 # FMA contraction on, 2-ulp division / sqrt (MUFU based), denormals flushed; sin/cos/pow/atan2/acos stay the accurate
 # library versions (no -use_fast_math).  See DESIGN.md "Numerics".  ILB_EXACT=1 builds the bit-faithful variant

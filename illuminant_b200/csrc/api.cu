@@ -74,9 +74,39 @@ bool ilb_make_df_geometry(const ilb_df* df, const ilb_df_uniforms& u, DFGeometry
     return true;
 }
 
+namespace {
+// the device build of include/ilb_detmath.h exactly as the kernels include it (ilb_device.cuh)
+__global__ void detmath_kernel(int function, const float* __restrict__ x, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i];
+    out[i] = function == 0 ? dm_sinf(v) : (function == 1 ? dm_cosf(v) : dm_acosf(v));
+}
+}  // namespace
+
 extern "C" {
 
 int ilb_abi_version(void) { return ILB_ABI_VERSION; }
+
+int ilb_debug_detmath(ilb_ctx* ctx, int function, const float* x, float* out, int count) {
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
+    if (function < 0 || function > 2 || count < 0 || (count > 0 && (!x || !out))) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad argument");
+    if (count == 0) return ILB_OK;
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    float* d = nullptr;
+    ILB_CUDA(ctx, cudaMalloc(&d, sizeof(float) * 2 * (size_t)count));
+    cudaError_t e = cudaMemcpyAsync(d, x, sizeof(float) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        detmath_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(function, d, d + count, count);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + count, sizeof(float) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return ilb_cuda_fail(ctx, e, "ilb_debug_detmath");
+    return ILB_OK;
+}
 
 int ilb_create(int device_ordinal, ilb_ctx** out_ctx) {
     if (!out_ctx) return ilb_fail(nullptr, ILB_ERR_INVALID_ARGUMENT, "out_ctx is null");
@@ -101,8 +131,30 @@ int ilb_create(int device_ordinal, ilb_ctx** out_ctx) {
         delete ctx;
         return ilb_cuda_fail(nullptr, e, "cudaStreamCreate");
     }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);
+    static const struct { const char* env; int value; } defaults[ILB_OPT_COUNT] = {
+        {"ILB_OPT_LIGHT_CONCURRENT", 1}, {"ILB_OPT_LIGHT_LINE_CTAS", 2}, {"ILB_OPT_LIGHT_OTHER_CTAS", 2},
+        {"ILB_OPT_LIGHT_LINE_HELPERS", 1}, {"ILB_OPT_LIGHT_OTHER_HELPERS", 3}};
+    for (int i = 0; i < ILB_OPT_COUNT; i++) {
+        const char* e = getenv(defaults[i].env);
+        ctx->opt[i] = e ? atoi(e) : defaults[i].value;
+    }
     live_add(ctx);
     *out_ctx = ctx;
+    return ILB_OK;
+}
+
+int ilb_set_option(ilb_ctx* ctx, int option, int value) {
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
+    if (option < 0 || option >= ILB_OPT_COUNT) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "unknown option %d", option);
+    if (value < 0 || value > 32) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "option %d: value %d outside [0,32]", option, value);
+    ctx->opt[option] = value;
+    return ILB_OK;
+}
+
+int ilb_get_option(const ilb_ctx* ctx, int option, int* out_value) {
+    if (!ctx || !out_value || option < 0 || option >= ILB_OPT_COUNT) return ILB_ERR_INVALID_ARGUMENT;
+    *out_value = ctx->opt[option];
     return ILB_OK;
 }
 
@@ -114,10 +166,19 @@ void ilb_destroy(ilb_ctx* ctx) {
     while (!ctx->systems.empty()) ilb_particles_destroy(ctx->systems.back());
     if (ctx->gbuffer && ctx->gbuffer_owned) cudaFree(ctx->gbuffer);
     if (ctx->d_lights) cudaFree(ctx->d_lights);
-    if (ctx->h_lights) cudaFreeHost(ctx->h_lights);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->h_lights[i]) cudaFreeHost(ctx->h_lights[i]);
+        if (ctx->ev_lights[i]) cudaEventDestroy(ctx->ev_lights[i]);
+    }
     if (ctx->d_lightmap) cudaFree(ctx->d_lightmap);
     if (ctx->d_probe_in) cudaFree(ctx->d_probe_in);
     if (ctx->d_accum) cudaFree(ctx->d_accum);
+    if (ctx->d_accum2) cudaFree(ctx->d_accum2);
+    if (ctx->d_tilework) cudaFree(ctx->d_tilework);
+    if (ctx->light_aux[0]) {
+        for (int i = 0; i < 3; i++) { cudaStreamDestroy(ctx->light_aux[i]); cudaEventDestroy(ctx->ev_light_join[i]); }
+        cudaEventDestroy(ctx->ev_light_fork);
+    }
     if (ctx->d_resolve_in) cudaFree(ctx->d_resolve_in);
     if (ctx->d_resolve_albedo) cudaFree(ctx->d_resolve_albedo);
     if (ctx->d_resolve_out) cudaFree(ctx->d_resolve_out);
@@ -415,7 +476,17 @@ int ilb_update_light_probes(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* 
     if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
     return ilb_probes_launch(ctx, df, frame, batches, batch_count, vertices, vertex_count, probe_positions, probe_normals, probe_count,
-                             output_format, probes_out);
+                             output_format, probes_out, nullptr);
+}
+
+int ilb_update_light_probes_device(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches, int batch_count,
+                                   const ilb_light_vertex* vertices, int vertex_count, const ilb_float4* probe_positions,
+                                   const ilb_float4* probe_normals, int probe_count, int output_format, void* d_probes_out) {
+    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!d_probes_out) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "d_probes_out is null");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ilb_probes_launch(ctx, df, frame, batches, batch_count, vertices, vertex_count, probe_positions, probe_normals, probe_count,
+                             output_format, nullptr, d_probes_out);
 }
 
 // ---------------------------------------------------------------------------------------------- particles
@@ -459,6 +530,7 @@ void ilb_particles_destroy(ilb_psys* ps) {
         if (ps->buf[i]) cudaFree(ps->buf[i]);
     if (ps->rng) cudaFree(ps->rng);
     if (ps->noise_table) cudaFree(ps->noise_table);
+    if (ps->escape_table) cudaFree(ps->escape_table);
     if (ps->positions) cudaFree(ps->positions);
     if (ps->pattern) cudaFree(ps->pattern);
     ilb_raster_release(ps);
@@ -468,7 +540,7 @@ void ilb_particles_destroy(ilb_psys* ps) {
 }
 
 int ilb_particles_set_randomness(ilb_psys* ps, const ilb_float4* table, int w, int h) {
-    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ps || !live_has(ps)) return ILB_ERR_INVALID_ARGUMENT;
     ilb_ctx* ctx = ps->ctx;
     if (!table || w <= 0 || h <= 0) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad randomness table");
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -484,7 +556,7 @@ int ilb_particles_set_randomness(ilb_psys* ps, const ilb_float4* table, int w, i
 }
 
 int ilb_particles_set_life_ramp(ilb_psys* ps, const ilb_float4* texels, int w, int h) {
-    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ps || !live_has(ps)) return ILB_ERR_INVALID_ARGUMENT;
     ilb_ctx* ctx = ps->ctx;
     if (texels && (w <= 0 || h <= 0 || w > 16384 || h > 16384)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad life ramp size %dx%d", w, h);
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -502,21 +574,21 @@ int ilb_particles_set_life_ramp(ilb_psys* ps, const ilb_float4* texels, int w, i
 }
 
 int ilb_particles_set_collision_field(ilb_psys* ps, ilb_df* df) {
-    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ps || !live_has(ps)) return ILB_ERR_INVALID_ARGUMENT;
     if (df && (!live_has(df) || df->ctx != ps->ctx)) return ilb_fail(ps->ctx, ILB_ERR_INVALID_ARGUMENT, "distance field is released or belongs to another context");
     ps->field = df;
     return ILB_OK;
 }
 
 int ilb_particles_set_live_chunks(ilb_psys* ps, int count) {
-    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ps || !live_has(ps)) return ILB_ERR_INVALID_ARGUMENT;
     if (count < 0 || count > ps->max_chunks) return ilb_fail(ps->ctx, ILB_ERR_INVALID_ARGUMENT, "live chunk count %d outside [0,%d]", count, ps->max_chunks);
     ps->live_chunks = count;
     return ILB_OK;
 }
 
 int ilb_particles_upload_chunk(ilb_psys* ps, int chunk, const ilb_float4* p, const ilb_float4* v, const ilb_float4* a) {
-    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ps || !live_has(ps)) return ILB_ERR_INVALID_ARGUMENT;
     ilb_ctx* ctx = ps->ctx;
     if (chunk < 0 || chunk >= ps->max_chunks) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "chunk %d outside [0,%d)", chunk, ps->max_chunks);
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -529,7 +601,7 @@ int ilb_particles_upload_chunk(ilb_psys* ps, int chunk, const ilb_float4* p, con
 }
 
 int ilb_particles_upload_buffer(ilb_psys* ps, int chunk, int which, const ilb_float4* data) {
-    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ps || !live_has(ps)) return ILB_ERR_INVALID_ARGUMENT;
     ilb_ctx* ctx = ps->ctx;
     if (!data || which < 0 || which > 4) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null data or bad buffer index %d", which);
     if (chunk < 0 || chunk >= ps->max_chunks) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "chunk %d out of range [0,%d)", chunk, ps->max_chunks);
@@ -540,7 +612,7 @@ int ilb_particles_upload_buffer(ilb_psys* ps, int chunk, int which, const ilb_fl
 }
 
 int ilb_particles_download_chunk(ilb_psys* ps, int chunk, ilb_float4* p, ilb_float4* v, ilb_float4* a, ilb_float4* rc, ilb_float4* rd) {
-    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ps || !live_has(ps)) return ILB_ERR_INVALID_ARGUMENT;
     ilb_ctx* ctx = ps->ctx;
     if (chunk < 0 || chunk >= ps->max_chunks) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "chunk %d outside [0,%d)", chunk, ps->max_chunks);
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -554,14 +626,14 @@ int ilb_particles_download_chunk(ilb_psys* ps, int chunk, ilb_float4* p, ilb_flo
 
 int ilb_particles_step(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spawn* spawns, int spawn_count, const ilb_op* ops,
                        int op_count, int steps) {
-    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ps || !live_has(ps)) return ILB_ERR_INVALID_ARGUMENT;
     ILB_CUDA(ps->ctx, cudaSetDevice(ps->ctx->device));
     return ilb_particles_launch(ps, u, spawns, nullptr, spawn_count, ops, op_count, steps);
 }
 
 int ilb_particles_step_sources(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spawn* spawns, const ilb_spawn_source* sources,
                                int spawn_count, const ilb_op* ops, int op_count, int steps) {
-    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ps || !live_has(ps)) return ILB_ERR_INVALID_ARGUMENT;
     ILB_CUDA(ps->ctx, cudaSetDevice(ps->ctx->device));
     if (sources)
         for (int i = 0; i < spawn_count; i++)
@@ -572,13 +644,13 @@ int ilb_particles_step_sources(ilb_psys* ps, const ilb_psys_uniforms* u, const i
 
 // ---------------------------------------------------------------------------------------------- particle rasterisation (N2)
 int ilb_particles_render_device(ilb_psys* ps, const ilb_particle_render* params, const void* d_texture, void* d_target) {
-    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ps || !live_has(ps)) return ILB_ERR_INVALID_ARGUMENT;
     ILB_CUDA(ps->ctx, cudaSetDevice(ps->ctx->device));
     return ilb_raster_launch(ps, params, d_texture, d_target);
 }
 
 int ilb_particles_render(ilb_psys* ps, const ilb_particle_render* r, const void* texture, void* target) {
-    if (!ps) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ps || !live_has(ps)) return ILB_ERR_INVALID_ARGUMENT;
     ilb_ctx* ctx = ps->ctx;
     if (!r || !target) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -607,12 +679,12 @@ int ilb_particles_render(ilb_psys* ps, const ilb_particle_render* r, const void*
 }
 
 void* ilb_particles_device_buffer(ilb_psys* ps, int which) {
-    if (!ps || which < 0 || which > 4) return nullptr;
+    if (!ps || !live_has(ps) || which < 0 || which > 4) return nullptr;
     return ps->buf[which];
 }
 
 int ilb_particles_count_live(ilb_psys* ps, int64_t* out_count) {
-    if (!ps || !out_count) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ps || !out_count || !live_has(ps)) return ILB_ERR_INVALID_ARGUMENT;
     ILB_CUDA(ps->ctx, cudaSetDevice(ps->ctx->device));
     return ilb_particles_count_launch(ps, out_count);
 }

@@ -33,11 +33,13 @@ ILB_DEV float bezierScalar(float a, float b, float c, float d, float count, floa
     return lerpf(abbc, bccd, t);
 }
 ILB_DEV float evaluateBezier1(const ilb_bezier1& b, float value) {  // :97-101
+    if (b.RangeAndCount.z <= 1.5f) return b.ABCD.x;  // uniform: a one-point curve (the default) never looks at t
     float t;
     const float count = tForScaledBezier(b.RangeAndCount, value, t);
     return bezierScalar(b.ABCD.x, b.ABCD.y, b.ABCD.z, b.ABCD.w, count, t);
 }
 ILB_DEV f4 evaluateBezier4(const ilb_bezier4& b, float value) {  // :141-177
+    if (b.RangeAndCount.z <= 1.5f) return mk4(b.A);  // uniform: a one-point curve (the default) never looks at t
     float t;
     const float count = tForScaledBezier(b.RangeAndCount, value, t);
     return mk4(bezierScalar(b.A.x, b.B.x, b.C.x, b.D.x, count, t), bezierScalar(b.A.y, b.B.y, b.C.y, b.D.y, count, t),

@@ -31,8 +31,10 @@ struct ilb_ctx {
     // per-frame staging
     void* d_lights = nullptr;
     size_t d_lights_capacity = 0;
-    void* h_lights = nullptr;  // pinned
-    size_t h_lights_capacity = 0;
+    void* h_lights[2] = {nullptr, nullptr};  // pinned, alternating (uploadLights)
+    size_t h_lights_capacity[2] = {0, 0};
+    cudaEvent_t ev_lights[2] = {nullptr, nullptr};
+    int h_lights_next = 0;
     void* d_lightmap = nullptr;  // staging for host-output entry points
     size_t d_lightmap_capacity = 0;
     void* d_probe_in = nullptr;
@@ -43,8 +45,16 @@ struct ilb_ctx {
     void* d_resolve_albedo = nullptr; size_t d_resolve_albedo_capacity = 0;
     void* d_resolve_out = nullptr;  size_t d_resolve_out_capacity = 0;
     void* d_luminance[2] = {nullptr, nullptr}; size_t d_luminance_capacity[2] = {0, 0};
-    void* d_accum = nullptr;     // fp32 sums handed from the line-light pass to the sphere / directional pass
+    void* d_accum = nullptr;     // fp32 sums of the line-light pass (handed to / combined with the sphere + directional pass)
     size_t d_accum_capacity = 0;
+    // concurrent lighting passes (lighting.cu, lightingLaunchRows): the other pass's fp32 sums, tile queues + arrival
+    // counters, the streams of the second pass and of the two helper grids, fork / join events
+    void* d_accum2 = nullptr;    size_t d_accum2_capacity = 0;
+    void* d_tilework = nullptr;  size_t d_tilework_capacity = 0;
+    cudaStream_t light_aux[3] = {};
+    cudaEvent_t ev_light_fork = nullptr, ev_light_join[3] = {};
+    int sm_count = 148;
+    int opt[ILB_OPT_COUNT] = {};  // tuning knobs, ilb_set_option
     // ParticleLightSources applied to every frame until replaced (ilb_lighting_set_particle_lights)
     std::vector<ilb_particle_light_source> particle_lights;
     void* d_plight_scratch = nullptr;
@@ -92,6 +102,7 @@ struct ilb_psys {
     uint8_t* pattern = nullptr;     // packed mip chain of an ILB_SPAWN_PATTERN spawn's texture
     size_t pattern_capacity = 0;
     float4* noise_table = nullptr;  // 2 * per_chunk float4, see noise_table_kernel
+    float2* escape_table = nullptr; // per_chunk float2, see escape_table_kernel
     unsigned long long* d_count = nullptr;
     bool use_tma = false;  // ILB_PARTICLE_TMA=1 selects the TMA-staged persistent step kernel (measured 22 % slower: the
                            // chain is issue-bound and tile-lockstep adds barrier stalls; the direct kernel is the default)
@@ -120,7 +131,7 @@ int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* fram
                         int output_count, bool outputs_are_full_frames);
 int ilb_probes_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches,
                       int batch_count, const ilb_light_vertex* vertices, int vertex_count, const ilb_float4* positions,
-                      const ilb_float4* normals, int probe_count, int output_format, void* probes_out_host);
+                      const ilb_float4* normals, int probe_count, int output_format, void* probes_out_host, void* d_probes_out);
 int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches,
                                  int batch_count, const ilb_light_vertex* vertices, int vertex_count, int gw, int gh, int gfmt,
                                  const void* gbuffer_host, void* lightmap_out_host);

@@ -73,6 +73,10 @@ struct LightingParams {
     int tiles_x, tiles_y;
     const float4* accum_in;  // fp32 sums of an earlier pass over this row band (nullptr: start from `clear`)
     float4* accum_out;       // leave the fp32 sums here instead of storing the lightmap (nullptr: final pass)
+    // concurrent passes (light_accumulate_persistent_kernel): this pass's tile queue, and the per-tile arrival counters of
+    // the two passes -- then accum_out is this pass's scratch and accum_in the other pass's
+    unsigned* tile_counter;
+    unsigned* tile_done;
 };
 
 struct Pixel {
@@ -112,6 +116,7 @@ ILB_DEV TraceConfig makeTraceConfig(const DLight& L, float rampX, float rampY, f
 struct Trace {  // TraceState :31-35
     f3 origin, direction;
     float t, len, vis;
+    float tSafe;  // lineTraceMarch: see safeInsideLimit
 };
 
 // returns true when the marched interval t < len stays on the segment start -> end
@@ -136,19 +141,36 @@ ILB_DEV float traceStep(const TraceConfig& c, float d, float offset, float& vis)
 }
 
 ILB_DEV float traceFinal(const TraceConfig& c, float visibility) {  // :182-188
-    return powf(saturatef(saturatef(visibility - FULLY_SHADOWED_THRESHOLD) / (UNSHADOWED_THRESHOLD - FULLY_SHADOWED_THRESHOLD)),
-                c.power);
+    const float v = saturatef(saturatef(visibility - FULLY_SHADOWED_THRESHOLD) / (UNSHADOWED_THRESHOLD - FULLY_SHADOWED_THRESHOLD));
+    if (c.power == 1.0f) return v;  // uniform per light: OcclusionToOpacityPower defaults to 1 (pow(v, 1) == v)
+    return powf(v, c.power);
+}
+
+// Largest ray parameter up to which origin + direction * t provably stays inside the field volume (a conservative bound:
+// 0.05 px of slack on every face covers the rounding of the per-sample position, which is below 1e-3 px for coordinates
+// up to 8192).  The march then tests `t <= tSafe` (one compare) instead of the six-compare volume test per sample; beyond
+// the bound it samples through the general path, which is correct everywhere, so the bits never depend on the bound.
+ILB_DEV float safeInsideLimit(const DFGeometry& g, f3 o, f3 d) {
+    const float m = 0.05f;
+    const float oz = o.z - g.zOffset;
+    if (!((o.x >= m) && (o.x <= g.ex - m) && (o.y >= m) && (o.y <= g.ey - m) && (oz >= m) && (oz <= g.ez - m))) return -1.0f;
+    const float BIG = 3.0e38f;
+    const float tx = (d.x > 0.0f) ? __fdividef((g.ex - m) - o.x, d.x) : ((d.x < 0.0f) ? __fdividef(m - o.x, d.x) : BIG);
+    const float ty = (d.y > 0.0f) ? __fdividef((g.ey - m) - o.y, d.y) : ((d.y < 0.0f) ? __fdividef(m - o.y, d.y) : BIG);
+    const float tz = (d.z > 0.0f) ? __fdividef((g.ez - m) - oz, d.z) : ((d.z < 0.0f) ? __fdividef(m - oz, d.z) : BIG);
+    return fminf(fminf(tx, ty), tz) * (1.0f - 3.0e-5f);
 }
 
 template <int FIELD, bool INSIDE>
 ILB_DEV void coneTraceMarch(const DFGeometry& g, const TraceConfig& c, Trace& a, float& stepsRemaining) {
     float liveness = 1.0f;
+    // a ray that ends outside the volume still spends most of its samples inside it: there the clamp is the
+    // identity and the distance-to-volume term is exactly 0, so the short sampler gives the same bits
+    const float tSafe = INSIDE ? 0.0f : safeInsideLimit(g, a.origin, a.direction);
     while (liveness > 0.0f) {
         stepsRemaining -= 1.0f;
         const f3 sp = xadd3(a.origin, xscale3(a.direction, a.t));  // coneTraceAdvance :73-82
-        // a ray that ends outside the volume still spends most of its samples inside it: there the clamp is the
-        // identity and the distance-to-volume term is exactly 0, so the short sampler gives the same bits
-        const float d = (INSIDE || insideField(g, sp)) ? sampleFieldT<FIELD, true>(g, sp) : sampleFieldT<FIELD, false>(g, sp);
+        const float d = (INSIDE || (a.t <= tSafe)) ? sampleFieldT<FIELD, true>(g, sp) : sampleFieldT<FIELD, false>(g, sp);
         a.t = xadd(a.t, traceStep(c, d, a.t, a.vis));
         // liveness = stepsRemaining * saturate(vis - 0.075) * saturate(len - t) > 0 (ConeTrace.fxh:168-176): a product of
         // non-negative factors that cannot underflow (a non-zero factor is at least one ulp of 0.075 resp. of t >= 0.5), so it
@@ -160,11 +182,14 @@ ILB_DEV void coneTraceMarch(const DFGeometry& g, const TraceConfig& c, Trace& a,
 template <int FIELD, bool FAST>
 ILB_DEV float coneTrace(const DFGeometry& g, const DLight& L, f3 lightCenter, float rampX, float rampY,
                         float growthFactor, f3 shaded, bool enable, Guard& bad) {  // coneTrace :141-191
-    Trace a;
-    const bool onSegment = traceInit<FAST>(a, shaded, lightCenter, rampX, bad);
+    // a disabled trace returns 1 whatever its state (ConeTrace.fxh:159,190): its set-up (a normalisation and three IEEE
+    // divisions) is only run for the pixels that march
+    if (!enable) return 1.0f;
     const TraceConfig c = makeTraceConfig(L, rampX, rampY, growthFactor);
-    float stepsRemaining = c.stepLimit;
-    if (L.hasField && enable) {
+    float stepsRemaining = c.stepLimit, vis = 1.0f;
+    if (L.hasField) {
+        Trace a;
+        const bool onSegment = traceInit<FAST>(a, shaded, lightCenter, rampX, bad);
         // every sample lies on the segment shaded -> lightCenter (t < len <= |v|); the field volume is convex, so when both
         // ends are inside every sample is inside and the clamp / distance-to-volume work of the sampler is skipped
         const bool inside = onSegment && insideField(g, shaded) && insideField(g, lightCenter);
@@ -174,15 +199,15 @@ ILB_DEV float coneTrace(const DFGeometry& g, const DLight& L, f3 lightCenter, fl
         if (inside) coneTraceMarch<FIELD, true>(g, c, a, stepsRemaining);
         else coneTraceMarch<FIELD, false>(g, c, a, stepsRemaining);
 #endif
+        vis = a.vis;
     }
-    const float visibility = fminf(a.vis, stepsRemaining / MAX_STEP_RAMP_WINDOW);
-    return enable ? traceFinal(c, visibility) : 1.0f;
+    return traceFinal(c, fminf(vis, stepsRemaining / MAX_STEP_RAMP_WINDOW));
 }
 
 template <int FIELD, bool INSIDE>
 ILB_DEV float traceAdvanceEx(const DFGeometry& g, const TraceConfig& c, Trace& s) {  // coneTraceAdvanceEx :84-96
     const f3 sp = xadd3(s.origin, xscale3(s.direction, s.t));
-    const float d = (INSIDE || insideField(g, sp)) ? sampleFieldT<FIELD, true>(g, sp) : sampleFieldT<FIELD, false>(g, sp);
+    const float d = (INSIDE || (s.t <= s.tSafe)) ? sampleFieldT<FIELD, true>(g, sp) : sampleFieldT<FIELD, false>(g, sp);
     s.t = fminf(xadd(s.t, traceStep(c, d, s.t, s.vis)), s.len);
     // saturate(vis - 0.075) * saturate((len - t) * 100): only its sign is used (lineConeTrace sums three of these and
     // multiplies by stepsRemaining); positive exactly when both factors are (no underflow, see coneTraceMarch)
@@ -310,6 +335,11 @@ ILB_DEV float lineLightOpacity(f3 wp, f3 wn, f3 P0, f3 P1, float lightRadius, co
 template <int FIELD, bool INSIDE>
 ILB_DEV void lineTraceMarch(const DFGeometry& g, const TraceConfig& cfg, Trace& a, Trace& b, Trace& c, float& stepsRemaining) {
     float liveness = 1.0f;
+    if (!INSIDE) {
+        a.tSafe = safeInsideLimit(g, a.origin, a.direction);
+        b.tSafe = safeInsideLimit(g, b.origin, b.direction);
+        c.tSafe = safeInsideLimit(g, c.origin, c.direction);
+    }
     while (liveness > 0.0f) {
         const float stepLiveness = traceAdvanceEx<FIELD, INSIDE>(g, cfg, a) + traceAdvanceEx<FIELD, INSIDE>(g, cfg, b) + traceAdvanceEx<FIELD, INSIDE>(g, cfg, c);
         stepsRemaining -= 1.0f;
@@ -320,16 +350,19 @@ ILB_DEV void lineTraceMarch(const DFGeometry& g, const TraceConfig& cfg, Trace& 
 template <int FIELD, bool FAST>
 ILB_DEV float lineConeTrace(const DFGeometry& g, const DLight& L, const DLine& D, f3 start, float u, float rampX, float rampY,
                             f3 shaded, bool enable, Guard& bad) {  // LineLightCore.fxh:17-68
-    Trace a, b, c;
-    const f3 delta = xyz(mk4(D.ab));
-    const float offset = D.center.w;
-    const f3 ta = xadd3(start, xscale3(delta, saturatef(xsub(u, offset)))), tb = xadd3(start, xscale3(delta, u));
-    const f3 tc = xadd3(start, xscale3(delta, saturatef(xadd(u, offset))));
-    const bool sa = traceInit<FAST>(a, shaded, ta, rampX, bad), sb = traceInit<FAST>(b, shaded, tb, rampX, bad);
-    const bool sc = traceInit<FAST>(c, shaded, tc, rampX, bad);
+    // a disabled trace returns 1 whatever its state (LineLightCore.fxh:62-67): most pixels of a line light's full-screen quad
+    // lie in its far field (pre-trace opacity below 0.75 / 255) and skip the set-up of the three traces altogether
+    if (!enable) return 1.0f;
     const TraceConfig cfg = makeTraceConfig(L, rampX, rampY, 1.0f);
-    float stepsRemaining = cfg.stepLimit;
-    if (L.hasField && enable) {
+    float stepsRemaining = cfg.stepLimit, visSum = 3.0f;
+    if (L.hasField) {
+        Trace a, b, c;
+        const f3 delta = xyz(mk4(D.ab));
+        const float offset = D.center.w;
+        const f3 ta = xadd3(start, xscale3(delta, saturatef(xsub(u, offset)))), tb = xadd3(start, xscale3(delta, u));
+        const f3 tc = xadd3(start, xscale3(delta, saturatef(xadd(u, offset))));
+        const bool sa = traceInit<FAST>(a, shaded, ta, rampX, bad), sb = traceInit<FAST>(b, shaded, tb, rampX, bad);
+        const bool sc = traceInit<FAST>(c, shaded, tc, rampX, bad);
         // t is clamped to len <= |target - shaded| for all three traces: samples stay on their segments
         const bool inside = sa && sb && sc && insideField(g, shaded) && insideField(g, ta) && insideField(g, tb) && insideField(g, tc);
 #if ILB_NO_INSIDE_PATH
@@ -338,9 +371,9 @@ ILB_DEV float lineConeTrace(const DFGeometry& g, const DLight& L, const DLine& D
         if (inside) lineTraceMarch<FIELD, true>(g, cfg, a, b, c, stepsRemaining);
         else lineTraceMarch<FIELD, false>(g, cfg, a, b, c, stepsRemaining);
 #endif
+        visSum = a.vis + b.vis + c.vis;
     }
-    const float visibility = fminf((a.vis + b.vis + c.vis) / 3.0f, stepsRemaining / MAX_STEP_RAMP_WINDOW);
-    return enable ? traceFinal(cfg, visibility) : 1.0f;
+    return traceFinal(cfg, fminf(visSum / 3.0f, stepsRemaining / MAX_STEP_RAMP_WINDOW));
 }
 
 template <int FIELD, bool FAST>
@@ -591,27 +624,30 @@ ILB_DEV float warpMax(float v) {
 #define ILB_LIGHT_MINBLOCKS_NOLINE 5
 #endif
 // TYPES: the light types this pass shades (lights of other types are dropped by the tile culling).  A frame is one
-// pass over all types, or -- ILB_SPLIT_PASSES, the default when line lights are present -- a line-light pass that
-// leaves its fp32 sums in P.accum_out followed by a sphere + directional pass that starts from them.
-template <int FIELD, int TYPES>
-__global__ void __launch_bounds__(TILE_THREADS, (TYPES & ILB_LIGHT_LINE) ? ILB_LIGHT_MINBLOCKS : ILB_LIGHT_MINBLOCKS_NOLINE)
-light_accumulate_kernel(const __grid_constant__ LightingParams P) {
-    __shared__ float s_box[TILE_WARPS][6];
-    __shared__ int s_warpCount[TILE_WARPS];
-    __shared__ uint16_t s_list[TILE_THREADS];
-    __shared__ int s_listCount;
+// pass over all types, or -- when line lights and other lights are both present -- a line-light pass and a sphere +
+// directional pass with their own register budgets (see lightingLaunchRows for how the two are scheduled).
+struct TileSmem {
+    float box[TILE_WARPS][6];
+    int warpCount[TILE_WARPS];
+    uint16_t list[TILE_THREADS];
+    uint8_t mask[TILE_THREADS];  // per listed light: bit w set when the light can reach warp w's 8x4 pixel block
+    int listCount;
+    unsigned next, arrival;      // persistent CTAs: the tile taken from the queue, this pass's arrival rank at the tile
+};
 
+template <int FIELD, int TYPES>
+ILB_DEV void shadeTile(const LightingParams& P, unsigned tile, TileSmem& S) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // a warp covers an 8x4 pixel patch: neighbouring lanes trace neighbouring rays (coherent DF footprints)
     int tileX, tileY;
     if (ILB_SWIZZLE > 1) {
-        const int band = blockIdx.x / (ILB_SWIZZLE * P.tiles_x), inband = blockIdx.x % (ILB_SWIZZLE * P.tiles_x);
+        const int band = tile / (ILB_SWIZZLE * P.tiles_x), inband = tile % (ILB_SWIZZLE * P.tiles_x);
         const int rowsInBand = min(ILB_SWIZZLE, P.tiles_y - band * ILB_SWIZZLE);
         tileX = inband / rowsInBand;
         tileY = band * ILB_SWIZZLE + inband % rowsInBand;
     } else {
-        tileX = blockIdx.x % P.tiles_x;
-        tileY = blockIdx.x / P.tiles_x;
+        tileX = tile % P.tiles_x;
+        tileY = tile / P.tiles_x;
     }
     const int px = tileX * TILE_W + (warp & 1) * 8 + (lane & 7);
     const int py = P.row_begin + tileY * TILE_H + (warp >> 1) * 4 + (lane >> 3);
@@ -630,15 +666,15 @@ light_accumulate_kernel(const __grid_constant__ LightingParams P) {
     by0 = warpMin(by0); by1 = warpMax(by1);
     bz0 = warpMin(bz0); bz1 = warpMax(bz1);
     if (lane == 0) {
-        s_box[warp][0] = bx0; s_box[warp][1] = bx1; s_box[warp][2] = by0;
-        s_box[warp][3] = by1; s_box[warp][4] = bz0; s_box[warp][5] = bz1;
+        S.box[warp][0] = bx0; S.box[warp][1] = bx1; S.box[warp][2] = by0;
+        S.box[warp][3] = by1; S.box[warp][4] = bz0; S.box[warp][5] = bz1;
     }
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < TILE_WARPS; w++) {
-        bx0 = fminf(bx0, s_box[w][0]); bx1 = fmaxf(bx1, s_box[w][1]);
-        by0 = fminf(by0, s_box[w][2]); by1 = fmaxf(by1, s_box[w][3]);
-        bz0 = fminf(bz0, s_box[w][4]); bz1 = fmaxf(bz1, s_box[w][5]);
+        bx0 = fminf(bx0, S.box[w][0]); bx1 = fmaxf(bx1, S.box[w][1]);
+        by0 = fminf(by0, S.box[w][2]); by1 = fmaxf(by1, S.box[w][3]);
+        bz0 = fminf(bz0, S.box[w][4]); bz1 = fmaxf(bz1, S.box[w][5]);
     }
     const int tx0 = tileX * TILE_W, tx1 = tx0 + TILE_W - 1;
     const int ty0 = P.row_begin + tileY * TILE_H, ty1 = ty0 + TILE_H - 1;
@@ -649,7 +685,7 @@ light_accumulate_kernel(const __grid_constant__ LightingParams P) {
 
     float accR = P.clear.x, accG = P.clear.y, accB = P.clear.z, accA = P.clear.w;
     const size_t scratchIndex = (size_t)(py - P.row_begin) * (size_t)P.width + (size_t)px;
-    if (P.accum_in && valid) {
+    if (P.accum_in && !P.tile_done && valid) {
         const float4 a = P.accum_in[scratchIndex];
         accR = a.x; accG = a.y; accB = a.z; accA = a.w;
     }
@@ -658,6 +694,7 @@ light_accumulate_kernel(const __grid_constant__ LightingParams P) {
         // ---- cull: thread t tests light base+t against the tile
         const int li = base + tid;
         bool keep = false;
+        unsigned warpMask = 0xFFu;
         if (li < P.nlights) {
             const DLight* L = P.lights + li;
             const int4 r = __ldg(reinterpret_cast<const int4*>(&L->px0));
@@ -672,27 +709,48 @@ light_accumulate_kernel(const __grid_constant__ LightingParams P) {
                 const float dz = fmaxf(fmaxf(bz0 - c.z, c.z - bz1), 0.0f);
                 const float reach = pr.x + fmaxf(pr.y, 1.0f) + 1.0f;
                 keep = (dx * dx + dy * dy + dz * dz) <= reach * reach;
+#if !ILB_NO_WARP_CULL
+                if (keep) {  // second level: the same two tests against every warp's own 8x4 block (pixel rectangle, world AABB)
+                    warpMask = 0u;
+#pragma unroll
+                    for (int w = 0; w < TILE_WARPS; w++) {
+                        const int wx0 = tx0 + (w & 1) * 8, wy0 = ty0 + (w >> 1) * 4;
+                        const float ex = fmaxf(fmaxf(S.box[w][0] - c.x, c.x - S.box[w][1]), 0.0f);
+                        const float ey = fmaxf(fmaxf(S.box[w][2] - c.y, c.y - S.box[w][3]), 0.0f) * fabsf(mo.z);
+                        const float ez = fmaxf(fmaxf(S.box[w][4] - c.z, c.z - S.box[w][5]), 0.0f);
+                        const bool hit = (r.x <= wx0 + 7) && (r.z >= wx0) && (r.y <= wy0 + 3) && (r.w >= wy0) && (S.box[w][0] <= S.box[w][1]) &&
+                                         ((ex * ex + ey * ey + ez * ez) <= reach * reach);
+                        warpMask |= hit ? (1u << w) : 0u;
+                    }
+                    keep = warpMask != 0u;
+                }
+#endif
             }
         }
         // ---- ordered compaction (draw order is kept so accumulation order matches the reference)
         const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
-        if (lane == 0) s_warpCount[warp] = __popc(ballot);
+        if (lane == 0) S.warpCount[warp] = __popc(ballot);
         __syncthreads();
         int offset = 0, total = 0;
 #pragma unroll
         for (int w = 0; w < TILE_WARPS; w++) {
-            const int c = s_warpCount[w];
+            const int c = S.warpCount[w];
             if (w < warp) offset += c;
             total += c;
         }
-        if (keep) s_list[offset + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)tid;
-        if (tid == 0) s_listCount = total;
+        if (keep) {
+            const int slot = offset + __popc(ballot & ((1u << lane) - 1u));
+            S.list[slot] = (uint16_t)tid;
+            S.mask[slot] = (uint8_t)warpMask;
+        }
+        if (tid == 0) S.listCount = total;
         __syncthreads();
 
         // ---- shade
-        const int n = s_listCount;
+        const int n = S.listCount;
         for (int k = 0; k < n; k++) {
-            const int lightIndex = base + (int)s_list[k];
+            if ((TYPES & ILB_LIGHT_SPHERE) && !((S.mask[k] >> warp) & 1u)) continue;  // warp-uniform: this block is out of the light's reach
+            const int lightIndex = base + (int)S.list[k];
             const DLight L = loadLight(P.lights, lightIndex);
             if (shade && coverage(L, wx, wy)) {
                 f3 rgb;
@@ -705,9 +763,55 @@ light_accumulate_kernel(const __grid_constant__ LightingParams P) {
         if (base + TILE_THREADS < P.nlights) __syncthreads();  // the list is rebuilt only when another round follows
     }
 
+    const size_t outIndex = (size_t)(py - P.out_row_base) * (size_t)P.width + (size_t)px;
+    if (P.tile_done) {
+        // Concurrent passes: each pass leaves its fp32 sums of the tile in its own scratch buffer; the pass that arrives
+        // second at the tile adds the two (line sums + other sums, a fixed operand order whoever arrives last) and stores
+        // the lightmap texel.  Release: scratch stores -> fence -> arrival counter; acquire: counter -> fence -> L2 loads.
+        if (valid) P.accum_out[scratchIndex] = make_float4(accR, accG, accB, accA);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) S.arrival = atomicAdd(P.tile_done + tile, 1u);
+        __syncthreads();
+        if (S.arrival != 0u) {
+            __threadfence();
+            if (valid) {
+                const float4 o = __ldcg(P.accum_in + scratchIndex);
+                storeTexel(P, outIndex, accR + o.x, accG + o.y, accB + o.z, accA + o.w);
+            }
+        }
+        return;
+    }
     if (!valid) return;
     if (P.accum_out) P.accum_out[scratchIndex] = make_float4(accR, accG, accB, accA);
-    else storeTexel(P, (size_t)(py - P.out_row_base) * (size_t)P.width + (size_t)px, accR, accG, accB, accA);
+    else storeTexel(P, outIndex, accR, accG, accB, accA);
+}
+
+template <int FIELD, int TYPES>
+__global__ void __launch_bounds__(TILE_THREADS, (TYPES & ILB_LIGHT_LINE) ? ILB_LIGHT_MINBLOCKS : ILB_LIGHT_MINBLOCKS_NOLINE)
+light_accumulate_kernel(const __grid_constant__ LightingParams P) {
+    __shared__ TileSmem S;
+    shadeTile<FIELD, TYPES>(P, blockIdx.x, S);
+}
+
+// Persistent form: a fixed number of resident CTAs per SM takes tiles from a queue (one atomic counter per pass), so that
+// the line-light pass (issue-bound, 80 registers) and the sphere + directional pass (latency-bound on its gathers, 48
+// registers) can be co-resident on every SM -- two CTAs of each fill the register file exactly -- and run side by side
+// instead of back to back.  "Helper" grids of the same kernels, launched behind the main grids, become resident when one
+// pass runs out of tiles and its CTAs exit, so the surviving pass gets its full occupancy back for the tail.
+template <int FIELD, int TYPES>
+__global__ void __launch_bounds__(TILE_THREADS, (TYPES & ILB_LIGHT_LINE) ? ILB_LIGHT_MINBLOCKS : ILB_LIGHT_MINBLOCKS_NOLINE)
+light_accumulate_persistent_kernel(const __grid_constant__ LightingParams P) {
+    __shared__ TileSmem S;
+    const unsigned ntiles = (unsigned)P.tiles_x * (unsigned)P.tiles_y;
+    for (;;) {
+        __syncthreads();  // the previous tile's shared state is no longer read
+        if (threadIdx.x == 0) S.next = atomicAdd(P.tile_counter, 1u);
+        __syncthreads();
+        const unsigned tile = S.next;
+        if (tile >= ntiles) return;
+        shadeTile<FIELD, TYPES>(P, tile, S);
+    }
 }
 
 // ---- light probes (L11): SphereLightProbe.fx:19-44, DirectionalLight.fx:163-190, LineLightProbe.fx:23-48 ----------
@@ -724,36 +828,55 @@ struct ProbeParams {
     void* out;
 };
 
+// One CTA per probe, one thread per light (rounds of PROBE_THREADS lights): the light-probe responses -- each with its own
+// cone trace -- are evaluated in parallel and summed by one thread in draw order, so the sums are the ones a serial loop
+// over the lights gives (the reference draws one additive pass per light into the probe target).
+constexpr int PROBE_THREADS = 128;
 template <int FIELD>
-__global__ void __launch_bounds__(128) probe_accumulate_kernel(const __grid_constant__ ProbeParams P) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.nprobes) return;
+__global__ void __launch_bounds__(PROBE_THREADS) probe_accumulate_kernel(const __grid_constant__ ProbeParams P) {
+    __shared__ float4 s_contribution[PROBE_THREADS];  // rgb, w = 1 when the light's fragment was not discarded
+    const int i = blockIdx.x, tid = threadIdx.x;
     const float4 ps = __ldg(P.positions + i), ns = __ldg(P.normals + i);  // sampleLightProbeBuffer LightCommon.fxh:233-254
     float accR = 0.0f, accG = 0.0f, accB = 0.0f, accA = 0.0f;
-    if (ps.w > 0.0f) {
+    if (ps.w > 0.0f) {  // uniform over the CTA
         const f3 p = mk3(ps.x, ps.y, ps.z), n = mk3(ns.x, ns.y, ns.z);
-        for (int k = 0; k < P.nlights; k++) {
-            const DLight L = loadLight(P.lights, k);
-            float4 props = L.props, more = L.more;
-            more.x = 0.0f;
-            more.w = 0.0f;
-            float core;
-            bool lit;
-            Guard bad = guardInit();  // probes are few: plain IEEE x-ops (FAST = false), no guard
-            if (L.type == ILB_LIGHT_DIRECTIONAL) {
-                props.x *= ns.w;
-                lit = directionalCore<FIELD, false>(P.df, L, p, n, L.color2, props, more, core, bad);
-            } else {  // sphere, and line lights shaded as spheres at LightPosition1 (reference quirk, LineLightProbe.fx:4)
-                props.w *= ns.w;
-                lit = sphereCore<FIELD, false>(P.df, L, P.lightOcclusion, p, n, mk3(L.pos1.x, L.pos1.y, L.pos1.z), props, more, core, bad);
+        for (int base = 0; base < P.nlights; base += PROBE_THREADS) {
+            const int k = base + tid;
+            float4 contribution = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (k < P.nlights) {
+                const DLight L = loadLight(P.lights, k);
+                float4 props = L.props, more = L.more;
+                more.x = 0.0f;
+                more.w = 0.0f;
+                float core;
+                bool lit;
+                Guard bad = guardInit();  // probes are few: plain IEEE x-ops (FAST = false), no guard
+                if (L.type == ILB_LIGHT_DIRECTIONAL) {
+                    props.x *= ns.w;
+                    lit = directionalCore<FIELD, false>(P.df, L, p, n, L.color2, props, more, core, bad);
+                } else {  // sphere, and line lights shaded as spheres at LightPosition1 (reference quirk, LineLightProbe.fx:4)
+                    props.w *= ns.w;
+                    lit = sphereCore<FIELD, false>(P.df, L, P.lightOcclusion, p, n, mk3(L.pos1.x, L.pos1.y, L.pos1.z), props, more, core, bad);
+                }
+                if (lit) {
+                    const float opacity = ps.w * core;
+                    const f3 rgb = mk3(L.color1.x, L.color1.y, L.color1.z) * L.color1.w * opacity;
+                    contribution = make_float4(rgb.x, rgb.y, rgb.z, 1.0f);
+                }
             }
-            if (lit) {
-                const float opacity = ps.w * core;
-                const f3 rgb = mk3(L.color1.x, L.color1.y, L.color1.z) * L.color1.w * opacity;
-                accR += rgb.x; accG += rgb.y; accB += rgb.z; accA += 1.0f;
+            s_contribution[tid] = contribution;
+            __syncthreads();
+            if (tid == 0) {
+                const int n_round = min(PROBE_THREADS, P.nlights - base);
+                for (int j = 0; j < n_round; j++) {
+                    const float4 c = s_contribution[j];
+                    if (c.w != 0.0f) { accR += c.x; accG += c.y; accB += c.z; accA += 1.0f; }
+                }
             }
+            __syncthreads();
         }
     }
+    if (tid != 0) return;
     if (P.out_format == ILB_FORMAT_FLOAT4) {
         reinterpret_cast<float4*>(P.out)[i] = make_float4(accR, accG, accB, accA);
     } else {
@@ -887,14 +1010,24 @@ int uploadLights(ilb_ctx* ctx, const std::vector<DLight>& lights, const std::vec
     const size_t lineBytes = std::max<size_t>(n, 1) * sizeof(DLine), hostBytes = lineBytes + std::max<size_t>(n, 1) * sizeof(DLight);
     int rc = ilb_reserve(ctx, &ctx->d_lights, &ctx->d_lights_capacity, hostBytes + extra * sizeof(DLight), false);
     if (rc) return rc;
-    rc = ilb_reserve(ctx, &ctx->h_lights, &ctx->h_lights_capacity, hostBytes, true);
-    if (rc) return rc;
-    // the pinned staging buffer is reused every frame: wait for the previous frame's copy
-    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // two pinned staging buffers alternate, each guarded by the event recorded behind its last copy: a frame never waits
+    // for the stream unless the copy issued two frames ago is still pending
+    const int slot = ctx->h_lights_next;
+    ctx->h_lights_next ^= 1;
+    if (!ctx->ev_lights[slot]) ILB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_lights[slot], cudaEventDisableTiming));
+    else ILB_CUDA(ctx, cudaEventSynchronize(ctx->ev_lights[slot]));
+    if (ctx->h_lights_capacity[slot] < hostBytes || !ctx->h_lights[slot]) {
+        if (ctx->h_lights[slot]) cudaFreeHost(ctx->h_lights[slot]);
+        ctx->h_lights[slot] = nullptr;
+        ctx->h_lights_capacity[slot] = 0;
+        ILB_CUDA(ctx, cudaMallocHost(&ctx->h_lights[slot], hostBytes * 2));
+        ctx->h_lights_capacity[slot] = hostBytes * 2;
+    }
     if (n) {
-        memcpy(ctx->h_lights, lines.data(), n * sizeof(DLine));
-        memcpy(reinterpret_cast<char*>(ctx->h_lights) + lineBytes, lights.data(), n * sizeof(DLight));
-        ILB_CUDA(ctx, cudaMemcpyAsync(ctx->d_lights, ctx->h_lights, hostBytes, cudaMemcpyHostToDevice, ctx->stream));
+        memcpy(ctx->h_lights[slot], lines.data(), n * sizeof(DLine));
+        memcpy(reinterpret_cast<char*>(ctx->h_lights[slot]) + lineBytes, lights.data(), n * sizeof(DLight));
+        ILB_CUDA(ctx, cudaMemcpyAsync(ctx->d_lights, ctx->h_lights[slot], hostBytes, cudaMemcpyHostToDevice, ctx->stream));
+        ILB_CUDA(ctx, cudaEventRecord(ctx->ev_lights[slot], ctx->stream));
     }
     *d_lines = reinterpret_cast<const DLine*>(ctx->d_lights);
     *d_lights = reinterpret_cast<const DLight*>(reinterpret_cast<const char*>(ctx->d_lights) + lineBytes);
@@ -1164,7 +1297,58 @@ int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin
             light_accumulate_kernel<0, TYPES><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);                            \
         ctx->launches++;                                                                                              \
     } while (0)
-    if (split) {
+    const bool concurrent = ctx->opt[ILB_OPT_LIGHT_CONCURRENT] != 0 &&  // every pass needs at least one grid, or its tiles are never shaded
+                            ctx->opt[ILB_OPT_LIGHT_LINE_CTAS] + ctx->opt[ILB_OPT_LIGHT_LINE_HELPERS] > 0 &&
+                            ctx->opt[ILB_OPT_LIGHT_OTHER_CTAS] + ctx->opt[ILB_OPT_LIGHT_OTHER_HELPERS] > 0;
+    if (split && concurrent) {
+        // both passes at once: persistent grids sized to be co-resident, one tile queue per pass, the pass that reaches a
+        // tile second adds the two fp32 partial sums and stores the texel (see light_accumulate_persistent_kernel)
+        const size_t bytes = sizeof(float4) * (size_t)P.width * (size_t)(row_end - row_begin);
+        int rc = ilb_reserve(ctx, &ctx->d_accum, &ctx->d_accum_capacity, bytes, false);
+        if (rc) return rc;
+        rc = ilb_reserve(ctx, &ctx->d_accum2, &ctx->d_accum2_capacity, bytes, false);
+        if (rc) return rc;
+        rc = ilb_reserve(ctx, &ctx->d_tilework, &ctx->d_tilework_capacity, sizeof(unsigned) * ((size_t)tiles + 2), false);
+        if (rc) return rc;
+        if (!ctx->light_aux[0]) {
+            for (int i = 0; i < 3; i++) {
+                ILB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->light_aux[i], cudaStreamNonBlocking));
+                ILB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_light_join[i], cudaEventDisableTiming));
+            }
+            ILB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_light_fork, cudaEventDisableTiming));
+        }
+        unsigned* work = reinterpret_cast<unsigned*>(ctx->d_tilework);
+        ILB_CUDA(ctx, cudaMemsetAsync(work, 0, sizeof(unsigned) * ((size_t)tiles + 2), ctx->stream));
+        ILB_CUDA(ctx, cudaEventRecord(ctx->ev_light_fork, ctx->stream));
+        for (int i = 0; i < 3; i++) ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->light_aux[i], ctx->ev_light_fork, 0));
+        LightingParams PL = P, PS = P;
+        PL.accum_out = reinterpret_cast<float4*>(ctx->d_accum); PL.accum_in = reinterpret_cast<const float4*>(ctx->d_accum2);
+        PS.accum_out = reinterpret_cast<float4*>(ctx->d_accum2); PS.accum_in = reinterpret_cast<const float4*>(ctx->d_accum);
+        PL.tile_counter = work; PS.tile_counter = work + 1;
+        PL.tile_done = PS.tile_done = work + 2;
+        PS.clear = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // the clear colour enters through the line-light sums
+        const unsigned sms = (unsigned)ctx->sm_count;
+        auto grid = [&](int perSm) { return std::min<unsigned>(tiles, sms * (unsigned)std::max(perSm, 0)); };
+#define ILB_LIGHT_PERSIST(PARAMS, TYPES, GRID, STREAM)                                                                 \
+    do {                                                                                                              \
+        if ((GRID) > 0) {                                                                                             \
+            if (P.df.planes && (planesMask & (((TYPES) & ILB_LIGHT_LINE) ? 1 : 2)))                                   \
+                light_accumulate_persistent_kernel<1, TYPES><<<(GRID), TILE_THREADS, 0, (STREAM)>>>(PARAMS);          \
+            else                                                                                                      \
+                light_accumulate_persistent_kernel<0, TYPES><<<(GRID), TILE_THREADS, 0, (STREAM)>>>(PARAMS);          \
+            ctx->launches++;                                                                                          \
+        }                                                                                                             \
+    } while (0)
+        ILB_LIGHT_PERSIST(PL, ILB_LIGHT_LINE, grid(ctx->opt[ILB_OPT_LIGHT_LINE_CTAS]), ctx->stream);
+        ILB_LIGHT_PERSIST(PS, NOLINE, grid(ctx->opt[ILB_OPT_LIGHT_OTHER_CTAS]), ctx->light_aux[0]);
+        ILB_LIGHT_PERSIST(PL, ILB_LIGHT_LINE, grid(ctx->opt[ILB_OPT_LIGHT_LINE_HELPERS]), ctx->light_aux[1]);
+        ILB_LIGHT_PERSIST(PS, NOLINE, grid(ctx->opt[ILB_OPT_LIGHT_OTHER_HELPERS]), ctx->light_aux[2]);
+#undef ILB_LIGHT_PERSIST
+        for (int i = 0; i < 3; i++) {
+            ILB_CUDA(ctx, cudaEventRecord(ctx->ev_light_join[i], ctx->light_aux[i]));
+            ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_light_join[i], 0));
+        }
+    } else if (split) {
         const size_t bytes = sizeof(float4) * (size_t)P.width * (size_t)(row_end - row_begin);
         const int rc = ilb_reserve(ctx, &ctx->d_accum, &ctx->d_accum_capacity, bytes, false);
         if (rc) return rc;
@@ -1265,8 +1449,8 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
 
 int ilb_probes_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const ilb_light_batch* batches, int batch_count,
                       const ilb_light_vertex* vertices, int vertex_count, const ilb_float4* positions, const ilb_float4* normals,
-                      int probe_count, int output_format, void* probes_out_host) {
-    if (!f || !positions || !normals || !probes_out_host || probe_count < 0) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
+                      int probe_count, int output_format, void* probes_out_host, void* d_probes_out) {
+    if (!f || !positions || !normals || (!probes_out_host && !d_probes_out) || probe_count < 0) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
     if (output_format != ILB_FORMAT_FLOAT4 && output_format != ILB_FORMAT_HALF4) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "probe output must be FLOAT4 or HALF4");
     if (df && df->ctx != ctx) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "distance field belongs to another context");
     if (probe_count == 0) return ILB_OK;
@@ -1299,11 +1483,12 @@ int ilb_probes_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, con
     P.normals = reinterpret_cast<const float4*>(base + in_bytes);
     P.nprobes = probe_count;
     P.out_format = output_format;
-    P.out = base + 2 * in_bytes;
-    if (P.df.planes) probe_accumulate_kernel<1><<<(probe_count + 127) / 128, 128, 0, ctx->stream>>>(P);
-    else probe_accumulate_kernel<0><<<(probe_count + 127) / 128, 128, 0, ctx->stream>>>(P);
+    P.out = d_probes_out ? d_probes_out : base + 2 * in_bytes;
+    if (P.df.planes) probe_accumulate_kernel<1><<<probe_count, PROBE_THREADS, 0, ctx->stream>>>(P);
+    else probe_accumulate_kernel<0><<<probe_count, PROBE_THREADS, 0, ctx->stream>>>(P);
     ctx->launches++;
     ILB_CUDA(ctx, cudaGetLastError());
+    if (d_probes_out) return ILB_OK;  // asynchronous: the caller reads the texels in stream order
     ILB_CUDA(ctx, cudaMemcpyAsync(probes_out_host, P.out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ILB_OK;

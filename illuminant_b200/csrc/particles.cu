@@ -60,6 +60,7 @@ struct StepParams {
     const float4* lifeRamp;    // LifeRampTexture (float4 texels) or nullptr
     int lifeRampW, lifeRampH;
     const float4* noiseTable;  // fast chains: positionDelta[per_chunk] then velocityDelta[per_chunk] of the chain's Noise op (noise_table_kernel)
+    const float2* escapeTable; // fast chains: the fallback escape direction of every texel of a chunk (escape_table_kernel)
 };
 
 #define PATTERN_MAX_LEVELS 15  // up to 16384 x 16384
@@ -353,7 +354,7 @@ ILB_DEV f3 cooperativeNormal4(const DFGeometry& g, float texelZ, f3 position, bo
 // COOP: every lane of the warp runs through this call together (the normal estimation is shared across lanes, see
 // cooperativeNormal4); COOP = false is the per-lane form for the divergent fallback call.
 template <bool COLLIDE, int FM, bool FAST, bool COOP>
-ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f4 oldVelocity, f4& outP, f4& outV, bool& needAttr, unsigned char* warpSlots, Guard& bad) {
+ILB_DEV bool updateTail(const StepParams& P, float x, float y, unsigned li, f4 oldPosition, f4 oldVelocity, f4& outP, f4& outV, bool& needAttr, unsigned char* warpSlots, Guard& bad) {
     const ilb_psys_uniforms& u = P.u;
     outP = mk4(0.0f);
     outV = mk4(0.0f);
@@ -433,9 +434,16 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, f4 oldPosition, f
             normal = mk3(normal.x, normal.y, xmul(normal.z, 0.0f));
             f3 escapeVector;
             if (tlengthdir3z<FAST>(normal, escapeVector, bad) < 0.33f) {
-                float s, c;
-                dm_sincosf(xadd(xdivz(x, 67.0f), xdivz(y, 13.0f)), &s, &c);
-                escapeVector = tnormalize3z<FAST>(mk3(s, c, 0.0f), bad);
+                // normalize(float3(sin(a), cos(a), 0)), a = x / 67 + y / 13: a function of the particle's texel alone, so the
+                // fast chains read it from a table built once per system (two range reductions and four polynomials otherwise)
+                if (FAST && P.escapeTable) {
+                    const float2 e = __ldg(P.escapeTable + li);
+                    escapeVector = mk3(e.x, e.y, 0.0f);
+                } else {
+                    float s, c;
+                    dm_sincosf(xadd(xdivz(x, 67.0f), xdivz(y, 13.0f)), &s, &c);
+                    escapeVector = tnormalize3z<FAST>(mk3(s, c, 0.0f), bad);
+                }
             }
             newVelocity = mk4(xscale3(xscale3(escapeVector, escapeSpeed), 0.33f), 3.0f);
             newPosition = xadd3(op, xscale3(xyz(newVelocity), dts));
@@ -516,7 +524,7 @@ ILB_DEV void stepParticle(const StepParams& P, float x, float y, unsigned li, f4
         if (K1 > 0) applyOp<K1, FAST>(P, P.ops[1], P.od[1], x, y, li, pos, vel, bad);
         if (K2 > 0) applyOp<K2, FAST>(P, P.ops[2], P.od[2], x, y, li, pos, vel, bad);
     }
-    updateTail<COLLIDE, FM, FAST, COOP>(P, x, y, pos, vel, outP, outV, needAttr, warpSlots, bad);
+    updateTail<COLLIDE, FM, FAST, COOP>(P, x, y, li, pos, vel, outP, outV, needAttr, warpSlots, bad);
 }
 
 // The IEEE re-evaluation of a particle whose fast evaluation tripped a range guard (operand of a square root or a
@@ -701,6 +709,20 @@ __global__ void __launch_bounds__(STEP_THREADS) noise_table_kernel(const __grid_
     noiseDeltas(P.rng, P.rng_w, P.rng_h, P.n, x, y, positionDelta, velocityDelta);
     P.table[i] = to_float4(positionDelta);
     P.table[P.per_chunk + i] = to_float4(velocityDelta);
+}
+
+// ---- escape-direction table ------------------------------------------------------------------------------------------
+// UpdateParticleSystemWithDistanceField.fx:104-110: a particle stuck inside an obstruction whose field gradient is too flat
+// escapes along normalize(float3(sin(a), cos(a), 0)) with a = x / 67 + y / 13 -- a function of its texel only.
+__global__ void __launch_bounds__(STEP_THREADS) escape_table_kernel(float2* __restrict__ table, unsigned per_chunk, int chunk_size) {
+    const unsigned i = blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (i >= per_chunk) return;
+    const float x = (float)(i % (unsigned)chunk_size), y = (float)(i / (unsigned)chunk_size);
+    float s, c;
+    dm_sincosf(xadd(xdivz(x, 67.0f), xdivz(y, 13.0f)), &s, &c);
+    Guard bad = guardInit();
+    const f3 e = tnormalize3z<false>(mk3(s, c, 0.0f), bad);
+    table[i] = make_float2(e.x, e.y);
 }
 
 // ---- spawner (SpawnerCommon.fxh, SpawnParticles.fx:10-30) -----------------------------------------------------
@@ -933,7 +955,9 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
     if (needsRng && !ps->rng) return ilb_fail(ctx, ILB_ERR_INVALID_OPERATION, "the randomness texture was not set");
 
     for (int step = 0; step < steps; step++) {
-        for (int si = 0; si < spawn_count; si++) {
+        // the spawn list describes ONE tick's spawns (index ranges, RandomnessOffset, feedback source index): it is applied
+        // before the first update only; the remaining `steps - 1` updates age the particles without re-initialising them
+        for (int si = 0; si < (step == 0 ? spawn_count : 0); si++) {
             const ilb_spawn& s = spawns[si];
             if (s.chunk < 0 || s.chunk >= ps->live_chunks) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "spawn %d: chunk %d is not live", si, s.chunk);
             const int kind = sources ? sources[si].kind : ILB_SPAWN_INLINE;
@@ -1131,6 +1155,14 @@ int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spa
             noise_table_kernel<<<(unsigned)((ps->per_chunk + STEP_THREADS - 1) / STEP_THREADS), STEP_THREADS, 0, ctx->stream>>>(NT);
             ctx->launches++;
             SP.noiseTable = ps->noise_table;
+            if (collide) {
+                if (!ps->escape_table) {
+                    ILB_CUDA(ctx, cudaMalloc(&ps->escape_table, sizeof(float2) * ps->per_chunk));
+                    escape_table_kernel<<<(unsigned)((ps->per_chunk + STEP_THREADS - 1) / STEP_THREADS), STEP_THREADS, 0, ctx->stream>>>(ps->escape_table, (unsigned)ps->per_chunk, ps->chunk_size);
+                    ctx->launches++;
+                }
+                SP.escapeTable = ps->escape_table;
+            }
         }
         const int fm = collide ? ((planes ? 2 : 0) | (ilb_field_is_flat(SP.df) ? 1 : 0)) : 0;  // field mode, see sampleField
 #define ILB_STAGED(C, A, B, D, FM)                                                                                          \

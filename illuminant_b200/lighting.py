@@ -442,6 +442,30 @@ class LightingRenderer:
         return out
 
 
+    def pack_probes(self):
+        """Probe positions / normals as UpdateLightProbeTexture uploads them (LightingRenderer.LightProbes.cs:88-110)."""
+        n = len(self.Probes)
+        pos = np.zeros((max(n, 1), 4), dtype=np.float32)
+        nrm = np.zeros((max(n, 1), 4), dtype=np.float32)
+        for i, p in enumerate(self.Probes):
+            pos[i] = list(p.Position) + [1.0]
+            nrm[i] = (list(p.Normal) if p.Normal is not None else [0, 0, 0]) + [1.0 if p.EnableShadows else 0.0]
+        return pos, nrm, n
+
+    def UpdateLightProbesDevice(self, d_out: int, packed=None, probes=None, intensityScale: float = 1.0, float4: bool = False):
+        """Asynchronous UpdateLightProbes: half4 (or float4) texels into the device buffer `d_out`, in stream order."""
+        pos, nrm, n = probes if probes is not None else self.pack_probes()
+        if n == 0:
+            return
+        frame = self.build_frame(intensityScale)
+        batches, nb, verts, nv = packed if packed is not None else self.build_batches(intensityScale)
+        df = self.DistanceField.handle if (self.DistanceField is not None and self.DistanceField.handle) else None
+        self.ctx.check(self.ctx.lib.ilb_update_light_probes_device(self.ctx.handle, df, C.byref(frame), C.cast(batches, C.c_void_p), nb,
+                                                                   C.cast(verts, C.c_void_p), nv, pos.ctypes.data_as(C.c_void_p),
+                                                                   nrm.ctypes.data_as(C.c_void_p), n, FORMAT_FLOAT4 if float4 else FORMAT_HALF4,
+                                                                   C.c_void_p(int(d_out))))
+
+
 def encode_gbuffer(normal: np.ndarray, relativeY: np.ndarray, z: np.ndarray, enableShadows: np.ndarray | bool = True,
                    fullbright: np.ndarray | bool = False, dead: np.ndarray | bool = False) -> np.ndarray:
     """Vectorised encodeGBufferSample (Shaders/GBufferShaderCommon.fxh:10-35, EnvironmentCommon.fxh:34-40) -> float32 [...,4].

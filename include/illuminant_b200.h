@@ -64,6 +64,24 @@ ILB_API void* ilb_stream(ilb_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench gpu_launches). */
 ILB_API uint64_t ilb_launch_count(const ilb_ctx* ctx);
 
+/* Scheduling knobs of the kernels (never results: every setting produces the same bits).  Defaults are the measured
+ * best on B200; the environment variable ILB_OPT_<NAME> overrides a default at ilb_create. */
+typedef enum ilb_option {
+    ILB_OPT_LIGHT_CONCURRENT = 0,   /* 1: run the line-light pass and the sphere + directional pass side by side (default) */
+    ILB_OPT_LIGHT_LINE_CTAS = 1,    /* resident line-pass CTAs per SM while both passes run (default 2) */
+    ILB_OPT_LIGHT_OTHER_CTAS = 2,   /* resident sphere + directional CTAs per SM while both passes run (default 2) */
+    ILB_OPT_LIGHT_LINE_HELPERS = 3, /* extra line-pass CTAs per SM that start when the other pass has drained (default 1) */
+    ILB_OPT_LIGHT_OTHER_HELPERS = 4,/* extra sphere + directional CTAs per SM for the opposite case (default 3) */
+    ILB_OPT_COUNT = 5
+} ilb_option;
+ILB_API int ilb_set_option(ilb_ctx* ctx, int option, int value);
+ILB_API int ilb_get_option(const ilb_ctx* ctx, int option, int* out_value);
+
+/* Diagnostic: evaluates the kernels' own device build of the deterministic sin / cos / acos (include/ilb_detmath.h) on
+ * `count` host values, so that tests can compare it bit for bit with the host build of the same header.
+ * function: 0 dm_sinf, 1 dm_cosf, 2 dm_acosf. */
+ILB_API int ilb_debug_detmath(ilb_ctx* ctx, int function, const float* x, float* out, int count);
+
 /* --------------------------------------------------------- distance field (L1) */
 
 /* The `Uniforms.DistanceField` struct (Uniforms.cs:79-108, 5 x float4) followed by
@@ -221,6 +239,13 @@ ILB_API int ilb_update_light_probes(ilb_ctx* ctx, ilb_df* df, const ilb_lighting
                                     const ilb_light_vertex* vertices, int vertex_count,
                                     const ilb_float4* probe_positions, const ilb_float4* probe_normals,
                                     int probe_count, int output_format, void* probes_out);
+/* Same, asynchronous: the texels go to a DEVICE buffer in stream order (the reference reads its probe target back later,
+ * LightingRenderer.LightProbes.cs:88-110).  Positions / normals are host arrays, copied before the call returns. */
+ILB_API int ilb_update_light_probes_device(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame,
+                                           const ilb_light_batch* batches, int batch_count,
+                                           const ilb_light_vertex* vertices, int vertex_count,
+                                           const ilb_float4* probe_positions, const ilb_float4* probe_normals,
+                                           int probe_count, int output_format, void* d_probes_out);
 
 /* ------------------------------------------ "next" row N3: lightmap resolve / luminance */
 
@@ -435,7 +460,8 @@ ILB_API int ilb_particles_upload_buffer(ilb_psys* psys, int chunk, int which, co
 ILB_API int ilb_particles_set_live_chunks(ilb_psys* psys, int count);
 /* One ParticleSystem.Update (ParticleSystem.cs:634, replacing the RunSpawner/UpdateChunk loop :725-745):
  * spawners first, then for every live chunk the transforms in order, then UpdatePositions /
- * UpdateWithDistanceField.  `steps` repeats the same update (fixed uniforms) steps times. Asynchronous. */
+ * UpdateWithDistanceField.  `steps` repeats the same update (fixed uniforms) steps times; the spawn list is one tick's
+ * spawns and is applied before the first of them only.  Asynchronous. */
 ILB_API int ilb_particles_step(ilb_psys* psys, const ilb_psys_uniforms* uniforms,
                                const ilb_spawn* spawns, int spawn_count,
                                const ilb_op* ops, int op_count, int steps);

@@ -46,6 +46,8 @@ void orc_encode_gbuffer_sample(const float* normal, float relativeY, float z, in
 int orc_resolve_lighting(const ilb_resolve* p, const float* lightmap, const float* albedo, float* out);
 /* N3: luminance buffer level `level` ((w/2 >> level) x (h/2 >> level) floats) of a fp32-decoded lightmap. */
 int orc_compute_luminance(const float* lightmap, int w, int h, int level, float* out);
+/* The host build of include/ilb_detmath.h (what every oracle function above calls): function 0 dm_sinf, 1 dm_cosf, 2 dm_acosf. */
+void orc_detmath(int function, const float* x, float* out, long n);
 void orc_float_to_half(const float* in, uint16_t* out, long n);
 void orc_half_to_float(const uint16_t* in, float* out, long n);
 #ifdef __cplusplus

@@ -76,6 +76,8 @@ def lib():
         L.orc_resolve_lighting.argtypes = [C.POINTER(_abi.Resolve), P, P, P]
         L.orc_compute_luminance.restype = C.c_int
         L.orc_compute_luminance.argtypes = [P, C.c_int, C.c_int, C.c_int, P]
+        L.orc_detmath.restype = None
+        L.orc_detmath.argtypes = [C.c_int, P, P, C.c_long]
         L.orc_float_to_half.restype = None
         L.orc_float_to_half.argtypes = [P, P, C.c_long]
         L.orc_half_to_float.restype = None
@@ -253,6 +255,14 @@ def encode_gbuffer_sample(normal, relative_y, z, dead=False, enable_shadows=True
     n = _f3(normal)
     out = np.zeros(4, np.float32)
     lib().orc_encode_gbuffer_sample(_ptr(n), relative_y, z, int(dead), int(enable_shadows), int(fullbright), _ptr(out))
+    return out
+
+
+def detmath(function: str, x: np.ndarray) -> np.ndarray:
+    """The host build of include/ilb_detmath.h: function in ("sin", "cos", "acos")."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    lib().orc_detmath({"sin": 0, "cos": 1, "acos": 2}[function], _ptr(x), _ptr(out), x.size)
     return out
 
 

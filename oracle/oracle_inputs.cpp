@@ -14,6 +14,10 @@ using namespace hlsl;
 
 extern "C" {
 
+void orc_detmath(int function, const float* x, float* out, long n) {
+    for (long i = 0; i < n; i++) out[i] = function == 0 ? dm_sinf(x[i]) : (function == 1 ? dm_cosf(x[i]) : dm_acosf(x[i]));
+}
+
 // RenderDistanceField for analytic obstructions: per physical slice p the texel (r,g,b,a) holds encoded
 // distances at z = SliceIndexToZ(3p..3p+3) (Lighting/LightingRenderer.DistanceField.cs:32-35, :347-400);
 // slice cleared to 0 (Shaders/ClearDistanceField.fx:27-39); each obstruction's quad covers

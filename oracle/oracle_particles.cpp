@@ -800,7 +800,8 @@ int orc_particles_step_sources(float* P, float* V, float* A, float* RC, float* R
     float *pPrev = P, *vPrev = V, *pCurr = P2.data(), *vCurr = V2.data();
 
     for (int step = 0; step < steps; step++) {
-        for (int si = 0; si < nspawns; si++) {
+        // the spawn list is one tick's spawns (ParticleSystem.Update runs its spawners once per update): first step only
+        for (int si = 0; si < (step == 0 ? nspawns : 0); si++) {
             const ilb_spawn& s = spawns[si];
             if (s.chunk < 0 || s.chunk >= live_chunks) return ILB_ERR_INVALID_ARGUMENT;
             const int kind = sources ? sources[si].kind : ILB_SPAWN_INLINE;

@@ -4,7 +4,7 @@ import pytest
 
 import illuminant_b200 as ib
 from illuminant_b200 import scenes
-from helpers import PARTICLE_ATOL, particle_err
+from helpers import check_particles
 
 pytestmark = pytest.mark.gpu
 
@@ -33,11 +33,7 @@ def _run_both(ctx, oracle, ps, chunk_size, steps, tex=None, seed=3, max_chunks=4
 
 
 def _check(gpu, ref, what=""):
-    names = ("position", "velocity", "attributes", "renderColor", "renderData")
-    for g, r, n in zip(gpu, ref, names):
-        assert not np.isnan(g).any(), f"{what} {n} NaN"
-        e = particle_err(g, r)
-        assert e <= PARTICLE_ATOL, f"{what} {n}: err {e:.3e}"
+    check_particles(gpu, ref, what)
 
 
 def test_ballistic_no_transforms_closed_form(ctx, oracle):
@@ -219,12 +215,7 @@ def test_planes_match_atlas_bit_for_bit(ctx, monkeypatch):
 
 
 def _check_nan_aware(gpu, ref):
-    for g, r_, n in zip(gpu, ref, ("position", "velocity", "attributes", "renderColor", "renderData")):
-        assert np.array_equal(np.isnan(g), np.isnan(r_)), n
-        ok = np.isfinite(r_) & np.isfinite(g)
-        assert np.array_equal(np.isfinite(g), np.isfinite(r_)), n
-        e = particle_err(g[ok], r_[ok])
-        assert e <= PARTICLE_ATOL, f"{n}: err {e:.3e}"
+    check_particles(gpu, ref, "degenerate", allow_nan=True)
 
 
 def test_degenerate_vectors_take_the_ieee_fallback(ctx, oracle):

@@ -6,7 +6,7 @@ import pytest
 
 import illuminant_b200 as ib
 from illuminant_b200 import _abi
-from helpers import PARTICLE_ATOL, particle_err
+from helpers import check_particles
 
 f32 = np.float32
 CS = 32          # chunk size
@@ -114,10 +114,7 @@ def test_feedback_spawn_known_answers(oracle):
 
 # ------------------------------------------------------------------------------------------------------------------- GPU
 def _check(gpu, ref, what):
-    for g, r, n in zip(gpu, ref, ("position", "velocity", "attributes", "renderColor", "renderData")):
-        assert not np.isnan(g).any(), f"{what} {n} NaN"
-        e = particle_err(g, r)
-        assert e <= PARTICLE_ATOL, f"{what} {n}: err {e:.3e}"
+    check_particles(gpu, ref, what)
 
 
 @pytest.mark.gpu
