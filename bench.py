@@ -5,13 +5,20 @@ of the reference algorithm).
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload both|lighting|particles]
 
 Primary metric: lit Mpixels/s on config C4 (3840x2160, 128 mixed Sphere/Directional/Line lights + 256 light probes,
-9-slice distance field); a "step" is one RenderLighting of the whole frame (+ the probe update).  The second hot path
-is reported in the same JSON line under "particles": Mparticle-steps/s for 8M particles (32 chunks x 512^2) per GPU
-through Spawner+Gravity+Noise+FMA+SDF collision; a step is one ParticleSystem.Update.
+9-slice distance field); a "step" is one RenderLighting of the whole frame PLUS the UpdateLightProbes of the same frame,
+both inside the timed region.  At N > 1 the frame is cut into row bands of equal MEASURED cost (calibrated before the
+timed region, sharding.rebalance_rows), every rank stores its band into every rank's full-frame buffer from inside the
+kernel (NVLink peer stores), and a symmetric-memory barrier ends the step.  The second hot path is reported in the same
+JSON line under "particles": Mparticle-steps/s for 8M particles (32 chunks x 512^2) per GPU through
+Spawner(60 000 / s)+Gravity+Noise+FMA+SDF collision; a step is one ParticleSystem.Update (spawn kernel, Noise table kernel,
+step kernel).  The particles the Spawner adds during the run are updated too but NOT counted in the metric.
 
 Timing: W >= 3 warm-up steps, then exactly K steps bracketed by barrier + synchronize, timed with CUDA events on the
 library's stream, max over ranks.  Inputs are larger than L2 (C4: 265 MB field + 133 MB G-buffer; particles: 640 MB of
 state), so every step streams from HBM -- no L2 flush needed (config.l2 says so).
+
+roofline.traffic is measured in the run: rank 0 profiles the same launches under `ncu --metrics dram__bytes_*` in a child
+process (byte counters only; no timing is ever taken under the profiler); null when ncu is unavailable.
 """
 from __future__ import annotations
 
@@ -126,26 +133,31 @@ def dist_env():
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm
-def cpu_lighting_sample(oracle, scenes, ib, scene, target_seconds: float):
-    """Times the oracle (reference algorithm, multi-pass, all host threads) on a band of rows of the same frame."""
-    df = scenes.make_distance_field(None, scene)
-    tex = oracle.generate_distance_field(df, scene.obstructions)
-    df.ValidSliceCount, df.handle = df.SliceCount, 1
-    r = ib.LightingRenderer(None, scene.environment, scene.configuration)
-    r.DistanceField, r._gbuffer_shape = df, scene.gbuffer.shape[:2]
-    batches, nb, verts, nv = r.build_batches()
-    mid = scene.height // 2
+ROW_STRIDE = 8   # the CPU arm shades every 8th row of the WHOLE frame per step (offset = step mod 8): 8 steps cover the frame once
 
-    def run(rows):
-        frame = r.build_frame(1.0, (mid - rows // 2, mid - rows // 2 + rows))
+
+class CpuLighting:
+    """The oracle (reference algorithm, multi-pass, all host threads) on the C4 frame.  Lights are clustered, so a band of
+    adjacent rows is not representative of the frame; a step here is a strided sample of rows spread over the whole frame."""
+
+    def __init__(self, oracle, scenes, ib, scene):
+        self.oracle, self.scene = oracle, scene
+        df = scenes.make_distance_field(None, scene)
+        self.tex = oracle.generate_distance_field(df, scene.obstructions)
+        df.ValidSliceCount, df.handle = df.SliceCount, 1
+        self.df = df
+        r = ib.LightingRenderer(None, scene.environment, scene.configuration)
+        r.DistanceField, r._gbuffer_shape = df, scene.gbuffer.shape[:2]
+        self.r = r
+        self.packed = r.build_batches()
+
+    def strided_step(self, step: int, stride: int = ROW_STRIDE):
+        """(rows shaded, seconds) for rows step % stride, + stride, ... of the whole frame."""
+        batches, nb, verts, nv = self.packed
+        frame = self.r.build_frame(1.0, (step % stride, self.scene.height))
         t = time.perf_counter()
-        oracle.render_lighting(tex, scene.gbuffer, frame, batches, nb, verts, nv)
-        return time.perf_counter() - t
-    rows = 4
-    t = run(rows)
-    rows = int(min(scene.height, max(4, rows * target_seconds / max(t, 1e-3))))
-    t = run(rows)
-    return rows * scene.width / t / 1e6, rows, t
+        out = self.oracle.render_lighting(self.tex, self.scene.gbuffer, frame, batches, nb, verts, nv, row_stride=stride)
+        return out.shape[0], time.perf_counter() - t
 
 
 def cpu_particle_sample(oracle, scenes, ib, tex, df_desc, target_seconds: float):
@@ -175,29 +187,22 @@ def run_reference(args):
     oracle.lib()
     cores = oracle.threads()
     scene = scenes.config_c4()
-    df = scenes.make_distance_field(None, scene)
-    tex = oracle.generate_distance_field(df, scene.obstructions)
-    df.ValidSliceCount, df.handle = df.SliceCount, 1
-    r = ib.LightingRenderer(None, scene.environment, scene.configuration)
-    r.DistanceField, r._gbuffer_shape = df, scene.gbuffer.shape[:2]
-    batches, nb, verts, nv = r.build_batches()
-    rows = 8   # bounded sample per step: an 8-row band around the middle of the 4K frame, all 128 lights
-    mid = scene.height // 2
-    frame = r.build_frame(1.0, (mid - rows // 2, mid + rows // 2))
-    times = []
+    cpu = CpuLighting(oracle, scenes, ib, scene)
+    times, rows = [], 0
     for i in range(args.warmup + args.steps):
-        t = time.perf_counter()
-        oracle.render_lighting(tex, scene.gbuffer, frame, batches, nb, verts, nv)
+        n, t = cpu.strided_step(i)
         if i >= args.warmup:
-            times.append(time.perf_counter() - t)
+            times.append(t)
+            rows += n
     total = sum(times)
-    value = rows * scene.width * args.steps / total / 1e6
-    pvalue, psteps, pt = cpu_particle_sample(oracle, scenes, ib, tex, df, 6.0) if args.workload != "lighting" else (None, 0, 0)
-    sample = f"{rows}-row band ({rows * scene.width} px) of the 3840x2160 / 128-light frame per step"
+    value = rows * scene.width / total / 1e6
+    pvalue, psteps, pt = cpu_particle_sample(oracle, scenes, ib, cpu.tex, cpu.df, 6.0) if args.workload != "lighting" else (None, 0, 0)
+    sample = (f"every {ROW_STRIDE}th row of the whole 3840x2160 / 128-light frame per step ({scene.height // ROW_STRIDE} rows, "
+              f"{scene.height // ROW_STRIDE * scene.width} px; the row offset advances each step, {ROW_STRIDE} steps cover the frame once)")
     line = {"impl": "reference", "metric": "lit Mpixels/s (4K, 128 lights)", "value": value, "unit": "Mpixels/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C4 3840x2160, 96 sphere + 8 directional + 24 line lights, 9-slice DF", "sample": sample},
+            "config": {"workload": C4_WORKLOAD, "sample": sample},
             "cpu_baseline": {"value": value, "unit": "Mpixels/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "particles": None if pvalue is None else {"metric": "Mparticle-steps/s", "value": pvalue, "unit": "Mparticle-steps/s",
@@ -207,11 +212,50 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+C4_WORKLOAD = "C4: 3840x2160, 96 sphere + 8 directional + 24 line lights, 256 probes, 9-slice 3840x2160 distance field"
+
+
+# ---------------------------------------------------------------------------------------------------- DRAM traffic (ncu child)
+def measure_traffic(what: str, pattern: str, skip: int, count: int, extra=()):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `count` launches matching `pattern` of profiles/microbench/profile_hot.py,
+    counted by ncu in a child process.  Byte counters only -- nothing timed under the profiler is ever reported.  Returns
+    (bytes, None) or (None, reason)."""
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not Path(ncu).exists():
+        return None, "ncu not found"
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", f"regex:{pattern}", "-s", str(skip),
+           "-c", str(count), "--csv", sys.executable, str(ROOT / "profiles" / "microbench" / "profile_hot.py"), what, *[str(e) for e in extra]]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    except Exception as e:   # noqa: BLE001
+        return None, f"ncu failed: {type(e).__name__}"
+    import csv, io
+    total, seen = 0.0, 0
+    rows = [r for r in csv.reader(io.StringIO(res.stdout)) if len(r) > 5]
+    if not rows:
+        return None, "ncu printed no counters (profiling not permitted on this box?)"
+    hdr = rows[0]
+    try:
+        ni, ui, vi = hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value")
+    except ValueError:
+        return None, "unexpected ncu output"
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for r in rows[1:]:
+        if r[ni].startswith("dram__bytes_"):
+            total += float(r[vi].replace(",", "")) * scale.get(r[ui], 1.0)
+            seen += 1
+    if seen < 2 * count:
+        return None, f"ncu saw {seen // 2} of {count} launches"
+    return total, None
+
+
 # ---------------------------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
     import illuminant_b200 as ib
-    from illuminant_b200 import _abi, build, scenes
+    from illuminant_b200 import _abi, build, scenes, sharding
     rank, local_rank, world = dist_env()
     if world > 1:
         import torch.distributed as dist
@@ -232,31 +276,65 @@ def run_ours(args):
         ctx.synchronize()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms: float) -> float:
+    def reduce_ranks(v: float, op="max") -> float:
         if dist is None:
-            return ms
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return v
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.MIN)
         return float(t.item())
 
-    def timed(step_fn, steps, warmup):
+    def gather_ranks(v: float):
+        if dist is None:
+            return [v]
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
+    def timed(step_fn, steps, warmup, sync=True):
         """Returns (total ms of `steps` steps, per-step ms list) measured with CUDA events on the library's stream."""
         with torch.cuda.stream(stream):
             for _ in range(warmup):
                 step_fn()
-            barrier()
+            if sync:
+                barrier()
+            else:
+                ctx.synchronize()
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
             evs[0].record(stream)
             for i in range(steps):
                 step_fn()
                 evs[i + 1].record(stream)
-            barrier()
+            if sync:
+                barrier()
+            else:
+                ctx.synchronize()
+                torch.cuda.synchronize()
         per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
         return evs[0].elapsed_time(evs[steps]), per
 
-    sampler = ClockSampler(local_rank)
     scene = scenes.config_c4()
     W, H = scene.width, scene.height
+    peers = {"ptrs": None, "hdl": None, "full": None, "gather": "none"}
+
+    def lighting_buffers():
+        """The full-frame lit buffer every rank ends a step with.  Preferred: symmetric memory, so that the kernel itself stores
+        every finished texel into the buffer of EVERY rank through NVLink peer mappings; fallback: NCCL all-gather of bands."""
+        if dist is not None and args.gather in ("auto", "peers"):
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                full = symm_mem.empty((H, W, 4), dtype=torch.float16, device=torch.device("cuda", local_rank))
+                hdl = symm_mem.rendezvous(full, dist.group.WORLD)
+                peers.update(ptrs=[int(p) for p in hdl.buffer_ptrs], hdl=hdl, full=full,
+                             gather="peer-stores (in-kernel all-gather over NVLink) + symmetric-memory barrier")
+                return
+            except Exception as e:   # noqa: BLE001
+                if args.gather == "peers":
+                    raise
+                print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
+        rows_per = sharding.band_height(H, world)
+        peers.update(full=torch.empty((rows_per * world, W, 4), dtype=torch.float16, device="cuda"),
+                     gather="nccl all_gather_into_tensor" if dist is not None else "none")
 
     # ------------------------------------------------------------------ lighting
     if args.workload in ("both", "lighting"):
@@ -267,72 +345,103 @@ def run_ours(args):
         renderer.Probes = scene.probes
         gb_host = torch.from_numpy(scene.gbuffer).pin_memory()
         renderer.SetGBuffer(gb_host.numpy())
-        from illuminant_b200 import sharding
-        rows_per = sharding.band_height(H, world)
-        r0, r1 = sharding.row_band(rank, world, H)
-        # Reassembly of the lit buffer.  Preferred: the kernel itself stores every finished texel into
-        # the full-frame buffer of EVERY rank through NVLink peer mappings (torch symmetric memory provides the mapped
-        # pointers), followed by a device-side barrier -- compute and all-gather are one kernel.  Fallback: a plain NCCL
-        # all-gather of the row bands.
-        gather, hdl, peer_ptrs = "none", None, None
-        if dist is not None and args.gather in ("auto", "peers"):
-            try:
-                import torch.distributed._symmetric_memory as symm_mem
-                full = symm_mem.empty((rows_per * world, W, 4), dtype=torch.float16, device=torch.device("cuda", local_rank))
-                hdl = symm_mem.rendezvous(full, dist.group.WORLD)
-                peer_ptrs = [int(p) for p in hdl.buffer_ptrs]
-                gather = "peer-stores (in-kernel all-gather over NVLink) + symmetric-memory barrier"
-            except Exception as e:   # noqa: BLE001
-                if args.gather == "peers":
-                    raise
-                hdl, peer_ptrs = None, None
-                print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
-        if peer_ptrs is None:
-            full = torch.empty((rows_per * world, W, 4), dtype=torch.float16, device="cuda")
-            if dist is not None:
-                gather = "nccl all_gather_into_tensor"
-        band = full[rank * rows_per:(rank + 1) * rows_per]
+        lighting_buffers()
+        full = peers["full"]
         packed = renderer.build_batches()
+        probes_packed = renderer.pack_probes()
+        d_probes = torch.zeros((max(probes_packed[2], 1), 4), dtype=torch.float16, device="cuda")
+        bounds = [sharding.row_band(k, world, H)[0] for k in range(world)] + [H]
+        scratch = torch.empty((H, W, 4), dtype=torch.float16, device="cuda")   # kernel-only timing target (any band fits)
+
+        def my_rows():
+            return bounds[rank], bounds[rank + 1]
+
+        def band_kernel_ms(reps=2):
+            r0, r1 = my_rows()
+            if r1 <= r0:
+                return 0.0
+            ms, _ = timed(lambda: renderer.RenderLightingDevice(scratch.data_ptr(), rows=(r0, r1), packed=packed), reps, 1, sync=False)
+            return ms / reps
+
+        # Row bands of equal measured cost (lights are clustered: equal-height bands finish at different times and the frame
+        # waits for the slowest rank).  Needs the peer-store gather, which leaves the band edges free.
+        calibration = None
+        if dist is not None and peers["ptrs"] is not None and not args.equal_bands:
+            history = []
+            for _ in range(4):
+                times = gather_ranks(band_kernel_ms())
+                history.append({"bounds": list(bounds), "band_ms": [round(t, 4) for t in times]})
+                bounds = sharding.rebalance_rows(bounds, times, H, quantum=4)
+            calibration = history
+        r0, r1 = my_rows()
         launches0 = ctx.launch_count
 
         def light_step():
-            if peer_ptrs is not None:
-                renderer.RenderLightingPeers(peer_ptrs, rows=(r0, r1), packed=packed)
-                hdl.barrier(channel=0)
+            if peers["ptrs"] is not None:
+                renderer.RenderLightingPeers(peers["ptrs"], rows=(r0, r1), packed=packed)
             else:
-                renderer.RenderLightingDevice(band.data_ptr(), rows=(r0, r1), packed=packed)
-                if dist is not None:   # one all-gather of row bands reassembles the lit buffer on every rank
-                    dist.all_gather_into_tensor(full, band)
+                renderer.RenderLightingDevice(full[r0:].data_ptr(), rows=(r0, r1), packed=packed)
+            if rank == 0:   # UpdateLightProbes of the same frame (256 probes x 128 lights): rank 0, asynchronous, inside the timed step
+                renderer.UpdateLightProbesDevice(d_probes.data_ptr(), packed=packed, probes=probes_packed)
+            if peers["ptrs"] is not None:
+                peers["hdl"].barrier(channel=0)
+            elif dist is not None:   # one all-gather of row bands reassembles the lit buffer on every rank
+                dist.all_gather_into_tensor(full, full[r0:r0 + sharding.band_height(H, world)])
 
+        sampler = ClockSampler(local_rank)
         sampler.start()
         total_ms, per = timed(light_step, args.steps, args.warmup)
         clocks = sampler.stop()
         launches = (ctx.launch_count - launches0) * args.steps // (args.steps + args.warmup)
-        total_ms = max_over_ranks(total_ms)
+        total_ms = reduce_ranks(total_ms)
         ms_step = total_ms / args.steps
         mpx = W * H / (ms_step * 1e-3) / 1e6
-        # kernel-only duration (no collective) for the roofline: time the band kernel alone
-        k_ms, _ = timed(lambda: renderer.RenderLightingDevice(band.data_ptr(), rows=(r0, r1), packed=packed), max(3, args.steps // 2), 1)
-        k_ms = k_ms / max(3, args.steps // 2)
-        achieved = LIGHT_BYTES_PER_PIXEL * W * (r1 - r0) / (k_ms * 1e-3) / 1e9
-        traffic = None
-        tp = ROOT / "profiles" / "traffic.json"
-        if tp.exists():
-            try:
-                traffic = json.loads(tp.read_text()).get("light_accumulate_kernel")
-            except Exception:
-                traffic = None
+        # kernel-only duration of this rank's band (no probes, no collective) for the roofline; all ranks' values are reported
+        k_ms = band_kernel_ms(max(3, args.steps // 2))
+        rank_kernel_ms = gather_ranks(k_ms)
+        t0 = time.perf_counter()
+        renderer.UpdateLightProbesDevice(d_probes.data_ptr(), packed=packed, probes=probes_packed)
+        ctx.synchronize()
+        probes_host_ms = (time.perf_counter() - t0) * 1e3
+        p_ms, _ = timed(lambda: renderer.UpdateLightProbesDevice(d_probes.data_ptr(), packed=packed, probes=probes_packed), 5, 1, sync=False)
+        achieved = LIGHT_BYTES_PER_PIXEL * W * (r1 - r0) / (max(k_ms, 1e-6) * 1e-3) / 1e9
 
-        # end to end through the public API with HOST buffers: per step the G-buffer (the per-frame input) goes
-        # host->device from pinned memory and the lightmap band comes back into pinned host memory
-        out_host = torch.empty((max(r1 - r0, 1), W, 4), dtype=torch.float16).pin_memory()
+        # end to end through the C-ABI with HOST buffers: per step this frame's G-buffer goes host->device from pinned memory and
+        # the lit buffer comes back into pinned host memory.  N = 1: one ilb_render_lighting_frame call (copies pipelined behind
+        # the kernels over row bands).  N > 1: every rank uploads the G-buffer rows of its band, renders it with the in-kernel
+        # peer-store gather, and RANK 0 downloads the REASSEMBLED full frame.
         frame = renderer.build_frame(1.0, (r0, r1))
         batches, nb, verts, nv = packed
-        gb_ptr, out_ptr = C.c_void_p(gb_host.data_ptr()), C.c_void_p(out_host.data_ptr())
+        probes_out_host = torch.zeros((max(probes_packed[2], 1), 4), dtype=torch.float16).pin_memory()
+        if dist is None:
+            out_host = torch.empty((H, W, 4), dtype=torch.float16).pin_memory()
+            gb_ptr, out_ptr = C.c_void_p(gb_host.data_ptr()), C.c_void_p(out_host.data_ptr())
 
-        def e2e_step():   # one C-ABI call per frame: G-buffer up, shade, lightmap down (pipelined over row bands inside)
-            ctx.check(ctx.lib.ilb_render_lighting_frame(ctx.handle, df.handle, C.byref(frame), C.cast(batches, C.c_void_p), nb,
-                                                        C.cast(verts, C.c_void_p), nv, W, H, _abi.FORMAT_FLOAT4, gb_ptr, out_ptr))
+            def e2e_step():
+                ctx.check(ctx.lib.ilb_render_lighting_frame(ctx.handle, df.handle, C.byref(frame), C.cast(batches, C.c_void_p), nb,
+                                                            C.cast(verts, C.c_void_p), nv, W, H, _abi.FORMAT_FLOAT4, gb_ptr, out_ptr))
+                renderer.UpdateLightProbesDevice(d_probes.data_ptr(), packed=packed, probes=probes_packed)
+                with torch.cuda.stream(stream):
+                    probes_out_host.copy_(d_probes, non_blocking=True)
+                ctx.synchronize()
+            h2d, d2h = H * W * 16 + nv * 128 + probes_packed[2] * 32, H * W * 8 + probes_packed[2] * 8
+            e2e_note = "one ilb_render_lighting_frame call per frame + probe update and read-back"
+        else:
+            out_host = torch.empty((H, W, 4), dtype=torch.float16).pin_memory() if rank == 0 else None
+            gb_rows = gb_host[r0:r1] if r1 > r0 else gb_host[:1]
+
+            def e2e_step():
+                if r1 > r0:
+                    ctx.check(ctx.lib.ilb_gbuffer_upload_rows(ctx.handle, W, H, _abi.FORMAT_FLOAT4, r0, r1, C.c_void_p(gb_rows.data_ptr())))
+                light_step()
+                if rank == 0:
+                    with torch.cuda.stream(stream):
+                        out_host.copy_(full[:H], non_blocking=True)
+                        probes_out_host.copy_(d_probes, non_blocking=True)
+                ctx.synchronize()
+            h2d = H * W * 16 + world * nv * 128 + probes_packed[2] * 32     # all ranks' band uploads together = one G-buffer
+            d2h = H * W * 8 + probes_packed[2] * 8
+            e2e_note = "per-rank G-buffer band upload, in-kernel gather, rank 0 downloads the reassembled full frame"
         e_steps = max(3, args.steps // 2)
         for _ in range(2):
             e2e_step()
@@ -341,19 +450,30 @@ def run_ours(args):
         for _ in range(e_steps):
             e2e_step()
         barrier()
-        e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e_steps)
+        e_ms = reduce_ranks((time.perf_counter() - t0) * 1e3 / e_steps)
+        if dist is not None:
+            renderer.SetGBuffer(gb_host.numpy())    # the band uploads left the other rows as they were; restore for what follows
+
+        traffic, traffic_note = None, "not measured"
+        if rank == 0 and not args.no_traffic:
+            traffic, why = measure_traffic("light", "light_accumulate", 2, 2, (2, r0, r1))
+            traffic_note = why or "ncu dram__bytes_read.sum + dram__bytes_write.sum of this rank's two lighting launches, measured in this run"
         result.update({
             "metric": "lit Mpixels/s (4K, 128 lights)", "value": mpx, "unit": "Mpixels/s", "ms_per_step": ms_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "light_accumulate_kernel (line-light pass + sphere/directional pass, both launches of the step)",
+                         "traffic_source": traffic_note,
+                         "kernel": "light_accumulate_kernel (line-light pass + sphere/directional pass, both launches of this rank's band)",
                          "kernel_ms": k_ms, "algorithmic_bytes_per_pixel": LIGHT_BYTES_PER_PIXEL, "peak_source": peak_src,
-                         "note": "per-pixel work is O(lights x trace steps): issue- and latency-bound, not HBM-bound (see DESIGN.md); "
-                                 "traffic = ncu DRAM bytes of both passes (the expanded distance-field planes trade traffic for instructions)"},
-            "e2e": {"value": W * H / (e_ms * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": int((r1 - r0) * W * 16 + nv * 128),
-                    "d2h_bytes_per_step": int(out_host.numel() * 2), "ms_per_step": e_ms},
-            "gpu_launches": int(launches), "clocks": clocks, "gather": gather,
+                         "note": "per-pixel work is O(lights x trace steps): issue- and latency-bound, not HBM-bound (see DESIGN.md)"},
+            "e2e": {"value": W * H / (e_ms * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e_ms, "what": e2e_note},
+            "gpu_launches": int(launches), "clocks": clocks, "gather": peers["gather"],
+            "probes": {"kernel_ms": p_ms / 5, "host_call_ms": probes_host_ms, "in_timed_step": True, "count": probes_packed[2]},
+            "bands": {"bounds": list(bounds), "rank_kernel_ms": [round(t, 4) for t in rank_kernel_ms], "calibration": calibration},
         })
         if world > 1:   # checksum of the reassembled frame: every rank must hold the same lit buffer
+            light_step()
+            barrier()
             chk = torch.tensor([float(full[:H].float().sum().item())], device="cuda", dtype=torch.float64)
             lo, hi = chk.clone(), chk.clone()
             dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
@@ -362,10 +482,7 @@ def run_ours(args):
             renderer.RenderLightingDevice(whole.data_ptr(), rows=(0, H), packed=packed)
             barrier()
             result["gather_matches_single_gpu"] = bool(torch.equal(whole.view(torch.int16), full[:H].view(torch.int16)))
-        # probes (config 4's "GI probes"): timed separately, tiny
-        t0 = time.perf_counter()
-        renderer.UpdateLightProbes()
-        result["probes_ms"] = (time.perf_counter() - t0) * 1e3
+            del whole
 
         # N3: resolve of the lit buffer -- HalfVector4 lightmap + Color albedo -> Color backbuffer, tone-mapped.
         # A streaming kernel: 16 algorithmic bytes per pixel.  Two buffer sets alternate (2 x 133 MB > L2) so every launch
@@ -374,7 +491,7 @@ def run_ours(args):
             from illuminant_b200 import hdr as hdr_mod
             hdr_cfg = ib.HDRConfiguration(Mode=ib.HDRMode.ToneMap, Exposure=1.2, ToneMapping=ib.ToneMappingConfiguration(WhitePoint=3.0))
             rp = hdr_mod.pack_resolve(W, H, _abi.FORMAT_HALF4, hdr_cfg, _abi.FORMAT_RGBA8, _abi.FORMAT_RGBA8)
-            lms = [full[:H].contiguous(), full[:H].clone()]
+            lms = [full[:H].contiguous().clone(), full[:H].clone()]
             als = [torch.randint(0, 256, (H, W, 4), dtype=torch.uint8, device="cuda") for _ in range(2)]
             outs = [torch.empty((H, W, 4), dtype=torch.uint8, device="cuda") for _ in range(2)]
             flip = {"i": 0}
@@ -387,7 +504,7 @@ def run_ours(args):
                     ctx.check(ctx.lib.ilb_resolve_lighting_device(ctx.handle, C.byref(rp), C.c_void_p(lms[i].data_ptr()),
                                                                   C.c_void_p(als[i].data_ptr()), C.c_void_p(outs[i].data_ptr())))
             r_steps = max(20, 2 * args.steps)
-            r_total, r_per = timed(resolve_step, r_steps, 3)
+            r_total, r_per = timed(resolve_step, r_steps, 3, sync=False)
             r_ms = float(np.median(r_per)) / R_INNER
             r_ach = 16 * W * H / (r_ms * 1e-3) / 1e9
             result["resolve"] = {"metric": "resolved Mpixels/s (4K, tone-mapped, with albedo)", "value": W * H / (r_ms * 1e-3) / 1e6,
@@ -399,18 +516,22 @@ def run_ours(args):
         except Exception as e:   # noqa: BLE001 -- the headline must not depend on the N3 side measurement
             result["resolve"] = {"error": f"{type(e).__name__}: {e}"}
 
-    # ------------------------------------------------------------------ particles (weak: 8M particles per GPU)
+    # ------------------------------------------------------------------ particles
+    def particle_system(count, chunk, nchunks, field, seed, headroom=2):
+        ps = scenes.particle_scene(seed, count, chunk, 1920, 1080, steps_hint=1000, collision_field=field, spawn_rate=60000.0)
+        engine = ib.ParticleEngine(ctx, ib.ParticleEngineConfiguration(ChunkSize=chunk, RandomSeed=0xB200))
+        system = ib.ParticleSystem(engine, ps.configuration, maxChunks=nchunks + headroom)   # headroom: chunks for the Spawner to fill
+        system.Transforms = ps.transforms
+        system.Spawn(ps.positions, ps.velocities, ps.attributes)
+        return ps, system
+
     if args.workload in ("both", "particles"):
         chunk, nchunks = 512, 32
         count = chunk * chunk * nchunks
         pscene_field = scenes.lighting_scene(1, 1920, 1080, 0)
         pdf = scenes.make_distance_field(ctx, pscene_field, resolution=0.25)   # quarter-res field like SimpleParticles.cs:216-219
         pdf.Rasterize(pscene_field.obstructions)
-        ps = scenes.particle_scene(2 + rank, count, chunk, 1920, 1080, steps_hint=1000, collision_field=pdf, spawn_rate=0.0)
-        engine = ib.ParticleEngine(ctx, ib.ParticleEngineConfiguration(ChunkSize=chunk, RandomSeed=0xB200))
-        system = ib.ParticleSystem(engine, ps.configuration, maxChunks=nchunks)
-        system.Transforms = ps.transforms
-        system.Spawn(ps.positions, ps.velocities, ps.attributes)
+        ps, system = particle_system(count, chunk, nchunks, pdf, 2 + rank)      # weak: 8M particles per GPU
         state = {"now": 0.0}
         launches0 = ctx.launch_count
 
@@ -424,7 +545,7 @@ def run_ours(args):
         total_ms, per = timed(particle_step, p_steps, p_warm)
         pclocks = sampler2.stop()
         p_launches = (ctx.launch_count - launches0) * p_steps // (p_steps + p_warm)
-        total_ms = max_over_ranks(total_ms)
+        total_ms = reduce_ranks(total_ms)
         ms_step = total_ms / p_steps
         mps = count * world / (ms_step * 1e-3) / 1e6
         achieved = PARTICLE_BYTES_PER_STEP * count / (float(np.median(per)) * 1e-3) / 1e9
@@ -440,22 +561,22 @@ def run_ours(args):
         for _ in range(p_steps):
             p_e2e_step()
         barrier()
-        e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / p_steps)
-        ptraffic = None
-        tp = ROOT / "profiles" / "traffic.json"
-        if tp.exists():
-            try:
-                ptraffic = json.loads(tp.read_text()).get("particle_step_kernel")
-            except Exception:
-                ptraffic = None
+        e_ms = reduce_ranks((time.perf_counter() - t0) * 1e3 / p_steps)
+        ptraffic, ptraffic_note = None, "not measured"
+        if rank == 0 and not args.no_traffic:
+            ptraffic, why = measure_traffic("particles", "particle_step_kernel", 4, 1, (5,))
+            ptraffic_note = why or "ncu dram__bytes_read.sum + dram__bytes_write.sum of one particle_step_kernel launch, measured in this run"
         result["particles"] = {
             "metric": "Mparticle-steps/s", "value": mps, "unit": "Mparticle-steps/s", "ms_per_step": ms_step, "steps": p_steps, "scaling": "weak",
-            "config": {"workload": f"{count} particles per GPU (32 chunks x 512^2), Gravity(4)+Noise+FMA+UpdateWithDistanceField, dt 1/60",
-                       "live_fraction": system.LiveCount / count},
+            "config": {"workload": f"{count} particles per GPU (32 chunks x 512^2 + spawn headroom), Spawner(60000/s)+Gravity(4)+Noise+FMA+UpdateWithDistanceField, dt 1/60",
+                       "live_particles_at_end": int(live.value), "live_chunks_at_end": system.LiveChunkCount,
+                       "counted_per_step": count, "note": "particles added by the Spawner during the run are updated but not counted"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ptraffic,
-                         "kernel": "particle_step_kernel<COLLIDE, Gravity, Noise, FMA>", "algorithmic_bytes_per_particle_step": PARTICLE_BYTES_PER_STEP, "peak_source": peak_src},
+                         "traffic_source": ptraffic_note,
+                         "kernel": "particle_step_kernel<COLLIDE, Gravity, Noise, FMA> (+ spawn and Noise-table launches of the step)",
+                         "algorithmic_bytes_per_particle_step": PARTICLE_BYTES_PER_STEP, "peak_source": peak_src},
             "e2e": {"value": count * world / (e_ms * 1e-3) / 1e6, "unit": "Mparticle-steps/s",
-                    "h2d_bytes_per_step": int(C.sizeof(_abi.PsysUniforms) + 3 * C.sizeof(_abi.Op)), "d2h_bytes_per_step": 8, "ms_per_step": e_ms},
+                    "h2d_bytes_per_step": int(C.sizeof(_abi.PsysUniforms) + 3 * C.sizeof(_abi.Op) + C.sizeof(_abi.Spawn)), "d2h_bytes_per_step": 8, "ms_per_step": e_ms},
             "gpu_launches": int(p_launches), "clocks": pclocks,
         }
 
@@ -469,7 +590,7 @@ def run_ours(args):
             def render_step():
                 ctx.check(ctx.lib.ilb_particles_render_device(system.handle, C.byref(rparams), None, C.c_void_p(rtarget.data_ptr())))
             rn = 10
-            _, rper = timed(render_step, rn, 2)
+            _, rper = timed(render_step, rn, 2, sync=False)
             rms = float(np.median(rper))
             rbytes = 48 * count + 8 * W * H
             result["render"] = {"metric": "rasterised Mparticles/s (8M particles per GPU -> 4K half4 target, additive)",
@@ -492,32 +613,57 @@ def run_ours(args):
         c5r.DistanceField = df                      # particles and lights share the same 4K field
         c5r._gbuffer_shape = renderer._gbuffer_shape
         c5packed = c5r.build_batches()
-        system.Configuration.Collision.DistanceField = df
+        eq0, eq1 = (r0, r1) if dist is None else sharding.row_band(rank, world, H)   # C5's lights are spread differently: equal bands
 
-        def frame_step():
-            particle_step()
-            if peer_ptrs is not None:
-                c5r.RenderLightingPeers(peer_ptrs, rows=(r0, r1), packed=c5packed)
-                hdl.barrier(channel=0)
+        def c5_lighting():
+            if peers["ptrs"] is not None:
+                c5r.RenderLightingPeers(peers["ptrs"], rows=(eq0, eq1), packed=c5packed)
+                peers["hdl"].barrier(channel=0)
             else:
-                c5r.RenderLightingDevice(band.data_ptr(), rows=(r0, r1), packed=c5packed)
+                c5r.RenderLightingDevice(full[eq0:].data_ptr(), rows=(eq0, eq1), packed=c5packed)
                 if dist is not None:
-                    dist.all_gather_into_tensor(full, band)
-        f_steps = max(args.steps, 10)
-        total_ms, _ = timed(frame_step, f_steps, 3)
-        ms_frame = max_over_ranks(total_ms) / f_steps
-        result["combined_c5"] = {"metric": "frames/s (8M particles per GPU + 64-light 4K lighting)", "value": 1e3 / ms_frame, "unit": "frames/s",
-                                 "ms_per_frame": ms_frame, "lit_mpixels_per_s": W * H / (ms_frame * 1e-3) / 1e6,
-                                 "mparticle_steps_per_s": count * world / (ms_frame * 1e-3) / 1e6, "steps": f_steps}
+                    dist.all_gather_into_tensor(full, full[eq0:eq0 + sharding.band_height(H, world)])
+
+        def c5_loop(update, n_particles, label):
+            def frame_step():
+                update()
+                c5_lighting()
+            f_steps = max(args.steps, 10)
+            total_ms, _ = timed(frame_step, f_steps, 3)
+            ms_frame = reduce_ranks(total_ms) / f_steps
+            return {"metric": f"frames/s ({label} + 64-light 4K lighting)", "value": 1e3 / ms_frame, "unit": "frames/s",
+                    "ms_per_frame": ms_frame, "lit_mpixels_per_s": W * H / (ms_frame * 1e-3) / 1e6,
+                    "mparticle_steps_per_s": n_particles / (ms_frame * 1e-3) / 1e6, "steps": f_steps}
+
+        system.Configuration.Collision.DistanceField = df
+        result["combined_c5"] = dict(c5_loop(particle_step, count * world, "8M particles per GPU"), scaling="weak (particles) / strong (lighting)")
+        # C5 as BASELINE.json words it: 8M particles IN TOTAL, chunk ranges sharded over the ranks (32 chunks -> 4 per GPU at N = 8)
+        c0, c1 = sharding.chunk_range(rank, world, nchunks)
+        sps, ssys = particle_system(chunk * chunk * (c1 - c0), chunk, c1 - c0, df, 40 + rank)
+        sstate = {"now": 0.0}
+
+        def strong_step():
+            sstate["now"] += sps.dt
+            ssys.Update(sstate["now"], sps.dt)
+        result["combined_c5_strong"] = dict(c5_loop(strong_step, count, "8M particles in total, chunk ranges sharded"),
+                                            scaling="strong", chunks_per_rank=c1 - c0)
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
         cores = oracle.threads()
         if "metric" in result:
-            v, rows, t = cpu_lighting_sample(oracle, scenes, ib, scene, 12.0)
-            result["cpu_baseline"] = {"value": v, "unit": "Mpixels/s", "cores": cores, "kind": "port",
-                                      "sample": f"{rows}-row band ({rows * W} px) of the same 4K / 128-light frame, {t:.1f} s"}
+            cpu = CpuLighting(oracle, scenes, ib, scene)
+            t_all, rows_all = 0.0, 0
+            for step in range(ROW_STRIDE):          # the whole frame once, in 8 strided passes; stops early past 20 s
+                n, t = cpu.strided_step(step)
+                t_all += t
+                rows_all += n
+                if t_all > 20.0:
+                    break
+            result["cpu_baseline"] = {"value": rows_all * W / t_all / 1e6, "unit": "Mpixels/s", "cores": cores, "kind": "port",
+                                      "sample": f"{rows_all} rows ({rows_all * W} px) of the same 4K / 128-light frame, every {ROW_STRIDE}th row "
+                                                f"per pass, {t_all:.1f} s"}
         if "particles" in result:
             cdf = scenes.make_distance_field(None, pscene_field, resolution=0.25)
             ctex = oracle.generate_distance_field(cdf, pscene_field.obstructions)
@@ -534,11 +680,11 @@ def run_ours(args):
         line = {"metric": result.get("metric"), "value": result.get("value"), "unit": result.get("unit"), "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": result.get("ms_per_step"), "higher_is_better": True,
                 "scaling": "strong" if primary else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "C4: 3840x2160, 96 sphere + 8 directional + 24 line lights, 256 probes, 9-slice 3840x2160 distance field"
-                           if primary else result.get("config", {}).get("workload"),
-                           "parallelism": f"row bands x{world}, gather: {result.get('gather', 'none')}" if primary else f"chunk ranges x{world}, no collective",
+                "config": {"workload": C4_WORKLOAD if primary else result.get("config", {}).get("workload"),
+                           "parallelism": f"row bands of equal measured cost x{world}, gather: {result.get('gather', 'none')}" if primary else f"chunk ranges x{world}, no collective",
                            "l2": "inputs larger than L2 (no flush)"}}
-        for k in ("roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "gather_checksum_equal", "gather_matches_single_gpu", "particles", "combined_c5", "probes_ms", "resolve", "render"):
+        for k in ("roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "gather_checksum_equal", "gather_matches_single_gpu", "probes", "bands",
+                  "particles", "combined_c5", "combined_c5_strong", "resolve", "render"):
             if k in result:
                 line[k] = result[k]
         print(json.dumps(line), flush=True)
@@ -555,6 +701,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="both", choices=["both", "lighting", "particles"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu child process that counts DRAM bytes")
+    ap.add_argument("--equal-bands", action="store_true", help="N>1: equal-height row bands instead of bands of equal measured cost")
     ap.add_argument("--gather", default="auto", choices=["auto", "peers", "nccl"], help="N>1 lit-buffer reassembly")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -193,6 +193,7 @@ _PROTOTYPES = [
     ("ilb_df_generate", C.c_int, [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DFUniforms), P, C.c_int, C.POINTER(P)]),
     ("ilb_gbuffer_upload", C.c_int, [P, C.c_int, C.c_int, C.c_int, P]),
     ("ilb_gbuffer_upload_device", C.c_int, [P, C.c_int, C.c_int, C.c_int, P]),
+    ("ilb_gbuffer_upload_rows", C.c_int, [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P]),
     ("ilb_render_lighting", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, P]),
     ("ilb_render_lighting_frame", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_int, P, P]),
     ("ilb_lighting_set_particle_lights", C.c_int, [P, P, C.c_int]),

@@ -133,7 +133,7 @@ int ilb_create(int device_ordinal, ilb_ctx** out_ctx) {
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);
     static const struct { const char* env; int value; } defaults[ILB_OPT_COUNT] = {
-        {"ILB_OPT_LIGHT_CONCURRENT", 1}, {"ILB_OPT_LIGHT_LINE_CTAS", 2}, {"ILB_OPT_LIGHT_OTHER_CTAS", 2},
+        {"ILB_OPT_LIGHT_CONCURRENT", 0}, {"ILB_OPT_LIGHT_LINE_CTAS", 2}, {"ILB_OPT_LIGHT_OTHER_CTAS", 2},
         {"ILB_OPT_LIGHT_LINE_HELPERS", 1}, {"ILB_OPT_LIGHT_OTHER_HELPERS", 3}};
     for (int i = 0; i < ILB_OPT_COUNT; i++) {
         const char* e = getenv(defaults[i].env);
@@ -338,6 +338,24 @@ static int gbuffer_set(ilb_ctx* ctx, int w, int h, int fmt, const void* data, bo
     ILB_CUDA(ctx, cudaMemcpyAsync(ctx->gbuffer, data, bytes, device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
     if (!device) ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // caller-owned pageable memory
     ctx->gb_w = w; ctx->gb_h = h; ctx->gb_fmt = fmt;
+    return ILB_OK;
+}
+
+int ilb_gbuffer_upload_rows(ilb_ctx* ctx, int w, int h, int fmt, int row_begin, int row_end, const void* rows) {
+    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!rows || w <= 0 || h <= 0 || row_begin < 0 || row_end > h || row_begin > row_end) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad G-buffer rows [%d,%d) of %dx%d", row_begin, row_end, w, h);
+    if (fmt != ILB_FORMAT_FLOAT4 && fmt != ILB_FORMAT_HALF4) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "G-buffer format must be FLOAT4 or HALF4");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t texel = ilb_format_bytes(fmt), bytes = texel * (size_t)w * (size_t)h;
+    if (!ctx->gbuffer_owned) { ctx->gbuffer = nullptr; ctx->gbuffer_capacity = 0; }
+    const bool fresh = !ctx->gbuffer || ctx->gb_w != w || ctx->gb_h != h || ctx->gb_fmt != fmt;
+    int rc = ilb_reserve(ctx, &ctx->gbuffer, &ctx->gbuffer_capacity, bytes, false);
+    if (rc) return rc;
+    ctx->gbuffer_owned = true;
+    if (fresh) ILB_CUDA(ctx, cudaMemsetAsync(ctx->gbuffer, 0, bytes, ctx->stream));  // rows that are never uploaded hold zeros
+    ctx->gb_w = w; ctx->gb_h = h; ctx->gb_fmt = fmt;
+    const size_t off = texel * (size_t)w * (size_t)row_begin, n = texel * (size_t)w * (size_t)(row_end - row_begin);
+    if (n) ILB_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<char*>(ctx->gbuffer) + off, rows, n, cudaMemcpyHostToDevice, ctx->stream));
     return ILB_OK;
 }
 

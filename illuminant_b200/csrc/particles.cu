@@ -574,6 +574,11 @@ __global__ void __launch_bounds__(STEP_THREADS, ILB_PARTICLE_MINBLOCKS) particle
     float x, y;
     const unsigned li = particleXY(P, gi, x, y);
     const f4 inP = inRange ? mk4(P.P[gi]) : mk4(0.0f), inV = inRange ? mk4(P.V[gi]) : mk4(0.0f);
+#if !ILB_NO_ATTR_PREFETCH
+    // the attributes are only needed by the render outputs at the very end: start pulling a live particle's texel towards L2 now,
+    // so that the dependent load behind ~1000 instructions of chain does not pay the DRAM latency (dead particles fetch nothing)
+    if (inRange && P.u.write_render_outputs && inP.w > 0.0f) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.A + gi));
+#endif
     stepParticleGuarded<COLLIDE, K0, K1, K2, FM>(P, x, y, li, inP, inV, outP, outV, needAttr, s_slots + (threadIdx.x & ~31u));
     if (!inRange) return;
     P.P[gi] = to_float4(outP);

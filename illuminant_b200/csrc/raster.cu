@@ -247,9 +247,9 @@ __global__ void __launch_bounds__(RBATCH) raster_shade_kernel(const __grid_const
             boxes[threadIdx.x] = make_int4(x0, y0, x1, y1);
         }
         __syncthreads();
-#ifdef ILB_RASTER_BALLOT
-        // EXPERIMENTAL (not in the default build; ILB_DEFINES=ILB_RASTER_BALLOT): each lane tests one staged quad's box against the
-        // warp's block, one ballot per 32 quads, and the warp visits only the set bits -- in ascending order, so the draw order holds.
+        // each lane tests one staged quad's box against the warp's block, one ballot per 32 quads, and the warp visits only the set
+        // bits -- in ascending order, so the draw order holds (measured on 8 M small quads: 4.34 -> 2.99 ms per render against a
+        // warp-uniform test per quad)
         for (unsigned k0 = 0; k0 < n; k0 += 32) {
             bool hit = false;
             if (k0 + lane < n) {
@@ -260,12 +260,6 @@ __global__ void __launch_bounds__(RBATCH) raster_shade_kernel(const __grid_const
             while (hits) {
                 const unsigned k = k0 + (unsigned)(__ffs(hits) - 1);
                 hits &= hits - 1;
-#else
-        for (unsigned k = 0; k < n; k++) {
-            {
-                const int4 box = boxes[k];
-                if (box.z < bx0 || box.x > bx0 + 7 || box.w < by0 || box.y > by0 + 3) continue;  // warp-uniform
-#endif
             const Sprite& s = batch[k];
             const float dx = xsub(pcx, s.cx), dy = xsub(pcy, s.cy);
             const float u = xadd(xmul(dx, s.m00), xmul(dy, s.m01)), v = xadd(xmul(dx, s.m10), xmul(dy, s.m11));

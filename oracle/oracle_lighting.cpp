@@ -703,13 +703,23 @@ extern "C" {
 int orc_render_lighting(const uint16_t* df_tex, int tw, int th, const void* gbuffer, int gw, int gh, int gfmt,
                         const ilb_lighting_frame* f, const ilb_light_batch* batches, int nbatches,
                         const ilb_light_vertex* verts, int nverts, float* out, int nthreads) {
+    return orc_render_lighting_strided(df_tex, tw, th, gbuffer, gw, gh, gfmt, f, batches, nbatches, verts, nverts, 1, out, nthreads);
+}
+
+// The same passes over rows row_begin, row_begin + row_stride, ... < row_end only (a sample of rows spread over a frame
+// whose cost is not uniform); `out` holds those rows packed: width * ceil((row_end - row_begin) / row_stride) float4.
+int orc_render_lighting_strided(const uint16_t* df_tex, int tw, int th, const void* gbuffer, int gw, int gh, int gfmt,
+                                const ilb_lighting_frame* f, const ilb_light_batch* batches, int nbatches,
+                                const ilb_light_vertex* verts, int nverts, int row_stride, float* out, int nthreads) {
+    if (row_stride < 1) return ILB_ERR_INVALID_ARGUMENT;
     const int W = f->width, r0 = f->row_begin, r1 = f->row_end;
+    const int nrows = (r1 - r0 + row_stride - 1) / row_stride;
     Frame fr = makeFrame(f, gbuffer, gw, gh, gfmt);
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #pragma omp parallel for schedule(static)
-    for (int y = r0; y < r1; y++)
+    for (int yi = 0; yi < nrows; yi++)
         for (int x = 0; x < W; x++) {
-            float* o = out + 4 * ((size_t)(y - r0) * W + x);
+            float* o = out + 4 * ((size_t)yi * W + x);
             o[0] = f->ClearColor.x; o[1] = f->ClearColor.y; o[2] = f->ClearColor.z; o[3] = f->ClearColor.w;
         }
     for (int b = 0; b < nbatches; b++) {
@@ -721,8 +731,9 @@ int orc_render_lighting(const uint16_t* df_tex, int tw, int th, const void* gbuf
             if (vi < 0 || vi >= nverts) return ILB_ERR_INVALID_ARGUMENT;
             const ilb_light_vertex& v = verts[vi];
 #pragma omp parallel for collapse(2) schedule(dynamic, 256)
-            for (int y = r0; y < r1; y++)
+            for (int yi = 0; yi < nrows; yi++)
                 for (int x = 0; x < W; x++) {
+                    const int y = r0 + yi * row_stride;
                     float4 result;
                     bool lit = false;
                     float2 vpos((float)x, (float)y);
@@ -748,7 +759,7 @@ int orc_render_lighting(const uint16_t* df_tex, int tw, int th, const void* gbuf
                             break;
                     }
                     if (lit) {
-                        float* o = out + 4 * ((size_t)(y - r0) * W + x);
+                        float* o = out + 4 * ((size_t)yi * W + x);
                         o[0] += result.x; o[1] += result.y; o[2] += result.z; o[3] += result.w;
                     }
                 }

@@ -193,3 +193,15 @@ def test_histogram_matches_scalar_transcription(ignore):
     assert sum(b["Count"] for b in h.Buckets) == h.SampleCount
     h.Clear()
     assert h.SampleCount == 0 and h.GetPercentile(50) == (False, 0, 0)
+
+
+def test_unorm8_decode_by_reciprocal_and_one_correction_is_the_ieee_quotient():
+    """resolve.cu decodes UNORM8 albedo / target texels as q = c * fl(1/255), rho = c - 255 q (one FMA, exact),
+    q' = fl(q + rho * fl(1/255)) instead of an IEEE division: the same bits as c / 255 for all 256 inputs."""
+    r = np.float32(1.0) / np.float32(255.0)
+    for c in range(256):
+        q = np.float32(np.float32(c) * r)
+        rho = np.float64(c) - 255.0 * np.float64(q)                  # exact in double, exactly representable in fp32
+        assert np.float64(np.float32(rho)) == rho
+        q2 = np.float32(np.float64(q) + rho * np.float64(r))         # the FMA: exact sum in double, one rounding to fp32
+        assert q2 == np.float32(c) / np.float32(255.0), c
