@@ -356,11 +356,15 @@ def run_ours(args):
         def my_rows():
             return bounds[rank], bounds[rank + 1]
 
-        def band_kernel_ms(reps=2):
+        def band_kernel_ms(reps=2, with_probes=False):
             r0, r1 = my_rows()
-            if r1 <= r0:
-                return 0.0
-            ms, _ = timed(lambda: renderer.RenderLightingDevice(scratch.data_ptr(), rows=(r0, r1), packed=packed), reps, 1, sync=False)
+
+            def work():
+                if r1 > r0:
+                    renderer.RenderLightingDevice(scratch.data_ptr(), rows=(r0, r1), packed=packed)
+                if with_probes and rank == 0:   # what rank 0 does on top of its band inside a step
+                    renderer.UpdateLightProbesDevice(d_probes.data_ptr(), packed=packed, probes=probes_packed)
+            ms, _ = timed(work, reps, 1, sync=False)
             return ms / reps
 
         # Row bands of equal measured cost (lights are clustered: equal-height bands finish at different times and the frame
@@ -369,7 +373,7 @@ def run_ours(args):
         if dist is not None and peers["ptrs"] is not None and not args.equal_bands:
             history = []
             for _ in range(4):
-                times = gather_ranks(band_kernel_ms())
+                times = gather_ranks(band_kernel_ms(4, with_probes=True))
                 history.append({"bounds": list(bounds), "band_ms": [round(t, 4) for t in times]})
                 bounds = sharding.rebalance_rows(bounds, times, H, quantum=4)
             calibration = history
