@@ -219,6 +219,9 @@ _PROTOTYPES = [
     ("ilb_particles_render_device", C.c_int, [P, C.POINTER(ParticleRender), P, P]),
     ("ilb_particles_device_buffer", P, [P, C.c_int]),
     ("ilb_particles_count_live", C.c_int, [P, C.POINTER(C.c_int64)]),
+    ("ilb_particles_request_chunk_liveness", C.c_int, [P]),
+    ("ilb_particles_poll_chunk_liveness", C.c_int, [P, C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int), C.c_int]),
+    ("ilb_particles_remove_chunk", C.c_int, [P, C.c_int]),
 ]
 EXPORTED_SYMBOLS = [p[0] for p in _PROTOTYPES]
 

@@ -554,6 +554,9 @@ void ilb_particles_destroy(ilb_psys* ps) {
     ilb_raster_release(ps);
     if (ps->life_ramp) cudaFree(ps->life_ramp);
     if (ps->d_count) cudaFree(ps->d_count);
+    if (ps->d_chunk_counts) cudaFree(ps->d_chunk_counts);
+    if (ps->h_chunk_counts) cudaFreeHost(ps->h_chunk_counts);
+    if (ps->ev_chunk_counts) cudaEventDestroy(ps->ev_chunk_counts);
     delete ps;
 }
 
@@ -705,6 +708,25 @@ int ilb_particles_count_live(ilb_psys* ps, int64_t* out_count) {
     if (!ps || !out_count || !live_has(ps)) return ILB_ERR_INVALID_ARGUMENT;
     ILB_CUDA(ps->ctx, cudaSetDevice(ps->ctx->device));
     return ilb_particles_count_launch(ps, out_count);
+}
+
+int ilb_particles_request_chunk_liveness(ilb_psys* ps) {
+    if (!ps || !live_has(ps)) return ILB_ERR_INVALID_ARGUMENT;
+    ILB_CUDA(ps->ctx, cudaSetDevice(ps->ctx->device));
+    return ilb_particles_liveness_request(ps);
+}
+
+int ilb_particles_poll_chunk_liveness(ilb_psys* ps, int64_t* counts, int capacity, int* out_count, int wait) {
+    if (!ps || !live_has(ps)) return ILB_ERR_INVALID_ARGUMENT;
+    if (!counts || !out_count || capacity < 0) return ilb_fail(ps->ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
+    ILB_CUDA(ps->ctx, cudaSetDevice(ps->ctx->device));
+    return ilb_particles_liveness_poll(ps, counts, capacity, out_count, wait);
+}
+
+int ilb_particles_remove_chunk(ilb_psys* ps, int chunk) {
+    if (!ps || !live_has(ps)) return ILB_ERR_INVALID_ARGUMENT;
+    ILB_CUDA(ps->ctx, cudaSetDevice(ps->ctx->device));
+    return ilb_particles_remove(ps, chunk);
 }
 
 }  // extern "C"

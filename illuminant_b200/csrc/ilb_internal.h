@@ -104,6 +104,12 @@ struct ilb_psys {
     float4* noise_table = nullptr;  // 2 * per_chunk float4, see noise_table_kernel
     float2* escape_table = nullptr; // per_chunk float2, see escape_table_kernel
     unsigned long long* d_count = nullptr;
+    // per-chunk liveness, read back asynchronously (ilb_particles_request_chunk_liveness / _poll_chunk_liveness)
+    unsigned long long* d_chunk_counts = nullptr;
+    unsigned long long* h_chunk_counts = nullptr;  // pinned
+    cudaEvent_t ev_chunk_counts = nullptr;
+    int liveness_chunks = 0;
+    bool liveness_pending = false;
     bool use_tma = false;  // ILB_PARTICLE_TMA=1 selects the TMA-staged persistent step kernel (measured 22 % slower: the
                            // chain is issue-bound and tile-lockstep adds barrier stalls; the direct kernel is the default)
     int sm_count = 148;
@@ -150,3 +156,6 @@ int ilb_dfgen_launch(ilb_ctx* ctx, uint2* tex, const uint2* base, int tw, int th
 int ilb_particles_launch(ilb_psys* psys, const ilb_psys_uniforms* u, const ilb_spawn* spawns, const ilb_spawn_source* sources,
                          int spawn_count, const ilb_op* ops, int op_count, int steps);
 int ilb_particles_count_launch(ilb_psys* psys, int64_t* out);
+int ilb_particles_liveness_request(ilb_psys* psys);
+int ilb_particles_liveness_poll(ilb_psys* psys, int64_t* counts, int capacity, int* out_count, int wait);
+int ilb_particles_remove(ilb_psys* psys, int chunk);

@@ -939,7 +939,68 @@ __global__ void __launch_bounds__(256) particle_count_live_kernel(const float4* 
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, (unsigned long long)local);
 }
 
+// per-chunk liveness (ParticleLiveness.cs:80-106 reads one occlusion-query count per chunk): blockIdx.y = chunk
+__global__ void __launch_bounds__(256) particle_count_chunks_kernel(const float4* __restrict__ P, unsigned per_chunk, unsigned long long* out) {
+    const float4* base = P + (size_t)blockIdx.y * per_chunk;
+    unsigned local = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < per_chunk; i += gridDim.x * blockDim.x) local += (__ldg(base + i).w > 0.0f) ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(out + blockIdx.y, (unsigned long long)local);
+}
+
 }  // namespace
+
+int ilb_particles_liveness_request(ilb_psys* ps) {
+    ilb_ctx* ctx = ps->ctx;
+    if (!ps->d_chunk_counts) {
+        ILB_CUDA(ctx, cudaMalloc(&ps->d_chunk_counts, sizeof(unsigned long long) * (size_t)ps->max_chunks));
+        ILB_CUDA(ctx, cudaMallocHost(&ps->h_chunk_counts, sizeof(unsigned long long) * (size_t)ps->max_chunks));
+        ILB_CUDA(ctx, cudaEventCreateWithFlags(&ps->ev_chunk_counts, cudaEventDisableTiming));
+    }
+    ps->liveness_chunks = ps->live_chunks;
+    ps->liveness_pending = true;
+    if (ps->live_chunks > 0) {
+        ILB_CUDA(ctx, cudaMemsetAsync(ps->d_chunk_counts, 0, sizeof(unsigned long long) * (size_t)ps->live_chunks, ctx->stream));
+        const unsigned bx = (unsigned)std::min<size_t>((ps->per_chunk + 1023) / 1024, 64);
+        particle_count_chunks_kernel<<<dim3(bx, (unsigned)ps->live_chunks), 256, 0, ctx->stream>>>(ps->buf[0], (unsigned)ps->per_chunk, ps->d_chunk_counts);
+        ctx->launches++;
+        ILB_CUDA(ctx, cudaGetLastError());
+        ILB_CUDA(ctx, cudaMemcpyAsync(ps->h_chunk_counts, ps->d_chunk_counts, sizeof(unsigned long long) * (size_t)ps->live_chunks, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ILB_CUDA(ctx, cudaEventRecord(ps->ev_chunk_counts, ctx->stream));
+    return ILB_OK;
+}
+
+int ilb_particles_liveness_poll(ilb_psys* ps, int64_t* counts, int capacity, int* out_count, int wait) {
+    ilb_ctx* ctx = ps->ctx;
+    *out_count = -1;
+    if (!ps->liveness_pending) return ILB_OK;
+    cudaError_t e = wait ? cudaEventSynchronize(ps->ev_chunk_counts) : cudaEventQuery(ps->ev_chunk_counts);
+    if (e == cudaErrorNotReady) return ILB_OK;
+    if (e != cudaSuccess) return ilb_cuda_fail(ctx, e, "liveness event");
+    if (capacity < ps->liveness_chunks) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "counts has room for %d chunks, the request covered %d", capacity, ps->liveness_chunks);
+    for (int i = 0; i < ps->liveness_chunks; i++) counts[i] = (int64_t)ps->h_chunk_counts[i];
+    *out_count = ps->liveness_chunks;
+    ps->liveness_pending = false;
+    return ILB_OK;
+}
+
+// Reap (ParticleLiveness.cs:121-129): the chunk leaves the system's ordered chunk list.  Chunks are slots of contiguous
+// slabs here (one kernel launch covers all live chunks), so the later chunks move down one slot, in order.
+int ilb_particles_remove(ilb_psys* ps, int chunk) {
+    ilb_ctx* ctx = ps->ctx;
+    if (chunk < 0 || chunk >= ps->live_chunks) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "chunk %d is not live", chunk);
+    const size_t bytes = sizeof(float4) * ps->per_chunk;
+    for (int b = 0; b < 5; b++) {
+        for (int c = chunk; c + 1 < ps->live_chunks; c++)   // ascending, slot by slot: source and destination never overlap
+            ILB_CUDA(ctx, cudaMemcpyAsync(ps->buf[b] + (size_t)c * ps->per_chunk, ps->buf[b] + (size_t)(c + 1) * ps->per_chunk, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        ILB_CUDA(ctx, cudaMemsetAsync(ps->buf[b] + (size_t)(ps->live_chunks - 1) * ps->per_chunk, 0, bytes, ctx->stream));
+    }
+    ps->live_chunks--;
+    ps->liveness_pending = false;   // a pending request counted the old slot order
+    return ILB_OK;
+}
 
 int ilb_particles_launch(ilb_psys* ps, const ilb_psys_uniforms* u, const ilb_spawn* spawns, const ilb_spawn_source* sources,
                          int spawn_count, const ilb_op* ops, int op_count, int steps) {

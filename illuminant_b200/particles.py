@@ -702,6 +702,7 @@ def generate_randomness_texture(seed: Optional[int]) -> np.ndarray:
 class ParticleSystem:
     """ParticleSystem(engine, configuration) -- ParticleSystem.cs:242-330 / Update :634-760."""
     MaxChunkCount = 64  # ParticleSystem.cs:49 (the capacity passed to the library may be larger, see `maxChunks`)
+    LivenessCheckInterval = 4   # ParticleLiveness.cs:14
 
     def __init__(self, engine: ParticleEngine, configuration: Optional[ParticleSystemConfiguration] = None, maxChunks: Optional[int] = None):
         self.Engine = engine
@@ -720,6 +721,13 @@ class ParticleSystem:
         self._chunk_consumed: List[int] = []           # Chunk.TotalConsumedForFeedback (== FeedbackSourceIndex)
         self._chunk_no_longer_target: List[bool] = []  # Chunk.NoLongerASpawnTarget
         self._chunk_is_feedback: List[bool] = []       # Chunk.IsFeedbackSource (set on the chunks a FeedbackSpawner fills)
+        self._chunk_live_count: List[Optional[int]] = []   # LivenessInfo.Count (ParticleLiveness.cs:24-28); None until a count arrives
+        self._chunk_dead_frames: List[int] = []            # LivenessInfo.DeadFrameCount
+        self._chunk_reap: List[bool] = []                  # member of ChunksToReap
+        self.DeadFrameThreshold = self.LivenessCheckInterval * 4   # ParticleLiveness.cs:22
+        self._frames_until_liveness = 0                    # FramesUntilNextLivenessCheck
+        self.IsClearPending = False
+        self.ReapedChunkCount = 0
         self._spawn_target = -1
         self._feedback_spawn_target = -1               # CurrentFeedbackSpawnTarget
         self._feedback_source = -1                     # CurrentFeedbackSource
@@ -760,6 +768,10 @@ class ParticleSystem:
             self._chunk_consumed.append(0)
             self._chunk_no_longer_target.append(self._chunk_next_offset[c] >= self.ChunkMaximumCount)
             self._chunk_is_feedback.append(False)
+        for c in range(len(self._chunk_live_count), len(self._chunk_next_offset)):
+            self._chunk_live_count.append(None)   # GetLivenessInfo starts from TotalSpawned; nothing is known before the first count
+            self._chunk_dead_frames.append(0)
+            self._chunk_reap.append(False)
 
     def _create_chunk(self) -> int:  # CreateChunk (ParticleSystem.cs:520-545)
         if len(self._chunk_next_offset) >= self.MaxChunks:
@@ -770,6 +782,61 @@ class ParticleSystem:
         if self.handle:
             self.ctx.check(self.ctx.lib.ilb_particles_set_live_chunks(self.handle, len(self._chunk_next_offset)))
         return len(self._chunk_next_offset) - 1
+
+    # ---- liveness and reaping (ParticleLiveness.cs:30-129, ParticleSystem.cs:529-545, :675, :702-714) -----------------------
+    def Clear(self) -> None:
+        """ParticleSystem.Clear (ParticleSystem.cs:529-545): every chunk is reaped at the top of the next Update."""
+        self._sync_chunk_lists()
+        self.IsClearPending = True
+        for c in range(self.LiveChunkCount):
+            self._chunk_reap[c] = True
+
+    def _process_liveness(self, counts) -> None:
+        """ProcessLatestLivenessInfo (ParticleLiveness.cs:46-78) for the chunks a liveness request covered."""
+        self._sync_chunk_lists()
+        for c, n in enumerate(counts):
+            if c >= self.LiveChunkCount:
+                break
+            self._chunk_live_count[c] = int(n)
+            self._chunk_dead_frames[c] = self._chunk_dead_frames[c] + 1 if n <= 0 else 0
+            if self._chunk_dead_frames[c] >= self.DeadFrameThreshold:
+                self._chunk_reap[c] = True
+
+    def _poll_liveness(self, wait: bool = False) -> bool:
+        if self.handle is None:
+            return False
+        counts = (C.c_int64 * max(self.MaxChunks, 1))()
+        n = C.c_int(-1)
+        self.ctx.check(self.ctx.lib.ilb_particles_poll_chunk_liveness(self.handle, counts, self.MaxChunks, C.byref(n), 1 if wait else 0))
+        if n.value < 0:
+            return False
+        self._process_liveness([counts[i] for i in range(n.value)])
+        return True
+
+    def _reap_chunk(self, c: int) -> None:
+        """Reap (ParticleLiveness.cs:121-129): the chunk leaves the ordered chunk list; later chunks keep their order."""
+        if self.handle is not None:
+            self.ctx.check(self.ctx.lib.ilb_particles_remove_chunk(self.handle, c))
+        for lst in (self._chunk_next_offset, self._chunk_total_spawned, self._chunk_consumed, self._chunk_no_longer_target,
+                    self._chunk_is_feedback, self._chunk_live_count, self._chunk_dead_frames, self._chunk_reap):
+            del lst[c]
+        fix = lambda i: -1 if i == c else (i - 1 if i > c else i)
+        self._spawn_target, self._feedback_spawn_target, self._feedback_source = (fix(self._spawn_target), fix(self._feedback_spawn_target),
+                                                                                  fix(self._feedback_source))
+        self.ReapedChunkCount += 1
+
+    def _update_live_count_and_reap(self) -> None:
+        """UpdateLiveCountAndReapDeadChunks (ParticleLiveness.cs:80-106) + the pending Clear (ParticleSystem.cs:702-714)."""
+        self._sync_chunk_lists()
+        self._poll_liveness()
+        for c in reversed(range(self.LiveChunkCount)):
+            if self._chunk_reap[c]:
+                self._reap_chunk(c)
+        if self.IsClearPending:
+            for c in reversed(range(self.LiveChunkCount)):
+                self._reap_chunk(c)
+            self.IsClearPending = False
+            self.TotalSpawnCount = 0
 
     def Spawn(self, positions: np.ndarray, velocities: np.ndarray, attributes: np.ndarray) -> int:
         """Spawn(count, initializer) (ParticleSpawning.cs:61-113): fills NEW chunks with caller-provided state
@@ -955,10 +1022,18 @@ class ParticleSystem:
         dt = deltaTimeSeconds if deltaTimeSeconds is not None else self._delta_time(now)
         self.Now = now
         self.LastUpdateTimeSeconds = now
+        self._update_live_count_and_reap()                 # ParticleSystem.cs:675
+        computingLiveness = self._frames_until_liveness <= 0   # :716-720 (`FramesUntilNextLivenessCheck-- <= 0`)
+        self._frames_until_liveness -= 1
+        if computingLiveness:
+            self._frames_until_liveness = self.LivenessCheckInterval
         spawns = self.plan_spawns(now, dt)
         ops = self.plan_ops(now)
         u = self.system_uniforms(dt)
         self.step_packed(u, spawns, ops, 1, self.last_sources)
+        if computingLiveness and self.handle is not None and self.LiveChunkCount > 0:
+            # ComputeLiveness (:752, ParticleLiveness.cs:131-141): counted behind this update, read back on a later frame
+            self.ctx.check(self.ctx.lib.ilb_particles_request_chunk_liveness(self.handle))
 
     def step_packed(self, u: PsysUniforms, spawns, ops, steps: int = 1, sources=None) -> None:
         """`sources`: None (every spawn is inline) or one ilb_spawn_source / None per spawn (ilb_particles_step_sources)."""

@@ -481,6 +481,18 @@ ILB_API void* ilb_particles_device_buffer(ilb_psys* psys, int which);
 /* Count particles with life > 0 in chunks [0, live) (CountLiveParticles.fx equivalent); synchronous. */
 ILB_API int ilb_particles_count_live(ilb_psys* psys, int64_t* out_count);
 
+/* Chunk liveness and reaping (ParticleLiveness.cs:14-129, ParticleSystem.cs:675, :702-714).  The reference counts the live
+ * particles of every chunk with occlusion queries every LivenessCheckInterval frames, reads the counts back some frames later
+ * and reaps chunks that stayed empty for DeadFrameThreshold checks, so that a continuous spawner never runs out of chunks.
+ *   request: queues one count per live chunk behind the work already submitted; asynchronous.
+ *   poll:    *out_count = number of chunks the last request covered and counts[0..*out_count) when its results have arrived
+ *            (wait != 0 blocks until they have), -1 when there is none or it is still in flight.
+ *   remove:  reaps `chunk`: the chunks behind it move down one slot, keeping their order (and their draw order); a request
+ *            in flight is dropped, because it counted the old slots. */
+ILB_API int ilb_particles_request_chunk_liveness(ilb_psys* psys);
+ILB_API int ilb_particles_poll_chunk_liveness(ilb_psys* psys, int64_t* counts, int capacity, int* out_count, int wait);
+ILB_API int ilb_particles_remove_chunk(ilb_psys* psys, int chunk);
+
 /* ------------------------------------------ "next" row N2: particle rasterisation (ParticleSystem.Render) */
 
 typedef enum ilb_blend {

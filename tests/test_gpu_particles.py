@@ -261,3 +261,59 @@ def test_life_ramp_texture(ctx, oracle):
         _, plain, _ = _run_both(ctx, oracle, fresh, 128, 4)
         assert not np.allclose(gpu[3], plain[3])      # the ramp really changes renderColor
         assert np.array_equal(gpu[0], plain[0])       # ... and nothing else
+
+
+def test_dead_chunks_are_reaped_so_a_continuous_spawner_never_runs_out(ctx):
+    """chunks were only ever appended, so a continuous Spawner stopped for good after MaxChunks * ChunkSize^2
+    spawns.  With the reference's liveness check every LivenessCheckInterval frames and reaping after DeadFrameThreshold empty
+    results (ParticleLiveness.cs:14-129, ParticleSystem.cs:675) a short-lived stream keeps spawning for ever."""
+    from illuminant_b200.particles import Formula, Spawner
+    chunk = 16
+    engine = ib.ParticleEngine(ctx, ib.ParticleEngineConfiguration(ChunkSize=chunk, RandomSeed=5))
+    cfg = ib.ParticleSystemConfiguration(LifeDecayPerSecond=1.0)
+    system = ib.ParticleSystem(engine, cfg, maxChunks=4)           # capacity 4 * 256 = 1024 particles
+    system.DeadFrameThreshold = 2
+    system.Transforms = [Spawner(MinRate=3000.0, MaxRate=3000.0, Seed=1, Position=Formula(Constant=(50.0, 50.0, 0.0), RandomScale=(20.0, 20.0, 0.0)),
+                                 Velocity=Formula(Constant=(1.0, 0.0, 0.0)), Life=(0.12, 0.0, 0.0), ColorConstant=(1.0, 1.0, 1.0, 1.0))]
+    dt, now, peak = 1 / 60.0, 0.0, 0
+    for frame in range(400):
+        now += dt
+        system.Update(now, dt)
+        if frame % 7 == 0:
+            system._poll_liveness(wait=True)                      # a slow consumer would see the counts a few frames late; either works
+        peak = max(peak, system.LiveChunkCount)
+    spawner = system.Transforms[0]
+    assert spawner.TotalSpawned > 6 * 1024, spawner.TotalSpawned   # up to 50 per frame for 400 frames: far past the capacity of 1024
+    assert system.ReapedChunkCount >= 15 and peak <= 4
+    live = system.LiveCount
+    assert 100 <= live <= 420, live                                # ~7 frames of life at up to 50 per frame stay alive
+    # the reaped slots were zeroed and the survivors kept their order: every live chunk holds only live-or-zero texels
+    for c in range(system.LiveChunkCount):
+        p, v, a, rc, rd = system.ReadChunk(c)
+        dead = p[:, 3] <= 0
+        assert np.isfinite(p).all() and (p[dead][:, 3] <= 0).all()
+    system.Clear()
+    system.Update(now + dt, dt)
+    assert system.LiveChunkCount <= 1 and system.LiveCount <= 60   # only this update's spawn survives the Clear
+
+
+def test_removing_a_chunk_keeps_the_order_of_the_others(ctx):
+    chunk = 16
+    engine = ib.ParticleEngine(ctx, ib.ParticleEngineConfiguration(ChunkSize=chunk, RandomSeed=5))
+    system = ib.ParticleSystem(engine, ib.ParticleSystemConfiguration(), maxChunks=5)
+    per = chunk * chunk
+    rs = np.random.RandomState(3)
+    P = rs.uniform(1.0, 9.0, (4 * per, 4)).astype(np.float32)
+    V = rs.uniform(-1.0, 1.0, (4 * per, 4)).astype(np.float32)
+    A = rs.uniform(0.0, 1.0, (4 * per, 4)).astype(np.float32)
+    system.Spawn(P, V, A)
+    system._sync_chunk_lists()
+    system._reap_chunk(1)
+    assert system.LiveChunkCount == 3
+    for new, old in enumerate((0, 2, 3)):
+        p, v, a, _, _ = system.ReadChunk(new)
+        sl = slice(old * per, (old + 1) * per)
+        assert np.array_equal(p, P[sl]) and np.array_equal(v, V[sl]) and np.array_equal(a, A[sl])
+    p, v, a, rc, rd = system.ReadChunk(3)                           # the vacated slot is zeroed for the next CreateChunk
+    assert not p.any() and not v.any() and not a.any()
+    assert system.LiveCount == 3 * per

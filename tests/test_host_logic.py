@@ -293,3 +293,33 @@ def test_dynamic_distance_field_is_a_distance_field():
     df = ib.DynamicDistanceField(None, 320, 200, 128.0, 8)
     assert (df.SliceCount, df.PhysicalSliceCount, df.TextureWidth, df.TextureHeight) == (9, 3, 640, 400)
     assert df.static_handle is None
+
+
+def test_chunk_reaping_bookkeeping_without_a_device():
+    """ParticleLiveness.cs:46-129 on the host mirror: a chunk whose count stays 0 for DeadFrameThreshold liveness results is
+    reaped at the top of the next update; the chunk lists and the spawn-target indices follow the shift."""
+    import illuminant_b200 as ib
+    engine = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=16))
+    system = ib.ParticleSystem(engine, ib.ParticleSystemConfiguration(), maxChunks=4)
+    for _ in range(3):
+        system._create_chunk()
+    system._chunk_next_offset[:] = [256, 256, 40]
+    system._chunk_total_spawned[:] = [256, 256, 40]
+    system._spawn_target = 2
+    system._feedback_source = 1
+    for k in range(system.DeadFrameThreshold - 1):
+        system._process_liveness([5, 0, 7])
+    assert system._chunk_reap == [False, False, False] and system._chunk_dead_frames == [0, system.DeadFrameThreshold - 1, 0]
+    system._process_liveness([5, 3, 7])                      # one live result resets the count
+    assert system._chunk_dead_frames[1] == 0
+    for k in range(system.DeadFrameThreshold):
+        system._process_liveness([5, 0, 7])
+    assert system._chunk_reap == [False, True, False]
+    system._update_live_count_and_reap()
+    assert system.LiveChunkCount == 2 and system._chunk_next_offset == [256, 40] and system._chunk_live_count == [5, 7]
+    assert system._spawn_target == 1 and system._feedback_source == -1 and system.ReapedChunkCount == 1
+    assert system._create_chunk() == 2 and system._create_chunk() == 3 and system._create_chunk() == -1   # a slot was freed
+    system.TotalSpawnCount = 99
+    system.Clear()
+    system._update_live_count_and_reap()
+    assert system.LiveChunkCount == 0 and system.TotalSpawnCount == 0 and not system.IsClearPending and system._spawn_target == -1
