@@ -3,7 +3,8 @@ the LightingRenderer SDF cone-trace and the ParticleEngine update chain, behind 
 include/illuminant_b200.h.  This package is the host-side mirror of the reference API for those paths."""
 from ._abi import (Context, IlluminantError, EXPORTED_SYMBOLS, LIB_PATH, load_library,
                    FORMAT_FLOAT4, FORMAT_HALF4, FORMAT_RGBA8)
-from .distance_field import DistanceField, DynamicDistanceField, LightObstruction, LightObstructionType, RendererQualitySettings
+from .distance_field import (DistanceField, DynamicDistanceField, LightObstruction, LightObstructionType, RendererQualitySettings,
+                             SimpleHeightVolume)
 from .lighting import (DirectionalLightSource, LightingEnvironment, LightingRenderer, LightProbe, LightSourceRampMode,
                        LineLightSource, ParticleLightSource, RendererConfiguration, ShadowFilter, SphereLightSource, encode_gbuffer)
 from .hdr import (DitheringSettings, GammaCompressionConfiguration, HDRConfiguration, HDRMode, Histogram, RenderedLighting,

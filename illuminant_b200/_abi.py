@@ -161,6 +161,10 @@ class ParticleRender(C.Structure):  # ilb_particle_render
                 ("reserved", C.c_float * 3)]
 
 
+class HeightVolumeStruct(C.Structure):  # ilb_height_volume
+    _fields_ = [("first_edge", C.c_int32), ("edge_count", C.c_int32), ("z_base", C.c_float), ("height", C.c_float), ("bounds", C.c_float * 4)]
+
+
 class IlluminantError(RuntimeError):
     """Raised for every non-zero ilb_status; `.code` carries the status."""
 
@@ -190,6 +194,8 @@ _PROTOTYPES = [
     ("ilb_df_download", C.c_int, [P, P, C.c_size_t]),
     ("ilb_df_destroy", None, [P]),
     ("ilb_df_update_dynamic", C.c_int, [P, P, C.c_int, C.c_int, C.c_int, C.POINTER(DFUniforms), P, C.c_int]),
+    ("ilb_df_create_empty", C.c_int, [P, C.c_int, C.c_int, C.POINTER(P)]),
+    ("ilb_df_update_slices", C.c_int, [P, P, C.c_int, C.c_int, C.c_int, C.POINTER(DFUniforms), P, C.c_int, P, C.c_int, P, C.c_int, C.c_int, C.c_int]),
     ("ilb_df_generate", C.c_int, [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DFUniforms), P, C.c_int, C.POINTER(P)]),
     ("ilb_gbuffer_upload", C.c_int, [P, C.c_int, C.c_int, C.c_int, P]),
     ("ilb_gbuffer_upload_device", C.c_int, [P, C.c_int, C.c_int, C.c_int, P]),

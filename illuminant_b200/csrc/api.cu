@@ -267,7 +267,11 @@ int ilb_df_generate(ilb_ctx* ctx, int tw, int th, int slice_w, int slice_h, int 
     if (!u || count < 0 || (count > 0 && !obstructions)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
     int rc = df_alloc(ctx, tw, th, 0, false, out_df);
     if (rc) return rc;
-    rc = ilb_dfgen_launch(ctx, (*out_df)->tex, nullptr, tw, th, slice_w, slice_h, slice_count, u, obstructions, count);
+    // slices the atlas has room for but the field does not use stay cleared
+    cudaError_t ce = cudaMemsetAsync((*out_df)->tex, 0, (size_t)8 * tw * th, ctx->stream);
+    rc = ce != cudaSuccess ? ilb_cuda_fail(ctx, ce, "clear distance field")
+                           : ilb_dfgen_launch(ctx, (*out_df)->tex, nullptr, tw, th, slice_w, slice_h, slice_count, u, obstructions, count, nullptr, 0,
+                                              nullptr, 0, 0, (slice_count + 2) / 3);
     if (rc) {
         ilb_df_destroy(*out_df);
         *out_df = nullptr;
@@ -286,7 +290,29 @@ int ilb_df_update_dynamic(ilb_df* df, const ilb_df* static_df, int slice_w, int 
     if (!u || count < 0 || (count > 0 && !obstructions)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
     df->version++;  // derived planes are rebuilt (in place) the next time the field is sampled
-    return ilb_dfgen_launch(ctx, df->tex, static_df->tex, df->tw, df->th, slice_w, slice_h, slice_count, u, obstructions, count);
+    return ilb_dfgen_launch(ctx, df->tex, static_df->tex, df->tw, df->th, slice_w, slice_h, slice_count, u, obstructions, count, nullptr, 0, nullptr,
+                            0, 0, (slice_count + 2) / 3);
+}
+
+int ilb_df_create_empty(ilb_ctx* ctx, int tw, int th, ilb_df** out_df) {
+    int rc = df_alloc(ctx, tw, th, 0, false, out_df);
+    if (rc) return rc;
+    ILB_CUDA(ctx, cudaMemsetAsync((*out_df)->tex, 0, (size_t)8 * tw * th, ctx->stream));
+    return ILB_OK;
+}
+
+int ilb_df_update_slices(ilb_df* df, const ilb_df* static_df, int slice_w, int slice_h, int slice_count, const ilb_df_uniforms* u,
+                         const ilb_obstruction* obstructions, int obstruction_count, const ilb_height_volume* volumes, int volume_count,
+                         const ilb_float4* edges, int edge_count, int first_physical_slice, int physical_slice_count) {
+    if (!df || !live_has(df)) return ILB_ERR_INVALID_ARGUMENT;
+    ilb_ctx* ctx = df->ctx;
+    if (static_df && (!live_has(static_df) || static_df->ctx != ctx || static_df == df || static_df->tw != df->tw || static_df->th != df->th))
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "static field is released, the same as the field, of another size or of another context");
+    if (!u || obstruction_count < 0 || (obstruction_count > 0 && !obstructions)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    df->version++;
+    return ilb_dfgen_launch(ctx, df->tex, static_df ? static_df->tex : nullptr, df->tw, df->th, slice_w, slice_h, slice_count, u, obstructions,
+                            obstruction_count, volumes, volume_count, edges, edge_count, first_physical_slice, physical_slice_count);
 }
 
 int ilb_df_download(ilb_df* df, uint16_t* rgba64, size_t bytes) {

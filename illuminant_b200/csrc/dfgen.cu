@@ -16,14 +16,42 @@ struct DFGenParams {
     float maxEnc, zOffset, depth, invX, invY;
     const ilb_obstruction* obs;
     int count;
+    const ilb_height_volume* volumes;  // height volumes (DistanceField.fx) and their packed edges
+    const float4* edges;
+    int nvolumes;
+    int first_physical;                // the launch covers physical slices [first_physical, first_physical + gridDim.z)
 };
+
+// ---- Shaders/DistanceField.fx: signed distance to an extruded polygon ------------------------------------------------
+// sdPolygonInit / sdPolygonVertex (un-vendored sq/Fracture SDF2D.fxh) restated from the published sdPolygon they implement:
+// d = squared distance to the closest edge, s flips for every edge the ray from p towards +x crosses; the shader passes
+// (vi, vj) = (edge end, edge start) (DistanceField.fx:88,94).  The crossing test compares two products exactly (x-ops): a
+// fused multiply-add on one side could flip the sign for points on an edge's supporting line.
+ILB_DEV void sdPolygonVertex(f2 p, f2 vi, f2 vj, float& d, float& s) {
+    const f2 e = vj - vi, w = p - vi;
+    const float t = fminf(fmaxf(dot2(w, e) / dot2(e, e), 0.0f), 1.0f);
+    const f2 b = w - e * t;
+    d = fminf(d, dot2(b, b));
+    const bool c0 = p.y >= vi.y, c1 = p.y < vj.y, c2 = xmul(e.x, w.y) > xmul(e.y, w.x);
+    if ((c0 && c1 && c2) || (!c0 && !c1 && !c2)) s = -s;
+}
+ILB_DEV float computeDistanceZ(float sliceZ, float z0, float z1) {  // :47-55
+    if (sliceZ >= z0) return (sliceZ <= z1) ? fmaxf(sliceZ - z1, z0 - sliceZ) : (sliceZ - z1);
+    return z0 - sliceZ;
+}
+ILB_DEV float finalEval(float z, float z0, float z1, float distanceSq, float sign) {  // :57-74, PolygonXyBias 1.5 (:13)
+    const float distanceZ = computeDistanceZ(z, z0, z1);
+    const float distanceXy = (sqrtf(distanceSq) * sign) + 1.5f;
+    if (distanceXy <= 0.0f) return (distanceZ <= 0.0f) ? (distanceXy + distanceZ) : distanceZ;
+    return fmaxf(distanceXy, 0.0f) + fmaxf(distanceZ, 0.0f);
+}
 
 constexpr int GEN_TILE = 16;
 
 __global__ void __launch_bounds__(GEN_TILE * GEN_TILE) df_generate_kernel(const __grid_constant__ DFGenParams P) {
     __shared__ uint16_t s_list[GEN_TILE * GEN_TILE];
     __shared__ int s_warpCount[8];
-    const int p = blockIdx.z;  // physical slice
+    const int p = P.first_physical + blockIdx.z;  // physical slice
     const int tid = threadIdx.y * GEN_TILE + threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int x = blockIdx.x * GEN_TILE + threadIdx.x, y = blockIdx.y * GEN_TILE + threadIdx.y;
     const bool valid = (x < P.slice_w) && (y < P.slice_h);
@@ -81,6 +109,26 @@ __global__ void __launch_bounds__(GEN_TILE * GEN_TILE) df_generate_kernel(const 
         }
         __syncthreads();
     }
+    // height volumes, in list order (RenderDistanceFieldHeightVolumes, LightingRenderer.DistanceField.cs:185-260): the quad is the
+    // polygon's bounds expanded by DistanceLimit = 520 (LightingRenderer.cs:316), MAX-blended like the analytic obstructions
+    if (valid) {
+        for (int v = 0; v < P.nvolumes; v++) {
+            const ilb_height_volume& hv = P.volumes[v];
+            if (wx < hv.bounds[0] - 520.0f || wx > hv.bounds[2] + 520.0f || wy < hv.bounds[1] - 520.0f || wy > hv.bounds[3] + 520.0f) continue;
+            const float4* e = P.edges + hv.first_edge;
+            const f2 xy = mk2(wx, wy);
+            float4 edge = __ldg(e);
+            float d = dot2(xy - mk2(edge.z, edge.w), xy - mk2(edge.z, edge.w)), sgn = 1.0f;   // sdPolygonInit
+            sdPolygonVertex(xy, mk2(edge.z, edge.w), mk2(edge.x, edge.y), d, sgn);
+            for (int j = 1; j < hv.edge_count; j++) {
+                edge = __ldg(e + j);
+                sdPolygonVertex(xy, mk2(edge.z, edge.w), mk2(edge.x, edge.y), d, sgn);
+            }
+            const float z0 = hv.z_base, z1 = hv.z_base + hv.height;
+#pragma unroll
+            for (int z = 0; z < 4; z++) best[z] = fmaxf(best[z], ILB_DISTANCE_ZERO - (finalEval(sliceZ[z], z0, z1, d, sgn) / P.maxEnc));
+        }
+    }
     if (valid) {
         uint32_t q[4];
 #pragma unroll
@@ -93,7 +141,8 @@ __global__ void __launch_bounds__(GEN_TILE * GEN_TILE) df_generate_kernel(const 
 }  // namespace
 
 int ilb_dfgen_launch(ilb_ctx* ctx, uint2* tex, const uint2* base, int tw, int th, int slice_w, int slice_h, int slice_count,
-                     const ilb_df_uniforms* u, const ilb_obstruction* obs, int count) {
+                     const ilb_df_uniforms* u, const ilb_obstruction* obs, int count, const ilb_height_volume* volumes, int volume_count,
+                     const ilb_float4* edges, int edge_count, int first_physical, int physical_count) {
     DFGenParams P;
     memset(&P, 0, sizeof(P));
     P.tex = tex; P.base = base; P.tw = tw; P.th = th; P.slice_w = slice_w; P.slice_h = slice_h; P.slice_count = slice_count;
@@ -104,22 +153,42 @@ int ilb_dfgen_launch(ilb_ctx* ctx, uint2* tex, const uint2* base, int tw, int th
     const int rows = (P.physical + P.columns - 1) / P.columns;
     if (P.columns * slice_w > tw || rows * slice_h > th)
         return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "atlas %dx%d too small for %d slices of %dx%d in %d columns", tw, th, P.physical, slice_w, slice_h, P.columns);
+    if (first_physical < 0 || physical_count < 0 || first_physical + physical_count > P.physical)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "physical slices [%d,+%d) outside [0,%d)", first_physical, physical_count, P.physical);
+    if (volume_count < 0 || edge_count < 0 || (volume_count > 0 && (!volumes || !edges)))
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null height-volume arrays");
+    for (int v = 0; v < volume_count; v++)
+        if (volumes[v].edge_count < 1 || volumes[v].first_edge < 0 || volumes[v].first_edge + volumes[v].edge_count > edge_count)
+            return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "height volume %d: edges [%d,+%d) outside [0,%d)", v, volumes[v].first_edge, volumes[v].edge_count, edge_count);
+    if (physical_count == 0) return ILB_OK;
     P.maxEnc = u->Extent.w; P.zOffset = u->ConeAndMisc.y; P.depth = u->Extent.z;
     P.invX = u->ConeAndMisc.w; P.invY = u->StepAndMisc2.w;
-    ilb_obstruction* d_obs = nullptr;
-    if (count > 0) {
-        ILB_CUDA(ctx, cudaMallocAsync(&d_obs, sizeof(ilb_obstruction) * (size_t)count, ctx->stream));
-        ILB_CUDA(ctx, cudaMemcpyAsync(d_obs, obs, sizeof(ilb_obstruction) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    P.first_physical = first_physical;
+    // one staging allocation for the three host arrays (obstructions, volumes, edges), released on every path
+    const size_t obsBytes = sizeof(ilb_obstruction) * (size_t)count, volBytes = sizeof(ilb_height_volume) * (size_t)volume_count;
+    const size_t obsPad = (obsBytes + 15) & ~(size_t)15, volPad = (volBytes + 15) & ~(size_t)15, edgeBytes = sizeof(float4) * (size_t)edge_count;
+    char* d_stage = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (obsPad + volPad + edgeBytes > 0) {
+        e = cudaMallocAsync(reinterpret_cast<void**>(&d_stage), obsPad + volPad + edgeBytes, ctx->stream);
+        if (e != cudaSuccess) return ilb_cuda_fail(ctx, e, "allocate distance-field generation inputs");
+        if (obsBytes) e = cudaMemcpyAsync(d_stage, obs, obsBytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && volBytes) e = cudaMemcpyAsync(d_stage + obsPad, volumes, volBytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && edgeBytes) e = cudaMemcpyAsync(d_stage + obsPad + volPad, edges, edgeBytes, cudaMemcpyHostToDevice, ctx->stream);
     }
-    P.obs = d_obs; P.count = count;
-    if (base) ILB_CUDA(ctx, cudaMemcpyAsync(tex, base, sizeof(uint2) * (size_t)tw * (size_t)th, cudaMemcpyDeviceToDevice, ctx->stream));
-    else ILB_CUDA(ctx, cudaMemsetAsync(tex, 0, sizeof(uint2) * (size_t)tw * (size_t)th, ctx->stream));
-    const dim3 grid((slice_w + GEN_TILE - 1) / GEN_TILE, (slice_h + GEN_TILE - 1) / GEN_TILE, P.physical);
-    df_generate_kernel<<<grid, dim3(GEN_TILE, GEN_TILE), 0, ctx->stream>>>(P);
-    ctx->launches++;
-    ILB_CUDA(ctx, cudaGetLastError());
-    if (d_obs) ILB_CUDA(ctx, cudaFreeAsync(d_obs, ctx->stream));
-    // obs is caller-owned host memory read by an async copy: finish before returning
-    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (e == cudaSuccess) {
+        P.obs = reinterpret_cast<const ilb_obstruction*>(d_stage); P.count = count;
+        P.volumes = reinterpret_cast<const ilb_height_volume*>(d_stage + obsPad); P.nvolumes = volume_count;
+        P.edges = reinterpret_cast<const float4*>(d_stage + obsPad + volPad);
+        // the kernel writes every texel of the slices it covers (clear value = 0 or the static texel), nothing else
+        const dim3 grid((slice_w + GEN_TILE - 1) / GEN_TILE, (slice_h + GEN_TILE - 1) / GEN_TILE, physical_count);
+        df_generate_kernel<<<grid, dim3(GEN_TILE, GEN_TILE), 0, ctx->stream>>>(P);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (d_stage) cudaFreeAsync(d_stage, ctx->stream);
+    // the inputs are caller-owned host memory read by asynchronous copies: finish before returning
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return ilb_cuda_fail(ctx, e, "distance-field generation");
     return ILB_OK;
 }

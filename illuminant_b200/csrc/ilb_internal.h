@@ -151,7 +151,8 @@ int ilb_raster_launch(ilb_psys* psys, const ilb_particle_render* params, const v
 void ilb_raster_release(ilb_psys* psys);
 // dfgen.cu
 int ilb_dfgen_launch(ilb_ctx* ctx, uint2* tex, const uint2* base, int tw, int th, int slice_w, int slice_h, int slice_count,
-                     const ilb_df_uniforms* u, const ilb_obstruction* obs, int count);
+                     const ilb_df_uniforms* u, const ilb_obstruction* obs, int count, const ilb_height_volume* volumes, int volume_count,
+                     const ilb_float4* edges, int edge_count, int first_physical, int physical_count);
 // particles.cu
 int ilb_particles_launch(ilb_psys* psys, const ilb_psys_uniforms* u, const ilb_spawn* spawns, const ilb_spawn_source* sources,
                          int spawn_count, const ilb_op* ops, int op_count, int steps);

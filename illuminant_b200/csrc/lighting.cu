@@ -1430,6 +1430,8 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
         ILB_CUDA(ctx, cudaMemcpyAsync(gdst + goff, gsrc + goff, gn, cudaMemcpyHostToDevice, ctx->copy_in));
         ILB_CUDA(ctx, cudaEventRecord(ctx->ev_in[nb], ctx->copy_in));
     }
+    // every band's kernels are queued before the first download: with PAGEABLE caller buffers cudaMemcpyAsync blocks the host
+    // until its copy is done, which must not hold back the launches of the bands behind it (pinned buffers never block)
     nb = 0;
     for (int r0 = f->row_begin; r0 < f->row_end; r0 += bandRows, nb++) {
         const int r1 = std::min(r0 + bandRows, f->row_end);
@@ -1438,6 +1440,10 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
         rc = lightingLaunchRows(ctx, prep, r0, r1, outs, 1, f->row_begin);
         if (rc) return rc;
         ILB_CUDA(ctx, cudaEventRecord(ctx->ev_done[nb], ctx->stream));
+    }
+    nb = 0;
+    for (int r0 = f->row_begin; r0 < f->row_end; r0 += bandRows, nb++) {
+        const int r1 = std::min(r0 + bandRows, f->row_end);
         ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[nb], 0));
         const size_t loff = ltexel * (size_t)f->width * (size_t)(r0 - f->row_begin), ln = ltexel * (size_t)f->width * (size_t)(r1 - r0);
         ILB_CUDA(ctx, cudaMemcpyAsync(lhost + loff, ldev + loff, ln, cudaMemcpyDeviceToHost, ctx->copy_out));

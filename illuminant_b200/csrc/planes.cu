@@ -131,12 +131,19 @@ int ilb_planes_attach(ilb_ctx* ctx, ilb_df* df, const ilb_df_uniforms& u, DFGeom
         cudaFree(P.planes);
         return ILB_OK;
     }
-    ILB_CUDA(ctx, cudaMemcpyAsync(P.vtab, vtab.data(), sizeof(float4) * (size_t)nv, cudaMemcpyHostToDevice, ctx->stream));
-    B.tex = df->tex; B.planes = P.planes;
-    B.tw = df->tw; B.th = df->th; B.sw = sw; B.sh = sh; B.pw = pw; B.ph = ph; B.nv = nv;
-    df_planes_build_kernel<<<dim3((pw + 255) / 256, ph, nv), 256, 0, ctx->stream>>>(B);
-    ILB_CUDA(ctx, cudaGetLastError());
-    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // vtab is a host vector
+    cudaError_t e = cudaMemcpyAsync(P.vtab, vtab.data(), sizeof(float4) * (size_t)nv, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        B.tex = df->tex; B.planes = P.planes;
+        B.tw = df->tw; B.th = df->th; B.sw = sw; B.sh = sh; B.pw = pw; B.ph = ph; B.nv = nv;
+        df_planes_build_kernel<<<dim3((pw + 255) / 256, ph, nv), 256, 0, ctx->stream>>>(B);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // vtab is a host vector
+    if (e != cudaSuccess) {  // nothing was attached yet: release the derived copy before reporting
+        cudaFree(P.planes);
+        cudaFree(P.vtab);
+        return ilb_cuda_fail(ctx, e, "build the expanded distance-field planes");
+    }
     P.pitch = pw;
     const float key[10] = {g->sliceSizeX, g->sliceSizeY, g->texelSizeX, g->texelSizeY, g->ex, g->ey, g->maxValidZ, g->zToSlice,
                            g->invSliceCountXTimesOneThird, g->sliceCount};

@@ -156,6 +156,7 @@ class LightProbe:  # Lighting/LightProbe.cs
 class LightingEnvironment:  # Lighting/LightingEnvironment.cs
     Lights: List[LightSource] = field(default_factory=list)
     Obstructions: List[LightObstruction] = field(default_factory=list)
+    HeightVolumes: list = field(default_factory=list)   # SimpleHeightVolume: only their distance-field footprint is in scope
     GroundZ: float = 0.0
     MaximumZ: float = 128.0
     ZToYMultiplier: float = 1.0
@@ -165,6 +166,7 @@ class LightingEnvironment:  # Lighting/LightingEnvironment.cs
 @dataclass
 class RendererConfiguration:  # Lighting/LightingRenderer.Configuration.cs:13-252
     MaximumRenderSize: Tuple[int, int] = (1920, 1080)
+    MaximumFieldUpdatesPerFrame: int = 1   # LightingRenderer.Configuration.cs:88-91: distance-field slices re-rasterised per frame
     HighQuality: bool = True            # HalfVector4 lightmap (LightingRenderer.cs:477-479)
     HighQualityGBuffer: bool = True     # Vector4 G-buffer (GBuffer.cs:31-39)
     StencilCulling: bool = False
@@ -259,6 +261,15 @@ class LightingRenderer:
         h, w = arr.shape[0], arr.shape[1]
         self.ctx.check(self.ctx.lib.ilb_gbuffer_upload(self.ctx.handle, w, h, fmt, arr.ctypes.data_as(C.c_void_p)))
         self._gbuffer_shape = (h, w)
+
+    def UpdateFields(self) -> int:
+        """The distance-field part of LightingRenderer.UpdateFields (LightingRenderer.cs:1949-1975 -> RenderDistanceField,
+        LightingRenderer.DistanceField.cs:19-31): re-rasterises at most Configuration.MaximumFieldUpdatesPerFrame invalid slices of
+        the field from Environment.Obstructions and Environment.HeightVolumes.  Returns the number of slice triplets rendered."""
+        df = self.DistanceField
+        if df is None or not df.NeedsRasterize:
+            return 0
+        return df.RenderDistanceField(self.Environment.Obstructions, self.Environment.HeightVolumes, self.Configuration.MaximumFieldUpdatesPerFrame)
 
     def SetGBufferDevice(self, device_ptr: int, width: int, height: int) -> None:
         fmt = FORMAT_FLOAT4 if self.Configuration.HighQualityGBuffer else FORMAT_HALF4

@@ -122,6 +122,33 @@ ILB_API int ilb_df_generate(ilb_ctx* ctx, int texture_width, int texture_height,
                             int slice_width, int slice_height, int slice_count,
                             const ilb_df_uniforms* u, const ilb_obstruction* obstructions, int count,
                             ilb_df** out_df);
+/* Height volumes (SDF/HeightVolume.cs, LightingRenderer.DistanceField.cs:185-260, Shaders/DistanceField.fx): an extruded
+ * polygon [z_base, z_base + height].  `edges` is the reference's VertexDataTexture: one float4 (a.x, a.y, b.x, b.y) per polygon
+ * edge j with a = p[j], b = p[wrap(j + 1)]; a volume owns edges [first_edge, first_edge + edge_count).  The volume's quad is
+ * its polygon bounds expanded by DistanceLimit = 520 (LightingRenderer.cs:316) and is MAX-blended like the analytic
+ * obstructions (LoadMaterials.cs:154-157).  The polygon distance itself (sdPolygonInit / sdPolygonVertex) lives in the
+ * un-vendored sq/Fracture SDF2D.fxh and is restated from its published definition (Quilez, "2D distance functions", sdPolygon:
+ * squared distance to the closest edge, sign flipped once per edge the horizontal ray from the point crosses). */
+typedef struct ilb_height_volume {
+    int32_t first_edge, edge_count;
+    float z_base, height;
+    float bounds[4];       /* polygon bounds: left, top, right, bottom */
+} ilb_height_volume;
+
+/* An atlas cleared to 0 (DistanceField.NeedClear, LightingRenderer.DistanceField.cs:51-55): every slice invalid. */
+ILB_API int ilb_df_create_empty(ilb_ctx* ctx, int texture_width, int texture_height, ilb_df** out_df);
+
+/* RenderDistanceFieldSliceTriplet (LightingRenderer.DistanceField.cs:80-152) for physical slices [first_physical_slice,
+ * first_physical_slice + physical_slice_count): each is cleared (to 0, or to the static field's texels when static_df is given:
+ * ClearDistanceField.fx:27-39), then the analytic obstructions and the height volumes are MAX-blended into it.  This is the
+ * incremental update of RenderDistanceFieldPartition (:415-464): the host mirror calls it for at most
+ * MaximumFieldUpdatesPerFrame slices per frame (LightingRenderer.Configuration.cs:88-91).  Texels of other slices are not
+ * touched.  In place, asynchronous; derived data (expanded planes) is refreshed lazily. */
+ILB_API int ilb_df_update_slices(ilb_df* df, const ilb_df* static_df, int slice_width, int slice_height, int slice_count,
+                                 const ilb_df_uniforms* uniforms, const ilb_obstruction* obstructions, int obstruction_count,
+                                 const ilb_height_volume* volumes, int volume_count, const ilb_float4* edges, int edge_count,
+                                 int first_physical_slice, int physical_slice_count);
+
 /* DynamicDistanceField (SDF/DistanceField.cs:248-310): the field a frame samples is the STATIC field with the dynamic
  * obstructions MAX-blended on top -- the slice is "cleared" to the static texture and only IsDynamic obstructions are
  * rasterised (LightingRenderer.DistanceField.cs:99-118, ClearDistanceField.fx:27-39).  Rewrites `df` in place from
@@ -201,8 +228,10 @@ ILB_API int ilb_render_lighting(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fra
  * LightingRenderer.RenderLighting reads through GBufferTexelSizeAndMisc, LightingRenderer.GBuffer.cs:520-534) goes up,
  * the frame is shaded, the lightmap comes down -- software-pipelined over row bands on three CUDA streams, so the
  * copies hide behind the kernels.  Equivalent to ilb_gbuffer_upload + ilb_render_lighting (bit-identical lightmap).
- * The G-buffer must have the frame's size and be screen-aligned (GBufferViewportRelative == 0); pinned host memory
- * makes the copies asynchronous.  Synchronous: returns when lightmap_out is complete. */
+ * The G-buffer must have the frame's size and be screen-aligned (GBufferViewportRelative == 0).  The overlap needs PINNED
+ * (page-locked) gbuffer / lightmap_out buffers -- cudaHostAlloc / cudaHostRegister, in C# a GCHandle-pinned array registered
+ * once at start-up; with pageable buffers the call is still correct (and all kernels are queued before the first download), but
+ * every copy is staged through the driver and blocks the caller.  Synchronous: returns when lightmap_out is complete. */
 ILB_API int ilb_render_lighting_frame(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame,
                                       const ilb_light_batch* batches, int batch_count,
                                       const ilb_light_vertex* vertices, int vertex_count,

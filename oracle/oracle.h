@@ -44,6 +44,13 @@ int orc_particles_render(const float* P, const float* RD, const float* RC, long 
                          const uint8_t* texture, float* target);
 int orc_generate_distance_field(uint16_t* out_rgba64, const uint16_t* base_rgba64 /* static field or NULL */, int tw, int th, int slice_w, int slice_h, int slice_count,
                                 const ilb_df_uniforms* u, const ilb_obstruction* obs, int count, int nthreads);
+/* The same for physical slices [first_physical, first_physical + physical_count) only, IN PLACE on `tex` (other slices keep their
+ * texels), with height volumes (Shaders/DistanceField.fx, see ilb_height_volume). */
+int orc_update_distance_field_slices(uint16_t* tex, const uint16_t* base, int tw, int th, int slice_w, int slice_h, int slice_count,
+                                     const ilb_df_uniforms* u, const ilb_obstruction* obs, int count, const ilb_height_volume* volumes,
+                                     int nvolumes, const ilb_float4* edges, int nedges, int first_physical, int physical_count, int nthreads);
+/* signed distance of one point to a height volume at slice depth z (computeSliceDistances / finalEval of DistanceField.fx) */
+float orc_height_volume_distance(const ilb_height_volume* volume, const ilb_float4* edges, float x, float y, float z);
 void orc_encode_gbuffer_sample(const float* normal, float relativeY, float z, int dead, int enableShadows, int fullbright, float* out4);
 /* N3: Resolve.fx / HDR.fxh on fp32-decoded texels (lightmap, albedo: w*h*4 floats; albedo may be NULL); out: w*h*4 floats, not quantised. */
 int orc_resolve_lighting(const ilb_resolve* p, const float* lightmap, const float* albedo, float* out);

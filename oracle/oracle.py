@@ -254,6 +254,42 @@ def generate_distance_field(df, obstructions, nthreads=0, base=None) -> np.ndarr
     return out
 
 
+def update_distance_field_slices(tex, df, obstructions, height_volumes, first_physical: int, physical_count: int, base=None, nthreads=0) -> np.ndarray:
+    """RenderDistanceFieldSliceTriplet for physical slices [first, first + count) IN PLACE on `tex` (uint16 [TH, TW, 4]), with
+    height volumes; `base`: the static field of a DynamicDistanceField or None."""
+    from illuminant_b200.distance_field import pack_height_volumes, pack_obstructions
+    obs = pack_obstructions(obstructions)
+    vols, nv, edges, ne = pack_height_volumes(height_volumes)
+    saved = df.ValidSliceCount
+    df.ValidSliceCount = df.SliceCount
+    u = df.uniforms()
+    df.ValidSliceCount = saved
+    assert tex.dtype == np.uint16 and tex.flags["C_CONTIGUOUS"] and tex.shape == (df.TextureHeight, df.TextureWidth, 4)
+    if base is not None:
+        base = np.ascontiguousarray(base, dtype=np.uint16)
+    L = lib()
+    L.orc_update_distance_field_slices.restype = C.c_int
+    L.orc_update_distance_field_slices.argtypes = [P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DFUniforms), P, C.c_int, P, C.c_int, P,
+                                                   C.c_int, C.c_int, C.c_int, C.c_int]
+    rc = L.orc_update_distance_field_slices(_ptr(tex), _ptr(base), df.TextureWidth, df.TextureHeight, df.SliceWidth, df.SliceHeight, df.SliceCount,
+                                            C.byref(u), C.cast(obs, P) if len(obstructions) else None, len(obstructions),
+                                            C.cast(vols, P) if nv else None, nv, C.cast(edges, P) if ne else None, ne, first_physical,
+                                            physical_count, nthreads or threads())
+    if rc != 0:
+        raise RuntimeError(f"orc_update_distance_field_slices failed: {rc}")
+    return tex
+
+
+def height_volume_distance(volume, x: float, y: float, z: float) -> float:
+    """finalEval(z, zRange, sdPolygon(xy)) of Shaders/DistanceField.fx for one SimpleHeightVolume."""
+    from illuminant_b200.distance_field import pack_height_volumes
+    vols, nv, edges, ne = pack_height_volumes([volume])
+    L = lib()
+    L.orc_height_volume_distance.restype = C.c_float
+    L.orc_height_volume_distance.argtypes = [P, P, C.c_float, C.c_float, C.c_float]
+    return float(L.orc_height_volume_distance(C.cast(vols, P), C.cast(edges, P), x, y, z))
+
+
 def encode_gbuffer_sample(normal, relative_y, z, dead=False, enable_shadows=True, fullbright=False) -> np.ndarray:
     n = _f3(normal)
     out = np.zeros(4, np.float32)

@@ -28,15 +28,76 @@ void orc_detmath(int function, const float* x, float* out, long n) {
 // (ClearDistanceField.fx:27-39 with ClearTexture = StaticTexture, LightingRenderer.DistanceField.cs:113-118) instead of 0.
 int orc_generate_distance_field(uint16_t* out, const uint16_t* base, int tw, int th, int slice_w, int slice_h, int slice_count,
                                 const ilb_df_uniforms* u, const ilb_obstruction* obs, int count, int nthreads) {
+    if (base) memcpy(out, base, sizeof(uint16_t) * 4 * (size_t)tw * th);
+    else memset(out, 0, sizeof(uint16_t) * 4 * (size_t)tw * th);
+    return orc_update_distance_field_slices(out, base, tw, th, slice_w, slice_h, slice_count, u, obs, count, nullptr, 0, nullptr, 0, 0,
+                                            (slice_count + 2) / 3, nthreads);
+}
+
+}  // extern "C"
+
+namespace {
+// ---- Shaders/DistanceField.fx (height volumes) ---------------------------------------------------------------------
+// sdPolygonInit / sdPolygonVertex: sq/Fracture SDF2D.fxh is not vendored; restated from the published definition it
+// implements (Quilez, sdPolygon): d = squared distance to the closest edge, s flips for every edge that the ray from p
+// towards +x crosses.  vi / vj are passed as (b, a) by the shader (DistanceField.fx:88,94): vi = edge end, vj = edge start.
+void sdPolygonVertex(float2 p, float2 vi, float2 vj, float& d, float& s) {
+    float2 e = vj - vi, w = p - vi;
+    float2 b = w - e * clamp(dot(w, e) / dot(e, e), 0.0f, 1.0f);
+    d = fminf(d, dot(b, b));
+    bool c0 = p.y >= vi.y, c1 = p.y < vj.y, c2 = (e.x * w.y) > (e.y * w.x);
+    if ((c0 && c1 && c2) || (!c0 && !c1 && !c2)) s = -s;
+}
+void sdPolygonInit(float2 p, float2 vi, float2 vj, float& d, float& s) {
+    d = dot(p - vi, p - vi);
+    s = 1.0f;
+    sdPolygonVertex(p, vi, vj, d, s);
+}
+float computeDistanceZ(float sliceZ, float2 zRange) {  // :47-55
+    if (sliceZ >= zRange.x) {
+        if (sliceZ <= zRange.y) return fmaxf(sliceZ - zRange.y, zRange.x - sliceZ);
+        return sliceZ - zRange.y;
+    }
+    return zRange.x - sliceZ;
+}
+float finalEval(float z, float2 zRange, float resultDistanceSq, float sign) {  // :57-74, PolygonXyBias 1.5 (:13)
+    float distanceZ = computeDistanceZ(z, zRange);
+    float distanceXy = (sqrtf(resultDistanceSq) * sign) + 1.5f;
+    if (distanceXy <= 0) {
+        if (distanceZ <= 0) return distanceXy + distanceZ;
+        return distanceZ;
+    }
+    return fmaxf(distanceXy, 0.0f) + fmaxf(distanceZ, 0.0f);
+}
+void polygonDistance(const ilb_height_volume& hv, const ilb_float4* edges, float2 xy, float& d, float& s) {  // computeSliceDistances :76-93
+    const ilb_float4* e = edges + hv.first_edge;
+    sdPolygonInit(xy, float2(e[0].z, e[0].w), float2(e[0].x, e[0].y), d, s);
+    for (int j = 1; j < hv.edge_count; j++) sdPolygonVertex(xy, float2(e[j].z, e[j].w), float2(e[j].x, e[j].y), d, s);
+}
+}  // namespace
+
+extern "C" {
+
+float orc_height_volume_distance(const ilb_height_volume* hv, const ilb_float4* edges, float x, float y, float z) {
+    float d, s;
+    polygonDistance(*hv, edges, float2(x, y), d, s);
+    return finalEval(z, float2(hv->z_base, hv->z_base + hv->height), d, s);
+}
+
+int orc_update_distance_field_slices(uint16_t* out, const uint16_t* base, int tw, int th, int slice_w, int slice_h, int slice_count,
+                                     const ilb_df_uniforms* u, const ilb_obstruction* obs, int count, const ilb_height_volume* volumes,
+                                     int nvolumes, const ilb_float4* edges, int nedges, int first_physical, int physical_count, int nthreads) {
     if (nthreads > 0) omp_set_num_threads(nthreads);
     const int physical = (slice_count + 2) / 3;
     const int columns = (int)u->TextureSliceCount.x;
     const float maxEnc = u->Extent.w, zOffset = u->ConeAndMisc.y, depth = u->Extent.z;
     const float invX = u->ConeAndMisc.w, invY = u->StepAndMisc2.w;
     const float DISTANCE_ZERO = 192.0f / 255.0f;
-    if (base) memcpy(out, base, sizeof(uint16_t) * 4 * (size_t)tw * th);
-    else memset(out, 0, sizeof(uint16_t) * 4 * (size_t)tw * th);
-    for (int p = 0; p < physical; p++) {
+    const float DistanceLimit = 520.0f;  // LightingRenderer.cs:316
+    if (first_physical < 0 || physical_count < 0 || first_physical + physical_count > physical || columns < 1) return ILB_ERR_INVALID_ARGUMENT;
+    for (int v = 0; v < nvolumes; v++)
+        if (volumes[v].edge_count < 1 || volumes[v].first_edge < 0 || volumes[v].first_edge + volumes[v].edge_count > nedges) return ILB_ERR_INVALID_ARGUMENT;
+    for (int p = first_physical; p < first_physical + physical_count; p++) {
         const int ox = (p % columns) * slice_w, oy = (p / columns) * slice_h;
         if (ox + slice_w > tw || oy + slice_h > th) return ILB_ERR_INVALID_ARGUMENT;
         float sliceZ[4];
@@ -61,6 +122,19 @@ int orc_generate_distance_field(uint16_t* out, const uint16_t* base, int tw, int
                         float wp[3] = {wx, wy, sliceZ[k]};
                         float d = orc_evaluate_by_type_id(o.type, wp, o.center, o.size, o.rotation);
                         float e = DISTANCE_ZERO - (d / maxEnc);
+                        best[k] = fmaxf(best[k], e);
+                    }
+                }
+                for (int v = 0; v < nvolumes; v++) {  // RenderDistanceFieldHeightVolumes (LightingRenderer.DistanceField.cs:185-260)
+                    const ilb_height_volume& hv = volumes[v];
+                    if (wx < hv.bounds[0] - DistanceLimit || wx > hv.bounds[2] + DistanceLimit || wy < hv.bounds[1] - DistanceLimit ||
+                        wy > hv.bounds[3] + DistanceLimit)
+                        continue;
+                    float d2, sgn;
+                    polygonDistance(hv, edges, float2(wx, wy), d2, sgn);
+                    float2 zRange(hv.z_base, hv.z_base + hv.height);
+                    for (int k = 0; k < 4; k++) {
+                        float e = DISTANCE_ZERO - (finalEval(sliceZ[k], zRange, d2, sgn) / maxEnc);   // encodeDistance
                         best[k] = fmaxf(best[k], e);
                     }
                 }

@@ -128,3 +128,54 @@ def test_c5_8m_particles_chunk_sharding_is_exact(ctx):
         for a, b in zip(part.ReadChunk(k), whole.ReadChunk(c0 + k)):
             assert np.array_equal(a, b)
     assert whole.LiveCount == count
+
+
+def test_c5_combined_frame_loop_matches_oracle_frame_by_frame(ctx, oracle):
+    """Config C5's loop (TestGame/TestGame/Scenes/ParticleLights.cs:333-378) at a size the oracle finishes in seconds: every frame
+    updates the particle system (Spawner + Gravity + Noise + FMA, collision against the LIGHTING field) and then renders the
+    lighting, whose light list includes one sphere light per live particle (ParticleLightSource) read from the state the update
+    just produced.  Both halves are compared with the oracle every frame, so a stale or mis-ordered hand-over would show."""
+    from illuminant_b200._abi import LightBatch, LightVertex
+    s = scenes.lighting_scene(61, 288, 176, 4, n_directional=1, n_line=1, ramp=(60.0, 180.0), float4_lightmap=True)
+    df = scenes.make_distance_field(ctx, s)
+    df.Rasterize(s.obstructions)
+    tex = df.Save()
+    chunk, n0 = 32, 600
+    ps = scenes.particle_scene(61, n0, chunk, 288, 176, steps_hint=40, collision_field=df, spawn_rate=1800.0)
+    engine = ib.ParticleEngine(ctx, ib.ParticleEngineConfiguration(ChunkSize=chunk, RandomSeed=61))
+    system = ib.ParticleSystem(engine, ps.configuration, maxChunks=4)
+    system.Transforms = ps.transforms
+    system.Spawn(ps.positions, ps.velocities, ps.attributes)
+    template = ib.SphereLightSource(Radius=2.0, RampLength=18.0, Color=(0.8, 0.6, 0.4, 0.5), CastsShadows=True)
+    pls = ib.ParticleLightSource(Template=template, System=system)
+    s.environment.Lights.append(pls)
+    r = ib.LightingRenderer(ctx, s.environment, s.configuration)
+    r.DistanceField = df
+    r.SetGBuffer(s.gbuffer)
+    per = chunk * chunk
+    P, V, A = (np.zeros((per, 4), np.float32) for _ in range(3))
+    P[:n0], V[:n0], A[:n0] = ps.positions, ps.velocities, ps.attributes
+    now = 0.0
+    for frame_index in range(3):
+        now += ps.dt
+        spawns, ops, u = system.plan_spawns(now, ps.dt), system.plan_ops(now), system.system_uniforms(ps.dt)
+        live = system.LiveChunkCount
+        if P.shape[0] < live * per:
+            P, V, A = (np.concatenate([a, np.zeros((live * per - a.shape[0], 4), np.float32)]) for a in (P, V, A))
+        system.step_packed(u, spawns, ops, 1)
+        P, V, A, RC, RD = oracle.particles_step(P, V, A, chunk, u, spawns, ops, engine.RandomnessTexture, tex, 1)
+        gpu_state = [np.concatenate(x) for x in zip(*[system.ReadChunk(c) for c in range(live)])]
+        check_particles(gpu_state, (P, V, A, RC, RD), f"frame {frame_index}")
+        lightmap = r.RenderLighting()
+        frame = r.build_frame()
+        batches, nb, verts, nv = r.build_batches()
+        pv = pls.light_vertices(P, A, True)                    # the oracle's particle state -> the oracle's particle lights
+        assert len(pv) > 300
+        allv = (LightVertex * (nv + len(pv)))(*([verts[i] for i in range(nv)] + pv))
+        allb = (LightBatch * (nb + 1))(*[batches[i] for i in range(nb)])
+        allb[nb].light_type, allb[nb].first_vertex, allb[nb].vertex_count = 3, nv, len(pv)
+        allb[nb].df = r._df_uniforms(None)
+        ref = oracle.render_lighting(tex, s.gbuffer, frame, allb, nb + 1, allv, nv + len(pv))
+        err = lighting_rel_err(lightmap, ref)
+        assert err.max() <= LIGHTING_RTOL, f"frame {frame_index}: max rel err {err.max():.3e}"
+        assert np.array_equal(lightmap[..., 3], ref[..., 3])
