@@ -358,7 +358,9 @@ class LightingRenderer:
             return
         hasDF = self.DistanceField is not None and self.DistanceField.handle is not None
         srcs = [l for l in self.Environment.Lights if l.Enabled and l.TypeID == LIGHT_PARTICLE and l.IsActive and l.System is not None]
-        if not srcs and not getattr(self, "_had_particle_lights", False):
+        # the library keeps the sources on the CONTEXT until they are replaced: a renderer without particle lights must clear
+        # what another renderer of the same context registered, or its frames would be lit by that renderer's particles
+        if not srcs and not getattr(self.ctx, "_particle_lights_registered", False):
             return
         arr = (_abi.ParticleLightSourceStruct * max(len(srcs), 1))()
         for i, l in enumerate(srcs):
@@ -366,7 +368,7 @@ class LightingRenderer:
             arr[i].LightProperties, arr[i].MoreLightProperties, arr[i].LightColor, arr[i].LightSpecularColor = l.uniforms(hasDF)
             arr[i].df = self._df_uniforms(l.Template.Quality)
         self.ctx.check(self.ctx.lib.ilb_lighting_set_particle_lights(self.ctx.handle, C.cast(arr, C.c_void_p) if srcs else None, len(srcs)))
-        self._had_particle_lights = bool(srcs)
+        self.ctx._particle_lights_registered = bool(srcs)
 
     # ---- the hot path -----------------------------------------------------------------------------------------
     def RenderLighting(self, intensityScale: float = 1.0, rows: Optional[Tuple[int, int]] = None) -> np.ndarray:

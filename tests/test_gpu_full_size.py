@@ -179,3 +179,11 @@ def test_c5_combined_frame_loop_matches_oracle_frame_by_frame(ctx, oracle):
         err = lighting_rel_err(lightmap, ref)
         assert err.max() <= LIGHTING_RTOL, f"frame {frame_index}: max rel err {err.max():.3e}"
         assert np.array_equal(lightmap[..., 3], ref[..., 3])
+    # another renderer of the same context without particle lights must not inherit them (they are registered per context)
+    s.environment.Lights.remove(pls)
+    r2 = ib.LightingRenderer(ctx, s.environment, s.configuration)
+    r2.DistanceField = df
+    r2.SetGBuffer(s.gbuffer)
+    plain = r2.RenderLighting()
+    ref = oracle_lightmap(oracle, r2, tex, s)
+    assert lighting_rel_err(plain, ref).max() <= LIGHTING_RTOL and np.array_equal(plain[..., 3], ref[..., 3])
