@@ -174,7 +174,7 @@ class IlluminantError(RuntimeError):
 
 
 # ilb_option
-OPT_LIGHT_CONCURRENT, OPT_LIGHT_LINE_CTAS, OPT_LIGHT_OTHER_CTAS, OPT_LIGHT_LINE_HELPERS, OPT_LIGHT_OTHER_HELPERS = range(5)
+OPT_LIGHT_CONCURRENT, OPT_LIGHT_LINE_CTAS, OPT_LIGHT_OTHER_CTAS, OPT_LIGHT_LINE_HELPERS, OPT_LIGHT_OTHER_HELPERS, OPT_LIGHT_PDL = range(6)
 
 # every symbol include/illuminant_b200.h declares: (name, restype, argtypes)
 P = C.c_void_p

@@ -685,10 +685,6 @@ ILB_DEV void shadeTile(const LightingParams& P, unsigned tile, TileSmem& S) {
 
     float accR = P.clear.x, accG = P.clear.y, accB = P.clear.z, accA = P.clear.w;
     const size_t scratchIndex = (size_t)(py - P.row_begin) * (size_t)P.width + (size_t)px;
-    if (P.accum_in && !P.tile_done && valid) {
-        const float4 a = P.accum_in[scratchIndex];
-        accR = a.x; accG = a.y; accB = a.z; accA = a.w;
-    }
 
     for (int base = 0; base < P.nlights; base += TILE_THREADS) {
         // ---- cull: thread t tests light base+t against the tile
@@ -782,15 +778,31 @@ ILB_DEV void shadeTile(const LightingParams& P, unsigned tile, TileSmem& S) {
         }
         return;
     }
+    if (P.accum_in) {
+        // second pass of a split frame: this pass summed its own lights from zero and now adds the first pass's sums (line sums +
+        // these sums, the operand order of the concurrent mode as well).  Under programmatic dependent launch the CTAs of this
+        // pass start while the first pass's last wave is still running and meet it here.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (valid) {
+            const float4 a = P.accum_in[scratchIndex];
+            accR = a.x + accR; accG = a.y + accG; accB = a.z + accB; accA = a.w + accA;
+        }
+    }
     if (!valid) return;
     if (P.accum_out) P.accum_out[scratchIndex] = make_float4(accR, accG, accB, accA);
     else storeTexel(P, outIndex, accR, accG, accB, accA);
 }
 
+// resident CTAs per SM for this pass's register budget (the budgets above are stated for 256-thread CTAs)
+#define ILB_LIGHT_CTAS(TYPES) ((((TYPES) & ILB_LIGHT_LINE) ? ILB_LIGHT_MINBLOCKS : ILB_LIGHT_MINBLOCKS_NOLINE) * (256 / TILE_THREADS))
+
 template <int FIELD, int TYPES>
-__global__ void __launch_bounds__(TILE_THREADS, (TYPES & ILB_LIGHT_LINE) ? ILB_LIGHT_MINBLOCKS : ILB_LIGHT_MINBLOCKS_NOLINE)
+__global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_CTAS(TYPES))
 light_accumulate_kernel(const __grid_constant__ LightingParams P) {
     __shared__ TileSmem S;
+    // first pass of a split frame: the second pass may be scheduled as soon as every CTA of this grid has started, i.e. into
+    // the idle SM slots of this grid's last wave (it waits for this grid's results only at its very end, see shadeTile)
+    if (P.accum_out && !P.tile_done) asm volatile("griddepcontrol.launch_dependents;");
     shadeTile<FIELD, TYPES>(P, blockIdx.x, S);
 }
 
@@ -800,7 +812,7 @@ light_accumulate_kernel(const __grid_constant__ LightingParams P) {
 // instead of back to back.  "Helper" grids of the same kernels, launched behind the main grids, become resident when one
 // pass runs out of tiles and its CTAs exit, so the surviving pass gets its full occupancy back for the tail.
 template <int FIELD, int TYPES>
-__global__ void __launch_bounds__(TILE_THREADS, (TYPES & ILB_LIGHT_LINE) ? ILB_LIGHT_MINBLOCKS : ILB_LIGHT_MINBLOCKS_NOLINE)
+__global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_CTAS(TYPES))
 light_accumulate_persistent_kernel(const __grid_constant__ LightingParams P) {
     __shared__ TileSmem S;
     const unsigned ntiles = (unsigned)P.tiles_x * (unsigned)P.tiles_y;
@@ -1356,7 +1368,22 @@ int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin
         ILB_LIGHT_LAUNCH(ILB_LIGHT_LINE);
         P.accum_in = P.accum_out;
         P.accum_out = nullptr;
-        ILB_LIGHT_LAUNCH(NOLINE);
+        P.clear = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // the clear colour entered through the line-light sums
+        if (ctx->opt[ILB_OPT_LIGHT_PDL]) {
+            // programmatic dependent launch: the second pass's CTAs fill the SM slots the first pass's last wave leaves idle
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(tiles); cfg.blockDim = dim3(TILE_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            if (P.df.planes && (planesMask & 2)) ILB_CUDA(ctx, cudaLaunchKernelEx(&cfg, light_accumulate_kernel<1, NOLINE>, P));
+            else ILB_CUDA(ctx, cudaLaunchKernelEx(&cfg, light_accumulate_kernel<0, NOLINE>, P));
+            ctx->launches++;
+        } else {
+            ILB_LIGHT_LAUNCH(NOLINE);
+        }
     } else if (prep.nline == 0) {
         ILB_LIGHT_LAUNCH(NOLINE);
     } else {

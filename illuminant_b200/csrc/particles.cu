@@ -607,27 +607,6 @@ struct __align__(128) StageSmem {
     unsigned long long full[STAGES];   // mbarriers
 };
 
-ILB_DEV uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-ILB_DEV void mbarInit(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
-}
-ILB_DEV void mbarExpectTx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
-}
-ILB_DEV void mbarWait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n.reg .pred p;\nWAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
-}
-ILB_DEV void bulkLoad(void* smemDst, const void* gmemSrc, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(smemDst)),
-                 "l"(gmemSrc), "r"(bytes), "r"(smemAddr(bar)) : "memory");
-}
-ILB_DEV void bulkStore(void* gmemDst, const void* smemSrc, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmemDst), "r"(smemAddr(smemSrc)), "r"(bytes) : "memory");
-}
-
 template <bool COLLIDE, int K0, int K1, int K2, int FM>
 __global__ void __launch_bounds__(STEP_THREADS, 3) particle_step_tma_kernel(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];

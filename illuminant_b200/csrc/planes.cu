@@ -39,6 +39,73 @@ __global__ void __launch_bounds__(256) df_planes_build_kernel(const __grid_const
     P.planes[((size_t)v * P.ph + py) * P.pw + px] = make_float4(lo0, hi0, xsub(lo1, lo0), xsub(hi1, hi0));
 }
 
+// TMA-staged form: the three virtual slices 3c, 3c + 1, 3c + 2 read the SAME atlas texels (channel pairs (r, g), (g, b),
+// (b, a) of physical slice c), and every entry needs its right-hand neighbour as well, so each atlas texel feeds six plane
+// entries.  One elected thread stages the CTA's run of an atlas row (257 texels, about 2 KB) into shared memory with a single
+// bulk asynchronous copy (cp.async.bulk, completion on an mbarrier; SASS: UBLKCP) and the 256 threads emit up to three 16-byte
+// entries each from it: the atlas is read once and only by the copy engine, the threads issue stores only.  CTAs whose run
+// crosses the U wrap of the atlas, or whose 16-byte aligned run would leave the allocation, take the direct loads instead
+// (a few columns at the atlas edges) -- both forms run the same arithmetic, so the planes are bit-identical.
+constexpr int BUILD_THREADS = 256;
+__global__ void __launch_bounds__(BUILD_THREADS) df_planes_build_tma_kernel(const __grid_constant__ PlaneBuildParams P) {
+    __shared__ __align__(16) uint2 s_row[BUILD_THREADS + 4];
+    __shared__ unsigned long long s_bar;
+    const int tid = threadIdx.x, px = blockIdx.x * BUILD_THREADS + tid, py = blockIdx.y, c = blockIdx.z;  // c: physical slice
+    const int v0 = 3 * c;
+    const int ay = min(max(P.row[v0] * P.sh + (py - HALO), 0), P.th - 1);            // V clamps
+    // atlas x of this CTA's first entry; U wraps modulo the atlas width (that is also how a slice index reaches the cells of the
+    // atlas's second and later rows: col = v / 3 runs past the column count, DistanceFieldCommon.fxh:273-281, :327-337)
+    long long first = ((long long)P.col[v0] * P.sw + (long long)blockIdx.x * BUILD_THREADS - HALO) % P.tw;
+    if (first < 0) first += P.tw;
+    const int count = min(BUILD_THREADS, P.pw - blockIdx.x * BUILD_THREADS) + 1;     // texels the CTA reads: its entries + one neighbour
+    const long long g0 = (long long)ay * P.tw + first, ga = g0 & ~1LL;               // 16-byte aligned start (the atlas is 256-byte aligned)
+    const long long gend = (g0 + count + 1) & ~1LL;
+    const bool staged = (first + count <= P.tw) && (gend <= (long long)P.tw * P.th); // uniform over the CTA: the run does not wrap
+    uint2 t0, t1;
+    if (staged) {
+        if (tid == 0) {
+            mbarInit(&s_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const unsigned bytes = (unsigned)(gend - ga) * (unsigned)sizeof(uint2);
+            mbarExpectTx(&s_bar, bytes);
+            bulkLoad(s_row, P.tex + ga, bytes, &s_bar);
+        }
+        __syncthreads();          // the barrier is initialised before anyone waits on it
+        mbarWait(&s_bar, 0);
+        const int at = (int)(g0 - ga) + tid;
+        if (px < P.pw) { t0 = s_row[at]; t1 = s_row[at + 1]; }
+    } else if (px < P.pw) {       // the run crosses the wrap: per-thread loads
+        const int ax = (int)((first + tid) % P.tw);
+        int ax1 = ax + 1;
+        if (ax1 == P.tw) ax1 = 0;
+        t0 = __ldg(P.tex + (size_t)ay * P.tw + ax);
+        t1 = __ldg(P.tex + (size_t)ay * P.tw + ax1);
+    }
+    if (px >= P.pw) return;
+    const float k = 1.0f / 65535.0f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const int v = v0 + j;
+        if (v >= P.nv) break;
+        const uint32_t sel = 0x3210u + 0x2222u * (uint32_t)j;
+        const uint32_t p0 = __byte_perm(t0.x, t0.y, sel), p1 = __byte_perm(t1.x, t1.y, sel);
+        const float lo0 = xmul(u16lo(p0), k), hi0 = xmul(u16hi(p0), k), lo1 = xmul(u16lo(p1), k), hi1 = xmul(u16hi(p1), k);
+        __stcs(P.planes + ((size_t)v * P.ph + py) * P.pw + px, make_float4(lo0, hi0, xsub(lo1, lo0), xsub(hi1, hi0)));
+    }
+}
+
+// ILB_PLANES_TMA=0 selects the one-thread-per-entry kernel (A/B and the bit-identity test)
+void launchPlaneBuild(ilb_ctx* ctx, const PlaneBuildParams& B) {
+    bool tma = true;
+    if (const char* e = getenv("ILB_PLANES_TMA")) tma = e[0] != '0';
+    // the staged kernel assumes what the host arithmetic of ilb_planes_attach guarantees for regular atlases: the three virtual
+    // slices of a physical slice share their cell
+    for (int v = 0; v < B.nv && tma; v++) tma = (B.col[v] == B.col[3 * (v / 3)]) && (B.row[v] == B.row[3 * (v / 3)]);
+    if (tma) df_planes_build_tma_kernel<<<dim3((B.pw + BUILD_THREADS - 1) / BUILD_THREADS, B.ph, (B.nv + 2) / 3), BUILD_THREADS, 0, ctx->stream>>>(B);
+    else df_planes_build_kernel<<<dim3((B.pw + 255) / 256, B.ph, B.nv), 256, 0, ctx->stream>>>(B);
+    ctx->launches++;
+}
+
 bool sameKey(const ilb_df_planes& p, const DFGeometry& g) {
     return p.key[0] == g.sliceSizeX && p.key[1] == g.sliceSizeY && p.key[2] == g.texelSizeX && p.key[3] == g.texelSizeY &&
            p.key[4] == g.ex && p.key[5] == g.ey && p.key[6] == g.maxValidZ && p.key[7] == g.zToSlice &&
@@ -113,7 +180,7 @@ int ilb_planes_attach(ilb_ctx* ctx, ilb_df* df, const ilb_df_uniforms& u, DFGeom
     if (stale && stale->nv == nv && stale->sw == sw && stale->sh == sh) {
         B.tex = df->tex; B.planes = stale->planes;
         B.tw = df->tw; B.th = df->th; B.sw = sw; B.sh = sh; B.pw = pw; B.ph = ph; B.nv = nv;
-        df_planes_build_kernel<<<dim3((pw + 255) / 256, ph, nv), 256, 0, ctx->stream>>>(B);
+        launchPlaneBuild(ctx, B);
         ILB_CUDA(ctx, cudaGetLastError());
         stale->version = df->version;
         g->planes = stale->planes; g->vtab = stale->vtab; g->pitch = stale->pitch;
@@ -135,7 +202,7 @@ int ilb_planes_attach(ilb_ctx* ctx, ilb_df* df, const ilb_df_uniforms& u, DFGeom
     if (e == cudaSuccess) {
         B.tex = df->tex; B.planes = P.planes;
         B.tw = df->tw; B.th = df->th; B.sw = sw; B.sh = sh; B.pw = pw; B.ph = ph; B.nv = nv;
-        df_planes_build_kernel<<<dim3((pw + 255) / 256, ph, nv), 256, 0, ctx->stream>>>(B);
+        launchPlaneBuild(ctx, B);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // vtab is a host vector

@@ -74,7 +74,9 @@ typedef enum ilb_option {
     ILB_OPT_LIGHT_OTHER_CTAS = 2,   /* resident sphere + directional CTAs per SM while both passes run (default 2) */
     ILB_OPT_LIGHT_LINE_HELPERS = 3, /* extra line-pass CTAs per SM that start when the other pass has drained (default 1) */
     ILB_OPT_LIGHT_OTHER_HELPERS = 4,/* extra sphere + directional CTAs per SM for the opposite case (default 3) */
-    ILB_OPT_COUNT = 5
+    ILB_OPT_LIGHT_PDL = 5,          /* 1: the sphere + directional pass is a programmatic dependent launch of the line-light pass:
+                                     * its CTAs start in the idle slots of the first pass's last wave (default 1) */
+    ILB_OPT_COUNT = 6
 } ilb_option;
 ILB_API int ilb_set_option(ilb_ctx* ctx, int option, int value);
 ILB_API int ilb_get_option(const ilb_ctx* ctx, int option, int* out_value);
