@@ -223,6 +223,7 @@ _PROTOTYPES = [
     ("ilb_particles_step_sources", C.c_int, [P, C.POINTER(PsysUniforms), P, P, C.c_int, P, C.c_int, C.c_int]),
     ("ilb_particles_render", C.c_int, [P, C.POINTER(ParticleRender), P, P]),
     ("ilb_particles_render_device", C.c_int, [P, C.POINTER(ParticleRender), P, P]),
+    ("ilb_particles_composite_layers", C.c_int, [P, C.POINTER(P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, C.POINTER(P), C.c_int]),
     ("ilb_particles_device_buffer", P, [P, C.c_int]),
     ("ilb_particles_count_live", C.c_int, [P, C.POINTER(C.c_int64)]),
     ("ilb_particles_request_chunk_liveness", C.c_int, [P]),

@@ -725,6 +725,15 @@ int ilb_particles_render(ilb_psys* ps, const ilb_particle_render* r, const void*
     return ILB_OK;
 }
 
+int ilb_particles_composite_layers(ilb_ctx* ctx, const void* const* d_layers, int layer_count, int width, int height, int row_begin,
+                                   int row_end, int blend, int target_format, const ilb_float4* clear_color, void* const* d_targets,
+                                   int target_count) {
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ilb_raster_composite(ctx, d_layers, layer_count, width, height, row_begin, row_end, blend, target_format, clear_color, d_targets,
+                                target_count);
+}
+
 void* ilb_particles_device_buffer(ilb_psys* ps, int which) {
     if (!ps || !live_has(ps) || which < 0 || which > 4) return nullptr;
     return ps->buf[which];

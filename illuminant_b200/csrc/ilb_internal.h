@@ -149,6 +149,8 @@ size_t ilb_format_bytes(int format);
 // raster.cu (N2)
 int ilb_raster_launch(ilb_psys* psys, const ilb_particle_render* params, const void* d_texture, void* d_target);
 void ilb_raster_release(ilb_psys* psys);
+int ilb_raster_composite(ilb_ctx* ctx, const void* const* d_layers, int layer_count, int width, int height, int row_begin, int row_end,
+                         int blend, int target_format, const ilb_float4* clear_color, void* const* d_targets, int target_count);
 // dfgen.cu
 int ilb_dfgen_launch(ilb_ctx* ctx, uint2* tex, const uint2* base, int tw, int th, int slice_w, int slice_h, int slice_count,
                      const ilb_df_uniforms* u, const ilb_obstruction* obs, int count, const ilb_height_volume* volumes, int volume_count,

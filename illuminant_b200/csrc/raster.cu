@@ -292,6 +292,34 @@ __global__ void __launch_bounds__(RBATCH) raster_shade_kernel(const __grid_const
     if (inside) storeTarget(R.target, R.fmt, pi, acc);
 }
 
+// ---- multi-GPU ParticleSystem.Render: composite of per-rank layers ---------------------------------------------------------
+// Chunks are sharded over the ranks in contiguous ranges, i.e. in DRAW ORDER, so rank k's chunks come
+// after rank k - 1's.  Every rank renders its chunks over a TRANSPARENT float4 layer with ilb_particles_render_device; the image
+// the reference would draw is the layers composited in rank order: premultiplied "over" is associative (AlphaBlend), additive
+// blending is a sum.  This kernel composites rows [row_begin, row_end) -- each rank takes one band -- reading the band of EVERY
+// rank's layer through its peer mapping (P2P loads over NVLink) and storing the finished texels into EVERY rank's target (peer
+// stores): the reduce-scatter and the all-gather of the image in one launch, no NCCL call on the data path.
+constexpr int MAX_LAYERS = 8;
+struct CompositeParams {
+    const float4* layers[MAX_LAYERS];
+    void* targets[MAX_LAYERS];
+    int nlayers, ntargets, W, row_begin, row_end, fmt, blend, clear;
+    float4 clearColor;
+};
+__global__ void __launch_bounds__(256) raster_composite_kernel(const __grid_constant__ CompositeParams C) {
+    const size_t n = (size_t)C.W * (size_t)(C.row_end - C.row_begin), base = (size_t)C.W * (size_t)C.row_begin;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pi = base + i;
+        f4 acc = C.clear ? mk4(C.clearColor) : loadTarget(C.targets[0], C.fmt, pi);
+        for (int k = 0; k < C.nlayers; k++) {   // rank order == draw order
+            const f4 l = mk4(__ldcs(C.layers[k] + pi));
+            if (C.blend == ILB_BLEND_ALPHA) acc = xadd4(l, xscale4(acc, xsub(1.0f, l.w)));
+            else acc = xadd4(l, acc);
+        }
+        for (int t = 0; t < C.ntargets; t++) storeTarget(C.targets[t], C.fmt, pi, acc);
+    }
+}
+
 int reserveU32(ilb_ctx* ctx, unsigned** p, size_t* cap, size_t count) {
     return ilb_reserve(ctx, reinterpret_cast<void**>(p), cap, std::max<size_t>(count, 4) * sizeof(unsigned), false);
 }
@@ -381,6 +409,38 @@ int ilb_raster_launch(ilb_psys* ps, const ilb_particle_render* r, const void* d_
         ILB_CUDA(ctx, cudaGetLastError());
     }
     raster_shade_kernel<<<(unsigned)tiles, RBATCH, 0, ctx->stream>>>(R);
+    ctx->launches++;
+    ILB_CUDA(ctx, cudaGetLastError());
+    return ILB_OK;
+}
+
+int ilb_raster_composite(ilb_ctx* ctx, const void* const* d_layers, int layer_count, int width, int height, int row_begin, int row_end,
+                         int blend, int target_format, const ilb_float4* clear_color, void* const* d_targets, int target_count) {
+    if (!d_layers || !d_targets || layer_count < 1 || layer_count > MAX_LAYERS || target_count < 1 || target_count > MAX_LAYERS)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "1..%d layers and targets", MAX_LAYERS);
+    if (width <= 0 || height <= 0 || row_begin < 0 || row_end > height || row_begin > row_end)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad rows [%d,%d) of %dx%d", row_begin, row_end, width, height);
+    if (blend != ILB_BLEND_ALPHA && blend != ILB_BLEND_ADDITIVE)
+        return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "only AlphaBlend and Additive layers composite (an Opaque layer has no coverage mask)");
+    if (target_format != ILB_FORMAT_FLOAT4 && target_format != ILB_FORMAT_HALF4 && target_format != ILB_FORMAT_RGBA8)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad target format %d", target_format);
+    if (row_begin == row_end) return ILB_OK;
+    CompositeParams C;
+    memset(&C, 0, sizeof(C));
+    for (int k = 0; k < layer_count; k++) {
+        if (!d_layers[k]) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null layer %d", k);
+        C.layers[k] = reinterpret_cast<const float4*>(d_layers[k]);
+    }
+    for (int t = 0; t < target_count; t++) {
+        if (!d_targets[t]) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null target %d", t);
+        C.targets[t] = d_targets[t];
+    }
+    C.nlayers = layer_count; C.ntargets = target_count; C.W = width; C.row_begin = row_begin; C.row_end = row_end;
+    C.fmt = target_format; C.blend = blend; C.clear = clear_color ? 1 : 0;
+    if (clear_color) C.clearColor = make_float4(clear_color->x, clear_color->y, clear_color->z, clear_color->w);
+    const size_t n = (size_t)width * (size_t)(row_end - row_begin);
+    const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16);
+    raster_composite_kernel<<<grid, 256, 0, ctx->stream>>>(C);
     ctx->launches++;
     ILB_CUDA(ctx, cudaGetLastError());
     return ILB_OK;

@@ -1119,6 +1119,15 @@ class ParticleSystem:
         self.ctx.check(self.ctx.lib.ilb_particles_render(self.handle, C.byref(r), tex_ptr, target.ctypes.data_as(C.c_void_p)))
         return target
 
+    def RenderLayerDevice(self, d_layer: int, width: int, height: int, blendState: str = "AlphaBlend",
+                          renderParams: Optional[ParticleRenderParameters] = None, viewportPosition=(0.0, 0.0), viewportScale=(1.0, 1.0)) -> None:
+        """This system's chunks rendered over a TRANSPARENT float4 layer at the device pointer `d_layer` ([H, W, 4] float32): one
+        rank's share of a multi-GPU ParticleSystem.Render (see composite_layers).  Asynchronous."""
+        if self.Configuration.Appearance.Texture is not None:
+            raise _abi.IlluminantError(_abi.ERR_UNSUPPORTED, "RenderLayerDevice renders untextured materials; pass the texture through ilb_particles_render_device")
+        r = self.render_params(width, height, blendState, renderParams, viewportPosition, viewportScale, (0.0, 0.0, 0.0, 0.0), _abi.FORMAT_FLOAT4)
+        self.ctx.check(self.ctx.lib.ilb_particles_render_device(self.handle, C.byref(r), None, C.c_void_p(int(d_layer))))
+
     def Dispose(self):
         if self.handle:
             self.ctx.lib.ilb_particles_destroy(self.handle)
@@ -1129,6 +1138,18 @@ class ParticleSystem:
             self.Dispose()
         except Exception:
             pass
+
+
+def composite_layers(ctx, layer_ptrs, width: int, height: int, rows, blendState: str, target_format: int, clearColor, target_ptrs) -> None:
+    """Composites rows [rows[0], rows[1]) of the per-rank layers (device pointers in rank == draw order; peer-mapped pointers of
+    other ranks are read over NVLink) onto `clearColor` (None: onto the contents of target_ptrs[0]) and stores the band into every
+    target of `target_ptrs` (ilb_particles_composite_layers).  Asynchronous on the context's stream."""
+    layers = (C.c_void_p * len(layer_ptrs))(*[C.c_void_p(int(p)) for p in layer_ptrs])
+    targets = (C.c_void_p * len(target_ptrs))(*[C.c_void_p(int(p)) for p in target_ptrs])
+    clear = Float4(*clearColor) if clearColor is not None else None
+    blend = {"AlphaBlend": _abi.BLEND_ALPHA, "Additive": _abi.BLEND_ADDITIVE, "Opaque": _abi.BLEND_OPAQUE}[blendState]
+    ctx.check(ctx.lib.ilb_particles_composite_layers(ctx.handle, layers, len(layer_ptrs), int(width), int(height), int(rows[0]), int(rows[1]), blend,
+                                                     int(target_format), C.byref(clear) if clear is not None else None, targets, len(target_ptrs)))
 
 
 def collision_field_uniforms(df: DistanceField, fullFieldAddressing: bool = False):

@@ -573,6 +573,18 @@ ILB_API int ilb_particles_render(ilb_psys* psys, const ilb_particle_render* para
  * the quad/tile pair count. */
 ILB_API int ilb_particles_render_device(ilb_psys* psys, const ilb_particle_render* params, const void* d_texture, void* d_target);
 
+/* Multi-GPU ParticleSystem.Render.  Chunk ranges are sharded over the ranks in draw order, so the frame the reference would draw
+ * is every rank's chunks rendered over a TRANSPARENT float4 layer (ilb_particles_render_device with clear = 1, ClearColor = 0,
+ * target_format = ILB_FORMAT_FLOAT4) and the layers composited in rank order: premultiplied "over" is associative (AlphaBlend),
+ * additive blending is a sum (ILB_BLEND_OPAQUE layers carry no coverage: ILB_ERR_UNSUPPORTED).  This call composites rows
+ * [row_begin, row_end) -- a rank's band -- of `layer_count` layers (device pointers, rank order; peer-mapped pointers of the
+ * other ranks' layers are read over NVLink) onto clear_color (NULL: onto the current contents of d_targets[0]) and stores the
+ * texels in target_format into every buffer of d_targets (peer-mapped full-frame targets: every rank ends with the whole
+ * image).  Asynchronous; the caller orders it behind all ranks' layer renders (a barrier) like the lighting gather. */
+ILB_API int ilb_particles_composite_layers(ilb_ctx* ctx, const void* const* d_layers, int layer_count, int width, int height,
+                                           int row_begin, int row_end, int blend, int target_format,
+                                           const ilb_float4* clear_color, void* const* d_targets, int target_count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -217,3 +217,55 @@ def test_gpu_render_checksum_property_at_4k(ctx):
     np.add.at(counts, (yi[on], xi[on]), 1.0)
     assert np.array_equal(out[..., 0], counts) and np.array_equal(out[..., 3], counts)
     assert float(out[..., 1].sum(dtype=np.float64)) == float(on.sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("blend", ["AlphaBlend", "Additive"])
+def test_gpu_layers_of_chunk_ranges_composite_to_the_whole_render(ctx, oracle, blend):
+    """Multi-GPU ParticleSystem.Render on one device: the chunks of a system are split into three contiguous ranges ("ranks"),
+    each range is rendered over a transparent float4 layer, and the layers are composited in range order -- band by band, as the
+    ranks would -- onto the clear colour.  Premultiplied "over" is associative and additive blending is a sum, so the result is
+    the single render of all chunks up to fp32 reassociation; the oracle (one pass over all particles) is the reference."""
+    import torch
+    from illuminant_b200.particles import composite_layers
+    w, h, n, chunk = 160, 96, 2700, 16
+    params = ib.ParticleRenderParameters(Origin=(0.5, 0.25), Scale=(1.1, 0.9))
+    clear = (0.05, 0.1, 0.0, 0.2)
+    P, RD, RC = _random_state(n, w, h, seed=17, size_range=(2.0, 12.0))
+    whole = _system(ctx, chunk=chunk, max_chunks=12, Rounded=True)
+    Pf, RDf, RCf = _upload(whole, P, RD, RC)
+    nchunks, per = whole.LiveChunkCount, chunk * chunk
+    assert nchunks == 11
+    ref = oracle.particles_render(Pf, RDf, RCf, whole.render_params(w, h, blend, params, clearColor=clear))
+    single = whole.Render(w, h, None, blend, params, clearColor=clear)
+    _compare(single, ref, f"single render {blend}", exact_coverage=False)
+    layers, systems = [], []
+    for c0, c1 in ((0, 4), (4, 8), (8, 11)):                         # sharding.chunk_range(rank, 3, 11)
+        part = _system(ctx, chunk=chunk, max_chunks=4, Rounded=True)
+        sl = slice(c0 * per, c1 * per)
+        _upload(part, Pf[sl], RDf[sl], RCf[sl])
+        layer = torch.empty((h, w, 4), dtype=torch.float32, device="cuda")
+        part.RenderLayerDevice(layer.data_ptr(), w, h, blend, params)
+        layers.append(layer)
+        systems.append(part)
+    target = torch.full((h, w, 4), 7.0, dtype=torch.float32, device="cuda")
+    for r0, r1 in ((0, 32), (32, 64), (64, 96)):                      # each "rank" composites its own row band of every layer
+        composite_layers(ctx, [l.data_ptr() for l in layers], w, h, (r0, r1), blend, _abi.FORMAT_FLOAT4, clear, [target.data_ptr()])
+    ctx.synchronize()
+    got = target.cpu().numpy()
+    _compare(got, ref, f"composited layers {blend}", exact_coverage=False)
+    assert np.abs(got - single).max() <= 2e-6                         # the same image as the one-GPU render, up to reassociation
+    # over an existing target (clear_color = NULL) and into a half4 target
+    base = torch.rand((h, w, 4), dtype=torch.float32, device="cuda")
+    expect = base.clone()
+    for l in layers:
+        expect = l + expect * (1.0 - l[..., 3:4]) if blend == "AlphaBlend" else l + expect
+    composite_layers(ctx, [l.data_ptr() for l in layers], w, h, (0, h), blend, _abi.FORMAT_FLOAT4, None, [base.data_ptr()])
+    ctx.synchronize()
+    assert torch.allclose(base, expect, rtol=0, atol=2e-6)
+    half = torch.zeros((h, w, 4), dtype=torch.float16, device="cuda")
+    composite_layers(ctx, [l.data_ptr() for l in layers], w, h, (0, h), blend, _abi.FORMAT_HALF4, clear, [half.data_ptr()])
+    ctx.synchronize()
+    assert torch.equal(half, target.half())
+    with pytest.raises(ib.IlluminantError):
+        composite_layers(ctx, [l.data_ptr() for l in layers], w, h, (0, h), "Opaque", _abi.FORMAT_FLOAT4, clear, [target.data_ptr()])
