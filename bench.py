@@ -609,6 +609,32 @@ def run_ours(args):
         except Exception as e:   # noqa: BLE001 -- the headline must not depend on the N2 side measurement
             result["render"] = {"error": f"{type(e).__name__}: {e}"}
 
+        # N2 at N > 1: every rank renders its chunks (rank order = draw order) over a transparent float4 layer, then composites its
+        # row band of ALL ranks' layers (P2P loads over NVLink) and stores the band into every rank's target (peer stores).
+        if dist is not None and peers["ptrs"] is not None:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                from illuminant_b200.particles import composite_layers
+                layer = symm_mem.empty((H, W, 4), dtype=torch.float32, device=torch.device("cuda", local_rank))
+                lhdl = symm_mem.rendezvous(layer, dist.group.WORLD)
+                layer_ptrs = [int(p) for p in lhdl.buffer_ptrs]
+                b0, b1 = sharding.row_band(rank, world, H)
+
+                def sharded_render_step():
+                    system.RenderLayerDevice(layer.data_ptr(), W, H, "Additive", ib.ParticleRenderParameters(Scale=(2.0, 2.0)))
+                    lhdl.barrier(channel=0)                      # every rank's layer is complete
+                    composite_layers(ctx, layer_ptrs, W, H, (b0, b1), "Additive", _abi.FORMAT_HALF4, (0.0, 0.0, 0.0, 0.0), peers["ptrs"])
+                    peers["hdl"].barrier(channel=0)              # every rank holds the whole image
+                sn = 10
+                s_total, _ = timed(sharded_render_step, sn, 2)
+                s_ms = reduce_ranks(s_total) / sn
+                result["render_sharded"] = {"metric": f"rasterised Mparticles/s ({count} particles per GPU, layers composited over NVLink into every rank's 4K half4 target)",
+                                            "value": count * world / (s_ms * 1e-3) / 1e6, "unit": "Mparticles/s", "ms_per_step": s_ms, "steps": sn,
+                                            "lit_fraction": float((peers["full"][:H, :, 3] > 0).float().mean().item())}
+                del layer
+            except Exception as e:   # noqa: BLE001 -- a side measurement
+                result["render_sharded"] = {"error": f"{type(e).__name__}: {e}"}
+
     # ------------------------------------------------------------------ combined frame loop (config C5)
     if args.workload == "both":
         # ParticleLights.cs:333-378: System.Update (collision against the lighting field) -> RenderLighting -> reassemble.
@@ -688,7 +714,7 @@ def run_ours(args):
                            "parallelism": f"row bands of equal measured cost x{world}, gather: {result.get('gather', 'none')}" if primary else f"chunk ranges x{world}, no collective",
                            "l2": "inputs larger than L2 (no flush)"}}
         for k in ("roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "gather_checksum_equal", "gather_matches_single_gpu", "probes", "bands",
-                  "particles", "combined_c5", "combined_c5_strong", "resolve", "render"):
+                  "particles", "combined_c5", "combined_c5_strong", "resolve", "render", "render_sharded"):
             if k in result:
                 line[k] = result[k]
         print(json.dumps(line), flush=True)

@@ -1440,9 +1440,18 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
     rc = lightingPrepare(ctx, df, f, batches, batch_count, vertices, vertex_count, &prep);
     if (rc) return rc;
     if (rows == 0) return ILB_OK;
-    // bands of whole tile rows; the first band is short so that the first kernel starts early, the last so that the
-    // final download is short
-    int bandRows = ((rows + ILB_PIPELINE_BANDS - 1) / ILB_PIPELINE_BANDS + TILE_H - 1) / TILE_H * TILE_H;
+    // Bands of whole tile rows with heights 1 : 2 : 3 : 4 : 3 : 2 : 1 -- the first band is short so that the first kernel starts
+    // after 1/16 of the upload, the last so that only 1/16 of the download is left when the last kernel ends, the middle ones
+    // long so that few kernel tails are paid.
+    static const int kShare[7] = {1, 2, 3, 4, 3, 2, 1};
+    static_assert(ILB_PIPELINE_BANDS >= 7, "one event pair per band");
+    int edge[8];
+    edge[0] = f->row_begin;
+    for (int b = 0, acc = 0; b < 7; b++) {
+        acc += kShare[b];
+        const int e = f->row_begin + (int)(((long long)rows * acc / 16 + TILE_H - 1) / TILE_H * TILE_H);
+        edge[b + 1] = (b == 6) ? f->row_end : std::min(std::max(e, edge[b]), f->row_end);
+    }
     const char* gsrc = reinterpret_cast<const char*>(gbuffer_host);
     char* gdst = reinterpret_cast<char*>(ctx->gbuffer);
     char* ldev = reinterpret_cast<char*>(ctx->d_lightmap);
@@ -1450,28 +1459,28 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
     // everything already queued on the main stream (earlier frames, uploads) must be done before the G-buffer is overwritten
     ILB_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], ctx->stream));
     ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_done[0], 0));
-    int nb = 0;
-    for (int r0 = f->row_begin; r0 < f->row_end; r0 += bandRows, nb++) {
-        const int r1 = std::min(r0 + bandRows, f->row_end);
+    for (int b = 0; b < 7; b++) {
+        const int r0 = edge[b], r1 = edge[b + 1];
+        if (r1 <= r0) continue;
         const size_t goff = gtexel * (size_t)gw * (size_t)r0, gn = gtexel * (size_t)gw * (size_t)(r1 - r0);
         ILB_CUDA(ctx, cudaMemcpyAsync(gdst + goff, gsrc + goff, gn, cudaMemcpyHostToDevice, ctx->copy_in));
-        ILB_CUDA(ctx, cudaEventRecord(ctx->ev_in[nb], ctx->copy_in));
+        ILB_CUDA(ctx, cudaEventRecord(ctx->ev_in[b], ctx->copy_in));
     }
     // every band's kernels are queued before the first download: with PAGEABLE caller buffers cudaMemcpyAsync blocks the host
     // until its copy is done, which must not hold back the launches of the bands behind it (pinned buffers never block)
-    nb = 0;
-    for (int r0 = f->row_begin; r0 < f->row_end; r0 += bandRows, nb++) {
-        const int r1 = std::min(r0 + bandRows, f->row_end);
-        ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[nb], 0));
+    for (int b = 0; b < 7; b++) {
+        const int r0 = edge[b], r1 = edge[b + 1];
+        if (r1 <= r0) continue;
+        ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
         void* outs[1] = {ctx->d_lightmap};
         rc = lightingLaunchRows(ctx, prep, r0, r1, outs, 1, f->row_begin);
         if (rc) return rc;
-        ILB_CUDA(ctx, cudaEventRecord(ctx->ev_done[nb], ctx->stream));
+        ILB_CUDA(ctx, cudaEventRecord(ctx->ev_done[b], ctx->stream));
     }
-    nb = 0;
-    for (int r0 = f->row_begin; r0 < f->row_end; r0 += bandRows, nb++) {
-        const int r1 = std::min(r0 + bandRows, f->row_end);
-        ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[nb], 0));
+    for (int b = 0; b < 7; b++) {
+        const int r0 = edge[b], r1 = edge[b + 1];
+        if (r1 <= r0) continue;
+        ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[b], 0));
         const size_t loff = ltexel * (size_t)f->width * (size_t)(r0 - f->row_begin), ln = ltexel * (size_t)f->width * (size_t)(r1 - r0);
         ILB_CUDA(ctx, cudaMemcpyAsync(lhost + loff, ldev + loff, ln, cudaMemcpyDeviceToHost, ctx->copy_out));
     }
