@@ -161,6 +161,11 @@ class ParticleRender(C.Structure):  # ilb_particle_render
                 ("reserved", C.c_float * 3)]
 
 
+class ResolvePlacement(C.Structure):  # ilb_resolve_placement
+    _fields_ = [("target_width", C.c_int32), ("target_height", C.c_int32), ("Position", C.c_float * 2), ("Scale", C.c_float * 2),
+                ("AlbedoRegion", C.c_float * 4), ("albedo_width", C.c_int32), ("albedo_height", C.c_int32)]
+
+
 class HeightVolumeStruct(C.Structure):  # ilb_height_volume
     _fields_ = [("first_edge", C.c_int32), ("edge_count", C.c_int32), ("z_base", C.c_float), ("height", C.c_float), ("bounds", C.c_float * 4)]
 
@@ -209,6 +214,8 @@ _PROTOTYPES = [
     ("ilb_update_light_probes_device", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, P, P, C.c_int, C.c_int, P]),
     ("ilb_resolve_lighting", C.c_int, [P, C.POINTER(Resolve), P, P, P]),
     ("ilb_resolve_lighting_device", C.c_int, [P, C.POINTER(Resolve), P, P, P]),
+    ("ilb_resolve_lighting_placed", C.c_int, [P, C.POINTER(Resolve), C.POINTER(ResolvePlacement), P, P, P]),
+    ("ilb_resolve_lighting_placed_device", C.c_int, [P, C.POINTER(Resolve), C.POINTER(ResolvePlacement), P, P, P]),
     ("ilb_compute_luminance", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, C.c_int, P]),
     ("ilb_particles_create", C.c_int, [P, C.c_int, C.c_int, C.POINTER(P)]),
     ("ilb_particles_destroy", None, [P]),

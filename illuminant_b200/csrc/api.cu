@@ -494,6 +494,47 @@ int ilb_resolve_lighting(ilb_ctx* ctx, const ilb_resolve* params, const void* li
     return ILB_OK;
 }
 
+int ilb_resolve_lighting_placed_device(ilb_ctx* ctx, const ilb_resolve* params, const ilb_resolve_placement* placement, const void* d_lightmap,
+                                       const void* d_albedo, void* d_target) {
+    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!params || !placement || !d_lightmap || !d_target) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ilb_resolve_placed_launch(ctx, params, placement, d_lightmap, d_albedo, d_target);
+}
+
+int ilb_resolve_lighting_placed(ilb_ctx* ctx, const ilb_resolve* params, const ilb_resolve_placement* pl, const void* lightmap, const void* albedo,
+                                void* target) {
+    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!params || !pl || !target) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
+    if (pl->target_width <= 0 || pl->target_height <= 0) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad target size");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void* d_lm = nullptr;
+    int rc = resolve_source(ctx, params->width, params->height, params->lightmap_format, lightmap, &d_lm);
+    if (rc) return rc;
+    const void* d_al = nullptr;
+    if (albedo) {
+        if (params->albedo_format != ILB_FORMAT_FLOAT4 && params->albedo_format != ILB_FORMAT_RGBA8)
+            return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "albedo format must be RGBA8 or FLOAT4");
+        if (pl->albedo_width <= 0 || pl->albedo_height <= 0) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad albedo size");
+        const size_t abytes = ilb_format_bytes(params->albedo_format) * (size_t)pl->albedo_width * (size_t)pl->albedo_height;
+        rc = ilb_reserve(ctx, &ctx->d_resolve_albedo, &ctx->d_resolve_albedo_capacity, abytes, false);
+        if (rc) return rc;
+        ILB_CUDA(ctx, cudaMemcpyAsync(ctx->d_resolve_albedo, albedo, abytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_al = ctx->d_resolve_albedo;
+    }
+    if (params->output_format != ILB_FORMAT_FLOAT4 && params->output_format != ILB_FORMAT_RGBA8)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "output format must be RGBA8 or FLOAT4");
+    const size_t obytes = ilb_format_bytes(params->output_format) * (size_t)pl->target_width * (size_t)pl->target_height;
+    rc = ilb_reserve(ctx, &ctx->d_resolve_out, &ctx->d_resolve_out_capacity, obytes, false);
+    if (rc) return rc;
+    ILB_CUDA(ctx, cudaMemcpyAsync(ctx->d_resolve_out, target, obytes, cudaMemcpyHostToDevice, ctx->stream));   // pixels outside the quad are kept
+    rc = ilb_resolve_placed_launch(ctx, params, pl, d_lm, d_al, ctx->d_resolve_out);
+    if (rc) return rc;
+    ILB_CUDA(ctx, cudaMemcpyAsync(target, ctx->d_resolve_out, obytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ILB_OK;
+}
+
 int ilb_compute_luminance(ilb_ctx* ctx, int width, int height, int lightmap_format, const void* lightmap, int level, float* out_luminance) {
     if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
     if (!out_luminance) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");

@@ -143,6 +143,8 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
                                  const void* gbuffer_host, void* lightmap_out_host);
 // resolve.cu (N3)
 int ilb_resolve_launch(ilb_ctx* ctx, const ilb_resolve* params, const void* d_lightmap, const void* d_albedo, void* d_output);
+int ilb_resolve_placed_launch(ilb_ctx* ctx, const ilb_resolve* params, const ilb_resolve_placement* placement, const void* d_lightmap,
+                              const void* d_albedo, void* d_target);
 int ilb_luminance_launch(ilb_ctx* ctx, int width, int height, int lightmap_format, const void* d_lightmap, int level,
                          float* out_host);
 size_t ilb_format_bytes(int format);

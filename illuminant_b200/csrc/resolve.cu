@@ -159,6 +159,46 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Re
     }
 }
 
+// ---- scaled / offset resolve (ResolveLighting drawn as a quad, LightingRenderer.cs:1537-1645) ------------------------------
+struct PlacedParams {
+    ResolveParams R;
+    int lw, lh, aw, ah, tw, th;     // lightmap, albedo, target sizes
+    int x0, y0, x1, y1;             // target pixels whose centre can lie inside the quad (half-open)
+    float px, py, qw, qh;           // quad position and size in target pixels
+    float u0, v0, u1, v1;           // albedo region
+    float uvox, uvoy;               // LightmapUVOffset
+};
+// LINEAR / CLAMP fetch, fp32 weights, individually rounded operations (the oracle's sampleLinearClamp)
+ILB_DEV f4 sampleLinearClamp(const void* tex, int fmt, int w, int h, float u, float v) {
+    const float x = xsub(xmul(u, (float)w), 0.5f), y = xsub(xmul(v, (float)h), 0.5f);
+    const float x0f = floorf(x), y0f = floorf(y);
+    const float fx = xsub(x, x0f), fy = xsub(y, y0f);
+    const int xa = min(max((int)x0f, 0), w - 1), xb = min(max((int)x0f + 1, 0), w - 1);
+    const int ya = min(max((int)y0f, 0), h - 1), yb = min(max((int)y0f + 1, 0), h - 1);
+    const f4 t00 = loadTexel(tex, fmt, (unsigned long long)ya * w + xa), t10 = loadTexel(tex, fmt, (unsigned long long)ya * w + xb);
+    const f4 t01 = loadTexel(tex, fmt, (unsigned long long)yb * w + xa), t11 = loadTexel(tex, fmt, (unsigned long long)yb * w + xb);
+    return xlerp4(xlerp4(t00, t10, fx), xlerp4(t01, t11, fx), fy);
+}
+template <int MODE, bool ALBEDO>
+__global__ void __launch_bounds__(256) resolve_placed_kernel(const __grid_constant__ PlacedParams P) {
+    const int x = P.x0 + blockIdx.x * 32 + (threadIdx.x & 31), y = P.y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= P.x1 || y >= P.y1) return;
+    const float tx = xdiv(xsub(xadd((float)x, 0.5f), P.px), P.qw), ty = xdiv(xsub(xadd((float)y, 0.5f), P.py), P.qh);
+    if (!(tx >= 0.0f && tx < 1.0f && ty >= 0.0f && ty < 1.0f)) return;     // the pixel centre is outside the quad
+    const float lu = fminf(fmaxf(xadd(tx, P.uvox), 0.0f), 1.0f), lv = fminf(fmaxf(xadd(ty, P.uvoy), 0.0f), 1.0f);
+    const f4 light = sampleLinearClamp(P.R.lightmap, P.R.lm_fmt, P.lw, P.lh, lu, lv);
+    f4 albedo = mk4(0.0f);
+    if (ALBEDO) {
+        const float au = fminf(fmaxf(xadd(P.u0, xmul(tx, xsub(P.u1, P.u0))), P.u0), P.u1);
+        const float av = fminf(fmaxf(xadd(P.v0, xmul(ty, xsub(P.v1, P.v0))), P.v0), P.v1);
+        albedo = sampleLinearClamp(P.R.albedo, P.R.al_fmt, P.aw, P.ah, au, av);
+    }
+    const f4 r = resolvePixel<MODE, ALBEDO>(P.R, light, albedo);
+    const size_t i = (size_t)y * (size_t)P.tw + (size_t)x;
+    if (P.R.out_fmt == ILB_FORMAT_RGBA8) reinterpret_cast<uint32_t*>(P.R.out)[i] = packRgba8(r);
+    else reinterpret_cast<float4*>(P.R.out)[i] = to_float4(r);
+}
+
 // ---- luminance ------------------------------------------------------------------------------------------------------
 // CalculateLuminancePixelShader (Resolve.fx:219-234) drawn into the half-size Single target (LightingRenderer.cs:839-898):
 // texel (x, y) point-samples lightmap texel (2x+1, 2y+1).  Individually rounded products / sums: bit-identical to the oracle.
@@ -190,7 +230,8 @@ void launchResolve(ilb_ctx* ctx, const ResolveParams& P, bool vec, int grid) {
 
 }  // namespace
 
-int ilb_resolve_launch(ilb_ctx* ctx, const ilb_resolve* r, const void* d_lightmap, const void* d_albedo, void* d_output) {
+static int fillResolveParams(ilb_ctx* ctx, const ilb_resolve* r, const void* d_lightmap, const void* d_albedo, void* d_output, bool placed,
+                             ResolveParams* out) {
     if (r->width <= 0 || r->height <= 0) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad size %dx%d", r->width, r->height);
     if (r->lightmap_format != ILB_FORMAT_FLOAT4 && r->lightmap_format != ILB_FORMAT_HALF4 && r->lightmap_format != ILB_FORMAT_RGBA8)
         return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad lightmap format %d", r->lightmap_format);
@@ -199,11 +240,11 @@ int ilb_resolve_launch(ilb_ctx* ctx, const ilb_resolve* r, const void* d_lightma
     if (r->output_format != ILB_FORMAT_FLOAT4 && r->output_format != ILB_FORMAT_RGBA8)
         return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "output format must be RGBA8 or FLOAT4");
     if (r->hdr_mode < ILB_HDR_NONE || r->hdr_mode > ILB_HDR_TONE_MAP) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad hdr_mode %d", r->hdr_mode);
-    if (r->LightmapUVOffset[0] != 0.0f || r->LightmapUVOffset[1] != 0.0f)
-        return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "LightmapUVOffset != 0 (scaled / offset resolves are outside the hot-path scope)");
+    if (!placed && (r->LightmapUVOffset[0] != 0.0f || r->LightmapUVOffset[1] != 0.0f))
+        return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "LightmapUVOffset != 0 needs the scaled / offset resolve (ilb_resolve_lighting_placed)");
     if (r->DitheringStrength != 0.0f)
         return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "DitheringStrength != 0 (ApplyDither lives in the un-vendored sq/Fracture DitherCommon.fxh)");
-    ResolveParams P;
+    ResolveParams& P = *out;
     memset(&P, 0, sizeof(P));
     P.lightmap = d_lightmap; P.albedo = d_albedo; P.out = d_output;
     P.n = (unsigned long long)r->width * (unsigned long long)r->height;
@@ -214,6 +255,52 @@ int ilb_resolve_launch(ilb_ctx* ctx, const ilb_resolve* r, const void* d_lightma
     P.middleGray = r->MiddleGray; P.averageLuminance = r->AverageLuminance; P.maxLumSq = r->MaximumLuminanceSquared;
     P.invWhiteScale = 1.0f / hostTonemap1(r->WhitePoint);
     P.albedoIsSRGB = r->AlbedoIsSRGB != 0.0f; P.resolveToSRGB = r->ResolveToSRGB != 0.0f;
+    return ILB_OK;
+}
+
+int ilb_resolve_placed_launch(ilb_ctx* ctx, const ilb_resolve* r, const ilb_resolve_placement* pl, const void* d_lightmap, const void* d_albedo,
+                              void* d_target) {
+    if (!pl || pl->target_width <= 0 || pl->target_height <= 0) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad placement");
+    if (d_albedo && (pl->albedo_width <= 0 || pl->albedo_height <= 0)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad albedo size");
+    PlacedParams P;
+    memset(&P, 0, sizeof(P));
+    int rc = fillResolveParams(ctx, r, d_lightmap, d_albedo, d_target, true, &P.R);
+    if (rc) return rc;
+    P.lw = r->width; P.lh = r->height; P.aw = pl->albedo_width; P.ah = pl->albedo_height; P.tw = pl->target_width; P.th = pl->target_height;
+    P.u0 = pl->AlbedoRegion[0]; P.v0 = pl->AlbedoRegion[1]; P.u1 = pl->AlbedoRegion[2]; P.v1 = pl->AlbedoRegion[3];
+    P.px = pl->Position[0]; P.py = pl->Position[1];
+    P.qw = (d_albedo ? (P.u1 - P.u0) * (float)P.aw : (float)P.lw) * pl->Scale[0];
+    P.qh = (d_albedo ? (P.v1 - P.v0) * (float)P.ah : (float)P.lh) * pl->Scale[1];
+    P.uvox = r->LightmapUVOffset[0]; P.uvoy = r->LightmapUVOffset[1];
+    if (!(P.qw > 0.0f) || !(P.qh > 0.0f)) return ILB_OK;   // an empty quad draws nothing
+    // conservative pixel box of the quad (the kernel decides per pixel centre)
+    auto lo = [](float v, int n) { return (int)std::fmin(std::fmax(std::floor(v - 1.0f), 0.0f), (float)n); };
+    auto hi = [](float v, int n) { return (int)std::fmin(std::fmax(std::ceil(v + 1.0f), 0.0f), (float)n); };
+    P.x0 = lo(P.px, P.tw); P.x1 = hi(P.px + P.qw, P.tw); P.y0 = lo(P.py, P.th); P.y1 = hi(P.py + P.qh, P.th);
+    if (P.x1 <= P.x0 || P.y1 <= P.y0) return ILB_OK;
+    const dim3 grid((P.x1 - P.x0 + 31) / 32, (P.y1 - P.y0 + 7) / 8);
+    const bool albedo = d_albedo != nullptr;
+#define ILB_PLACED(MODE, ALB) resolve_placed_kernel<MODE, ALB><<<grid, 256, 0, ctx->stream>>>(P)
+    switch (r->hdr_mode * 2 + (albedo ? 1 : 0)) {
+        case 0: ILB_PLACED(ILB_HDR_NONE, false); break;
+        case 1: ILB_PLACED(ILB_HDR_NONE, true); break;
+        case 2: ILB_PLACED(ILB_HDR_GAMMA_COMPRESS, false); break;
+        case 3: ILB_PLACED(ILB_HDR_GAMMA_COMPRESS, true); break;
+        case 4: ILB_PLACED(ILB_HDR_TONE_MAP, false); break;
+        default: ILB_PLACED(ILB_HDR_TONE_MAP, true); break;
+    }
+#undef ILB_PLACED
+    ctx->launches++;
+    ILB_CUDA(ctx, cudaGetLastError());
+    return ILB_OK;
+}
+
+int ilb_resolve_launch(ilb_ctx* ctx, const ilb_resolve* r, const void* d_lightmap, const void* d_albedo, void* d_output) {
+    ResolveParams P;
+    {
+        const int rc = fillResolveParams(ctx, r, d_lightmap, d_albedo, d_output, false, &P);
+        if (rc) return rc;
+    }
     const bool vec = (((uintptr_t)d_lightmap | (uintptr_t)d_albedo | (uintptr_t)d_output) & 15u) == 0;
     // enough 256-thread CTAs for every group of four pixels, capped at 8 waves of 148 SMs x 8 resident CTAs (grid-stride)
     const unsigned long long work = vec ? std::max<unsigned long long>(P.n >> 2, 1) : P.n;

@@ -236,6 +236,39 @@ class RenderedLighting:  # LightingRenderer.HDR.cs:69-212
         ctx.check(ctx.lib.ilb_resolve_lighting(ctx.handle, C.byref(params), lm_ptr, al_ptr, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def ResolvePlaced(self, target: np.ndarray, position=(0.0, 0.0), scale=(1.0, 1.0), albedo: Optional[np.ndarray] = None,
+                      albedoRegion=(0.0, 0.0, 1.0, 1.0), hdr: Optional[HDRConfiguration] = None, lightmap: Optional[np.ndarray] = None,
+                      uvOffset: Tuple[float, float] = (0.0, 0.0)) -> np.ndarray:
+        """RenderedLighting.Resolve with a position, a scale and an albedo region (LightingRenderer.HDR.cs:101-152 ->
+        ResolveLighting, LightingRenderer.cs:1537-1645): the resolve drawn as a quad into `target` (uint8 or float32 [H, W, 4] of
+        any size); returns the updated copy.  Without albedo pass scale / RenderScale like the reference (:1635)."""
+        if not self.IsValid:
+            raise _abi.IlluminantError(_abi.ERR_INVALID_OPERATION, "Invalid")
+        ctx = self.Renderer.ctx
+        lm_ptr, lm_fmt, w, h = None, self.LightmapFormat, self.Width, self.Height
+        if lightmap is not None:
+            lightmap, lm_fmt = _texels(lightmap, "lightmap")
+            h, w = lightmap.shape[0], lightmap.shape[1]
+            lm_ptr = lightmap.ctypes.data_as(C.c_void_p)
+        target, out_fmt = _texels(np.array(target, copy=True, order="C"), "target")
+        if out_fmt == FORMAT_HALF4:
+            raise _abi.IlluminantError(_abi.ERR_INVALID_ARGUMENT, "target must be uint8 or float32 texels")
+        pl = _abi.ResolvePlacement()
+        pl.target_width, pl.target_height = target.shape[1], target.shape[0]
+        pl.Position[:] = [float(position[0]), float(position[1])]
+        pl.Scale[:] = [float(scale[0]), float(scale[1])]
+        pl.AlbedoRegion[:] = [float(v) for v in albedoRegion]
+        al_ptr, al_fmt = None, FORMAT_RGBA8
+        if albedo is not None:
+            albedo, al_fmt = _texels(albedo, "albedo")
+            if al_fmt == FORMAT_HALF4:
+                raise _abi.IlluminantError(_abi.ERR_INVALID_ARGUMENT, "albedo must be uint8 or float32 texels")
+            pl.albedo_width, pl.albedo_height = albedo.shape[1], albedo.shape[0]
+            al_ptr = albedo.ctypes.data_as(C.c_void_p)
+        params = pack_resolve(w, h, lm_fmt, hdr, al_fmt, out_fmt, uvOffset)
+        ctx.check(ctx.lib.ilb_resolve_lighting_placed(ctx.handle, C.byref(params), C.byref(pl), lm_ptr, al_ptr, target.ctypes.data_as(C.c_void_p)))
+        return target
+
     def ComputeLuminance(self, level: int, lightmap: Optional[np.ndarray] = None) -> np.ndarray:
         """Level `level` of the luminance buffer (UpdateLuminanceBuffer + mips): float32 [(H/2) >> level, (W/2) >> level]."""
         ctx = self.Renderer.ctx

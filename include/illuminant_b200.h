@@ -327,6 +327,28 @@ ILB_API int ilb_resolve_lighting(ilb_ctx* ctx, const ilb_resolve* params, const 
 /* Same with DEVICE pointers (16-byte aligned); asynchronous on ilb_stream(ctx). */
 ILB_API int ilb_resolve_lighting_device(ilb_ctx* ctx, const ilb_resolve* params, const void* d_lightmap, const void* d_albedo,
                                         void* d_output);
+
+/* Scaled / offset resolve: ResolveLighting draws the resolve as a bitmap quad at `Position` with `Scale` into a render target of
+ * any size (LightingRenderer.cs:1537-1645; RenderedLighting.Resolve passes position, scale and the albedo region through).
+ * With albedo the quad is the albedo region in texels times Scale; without, the lightmap's render size (params->width x
+ * height) times Scale (the caller divides by RenderScale like :1635).  Every target pixel whose CENTRE lies inside the quad is
+ * written (BlendState.Opaque), the others keep their contents.  Both textures are sampled LINEAR / CLAMP at the interpolated
+ * texture coordinates (fp32 bilinear weights, the convention of the distance-field sampler), the lightmap at its coordinate plus
+ * params->LightmapUVOffset, each clamped to its region (Resolve.fx:30-36, :47-53).  In the screen-aligned 1:1 case (Position 0,
+ * Scale 1, target == lightmap size) the result equals ilb_resolve_lighting up to the fp32 rounding of the texture coordinates
+ * (the neighbouring texel enters with a weight of a few 1e-7). */
+typedef struct ilb_resolve_placement {
+    int32_t target_width, target_height;
+    float Position[2];
+    float Scale[2];
+    float AlbedoRegion[4];          /* u0, v0, u1, v1 (Bounds.Unit = 0, 0, 1, 1) */
+    int32_t albedo_width, albedo_height;
+} ilb_resolve_placement;
+/* target: target_width x target_height texels of params->output_format, read (pixels outside the quad) and written. */
+ILB_API int ilb_resolve_lighting_placed(ilb_ctx* ctx, const ilb_resolve* params, const ilb_resolve_placement* placement,
+                                        const void* lightmap, const void* albedo, void* target);
+ILB_API int ilb_resolve_lighting_placed_device(ilb_ctx* ctx, const ilb_resolve* params, const ilb_resolve_placement* placement,
+                                               const void* d_lightmap, const void* d_albedo, void* d_target);
 /* UpdateLuminanceBuffer + the mip chain TryComputeHistogram reads (LightingRenderer.cs:855-898, LightingRenderer.HDR.cs:154-186):
  * level 0 is (width/2) x (height/2) SurfaceFormat.Single texels, texel (x,y) = dot(lightmap texel (2x+1, 2y+1).rgb,
  * (0.299, 0.587, 0.144)) (CalculateLuminancePixelShader, Resolve.fx:219-234; point-sampled at the half-size target's pixel

@@ -54,6 +54,10 @@ float orc_height_volume_distance(const ilb_height_volume* volume, const ilb_floa
 void orc_encode_gbuffer_sample(const float* normal, float relativeY, float z, int dead, int enableShadows, int fullbright, float* out4);
 /* N3: Resolve.fx / HDR.fxh on fp32-decoded texels (lightmap, albedo: w*h*4 floats; albedo may be NULL); out: w*h*4 floats, not quantised. */
 int orc_resolve_lighting(const ilb_resolve* p, const float* lightmap, const float* albedo, float* out);
+/* N3: the resolve drawn as a quad at placement->Position with placement->Scale into a target of any size (ResolveLighting,
+ * LightingRenderer.cs:1537-1645): lightmap w*h*4 floats, albedo (nullable) albedo_width*albedo_height*4 floats, target
+ * target_width*target_height*4 floats read and written (pixels outside the quad keep their contents). */
+int orc_resolve_lighting_placed(const ilb_resolve* p, const ilb_resolve_placement* place, const float* lightmap, const float* albedo, float* target);
 /* N3: luminance buffer level `level` ((w/2 >> level) x (h/2 >> level) floats) of a fp32-decoded lightmap. */
 int orc_compute_luminance(const float* lightmap, int w, int h, int level, float* out);
 /* The host build of include/ilb_detmath.h (what every oracle function above calls): function 0 dm_sinf, 1 dm_cosf, 2 dm_acosf. */

@@ -330,6 +330,20 @@ def resolve_lighting(params, lightmap, albedo=None) -> np.ndarray:
     return out
 
 
+def resolve_lighting_placed(params, placement, lightmap, albedo, target) -> np.ndarray:
+    """ResolveLighting as a quad at placement.Position with placement.Scale: float32 arrays; returns the updated copy of `target`."""
+    lm = np.ascontiguousarray(lightmap, dtype=np.float32)
+    al = np.ascontiguousarray(albedo, dtype=np.float32) if albedo is not None else None
+    out = np.array(target, dtype=np.float32, copy=True, order="C")
+    L = lib()
+    L.orc_resolve_lighting_placed.restype = C.c_int
+    L.orc_resolve_lighting_placed.argtypes = [C.POINTER(_abi.Resolve), C.POINTER(_abi.ResolvePlacement), P, P, P]
+    rc = L.orc_resolve_lighting_placed(C.byref(params), C.byref(placement), _ptr(lm), _ptr(al), _ptr(out))
+    if rc != 0:
+        raise RuntimeError(f"orc_resolve_lighting_placed failed: {rc}")
+    return out
+
+
 def compute_luminance(lightmap, level: int) -> np.ndarray:
     lm = np.asarray(lightmap)
     lm = np.ascontiguousarray(lm.astype(np.float32) / np.float32(255.0)) if lm.dtype == np.uint8 else np.ascontiguousarray(lm, dtype=np.float32)

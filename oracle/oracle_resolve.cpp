@@ -7,6 +7,7 @@
 // (sRGBCommon.fxh) are restated here from the published IEC 61966-2-1 transfer functions applied to the un-premultiplied
 // colour; ApplyDither (DitherCommon.fxh) is the identity at the handler's default Strength 0 (LightingRenderer.cs:1489-1494),
 // the only value the boundary accepts.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -109,6 +110,57 @@ extern "C" int orc_resolve_lighting(const ilb_resolve* p, const float* lightmap,
         float4 r = resolvePixel(P, float4(l[0], l[1], l[2], l[3]), albedo ? albedo + 4 * i : nullptr);
         out[4 * i + 0] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
     }
+    return 0;
+}
+
+namespace {
+// LINEAR / CLAMP fetch at texture coordinates (u, v) of a w x h float4 texture: fp32 bilinear weights
+float4 sampleLinearClamp(const float* tex, int w, int h, float u, float v) {
+    const float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
+    const float x0f = floorf(x), y0f = floorf(y);
+    const float fx = x - x0f, fy = y - y0f;
+    auto at = [&](int ix, int iy) {
+        ix = std::min(std::max(ix, 0), w - 1);
+        iy = std::min(std::max(iy, 0), h - 1);
+        const float* t = tex + 4 * ((size_t)iy * w + ix);
+        return float4(t[0], t[1], t[2], t[3]);
+    };
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const float4 top = lerp(at(x0, y0), at(x0 + 1, y0), fx), bottom = lerp(at(x0, y0 + 1), at(x0 + 1, y0 + 1), fx);
+    return lerp(top, bottom, fy);
+}
+}  // namespace
+
+extern "C" int orc_resolve_lighting_placed(const ilb_resolve* p, const ilb_resolve_placement* place, const float* lightmap, const float* albedo,
+                                           float* target) {
+    if (!p || !place || !lightmap || !target) return -1;
+    ilb_resolve P = *p;
+    if (P.InverseScaleFactor == 0.0f) P.InverseScaleFactor = 1.0f;
+    const float u0 = place->AlbedoRegion[0], v0 = place->AlbedoRegion[1], u1 = place->AlbedoRegion[2], v1 = place->AlbedoRegion[3];
+    // the quad: the first texture's region in texels times Scale (BitmapDrawCall), at Position
+    const float qw = (albedo ? (u1 - u0) * (float)place->albedo_width : (float)P.width) * place->Scale[0];
+    const float qh = (albedo ? (v1 - v0) * (float)place->albedo_height : (float)P.height) * place->Scale[1];
+    if (!(qw > 0.0f) || !(qh > 0.0f)) return 0;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < place->target_height; y++)
+        for (int x = 0; x < place->target_width; x++) {
+            const float tx = (((float)x + 0.5f) - place->Position[0]) / qw, ty = (((float)y + 0.5f) - place->Position[1]) / qh;
+            if (!(tx >= 0.0f && tx < 1.0f && ty >= 0.0f && ty < 1.0f)) continue;
+            // texCoord2 over the lightmap region (0, 0)-(1, 1) plus LightmapUVOffset, clamped to it (Resolve.fx:35-36, :52-53)
+            const float lu = fminf(fmaxf(tx + P.LightmapUVOffset[0], 0.0f), 1.0f), lv = fminf(fmaxf(ty + P.LightmapUVOffset[1], 0.0f), 1.0f);
+            const float4 light = sampleLinearClamp(lightmap, P.width, P.height, lu, lv);
+            float a4[4];
+            const float* ap = nullptr;
+            if (albedo) {
+                const float au = fminf(fmaxf(u0 + tx * (u1 - u0), u0), u1), av = fminf(fmaxf(v0 + ty * (v1 - v0), v0), v1);
+                const float4 a = sampleLinearClamp(albedo, place->albedo_width, place->albedo_height, au, av);
+                a4[0] = a.x; a4[1] = a.y; a4[2] = a.z; a4[3] = a.w;
+                ap = a4;
+            }
+            const float4 r = resolvePixel(P, light, ap);
+            float* o = target + 4 * ((size_t)y * place->target_width + x);
+            o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
+        }
     return 0;
 }
 

@@ -160,3 +160,30 @@ def test_resolve_error_behaviour(ctx):
         assert e.value.code == _abi.ERR_INVALID_OPERATION
     finally:
         c2.close()
+
+
+@pytest.mark.parametrize("name", ["none", "tone-map-srgb"])
+@pytest.mark.parametrize("with_albedo", [False, True])
+def test_placed_resolve_matches_oracle(ctx, oracle, name, with_albedo):
+    """Scaled / offset resolve (ResolveLighting as a quad, LightingRenderer.cs:1537-1645) against the oracle: magnified and
+    minified, off the target's edges, an albedo sub-region, a LightmapUVOffset; pixels outside the quad are untouched."""
+    from illuminant_b200 import hdr as H
+    w, h, tw, th = 96, 54, 200, 120
+    lm, al = _inputs(31, w, h, np.float16, np.uint8)
+    al = al[:40, :64].copy() if with_albedo else None
+    rl = _rendered(ctx, w, h)
+    target = np.random.RandomState(2).rand(th, tw, 4).astype(np.float32)
+    for position, scale, region, uv in (((10.5, 7.25), (1.9, 2.1), (0.0, 0.0, 1.0, 1.0), (0.0, 0.0)),
+                                        ((-30.0, -11.0), (0.6, 0.45), (0.25, 0.125, 0.875, 1.0), (0.01, -0.02)),
+                                        ((150.0, 90.0), (3.0, 3.0), (0.0, 0.0, 0.5, 0.5), (0.0, 0.0))):
+        gpu = rl.ResolvePlaced(target, position, scale, al, region, HDRS[name], lightmap=lm, uvOffset=uv)
+        params = H.pack_resolve(w, h, _abi.FORMAT_FLOAT4, HDRS[name], _abi.FORMAT_FLOAT4, _abi.FORMAT_FLOAT4, uvOffset=uv)
+        pl = _abi.ResolvePlacement()
+        pl.target_width, pl.target_height = tw, th
+        pl.Position[:], pl.Scale[:], pl.AlbedoRegion[:] = position, scale, region
+        if al is not None:
+            pl.albedo_width, pl.albedo_height = al.shape[1], al.shape[0]
+        ref = oracle.resolve_lighting_placed(params, pl, lm.astype(np.float32), al.astype(np.float32) / 255 if al is not None else None, target)
+        _check(gpu, ref, f"placed {name} albedo={with_albedo} at {position}")
+        untouched = ref == target
+        assert np.array_equal(gpu[untouched], target[untouched]) and 0.02 < 1.0 - untouched.all(axis=2).mean() < 0.9

@@ -205,3 +205,50 @@ def test_unorm8_decode_by_reciprocal_and_one_correction_is_the_ieee_quotient():
         assert np.float64(np.float32(rho)) == rho
         q2 = np.float32(np.float64(q) + rho * np.float64(r))         # the FMA: exact sum in double, one rounding to fp32
         assert q2 == np.float32(c) / np.float32(255.0), c
+
+
+# ---- scaled / offset resolve (ResolveLighting drawn as a quad, LightingRenderer.cs:1537-1645) -------------------------------
+def _placement(tw, th, position=(0.0, 0.0), scale=(1.0, 1.0), region=(0.0, 0.0, 1.0, 1.0), albedo=None):
+    pl = _abi.ResolvePlacement()
+    pl.target_width, pl.target_height = tw, th
+    pl.Position[:] = position
+    pl.Scale[:] = scale
+    pl.AlbedoRegion[:] = region
+    if albedo is not None:
+        pl.albedo_width, pl.albedo_height = albedo.shape[1], albedo.shape[0]
+    return pl
+
+
+def test_placed_resolve_known_answers(oracle):
+    rs = np.random.RandomState(4)
+    lm = (rs.rand(6, 8, 4) * 2).astype(np.float32)
+    # 1:1 placement: the plain resolve up to the rounding of the texture coordinates
+    same = oracle.resolve_lighting_placed(_params(8, 6), _placement(8, 6), lm, None, np.full((6, 8, 4), 9.0, np.float32))
+    assert np.allclose(same, oracle.resolve_lighting(_params(8, 6), lm), rtol=0, atol=2e-6)
+    # a constant lightmap stays constant under any scale; pixels outside the quad keep the target's contents
+    const = np.full((6, 8, 4), 0.25, np.float32)
+    out = oracle.resolve_lighting_placed(_params(8, 6), _placement(40, 30, position=(4.0, 3.0), scale=(2.5, 3.0)), const, None,
+                                         np.full((30, 40, 4), -1.0, np.float32))
+    inside = np.zeros((30, 40), bool)
+    inside[3:21, 4:24] = True                                    # quad: 8 * 2.5 = 20 wide, 6 * 3 = 18 tall at (4, 3)
+    assert np.allclose(out[inside][:, :3], 0.25, atol=1e-7) and np.all(out[inside][:, 3] == 1.0) and np.all(out[~inside] == -1.0)
+    # a horizontal ramp magnified 4x: LINEAR sampling interpolates between texel centres and clamps at the edges
+    ramp = np.zeros((1, 4, 4), np.float32)
+    ramp[0, :, 0] = [0.0, 1.0, 2.0, 3.0]
+    out = oracle.resolve_lighting_placed(_params(4, 1), _placement(16, 1, scale=(4.0, 1.0)), ramp, None, np.zeros((1, 16, 4), np.float32))
+    centres = (np.arange(16) + 0.5) / 4.0 - 0.5                  # texel-space coordinate of every output pixel centre
+    assert np.allclose(out[0, :, 0], np.clip(centres, 0.0, 3.0), atol=1e-6)
+    # LightmapUVOffset shifts the lightmap fetch by whole texels when it is k / width
+    p = H.pack_resolve(4, 1, _abi.FORMAT_FLOAT4, None, _abi.FORMAT_FLOAT4, _abi.FORMAT_FLOAT4, uvOffset=(0.25, 0.0))
+    out = oracle.resolve_lighting_placed(p, _placement(4, 1), ramp, None, np.zeros((1, 4, 4), np.float32))
+    assert np.allclose(out[0, :, 0], [1.0, 2.0, 3.0, 3.0], atol=1e-6)
+    # with albedo the quad is the albedo REGION in texels times the scale, and both textures stretch over it
+    al = np.zeros((4, 4, 4), np.float32)
+    al[..., 3] = 1.0
+    al[:, 2:, :3] = 0.5                                          # right half of the sheet is grey
+    light = np.full((2, 2, 4), 0.5, np.float32)                  # x 2 = 1: albedo passes through
+    light[..., 3] = 1.0
+    pl = _placement(12, 8, position=(2.0, 1.0), scale=(3.0, 1.5), region=(0.5, 0.0, 1.0, 1.0), albedo=al)
+    out = oracle.resolve_lighting_placed(_params(2, 2), pl, light, al, np.zeros((8, 12, 4), np.float32))
+    assert np.allclose(out[1:7, 3:8, :3], 0.5, atol=1e-6) and not out[:, 8:].any() and not out[7:].any()   # 2 texels * 3 = 6 wide, 4 * 1.5 = 6 tall
+    assert np.allclose(out[1:7, 2, :3], 1.0 / 3.0, atol=1e-6)   # the bilinear footprint of the first column reaches the black texel left of the region
