@@ -194,7 +194,7 @@ void ilb_destroy(ilb_ctx* ctx) {
 }
 
 const char* ilb_last_error(const ilb_ctx* ctx) {
-    if (ctx) return ctx->last_error.c_str();
+    if (ctx && live_has(ctx)) return ctx->last_error.c_str();
     std::lock_guard<std::mutex> lock(g_error_mutex);
     static thread_local std::string copy;
     copy = g_create_error;
@@ -202,18 +202,18 @@ const char* ilb_last_error(const ilb_ctx* ctx) {
 }
 
 int ilb_synchronize(ilb_ctx* ctx) {
-    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
     ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ILB_OK;
 }
 
-void* ilb_stream(ilb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
-uint64_t ilb_launch_count(const ilb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* ilb_stream(ilb_ctx* ctx) { return (ctx && live_has(ctx)) ? (void*)ctx->stream : nullptr; }
+uint64_t ilb_launch_count(const ilb_ctx* ctx) { return (ctx && live_has(ctx)) ? ctx->launches : 0; }
 
 // ---------------------------------------------------------------------------------------------- distance field
 static int df_alloc(ilb_ctx* ctx, int tw, int th, size_t bytes, bool check_bytes, ilb_df** out_df) {
-    if (!ctx || !out_df) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !live_has(ctx) || !out_df) return ILB_ERR_INVALID_ARGUMENT;
     *out_df = nullptr;
     if (tw <= 0 || th <= 0 || tw > 8192 || th > 8192)  // DistanceField.MaxSurfaceSize, SDF/DistanceField.cs:19
         return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "atlas %dx%d outside (0,8192]", tw, th);
@@ -341,7 +341,7 @@ void ilb_df_destroy(ilb_df* df) {
 
 // ---------------------------------------------------------------------------------------------- G-buffer
 static int gbuffer_set(ilb_ctx* ctx, int w, int h, int fmt, const void* data, bool device) {
-    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!data) {  // G-buffer disabled (Configuration.EnableGBuffer == false)
         ctx->gb_w = ctx->gb_h = 0;
@@ -368,7 +368,7 @@ static int gbuffer_set(ilb_ctx* ctx, int w, int h, int fmt, const void* data, bo
 }
 
 int ilb_gbuffer_upload_rows(ilb_ctx* ctx, int w, int h, int fmt, int row_begin, int row_end, const void* rows) {
-    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
     if (!rows || w <= 0 || h <= 0 || row_begin < 0 || row_end > h || row_begin > row_end) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad G-buffer rows [%d,%d) of %dx%d", row_begin, row_end, w, h);
     if (fmt != ILB_FORMAT_FLOAT4 && fmt != ILB_FORMAT_HALF4) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "G-buffer format must be FLOAT4 or HALF4");
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -391,7 +391,7 @@ int ilb_gbuffer_upload_device(ilb_ctx* ctx, int w, int h, int fmt, const void* d
 // ---------------------------------------------------------------------------------------------- lighting
 int ilb_render_lighting_device(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches,
                                int batch_count, const ilb_light_vertex* vertices, int vertex_count, void* d_lightmap_out) {
-    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
     void* outs[1] = {d_lightmap_out};
     return ilb_lighting_launch(ctx, df, frame, batches, batch_count, vertices, vertex_count, outs, 1, false);
@@ -400,7 +400,7 @@ int ilb_render_lighting_device(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fram
 int ilb_render_lighting_peers(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches,
                               int batch_count, const ilb_light_vertex* vertices, int vertex_count, void* const* d_peer_lightmaps,
                               int peer_count) {
-    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
     if (!d_peer_lightmaps) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "d_peer_lightmaps is null");
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
     return ilb_lighting_launch(ctx, df, frame, batches, batch_count, vertices, vertex_count, d_peer_lightmaps, peer_count, true);
@@ -408,7 +408,7 @@ int ilb_render_lighting_peers(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame
 
 int ilb_render_lighting(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches, int batch_count,
                         const ilb_light_vertex* vertices, int vertex_count, void* lightmap_out) {
-    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
     if (!frame || !lightmap_out) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (frame->width <= 0 || frame->row_end < frame->row_begin) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad frame geometry");
@@ -428,7 +428,7 @@ int ilb_render_lighting(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* fram
 int ilb_render_lighting_frame(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches, int batch_count,
                               const ilb_light_vertex* vertices, int vertex_count, int gbuffer_width, int gbuffer_height, int gbuffer_format,
                               const void* gbuffer, void* lightmap_out) {
-    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->lm_fmt = -1;
     const int rc = ilb_lighting_frame_from_host(ctx, df, frame, batches, batch_count, vertices, vertex_count, gbuffer_width, gbuffer_height,
@@ -458,14 +458,14 @@ static int resolve_source(ilb_ctx* ctx, int w, int h, int fmt, const void* light
 }
 
 int ilb_resolve_lighting_device(ilb_ctx* ctx, const ilb_resolve* params, const void* d_lightmap, const void* d_albedo, void* d_output) {
-    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
     if (!params || !d_lightmap || !d_output) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
     return ilb_resolve_launch(ctx, params, d_lightmap, d_albedo, d_output);
 }
 
 int ilb_resolve_lighting(ilb_ctx* ctx, const ilb_resolve* params, const void* lightmap, const void* albedo, void* output) {
-    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
     if (!params || !output) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
     const void* d_lm = nullptr;
@@ -496,7 +496,7 @@ int ilb_resolve_lighting(ilb_ctx* ctx, const ilb_resolve* params, const void* li
 
 int ilb_resolve_lighting_placed_device(ilb_ctx* ctx, const ilb_resolve* params, const ilb_resolve_placement* placement, const void* d_lightmap,
                                        const void* d_albedo, void* d_target) {
-    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
     if (!params || !placement || !d_lightmap || !d_target) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
     return ilb_resolve_placed_launch(ctx, params, placement, d_lightmap, d_albedo, d_target);
@@ -504,7 +504,7 @@ int ilb_resolve_lighting_placed_device(ilb_ctx* ctx, const ilb_resolve* params, 
 
 int ilb_resolve_lighting_placed(ilb_ctx* ctx, const ilb_resolve* params, const ilb_resolve_placement* pl, const void* lightmap, const void* albedo,
                                 void* target) {
-    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
     if (!params || !pl || !target) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
     if (pl->target_width <= 0 || pl->target_height <= 0) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad target size");
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -536,7 +536,7 @@ int ilb_resolve_lighting_placed(ilb_ctx* ctx, const ilb_resolve* params, const i
 }
 
 int ilb_compute_luminance(ilb_ctx* ctx, int width, int height, int lightmap_format, const void* lightmap, int level, float* out_luminance) {
-    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
     if (!out_luminance) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
     const void* d_lm = nullptr;
@@ -546,7 +546,7 @@ int ilb_compute_luminance(ilb_ctx* ctx, int width, int height, int lightmap_form
 }
 
 int ilb_lighting_set_particle_lights(ilb_ctx* ctx, const ilb_particle_light_source* sources, int count) {
-    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
     if (count < 0 || (count > 0 && !sources)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null or negative argument");
     for (int i = 0; i < count; i++)
         if (!sources[i].system || !live_has(sources[i].system) || sources[i].system->ctx != ctx)
@@ -558,7 +558,7 @@ int ilb_lighting_set_particle_lights(ilb_ctx* ctx, const ilb_particle_light_sour
 int ilb_update_light_probes(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches, int batch_count,
                             const ilb_light_vertex* vertices, int vertex_count, const ilb_float4* probe_positions,
                             const ilb_float4* probe_normals, int probe_count, int output_format, void* probes_out) {
-    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
     return ilb_probes_launch(ctx, df, frame, batches, batch_count, vertices, vertex_count, probe_positions, probe_normals, probe_count,
                              output_format, probes_out, nullptr);
@@ -567,7 +567,7 @@ int ilb_update_light_probes(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* 
 int ilb_update_light_probes_device(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches, int batch_count,
                                    const ilb_light_vertex* vertices, int vertex_count, const ilb_float4* probe_positions,
                                    const ilb_float4* probe_normals, int probe_count, int output_format, void* d_probes_out) {
-    if (!ctx) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
     if (!d_probes_out) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "d_probes_out is null");
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
     return ilb_probes_launch(ctx, df, frame, batches, batch_count, vertices, vertex_count, probe_positions, probe_normals, probe_count,
@@ -576,7 +576,7 @@ int ilb_update_light_probes_device(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_
 
 // ---------------------------------------------------------------------------------------------- particles
 int ilb_particles_create(ilb_ctx* ctx, int chunk_size, int max_chunks, ilb_psys** out_psys) {
-    if (!ctx || !out_psys) return ILB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !live_has(ctx) || !out_psys) return ILB_ERR_INVALID_ARGUMENT;
     *out_psys = nullptr;
     if (chunk_size < 16 || chunk_size > 4096 || max_chunks < 1)
         return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "chunk_size %d / max_chunks %d out of range", chunk_size, max_chunks);

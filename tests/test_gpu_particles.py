@@ -317,3 +317,33 @@ def test_removing_a_chunk_keeps_the_order_of_the_others(ctx):
     p, v, a, rc, rd = system.ReadChunk(3)                           # the vacated slot is zeroed for the next CreateChunk
     assert not p.any() and not v.any() and not a.any()
     assert system.LiveCount == 3 * per
+
+
+def test_stale_handles_are_rejected_not_dereferenced():
+    """ilb_destroy releases a context's fields and particle systems; a later call through any stale handle must come back as
+    ILB_ERR_INVALID_ARGUMENT instead of touching freed memory (a Python ParticleSystem can outlive its Context)."""
+    import ctypes as C
+    from illuminant_b200 import _abi
+    ctx2 = ib.Context(0)
+    lib = ctx2.lib
+    ps, df = C.c_void_p(), C.c_void_p()
+    assert lib.ilb_particles_create(ctx2.handle, 16, 2, C.byref(ps)) == 0
+    assert lib.ilb_df_create_empty(ctx2.handle, 32, 32, C.byref(df)) == 0
+    stale_ctx = C.c_void_p(ctx2.handle.value)
+    ctx2.close()
+    count, n, v = C.c_int64(0), C.c_int(0), C.c_int(0)
+    u = _abi.PsysUniforms()
+    assert lib.ilb_particles_count_live(ps, C.byref(count)) == _abi.ERR_INVALID_ARGUMENT
+    assert lib.ilb_particles_step(ps, C.byref(u), None, 0, None, 0, 1) == _abi.ERR_INVALID_ARGUMENT
+    assert lib.ilb_particles_set_live_chunks(ps, 1) == _abi.ERR_INVALID_ARGUMENT
+    assert lib.ilb_particles_request_chunk_liveness(ps) == _abi.ERR_INVALID_ARGUMENT
+    assert lib.ilb_particles_remove_chunk(ps, 0) == _abi.ERR_INVALID_ARGUMENT
+    assert lib.ilb_particles_device_buffer(ps, 0) is None
+    buf = (C.c_uint16 * (32 * 32 * 4))()
+    assert lib.ilb_df_download(df, buf, 32 * 32 * 8) == _abi.ERR_INVALID_ARGUMENT
+    assert lib.ilb_synchronize(stale_ctx) == _abi.ERR_INVALID_ARGUMENT
+    assert lib.ilb_set_option(stale_ctx, 0, 1) == _abi.ERR_INVALID_ARGUMENT
+    assert lib.ilb_gbuffer_upload(stale_ctx, 4, 4, 0, buf) == _abi.ERR_INVALID_ARGUMENT
+    lib.ilb_particles_destroy(ps)      # no-ops
+    lib.ilb_df_destroy(df)
+    lib.ilb_destroy(stale_ctx)
