@@ -202,6 +202,40 @@ namespace Squared.Illuminant.Native {
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_render (IntPtr psys, ref IlbParticleRender parameters, void* textureOrNull, void* target);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_render_device (IntPtr psys, ref IlbParticleRender parameters, void* dTextureOrNull, void* dTarget);
 
+        // ---- round 2 -----------------------------------------------------------------------------------------------------
+        // scheduling knobs (ilb_option): never change results
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_set_option (IntPtr ctx, int option, int value);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_get_option (IntPtr ctx, int option, out int value);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_debug_detmath (IntPtr ctx, int function, float* x, float* result, int count);
+        // a rank's row band of the G-buffer (multi-GPU); asynchronous UpdateLightProbes into a device buffer
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_gbuffer_upload_rows (IntPtr ctx, int w, int h, int format, int rowBegin, int rowEnd, void* rows);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_update_light_probes_device (IntPtr ctx, IntPtr df, ref IlbLightingFrame frame, IlbLightBatch* batches, int batchCount, LightVertex* vertices, int vertexCount, Vector4* probePositions, Vector4* probeNormals, int probeCount, int outputFormat, void* dProbesOut);
+        // N1: height volumes and incremental slice updates (LightingRenderer.DistanceField.cs:80-260, :415-464)
+        [StructLayout(LayoutKind.Sequential, Pack = 4)]
+        public struct IlbHeightVolume {           // ilb_height_volume
+            public int FirstEdge, EdgeCount;
+            public float ZBase, Height;
+            public float BoundsLeft, BoundsTop, BoundsRight, BoundsBottom;
+        }
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_df_create_empty (IntPtr ctx, int w, int h, out IntPtr df);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_df_update_slices (IntPtr df, IntPtr staticDfOrNull, int sliceW, int sliceH, int sliceCount, ref IlbDFUniforms u, IlbObstruction* obstructions, int obstructionCount, IlbHeightVolume* volumes, int volumeCount, Vector4* edges, int edgeCount, int firstPhysicalSlice, int physicalSliceCount);
+        // chunk liveness and reaping (ParticleLiveness.cs)
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_request_chunk_liveness (IntPtr psys);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_poll_chunk_liveness (IntPtr psys, long* counts, int capacity, out int count, int wait);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_remove_chunk (IntPtr psys, int chunk);
+        // multi-GPU ParticleSystem.Render: per-rank transparent layers, composited band by band over peer mappings
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_composite_layers (IntPtr ctx, void** dLayers, int layerCount, int width, int height, int rowBegin, int rowEnd, int blend, int targetFormat, Vector4* clearColorOrNull, void** dTargets, int targetCount);
+        // N3: scaled / offset resolve (ResolveLighting drawn as a quad, LightingRenderer.cs:1537-1645)
+        [StructLayout(LayoutKind.Sequential, Pack = 4)]
+        public struct IlbResolvePlacement {       // ilb_resolve_placement
+            public int TargetWidth, TargetHeight;
+            public float PositionX, PositionY, ScaleX, ScaleY;
+            public float AlbedoU0, AlbedoV0, AlbedoU1, AlbedoV1;
+            public int AlbedoWidth, AlbedoHeight;
+        }
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_resolve_lighting_placed (IntPtr ctx, ref IlbResolve parameters, ref IlbResolvePlacement placement, void* lightmapOrNull, void* albedoOrNull, void* target);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_resolve_lighting_placed_device (IntPtr ctx, ref IlbResolve parameters, ref IlbResolvePlacement placement, void* dLightmap, void* dAlbedoOrNull, void* dTarget);
+
         /// <summary>Maps an ilb_status to the exception type the reference throws at the same place.</summary>
         public static void Check (IntPtr ctx, int status) {
             if (status == 0)
