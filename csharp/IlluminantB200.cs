@@ -202,6 +202,15 @@ namespace Squared.Illuminant.Native {
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_render (IntPtr psys, ref IlbParticleRender parameters, void* textureOrNull, void* target);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_render_device (IntPtr psys, ref IlbParticleRender parameters, void* dTextureOrNull, void* dTarget);
 
+        // device-pointer variants (interop with other CUDA code in the process, multi-GPU peer mappings) and introspection
+        [DllImport(DllName, CallingConvention = CC)] public static extern IntPtr ilb_stream (IntPtr ctx);
+        [DllImport(DllName, CallingConvention = CC)] public static extern ulong ilb_launch_count (IntPtr ctx);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_df_create_device (IntPtr ctx, int w, int h, void* dRgba64, UIntPtr bytes, out IntPtr df);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_gbuffer_upload_device (IntPtr ctx, int w, int h, int format, void* dData);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_render_lighting_device (IntPtr ctx, IntPtr df, ref IlbLightingFrame frame, IlbLightBatch* batches, int batchCount, LightVertex* vertices, int vertexCount, void* dLightmapOut);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_render_lighting_peers (IntPtr ctx, IntPtr df, ref IlbLightingFrame frame, IlbLightBatch* batches, int batchCount, LightVertex* vertices, int vertexCount, void** dPeerLightmaps, int peerCount);
+        [DllImport(DllName, CallingConvention = CC)] public static extern void* ilb_particles_device_buffer (IntPtr psys, int which);
+
         // ---- round 2 -----------------------------------------------------------------------------------------------------
         // scheduling knobs (ilb_option): never change results
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_set_option (IntPtr ctx, int option, int value);

@@ -81,3 +81,40 @@ def test_cuda_library_is_sm100a_with_lineinfo():
     from illuminant_b200 import _abi
     out = subprocess.run(["cuobjdump", "-lelf", str(_abi.LIB_PATH)], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_csharp_shim_binds_every_symbol_with_matching_struct_sizes():
+    """csharp/IlluminantB200.cs cannot be compiled here (no .NET), so it is checked textually: every symbol the header declares
+    has a DllImport, and every blittable struct it declares has the size of the matching C struct (summing the field sizes of
+    the Sequential, Pack = 4 layouts: int / float 4, Vector2 8, Vector3 12, Vector4 16, Matrix 64, long 8, `fixed float X[n]`)."""
+    from illuminant_b200 import _abi
+    cs = (ROOT / "csharp" / "IlluminantB200.cs").read_text()
+    imported = set(re.findall(r"public static extern \w+\*? (ilb_\w+) ?\(", cs))
+    assert imported == set(declared_symbols()), sorted(set(declared_symbols()) ^ imported)
+    sizes = {"int": 4, "float": 4, "long": 8, "Vector2": 8, "Vector3": 12, "Vector4": 16, "Matrix": 64, "IntPtr": 8,
+             "Uniforms.ClampedBezier1": C.sizeof(_abi.Bezier1), "Uniforms.ClampedBezier4": C.sizeof(_abi.Bezier4)}
+    mirrors = {"IlbDFUniforms": _abi.DFUniforms, "IlbLightBatch": _abi.LightBatch, "IlbLightingFrame": _abi.LightingFrame,
+               "IlbObstruction": _abi.Obstruction, "IlbPsysUniforms": _abi.PsysUniforms, "IlbArea": _abi.Area, "IlbGravity": _abi.GravityOp,
+               "IlbNoise": _abi.NoiseOp, "IlbFMA": _abi.FMAOp, "IlbMatrixMultiply": _abi.MatrixOp, "IlbSpawn": _abi.Spawn,
+               "IlbHeightVolume": _abi.HeightVolumeStruct, "IlbResolvePlacement": _abi.ResolvePlacement}
+    checked = 0
+    for name, body in re.findall(r"public (?:unsafe )?struct (\w+) \{(.*?)\n    \}|public (?:unsafe )?struct (\w+) \{(.*?)\n        \}", cs, flags=re.S) and \
+            [(m[0] or m[2], m[1] or m[3]) for m in re.findall(r"public (?:unsafe )?struct (\w+) \{(.*?)\n    \}|public (?:unsafe )?struct (\w+) \{(.*?)\n        \}", cs, flags=re.S)]:
+        if name not in mirrors:
+            continue
+        total = 0
+        for decl in re.findall(r"public ([^;()]+);", body):
+            decl = decl.split("//")[0].strip()
+            m = re.match(r"fixed (\w+) \w+\[([^\]]+)\]", decl)
+            if m:
+                total += sizes[m.group(1)] * eval(m.group(2))
+                continue
+            typ, names = decl.split(" ", 1)
+            if typ in sizes or typ in mirrors:
+                unit = sizes[typ] if typ in sizes else C.sizeof(mirrors[typ])
+                total += unit * len([n for n in names.split(",") if n.strip()])
+            else:
+                raise AssertionError(f"{name}: unknown field type {typ!r}")
+        assert total == C.sizeof(mirrors[name]), f"{name}: C# fields sum to {total} bytes, the C struct has {C.sizeof(mirrors[name])}"
+        checked += 1
+    assert checked >= 11, checked
