@@ -25,6 +25,9 @@ namespace {
 #ifndef ILB_TILE_H
 #define ILB_TILE_H 16
 #endif
+#ifndef ILB_SPLIT_MARCH
+#define ILB_SPLIT_MARCH 1   // rays that leave the field volume march in two loops (inside part, outside part), see coneTraceMarch
+#endif
 #ifndef ILB_SWIZZLE
 #define ILB_SWIZZLE 8   // CTAs walk down bands of this many tile rows (column-major inside a band): 2-D locality in L1/L2
 #endif
@@ -154,6 +157,9 @@ ILB_DEV float safeInsideLimit(const DFGeometry& g, f3 o, f3 d) {
     const float m = 0.05f;
     const float oz = o.z - g.zOffset;
     if (!((o.x >= m) && (o.x <= g.ex - m) && (o.y >= m) && (o.y <= g.ey - m) && (oz >= m) && (oz <= g.ez - m))) return -1.0f;
+    // a NaN direction (zero-length ray: its light-pixel is re-evaluated by the IEEE fallback) must not reach the short sampler,
+    // whose texel addressing (floorBiased) is only defined for finite coordinates
+    if (!((d.x == d.x) && (d.y == d.y) && (d.z == d.z))) return -1.0f;
     const float BIG = 3.0e38f;
     const float tx = (d.x > 0.0f) ? __fdividef((g.ex - m) - o.x, d.x) : ((d.x < 0.0f) ? __fdividef(m - o.x, d.x) : BIG);
     const float ty = (d.y > 0.0f) ? __fdividef((g.ey - m) - o.y, d.y) : ((d.y < 0.0f) ? __fdividef(m - o.y, d.y) : BIG);
@@ -161,22 +167,40 @@ ILB_DEV float safeInsideLimit(const DFGeometry& g, f3 o, f3 d) {
     return fminf(fminf(tx, ty), tz) * (1.0f - 3.0e-5f);
 }
 
+// one step of the march (coneTraceAdvance :73-82 + the loop condition :168-176); returns the liveness of the trace
+template <int FIELD, bool INSIDE>
+ILB_DEV bool coneTraceMarchStep(const DFGeometry& g, const TraceConfig& c, Trace& a, float& stepsRemaining) {
+    stepsRemaining -= 1.0f;
+    const f3 sp = xadd3(a.origin, xscale3(a.direction, a.t));
+    const float d = sampleFieldT<FIELD, INSIDE>(g, sp);
+    a.t = xadd(a.t, traceStep(c, d, a.t, a.vis));
+    // liveness = stepsRemaining * saturate(vis - 0.075) * saturate(len - t) > 0 (ConeTrace.fxh:168-176): a product of
+    // non-negative factors that cannot underflow (a non-zero factor is at least one ulp of 0.075 resp. of t >= 0.5), so it
+    // is positive exactly when every factor is
+    return (stepsRemaining > 0.0f) && (a.vis > FULLY_SHADOWED_THRESHOLD) && (a.len > a.t);
+}
+
 template <int FIELD, bool INSIDE>
 ILB_DEV void coneTraceMarch(const DFGeometry& g, const TraceConfig& c, Trace& a, float& stepsRemaining) {
-    float liveness = 1.0f;
+    bool live = true;
+#if ILB_SPLIT_MARCH
+    if (!INSIDE) {
+        // A ray that ends outside the volume still spends most of its samples inside it: there the clamp is the identity and the
+        // distance-to-volume term is exactly 0, so the short sampler gives the same bits.  t only grows, so the march is two
+        // loops -- the short sampler while t <= tSafe, the general one for the rest -- each with one copy of its sampler.
+        const float tSafe = safeInsideLimit(g, a.origin, a.direction);
+        while (live && (a.t <= tSafe)) live = coneTraceMarchStep<FIELD, true>(g, c, a, stepsRemaining);
+    }
+    while (live) live = coneTraceMarchStep<FIELD, INSIDE>(g, c, a, stepsRemaining);
+#else
     // a ray that ends outside the volume still spends most of its samples inside it: there the clamp is the
     // identity and the distance-to-volume term is exactly 0, so the short sampler gives the same bits
     const float tSafe = INSIDE ? 0.0f : safeInsideLimit(g, a.origin, a.direction);
-    while (liveness > 0.0f) {
-        stepsRemaining -= 1.0f;
-        const f3 sp = xadd3(a.origin, xscale3(a.direction, a.t));  // coneTraceAdvance :73-82
-        const float d = (INSIDE || (a.t <= tSafe)) ? sampleFieldT<FIELD, true>(g, sp) : sampleFieldT<FIELD, false>(g, sp);
-        a.t = xadd(a.t, traceStep(c, d, a.t, a.vis));
-        // liveness = stepsRemaining * saturate(vis - 0.075) * saturate(len - t) > 0 (ConeTrace.fxh:168-176): a product of
-        // non-negative factors that cannot underflow (a non-zero factor is at least one ulp of 0.075 resp. of t >= 0.5), so it
-        // is positive exactly when every factor is
-        liveness = ((stepsRemaining > 0.0f) && (a.vis > FULLY_SHADOWED_THRESHOLD) && (a.len > a.t)) ? 1.0f : 0.0f;
+    while (live) {
+        if (INSIDE || (a.t <= tSafe)) live = coneTraceMarchStep<FIELD, true>(g, c, a, stepsRemaining);
+        else live = coneTraceMarchStep<FIELD, false>(g, c, a, stepsRemaining);
     }
+#endif
 }
 
 template <int FIELD, bool FAST>

@@ -106,6 +106,11 @@ void launchPlaneBuild(ilb_ctx* ctx, const PlaneBuildParams& B) {
     ctx->launches++;
 }
 
+// the slice table as floorBiased() indexes it: entry (ILB_FLOOR_BIAS + v) of the returned pointer is entry v of the table
+const float4* biasedTable(const float4* vtab) {
+    return reinterpret_cast<const float4*>(reinterpret_cast<uintptr_t>(vtab) - (uintptr_t)ILB_FLOOR_BIAS * sizeof(float4));
+}
+
 bool sameKey(const ilb_df_planes& p, const DFGeometry& g) {
     return p.key[0] == g.sliceSizeX && p.key[1] == g.sliceSizeY && p.key[2] == g.texelSizeX && p.key[3] == g.texelSizeY &&
            p.key[4] == g.ex && p.key[5] == g.ey && p.key[6] == g.maxValidZ && p.key[7] == g.zToSlice &&
@@ -126,7 +131,7 @@ void ilb_planes_release(ilb_df* df) {
 // when the uniforms do not describe a regular column x row atlas, when an index could leave the halo, or when the
 // allocation does not fit.  `columns` / `rows` are TextureSliceCount.xy.
 int ilb_planes_attach(ilb_ctx* ctx, ilb_df* df, const ilb_df_uniforms& u, DFGeometry* g) {
-    g->planes = nullptr; g->vtab = nullptr; g->pitch = 0;
+    g->planes = nullptr; g->vtab = nullptr; g->vtabBiased = nullptr; g->pitch = 0;
     if (!df || !g->tex) return ILB_OK;
     if (const char* e = getenv("ILB_NO_PLANES"))  // read per call: the parity tests flip it to compare both samplers
         if (e[0] != '0') return ILB_OK;
@@ -134,7 +139,7 @@ int ilb_planes_attach(ilb_ctx* ctx, ilb_df* df, const ilb_df_uniforms& u, DFGeom
     for (ilb_df_planes& p : df->planes)
         if (sameKey(p, *g)) {
             if (p.version == df->version) {
-                g->planes = p.planes; g->vtab = p.vtab; g->pitch = p.pitch;
+                g->planes = p.planes; g->vtab = p.vtab; g->vtabBiased = biasedTable(p.vtab); g->pitch = p.pitch;
                 return ILB_OK;
             }
             stale = &p;  // the atlas was rewritten in place: same geometry, same allocation, new contents
@@ -172,9 +177,12 @@ int ilb_planes_attach(ilb_ctx* ctx, ilb_df* df, const ilb_df_uniforms& u, DFGeom
         if (lx0 < -HALO || lx1 > sw + HALO - 1 || ly0 < -HALO || ly1 + 1 > sh + HALO - 1) return ILB_OK;
         B.col[v] = col; B.row[v] = row;
         const int base = v * pw * ph + (HALO - row * sh) * pw + (HALO - col * sw);
-        float basef;
+        // .w: the same base for indices that still carry the bias of floorBiased() in both coordinates (ilb_device.cuh), modulo 2^32
+        const unsigned biased = (unsigned)base - (unsigned)ILB_FLOOR_BIAS * (unsigned)(pw + 1);
+        float basef, biasedf;
         memcpy(&basef, &base, sizeof(float));
-        vtab[(size_t)v] = make_float4(cu, rv, basef, 0.0f);
+        memcpy(&biasedf, &biased, sizeof(float));
+        vtab[(size_t)v] = make_float4(cu, rv, basef, biasedf);
     }
 
     if (stale && stale->nv == nv && stale->sw == sw && stale->sh == sh) {
@@ -183,7 +191,7 @@ int ilb_planes_attach(ilb_ctx* ctx, ilb_df* df, const ilb_df_uniforms& u, DFGeom
         launchPlaneBuild(ctx, B);
         ILB_CUDA(ctx, cudaGetLastError());
         stale->version = df->version;
-        g->planes = stale->planes; g->vtab = stale->vtab; g->pitch = stale->pitch;
+        g->planes = stale->planes; g->vtab = stale->vtab; g->vtabBiased = biasedTable(stale->vtab); g->pitch = stale->pitch;
         return ILB_OK;
     }
     ilb_df_planes P;
@@ -221,6 +229,6 @@ int ilb_planes_attach(ilb_ctx* ctx, ilb_df* df, const ilb_df_uniforms& u, DFGeom
         df->planes.erase(df->planes.begin());
     }
     df->planes.push_back(P);
-    g->planes = P.planes; g->vtab = P.vtab; g->pitch = P.pitch;
+    g->planes = P.planes; g->vtab = P.vtab; g->vtabBiased = biasedTable(P.vtab); g->pitch = P.pitch;
     return ILB_OK;
 }
