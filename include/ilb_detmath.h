@@ -11,8 +11,9 @@
  * 7.7e-8 against float64 libm); acos from Abramowitz & Stegun 4.4.46: absolute error below 5e-7 on [-1, 1] (measured
  * 4.3e-7, i.e. 1.8 ulp of pi).  tests/test_detmath.py asserts these bounds and, on the GPU, that the device build
  * returns the same bits as the host build.  Arguments must satisfy |x| < 1.6e9 (the octant index is an int).  Every
- * operation is an individually rounded IEEE fp32 add / multiply / sqrt through the DM_* macros, so the CPU build
- * (-ffp-contract=off) and the GPU build (__fadd_rn / __fmul_rn / __fsqrt_rn: never fused) agree bit for bit.
+ * operation is an individually rounded IEEE fp32 add / multiply / sqrt -- or, in the arc-cosine polynomial, an explicit
+ * fused multiply-add -- through the DM_* macros, so the CPU build (-ffp-contract=off: nothing is fused behind the
+ * source's back) and the GPU build (__fadd_rn / __fmul_rn / __fsqrt_rn / __fmaf_rn) agree bit for bit.
  *
  * Usage: define DM_FN (function qualifiers) and optionally DM_ADD / DM_MUL / DM_SQRT before including.
  */
@@ -28,6 +29,10 @@
 #define DM_SQRT(a) sqrtf(a)
 #endif
 #define DM_SUB(a, b) DM_ADD((a), -(b))
+/* the fused multiply-add of IEEE 754-2008 (one rounding): fmaf() on the host, __fmaf_rn on the device -- the same bits */
+#ifndef DM_FMA
+#define DM_FMA(a, b, c) __builtin_fmaf((a), (b), (c)) /* gcc / clang: no header, so no ::abs / ::fmod leak into the includer */
+#endif
 
 #define DM_FOPI 1.27323954473516f /* 4/pi */
 #define DM_DP1 0.78515625f
@@ -97,14 +102,14 @@ DM_FN void dm_sincosf(float x, float* s, float* c) {
 
 /* acos: Abramowitz & Stegun 4.4.46, acos(x) = sqrt(1 - x) * P7(x) on [0, 1] (|error| <= 2e-8 before rounding),
  * reflected for x < 0.  Branch-free apart from the final select; |x| > 1 gives sqrt(negative) = NaN like acos(). */
-DM_FN float dm_acos_poly(float x) { /* P7(|x|) */
-    float p = DM_ADD(DM_MUL(-0.0012624911f, x), 0.0066700901f);
-    p = DM_ADD(DM_MUL(p, x), -0.0170881256f);
-    p = DM_ADD(DM_MUL(p, x), 0.0308918810f);
-    p = DM_ADD(DM_MUL(p, x), -0.0501743046f);
-    p = DM_ADD(DM_MUL(p, x), 0.0889789874f);
-    p = DM_ADD(DM_MUL(p, x), -0.2145988016f);
-    return DM_ADD(DM_MUL(p, x), 1.5707963050f);
+DM_FN float dm_acos_poly(float x) { /* P7(|x|), Horner's rule in fused multiply-adds: 7 operations, 7 roundings */
+    float p = DM_FMA(-0.0012624911f, x, 0.0066700901f);
+    p = DM_FMA(p, x, -0.0170881256f);
+    p = DM_FMA(p, x, 0.0308918810f);
+    p = DM_FMA(p, x, -0.0501743046f);
+    p = DM_FMA(p, x, 0.0889789874f);
+    p = DM_FMA(p, x, -0.2145988016f);
+    return DM_FMA(p, x, 1.5707963050f);
 }
 /* s = sqrt(1 - |xx|), supplied by the caller (the kernels have a cheaper correctly rounded sqrt for in-range operands) */
 DM_FN float dm_acos_finish(float xx, float s) {

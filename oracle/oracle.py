@@ -24,7 +24,7 @@ P = C.c_void_p
 
 def build(force: bool = False) -> Path:
     srcs = [HERE / n for n in ("oracle_lighting.cpp", "oracle_particles.cpp", "oracle_inputs.cpp", "oracle_resolve.cpp", "hlsl.hpp", "oracle.h",
-                               "Makefile")] + [HERE.parent / "include" / "illuminant_b200.h"]
+                               "Makefile")] + [HERE.parent / "include" / "illuminant_b200.h", HERE.parent / "include" / "ilb_detmath.h"]
     if force or not LIB.exists() or any(s.stat().st_mtime > LIB.stat().st_mtime for s in srcs):
         res = subprocess.run(["make", "-C", str(HERE), "-B", "liboracle.so"], capture_output=True, text=True)
         if res.returncode != 0:
