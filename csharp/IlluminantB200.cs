@@ -23,7 +23,7 @@ namespace Squared.Illuminant.Native {
 
     [StructLayout(LayoutKind.Sequential)]
     public struct IlbLightBatch {                       // ilb_light_batch: one LightTypeRenderState draw (LightingRenderer.cs:1149-1166)
-        public int LightType, FirstVertex, VertexCount, Reserved;
+        public int LightType, FirstVertex, VertexCount, RampTexture;   // RampTexture: 0 or an ilb_ramp_texture_create id
         public IlbDFUniforms DF;
     }
 
@@ -244,6 +244,25 @@ namespace Squared.Illuminant.Native {
         }
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_resolve_lighting_placed (IntPtr ctx, ref IlbResolve parameters, ref IlbResolvePlacement placement, void* lightmapOrNull, void* albedoOrNull, void* target);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_resolve_lighting_placed_device (IntPtr ctx, ref IlbResolve parameters, ref IlbResolvePlacement placement, void* dLightmap, void* dAlbedoOrNull, void* dTarget);
+
+        // N3: HDRConfiguration.Dithering and the LUT-blended resolve (LUTResolve.fx; IlluminantMaterials.SetLUTBlending)
+        [StructLayout(LayoutKind.Sequential, Pack = 4)]
+        public struct IlbDithering {              // ilb_dithering <- Squared.Render.DitheringSettings (FrameIndex = DeviceManager.FrameIndex)
+            public float Strength, Unit, FrameIndex, BandSize, RangeMin, RangeMax;
+        }
+        [StructLayout(LayoutKind.Sequential, Pack = 4)]
+        public struct IlbLutBlending {            // ilb_lut_blending <- LUTBlendingConfiguration + ColorLUT.Resolution / RowCount
+            public int DarkResolution, BrightResolution, DarkRowCount, BrightRowCount;
+            public float DarkLevel, NeutralBandSize, BrightLevel, PerChannel, LUTOnly;
+            public Vector4 LUTOffsets;
+            public float Reserved;
+        }
+        // LightSource.RampTexture -> SphereLightWithDistanceRamp (a 1x1 texture means "no ramp", LightingRenderer.cs:819-827: pass 0)
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_ramp_texture_create (IntPtr ctx, int width, int height, int format, void* texels, out int id);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_ramp_texture_destroy (IntPtr ctx, int id);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_set_dithering (IntPtr ctx, IlbDithering* settingsOrNull);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_resolve_lighting_lut (IntPtr ctx, ref IlbResolve parameters, ref IlbLutBlending lut, void* darkLut, void* brightLut, void* lightmapOrNull, void* albedo, void* output);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_resolve_lighting_lut_device (IntPtr ctx, ref IlbResolve parameters, ref IlbLutBlending lut, void* dDarkLut, void* dBrightLut, void* dLightmap, void* dAlbedo, void* dOutput);
 
         /// <summary>Maps an ilb_status to the exception type the reference throws at the same place.</summary>
         public static void Check (IntPtr ctx, int status) {

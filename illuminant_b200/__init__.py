@@ -7,8 +7,8 @@ from .distance_field import (DistanceField, DynamicDistanceField, LightObstructi
                              SimpleHeightVolume)
 from .lighting import (DirectionalLightSource, LightingEnvironment, LightingRenderer, LightProbe, LightSourceRampMode,
                        LineLightSource, ParticleLightSource, RendererConfiguration, ShadowFilter, SphereLightSource, encode_gbuffer)
-from .hdr import (DitheringSettings, GammaCompressionConfiguration, HDRConfiguration, HDRMode, Histogram, RenderedLighting,
-                  ToneMappingConfiguration, pack_resolve)
+from .hdr import (ColorLUT, DitheringSettings, GammaCompressionConfiguration, HDRConfiguration, HDRMode, Histogram, LUTBlendingConfiguration,
+                  RenderedLighting, ToneMappingConfiguration, pack_resolve)
 from .particles import (FMA, AreaType, Attractor, AttractorType, Bezier4V, BezierF, FeedbackSpawner, Formula, FormulaType, Gravity, MatrixMultiply,
                         Noise, ParticleAppearance, ParticleCollision, ParticleColorLifeRamp, ParticleEngine, ParticleEngineConfiguration, ParticleRenderParameters, ParticleSystem,
                         ParticleSystemConfiguration, PatternSpawner, Spawner, TransformArea)

@@ -56,7 +56,7 @@ class LightVertex(C.Structure):
 
 
 class LightBatch(C.Structure):
-    _fields_ = [("light_type", C.c_int32), ("first_vertex", C.c_int32), ("vertex_count", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("light_type", C.c_int32), ("first_vertex", C.c_int32), ("vertex_count", C.c_int32), ("ramp_texture", C.c_int32),
                 ("df", DFUniforms)]
 
 
@@ -166,6 +166,17 @@ class ResolvePlacement(C.Structure):  # ilb_resolve_placement
                 ("AlbedoRegion", C.c_float * 4), ("albedo_width", C.c_int32), ("albedo_height", C.c_int32)]
 
 
+class Dithering(C.Structure):  # ilb_dithering
+    _fields_ = [("Strength", C.c_float), ("Unit", C.c_float), ("FrameIndex", C.c_float), ("BandSize", C.c_float), ("RangeMin", C.c_float),
+                ("RangeMax", C.c_float)]
+
+
+class LutBlending(C.Structure):  # ilb_lut_blending
+    _fields_ = [("dark_resolution", C.c_int32), ("bright_resolution", C.c_int32), ("dark_row_count", C.c_int32), ("bright_row_count", C.c_int32),
+                ("DarkLevel", C.c_float), ("NeutralBandSize", C.c_float), ("BrightLevel", C.c_float), ("PerChannel", C.c_float),
+                ("LUTOnly", C.c_float), ("LUTOffsets", C.c_float * 4), ("reserved", C.c_float)]
+
+
 class HeightVolumeStruct(C.Structure):  # ilb_height_volume
     _fields_ = [("first_edge", C.c_int32), ("edge_count", C.c_int32), ("z_base", C.c_float), ("height", C.c_float), ("bounds", C.c_float * 4)]
 
@@ -216,6 +227,11 @@ _PROTOTYPES = [
     ("ilb_resolve_lighting_device", C.c_int, [P, C.POINTER(Resolve), P, P, P]),
     ("ilb_resolve_lighting_placed", C.c_int, [P, C.POINTER(Resolve), C.POINTER(ResolvePlacement), P, P, P]),
     ("ilb_resolve_lighting_placed_device", C.c_int, [P, C.POINTER(Resolve), C.POINTER(ResolvePlacement), P, P, P]),
+    ("ilb_ramp_texture_create", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, C.POINTER(C.c_int32)]),
+    ("ilb_ramp_texture_destroy", C.c_int, [P, C.c_int32]),
+    ("ilb_set_dithering", C.c_int, [P, C.POINTER(Dithering)]),
+    ("ilb_resolve_lighting_lut", C.c_int, [P, C.POINTER(Resolve), C.POINTER(LutBlending), P, P, P, P, P]),
+    ("ilb_resolve_lighting_lut_device", C.c_int, [P, C.POINTER(Resolve), C.POINTER(LutBlending), P, P, P, P, P]),
     ("ilb_compute_luminance", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, C.c_int, P]),
     ("ilb_particles_create", C.c_int, [P, C.c_int, C.c_int, C.POINTER(P)]),
     ("ilb_particles_destroy", None, [P]),

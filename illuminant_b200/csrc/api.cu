@@ -182,6 +182,9 @@ void ilb_destroy(ilb_ctx* ctx) {
     if (ctx->d_resolve_in) cudaFree(ctx->d_resolve_in);
     if (ctx->d_resolve_albedo) cudaFree(ctx->d_resolve_albedo);
     if (ctx->d_resolve_out) cudaFree(ctx->d_resolve_out);
+    if (ctx->d_resolve_lut) cudaFree(ctx->d_resolve_lut);
+    if (ctx->d_ramp_table) cudaFree(ctx->d_ramp_table);
+    for (ilb_ctx::RampTexture& t : ctx->ramps) if (t.texels) cudaFree(t.texels);
     for (int i = 0; i < 2; i++) if (ctx->d_luminance[i]) cudaFree(ctx->d_luminance[i]);
     if (ctx->d_plight_scratch) cudaFree(ctx->d_plight_scratch);
     if (ctx->copy_in) {
@@ -488,6 +491,95 @@ int ilb_resolve_lighting(ilb_ctx* ctx, const ilb_resolve* params, const void* li
     rc = ilb_reserve(ctx, &ctx->d_resolve_out, &ctx->d_resolve_out_capacity, obytes, false);
     if (rc) return rc;
     rc = ilb_resolve_launch(ctx, params, d_lm, d_al, ctx->d_resolve_out);
+    if (rc) return rc;
+    ILB_CUDA(ctx, cudaMemcpyAsync(output, ctx->d_resolve_out, obytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ILB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- ramp textures
+int ilb_ramp_texture_create(ilb_ctx* ctx, int width, int height, int format, const void* texels, int32_t* out_id) {
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
+    if (!texels || !out_id || width <= 0 || height <= 0 || (size_t)width * (size_t)height > ((size_t)1 << 26))
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad ramp texture %dx%d", width, height);
+    if (format != ILB_FORMAT_RGBA8 && format != ILB_FORMAT_FLOAT4) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "ramp texture format must be RGBA8 or FLOAT4");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)width * (size_t)height;
+    std::vector<float> decoded(4 * n);   // the kernel samples float4 texels; UNORM8 -> float is c / 255
+    if (format == ILB_FORMAT_FLOAT4) memcpy(decoded.data(), texels, sizeof(float) * 4 * n);
+    else for (size_t i = 0; i < 4 * n; i++) decoded[i] = (float)reinterpret_cast<const unsigned char*>(texels)[i] / 255.0f;
+    ilb_ctx::RampTexture t;
+    t.w = width; t.h = height;
+    ILB_CUDA(ctx, cudaMalloc(&t.texels, sizeof(float4) * n));
+    const cudaError_t e = cudaMemcpy(t.texels, decoded.data(), sizeof(float4) * n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(t.texels); return ilb_cuda_fail(ctx, e, "upload a ramp texture"); }
+    size_t slot = ctx->ramps.size();
+    for (size_t i = 0; i < ctx->ramps.size(); i++) if (!ctx->ramps[i].texels) { slot = i; break; }   // reuse a destroyed id
+    if (slot == ctx->ramps.size()) ctx->ramps.push_back(t); else ctx->ramps[slot] = t;
+    ctx->ramp_table_dirty = true;
+    *out_id = (int32_t)slot + 1;
+    return ILB_OK;
+}
+
+int ilb_ramp_texture_destroy(ilb_ctx* ctx, int32_t id) {
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
+    if (id < 1 || (size_t)id > ctx->ramps.size() || !ctx->ramps[(size_t)id - 1].texels) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "unknown ramp texture %d", id);
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // a frame in flight may still sample it
+    cudaFree(ctx->ramps[(size_t)id - 1].texels);
+    ctx->ramps[(size_t)id - 1] = ilb_ctx::RampTexture();
+    ctx->ramp_table_dirty = true;
+    return ILB_OK;
+}
+
+int ilb_set_dithering(ilb_ctx* ctx, const ilb_dithering* settings) {
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
+    const ilb_dithering defaults = {0.0f, 255.0f, 0.0f, 1.0f, 0.0f, 1.0f};
+    ctx->dither = settings ? *settings : defaults;
+    if (!(ctx->dither.Unit > 0.0f) && ctx->dither.Unit != 0.0f) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "Dithering.Unit must be positive");
+    return ILB_OK;
+}
+
+int ilb_resolve_lighting_lut_device(ilb_ctx* ctx, const ilb_resolve* params, const ilb_lut_blending* lut, const void* d_dark_lut,
+                                    const void* d_bright_lut, const void* d_lightmap, const void* d_albedo, void* d_output) {
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
+    if (!params || !lut || !d_dark_lut || !d_bright_lut || !d_lightmap || !d_output) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!d_albedo) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "LUT blending is not compatible with this type of lighting resolve (no albedo)");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ilb_resolve_lut_launch(ctx, params, lut, d_dark_lut, d_bright_lut, d_lightmap, d_albedo, d_output);
+}
+
+int ilb_resolve_lighting_lut(ilb_ctx* ctx, const ilb_resolve* params, const ilb_lut_blending* lut, const void* dark_lut, const void* bright_lut,
+                             const void* lightmap, const void* albedo, void* output) {
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
+    if (!params || !lut || !dark_lut || !bright_lut || !output) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!albedo) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "LUT blending is not compatible with this type of lighting resolve (no albedo)");
+    if (lut->dark_resolution < 2 || lut->bright_resolution < 2 || lut->dark_row_count < 1 || lut->bright_row_count < 1 ||
+        lut->dark_resolution > 256 || lut->bright_resolution > 256 || lut->dark_row_count > 256 || lut->bright_row_count > 256)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad LUT geometry");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void* d_lm = nullptr;
+    int rc = resolve_source(ctx, params->width, params->height, params->lightmap_format, lightmap, &d_lm);
+    if (rc) return rc;
+    if (params->albedo_format != ILB_FORMAT_FLOAT4 && params->albedo_format != ILB_FORMAT_RGBA8)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "albedo format must be RGBA8 or FLOAT4");
+    if (params->output_format != ILB_FORMAT_FLOAT4 && params->output_format != ILB_FORMAT_RGBA8)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "output format must be RGBA8 or FLOAT4");
+    const size_t n = (size_t)params->width * (size_t)params->height;
+    const size_t abytes = ilb_format_bytes(params->albedo_format) * n, obytes = ilb_format_bytes(params->output_format) * n;
+    auto lutBytes = [](int res, int rows) { return (size_t)4 * (size_t)res * res * (size_t)res * rows; };
+    const size_t dbytes = (lutBytes(lut->dark_resolution, lut->dark_row_count) + 255) & ~(size_t)255, bbytes = lutBytes(lut->bright_resolution, lut->bright_row_count);
+    rc = ilb_reserve(ctx, &ctx->d_resolve_albedo, &ctx->d_resolve_albedo_capacity, abytes, false);
+    if (rc) return rc;
+    rc = ilb_reserve(ctx, &ctx->d_resolve_out, &ctx->d_resolve_out_capacity, obytes, false);
+    if (rc) return rc;
+    rc = ilb_reserve(ctx, &ctx->d_resolve_lut, &ctx->d_resolve_lut_capacity, dbytes + bbytes, false);
+    if (rc) return rc;
+    char* d_lut = reinterpret_cast<char*>(ctx->d_resolve_lut);
+    ILB_CUDA(ctx, cudaMemcpyAsync(ctx->d_resolve_albedo, albedo, abytes, cudaMemcpyHostToDevice, ctx->stream));
+    ILB_CUDA(ctx, cudaMemcpyAsync(d_lut, dark_lut, lutBytes(lut->dark_resolution, lut->dark_row_count), cudaMemcpyHostToDevice, ctx->stream));
+    ILB_CUDA(ctx, cudaMemcpyAsync(d_lut + dbytes, bright_lut, bbytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = ilb_resolve_lut_launch(ctx, params, lut, d_lut, d_lut + dbytes, d_lm, ctx->d_resolve_albedo, ctx->d_resolve_out);
     if (rc) return rc;
     ILB_CUDA(ctx, cudaMemcpyAsync(output, ctx->d_resolve_out, obytes, cudaMemcpyDeviceToHost, ctx->stream));
     ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

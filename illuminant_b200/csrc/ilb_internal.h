@@ -44,6 +44,12 @@ struct ilb_ctx {
     void* d_resolve_in = nullptr;   size_t d_resolve_in_capacity = 0;
     void* d_resolve_albedo = nullptr; size_t d_resolve_albedo_capacity = 0;
     void* d_resolve_out = nullptr;  size_t d_resolve_out_capacity = 0;
+    void* d_resolve_lut = nullptr;  size_t d_resolve_lut_capacity = 0;   // dark + bright ColorLUT texels of a host-to-host LUT resolve
+    // LightSource.RampTexture: id - 1 indexes `ramps`; `d_ramp_table` is the device copy of {texels, w, h} records (lighting.cu)
+    struct RampTexture { float4* texels = nullptr; int w = 0, h = 0; };
+    std::vector<RampTexture> ramps;
+    void* d_ramp_table = nullptr; size_t d_ramp_table_capacity = 0; bool ramp_table_dirty = true;
+    ilb_dithering dither = {0.0f, 255.0f, 0.0f, 1.0f, 0.0f, 1.0f};       // ilb_set_dithering; the handler's default
     void* d_luminance[2] = {nullptr, nullptr}; size_t d_luminance_capacity[2] = {0, 0};
     void* d_accum = nullptr;     // fp32 sums of the line-light pass (handed to / combined with the sphere + directional pass)
     size_t d_accum_capacity = 0;
@@ -145,6 +151,8 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
 int ilb_resolve_launch(ilb_ctx* ctx, const ilb_resolve* params, const void* d_lightmap, const void* d_albedo, void* d_output);
 int ilb_resolve_placed_launch(ilb_ctx* ctx, const ilb_resolve* params, const ilb_resolve_placement* placement, const void* d_lightmap,
                               const void* d_albedo, void* d_target);
+int ilb_resolve_lut_launch(ilb_ctx* ctx, const ilb_resolve* params, const ilb_lut_blending* lut, const void* d_dark, const void* d_bright,
+                           const void* d_lightmap, const void* d_albedo, void* d_output);
 int ilb_luminance_launch(ilb_ctx* ctx, int width, int height, int lightmap_format, const void* d_lightmap, int level,
                          float* out_host);
 size_t ilb_format_bytes(int format);

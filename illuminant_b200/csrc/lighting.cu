@@ -34,6 +34,8 @@ namespace {
 constexpr int TILE_W = 16, TILE_H = ILB_TILE_H, TILE_THREADS = TILE_W * TILE_H, TILE_WARPS = TILE_THREADS / 32;
 constexpr int MAX_OUTPUTS = 8;
 constexpr int ILB_LIGHT_PARTICLE_BIT = 8;  // DLight::type of a particle light (a bit for the TYPES masks; the public id, ILB_LIGHT_PARTICLE, is 3)
+constexpr int ILB_LIGHT_RAMP_BIT = 16;     // DLight::type of a sphere light drawn with a ramp texture = ILB_LIGHT_SPHERE | ILB_LIGHT_RAMP_BIT
+constexpr int ILB_LIGHT_TYPE_MASK = 15;
 
 // One light, flattened on the host from (batch, LightVertex): the LightVertex fields (Vertices.cs:10-39) plus
 // the batch's quality uniforms and the rasterised coverage of its quad.
@@ -59,6 +61,9 @@ struct __align__(16) DLine {
     float4 ab;      // (P1 - P0).xyz, dot(ab, ab)
 };
 
+// One LightSource.RampTexture as the kernel samples it (float4 texels; RampCommon.fxh:5-12: LINEAR, U CLAMP, V WRAP)
+struct RampTex { const float4* texels; int w, h, pad; };
+
 struct LightingParams {
     DFGeometry df;
     float4 envZAndScale, envZToY, gbTexelAndMisc, clear;
@@ -67,6 +72,7 @@ struct LightingParams {
     int gw, gh, gfmt;
     const DLight* lights;
     const DLine* lines;   // per-light line constants (valid for line lights)
+    const struct RampTex* ramps;  // ramp textures (SphereLightWithDistanceRamp); DLight::evenMore.y = 1-based index, 0 = none
     int nlights;
     int width, height, row_begin, row_end;
     int out_format, stencil;
@@ -285,7 +291,7 @@ ILB_DEV float computeAO(const DFGeometry& g, bool hasField, f3 p, f3 n, float ao
 // SphereLightPixelCore (SphereLightCore.fxh:58-158); returns false on discard
 template <int FIELD, bool FAST>
 ILB_DEV bool sphereCore(const DFGeometry& g, const DLight& L, float lightOcclusion, f3 p, f3 n, f3 center, float4 props,
-                        float4 more, float& opacity, Guard& bad) {
+                        float4 more, float& opacity, float& preTrace, Guard& bad) {
     const float distanceOpacity = sphereLightOpacity<FAST>(lightOcclusion, p, n, center, props, more.z, L.rcpRamp, bad);
     const bool visible = (distanceOpacity > 0.0f) && (p.x > -9999.0f);
     if (!visible) return false;
@@ -295,7 +301,26 @@ ILB_DEV bool sphereCore(const DFGeometry& g, const DLight& L, float lightOcclusi
     const bool traceShadows = (props.w != 0.0f) && (preTraceOpacity >= (0.75f / 255.0f));
     const float coneOpacity = coneTrace<FIELD, FAST>(g, L, center, props.x, props.y, 1.0f, xadd3(p, xscale3(n, 1.6f)), traceShadows, bad);
     opacity = preTraceOpacity * coneOpacity;
+    preTrace = preTraceOpacity;  // SphereLightPixelCoreWithRamp hands it to the ramp lookup (coneOpacity = opacity / preTrace is not exact: the caller keeps it)
     return true;
+}
+
+// SphereLightPixelEpilogueWithRamp (SphereLightCore.fxh:99-119): RampTexture(preTraceOpacity, (angle + offset) * rate).rgb.
+// Out of line: ramp-textured batches are rare and must not cost the sphere / directional pass registers.
+__device__ __noinline__ float4 rampLookup(const RampTex* ramps, int id, float preTraceOpacity, float dx, float dy, float offset, float rate) {
+    const RampTex t = ramps[id - 1];
+    const float angle = atan2f(dy, dx);
+    const float u = preTraceOpacity, v = (angle + offset) * rate;
+    const float x = u * (float)t.w - 0.5f, y = v * (float)t.h - 0.5f;
+    const float x0f = floorf(x), y0f = floorf(y);
+    const float fx = x - x0f, fy = y - y0f;
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const int xa = min(max(x0, 0), t.w - 1), xb = min(max(x0 + 1, 0), t.w - 1);          // U clamps
+    const int ya = ((y0 % t.h) + t.h) % t.h, yb = (((y0 + 1) % t.h) + t.h) % t.h;        // V wraps
+    const float4 t00 = __ldg(t.texels + (size_t)ya * t.w + xa), t10 = __ldg(t.texels + (size_t)ya * t.w + xb);
+    const float4 t01 = __ldg(t.texels + (size_t)yb * t.w + xa), t11 = __ldg(t.texels + (size_t)yb * t.w + xb);
+    const f4 top = lerp4(mk4(t00), mk4(t10), fx), bottom = lerp4(mk4(t01), mk4(t11), fx);
+    return to_float4(lerp4(top, bottom, fy));
 }
 
 // DirectionalLightPixelCore (DirectionalLight.fx:52-93, useOpacityRamp = false)
@@ -488,7 +513,7 @@ ILB_DEV Pixel decodePixel(const LightingParams& P, int px, int py) {
 //           (SphereLightCore.fxh:13-56): covX = X(0), X(1/7), X(6/7), X(1); covY likewise (2.5D shift applied to w<0.5)
 //   directional / line: one rectangle covX = (x0, x1), covY = (y0, y1) (DirectionalLight.fx:19-37, LineLightCore.fxh:122-173)
 ILB_DEV bool coverage(const DLight& L, float wx, float wy) {
-    if (L.type == ILB_LIGHT_SPHERE) {
+    if ((L.type & ILB_LIGHT_TYPE_MASK) == ILB_LIGHT_SPHERE) {
         const float4 X = L.covX, Y = L.covY;
         const bool a = (wx >= X.y) && (wx <= X.z) && (wy >= Y.x) && (wy <= Y.w);
         const bool b = (wx >= X.z) && (wx <= X.w) && (wy >= Y.y) && (wy <= Y.z);
@@ -521,17 +546,34 @@ ILB_DEV DLine loadLine(const DLine* lines, int i) {
 // One light at one pixel; returns false when the reference fragment would be discarded.
 // TYPES: bit mask of ilb_light_type values this instantiation can meet (other branches are compiled out)
 template <int FIELD, bool FAST, int TYPES>
-ILB_DEV bool shadeLight(const DFGeometry& df, float lightOcclusion, const DLight& L, const DLine* lines, int lightIndex, const Pixel& px,
-                        f3& rgb, Guard& bad) {
+ILB_DEV bool shadeLight(const DFGeometry& df, float lightOcclusion, const DLight& L, const DLight* lights, const DLine* lines, const RampTex* ramps,
+                        int lightIndex, const Pixel& px, f3& rgb, Guard& bad) {
     const float es = px.enableShadows ? 1.0f : 0.0f;
-    if ((TYPES & ILB_LIGHT_SPHERE) && (L.type == ILB_LIGHT_SPHERE || L.type == ILB_LIGHT_PARTICLE_BIT)) {  // SphereLightPixelShader SphereLight.fx:7-46, ParticleLightPixelShader ParticleLight.fx:84-118
+    if ((TYPES & ILB_LIGHT_SPHERE) && ((L.type & ILB_LIGHT_TYPE_MASK) == ILB_LIGHT_SPHERE || L.type == ILB_LIGHT_PARTICLE_BIT)) {  // SphereLightPixelShader SphereLight.fx:7-46, ParticleLightPixelShader ParticleLight.fx:84-118
         if (px.fullbright || shadowFilterRejects(L.evenMore.x, px.enableShadows)) return false;
         float4 props = L.props;
         props.w *= es;
         const f3 center = mk3(L.pos1.x, L.pos1.y, L.pos1.z);
-        float opacity;
-        if (!sphereCore<FIELD, FAST>(df, L, lightOcclusion, px.pos, px.normal, center, props, L.more, opacity, bad)) return false;
+        float opacity, preTrace;
+        if (!sphereCore<FIELD, FAST>(df, L, lightOcclusion, px.pos, px.normal, center, props, L.more, opacity, preTrace, bad)) return false;
         const float4 color = L.color1, spec = L.color2;
+        if (L.type & ILB_LIGHT_RAMP_BIT) {  // uniform per light: SphereLightWithDistanceRampPixelShader (SphereLight.fx:48-87)
+            // opacity3 = RampTexture(preTraceOpacity, angle).rgb * coneOpacity, coneOpacity = opacity / preTraceOpacity up to rounding;
+            // a pixel that was not discarded has preTraceOpacity > 0 (distanceOpacity > 0 and the AO factor >= 1 - AO opacity).
+            // The ramp's index, offset and rate are re-read from the light record (L1-resident) so that they do not occupy
+            // registers across the cone trace of every ordinary sphere light.
+            const float4 em = __ldg(&lights[lightIndex].evenMore);
+            const float4 r = rampLookup(ramps, (int)em.y, preTrace, px.pos.x - center.x, px.pos.y - center.y, em.z, em.w);
+            const float cone = (preTrace > 0.0f) ? opacity / preTrace : 0.0f;
+            f3 o3 = mk3(r.x, r.y, r.z) * cone;
+            rgb = mk3(color.x, color.y, color.z) * color.w * o3;
+            if (any3(mk3(spec.x, spec.y, spec.z))) {
+                const f3 lightDirection = px.pos - center;
+                const f3 h = normalize3(normalize3(px.camera - px.pos) - lightDirection);
+                rgb = rgb + (mk3(spec.x, spec.y, spec.z) * powf(saturatef(dot3(h, px.normal)), spec.w) * o3);
+            }
+            return true;
+        }
         rgb = (mk3(color.x, color.y, color.z) * color.w * opacity);
         if (any3(mk3(spec.x, spec.y, spec.z)) || L.type == ILB_LIGHT_PARTICLE_BIT) {  // CalcSphereLightSpecularity LightCommon.fxh:212-222
             const f3 lightDirection = px.pos - center;
@@ -569,7 +611,7 @@ ILB_DEV bool shadeLight(const DFGeometry& df, float lightOcclusion, const DLight
 // line: it is never on the hot path and must not cost the hot path registers.  Returns rgb, w = 1 when lit.
 template <int FIELD, int TYPES>
 __device__ __noinline__ float4 shadeLightExact(const DFGeometry* df, float lightOcclusion, const DLight* lights, const DLine* lines,
-                                               int lightIndex, float4 posShadows, float4 normalFullbright, float4 camera) {
+                                               const RampTex* ramps, int lightIndex, float4 posShadows, float4 normalFullbright, float4 camera) {
     Pixel px;
     px.pos = mk3(posShadows.x, posShadows.y, posShadows.z);
     px.normal = mk3(normalFullbright.x, normalFullbright.y, normalFullbright.z);
@@ -580,7 +622,7 @@ __device__ __noinline__ float4 shadeLightExact(const DFGeometry* df, float light
     const DLight L = loadLight(lights, lightIndex);
     f3 rgb = mk3(0.0f);
     Guard bad = guardInit();
-    const bool lit = shadeLight<FIELD, false, TYPES>(*df, lightOcclusion, L, lines, lightIndex, px, rgb, bad);
+    const bool lit = shadeLight<FIELD, false, TYPES>(*df, lightOcclusion, L, lights, lines, ramps, lightIndex, px, rgb, bad);
 #if ILB_BREAK_FALLBACK  // test hook: proves that a test reaches this path (tests/README: degenerate-geometry tests must fail with it)
     rgb.x += 1.0f;
 #endif
@@ -590,15 +632,15 @@ __device__ __noinline__ float4 shadeLightExact(const DFGeometry* df, float light
 // fast evaluation + fallback
 template <int FIELD, int TYPES>
 ILB_DEV bool shadeLightGuarded(const DFGeometry& df, float lightOcclusion, const DLight& L, const DLight* lights, const DLine* lines,
-                               int lightIndex, const Pixel& px, f3& rgb) {
+                               const RampTex* ramps, int lightIndex, const Pixel& px, f3& rgb) {
 #if ILB_NO_FAST_GUARD
     Guard bad = guardInit();
-    return shadeLight<FIELD, false, TYPES>(df, lightOcclusion, L, lines, lightIndex, px, rgb, bad);
+    return shadeLight<FIELD, false, TYPES>(df, lightOcclusion, L, lights, lines, ramps, lightIndex, px, rgb, bad);
 #else
     Guard bad = guardInit();
-    bool lit = shadeLight<FIELD, true, TYPES>(df, lightOcclusion, L, lines, lightIndex, px, rgb, bad);
+    bool lit = shadeLight<FIELD, true, TYPES>(df, lightOcclusion, L, lights, lines, ramps, lightIndex, px, rgb, bad);
     if (guardTripped(bad)) {
-        const float4 r = shadeLightExact<FIELD, TYPES>(&df, lightOcclusion, lights, lines, lightIndex,
+        const float4 r = shadeLightExact<FIELD, TYPES>(&df, lightOcclusion, lights, lines, ramps, lightIndex,
                                                 make_float4(px.pos.x, px.pos.y, px.pos.z, px.enableShadows ? 1.0f : 0.0f),
                                                 make_float4(px.normal.x, px.normal.y, px.normal.z, px.fullbright ? 1.0f : 0.0f),
                                                 make_float4(px.camera.x, px.camera.y, px.camera.z, 0.0f));
@@ -720,7 +762,7 @@ ILB_DEV void shadeTile(const LightingParams& P, unsigned tile, TileSmem& S) {
             const int4 r = __ldg(reinterpret_cast<const int4*>(&L->px0));
             const int type = __ldg(&L->type);
             keep = ((type & TYPES) != 0) && (r.x <= tx1) && (r.z >= tx0) && (r.y <= ty1) && (r.w >= ty0) && (bx0 <= bx1);
-            if ((TYPES & ILB_LIGHT_SPHERE) && keep && (type == ILB_LIGHT_SPHERE || type == ILB_LIGHT_PARTICLE_BIT)) {
+            if ((TYPES & ILB_LIGHT_SPHERE) && keep && ((type & ILB_LIGHT_TYPE_MASK) == ILB_LIGHT_SPHERE || type == ILB_LIGHT_PARTICLE_BIT)) {
                 // sphere lights reach radius + rampLength (radius + 1 in RampMode None): reject the tile when the
                 // closest point of its world AABB is farther (1 px of slack covers fp rounding)
                 const float4 c = __ldg(&L->pos1), pr = __ldg(&L->props), mo = __ldg(&L->more);
@@ -774,7 +816,7 @@ ILB_DEV void shadeTile(const LightingParams& P, unsigned tile, TileSmem& S) {
             const DLight L = loadLight(P.lights, lightIndex);
             if (shade && coverage(L, wx, wy)) {
                 f3 rgb;
-                if (shadeLightGuarded<FIELD, TYPES>(P.df, P.envZToY.z, L, P.lights, P.lines, lightIndex, pix, rgb)) {
+                if (shadeLightGuarded<FIELD, TYPES>(P.df, P.envZToY.z, L, P.lights, P.lines, P.ramps, lightIndex, pix, rgb)) {
                     // BlendState.Additive with PS alpha 1: rgb += src.rgb, a += 1 (LightingRenderer.cs:206)
                     accR += rgb.x; accG += rgb.y; accB += rgb.z; accA += 1.0f;
                 }
@@ -892,7 +934,8 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_accumulate_kernel(const _
                     lit = directionalCore<FIELD, false>(P.df, L, p, n, L.color2, props, more, core, bad);
                 } else {  // sphere, and line lights shaded as spheres at LightPosition1 (reference quirk, LineLightProbe.fx:4)
                     props.w *= ns.w;
-                    lit = sphereCore<FIELD, false>(P.df, L, P.lightOcclusion, p, n, mk3(L.pos1.x, L.pos1.y, L.pos1.z), props, more, core, bad);
+                    float preTrace;
+                    lit = sphereCore<FIELD, false>(P.df, L, P.lightOcclusion, p, n, mk3(L.pos1.x, L.pos1.y, L.pos1.z), props, more, core, preTrace, bad);
                 }
                 if (lit) {
                     const float opacity = ps.w * core;
@@ -930,7 +973,7 @@ inline float hlerp(float a, float b, float t) { return a + t * (b - a); }
 
 int flattenLights(ilb_ctx* ctx, const ilb_df* df, const ilb_lighting_frame* f, const ilb_light_batch* batches, int batch_count,
                   const ilb_light_vertex* verts, int vertex_count, std::vector<DLight>& out, std::vector<DLine>& lines,
-                  const ilb_df_uniforms** geometry) {
+                  const ilb_df_uniforms** geometry, bool allowRamps = true) {
     *geometry = nullptr;
     // correctly rounded reciprocal of a uniform divisor for udiv(); 0 selects udiv's IEEE division
     auto rcp = [](float y) { const float a = std::fabs(y); return (a >= 1.0e-30f && a <= 1.0e30f) ? 1.0f / y : 0.0f; };
@@ -944,6 +987,13 @@ int flattenLights(ilb_ctx* ctx, const ilb_df* df, const ilb_lighting_frame* f, c
             return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "light type %d is outside the hot-path scope (sphere=1, directional=2, line=4)", B.light_type);
         if (B.first_vertex < 0 || B.vertex_count < 0 || B.first_vertex + B.vertex_count > vertex_count)
             return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "batch %d vertex range [%d,+%d) outside [0,%d)", b, B.first_vertex, B.vertex_count, vertex_count);
+        if (B.ramp_texture != 0) {
+            if (B.light_type != ILB_LIGHT_SPHERE)
+                return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "batch %d: ramp textures are only supported on sphere lights (SphereLightWithDistanceRamp)", b);
+            if (B.ramp_texture < 0 || (size_t)B.ramp_texture > ctx->ramps.size() || !ctx->ramps[(size_t)B.ramp_texture - 1].texels)
+                return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "batch %d: unknown ramp texture %d", b, B.ramp_texture);
+            if (!allowRamps) return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "batch %d: ramp textures on light probes are outside the hot-path scope", b);
+        }
         const bool hasField = (df != nullptr) && (B.df.Extent.x > 0.0f);
         if (hasField) {
             if (*geometry) {
@@ -969,8 +1019,11 @@ int flattenLights(ilb_ctx* ctx, const ilb_df* df, const ilb_lighting_frame* f, c
             L.quality = make_float4(B.df.ConeAndMisc.x, B.df.ConeAndMisc.z, B.df.StepAndMisc2.x, B.df.Packed1.w);
             L.longStep = B.df.StepAndMisc2.z;
             L.hasField = hasField ? 1 : 0;
-            L.type = B.light_type;
+            L.type = B.light_type | (B.ramp_texture ? ILB_LIGHT_RAMP_BIT : 0);
             L.rcpRamp = rcp(v.LightProperties.y);
+            // EvenMoreLightProperties.y is always 0 on the host side (LightingRenderer.cs:1212-1214): the device record carries the
+            // batch's ramp texture there
+            L.evenMore.y = (float)B.ramp_texture;
             DLine D;
             memset(&D, 0, sizeof(D));
             if (B.light_type == ILB_LIGHT_LINE) {
@@ -1284,6 +1337,19 @@ int lightingPrepare(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const
         rc = ilb_planes_attach(ctx, df, *geometry, &P.df);
         if (rc) return rc;
     }
+    if (!ctx->ramps.empty()) {  // the ramp table: a few 16-byte records, re-uploaded when a texture was created or destroyed
+        const size_t bytes = sizeof(RampTex) * ctx->ramps.size();
+        rc = ilb_reserve(ctx, &ctx->d_ramp_table, &ctx->d_ramp_table_capacity, bytes, false);
+        if (rc) return rc;
+        if (ctx->ramp_table_dirty) {
+            std::vector<RampTex> table(ctx->ramps.size());
+            for (size_t i = 0; i < table.size(); i++) table[i] = RampTex{ctx->ramps[i].texels, ctx->ramps[i].w, ctx->ramps[i].h, 0};
+            ILB_CUDA(ctx, cudaMemcpyAsync(ctx->d_ramp_table, table.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+            ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `table` is a host vector
+            ctx->ramp_table_dirty = false;
+        }
+        P.ramps = reinterpret_cast<const RampTex*>(ctx->d_ramp_table);
+    }
     P.envZAndScale = h4(f->EnvironmentZAndScale);
     P.envZToY = h4(f->EnvironmentZToY);
     P.gbTexelAndMisc = h4(f->GBufferTexelSizeAndMisc);
@@ -1300,7 +1366,7 @@ int lightingPrepare(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const
     P.stencil = f->stencil_culling;
     out->nlights = (int)(lights.size() + extra);
     out->nline = 0;
-    for (const DLight& L : lights) out->nline += (L.type == ILB_LIGHT_LINE) ? 1 : 0;
+    for (const DLight& L : lights) out->nline += ((L.type & ILB_LIGHT_TYPE_MASK) == ILB_LIGHT_LINE) ? 1 : 0;
     return ILB_OK;
 }
 
@@ -1526,7 +1592,7 @@ int ilb_probes_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, con
     std::vector<DLight> lights;
     std::vector<DLine> lines;
     const ilb_df_uniforms* geometry = nullptr;
-    int rc = flattenLights(ctx, df, &fr, batches, batch_count, vertices, vertex_count, lights, lines, &geometry);
+    int rc = flattenLights(ctx, df, &fr, batches, batch_count, vertices, vertex_count, lights, lines, &geometry, false);
     if (rc) return rc;
     ProbeParams P;
     memset(&P, 0, sizeof(P));

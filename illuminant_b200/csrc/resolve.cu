@@ -30,6 +30,9 @@ struct ResolveParams {
     float middleGray, averageLuminance, maxLumSq;
     float invWhiteScale;  // 1 / Uncharted2Tonemap1(WhitePoint), host-evaluated (HDR.fxh:32-38, Resolve.fx:131)
     int albedoIsSRGB, resolveToSRGB;
+    // ApplyDither (convention of ilb_dithering): strength 0 = off
+    float ditherStrength, ditherUnit, ditherInvUnit, ditherPhase, ditherBand, ditherMin, ditherMax;
+    int width;  // row length, for the pixel coordinates the dither pattern needs
 };
 
 // ---- texel access ---------------------------------------------------------------------------------------------------
@@ -99,6 +102,26 @@ ILB_DEV f3 pow3u(f3 v, float e) {  // pow(x, 1) == x exactly: skip the three pow
     return mk3(powf(v.x, e), powf(v.y, e), powf(v.z, e));
 }
 
+// ApplyDither under the convention stated at ilb_dithering (the reference's lives in the un-vendored sq/Fracture): ordered
+// dithering to multiples of 1 / Unit with a 17-periodic threshold, blended by Strength, inside [RangeMin, RangeMax]
+ILB_DEV float ditherThreshold(const ResolveParams& P, int x, int y) {
+    // individually rounded: the threshold is compared against, so the oracle must see the same bits
+    const float s = xadd(xmul((float)((2 * x + 7 * y) % 17), 1.0f / 17.0f), P.ditherPhase);  // ditherPhase = frac(23 * ((FrameIndex mod 4) + 0.5) / 17)
+    return xmul(xsub(s, floorf(s)), P.ditherBand);
+}
+ILB_DEV float dither1(const ResolveParams& P, float c, float t) {
+    const float c8 = c * P.ditherUnit;
+    const float a = truncf(c8), b = ceilf(c8);
+    const float q = (((c8 - a) >= t) ? b : a) * P.ditherInvUnit;
+    return ((c >= P.ditherMin) && (c <= P.ditherMax)) ? lerpf(c, q, P.ditherStrength) : c;
+}
+ILB_DEV f4 applyDither(const ResolveParams& P, f4 c, unsigned long long pixel) {
+    if (P.ditherStrength == 0.0f) return c;  // uniform: the default
+    const int y = (int)(pixel / (unsigned long long)P.width), x = (int)(pixel - (unsigned long long)y * (unsigned long long)P.width);
+    const float t = ditherThreshold(P, x, y);
+    return mk4(dither1(P, c.x, t), dither1(P, c.y, t), dither1(P, c.z, t), c.w);
+}
+
 template <int MODE, bool ALBEDO>
 ILB_DEV f4 resolvePixel(const ResolveParams& P, f4 light, f4 albedo) {
     f4 result;
@@ -128,7 +151,7 @@ ILB_DEV f4 resolvePixel(const ResolveParams& P, f4 light, f4 albedo) {
         result = mk4(pow3u(rgb, P.gamma), result.w);
     }
     if (P.resolveToSRGB) result = pLinearToPSRGB(result);
-    return result;  // ApplyDither: identity at Strength 0 (the only value the boundary accepts)
+    return result;  // the caller applies ApplyDither (it knows the pixel's coordinates)
 }
 
 template <int MODE, bool ALBEDO, bool VEC>
@@ -141,7 +164,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Re
         loadTexels4(P.lightmap, P.lm_fmt, g, l);
         if (ALBEDO) loadTexels4(P.albedo, P.al_fmt, g, a);
 #pragma unroll
-        for (int k = 0; k < 4; k++) r[k] = resolvePixel<MODE, ALBEDO>(P, l[k], ALBEDO ? a[k] : mk4(0.0f));
+        for (int k = 0; k < 4; k++) r[k] = applyDither(P, resolvePixel<MODE, ALBEDO>(P, l[k], ALBEDO ? a[k] : mk4(0.0f)), 4 * g + k);
         if (P.out_fmt == ILB_FORMAT_RGBA8) {
             __stcs(reinterpret_cast<uint4*>(P.out) + g, make_uint4(packRgba8(r[0]), packRgba8(r[1]), packRgba8(r[2]), packRgba8(r[3])));
         } else {
@@ -153,7 +176,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Re
     for (unsigned long long i = (VEC ? (groups << 2) : 0ull) + tid; i < P.n; i += stride) {
         const f4 l = loadTexel(P.lightmap, P.lm_fmt, i);
         const f4 a = ALBEDO ? loadTexel(P.albedo, P.al_fmt, i) : mk4(0.0f);
-        const f4 r = resolvePixel<MODE, ALBEDO>(P, l, a);
+        const f4 r = applyDither(P, resolvePixel<MODE, ALBEDO>(P, l, a), i);
         if (P.out_fmt == ILB_FORMAT_RGBA8) reinterpret_cast<uint32_t*>(P.out)[i] = packRgba8(r);
         else reinterpret_cast<float4*>(P.out)[i] = to_float4(r);
     }
@@ -193,10 +216,89 @@ __global__ void __launch_bounds__(256) resolve_placed_kernel(const __grid_consta
         const float av = fminf(fmaxf(xadd(P.v0, xmul(ty, xsub(P.v1, P.v0))), P.v0), P.v1);
         albedo = sampleLinearClamp(P.R.albedo, P.R.al_fmt, P.aw, P.ah, au, av);
     }
-    const f4 r = resolvePixel<MODE, ALBEDO>(P.R, light, albedo);
     const size_t i = (size_t)y * (size_t)P.tw + (size_t)x;
+    const f4 r = applyDither(P.R, resolvePixel<MODE, ALBEDO>(P.R, light, albedo), i);  // P.R.width is the target's row length here
     if (P.R.out_fmt == ILB_FORMAT_RGBA8) reinterpret_cast<uint32_t*>(P.R.out)[i] = packRgba8(r);
     else reinterpret_cast<float4*>(P.R.out)[i] = to_float4(r);
+}
+
+// ---- LUT-blended resolve (LUTResolve.fx:57-135) ------------------------------------------------------------------------------
+struct LutParams {
+    ResolveParams R;
+    const void* dark;
+    const void* bright;
+    int dres, bres, drows, brows;      // LUTResolutionsAndRowCounts
+    float level0, neutral, level1;     // LUTLevels
+    int perChannel, lutOnly;
+    float off[4];                      // LUTOffsets
+};
+// LINEAR / CLAMP fetch of a ColorLUT texel (cached loads: every pixel reads the same few kilobytes)
+ILB_DEV f3 sampleLutLinearClamp(const void* tex, int w, int h, float u, float v) {
+    const float x = xsub(xmul(u, (float)w), 0.5f), y = xsub(xmul(v, (float)h), 0.5f);
+    const float x0f = floorf(x), y0f = floorf(y);
+    const float fx = xsub(x, x0f), fy = xsub(y, y0f);
+    const int xa = min(max((int)x0f, 0), w - 1), xb = min(max((int)x0f + 1, 0), w - 1);
+    const int ya = min(max((int)y0f, 0), h - 1), yb = min(max((int)y0f + 1, 0), h - 1);
+    const unsigned int* t = reinterpret_cast<const unsigned int*>(tex);
+    const f4 t00 = unpackRgba8(__ldg(t + ya * w + xa)), t10 = unpackRgba8(__ldg(t + ya * w + xb));
+    const f4 t01 = unpackRgba8(__ldg(t + yb * w + xa)), t11 = unpackRgba8(__ldg(t + yb * w + xb));
+    return xyz(xlerp4(xlerp4(t00, t10, fx), xlerp4(t01, t11, fx), fy));
+}
+// ReadLUT under the convention stated at ilb_lut_blending (sq/Fracture LUTCommon.fxh is un-vendored): strip layout, row 0
+ILB_DEV f3 readLUT(const void* tex, int res, int rows, f3 value, float offU, float offV) {
+    const float resm1 = (float)(res - 1);
+    const float blue = value.z * resm1;
+    const float s0 = floorf(blue), s1 = fminf(s0 + 1.0f, resm1), w = blue - s0;
+    const int tw = res * res, th = res * rows;
+    const float invW = 1.0f / (float)tw, invH = 1.0f / (float)th;
+    const float uIn = 0.5f + value.x * resm1, v = (0.5f + value.y * resm1) * invH + offV;
+    const f3 a = sampleLutLinearClamp(tex, tw, th, (s0 * (float)res + uIn) * invW + offU, v);
+    const f3 b = sampleLutLinearClamp(tex, tw, th, (s1 * (float)res + uIn) * invW + offU, v);
+    return lerp3(a, b, w);
+}
+ILB_DEV f4 lutResolvePixel(const LutParams& P, f4 light, f4 albedo) {  // LUTBlendedResolveWithAlbedoCommon :57-117 + the pixel shader :119-135
+    if (P.R.albedoIsSRGB) albedo = pSRGBToPLinear(albedo);
+    light = light * P.R.invScale2;
+    f3 weight = xyz(light);
+    const float bandWidth = saturatef(P.level1 - P.level0);
+    const float neutralBandWidth = fminf(P.neutral, bandWidth - 0.01f);
+    const bool hasNeutralBand = neutralBandWidth > 0.0f;
+    if (!P.perChannel || hasNeutralBand) {  // RgbToGray, LUTResolve.fx:16 (0.144 sic)
+        const float gray = weight.x * 0.299f + weight.y * 0.587f + weight.z * 0.144f;
+        weight = mk3(gray);
+    }
+    const f3 a = mk3(saturatef(albedo.x), saturatef(albedo.y), saturatef(albedo.z));
+    const f3 lut1 = readLUT(P.dark, P.dres, P.drows, a, P.off[0], P.off[1]), lut2 = readLUT(P.bright, P.bres, P.brows, a, P.off[2], P.off[3]);
+    f3 blended;
+    if (hasNeutralBand) {
+        const float transitionSize = (bandWidth - neutralBandWidth) * 0.5f;
+        const float v = weight.x - P.level0, v2 = v - transitionSize, v3 = v2 - neutralBandWidth;
+        const f3 val1 = lerp3(lut1, a, saturatef(v / transitionSize));
+        blended = lerp3(val1, lut2, saturatef(v3 / transitionSize));
+    } else {
+        if (P.level1 > P.level0) {
+            weight = max3(weight - P.level0, mk3(0.0f)) / (P.level1 - P.level0);
+            weight = mk3(saturatef(weight.x), saturatef(weight.y), saturatef(weight.z));
+        } else {
+            weight = weight - P.level0;
+            weight = mk3(saturatef(weight.x), saturatef(weight.y), saturatef(weight.z));
+        }
+        blended = lut1 + weight * (lut2 - lut1);
+    }
+    f3 rgb = P.lutOnly ? blended : blended * xyz(light);
+    rgb = max3(mk3(0.0f), rgb + P.R.offset) * P.R.exposure;
+    f4 result = mk4(pow3u(rgb, P.R.gamma), albedo.w);
+    if (P.R.resolveToSRGB) result = pLinearToPSRGB(result);
+    return result;
+}
+__global__ void __launch_bounds__(256) resolve_lut_kernel(const __grid_constant__ LutParams P) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.R.n; i += stride) {
+        const f4 l = loadTexel(P.R.lightmap, P.R.lm_fmt, i), a = loadTexel(P.R.albedo, P.R.al_fmt, i);
+        const f4 r = applyDither(P.R, lutResolvePixel(P, l, a), i);
+        if (P.R.out_fmt == ILB_FORMAT_RGBA8) reinterpret_cast<uint32_t*>(P.R.out)[i] = packRgba8(r);
+        else reinterpret_cast<float4*>(P.R.out)[i] = to_float4(r);
+    }
 }
 
 // ---- luminance ------------------------------------------------------------------------------------------------------
@@ -242,8 +344,6 @@ static int fillResolveParams(ilb_ctx* ctx, const ilb_resolve* r, const void* d_l
     if (r->hdr_mode < ILB_HDR_NONE || r->hdr_mode > ILB_HDR_TONE_MAP) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad hdr_mode %d", r->hdr_mode);
     if (!placed && (r->LightmapUVOffset[0] != 0.0f || r->LightmapUVOffset[1] != 0.0f))
         return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "LightmapUVOffset != 0 needs the scaled / offset resolve (ilb_resolve_lighting_placed)");
-    if (r->DitheringStrength != 0.0f)
-        return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "DitheringStrength != 0 (ApplyDither lives in the un-vendored sq/Fracture DitherCommon.fxh)");
     ResolveParams& P = *out;
     memset(&P, 0, sizeof(P));
     P.lightmap = d_lightmap; P.albedo = d_albedo; P.out = d_output;
@@ -255,6 +355,19 @@ static int fillResolveParams(ilb_ctx* ctx, const ilb_resolve* r, const void* d_l
     P.middleGray = r->MiddleGray; P.averageLuminance = r->AverageLuminance; P.maxLumSq = r->MaximumLuminanceSquared;
     P.invWhiteScale = 1.0f / hostTonemap1(r->WhitePoint);
     P.albedoIsSRGB = r->AlbedoIsSRGB != 0.0f; P.resolveToSRGB = r->ResolveToSRGB != 0.0f;
+    // ApplyDither: the context's settings (ilb_set_dithering), Strength overridden by a non-zero DitheringStrength of this call
+    const ilb_dithering& d = ctx->dither;
+    P.ditherStrength = (r->DitheringStrength != 0.0f) ? r->DitheringStrength : d.Strength;
+    P.ditherUnit = (d.Unit != 0.0f) ? d.Unit : 255.0f;
+    P.ditherInvUnit = 1.0f / P.ditherUnit;
+    P.ditherBand = (d.BandSize != 0.0f) ? d.BandSize : 1.0f;
+    P.ditherMin = d.RangeMin;
+    P.ditherMax = (d.RangeMax > d.RangeMin) ? d.RangeMax : 1.0f;
+    {
+        const float f = std::fmod(d.FrameIndex, 4.0f) + 0.5f, s = 23.0f * f / 17.0f;
+        P.ditherPhase = s - std::floor(s);
+    }
+    P.width = r->width;
     return ILB_OK;
 }
 
@@ -266,6 +379,7 @@ int ilb_resolve_placed_launch(ilb_ctx* ctx, const ilb_resolve* r, const ilb_reso
     memset(&P, 0, sizeof(P));
     int rc = fillResolveParams(ctx, r, d_lightmap, d_albedo, d_target, true, &P.R);
     if (rc) return rc;
+    P.R.width = pl->target_width;  // the dither pattern follows the target's pixel grid
     P.lw = r->width; P.lh = r->height; P.aw = pl->albedo_width; P.ah = pl->albedo_height; P.tw = pl->target_width; P.th = pl->target_height;
     P.u0 = pl->AlbedoRegion[0]; P.v0 = pl->AlbedoRegion[1]; P.u1 = pl->AlbedoRegion[2]; P.v1 = pl->AlbedoRegion[3];
     P.px = pl->Position[0]; P.py = pl->Position[1];
@@ -314,6 +428,28 @@ int ilb_resolve_launch(ilb_ctx* ctx, const ilb_resolve* r, const void* d_lightma
         case 4: launchResolve<ILB_HDR_TONE_MAP, false>(ctx, P, vec, grid); break;
         default: launchResolve<ILB_HDR_TONE_MAP, true>(ctx, P, vec, grid); break;
     }
+    ctx->launches++;
+    ILB_CUDA(ctx, cudaGetLastError());
+    return ILB_OK;
+}
+
+int ilb_resolve_lut_launch(ilb_ctx* ctx, const ilb_resolve* r, const ilb_lut_blending* lut, const void* d_dark, const void* d_bright,
+                           const void* d_lightmap, const void* d_albedo, void* d_output) {
+    if (r->hdr_mode != ILB_HDR_NONE) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "LUT blending is not compatible with this type of lighting resolve");
+    if (lut->dark_resolution < 2 || lut->bright_resolution < 2 || lut->dark_row_count < 1 || lut->bright_row_count < 1 ||
+        lut->dark_resolution > 256 || lut->bright_resolution > 256)
+        return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad LUT geometry");
+    LutParams P;
+    memset(&P, 0, sizeof(P));
+    const int rc = fillResolveParams(ctx, r, d_lightmap, d_albedo, d_output, false, &P.R);
+    if (rc) return rc;
+    P.dark = d_dark; P.bright = d_bright;
+    P.dres = lut->dark_resolution; P.bres = lut->bright_resolution; P.drows = lut->dark_row_count; P.brows = lut->bright_row_count;
+    P.level0 = lut->DarkLevel; P.neutral = lut->NeutralBandSize; P.level1 = lut->BrightLevel;
+    P.perChannel = lut->PerChannel != 0.0f; P.lutOnly = lut->LUTOnly != 0.0f;
+    for (int k = 0; k < 4; k++) P.off[k] = lut->LUTOffsets[k];
+    const int grid = (int)std::min<unsigned long long>((P.R.n + 255) / 256, 148ull * 8 * 8);
+    resolve_lut_kernel<<<grid, 256, 0, ctx->stream>>>(P);
     ctx->launches++;
     ILB_CUDA(ctx, cudaGetLastError());
     return ILB_OK;

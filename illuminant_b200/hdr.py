@@ -36,9 +36,58 @@ class ToneMappingConfiguration:  # :220-222
 
 
 @dataclass
-class DitheringSettings:  # Squared.Render (un-vendored sq/Fracture); only the two members the resolve handler sets (:1489-1494)
+class DitheringSettings:  # Squared.Render (un-vendored sq/Fracture); Unit / Strength / FrameIndex are what the resolve handler sets (:1489-1497)
     Unit: float = 255.0
     Strength: float = 0.0
+    FrameIndex: float = 0.0   # the handler overwrites it with DeviceManager.FrameIndex
+    BandSize: float = 1.0
+    RangeMin: float = 0.0
+    RangeMax: float = 1.0
+
+    def pack(self) -> "_abi.Dithering":
+        d = _abi.Dithering()
+        d.Strength, d.Unit, d.FrameIndex = float(self.Strength), float(self.Unit), float(self.FrameIndex)
+        d.BandSize, d.RangeMin, d.RangeMax = float(self.BandSize), float(self.RangeMin), float(self.RangeMax)
+        return d
+
+
+@dataclass
+class ColorLUT:  # Squared.Render.ColorLUT (un-vendored): a SurfaceFormat.Color strip texture, (Resolution^2) x (Resolution * RowCount) texels
+    Texture: np.ndarray          # uint8 [Resolution * RowCount, Resolution * Resolution, 4]
+    Resolution: int
+    RowCount: int = 1
+
+    @staticmethod
+    def Identity(resolution: int = 16) -> "ColorLUT":
+        """The neutral table: texel (b * res + r, g) = (r, g, b) / (res - 1)."""
+        res = int(resolution)
+        t = np.zeros((res, res * res, 4), np.uint8)
+        ramp = np.round(np.arange(res) * 255.0 / (res - 1)).astype(np.uint8)
+        for b in range(res):
+            t[:, b * res:(b + 1) * res, 0] = ramp[None, :]
+            t[:, b * res:(b + 1) * res, 1] = ramp[:, None]
+            t[:, b * res:(b + 1) * res, 2] = ramp[b]
+        t[..., 3] = 255
+        return ColorLUT(t, res, 1)
+
+
+@dataclass
+class LUTBlendingConfiguration:  # LightingRenderer.HDR.cs:260-273
+    DarkLUT: ColorLUT = None
+    BrightLUT: ColorLUT = None
+    PerChannel: bool = False
+    LUTOnly: bool = False
+    DarkLevel: float = 0.0
+    NeutralBandSize: float = 0.0
+    BrightLevel: float = 1.0     # stored as _BrightLevelMinus1 so that default(LUTBlendingConfiguration) means 1
+
+    def pack(self) -> "_abi.LutBlending":  # IlluminantMaterials.SetLUTBlending, IlluminantMaterials.cs:139-149
+        b = _abi.LutBlending()
+        b.dark_resolution, b.bright_resolution = int(self.DarkLUT.Resolution), int(self.BrightLUT.Resolution)
+        b.dark_row_count, b.bright_row_count = int(self.DarkLUT.RowCount), int(self.BrightLUT.RowCount)
+        b.DarkLevel, b.NeutralBandSize, b.BrightLevel = float(self.DarkLevel), float(self.NeutralBandSize), float(self.BrightLevel)
+        b.PerChannel, b.LUTOnly = (1.0 if self.PerChannel else 0.0), (1.0 if self.LUTOnly else 0.0)
+        return b
 
 
 @dataclass
@@ -212,13 +261,22 @@ class RenderedLighting:  # LightingRenderer.HDR.cs:69-212
     def IsValid(self) -> bool:
         return self.Renderer is not None and self.Renderer.ctx is not None
 
+    def _bind_dithering(self, ctx, hdr: Optional[HDRConfiguration]) -> None:
+        """LightingResolveHandler._Before (:1489-1497): the configuration's DitheringSettings or {Unit 255, Strength 0}."""
+        ds = hdr.Dithering if (hdr is not None and hdr.Dithering is not None) else None
+        ctx.check(ctx.lib.ilb_set_dithering(ctx.handle, C.byref(ds.pack()) if ds is not None else None))
+
     def Resolve(self, albedo: Optional[np.ndarray] = None, hdr: Optional[HDRConfiguration] = None, float4: bool = False,
-                lightmap: Optional[np.ndarray] = None, uvOffset: Tuple[float, float] = (0.0, 0.0)) -> np.ndarray:
+                lightmap: Optional[np.ndarray] = None, uvOffset: Tuple[float, float] = (0.0, 0.0),
+                lutBlending: Optional[LUTBlendingConfiguration] = None) -> np.ndarray:
         """RenderedLighting.Resolve at 1:1 (position 0, scale 1): uint8 [H, W, 4] backbuffer texels (float32 with float4=True).
-        `lightmap` = None resolves the lightmap resident on the device from the last frame; an array resolves those texels."""
+        `lightmap` = None resolves the lightmap resident on the device from the last frame; an array resolves those texels.
+        `lutBlending` selects the LUT-blended material like ResolveLighting (LightingRenderer.cs:1558-1561): it needs an albedo and
+        HDRMode.None."""
         if not self.IsValid:
             raise _abi.IlluminantError(_abi.ERR_INVALID_OPERATION, "Invalid")
         ctx = self.Renderer.ctx
+        self._bind_dithering(ctx, hdr)
         lm_ptr, lm_fmt, w, h = None, self.LightmapFormat, self.Width, self.Height
         if lightmap is not None:
             lightmap, lm_fmt = _texels(lightmap, "lightmap")
@@ -233,6 +291,17 @@ class RenderedLighting:  # LightingRenderer.HDR.cs:69-212
         out_fmt = FORMAT_FLOAT4 if float4 else FORMAT_RGBA8
         params = pack_resolve(w, h, lm_fmt, hdr, al_fmt, out_fmt, uvOffset)
         out = np.empty((h, w, 4), dtype=_NP[out_fmt])
+        if lutBlending is not None and albedo is not None and params.hdr_mode == HDRMode.None_:
+            lut = lutBlending.pack()
+            dark, bright = (np.ascontiguousarray(t.Texture, dtype=np.uint8) for t in (lutBlending.DarkLUT, lutBlending.BrightLUT))
+            for t, l in ((dark, lutBlending.DarkLUT), (bright, lutBlending.BrightLUT)):
+                if t.shape != (l.Resolution * l.RowCount, l.Resolution * l.Resolution, 4):
+                    raise _abi.IlluminantError(_abi.ERR_INVALID_ARGUMENT, "a ColorLUT texture is [Resolution * RowCount, Resolution^2, 4] uint8 texels")
+            ctx.check(ctx.lib.ilb_resolve_lighting_lut(ctx.handle, C.byref(params), C.byref(lut), dark.ctypes.data_as(C.c_void_p),
+                                                       bright.ctypes.data_as(C.c_void_p), lm_ptr, al_ptr, out.ctypes.data_as(C.c_void_p)))
+            return out
+        if lutBlending is not None and albedo is not None:  # LightingRenderer.cs:1593-1594
+            raise _abi.IlluminantError(_abi.ERR_INVALID_ARGUMENT, "LUT blending is not compatible with this type of lighting resolve.")
         ctx.check(ctx.lib.ilb_resolve_lighting(ctx.handle, C.byref(params), lm_ptr, al_ptr, out.ctypes.data_as(C.c_void_p)))
         return out
 
@@ -266,6 +335,7 @@ class RenderedLighting:  # LightingRenderer.HDR.cs:69-212
             pl.albedo_width, pl.albedo_height = albedo.shape[1], albedo.shape[0]
             al_ptr = albedo.ctypes.data_as(C.c_void_p)
         params = pack_resolve(w, h, lm_fmt, hdr, al_fmt, out_fmt, uvOffset)
+        self._bind_dithering(ctx, hdr)
         ctx.check(ctx.lib.ilb_resolve_lighting_placed(ctx.handle, C.byref(params), C.byref(pl), lm_ptr, al_ptr, target.ctypes.data_as(C.c_void_p)))
         return target
 

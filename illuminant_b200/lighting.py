@@ -42,6 +42,7 @@ class LightSource:  # LightSource.cs:58-82
     Quality: Optional[RendererQualitySettings] = None
     Enabled: bool = True
     SortKey: int = 0
+    RampTexture: Optional[np.ndarray] = None   # LightSource.cs:182-193: uint8 / float32 [H, W, 4]; 1x1 means "no ramp" (LightingRenderer.cs:819-827)
 
     @property
     def RampOffsetForGPU(self) -> float:
@@ -334,16 +335,18 @@ class LightingRenderer:
             if v is None:
                 continue
             q = l.Quality or self.Configuration.DefaultQuality
-            key = (l.TypeID, id(q))
+            ramp = self._ramp_texture_id(getattr(l, "RampTexture", None))
+            key = (l.TypeID, id(q), ramp)      # LightTypeRenderStateKey: type, ramp texture, quality (LightingRenderer.cs:44-90)
             if key not in groups:
-                groups[key] = (l.TypeID, q, [])
+                groups[key] = (l.TypeID, q, [], ramp)
             groups[key][2].append(v)
         n = sum(len(g[2]) for g in groups.values())
         verts = (LightVertex * max(n, 1))()
         batches = (LightBatch * max(len(groups), 1))()
         i = 0
-        for b, (typ, q, vs) in enumerate(groups.values()):
+        for b, (typ, q, vs, ramp) in enumerate(groups.values()):
             batches[b].light_type = typ
+            batches[b].ramp_texture = ramp
             batches[b].first_vertex = i
             batches[b].vertex_count = len(vs)
             batches[b].df = self._df_uniforms(q)
@@ -351,6 +354,35 @@ class LightingRenderer:
                 verts[i] = v
                 i += 1
         return batches, len(groups), verts, n
+
+    def _ramp_texture_id(self, texture) -> int:
+        """The library id of a light's ramp texture (uploaded once per array object); 0 for none and for 1x1 textures.  Without a
+        context (CPU-side packing for the oracle) ids are assigned in first-use order; `ramp_textures` lists the arrays by id."""
+        if texture is None:
+            return 0
+        t = np.asarray(texture)
+        if t.shape[0] == 1 and t.shape[1] == 1:
+            return 0
+        cache = self.__dict__.setdefault("_ramp_ids", {})
+        if id(texture) in cache:
+            return cache[id(texture)][0]
+        if t.dtype == np.uint8:
+            arr, fmt = np.ascontiguousarray(t), FORMAT_RGBA8
+        else:
+            arr, fmt = np.ascontiguousarray(t, dtype=np.float32), FORMAT_FLOAT4
+        if self.ctx is not None:
+            rid = C.c_int32(0)
+            self.ctx.check(self.ctx.lib.ilb_ramp_texture_create(self.ctx.handle, arr.shape[1], arr.shape[0], fmt, arr.ctypes.data_as(C.c_void_p), C.byref(rid)))
+            rid = int(rid.value)
+        else:
+            rid = len(cache) + 1
+        cache[id(texture)] = (rid, texture)   # keeps the array alive, so its id() stays unique
+        return rid
+
+    @property
+    def ramp_textures(self):
+        """[(id, array)] of the ramp textures seen by build_batches so far."""
+        return sorted(self.__dict__.get("_ramp_ids", {}).values(), key=lambda p: p[0])
 
     def _sync_particle_lights(self) -> None:
         """Hands the enabled, active ParticleLightSources to the library (LightingRenderer.cs:1126-1144)."""

@@ -200,9 +200,19 @@ typedef struct ilb_light_batch {
     int32_t light_type;   /* ilb_light_type */
     int32_t first_vertex;
     int32_t vertex_count;
-    int32_t reserved;
+    int32_t ramp_texture; /* 0, or an ilb_ramp_texture_create id: LightTypeRenderStateKey.RampTexture (LightingRenderer.cs:50, :150-158) */
     ilb_df_uniforms df;   /* Extent.x <= 0 == rendered without a distance field */
 } ilb_light_batch;
+
+/* LightSource.RampTexture (LightSource.cs:182-193): a sphere-light batch with a ramp texture is drawn with the
+ * SphereLightWithDistanceRamp material (Shaders/SphereLight.fx:48-87, SphereLightCore.fxh:99-119, :160-199): the light's rgb is
+ * RampTexture(preTraceOpacity, (atan2(dy, dx) + EvenMoreLightProperties.z) * EvenMoreLightProperties.w).rgb * coneOpacity
+ * instead of the scalar opacity; RampTextureSampler is LINEAR, U CLAMP, V WRAP (RampCommon.fxh:5-12).  A 1x1 texture means
+ * "no ramp" in the reference (LightingRenderer.cs:819-827): pass ramp_texture = 0 for it.  texels: width*height of `format`
+ * (ILB_FORMAT_RGBA8 or ILB_FORMAT_FLOAT4), host memory.  Ramp textures on directional lights (DirectionalLightWithRamp) and on
+ * light probes are outside the hot-path scope: ILB_ERR_UNSUPPORTED. */
+ILB_API int ilb_ramp_texture_create(ilb_ctx* ctx, int width, int height, int format, const void* texels, int32_t* out_id);
+ILB_API int ilb_ramp_texture_destroy(ilb_ctx* ctx, int32_t id);
 
 /* Per-frame uniforms of the light pass. */
 typedef struct ilb_lighting_frame {
@@ -301,8 +311,8 @@ typedef enum ilb_hdr_mode { /* HDRMode, LightingRenderer.HDR.cs:269-273 */
  * Scope: the screen-aligned 1:1 resolve (RenderedLighting.Resolve with width/height = the lightmap's size, position 0;
  * with the LinearClamp sampler that fetches exactly one texel per pixel) -- LightmapUVOffset must be (0,0) and the
  * albedo has the lightmap's size.  ApplyDither (Resolve.fx:88) lives in the un-vendored sq/Fracture (DitherCommon.fxh);
- * the handler's default is Strength 0 (:1489-1494), i.e. the identity -- DitheringStrength must be 0.  LUT blending
- * (LUTResolve.fx) is out of scope.  Other values return ILB_ERR_UNSUPPORTED. */
+ * the handler's default is Strength 0 (:1489-1494), i.e. the identity; a non-zero DitheringStrength (or ilb_set_dithering) dithers
+ * under the convention stated at ilb_dithering.  LUT blending (LUTResolve.fx) is ilb_resolve_lighting_lut. */
 typedef struct ilb_resolve {
     int32_t width, height;     /* lightmap (= output) size in pixels */
     int32_t lightmap_format;   /* ilb_format of the lightmap: HALF4, RGBA8 or FLOAT4 */
@@ -349,6 +359,47 @@ ILB_API int ilb_resolve_lighting_placed(ilb_ctx* ctx, const ilb_resolve* params,
                                         const void* lightmap, const void* albedo, void* target);
 ILB_API int ilb_resolve_lighting_placed_device(ilb_ctx* ctx, const ilb_resolve* params, const ilb_resolve_placement* placement,
                                                const void* d_lightmap, const void* d_albedo, void* d_target);
+/* HDRConfiguration.Dithering (LightingRenderer.HDR.cs:212; the resolve handler binds it as the `Dithering` uniform with
+ * FrameIndex = DeviceManager.FrameIndex, LightingRenderer.cs:1489-1497).  DitheringSettings and ApplyDither live in the
+ * un-vendored sq/Fracture (Squared.Render, DitherCommon.fxh), so what this library computes is a stated CONVENTION, the same
+ * in the kernels and in the oracle -- ordered dithering to multiples of 1 / Unit with the 17-periodic threshold pattern:
+ *     t      = frac((2 * x + 7 * y + 23 * ((FrameIndex mod 4) + 0.5)) / 17)             (x, y = integer pixel coordinates, VPOS)
+ *     rgb8   = rgb * Unit;  a = trunc(rgb8);  b = ceil(rgb8)
+ *     q      = ((rgb8 - a) >= t * BandSize ? b : a) / Unit
+ *     result = RangeMin <= rgb <= RangeMax ? lerp(rgb, q, Strength) : rgb                 (per channel)
+ * Defaults for members left 0: Unit 255, BandSize 1, RangeMax 1.  Strength 0 is the identity (the handler's default). */
+typedef struct ilb_dithering {
+    float Strength, Unit, FrameIndex, BandSize, RangeMin, RangeMax;
+} ilb_dithering;
+/* Settings of every later resolve on this context; NULL restores the default (Strength 0).  A non-zero
+ * ilb_resolve.DitheringStrength overrides Strength for that call. */
+ILB_API int ilb_set_dithering(ilb_ctx* ctx, const ilb_dithering* settings);
+
+/* LUT-blended resolve: {Screen,World}SpaceLUTBlendedLightingResolveWithAlbedo (Shaders/LUTResolve.fx:57-135), chosen by
+ * ResolveLighting when a LUTBlendingConfiguration is given, an albedo is bound and the HDR mode is None
+ * (LightingRenderer.cs:1558-1561, :1576-1579).  Members as IlluminantMaterials.SetLUTBlending packs them
+ * (IlluminantMaterials.cs:139-149): LUTResolutionsAndRowCounts = (dark res, bright res, dark rows, bright rows), LUTLevels =
+ * (DarkLevel, NeutralBandSize, BrightLevel); LUTOffsets is never set by the reference (0).  A ColorLUT texture is
+ * SurfaceFormat.Color, (resolution * resolution) x (resolution * row_count) texels.  ReadLUT lives in the un-vendored
+ * sq/Fracture (LUTCommon.fxh); the CONVENTION here is the usual strip layout -- slice b of row 0 occupies columns
+ * [b * res, (b + 1) * res), red runs along x and green along y inside a slice at texel centres 0.5 + c * (res - 1), the two
+ * slices around blue * (res - 1) are fetched LINEAR / CLAMP and blended by the fraction; LUTOffsets.xy / .zw are added to the
+ * dark / bright (u, v). */
+typedef struct ilb_lut_blending {
+    int32_t dark_resolution, bright_resolution, dark_row_count, bright_row_count;
+    float DarkLevel, NeutralBandSize, BrightLevel;
+    float PerChannel, LUTOnly;                    /* 0 / 1 */
+    float LUTOffsets[4];
+    float reserved;
+} ilb_lut_blending;
+/* params->hdr_mode must be ILB_HDR_NONE and albedo must be given (the reference throws otherwise, :1593-1594).  dark_lut /
+ * bright_lut: RGBA8 texels, HOST memory; the other pointers as for ilb_resolve_lighting.  Synchronous. */
+ILB_API int ilb_resolve_lighting_lut(ilb_ctx* ctx, const ilb_resolve* params, const ilb_lut_blending* lut, const void* dark_lut,
+                                     const void* bright_lut, const void* lightmap, const void* albedo, void* output);
+/* Same with DEVICE pointers for all five buffers; asynchronous on ilb_stream(ctx). */
+ILB_API int ilb_resolve_lighting_lut_device(ilb_ctx* ctx, const ilb_resolve* params, const ilb_lut_blending* lut, const void* d_dark_lut,
+                                            const void* d_bright_lut, const void* d_lightmap, const void* d_albedo, void* d_output);
+
 /* UpdateLuminanceBuffer + the mip chain TryComputeHistogram reads (LightingRenderer.cs:855-898, LightingRenderer.HDR.cs:154-186):
  * level 0 is (width/2) x (height/2) SurfaceFormat.Single texels, texel (x,y) = dot(lightmap texel (2x+1, 2y+1).rgb,
  * (0.299, 0.587, 0.144)) (CalculateLuminancePixelShader, Resolve.fx:219-234; point-sampled at the half-size target's pixel

@@ -57,6 +57,14 @@ int orc_resolve_lighting(const ilb_resolve* p, const float* lightmap, const floa
 /* N3: the resolve drawn as a quad at placement->Position with placement->Scale into a target of any size (ResolveLighting,
  * LightingRenderer.cs:1537-1645): lightmap w*h*4 floats, albedo (nullable) albedo_width*albedo_height*4 floats, target
  * target_width*target_height*4 floats read and written (pixels outside the quad keep their contents). */
+/* SphereLightWithDistanceRamp: the ramp textures (float4 texels, kept by reference) that ilb_light_batch.ramp_texture = id
+ * (1-based) selects in later orc_render_lighting calls. */
+void orc_set_ramp_textures(int count, const float* const* texels, const int* widths, const int* heights);
+/* N3: ApplyDither settings of every later orc_resolve_* call (NULL = the handler's default, Strength 0); LUT-blended resolve
+ * (LUTResolve.fx); textures are float4 texels. */
+void orc_set_dithering(const ilb_dithering* d);
+int orc_resolve_lighting_lut(const ilb_resolve* p, const ilb_lut_blending* lut, const float* dark, const float* bright, const float* lightmap,
+                             const float* albedo, float* out);
 int orc_resolve_lighting_placed(const ilb_resolve* p, const ilb_resolve_placement* place, const float* lightmap, const float* albedo, float* target);
 /* N3: luminance buffer level `level` ((w/2 >> level) x (h/2 >> level) floats) of a fp32-decoded lightmap. */
 int orc_compute_luminance(const float* lightmap, int w, int h, int level, float* out);

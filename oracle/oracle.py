@@ -121,6 +121,30 @@ def render_lighting(df_tex, gbuffer, frame: LightingFrame, batches, nb, verts, n
     return out
 
 
+_ramp_keepalive = []
+
+
+def set_ramp_textures(textures) -> None:
+    """The ramp textures ilb_light_batch.ramp_texture refers to: a list of (id, array) with ids 1..n (LightingRenderer.ramp_textures),
+    or [] / None.  uint8 texels decode as c / 255."""
+    global _ramp_keepalive
+    textures = sorted(textures or [], key=lambda p: p[0])
+    arrays = []
+    for k, (rid, t) in enumerate(textures):
+        assert rid == k + 1, "ramp texture ids must be 1..n"
+        t = np.asarray(t)
+        arrays.append(np.ascontiguousarray(t.astype(np.float32) / np.float32(255.0)) if t.dtype == np.uint8 else np.ascontiguousarray(t, dtype=np.float32))
+    n = len(arrays)
+    ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrays])
+    ws = (C.c_int * max(n, 1))(*[a.shape[1] for a in arrays])
+    hs = (C.c_int * max(n, 1))(*[a.shape[0] for a in arrays])
+    L = lib()
+    L.orc_set_ramp_textures.restype = None
+    L.orc_set_ramp_textures.argtypes = [C.c_int, P, P, P]
+    L.orc_set_ramp_textures(n, C.cast(ptrs, P), C.cast(ws, P), C.cast(hs, P))
+    _ramp_keepalive = arrays     # the oracle keeps the texels by reference
+
+
 def update_light_probes(df_tex, frame, batches, nb, verts, nv, positions, normals) -> np.ndarray:
     tw = th = 0
     if df_tex is not None:
@@ -327,6 +351,34 @@ def resolve_lighting(params, lightmap, albedo=None) -> np.ndarray:
     rc = lib().orc_resolve_lighting(C.byref(params), _ptr(lm), _ptr(al), _ptr(out))
     if rc != 0:
         raise RuntimeError(f"orc_resolve_lighting failed: {rc}")
+    return out
+
+
+def set_dithering(settings=None) -> None:
+    """ApplyDither settings (an _abi.Dithering, or None for the handler's default) of every later resolve_* call."""
+    L = lib()
+    L.orc_set_dithering.restype = None
+    L.orc_set_dithering.argtypes = [P]
+    L.orc_set_dithering(C.byref(settings) if settings is not None else None)
+
+
+def _decode_texels(a):
+    a = np.asarray(a)
+    if a.dtype == np.uint8:
+        return np.ascontiguousarray(a.astype(np.float32) / np.float32(255.0))
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def resolve_lighting_lut(params, lut, dark, bright, lightmap, albedo) -> np.ndarray:
+    """LUTResolve.fx on fp32-decoded texels; dark / bright: the two ColorLUT textures [res * rows, res * res, 4]."""
+    dk, br, lm, al = (_decode_texels(a) for a in (dark, bright, lightmap, albedo))
+    out = np.empty((params.height, params.width, 4), dtype=np.float32)
+    L = lib()
+    L.orc_resolve_lighting_lut.restype = C.c_int
+    L.orc_resolve_lighting_lut.argtypes = [C.POINTER(_abi.Resolve), C.POINTER(_abi.LutBlending), P, P, P, P, P]
+    rc = L.orc_resolve_lighting_lut(C.byref(params), C.byref(lut), _ptr(dk), _ptr(br), _ptr(lm), _ptr(al), _ptr(out))
+    if rc != 0:
+        raise RuntimeError(f"orc_resolve_lighting_lut failed: {rc}")
     return out
 
 

@@ -382,7 +382,7 @@ float computeAO(const DistanceField& df, float3 shadedPixelPosition, float3 shad
 // returns false when the fragment is discarded
 bool SphereLightPixelCore(const Frame& fr, const DistanceField& df, float3 shadedPixelPosition,
                           float3 shadedPixelNormal, float3 lightCenter, float4 lightProperties,
-                          float4 moreLightProperties, float& opacity) {  // SphereLightCore.fxh:58-158
+                          float4 moreLightProperties, float& opacity, float* preTrace = nullptr, float* cone = nullptr) {  // SphereLightCore.fxh:58-158
     const float SELF_OCCLUSION_HACK = 1.6f;
     const float SHADOW_OPACITY_THRESHOLD = (0.75f / 255.0f);
     // prologue :58-80
@@ -400,7 +400,33 @@ bool SphereLightPixelCore(const Frame& fr, const DistanceField& df, float3 shade
                                   float2(df.getConeGrowthFactor(), moreLightProperties.y),
                                   shadedPixelPosition + (SELF_OCCLUSION_HACK * shadedPixelNormal), traceShadows);
     opacity = preTraceOpacity * coneOpacity;  // epilogue :82-97
+    if (preTrace) *preTrace = preTraceOpacity;  // SphereLightPixelCoreWithRamp (:160-199) hands both to its epilogue
+    if (cone) *cone = coneOpacity;
     return true;
+}
+
+// ---- ramp textures (RampCommon.fxh): RampTextureSampler = LINEAR min / mag, U CLAMP, V WRAP; fp32 bilinear weights
+struct RampTexture { const float* texels; int w, h; };
+std::vector<RampTexture> g_ramps;  // id - 1 -> texture (orc_set_ramp_textures)
+float4 SampleFromRamp2(const RampTexture& t, float2 xy) {  // RampCommon.fxh:19-21
+    const float x = xy.x * (float)t.w - 0.5f, y = xy.y * (float)t.h - 0.5f;
+    const float x0f = floorf(x), y0f = floorf(y);
+    const float fx = x - x0f, fy = y - y0f;
+    auto at = [&](int ix, int iy) {
+        ix = std::min(std::max(ix, 0), t.w - 1);
+        iy = ((iy % t.h) + t.h) % t.h;
+        const float* q = t.texels + 4 * ((size_t)iy * t.w + ix);
+        return float4(q[0], q[1], q[2], q[3]);
+    };
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const float4 top = lerp(at(x0, y0), at(x0 + 1, y0), fx), bottom = lerp(at(x0, y0 + 1), at(x0 + 1, y0 + 1), fx);
+    return lerp(top, bottom, fy);
+}
+// SphereLightPixelEpilogueWithRamp (SphereLightCore.fxh:99-119)
+float3 SphereLightPixelEpilogueWithRamp(const RampTexture& ramp, float preTraceOpacity, float coneOpacity, float3 distanceToCenter,
+                                        float4 evenMoreLightProperties) {
+    float angle = atan2f(distanceToCenter.y, distanceToCenter.x);
+    return SampleFromRamp2(ramp, float2(preTraceOpacity, (angle + evenMoreLightProperties.z) * evenMoreLightProperties.w)).xyz() * coneOpacity;
 }
 
 // Rasterised coverage of the sphere-light geometry: SphereLightVertexShader (SphereLightCore.fxh:13-56)
@@ -433,7 +459,7 @@ bool sphereLightCovers(const Frame& fr, const ilb_light_vertex& v, float px, flo
 }
 
 bool SphereLightPixelShader(const Frame& fr, const DistanceField& df, const ilb_light_vertex& v, float2 vpos,
-                            float4& result) {  // SphereLight.fx:7-46
+                            float4& result, int rampTexture = 0) {  // SphereLight.fx:7-46; with a ramp texture :48-87
     float3 lightCenter(v.LightPosition1.x, v.LightPosition1.y, v.LightPosition1.z);
     float4 lightProperties = f4(v.LightProperties), moreLightProperties = f4(v.MoreLightProperties);
     float4 color = f4(v.Color1), specular = f4(v.Color2), evenMoreLightProperties = f4(v.EvenMoreLightProperties);
@@ -444,12 +470,18 @@ bool SphereLightPixelShader(const Frame& fr, const DistanceField& df, const ilb_
     if (fullbright || checkShadowFilter(evenMoreLightProperties, enableShadows)) return false;
     lightProperties.w *= enableShadows ? 1.0f : 0.0f;
 
-    float opacity;
+    float opacity, preTraceOpacity, coneOpacity;
     if (!SphereLightPixelCore(fr, df, shadedPixelPosition, shadedPixelNormal, lightCenter, lightProperties,
-                              moreLightProperties, opacity))
+                              moreLightProperties, opacity, &preTraceOpacity, &coneOpacity))
         return false;
     float specularity = CalcSphereLightSpecularity(cameraPosition, shadedPixelPosition, shadedPixelNormal,
                                                    lightCenter, specular.w);
+    if (rampTexture > 0 && rampTexture <= (int)g_ramps.size()) {  // SphereLightWithDistanceRampPixelShader SphereLight.fx:48-87
+        float3 opacity3 = SphereLightPixelEpilogueWithRamp(g_ramps[rampTexture - 1], preTraceOpacity, coneOpacity,
+                                                           shadedPixelPosition - lightCenter, evenMoreLightProperties);
+        result = float4((color.xyz() * color.w * opacity3) + (specular.xyz() * specularity * opacity3), 1);
+        return true;
+    }
     float3 rgb = (color.xyz() * color.w * opacity) + (specular.xyz() * specularity * opacity);
     result = float4(rgb, 1);
     return true;
@@ -697,6 +729,12 @@ Frame makeFrame(const ilb_lighting_frame* f, const void* gbuffer, int gw, int gh
 
 extern "C" {
 
+// The ramp textures ilb_light_batch.ramp_texture refers to (id - 1 indexes the arrays): float4 texels, kept by reference.
+void orc_set_ramp_textures(int count, const float* const* texels, const int* widths, const int* heights) {
+    g_ramps.clear();
+    for (int i = 0; i < count; i++) g_ramps.push_back(RampTexture{texels[i], widths[i], heights[i]});
+}
+
 // RenderLighting (Lighting/LightingRenderer.cs:917-1168) in the reference's multi-pass form:
 // clear to ambient, then one full-band pass per light with additive blend (BlendState.Additive:
 // rgb += src.rgb * src.a(=1), a += 1).  Output: fp32 float4, width*(row_end-row_begin).
@@ -744,7 +782,7 @@ int orc_render_lighting_strided(const uint16_t* df_tex, int tw, int th, const vo
                     }
                     switch (batch.light_type) {
                         case ILB_LIGHT_SPHERE:
-                            lit = sphereLightCovers(fr, v, (float)x, (float)y) && SphereLightPixelShader(fr, df, v, vpos, result);
+                            lit = sphereLightCovers(fr, v, (float)x, (float)y) && SphereLightPixelShader(fr, df, v, vpos, result, batch.ramp_texture);
                             break;
                         case ILB_LIGHT_DIRECTIONAL:
                             lit = directionalLightCovers(fr, v, (float)x, (float)y) && DirectionalLightPixelShader(fr, df, v, vpos, result);

@@ -5,8 +5,9 @@
 // PARITY UNPINNED (like the rest of the oracle): the reference holds no tests or fixtures for this path, and three helpers
 // it calls live in the un-vendored, un-pinned sq/Fracture (Squared/RenderLib/Shaders): pSRGBToPLinear / pLinearToPSRGB
 // (sRGBCommon.fxh) are restated here from the published IEC 61966-2-1 transfer functions applied to the un-premultiplied
-// colour; ApplyDither (DitherCommon.fxh) is the identity at the handler's default Strength 0 (LightingRenderer.cs:1489-1494),
-// the only value the boundary accepts.
+// colour; ApplyDither (DitherCommon.fxh) is the identity at the handler's default Strength 0 (LightingRenderer.cs:1489-1494) and
+// otherwise follows the CONVENTION stated at ilb_dithering in include/illuminant_b200.h; ReadLUT (LUTCommon.fxh) follows the
+// convention stated at ilb_lut_blending.  Neither of the two can be checked against the reference's source.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -57,6 +58,26 @@ float3 Uncharted2Tonemap(float3 rgb) {  // HDR.fxh:40-46
 
 float3 pow3(float3 v, float e) { return float3(powf(v.x, e), powf(v.y, e), powf(v.z, e)); }
 
+// ---- ApplyDither: the convention of ilb_dithering (the reference's lives in the un-vendored sq/Fracture DitherCommon.fxh)
+ilb_dithering g_dither = {0.0f, 255.0f, 0.0f, 1.0f, 0.0f, 1.0f};
+float3 ApplyDither(const ilb_resolve& P, float3 rgb, int x, int y) {
+    const float strength = (P.DitheringStrength != 0.0f) ? P.DitheringStrength : g_dither.Strength;
+    if (strength == 0.0f) return rgb;
+    const float unit = (g_dither.Unit != 0.0f) ? g_dither.Unit : 255.0f, invUnit = 1.0f / unit;
+    const float band = (g_dither.BandSize != 0.0f) ? g_dither.BandSize : 1.0f;
+    const float lo = g_dither.RangeMin, hi = (g_dither.RangeMax > g_dither.RangeMin) ? g_dither.RangeMax : 1.0f;
+    const float f = fmodf(g_dither.FrameIndex, 4.0f) + 0.5f, ph = 23.0f * f / 17.0f, phase = ph - floorf(ph);
+    const float s = (float)((2 * x + 7 * y) % 17) * (1.0f / 17.0f) + phase;
+    const float t = (s - floorf(s)) * band;
+    auto one = [&](float c) {
+        const float c8 = c * unit;
+        const float a = truncf(c8), b = ceilf(c8);
+        const float q = (((c8 - a) >= t) ? b : a) * invUnit;
+        return ((c >= lo) && (c <= hi)) ? c + strength * (q - c) : c;
+    };
+    return float3(one(rgb.x), one(rgb.y), one(rgb.z));
+}
+
 // ---- Resolve.fx
 float4 ResolveCommon(const ilb_resolve& P, float4 color) {  // Resolve.fx:30-45 (texel fetch done by the caller)
     float4 result = color * P.InverseScaleFactor;
@@ -93,9 +114,9 @@ float4 resolvePixel(const ilb_resolve& P, float4 light, const float* albedoTexel
             break;
     }
     if (P.ResolveToSRGB != 0.0f) result = pLinearToPSRGB(result);
-    // ApplyDither(result.rgb, vpos): identity at DitheringStrength == 0
-    return result;
+    return result;  // the callers apply ApplyDither(result.rgb, vpos)
 }
+float4 dithered(const ilb_resolve& P, float4 c, int x, int y) { return float4(ApplyDither(P, c.xyz(), x, y), c.w); }
 
 }  // namespace
 
@@ -107,7 +128,7 @@ extern "C" int orc_resolve_lighting(const ilb_resolve* p, const float* lightmap,
 #pragma omp parallel for schedule(static)
     for (long i = 0; i < n; i++) {
         const float* l = lightmap + 4 * i;
-        float4 r = resolvePixel(P, float4(l[0], l[1], l[2], l[3]), albedo ? albedo + 4 * i : nullptr);
+        float4 r = dithered(P, resolvePixel(P, float4(l[0], l[1], l[2], l[3]), albedo ? albedo + 4 * i : nullptr), (int)(i % P.width), (int)(i / P.width));
         out[4 * i + 0] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
     }
     return 0;
@@ -157,10 +178,88 @@ extern "C" int orc_resolve_lighting_placed(const ilb_resolve* p, const ilb_resol
                 a4[0] = a.x; a4[1] = a.y; a4[2] = a.z; a4[3] = a.w;
                 ap = a4;
             }
-            const float4 r = resolvePixel(P, light, ap);
+            const float4 r = dithered(P, resolvePixel(P, light, ap), x, y);
             float* o = target + 4 * ((size_t)y * place->target_width + x);
             o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
         }
+    return 0;
+}
+
+extern "C" void orc_set_dithering(const ilb_dithering* d) {
+    const ilb_dithering defaults = {0.0f, 255.0f, 0.0f, 1.0f, 0.0f, 1.0f};
+    g_dither = d ? *d : defaults;
+}
+
+namespace {
+// ReadLUT: the convention of ilb_lut_blending (sq/Fracture LUTCommon.fxh is un-vendored).  `tex`: float4 texels
+float3 ReadLUT(const float* tex, int res, int rows, float3 value, float offU, float offV) {
+    const float resm1 = (float)(res - 1);
+    const float blue = value.z * resm1;
+    const float s0 = floorf(blue), s1 = fminf(s0 + 1.0f, resm1), w = blue - s0;
+    const int tw = res * res, th = res * rows;
+    const float invW = 1.0f / (float)tw, invH = 1.0f / (float)th;
+    const float uIn = 0.5f + value.x * resm1, v = (0.5f + value.y * resm1) * invH + offV;
+    const float3 a = sampleLinearClamp(tex, tw, th, (s0 * (float)res + uIn) * invW + offU, v).xyz();
+    const float3 b = sampleLinearClamp(tex, tw, th, (s1 * (float)res + uIn) * invW + offU, v).xyz();
+    return lerp(a, b, w);
+}
+const float3 RgbToGrayLUT = float3(0.299f, 0.587f, 0.144f);  // LUTResolve.fx:16 (sic)
+}  // namespace
+
+// LUTBlendedResolveWithAlbedoCommon (LUTResolve.fx:57-117) + LUTBlendedLightingResolveWithAlbedoPixelShader (:119-135), 1:1
+extern "C" int orc_resolve_lighting_lut(const ilb_resolve* p, const ilb_lut_blending* lut, const float* dark, const float* bright,
+                                        const float* lightmap, const float* albedoTex, float* out) {
+    if (!p || !lut || !dark || !bright || !lightmap || !albedoTex || !out) return -1;
+    if (p->hdr_mode != ILB_HDR_NONE) return -2;  // "LUT blending is not compatible with this type of lighting resolve"
+    ilb_resolve P = *p;
+    if (P.InverseScaleFactor == 0.0f) P.InverseScaleFactor = 1.0f;
+    const float3 LUTLevels = float3(lut->DarkLevel, lut->NeutralBandSize, lut->BrightLevel);
+    const long n = (long)P.width * P.height;
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; i++) {
+        float4 light = float4(lightmap[4 * i], lightmap[4 * i + 1], lightmap[4 * i + 2], lightmap[4 * i + 3]);
+        float4 albedo = float4(albedoTex[4 * i], albedoTex[4 * i + 1], albedoTex[4 * i + 2], albedoTex[4 * i + 3]);
+        if (P.AlbedoIsSRGB != 0.0f) albedo = pSRGBToPLinear(albedo);
+        light *= P.InverseScaleFactor * 2;
+        float3 weight = light.xyz();
+        float bandWidth = saturate(LUTLevels.z - LUTLevels.x);
+        float neutralBandWidth = fminf(LUTLevels.y, bandWidth - 0.01f);
+        bool hasNeutralBand = (neutralBandWidth > 0);
+        bool normalize = !(lut->PerChannel != 0.0f) || hasNeutralBand;
+        if (normalize) {
+            weight *= RgbToGrayLUT;
+            weight = float3(weight.x + weight.y + weight.z);
+        }
+        float3 a = saturate(albedo.xyz());
+        float3 lutValue1 = ReadLUT(dark, lut->dark_resolution, lut->dark_row_count, a, lut->LUTOffsets[0], lut->LUTOffsets[1]);
+        float3 lutValue2 = ReadLUT(bright, lut->bright_resolution, lut->bright_row_count, a, lut->LUTOffsets[2], lut->LUTOffsets[3]);
+        float3 blendedValue;
+        if (hasNeutralBand) {
+            float transitionSize = (bandWidth - neutralBandWidth) * 0.5f;
+            float v = weight.x - LUTLevels.x, v2 = v - transitionSize, v3 = v2 - neutralBandWidth;
+            float3 val1 = lerp(lutValue1, a, saturate(v / transitionSize));
+            blendedValue = lerp(val1, lutValue2, saturate(v3 / transitionSize));
+        } else {
+            if (LUTLevels.z > LUTLevels.x) {
+                weight = weight - LUTLevels.x;
+                weight = max(float3(0.0f), weight);
+                weight = weight / (LUTLevels.z - LUTLevels.x);
+                weight = saturate(weight);
+            } else {  // HACK (:105-108)
+                weight = weight - LUTLevels.x;
+                weight = saturate(weight);
+            }
+            blendedValue = lutValue1 + weight * (lutValue2 - lutValue1);  // lerp with a per-channel weight
+        }
+        float4 result = float4(blendedValue * ((lut->LUTOnly != 0.0f) ? float3(1.0f) : light.xyz()), albedo.w);
+        float3 rgb = max(float3(0.0f), result.xyz() + P.Offset);
+        rgb *= (P.ExposureMinusOne + 1);
+        rgb = pow3(rgb, P.GammaMinusOne + 1);
+        result = float4(rgb, result.w);
+        if (P.ResolveToSRGB != 0.0f) result = pLinearToPSRGB(result);
+        result = dithered(P, result, (int)(i % P.width), (int)(i / P.width));
+        out[4 * i + 0] = result.x; out[4 * i + 1] = result.y; out[4 * i + 2] = result.z; out[4 * i + 3] = result.w;
+    }
     return 0;
 }
 

@@ -55,10 +55,12 @@ def test_struct_layouts_match_the_header(tmp_path):
              "ilb_light_vertex": _abi.LightVertex, "ilb_light_batch": _abi.LightBatch, "ilb_lighting_frame": _abi.LightingFrame,
              "ilb_bezier1": _abi.Bezier1, "ilb_bezier4": _abi.Bezier4, "ilb_psys_uniforms": _abi.PsysUniforms, "ilb_area": _abi.Area,
              "ilb_gravity": _abi.GravityOp, "ilb_noise": _abi.NoiseOp, "ilb_fma": _abi.FMAOp, "ilb_matrix_multiply": _abi.MatrixOp,
-             "ilb_op": _abi.Op, "ilb_spawn": _abi.Spawn, "ilb_resolve": _abi.Resolve, "ilb_spawn_source": _abi.SpawnSource, "ilb_particle_render": _abi.ParticleRender}
+             "ilb_op": _abi.Op, "ilb_spawn": _abi.Spawn, "ilb_resolve": _abi.Resolve, "ilb_spawn_source": _abi.SpawnSource, "ilb_particle_render": _abi.ParticleRender,
+             "ilb_dithering": _abi.Dithering, "ilb_lut_blending": _abi.LutBlending}
     probes = {"ilb_lighting_frame": ["ClearColor", "ViewportPosition", "stencil_culling"], "ilb_psys_uniforms": ["CollisionField", "has_collision_field"],
               "ilb_spawn": ["AttributeDiscardThreshold", "PositionMatrix"], "ilb_noise": ["VelocityScale", "RandomnessTexel"], "ilb_op": ["u"],
-              "ilb_light_batch": ["df"], "ilb_spawn_source": ["positions", "source_system", "source_chunk", "SourceLifeRange", "pattern_texels", "StepWidthAndSizeScale", "CenteringOffset"], "ilb_particle_render": ["ClearColor", "RoundingPowerFromLife", "ViewportScale", "StippleFactor"], "ilb_resolve": ["InverseScaleFactor", "WhitePoint", "DitheringStrength"], "ilb_gravity": ["AttractorRadiusesAndStrengths"]}
+              "ilb_light_batch": ["df"], "ilb_spawn_source": ["positions", "source_system", "source_chunk", "SourceLifeRange", "pattern_texels", "StepWidthAndSizeScale", "CenteringOffset"], "ilb_particle_render": ["ClearColor", "RoundingPowerFromLife", "ViewportScale", "StippleFactor"], "ilb_resolve": ["InverseScaleFactor", "WhitePoint", "DitheringStrength"], "ilb_gravity": ["AttractorRadiusesAndStrengths"],
+              "ilb_dithering": ["RangeMax"], "ilb_lut_blending": ["BrightLevel", "LUTOffsets"]}
     src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
     for n in names:
         src.append(f'printf("{n} %zu\\n", sizeof({n}));')
@@ -96,7 +98,8 @@ def test_csharp_shim_binds_every_symbol_with_matching_struct_sizes():
     mirrors = {"IlbDFUniforms": _abi.DFUniforms, "IlbLightBatch": _abi.LightBatch, "IlbLightingFrame": _abi.LightingFrame,
                "IlbObstruction": _abi.Obstruction, "IlbPsysUniforms": _abi.PsysUniforms, "IlbArea": _abi.Area, "IlbGravity": _abi.GravityOp,
                "IlbNoise": _abi.NoiseOp, "IlbFMA": _abi.FMAOp, "IlbMatrixMultiply": _abi.MatrixOp, "IlbSpawn": _abi.Spawn,
-               "IlbHeightVolume": _abi.HeightVolumeStruct, "IlbResolvePlacement": _abi.ResolvePlacement}
+               "IlbHeightVolume": _abi.HeightVolumeStruct, "IlbResolvePlacement": _abi.ResolvePlacement,
+               "IlbDithering": _abi.Dithering, "IlbLutBlending": _abi.LutBlending}
     checked = 0
     for name, body in re.findall(r"public (?:unsafe )?struct (\w+) \{(.*?)\n    \}|public (?:unsafe )?struct (\w+) \{(.*?)\n        \}", cs, flags=re.S) and \
             [(m[0] or m[2], m[1] or m[3]) for m in re.findall(r"public (?:unsafe )?struct (\w+) \{(.*?)\n    \}|public (?:unsafe )?struct (\w+) \{(.*?)\n        \}", cs, flags=re.S)]:
