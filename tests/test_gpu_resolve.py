@@ -143,9 +143,11 @@ def test_resolve_error_behaviour(ctx):
     with pytest.raises(ib.IlluminantError) as e:
         rl.Resolve(lightmap=lm, uvOffset=(0.5, 0.0))
     assert e.value.code == _abi.ERR_UNSUPPORTED
-    with pytest.raises(ib.IlluminantError) as e:
-        rl.Resolve(lightmap=lm, hdr=ib.HDRConfiguration(Dithering=ib.DitheringSettings(Strength=1.0)))
-    assert e.value.code == _abi.ERR_UNSUPPORTED and "DitherCommon" in str(e.value)
+    with pytest.raises(ib.IlluminantError) as e:     # LUT blending needs HDRMode.None (LightingRenderer.cs:1593-1594)
+        lut = ib.LUTBlendingConfiguration(ib.ColorLUT.Identity(4), ib.ColorLUT.Identity(4))
+        rl.Resolve(np.zeros((16, 16, 4), np.uint8), lightmap=lm, lutBlending=lut,
+                   hdr=ib.HDRConfiguration(Mode=ib.HDRMode.GammaCompress, GammaCompression=ib.GammaCompressionConfiguration(0.5, 0.5, 2.0)))
+    assert e.value.code == _abi.ERR_INVALID_ARGUMENT and "LUT blending" in str(e.value)
     with pytest.raises(ib.IlluminantError) as e:
         rl.Resolve(np.zeros((8, 8, 4), np.uint8), lightmap=lm)
     assert e.value.code == _abi.ERR_INVALID_ARGUMENT
