@@ -190,7 +190,8 @@ class IlluminantError(RuntimeError):
 
 
 # ilb_option
-OPT_LIGHT_CONCURRENT, OPT_LIGHT_LINE_CTAS, OPT_LIGHT_OTHER_CTAS, OPT_LIGHT_LINE_HELPERS, OPT_LIGHT_OTHER_HELPERS, OPT_LIGHT_PDL = range(6)
+(OPT_LIGHT_CONCURRENT, OPT_LIGHT_LINE_CTAS, OPT_LIGHT_OTHER_CTAS, OPT_LIGHT_LINE_HELPERS, OPT_LIGHT_OTHER_HELPERS, OPT_LIGHT_PDL,
+ OPT_LIGHT_CONST_BANK) = range(7)
 
 # every symbol include/illuminant_b200.h declares: (name, restype, argtypes)
 P = C.c_void_p

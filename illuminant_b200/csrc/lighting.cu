@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include <cuda_fp16.h>
 
@@ -60,6 +61,15 @@ struct __align__(16) DLine {
     float4 center;  // lightCenter.xyz, offset = max(saturate((radius + 1) / |P1 - P0|), 0.03)
     float4 ab;      // (P1 - P0).xyz, dot(ab, ab)
 };
+
+// The frame's light records in the constant bank (frames of up to ILB_CONST_LIGHTS lights; larger lists -- particle lights --
+// stay in global memory).  Every lane of a warp shades the same light at the same time, so a constant-bank read is a
+// broadcast; what it buys over the global copy is REGISTERS: a field read with LDC c[3][index + offset] is re-read where it
+// is used (after the cone trace: colour, specular, ...) instead of being loaded up front and kept -- or spilled -- across the
+// march.  The culling phase (one light per THREAD) and the out-of-line IEEE fallback keep reading the global copy.
+constexpr int ILB_CONST_LIGHTS = 256;
+__constant__ DLight c_lights[ILB_CONST_LIGHTS];
+__constant__ DLine c_lines[ILB_CONST_LIGHTS];
 
 // One LightSource.RampTexture as the kernel samples it (float4 texels; RampCommon.fxh:5-12: LINEAR, U CLAMP, V WRAP)
 struct RampTex { const float4* texels; int w, h, pad; };
@@ -545,7 +555,8 @@ ILB_DEV DLine loadLine(const DLine* lines, int i) {
 
 // One light at one pixel; returns false when the reference fragment would be discarded.
 // TYPES: bit mask of ilb_light_type values this instantiation can meet (other branches are compiled out)
-template <int FIELD, bool FAST, int TYPES>
+// CL: the light records of this frame are in the constant bank (c_lights / c_lines) and L refers into it
+template <int FIELD, bool FAST, int TYPES, bool CL>
 ILB_DEV bool shadeLight(const DFGeometry& df, float lightOcclusion, const DLight& L, const DLight* lights, const DLine* lines, const RampTex* ramps,
                         int lightIndex, const Pixel& px, f3& rgb, Guard& bad) {
     const float es = px.enableShadows ? 1.0f : 0.0f;
@@ -595,7 +606,9 @@ ILB_DEV bool shadeLight(const DFGeometry& df, float lightOcclusion, const DLight
         float4 props = L.props;
         props.w *= es;
         float u, opacity;
-        const DLine D = loadLine(lines, lightIndex);
+        DLine Dg;
+        if (!CL) Dg = loadLine(lines, lightIndex);
+        const DLine& D = CL ? c_lines[lightIndex] : Dg;
         if (!lineCore<FIELD, FAST>(df, L, D, px.pos, px.normal, mk3(L.pos1.x, L.pos1.y, L.pos1.z), mk3(L.pos2.x, L.pos2.y, L.pos2.z), props,
                                    L.more, u, opacity, bad))
             return false;
@@ -622,7 +635,7 @@ __device__ __noinline__ float4 shadeLightExact(const DFGeometry* df, float light
     const DLight L = loadLight(lights, lightIndex);
     f3 rgb = mk3(0.0f);
     Guard bad = guardInit();
-    const bool lit = shadeLight<FIELD, false, TYPES>(*df, lightOcclusion, L, lights, lines, ramps, lightIndex, px, rgb, bad);
+    const bool lit = shadeLight<FIELD, false, TYPES, false>(*df, lightOcclusion, L, lights, lines, ramps, lightIndex, px, rgb, bad);
 #if ILB_BREAK_FALLBACK  // test hook: proves that a test reaches this path (tests/README: degenerate-geometry tests must fail with it)
     rgb.x += 1.0f;
 #endif
@@ -630,15 +643,15 @@ __device__ __noinline__ float4 shadeLightExact(const DFGeometry* df, float light
 }
 
 // fast evaluation + fallback
-template <int FIELD, int TYPES>
+template <int FIELD, int TYPES, bool CL>
 ILB_DEV bool shadeLightGuarded(const DFGeometry& df, float lightOcclusion, const DLight& L, const DLight* lights, const DLine* lines,
                                const RampTex* ramps, int lightIndex, const Pixel& px, f3& rgb) {
 #if ILB_NO_FAST_GUARD
     Guard bad = guardInit();
-    return shadeLight<FIELD, false, TYPES>(df, lightOcclusion, L, lights, lines, ramps, lightIndex, px, rgb, bad);
+    return shadeLight<FIELD, false, TYPES, CL>(df, lightOcclusion, L, lights, lines, ramps, lightIndex, px, rgb, bad);
 #else
     Guard bad = guardInit();
-    bool lit = shadeLight<FIELD, true, TYPES>(df, lightOcclusion, L, lights, lines, ramps, lightIndex, px, rgb, bad);
+    bool lit = shadeLight<FIELD, true, TYPES, CL>(df, lightOcclusion, L, lights, lines, ramps, lightIndex, px, rgb, bad);
     if (guardTripped(bad)) {
         const float4 r = shadeLightExact<FIELD, TYPES>(&df, lightOcclusion, lights, lines, ramps, lightIndex,
                                                 make_float4(px.pos.x, px.pos.y, px.pos.z, px.enableShadows ? 1.0f : 0.0f),
@@ -701,7 +714,7 @@ struct TileSmem {
     unsigned next, arrival;      // persistent CTAs: the tile taken from the queue, this pass's arrival rank at the tile
 };
 
-template <int FIELD, int TYPES>
+template <int FIELD, int TYPES, bool CL>
 ILB_DEV void shadeTile(const LightingParams& P, unsigned tile, TileSmem& S) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // a warp covers an 8x4 pixel patch: neighbouring lanes trace neighbouring rays (coherent DF footprints)
@@ -813,10 +826,12 @@ ILB_DEV void shadeTile(const LightingParams& P, unsigned tile, TileSmem& S) {
         for (int k = 0; k < n; k++) {
             if ((TYPES & ILB_LIGHT_SPHERE) && !((S.mask[k] >> warp) & 1u)) continue;  // warp-uniform: this block is out of the light's reach
             const int lightIndex = base + (int)S.list[k];
-            const DLight L = loadLight(P.lights, lightIndex);
+            DLight Lg;
+            if (!CL) Lg = loadLight(P.lights, lightIndex);
+            const DLight& L = CL ? c_lights[lightIndex] : Lg;
             if (shade && coverage(L, wx, wy)) {
                 f3 rgb;
-                if (shadeLightGuarded<FIELD, TYPES>(P.df, P.envZToY.z, L, P.lights, P.lines, P.ramps, lightIndex, pix, rgb)) {
+                if (shadeLightGuarded<FIELD, TYPES, CL>(P.df, P.envZToY.z, L, P.lights, P.lines, P.ramps, lightIndex, pix, rgb)) {
                     // BlendState.Additive with PS alpha 1: rgb += src.rgb, a += 1 (LightingRenderer.cs:206)
                     accR += rgb.x; accG += rgb.y; accB += rgb.z; accA += 1.0f;
                 }
@@ -862,14 +877,14 @@ ILB_DEV void shadeTile(const LightingParams& P, unsigned tile, TileSmem& S) {
 // resident CTAs per SM for this pass's register budget (the budgets above are stated for 256-thread CTAs)
 #define ILB_LIGHT_CTAS(TYPES) ((((TYPES) & ILB_LIGHT_LINE) ? ILB_LIGHT_MINBLOCKS : ILB_LIGHT_MINBLOCKS_NOLINE) * (256 / TILE_THREADS))
 
-template <int FIELD, int TYPES>
+template <int FIELD, int TYPES, bool CL>
 __global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_CTAS(TYPES))
 light_accumulate_kernel(const __grid_constant__ LightingParams P) {
     __shared__ TileSmem S;
     // first pass of a split frame: the second pass may be scheduled as soon as every CTA of this grid has started, i.e. into
     // the idle SM slots of this grid's last wave (it waits for this grid's results only at its very end, see shadeTile)
     if (P.accum_out && !P.tile_done) asm volatile("griddepcontrol.launch_dependents;");
-    shadeTile<FIELD, TYPES>(P, blockIdx.x, S);
+    shadeTile<FIELD, TYPES, CL>(P, blockIdx.x, S);
 }
 
 // Persistent form: a fixed number of resident CTAs per SM takes tiles from a queue (one atomic counter per pass), so that
@@ -888,7 +903,7 @@ light_accumulate_persistent_kernel(const __grid_constant__ LightingParams P) {
         __syncthreads();
         const unsigned tile = S.next;
         if (tile >= ntiles) return;
-        shadeTile<FIELD, TYPES>(P, tile, S);
+        shadeTile<FIELD, TYPES, false>(P, tile, S);
     }
 }
 
@@ -1093,8 +1108,19 @@ int flattenLights(ilb_ctx* ctx, const ilb_df* df, const ilb_lighting_frame* f, c
 
 // device layout: DLine[n] (host lights only) followed by DLight[n + extra]; the `extra` records are appended on the device
 // (particle lights)
+std::mutex g_constBankMutex;
+cudaEvent_t g_constBankLastUse = nullptr;   // behind the most recent launch (of any context) that reads c_lights / c_lines
+
+// records that the work queued on ctx->stream so far reads the constant-bank light records
+int constBankMarkUse(ilb_ctx* ctx) {
+    std::lock_guard<std::mutex> lock(g_constBankMutex);
+    if (!g_constBankLastUse) ILB_CUDA(ctx, cudaEventCreateWithFlags(&g_constBankLastUse, cudaEventDisableTiming));
+    ILB_CUDA(ctx, cudaEventRecord(g_constBankLastUse, ctx->stream));
+    return ILB_OK;
+}
+
 int uploadLights(ilb_ctx* ctx, const std::vector<DLight>& lights, const std::vector<DLine>& lines, size_t extra, const DLight** d_lights,
-                 const DLine** d_lines) {
+                 const DLine** d_lines, bool toConstantBank = false) {
     const size_t n = lights.size();
     const size_t lineBytes = std::max<size_t>(n, 1) * sizeof(DLine), hostBytes = lineBytes + std::max<size_t>(n, 1) * sizeof(DLight);
     int rc = ilb_reserve(ctx, &ctx->d_lights, &ctx->d_lights_capacity, hostBytes + extra * sizeof(DLight), false);
@@ -1116,6 +1142,16 @@ int uploadLights(ilb_ctx* ctx, const std::vector<DLight>& lights, const std::vec
         memcpy(ctx->h_lights[slot], lines.data(), n * sizeof(DLine));
         memcpy(reinterpret_cast<char*>(ctx->h_lights[slot]) + lineBytes, lights.data(), n * sizeof(DLight));
         ILB_CUDA(ctx, cudaMemcpyAsync(ctx->d_lights, ctx->h_lights[slot], hostBytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (toConstantBank) {
+            // The constant bank belongs to the module, i.e. to every context of the process on this device: the kernels of
+            // another context's frame that still read it must have finished before it is overwritten (same-stream work is
+            // ordered anyway).  One process-wide event, recorded behind every lighting launch that reads the bank.
+            std::lock_guard<std::mutex> lock(g_constBankMutex);
+            if (g_constBankLastUse) ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, g_constBankLastUse, 0));
+            const char* staged = reinterpret_cast<const char*>(ctx->h_lights[slot]);
+            ILB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_lines, staged, n * sizeof(DLine), 0, cudaMemcpyHostToDevice, ctx->stream));
+            ILB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_lights, staged + lineBytes, n * sizeof(DLight), 0, cudaMemcpyHostToDevice, ctx->stream));
+        }
         ILB_CUDA(ctx, cudaEventRecord(ctx->ev_lights[slot], ctx->stream));
     }
     *d_lines = reinterpret_cast<const DLine*>(ctx->d_lights);
@@ -1247,6 +1283,7 @@ namespace {
 struct LightingPrepared {
     LightingParams P;   // everything but the row band and the outputs
     int nline = 0, nlights = 0;
+    bool constBank = false;   // the frame's light records are in c_lights / c_lines as well
 };
 
 // Per-frame work that does not depend on the row band: validate, flatten + upload the light list, resolve the field.
@@ -1319,7 +1356,8 @@ int lightingPrepare(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const
         if (extra > ((size_t)1 << 20))
             return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "%zu particle lights in one frame (limit 1048576): the tile culling is brute force over the light list", extra);
     }
-    rc = uploadLights(ctx, lights, lines, extra, &P.lights, &P.lines);
+    out->constBank = ctx->opt[ILB_OPT_LIGHT_CONST_BANK] != 0 && !lights.empty() && lights.size() + extra <= (size_t)ILB_CONST_LIGHTS;
+    rc = uploadLights(ctx, lights, lines, extra, &P.lights, &P.lines, out->constBank);
     if (rc) return rc;
     {
         size_t at = lights.size();
@@ -1331,6 +1369,9 @@ int lightingPrepare(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const
             at += pd.count;
         }
         ILB_CUDA(ctx, cudaGetLastError());
+        if (out->constBank && extra)   // the particle-light records were written on the device: append them to the bank from there
+            ILB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_lights, P.lights + lights.size(), extra * sizeof(DLight), lights.size() * sizeof(DLight),
+                                                  cudaMemcpyDeviceToDevice, ctx->stream));
     }
     if (geometry) {
         if (!ilb_make_df_geometry(df, *geometry, &P.df)) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad distance-field uniforms");
@@ -1393,10 +1434,12 @@ int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin
     if (const char* e = getenv("ILB_PLANES_MASK")) planesMask = atoi(e);
 #define ILB_LIGHT_LAUNCH(TYPES)                                                                                       \
     do {                                                                                                              \
-        if (P.df.planes && (planesMask & (((TYPES) & ILB_LIGHT_LINE) ? 1 : 2)))                                       \
-            light_accumulate_kernel<1, TYPES><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);                            \
-        else                                                                                                          \
-            light_accumulate_kernel<0, TYPES><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);                            \
+        if (P.df.planes && (planesMask & (((TYPES) & ILB_LIGHT_LINE) ? 1 : 2))) {                                     \
+            if (prep.constBank) light_accumulate_kernel<1, TYPES, true><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);  \
+            else light_accumulate_kernel<1, TYPES, false><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);                \
+        } else {                                                                                                      \
+            light_accumulate_kernel<0, TYPES, false><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);                     \
+        }                                                                                                             \
         ctx->launches++;                                                                                              \
     } while (0)
     const bool concurrent = ctx->opt[ILB_OPT_LIGHT_CONCURRENT] != 0 &&  // every pass needs at least one grid, or its tiles are never shaded
@@ -1468,8 +1511,12 @@ int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;
-            if (P.df.planes && (planesMask & 2)) ILB_CUDA(ctx, cudaLaunchKernelEx(&cfg, light_accumulate_kernel<1, NOLINE>, P));
-            else ILB_CUDA(ctx, cudaLaunchKernelEx(&cfg, light_accumulate_kernel<0, NOLINE>, P));
+            if (P.df.planes && (planesMask & 2)) {
+                if (prep.constBank) ILB_CUDA(ctx, cudaLaunchKernelEx(&cfg, light_accumulate_kernel<1, NOLINE, true>, P));
+                else ILB_CUDA(ctx, cudaLaunchKernelEx(&cfg, light_accumulate_kernel<1, NOLINE, false>, P));
+            } else {
+                ILB_CUDA(ctx, cudaLaunchKernelEx(&cfg, light_accumulate_kernel<0, NOLINE, false>, P));
+            }
             ctx->launches++;
         } else {
             ILB_LIGHT_LAUNCH(NOLINE);
@@ -1481,6 +1528,7 @@ int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin
     }
 #undef ILB_LIGHT_LAUNCH
     ILB_CUDA(ctx, cudaGetLastError());
+    if (prep.constBank) return constBankMarkUse(ctx);
     return ILB_OK;
 }
 

@@ -76,7 +76,10 @@ typedef enum ilb_option {
     ILB_OPT_LIGHT_OTHER_HELPERS = 4,/* extra sphere + directional CTAs per SM for the opposite case (default 3) */
     ILB_OPT_LIGHT_PDL = 5,          /* 1: the sphere + directional pass is a programmatic dependent launch of the line-light pass:
                                      * its CTAs start in the idle slots of the first pass's last wave (default 1) */
-    ILB_OPT_COUNT = 6
+    ILB_OPT_LIGHT_CONST_BANK = 6,   /* 1: frames of up to 256 lights keep their light records in the constant bank as well, so that the
+                                     * per-pixel light loop re-reads a field where it uses it instead of holding the whole record in
+                                     * registers across the cone trace (default 1) */
+    ILB_OPT_COUNT = 7
 } ilb_option;
 ILB_API int ilb_set_option(ilb_ctx* ctx, int option, int value);
 ILB_API int ilb_get_option(const ilb_ctx* ctx, int option, int* out_value);
