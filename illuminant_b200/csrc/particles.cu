@@ -477,6 +477,9 @@ ILB_DEV bool updateTail(const StepParams& P, float x, float y, unsigned li, f4 o
 #ifndef ILB_PARTICLE_MINBLOCKS
 #define ILB_PARTICLE_MINBLOCKS 5
 #endif
+#ifndef ILB_PARTICLE_PREFETCH_CTAS
+#define ILB_PARTICLE_PREFETCH_CTAS (148 * ILB_PARTICLE_MINBLOCKS)
+#endif
 
 template <int KIND, bool FAST>
 ILB_DEV void applyOp(const StepParams& P, const ilb_op& op, const OpDerived& d, float x, float y, unsigned li, f4& pos, f4& vel, Guard& bad) {
@@ -574,6 +577,18 @@ __global__ void __launch_bounds__(STEP_THREADS, ILB_PARTICLE_MINBLOCKS) particle
     float x, y;
     const unsigned li = particleXY(P, gi, x, y);
     const f4 inP = inRange ? mk4(P.P[gi]) : mk4(0.0f), inV = inRange ? mk4(P.V[gi]) : mk4(0.0f);
+#if ILB_PARTICLE_PREFETCH_CTAS > 0
+    // CTAs start in block order and ILB_PARTICLE_PREFETCH_CTAS of them are resident at a time (148 SMs x 5), so the CTA that
+    // takes this one's place runs about one CTA lifetime from now: pull its PositionAndLife / Velocity lines towards L2 now (one
+    // lane per 128-byte line), so that its first loads -- which nothing can overlap within the warp -- hit L2 instead of HBM
+    if ((threadIdx.x & 7u) == 0u) {
+        const unsigned long long ahead = (unsigned long long)gi + (unsigned long long)ILB_PARTICLE_PREFETCH_CTAS * STEP_THREADS;
+        if (ahead < P.total) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.P + ahead));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.V + ahead));
+        }
+    }
+#endif
 #if !ILB_NO_ATTR_PREFETCH
     // the attributes are only needed by the render outputs at the very end: start pulling a live particle's texel towards L2 now,
     // so that the dependent load behind ~1000 instructions of chain does not pay the DRAM latency (dead particles fetch nothing)
