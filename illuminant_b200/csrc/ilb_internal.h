@@ -35,6 +35,10 @@ struct ilb_ctx {
     size_t h_lights_capacity[2] = {0, 0};
     cudaEvent_t ev_lights[2] = {nullptr, nullptr};
     int h_lights_next = 0;
+    // what d_lights currently holds (uploadLights skips the copies of a frame whose flattened light list is unchanged)
+    std::vector<char> lights_cache;
+    const void* lights_cache_ptr = nullptr;
+    unsigned long long lights_cache_const_epoch = 0;   // epoch of the constant bank that holds the same list; 0 = not in the bank
     void* d_lightmap = nullptr;  // staging for host-output entry points
     size_t d_lightmap_capacity = 0;
     void* d_probe_in = nullptr;

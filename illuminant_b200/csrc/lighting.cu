@@ -1110,6 +1110,7 @@ int flattenLights(ilb_ctx* ctx, const ilb_df* df, const ilb_lighting_frame* f, c
 // (particle lights)
 std::mutex g_constBankMutex;
 cudaEvent_t g_constBankLastUse = nullptr;   // behind the most recent launch (of any context) that reads c_lights / c_lines
+unsigned long long g_constBankEpoch = 0;    // bumped by every upload into the bank: a context's cached list is there only while its epoch is current
 
 // records that the work queued on ctx->stream so far reads the constant-bank light records
 int constBankMarkUse(ilb_ctx* ctx) {
@@ -1125,6 +1126,21 @@ int uploadLights(ilb_ctx* ctx, const std::vector<DLight>& lights, const std::vec
     const size_t lineBytes = std::max<size_t>(n, 1) * sizeof(DLine), hostBytes = lineBytes + std::max<size_t>(n, 1) * sizeof(DLight);
     int rc = ilb_reserve(ctx, &ctx->d_lights, &ctx->d_lights_capacity, hostBytes + extra * sizeof(DLight), false);
     if (rc) return rc;
+    *d_lines = reinterpret_cast<const DLine*>(ctx->d_lights);
+    *d_lights = reinterpret_cast<const DLight*>(reinterpret_cast<const char*>(ctx->d_lights) + lineBytes);
+    // Lights that did not change since the last upload (static lights, and the probe update that follows a frame with the same
+    // list) are not copied again: the flattened records are compared with what the device copy -- and, when asked for, the
+    // constant bank, which another context may have overwritten since (epoch) -- already hold.
+    const size_t lb = n * sizeof(DLine), gb = n * sizeof(DLight);
+    if (n && ctx->lights_cache_ptr == ctx->d_lights && ctx->lights_cache.size() == lb + gb &&
+        memcmp(ctx->lights_cache.data(), lines.data(), lb) == 0 && memcmp(ctx->lights_cache.data() + lb, lights.data(), gb) == 0) {
+        bool bankOk = !toConstantBank;
+        if (toConstantBank) {
+            std::lock_guard<std::mutex> lock(g_constBankMutex);
+            bankOk = ctx->lights_cache_const_epoch != 0 && ctx->lights_cache_const_epoch == g_constBankEpoch;
+        }
+        if (bankOk) return ILB_OK;
+    }
     // two pinned staging buffers alternate, each guarded by the event recorded behind its last copy: a frame never waits
     // for the stream unless the copy issued two frames ago is still pending
     const int slot = ctx->h_lights_next;
@@ -1151,11 +1167,16 @@ int uploadLights(ilb_ctx* ctx, const std::vector<DLight>& lights, const std::vec
             const char* staged = reinterpret_cast<const char*>(ctx->h_lights[slot]);
             ILB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_lines, staged, n * sizeof(DLine), 0, cudaMemcpyHostToDevice, ctx->stream));
             ILB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_lights, staged + lineBytes, n * sizeof(DLight), 0, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->lights_cache_const_epoch = ++g_constBankEpoch;
+        } else {
+            ctx->lights_cache_const_epoch = 0;
         }
         ILB_CUDA(ctx, cudaEventRecord(ctx->ev_lights[slot], ctx->stream));
+        ctx->lights_cache.resize(lb + gb);
+        memcpy(ctx->lights_cache.data(), lines.data(), lb);
+        memcpy(ctx->lights_cache.data() + lb, lights.data(), gb);
+        ctx->lights_cache_ptr = ctx->d_lights;
     }
-    *d_lines = reinterpret_cast<const DLine*>(ctx->d_lights);
-    *d_lights = reinterpret_cast<const DLight*>(reinterpret_cast<const char*>(ctx->d_lights) + lineBytes);
     return ILB_OK;
 }
 

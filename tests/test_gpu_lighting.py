@@ -322,3 +322,33 @@ def test_particle_light_source(ctx, oracle):
     pls.Enabled = True
     bands = [r.RenderLighting(rows=(a, b)) for a, b in ((0, 64), (64, 200))]
     assert np.array_equal(np.concatenate(bands, axis=0), gpu)
+
+
+def test_light_list_caching_and_the_shared_constant_bank(ctx):
+    """The flattened light records are uploaded only when they change, and frames of up to 256 lights read them from the
+    constant bank -- which belongs to the module, i.e. to every context of the process.  Two contexts that render different
+    light lists alternately, a light that moves between two frames, and the option switched off must all give the same bits
+    as a fresh render."""
+    from illuminant_b200 import _abi
+    sa = scenes.lighting_scene(51, 160, 96, 5, n_directional=1, n_line=1, ramp=(50.0, 140.0), float4_lightmap=True)
+    sb = scenes.lighting_scene(52, 160, 96, 3, n_line=2, ramp=(60.0, 120.0), float4_lightmap=True)
+    ra, _ = make_renderer(ctx, sa)
+    c2 = ib.Context(0)
+    try:
+        rb, _ = make_renderer(c2, sb)
+        a0, b0 = ra.RenderLighting(), rb.RenderLighting()
+        for _ in range(3):      # unchanged lists: nothing is uploaded, and each context finds the other's records in the bank
+            assert np.array_equal(ra.RenderLighting(), a0) and np.array_equal(rb.RenderLighting(), b0)
+        ctx.set_option(_abi.OPT_LIGHT_CONST_BANK, 0)
+        assert np.array_equal(ra.RenderLighting(), a0)          # the global-memory path: same bits
+        ctx.set_option(_abi.OPT_LIGHT_CONST_BANK, 1)
+        assert np.array_equal(ra.RenderLighting(), a0)
+        light = sa.environment.Lights[0]
+        x, y, z = light.Position
+        light.Position = (x + 7.0, y - 3.0, z)
+        a1 = ra.RenderLighting()
+        assert not np.array_equal(a1, a0)                        # the moved light was uploaded
+        light.Position = (x, y, z)
+        assert np.array_equal(ra.RenderLighting(), a0) and np.array_equal(rb.RenderLighting(), b0)
+    finally:
+        c2.close()
