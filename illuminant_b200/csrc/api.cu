@@ -187,6 +187,7 @@ void ilb_destroy(ilb_ctx* ctx) {
     for (ilb_ctx::RampTexture& t : ctx->ramps) if (t.texels) cudaFree(t.texels);
     for (int i = 0; i < 2; i++) if (ctx->d_luminance[i]) cudaFree(ctx->d_luminance[i]);
     if (ctx->d_plight_scratch) cudaFree(ctx->d_plight_scratch);
+    if (ctx->band_stream) { cudaStreamDestroy(ctx->band_stream); cudaEventDestroy(ctx->ev_band_fork); cudaEventDestroy(ctx->ev_band_join); }
     if (ctx->copy_in) {
         cudaStreamDestroy(ctx->copy_in);
         cudaStreamDestroy(ctx->copy_out);

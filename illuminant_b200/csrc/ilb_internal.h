@@ -71,6 +71,8 @@ struct ilb_ctx {
     size_t d_plight_scratch_capacity = 0;
     // host-to-host frame pipeline (ilb_render_lighting_frame): upload / download streams and per-band events
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaStream_t band_stream = nullptr;                        // second compute lane of the pipelined host-to-host frame
+    cudaEvent_t ev_band_fork = nullptr, ev_band_join = nullptr;
     cudaEvent_t ev_in[ILB_PIPELINE_BANDS] = {}, ev_done[ILB_PIPELINE_BANDS] = {};
 };
 

@@ -1112,11 +1112,11 @@ std::mutex g_constBankMutex;
 cudaEvent_t g_constBankLastUse = nullptr;   // behind the most recent launch (of any context) that reads c_lights / c_lines
 unsigned long long g_constBankEpoch = 0;    // bumped by every upload into the bank: a context's cached list is there only while its epoch is current
 
-// records that the work queued on ctx->stream so far reads the constant-bank light records
-int constBankMarkUse(ilb_ctx* ctx) {
+// records that the work queued on `stream` so far reads the constant-bank light records
+int constBankMarkUse(ilb_ctx* ctx, cudaStream_t stream) {
     std::lock_guard<std::mutex> lock(g_constBankMutex);
     if (!g_constBankLastUse) ILB_CUDA(ctx, cudaEventCreateWithFlags(&g_constBankLastUse, cudaEventDisableTiming));
-    ILB_CUDA(ctx, cudaEventRecord(g_constBankLastUse, ctx->stream));
+    ILB_CUDA(ctx, cudaEventRecord(g_constBankLastUse, stream));
     return ILB_OK;
 }
 
@@ -1433,8 +1433,13 @@ int lightingPrepare(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const
 }
 
 // Shades rows [row_begin, row_end) of a prepared frame into d_outputs (band buffers whose row 0 is `out_row_base`).
+// `lane` 1 runs the band on ctx->band_stream with its own scratch sums, so that the kernels of two neighbouring bands of a
+// pipelined frame can be resident together (the tail of one band's last wave is filled by the next band's CTAs).
 int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin, int row_end, void* const* d_outputs, int output_count,
-                       int out_row_base) {
+                       int out_row_base, int lane = 0) {
+    const cudaStream_t st = lane ? ctx->band_stream : ctx->stream;
+    void** accumBuffer = lane ? &ctx->d_accum2 : &ctx->d_accum;
+    size_t* accumCapacity = lane ? &ctx->d_accum2_capacity : &ctx->d_accum_capacity;
     if (output_count < 1 || output_count > MAX_OUTPUTS) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "1..%d outputs", MAX_OUTPUTS);
     if (row_begin >= row_end) return ILB_OK;
     LightingParams P = prep.P;
@@ -1456,17 +1461,17 @@ int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin
 #define ILB_LIGHT_LAUNCH(TYPES)                                                                                       \
     do {                                                                                                              \
         if (P.df.planes && (planesMask & (((TYPES) & ILB_LIGHT_LINE) ? 1 : 2))) {                                     \
-            if (prep.constBank) light_accumulate_kernel<1, TYPES, true><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);  \
-            else light_accumulate_kernel<1, TYPES, false><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);                \
+            if (prep.constBank) light_accumulate_kernel<1, TYPES, true><<<tiles, TILE_THREADS, 0, st>>>(P);           \
+            else light_accumulate_kernel<1, TYPES, false><<<tiles, TILE_THREADS, 0, st>>>(P);                         \
         } else {                                                                                                      \
-            light_accumulate_kernel<0, TYPES, false><<<tiles, TILE_THREADS, 0, ctx->stream>>>(P);                     \
+            light_accumulate_kernel<0, TYPES, false><<<tiles, TILE_THREADS, 0, st>>>(P);                              \
         }                                                                                                             \
         ctx->launches++;                                                                                              \
     } while (0)
     const bool concurrent = ctx->opt[ILB_OPT_LIGHT_CONCURRENT] != 0 &&  // every pass needs at least one grid, or its tiles are never shaded
                             ctx->opt[ILB_OPT_LIGHT_LINE_CTAS] + ctx->opt[ILB_OPT_LIGHT_LINE_HELPERS] > 0 &&
                             ctx->opt[ILB_OPT_LIGHT_OTHER_CTAS] + ctx->opt[ILB_OPT_LIGHT_OTHER_HELPERS] > 0;
-    if (split && concurrent) {
+    if (split && concurrent && lane == 0) {
         // both passes at once: persistent grids sized to be co-resident, one tile queue per pass, the pass that reaches a
         // tile second adds the two fp32 partial sums and stores the texel (see light_accumulate_persistent_kernel)
         const size_t bytes = sizeof(float4) * (size_t)P.width * (size_t)(row_end - row_begin);
@@ -1516,9 +1521,9 @@ int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin
         }
     } else if (split) {
         const size_t bytes = sizeof(float4) * (size_t)P.width * (size_t)(row_end - row_begin);
-        const int rc = ilb_reserve(ctx, &ctx->d_accum, &ctx->d_accum_capacity, bytes, false);
+        const int rc = ilb_reserve(ctx, accumBuffer, accumCapacity, bytes, false);
         if (rc) return rc;
-        P.accum_out = reinterpret_cast<float4*>(ctx->d_accum);
+        P.accum_out = reinterpret_cast<float4*>(*accumBuffer);
         ILB_LIGHT_LAUNCH(ILB_LIGHT_LINE);
         P.accum_in = P.accum_out;
         P.accum_out = nullptr;
@@ -1527,7 +1532,7 @@ int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin
             // programmatic dependent launch: the second pass's CTAs fill the SM slots the first pass's last wave leaves idle
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof(cfg));
-            cfg.gridDim = dim3(tiles); cfg.blockDim = dim3(TILE_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+            cfg.gridDim = dim3(tiles); cfg.blockDim = dim3(TILE_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -1549,7 +1554,7 @@ int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin
     }
 #undef ILB_LIGHT_LAUNCH
     ILB_CUDA(ctx, cudaGetLastError());
-    if (prep.constBank) return constBankMarkUse(ctx);
+    if (prep.constBank) return constBankMarkUse(ctx, st);
     return ILB_OK;
 }
 
@@ -1611,6 +1616,32 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
         const int e = f->row_begin + (int)(((long long)rows * acc / 16 + TILE_H - 1) / TILE_H * TILE_H);
         edge[b + 1] = (b == 6) ? f->row_end : std::min(std::max(e, edge[b]), f->row_end);
     }
+    // Two compute lanes: even bands run on the context's stream, odd bands on band_stream with their own scratch sums, so the
+    // CTAs of band b + 1 fill the SM slots that the last wave of band b leaves idle (kernels of one stream run back to back,
+    // and every band would otherwise pay the tails of both of its passes).  ILB_BAND_LANES=1 restores the single lane.
+    int lanes = 2;
+    if (const char* e = getenv("ILB_BAND_LANES")) lanes = atoi(e) >= 2 ? 2 : 1;
+    const bool splitFrame = prep.nline > 0 && prep.nline < prep.nlights;
+    if (ctx->opt[ILB_OPT_LIGHT_CONCURRENT] != 0 && splitFrame) lanes = 1;   // the co-resident pass mode owns both scratch buffers
+    if (lanes == 2) {
+        if (!ctx->band_stream) {
+            ILB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->band_stream, cudaStreamNonBlocking));
+            ILB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_band_fork, cudaEventDisableTiming));
+            ILB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_band_join, cudaEventDisableTiming));
+        }
+        if (splitFrame) {   // both scratch buffers at their final size before anything is in flight
+            int maxRows = 0;
+            for (int b = 0; b < 7; b++) maxRows = std::max(maxRows, edge[b + 1] - edge[b]);
+            const size_t bytes = sizeof(float4) * (size_t)f->width * (size_t)std::max(maxRows, 1);
+            rc = ilb_reserve(ctx, &ctx->d_accum, &ctx->d_accum_capacity, bytes, false);
+            if (rc) return rc;
+            rc = ilb_reserve(ctx, &ctx->d_accum2, &ctx->d_accum2_capacity, bytes, false);
+            if (rc) return rc;
+        }
+        // the second lane starts behind everything the frame's preparation queued on the context's stream (light records)
+        ILB_CUDA(ctx, cudaEventRecord(ctx->ev_band_fork, ctx->stream));
+        ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->band_stream, ctx->ev_band_fork, 0));
+    }
     const char* gsrc = reinterpret_cast<const char*>(gbuffer_host);
     char* gdst = reinterpret_cast<char*>(ctx->gbuffer);
     char* ldev = reinterpret_cast<char*>(ctx->d_lightmap);
@@ -1630,11 +1661,17 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
     for (int b = 0; b < 7; b++) {
         const int r0 = edge[b], r1 = edge[b + 1];
         if (r1 <= r0) continue;
-        ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
+        const int lane = (lanes == 2) ? (b & 1) : 0;
+        const cudaStream_t st = lane ? ctx->band_stream : ctx->stream;
+        ILB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_in[b], 0));
         void* outs[1] = {ctx->d_lightmap};
-        rc = lightingLaunchRows(ctx, prep, r0, r1, outs, 1, f->row_begin);
+        rc = lightingLaunchRows(ctx, prep, r0, r1, outs, 1, f->row_begin, lane);
         if (rc) return rc;
-        ILB_CUDA(ctx, cudaEventRecord(ctx->ev_done[b], ctx->stream));
+        ILB_CUDA(ctx, cudaEventRecord(ctx->ev_done[b], st));
+    }
+    if (lanes == 2) {   // later work on the context's stream is ordered behind both lanes
+        ILB_CUDA(ctx, cudaEventRecord(ctx->ev_band_join, ctx->band_stream));
+        ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_band_join, 0));
     }
     for (int b = 0; b < 7; b++) {
         const int r0 = edge[b], r1 = edge[b + 1];
