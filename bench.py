@@ -431,21 +431,56 @@ def run_ours(args):
             h2d, d2h = H * W * 16 + nv * 128 + probes_packed[2] * 32, H * W * 8 + probes_packed[2] * 8
             e2e_note = "one ilb_render_lighting_frame call per frame + probe update and read-back"
         else:
+            # N > 1, host to host: every rank's band is cut into `rounds` sub-bands of whole tile rows.  Per round a rank uploads the
+            # sub-band's G-buffer rows (ilb_gbuffer_upload_rows: upload stream, behind nothing but the work that touches those rows),
+            # renders it with the in-kernel peer-store gather, and a symmetric-memory barrier closes the round on every rank; RANK 0
+            # then downloads the round's rows of ALL ranks from its reassembled buffer on a copy stream while the next round computes.
             out_host = torch.empty((H, W, 4), dtype=torch.float16).pin_memory() if rank == 0 else None
-            gb_rows = gb_host[r0:r1] if r1 > r0 else gb_host[:1]
+            rounds = 4 if world <= 2 else 2
+            all_bounds = list(bounds)
+
+            def cut(a, b):   # `rounds` pieces of whole 16-row tile rows
+                edges = [a + min(b - a, ((b - a) * k // rounds + 15) // 16 * 16) for k in range(rounds)] + [b]
+                return [(edges[k], edges[k + 1]) for k in range(rounds)]
+            pieces = [cut(all_bounds[k], all_bounds[k + 1]) for k in range(world)]
+            copy_out = torch.cuda.Stream(device=local_rank)
+            ev_round = [torch.cuda.Event() for _ in range(rounds)]
+            use_peers = peers["ptrs"] is not None
 
             def e2e_step():
-                if r1 > r0:
-                    ctx.check(ctx.lib.ilb_gbuffer_upload_rows(ctx.handle, W, H, _abi.FORMAT_FLOAT4, r0, r1, C.c_void_p(gb_rows.data_ptr())))
-                light_step()
-                if rank == 0:
-                    with torch.cuda.stream(stream):
-                        out_host.copy_(full[:H], non_blocking=True)
+                with torch.cuda.stream(stream):
+                    for k in range(rounds):
+                        a, b = pieces[rank][k]
+                        if b > a:
+                            ctx.check(ctx.lib.ilb_gbuffer_upload_rows(ctx.handle, W, H, _abi.FORMAT_FLOAT4, a, b, C.c_void_p(gb_host[a:b].data_ptr())))
+                            if use_peers:
+                                renderer.RenderLightingPeers(peers["ptrs"], rows=(a, b), packed=packed)
+                            else:
+                                renderer.RenderLightingDevice(full[a:].data_ptr(), rows=(a, b), packed=packed)
+                        if k == 0 and rank == 0:
+                            renderer.UpdateLightProbesDevice(d_probes.data_ptr(), packed=packed, probes=probes_packed)
+                        if use_peers:
+                            peers["hdl"].barrier(channel=0)
+                        if rank == 0 and use_peers:
+                            ev_round[k].record(stream)
+                            copy_out.wait_event(ev_round[k])
+                            with torch.cuda.stream(copy_out):
+                                for q in range(world):
+                                    qa, qb = pieces[q][k]
+                                    if qb > qa:
+                                        out_host[qa:qb].copy_(full[qa:qb], non_blocking=True)
+                    if not use_peers:   # NCCL fallback: one all-gather of equal bands, then the download
+                        dist.all_gather_into_tensor(full, full[r0:r0 + sharding.band_height(H, world)])
+                        if rank == 0:
+                            out_host.copy_(full[:H], non_blocking=True)
+                    if rank == 0:
                         probes_out_host.copy_(d_probes, non_blocking=True)
                 ctx.synchronize()
+                copy_out.synchronize()
             h2d = H * W * 16 + world * nv * 128 + probes_packed[2] * 32     # all ranks' band uploads together = one G-buffer
             d2h = H * W * 8 + probes_packed[2] * 8
-            e2e_note = "per-rank G-buffer band upload, in-kernel gather, rank 0 downloads the reassembled full frame"
+            e2e_note = (f"per-rank G-buffer band upload and render in {rounds} rounds (in-kernel gather + barrier per round), rank 0 downloads the "
+                        "reassembled full frame round by round behind the next round's kernels")
         e_steps = max(3, args.steps // 2)
         for _ in range(2):
             e2e_step()
@@ -457,6 +492,12 @@ def run_ours(args):
         e_ms = reduce_ranks((time.perf_counter() - t0) * 1e3 / e_steps)
         if dist is not None:
             renderer.SetGBuffer(gb_host.numpy())    # the band uploads left the other rows as they were; restore for what follows
+            if rank == 0:   # the frame that arrived on the host is the unsharded render, bit for bit
+                whole = torch.empty((H, W, 4), dtype=torch.float16, device="cuda")
+                renderer.RenderLightingDevice(whole.data_ptr(), rows=(0, H), packed=packed)
+                ctx.synchronize()
+                result["e2e_host_frame_matches_single_gpu"] = bool(torch.equal(whole.cpu().view(torch.int16), out_host.view(torch.int16)))
+                del whole
 
         traffic, traffic_note = None, "not measured"
         if rank == 0 and not args.no_traffic:
@@ -713,7 +754,7 @@ def run_ours(args):
                 "config": {"workload": C4_WORKLOAD if primary else result.get("config", {}).get("workload"),
                            "parallelism": f"row bands of equal measured cost x{world}, gather: {result.get('gather', 'none')}" if primary else f"chunk ranges x{world}, no collective",
                            "l2": "inputs larger than L2 (no flush)"}}
-        for k in ("roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "gather_checksum_equal", "gather_matches_single_gpu", "probes", "bands",
+        for k in ("roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "gather_checksum_equal", "gather_matches_single_gpu", "e2e_host_frame_matches_single_gpu", "probes", "bands",
                   "particles", "combined_c5", "combined_c5_strong", "resolve", "render", "render_sharded"):
             if k in result:
                 line[k] = result[k]

@@ -84,6 +84,17 @@ __global__ void detmath_kernel(int function, const float* __restrict__ x, float*
 }
 }  // namespace
 
+int ilb_gbuffer_note_user(ilb_ctx* ctx, int row_begin, int row_end) {
+    ilb_ctx::GBufferUser& u = ctx->gb_users[ctx->gb_user_next];
+    ctx->gb_user_next = (ctx->gb_user_next + 1) % 8;
+    if (!u.done) ILB_CUDA(ctx, cudaEventCreateWithFlags(&u.done, cudaEventDisableTiming));
+    // a slot that is reused keeps the rows of the launch it replaces: this launch is later in the stream, so its event covers both
+    if (u.live) { row_begin = std::min(row_begin, u.row_begin); row_end = std::max(row_end, u.row_end); }
+    ILB_CUDA(ctx, cudaEventRecord(u.done, ctx->stream));
+    u.row_begin = row_begin; u.row_end = row_end; u.live = true;
+    return ILB_OK;
+}
+
 extern "C" {
 
 int ilb_abi_version(void) { return ILB_ABI_VERSION; }
@@ -187,6 +198,8 @@ void ilb_destroy(ilb_ctx* ctx) {
     for (ilb_ctx::RampTexture& t : ctx->ramps) if (t.texels) cudaFree(t.texels);
     for (int i = 0; i < 2; i++) if (ctx->d_luminance[i]) cudaFree(ctx->d_luminance[i]);
     if (ctx->d_plight_scratch) cudaFree(ctx->d_plight_scratch);
+    for (ilb_ctx::GBufferUser& u : ctx->gb_users) if (u.done) cudaEventDestroy(u.done);
+    for (cudaEvent_t e : ctx->ev_rows_uploaded) if (e) cudaEventDestroy(e);
     if (ctx->band_stream) { cudaStreamDestroy(ctx->band_stream); cudaEventDestroy(ctx->ev_band_fork); cudaEventDestroy(ctx->ev_band_join); }
     if (ctx->copy_in) {
         cudaStreamDestroy(ctx->copy_in);
@@ -368,6 +381,7 @@ static int gbuffer_set(ilb_ctx* ctx, int w, int h, int fmt, const void* data, bo
     ILB_CUDA(ctx, cudaMemcpyAsync(ctx->gbuffer, data, bytes, device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
     if (!device) ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // caller-owned pageable memory
     ctx->gb_w = w; ctx->gb_h = h; ctx->gb_fmt = fmt;
+    if (device) return ilb_gbuffer_note_user(ctx, 0, h);   // a later row upload must not overtake this copy
     return ILB_OK;
 }
 
@@ -382,10 +396,36 @@ int ilb_gbuffer_upload_rows(ilb_ctx* ctx, int w, int h, int fmt, int row_begin, 
     int rc = ilb_reserve(ctx, &ctx->gbuffer, &ctx->gbuffer_capacity, bytes, false);
     if (rc) return rc;
     ctx->gbuffer_owned = true;
-    if (fresh) ILB_CUDA(ctx, cudaMemsetAsync(ctx->gbuffer, 0, bytes, ctx->stream));  // rows that are never uploaded hold zeros
+    if (fresh) {  // rows that are never uploaded hold zeros
+        ILB_CUDA(ctx, cudaMemsetAsync(ctx->gbuffer, 0, bytes, ctx->stream));
+        for (ilb_ctx::GBufferUser& u : ctx->gb_users) u.live = false;   // they used the buffer this one replaces
+        const int rc2 = ilb_gbuffer_note_user(ctx, 0, h);
+        if (rc2) return rc2;
+    }
     ctx->gb_w = w; ctx->gb_h = h; ctx->gb_fmt = fmt;
     const size_t off = texel * (size_t)w * (size_t)row_begin, n = texel * (size_t)w * (size_t)(row_end - row_begin);
-    if (n) ILB_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<char*>(ctx->gbuffer) + off, rows, n, cudaMemcpyHostToDevice, ctx->stream));
+    if (!n) return ILB_OK;
+    // The copy runs on the upload stream, behind exactly the queued work that touches these rows (a band whose kernels are
+    // still running does not hold back the upload of the next band), and the context's stream continues behind the copy.
+    if (!ctx->copy_in) {
+        ILB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        ILB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < ILB_PIPELINE_BANDS; i++) {
+            ILB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+            ILB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    for (ilb_ctx::GBufferUser& u : ctx->gb_users) {
+        if (!u.live) continue;
+        if (cudaEventQuery(u.done) == cudaSuccess) { u.live = false; continue; }
+        if (u.row_begin < row_end && row_begin < u.row_end) ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, u.done, 0));
+    }
+    ILB_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<char*>(ctx->gbuffer) + off, rows, n, cudaMemcpyHostToDevice, ctx->copy_in));
+    cudaEvent_t& up = ctx->ev_rows_uploaded[ctx->ev_rows_next];
+    ctx->ev_rows_next = (ctx->ev_rows_next + 1) % 8;
+    if (!up) ILB_CUDA(ctx, cudaEventCreateWithFlags(&up, cudaEventDisableTiming));
+    ILB_CUDA(ctx, cudaEventRecord(up, ctx->copy_in));
+    ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, up, 0));
     return ILB_OK;
 }
 

@@ -71,6 +71,13 @@ struct ilb_ctx {
     size_t d_plight_scratch_capacity = 0;
     // host-to-host frame pipeline (ilb_render_lighting_frame): upload / download streams and per-band events
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    // ilb_gbuffer_upload_rows copies on the upload stream (copy_in); it only waits for queued work that touches the same rows:
+    // the lighting launches (and whole-buffer uploads) still in flight are remembered with the rows they read
+    struct GBufferUser { cudaEvent_t done = nullptr; int row_begin = 0, row_end = 0; bool live = false; };
+    GBufferUser gb_users[8];
+    int gb_user_next = 0;
+    cudaEvent_t ev_rows_uploaded[8] = {};
+    int ev_rows_next = 0;
     cudaStream_t band_stream = nullptr;                        // second compute lane of the pipelined host-to-host frame
     cudaEvent_t ev_band_fork = nullptr, ev_band_join = nullptr;
     cudaEvent_t ev_in[ILB_PIPELINE_BANDS] = {}, ev_done[ILB_PIPELINE_BANDS] = {};
@@ -162,6 +169,8 @@ int ilb_resolve_lut_launch(ilb_ctx* ctx, const ilb_resolve* params, const ilb_lu
 int ilb_luminance_launch(ilb_ctx* ctx, int width, int height, int lightmap_format, const void* d_lightmap, int level,
                          float* out_host);
 size_t ilb_format_bytes(int format);
+// api.cu: remembers that work queued on ctx->stream so far reads (or writes) G-buffer rows [row_begin, row_end)
+int ilb_gbuffer_note_user(ilb_ctx* ctx, int row_begin, int row_end);
 // raster.cu (N2)
 int ilb_raster_launch(ilb_psys* psys, const ilb_particle_render* params, const void* d_texture, void* d_target);
 void ilb_raster_release(ilb_psys* psys);

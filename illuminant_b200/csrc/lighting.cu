@@ -1566,7 +1566,13 @@ int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, c
     LightingPrepared prep;
     int rc = lightingPrepare(ctx, df, f, batches, batch_count, vertices, vertex_count, &prep);
     if (rc) return rc;
-    return lightingLaunchRows(ctx, prep, f->row_begin, f->row_end, d_outputs, output_count, outputs_are_full_frames ? 0 : f->row_begin);
+    rc = lightingLaunchRows(ctx, prep, f->row_begin, f->row_end, d_outputs, output_count, outputs_are_full_frames ? 0 : f->row_begin);
+    if (rc) return rc;
+    // the kernels read the G-buffer texels of their own rows only (decodePixel); with a G-buffer of another size the mapping is
+    // not one to one, so the launch counts as a reader of every row
+    const bool oneToOne = ctx->gbuffer && ctx->gb_w == f->width && ctx->gb_h == f->height && f->GBufferViewportRelative == 0.0f;
+    if (ctx->gbuffer) return ilb_gbuffer_note_user(ctx, oneToOne ? f->row_begin : 0, oneToOne ? f->row_end : ctx->gb_h);
+    return ILB_OK;
 }
 
 // Host-to-host frame: G-buffer band up, shade, lightmap band down, software-pipelined over row bands on three streams
