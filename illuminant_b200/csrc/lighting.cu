@@ -456,8 +456,9 @@ ILB_DEV float4 loadGBufferTexel(const LightingParams& P, int ix, int iy) {
     ix = min(max(ix, 0), P.gw - 1);
     iy = min(max(iy, 0), P.gh - 1);
     const size_t i = (size_t)iy * (size_t)P.gw + (size_t)ix;
-    if (P.gfmt == ILB_FORMAT_FLOAT4) return __ldg((const float4*)P.gbuffer + i);
-    const uint2 raw = __ldg((const uint2*)P.gbuffer + i);
+    // streaming loads: a G-buffer texel is read once per pass and should not displace distance-field lines from L2
+    if (P.gfmt == ILB_FORMAT_FLOAT4) return __ldcs((const float4*)P.gbuffer + i);
+    const uint2 raw = __ldcs((const uint2*)P.gbuffer + i);
     const __half2 lo = *reinterpret_cast<const __half2*>(&raw.x), hi = *reinterpret_cast<const __half2*>(&raw.y);
     const float2 a = __half22float2(lo), b = __half22float2(hi);
     return make_float4(a.x, a.y, b.x, b.y);
@@ -865,12 +866,12 @@ ILB_DEV void shadeTile(const LightingParams& P, unsigned tile, TileSmem& S) {
         // pass start while the first pass's last wave is still running and meet it here.
         asm volatile("griddepcontrol.wait;" ::: "memory");
         if (valid) {
-            const float4 a = P.accum_in[scratchIndex];
+            const float4 a = __ldcs(P.accum_in + scratchIndex);   // written once, read once: streaming
             accR = a.x + accR; accG = a.y + accG; accB = a.z + accB; accA = a.w + accA;
         }
     }
     if (!valid) return;
-    if (P.accum_out) P.accum_out[scratchIndex] = make_float4(accR, accG, accB, accA);
+    if (P.accum_out) __stcs(P.accum_out + scratchIndex, make_float4(accR, accG, accB, accA));
     else storeTexel(P, outIndex, accR, accG, accB, accA);
 }
 
