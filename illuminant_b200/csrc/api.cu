@@ -145,7 +145,8 @@ int ilb_create(int device_ordinal, ilb_ctx** out_ctx) {
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);
     static const struct { const char* env; int value; } defaults[ILB_OPT_COUNT] = {
         {"ILB_OPT_LIGHT_CONCURRENT", 0}, {"ILB_OPT_LIGHT_LINE_CTAS", 2}, {"ILB_OPT_LIGHT_OTHER_CTAS", 2},
-        {"ILB_OPT_LIGHT_LINE_HELPERS", 1}, {"ILB_OPT_LIGHT_OTHER_HELPERS", 3}, {"ILB_OPT_LIGHT_PDL", 1}, {"ILB_OPT_LIGHT_CONST_BANK", 1}};
+        {"ILB_OPT_LIGHT_LINE_HELPERS", 1}, {"ILB_OPT_LIGHT_OTHER_HELPERS", 3}, {"ILB_OPT_LIGHT_PDL", 1}, {"ILB_OPT_LIGHT_CONST_BANK", 1},
+        {"ILB_OPT_LIGHT_SPLIT_BAND", 1}};
     for (int i = 0; i < ILB_OPT_COUNT; i++) {
         const char* e = getenv(defaults[i].env);
         ctx->opt[i] = e ? atoi(e) : defaults[i].value;

@@ -1567,8 +1567,37 @@ int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, c
     LightingPrepared prep;
     int rc = lightingPrepare(ctx, df, f, batches, batch_count, vertices, vertex_count, &prep);
     if (rc) return rc;
-    rc = lightingLaunchRows(ctx, prep, f->row_begin, f->row_end, d_outputs, output_count, outputs_are_full_frames ? 0 : f->row_begin);
-    if (rc) return rc;
+    const int rows = f->row_end - f->row_begin, outBase = outputs_are_full_frames ? 0 : f->row_begin;
+    const bool splitFrame = prep.nline > 0 && prep.nline < prep.nlights;
+    if (ctx->opt[ILB_OPT_LIGHT_SPLIT_BAND] != 0 && rows >= 4 * TILE_H && 2 * rows < f->height &&
+        !(ctx->opt[ILB_OPT_LIGHT_CONCURRENT] != 0 && splitFrame)) {
+        // A band of a sharded frame: its two halves run on two compute lanes (see lightingLaunchRows), the stream continues
+        // behind both.  Whole frames are long enough for their tails not to matter and keep the single launch pair.
+        const int mid = f->row_begin + ((rows / 2 + TILE_H - 1) / TILE_H) * TILE_H;
+        if (!ctx->band_stream) {
+            ILB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->band_stream, cudaStreamNonBlocking));
+            ILB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_band_fork, cudaEventDisableTiming));
+            ILB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_band_join, cudaEventDisableTiming));
+        }
+        if (splitFrame) {   // both scratch buffers at their final size before anything is in flight
+            const size_t bytes = sizeof(float4) * (size_t)f->width * (size_t)std::max(mid - f->row_begin, f->row_end - mid);
+            rc = ilb_reserve(ctx, &ctx->d_accum, &ctx->d_accum_capacity, bytes, false);
+            if (rc) return rc;
+            rc = ilb_reserve(ctx, &ctx->d_accum2, &ctx->d_accum2_capacity, bytes, false);
+            if (rc) return rc;
+        }
+        ILB_CUDA(ctx, cudaEventRecord(ctx->ev_band_fork, ctx->stream));
+        ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->band_stream, ctx->ev_band_fork, 0));
+        rc = lightingLaunchRows(ctx, prep, f->row_begin, mid, d_outputs, output_count, outBase, 0);
+        if (rc) return rc;
+        rc = lightingLaunchRows(ctx, prep, mid, f->row_end, d_outputs, output_count, outBase, 1);
+        if (rc) return rc;
+        ILB_CUDA(ctx, cudaEventRecord(ctx->ev_band_join, ctx->band_stream));
+        ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_band_join, 0));
+    } else {
+        rc = lightingLaunchRows(ctx, prep, f->row_begin, f->row_end, d_outputs, output_count, outBase);
+        if (rc) return rc;
+    }
     // the kernels read the G-buffer texels of their own rows only (decodePixel); with a G-buffer of another size the mapping is
     // not one to one, so the launch counts as a reader of every row
     const bool oneToOne = ctx->gbuffer && ctx->gb_w == f->width && ctx->gb_h == f->height && f->GBufferViewportRelative == 0.0f;

@@ -41,18 +41,25 @@ ILB_DEV f4 unpackHalf4(uint2 v) {
     const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
     return mk4(lo.x, lo.y, hi.x, hi.y);
 }
+// Byte k of `v` as a float without the conversion pipe: the byte-permute builds the bit pattern of 8388608 + c (0x4B0000cc),
+// one exact subtraction leaves c.
+template <int K>
+ILB_DEV float byteToFloat(uint32_t v) { return __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540u | K)) - 8388608.0f; }
 ILB_DEV f4 unpackRgba8(uint32_t v) {  // UNORM8 -> float is c / 255
     // q = c * fl(1 / 255) followed by one Markstein correction is the correctly rounded c / 255 for every c in 0..255 (checked
     // exhaustively in exact arithmetic, tests/test_resolve_oracle.py): 3 instructions instead of an IEEE division per channel --
     // four per albedo texel were the largest ALU item of the tone-mapped resolve (59.8 -> 45.6 us per 4K frame)
     const float r255 = 1.0f / 255.0f;
-    return mk4(udiv((float)(v & 255u), 255.0f, r255), udiv((float)((v >> 8) & 255u), 255.0f, r255), udiv((float)((v >> 16) & 255u), 255.0f, r255),
-               udiv((float)(v >> 24), 255.0f, r255));
+    return mk4(udiv(byteToFloat<0>(v), 255.0f, r255), udiv(byteToFloat<1>(v), 255.0f, r255), udiv(byteToFloat<2>(v), 255.0f, r255),
+               udiv(byteToFloat<3>(v), 255.0f, r255));
 }
-ILB_DEV uint32_t packRgba8(f4 c) {  // float -> UNORM8: round to nearest, NaN -> 0 (saturatef)
-    const uint32_t R = (uint32_t)(saturatef(c.x) * 255.0f + 0.5f), G = (uint32_t)(saturatef(c.y) * 255.0f + 0.5f);
-    const uint32_t B = (uint32_t)(saturatef(c.z) * 255.0f + 0.5f), A = (uint32_t)(saturatef(c.w) * 255.0f + 0.5f);
-    return R | (G << 8) | (B << 16) | (A << 24);
+// float -> UNORM8: floor(saturate(c) * 255 + 0.5), NaN -> 0 (saturatef).  The truncation is a round-toward-zero add of 2^23
+// (the integer lands in the low mantissa bits: t < 256.5), again without the conversion pipe; three byte-permutes gather the bytes.
+ILB_DEV uint32_t unorm8Bits(float c) { return __float_as_uint(__fadd_rz(saturatef(c) * 255.0f + 0.5f, 8388608.0f)); }
+ILB_DEV uint32_t packRgba8(f4 c) {
+    const uint32_t rg = __byte_perm(unorm8Bits(c.x), unorm8Bits(c.y), 0x3340u);   // bytes: r, g, *, *
+    const uint32_t ba = __byte_perm(unorm8Bits(c.z), unorm8Bits(c.w), 0x3340u);
+    return __byte_perm(rg, ba, 0x5410u);
 }
 ILB_DEV f4 loadTexel(const void* base, int fmt, unsigned long long i) {
     if (fmt == ILB_FORMAT_HALF4) return unpackHalf4(__ldcs(reinterpret_cast<const uint2*>(base) + i));

@@ -79,7 +79,10 @@ typedef enum ilb_option {
     ILB_OPT_LIGHT_CONST_BANK = 6,   /* 1: frames of up to 256 lights keep their light records in the constant bank as well, so that the
                                      * per-pixel light loop re-reads a field where it uses it instead of holding the whole record in
                                      * registers across the cone trace (default 1) */
-    ILB_OPT_COUNT = 7
+    ILB_OPT_LIGHT_SPLIT_BAND = 7,   /* 1: a device-to-device render of fewer than half of the frame's rows (one rank's band of a sharded
+                                     * frame) is cut into two halves on two compute lanes, so that each half's last wave is filled by
+                                     * the other half's CTAs (default 1) */
+    ILB_OPT_COUNT = 8
 } ilb_option;
 ILB_API int ilb_set_option(ilb_ctx* ctx, int option, int value);
 ILB_API int ilb_get_option(const ilb_ctx* ctx, int option, int* out_value);
