@@ -381,12 +381,29 @@ ILB_DEV float lineLightOpacity(f3 wp, f3 wn, f3 P0, f3 P1, float lightRadius, co
     const f3 p2 = xsub3(P1, ru), p3 = xadd3(P1, ru);
     const f3 v0 = xsub3(p0, wp), v1 = xsub3(p1, wp), v2 = xsub3(p2, wp), v3 = xsub3(p3, wp);
     const float solidAngle = rectangleSolidAngle<FAST>(v0, v1, v2, v3, bad);
-    const float sum = xadd(xadd(xadd(xadd(saturatef(xdot3(tnormalize3<FAST>(v0, bad), wn)), saturatef(xdot3(tnormalize3<FAST>(v1, bad), wn))),
-                                     saturatef(xdot3(tnormalize3<FAST>(v2, bad), wn))),
-                                saturatef(xdot3(tnormalize3<FAST>(v3, bad), wn))),
-                           saturatef(xdot3(tnormalize3<FAST>(xsub3(lightCenter, wp), bad), wn)));
+    float sum, forwardDotN;
+    if (FAST && (wn.x == 0.0f) && (wn.y == 0.0f)) {
+        // A surface that faces straight up or down (floors, the tops of raised boxes: most pixels of a top-down scene; the
+        // branch is all but warp-uniform).  dot(normalize(v), n) = (0 * nx' + 0 * ny') + nz' * n.z, and a finite x times zero
+        // plus a finite y times zero is a zero of either sign, which adds nothing to a non-zero product and leaves a zero
+        // product a zero that saturate() maps to +0 either way: only the z component of each normalised vector is needed,
+        // with the same bits (a non-finite component trips the range guard, and the fallback takes the general form below).
+        auto nz = [&](f3 v) {
+            const float d = xdot3(v, v);
+            guardOperand(bad, d);
+            return saturatef(xmul(xmul(v.z, grcp_core(gsqrt_core(d))), wn.z));
+        };
+        sum = xadd(xadd(xadd(xadd(nz(v0), nz(v1)), nz(v2)), nz(v3)), nz(xsub3(lightCenter, wp)));
+        forwardDotN = saturatef(xmul(forward.z, wn.z));
+    } else {
+        sum = xadd(xadd(xadd(xadd(saturatef(xdot3(tnormalize3<FAST>(v0, bad), wn)), saturatef(xdot3(tnormalize3<FAST>(v1, bad), wn))),
+                                  saturatef(xdot3(tnormalize3<FAST>(v2, bad), wn))),
+                             saturatef(xdot3(tnormalize3<FAST>(v3, bad), wn))),
+                        saturatef(xdot3(tnormalize3<FAST>(xsub3(lightCenter, wp), bad), wn)));
+        forwardDotN = saturatef(xdot3(forward, wn));
+    }
     float illuminance = xmul(xmul(solidAngle, 0.2f), sum);
-    const float illuminanceSphere = xmul(xmul(ILB_PI, saturatef(xdot3(forward, wn))), xdiv(xmul(lightRadius, lightRadius), sqrSphereDistance));
+    const float illuminanceSphere = xmul(xmul(ILB_PI, forwardDotN), xdiv(xmul(lightRadius, lightRadius), sqrSphereDistance));
     illuminance = xadd(illuminance, illuminanceSphere);
     return saturatef(illuminance);
 }
@@ -569,7 +586,9 @@ ILB_DEV bool shadeLight(const DFGeometry& df, float lightOcclusion, const DLight
         float opacity, preTrace;
         if (!sphereCore<FIELD, FAST>(df, L, lightOcclusion, px.pos, px.normal, center, props, L.more, opacity, preTrace, bad)) return false;
         const float4 color = L.color1, spec = L.color2;
-        if (L.type & ILB_LIGHT_RAMP_BIT) {  // uniform per light: SphereLightWithDistanceRampPixelShader (SphereLight.fx:48-87)
+        // (instantiations without the ramp bit in TYPES serve the frames that have no ramp-textured light: the branch and the
+        // registers it keeps alive cost the sphere / directional pass 0.6 % when compiled in)
+        if ((TYPES & ILB_LIGHT_RAMP_BIT) && (L.type & ILB_LIGHT_RAMP_BIT)) {  // uniform per light: SphereLightWithDistanceRampPixelShader (SphereLight.fx:48-87)
             // opacity3 = RampTexture(preTraceOpacity, angle).rgb * coneOpacity, coneOpacity = opacity / preTraceOpacity up to rounding;
             // a pixel that was not discarded has preTraceOpacity > 0 (distanceOpacity > 0 and the AO factor >= 1 - AO opacity).
             // The ramp's index, offset and rate are re-read from the light record (L1-resident) so that they do not occupy
@@ -1305,6 +1324,7 @@ namespace {
 struct LightingPrepared {
     LightingParams P;   // everything but the row band and the outputs
     int nline = 0, nlights = 0;
+    bool hasRamp = false;     // a sphere-light batch with a ramp texture: the instantiations with ILB_LIGHT_RAMP_BIT in TYPES
     bool constBank = false;   // the frame's light records are in c_lights / c_lines as well
 };
 
@@ -1429,7 +1449,10 @@ int lightingPrepare(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const
     P.stencil = f->stencil_culling;
     out->nlights = (int)(lights.size() + extra);
     out->nline = 0;
-    for (const DLight& L : lights) out->nline += ((L.type & ILB_LIGHT_TYPE_MASK) == ILB_LIGHT_LINE) ? 1 : 0;
+    for (const DLight& L : lights) {
+        out->nline += ((L.type & ILB_LIGHT_TYPE_MASK) == ILB_LIGHT_LINE) ? 1 : 0;
+        out->hasRamp = out->hasRamp || (L.type & ILB_LIGHT_RAMP_BIT) != 0;
+    }
     return ILB_OK;
 }
 
@@ -1461,7 +1484,12 @@ int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin
     if (const char* e = getenv("ILB_PLANES_MASK")) planesMask = atoi(e);
 #define ILB_LIGHT_LAUNCH(TYPES)                                                                                       \
     do {                                                                                                              \
-        if (P.df.planes && (planesMask & (((TYPES) & ILB_LIGHT_LINE) ? 1 : 2))) {                                     \
+        if (prep.hasRamp && ((TYPES) & ILB_LIGHT_SPHERE)) {                                                           \
+            if (P.df.planes && (planesMask & 2))                                                                      \
+                light_accumulate_kernel<1, (TYPES) | ILB_LIGHT_RAMP_BIT, false><<<tiles, TILE_THREADS, 0, st>>>(P);   \
+            else                                                                                                      \
+                light_accumulate_kernel<0, (TYPES) | ILB_LIGHT_RAMP_BIT, false><<<tiles, TILE_THREADS, 0, st>>>(P);   \
+        } else if (P.df.planes && (planesMask & (((TYPES) & ILB_LIGHT_LINE) ? 1 : 2))) {                              \
             if (prep.constBank) light_accumulate_kernel<1, TYPES, true><<<tiles, TILE_THREADS, 0, st>>>(P);           \
             else light_accumulate_kernel<1, TYPES, false><<<tiles, TILE_THREADS, 0, st>>>(P);                         \
         } else {                                                                                                      \
@@ -1472,7 +1500,7 @@ int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin
     const bool concurrent = ctx->opt[ILB_OPT_LIGHT_CONCURRENT] != 0 &&  // every pass needs at least one grid, or its tiles are never shaded
                             ctx->opt[ILB_OPT_LIGHT_LINE_CTAS] + ctx->opt[ILB_OPT_LIGHT_LINE_HELPERS] > 0 &&
                             ctx->opt[ILB_OPT_LIGHT_OTHER_CTAS] + ctx->opt[ILB_OPT_LIGHT_OTHER_HELPERS] > 0;
-    if (split && concurrent && lane == 0) {
+    if (split && concurrent && lane == 0 && !prep.hasRamp) {
         // both passes at once: persistent grids sized to be co-resident, one tile queue per pass, the pass that reaches a
         // tile second adds the two fp32 partial sums and stores the texel (see light_accumulate_persistent_kernel)
         const size_t bytes = sizeof(float4) * (size_t)P.width * (size_t)(row_end - row_begin);
@@ -1529,7 +1557,7 @@ int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin
         P.accum_in = P.accum_out;
         P.accum_out = nullptr;
         P.clear = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // the clear colour entered through the line-light sums
-        if (ctx->opt[ILB_OPT_LIGHT_PDL]) {
+        if (ctx->opt[ILB_OPT_LIGHT_PDL] && !prep.hasRamp) {
             // programmatic dependent launch: the second pass's CTAs fill the SM slots the first pass's last wave leaves idle
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof(cfg));

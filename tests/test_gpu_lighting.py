@@ -352,3 +352,26 @@ def test_light_list_caching_and_the_shared_constant_bank(ctx):
         assert np.array_equal(ra.RenderLighting(), a0) and np.array_equal(rb.RenderLighting(), b0)
     finally:
         c2.close()
+
+
+def test_line_lights_on_tilted_and_flat_surfaces(ctx, oracle):
+    """The line light's opacity has a short form for surfaces whose normal has no x / y component (floors, box tops) and the
+    general form for everything else: a G-buffer that mixes both inside every warp, normals that point away from the light,
+    and missing normals must all match the oracle (which only has the general form), alpha counts exactly."""
+    s = scenes.lighting_scene(53, 224, 144, 2, n_directional=1, n_line=4, ramp=(60.0, 160.0), float4_lightmap=True)
+    rs = np.random.RandomState(12)
+    h, w = s.gbuffer.shape[:2]
+    z = rs.uniform(0, 30, (h, w)).astype(np.float32)
+    n = np.zeros((h, w, 3), np.float32)
+    n[..., 2] = 1
+    tilt = rs.rand(h, w) < 0.5
+    v = rs.normal(size=(h, w, 3)).astype(np.float32)
+    v /= np.linalg.norm(v, axis=-1, keepdims=True)
+    n[tilt] = v[tilt]                       # any direction, also facing down
+    n[rs.rand(h, w) < 0.1] = np.array([0, 0, -1], np.float32)
+    n[rs.rand(h, w) < 0.05] = 0             # "no normal" pixels
+    s.gbuffer = ib.encode_gbuffer(n, np.zeros((h, w), np.float32), z)
+    r, tex = make_renderer(ctx, s)
+    gpu, ref = r.RenderLighting(), oracle_lightmap(oracle, r, tex, s)
+    _check(gpu, ref, "line lights, mixed normals")
+    assert np.array_equal(gpu[..., 3], ref[..., 3])
