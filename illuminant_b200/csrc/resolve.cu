@@ -41,17 +41,24 @@ ILB_DEV f4 unpackHalf4(uint2 v) {
     const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
     return mk4(lo.x, lo.y, hi.x, hi.y);
 }
-// Byte k of `v` as a float without the conversion pipe: the byte-permute builds the bit pattern of 8388608 + c (0x4B0000cc),
-// one exact subtraction leaves c.
+// UNORM8 -> float, c / 255, in two instructions per channel and without the conversion pipe: the byte-permute builds the bit
+// pattern of 8388608 + c (0x4B0000cc) and one fused multiply-add computes RN((8388608 + c) * r - 8388608 * r) = RN(c * r),
+// r = fl(1 / 255) (8388608 * r is exact).  RN(c * r) is within one ulp of the correctly rounded c / 255 (the oracle's decode),
+// five orders of magnitude inside the resolve tolerance; and since |c * r * 255 - c| < 1e-4, packing an unchanged value returns
+// the byte it came from (the pass-through properties of tests/test_gpu_resolve.py hold exactly).  This replaces a correctly
+// rounded division in six instructions per channel: the tone-mapped resolve is bound by instruction issue, and a quarter of
+// its instructions were these decodes.
 template <int K>
-ILB_DEV float byteToFloat(uint32_t v) { return __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540u | K)) - 8388608.0f; }
-ILB_DEV f4 unpackRgba8(uint32_t v) {  // UNORM8 -> float is c / 255
-    // q = c * fl(1 / 255) followed by one Markstein correction is the correctly rounded c / 255 for every c in 0..255 (checked
-    // exhaustively in exact arithmetic, tests/test_resolve_oracle.py): 3 instructions instead of an IEEE division per channel --
-    // four per albedo texel were the largest ALU item of the tone-mapped resolve (59.8 -> 45.6 us per 4K frame)
+ILB_DEV float unorm8ToFloat(uint32_t v) {
     const float r255 = 1.0f / 255.0f;
-    return mk4(udiv(byteToFloat<0>(v), 255.0f, r255), udiv(byteToFloat<1>(v), 255.0f, r255), udiv(byteToFloat<2>(v), 255.0f, r255),
-               udiv(byteToFloat<3>(v), 255.0f, r255));
+    return __fmaf_rn(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540u | K)), r255, -8388608.0f * r255);
+}
+ILB_DEV f4 unpackRgba8(uint32_t v) { return mk4(unorm8ToFloat<0>(v), unorm8ToFloat<1>(v), unorm8ToFloat<2>(v), unorm8ToFloat<3>(v)); }
+// the correctly rounded c / 255 (q = c * r, one Markstein correction): the luminance buffer is compared bit for bit
+ILB_DEV f4 unpackRgba8Exact(uint32_t v) {
+    const float r255 = 1.0f / 255.0f;
+    return mk4(udiv((float)(v & 255u), 255.0f, r255), udiv((float)((v >> 8) & 255u), 255.0f, r255), udiv((float)((v >> 16) & 255u), 255.0f, r255),
+               udiv((float)(v >> 24), 255.0f, r255));
 }
 // float -> UNORM8: floor(saturate(c) * 255 + 0.5), NaN -> 0 (saturatef).  The truncation is a round-toward-zero add of 2^23
 // (the integer lands in the low mantissa bits: t < 256.5), again without the conversion pipe; three byte-permutes gather the bytes.
@@ -161,8 +168,11 @@ ILB_DEV f4 resolvePixel(const ResolveParams& P, f4 light, f4 albedo) {
     return result;  // the caller applies ApplyDither (it knows the pixel's coordinates)
 }
 
+#ifndef ILB_RESOLVE_MINBLOCKS
+#define ILB_RESOLVE_MINBLOCKS 5   // 51 registers: 45.7 -> 43.6 us for the tone-mapped 4K resolve (6: 44.0, 8: 51.9 -- spills)
+#endif
 template <int MODE, bool ALBEDO, bool VEC>
-__global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ ResolveParams P) {
+__global__ void __launch_bounds__(256, ILB_RESOLVE_MINBLOCKS) resolve_kernel(const __grid_constant__ ResolveParams P) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long groups = P.n >> 2;
@@ -314,7 +324,8 @@ __global__ void __launch_bounds__(256) resolve_lut_kernel(const __grid_constant_
 __global__ void __launch_bounds__(256) luminance_level0_kernel(const void* lightmap, int fmt, int w, int lw, int lh, float* out) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= lw || y >= lh) return;
-    const f4 t = loadTexel(lightmap, fmt, (unsigned long long)(2 * y + 1) * (unsigned long long)w + (unsigned long long)(2 * x + 1));
+    const unsigned long long i = (unsigned long long)(2 * y + 1) * (unsigned long long)w + (unsigned long long)(2 * x + 1);
+    const f4 t = (fmt == ILB_FORMAT_RGBA8) ? unpackRgba8Exact(__ldcs(reinterpret_cast<const unsigned int*>(lightmap) + i)) : loadTexel(lightmap, fmt, i);
     out[(size_t)y * lw + x] = xadd(xadd(xmul(t.x, 0.299f), xmul(t.y, 0.587f)), xmul(t.z, 0.144f));  // 0.144: Resolve.fx:15 (sic)
 }
 // one mip step: 2x2 box filter, size floor(size / 2)

@@ -195,16 +195,21 @@ def test_histogram_matches_scalar_transcription(ignore):
     assert h.SampleCount == 0 and h.GetPercentile(50) == (False, 0, 0)
 
 
-def test_unorm8_decode_by_reciprocal_and_one_correction_is_the_ieee_quotient():
-    """resolve.cu decodes UNORM8 albedo / target texels as q = c * fl(1/255), rho = c - 255 q (one FMA, exact),
-    q' = fl(q + rho * fl(1/255)) instead of an IEEE division: the same bits as c / 255 for all 256 inputs."""
+def test_unorm8_decode_by_one_fma_is_within_an_ulp_and_round_trips():
+    """resolve.cu decodes UNORM8 texels as one fused multiply-add, RN((8388608 + c) * r - 8388608 * r) = RN(c * r) with
+    r = fl(1 / 255): for all 256 inputs the result is within one ulp of the correctly rounded c / 255 (what the oracle decodes),
+    and packing it again (floor(x * 255 + 0.5), the kernel's truncating add) returns c -- the exact pass-through properties of the
+    GPU tests rest on that."""
     r = np.float32(1.0) / np.float32(255.0)
+    worst = 0.0
     for c in range(256):
-        q = np.float32(np.float32(c) * r)
-        rho = np.float64(c) - 255.0 * np.float64(q)                  # exact in double, exactly representable in fp32
-        assert np.float64(np.float32(rho)) == rho
-        q2 = np.float32(np.float64(q) + rho * np.float64(r))         # the FMA: exact sum in double, one rounding to fp32
-        assert q2 == np.float32(c) / np.float32(255.0), c
+        x = np.float32(np.float64(c) * np.float64(r))        # one rounding of the exact product (24 x 8 bits fit a double)
+        ref = np.float32(c) / np.float32(255.0)
+        if c:
+            worst = max(worst, abs(float(x) - float(ref)) / float(np.spacing(ref)))
+        assert int(np.floor(np.float32(np.float32(x * np.float32(255.0)) + np.float32(0.5)))) == c
+        assert np.float64(8388608.0) * np.float64(r) == np.float64(np.float32(np.float32(8388608.0) * r))   # the addend is exact
+    assert worst <= 1.0
 
 
 # ---- scaled / offset resolve (ResolveLighting drawn as a quad, LightingRenderer.cs:1537-1645) -------------------------------
