@@ -14,7 +14,7 @@
 struct ilb_df;
 struct ilb_psys;
 
-#define ILB_PIPELINE_BANDS 8
+#define ILB_PIPELINE_BANDS 12
 
 struct ilb_ctx {
     int device = -1;

@@ -1668,17 +1668,23 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
     rc = lightingPrepare(ctx, df, f, batches, batch_count, vertices, vertex_count, &prep);
     if (rc) return rc;
     if (rows == 0) return ILB_OK;
-    // Bands of whole tile rows with heights 1 : 2 : 3 : 4 : 3 : 2 : 1 -- the first band is short so that the first kernel starts
-    // after 1/16 of the upload, the last so that only 1/16 of the download is left when the last kernel ends, the middle ones
-    // long so that few kernel tails are paid.
-    static const int kShare[7] = {1, 2, 3, 4, 3, 2, 1};
-    static_assert(ILB_PIPELINE_BANDS >= 7, "one event pair per band");
-    int edge[8];
+    // Bands of whole tile rows with heights 1 : 2 : 4 : 6 : 6 : 6 : 4 : 2 : 1 -- the first band is short so that the first kernel
+    // starts after 1/32 of the upload, the last so that only 1/32 of the download is left when the last kernel ends, the middle
+    // ones long so that few launches are paid (7.82 -> 7.69 ms per C4 frame against the 7-band split 1 : 2 : 3 : 4 : 3 : 2 : 1).
+    // ILB_BAND_SHARES selects the split (dev knob): 0 = 1:2:3:4:3:2:1 of 16, 1 (default) = 1:2:4:6:6:6:4:2:1 of 32
+    static const int kShares[2][9] = {{1, 2, 3, 4, 3, 2, 1, 0, 0}, {1, 2, 4, 6, 6, 6, 4, 2, 1}};
+    static const int kCount[2] = {7, 9}, kTotal[2] = {16, 32};
+    int which = 1;
+    if (const char* e = getenv("ILB_BAND_SHARES")) which = atoi(e) == 0 ? 0 : 1;
+    const int* kShare = kShares[which];
+    const int NB = kCount[which], total = kTotal[which];
+    static_assert(ILB_PIPELINE_BANDS >= 9, "one event pair per band");
+    int edge[10];
     edge[0] = f->row_begin;
-    for (int b = 0, acc = 0; b < 7; b++) {
+    for (int b = 0, acc = 0; b < NB; b++) {
         acc += kShare[b];
-        const int e = f->row_begin + (int)(((long long)rows * acc / 16 + TILE_H - 1) / TILE_H * TILE_H);
-        edge[b + 1] = (b == 6) ? f->row_end : std::min(std::max(e, edge[b]), f->row_end);
+        const int e = f->row_begin + (int)(((long long)rows * acc / total + TILE_H - 1) / TILE_H * TILE_H);
+        edge[b + 1] = (b == NB - 1) ? f->row_end : std::min(std::max(e, edge[b]), f->row_end);
     }
     // Two compute lanes: even bands run on the context's stream, odd bands on band_stream with their own scratch sums, so the
     // CTAs of band b + 1 fill the SM slots that the last wave of band b leaves idle (kernels of one stream run back to back,
@@ -1695,7 +1701,7 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
         }
         if (splitFrame) {   // both scratch buffers at their final size before anything is in flight
             int maxRows = 0;
-            for (int b = 0; b < 7; b++) maxRows = std::max(maxRows, edge[b + 1] - edge[b]);
+            for (int b = 0; b < NB; b++) maxRows = std::max(maxRows, edge[b + 1] - edge[b]);
             const size_t bytes = sizeof(float4) * (size_t)f->width * (size_t)std::max(maxRows, 1);
             rc = ilb_reserve(ctx, &ctx->d_accum, &ctx->d_accum_capacity, bytes, false);
             if (rc) return rc;
@@ -1713,7 +1719,7 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
     // everything already queued on the main stream (earlier frames, uploads) must be done before the G-buffer is overwritten
     ILB_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], ctx->stream));
     ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_done[0], 0));
-    for (int b = 0; b < 7; b++) {
+    for (int b = 0; b < NB; b++) {
         const int r0 = edge[b], r1 = edge[b + 1];
         if (r1 <= r0) continue;
         const size_t goff = gtexel * (size_t)gw * (size_t)r0, gn = gtexel * (size_t)gw * (size_t)(r1 - r0);
@@ -1722,7 +1728,7 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
     }
     // every band's kernels are queued before the first download: with PAGEABLE caller buffers cudaMemcpyAsync blocks the host
     // until its copy is done, which must not hold back the launches of the bands behind it (pinned buffers never block)
-    for (int b = 0; b < 7; b++) {
+    for (int b = 0; b < NB; b++) {
         const int r0 = edge[b], r1 = edge[b + 1];
         if (r1 <= r0) continue;
         const int lane = (lanes == 2) ? (b & 1) : 0;
@@ -1737,7 +1743,7 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
         ILB_CUDA(ctx, cudaEventRecord(ctx->ev_band_join, ctx->band_stream));
         ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_band_join, 0));
     }
-    for (int b = 0; b < 7; b++) {
+    for (int b = 0; b < NB; b++) {
         const int r0 = edge[b], r1 = edge[b + 1];
         if (r1 <= r0) continue;
         ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[b], 0));
