@@ -337,7 +337,12 @@ __device__ __noinline__ float4 rampLookup(const RampTex* ramps, int id, float pr
 template <int FIELD, bool FAST>
 ILB_DEV bool directionalCore(const DFGeometry& g, const DLight& L, f3 p, f3 n, float4 dir, float4 props, float4 more,
                              float& opacity, Guard& bad) {
-    float lightOpacity = (dir.w < 0.1f) ? 1.0f : normalFactorEx<350>(mk3(dir.x, dir.y, dir.z), n);
+    // On a surface that faces straight up (floors, box tops) the normal factor of a directional light depends on the light
+    // alone: the host evaluated it once (flattenLights, same operations, the oracle's own powf) into the record's spare word
+    float lightOpacity;
+    if (dir.w < 0.1f) lightOpacity = 1.0f;
+    else if ((n.x == 0.0f) && (n.y == 0.0f) && (n.z == 1.0f)) lightOpacity = L.covX.z;
+    else lightOpacity = normalFactorEx<350>(mk3(dir.x, dir.y, dir.z), n);
     const bool visible = (p.x > -9999.0f);
     const float aoRadius = xmul(more.x, fmaxf(0.0f, n.z));
     lightOpacity *= computeAO<FIELD>(g, L.hasField != 0, p, n, aoRadius, more.w, visible);
@@ -1098,7 +1103,12 @@ int flattenLights(ilb_ctx* ctx, const ilb_df* df, const ilb_lighting_frame* f, c
                 by1 = std::max(std::max(L.covY.x, L.covY.y), std::max(L.covY.z, L.covY.w));
             } else if (B.light_type == ILB_LIGHT_DIRECTIONAL) {  // DirectionalLight.fx:19-37
                 bx0 = v.LightPosition1.x; bx1 = v.LightPosition2.x; by0 = v.LightPosition1.y; by1 = v.LightPosition2.y;
-                L.covX = make_float4(bx0, bx1, 0, 0);
+                // computeNormalFactorEx(direction, (0, 0, 1), 0.35, 0.35) (LightCommon.fxh:154-165): dot(-direction, n) = -direction.z
+                // exactly for n = (0, 0, 1) and a finite direction; individually rounded like normalFactorEx<350>
+                const float dz = -v.Color2.z, range = 0.35f;
+                const float q = (dz + range) / range;
+                const float flatFactor = std::pow(std::fmin(std::fmax(q, 0.0f), 1.0f), 0.85f);
+                L.covX = make_float4(bx0, bx1, flatFactor, 0);
                 L.covY = make_float4(by0, by1, 0, 0);
             } else {  // LineLightVertexShader LineLightCore.fxh:122-173 (bounds are +-9999 around the segment)
                 const float radius = v.LightProperties.x + v.LightProperties.y + 1;
