@@ -258,13 +258,22 @@ ILB_DEV float traceAdvanceEx(const DFGeometry& g, const TraceConfig& c, Trace& s
 // ---- light response (LightCommon.fxh, AOCommon.fxh) ---------------------------------------------------------
 #define DOT_EXPONENT 0.85f
 
-template <int RANGE_1000>  // offset == range == RANGE_1000 / 1000 (0.15 for sphere lights, 0.35 for directional lights)
+// Division by a per-light / per-shader constant whose reciprocal is at hand.  FAST: the three-instruction Markstein form (udiv),
+// which equals div.rn for every FINITE dividend whose quotient does not overflow -- but turns an infinite dividend into NaN
+// (inf * r - y * inf) where div.rn gives +-inf, and saturate() maps those to different ends of [0, 1].  Infinite operands only
+// come from non-finite G-buffer texels (a HalfVector4 G-buffer stores its "dead" marker -99999 as -inf); they also trip the
+// range guard of the square roots next to every one of these divisions, so the re-evaluation (FAST = false) is where they are
+// seen, and it divides the IEEE way.
+template <bool FAST>
+ILB_DEV float ldiv(float x, float y, float r) { return FAST ? udiv(x, y, r) : xdivz(x, y); }
+
+template <int RANGE_1000, bool FAST>  // offset == range == RANGE_1000 / 1000 (0.15 for sphere lights, 0.35 for directional lights)
 ILB_DEV float normalFactorEx(f3 lightNormal, f3 n) {  // computeNormalFactorEx :154-165
     if (!any3(n)) return 1.0f;
     constexpr float range = (float)RANGE_1000 / 1000.0f;
     static_assert(RANGE_1000 == 150 || RANGE_1000 == 350, "the two call sites of the reference");
     const float d = xdot3(-lightNormal, n);  // exact: its sign decides `visible` (discard / alpha count)
-    return powf(saturatef(udiv(xadd(d, range), range, 1.0f / range)), DOT_EXPONENT);
+    return powf(saturatef(ldiv<FAST>(xadd(d, range), range, 1.0f / range)), DOT_EXPONENT);
 }
 
 template <bool FAST>
@@ -273,10 +282,10 @@ ILB_DEV float sphereLightOpacity(float lightOcclusion, f3 p, f3 n, f3 center, fl
     f3 d3 = xsub3(p, center);
     d3.y = xmul(d3.y, yFactor);
     const float distance = tlength3<FAST>(d3, bad);
-    float distanceFactor = xsub(1.0f, saturatef(udiv(xsub(distance, props.x), props.y, rRamp)));
+    float distanceFactor = xsub(1.0f, saturatef(ldiv<FAST>(xsub(distance, props.x), props.y, rRamp)));
     if (lightOcclusion > 0.0f) distanceFactor = xmul(distanceFactor, xsub(1.0f, saturatef(xdiv(d3.z, lightOcclusion))));
     const f3 lightNormal = xdivs3(d3, distance);
-    float normalFactor = normalFactorEx<150>(lightNormal, n);
+    float normalFactor = normalFactorEx<150, FAST>(lightNormal, n);
     if (props.z >= 2.0f) {
         distanceFactor = xsub(1.0f, saturatef(xsub(distance, props.x)));
         normalFactor = 1.0f;
@@ -343,7 +352,7 @@ ILB_DEV bool directionalCore(const DFGeometry& g, const DLight& L, f3 p, f3 n, f
     float lightOpacity;
     if (dir.w < 0.1f) lightOpacity = 1.0f;
     else if ((n.x == 0.0f) && (n.y == 0.0f) && (n.z == 1.0f)) lightOpacity = L.covX.z;
-    else lightOpacity = normalFactorEx<350>(mk3(dir.x, dir.y, dir.z), n);
+    else lightOpacity = normalFactorEx<350, FAST>(mk3(dir.x, dir.y, dir.z), n);
     const bool visible = (p.x > -9999.0f);
     const float aoRadius = xmul(more.x, fmaxf(0.0f, n.z));
     lightOpacity *= computeAO<FIELD>(g, L.hasField != 0, p, n, aoRadius, more.w, visible);
@@ -376,7 +385,7 @@ template <bool FAST>
 ILB_DEV float lineLightOpacity(f3 wp, f3 wn, f3 P0, f3 P1, float lightRadius, const DLine& D, f3& spherePosition, float& u, Guard& bad) {  // FBPBR.fxh:53-101
     const f3 lightLeft = xyz(mk4(D.left)), lightCenter = xyz(mk4(D.center)), ab = xyz(mk4(D.ab));
     // closestPointOnLineSegment3 DistanceFieldCommon.fxh:151-155 (exact: u places the three trace targets)
-    u = saturatef(udiv(xdot3(xsub3(wp, P0), ab), D.ab.w, D.left.w));
+    u = saturatef(ldiv<FAST>(xdot3(xsub3(wp, P0), ab), D.ab.w, D.left.w));
     spherePosition = xadd3(P0, xscale3(ab, u));
     const f3 sphereUnormL = xsub3(spherePosition, wp);
     const float sqrSphereDistance = xdot3(sphereUnormL, sphereUnormL);
@@ -611,12 +620,14 @@ ILB_DEV bool shadeLight(const DFGeometry& df, float lightOcclusion, const DLight
             }
             return true;
         }
-        rgb = (mk3(color.x, color.y, color.z) * color.w * opacity);
+        // colour products and the accumulation are individually rounded (the oracle's operations): every instantiation of the
+        // kernel -- atlas / planes, constant bank or not, one pass or two -- then lands on the same bits
+        rgb = xscale3(xscale3(mk3(color.x, color.y, color.z), color.w), opacity);
         if (any3(mk3(spec.x, spec.y, spec.z)) || L.type == ILB_LIGHT_PARTICLE_BIT) {  // CalcSphereLightSpecularity LightCommon.fxh:212-222
             const f3 lightDirection = px.pos - center;
             const f3 h = normalize3(normalize3(px.camera - px.pos) - lightDirection);
             const float specularity = powf(saturatef(dot3(h, px.normal)), spec.w);
-            rgb = rgb + (mk3(spec.x, spec.y, spec.z) * specularity * opacity);
+            rgb = xadd3(rgb, xscale3(xscale3(mk3(spec.x, spec.y, spec.z), specularity), opacity));
         }
         return true;
     } else if ((TYPES & ILB_LIGHT_DIRECTIONAL) && L.type == ILB_LIGHT_DIRECTIONAL) {  // DirectionalLightPixelShader DirectionalLight.fx:95-127
@@ -625,7 +636,7 @@ ILB_DEV bool shadeLight(const DFGeometry& df, float lightOcclusion, const DLight
         props.x *= es;
         float opacity;
         if (!directionalCore<FIELD, FAST>(df, L, px.pos, px.normal, L.color2, props, L.more, opacity, bad)) return false;
-        rgb = mk3(L.color1.x, L.color1.y, L.color1.z) * L.color1.w * opacity;
+        rgb = xscale3(xscale3(mk3(L.color1.x, L.color1.y, L.color1.z), L.color1.w), opacity);
         return true;
     } else if (TYPES & ILB_LIGHT_LINE) {  // LineLightPixelShader LineLight.fx:7-42
         if (px.fullbright) return false;
@@ -638,8 +649,8 @@ ILB_DEV bool shadeLight(const DFGeometry& df, float lightOcclusion, const DLight
         if (!lineCore<FIELD, FAST>(df, L, D, px.pos, px.normal, mk3(L.pos1.x, L.pos1.y, L.pos1.z), mk3(L.pos2.x, L.pos2.y, L.pos2.z), props,
                                    L.more, u, opacity, bad))
             return false;
-        const f4 color = lerp4(mk4(L.color1), mk4(L.color2), u);
-        rgb = mk3(color.x, color.y, color.z) * color.w * opacity;
+        const f4 color = xlerp4(mk4(L.color1), mk4(L.color2), u);
+        rgb = xscale3(xscale3(mk3(color.x, color.y, color.z), color.w), opacity);
         return true;
     }
     return false;
@@ -859,7 +870,7 @@ ILB_DEV void shadeTile(const LightingParams& P, unsigned tile, TileSmem& S) {
                 f3 rgb;
                 if (shadeLightGuarded<FIELD, TYPES, CL>(P.df, P.envZToY.z, L, P.lights, P.lines, P.ramps, lightIndex, pix, rgb)) {
                     // BlendState.Additive with PS alpha 1: rgb += src.rgb, a += 1 (LightingRenderer.cs:206)
-                    accR += rgb.x; accG += rgb.y; accB += rgb.z; accA += 1.0f;
+                    accR = xadd(accR, rgb.x); accG = xadd(accG, rgb.y); accB = xadd(accB, rgb.z); accA += 1.0f;
                 }
             }
         }
