@@ -64,7 +64,9 @@ ILB_API void* ilb_stream(ilb_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench gpu_launches). */
 ILB_API uint64_t ilb_launch_count(const ilb_ctx* ctx);
 
-/* Scheduling knobs of the kernels (never results: every setting produces the same bits).  Defaults are the measured
+/* Scheduling knobs of the kernels, never results: light counts, discards, distance-field samples, march steps and particle
+ * state are the same bits under every setting; ILB_OPT_LIGHT_CONST_BANK selects another instantiation of the light kernel, whose
+ * smooth factors (ambient occlusion, specular) may differ in the last bit or two.  Defaults are the measured
  * best on B200; the environment variable ILB_OPT_<NAME> overrides a default at ilb_create. */
 typedef enum ilb_option {
     ILB_OPT_LIGHT_CONCURRENT = 0,   /* 1: run the line-light pass and the sphere + directional pass side by side as co-resident

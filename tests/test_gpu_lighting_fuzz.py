@@ -105,13 +105,18 @@ def test_random_scene_matches_the_oracle(ctx, oracle, seed):
     worst = np.unravel_index(np.argmax(err), err.shape)
     assert err.max() <= LIGHTING_RTOL, f"seed {seed}: max rel err {err.max():.3e} at {worst}: gpu {gpu[worst]} ref {ref[worst]}"
     assert np.array_equal(gpu[..., 3], ref[..., 3]), f"seed {seed}: {int((gpu[..., 3] != ref[..., 3]).sum())} pixels with a different light count"
-    # the same frame without the constant-bank light records and as two row bands: same bits
+    # the same frame without the constant-bank light records: another instantiation of the kernel, whose smooth factors (AO,
+    # specular: plain operators, contracted as the compiler sees fit) may differ in the last bits -- light counts may not
     from illuminant_b200 import _abi
     ctx.set_option(_abi.OPT_LIGHT_CONST_BANK, 0)
     try:
-        assert np.array_equal(r.RenderLighting(), gpu, equal_nan=True)
+        other = r.RenderLighting()
     finally:
         ctx.set_option(_abi.OPT_LIGHT_CONST_BANK, 1)
+    assert np.array_equal(other[..., 3], gpu[..., 3])
+    d = lighting_rel_err(np.nan_to_num(other), np.nan_to_num(gpu))
+    assert d.max() <= 2e-6, f"seed {seed}: constant bank on / off differ by {d.max():.3e}"
+    # ... and as two row bands (the same instantiation): the same bits
     h = gpu.shape[0]
     cut = (h // 2 + 15) // 16 * 16
     halves = np.concatenate([r.RenderLighting(rows=(0, cut)), r.RenderLighting(rows=(cut, h))], axis=0)
