@@ -8,7 +8,9 @@ Primary metric: lit Mpixels/s on config C4 (3840x2160, 128 mixed Sphere/Directio
 9-slice distance field); a "step" is one RenderLighting of the whole frame PLUS the UpdateLightProbes of the same frame,
 both inside the timed region.  At N > 1 the frame is cut into row bands of equal MEASURED cost (calibrated before the
 timed region, sharding.rebalance_rows), every rank stores its band into every rank's full-frame buffer from inside the
-kernel (NVLink peer stores), and a symmetric-memory barrier ends the step.  The second hot path is reported in the same
+kernel (NVLink peer stores), and a symmetric-memory barrier ends the step.  The host-to-host number (`e2e`) at N > 1 is one
+ilb_render_lighting_frame call per rank on its band, the lightmap rows of every rank landing in one page-locked shared-memory
+host frame that rank 0 consumes (sharding.SharedHostFrame: no collective on that leg).  The second hot path is reported in the same
 JSON line under "particles": Mparticle-steps/s for 8M particles (32 chunks x 512^2) per GPU through
 Spawner(60 000 / s)+Gravity+Noise+FMA+SDF collision; a step is one ParticleSystem.Update (spawn kernel, Noise table kernel,
 step kernel).  The particles the Spawner adds during the run are updated too but NOT counted in the metric.
@@ -441,56 +443,38 @@ def run_ours(args):
             h2d, d2h = H * W * 16 + nv * 128 + probes_packed[2] * 32, H * W * 8 + probes_packed[2] * 8
             e2e_note = "one ilb_render_lighting_frame call per frame + probe update and read-back"
         else:
-            # N > 1, host to host: every rank's band is cut into `rounds` sub-bands of whole tile rows.  Per round a rank uploads the
-            # sub-band's G-buffer rows (ilb_gbuffer_upload_rows: upload stream, behind nothing but the work that touches those rows),
-            # renders it with the in-kernel peer-store gather, and a symmetric-memory barrier closes the round on every rank; RANK 0
-            # then downloads the round's rows of ALL ranks from its reassembled buffer on a copy stream while the next round computes.
-            out_host = torch.empty((H, W, 4), dtype=torch.float16).pin_memory() if rank == 0 else None
-            rounds = 4 if world <= 2 else 2
-            all_bounds = list(bounds)
-
-            def cut(a, b):   # `rounds` pieces of whole 16-row tile rows
-                edges = [a + min(b - a, ((b - a) * k // rounds + 15) // 16 * 16) for k in range(rounds)] + [b]
-                return [(edges[k], edges[k + 1]) for k in range(rounds)]
-            pieces = [cut(all_bounds[k], all_bounds[k + 1]) for k in range(world)]
-            copy_out = torch.cuda.Stream(device=local_rank)
-            ev_round = [torch.cuda.Event() for _ in range(rounds)]
-            use_peers = peers["ptrs"] is not None
+            # N > 1, host to host: every rank makes ONE ilb_render_lighting_frame call for its band (its G-buffer rows go up from
+            # pinned memory, its rows of the lightmap come down, both pipelined behind the kernels inside the call) whose
+            # `lightmap_out` points into ONE host frame shared by the node's ranks (POSIX shared memory, page-locked on every rank
+            # with ilb_host_register).  The frame is reassembled in RANK 0's host memory by the copy engines of all GPUs over
+            # their own PCIe links: no collective and no GPU barrier on this leg.  Per frame, a sequence number per rank in the
+            # same mapping tells rank 0 that the rank's band is in place; rank 0 takes the frame and releases it.
+            port = os.environ.get("MASTER_PORT", "0")
+            shared = sharding.SharedHostFrame(f"ilb_bench_frame_{port}", H, W, 4, "float16", rank, world, ctx=ctx)
+            out_host = torch.from_numpy(shared.frame)
+            gb_ptr, out_ptr = C.c_void_p(gb_host.data_ptr()), C.c_void_p(shared.rows(r0, r1).ctypes.data if r1 > r0 else shared.frame.ctypes.data)
+            seq = {"n": 0}
 
             def e2e_step():
-                with torch.cuda.stream(stream):
-                    for k in range(rounds):
-                        a, b = pieces[rank][k]
-                        if b > a:
-                            ctx.check(ctx.lib.ilb_gbuffer_upload_rows(ctx.handle, W, H, _abi.FORMAT_FLOAT4, a, b, C.c_void_p(gb_host[a:b].data_ptr())))
-                            if use_peers:
-                                renderer.RenderLightingPeers(peers["ptrs"], rows=(a, b), packed=packed)
-                            else:
-                                renderer.RenderLightingDevice(full[a:].data_ptr(), rows=(a, b), packed=packed)
-                        if k == 0 and rank == 0:
-                            renderer.UpdateLightProbesDevice(d_probes.data_ptr(), packed=packed, probes=probes_packed)
-                        if use_peers:
-                            peers["hdl"].barrier(channel=0)
-                        if rank == 0 and use_peers:
-                            ev_round[k].record(stream)
-                            copy_out.wait_event(ev_round[k])
-                            with torch.cuda.stream(copy_out):
-                                for q in range(world):
-                                    qa, qb = pieces[q][k]
-                                    if qb > qa:
-                                        out_host[qa:qb].copy_(full[qa:qb], non_blocking=True)
-                    if not use_peers:   # NCCL fallback: one all-gather of equal bands, then the download
-                        dist.all_gather_into_tensor(full, full[r0:r0 + sharding.band_height(H, world)])
-                        if rank == 0:
-                            out_host.copy_(full[:H], non_blocking=True)
-                    if rank == 0:
+                seq["n"] += 1
+                n = seq["n"]
+                shared.begin(n)
+                if r1 > r0:
+                    ctx.check(ctx.lib.ilb_render_lighting_frame(ctx.handle, df.handle, C.byref(frame), C.cast(batches, C.c_void_p), nb,
+                                                                C.cast(verts, C.c_void_p), nv, W, H, _abi.FORMAT_FLOAT4, gb_ptr, out_ptr))
+                shared.publish(n)
+                if rank == 0:
+                    renderer.UpdateLightProbesDevice(d_probes.data_ptr(), packed=packed, probes=probes_packed)
+                    with torch.cuda.stream(stream):
                         probes_out_host.copy_(d_probes, non_blocking=True)
-                ctx.synchronize()
-                copy_out.synchronize()
+                    ctx.synchronize()
+                    shared.wait_complete(n)      # the whole frame is in rank 0's host memory here
+                    shared.release(n)
             h2d = H * W * 16 + world * nv * 128 + probes_packed[2] * 32     # all ranks' band uploads together = one G-buffer
             d2h = H * W * 8 + probes_packed[2] * 8
-            e2e_note = (f"per-rank G-buffer band upload and render in {rounds} rounds (in-kernel gather + barrier per round), rank 0 downloads the "
-                        "reassembled full frame round by round behind the next round's kernels")
+            e2e_note = ("one ilb_render_lighting_frame call per rank on its row band; every rank's lightmap rows land directly in one "
+                        "page-locked shared-memory host frame owned by rank 0 (no collective, no GPU barrier); rank 0 waits for "
+                        "every rank's band of the frame, then releases it")
         e_steps = max(3, args.steps // 2)
         for _ in range(2):
             e2e_step()
@@ -508,6 +492,9 @@ def run_ours(args):
                 ctx.synchronize()
                 result["e2e_host_frame_matches_single_gpu"] = bool(torch.equal(whole.cpu().view(torch.int16), out_host.view(torch.int16)))
                 del whole
+            del out_host
+            barrier()
+            shared.close()
 
         traffic, traffic_note = None, "not measured"
         if rank == 0 and not args.no_traffic:

@@ -204,6 +204,9 @@ namespace Squared.Illuminant.Native {
 
         // device-pointer variants (interop with other CUDA code in the process, multi-GPU peer mappings) and introspection
         [DllImport(DllName, CallingConvention = CC)] public static extern IntPtr ilb_stream (IntPtr ctx);
+        // page-locks caller memory (pinned arrays, MemoryMappedFile views) so that frame copies run by DMA; see INTEGRATION.md
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_host_register (IntPtr ctx, void* hostPtr, UIntPtr bytes);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_host_unregister (IntPtr ctx, void* hostPtr);
         [DllImport(DllName, CallingConvention = CC)] public static extern ulong ilb_launch_count (IntPtr ctx);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_df_create_device (IntPtr ctx, int w, int h, void* dRgba64, UIntPtr bytes, out IntPtr df);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_gbuffer_upload_device (IntPtr ctx, int w, int h, int format, void* dData);

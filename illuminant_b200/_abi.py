@@ -202,6 +202,8 @@ _PROTOTYPES = [
     ("ilb_last_error", C.c_char_p, [P]),
     ("ilb_synchronize", C.c_int, [P]),
     ("ilb_stream", P, [P]),
+    ("ilb_host_register", C.c_int, [P, P, C.c_size_t]),
+    ("ilb_host_unregister", C.c_int, [P, P]),
     ("ilb_launch_count", C.c_uint64, [P]),
     ("ilb_set_option", C.c_int, [P, C.c_int, C.c_int]),
     ("ilb_get_option", C.c_int, [P, C.c_int, C.POINTER(C.c_int)]),
@@ -309,6 +311,13 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.ilb_launch_count(self.handle))
+
+    def host_register(self, ptr: int, nbytes: int):
+        """Page-locks caller memory for asynchronous copies (ilb_host_register)."""
+        self.check(self.lib.ilb_host_register(self.handle, C.c_void_p(int(ptr)), C.c_size_t(int(nbytes))))
+
+    def host_unregister(self, ptr: int):
+        self.check(self.lib.ilb_host_unregister(self.handle, C.c_void_p(int(ptr))))
 
     def set_option(self, option: int, value: int):
         """Scheduling knobs (ilb_option): never change results."""

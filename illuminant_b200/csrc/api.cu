@@ -226,6 +226,27 @@ int ilb_synchronize(ilb_ctx* ctx) {
     return ILB_OK;
 }
 
+int ilb_host_register(ilb_ctx* ctx, void* host_ptr, size_t bytes) {
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
+    if (!host_ptr || !bytes) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null host range");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { (void)cudaGetLastError(); return ILB_OK; }
+    ILB_CUDA(ctx, e);
+    return ILB_OK;
+}
+
+int ilb_host_unregister(ilb_ctx* ctx, void* host_ptr) {
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
+    if (!host_ptr) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null host range");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // nothing of this context may still be copying from / into the range
+    const cudaError_t e = cudaHostUnregister(host_ptr);
+    if (e == cudaErrorHostMemoryNotRegistered) { (void)cudaGetLastError(); return ILB_OK; }
+    ILB_CUDA(ctx, e);
+    return ILB_OK;
+}
+
 void* ilb_stream(ilb_ctx* ctx) { return (ctx && live_has(ctx)) ? (void*)ctx->stream : nullptr; }
 uint64_t ilb_launch_count(const ilb_ctx* ctx) { return (ctx && live_has(ctx)) ? ctx->launches : 0; }
 

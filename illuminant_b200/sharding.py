@@ -54,3 +54,127 @@ def rebalance_rows(bounds, times, height: int, quantum: int = 16):
         new.append(edge)
     new.append(height)
     return new
+
+
+class SharedHostFrame:
+    """The reassembled frame in HOST memory of one node, written by every rank directly (section 8e, host-to-host leg).
+
+    One process per GPU shares the node's host memory: rank 0 creates a POSIX shared-memory object, every rank maps it and
+    page-locks the mapping (`ilb_host_register`), and each rank passes `rows(r0, r1)` of it as `lightmap_out` of its
+    `ilb_render_lighting_frame` call -- its band of the lit buffer goes from its GPU into the consumer's frame over its own PCIe
+    link, so the frame is reassembled by the copy engines of all GPUs at once instead of being gathered on one GPU and
+    downloaded by it alone.  No collective, no GPU barrier: a sequence number per rank in the same mapping says "my band of frame
+    s is in place", and the consumer's number says "frame s has been taken, its memory may be overwritten".
+
+    Layout: 4096-byte header (int64 slot 8*k = sequence number of rank k, slot 8*world = the consumer's), then the frame.
+    """
+    HEADER = 4096
+
+    def __init__(self, name: str, height: int, width: int, channels: int, dtype, rank: int, world: int, ctx=None,
+                 timeout_s: float = 60.0):
+        import mmap
+        import os
+        import time
+
+        import numpy as np
+        self.rank, self.world, self.ctx = int(rank), int(world), ctx
+        self.shape, self.dtype = (int(height), int(width), int(channels)), np.dtype(dtype)
+        if 8 * (self.world + 1) * 8 > self.HEADER:
+            raise ValueError("too many ranks for the header")
+        nbytes = self.HEADER + int(np.prod(self.shape)) * self.dtype.itemsize
+        self.path = os.path.join("/dev/shm", name)
+        self.owner = self.rank == 0
+        if self.owner:
+            try:
+                os.unlink(self.path)
+            except FileNotFoundError:
+                pass
+            fd = os.open(self.path + ".tmp", os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
+            os.ftruncate(fd, nbytes)
+            os.rename(self.path + ".tmp", self.path)      # appears under its name only at full size, zero-filled
+        else:
+            deadline = time.monotonic() + timeout_s
+            while True:
+                try:
+                    fd = os.open(self.path, os.O_RDWR)
+                    if os.fstat(fd).st_size == nbytes:
+                        break
+                    os.close(fd)
+                except FileNotFoundError:
+                    pass
+                if time.monotonic() > deadline:
+                    raise TimeoutError(f"shared host frame {self.path} did not appear")
+                time.sleep(0.005)
+        self._map = mmap.mmap(fd, nbytes)
+        os.close(fd)
+        self._bytes = np.frombuffer(self._map, dtype=np.uint8)
+        self.seq = self._bytes[:self.HEADER].view(np.int64)
+        self.frame = self._bytes[self.HEADER:].view(self.dtype).reshape(self.shape)
+        self.registered = False
+        if ctx is not None:
+            ctx.host_register(self._bytes.ctypes.data, nbytes)
+            self.registered = True
+
+    def rows(self, r0: int, r1: int):
+        """The view a rank passes as `lightmap_out` for its band [r0, r1)."""
+        return self.frame[r0:r1]
+
+    @staticmethod
+    def _spin(pred, timeout_s: float, what: str):
+        import os
+        import time
+        deadline = None
+        n = 0
+        while not pred():
+            n += 1
+            if n & 0x3ff == 0:
+                os.sched_yield()
+                if deadline is None:
+                    deadline = time.monotonic() + timeout_s
+                elif time.monotonic() > deadline:
+                    raise TimeoutError(what)
+
+    def begin(self, s: int, timeout_s: float = 60.0):
+        """Blocks until frame s - 1 has been taken by the consumer (its memory is about to be overwritten)."""
+        slot = 8 * self.world
+        self._spin(lambda: int(self.seq[slot]) >= s - 1, timeout_s, f"frame {s - 1} was never released")
+
+    def publish(self, s: int):
+        """This rank's band of frame s is complete in the shared frame (call after the synchronous frame call returned)."""
+        self.seq[8 * self.rank] = s
+
+    def wait_complete(self, s: int, timeout_s: float = 60.0):
+        """Consumer: blocks until every rank has published frame s."""
+        slots = [8 * k for k in range(self.world)]
+        self._spin(lambda: all(int(self.seq[i]) >= s for i in slots), timeout_s, f"frame {s} incomplete")
+
+    def release(self, s: int):
+        """Consumer: frame s has been taken."""
+        self.seq[8 * self.world] = s
+
+    def close(self):
+        import os
+        if getattr(self, "_map", None) is None:
+            return
+        if self.registered and self.ctx is not None:
+            try:
+                self.ctx.host_unregister(self._bytes.ctypes.data)
+            except Exception:   # noqa: BLE001  (context already gone at interpreter exit)
+                pass
+        self.seq = self.frame = self._bytes = None
+        try:
+            self._map.close()
+        except BufferError:
+            pass
+        self._map = None
+        if self.owner:
+            try:
+                os.unlink(self.path)
+            except FileNotFoundError:
+                pass
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # noqa: BLE001
+            pass

@@ -63,6 +63,14 @@ ILB_API int ilb_synchronize(ilb_ctx* ctx);
 ILB_API void* ilb_stream(ilb_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench gpu_launches). */
 ILB_API uint64_t ilb_launch_count(const ilb_ctx* ctx);
+/* Page-locks `bytes` of caller memory at `host_ptr` (a GCHandle-pinned managed array, a native allocation, or a mapping of
+ * shared memory -- MemoryMappedFile / shm_open) for every CUDA context of the process, so that the copies of
+ * ilb_render_lighting_frame and ilb_gbuffer_upload_rows run asynchronously by DMA instead of being staged.  One node, one
+ * process per GPU: when `lightmap_out` of every rank points into ONE shared mapping registered on every rank, each rank's band
+ * of the frame goes from its GPU straight into the host frame of the consumer over the rank's own PCIe link -- the reassembled
+ * frame reaches the host without passing through one GPU.  Unregister before the memory is freed or unmapped. */
+ILB_API int ilb_host_register(ilb_ctx* ctx, void* host_ptr, size_t bytes);
+ILB_API int ilb_host_unregister(ilb_ctx* ctx, void* host_ptr);
 
 /* Scheduling knobs of the kernels, never results: light counts, discards, distance-field samples, march steps and particle
  * state are the same bits under every setting; ILB_OPT_LIGHT_CONST_BANK selects another instantiation of the light kernel, whose

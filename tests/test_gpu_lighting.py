@@ -211,6 +211,52 @@ def test_pipelined_host_frame_equals_upload_plus_render(ctx):
             assert np.array_equal(got.view(np.uint16), want.view(np.uint16))
 
 
+def test_bands_land_in_one_registered_shared_host_frame(ctx):
+    """The host-to-host leg at N > 1 on one device: the bands of a frame, each rendered by its own ilb_render_lighting_frame
+    call straight into its rows of ONE page-locked shared-memory host frame (ilb_host_register), reassemble the unsharded
+    lightmap bit for bit -- under every split of the pipeline bands; registering twice and unregistering unknown memory are
+    harmless; null ranges are rejected."""
+    import os
+    from illuminant_b200 import sharding
+    from illuminant_b200._abi import IlluminantError
+    w, h = 640, 403
+    s = scenes.lighting_scene(37, w, h, 6, n_directional=1, n_line=1, ramp=(60.0, 260.0))
+    df = scenes.make_distance_field(ctx, s)
+    df.Rasterize(s.obstructions)
+    r = ib.LightingRenderer(ctx, s.environment, s.configuration)
+    r.DistanceField = df
+    r.SetGBuffer(s.gbuffer)
+    want = r.RenderLighting()
+    shared = sharding.SharedHostFrame(f"ilb_test_gpu_frame_{os.getpid()}", h, w, 4, want.dtype, 0, 1, ctx=ctx)
+    try:
+        ctx.host_register(shared.frame.ctypes.data - shared.HEADER, shared.HEADER + shared.frame.nbytes)   # already registered: fine
+        gb = np.ascontiguousarray(s.gbuffer)
+        old = os.environ.get("ILB_BAND_SHARES")
+        try:
+            for split in (None, "0", "1", "2", "3", "4"):
+                if split is None:
+                    os.environ.pop("ILB_BAND_SHARES", None)
+                else:
+                    os.environ["ILB_BAND_SHARES"] = split
+                shared.frame[...] = 0
+                r.SetGBuffer(np.zeros_like(s.gbuffer))
+                for k in range(3):
+                    r0, r1 = sharding.row_band(k, 3, h)
+                    r.RenderLightingFrame(gb, rows=(r0, r1), out=shared.rows(r0, r1))
+                assert np.array_equal(shared.frame.view(np.uint16), want.view(np.uint16)), split
+        finally:
+            if old is None:
+                os.environ.pop("ILB_BAND_SHARES", None)
+            else:
+                os.environ["ILB_BAND_SHARES"] = old
+        with pytest.raises(IlluminantError):
+            ctx.host_register(0, 4096)
+        scratch = np.zeros(8192, np.uint8)
+        ctx.host_unregister(scratch.ctypes.data)      # never registered: nothing to do
+    finally:
+        shared.close()
+
+
 def test_degenerate_geometry_takes_the_ieee_fallback(ctx, oracle):
     """Operands outside the fast window of the deferred-guard square roots / reciprocals (zero-length vectors: a light
     exactly at a shaded point, at a trace origin, a pixel on a line light's axis, a zero-length line light) must come out

@@ -61,3 +61,62 @@ def test_two_rank_sharding_matches_single_rank(tmp_path, oracle):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def _host_frame_worker(rank, world, name, outdir):
+    """The host-to-host leg of bench.py at N > 1 without a device: every rank writes its band of three consecutive frames into
+    the one shared host frame (here the oracle stands in for ilb_render_lighting_frame), rank 0 consumes each complete frame."""
+    sys.path.insert(0, str(ROOT))
+    os.environ["OMP_NUM_THREADS"] = "2"
+    import illuminant_b200 as ib
+    from illuminant_b200 import scenes, sharding
+    from oracle import oracle
+    s = scenes.lighting_scene(92, 64, 45, 2, float4_lightmap=True)
+    df = scenes.make_distance_field(None, s)
+    tex = oracle.generate_distance_field(df, s.obstructions)
+    df.ValidSliceCount, df.handle = df.SliceCount, 1
+    r = ib.LightingRenderer(None, s.environment, s.configuration)
+    r.DistanceField, r._gbuffer_shape = df, s.gbuffer.shape[:2]
+    shared = sharding.SharedHostFrame(name, s.height, s.width, 4, np.float32, rank, world)
+    r0, r1 = sharding.row_band(rank, world, s.height)
+    for seq in (1, 2, 3):
+        scale = float(seq)            # a different frame every time: a stale band would be noticed
+        batches, nb, verts, nv = r.build_batches(scale)
+        shared.begin(seq)
+        shared.rows(r0, r1)[...] = oracle.render_lighting(tex, s.gbuffer, r.build_frame(scale, (r0, r1)), batches, nb, verts, nv, nthreads=2)
+        shared.publish(seq)
+        if rank == 0:
+            shared.wait_complete(seq)
+            whole = oracle.render_lighting(tex, s.gbuffer, r.build_frame(scale), batches, nb, verts, nv, nthreads=2)
+            assert np.array_equal(shared.frame, whole), seq
+            shared.release(seq)
+    (Path(outdir) / f"hf{rank}").write_text("ok")
+    if rank == 0:   # the others may still be mapping / unmapping; the name can go, the memory lives until the last unmap
+        shared.wait_complete(3)
+    shared.close()
+
+
+def test_shared_host_frame_is_reassembled_by_the_ranks_themselves(tmp_path, oracle):
+    name = f"ilb_test_frame_{os.getpid()}"
+    mp.spawn(_host_frame_worker, args=(2, name, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "hf0").exists() and (tmp_path / "hf1").exists()
+    assert not os.path.exists(os.path.join("/dev/shm", name))
+
+
+def test_shared_host_frame_single_rank_protocol():
+    from illuminant_b200 import sharding
+    name = f"ilb_test_frame1_{os.getpid()}"
+    f = sharding.SharedHostFrame(name, 8, 4, 4, np.float16, 0, 1)
+    assert f.frame.shape == (8, 4, 4) and f.frame.dtype == np.float16 and not f.frame.any()
+    assert f.frame.ctypes.data % 4096 == 0          # page-aligned behind the header: page-lockable as one range
+    f.begin(1)
+    f.rows(2, 5)[...] = 1.0
+    f.publish(1)
+    f.wait_complete(1)
+    assert float(f.frame.sum()) == 3 * 4 * 4
+    with pytest.raises(TimeoutError):
+        f.begin(3, timeout_s=0.05)                   # frame 2 was never released
+    f.release(2)
+    f.begin(3)
+    f.close()
+    assert not os.path.exists(os.path.join("/dev/shm", name))
