@@ -221,12 +221,14 @@ C4_WORKLOAD = "C4: 3840x2160, 96 sphere + 8 directional + 24 line lights, 256 pr
 def measure_traffic(what: str, pattern: str, skip: int, count: int, extra=()):
     """dram__bytes_read.sum + dram__bytes_write.sum of `count` launches matching `pattern` of profiles/microbench/profile_hot.py,
     counted by ncu in a child process.  Byte counters only -- nothing timed under the profiler is ever reported.  Returns
-    (bytes, None) or (None, reason)."""
+    (bytes, None) or (None, reason); the warp-instruction count of the same launches (smsp__inst_executed.sum) is left in
+    measure_traffic.instructions (None when it was not reported)."""
+    measure_traffic.instructions = None
     import shutil
     ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
     if not Path(ncu).exists():
         return None, "ncu not found"
-    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", f"regex:{pattern}", "-s", str(skip),
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum", "--clock-control", "none", "-k", f"regex:{pattern}", "-s", str(skip),
            "-c", str(count), "--csv", sys.executable, str(ROOT / "profiles" / "microbench" / "profile_hot.py"), what, *[str(e) for e in extra]]
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
     try:
@@ -244,13 +246,33 @@ def measure_traffic(what: str, pattern: str, skip: int, count: int, extra=()):
     except ValueError:
         return None, "unexpected ncu output"
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    insts, iseen = 0.0, 0
     for r in rows[1:]:
         if r[ni].startswith("dram__bytes_"):
             total += float(r[vi].replace(",", "")) * scale.get(r[ui], 1.0)
             seen += 1
+        elif r[ni].startswith("smsp__inst_executed"):
+            insts += float(r[vi].replace(",", ""))
+            iseen += 1
     if seen < 2 * count:
         return None, f"ncu saw {seen // 2} of {count} launches"
+    if iseen == count:
+        measure_traffic.instructions = insts
     return total, None
+
+
+def issue_roofline(warp_instructions, kernel_ms, clocks, device):
+    """What bounds the two hot kernels is the instruction issue rate, not HBM: the warp-instructions of
+    the launches (counted by ncu in the run) over the kernel time (CUDA events, no profiler), against the 4 issue slots per SM
+    and cycle at the SM clock sampled during the timed region.  Reported NEXT TO the HBM roofline the contract asks for."""
+    if not warp_instructions or not kernel_ms or not clocks or not clocks.get("sm_mhz"):
+        return None
+    import torch
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    peak = sms * 4 * float(clocks["sm_mhz"]) * 1e6 / 1e9
+    achieved = warp_instructions / (kernel_ms * 1e-3) / 1e9
+    return {"bound": "issue", "warp_instructions": warp_instructions, "achieved": achieved, "peak": peak, "unit": "G warp-instructions/s",
+            "frac": achieved / peak, "peak_source": f"{sms} SMs x 4 schedulers x {clocks['sm_mhz']:.0f} MHz (sampled under load)"}
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
@@ -500,6 +522,7 @@ def run_ours(args):
         if rank == 0 and not args.no_traffic:
             traffic, why = measure_traffic("light", "light_accumulate", 2, 2, (2, r0, r1))
             traffic_note = why or "ncu dram__bytes_read.sum + dram__bytes_write.sum of this rank's two lighting launches, measured in this run"
+            result["roofline_issue"] = issue_roofline(measure_traffic.instructions, k_ms, clocks, local_rank)
         result.update({
             "metric": "lit Mpixels/s (4K, 128 lights)", "value": mpx, "unit": "Mpixels/s", "ms_per_step": ms_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -608,6 +631,7 @@ def run_ours(args):
         if rank == 0 and not args.no_traffic:
             ptraffic, why = measure_traffic("particles", "particle_step_kernel", 4, 1, (5,))
             ptraffic_note = why or "ncu dram__bytes_read.sum + dram__bytes_write.sum of one particle_step_kernel launch, measured in this run"
+            p_issue = issue_roofline(measure_traffic.instructions, ms_step, pclocks, local_rank)
         result["particles"] = {
             "metric": "Mparticle-steps/s", "value": mps, "unit": "Mparticle-steps/s", "ms_per_step": ms_step, "steps": p_steps, "scaling": "weak",
             "config": {"workload": f"{count} particles per GPU (32 chunks x 512^2 + spawn headroom), Spawner(60000/s)+Gravity(4)+Noise+FMA+UpdateWithDistanceField, dt 1/60",
@@ -621,6 +645,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(C.sizeof(_abi.PsysUniforms) + 3 * C.sizeof(_abi.Op) + C.sizeof(_abi.Spawn)), "d2h_bytes_per_step": 8, "ms_per_step": e_ms},
             "gpu_launches": int(p_launches), "clocks": pclocks,
         }
+        if rank == 0 and not args.no_traffic and p_issue:
+            result["particles"]["roofline_issue"] = p_issue
 
         # N2: ParticleSystem.Render of the same 8M particles into a 4K half4 target, additive (the whole
         # render: vertex work, binning, stable sort, ordered per-tile shading).  Reported next to the headline, never part of it.
@@ -751,7 +777,7 @@ def run_ours(args):
                 "config": {"workload": C4_WORKLOAD if primary else result.get("config", {}).get("workload"),
                            "parallelism": f"row bands of equal measured cost x{world}, gather: {result.get('gather', 'none')}" if primary else f"chunk ranges x{world}, no collective",
                            "l2": "inputs larger than L2 (no flush)"}}
-        for k in ("roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "gather_checksum_equal", "gather_matches_single_gpu", "e2e_host_frame_matches_single_gpu", "probes", "bands",
+        for k in ("roofline", "roofline_issue", "cpu_baseline", "e2e", "gpu_launches", "clocks", "gather_checksum_equal", "gather_matches_single_gpu", "e2e_host_frame_matches_single_gpu", "probes", "bands",
                   "particles", "combined_c5", "combined_c5_strong", "resolve", "render", "render_sharded"):
             if k in result:
                 line[k] = result[k]

@@ -1693,14 +1693,16 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
     // Bands of whole tile rows with heights 1 : 2 : 4 : 6 : 6 : 6 : 4 : 2 : 1 -- the first band is short so that the first kernel
     // starts after 1/32 of the upload, the last so that only 1/32 of the download is left when the last kernel ends, the middle
     // ones long so that few launches are paid (7.82 -> 7.69 ms per C4 frame against the 7-band split 1 : 2 : 3 : 4 : 3 : 2 : 1).
-    // A short frame -- a rank's band of a sharded frame, a small render target -- takes a coarser split, so that no band is less
-    // than about a wave and a half of CTAs (740 are resident at a time): 7 bands below 16 000 tiles, 4 below 6 000, 2 below 2 500.
+    // A rank's band of a frame sharded over 8 GPUs (270 rows, 4 080 tiles) still does best with the 9-band split, although a band is
+    // then less than a wave of CTAs -- the two compute lanes interleave neighbouring bands, and what counts is how early the first
+    // kernel starts and how little is left to download after the last (measured at 8 GPUs: 1 band 2.26 ms per host-to-host
+    // frame, 2 bands 1.75, 4 bands 1.60, 7 bands 1.56, 9 bands 1.52).  Only small render targets take a coarser split.
     // ILB_BAND_SHARES selects the split (dev knob): 0 = 1:2:3:4:3:2:1, 1 = 1:2:4:6:6:6:4:2:1, 2 = 1:2:2:1, 3 = 1:1, 4 = one band
     static const int kShares[5][9] = {{1, 2, 3, 4, 3, 2, 1, 0, 0}, {1, 2, 4, 6, 6, 6, 4, 2, 1}, {1, 2, 2, 1, 0, 0, 0, 0, 0}, {1, 1, 0, 0, 0, 0, 0, 0, 0},
                                       {1, 0, 0, 0, 0, 0, 0, 0, 0}};
     static const int kCount[5] = {7, 9, 4, 2, 1}, kTotal[5] = {16, 32, 6, 2, 1};
     const long long tiles = (long long)((rows + TILE_H - 1) / TILE_H) * ((f->width + TILE_W - 1) / TILE_W);
-    int which = tiles >= 16000 ? 1 : tiles >= 6000 ? 0 : tiles >= 2500 ? 2 : 3;
+    int which = tiles >= 2500 ? 1 : tiles >= 600 ? 2 : 3;
     if (const char* e = getenv("ILB_BAND_SHARES")) { const int v = atoi(e); if (v >= 0 && v <= 4) which = v; }
     const int* kShare = kShares[which];
     const int NB = kCount[which], total = kTotal[which];
