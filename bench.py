@@ -472,7 +472,11 @@ def run_ours(args):
             # their own PCIe links: no collective and no GPU barrier on this leg.  Per frame, a sequence number per rank in the
             # same mapping tells rank 0 that the rank's band is in place; rank 0 takes the frame and releases it.
             port = os.environ.get("MASTER_PORT", "0")
-            shared = sharding.SharedHostFrame(f"ilb_bench_frame_{port}", H, W, 4, "float16", rank, world, ctx=ctx)
+            shared = None
+            for turn in (0, 1):      # rank 0 creates the object (replacing a stale one of a crashed run) before anyone else opens it
+                if (rank == 0) == (turn == 0):
+                    shared = sharding.SharedHostFrame(f"ilb_bench_frame_{port}", H, W, 4, "float16", rank, world, ctx=ctx)
+                barrier()
             out_host = torch.from_numpy(shared.frame)
             gb_ptr, out_ptr = C.c_void_p(gb_host.data_ptr()), C.c_void_p(shared.rows(r0, r1).ctypes.data if r1 > r0 else shared.frame.ctypes.data)
             seq = {"n": 0}

@@ -912,7 +912,11 @@ ILB_DEV void shadeTile(const LightingParams& P, unsigned tile, TileSmem& S) {
 }
 
 // resident CTAs per SM for this pass's register budget (the budgets above are stated for 256-thread CTAs)
+#if defined(ILB_LIGHT_CTAS_LINE) && defined(ILB_LIGHT_CTAS_NOLINE)   // dev knob: resident CTAs per SM stated directly (for other tile heights)
+#define ILB_LIGHT_CTAS(TYPES) (((TYPES) & ILB_LIGHT_LINE) ? ILB_LIGHT_CTAS_LINE : ILB_LIGHT_CTAS_NOLINE)
+#else
 #define ILB_LIGHT_CTAS(TYPES) ((((TYPES) & ILB_LIGHT_LINE) ? ILB_LIGHT_MINBLOCKS : ILB_LIGHT_MINBLOCKS_NOLINE) * (256 / TILE_THREADS))
+#endif
 
 template <int FIELD, int TYPES, bool CL>
 __global__ void __launch_bounds__(TILE_THREADS, ILB_LIGHT_CTAS(TYPES))
