@@ -191,7 +191,7 @@ class IlluminantError(RuntimeError):
 
 # ilb_option
 (OPT_LIGHT_CONCURRENT, OPT_LIGHT_LINE_CTAS, OPT_LIGHT_OTHER_CTAS, OPT_LIGHT_LINE_HELPERS, OPT_LIGHT_OTHER_HELPERS, OPT_LIGHT_PDL,
- OPT_LIGHT_CONST_BANK, OPT_LIGHT_SPLIT_BAND) = range(8)
+ OPT_LIGHT_CONST_BANK, OPT_LIGHT_SPLIT_BAND, OPT_LIGHT_TILE_ORDER) = range(9)
 
 # every symbol include/illuminant_b200.h declares: (name, restype, argtypes)
 P = C.c_void_p

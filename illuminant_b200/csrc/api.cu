@@ -146,7 +146,7 @@ int ilb_create(int device_ordinal, ilb_ctx** out_ctx) {
     static const struct { const char* env; int value; } defaults[ILB_OPT_COUNT] = {
         {"ILB_OPT_LIGHT_CONCURRENT", 0}, {"ILB_OPT_LIGHT_LINE_CTAS", 2}, {"ILB_OPT_LIGHT_OTHER_CTAS", 2},
         {"ILB_OPT_LIGHT_LINE_HELPERS", 1}, {"ILB_OPT_LIGHT_OTHER_HELPERS", 3}, {"ILB_OPT_LIGHT_PDL", 1}, {"ILB_OPT_LIGHT_CONST_BANK", 1},
-        {"ILB_OPT_LIGHT_SPLIT_BAND", 1}};
+        {"ILB_OPT_LIGHT_SPLIT_BAND", 1}, {"ILB_OPT_LIGHT_TILE_ORDER", 0}};
     for (int i = 0; i < ILB_OPT_COUNT; i++) {
         const char* e = getenv(defaults[i].env);
         ctx->opt[i] = e ? atoi(e) : defaults[i].value;
@@ -187,6 +187,11 @@ void ilb_destroy(ilb_ctx* ctx) {
     if (ctx->d_accum) cudaFree(ctx->d_accum);
     if (ctx->d_accum2) cudaFree(ctx->d_accum2);
     if (ctx->d_tilework) cudaFree(ctx->d_tilework);
+    for (ilb_ctx::TileOrder& t : ctx->tile_orders) {
+        if (t.h) cudaFreeHost(t.h);
+        if (t.d) cudaFree(t.d);
+        for (cudaEvent_t e : t.used) if (e) cudaEventDestroy(e);
+    }
     if (ctx->light_aux[0]) {
         for (int i = 0; i < 3; i++) { cudaStreamDestroy(ctx->light_aux[i]); cudaEventDestroy(ctx->ev_light_join[i]); }
         cudaEventDestroy(ctx->ev_light_fork);

@@ -65,6 +65,18 @@ struct ilb_ctx {
     cudaEvent_t ev_light_fork = nullptr, ev_light_join[3] = {};
     int sm_count = 148;
     int opt[ILB_OPT_COUNT] = {};  // tuning knobs, ilb_set_option
+    // heaviest-first tile orders of the sphere + directional pass (lighting.cu, tileOrderFor): a ring of cached orders keyed by the
+    // frame geometry and the sphere lights' pixel rectangles, each with its own pinned staging and device copy; `used[lane]` is
+    // recorded behind the last launch of that compute lane that reads the slot, and waited for before the slot is given away
+    struct TileOrder {
+        std::vector<int> key;
+        unsigned* h = nullptr; unsigned* d = nullptr;
+        size_t capacity = 0;
+        cudaEvent_t used[2] = {nullptr, nullptr};
+        unsigned long long stamp = 0;
+    };
+    TileOrder tile_orders[32];
+    unsigned long long tile_order_clock = 0;
     // ParticleLightSources applied to every frame until replaced (ilb_lighting_set_particle_lights)
     std::vector<ilb_particle_light_source> particle_lights;
     void* d_plight_scratch = nullptr;

@@ -90,6 +90,7 @@ struct LightingParams {
     void* outs[MAX_OUTPUTS];
     int nouts;
     int out_row_base;  // row index of outs[] row 0 (row_begin for band buffers, 0 for full frames)
+    const unsigned* tile_order;  // heaviest-first permutation of the tile indices (ILB_OPT_LIGHT_TILE_ORDER), or null
     int tiles_x, tiles_y;
     const float4* accum_in;  // fp32 sums of an earlier pass over this row band (nullptr: start from `clear`)
     float4* accum_out;       // leave the fp32 sums here instead of storing the lightmap (nullptr: final pass)
@@ -925,7 +926,7 @@ light_accumulate_kernel(const __grid_constant__ LightingParams P) {
     // first pass of a split frame: the second pass may be scheduled as soon as every CTA of this grid has started, i.e. into
     // the idle SM slots of this grid's last wave (it waits for this grid's results only at its very end, see shadeTile)
     if (P.accum_out && !P.tile_done) asm volatile("griddepcontrol.launch_dependents;");
-    shadeTile<FIELD, TYPES, CL>(P, blockIdx.x, S);
+    shadeTile<FIELD, TYPES, CL>(P, P.tile_order ? __ldg(P.tile_order + blockIdx.x) : blockIdx.x, S);
 }
 
 // Persistent form: a fixed number of resident CTAs per SM takes tiles from a queue (one atomic counter per pass), so that
@@ -1352,6 +1353,7 @@ struct LightingPrepared {
     int nline = 0, nlights = 0;
     bool hasRamp = false;     // a sphere-light batch with a ramp texture: the instantiations with ILB_LIGHT_RAMP_BIT in TYPES
     bool constBank = false;   // the frame's light records are in c_lights / c_lines as well
+    std::vector<int> sphereRects;   // px0, py0, px1, py1 of every sphere light of the host list: what tileOrderFor counts per tile
 };
 
 // Per-frame work that does not depend on the row band: validate, flatten + upload the light list, resolve the field.
@@ -1478,8 +1480,114 @@ int lightingPrepare(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const
     for (const DLight& L : lights) {
         out->nline += ((L.type & ILB_LIGHT_TYPE_MASK) == ILB_LIGHT_LINE) ? 1 : 0;
         out->hasRamp = out->hasRamp || (L.type & ILB_LIGHT_RAMP_BIT) != 0;
+        if ((L.type & ILB_LIGHT_TYPE_MASK) == ILB_LIGHT_SPHERE) {
+            const int r[4] = {L.px0, L.py0, L.px1, L.py1};
+            out->sphereRects.insert(out->sphereRects.end(), r, r + 4);
+        }
     }
     return ILB_OK;
+}
+
+// ILB_OPT_LIGHT_TILE_ORDER: the tile indices of rows [row_begin, row_end) sorted by the number of sphere-light quads that
+// cover the tile, heaviest first, equal tiles in their traversal order (a stable counting sort, so the 2-D locality of the
+// traversal survives inside every class).  The per-pixel cost of the sphere + directional pass is a serial loop over the tile's
+// lights, so a tile under a cluster of lights runs several times as long as an empty one: started last it would keep a few SMs
+// busy while the rest of the device idles.  Counted on the host from the light list (a 2-D difference array over the tiles: a
+// few microseconds per band), cached per (geometry, rectangles) in a ring of slots that own their staging and device memory.
+// Purely a launch-order hint: a missing or stale order costs time, never results.  Returns null when there is nothing to sort.
+const unsigned* tileOrderFor(ilb_ctx* ctx, const LightingPrepared& prep, int width, int row_begin, int row_end, int lane, cudaStream_t st) {
+    const int tiles_x = (width + TILE_W - 1) / TILE_W, tiles_y = (row_end - row_begin + TILE_H - 1) / TILE_H;
+    const size_t tiles = (size_t)tiles_x * (size_t)tiles_y;
+    if (prep.sphereRects.empty() || tiles < 512) return nullptr;
+    constexpr int SLOTS = (int)(sizeof(ctx->tile_orders) / sizeof(ctx->tile_orders[0]));
+    std::vector<int> key;
+    key.reserve(prep.sphereRects.size() + 3);
+    key.push_back(width); key.push_back(row_begin); key.push_back(row_end);
+    key.insert(key.end(), prep.sphereRects.begin(), prep.sphereRects.end());
+    ilb_ctx::TileOrder* slot = nullptr;
+    for (int i = 0; i < SLOTS; i++)
+        if (ctx->tile_orders[i].d && ctx->tile_orders[i].key == key) { slot = &ctx->tile_orders[i]; break; }
+    const bool hit = slot != nullptr;
+    if (!hit) {
+        slot = &ctx->tile_orders[0];
+        for (int i = 1; i < SLOTS; i++)
+            if (ctx->tile_orders[i].stamp < slot->stamp) slot = &ctx->tile_orders[i];
+        for (int l = 0; l < 2; l++)   // kernels that still read the order this slot held
+            if (slot->used[l] && cudaEventSynchronize(slot->used[l]) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+        if (slot->capacity < tiles) {
+            if (slot->h) cudaFreeHost(slot->h);
+            if (slot->d) cudaFree(slot->d);
+            slot->h = slot->d = nullptr; slot->capacity = 0; slot->key.clear();
+            const size_t want = tiles + tiles / 2;
+            if (cudaMallocHost(reinterpret_cast<void**>(&slot->h), want * sizeof(unsigned)) != cudaSuccess ||
+                cudaMalloc(reinterpret_cast<void**>(&slot->d), want * sizeof(unsigned)) != cudaSuccess) {
+                (void)cudaGetLastError();
+                if (slot->h) cudaFreeHost(slot->h);
+                slot->h = slot->d = nullptr;
+                return nullptr;
+            }
+            slot->capacity = want;
+        }
+        // sphere-light quads per tile: 2-D difference array, then prefix sums
+        const int dw = tiles_x + 1;
+        std::vector<int> cnt((size_t)(tiles_y + 1) * (size_t)dw, 0);
+        for (size_t i = 0; i + 3 < prep.sphereRects.size(); i += 4) {
+            const int x0 = std::max(prep.sphereRects[i], 0), y0 = std::max(prep.sphereRects[i + 1], row_begin);
+            const int x1 = std::min(prep.sphereRects[i + 2], width - 1), y1 = std::min(prep.sphereRects[i + 3], row_end - 1);
+            if (x0 > x1 || y0 > y1) continue;
+            const int tx0 = x0 / TILE_W, tx1 = x1 / TILE_W, ty0 = (y0 - row_begin) / TILE_H, ty1 = (y1 - row_begin) / TILE_H;
+            cnt[(size_t)ty0 * dw + tx0]++; cnt[(size_t)ty0 * dw + tx1 + 1]--;
+            cnt[(size_t)(ty1 + 1) * dw + tx0]--; cnt[(size_t)(ty1 + 1) * dw + tx1 + 1]++;
+        }
+        int most = 0;
+        for (int y = 0; y < tiles_y; y++)
+            for (int x = 0; x < tiles_x; x++) {
+                int v = cnt[(size_t)y * dw + x];
+                if (x) v += cnt[(size_t)y * dw + x - 1];
+                if (y) v += cnt[(size_t)(y - 1) * dw + x];
+                if (x && y) v -= cnt[(size_t)(y - 1) * dw + x - 1];
+                cnt[(size_t)y * dw + x] = v;
+                most = std::max(most, v);
+            }
+        // stable counting sort of the kernel's linear tile indices (the traversal of shadeTile), heaviest class first
+        auto tileCount = [&](unsigned tile) {
+            int tileX, tileY;
+            if (ILB_SWIZZLE > 1) {
+                const int band = (int)(tile / (unsigned)(ILB_SWIZZLE * tiles_x)), inband = (int)(tile % (unsigned)(ILB_SWIZZLE * tiles_x));
+                const int rowsInBand = std::min(ILB_SWIZZLE, tiles_y - band * ILB_SWIZZLE);
+                tileX = inband / rowsInBand;
+                tileY = band * ILB_SWIZZLE + inband % rowsInBand;
+            } else {
+                tileX = (int)(tile % (unsigned)tiles_x);
+                tileY = (int)(tile / (unsigned)tiles_x);
+            }
+            return cnt[(size_t)tileY * dw + tileX];
+        };
+        std::vector<unsigned> start((size_t)most + 2, 0u);
+        for (unsigned t = 0; t < (unsigned)tiles; t++) start[(size_t)(most - tileCount(t)) + 1]++;
+        for (size_t c = 1; c < start.size(); c++) start[c] += start[c - 1];
+        for (unsigned t = 0; t < (unsigned)tiles; t++) slot->h[start[(size_t)(most - tileCount(t))]++] = t;
+        if (most == 0) { slot->key.clear(); return nullptr; }   // no quad touches the band: the traversal order is as good as any
+        if (cudaMemcpyAsync(slot->d, slot->h, tiles * sizeof(unsigned), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            (void)cudaGetLastError();
+            slot->key.clear();
+            return nullptr;
+        }
+        slot->key = std::move(key);
+    }
+    slot->stamp = ++ctx->tile_order_clock;
+    return slot->d;
+}
+
+// records that the launches queued on lane `lane` so far read the order (see ilb_ctx::TileOrder)
+void tileOrderMarkUse(ilb_ctx* ctx, const unsigned* order, int lane, cudaStream_t st) {
+    for (ilb_ctx::TileOrder& t : ctx->tile_orders) {
+        if (t.d != order) continue;
+        cudaEvent_t& e = t.used[lane ? 1 : 0];
+        if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); e = nullptr; return; }
+        if (cudaEventRecord(e, st) != cudaSuccess) (void)cudaGetLastError();
+        return;
+    }
 }
 
 // Shades rows [row_begin, row_end) of a prepared frame into d_outputs (band buffers whose row 0 is `out_row_base`).
@@ -1506,6 +1614,7 @@ int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin
     constexpr int NOLINE = ILB_LIGHT_SPHERE | ILB_LIGHT_DIRECTIONAL | ILB_LIGHT_PARTICLE_BIT, ALL = NOLINE | ILB_LIGHT_LINE;
     bool split = prep.nline > 0 && prep.nline < prep.nlights;
     if (const char* e = getenv("ILB_SPLIT_PASSES")) split = split && e[0] != '0';
+    const unsigned* order = nullptr;   // ILB_OPT_LIGHT_TILE_ORDER: heaviest tiles of the sphere + directional pass first
     int planesMask = 3;  // dev knob: bit 0 = line pass samples the planes, bit 1 = sphere / directional pass does
     if (const char* e = getenv("ILB_PLANES_MASK")) planesMask = atoi(e);
 #define ILB_LIGHT_LAUNCH(TYPES)                                                                                       \
@@ -1578,10 +1687,14 @@ int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin
         const size_t bytes = sizeof(float4) * (size_t)P.width * (size_t)(row_end - row_begin);
         const int rc = ilb_reserve(ctx, accumBuffer, accumCapacity, bytes, false);
         if (rc) return rc;
+        // (an upload of the order is queued here, ahead of the line pass: nothing may sit between the two launches of the
+        // programmatic dependent pair)
+        order = (ctx->opt[ILB_OPT_LIGHT_TILE_ORDER] != 0) ? tileOrderFor(ctx, prep, P.width, row_begin, row_end, lane, st) : nullptr;
         P.accum_out = reinterpret_cast<float4*>(*accumBuffer);
         ILB_LIGHT_LAUNCH(ILB_LIGHT_LINE);
         P.accum_in = P.accum_out;
         P.accum_out = nullptr;
+        P.tile_order = order;
         P.clear = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // the clear colour entered through the line-light sums
         if (ctx->opt[ILB_OPT_LIGHT_PDL] && !prep.hasRamp) {
             // programmatic dependent launch: the second pass's CTAs fill the SM slots the first pass's last wave leaves idle
@@ -1603,12 +1716,15 @@ int lightingLaunchRows(ilb_ctx* ctx, const LightingPrepared& prep, int row_begin
             ILB_LIGHT_LAUNCH(NOLINE);
         }
     } else if (prep.nline == 0) {
+        P.tile_order = order = (ctx->opt[ILB_OPT_LIGHT_TILE_ORDER] != 0) ? tileOrderFor(ctx, prep, P.width, row_begin, row_end, lane, st) : nullptr;
         ILB_LIGHT_LAUNCH(NOLINE);
     } else {
+        P.tile_order = order = (ctx->opt[ILB_OPT_LIGHT_TILE_ORDER] != 0) ? tileOrderFor(ctx, prep, P.width, row_begin, row_end, lane, st) : nullptr;
         ILB_LIGHT_LAUNCH(ALL);
     }
 #undef ILB_LIGHT_LAUNCH
     ILB_CUDA(ctx, cudaGetLastError());
+    if (order) tileOrderMarkUse(ctx, order, lane, st);
     if (prep.constBank) return constBankMarkUse(ctx, st);
     return ILB_OK;
 }

@@ -257,6 +257,40 @@ def test_bands_land_in_one_registered_shared_host_frame(ctx):
         shared.close()
 
 
+def test_heaviest_first_tile_order_is_only_a_schedule(ctx):
+    """ILB_OPT_LIGHT_TILE_ORDER starts the tiles under the most sphere-light quads first: same bits with the option on and off,
+    for whole frames, bands and mixed / sphere-only light lists; moving a light makes a new order (more moves than the cache
+    has slots: slots are recycled while frames are in flight)."""
+    from illuminant_b200 import _abi
+    w, h = 800, 480      # 50 x 30 tiles: above the 512-tile threshold
+    for n_line in (1, 0):
+        s = scenes.lighting_scene(41 + n_line, w, h, 10, n_directional=1, n_line=n_line, ramp=(40.0, 160.0))
+        df = scenes.make_distance_field(ctx, s)
+        df.Rasterize(s.obstructions)
+        r = ib.LightingRenderer(ctx, s.environment, s.configuration)
+        r.DistanceField = df
+        r.SetGBuffer(s.gbuffer)
+        try:
+            for rows in (None, (16, h - 21)):
+                ctx.set_option(_abi.OPT_LIGHT_TILE_ORDER, 0)
+                want = r.RenderLighting(rows=rows)
+                ctx.set_option(_abi.OPT_LIGHT_TILE_ORDER, 1)
+                for _ in range(2):     # miss, then hit
+                    got = r.RenderLighting(rows=rows)
+                    assert np.array_equal(got.view(np.uint16), want.view(np.uint16)), (n_line, rows)
+            light = next(l for l in s.environment.Lights if isinstance(l, ib.SphereLightSource))
+            x0 = light.Position[0]
+            for k in range(40):
+                light.Position = (x0 + 3.0 * k,) + tuple(light.Position[1:])
+                ctx.set_option(_abi.OPT_LIGHT_TILE_ORDER, 1)
+                got = r.RenderLighting()
+                if k % 13 == 0:
+                    ctx.set_option(_abi.OPT_LIGHT_TILE_ORDER, 0)
+                    assert np.array_equal(got.view(np.uint16), r.RenderLighting().view(np.uint16)), k
+        finally:
+            ctx.set_option(_abi.OPT_LIGHT_TILE_ORDER, 0)
+
+
 def test_degenerate_geometry_takes_the_ieee_fallback(ctx, oracle):
     """Operands outside the fast window of the deferred-guard square roots / reciprocals (zero-length vectors: a light
     exactly at a shaded point, at a trace origin, a pixel on a line light's axis, a zero-length line light) must come out
