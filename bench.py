@@ -524,8 +524,13 @@ def run_ours(args):
 
         traffic, traffic_note = None, "not measured"
         if rank == 0 and not args.no_traffic:
-            traffic, why = measure_traffic("light", "light_accumulate", 2, 2, (2, r0, r1))
-            traffic_note = why or "ncu dram__bytes_read.sum + dram__bytes_write.sum of this rank's two lighting launches, measured in this run"
+            l0 = ctx.launch_count      # launches of one render of this rank's band: 2, or 4 when the band runs as two halves
+            renderer.RenderLightingDevice(scratch.data_ptr(), rows=(r0, r1), packed=packed)
+            ctx.synchronize()
+            per_band = max(int(ctx.launch_count - l0), 1)
+            traffic, why = measure_traffic("light", "light_accumulate", per_band, per_band, (2, r0, r1))
+            traffic_note = why or (f"ncu dram__bytes_read.sum + dram__bytes_write.sum of the {per_band} lighting launches of this rank's band, "
+                                   "measured in this run")
             result["roofline_issue"] = issue_roofline(measure_traffic.instructions, k_ms, clocks, local_rank)
         result.update({
             "metric": "lit Mpixels/s (4K, 128 lights)", "value": mpx, "unit": "Mpixels/s", "ms_per_step": ms_step,
