@@ -472,35 +472,81 @@ def run_ours(args):
             # their own PCIe links: no collective and no GPU barrier on this leg.  Per frame, a sequence number per rank in the
             # same mapping tells rank 0 that the rank's band is in place; rank 0 takes the frame and releases it.
             port = os.environ.get("MASTER_PORT", "0")
-            shared = None
-            for turn in (0, 1):      # rank 0 creates the object (replacing a stale one of a crashed run) before anyone else opens it
-                if (rank == 0) == (turn == 0):
-                    shared = sharding.SharedHostFrame(f"ilb_bench_frame_{port}", H, W, 4, "float16", rank, world, ctx=ctx)
-                barrier()
-            out_host = torch.from_numpy(shared.frame)
-            gb_ptr, out_ptr = C.c_void_p(gb_host.data_ptr()), C.c_void_p(shared.rows(r0, r1).ctypes.data if r1 > r0 else shared.frame.ctypes.data)
+            shared, shared_err = None, ""
+            nbytes = H * W * 8 + sharding.SharedHostFrame.HEADER
+            try:
+                st = os.statvfs("/dev/shm")
+                room = st.f_bavail * st.f_frsize >= nbytes + (16 << 20)
+            except OSError:
+                room = False
+            if room and os.environ.get("ILB_BENCH_NO_SHARED_FRAME") != "1":
+                for turn in (0, 1):      # rank 0 creates the object (replacing a stale one of a crashed run) before anyone else opens it
+                    if (rank == 0) == (turn == 0):
+                        try:
+                            shared = sharding.SharedHostFrame(f"ilb_bench_frame_{port}", H, W, 4, "float16", rank, world, ctx=ctx, timeout_s=10.0)
+                        except Exception as e:   # noqa: BLE001  (no room after all, page-locking refused, ...)
+                            shared_err = f"{type(e).__name__}: {e}"
+                    barrier()
+            else:
+                shared_err = "no room in /dev/shm" if not room else "disabled by ILB_BENCH_NO_SHARED_FRAME"
+            if reduce_ranks(1.0 if shared is not None else 0.0, op="min") < 0.5:   # all ranks or none
+                if shared is not None:
+                    shared.close()
+                shared = None
             seq = {"n": 0}
+            if shared is not None:
+                out_host = torch.from_numpy(shared.frame)
+                gb_ptr, out_ptr = C.c_void_p(gb_host.data_ptr()), C.c_void_p(shared.rows(r0, r1).ctypes.data if r1 > r0 else shared.frame.ctypes.data)
 
-            def e2e_step():
-                seq["n"] += 1
-                n = seq["n"]
-                shared.begin(n)
-                if r1 > r0:
-                    ctx.check(ctx.lib.ilb_render_lighting_frame(ctx.handle, df.handle, C.byref(frame), C.cast(batches, C.c_void_p), nb,
-                                                                C.cast(verts, C.c_void_p), nv, W, H, _abi.FORMAT_FLOAT4, gb_ptr, out_ptr))
-                shared.publish(n)
+                def e2e_step():
+                    seq["n"] += 1
+                    n = seq["n"]
+                    shared.begin(n)
+                    if r1 > r0:
+                        ctx.check(ctx.lib.ilb_render_lighting_frame(ctx.handle, df.handle, C.byref(frame), C.cast(batches, C.c_void_p), nb,
+                                                                    C.cast(verts, C.c_void_p), nv, W, H, _abi.FORMAT_FLOAT4, gb_ptr, out_ptr))
+                    shared.publish(n)
+                    if rank == 0:
+                        renderer.UpdateLightProbesDevice(d_probes.data_ptr(), packed=packed, probes=probes_packed)
+                        with torch.cuda.stream(stream):
+                            probes_out_host.copy_(d_probes, non_blocking=True)
+                        ctx.synchronize()
+                        shared.wait_complete(n)      # the whole frame is in rank 0's host memory here
+                        shared.release(n)
+                e2e_note = ("one ilb_render_lighting_frame call per rank on its row band; every rank's lightmap rows land directly in one "
+                            "page-locked shared-memory host frame owned by rank 0 (no collective, no GPU barrier); rank 0 waits for "
+                            "every rank's band of the frame, then releases it")
+            else:
+                # Fallback (no shared host frame on this box: the reason is in the note): every rank uploads its G-buffer rows and
+                # renders its band with the device-side gather, rank 0 downloads the reassembled frame from its own device alone.
                 if rank == 0:
-                    renderer.UpdateLightProbesDevice(d_probes.data_ptr(), packed=packed, probes=probes_packed)
+                    print(f"[bench] shared host frame unavailable ({shared_err}); rank 0 downloads the gathered frame", file=sys.stderr)
+                out_host = torch.empty((H, W, 4), dtype=torch.float16).pin_memory() if rank == 0 else None
+                use_peers = peers["ptrs"] is not None
+
+                def e2e_step():
                     with torch.cuda.stream(stream):
-                        probes_out_host.copy_(d_probes, non_blocking=True)
+                        if r1 > r0:
+                            ctx.check(ctx.lib.ilb_gbuffer_upload_rows(ctx.handle, W, H, _abi.FORMAT_FLOAT4, r0, r1, C.c_void_p(gb_host[r0:r1].data_ptr())))
+                            if use_peers:
+                                renderer.RenderLightingPeers(peers["ptrs"], rows=(r0, r1), packed=packed)
+                            else:
+                                renderer.RenderLightingDevice(full[r0:].data_ptr(), rows=(r0, r1), packed=packed)
+                        if rank == 0:
+                            renderer.UpdateLightProbesDevice(d_probes.data_ptr(), packed=packed, probes=probes_packed)
+                        if use_peers:
+                            peers["hdl"].barrier(channel=0)
+                        else:
+                            dist.all_gather_into_tensor(full, full[r0:r0 + sharding.band_height(H, world)])
+                        if rank == 0:
+                            out_host.copy_(full[:H], non_blocking=True)
+                            probes_out_host.copy_(d_probes, non_blocking=True)
                     ctx.synchronize()
-                    shared.wait_complete(n)      # the whole frame is in rank 0's host memory here
-                    shared.release(n)
+                    torch.cuda.synchronize()
+                e2e_note = (f"shared host frame unavailable ({shared_err}): per-rank G-buffer band upload and render with the device-side gather, "
+                            "rank 0 downloads the reassembled full frame")
             h2d = H * W * 16 + world * nv * 128 + probes_packed[2] * 32     # all ranks' band uploads together = one G-buffer
             d2h = H * W * 8 + probes_packed[2] * 8
-            e2e_note = ("one ilb_render_lighting_frame call per rank on its row band; every rank's lightmap rows land directly in one "
-                        "page-locked shared-memory host frame owned by rank 0 (no collective, no GPU barrier); rank 0 waits for "
-                        "every rank's band of the frame, then releases it")
         e_steps = max(3, args.steps // 2)
         for _ in range(2):
             e2e_step()
@@ -520,7 +566,8 @@ def run_ours(args):
                 del whole
             del out_host
             barrier()
-            shared.close()
+            if shared is not None:
+                shared.close()
 
         traffic, traffic_note = None, "not measured"
         if rank == 0 and not args.no_traffic:
