@@ -456,11 +456,13 @@ def run_ours(args):
             gb_ptr, out_ptr = C.c_void_p(gb_host.data_ptr()), C.c_void_p(out_host.data_ptr())
 
             def e2e_step():
-                ctx.check(ctx.lib.ilb_render_lighting_frame(ctx.handle, df.handle, C.byref(frame), C.cast(batches, C.c_void_p), nb,
-                                                            C.cast(verts, C.c_void_p), nv, W, H, _abi.FORMAT_FLOAT4, gb_ptr, out_ptr))
+                # the probe update and its read-back are queued first (asynchronous, independent of the lightmap): they run while
+                # the frame's first G-buffer rows are on their way up, and the frame call's final synchronisation covers them
                 renderer.UpdateLightProbesDevice(d_probes.data_ptr(), packed=packed, probes=probes_packed)
                 with torch.cuda.stream(stream):
                     probes_out_host.copy_(d_probes, non_blocking=True)
+                ctx.check(ctx.lib.ilb_render_lighting_frame(ctx.handle, df.handle, C.byref(frame), C.cast(batches, C.c_void_p), nb,
+                                                            C.cast(verts, C.c_void_p), nv, W, H, _abi.FORMAT_FLOAT4, gb_ptr, out_ptr))
                 ctx.synchronize()
             h2d, d2h = H * W * 16 + nv * 128 + probes_packed[2] * 32, H * W * 8 + probes_packed[2] * 8
             e2e_note = "one ilb_render_lighting_frame call per frame + probe update and read-back"
@@ -502,14 +504,15 @@ def run_ours(args):
                     seq["n"] += 1
                     n = seq["n"]
                     shared.begin(n)
+                    if rank == 0:   # queued ahead of the band (asynchronous; the frame call's final synchronisation covers them)
+                        renderer.UpdateLightProbesDevice(d_probes.data_ptr(), packed=packed, probes=probes_packed)
+                        with torch.cuda.stream(stream):
+                            probes_out_host.copy_(d_probes, non_blocking=True)
                     if r1 > r0:
                         ctx.check(ctx.lib.ilb_render_lighting_frame(ctx.handle, df.handle, C.byref(frame), C.cast(batches, C.c_void_p), nb,
                                                                     C.cast(verts, C.c_void_p), nv, W, H, _abi.FORMAT_FLOAT4, gb_ptr, out_ptr))
                     shared.publish(n)
                     if rank == 0:
-                        renderer.UpdateLightProbesDevice(d_probes.data_ptr(), packed=packed, probes=probes_packed)
-                        with torch.cuda.stream(stream):
-                            probes_out_host.copy_(d_probes, non_blocking=True)
                         ctx.synchronize()
                         shared.wait_complete(n)      # the whole frame is in rank 0's host memory here
                         shared.release(n)
