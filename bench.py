@@ -475,7 +475,7 @@ def run_ours(args):
             # same mapping tells rank 0 that the rank's band is in place; rank 0 takes the frame and releases it.
             port = os.environ.get("MASTER_PORT", "0")
             shared, shared_err = None, ""
-            nbytes = H * W * 8 + sharding.SharedHostFrame.HEADER
+            nbytes = 2 * H * W * 8 + sharding.SharedHostFrame.HEADER
             try:
                 st = os.statvfs("/dev/shm")
                 room = st.f_bavail * st.f_frsize >= nbytes + (16 << 20)
@@ -485,7 +485,7 @@ def run_ours(args):
                 for turn in (0, 1):      # rank 0 creates the object (replacing a stale one of a crashed run) before anyone else opens it
                     if (rank == 0) == (turn == 0):
                         try:
-                            shared = sharding.SharedHostFrame(f"ilb_bench_frame_{port}", H, W, 4, "float16", rank, world, ctx=ctx, timeout_s=10.0)
+                            shared = sharding.SharedHostFrame(f"ilb_bench_frame_{port}", H, W, 4, "float16", rank, world, ctx=ctx, timeout_s=10.0, depth=2)
                         except Exception as e:   # noqa: BLE001  (no room after all, page-locking refused, ...)
                             shared_err = f"{type(e).__name__}: {e}"
                     barrier()
@@ -497,8 +497,10 @@ def run_ours(args):
                 shared = None
             seq = {"n": 0}
             if shared is not None:
-                out_host = torch.from_numpy(shared.frame)
-                gb_ptr, out_ptr = C.c_void_p(gb_host.data_ptr()), C.c_void_p(shared.rows(r0, r1).ctypes.data if r1 > r0 else shared.frame.ctypes.data)
+                # two frames in the mapping: the other ranks work on frame n + 1 while rank 0 still holds frame n, so no rank ever
+                # waits for the hand-shake of the frame before (a consumer that double-buffers the lit frame, as a renderer does)
+                gb_ptr = C.c_void_p(gb_host.data_ptr())
+                out_ptrs = [C.c_void_p(shared.rows(r0, r1, k).ctypes.data if r1 > r0 else shared.frames[k].ctypes.data) for k in range(shared.depth)]
 
                 def e2e_step():
                     seq["n"] += 1
@@ -510,15 +512,15 @@ def run_ours(args):
                             probes_out_host.copy_(d_probes, non_blocking=True)
                     if r1 > r0:
                         ctx.check(ctx.lib.ilb_render_lighting_frame(ctx.handle, df.handle, C.byref(frame), C.cast(batches, C.c_void_p), nb,
-                                                                    C.cast(verts, C.c_void_p), nv, W, H, _abi.FORMAT_FLOAT4, gb_ptr, out_ptr))
+                                                                    C.cast(verts, C.c_void_p), nv, W, H, _abi.FORMAT_FLOAT4, gb_ptr, out_ptrs[n % shared.depth]))
                     shared.publish(n)
                     if rank == 0:
                         ctx.synchronize()
-                        shared.wait_complete(n)      # the whole frame is in rank 0's host memory here
+                        shared.wait_complete(n)      # the whole frame n is in rank 0's host memory here
                         shared.release(n)
-                e2e_note = ("one ilb_render_lighting_frame call per rank on its row band; every rank's lightmap rows land directly in one "
-                            "page-locked shared-memory host frame owned by rank 0 (no collective, no GPU barrier); rank 0 waits for "
-                            "every rank's band of the frame, then releases it")
+                e2e_note = ("one ilb_render_lighting_frame call per rank on its row band; every rank's lightmap rows land directly in a "
+                            "page-locked shared-memory host frame owned by rank 0 (two frame slots, no collective, no GPU barrier); rank 0 "
+                            "waits for every rank's band of frame n, then releases its slot; the other ranks may be one frame ahead")
             else:
                 # Fallback (no shared host frame on this box: the reason is in the note): every rank uploads its G-buffer rows and
                 # renders its band with the device-side gather, rank 0 downloads the reassembled frame from its own device alone.
@@ -565,9 +567,13 @@ def run_ours(args):
                 whole = torch.empty((H, W, 4), dtype=torch.float16, device="cuda")
                 renderer.RenderLightingDevice(whole.data_ptr(), rows=(0, H), packed=packed)
                 ctx.synchronize()
-                result["e2e_host_frame_matches_single_gpu"] = bool(torch.equal(whole.cpu().view(torch.int16), out_host.view(torch.int16)))
+                if shared is not None:    # every slot holds a complete frame (each was written at least once, zero-filled before)
+                    out_host = [torch.from_numpy(f) for f in shared.frames]
+                else:
+                    out_host = [out_host]
+                result["e2e_host_frame_matches_single_gpu"] = all(bool(torch.equal(whole.cpu().view(torch.int16), o.view(torch.int16))) for o in out_host)
                 del whole
-            del out_host
+            out_host = None
             barrier()
             if shared is not None:
                 shared.close()

@@ -66,12 +66,15 @@ class SharedHostFrame:
     downloaded by it alone.  No collective, no GPU barrier: a sequence number per rank in the same mapping says "my band of frame
     s is in place", and the consumer's number says "frame s has been taken, its memory may be overwritten".
 
-    Layout: 4096-byte header (int64 slot 8*k = sequence number of rank k, slot 8*world = the consumer's), then the frame.
+    `depth` > 1 keeps that many frames in the mapping (frame s lives in slot s % depth), so that the ranks can work on frame
+    s + 1 while the consumer still holds frame s: the producers then never wait for the consumer's hand-shake, only for a slot.
+
+    Layout: 4096-byte header (int64 slot 8*k = sequence number of rank k, slot 8*world = the consumer's), then the frame(s).
     """
     HEADER = 4096
 
     def __init__(self, name: str, height: int, width: int, channels: int, dtype, rank: int, world: int, ctx=None,
-                 timeout_s: float = 60.0):
+                 timeout_s: float = 60.0, depth: int = 1):
         import mmap
         import os
         import time
@@ -81,7 +84,10 @@ class SharedHostFrame:
         self.shape, self.dtype = (int(height), int(width), int(channels)), np.dtype(dtype)
         if 8 * (self.world + 1) * 8 > self.HEADER:
             raise ValueError("too many ranks for the header")
-        nbytes = self.HEADER + int(np.prod(self.shape)) * self.dtype.itemsize
+        self.depth = max(int(depth), 1)
+        frame_bytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        frame_bytes = (frame_bytes + 4095) // 4096 * 4096          # every frame starts on a page
+        nbytes = self.HEADER + self.depth * frame_bytes
         self.path = os.path.join("/dev/shm", name)
         self.owner = self.rank == 0
         if self.owner:
@@ -109,15 +115,22 @@ class SharedHostFrame:
         os.close(fd)
         self._bytes = np.frombuffer(self._map, dtype=np.uint8)
         self.seq = self._bytes[:self.HEADER].view(np.int64)
-        self.frame = self._bytes[self.HEADER:].view(self.dtype).reshape(self.shape)
+        used = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.frames = [self._bytes[self.HEADER + k * frame_bytes:self.HEADER + k * frame_bytes + used].view(self.dtype).reshape(self.shape)
+                       for k in range(self.depth)]
+        self.frame = self.frames[0]
         self.registered = False
         if ctx is not None:
             ctx.host_register(self._bytes.ctypes.data, nbytes)
             self.registered = True
 
-    def rows(self, r0: int, r1: int):
-        """The view a rank passes as `lightmap_out` for its band [r0, r1)."""
-        return self.frame[r0:r1]
+    def frame_of(self, s: int):
+        """The slot that holds frame s."""
+        return self.frames[s % self.depth]
+
+    def rows(self, r0: int, r1: int, s: int = 0):
+        """The view a rank passes as `lightmap_out` for its band [r0, r1) of frame s."""
+        return self.frames[s % self.depth][r0:r1]
 
     @staticmethod
     def _spin(pred, timeout_s: float, what: str):
@@ -135,9 +148,9 @@ class SharedHostFrame:
                     raise TimeoutError(what)
 
     def begin(self, s: int, timeout_s: float = 60.0):
-        """Blocks until frame s - 1 has been taken by the consumer (its memory is about to be overwritten)."""
+        """Blocks until frame s - depth has been taken by the consumer (its slot is about to be overwritten)."""
         slot = 8 * self.world
-        self._spin(lambda: int(self.seq[slot]) >= s - 1, timeout_s, f"frame {s - 1} was never released")
+        self._spin(lambda: int(self.seq[slot]) >= s - self.depth, timeout_s, f"frame {s - self.depth} was never released")
 
     def publish(self, s: int):
         """This rank's band of frame s is complete in the shared frame (call after the synchronous frame call returned)."""
@@ -161,7 +174,7 @@ class SharedHostFrame:
                 self.ctx.host_unregister(self._bytes.ctypes.data)
             except Exception:   # noqa: BLE001  (context already gone at interpreter exit)
                 pass
-        self.seq = self.frame = self._bytes = None
+        self.seq = self.frame = self.frames = self._bytes = None
         try:
             self._map.close()
         except BufferError:

@@ -63,7 +63,7 @@ def test_two_rank_sharding_matches_single_rank(tmp_path, oracle):
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
 
 
-def _host_frame_worker(rank, world, name, outdir):
+def _host_frame_worker(rank, world, name, outdir, depth=1):
     """The host-to-host leg of bench.py at N > 1 without a device: every rank writes its band of three consecutive frames into
     the one shared host frame (here the oracle stands in for ilb_render_lighting_frame), rank 0 consumes each complete frame."""
     sys.path.insert(0, str(ROOT))
@@ -77,28 +77,30 @@ def _host_frame_worker(rank, world, name, outdir):
     df.ValidSliceCount, df.handle = df.SliceCount, 1
     r = ib.LightingRenderer(None, s.environment, s.configuration)
     r.DistanceField, r._gbuffer_shape = df, s.gbuffer.shape[:2]
-    shared = sharding.SharedHostFrame(name, s.height, s.width, 4, np.float32, rank, world)
+    shared = sharding.SharedHostFrame(name, s.height, s.width, 4, np.float32, rank, world, depth=depth)
     r0, r1 = sharding.row_band(rank, world, s.height)
-    for seq in (1, 2, 3):
+    last = 5
+    for seq in range(1, last + 1):
         scale = float(seq)            # a different frame every time: a stale band would be noticed
         batches, nb, verts, nv = r.build_batches(scale)
-        shared.begin(seq)
-        shared.rows(r0, r1)[...] = oracle.render_lighting(tex, s.gbuffer, r.build_frame(scale, (r0, r1)), batches, nb, verts, nv, nthreads=2)
+        shared.begin(seq)             # with depth 2 the other rank may be one frame ahead of the consumer, never two
+        shared.rows(r0, r1, seq)[...] = oracle.render_lighting(tex, s.gbuffer, r.build_frame(scale, (r0, r1)), batches, nb, verts, nv, nthreads=2)
         shared.publish(seq)
         if rank == 0:
             shared.wait_complete(seq)
             whole = oracle.render_lighting(tex, s.gbuffer, r.build_frame(scale), batches, nb, verts, nv, nthreads=2)
-            assert np.array_equal(shared.frame, whole), seq
+            assert np.array_equal(shared.frame_of(seq), whole), seq
             shared.release(seq)
     (Path(outdir) / f"hf{rank}").write_text("ok")
     if rank == 0:   # the others may still be mapping / unmapping; the name can go, the memory lives until the last unmap
-        shared.wait_complete(3)
+        shared.wait_complete(last)
     shared.close()
 
 
-def test_shared_host_frame_is_reassembled_by_the_ranks_themselves(tmp_path, oracle):
-    name = f"ilb_test_frame_{os.getpid()}"
-    mp.spawn(_host_frame_worker, args=(2, name, str(tmp_path)), nprocs=2, join=True)
+@pytest.mark.parametrize("depth", [1, 2])
+def test_shared_host_frame_is_reassembled_by_the_ranks_themselves(tmp_path, oracle, depth):
+    name = f"ilb_test_frame_{os.getpid()}_{depth}"
+    mp.spawn(_host_frame_worker, args=(2, name, str(tmp_path), depth), nprocs=2, join=True)
     assert (tmp_path / "hf0").exists() and (tmp_path / "hf1").exists()
     assert not os.path.exists(os.path.join("/dev/shm", name))
 
@@ -119,4 +121,13 @@ def test_shared_host_frame_single_rank_protocol():
     f.release(2)
     f.begin(3)
     f.close()
+    g = sharding.SharedHostFrame(name, 8, 4, 4, np.float16, 0, 1, depth=2)      # two slots: frame s lives in slot s % 2
+    assert g.frame_of(1) is g.frames[1] and g.frame_of(2) is g.frames[0] and g.frames[1].ctypes.data % 4096 == 0
+    g.begin(1)
+    g.begin(2)                                       # one frame ahead of the consumer is allowed ...
+    with pytest.raises(TimeoutError):
+        g.begin(3, timeout_s=0.05)                   # ... two are not
+    g.rows(0, 8, 1)[...] = 2.0
+    assert not g.frames[0].any() and float(g.frame_of(1).sum()) == 2.0 * 8 * 4 * 4
+    g.close()
     assert not os.path.exists(os.path.join("/dev/shm", name))
