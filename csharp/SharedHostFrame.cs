@@ -6,7 +6,8 @@
 // passes Rows(r0) as `lightmapOut` of its own ilb_render_lighting_frame call with IlbLightingFrame.RowBegin / RowEnd = its
 // band.  Each rank's rows then travel from its GPU into this frame over the rank's own PCIe link: no collective, no GPU
 // barrier.  Layout: a 4096-byte header (int64 slot 8 * k = sequence number of rank k, slot 8 * world = the consumer's),
-// then height * width texels of HalfVector4.
+// then `depth` frames of height * width texels of HalfVector4, each starting on a page (frame s lives in slot s % depth: with
+// two slots the ranks work on frame s + 1 while the consumer still holds frame s).
 using System;
 using System.IO;
 using System.IO.MemoryMappedFiles;
@@ -15,18 +16,20 @@ using System.Threading;
 namespace Squared.Illuminant.Native {
     public sealed unsafe class SharedHostFrame : IDisposable {
         public const int HeaderBytes = 4096;
-        public readonly int Rank, World, Width, Height, TexelBytes;
+        public readonly int Rank, World, Width, Height, TexelBytes, Depth;
+        readonly long FrameBytes;
         readonly IntPtr Context;
         readonly MemoryMappedFile File;
         readonly MemoryMappedViewAccessor View;
         readonly byte* Base;
         readonly string Path;
 
-        public SharedHostFrame (IntPtr ctx, string name, int width, int height, int rank, int world, int texelBytes = 8) {
+        public SharedHostFrame (IntPtr ctx, string name, int width, int height, int rank, int world, int texelBytes = 8, int depth = 1) {
             if (8 * (world + 1) * 8 > HeaderBytes)
                 throw new ArgumentOutOfRangeException(nameof(world));
-            Context = ctx; Rank = rank; World = world; Width = width; Height = height; TexelBytes = texelBytes;
-            long bytes = HeaderBytes + (long)width * height * texelBytes;
+            Context = ctx; Rank = rank; World = world; Width = width; Height = height; TexelBytes = texelBytes; Depth = Math.Max(depth, 1);
+            FrameBytes = ((long)width * height * texelBytes + 4095) / 4096 * 4096;
+            long bytes = HeaderBytes + Depth * FrameBytes;
             Path = System.IO.Path.Combine("/dev/shm", name);
             if (rank == 0) {
                 // created under a temporary name and renamed, so that it appears at full size, zero-filled
@@ -49,8 +52,8 @@ namespace Squared.Illuminant.Native {
             B200.Check(ctx, B200.ilb_host_register(ctx, Base, (UIntPtr)(ulong)bytes));
         }
 
-        /// <summary>What a rank passes as lightmapOut for the band that starts at row rowBegin.</summary>
-        public void* Rows (int rowBegin) => Base + HeaderBytes + (long)rowBegin * Width * TexelBytes;
+        /// <summary>What a rank passes as lightmapOut for the band of frame s that starts at row rowBegin.</summary>
+        public void* Rows (int rowBegin, long s = 0) => Base + HeaderBytes + (s % Depth) * FrameBytes + (long)rowBegin * Width * TexelBytes;
 
         long* Slot (int index) => (long*)(Base + 64 * index);
 
@@ -64,8 +67,8 @@ namespace Squared.Illuminant.Native {
             }
         }
 
-        /// <summary>Blocks until frame s - 1 has been taken by the consumer: its memory is about to be overwritten.</summary>
-        public void Begin (long s) => Spin(() => Volatile.Read(ref *Slot(World)) >= s - 1, "frame " + (s - 1) + " was never released");
+        /// <summary>Blocks until frame s - Depth has been taken by the consumer: its slot is about to be overwritten.</summary>
+        public void Begin (long s) => Spin(() => Volatile.Read(ref *Slot(World)) >= s - Depth, "frame " + (s - Depth) + " was never released");
         /// <summary>This rank's band of frame s is in place (call after ilb_render_lighting_frame has returned).</summary>
         public void Publish (long s) => Volatile.Write(ref *Slot(Rank), s);
         /// <summary>Consumer: blocks until every rank has published frame s.</summary>
