@@ -451,21 +451,41 @@ def run_ours(args):
         frame = renderer.build_frame(1.0, (r0, r1))
         batches, nb, verts, nv = packed
         probes_out_host = torch.zeros((max(probes_packed[2], 1), 4), dtype=torch.float16).pin_memory()
+        e2e_drain = None
         if dist is None:
-            out_host = torch.empty((H, W, 4), dtype=torch.float16).pin_memory()
-            gb_ptr, out_ptr = C.c_void_p(gb_host.data_ptr()), C.c_void_p(out_host.data_ptr())
+            # Two frames in flight, as a renderer that double-buffers its lit frame has them: frame n is queued
+            # (ilb_render_lighting_frame_async: G-buffer up, shade, lightmap down into buffer n % 2) before frame n - 1 is waited
+            # for, so the fill and the drain of one frame's copy pipeline hide behind its neighbours.  Every step still uploads
+            # its G-buffer and downloads its lightmap and probes; the timed region ends when the last frame is on the host.
+            out_hosts = [torch.empty((H, W, 4), dtype=torch.float16).pin_memory() for _ in range(2)]
+            probes_hosts = [torch.zeros((max(probes_packed[2], 1), 4), dtype=torch.float16).pin_memory() for _ in range(2)]
+            gb_ptr, out_ptrs = C.c_void_p(gb_host.data_ptr()), [C.c_void_p(o.data_ptr()) for o in out_hosts]
+            fl = {"n": 0, "pending": 0}
 
             def e2e_step():
-                # the probe update and its read-back are queued first (asynchronous, independent of the lightmap): they run while
-                # the frame's first G-buffer rows are on their way up, and the frame call's final synchronisation covers them
+                n = fl["n"]
+                fl["n"] += 1
+                # the probe update and its read-back are queued first (asynchronous, independent of the lightmap); the frame's
+                # last download is behind them in stream order, so waiting for the frame covers them
                 renderer.UpdateLightProbesDevice(d_probes.data_ptr(), packed=packed, probes=probes_packed)
                 with torch.cuda.stream(stream):
-                    probes_out_host.copy_(d_probes, non_blocking=True)
-                ctx.check(ctx.lib.ilb_render_lighting_frame(ctx.handle, df.handle, C.byref(frame), C.cast(batches, C.c_void_p), nb,
-                                                            C.cast(verts, C.c_void_p), nv, W, H, _abi.FORMAT_FLOAT4, gb_ptr, out_ptr))
+                    probes_hosts[n % 2].copy_(d_probes, non_blocking=True)
+                ticket = C.c_uint64(0)
+                ctx.check(ctx.lib.ilb_render_lighting_frame_async(ctx.handle, df.handle, C.byref(frame), C.cast(batches, C.c_void_p), nb,
+                                                                  C.cast(verts, C.c_void_p), nv, W, H, _abi.FORMAT_FLOAT4, gb_ptr, out_ptrs[n % 2],
+                                                                  C.byref(ticket)))
+                if fl["pending"]:      # frame n - 1 is complete in host memory
+                    ctx.check(ctx.lib.ilb_render_lighting_frame_wait(ctx.handle, C.c_uint64(fl["pending"])))
+                fl["pending"] = int(ticket.value)
+
+            def e2e_drain():
+                if fl["pending"]:
+                    ctx.check(ctx.lib.ilb_render_lighting_frame_wait(ctx.handle, C.c_uint64(fl["pending"])))
+                    fl["pending"] = 0
                 ctx.synchronize()
             h2d, d2h = H * W * 16 + nv * 128 + probes_packed[2] * 32, H * W * 8 + probes_packed[2] * 8
-            e2e_note = "one ilb_render_lighting_frame call per frame + probe update and read-back"
+            e2e_note = ("one ilb_render_lighting_frame_async call per frame (+ probe update and read-back), two frames in flight: frame n is "
+                        "queued before frame n - 1 is waited for; every frame uploads its G-buffer and downloads its lightmap")
         else:
             # N > 1, host to host: every rank makes ONE ilb_render_lighting_frame call for its band (its G-buffer rows go up from
             # pinned memory, its rows of the lightmap come down, both pipelined behind the kernels inside the call) whose
@@ -502,25 +522,41 @@ def run_ours(args):
                 gb_ptr = C.c_void_p(gb_host.data_ptr())
                 out_ptrs = [C.c_void_p(shared.rows(r0, r1, k).ctypes.data if r1 > r0 else shared.frames[k].ctypes.data) for k in range(shared.depth)]
 
+                def e2e_finish(m, ticket):   # frame m of this rank is in the shared frame: publish it; rank 0 takes the whole frame
+                    if m <= 0:
+                        return
+                    if ticket:
+                        ctx.check(ctx.lib.ilb_render_lighting_frame_wait(ctx.handle, C.c_uint64(ticket)))
+                    shared.publish(m)
+                    if rank == 0:
+                        shared.wait_complete(m)      # the whole frame m is in rank 0's host memory here
+                        shared.release(m)
+
                 def e2e_step():
                     seq["n"] += 1
                     n = seq["n"]
-                    shared.begin(n)
-                    if rank == 0:   # queued ahead of the band (asynchronous; the frame call's final synchronisation covers them)
+                    shared.begin(n)                  # slot n % 2 is free: frame n - 2 has been taken
+                    if rank == 0:   # queued ahead of the band (asynchronous; the frame's last download is behind them in stream order)
                         renderer.UpdateLightProbesDevice(d_probes.data_ptr(), packed=packed, probes=probes_packed)
                         with torch.cuda.stream(stream):
                             probes_out_host.copy_(d_probes, non_blocking=True)
-                    if r1 > r0:
-                        ctx.check(ctx.lib.ilb_render_lighting_frame(ctx.handle, df.handle, C.byref(frame), C.cast(batches, C.c_void_p), nb,
-                                                                    C.cast(verts, C.c_void_p), nv, W, H, _abi.FORMAT_FLOAT4, gb_ptr, out_ptrs[n % shared.depth]))
-                    shared.publish(n)
-                    if rank == 0:
-                        ctx.synchronize()
-                        shared.wait_complete(n)      # the whole frame n is in rank 0's host memory here
-                        shared.release(n)
-                e2e_note = ("one ilb_render_lighting_frame call per rank on its row band; every rank's lightmap rows land directly in a "
-                            "page-locked shared-memory host frame owned by rank 0 (two frame slots, no collective, no GPU barrier); rank 0 "
-                            "waits for every rank's band of frame n, then releases its slot; the other ranks may be one frame ahead")
+                    ticket = C.c_uint64(0)
+                    if r1 > r0:     # this rank's band of frame n is queued before its band of frame n - 1 is waited for
+                        ctx.check(ctx.lib.ilb_render_lighting_frame_async(ctx.handle, df.handle, C.byref(frame), C.cast(batches, C.c_void_p), nb,
+                                                                          C.cast(verts, C.c_void_p), nv, W, H, _abi.FORMAT_FLOAT4, gb_ptr,
+                                                                          out_ptrs[n % shared.depth], C.byref(ticket)))
+                    e2e_finish(n - 1, seq.get("ticket", 0))
+                    seq["ticket"] = int(ticket.value)
+                    seq["open"] = n
+
+                def e2e_drain():
+                    if seq.get("open"):
+                        e2e_finish(seq["open"], seq.get("ticket", 0))
+                        seq["open"], seq["ticket"] = 0, 0
+                    ctx.synchronize()
+                e2e_note = ("one ilb_render_lighting_frame_async call per rank on its row band, two frames in flight; every rank's lightmap rows "
+                            "land directly in a page-locked shared-memory host frame owned by rank 0 (two frame slots, no collective, no GPU "
+                            "barrier); rank 0 waits for every rank's band of frame n, then releases its slot")
             else:
                 # Fallback (no shared host frame on this box: the reason is in the note): every rank uploads its G-buffer rows and
                 # renders its band with the device-side gather, rank 0 downloads the reassembled frame from its own device alone.
@@ -553,14 +589,40 @@ def run_ours(args):
             h2d = H * W * 16 + world * nv * 128 + probes_packed[2] * 32     # all ranks' band uploads together = one G-buffer
             d2h = H * W * 8 + probes_packed[2] * 8
         e_steps = max(3, args.steps // 2)
-        for _ in range(2):
-            e2e_step()
+        e2e_error = ""
+        try:
+            for _ in range(2):
+                e2e_step()
+            if e2e_drain is not None:
+                e2e_drain()
+        except Exception as e:   # noqa: BLE001  (a rank that lost the hand-shake must not take the device-timed line with it)
+            e2e_error = f"{type(e).__name__}: {e}"
         barrier()
         t0 = time.perf_counter()
-        for _ in range(e_steps):
-            e2e_step()
+        try:
+            if not e2e_error:
+                for _ in range(e_steps):
+                    e2e_step()
+                if e2e_drain is not None:    # the last frame in flight is on the host before the clock stops
+                    e2e_drain()
+        except Exception as e:   # noqa: BLE001
+            e2e_error = f"{type(e).__name__}: {e}"
         barrier()
         e_ms = reduce_ranks((time.perf_counter() - t0) * 1e3 / e_steps)
+        if reduce_ranks(1.0 if e2e_error else 0.0) > 0.5:    # on any rank: no host-to-host number rather than a wrong one
+            e_ms = float("nan")
+            e2e_note = "FAILED (" + (e2e_error or "on another rank") + "): " + e2e_note
+            print(f"[bench] rank {rank}: host-to-host leg failed: {e2e_error or 'on another rank'}", file=sys.stderr)
+            try:
+                ctx.synchronize()
+            except Exception:   # noqa: BLE001
+                pass
+        if dist is None:   # both host frames of the two-deep queue hold the frame a plain device render gives, bit for bit
+            whole = torch.empty((H, W, 4), dtype=torch.float16, device="cuda")
+            renderer.RenderLightingDevice(whole.data_ptr(), rows=(0, H), packed=packed)
+            ctx.synchronize()
+            result["e2e_host_frame_matches_device_render"] = all(bool(torch.equal(whole.cpu().view(torch.int16), o.view(torch.int16))) for o in out_hosts)
+            del whole
         if dist is not None:
             renderer.SetGBuffer(gb_host.numpy())    # the band uploads left the other rows as they were; restore for what follows
             if rank == 0:   # the frame that arrived on the host is the unsharded render, bit for bit
@@ -595,8 +657,8 @@ def run_ours(args):
                          "kernel": "light_accumulate_kernel (line-light pass + sphere/directional pass, both launches of this rank's band)",
                          "kernel_ms": k_ms, "algorithmic_bytes_per_pixel": LIGHT_BYTES_PER_PIXEL, "peak_source": peak_src,
                          "note": "per-pixel work is O(lights x trace steps): issue- and latency-bound, not HBM-bound (see DESIGN.md)"},
-            "e2e": {"value": W * H / (e_ms * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e_ms, "what": e2e_note},
+            "e2e": {"value": (W * H / (e_ms * 1e-3) / 1e6) if e_ms == e_ms else None, "unit": "Mpixels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e_ms if e_ms == e_ms else None, "what": e2e_note},
             "gpu_launches": int(launches), "clocks": clocks, "gather": peers["gather"],
             "probes": {"kernel_ms": p_ms / 5, "host_call_ms": probes_host_ms, "in_timed_step": True, "count": probes_packed[2]},
             "bands": {"bounds": list(bounds), "rank_kernel_ms": [round(t, 4) for t in rank_kernel_ms], "calibration": calibration},
@@ -842,7 +904,7 @@ def run_ours(args):
                 "config": {"workload": C4_WORKLOAD if primary else result.get("config", {}).get("workload"),
                            "parallelism": f"row bands of equal measured cost x{world}, gather: {result.get('gather', 'none')}" if primary else f"chunk ranges x{world}, no collective",
                            "l2": "inputs larger than L2 (no flush)"}}
-        for k in ("roofline", "roofline_issue", "cpu_baseline", "e2e", "gpu_launches", "clocks", "gather_checksum_equal", "gather_matches_single_gpu", "e2e_host_frame_matches_single_gpu", "probes", "bands",
+        for k in ("roofline", "roofline_issue", "cpu_baseline", "e2e", "gpu_launches", "clocks", "gather_checksum_equal", "gather_matches_single_gpu", "e2e_host_frame_matches_single_gpu", "e2e_host_frame_matches_device_render", "probes", "bands",
                   "particles", "combined_c5", "combined_c5_strong", "resolve", "render", "render_sharded"):
             if k in result:
                 line[k] = result[k]

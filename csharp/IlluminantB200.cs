@@ -144,6 +144,8 @@ namespace Squared.Illuminant.Native {
             public Vector4 LightProperties, MoreLightProperties, LightColor, LightSpecularColor;
             public IlbDFUniforms DF;
         }
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_render_lighting_frame_async (IntPtr ctx, IntPtr df, ref IlbLightingFrame frame, IlbLightBatch* batches, int batchCount, LightVertex* vertices, int vertexCount, int gbufferWidth, int gbufferHeight, int gbufferFormat, void* gbuffer, void* lightmapOut, out ulong ticket);
+        [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_render_lighting_frame_wait (IntPtr ctx, ulong ticket);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_lighting_set_particle_lights (IntPtr ctx, IlbParticleLightSource* sources, int count);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_update_light_probes (IntPtr ctx, IntPtr df, ref IlbLightingFrame frame, IlbLightBatch* batches, int batchCount, LightVertex* vertices, int vertexCount, Vector4* probePositions, Vector4* probeNormals, int probeCount, int outputFormat, void* probesOut);
         [DllImport(DllName, CallingConvention = CC)] public static extern int ilb_particles_create (IntPtr ctx, int chunkSize, int maxChunks, out IntPtr psys);

@@ -221,6 +221,9 @@ _PROTOTYPES = [
     ("ilb_gbuffer_upload_rows", C.c_int, [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P]),
     ("ilb_render_lighting", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, P]),
     ("ilb_render_lighting_frame", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_int, P, P]),
+    ("ilb_render_lighting_frame_async", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_int, P, P,
+                                                  C.POINTER(C.c_uint64)]),
+    ("ilb_render_lighting_frame_wait", C.c_int, [P, C.c_uint64]),
     ("ilb_lighting_set_particle_lights", C.c_int, [P, P, C.c_int]),
     ("ilb_render_lighting_device", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, P]),
     ("ilb_render_lighting_peers", C.c_int, [P, P, C.POINTER(LightingFrame), P, C.c_int, P, C.c_int, C.POINTER(P), C.c_int]),

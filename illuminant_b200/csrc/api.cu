@@ -85,6 +85,7 @@ __global__ void detmath_kernel(int function, const float* __restrict__ x, float*
 }  // namespace
 
 int ilb_gbuffer_note_user(ilb_ctx* ctx, int row_begin, int row_end) {
+    ctx->gb_generation++;   // a reader / writer of the G-buffer outside the frame pipeline (see ilb_ctx::ev_down)
     ilb_ctx::GBufferUser& u = ctx->gb_users[ctx->gb_user_next];
     ctx->gb_user_next = (ctx->gb_user_next + 1) % 8;
     if (!u.done) ILB_CUDA(ctx, cudaEventCreateWithFlags(&u.done, cudaEventDisableTiming));
@@ -173,6 +174,7 @@ int ilb_get_option(const ilb_ctx* ctx, int option, int* out_value) {
 void ilb_destroy(ilb_ctx* ctx) {
     if (!ctx || !live_take(ctx)) return;
     cudaSetDevice(ctx->device);
+    ilb_frames_drain(ctx);
     cudaStreamSynchronize(ctx->stream);
     while (!ctx->fields.empty()) ilb_df_destroy(ctx->fields.back());      // children die with their context
     while (!ctx->systems.empty()) ilb_particles_destroy(ctx->systems.back());
@@ -211,6 +213,8 @@ void ilb_destroy(ilb_ctx* ctx) {
         cudaStreamDestroy(ctx->copy_in);
         cudaStreamDestroy(ctx->copy_out);
         for (int i = 0; i < ILB_PIPELINE_BANDS; i++) { cudaEventDestroy(ctx->ev_in[i]); cudaEventDestroy(ctx->ev_done[i]); }
+        for (cudaEvent_t e : ctx->ev_down) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : ctx->ev_frame) if (e) cudaEventDestroy(e);
     }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -387,6 +391,8 @@ void ilb_df_destroy(ilb_df* df) {
 static int gbuffer_set(ilb_ctx* ctx, int w, int h, int fmt, const void* data, bool device) {
     if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    { const int rcd = ilb_frames_drain(ctx); if (rcd) return rcd; }   // frames in flight read / write the G-buffer
+    ctx->gb_generation++;
     if (!data) {  // G-buffer disabled (Configuration.EnableGBuffer == false)
         ctx->gb_w = ctx->gb_h = 0;
         if (ctx->gbuffer && ctx->gbuffer_owned) {
@@ -417,6 +423,8 @@ int ilb_gbuffer_upload_rows(ilb_ctx* ctx, int w, int h, int fmt, int row_begin, 
     if (!rows || w <= 0 || h <= 0 || row_begin < 0 || row_end > h || row_begin > row_end) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad G-buffer rows [%d,%d) of %dx%d", row_begin, row_end, w, h);
     if (fmt != ILB_FORMAT_FLOAT4 && fmt != ILB_FORMAT_HALF4) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "G-buffer format must be FLOAT4 or HALF4");
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    { const int rcd = ilb_frames_drain(ctx); if (rcd) return rcd; }
+    ctx->gb_generation++;
     const size_t texel = ilb_format_bytes(fmt), bytes = texel * (size_t)w * (size_t)h;
     if (!ctx->gbuffer_owned) { ctx->gbuffer = nullptr; ctx->gbuffer_capacity = 0; }
     const bool fresh = !ctx->gbuffer || ctx->gb_w != w || ctx->gb_h != h || ctx->gb_fmt != fmt;
@@ -503,9 +511,30 @@ int ilb_render_lighting_frame(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->lm_fmt = -1;
     const int rc = ilb_lighting_frame_from_host(ctx, df, frame, batches, batch_count, vertices, vertex_count, gbuffer_width, gbuffer_height,
-                                                gbuffer_format, gbuffer, lightmap_out);
+                                                gbuffer_format, gbuffer, lightmap_out, nullptr);
     if (rc == ILB_OK) { ctx->lm_w = frame->width; ctx->lm_rows = frame->row_end - frame->row_begin; ctx->lm_fmt = frame->lightmap_format; }
     return rc;
+}
+
+int ilb_render_lighting_frame_async(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches, int batch_count,
+                                    const ilb_light_vertex* vertices, int vertex_count, int gbuffer_width, int gbuffer_height, int gbuffer_format,
+                                    const void* gbuffer, void* lightmap_out, uint64_t* out_ticket) {
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
+    if (!out_ticket) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null ticket");
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->lm_fmt = -1;
+    unsigned long long ticket = 0;
+    const int rc = ilb_lighting_frame_from_host(ctx, df, frame, batches, batch_count, vertices, vertex_count, gbuffer_width, gbuffer_height,
+                                                gbuffer_format, gbuffer, lightmap_out, &ticket);
+    *out_ticket = ticket;
+    if (rc == ILB_OK) { ctx->lm_w = frame->width; ctx->lm_rows = frame->row_end - frame->row_begin; ctx->lm_fmt = frame->lightmap_format; }
+    return rc;
+}
+
+int ilb_render_lighting_frame_wait(ilb_ctx* ctx, uint64_t ticket) {
+    if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
+    ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ilb_lighting_frame_wait(ctx, ticket);
 }
 
 // ---------------------------------------------------------------------------------------------- resolve / luminance (N3)
@@ -514,6 +543,7 @@ static int resolve_source(ilb_ctx* ctx, int w, int h, int fmt, const void* light
     if (w <= 0 || h <= 0) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad size %dx%d", w, h);
     if (fmt != ILB_FORMAT_FLOAT4 && fmt != ILB_FORMAT_HALF4 && fmt != ILB_FORMAT_RGBA8) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad lightmap format %d", fmt);
     if (!lightmap_host) {
+        { const int rcd = ilb_frames_drain(ctx); if (rcd) return rcd; }   // the resident lightmap is the last frame's, complete
         if (ctx->lm_fmt < 0 || !ctx->d_lightmap) return ilb_fail(ctx, ILB_ERR_INVALID_OPERATION, "no resident lightmap: render a frame first or pass the texels");
         if (ctx->lm_w != w || ctx->lm_rows != h || ctx->lm_fmt != fmt)
             return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "resident lightmap is %dx%d format %d, asked for %dx%d format %d", ctx->lm_w, ctx->lm_rows, ctx->lm_fmt, w, h, fmt);

@@ -93,6 +93,15 @@ struct ilb_ctx {
     cudaStream_t band_stream = nullptr;                        // second compute lane of the pipelined host-to-host frame
     cudaEvent_t ev_band_fork = nullptr, ev_band_join = nullptr;
     cudaEvent_t ev_in[ILB_PIPELINE_BANDS] = {}, ev_done[ILB_PIPELINE_BANDS] = {};
+    // Frames in flight (ilb_render_lighting_frame_async): the next frame's bands are ordered behind the SAME band of the frame
+    // before it -- its upload behind that band's kernels (ev_done[b]), its kernels behind that band's download (ev_down[b]) --
+    // as long as the two frames share their geometry and nothing else touched the G-buffer in between (gb_generation is bumped by
+    // every other entry point that writes or reads it).  ev_frame[ticket % 4] sits behind the last download of frame `ticket`.
+    cudaEvent_t ev_down[ILB_PIPELINE_BANDS] = {}, ev_frame[4] = {};
+    unsigned long long frame_ticket = 0, frame_waited = 0;     // frames enqueued / known complete
+    unsigned long long gb_generation = 0, pipe_generation = ~0ull;
+    int pipe_edges[ILB_PIPELINE_BANDS + 1] = {}, pipe_nb = 0, pipe_lanes = 0, pipe_w = 0, pipe_h = 0, pipe_gfmt = -1, pipe_lfmt = -1;
+    void* pipe_gbuffer = nullptr; void* pipe_lightmap = nullptr;
 };
 
 #define ILB_MAX_VIRTUAL_SLICES 64
@@ -171,7 +180,9 @@ int ilb_probes_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame,
                       const ilb_float4* normals, int probe_count, int output_format, void* probes_out_host, void* d_probes_out);
 int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame, const ilb_light_batch* batches,
                                  int batch_count, const ilb_light_vertex* vertices, int vertex_count, int gw, int gh, int gfmt,
-                                 const void* gbuffer_host, void* lightmap_out_host);
+                                 const void* gbuffer_host, void* lightmap_out_host, unsigned long long* out_ticket);
+int ilb_lighting_frame_wait(ilb_ctx* ctx, unsigned long long ticket);
+int ilb_frames_drain(ilb_ctx* ctx);   // waits for every frame in flight; a no-op when there is none
 // resolve.cu (N3)
 int ilb_resolve_launch(ilb_ctx* ctx, const ilb_resolve* params, const void* d_lightmap, const void* d_albedo, void* d_output);
 int ilb_resolve_placed_launch(ilb_ctx* ctx, const ilb_resolve* params, const ilb_resolve_placement* placement, const void* d_lightmap,

@@ -1735,7 +1735,9 @@ int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, c
                         const ilb_light_vertex* vertices, int vertex_count, void* const* d_outputs, int output_count,
                         bool outputs_are_full_frames) {
     LightingPrepared prep;
-    int rc = lightingPrepare(ctx, df, f, batches, batch_count, vertices, vertex_count, &prep);
+    int rc = ilb_frames_drain(ctx);   // frames in flight share the scratch sums and the two compute lanes
+    if (rc) return rc;
+    rc = lightingPrepare(ctx, df, f, batches, batch_count, vertices, vertex_count, &prep);
     if (rc) return rc;
     const int rows = f->row_end - f->row_begin, outBase = outputs_are_full_frames ? 0 : f->row_begin;
     const bool splitFrame = prep.nline > 0 && prep.nline < prep.nlights;
@@ -1780,36 +1782,15 @@ int ilb_lighting_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, c
 // texel, so a band needs only its own rows).  Synchronous: returns when lightmap_out_host is complete.
 int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const ilb_light_batch* batches, int batch_count,
                                  const ilb_light_vertex* vertices, int vertex_count, int gw, int gh, int gfmt, const void* gbuffer_host,
-                                 void* lightmap_out_host) {
+                                 void* lightmap_out_host, unsigned long long* out_ticket) {
+    if (out_ticket) *out_ticket = 0;
     if (!f || !gbuffer_host || !lightmap_out_host) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "null argument");
     if (gfmt != ILB_FORMAT_FLOAT4 && gfmt != ILB_FORMAT_HALF4) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "G-buffer format must be FLOAT4 or HALF4");
     if (gw != f->width || gh != f->height)  // one texel per pixel, so that a row band of the frame needs the same rows of the G-buffer
         return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "pipelined frames need a G-buffer of the frame's size (%dx%d), got %dx%d", f->width, f->height, gw, gh);
     if (f->GBufferViewportRelative != 0.0f) return ilb_fail(ctx, ILB_ERR_UNSUPPORTED, "pipelined frames need a screen-aligned G-buffer");
-    const size_t gtexel = ilb_format_bytes(gfmt), ltexel = ilb_format_bytes(f->lightmap_format);
-    const size_t gbytes = gtexel * (size_t)gw * (size_t)gh;
-    if (!ctx->gbuffer_owned) { ctx->gbuffer = nullptr; ctx->gbuffer_capacity = 0; }
-    int rc = ilb_reserve(ctx, &ctx->gbuffer, &ctx->gbuffer_capacity, gbytes, false);
-    if (rc) return rc;
-    ctx->gbuffer_owned = true;
-    ctx->gb_w = gw; ctx->gb_h = gh; ctx->gb_fmt = gfmt;
     const int rows = f->row_end - f->row_begin;
     if (rows < 0 || f->row_begin < 0 || f->row_end > f->height) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "bad frame geometry");
-    const size_t lbytes = ltexel * (size_t)f->width * (size_t)std::max(rows, 1);
-    rc = ilb_reserve(ctx, &ctx->d_lightmap, &ctx->d_lightmap_capacity, std::max<size_t>(lbytes, 16), false);
-    if (rc) return rc;
-    if (!ctx->copy_in) {
-        ILB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
-        ILB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
-        for (int i = 0; i < ILB_PIPELINE_BANDS; i++) {
-            ILB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
-            ILB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
-        }
-    }
-    LightingPrepared prep;
-    rc = lightingPrepare(ctx, df, f, batches, batch_count, vertices, vertex_count, &prep);
-    if (rc) return rc;
-    if (rows == 0) return ILB_OK;
     // Bands of whole tile rows with heights 1 : 2 : 4 : 6 : 6 : 6 : 4 : 2 : 1 -- the first band is short so that the first kernel
     // starts after 1/32 of the upload, the last so that only 1/32 of the download is left when the last kernel ends, the middle
     // ones long so that few launches are paid (7.82 -> 7.69 ms per C4 frame against the 7-band split 1 : 2 : 3 : 4 : 3 : 2 : 1).
@@ -1834,6 +1815,48 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
         const int e = f->row_begin + (int)(((long long)rows * acc / total + TILE_H - 1) / TILE_H * TILE_H);
         edge[b + 1] = (b == NB - 1) ? f->row_end : std::min(std::max(e, edge[b]), f->row_end);
     }
+    // Frames in flight (ilb_render_lighting_frame_async): this frame may be queued behind the one before it band by band when both
+    // have the same geometry, buffers and band edges and nothing else has touched the G-buffer since; otherwise whatever is in
+    // flight is waited for first, and the frame starts behind everything queued on the context's stream, as a lone frame does.
+    const size_t gtexel0 = ilb_format_bytes(gfmt), ltexel0 = ilb_format_bytes(f->lightmap_format);
+    bool chained = ctx->frame_ticket > ctx->frame_waited && ctx->pipe_generation == ctx->gb_generation && ctx->gbuffer_owned &&
+                   ctx->gbuffer == ctx->pipe_gbuffer && ctx->d_lightmap == ctx->pipe_lightmap && ctx->pipe_w == f->width && ctx->pipe_h == f->height &&
+                   ctx->pipe_gfmt == gfmt && ctx->pipe_lfmt == f->lightmap_format && ctx->pipe_nb == NB &&
+                   ctx->gbuffer_capacity >= gtexel0 * (size_t)gw * (size_t)gh &&
+                   ctx->d_lightmap_capacity >= std::max<size_t>(ltexel0 * (size_t)f->width * (size_t)std::max(rows, 1), 16);
+    for (int b = 0; chained && b <= NB; b++) chained = ctx->pipe_edges[b] == edge[b];
+    if (getenv("ILB_NO_FRAME_CHAINING")) chained = false;   // dev knob
+    if (!chained) {
+        const int rcd = ilb_frames_drain(ctx);
+        if (rcd) return rcd;
+    }
+    ctx->pipe_generation = ~0ull;   // valid again only when this frame is queued completely
+    const size_t gtexel = ilb_format_bytes(gfmt), ltexel = ilb_format_bytes(f->lightmap_format);
+    const size_t gbytes = gtexel * (size_t)gw * (size_t)gh;
+    if (!ctx->gbuffer_owned) { ctx->gbuffer = nullptr; ctx->gbuffer_capacity = 0; }
+    int rc = ilb_reserve(ctx, &ctx->gbuffer, &ctx->gbuffer_capacity, gbytes, false);
+    if (rc) return rc;
+    ctx->gbuffer_owned = true;
+    ctx->gb_w = gw; ctx->gb_h = gh; ctx->gb_fmt = gfmt;
+    const size_t lbytes = ltexel * (size_t)f->width * (size_t)std::max(rows, 1);
+    rc = ilb_reserve(ctx, &ctx->d_lightmap, &ctx->d_lightmap_capacity, std::max<size_t>(lbytes, 16), false);
+    if (rc) return rc;
+    if (!ctx->copy_in) {
+        ILB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        ILB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < ILB_PIPELINE_BANDS; i++) {
+            ILB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+            ILB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    if (!ctx->ev_frame[0]) {
+        for (cudaEvent_t& e : ctx->ev_down) ILB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (cudaEvent_t& e : ctx->ev_frame) ILB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    LightingPrepared prep;
+    rc = lightingPrepare(ctx, df, f, batches, batch_count, vertices, vertex_count, &prep);
+    if (rc) return rc;
+    if (rows == 0) return ILB_OK;
     // Two compute lanes: even bands run on the context's stream, odd bands on band_stream with their own scratch sums, so the
     // CTAs of band b + 1 fill the SM slots that the last wave of band b leaves idle (kernels of one stream run back to back,
     // and every band would otherwise pay the tails of both of its passes).  ILB_BAND_LANES=1 restores the single lane.
@@ -1864,12 +1887,16 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
     char* gdst = reinterpret_cast<char*>(ctx->gbuffer);
     char* ldev = reinterpret_cast<char*>(ctx->d_lightmap);
     char* lhost = reinterpret_cast<char*>(lightmap_out_host);
-    // everything already queued on the main stream (earlier frames, uploads) must be done before the G-buffer is overwritten
-    ILB_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], ctx->stream));
-    ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_done[0], 0));
+    if (!chained) {   // everything already queued on the main stream (uploads, other renders) must be done before the G-buffer is overwritten
+        ILB_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], ctx->stream));
+        ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_done[0], 0));
+    }
     for (int b = 0; b < NB; b++) {
         const int r0 = edge[b], r1 = edge[b + 1];
         if (r1 <= r0) continue;
+        // chained: the rows of band b are free as soon as the kernels of band b of the frame before have run (the waits are queued
+        // before this frame records ev_done[b] again, so they refer to that frame)
+        if (chained) ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_done[b], 0));
         const size_t goff = gtexel * (size_t)gw * (size_t)r0, gn = gtexel * (size_t)gw * (size_t)(r1 - r0);
         ILB_CUDA(ctx, cudaMemcpyAsync(gdst + goff, gsrc + goff, gn, cudaMemcpyHostToDevice, ctx->copy_in));
         ILB_CUDA(ctx, cudaEventRecord(ctx->ev_in[b], ctx->copy_in));
@@ -1882,6 +1909,7 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
         const int lane = (lanes == 2) ? (b & 1) : 0;
         const cudaStream_t st = lane ? ctx->band_stream : ctx->stream;
         ILB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_in[b], 0));
+        if (chained) ILB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_down[b], 0));   // the lightmap rows of band b have been downloaded
         void* outs[1] = {ctx->d_lightmap};
         rc = lightingLaunchRows(ctx, prep, r0, r1, outs, 1, f->row_begin, lane);
         if (rc) return rc;
@@ -1897,11 +1925,38 @@ int ilb_lighting_frame_from_host(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_fr
         ILB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[b], 0));
         const size_t loff = ltexel * (size_t)f->width * (size_t)(r0 - f->row_begin), ln = ltexel * (size_t)f->width * (size_t)(r1 - r0);
         ILB_CUDA(ctx, cudaMemcpyAsync(lhost + loff, ldev + loff, ln, cudaMemcpyDeviceToHost, ctx->copy_out));
+        ILB_CUDA(ctx, cudaEventRecord(ctx->ev_down[b], ctx->copy_out));
     }
+    const unsigned long long ticket = ++ctx->frame_ticket;
+    ILB_CUDA(ctx, cudaEventRecord(ctx->ev_frame[ticket % 4], ctx->copy_out));
+    ctx->pipe_generation = ctx->gb_generation;
+    ctx->pipe_gbuffer = ctx->gbuffer; ctx->pipe_lightmap = ctx->d_lightmap;
+    ctx->pipe_w = f->width; ctx->pipe_h = f->height; ctx->pipe_gfmt = gfmt; ctx->pipe_lfmt = f->lightmap_format; ctx->pipe_nb = NB;
+    for (int b = 0; b <= NB; b++) ctx->pipe_edges[b] = edge[b];
+    if (out_ticket) { *out_ticket = ticket; return ILB_OK; }   // asynchronous: ilb_lighting_frame_wait(ticket)
     ILB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
     ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->frame_waited = ticket;
     return ILB_OK;
 }
+
+int ilb_lighting_frame_wait(ilb_ctx* ctx, unsigned long long ticket) {
+    if (ticket == 0 || ticket <= ctx->frame_waited) return ILB_OK;   // nothing was queued (an empty band), or known complete
+    if (ticket > ctx->frame_ticket) return ilb_fail(ctx, ILB_ERR_INVALID_ARGUMENT, "unknown frame ticket %llu", ticket);
+    // downloads complete in frame order, so a slot that a later frame has taken over still covers this one
+    ILB_CUDA(ctx, cudaEventSynchronize(ctx->ev_frame[ticket % 4]));
+    ctx->frame_waited = std::max(ctx->frame_waited, ticket);
+    return ILB_OK;
+}
+
+int ilb_frames_drain(ilb_ctx* ctx) {
+    if (ctx->frame_waited >= ctx->frame_ticket) return ILB_OK;
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
+    ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->frame_waited = ctx->frame_ticket;
+    return ILB_OK;
+}
+
 
 int ilb_probes_launch(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* f, const ilb_light_batch* batches, int batch_count,
                       const ilb_light_vertex* vertices, int vertex_count, const ilb_float4* positions, const ilb_float4* normals,

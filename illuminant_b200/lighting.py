@@ -445,6 +445,30 @@ class LightingRenderer:
         self._set_last_rendered(frame, intensityScale)
         return out
 
+    def RenderLightingFrameAsync(self, gbuffer: np.ndarray, out: np.ndarray, intensityScale: float = 1.0,
+                                 rows: Optional[Tuple[int, int]] = None, packed=None) -> int:
+        """`ilb_render_lighting_frame_async`: queues the frame and returns its ticket; `WaitLightingFrame(ticket)` returns when
+        `out` is complete.  `gbuffer` (a C-contiguous array of the G-buffer's dtype) and `out` must stay untouched until then
+        and be page-locked (`Context.host_register`) for the call to return before the copies have run."""
+        fmt = FORMAT_FLOAT4 if self.Configuration.HighQualityGBuffer else FORMAT_HALF4
+        want = np.float32 if fmt == FORMAT_FLOAT4 else np.float16
+        if gbuffer.dtype != want or not gbuffer.flags["C_CONTIGUOUS"] or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("asynchronous frames need C-contiguous arrays of the G-buffer's own dtype (no staging copy can outlive the call)")
+        gh, gw = gbuffer.shape[0], gbuffer.shape[1]
+        self._gbuffer_shape = (gh, gw)
+        frame = self.build_frame(intensityScale, rows)
+        batches, nb, verts, nv = packed if packed is not None else self.build_batches(intensityScale)
+        df = self.DistanceField.handle if (self.DistanceField is not None and self.DistanceField.handle) else None
+        ticket = C.c_uint64(0)
+        self.ctx.check(self.ctx.lib.ilb_render_lighting_frame_async(self.ctx.handle, df, C.byref(frame), C.cast(batches, C.c_void_p), nb,
+                                                                    C.cast(verts, C.c_void_p), nv, gw, gh, fmt, gbuffer.ctypes.data_as(C.c_void_p),
+                                                                    out.ctypes.data_as(C.c_void_p), C.byref(ticket)))
+        self._set_last_rendered(frame, intensityScale)
+        return int(ticket.value)
+
+    def WaitLightingFrame(self, ticket: int) -> None:
+        self.ctx.check(self.ctx.lib.ilb_render_lighting_frame_wait(self.ctx.handle, C.c_uint64(int(ticket))))
+
     def RenderLightingDevice(self, device_ptr: int, intensityScale: float = 1.0, rows: Optional[Tuple[int, int]] = None,
                              packed=None) -> None:
         """Asynchronous variant writing rows [row_begin,row_end) to a device buffer that starts at row_begin."""

@@ -270,6 +270,21 @@ ILB_API int ilb_render_lighting_frame(ilb_ctx* ctx, ilb_df* df, const ilb_lighti
                                       const ilb_light_vertex* vertices, int vertex_count,
                                       int gbuffer_width, int gbuffer_height, int gbuffer_format, const void* gbuffer,
                                       void* lightmap_out);
+/* The same frame without the final wait: the call returns as soon as the frame is queued, *out_ticket names it, and
+ * ilb_render_lighting_frame_wait(ctx, ticket) returns when its lightmap_out is complete (tickets complete in order; 0 = nothing
+ * was queued, e.g. an empty row band).  A renderer that double-buffers its lit frame queues frame n + 1 before it waits for
+ * frame n: consecutive frames of the same geometry are then chained band by band on the device -- the G-buffer rows of band b
+ * of frame n + 1 go up as soon as the kernels of band b of frame n have run, its kernels start as soon as that band's lightmap
+ * rows have gone down -- so the fill and drain of one frame's pipeline hide behind its neighbours.  Until the wait returns the
+ * caller must leave `gbuffer` and `lightmap_out` alone (frames in flight need distinct lightmap_out buffers; both must be
+ * page-locked for the call to be asynchronous at all).  Every other lighting, G-buffer or resolve entry point of the context
+ * first waits for the frames in flight; light probes and particle systems do not. */
+ILB_API int ilb_render_lighting_frame_async(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame,
+                                            const ilb_light_batch* batches, int batch_count,
+                                            const ilb_light_vertex* vertices, int vertex_count,
+                                            int gbuffer_width, int gbuffer_height, int gbuffer_format, const void* gbuffer,
+                                            void* lightmap_out, uint64_t* out_ticket);
+ILB_API int ilb_render_lighting_frame_wait(ilb_ctx* ctx, uint64_t ticket);
 /* Same with a DEVICE output pointer; asynchronous on ilb_stream(ctx). */
 ILB_API int ilb_render_lighting_device(ilb_ctx* ctx, ilb_df* df, const ilb_lighting_frame* frame,
                                        const ilb_light_batch* batches, int batch_count,

@@ -257,6 +257,74 @@ def test_bands_land_in_one_registered_shared_host_frame(ctx):
         shared.close()
 
 
+def test_frames_in_flight_are_chained_band_by_band(ctx):
+    """ilb_render_lighting_frame_async / _wait: several frames queued before the first is waited for -- every frame with its own
+    G-buffer and its own light list, into its own page-locked output -- give the bits of the synchronous call; other entry points
+    in between (a G-buffer upload, a plain render, a frame of another size) first wait for what is in flight; tickets of frames
+    that are long complete, of empty bands and unknown tickets behave as documented."""
+    from illuminant_b200._abi import IlluminantError
+    w, h = 640, 403
+    rng = np.random.RandomState(5)
+    base = scenes.lighting_scene(51, w, h, 6, n_directional=1, n_line=1, ramp=(60.0, 260.0))
+    df = scenes.make_distance_field(ctx, base)
+    df.Rasterize(base.obstructions)
+    r = ib.LightingRenderer(ctx, base.environment, base.configuration)
+    r.DistanceField = df
+    gbs, wants = [], []
+    sphere = next(l for l in base.environment.Lights if isinstance(l, ib.SphereLightSource))
+    x0 = sphere.Position[0]
+    n_frames = 6
+    for k in range(n_frames):      # frame k: its own G-buffer (rows shuffled in blocks) and a moved light
+        gb = np.ascontiguousarray(np.roll(base.gbuffer, 16 * k, axis=0), dtype=np.float32 if base.configuration.HighQualityGBuffer else np.float16)
+        sphere.Position = (x0 + 7.0 * k,) + tuple(sphere.Position[1:])
+        gbs.append(gb)
+        wants.append(r.RenderLightingFrame(gb).copy())
+    pinned = [np.zeros_like(wants[0]) for _ in range(n_frames)]
+    for a in gbs + pinned:
+        ctx.host_register(a.ctypes.data, a.nbytes)
+    try:
+        for rows in (None, (32, h - 40)):
+            for o in pinned:
+                o[...] = 0
+            tickets = []
+            for k in range(n_frames):      # all queued before the first wait: up to six frames in flight
+                sphere.Position = (x0 + 7.0 * k,) + tuple(sphere.Position[1:])
+                out = pinned[k] if rows is None else pinned[k][rows[0]:rows[1]]
+                tickets.append(r.RenderLightingFrameAsync(gbs[k], out, rows=rows))
+            assert tickets == sorted(tickets) and len(set(tickets)) == n_frames
+            for k in reversed(range(n_frames)):    # waiting out of order is allowed
+                r.WaitLightingFrame(tickets[k])
+                want = wants[k] if rows is None else wants[k][rows[0]:rows[1]]
+                got = pinned[k] if rows is None else pinned[k][rows[0]:rows[1]]
+                assert np.array_equal(got.view(np.uint16), want.view(np.uint16)), (rows, k)
+            r.WaitLightingFrame(tickets[0])        # long complete: returns at once
+        # other entry points between frames in flight
+        sphere.Position = (x0,) + tuple(sphere.Position[1:])
+        t0 = r.RenderLightingFrameAsync(gbs[0], pinned[0])
+        r.SetGBuffer(gbs[1])                       # waits for t0, then replaces the G-buffer
+        plain = r.RenderLighting()                 # renders from gbs[1]
+        t1 = r.RenderLightingFrameAsync(gbs[2], pinned[2])
+        t2 = r.RenderLightingFrameAsync(gbs[3], pinned[3], rows=(0, 160))     # another geometry: not chained
+        r.WaitLightingFrame(t2)
+        r.WaitLightingFrame(t1)
+        r.WaitLightingFrame(t0)
+        sphere.Position = (x0,) + tuple(sphere.Position[1:])
+        for k, got in ((0, pinned[0]), (2, pinned[2])):
+            assert np.array_equal(got.view(np.uint16), r.RenderLightingFrame(gbs[k]).view(np.uint16)), k
+        assert np.array_equal(pinned[3][:160].view(np.uint16), r.RenderLightingFrame(gbs[3], rows=(0, 160)).view(np.uint16))
+        assert np.array_equal(plain.view(np.uint16), r.RenderLightingFrame(gbs[1]).view(np.uint16))
+        assert r.RenderLightingFrameAsync(gbs[0], pinned[0][:0], rows=(48, 48)) == 0      # empty band: nothing queued
+        r.WaitLightingFrame(0)
+        with pytest.raises(IlluminantError):
+            r.WaitLightingFrame(10 ** 9)
+        with pytest.raises(ValueError):
+            r.RenderLightingFrameAsync(gbs[0][:, ::2], pinned[0])
+    finally:
+        ctx.synchronize()
+        for a in gbs + pinned:
+            ctx.host_unregister(a.ctypes.data)
+
+
 def test_heaviest_first_tile_order_is_only_a_schedule(ctx):
     """ILB_OPT_LIGHT_TILE_ORDER starts the tiles under the most sphere-light quads first: same bits with the option on and off,
     for whole frames, bands and mixed / sphere-only light lists; moving a light makes a new order (more moves than the cache
