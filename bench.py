@@ -8,9 +8,11 @@ Primary metric: lit Mpixels/s on config C4 (3840x2160, 128 mixed Sphere/Directio
 9-slice distance field); a "step" is one RenderLighting of the whole frame PLUS the UpdateLightProbes of the same frame,
 both inside the timed region.  At N > 1 the frame is cut into row bands of equal MEASURED cost (calibrated before the
 timed region, sharding.rebalance_rows), every rank stores its band into every rank's full-frame buffer from inside the
-kernel (NVLink peer stores), and a symmetric-memory barrier ends the step.  The host-to-host number (`e2e`) at N > 1 is one
-ilb_render_lighting_frame call per rank on its band, the lightmap rows of every rank landing in one page-locked shared-memory
-host frame that rank 0 consumes (sharding.SharedHostFrame: no collective on that leg).  The second hot path is reported in the same
+kernel (NVLink peer stores), and a symmetric-memory barrier ends the step.  The host-to-host number (`e2e`) goes through
+ilb_render_lighting_frame_async / _wait with HOST buffers, two frames in flight (frame n is queued before frame n - 1 is
+waited for; every frame uploads its G-buffer from pinned memory and downloads its lightmap and probes); at N > 1 it is one such
+call per rank on its band, the lightmap rows of every rank landing in one page-locked shared-memory host frame (two slots) that
+rank 0 consumes (sharding.SharedHostFrame: no collective on that leg).  The second hot path is reported in the same
 JSON line under "particles": Mparticle-steps/s for 8M particles (32 chunks x 512^2) per GPU through
 Spawner(60 000 / s)+Gravity+Noise+FMA+SDF collision; a step is one ParticleSystem.Update (spawn kernel, Noise table kernel,
 step kernel).  The particles the Spawner adds during the run are updated too but NOT counted in the metric.
