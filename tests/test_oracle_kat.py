@@ -231,6 +231,93 @@ def test_unobstructed_light_is_ambient_plus_falloff(oracle):
         assert lm[y, x, 3] == s.environment.Ambient[3] + (1.0 if op > 0 else 0.0)      # additive blend counts touching lights
 
 
+def _triangle_solid_angle(a, b, c):
+    """Van Oosterom & Strackee (1983): tan(omega / 2) = a . (b x c) / (|a||b||c| + (a.b)|c| + (a.c)|b| + (b.c)|a|) -- not the
+    dihedral-angle sum the shader uses, so agreement pins rectangleSolidAngle (FBPBR.fxh:33-51) from outside."""
+    la, lb, lc = np.linalg.norm(a), np.linalg.norm(b), np.linalg.norm(c)
+    num = float(np.dot(a, np.cross(b, c)))
+    den = la * lb * lc + np.dot(a, b) * lc + np.dot(a, c) * lb + np.dot(b, c) * la
+    return abs(2.0 * np.arctan2(num, den))
+
+
+def _line_light_opacity_f64(wp, n, P0, P1, radius):
+    """computeLineLightOpacity (FBPBR.fxh:53-101) in float64, the solid angle from two triangles."""
+    wp, n, P0, P1 = (np.asarray(v, np.float64) for v in (wp, n, P0, P1))
+    ab = P1 - P0
+    u = min(max(np.dot(wp - P0, ab) / np.dot(ab, ab), 0.0), 1.0)      # closestPointOnLineSegment3, DistanceFieldCommon.fxh:151-155
+    sphere = P0 + u * ab
+    left = ab / np.linalg.norm(ab)
+    forward = (sphere - wp) / np.linalg.norm(sphere - wp)
+    up = np.cross(left, forward)
+    p = [P0 + radius * up, P0 - radius * up, P1 - radius * up, P1 + radius * up]
+    v = [q - wp for q in p]
+    omega = _triangle_solid_angle(v[0], v[1], v[2]) + _triangle_solid_angle(v[0], v[2], v[3])
+    sat = lambda x: min(max(x, 0.0), 1.0)     # noqa: E731
+    total = sum(sat(np.dot(q / np.linalg.norm(q), n)) for q in v) + sat(np.dot((0.5 * (P0 + P1) - wp) / np.linalg.norm(0.5 * (P0 + P1) - wp), n))
+    illum = omega * 0.2 * total
+    d = sphere - wp
+    illum += np.pi * sat(np.dot(d / np.linalg.norm(d), n)) * (radius * radius) / np.dot(d, d)
+    return sat(illum), u
+
+
+def test_unobstructed_line_light_matches_an_independent_solid_angle(oracle):
+    """No obstructions, no G-buffer (flat ground, normal +z): lightmap = ambient + lerp(StartColor, EndColor, u).rgb * a *
+    computeLineLightOpacity, the latter evaluated in float64 with the rectangle's solid angle taken from the Van Oosterom-Strackee
+    triangle formula instead of the shader's sum of four dihedral angles.  The four arc-cosines nearly cancel in fp32, hence
+    the tolerance (3e-4 of the opacity, far below a wrong formula, which is off by tens of per cent)."""
+    s = scenes.lighting_scene(0, 64, 40, 0, float4_lightmap=True)
+    s.configuration.EnableGBuffer = False
+    P0, P1, radius = (14.0, 12.0, 22.0), (49.0, 27.0, 31.0), 5.0
+    light = ib.LineLightSource(StartPosition=P0, EndPosition=P1, Radius=radius, StartColor=(1.0, 0.5, 0.25, 0.8), EndColor=(0.2, 0.9, 0.6, 0.5),
+                               CastsShadows=True)
+    s.environment.Lights = [light]
+    df = scenes.make_distance_field(None, s)
+    tex = np.zeros((df.TextureHeight, df.TextureWidth, 4), np.uint16)    # cleared field: nothing occludes
+    df.ValidSliceCount, df.handle = df.SliceCount, 1
+    r = ib.LightingRenderer(None, s.environment, s.configuration)
+    r.DistanceField = df
+    frame = r.build_frame()
+    batches, nb, verts, nv = r.build_batches()
+    lm = oracle.render_lighting(tex, None, frame, batches, nb, verts, nv)
+    c0, c1 = np.array(light.StartColor, np.float64), np.array(light.EndColor, np.float64)
+    seen = []
+    for (x, y) in [(14, 12), (31, 19), (49, 27), (5, 35), (60, 3), (0, 0), (63, 39), (30, 5)]:
+        op, u = _line_light_opacity_f64((x + 0.5, y + 0.5, 0.0), (0.0, 0.0, 1.0), P0, P1, radius)
+        col = c0 + (c1 - c0) * u
+        want = np.array(s.environment.Ambient[:3], np.float64) + col[:3] * col[3] * op
+        got = lm[y, x, :3].astype(np.float64)
+        assert np.allclose(got, want, rtol=0, atol=3e-4 * max(op, 1e-3) + 2e-6), (x, y, got, want, op)
+        assert lm[y, x, 3] == s.environment.Ambient[3] + (1.0 if op > 0 else 0.0)
+        seen.append(op)
+    assert max(seen) > 0.4 and 0.0 < min(seen) < 0.15          # under the light and far from it
+
+
+def test_unobstructed_directional_light_is_ambient_plus_normal_factor(oracle):
+    """No obstructions, no G-buffer (normal +z): every pixel = ambient + color.rgb * color.a * pow(saturate((dot(-dir, n) + 0.35) /
+    0.35), 0.85) (computeDirectionalLightOpacity / computeNormalFactorEx, LightCommon.fxh:154-165, :224-231), evaluated in
+    float64 -- light from above (factor 1), grazing from below the horizon (inside the ramp) and from straight below (0)."""
+    for direction, inside in (((0.3, 0.2, -0.9327379), False), ((0.6, 0.742294, 0.2987), True), ((0.8, 0.5244044, 0.2915), True), ((0.0, 0.0, 1.0), False)):
+        s = scenes.lighting_scene(0, 32, 24, 0, float4_lightmap=True)
+        s.configuration.EnableGBuffer = False
+        light = ib.DirectionalLightSource(Color=(0.9, 0.6, 0.3, 0.7), CastsShadows=True)
+        light.Direction = direction
+        s.environment.Lights = [light]
+        df = scenes.make_distance_field(None, s)
+        tex = np.zeros((df.TextureHeight, df.TextureWidth, 4), np.uint16)
+        df.ValidSliceCount, df.handle = df.SliceCount, 1
+        r = ib.LightingRenderer(None, s.environment, s.configuration)
+        r.DistanceField = df
+        batches, nb, verts, nv = r.build_batches()
+        lm = oracle.render_lighting(tex, None, r.build_frame(), batches, nb, verts, nv)
+        d = np.array(light.Direction, np.float64)
+        d = d / np.linalg.norm(d)
+        factor = min(max((-d[2] + 0.35) / 0.35, 0.0), 1.0) ** 0.85
+        assert (0.0 < factor < 1.0) == inside
+        want = np.array(s.environment.Ambient[:3], np.float64) + np.array([0.9, 0.6, 0.3]) * 0.7 * factor
+        assert np.allclose(lm[..., :3].reshape(-1, 3), want, rtol=0, atol=2e-5), (direction, lm[0, 0], want)
+        assert np.all(lm[..., 3] == s.environment.Ambient[3] + 1.0)      # a directional light never discards a visible pixel
+
+
 # ---- closed forms, particles --------------------------------------------------------------------------------------
 def test_ballistic_particles_closed_form(oracle):
     """friction 0, no transforms, no field: p(t) = p0 + v t, life linear, dead particles become zeros."""
@@ -276,6 +363,64 @@ def test_gravity_single_linear_attractor(oracle):
     P2, V2, *_ = oracle.particles_step(P, V, A, 16, system.system_uniforms(dt), [], system.plan_ops(0.0), engine.RandomnessTexture, None, 1)
     assert V2[0, 0] == pytest.approx((1 - 10 / 40.0) * dt * 6.0, rel=1e-5) and V2[0, 1] == 0        # Gravity.fx:36-48
     assert V2[1, 0] == 0.0 and V2[1, 3] == 3.0       # untouched (only UpdateWithDistanceField counts the delay down)
+
+
+def test_fma_transform_closed_form(oracle):
+    """FMA.fx:15-51 + PS_Update (UpdateParticleSystem.fx:9-38) in float64: with no area the weight is Strength, the lerp
+    parameter weight * getDeltaTime() / TimeDivisor = Strength * dt * CyclesPerSecond (both carry VelocityConstantScale), the
+    position then advances by the NEW velocity times dt; a dead particle and one outside the category filter pass through."""
+    engine = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=16))
+    cfg = ib.ParticleSystemConfiguration(Friction=0.0, LifeDecayPerSecond=0.0, MaximumVelocity=1000.0)
+    system = ib.ParticleSystem(engine, cfg, maxChunks=1)
+    fma = ib.FMA(CyclesPerSecond=10, PositionAdd=(1.0, 2.0, 3.0), PositionMultiply=(2.0, 1.0, 0.5), VelocityAdd=(0.0, 5.0, 0.0),
+                 VelocityMultiply=(0.5, 0.5, 0.5), Strength=0.8, CategoryFilter=(0.0, 1.0))
+    system.Transforms = [fma]
+    P = np.zeros((256, 4), np.float32); V = np.zeros((256, 4), np.float32); A = np.ones((256, 4), np.float32)
+    P[0] = [3, 4, 5, 1]; V[0] = [10, -20, 5, 0]
+    P[1] = [3, 4, 5, 1]; V[1] = [10, -20, 5, 2]      # category 2: outside the filter, only the update tail moves it
+    dt = 0.02
+    P2, V2, *_ = oracle.particles_step(P, V, A, 16, system.system_uniforms(dt), [], system.plan_ops(0.0), engine.RandomnessTexture, None, 1)
+    t = 0.8 * dt * 10.0
+    p0, v0 = np.array([3.0, 4.0, 5.0]), np.array([10.0, -20.0, 5.0])
+    p1 = p0 + t * (p0 * np.array([2.0, 1.0, 0.5]) + np.array([1.0, 2.0, 3.0]) - p0)
+    v1 = v0 + t * (v0 * 0.5 + np.array([0.0, 5.0, 0.0]) - v0)
+    assert np.allclose(V2[0, :3], v1, rtol=2e-6) and V2[0, 3] == 0.0
+    assert np.allclose(P2[0, :3], p1 + v1 * dt, rtol=2e-6) and P2[0, 3] == 1.0
+    assert np.allclose(V2[1, :3], v0, rtol=2e-6) and V2[1, 3] == 2.0
+    assert np.allclose(P2[1, :3], p0 + v0 * dt, rtol=2e-6)
+    assert not P2[2:].any() and not V2[2:].any()       # dead particles stay cleared
+
+
+def test_collision_tail_closed_forms(oracle):
+    """PS_Update of UpdateParticleSystemWithDistanceField.fx:29-147 by hand.  In a cleared field (every sample decodes to
+    96.4 px: nothing within reach) a particle flies p + v * dt and its bounce delay counts down by one; a particle that flies
+    straight at the face of a box stops where the sampled distance first drops below CollisionDistance -- never inside the
+    box -- and leaves with a reflected velocity of |v| * BounceVelocityMultiplier, velocity.w = 3 (the bounce delay) and its
+    life reduced by LifePenalty."""
+    df = _field(128, 128, 64.0, 9)
+    df.ValidSliceCount, df.handle = df.SliceCount, 1
+    engine = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=16))
+    cfg = ib.ParticleSystemConfiguration(Friction=0.0, LifeDecayPerSecond=0.0, MaximumVelocity=10000.0)
+    cfg.Collision = ib.ParticleCollision(DistanceField=df, DistanceFieldMaximumZ=64.0, EscapeVelocity=50.0, BounceVelocityMultiplier=0.5,
+                                         Distance=1.0, LifePenalty=0.25)
+    system = ib.ParticleSystem(engine, cfg, maxChunks=1)
+    system.Transforms = []
+    dt = 0.02
+    P = np.zeros((256, 4), np.float32); V = np.zeros((256, 4), np.float32); A = np.ones((256, 4), np.float32)
+    P[0] = [20, 30, 8, 1]; V[0] = [100, -50, 25, 2]
+    cleared = np.zeros((df.TextureHeight, df.TextureWidth, 4), np.uint16)
+    P2, V2, *_ = oracle.particles_step(P, V, A, 16, system.system_uniforms(dt), [], system.plan_ops(0.0), engine.RandomnessTexture, cleared, 1)
+    assert np.allclose(P2[0, :3], P[0, :3] + V[0, :3] * dt, rtol=2e-6) and P2[0, 3] == 1.0
+    assert np.allclose(V2[0, :3], V[0, :3], rtol=2e-6) and V2[0, 3] == 1.0            # bounce delay 2 -> 1
+    # a wall: box of half size 10 centred at x = 80; its -x face is the plane x = 70
+    box = ib.LightObstruction(ib.LightObstructionType.Box, (80.0, 64.0, 0.0), (10.0, 40.0, 200.0))
+    tex = oracle.generate_distance_field(df, [box])
+    P[0] = [60, 64, 8, 1]; V[0] = [1000, 0, 0, 0]        # 20 px per step, 10 px in front of the face, category 0 = bounces
+    P2, V2, *_ = oracle.particles_step(P, V, A, 16, system.system_uniforms(dt), [], system.plan_ops(0.0), engine.RandomnessTexture, tex, 1)
+    assert 60.0 <= P2[0, 0] <= 70.0 and abs(P2[0, 1] - 64.0) < 1e-3 and abs(P2[0, 2] - 8.0) < 1e-3     # stopped in front of the face
+    assert P2[0, 0] >= 70.0 - 1.0 - 16.0                                                              # after at most one back-off
+    assert V2[0, 0] == pytest.approx(-1000.0 * 0.5, rel=2e-3) and abs(V2[0, 1]) < 2.0 and abs(V2[0, 2]) < 2.0   # reflected off the x face
+    assert V2[0, 3] == 3.0 and P2[0, 3] == pytest.approx(1.0 - 0.25, abs=1e-6)
 
 
 def test_area_weight_quirk_scalar_rotation(oracle):
