@@ -292,6 +292,38 @@ def test_unobstructed_line_light_matches_an_independent_solid_angle(oracle):
     assert max(seen) > 0.4 and 0.0 < min(seen) < 0.15          # under the light and far from it
 
 
+def test_ambient_occlusion_closed_form(oracle):
+    """computeAO (AOCommon.fxh:1-20) by hand: on flat ground next to a tall box the sample at p + (0, 0, n.z * radius) is D px from
+    the box's face (as the field stores it), so the light's opacity is multiplied by (1 - o) + o * (1 - (1 - D / radius)^2); beyond
+    the radius by 1.
+    The light casts no shadows, so nothing else of the field enters."""
+    s = scenes.lighting_scene(0, 96, 64, 0, float4_lightmap=True)
+    s.configuration.EnableGBuffer = False
+    box = ib.LightObstruction(ib.LightObstructionType.Box, (70.0, 32.0, 0.0), (10.0, 60.0, 400.0))     # face at x = 60, spans every slice
+    light = ib.SphereLightSource(Position=(30.0, 32.0, 40.0), Radius=10.0, RampLength=120.0, Color=(1.0, 0.8, 0.6, 1.0), CastsShadows=False,
+                                 AmbientOcclusionRadius=20.0, AmbientOcclusionOpacity=0.6)
+    s.environment.Lights = [light]
+    s.obstructions = [box]
+    df = scenes.make_distance_field(None, s)
+    tex = oracle.generate_distance_field(df, [box])
+    df.ValidSliceCount, df.handle = df.SliceCount, 1
+    r = ib.LightingRenderer(None, s.environment, s.configuration)
+    r.DistanceField = df
+    frame = r.build_frame()
+    batches, nb, verts, nv = r.build_batches()
+    lm = oracle.render_lighting(tex, None, frame, batches, nb, verts, nv)
+    factors = []
+    for x in (20, 39, 45, 52, 57):
+        pos = (x + 0.5, 32.5, 0.0)
+        D = 60.0 - x      # the sample at the pixel centre reads field texel x, which holds the distance at x (test_distance_field_generation_box_slice)
+        ao = 1.0 if D >= 20.0 else (1.0 - 0.6) + 0.6 * (1.0 - (1.0 - D / 20.0) ** 2)
+        op = oracle.sphere_light_opacity(frame, pos, (0, 0, 1), light.Position, (10.0, 120.0, 0, 0))
+        want = np.array(s.environment.Ambient[:3], np.float64) + np.array([1.0, 0.8, 0.6]) * op * ao
+        assert np.allclose(lm[32, x, :3], want, rtol=0, atol=2e-3 * op), (x, lm[32, x], want, ao)
+        factors.append(ao)
+    assert factors[0] == 1.0 and factors[-1] < 0.6          # out of reach, and deep in the corner
+
+
 def test_unobstructed_directional_light_is_ambient_plus_normal_factor(oracle):
     """No obstructions, no G-buffer (normal +z): every pixel = ambient + color.rgb * color.a * pow(saturate((dot(-dir, n) + 0.35) /
     0.35), 0.85) (computeDirectionalLightOpacity / computeNormalFactorEx, LightCommon.fxh:154-165, :224-231), evaluated in
