@@ -455,6 +455,70 @@ def test_collision_tail_closed_forms(oracle):
     assert V2[0, 3] == 3.0 and P2[0, 3] == pytest.approx(1.0 - 0.25, abs=1e-6)
 
 
+@pytest.mark.parametrize("replace", [True, False])
+def test_noise_transform_closed_form(oracle, replace):
+    """PS_Noise (Noise.fx:28-72) + PS_Update in float64 over a CONSTANT randomness table (every lookup returns the same texel,
+    so the four random vectors are known): delta = sign(r + offset) * max(|r + offset|, minimum) * scale; the position is
+    lerped by t = Strength * dt * CyclesPerSecond; the velocity is lerped towards the delta by the WEIGHT (ReplaceOldVelocity)
+    or towards old + delta by t, plus normalize(old velocity) * the speed delta."""
+    engine = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=16))
+    cfg = ib.ParticleSystemConfiguration(Friction=0.0, LifeDecayPerSecond=0.0, MaximumVelocity=10000.0)
+    system = ib.ParticleSystem(engine, cfg, maxChunks=1)
+    noise = ib.Noise(CyclesPerSecond=5, PositionOffset=(-0.5, -0.5, -0.5, -0.5), PositionMinimum=(0.0, 0.4, 0.0, 0.0), PositionScale=(8.0, 4.0, 2.0, 0.0),
+                     VelocityOffset=(-0.5, 0.25, -0.5), VelocityMinimum=(0.0, 0.0, 0.5), VelocityScale=(100.0, 50.0, 20.0),
+                     SpeedOffset=0.25, SpeedMinimum=0.0, SpeedScale=10.0, ReplaceOldVelocity=replace, Strength=0.5)
+    system.Transforms = [noise]
+    texel = np.array([0.75, 0.25, 0.625, 0.125], np.float32)
+    table = np.broadcast_to(texel, engine.RandomnessTexture.shape).copy()
+    P = np.zeros((256, 4), np.float32); V = np.zeros((256, 4), np.float32); A = np.ones((256, 4), np.float32)
+    P[0] = [30, 40, 5, 1]; V[0] = [30, 0, 40, 0]
+    dt = 0.02
+    P2, V2, *_ = oracle.particles_step(P, V, A, 16, system.system_uniforms(dt), [], system.plan_ops(0.0), table, None, 1)
+    r = texel.astype(np.float64)
+
+    def delta(offset, minimum, scale):
+        d = r + np.array(offset, np.float64)
+        return np.sign(d) * np.maximum(np.abs(d), np.array(minimum, np.float64)) * np.array(scale, np.float64)
+    dp = delta((-0.5, -0.5, -0.5, -0.5), (0.0, 0.4, 0.0, 0.0), (8.0, 4.0, 2.0, 0.0))
+    dv = delta((-0.5, 0.25, -0.5, 0.25), (0.0, 0.0, 0.5, 0.0), (100.0, 50.0, 20.0, 10.0))
+    assert dp[1] == pytest.approx(-0.4 * 4.0) and dv[2] == pytest.approx(0.5 * 20.0)      # both minimums engage
+    weight, t = 0.5, 0.5 * dt * 5.0
+    p0, v0 = np.array([30.0, 40.0, 5.0]), np.array([30.0, 0.0, 40.0])
+    p1 = p0 + t * dp[:3]
+    v1 = (v0 + weight * (dv[:3] - v0)) if replace else (v0 + t * dv[:3])
+    v1 = v1 + v0 / np.linalg.norm(v0) * dv[3]
+    assert np.allclose(V2[0, :3], v1, rtol=3e-6, atol=1e-5) and V2[0, 3] == 0.0
+    assert np.allclose(P2[0, :3], p1 + v1 * dt, rtol=3e-6) and P2[0, 3] == pytest.approx(1.0 + t * dp[3])
+
+
+def test_render_data_closed_form(oracle):
+    """computeRenderData (UpdateCommon.fxh:97-117) by hand with the default ramps (all 1) and OpacityFromLife: renderColor =
+    attributes * (1, 1, 1, life / OpacityFromLife) with alpha saturated and rgb premultiplied; renderData = (size 1, atan2 of the
+    velocity brought into [0, 2 pi) + life * RotationFromLife + index * RotationFromIndex, max(|v|, 1e-4), velocity.w), index =
+    x + y * 256 (the reference's own "FIXME" constant, whatever the chunk size)."""
+    import math
+    engine = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=16))
+    cfg = ib.ParticleSystemConfiguration(Friction=0.0, LifeDecayPerSecond=0.0, MaximumVelocity=10000.0, RotationFromVelocity=True,
+                                         RotationFromLife=30.0, RotationFromIndex=2.0, OpacityFromLife=4.0)
+    system = ib.ParticleSystem(engine, cfg, maxChunks=1)
+    system.Transforms = []
+    P = np.zeros((256, 4), np.float32); V = np.zeros((256, 4), np.float32); A = np.zeros((256, 4), np.float32)
+    i = 3 + 2 * 16                                   # texel (3, 2) of the 16 x 16 chunk
+    P[i] = [10, 20, 0, 2.0]; V[i] = [30, -40, 0, 1.0]; A[i] = [0.8, 0.6, 0.4, 0.9]
+    P[5] = [1, 1, 0, 8.0]; V[5] = [0.001, 0.002, 0, 0]; A[5] = [1, 1, 1, 1]     # slow (no rotation from velocity), alpha saturates
+    P2, V2, A2, RC, RD = oracle.particles_step(P, V, A, 16, system.system_uniforms(0.02), [], system.plan_ops(0.0), engine.RandomnessTexture, None, 1)
+    alpha = min(max(0.9 * (2.0 / 4.0), 0.0), 1.0)
+    assert np.allclose(RC[i], [0.8 * alpha, 0.6 * alpha, 0.4 * alpha, alpha], rtol=2e-6)
+    angle = math.atan2(-40.0, 30.0) + 2.0 * math.pi
+    index = 3 + 2 * 256
+    assert RD[i, 0] == pytest.approx(1.0, rel=1e-6)
+    assert RD[i, 1] == pytest.approx(angle + 2.0 * math.radians(30.0) + index * math.radians(2.0), rel=3e-6)
+    assert RD[i, 2] == pytest.approx(50.0, rel=1e-6) and RD[i, 3] == 1.0
+    assert np.allclose(RC[5], [1, 1, 1, 1]) and RD[5, 1] == pytest.approx(8.0 * math.radians(30.0) + 5 * math.radians(2.0), rel=3e-6)
+    assert RD[5, 2] == pytest.approx(math.hypot(0.001, 0.002), rel=1e-5)
+    assert not RC[0].any() and not RD[0].any()       # dead particle
+
+
 def test_area_weight_quirk_scalar_rotation(oracle):
     """AreaRotation is a scalar broadcast into a quaternion (FMA.fx:11,17): rotation 0 collapses the local position to 0,
     so the weight is `Strength` everywhere (distance = -min size); a unit quaternion would be the identity."""
