@@ -166,6 +166,51 @@ def test_cone_trace_closed_forms(oracle):
     assert steps == 2 and v == 0.0
 
 
+def _cone_trace_constant_field_f64(d0, start, end, light_radius, ramp_length, q):
+    """coneTrace (ConeTrace.fxh:13-71, 120-191) in float64 over a field whose distance is d0 everywhere, written from the shader
+    text with its own constants; returns (result, steps taken)."""
+    MIN_CONE_RADIUS, WINDOW, T0, DARK, LIT, HACK = 0.33, 2.0, 0.5, 0.075, 0.95, 1.5
+    length = math.dist(start, end)
+    t, limit, vis = T0, max(length - light_radius, 1.0), 1.0
+    max_radius = min(max(light_radius, MIN_CONE_RADIUS), q.MaxConeRadius)
+    growth = max_radius / max(ramp_length, 16.0) * 1.0
+    min_step = max(1.0, q.MinStepSize)
+    steps_remaining, live, steps = float(q.MaxStepCount), 1.0, 0
+    sat = lambda x: min(max(x, 0.0), 1.0)     # noqa: E731
+    while live > 0:
+        steps_remaining -= 1
+        steps += 1
+        vis = min(vis, (d0 + HACK) / min(growth * t + MIN_CONE_RADIUS, max_radius))
+        t += max(abs(d0) * q.LongStepFactor, min_step)
+        live = steps_remaining * sat(vis - DARK) * sat(limit - t)
+    v = min(vis, steps_remaining / WINDOW)
+    return sat(sat(v - DARK) / (LIT - DARK)) ** q.OcclusionToOpacityPower, steps
+
+
+def test_cone_trace_penumbra_over_a_constant_field(oracle):
+    """Partial shadow: over a field that reads d0 everywhere the visibility is (d0 + 1.5) / cone radius at the last sample, the
+    radius growing by maxRadius / rampLength per pixel from 0.33 up to the light's radius (capped at MaxConeRadius); the march
+    advances by max(|d0| * LongStepFactor, MinStepSize).  The float64 restatement above must give the oracle's value and step
+    count for light radii below / above MaxConeRadius, a non-default quality, a negative distance and a small step budget."""
+    df = _field(128, 96, 128.0, 9)
+    tex0 = np.zeros((df.TextureHeight, df.TextureWidth, 4), np.uint16)
+    start, end = (10.0, 12.0, 2.0), (100.0, 70.0, 30.0)
+    cases = [(3.0, 8.0, 100.0, ib.RendererQualitySettings()), (6.0, 40.0, 60.0, ib.RendererQualitySettings()),
+             (1.0, 12.0, 10.0, ib.RendererQualitySettings(MinStepSize=5.0, LongStepFactor=0.5, MaxStepCount=40, MaxConeRadius=16, OcclusionToOpacityPower=2.0)),
+             (-0.5, 8.0, 100.0, ib.RendererQualitySettings()), (2.0, 4.0, 200.0, ib.RendererQualitySettings(MinStepSize=1.0, MaxStepCount=12))]
+    seen = []
+    for d0, radius, ramp, q in cases:
+        code = int(round((192.0 / 255.0 - d0 / 128.0) * 65535))
+        tex = np.full_like(tex0, code)
+        d_stored = (192.0 / 255.0 - code / 65535.0) * 128.0          # what the texel decodes to (quantised to 1/512 px)
+        want, want_steps = _cone_trace_constant_field_f64(d_stored, start, end, radius, ramp, q)
+        got, steps = oracle.cone_trace(tex, df.uniforms(q), end, radius, ramp, start)
+        assert steps == want_steps, (d0, radius, steps, want_steps)
+        assert got == pytest.approx(want, abs=2e-5), (d0, radius, got, want)
+        seen.append(want)
+    assert 0.05 < seen[0] < 0.95 and 0.05 < seen[1] < 0.95 and 0.0 < seen[3] < 0.1    # real penumbrae; just inside a surface is nearly dark
+
+
 def test_sphere_light_opacity_closed_forms(oracle):
     s = scenes.lighting_scene(0, 32, 32, 0)
     r = ib.LightingRenderer(None, s.environment, s.configuration)
