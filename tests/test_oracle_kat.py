@@ -564,6 +564,52 @@ def test_render_data_closed_form(oracle):
     assert not RC[0].any() and not RD[0].any()       # dead particle
 
 
+def test_gravity_mixed_attractors_and_the_acceleration_clamp(oracle):
+    """Gravity.fx:12-61 in float64: a Physical attractor (1 / max(|d|^2 - radius, 0.001), not time-scaled), a Linear and an
+    Exponential one (time-scaled falloffs) are summed, the sum is clamped to MaximumAcceleration * dt, and the new velocity is
+    capped per component at MaximumVelocity."""
+    engine = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=16))
+    attractors = [ib.Attractor(Position=(40, 10, 0), Radius=50.0, Strength=300.0, Type=ib.AttractorType.Physical),
+                  ib.Attractor(Position=(0, 60, 20), Radius=120.0, Strength=900.0, Type=ib.AttractorType.Linear),
+                  ib.Attractor(Position=(-30, -30, 10), Radius=90.0, Strength=1500.0, Type=ib.AttractorType.Exponential)]
+    dt = 0.02
+    p0, v0 = np.array([5.0, 8.0, 2.0]), np.array([3.0, -2.0, 1.0])
+
+    def expected(max_accel, max_velocity):
+        acc = np.zeros(3)
+        for a in attractors:
+            to = np.array(a.Position, np.float64) - p0
+            dist = np.linalg.norm(to)
+            if a.Type == ib.AttractorType.Physical:
+                att = 1.0 / max(np.dot(to, to) - a.Radius, 0.001)
+            else:
+                att = 1.0 - min(max(dist / a.Radius, 0.0), 1.0)
+                if a.Type == ib.AttractorType.Exponential:
+                    att *= att
+                att = att * dt          # getDeltaTime() / VelocityConstantScale
+            acc += to / dist * att * a.Strength
+        cap = max_accel * dt
+        if np.linalg.norm(acc) > cap:
+            acc = acc / np.linalg.norm(acc) * cap
+        return np.minimum(max_velocity, v0 + acc), np.linalg.norm(acc)
+
+    for max_accel, max_velocity, clamped in ((1.0e6, 1000.0, False), (200.0, 1000.0, True), (1.0e6, 4.0, False)):
+        cfg = ib.ParticleSystemConfiguration(Friction=0.0, LifeDecayPerSecond=0.0, MaximumVelocity=max_velocity)
+        system = ib.ParticleSystem(engine, cfg, maxChunks=1)
+        system.Transforms = [ib.Gravity(MaximumAcceleration=max_accel, Attractors=attractors)]
+        P = np.zeros((256, 4), np.float32); V = np.zeros((256, 4), np.float32); A = np.ones((256, 4), np.float32)
+        P[0] = [*p0, 1]; V[0] = [*v0, 0]
+        P2, V2, *_ = oracle.particles_step(P, V, A, 16, system.system_uniforms(dt), [], system.plan_ops(0.0), engine.RandomnessTexture, None, 1)
+        want, acc_len = expected(max_accel, max_velocity)
+        assert (acc_len == pytest.approx(max_accel * dt)) == clamped
+        if max_velocity > 100.0:      # (the update tail rescales a velocity longer than MaximumVelocity: checked on the op's output otherwise)
+            assert np.allclose(V2[0, :3], want, rtol=3e-6), (max_accel, V2[0], want)
+            assert np.allclose(P2[0, :3], p0 + want * dt, rtol=3e-6)
+        else:
+            capped = want / np.linalg.norm(want) * min(np.linalg.norm(want), max_velocity)     # applyFrictionAndMaximum, UpdateCommon.fxh:20-35
+            assert np.any(want == max_velocity) and np.allclose(V2[0, :3], capped, rtol=3e-6), (V2[0], want, capped)
+
+
 def test_area_weight_quirk_scalar_rotation(oracle):
     """AreaRotation is a scalar broadcast into a quaternion (FMA.fx:11,17): rotation 0 collapses the local position to 0,
     so the weight is `Strength` everywhere (distance = -min size); a unit quaternion would be the identity."""
