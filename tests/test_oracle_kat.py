@@ -610,6 +610,42 @@ def test_gravity_mixed_attractors_and_the_acceleration_clamp(oracle):
             assert np.any(want == max_velocity) and np.allclose(V2[0, :3], capped, rtol=3e-6), (V2[0], want, capped)
 
 
+def test_spawner_linear_formulas_closed_form(oracle):
+    """PS_Spawn (SpawnParticles.fx:10-30) -> Spawn_Stage1 / Spawn_Stage2 / evaluateFormula (SpawnerCommon.fxh:62-70, 119-188) by
+    hand over a CONSTANT randomness table (random1 = random2 = random3 = the texel): every spawned particle gets position =
+    constant + (r + offset) * scale with the life formula in .w, velocity likewise with the category in .w, attributes =
+    ColorConstant + (r + ColorOffset) * ColorRandomScale; the update pass of the same tick then advances it by velocity * dt.
+    Exactly rate * dt particles appear, in index order from the start of the chunk; the rest of the chunk stays dead."""
+    engine = ib.ParticleEngine(None, ib.ParticleEngineConfiguration(ChunkSize=16))
+    cfg = ib.ParticleSystemConfiguration(Friction=0.0, LifeDecayPerSecond=0.0, MaximumVelocity=10000.0)
+    system = ib.ParticleSystem(engine, cfg, maxChunks=1)
+    spawner = ib.Spawner(MinRate=500.0, MaxRate=500.0,
+                         Position=ib.Formula(Constant=(10.0, 20.0, 5.0), RandomScale=(4.0, 2.0, 1.0), Offset=(-0.5, -0.5, 0.0), Type=ib.FormulaType.Linear),
+                         Velocity=ib.Formula(Constant=(1.0, 2.0, 3.0), RandomScale=(10.0, 20.0, 40.0), Offset=(0.0, -1.0, 0.25), Type=ib.FormulaType.Linear),
+                         Life=(2.0, 1.0, -0.5), Category=(0.0, 0.0, 0.0), ColorConstant=(0.5, 0.5, 0.5, 1.0), ColorRandomScale=(0.1, 0.2, 0.4, 0.0))
+    system.Transforms = [spawner]
+    texel = np.array([0.75, 0.25, 0.625, 0.125], np.float32)
+    table = np.broadcast_to(texel, engine.RandomnessTexture.shape).copy()
+    dt = 0.02
+    spawns, ops, u = system.plan_spawns(dt, dt), system.plan_ops(dt), system.system_uniforms(dt)
+    assert system.LiveChunkCount == 1
+    P = np.zeros((256, 4), np.float32); V = np.zeros((256, 4), np.float32); A = np.zeros((256, 4), np.float32)
+    P2, V2, A2, *_ = oracle.particles_step(P, V, A, 16, u, spawns, ops, table, None, 1)
+    r = texel.astype(np.float64)
+    pos = np.array([10.0, 20.0, 5.0]) + (r[:3] + np.array([-0.5, -0.5, 0.0])) * np.array([4.0, 2.0, 1.0])
+    vel = np.array([1.0, 2.0, 3.0]) + (r[:3] + np.array([0.0, -1.0, 0.25])) * np.array([10.0, 20.0, 40.0])
+    life = 2.0 + (r[3] - 0.5) * 1.0
+    col = np.array([0.5, 0.5, 0.5, 1.0]) + r * np.array([0.1, 0.2, 0.4, 0.0])
+    n = int(round(500.0 * dt))
+    live = P2[:, 3] > 0
+    assert live.sum() == n and live[:n].all()
+    for i in range(n):
+        assert np.allclose(V2[i], [*vel, 0.0], rtol=3e-6), (i, V2[i])
+        assert np.allclose(P2[i], [*(pos + vel * dt), life], rtol=3e-6), (i, P2[i])
+        assert np.allclose(A2[i], col, rtol=3e-6)
+    assert not P2[n:].any() and not V2[n:].any()
+
+
 def test_area_weight_quirk_scalar_rotation(oracle):
     """AreaRotation is a scalar broadcast into a quaternion (FMA.fx:11,17): rotation 0 collapses the local position to 0,
     so the weight is `Strength` everywhere (distance = -min size); a unit quaternion would be the identity."""
