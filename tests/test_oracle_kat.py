@@ -369,6 +369,39 @@ def test_ambient_occlusion_closed_form(oracle):
     assert factors[0] == 1.0 and factors[-1] < 0.6          # out of reach, and deep in the corner
 
 
+def test_sphere_light_specular_closed_form(oracle):
+    """SphereLightPixelShader (SphereLight.fx:7-46) + CalcSphereLightSpecularity (LightCommon.fxh:212-222) by hand, without a
+    G-buffer: the camera sits straight above the pixel at MaximumZ + 0.01, h = normalize(normalize(camera - p) - (p - light)) --
+    the light direction is NOT normalised in the reference -- and the light adds specular.rgb * pow(saturate(dot(h, n)), power)
+    * opacity on top of color.rgb * color.a * opacity."""
+    s = scenes.lighting_scene(0, 48, 32, 0, float4_lightmap=True)
+    s.configuration.EnableGBuffer = False
+    light = ib.SphereLightSource(Position=(20.0, 12.0, 30.0), Radius=6.0, RampLength=60.0, Color=(1.0, 0.5, 0.25, 0.8), CastsShadows=False,
+                                 SpecularColor=(0.3, 0.6, 0.9), SpecularPower=6.0)
+    s.environment.Lights = [light]
+    df = scenes.make_distance_field(None, s)
+    tex = np.zeros((df.TextureHeight, df.TextureWidth, 4), np.uint16)
+    df.ValidSliceCount, df.handle = df.SliceCount, 1
+    r = ib.LightingRenderer(None, s.environment, s.configuration)
+    r.DistanceField = df
+    frame = r.build_frame()
+    batches, nb, verts, nv = r.build_batches()
+    lm = oracle.render_lighting(tex, None, frame, batches, nb, verts, nv)
+    seen = []
+    for (x, y) in [(20, 12), (28, 18), (8, 5), (40, 28)]:
+        p = np.array([x + 0.5, y + 0.5, 0.0])
+        cam = np.array([x + 0.5, y + 0.5, s.environment.MaximumZ + 0.01])
+        to_cam = (cam - p) / np.linalg.norm(cam - p)
+        h = to_cam - (p - np.array(light.Position, np.float64))
+        h /= np.linalg.norm(h)
+        spec = min(max(h[2], 0.0), 1.0) ** 6.0
+        op = oracle.sphere_light_opacity(frame, tuple(p), (0, 0, 1), light.Position, (6.0, 60.0, 0, 0))
+        want = np.array(s.environment.Ambient[:3], np.float64) + (np.array([1.0, 0.5, 0.25]) * 0.8 + np.array([0.3, 0.6, 0.9]) * spec) * op
+        assert np.allclose(lm[y, x, :3], want, rtol=0, atol=2e-4), (x, y, lm[y, x], want, spec)
+        seen.append(spec)
+    assert seen[0] > 0.99 and 0.0 < min(seen) < 0.9        # under the light the half vector is the normal; it falls off sideways
+
+
 def test_unobstructed_directional_light_is_ambient_plus_normal_factor(oracle):
     """No obstructions, no G-buffer (normal +z): every pixel = ambient + color.rgb * color.a * pow(saturate((dot(-dir, n) + 0.35) /
     0.35), 0.85) (computeDirectionalLightOpacity / computeNormalFactorEx, LightCommon.fxh:154-165, :224-231), evaluated in
