@@ -402,6 +402,36 @@ def test_sphere_light_specular_closed_form(oracle):
     assert seen[0] > 0.99 and 0.0 < min(seen) < 0.9        # under the light the half vector is the normal; it falls off sideways
 
 
+def test_light_probes_closed_form(oracle):
+    """SphereLightProbePixelShader (SphereLightProbe.fx:19-44) by hand in a cleared field: a probe is cleared to 0 (no ambient),
+    then every light adds color.rgb * color.a * probe opacity * computeSphereLightOpacity at the probe's position and normal
+    (ambient occlusion switched off for probes); two lights add up, alpha counts them."""
+    s = scenes.lighting_scene(0, 64, 48, 0, float4_lightmap=True)
+    lights = [ib.SphereLightSource(Position=(20.0, 12.0, 30.0), Radius=6.0, RampLength=80.0, Color=(1.0, 0.5, 0.25, 0.8), CastsShadows=True,
+                                   AmbientOcclusionRadius=12.0),
+              ib.SphereLightSource(Position=(50.0, 40.0, 10.0), Radius=4.0, RampLength=70.0, Color=(0.2, 0.9, 0.4, 0.5), CastsShadows=False)]
+    s.environment.Lights = lights
+    df = scenes.make_distance_field(None, s)
+    tex = np.zeros((df.TextureHeight, df.TextureWidth, 4), np.uint16)
+    df.ValidSliceCount, df.handle = df.SliceCount, 1
+    r = ib.LightingRenderer(None, s.environment, s.configuration)
+    r.DistanceField = df
+    frame = r.build_frame()
+    batches, nb, verts, nv = r.build_batches()
+    positions = np.array([[22.0, 14.0, 5.0, 1.0], [40.0, 30.0, 0.0, 1.0], [60.0, 5.0, 20.0, 1.0]], np.float32)     # xyz, opacity
+    normals = np.array([[0.0, 0.0, 1.0, 1.0], [0.6, 0.0, 0.8, 1.0], [0.0, -1.0, 0.0, 0.0]], np.float32)             # xyz, enable shadows
+    out = oracle.update_light_probes(tex, frame, batches, nb, verts, nv, positions, normals)
+    for k in range(3):
+        want, touched = np.zeros(3), 0
+        for L in lights:
+            op = oracle.sphere_light_opacity(frame, tuple(positions[k, :3]), tuple(normals[k, :3]), L.Position, (L.Radius, L.RampLength, 0, 0))
+            want += np.array(L.Color[:3], np.float64) * L.Color[3] * op
+            touched += 1 if op > 0 else 0
+        assert np.allclose(out[k, :3], want, rtol=0, atol=3e-6), (k, out[k], want)
+        assert out[k, 3] == touched
+    assert out[0, :3].max() > 0.3
+
+
 def test_unobstructed_directional_light_is_ambient_plus_normal_factor(oracle):
     """No obstructions, no G-buffer (normal +z): every pixel = ambient + color.rgb * color.a * pow(saturate((dot(-dir, n) + 0.35) /
     0.35), 0.85) (computeDirectionalLightOpacity / computeNormalFactorEx, LightCommon.fxh:154-165, :224-231), evaluated in
