@@ -231,6 +231,7 @@ const char* ilb_last_error(const ilb_ctx* ctx) {
 int ilb_synchronize(ilb_ctx* ctx) {
     if (!ctx || !live_has(ctx)) return ILB_ERR_INVALID_ARGUMENT;
     ILB_CUDA(ctx, cudaSetDevice(ctx->device));
+    { const int rcd = ilb_frames_drain(ctx); if (rcd) return rcd; }   // frames in flight finish on the download stream
     ILB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ILB_OK;
 }

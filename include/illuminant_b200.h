@@ -58,6 +58,7 @@ ILB_API int ilb_create(int device_ordinal, ilb_ctx** out_ctx);
 ILB_API void ilb_destroy(ilb_ctx* ctx);
 /* Last error message of this context; ctx == NULL returns the last creation error. */
 ILB_API const char* ilb_last_error(const ilb_ctx* ctx);
+/* Returns when everything queued on the context has run, frames in flight (ilb_render_lighting_frame_async) included. */
 ILB_API int ilb_synchronize(ilb_ctx* ctx);
 /* The CUDA stream (cudaStream_t) all work of this context is enqueued on. */
 ILB_API void* ilb_stream(ilb_ctx* ctx);
